@@ -1,0 +1,316 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY (never imported by the product package).
+
+ctypes doors onto
+  * oracle/liboracle.so                 our C restatement (oracle/skat_oracle.c)
+  * oracle/_ref/libmixchisq_ref.so      the REFERENCE's own Davies/Liu code, compiled in place
+  * oracle/_ref/libgsl_ref.so           GSL 1.16 from the tarball the reference vendors
+plus the numpy/scipy restatement of SKAT-O (regression/SkatO.cpp) and of the synthetic-data
+stream of SURVEY.md section 8(d) (so that the oracle can regenerate on the host exactly the
+genotypes the device generator wrote).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dbl_p = C.POINTER(C.c_double)
+_int_p = C.POINTER(C.c_int)
+
+
+def _p(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class SkatOut(C.Structure):
+    _fields_ = [("Q", C.c_double), ("pvalue", C.c_double), ("p_davies", C.c_double),
+                ("p_liu", C.c_double), ("fault", C.c_int), ("n_lambda", C.c_int)]
+
+
+class GeneOut(C.Structure):
+    _fields_ = [("m_poly", C.c_int), ("status", C.c_int), ("skat", SkatOut),
+                ("cmc_nonref", C.c_int),
+                ("cmc_U", C.c_double), ("cmc_V", C.c_double), ("cmc_stat", C.c_double),
+                ("cmc_p", C.c_double), ("cmc_ok", C.c_int),
+                ("zeg_U", C.c_double), ("zeg_V", C.c_double), ("zeg_stat", C.c_double),
+                ("zeg_p", C.c_double), ("zeg_ok", C.c_int)]
+
+
+def build(native: bool = False) -> str:
+    """Compile the checker (make -C oracle).  `native` additionally builds liboracle_native.so
+    with -march=native on THIS machine (used by the CPU-baseline timing legs)."""
+    targets = ["all"] + (["liboracle_native.so"] if native else [])
+    subprocess.run(["make", "-s", "-C", _HERE] + targets, check=True)
+    return os.path.join(_HERE, "liboracle_native.so" if native else "liboracle.so")
+
+
+_lib_cache = {}
+
+
+def lib(native: bool = False):
+    key = "native" if native else "portable"
+    if key in _lib_cache:
+        return _lib_cache[key]
+    path = os.path.join(_HERE, "liboracle_native.so" if native else "liboracle.so")
+    if not os.path.exists(path):
+        build(native)
+    L = C.CDLL(path)
+    L.orc_qf.restype = C.c_double
+    L.orc_qf.argtypes = [_dbl_p, _dbl_p, _int_p, C.c_int, C.c_double, C.c_double, C.c_int,
+                         C.c_double, _dbl_p, _int_p]
+    L.orc_mixchisq_pvalue.restype = C.c_double
+    L.orc_mixchisq_pvalue.argtypes = [_dbl_p, C.c_int, C.c_double, _int_p]
+    L.orc_liu_pvalue.restype = C.c_double
+    L.orc_liu_pvalue.argtypes = [_dbl_p, C.c_int, C.c_double]
+    L.orc_gamma_q.restype = C.c_double
+    L.orc_gamma_q.argtypes = [C.c_double, C.c_double]
+    L.orc_chisq_q.restype = C.c_double
+    L.orc_chisq_q.argtypes = [C.c_double, C.c_double]
+    L.orc_beta_pdf.restype = C.c_double
+    L.orc_beta_pdf.argtypes = [C.c_double] * 3
+    L.orc_skat_weight.restype = C.c_double
+    L.orc_skat_weight.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
+    L.orc_sym_eigenvalues.restype = None
+    L.orc_sym_eigenvalues.argtypes = [C.c_int, _dbl_p, _dbl_p]
+    L.orc_fit_null_linear.restype = C.c_int
+    L.orc_fit_null_linear.argtypes = [C.c_int64, C.c_int, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p,
+                                      _dbl_p]
+    L.orc_flip_minor_polymorphic.restype = C.c_int
+    L.orc_flip_minor_polymorphic.argtypes = [C.c_int64, C.c_int, _dbl_p, _dbl_p, _int_p, _int_p]
+    for name in ("orc_skat_reduced64", "orc_skat_faithful32"):
+        f = getattr(L, name)
+        f.restype = C.c_int
+    L.orc_skat_reduced64.argtypes = [C.c_int64, C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, _dbl_p,
+                                     _dbl_p, C.POINTER(SkatOut), _dbl_p]
+    L.orc_skat_faithful32.argtypes = [C.c_int, C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, _dbl_p,
+                                      _dbl_p, C.POINTER(SkatOut), _dbl_p]
+    L.orc_cmc_collapse.restype = None
+    L.orc_cmc_collapse.argtypes = [C.c_int64, C.c_int, _dbl_p, _dbl_p]
+    L.orc_zeggini_collapse.restype = None
+    L.orc_zeggini_collapse.argtypes = [C.c_int64, C.c_int, _dbl_p, _dbl_p]
+    L.orc_nonref_sites.restype = C.c_int
+    L.orc_nonref_sites.argtypes = [C.c_int64, _dbl_p]
+    L.orc_score_test_1.restype = C.c_int
+    L.orc_score_test_1.argtypes = [C.c_int64, C.c_int, _dbl_p, _dbl_p, C.c_double, _dbl_p, _dbl_p,
+                                   _dbl_p, _dbl_p, _dbl_p]
+    L.orc_gene.restype = C.c_int
+    L.orc_gene.argtypes = [C.c_int64, C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, _dbl_p, C.c_double,
+                           C.c_double, C.c_double, C.POINTER(GeneOut), _dbl_p]
+    L.orc_gene_batch.restype = C.c_int
+    L.orc_gene_batch.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p,
+                                 _dbl_p, C.c_double, C.c_double, C.c_double, C.POINTER(GeneOut),
+                                 C.c_int]
+    L.orc_max_threads.restype = C.c_int
+    _lib_cache[key] = L
+    return L
+
+
+def ref_mix():
+    """The reference's own MixtureChiSquare (None when oracle/_ref was never built)."""
+    if "mix" not in _lib_cache:
+        path = os.path.join(_HERE, "_ref", "libmixchisq_ref.so")
+        if not os.path.exists(path):
+            _lib_cache["mix"] = None
+        else:
+            L = C.CDLL(path)
+            L.ref_mixchisq_pvalue.restype = C.c_double
+            L.ref_mixchisq_pvalue.argtypes = [_dbl_p, C.c_int, C.c_double]
+            L.ref_liu_pvalue.restype = C.c_double
+            L.ref_liu_pvalue.argtypes = [_dbl_p, C.c_int, C.c_double]
+            L.ref_qf.restype = C.c_double
+            L.ref_qf.argtypes = [_dbl_p, _dbl_p, _int_p, C.c_int, C.c_double, C.c_double, C.c_int,
+                                 C.c_double, _dbl_p, _int_p]
+            _lib_cache["mix"] = L
+    return _lib_cache["mix"]
+
+
+_QAGS_CB = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
+
+
+def ref_gsl():
+    """GSL 1.16 as vendored by the reference (None when oracle/_ref was never built)."""
+    if "gsl" not in _lib_cache:
+        path = os.path.join(_HERE, "_ref", "libgsl_ref.so")
+        if not os.path.exists(path):
+            _lib_cache["gsl"] = None
+        else:
+            L = C.CDLL(path)
+            for n, na in (("ref_gsl_ran_beta_pdf", 3), ("ref_gsl_cdf_chisq_Q", 2),
+                          ("ref_gsl_cdf_chisq_P", 2), ("ref_gsl_cdf_chisq_Qinv", 2),
+                          ("ref_gsl_ran_chisq_pdf", 2)):
+                f = getattr(L, n)
+                f.restype = C.c_double
+                f.argtypes = [C.c_double] * na
+            L.ref_gsl_qags.restype = C.c_int
+            L.ref_gsl_qags.argtypes = [_QAGS_CB, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                       C.c_double, C.c_int, _dbl_p, _dbl_p, _int_p]
+            _lib_cache["gsl"] = L
+    return _lib_cache["gsl"]
+
+
+# ------------------------------------------------------------------------------------------------
+# thin numpy-level helpers
+# ------------------------------------------------------------------------------------------------
+def qf(lam, Q, lim=10000, acc=1e-6, which="oracle"):
+    """Davies qf() -> (value, ifault, trace[7]).  which = 'oracle' | 'reference'."""
+    lam = np.ascontiguousarray(lam, dtype=np.float64)
+    n = len(lam)
+    nc = np.zeros(n)
+    df = np.ones(n, dtype=np.int32)
+    trace = np.zeros(7)
+    fault = C.c_int(0)
+    if which == "oracle":
+        v = lib().orc_qf(_p(lam), _p(nc), _p(df, C.c_int), n, 0.0, float(Q), int(lim), float(acc),
+                         _p(trace), C.byref(fault))
+    else:
+        v = ref_mix().ref_qf(_p(lam), _p(nc), _p(df, C.c_int), n, 0.0, float(Q), int(lim),
+                             float(acc), _p(trace), C.byref(fault))
+    return v, fault.value, trace
+
+
+def mix_pvalue(lam, Q, which="oracle"):
+    lam = np.ascontiguousarray(lam, dtype=np.float64)
+    if which == "oracle":
+        fault = C.c_int(0)
+        p = lib().orc_mixchisq_pvalue(_p(lam), len(lam), float(Q), C.byref(fault))
+        return p, fault.value
+    return ref_mix().ref_mixchisq_pvalue(_p(lam), len(lam), float(Q)), None
+
+
+def liu_pvalue(lam, Q, which="oracle"):
+    lam = np.ascontiguousarray(lam, dtype=np.float64)
+    if which == "oracle":
+        return lib().orc_liu_pvalue(_p(lam), len(lam), float(Q))
+    return ref_mix().ref_liu_pvalue(_p(lam), len(lam), float(Q))
+
+
+def skat_final_pvalue(lam, Q, which="oracle"):
+    """Skat.cpp:100-103: Davies, then Liu when p<=0 or p==1."""
+    p, fault = mix_pvalue(lam, Q, which)
+    if p <= 0.0 or p == 1.0:
+        p = liu_pvalue(lam, Q, which)
+    return p, fault
+
+
+def sym_eigenvalues(a):
+    a = np.array(a, dtype=np.float64, order="C")
+    n = a.shape[0]
+    ev = np.zeros(n)
+    lib().orc_sym_eigenvalues(n, _p(a), _p(ev))
+    return ev
+
+
+def fit_null_linear(X, y):
+    """X: (N, C) any layout; returns dict(resid, sigma2, xtx_inv, beta)."""
+    Xc = np.asfortranarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    N, Cc = Xc.shape
+    resid = np.zeros(N)
+    s2 = C.c_double(0)
+    xi = np.zeros((Cc, Cc))
+    beta = np.zeros(Cc)
+    rc = lib().orc_fit_null_linear(N, Cc, _p(Xc), _p(y), _p(resid), C.byref(s2), _p(xi), _p(beta))
+    if rc:
+        raise RuntimeError("null model: X'X not positive definite")
+    return dict(resid=resid, sigma2=s2.value, xtx_inv=xi, beta=beta)
+
+
+def gene(G_raw, af, X, resid, sigma2, beta1=1.0, beta2=25.0, native=False):
+    """Whole-gene oracle.  G_raw (N, M) doubles (unflipped, imputed), af per ORIGINAL column."""
+    Gc = np.asfortranarray(G_raw, dtype=np.float64)
+    Xc = np.asfortranarray(X, dtype=np.float64)
+    N, M = Gc.shape
+    out = GeneOut()
+    lam = np.zeros(max(M, 1))
+    af = np.ascontiguousarray(af, dtype=np.float64)
+    resid = np.ascontiguousarray(resid, dtype=np.float64)
+    lib(native).orc_gene(N, M, Xc.shape[1], _p(Gc), _p(af), _p(Xc), _p(resid), float(sigma2),
+                         float(beta1), float(beta2), C.byref(out), _p(lam))
+    return out, lam[: out.skat.n_lambda].copy()
+
+
+def gene_batch(G_all, af_all, X, resid, sigma2, threads=1, beta1=1.0, beta2=25.0, native=False):
+    """G_all: (n_genes, M, N) C-contiguous == each gene N x M column-major."""
+    G_all = np.ascontiguousarray(G_all, dtype=np.float64)
+    ng, M, N = G_all.shape
+    Xc = np.asfortranarray(X, dtype=np.float64)
+    out = (GeneOut * ng)()
+    af_all = np.ascontiguousarray(af_all, dtype=np.float64)
+    resid = np.ascontiguousarray(resid, dtype=np.float64)
+    lib(native).orc_gene_batch(N, M, Xc.shape[1], ng, _p(G_all), _p(af_all), _p(Xc), _p(resid),
+                               float(sigma2), float(beta1), float(beta2), out, int(threads))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Synthetic data stream -- the HOST twin of rvtests_b200/csrc/synth.cuh.
+# Counter-based: genotype(variant v, sample i) depends only on (seed, v, i), so any subset can be
+# regenerated anywhere.  mix64 is the splitmix64 finaliser.
+# ------------------------------------------------------------------------------------------------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix64(z):
+    z = np.asarray(z, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def synth_variant_key(seed, vid):
+    with np.errstate(over="ignore"):
+        return _mix64(np.uint64(seed) + np.asarray(vid, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+
+
+def synth_maf(seed, vid, lo=1e-4, hi=0.05):
+    """MAF_j ~ log-uniform[lo, hi] from the variant key (fp64 on the host; the device only ever
+    sees the integer thresholds derived from it)."""
+    k = _mix64(synth_variant_key(seed, vid) ^ np.uint64(0xA5A5A5A5A5A5A5A5))
+    u = (k >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return lo * (hi / lo) ** u
+
+
+def synth_thresholds(maf):
+    """uint32 thresholds t0,t1: g = (h>=t0) + (h>=t1) with h the 32-bit hash, HWE proportions."""
+    maf = np.asarray(maf, dtype=np.float64)
+    q0 = (1.0 - maf) ** 2
+    q01 = q0 + 2.0 * maf * (1.0 - maf)
+    t0 = np.minimum(np.floor(q0 * 4294967296.0), 4294967295.0).astype(np.uint64).astype(np.uint32)
+    t1 = np.minimum(np.floor(q01 * 4294967296.0), 4294967295.0).astype(np.uint64).astype(np.uint32)
+    return t0, t1
+
+
+def synth_genotypes(seed, vid, N, maf=None):
+    """(len(vid), N) int8 genotypes in {0,1,2}."""
+    vid = np.atleast_1d(np.asarray(vid, dtype=np.uint64))
+    if maf is None:
+        maf = synth_maf(seed, vid)
+    t0, t1 = synth_thresholds(maf)
+    key = synth_variant_key(seed, vid)[:, None]
+    i = np.arange(N, dtype=np.uint64)[None, :]
+    with np.errstate(over="ignore"):
+        h = (_mix64(key + i * np.uint64(0xD1B54A32D192ED03)) >> np.uint64(32)).astype(np.uint32)
+    return ((h >= t0[:, None]).astype(np.int8) + (h >= t1[:, None]).astype(np.int8))
+
+
+def synth_covariates(seed, N, C=3):
+    """Intercept + (C-1) N(0,1) covariates and the null quantitative trait
+    y = 0.5 x1 - 0.3 x2 + N(0,1)   (SURVEY.md 8(d))."""
+    rng = np.random.Generator(np.random.Philox(key=int(seed)))
+    X = np.ones((N, C))
+    if C > 1:
+        X[:, 1:] = rng.standard_normal((N, C - 1))
+    y = rng.standard_normal(N)
+    if C > 1:
+        y = y + 0.5 * X[:, 1]
+    if C > 2:
+        y = y - 0.3 * X[:, 2]
+    return X, y
