@@ -1,0 +1,138 @@
+/*
+ * rvtests_b200.h -- C ABI of the B200-native rvtests gene engine (librvtests_b200.so).
+ *
+ * The reference (zhanxw/rvtests @ 8defd6f) has no FFI on this path: its plugin surface is the C++
+ * abstract class ModelFitter (src/ModelFitter.h:17-75) whose fit(DataConsolidator*) pulls
+ * Matrix/Vector views (base/MathMatrix.h:33-111) and calls the pimpl statistics classes
+ *   Skat::Fit                      regression/Skat.h:26-38      / Skat.cpp:29-105
+ *   SkatO::Fit                     regression/SkatO.h:28-39     / SkatO.cpp:101-281
+ *   LinearRegression::FitLinearModel            regression/LinearRegression.cpp:20-69
+ *   LinearRegressionScoreTest::TestCovariate    regression/LinearRegressionScoreTest.cpp:173-263
+ *   cmcCollapse / zegginiCollapse               src/Model.cpp:73-89, 115-130
+ *   getFlippedToMinorPolymorphicGenotype        src/DataConsolidator.h:128-132, .cpp:46-142
+ * The entry points below are what a C++ adapter with the ModelFitter signature binds instead of
+ * those classes (rvtests_b200/host/*.h are such adapters; INTEGRATION.md shows the registration a
+ * maintainer adds to src/ModelManager.cpp).  Plain pointers and sizes only; no C++ / torch types.
+ *
+ * Threading: one host thread per context (the reference's model loop is single-threaded,
+ * src/Main.cpp:1249-1253).  All functions return RVT_OK (0) or a negative RVT_E_* code;
+ * rvt_last_error() gives the message.  There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails with RVT_E_CUDA.
+ */
+#ifndef RVTESTS_B200_H_
+#define RVTESTS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVT_OK 0
+#define RVT_E_BADARG (-1)
+#define RVT_E_CUDA (-2)
+#define RVT_E_STATE (-3)
+#define RVT_E_UNSUPPORTED (-4)
+#define RVT_E_NUMERIC (-5)
+
+/* per-gene status (rvt_gene_result.status) */
+#define RVT_GENE_OK 0
+#define RVT_GENE_NA 2           /* no polymorphic variant: fit() == -1, output "NA" (src/Model.h:2637-2640) */
+#define RVT_GENE_BADFLAGS 4     /* caller-supplied flip/skip flags contradict the data */
+#define RVT_GENE_BADVALUE 5     /* a genotype outside {0,1,2} reached the hard-call path */
+
+/* engine selection for rvt_set_option("engine") */
+#define RVT_ENGINE_AUTO 0
+#define RVT_ENGINE_SIMT 1       /* dp4a CUDA-core sweep */
+#define RVT_ENGINE_TC 2         /* tcgen05 (kind::i8) tensor-core sweep, TMA-fed */
+
+typedef struct rvt_ctx rvt_ctx;
+
+/* One record per gene, in push order.  Field <- reference source of the value:
+ *   Q, p_skat            SkatTest::writeOutput "%g\t%g" (src/Model.h:2743): Skat::GetQ, pValue
+ *   p_davies/fault/p_liu MixtureChiSquare::getPvalue / getLiuPvalue (regression/MixtureChiSquare.cpp)
+ *   cmc_nonref, cmc_p    CMCTest::writeOutput NonRefSite, Pvalue (src/Model.h:865-900)
+ *   zeg_p                ZegginiTest::writeOutput Pvalue (src/Model.h:1223-1234)
+ *   *_U, *_V, *_stat     LinearRegressionScoreTest U, V, stat (LinearRegressionScoreTest.cpp:213-258)
+ *   skato_*              SkatOTest::writeOutput Q, rho, Pvalue (src/Model.h:2866-2875)
+ */
+typedef struct rvt_gene_result {
+  double Q;
+  double p_skat;
+  double p_davies;
+  double p_liu;
+  int32_t davies_fault;
+  int32_t n_lambda;
+  int32_t m_poly;
+  int32_t status;
+  int32_t cmc_nonref;
+  int32_t cmc_ok;
+  double cmc_U, cmc_V, cmc_stat, cmc_p;
+  int32_t zeg_ok;
+  int32_t skato_ok;
+  double zeg_U, zeg_V, zeg_stat, zeg_p;
+  double skato_Q, skato_rho, skato_p;
+  double lambda_max;   /* largest kept eigenvalue (diagnostic) */
+} rvt_gene_result;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int rvt_ctx_create(int device, rvt_ctx** out);
+void rvt_ctx_destroy(rvt_ctx* ctx);
+const char* rvt_last_error(const rvt_ctx* ctx);
+/* keys: "beta1","beta2" (Beta weight, src/ModelManager.cpp:169-175), "engine", "splits" (0=auto),
+ * "skato" (0/1), "stream_ptr" (cudaStream_t as integer; default stream 0 of the context) */
+int rvt_set_option(rvt_ctx* ctx, const char* key, double value);
+double rvt_get_info(const rvt_ctx* ctx, const char* key);
+
+/* ---- null model: replaces LinearRegression::FitLinearModel(cov, phenoVec) -------------------
+ * X: N x C column-major doubles INCLUDING the intercept as column 0 (the matrix produced by
+ * copyCovariateAndIntercept, src/ModelUtil.h:102-130); y: N.  Host pointers.  binary != 0
+ * (logistic null) is RVT_E_UNSUPPORTED in this build. */
+int rvt_set_null_model(rvt_ctx* ctx, int64_t N, int C, const double* X, const double* y, int binary);
+/* same, X and y already in device memory */
+int rvt_set_null_model_dev(rvt_ctx* ctx, int64_t N, int C, const double* dX, const double* dy);
+/* resid (N doubles, host, may be NULL), sigma2, xtx_inv (C*C row-major, may be NULL) */
+int rvt_get_null_model(rvt_ctx* ctx, double* resid, double* sigma2, double* xtx_inv);
+
+/* ---- genes ---------------------------------------------------------------------------------
+ * rvt_gene_push_f64: the reference boundary -- G is dc->getGenotype(): N x M column-major doubles
+ *   on the host, imputed, NOT yet flipped (the engine performs convertToMinorAlleleCount +
+ *   removeMonomorphicMarker itself).  af: M allele frequencies in the caller's column order
+ *   (GenotypeCounter::getAF) or NULL (then AF = column mean / 2 of the kept columns).
+ * rvt_gene_push_i8: same, hard calls as int8 [M][ld] variant-major on the host.
+ * rvt_gene_push_dev_i8: block already in device memory (zero-copy; must stay valid until flush).
+ *   flags: NULL (engine counts the rows itself) or M bytes 0 normal / 1 flip-to-minor / 2 skip.
+ * Each push appends one gene; results come back from rvt_flush in push order. */
+int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af);
+int rvt_gene_push_i8(rvt_ctx* ctx, const int8_t* G, int M, int64_t ld, const double* af);
+int rvt_gene_push_dev_i8(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const double* af,
+                         const uint8_t* flags);
+/* number of genes pushed and not yet flushed */
+int rvt_pending(const rvt_ctx* ctx);
+/* run the sweep + per-gene statistics for every pending gene; out: host array of `cap` records */
+int rvt_flush(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out);
+/* as rvt_flush but leaves the records in device memory (d_out: device pointer, cap records);
+ * asynchronous on the context stream -- used by the multi-GPU gather */
+int rvt_flush_dev(rvt_ctx* ctx, rvt_gene_result* d_out, int cap, int* n_out);
+
+/* ---- device-resident synthetic cohort (SURVEY.md 8(d) stream; bench + tests) -----------------
+ * Generates n_genes x M variants x N samples of HWE genotypes directly in HBM (packed int8),
+ * variant ids first_vid .. first_vid + n_genes*M - 1, with per-variant uint32 thresholds t0,t1 and
+ * 64-bit keys supplied by the host (oracle/oracle.py synth_* reproduces the same stream).
+ * The genes stay loaded: rvt_run_loaded() pushes all of them (zero-copy) and flushes. */
+int rvt_synth_load(rvt_ctx* ctx, int n_genes, int M, const uint64_t* keys, const uint32_t* t0,
+                   const uint32_t* t1);
+int rvt_loaded_genes(const rvt_ctx* ctx);
+int rvt_run_loaded(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, int results_on_device);
+/* copy rows [row0,row0+rows) x samples [0,N) of the loaded arena back to the host (tests) */
+int rvt_loaded_read(rvt_ctx* ctx, int64_t row0, int rows, int8_t* out /*rows x N*/);
+
+/* ---- measurement hooks ----------------------------------------------------------------------- */
+/* device milliseconds of the last flush: [0] sweep kernel(s), [1] finalize kernel(s), [2] whole
+ * flush on the context stream (CUDA events), [3] number of kernel launches */
+int rvt_last_timing(const rvt_ctx* ctx, double out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVTESTS_B200_H_ */

@@ -1,0 +1,209 @@
+// finalize.cuh -- K2/K3: everything after the genotype sweep, one CTA per gene, O(M^3), fp64.
+//
+// From the exact integer sums of the sweep it rebuilds, per gene,
+//   flip-to-minor + monomorphic removal   src/DataConsolidator.cpp:46-69, 94-142 (done
+//                                         algebraically: g' = 2-g is an affine map of the sums)
+//   Beta weights                          src/Model.h:2644-2661 (with the caller-order AF lookup
+//                                         of src/DataConsolidator.cpp:527-529 when af is given)
+//   Q = sum_j w_j (g_j'r)^2               regression/Skat.cpp:47-52
+//   K = W^1/2 (G'VG - G'VX (X'VX)^-1 X'VG) W^1/2,  V = sigma2 I     Skat.cpp:55-76
+//   eigenvalues, top-down > 1e-30         Skat.cpp:84-98
+//   Davies -> (p<=0 or p==1) -> Liu       Skat.cpp:100-103, regression/MixtureChiSquare.cpp
+//   CMC / Zeggini score tests             regression/LinearRegressionScoreTest.cpp:209-261,
+//                                         NonRefSite src/Model.h:894-900
+#pragma once
+#include "../../include/rvtests_b200.h"
+#include "common.cuh"
+#include "eigen.cuh"
+
+namespace rvt {
+
+constexpr int kFinThreads = 128;
+constexpr int kKld = kTileRows + 1;  // padded leading dimension of K in shared memory
+// dynamic shared memory: reduced tile (int64) + K (fp64)
+constexpr int kFinSmem = kTileRows * kMaxNC * 8 + kTileRows * kKld * 8;
+
+__device__ __forceinline__ long long recombine4(const long long* d) {
+  return d[0] + (d[1] << 8) + (d[2] << 16) + (d[3] << 24);
+}
+
+__global__ void __launch_bounds__(kFinThreads)
+k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __restrict__ rowflags,
+           const double* __restrict__ af, const RowCounts* __restrict__ counts,
+           const NullModel* __restrict__ nm, EngineParams prm, int S,
+           const SweepPartial* __restrict__ parts, rvt_gene_result* __restrict__ res) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  long long* D = reinterpret_cast<long long*>(dyn);                       // [64][NC]
+  double* K = reinterpret_cast<double*>(dyn + kTileRows * kMaxNC * 8);    // [64][kKld]
+  __shared__ double s_red[64];
+  __shared__ double s_cs[kTileRows + 2];
+  __shared__ double s_ev[kTileRows], s_lam[kTileRows];
+  __shared__ int s_th[kTileRows];
+  __shared__ long long s_coll[kCollapseN];
+  __shared__ long long s_craw[kTileRows];
+  __shared__ int s_idx[kTileRows], s_flip[kTileRows];
+  __shared__ double s_s[kTileRows], s_sw[kTileRows], s_B[kTileRows][kMaxC];
+  __shared__ int s_Mp, s_bad;
+  __shared__ double s_Q;
+
+  const int g = blockIdx.x;
+  if (g >= n_genes) return;
+  const int tid = threadIdx.x;
+  const GeneDesc gd = genes[g];
+  const int M = gd.M;
+  const int64_t N = nm->N;
+  const int C = nm->C, ER = nm->ER, NC = kTileRows + ER;
+  const double sigma2 = nm->sigma2;
+  BlockPar par{s_red};
+
+  // 1. reduce the splits (int64)
+  for (int idx = tid; idx < M * NC; idx += kFinThreads) {
+    const int i = idx / NC, j = idx - i * NC;
+    long long s = 0;
+    for (int sp = 0; sp < S; ++sp) s += parts[(size_t)g * S + sp].d[i][j];
+    D[i * NC + j] = s;
+  }
+  if (tid < 2 * (ER + 1)) {
+    long long s = 0;
+    for (int sp = 0; sp < S; ++sp) s += parts[(size_t)g * S + sp].coll[tid];
+    s_coll[tid] = s;
+  }
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+
+  // 2. per-variant counts -> flip / monomorphic, cross-checked with the flags the sweep used
+  if (tid < M) {
+    // intercept = vector 1 (X column 0): fixed-point image of 1.0 is 2^e exactly
+    long long cint = recombine4(&D[tid * NC + kTileRows + 4]);
+    double cd = (double)cint * nm->scale[1];
+    long long c = llrint(cd);
+    long long ajj = D[tid * NC + tid];
+    long long n2 = (ajj - c) / 2, n1 = c - 2 * n2, n0 = N - n1 - n2;
+    int flip = c > N;
+    int mono = (n0 == N) || (n1 == N) || (n2 == N);
+    uint8_t expect = mono ? kRowSkip : (flip ? kRowFlipped : kRowNormal);
+    if (rowflags[gd.var0 + tid] != expect) atomicExch(&s_bad, 1);
+    if ((ajj - c) & 1 || n0 < 0 || n1 < 0 || n2 < 0) atomicExch(&s_bad, 2);
+    if (gd.counted && counts[gd.var0 + tid].bad > 0) atomicExch(&s_bad, 2);
+    s_craw[tid] = c;
+    s_flip[tid] = mono ? -1 : flip;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int mp = 0;
+    for (int j = 0; j < M; ++j)
+      if (s_flip[j] >= 0) s_idx[mp++] = j;
+    s_Mp = mp;
+  }
+  __syncthreads();
+  const int Mp = s_Mp;
+
+  // 3. real-valued score vector, covariate cross-products, weights (kept variants, minor-coded)
+  if (tid < Mp) {
+    const int j = s_idx[tid];
+    const int fl = s_flip[j];
+    long long sint = recombine4(&D[j * NC + kTileRows]);
+    if (fl) sint = 2 * nm->vsum[0] - sint;
+    s_s[tid] = (double)sint * nm->scale[0];
+    for (int l = 0; l < C; ++l) {
+      long long b = recombine4(&D[j * NC + kTileRows + 4 * (l + 1)]);
+      if (fl) b = 2 * nm->vsum[l + 1] - b;
+      s_B[tid][l] = (double)b * nm->scale[l + 1];
+    }
+    double freq = gd.has_af ? af[gd.var0 + tid] : (double)s_craw[j] / (2.0 * (double)N);
+    double w = beta_weight(freq, prm.beta1, prm.beta2, true);
+    s_sw[tid] = sqrt(w);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double q = 0.0;
+    for (int i = 0; i < Mp; ++i) q += (s_sw[i] * s_sw[i]) * s_s[i] * s_s[i];
+    s_Q = q;
+  }
+  // 4. K = W^1/2 sigma2 (A' - B' (X'X)^-1 B'^T) W^1/2   (upper triangle, mirrored)
+  for (int idx = tid; idx < Mp * Mp; idx += kFinThreads) {
+    const int i = idx / Mp, k = idx - i * Mp;
+    if (k < i) continue;
+    const int ji = s_idx[i], jk = s_idx[k];
+    const int fi = s_flip[ji], fk = s_flip[jk];
+    long long a = D[ji * NC + jk];
+    const long long ci = s_craw[ji], ck = s_craw[jk];
+    if (fi && fk)
+      a = 4 * N - 2 * ci - 2 * ck + a;
+    else if (fi)
+      a = 2 * ck - a;
+    else if (fk)
+      a = 2 * ci - a;
+    double t = 0.0;
+    for (int l = 0; l < C; ++l) {
+      double u = 0.0;
+      for (int m = 0; m < C; ++m) u += nm->xtx_inv[l * C + m] * s_B[k][m];
+      t += s_B[i][l] * u;
+    }
+    double v = s_sw[i] * s_sw[k] * sigma2 * ((double)a - t);
+    K[i * kKld + k] = v;
+    K[k * kKld + i] = v;
+  }
+  __syncthreads();
+
+  // 5. eigenvalues, descending, keep > 1e-30 from the top (Skat.cpp:84-98)
+  double p_dav = -1.0, p_liu = 1.0, p_fin = 1.0, lam_max = 0.0;
+  int fault = 0, r = 0;
+  if (Mp > 0) {
+    jacobi_eigenvalues(K, Mp, kKld, s_cs, par);
+    __syncthreads();
+    if (tid < Mp) s_ev[tid] = K[tid * kKld + tid];
+    __syncthreads();
+    sort_descending(s_ev, Mp, s_lam, par);
+    const int r_ub = (N < (int64_t)Mp) ? (int)N : Mp;
+    while (r < r_ub && s_lam[r] > 1e-30) ++r;
+    lam_max = r ? s_lam[0] : 0.0;
+    // 6. p-value
+    const double Q = s_Q;
+    p_dav = mixchisq_pvalue(s_lam, r, Q, s_th, &fault, par);
+    p_liu = liu_pvalue(s_lam, r, Q);
+    p_fin = p_dav;
+    if (p_fin <= 0.0 || p_fin == 1.0) p_fin = p_liu;
+  }
+
+  // 7. burden score tests (m = 1)
+  if (tid == 0) {
+    rvt_gene_result o;
+    memset(&o, 0, sizeof(o));
+    o.m_poly = Mp;
+    o.status = (Mp == 0) ? RVT_GENE_NA : RVT_GENE_OK;
+    if (s_bad == 1) o.status = RVT_GENE_BADFLAGS;
+    if (s_bad == 2) o.status = RVT_GENE_BADVALUE;
+    o.Q = s_Q;
+    o.p_skat = p_fin;
+    o.p_davies = p_dav;
+    o.p_liu = p_liu;
+    o.davies_fault = fault;
+    o.n_lambda = r;
+    o.lambda_max = lam_max;
+    for (int which = 0; which < 2; ++which) {  // 0 zeggini, 1 cmc
+      const long long* cl = s_coll + which * (ER + 1);
+      double U = (double)recombine4(cl) * nm->scale[0];
+      double SZ[kMaxC];
+      for (int l = 0; l < C; ++l) SZ[l] = (double)recombine4(cl + 4 * (l + 1)) * nm->scale[l + 1];
+      double SS = (double)cl[ER];
+      double q = 0.0;
+      for (int l = 0; l < C; ++l)
+        for (int m = 0; m < C; ++m) q += SZ[l] * nm->xtx_inv[l * C + m] * SZ[m];
+      SS -= q;
+      double V = SS * sigma2;
+      double stat = U * ((1.0 / SS) / sigma2) * U;
+      int ok = (Mp > 0) && !(stat < 0.0) && (stat == stat);
+      double p = ok ? chisq_q(stat, 1.0) : nan("");
+      if (which == 0) {
+        o.zeg_U = U; o.zeg_V = V; o.zeg_stat = stat; o.zeg_p = p; o.zeg_ok = ok;
+      } else {
+        o.cmc_U = U; o.cmc_V = V; o.cmc_stat = stat; o.cmc_p = p; o.cmc_ok = ok;
+        o.cmc_nonref = (int)cl[ER];
+      }
+    }
+    res[g] = o;
+  }
+}
+
+}  // namespace rvt

@@ -1,0 +1,155 @@
+// prep.cuh -- K0: getting genotypes into the packed device layout, plus the synthetic cohort.
+//
+//   k_synth_rows     counter-based HWE genotype generator; host twin:
+//                    oracle/oracle.py synth_genotypes().  Writes int8 rows + per-row counts.
+//   k_count_rows     per-row counts (#1, #2, #invalid) of caller-supplied int8 blocks
+//   k_pack_f64       reference boundary: N x M column-major doubles (base/MathMatrix.h:33-41)
+//                    -> int8 rows + counts; non-{0,1,2} values are counted as invalid
+//   k_flags_from_counts  flip-to-minor / monomorphic flags + allele frequency from the counts:
+//                    convertToMinorAlleleCount (colsum > N => flip, src/DataConsolidator.cpp:46-69),
+//                    isMonomorphicMarker (:94-116), GenotypeCounter::getAF (src/GenotypeCounter.h:46-52)
+#pragma once
+#include "common.cuh"
+
+namespace rvt {
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// grid: (ceil(ld/16/256), rows).  One thread = 16 consecutive samples of one row.
+__global__ void __launch_bounds__(256)
+k_synth_rows(int8_t* __restrict__ arena, int64_t ld, int64_t N, const unsigned long long* __restrict__ keys,
+             const uint32_t* __restrict__ t0, const uint32_t* __restrict__ t1, RowCounts* __restrict__ counts) {
+  const int64_t row = blockIdx.y;
+  const int64_t c16 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i0 = c16 * 16;
+  int n1 = 0, n2 = 0;
+  if (i0 < ld) {
+    const unsigned long long key = keys[row];
+    const uint32_t a = t0[row], b = t1[row];
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int64_t i = i0 + 4 * q + s;
+        uint32_t gq = 0;
+        if (i < N) {
+          uint32_t h = (uint32_t)(mix64(key + (unsigned long long)i * 0xD1B54A32D192ED03ull) >> 32);
+          gq = (h >= a) + (h >= b);
+        }
+        n1 += (gq == 1);
+        n2 += (gq == 2);
+        word |= gq << (8 * s);
+      }
+      w[q] = word;
+    }
+    *reinterpret_cast<uint4*>(arena + (size_t)row * ld + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (n1 | n2)) {
+    atomicAdd(&counts[row].n1, n1);
+    atomicAdd(&counts[row].n2, n2);
+  }
+}
+
+// grid: (ceil(N/16/256), rows); base + row*ld must be 16-byte aligned.
+__global__ void __launch_bounds__(256)
+k_count_rows(const int8_t* __restrict__ base, int64_t ld, int64_t N, RowCounts* __restrict__ counts) {
+  const int64_t row = blockIdx.y;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  int n1 = 0, n2 = 0, bad = 0;
+  if (i0 < N) {
+    const int8_t* p = base + (size_t)row * ld + i0;
+    if (i0 + 16 <= N) {
+      uint4 v = *reinterpret_cast<const uint4*>(p);
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          uint32_t gq = (w[q] >> (8 * s)) & 0xFF;
+          n1 += (gq == 1);
+          n2 += (gq == 2);
+          bad += (gq > 2);
+        }
+    } else {
+      for (int64_t i = i0; i < N; ++i) {
+        uint32_t gq = (uint8_t)p[i - i0];
+        n1 += (gq == 1);
+        n2 += (gq == 2);
+        bad += (gq > 2);
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (n1 | n2 | bad)) {
+    atomicAdd(&counts[row].n1, n1);
+    atomicAdd(&counts[row].n2, n2);
+    atomicAdd(&counts[row].bad, bad);
+  }
+}
+
+// grid: (ceil(ld/4/256), M).  src: N x M column-major doubles; dst: int8 [M][ld] (zero padded).
+__global__ void __launch_bounds__(256)
+k_pack_f64(const double* __restrict__ src, int64_t N, int8_t* __restrict__ dst, int64_t ld,
+           RowCounts* __restrict__ counts) {
+  const int64_t row = blockIdx.y;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  int n1 = 0, n2 = 0, bad = 0;
+  if (i0 < ld) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int64_t i = i0 + s;
+      uint32_t gq = 0;
+      if (i < N) {
+        double v = src[(size_t)row * N + i];
+        if (v == 0.0) gq = 0;
+        else if (v == 1.0) gq = 1;
+        else if (v == 2.0) gq = 2;
+        else { gq = 0; bad += 1; }
+      }
+      n1 += (gq == 1);
+      n2 += (gq == 2);
+      word |= gq << (8 * s);
+    }
+    *reinterpret_cast<uint32_t*>(dst + (size_t)row * ld + i0) = word;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (n1 | n2 | bad)) {
+    atomicAdd(&counts[row].n1, n1);
+    atomicAdd(&counts[row].n2, n2);
+    atomicAdd(&counts[row].bad, bad);
+  }
+}
+
+// one thread per row
+__global__ void k_flags_from_counts(int64_t n_rows, int64_t N, const RowCounts* __restrict__ counts,
+                                    uint8_t* __restrict__ flags, double* __restrict__ af_out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const long long n1 = counts[r].n1, n2 = counts[r].n2, n0 = N - n1 - n2;
+  const long long c = n1 + 2 * n2;
+  uint8_t f = (c > N) ? kRowFlipped : kRowNormal;
+  if (n0 == N || n1 == N || n2 == N) f = kRowSkip;
+  flags[r] = f;
+  if (af_out) af_out[r] = 0.5 * (double)c / (double)N;
+}
+
+}  // namespace rvt

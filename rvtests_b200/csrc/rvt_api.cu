@@ -1,0 +1,616 @@
+// rvt_api.cu -- the C ABI (include/rvtests_b200.h) of the B200 gene engine: context, null model,
+// gene queue, flush = [K0 flags] -> [K1 sweep] -> [K2/K3 finalize].  Host code here is plumbing
+// only (allocation, launches, copies); every number a test reports is computed on the GPU.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rvtests_b200.h"
+#include "common.cuh"
+#include "finalize.cuh"
+#include "null_model.cuh"
+#include "prep.cuh"
+#include "sweep_simt.cuh"
+#include "sweep_tc.cuh"
+
+using namespace rvt;
+
+namespace {
+struct Chunk {
+  uint8_t* p;
+  size_t cap, used;
+};
+}  // namespace
+
+struct rvt_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  char err[512] = {0};
+  int sm_count = 148;
+  // options
+  double beta1 = 1.0, beta2 = 25.0;
+  int engine = RVT_ENGINE_AUTO;
+  int splits = 0;
+  // null model
+  bool have_null = false;
+  int64_t N = 0;
+  int C = 0, ER = 0;
+  int64_t ldE = 0;
+  double *dX = nullptr, *dy = nullptr, *dresid = nullptr, *dnull_part = nullptr, *dbeta = nullptr;
+  int8_t* dE = nullptr;
+  NullModel* d_nm = nullptr;
+  NullModel h_nm;
+  int *d_shift = nullptr, *d_status = nullptr;
+  // pending genes
+  std::vector<GeneDesc> genes;
+  std::vector<uint8_t> userflags;  // per variant, 0xFF = derive from counts
+  std::vector<double> af;          // per variant (valid when gene.has_af)
+  std::vector<int64_t> count_slot; // per gene: offset into d_counts or -1
+  int64_t n_var = 0;
+  // device side arrays (grown on demand)
+  GeneDesc* d_genes = nullptr;
+  size_t cap_genes = 0;
+  uint8_t *d_flags = nullptr, *d_userflags = nullptr;
+  double* d_af = nullptr;
+  RowCounts* d_counts = nullptr;
+  size_t cap_var = 0;
+  SweepPartial* d_parts = nullptr;
+  size_t cap_parts = 0;
+  rvt_gene_result* d_res = nullptr;
+  size_t cap_res = 0;
+  unsigned int* d_counter = nullptr;
+  // staging
+  std::vector<Chunk> chunks;
+  double* d_stage64 = nullptr;
+  size_t cap_stage64 = 0;
+  // loaded synthetic cohort
+  int8_t* d_loaded = nullptr;
+  int64_t loaded_rows = 0, loaded_ld = 0;
+  int loaded_genes = 0, loaded_M = 0;
+  std::vector<uint8_t> loaded_flags;
+  std::vector<double> loaded_af;
+  TcSegments tc;
+  // timing
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double t_sweep = 0, t_fin = 0, t_total = 0, n_launch = 0;
+  int last_engine = 0, last_S = 0;
+};
+
+#define CTX_FAIL(code, ...)                              \
+  do {                                                   \
+    snprintf(ctx->err, sizeof(ctx->err), __VA_ARGS__);   \
+    return (code);                                       \
+  } while (0)
+
+static int ensure(rvt_ctx* ctx, void** p, size_t* cap, size_t need, size_t elem) {
+  if (need <= *cap) return RVT_OK;
+  size_t ncap = std::max(need, *cap * 2);
+  void* np = nullptr;
+  RVT_CUDA_OK(cudaMalloc(&np, ncap * elem));
+  if (*p) {
+    RVT_CUDA_OK(cudaMemcpyAsync(np, *p, *cap * elem, cudaMemcpyDeviceToDevice, ctx->stream));
+    RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    RVT_CUDA_OK(cudaFree(*p));
+  }
+  *p = np;
+  *cap = ncap;
+  return RVT_OK;
+}
+
+// per-variant device arrays share one capacity
+static int ensure_var(rvt_ctx* ctx, size_t need) {
+  if (need <= ctx->cap_var) return RVT_OK;
+  size_t ncap = std::max(need, ctx->cap_var * 2 + 1024);
+  auto grow = [&](void** p, size_t elem) -> int {
+    void* np = nullptr;
+    RVT_CUDA_OK(cudaMalloc(&np, ncap * elem));
+    RVT_CUDA_OK(cudaMemsetAsync(np, 0, ncap * elem, ctx->stream));
+    if (*p) {
+      RVT_CUDA_OK(cudaMemcpyAsync(np, *p, ctx->cap_var * elem, cudaMemcpyDeviceToDevice, ctx->stream));
+      RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      RVT_CUDA_OK(cudaFree(*p));
+    }
+    *p = np;
+    return RVT_OK;
+  };
+  int rc;
+  if ((rc = grow((void**)&ctx->d_flags, 1))) return rc;
+  if ((rc = grow((void**)&ctx->d_userflags, 1))) return rc;
+  if ((rc = grow((void**)&ctx->d_af, sizeof(double)))) return rc;
+  if ((rc = grow((void**)&ctx->d_counts, sizeof(RowCounts)))) return rc;
+  ctx->cap_var = ncap;
+  return RVT_OK;
+}
+
+static int arena_alloc(rvt_ctx* ctx, size_t bytes, uint8_t** out) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  for (auto& c : ctx->chunks)
+    if (c.cap - c.used >= bytes) {
+      *out = c.p + c.used;
+      c.used += bytes;
+      return RVT_OK;
+    }
+  Chunk c;
+  c.cap = std::max(bytes, (size_t)256 << 20);
+  c.used = bytes;
+  RVT_CUDA_OK(cudaMalloc((void**)&c.p, c.cap));
+  ctx->chunks.push_back(c);
+  *out = c.p;
+  return RVT_OK;
+}
+
+extern "C" {
+
+int rvt_ctx_create(int device, rvt_ctx** out) {
+  if (!out) return RVT_E_BADARG;
+  *out = nullptr;
+  rvt_ctx* ctx = new (std::nothrow) rvt_ctx();
+  if (!ctx) return RVT_E_CUDA;
+  *out = ctx;  // returned even on failure so that rvt_last_error() can explain
+  ctx->device = device;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    CTX_FAIL(RVT_E_CUDA, "no CUDA device available (%s): the engine has no CPU fallback",
+             cudaGetErrorString(e));
+  RVT_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  RVT_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  if (prop.major != 10)
+    CTX_FAIL(RVT_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+             prop.major, prop.minor);
+  RVT_CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (auto& ev : ctx->ev) RVT_CUDA_OK(cudaEventCreate(&ev));
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_nm, sizeof(NullModel)));
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_counter, sizeof(unsigned int) * 4));
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_shift, sizeof(int) * (kMaxC + 1)));
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_status, sizeof(int)));
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->dbeta, sizeof(double) * kMaxC));
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->dnull_part, sizeof(double) * kNullBlocks * kNullAcc));
+  RVT_CUDA_OK(cudaFuncSetAttribute(k_sweep_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, kSimtSmem));
+  RVT_CUDA_OK(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinSmem));
+  int rc = tc_init(&ctx->tc, ctx->err, sizeof(ctx->err));
+  if (rc) return rc;
+  return RVT_OK;
+}
+
+void rvt_ctx_destroy(rvt_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
+                  ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (auto& c : ctx->chunks) cudaFree(c.p);
+  for (auto& ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* rvt_last_error(const rvt_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
+  if (!ctx || !key) return RVT_E_BADARG;
+  std::string k(key);
+  if (k == "beta1") ctx->beta1 = value;
+  else if (k == "beta2") ctx->beta2 = value;
+  else if (k == "engine") {
+    int e = (int)value;
+    if (e < 0 || e > 2) CTX_FAIL(RVT_E_BADARG, "engine must be 0 (auto), 1 (simt) or 2 (tc)");
+    ctx->engine = e;
+  } else if (k == "splits") {
+    if (value < 0 || value > 64) CTX_FAIL(RVT_E_BADARG, "splits must be in 0..64");
+    ctx->splits = (int)value;
+  } else
+    CTX_FAIL(RVT_E_BADARG, "unknown option '%s'", key);
+  return RVT_OK;
+}
+
+double rvt_get_info(const rvt_ctx* ctx, const char* key) {
+  if (!ctx || !key) return -1;
+  std::string k(key);
+  if (k == "sm_count") return ctx->sm_count;
+  if (k == "last_engine") return ctx->last_engine;
+  if (k == "last_splits") return ctx->last_S;
+  if (k == "N") return (double)ctx->N;
+  if (k == "C") return ctx->C;
+  if (k == "ER") return ctx->ER;
+  if (k == "loaded_ld") return (double)ctx->loaded_ld;
+  if (k == "tc_available") return ctx->tc.encode ? 1 : 0;
+  return -1;
+}
+
+static int null_model_run(rvt_ctx* ctx) {
+  const int64_t N = ctx->N;
+  const int C = ctx->C;
+  ctx->ER = ((4 * (C + 1)) + 7) & ~7;
+  ctx->ldE = (N + 127) & ~(int64_t)127;
+  if (ctx->dresid) cudaFree(ctx->dresid);
+  if (ctx->dE) cudaFree(ctx->dE);
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->dresid, sizeof(double) * N));
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->dE, (size_t)ctx->ER * ctx->ldE));
+  RVT_CUDA_OK(cudaMemsetAsync(ctx->dE, 0, (size_t)ctx->ER * ctx->ldE, ctx->stream));
+  NullModel h;
+  memset(&h, 0, sizeof(h));
+  h.N = N;
+  h.C = C;
+  h.ER = ctx->ER;
+  h.ldE = ctx->ldE;
+  h.E = ctx->dE;
+  h.resid = ctx->dresid;
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_nm, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+  k_null_moments<<<kNullBlocks, kNullThreads, 0, ctx->stream>>>(N, C, ctx->dX, ctx->dy, ctx->dnull_part);
+  k_null_solve<<<1, 32, 0, ctx->stream>>>(C, kNullBlocks, ctx->dnull_part, ctx->d_nm, ctx->dbeta, ctx->d_status);
+  k_null_resid<<<kNullBlocks, kNullThreads, 0, ctx->stream>>>(N, C, ctx->dX, ctx->dy, ctx->dbeta, ctx->dresid,
+                                                             ctx->dnull_part);
+  k_null_finish<<<1, 32, 0, ctx->stream>>>(N, C, kNullBlocks, ctx->dnull_part, ctx->d_nm, ctx->d_shift);
+  k_build_E<<<kNullBlocks, kNullThreads, 0, ctx->stream>>>(N, C, ctx->dX, ctx->dresid, ctx->d_shift, ctx->dE,
+                                                          ctx->ldE, ctx->d_nm);
+  RVT_CUDA_OK(cudaGetLastError());
+  int status = 0;
+  RVT_CUDA_OK(cudaMemcpyAsync(&status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  RVT_CUDA_OK(cudaMemcpyAsync(&ctx->h_nm, ctx->d_nm, sizeof(NullModel), cudaMemcpyDeviceToHost, ctx->stream));
+  RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (status == 1) CTX_FAIL(RVT_E_NUMERIC, "null model: X'X is not positive definite");
+  if (status == 2)
+    CTX_FAIL(RVT_E_BADARG, "null model: column 0 of X must be the intercept (all ones), as produced by "
+                           "copyCovariateAndIntercept (src/ModelUtil.h:102-130)");
+  ctx->have_null = true;
+  int rc = tc_bind_null(&ctx->tc, ctx->dE, ctx->ER, N, ctx->ldE, ctx->err, sizeof(ctx->err));
+  if (rc) return rc;
+  return RVT_OK;
+}
+
+static int null_model_alloc(rvt_ctx* ctx, int64_t N, int C) {
+  if (N <= 0 || N > ((int64_t)1 << 31) - 256) CTX_FAIL(RVT_E_BADARG, "N out of range");
+  if (C < 1 || C > kMaxC) CTX_FAIL(RVT_E_UNSUPPORTED, "C=%d covariate columns (incl. intercept); this build supports 1..%d", C, kMaxC);
+  if (!ctx->genes.empty()) CTX_FAIL(RVT_E_STATE, "flush pending genes before changing the null model");
+  RVT_CUDA_OK(cudaSetDevice(ctx->device));
+  if (ctx->dX) cudaFree(ctx->dX);
+  if (ctx->dy) cudaFree(ctx->dy);
+  ctx->dX = ctx->dy = nullptr;
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->dX, sizeof(double) * N * C));
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->dy, sizeof(double) * N));
+  ctx->N = N;
+  ctx->C = C;
+  ctx->have_null = false;
+  return RVT_OK;
+}
+
+int rvt_set_null_model(rvt_ctx* ctx, int64_t N, int C, const double* X, const double* y, int binary) {
+  if (!ctx || !X || !y) return RVT_E_BADARG;
+  if (binary) CTX_FAIL(RVT_E_UNSUPPORTED, "binary traits (logistic null model) are not implemented in this build");
+  int rc = null_model_alloc(ctx, N, C);
+  if (rc) return rc;
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->dX, X, sizeof(double) * N * C, cudaMemcpyHostToDevice, ctx->stream));
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->dy, y, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+  return null_model_run(ctx);
+}
+
+int rvt_set_null_model_dev(rvt_ctx* ctx, int64_t N, int C, const double* dX, const double* dy) {
+  if (!ctx || !dX || !dy) return RVT_E_BADARG;
+  int rc = null_model_alloc(ctx, N, C);
+  if (rc) return rc;
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->dX, dX, sizeof(double) * N * C, cudaMemcpyDeviceToDevice, ctx->stream));
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->dy, dy, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx->stream));
+  return null_model_run(ctx);
+}
+
+int rvt_get_null_model(rvt_ctx* ctx, double* resid, double* sigma2, double* xtx_inv) {
+  if (!ctx) return RVT_E_BADARG;
+  if (!ctx->have_null) CTX_FAIL(RVT_E_STATE, "no null model set");
+  if (sigma2) *sigma2 = ctx->h_nm.sigma2;
+  if (xtx_inv) memcpy(xtx_inv, ctx->h_nm.xtx_inv, sizeof(double) * ctx->C * ctx->C);
+  if (resid) {
+    RVT_CUDA_OK(cudaMemcpyAsync(resid, ctx->dresid, sizeof(double) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+    RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  return RVT_OK;
+}
+
+// common tail of every push: append the descriptor and the per-variant side data
+static int push_common(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const double* af, const uint8_t* flags,
+                       bool counted, int seg, int64_t row0) {
+  GeneDesc gd;
+  memset(&gd, 0, sizeof(gd));
+  gd.g = dG;
+  gd.ld = ld;
+  gd.M = M;
+  gd.seg = seg;
+  gd.row0 = row0;
+  gd.var0 = ctx->n_var;
+  gd.has_af = af ? 1 : 0;
+  gd.counted = counted ? 1 : 0;
+  ctx->genes.push_back(gd);
+  ctx->count_slot.push_back(counted ? ctx->n_var : -1);
+  for (int j = 0; j < M; ++j) {
+    ctx->userflags.push_back(flags ? flags[j] : (uint8_t)0xFF);
+    ctx->af.push_back(af ? af[j] : 0.0);
+  }
+  ctx->n_var += M;
+  return RVT_OK;
+}
+
+static int push_check(rvt_ctx* ctx, int M) {
+  if (!ctx->have_null) CTX_FAIL(RVT_E_STATE, "set the null model before pushing genes");
+  if (M < 1) CTX_FAIL(RVT_E_BADARG, "gene with no variant (the reference returns -1 / NA: src/Model.h:2637-2640)");
+  if (M > kMaxM) CTX_FAIL(RVT_E_UNSUPPORTED, "M=%d variants; this build handles genes of up to %d variants", M, kMaxM);
+  RVT_CUDA_OK(cudaSetDevice(ctx->device));
+  return RVT_OK;
+}
+
+static void launch_count(rvt_ctx* ctx, const int8_t* d, int M, int64_t ld, RowCounts* counts) {
+  const int64_t per_row = (ctx->N + 16 * 256 - 1) / (16 * 256);
+  dim3 grid((unsigned)per_row, (unsigned)M);
+  k_count_rows<<<grid, 256, 0, ctx->stream>>>(d, ld, ctx->N, counts);
+}
+
+int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
+  if (!ctx || !G) return RVT_E_BADARG;
+  int rc = push_check(ctx, M);
+  if (rc) return rc;
+  const int64_t N = ctx->N, ld = (N + 127) & ~(int64_t)127;
+  size_t need = (size_t)N * M;
+  if (need > ctx->cap_stage64) {
+    if (ctx->d_stage64) {
+      RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_stage64);
+    }
+    RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_stage64, need * sizeof(double)));
+    ctx->cap_stage64 = need;
+  }
+  uint8_t* blk = nullptr;
+  if ((rc = arena_alloc(ctx, (size_t)M * ld, &blk))) return rc;
+  if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_stage64, G, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
+  dim3 grid((unsigned)((ld / 4 + 255) / 256), (unsigned)M);
+  k_pack_f64<<<grid, 256, 0, ctx->stream>>>(ctx->d_stage64, N, (int8_t*)blk, ld, ctx->d_counts + ctx->n_var);
+  RVT_CUDA_OK(cudaGetLastError());
+  // the staging buffer is reused by the next push: wait (pageable H2D is synchronous anyway)
+  RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return push_common(ctx, (const int8_t*)blk, M, ld, af, nullptr, true, -1, 0);
+}
+
+int rvt_gene_push_i8(rvt_ctx* ctx, const int8_t* G, int M, int64_t ld_in, const double* af) {
+  if (!ctx || !G) return RVT_E_BADARG;
+  int rc = push_check(ctx, M);
+  if (rc) return rc;
+  const int64_t N = ctx->N, ld = (N + 127) & ~(int64_t)127;
+  if (ld_in < N) CTX_FAIL(RVT_E_BADARG, "ld (%lld) < N (%lld)", (long long)ld_in, (long long)N);
+  uint8_t* blk = nullptr;
+  if ((rc = arena_alloc(ctx, (size_t)M * ld, &blk))) return rc;
+  if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
+  RVT_CUDA_OK(cudaMemsetAsync(blk, 0, (size_t)M * ld, ctx->stream));
+  RVT_CUDA_OK(cudaMemcpy2DAsync(blk, ld, G, ld_in, N, M, cudaMemcpyHostToDevice, ctx->stream));
+  RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
+  launch_count(ctx, (const int8_t*)blk, M, ld, ctx->d_counts + ctx->n_var);
+  RVT_CUDA_OK(cudaGetLastError());
+  return push_common(ctx, (const int8_t*)blk, M, ld, af, nullptr, true, -1, 0);
+}
+
+int rvt_gene_push_dev_i8(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const double* af, const uint8_t* flags) {
+  if (!ctx || !dG) return RVT_E_BADARG;
+  int rc = push_check(ctx, M);
+  if (rc) return rc;
+  if (ld < ctx->N || (ld & 15) || ((uintptr_t)dG & 15))
+    CTX_FAIL(RVT_E_BADARG, "device block must be 16-byte aligned with ld a multiple of 16 and >= N");
+  if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
+  if (!flags) {
+    RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
+    launch_count(ctx, dG, M, ld, ctx->d_counts + ctx->n_var);
+    RVT_CUDA_OK(cudaGetLastError());
+  }
+  return push_common(ctx, dG, M, ld, af, flags, flags == nullptr, -1, 0);
+}
+
+int rvt_pending(const rvt_ctx* ctx) { return ctx ? (int)ctx->genes.size() : 0; }
+
+// user flags override; otherwise derive from counts.  One thread per variant.
+__global__ void k_resolve_flags(int64_t n_var, int64_t N, const RowCounts* __restrict__ counts,
+                                const uint8_t* __restrict__ user, uint8_t* __restrict__ flags) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_var) return;
+  if (user[r] != 0xFF) {
+    flags[r] = user[r];
+    return;
+  }
+  const long long n1 = counts[r].n1, n2 = counts[r].n2, n0 = N - n1 - n2, c = n1 + 2 * n2;
+  uint8_t f = (c > N) ? kRowFlipped : kRowNormal;
+  if (n0 == N || n1 == N || n2 == N) f = kRowSkip;
+  flags[r] = f;
+}
+
+static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, bool to_device) {
+  if (!ctx) return RVT_E_BADARG;
+  const int n = (int)ctx->genes.size();
+  if (n_out) *n_out = 0;
+  if (n == 0) return RVT_OK;
+  if (!out || cap < n) CTX_FAIL(RVT_E_BADARG, "result buffer too small: %d pending genes, cap %d", n, cap);
+  RVT_CUDA_OK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure(ctx, (void**)&ctx->d_genes, &ctx->cap_genes, n, sizeof(GeneDesc)))) return rc;
+  if ((rc = ensure_var(ctx, ctx->n_var))) return rc;
+  const int64_t N = ctx->N;
+  int S = ctx->splits;
+  if (S <= 0) S = (int)std::min<int64_t>(16, std::max<int64_t>(1, (N + 65535) / 65536));
+  // samples per split: multiple of 512 (one TMA stage of the tensor-core kernel; 2 simt tiles)
+  int64_t chunk = (((N + S - 1) / S) + 511) & ~(int64_t)511;
+  S = (int)((N + chunk - 1) / chunk);
+  if (chunk > ((int64_t)1 << 22)) CTX_FAIL(RVT_E_UNSUPPORTED, "split of %lld samples exceeds the int32 accumulation bound; raise 'splits'", (long long)chunk);
+  const int batch = std::min(n, 2048);
+  if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)batch * S, sizeof(SweepPartial)))) return rc;
+  rvt_gene_result* d_res = out;
+  if (!to_device) {
+    if ((rc = ensure(ctx, (void**)&ctx->d_res, &ctx->cap_res, n, sizeof(rvt_gene_result)))) return rc;
+    d_res = ctx->d_res;
+  }
+  cudaStream_t st = ctx->stream;
+  RVT_CUDA_OK(cudaEventRecord(ctx->ev[0], st));
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_genes, ctx->genes.data(), sizeof(GeneDesc) * n, cudaMemcpyHostToDevice, st));
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_userflags, ctx->userflags.data(), ctx->n_var, cudaMemcpyHostToDevice, st));
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_af, ctx->af.data(), sizeof(double) * ctx->n_var, cudaMemcpyHostToDevice, st));
+  k_resolve_flags<<<(unsigned)((ctx->n_var + 255) / 256), 256, 0, st>>>(ctx->n_var, N, ctx->d_counts,
+                                                                         ctx->d_userflags, ctx->d_flags);
+  int launches = 1;
+  int engine = ctx->engine;
+  bool tc_ok = tc_usable(&ctx->tc, ctx->genes.data(), n);
+  if (engine == RVT_ENGINE_AUTO) engine = tc_ok ? RVT_ENGINE_TC : RVT_ENGINE_SIMT;
+  if (engine == RVT_ENGINE_TC && !tc_ok)
+    CTX_FAIL(RVT_E_UNSUPPORTED, "tensor-core engine requested but unavailable for these genes: %s", ctx->tc.why);
+  ctx->last_engine = engine;
+  ctx->last_S = S;
+  EngineParams prm{ctx->beta1, ctx->beta2};
+  float ms_sweep = 0.f, ms_fin = 0.f;
+  for (int b0 = 0; b0 < n; b0 += batch) {
+    const int nb = std::min(batch, n - b0);
+    RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), st));
+    RVT_CUDA_OK(cudaEventRecord(ctx->ev[2], st));
+    if (engine == RVT_ENGINE_SIMT) {
+      const int grid = std::min(nb * S, ctx->sm_count * 3);
+      k_sweep_simt<<<grid, kSimtThreads, kSimtSmem, st>>>(ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_nm, S, chunk,
+                                                          ctx->d_parts, ctx->d_counter);
+    } else {
+      rc = tc_launch(&ctx->tc, ctx->d_genes + b0, ctx->genes.data() + b0, nb, ctx->d_flags, ctx->d_nm, N, ctx->ER,
+                     S, chunk, ctx->d_parts, ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err));
+      if (rc) return rc;
+    }
+    RVT_CUDA_OK(cudaEventRecord(ctx->ev[3], st));
+    k_finalize<<<nb, kFinThreads, kFinSmem, st>>>(ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S,
+                                                  ctx->d_parts, d_res + b0);
+    RVT_CUDA_OK(cudaEventRecord(ctx->ev[4], st));
+    RVT_CUDA_OK(cudaGetLastError());
+    launches += 2;
+    if (n > batch || true) {
+      // per-batch timing needs the events resolved before they are re-recorded
+      RVT_CUDA_OK(cudaEventSynchronize(ctx->ev[4]));
+      float a = 0, b = 0;
+      RVT_CUDA_OK(cudaEventElapsedTime(&a, ctx->ev[2], ctx->ev[3]));
+      RVT_CUDA_OK(cudaEventElapsedTime(&b, ctx->ev[3], ctx->ev[4]));
+      ms_sweep += a;
+      ms_fin += b;
+    }
+  }
+  if (!to_device)
+    RVT_CUDA_OK(cudaMemcpyAsync(out, d_res, sizeof(rvt_gene_result) * n, cudaMemcpyDeviceToHost, st));
+  RVT_CUDA_OK(cudaEventRecord(ctx->ev[1], st));
+  RVT_CUDA_OK(cudaStreamSynchronize(st));
+  float tot = 0;
+  RVT_CUDA_OK(cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[1]));
+  ctx->t_sweep = ms_sweep;
+  ctx->t_fin = ms_fin;
+  ctx->t_total = tot;
+  ctx->n_launch = launches;
+  if (n_out) *n_out = n;
+  ctx->genes.clear();
+  ctx->userflags.clear();
+  ctx->af.clear();
+  ctx->count_slot.clear();
+  ctx->n_var = 0;
+  for (auto& c : ctx->chunks) c.used = 0;
+  return RVT_OK;
+}
+
+int rvt_flush(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out) { return flush_impl(ctx, out, cap, n_out, false); }
+int rvt_flush_dev(rvt_ctx* ctx, rvt_gene_result* d_out, int cap, int* n_out) {
+  return flush_impl(ctx, d_out, cap, n_out, true);
+}
+
+int rvt_synth_load(rvt_ctx* ctx, int n_genes, int M, const uint64_t* keys, const uint32_t* t0, const uint32_t* t1) {
+  if (!ctx || !keys || !t0 || !t1 || n_genes < 1) return RVT_E_BADARG;
+  int rc = push_check(ctx, M);
+  if (rc) return rc;
+  const int64_t N = ctx->N, ld = (N + 127) & ~(int64_t)127;
+  const int64_t rows = (int64_t)n_genes * M;
+  if (ctx->d_loaded) {
+    cudaFree(ctx->d_loaded);
+    ctx->d_loaded = nullptr;
+  }
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_loaded, (size_t)rows * ld));
+  unsigned long long* dk = nullptr;
+  uint32_t *d0 = nullptr, *d1 = nullptr;
+  RowCounts* dc = nullptr;
+  uint8_t* dfl = nullptr;
+  double* daf = nullptr;
+  RVT_CUDA_OK(cudaMalloc((void**)&dk, rows * 8));
+  RVT_CUDA_OK(cudaMalloc((void**)&d0, rows * 4));
+  RVT_CUDA_OK(cudaMalloc((void**)&d1, rows * 4));
+  RVT_CUDA_OK(cudaMalloc((void**)&dc, rows * sizeof(RowCounts)));
+  RVT_CUDA_OK(cudaMalloc((void**)&dfl, rows));
+  RVT_CUDA_OK(cudaMalloc((void**)&daf, rows * 8));
+  cudaStream_t st = ctx->stream;
+  RVT_CUDA_OK(cudaMemcpyAsync(dk, keys, rows * 8, cudaMemcpyHostToDevice, st));
+  RVT_CUDA_OK(cudaMemcpyAsync(d0, t0, rows * 4, cudaMemcpyHostToDevice, st));
+  RVT_CUDA_OK(cudaMemcpyAsync(d1, t1, rows * 4, cudaMemcpyHostToDevice, st));
+  RVT_CUDA_OK(cudaMemsetAsync(dc, 0, rows * sizeof(RowCounts), st));
+  const unsigned per_row = (unsigned)((ld / 16 + 255) / 256);
+  for (int64_t r0 = 0; r0 < rows; r0 += 32768) {
+    const unsigned nr = (unsigned)std::min<int64_t>(32768, rows - r0);
+    k_synth_rows<<<dim3(per_row, nr), 256, 0, st>>>(ctx->d_loaded + (size_t)r0 * ld, ld, N, dk + r0, d0 + r0, d1 + r0,
+                                                    dc + r0);
+  }
+  k_flags_from_counts<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(rows, N, dc, dfl, daf);
+  RVT_CUDA_OK(cudaGetLastError());
+  ctx->loaded_flags.resize(rows);
+  ctx->loaded_af.resize(rows);
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->loaded_flags.data(), dfl, rows, cudaMemcpyDeviceToHost, st));
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->loaded_af.data(), daf, rows * 8, cudaMemcpyDeviceToHost, st));
+  RVT_CUDA_OK(cudaStreamSynchronize(st));
+  cudaFree(dk); cudaFree(d0); cudaFree(d1); cudaFree(dc); cudaFree(dfl); cudaFree(daf);
+  ctx->loaded_rows = rows;
+  ctx->loaded_ld = ld;
+  ctx->loaded_genes = n_genes;
+  ctx->loaded_M = M;
+  rc = tc_bind_segment(&ctx->tc, 0, ctx->d_loaded, rows, N, ld, ctx->err, sizeof(ctx->err));
+  if (rc) return rc;
+  return RVT_OK;
+}
+
+int rvt_loaded_genes(const rvt_ctx* ctx) { return ctx ? ctx->loaded_genes : 0; }
+
+int rvt_run_loaded(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, int results_on_device) {
+  if (!ctx) return RVT_E_BADARG;
+  if (!ctx->d_loaded) CTX_FAIL(RVT_E_STATE, "no cohort loaded (rvt_synth_load)");
+  if (!ctx->genes.empty()) CTX_FAIL(RVT_E_STATE, "flush pending genes first");
+  const int M = ctx->loaded_M;
+  int rc = push_check(ctx, M);
+  if (rc) return rc;
+  if ((rc = ensure_var(ctx, (size_t)ctx->loaded_rows))) return rc;
+  ctx->genes.reserve(ctx->loaded_genes);
+  for (int g = 0; g < ctx->loaded_genes; ++g) {
+    const int64_t row0 = (int64_t)g * M;
+    // AF: the loader's counts, i.e. what GenotypeCounter::getAF hands to the fitters
+    push_common(ctx, ctx->d_loaded + (size_t)row0 * ctx->loaded_ld, M, ctx->loaded_ld, ctx->loaded_af.data() + row0,
+                ctx->loaded_flags.data() + row0, false, 0, row0);
+  }
+  return flush_impl(ctx, out, cap, n_out, results_on_device != 0);
+}
+
+int rvt_loaded_read(rvt_ctx* ctx, int64_t row0, int rows, int8_t* out) {
+  if (!ctx || !out) return RVT_E_BADARG;
+  if (!ctx->d_loaded || row0 < 0 || row0 + rows > ctx->loaded_rows) CTX_FAIL(RVT_E_BADARG, "rows out of range");
+  RVT_CUDA_OK(cudaMemcpy2DAsync(out, ctx->N, ctx->d_loaded + (size_t)row0 * ctx->loaded_ld, ctx->loaded_ld, ctx->N,
+                                rows, cudaMemcpyDeviceToHost, ctx->stream));
+  RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return RVT_OK;
+}
+
+int rvt_last_timing(const rvt_ctx* ctx, double out[4]) {
+  if (!ctx || !out) return RVT_E_BADARG;
+  out[0] = ctx->t_sweep;
+  out[1] = ctx->t_fin;
+  out[2] = ctx->t_total;
+  out[3] = ctx->n_launch;
+  return RVT_OK;
+}
+
+}  // extern "C"

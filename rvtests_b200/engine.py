@@ -1,0 +1,212 @@
+"""ctypes mirror of include/rvtests_b200.h (names, argument meaning and error behaviour follow
+the C ABI one to one).  No arithmetic happens here."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import build as _build
+
+RVT_OK = 0
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
+GENE_OK, GENE_NA, GENE_BADFLAGS, GENE_BADVALUE = 0, 2, 4, 5
+
+
+class RvtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"rvtests_b200 error {code}: {msg}")
+        self.code = code
+
+
+class GeneResult(C.Structure):
+    """struct rvt_gene_result"""
+    _fields_ = [
+        ("Q", C.c_double), ("p_skat", C.c_double), ("p_davies", C.c_double), ("p_liu", C.c_double),
+        ("davies_fault", C.c_int32), ("n_lambda", C.c_int32), ("m_poly", C.c_int32),
+        ("status", C.c_int32), ("cmc_nonref", C.c_int32), ("cmc_ok", C.c_int32),
+        ("cmc_U", C.c_double), ("cmc_V", C.c_double), ("cmc_stat", C.c_double), ("cmc_p", C.c_double),
+        ("zeg_ok", C.c_int32), ("skato_ok", C.c_int32),
+        ("zeg_U", C.c_double), ("zeg_V", C.c_double), ("zeg_stat", C.c_double), ("zeg_p", C.c_double),
+        ("skato_Q", C.c_double), ("skato_rho", C.c_double), ("skato_p", C.c_double),
+        ("lambda_max", C.c_double),
+    ]
+
+
+RESULT_DTYPE = np.dtype([
+    ("Q", "f8"), ("p_skat", "f8"), ("p_davies", "f8"), ("p_liu", "f8"),
+    ("davies_fault", "i4"), ("n_lambda", "i4"), ("m_poly", "i4"), ("status", "i4"),
+    ("cmc_nonref", "i4"), ("cmc_ok", "i4"),
+    ("cmc_U", "f8"), ("cmc_V", "f8"), ("cmc_stat", "f8"), ("cmc_p", "f8"),
+    ("zeg_ok", "i4"), ("skato_ok", "i4"),
+    ("zeg_U", "f8"), ("zeg_V", "f8"), ("zeg_stat", "f8"), ("zeg_p", "f8"),
+    ("skato_Q", "f8"), ("skato_rho", "f8"), ("skato_p", "f8"), ("lambda_max", "f8"),
+])
+assert RESULT_DTYPE.itemsize == C.sizeof(GeneResult)
+
+EXPORTS = [
+    "rvt_ctx_create", "rvt_ctx_destroy", "rvt_last_error", "rvt_set_option", "rvt_get_info",
+    "rvt_set_null_model", "rvt_set_null_model_dev", "rvt_get_null_model",
+    "rvt_gene_push_f64", "rvt_gene_push_i8", "rvt_gene_push_dev_i8", "rvt_pending",
+    "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded",
+    "rvt_loaded_read", "rvt_last_timing",
+]
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+
+
+def load_library(rebuild: bool = False):
+    """dlopen the in-tree librvtests_b200.so (building it first when sources are newer)."""
+    global _lib
+    if _lib is not None and not rebuild:
+        return _lib
+    path = _build.build_lib(force=rebuild)
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.rvt_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.rvt_ctx_destroy.argtypes = [vp]
+    L.rvt_ctx_destroy.restype = None
+    L.rvt_last_error.argtypes = [vp]
+    L.rvt_last_error.restype = C.c_char_p
+    L.rvt_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    L.rvt_get_info.argtypes = [vp, C.c_char_p]
+    L.rvt_get_info.restype = C.c_double
+    L.rvt_set_null_model.argtypes = [vp, C.c_int64, C.c_int, _dp, _dp, C.c_int]
+    L.rvt_set_null_model_dev.argtypes = [vp, C.c_int64, C.c_int, vp, vp]
+    L.rvt_get_null_model.argtypes = [vp, _dp, _dp, _dp]
+    L.rvt_gene_push_f64.argtypes = [vp, _dp, C.c_int, _dp]
+    L.rvt_gene_push_i8.argtypes = [vp, vp, C.c_int, C.c_int64, _dp]
+    L.rvt_gene_push_dev_i8.argtypes = [vp, vp, C.c_int, C.c_int64, _dp, vp]
+    L.rvt_pending.argtypes = [vp]
+    L.rvt_flush.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
+    L.rvt_flush_dev.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
+    L.rvt_synth_load.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    L.rvt_loaded_genes.argtypes = [vp]
+    L.rvt_run_loaded.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.c_int]
+    L.rvt_loaded_read.argtypes = [vp, C.c_int64, C.c_int, vp]
+    L.rvt_last_timing.argtypes = [vp, _dp]
+    _lib = L
+    return L
+
+
+def _pd(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+class GeneEngine:
+    """One context on one GPU.  Mirrors the call sequence a ModelFitter adapter makes:
+    set_null_model (once) -> push genes -> flush."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        rc = self.L.rvt_ctx_create(device, C.byref(self.h))
+        if rc != RVT_OK:
+            msg = self.L.rvt_last_error(self.h).decode() if self.h else "context allocation failed"
+            if self.h:
+                self.L.rvt_ctx_destroy(self.h)
+                self.h = C.c_void_p()
+            raise RvtError(rc, msg)
+        self.N = 0
+        self.C = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rvt_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != RVT_OK:
+            raise RvtError(rc, self.L.rvt_last_error(self.h).decode())
+
+    def set_option(self, key: str, value: float):
+        self._chk(self.L.rvt_set_option(self.h, key.encode(), float(value)))
+
+    def info(self, key: str) -> float:
+        return self.L.rvt_get_info(self.h, key.encode())
+
+    def set_null_model(self, X, y, binary: bool = False):
+        """X: (N, C) incl. intercept column 0; y: (N,)"""
+        Xc = np.asfortranarray(X, dtype=np.float64)
+        yc = np.ascontiguousarray(y, dtype=np.float64)
+        self.N, self.C = Xc.shape
+        self._chk(self.L.rvt_set_null_model(self.h, self.N, self.C, _pd(Xc), _pd(yc), int(binary)))
+
+    def set_null_model_dev(self, N, Cc, dX_ptr, dy_ptr):
+        self.N, self.C = int(N), int(Cc)
+        self._chk(self.L.rvt_set_null_model_dev(self.h, self.N, self.C, dX_ptr, dy_ptr))
+
+    def get_null_model(self, want_resid=True):
+        resid = np.zeros(self.N) if want_resid else None
+        s2 = C.c_double(0)
+        xi = np.zeros((self.C, self.C))
+        self._chk(self.L.rvt_get_null_model(self.h, _pd(resid), C.byref(s2), _pd(xi)))
+        return dict(resid=resid, sigma2=s2.value, xtx_inv=xi)
+
+    def push_f64(self, G, af=None):
+        """G: (N, M) doubles as dc->getGenotype() (any layout; sent column-major)."""
+        Gc = np.asfortranarray(G, dtype=np.float64)
+        afc = None if af is None else np.ascontiguousarray(af, dtype=np.float64)
+        self._chk(self.L.rvt_gene_push_f64(self.h, _pd(Gc), Gc.shape[1], _pd(afc)))
+
+    def push_i8(self, Gt, af=None):
+        """Gt: (M, N) int8 variant-major hard calls."""
+        Gc = np.ascontiguousarray(Gt, dtype=np.int8)
+        afc = None if af is None else np.ascontiguousarray(af, dtype=np.float64)
+        self._chk(self.L.rvt_gene_push_i8(self.h, Gc.ctypes.data, Gc.shape[0], Gc.shape[1], _pd(afc)))
+
+    def push_dev_i8(self, dptr, M, ld, af=None, flags=None):
+        afc = None if af is None else np.ascontiguousarray(af, dtype=np.float64)
+        fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+        self._chk(self.L.rvt_gene_push_dev_i8(self.h, dptr, int(M), int(ld), _pd(afc),
+                                              None if fl is None else fl.ctypes.data))
+
+    def pending(self) -> int:
+        return self.L.rvt_pending(self.h)
+
+    def flush(self):
+        n = self.pending()
+        out = np.zeros(max(n, 1), dtype=RESULT_DTYPE)
+        got = C.c_int(0)
+        self._chk(self.L.rvt_flush(self.h, out.ctypes.data, len(out), C.byref(got)))
+        return out[: got.value]
+
+    def flush_dev(self, d_out_ptr, cap):
+        got = C.c_int(0)
+        self._chk(self.L.rvt_flush_dev(self.h, d_out_ptr, int(cap), C.byref(got)))
+        return got.value
+
+    def synth_load(self, keys, t0, t1, n_genes, M):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        t0 = np.ascontiguousarray(t0, dtype=np.uint32)
+        t1 = np.ascontiguousarray(t1, dtype=np.uint32)
+        assert len(keys) == n_genes * M
+        self._chk(self.L.rvt_synth_load(self.h, int(n_genes), int(M), keys.ctypes.data, t0.ctypes.data,
+                                        t1.ctypes.data))
+
+    def run_loaded(self, d_out_ptr=None):
+        n = self.L.rvt_loaded_genes(self.h)
+        got = C.c_int(0)
+        if d_out_ptr is None:
+            out = np.zeros(max(n, 1), dtype=RESULT_DTYPE)
+            self._chk(self.L.rvt_run_loaded(self.h, out.ctypes.data, len(out), C.byref(got), 0))
+            return out[: got.value]
+        self._chk(self.L.rvt_run_loaded(self.h, d_out_ptr, n, C.byref(got), 1))
+        return got.value
+
+    def loaded_read(self, row0, rows):
+        out = np.zeros((rows, self.N), dtype=np.int8)
+        self._chk(self.L.rvt_loaded_read(self.h, int(row0), int(rows), out.ctypes.data))
+        return out
+
+    def last_timing(self):
+        t = np.zeros(4)
+        self._chk(self.L.rvt_last_timing(self.h, _pd(t)))
+        return dict(sweep_ms=t[0], finalize_ms=t[1], total_ms=t[2], launches=int(t[3]))

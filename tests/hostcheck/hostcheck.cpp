@@ -1,0 +1,33 @@
+// tests/hostcheck/hostcheck.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the product's __host__ __device__ math headers (rvtests_b200/csrc/*.cuh) with g++
+// so that `pytest -m "not gpu"` can check their LOGIC against the oracle on the CPU.  The product
+// never links or calls this; its GPU kernels instantiate the same templates with a CTA-wide Par.
+#include <vector>
+#include "../../rvtests_b200/csrc/eigen.cuh"
+#include "../../rvtests_b200/csrc/skato_tail.cuh"
+
+extern "C" {
+double hc_gamma_q(double a, double x) { return rvt::gamma_q(a, x); }
+double hc_chisq_q(double x, double df) { return rvt::chisq_q(x, df); }
+double hc_beta_weight(double f, double b1, double b2, int sq) { return rvt::beta_weight(f, b1, b2, sq != 0); }
+double hc_liu(const double* lam, int n, double Q) { return rvt::liu_pvalue(lam, n, Q); }
+double hc_mixchisq(const double* lam, int n, double Q, int* fault) {
+  std::vector<int> th(n > 0 ? n : 1);
+  rvt::SerialPar par;
+  return rvt::mixchisq_pvalue(lam, n, Q, th.data(), fault, par);
+}
+double hc_qf(const double* lam, int n, double Q, int lim, double acc, int* fault) {
+  std::vector<int> th(n > 0 ? n : 1);
+  rvt::SerialPar par;
+  return rvt::davies_qf(lam, n, Q, lim, acc, th.data(), fault, par);
+}
+// eigenvalues, descending
+int hc_eigen(const double* a_in, int n, double* out) {
+  std::vector<double> a(a_in, a_in + (size_t)n * n), cs(n + 2), ev(n);
+  rvt::SerialPar par;
+  int sweeps = rvt::jacobi_eigenvalues(a.data(), n, n, cs.data(), par);
+  for (int i = 0; i < n; ++i) ev[i] = a[(size_t)i * n + i];
+  rvt::sort_descending(ev.data(), n, out, par);
+  return sweeps;
+}
+}

@@ -1,0 +1,185 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same seeded
+inputs.  Integer/count outputs bit exact; Q <= 1e-6 rel; p-values <= 1e-4 rel with the same
+Davies fault flag (BASELINE.json north_star tolerances)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from util import af_of, check_gene, make_problem, rel
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ENGINES = [1, 2]  # RVT_ENGINE_SIMT, RVT_ENGINE_TC
+
+
+def _oracle_gene(O, G, X, nm, af=None):
+    return O.gene(G.astype(float), af_of(G) if af is None else af, X, nm["resid"], nm["sigma2"])
+
+
+@pytest.fixture(scope="module")
+def eng(engine_cls):
+    e = engine_cls(0)
+    yield e
+    e.close()
+
+
+def _set_engine(eng, which):
+    if which == 2 and eng.info("tc_available") != 1:
+        pytest.skip("tensor-core engine not available in this build")
+    eng.set_option("engine", which)
+
+
+@pytest.mark.parametrize("which", ENGINES)
+def test_c1_anchor(eng, oracle, which):
+    _set_engine(eng, which)
+    a = json.load(open(os.path.join(GOLD, "c1_anchor.json")))
+    G = np.array(a["G"], dtype=np.int8)
+    X = np.ones((9, 1))
+    y = np.array(a["y"])
+    eng.set_null_model(X, y)
+    nm = eng.get_null_model()
+    assert nm["sigma2"] == pytest.approx(a["sigma2"], rel=1e-12)
+    eng.push_f64(G.astype(float), af_of(G))
+    r = eng.flush()[0]
+    assert r["Q"] == pytest.approx(a["Q"], rel=1e-8)
+    assert int(r["davies_fault"]) == 1
+    assert r["p_skat"] == pytest.approx(a["pvalue"], rel=1e-5)
+    assert int(r["cmc_nonref"]) == a["cmc_nonref"]
+    # what the reference prints (src/Model.h:2743 "%g\t%g")
+    assert "%g" % r["Q"] == "23.741" and "%g" % r["p_skat"] == "0.324321"
+
+
+def test_null_model_matches_oracle(eng, oracle):
+    O = oracle
+    for seed, N, C in ((1, 17, 1), (2, 1000, 3), (3, 40000, 5)):
+        X, y = O.synth_covariates(seed, N, C)
+        eng.set_null_model(X, y)
+        nm = eng.get_null_model()
+        ref = O.fit_null_linear(X, y)
+        assert rel(nm["sigma2"], ref["sigma2"]) <= 1e-12
+        assert np.max(np.abs(nm["resid"] - ref["resid"])) <= 1e-11
+        assert np.max(np.abs(nm["xtx_inv"] - ref["xtx_inv"])) <= 1e-12 * np.max(np.abs(ref["xtx_inv"]))
+
+
+CASES = [
+    # seed, N, M, C, n_mono, n_flip
+    (10, 50, 1, 1, 0, 0),
+    (11, 97, 5, 1, 1, 1),
+    (12, 1000, 30, 3, 2, 3),
+    (13, 1000, 64, 3, 0, 5),
+    (14, 4099, 50, 3, 3, 4),
+    (15, 20000, 50, 3, 0, 0),
+    (16, 513, 7, 2, 7, 0),      # every variant monomorphic -> NA
+    (17, 2048, 33, 4, 1, 1),
+]
+
+
+@pytest.mark.parametrize("which", ENGINES)
+@pytest.mark.parametrize("case", CASES)
+def test_push_f64_and_i8_vs_oracle(eng, oracle, which, case):
+    _set_engine(eng, which)
+    O = oracle
+    seed, N, M, C, n_mono, n_flip = case
+    maf = None if N >= 1000 else np.linspace(0.05, 0.4, M)
+    G, X, y = make_problem(O, seed, N, M, C, maf=maf, n_mono=n_mono, n_flip=n_flip)
+    eng.set_null_model(X, y)
+    nm = O.fit_null_linear(X, y)
+    af = af_of(G)
+    eng.push_f64(G.astype(float), af)          # reference boundary (double Matrix)
+    eng.push_i8(G.T.copy(), af)                # packed hard calls
+    eng.push_i8(G.T.copy(), None)              # AF derived by the engine
+    res = eng.flush()
+    ref, lam = _oracle_gene(O, G, X, nm)
+    check_gene(res[0], ref, lam, ctx=f"f64 {case}")
+    check_gene(res[1], ref, lam, ctx=f"i8 {case}")
+    # f64 and i8 paths share the integer pipeline: identical bits
+    for k in ("Q", "p_skat", "cmc_U", "zeg_U", "cmc_nonref", "lambda_max"):
+        assert res[0][k] == res[1][k], k
+    # without caller AF the engine uses the kept columns' own frequencies (no index quirk)
+    keep = [j for j in range(M) if G[:, j].min() != G[:, j].max()]
+    if keep:
+        af2 = np.zeros(M)
+        af2[: len(keep)] = af[keep]
+        ref2, lam2 = _oracle_gene(O, G, X, nm, af=af2)
+        check_gene(res[2], ref2, lam2, ctx=f"i8/noaf {case}")
+
+
+@pytest.mark.parametrize("which", ENGINES)
+def test_split_invariance_bitwise(eng, oracle, which):
+    """exact integer accumulation => the split count cannot change a single bit"""
+    _set_engine(eng, which)
+    O = oracle
+    G, X, y = make_problem(O, 21, 30000, 40, 3, n_flip=2)
+    eng.set_null_model(X, y)
+    outs = []
+    for s in (1, 3, 8):
+        eng.set_option("splits", s)
+        eng.push_i8(G.T.copy(), af_of(G))
+        outs.append(eng.flush()[0])
+    eng.set_option("splits", 0)
+    for o in outs[1:]:
+        assert o.tobytes() == outs[0].tobytes()
+
+
+def test_engines_agree_bitwise(eng, oracle):
+    if eng.info("tc_available") != 1:
+        pytest.skip("tensor-core engine not available")
+    O = oracle
+    G, X, y = make_problem(O, 22, 70000, 50, 3, n_flip=3, n_mono=1)
+    eng.set_null_model(X, y)
+    outs = []
+    for which in (1, 2):
+        eng.set_option("engine", which)
+        eng.push_i8(G.T.copy(), af_of(G))
+        outs.append(eng.flush()[0])
+    eng.set_option("engine", 0)
+    assert outs[0].tobytes() == outs[1].tobytes()
+
+
+@pytest.mark.parametrize("which", ENGINES)
+def test_loaded_synthetic_cohort(eng, oracle, which):
+    """device generator == host twin (bit exact), and the zero-copy loaded path == oracle"""
+    _set_engine(eng, which)
+    O = oracle
+    seed, N, M, ng, C = 20260925, 30011, 30, 6, 3
+    X, y = O.synth_covariates(seed, N, C)
+    eng.set_null_model(X, y)
+    nm = O.fit_null_linear(X, y)
+    vid = np.arange(ng * M, dtype=np.uint64)
+    maf = O.synth_maf(seed, vid)
+    t0, t1 = O.synth_thresholds(maf)
+    eng.synth_load(O.synth_variant_key(seed, vid), t0, t1, ng, M)
+    host = O.synth_genotypes(seed, vid, N, maf=maf)
+    dev = eng.loaded_read(0, ng * M)
+    assert np.array_equal(host, dev)
+    res = eng.run_loaded()
+    assert len(res) == ng
+    for g in range(ng):
+        Gg = host[g * M:(g + 1) * M].T
+        ref, lam = _oracle_gene(O, Gg, X, nm)
+        check_gene(res[g], ref, lam, ctx=f"loaded gene {g}")
+
+
+def test_bad_values_are_reported_not_computed(eng, oracle):
+    O = oracle
+    G, X, y = make_problem(O, 30, 500, 6, 1, maf=0.2)
+    eng.set_null_model(X, y)
+    Gd = G.astype(float)
+    Gd[3, 2] = 0.37  # an imputed dosage: not a hard call
+    eng.push_f64(Gd, af_of(G))
+    r = eng.flush()[0]
+    assert int(r["status"]) == 5  # RVT_GENE_BADVALUE (hard-call path only in this build)
+
+
+def test_errors_are_loud(eng):
+    import rvtests_b200
+    e2 = rvtests_b200.GeneEngine(0)
+    with pytest.raises(rvtests_b200.RvtError):
+        e2.push_i8(np.zeros((3, 10), dtype=np.int8))  # no null model yet
+    X = np.ones((10, 2))
+    X[:, 0] = 2.0
+    with pytest.raises(rvtests_b200.RvtError):
+        e2.set_null_model(X, np.arange(10.0))  # column 0 is not the intercept
+    e2.close()
