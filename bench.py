@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- gene-sets/sec of the per-gene SKAT (+CMC, Zeggini) hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU; torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host cores
+
+A "step" is one pass of the hot path over the genes resident on each GPU: for every gene one
+sweep over its packed N x M genotype block (K1), then eigenvalues + Davies/Liu + burden score tests
+(K2/K3), results left in HBM and (N>1) gathered once over NCCL.  Workload (weak scaling): each
+rank holds --genes genes of --samples x --variants synthetic HWE genotypes (SURVEY.md 8(d) stream,
+seed 20260925), i.e. BASELINE.json configs[2] (500k samples, 20 000 genes x 50 variants over 8 GPUs
+= 2 500 genes per GPU) at 8 ranks; the metric's "500k samples x 50 variants" at every N.
+The data set per rank (62.5 GB) is ~500x L2, so every step streams from HBM (no L2 flush needed).
+
+The one JSON line on stdout follows the driver contract; see DESIGN.md section 6 for how each
+field is measured.  oracle/ is used ONLY by the cpu_baseline leg and by --impl reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 20260925
+METRIC = "gene-sets/sec (SKAT, 500k samples x 50 variants)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples", type=int, default=500_000)
+    ap.add_argument("--variants", type=int, default=50)
+    ap.add_argument("--genes", type=int, default=2500, help="genes resident per GPU")
+    ap.add_argument("--covariates", type=int, default=3, help="columns of X incl. intercept")
+    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 dp4a, 2 tcgen05")
+    ap.add_argument("--e2e-genes", type=int, default=64, help="genes per step of the host-buffer (e2e) leg")
+    ap.add_argument("--cpu-genes", type=int, default=16, help="distinct genes of the CPU sample")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) > 8 and r[3].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) > 8 for i in range(4) if r[5 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+def cohort(args, rank):
+    """keys / thresholds of this rank's variants + the shared covariates and trait."""
+    from rvtests_b200.synth import variant_params, covariates
+    vid0 = rank * args.genes * args.variants
+    keys, t0, t1 = variant_params(SEED, vid0, args.genes * args.variants)
+    X, y = covariates(SEED, args.samples, args.covariates)
+    return keys, t0, t1, X, y
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import rvtests_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+
+    keys, t0, t1, X, y = cohort(args, rank)
+    eng = rvtests_b200.GeneEngine(local)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_option("engine", args.engine)
+    eng.set_null_model(X, y)
+    eng.synth_load(keys, t0, t1, args.genes, args.variants)
+
+    rec = rvtests_b200.engine.RESULT_DTYPE.itemsize
+    d_res = torch.empty(args.genes * rec, dtype=torch.uint8, device=dev)
+    d_all = torch.empty(world * args.genes * rec, dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def step():
+        n = eng.run_loaded(d_res.data_ptr())
+        if world > 1:
+            # the single collective of the path: one gather of the per-gene summary records
+            dist.all_gather_into_tensor(d_all, d_res)
+        return n
+
+    sweep_ms, fin_ms, launches = [], [], 0
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+        t = eng.last_timing()
+        sweep_ms.append(t["sweep_ms"])
+        fin_ms.append(t["finalize_ms"])
+        launches += t["launches"]
+    e1.record(stream)
+    torch.cuda.synchronize()
+    w1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax.item())
+    ms_per_step = ms_total / args.steps
+    value = world * args.genes / (ms_per_step * 1e-3)
+
+    out = None
+    if rank == 0:
+        res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=rvtests_b200.engine.RESULT_DTYPE)
+        pk = peaks()
+        hbm_peak = pk["hbm_gbs"] if pk else 6650.0
+        alg_bytes = float(args.genes) * args.samples * args.variants  # 1 byte per genotype
+        sweep_s = float(np.mean(sweep_ms)) * 1e-3
+        achieved = alg_bytes / sweep_s / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": "gene-sets/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "s8 x s8 -> s32 (exact) + f64 tail", "data": "synthetic",
+            "config": {"workload": f"SKAT+CMC+Zeggini, N={args.samples} samples x M={args.variants} variants, "
+                                   f"{args.genes} genes per GPU (BASELINE configs[2] sharded: 2500 genes/GPU), C={args.covariates}",
+                       "genes_per_gpu": args.genes, "samples": args.samples, "variants": args.variants,
+                       "covariates_incl_intercept": args.covariates, "kernel_flags": "skat[nPerm=0] + cmc + zeggini",
+                       "engine": {1: "dp4a", 2: "tcgen05.kind::i8"}.get(int(eng.info("last_engine")), "?"),
+                       "splits": int(eng.info("last_splits")),
+                       "l2_policy": "inputs (62.5 GB/rank at defaults) >> 126 MB L2; no flush needed",
+                       "parallelism": f"genes sharded over {world} rank(s), one NCCL all_gather of result records"},
+            "wall_ms_per_step": (w1 - w0) * 1e3 / args.steps,
+            "kernel_ms_per_step": {"sweep": float(np.mean(sweep_ms)), "finalize": float(np.mean(fin_ms))},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_sweep_tc" if int(eng.info("last_engine")) == 2 else "k_sweep_simt",
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if pk else "fallback 6.65 TB/s (of fallback)",
+                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": None},
+            "sanity": {"genes_ok": int((res["status"] == 0).sum()), "median_p_skat": float(np.median(res["p_skat"])),
+                       "davies_fault_frac": float((res["davies_fault"] != 0).mean())},
+        }
+    # ---- e2e: HOST buffers through the C ABI, H2D + D2H inside the timed region (rank-local, all ranks)
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, eng, torch, dist, world, rank, dev)
+    if rank == 0:
+        out["e2e"] = e2e
+        if not args.no_cpu and world == 1:
+            out["cpu_baseline"] = cpu_baseline(args, threads=os.cpu_count())
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, eng, torch, dist, world, rank, dev):
+    """same metric through rvt_gene_push_i8 (host, pinned) -> rvt_flush (results copied back)."""
+    import rvtests_b200
+    ng, M, N = args.e2e_genes, args.variants, args.samples
+    host = torch.empty((ng * M, N), dtype=torch.int8, pin_memory=True)
+    host.numpy()[:] = eng.loaded_read(0, ng * M)  # the same genotypes as the first resident genes
+    hn = host.numpy()
+    af = 0.5 * hn.reshape(ng, M, N).sum(axis=2, dtype=np.int64) / N
+
+    def step():
+        for g in range(ng):
+            eng.push_i8(hn[g * M:(g + 1) * M], af[g])
+        return eng.flush()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    sec = float(dt.item()) / reps
+    return {"value": world * ng / sec, "unit": "gene-sets/s",
+            "h2d_bytes_per_step": int(world * ng * M * N), "d2h_bytes_per_step": int(world * ng * rvtests_b200.engine.RESULT_DTYPE.itemsize),
+            "genes_per_step_per_gpu": ng, "host_format": "int8 variant-major hard calls, pinned host memory (rvt_gene_push_i8)",
+            "timing": "host wall clock around push+flush (copies inside), max over ranks"}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_problem(args):
+    from oracle import oracle as O
+    try:
+        O.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    from rvtests_b200.synth import variant_params, covariates
+    nd, M, N = args.cpu_genes, args.variants, args.samples
+    keys, t0, t1 = variant_params(SEED, 0, nd * M)
+    G = O.synth_rows_f64(keys, t0, t1, N, threads=0, native=native).reshape(nd, M, N)
+    X, y = covariates(SEED, N, args.covariates)
+    nm = O.fit_null_linear(X, y)
+    af = 0.5 * G.sum(axis=2) / N
+    return O, native, G, af, X, nm
+
+
+def time_cpu(O, native, G, af, X, nm, threads, seconds):
+    nd = G.shape[0]
+    # calibrate on one pass of `threads` tasks, then size the sample for ~`seconds` of work
+    idx = np.arange(max(threads, 1)) % nd
+    t = time.perf_counter()
+    O.gene_batch_idx(G, af, idx, X, nm["resid"], nm["sigma2"], threads=threads, native=native)
+    one = time.perf_counter() - t
+    reps = int(max(1, min(50, seconds / max(one, 1e-3))))
+    idx = np.arange(len(idx) * reps) % nd
+    t = time.perf_counter()
+    out = O.gene_batch_idx(G, af, idx, X, nm["resid"], nm["sigma2"], threads=threads, native=native)
+    dt = time.perf_counter() - t
+    return len(idx) / dt, len(idx), dt, out
+
+
+def cpu_baseline(args, threads):
+    O, native, G, af, X, nm = cpu_problem(args)
+    v, ntask, dt, _ = time_cpu(O, native, G, af, X, nm, threads, args.cpu_seconds)
+    v1, ntask1, dt1, _ = time_cpu(O, native, G, af, X, nm, 1, min(args.cpu_seconds, 6.0))
+    return {"value": v, "unit": "gene-sets/s", "cores": threads, "kind": "port",
+            "sample": f"{ntask} gene-tasks over {G.shape[0]} distinct genes of N={args.samples} x M={args.variants} "
+                      f"(fp64 column-major Matrix, 200 MB each) in {dt:.1f} s, OpenMP over genes, "
+                      f"oracle/skat_oracle.c {'-march=native' if native else 'x86-64-v3'}: reduced O(N M^2) algebra "
+                      "(the reference's own Skat.cpp is O(N^2) and cannot run at this N: SURVEY.md F2)",
+            "single_thread_value": v1, "single_thread_note": "the reference's gene loop is serial (src/Main.cpp:1221-1254)"}
+
+
+def run_reference(args):
+    """reference arm: the reference algorithm (oracle port; Skat.cpp itself needs Eigen, absent) on all
+    host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count()
+    O, native, G, af, X, nm = cpu_problem(args)
+    per_step = []
+    for k in range(args.warmup + args.steps):
+        v, ntask, dt, _ = time_cpu(O, native, G, af, X, nm, threads, max(2.0, args.cpu_seconds / max(args.steps, 1)))
+        if k >= args.warmup:
+            per_step.append((v, ntask, dt))
+    value = float(np.mean([p[0] for p in per_step]))
+    ms = float(np.mean([p[2] for p in per_step])) * 1e3
+    sample = (f"each step = {per_step[0][1]} gene-tasks over {G.shape[0]} distinct genes of N={args.samples} x "
+              f"M={args.variants}, OpenMP over genes on {threads} threads, oracle port "
+              f"({'-march=native' if native else 'x86-64-v3'})")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "gene-sets/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"SKAT+CMC+Zeggini, N={args.samples} samples x M={args.variants} variants, C={args.covariates}",
+                   "samples": args.samples, "variants": args.variants, "kernel_flags": "skat[nPerm=0] + cmc + zeggini"},
+        "cpu_baseline": {"value": value, "unit": "gene-sets/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "gene-sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

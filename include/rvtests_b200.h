@@ -80,9 +80,13 @@ int rvt_ctx_create(int device, rvt_ctx** out);
 void rvt_ctx_destroy(rvt_ctx* ctx);
 const char* rvt_last_error(const rvt_ctx* ctx);
 /* keys: "beta1","beta2" (Beta weight, src/ModelManager.cpp:169-175), "engine", "splits" (0=auto),
- * "skato" (0/1), "stream_ptr" (cudaStream_t as integer; default stream 0 of the context) */
+ * "skato" (0/1) */
 int rvt_set_option(rvt_ctx* ctx, const char* key, double value);
 double rvt_get_info(const rvt_ctx* ctx, const char* key);
+/* run on a caller-owned CUDA stream (cudaStream_t), e.g. the framework's current stream, so that
+ * the caller's events and collectives order with the engine's kernels; NULL restores the
+ * context's own stream */
+int rvt_set_stream(rvt_ctx* ctx, void* cuda_stream);
 
 /* ---- null model: replaces LinearRegression::FitLinearModel(cov, phenoVec) -------------------
  * X: N x C column-major doubles INCLUDING the intercept as column 0 (the matrix produced by
@@ -131,6 +135,9 @@ int rvt_loaded_read(rvt_ctx* ctx, int64_t row0, int rows, int8_t* out /*rows x N
 /* device milliseconds of the last flush: [0] sweep kernel(s), [1] finalize kernel(s), [2] whole
  * flush on the context stream (CUDA events), [3] number of kernel launches */
 int rvt_last_timing(const rvt_ctx* ctx, double out[4]);
+/* diagnostic: copy the raw sweep partials of the last flush's final batch (device layout, see
+ * rvtests_b200/csrc/common.cuh SweepPartial) to the host; returns the byte count via *bytes */
+int rvt_debug_partials(rvt_ctx* ctx, void* out, int64_t cap_bytes, int64_t* bytes);
 
 #ifdef __cplusplus
 }

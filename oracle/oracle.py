@@ -106,6 +106,12 @@ def lib(native: bool = False):
     L.orc_gene_batch.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p,
                                  _dbl_p, C.c_double, C.c_double, C.c_double, C.POINTER(GeneOut),
                                  C.c_int]
+    L.orc_gene_batch_idx.restype = C.c_int
+    L.orc_gene_batch_idx.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, _int_p, _dbl_p, _dbl_p, _dbl_p,
+                                     _dbl_p, C.c_double, C.c_double, C.c_double, C.POINTER(GeneOut),
+                                     C.c_int]
+    L.orc_synth_rows_f64.restype = None
+    L.orc_synth_rows_f64.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, _dbl_p, C.c_int]
     L.orc_max_threads.restype = C.c_int
     _lib_cache[key] = L
     return L
@@ -245,6 +251,32 @@ def gene_batch(G_all, af_all, X, resid, sigma2, threads=1, beta1=1.0, beta2=25.0
     resid = np.ascontiguousarray(resid, dtype=np.float64)
     lib(native).orc_gene_batch(N, M, Xc.shape[1], ng, _p(G_all), _p(af_all), _p(Xc), _p(resid),
                                float(sigma2), float(beta1), float(beta2), out, int(threads))
+    return out
+
+
+def gene_batch_idx(G_all, af_all, index, X, resid, sigma2, threads=1, beta1=1.0, beta2=25.0, native=False):
+    """tasks t -> gene index[t] of G_all (n_distinct, M, N); returns GeneOut array of len(index)."""
+    G_all = np.ascontiguousarray(G_all, dtype=np.float64)
+    nd, M, N = G_all.shape
+    index = np.ascontiguousarray(index, dtype=np.int32)
+    Xc = np.asfortranarray(X, dtype=np.float64)
+    out = (GeneOut * len(index))()
+    af_all = np.ascontiguousarray(af_all, dtype=np.float64)
+    resid = np.ascontiguousarray(resid, dtype=np.float64)
+    lib(native).orc_gene_batch_idx(N, M, Xc.shape[1], len(index), _p(index, C.c_int), _p(G_all), _p(af_all),
+                                   _p(Xc), _p(resid), float(sigma2), float(beta1), float(beta2), out,
+                                   int(threads))
+    return out
+
+
+def synth_rows_f64(keys, t0, t1, N, threads=0, native=False):
+    """C twin of the device generator: (len(keys), N) doubles."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    t0 = np.ascontiguousarray(t0, dtype=np.uint32)
+    t1 = np.ascontiguousarray(t1, dtype=np.uint32)
+    out = np.empty((len(keys), N), dtype=np.float64)
+    lib(native).orc_synth_rows_f64(len(keys), N, keys.ctypes.data, t0.ctypes.data, t1.ctypes.data, _p(out),
+                                   int(threads))
     return out
 
 

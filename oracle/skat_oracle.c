@@ -1073,6 +1073,50 @@ ORC_API int orc_gene_batch(int64_t N, int M, int C, int n_genes, const double* G
   return 0;
 }
 
+/* Same, but task t works on gene index[t] (lets a bounded set of distinct genes stand in for a
+ * long gene list when timing the CPU baseline: every task still streams its 8*N*M bytes). */
+ORC_API int orc_gene_batch_idx(int64_t N, int M, int C, int n_tasks, const int* index, const double* G_all,
+                               const double* af_all, const double* X, const double* resid,
+                               double sigma2, double beta1, double beta2, orc_gene_out* out,
+                               int threads) {
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+  for (int t = 0; t < n_tasks; ++t) {
+    const int g = index[t];
+    double* lam = (double*)malloc(sizeof(double) * M);
+    orc_gene(N, M, C, G_all + (size_t)g * N * M, af_all + (size_t)g * M, X, resid, sigma2, beta1,
+             beta2, &out[t], lam);
+    free(lam);
+  }
+  return 0;
+}
+
+/* Host twin of the device genotype generator (rvtests_b200/csrc/prep.cuh k_synth_rows): writes
+ * rows x N doubles (row-major == each variant contiguous) for the given keys / thresholds. */
+static inline uint64_t orc_mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+ORC_API void orc_synth_rows_f64(int64_t rows, int64_t N, const uint64_t* keys, const uint32_t* t0,
+                                const uint32_t* t1, double* out, int threads) {
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(static)
+#endif
+  for (int64_t r = 0; r < rows; ++r) {
+    const uint64_t key = keys[r];
+    const uint32_t a = t0[r], b = t1[r];
+    double* o = out + (size_t)r * N;
+    for (int64_t i = 0; i < N; ++i) {
+      uint32_t h = (uint32_t)(orc_mix64(key + (uint64_t)i * 0xD1B54A32D192ED03ull) >> 32);
+      o[i] = (double)((h >= a) + (h >= b));
+    }
+  }
+}
+
 ORC_API int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

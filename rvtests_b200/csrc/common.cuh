@@ -6,7 +6,7 @@
 //       reference's column-major Matrix (base/MathMatrix.h:33-41) at one byte per call.
 //       Rows of consecutive genes are stacked in one arena so that ONE TMA tensor map
 //       [total_rows][N] serves every gene of a segment.
-//   null-model digits "E"      : int8 [ER rows][ldE], ER = 4*(C+1) rounded up to 8.  Row 4*v+k is
+//   null-model digits "E"      : int8 [ER rows][ldE], ER = 4*(C+1) rounded up to 16.  Row 4*v+k is
 //       base-256 balanced digit k of the fixed-point image of vector v, v=0 the null residual r,
 //       v=1..C the covariate columns (column 0 = intercept).  value_i = (sum_k d_ik 256^k) 2^-e_v.
 //       With G in {0,1,2} and digits in [-128,127] every dot product the tests need
@@ -55,7 +55,7 @@ struct SweepPartial {
 struct NullModel {
   int64_t N;
   int32_t C;
-  int32_t ER;            // rows of E (multiple of 8)
+  int32_t ER;            // rows of E (16 or 32)
   int64_t ldE;           // bytes between rows of E
   const int8_t* E;       // digits
   const double* resid;   // N

@@ -20,16 +20,13 @@
 
 using namespace rvt;
 
-namespace {
-struct Chunk {
-  uint8_t* p;
-  size_t cap, used;
-};
-}  // namespace
+constexpr int kSegLoaded = 0;  // the synthetic / loaded cohort arena
+constexpr int kSegStaged = 1;  // genes staged from host buffers
 
 struct rvt_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
   char err[512] = {0};
   int sm_count = 148;
   // options
@@ -64,8 +61,9 @@ struct rvt_ctx {
   rvt_gene_result* d_res = nullptr;
   size_t cap_res = 0;
   unsigned int* d_counter = nullptr;
-  // staging
-  std::vector<Chunk> chunks;
+  // staging: one growable arena of int8 rows (row pitch stage_ld), TMA segment kSegStaged
+  int8_t* d_stage = nullptr;
+  int64_t stage_ld = 0, stage_cap_rows = 0, stage_used_rows = 0;
   double* d_stage64 = nullptr;
   size_t cap_stage64 = 0;
   // loaded synthetic cohort
@@ -79,6 +77,7 @@ struct rvt_ctx {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double t_sweep = 0, t_fin = 0, t_total = 0, n_launch = 0;
   int last_engine = 0, last_S = 0;
+  int64_t last_parts = 0;
 };
 
 #define CTX_FAIL(code, ...)                              \
@@ -127,20 +126,32 @@ static int ensure_var(rvt_ctx* ctx, size_t need) {
   return RVT_OK;
 }
 
-static int arena_alloc(rvt_ctx* ctx, size_t bytes, uint8_t** out) {
-  bytes = (bytes + 255) & ~(size_t)255;
-  for (auto& c : ctx->chunks)
-    if (c.cap - c.used >= bytes) {
-      *out = c.p + c.used;
-      c.used += bytes;
-      return RVT_OK;
+// rows for one staged gene; grows the arena (device-to-device copy, pending descriptors re-based)
+static int stage_alloc_rows(rvt_ctx* ctx, int M, int64_t ld, int64_t* row0) {
+  if (ctx->stage_ld != ld) {
+    if (ctx->stage_used_rows) CTX_FAIL(RVT_E_STATE, "internal: staging arena pitch changed with genes pending");
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    ctx->d_stage = nullptr;
+    ctx->stage_cap_rows = 0;
+    ctx->stage_ld = ld;
+  }
+  if (ctx->stage_used_rows + M > ctx->stage_cap_rows) {
+    int64_t ncap = std::max<int64_t>(ctx->stage_used_rows + M, ctx->stage_cap_rows * 2);
+    ncap = std::max<int64_t>(ncap, std::max<int64_t>(256, ((int64_t)64 << 20) / ld));
+    int8_t* np = nullptr;
+    RVT_CUDA_OK(cudaMalloc((void**)&np, (size_t)ncap * ld));
+    if (ctx->d_stage) {
+      RVT_CUDA_OK(cudaMemcpyAsync(np, ctx->d_stage, (size_t)ctx->stage_used_rows * ld, cudaMemcpyDeviceToDevice, ctx->stream));
+      RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      RVT_CUDA_OK(cudaFree(ctx->d_stage));
     }
-  Chunk c;
-  c.cap = std::max(bytes, (size_t)256 << 20);
-  c.used = bytes;
-  RVT_CUDA_OK(cudaMalloc((void**)&c.p, c.cap));
-  ctx->chunks.push_back(c);
-  *out = c.p;
+    for (auto& g : ctx->genes)
+      if (g.seg == kSegStaged) g.g = np + (size_t)g.row0 * ld;
+    ctx->d_stage = np;
+    ctx->stage_cap_rows = ncap;
+  }
+  *row0 = ctx->stage_used_rows;
+  ctx->stage_used_rows += M;
   return RVT_OK;
 }
 
@@ -165,7 +176,8 @@ int rvt_ctx_create(int device, rvt_ctx** out) {
   if (prop.major != 10)
     CTX_FAIL(RVT_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
              prop.major, prop.minor);
-  RVT_CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  RVT_CUDA_OK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
   for (auto& ev : ctx->ev) RVT_CUDA_OK(cudaEventCreate(&ev));
   RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_nm, sizeof(NullModel)));
   RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_counter, sizeof(unsigned int) * 4));
@@ -186,13 +198,12 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  for (auto& c : ctx->chunks) cudaFree(c.p);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 
@@ -215,6 +226,14 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   return RVT_OK;
 }
 
+int rvt_set_stream(rvt_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return RVT_E_BADARG;
+  RVT_CUDA_OK(cudaSetDevice(ctx->device));
+  RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return RVT_OK;
+}
+
 double rvt_get_info(const rvt_ctx* ctx, const char* key) {
   if (!ctx || !key) return -1;
   std::string k(key);
@@ -232,7 +251,7 @@ double rvt_get_info(const rvt_ctx* ctx, const char* key) {
 static int null_model_run(rvt_ctx* ctx) {
   const int64_t N = ctx->N;
   const int C = ctx->C;
-  ctx->ER = ((4 * (C + 1)) + 7) & ~7;
+  ctx->ER = ((4 * (C + 1)) + 15) & ~15;  // kind::i8 UMMA needs N = 64 + ER to be a multiple of 16
   ctx->ldE = (N + 127) & ~(int64_t)127;
   if (ctx->dresid) cudaFree(ctx->dresid);
   if (ctx->dE) cudaFree(ctx->dE);
@@ -368,17 +387,18 @@ int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
     RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_stage64, need * sizeof(double)));
     ctx->cap_stage64 = need;
   }
-  uint8_t* blk = nullptr;
-  if ((rc = arena_alloc(ctx, (size_t)M * ld, &blk))) return rc;
+  int64_t row0 = 0;
+  if ((rc = stage_alloc_rows(ctx, M, ld, &row0))) return rc;
+  int8_t* blk = ctx->d_stage + (size_t)row0 * ld;
   if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_stage64, G, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
   dim3 grid((unsigned)((ld / 4 + 255) / 256), (unsigned)M);
-  k_pack_f64<<<grid, 256, 0, ctx->stream>>>(ctx->d_stage64, N, (int8_t*)blk, ld, ctx->d_counts + ctx->n_var);
+  k_pack_f64<<<grid, 256, 0, ctx->stream>>>(ctx->d_stage64, N, blk, ld, ctx->d_counts + ctx->n_var);
   RVT_CUDA_OK(cudaGetLastError());
   // the staging buffer is reused by the next push: wait (pageable H2D is synchronous anyway)
   RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  return push_common(ctx, (const int8_t*)blk, M, ld, af, nullptr, true, -1, 0);
+  return push_common(ctx, blk, M, ld, af, nullptr, true, kSegStaged, row0);
 }
 
 int rvt_gene_push_i8(rvt_ctx* ctx, const int8_t* G, int M, int64_t ld_in, const double* af) {
@@ -387,15 +407,16 @@ int rvt_gene_push_i8(rvt_ctx* ctx, const int8_t* G, int M, int64_t ld_in, const 
   if (rc) return rc;
   const int64_t N = ctx->N, ld = (N + 127) & ~(int64_t)127;
   if (ld_in < N) CTX_FAIL(RVT_E_BADARG, "ld (%lld) < N (%lld)", (long long)ld_in, (long long)N);
-  uint8_t* blk = nullptr;
-  if ((rc = arena_alloc(ctx, (size_t)M * ld, &blk))) return rc;
+  int64_t row0 = 0;
+  if ((rc = stage_alloc_rows(ctx, M, ld, &row0))) return rc;
+  int8_t* blk = ctx->d_stage + (size_t)row0 * ld;
   if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
   RVT_CUDA_OK(cudaMemsetAsync(blk, 0, (size_t)M * ld, ctx->stream));
   RVT_CUDA_OK(cudaMemcpy2DAsync(blk, ld, G, ld_in, N, M, cudaMemcpyHostToDevice, ctx->stream));
   RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
-  launch_count(ctx, (const int8_t*)blk, M, ld, ctx->d_counts + ctx->n_var);
+  launch_count(ctx, blk, M, ld, ctx->d_counts + ctx->n_var);
   RVT_CUDA_OK(cudaGetLastError());
-  return push_common(ctx, (const int8_t*)blk, M, ld, af, nullptr, true, -1, 0);
+  return push_common(ctx, blk, M, ld, af, nullptr, true, kSegStaged, row0);
 }
 
 int rvt_gene_push_dev_i8(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const double* af, const uint8_t* flags) {
@@ -463,6 +484,10 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
                                                                          ctx->d_userflags, ctx->d_flags);
   int launches = 1;
   int engine = ctx->engine;
+  if (ctx->stage_used_rows > 0) {
+    rc = tc_bind_segment(&ctx->tc, kSegStaged, ctx->d_stage, ctx->stage_used_rows, N, ctx->stage_ld, ctx->err, sizeof(ctx->err));
+    if (rc) return rc;
+  }
   bool tc_ok = tc_usable(&ctx->tc, ctx->genes.data(), n);
   if (engine == RVT_ENGINE_AUTO) engine = tc_ok ? RVT_ENGINE_TC : RVT_ENGINE_SIMT;
   if (engine == RVT_ENGINE_TC && !tc_ok)
@@ -490,6 +515,7 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     RVT_CUDA_OK(cudaEventRecord(ctx->ev[4], st));
     RVT_CUDA_OK(cudaGetLastError());
     launches += 2;
+    ctx->last_parts = (int64_t)nb * S;
     if (n > batch || true) {
       // per-batch timing needs the events resolved before they are re-recorded
       RVT_CUDA_OK(cudaEventSynchronize(ctx->ev[4]));
@@ -516,7 +542,7 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   ctx->af.clear();
   ctx->count_slot.clear();
   ctx->n_var = 0;
-  for (auto& c : ctx->chunks) c.used = 0;
+  ctx->stage_used_rows = 0;
   return RVT_OK;
 }
 
@@ -570,7 +596,7 @@ int rvt_synth_load(rvt_ctx* ctx, int n_genes, int M, const uint64_t* keys, const
   ctx->loaded_ld = ld;
   ctx->loaded_genes = n_genes;
   ctx->loaded_M = M;
-  rc = tc_bind_segment(&ctx->tc, 0, ctx->d_loaded, rows, N, ld, ctx->err, sizeof(ctx->err));
+  rc = tc_bind_segment(&ctx->tc, kSegLoaded, ctx->d_loaded, rows, N, ld, ctx->err, sizeof(ctx->err));
   if (rc) return rc;
   return RVT_OK;
 }
@@ -590,7 +616,7 @@ int rvt_run_loaded(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, int 
     const int64_t row0 = (int64_t)g * M;
     // AF: the loader's counts, i.e. what GenotypeCounter::getAF hands to the fitters
     push_common(ctx, ctx->d_loaded + (size_t)row0 * ctx->loaded_ld, M, ctx->loaded_ld, ctx->loaded_af.data() + row0,
-                ctx->loaded_flags.data() + row0, false, 0, row0);
+                ctx->loaded_flags.data() + row0, false, kSegLoaded, row0);
   }
   return flush_impl(ctx, out, cap, n_out, results_on_device != 0);
 }
@@ -601,6 +627,16 @@ int rvt_loaded_read(rvt_ctx* ctx, int64_t row0, int rows, int8_t* out) {
   RVT_CUDA_OK(cudaMemcpy2DAsync(out, ctx->N, ctx->d_loaded + (size_t)row0 * ctx->loaded_ld, ctx->loaded_ld, ctx->N,
                                 rows, cudaMemcpyDeviceToHost, ctx->stream));
   RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return RVT_OK;
+}
+
+int rvt_debug_partials(rvt_ctx* ctx, void* out, int64_t cap_bytes, int64_t* bytes) {
+  if (!ctx || !bytes) return RVT_E_BADARG;
+  const int64_t need = (int64_t)ctx->last_parts * (int64_t)sizeof(SweepPartial);
+  *bytes = need;
+  if (!out) return RVT_OK;
+  if (cap_bytes < need) CTX_FAIL(RVT_E_BADARG, "partials need %lld bytes", (long long)need);
+  RVT_CUDA_OK(cudaMemcpy(out, ctx->d_parts, (size_t)need, cudaMemcpyDeviceToHost));
   return RVT_OK;
 }
 

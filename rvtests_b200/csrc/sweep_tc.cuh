@@ -1,17 +1,451 @@
-// sweep_tc.cuh -- K1 on the 5th-generation tensor cores (placeholder until the kernel lands).
+// sweep_tc.cuh -- K1 on the 5th-generation tensor cores: TMA -> SMEM -> tcgen05.mma (kind::i8,
+// s32 accumulators in TMEM) with the burden collapse riding on the same SMEM tiles.
+//
+// Same contract as sweep_simt.cuh (one SweepPartial per (gene, split), bit-identical numbers):
+//   D[64 x (64+ER)] += T_gene[64 x K] * [T_gene ; E]^T        regression/Skat.cpp:47-76 G'VG, G'r,
+//                                                             X'VG; LinearRegressionScoreTest.cpp:209-217
+// Why kind::i8 and not kind::f16: genotypes are 0/1/2 and the null-model vectors are carried as
+// base-256 digits (common.cuh), so the contraction is an exact integer GEMM.  sm_100a has int8
+// UMMA at twice the bf16 rate, the operands need no conversion pass (TMA lands them ready to use)
+// and the s32 accumulation is exact -- results do not depend on tiling or split order.
+//
+// CTA = 6 warps, persistent over units u = blockIdx.x + i*gridDim.x (static: units cost the same):
+//   warp 0      TMA producer: per stage 4 boxes of 128 samples, each box = gene tile 64 x 128 B
+//               (SWIZZLE_128B) immediately followed by the E tile ER x 128 B, so that the B operand
+//               of one UMMA is the contiguous (64+ER)-row tile.  OOB rows/samples are zero-filled.
+//   warp 1      MMA issuer: 4 UMMAs (K = 32 bytes) per box; tcgen05.commit frees the stage and,
+//               after the unit's last stage, publishes the TMEM accumulator (double-buffered).
+//   warps 2..5  consumers: (a) burden collapse of box (warp-2) of every stage straight from the
+//               swizzled SMEM tile, (b) epilogue: tcgen05.ld the accumulator of the finished unit
+//               (UMMA M=64 layout: row m at lane (m%16)+32*(m/16)) and store the SweepPartial.
+// Roofline class: HBM sweep, 1 byte per genotype: the tensor pipe needs
+// 128*(64+ER)/256 = 40 cycles per 32-sample slice, i.e. ~64 B/clk/SM, ~3x what HBM can deliver.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
+#include "sweep_simt.cuh"
+
 namespace rvt {
-struct TcSegments {
-  void* encode = nullptr;
-  char why[128] = "tensor-core sweep not built yet";
+
+constexpr int kTcThreads = 192;
+constexpr int kTcStages = 4;
+constexpr int kTcBoxes = 4;                 // boxes per stage == consumer warps
+constexpr int kTcBoxK = 128;                // samples per box (one 128-byte swizzle row)
+constexpr int kTcStageK = kTcBoxes * kTcBoxK;
+constexpr int kTcTmemCols = 256;            // 2 accumulators x 128 columns
+
+template <int ER>
+struct TcCfg {
+  static constexpr int kBoxBytes = kTileRows * 128 + ER * 128;
+  static constexpr int kStageBytes = kTcBoxes * kBoxBytes;
+  static constexpr int kSmem = kTcStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kNC = kTileRows + ER;
 };
-inline int tc_init(TcSegments*, char*, size_t) { return 0; }
-inline int tc_bind_null(TcSegments*, const int8_t*, int, int64_t, int64_t, char*, size_t) { return 0; }
-inline int tc_bind_segment(TcSegments*, int, const int8_t*, int64_t, int64_t, int64_t, char*, size_t) { return 0; }
-inline bool tc_usable(const TcSegments*, const GeneDesc*, int) { return false; }
-inline int tc_launch(TcSegments*, const GeneDesc*, const GeneDesc*, int, const uint8_t*, const NullModel*, int64_t, int,
-                     int, int64_t, SweepPartial*, unsigned int*, int, cudaStream_t, char*, size_t) {
-  return -4;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
+// LBO = 16 B (unused for a single swizzle row of K), SBO = 1024 B between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
+  const uint32_t hi = 64u | (1u << 14) | (2u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// byte offset of 4-byte word `w` (0..31) of row `r` inside a SWIZZLE_128B tile with 128-byte rows
+__device__ __forceinline__ uint32_t sw128_word_off(int r, int w) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((w >> 2) ^ (r & 7)) << 4) | ((w & 3) << 2)));
+}
+
+template <int ER>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_sweep_tc(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_e,
+           const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __restrict__ rowflags, int64_t N, int S,
+           int64_t chunk, SweepPartial* __restrict__ out) {
+  using Cfg = TcCfg<ER>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is required by SWIZZLE_128B (TMA destination and UMMA descriptors)
+  uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + kTcStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                    // [kTcStages]
+  uint64_t* empty = bars + kTcStages;       // [kTcStages]
+  uint64_t* tfull = bars + 2 * kTcStages;   // [2]
+  uint64_t* tempty = tfull + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  __shared__ uint32_t s_xf[4][kTileRows], s_mn[4][kTileRows], s_en[4][kTileRows];
+  __shared__ unsigned long long s_coll[2][kCollapseN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = n_genes * S;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < kTcStages; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], 1 + kTcBoxes);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tfull[a], 1);
+        mbar_init(&tempty[a], 4);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTcTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  if (threadIdx.x < 2 * kCollapseN) (&s_coll[0][0])[threadIdx.x] = 0ull;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int gi = u / S, sp = u - gi * S;
+        const int row0 = (int)genes[gi].row0;
+        const int64_t k0 = (int64_t)sp * chunk;
+        int64_t k1 = k0 + chunk;
+        if (k1 > N) k1 = N;
+        const int nsteps = (k1 > k0) ? (int)((k1 - k0 + kTcStageK - 1) / kTcStageK) : 0;
+        for (int ks = 0; ks < nsteps; ++ks, ++it) {
+          const int s = it % kTcStages;
+          const uint32_t ph = (it / kTcStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], Cfg::kStageBytes);
+          uint8_t* st = tiles + (size_t)s * Cfg::kStageBytes;
+          const int kb = (int)(k0 + (int64_t)ks * kTcStageK);
+#pragma unroll
+          for (int b = 0; b < kTcBoxes; ++b) {
+            tma_load_2d(st + b * Cfg::kBoxBytes, &map_g, kb + b * kTcBoxK, row0, &full[s]);
+            tma_load_2d(st + b * Cfg::kBoxBytes + kTileRows * 128, &map_e, kb + b * kTcBoxK, 0, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 64, N = 64 + ER
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cfg::kNC >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
+    uint32_t it = 0, ui = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+      const int gi = u / S, sp = u - gi * S;
+      const int64_t k0 = (int64_t)sp * chunk;
+      int64_t k1 = k0 + chunk;
+      if (k1 > N) k1 = N;
+      const int nsteps = (k1 > k0) ? (int)((k1 - k0 + kTcStageK - 1) / kTcStageK) : 0;
+      const int a = ui & 1;
+      mbar_wait(&tempty[a], ((ui >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)a * 128u;
+      for (int ks = 0; ks < nsteps; ++ks, ++it) {
+        const int s = it % kTcStages;
+        const uint32_t ph = (it / kTcStages) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_u32(tiles + (size_t)s * Cfg::kStageBytes);
+#pragma unroll
+          for (int b = 0; b < kTcBoxes; ++b) {
+            const uint64_t d0 = umma_desc_sw128(st + b * Cfg::kBoxBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // advance 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+              const uint64_t d = d0 + (uint64_t)(2 * k);
+              umma_i8(tmem_d, d, d, idesc, (ks | b | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[s]);
+          if (ks == nsteps - 1) umma_commit(&tfull[a]);
+        }
+        __syncwarp();
+      }
+      if (nsteps == 0 && lane == 0) umma_commit(&tfull[a]);  // degenerate unit: publish (stale) accumulator
+      __syncwarp();
+    }
+  } else {
+    // ===================== consumers: collapse + epilogue =====================
+    const int cw = warp - 2;       // box handled in every stage
+    const int q = warp & 3;        // TMEM lane quadrant this warp may read
+    uint32_t it = 0, ui = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+      const int gi = u / S, sp = u - gi * S;
+      const GeneDesc gd = genes[gi];
+      const int M = gd.M;
+      const int64_t k0 = (int64_t)sp * chunk;
+      int64_t k1 = k0 + chunk;
+      if (k1 > N) k1 = N;
+      const int nsteps = (k1 > k0) ? (int)((k1 - k0 + kTcStageK - 1) / kTcStageK) : 0;
+      for (int r = lane; r < kTileRows; r += 32) {
+        uint8_t f = (r < M) ? rowflags[gd.var0 + r] : (uint8_t)kRowSkip;
+        s_xf[cw][r] = (f == kRowFlipped) ? 0x01010101u : 0u;
+        s_mn[cw][r] = (f == kRowNormal) ? 0x01010101u : 0u;
+        s_en[cw][r] = (f == kRowSkip) ? 0u : 0x01010101u;
+      }
+      __syncwarp();
+      int cz[ER + 1], cc[ER + 1];
+#pragma unroll
+      for (int e = 0; e <= ER; ++e) cz[e] = cc[e] = 0;
+      for (int ks = 0; ks < nsteps; ++ks, ++it) {
+        const int s = it % kTcStages;
+        const uint32_t ph = (it / kTcStages) & 1;
+        mbar_wait(&full[s], ph);
+        const uint8_t* box = tiles + (size_t)s * Cfg::kStageBytes + cw * Cfg::kBoxBytes;
+        const int64_t ksamp = k0 + (int64_t)ks * kTcStageK + cw * kTcBoxK + 4 * lane;
+        uint32_t z = 0;
+        for (int r = 0; r < M; ++r) {
+          uint32_t w = *reinterpret_cast<const uint32_t*>(box + sw128_word_off(r, lane));
+          z += collapse_ind(w, s_xf[cw][r], s_mn[cw][r], s_en[cw][r]);
+        }
+        int64_t rem = k1 - ksamp;
+        uint32_t vm = rem >= 4 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - (int)rem))));
+        z &= vm;
+        const uint32_t c = ((z + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
+        const uint8_t* ebox = box + kTileRows * 128;
+#pragma unroll
+        for (int e = 0; e < ER; ++e) {
+          int ew = *reinterpret_cast<const int*>(ebox + sw128_word_off(e, lane));
+          cz[e] = __dp4a((int)z, ew, cz[e]);
+          cc[e] = __dp4a((int)c, ew, cc[e]);
+        }
+        cz[ER] = __dp4a((int)z, (int)z, cz[ER]);
+        cc[ER] = __dp4a((int)c, (int)c, cc[ER]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+      // ---- collapse sums of this unit: warp reduce (int64), combine the 4 warps through smem
+      const int cb = ui & 1;
+#pragma unroll
+      for (int e = 0; e <= ER; ++e) {
+        long long a = cz[e], b = cc[e];
+        for (int o = 16; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0) {
+          atomicAdd(&s_coll[cb][e], (unsigned long long)a);
+          atomicAdd(&s_coll[cb][(ER + 1) + e], (unsigned long long)b);
+        }
+      }
+      // ---- epilogue: accumulator of this unit -> SweepPartial
+      const int a = ui & 1;
+      mbar_wait(&tfull[a], (ui >> 1) & 1);
+      tc_fence_after();
+      SweepPartial* o = out + u;
+      const uint32_t taddr = tmem_base + (uint32_t)a * 128u + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c0 = 0; c0 < Cfg::kNC; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (lane < 16) {
+          const int row = 16 * q + lane;   // UMMA M=64: row m lives at lane (m%16) + 32*(m/16)
+          int4* dst = reinterpret_cast<int4*>(&o->d[row][c0]);
+          if (row < M) {
+            dst[0] = make_int4((int)v[0], (int)v[1], (int)v[2], (int)v[3]);
+            dst[1] = make_int4((int)v[4], (int)v[5], (int)v[6], (int)v[7]);
+            dst[2] = make_int4((int)v[8], (int)v[9], (int)v[10], (int)v[11]);
+            dst[3] = make_int4((int)v[12], (int)v[13], (int)v[14], (int)v[15]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[a]);
+      // all 4 consumer warps have added their collapse sums -> one warp writes them out
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      if (cw == 0) {
+        for (int i = lane; i < 2 * (ER + 1); i += 32) {
+          o->coll[i] = (long long)s_coll[cb][i];
+          s_coll[cb][i] = 0ull;
+        }
+      }
+      // s_coll[cb] is reused two units later; the bar.sync of the next unit orders that reuse
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(kTcTmemCols));
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcSegments {
+  void* encode = nullptr;   // cuTensorMapEncodeTiled through the runtime's driver entry point
+  char why[128] = "";
+  bool have_e = false;
+  int ER = 0;
+  CUtensorMap map_e;
+  static constexpr int kMaxSeg = 4;
+  bool have_seg[kMaxSeg] = {false, false, false, false};
+  CUtensorMap map_seg[kMaxSeg];
+};
+
+inline int tc_init(TcSegments* tc, char* err, size_t errlen) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+    snprintf(tc->why, sizeof(tc->why), "cuTensorMapEncodeTiled unavailable");
+    tc->encode = nullptr;
+    (void)cudaGetLastError();
+    return 0;  // the dp4a engine still works; an explicit engine=tc request fails loudly
+  }
+  tc->encode = fn;
+  e = cudaFuncSetAttribute(k_sweep_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32>::kSmem);
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "cudaFuncSetAttribute(k_sweep_tc): %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return 0;
+}
+
+inline int tc_make_map(TcSegments* tc, CUtensorMap* map, const void* base, int64_t rows, int64_t N, int64_t ld, int box_rows,
+                       char* err, size_t errlen) {
+  cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld};
+  cuuint32_t box[2] = {(cuuint32_t)kTcBoxK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((PFN_encodeTiled)tc->encode)(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box,
+                                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d) rows=%lld N=%lld ld=%lld", (int)r, (long long)rows, (long long)N,
+             (long long)ld);
+    return -2;
+  }
+  return 0;
+}
+
+inline int tc_bind_null(TcSegments* tc, const int8_t* E, int ER, int64_t N, int64_t ldE, char* err, size_t errlen) {
+  tc->have_e = false;
+  for (bool& b : tc->have_seg) b = false;  // segments are tied to N
+  if (!tc->encode) return 0;
+  if (ER != 16 && ER != 32) {
+    snprintf(tc->why, sizeof(tc->why), "ER=%d unsupported by the tensor-core sweep", ER);
+    return 0;
+  }
+  int rc = tc_make_map(tc, &tc->map_e, E, ER, N, ldE, ER, err, errlen);
+  if (rc) return rc;
+  tc->have_e = true;
+  tc->ER = ER;
+  return 0;
+}
+
+inline int tc_bind_segment(TcSegments* tc, int seg, const int8_t* base, int64_t rows, int64_t N, int64_t ld, char* err,
+                           size_t errlen) {
+  if (!tc->encode || seg < 0 || seg >= TcSegments::kMaxSeg) return 0;
+  tc->have_seg[seg] = false;
+  if (rows <= 0) return 0;
+  int rc = tc_make_map(tc, &tc->map_seg[seg], base, rows, N, ld, kTileRows, err, errlen);
+  if (rc) return rc;
+  tc->have_seg[seg] = true;
+  return 0;
+}
+
+inline bool tc_usable(TcSegments* tc, const GeneDesc* h_genes, int n) {
+  if (!tc->encode) return false;
+  if (!tc->have_e) {
+    if (!tc->why[0]) snprintf(tc->why, sizeof(tc->why), "null-model tensor map missing");
+    return false;
+  }
+  const int seg = h_genes[0].seg;
+  if (seg < 0 || seg >= TcSegments::kMaxSeg || !tc->have_seg[seg]) {
+    snprintf(tc->why, sizeof(tc->why), "genes are not in a TMA-mapped segment");
+    return false;
+  }
+  for (int i = 1; i < n; ++i)
+    if (h_genes[i].seg != seg) {
+      snprintf(tc->why, sizeof(tc->why), "genes span several segments");
+      return false;
+    }
+  return true;
+}
+
+inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_genes, int n, const uint8_t* d_flags,
+                     const NullModel* /*d_nm*/, int64_t N, int ER, int S, int64_t chunk, SweepPartial* d_parts,
+                     unsigned int* /*counter*/, int sm_count, cudaStream_t st, char* err, size_t errlen) {
+  const int seg = h_genes[0].seg;
+  const int grid = std::min(n * S, sm_count);
+  if (chunk % kTcStageK != 0) {
+    snprintf(err, errlen, "internal: chunk %lld is not a multiple of the TMA stage (%d)", (long long)chunk, kTcStageK);
+    return -3;
+  }
+  if (ER == 16)
+    k_sweep_tc<16><<<grid, kTcThreads, TcCfg<16>::kSmem, st>>>(tc->map_seg[seg], tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+  else
+    k_sweep_tc<32><<<grid, kTcThreads, TcCfg<32>::kSmem, st>>>(tc->map_seg[seg], tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "k_sweep_tc launch: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return 0;
+}
+
 }  // namespace rvt

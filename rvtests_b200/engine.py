@@ -46,10 +46,11 @@ assert RESULT_DTYPE.itemsize == C.sizeof(GeneResult)
 
 EXPORTS = [
     "rvt_ctx_create", "rvt_ctx_destroy", "rvt_last_error", "rvt_set_option", "rvt_get_info",
+    "rvt_set_stream",
     "rvt_set_null_model", "rvt_set_null_model_dev", "rvt_get_null_model",
     "rvt_gene_push_f64", "rvt_gene_push_i8", "rvt_gene_push_dev_i8", "rvt_pending",
     "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded",
-    "rvt_loaded_read", "rvt_last_timing",
+    "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
 ]
 
 _lib = None
@@ -72,6 +73,7 @@ def load_library(rebuild: bool = False):
     L.rvt_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     L.rvt_get_info.argtypes = [vp, C.c_char_p]
     L.rvt_get_info.restype = C.c_double
+    L.rvt_set_stream.argtypes = [vp, vp]
     L.rvt_set_null_model.argtypes = [vp, C.c_int64, C.c_int, _dp, _dp, C.c_int]
     L.rvt_set_null_model_dev.argtypes = [vp, C.c_int64, C.c_int, vp, vp]
     L.rvt_get_null_model.argtypes = [vp, _dp, _dp, _dp]
@@ -86,6 +88,7 @@ def load_library(rebuild: bool = False):
     L.rvt_run_loaded.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.c_int]
     L.rvt_loaded_read.argtypes = [vp, C.c_int64, C.c_int, vp]
     L.rvt_last_timing.argtypes = [vp, _dp]
+    L.rvt_debug_partials.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -128,6 +131,9 @@ class GeneEngine:
 
     def set_option(self, key: str, value: float):
         self._chk(self.L.rvt_set_option(self.h, key.encode(), float(value)))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._chk(self.L.rvt_set_stream(self.h, cuda_stream_ptr))
 
     def info(self, key: str) -> float:
         return self.L.rvt_get_info(self.h, key.encode())
@@ -205,6 +211,15 @@ class GeneEngine:
         out = np.zeros((rows, self.N), dtype=np.int8)
         self._chk(self.L.rvt_loaded_read(self.h, int(row0), int(rows), out.ctypes.data))
         return out
+
+    def debug_partials(self):
+        """raw SweepPartial records of the last batch: dict(d=(n,64,96) int32, coll=(n,66) int64)"""
+        nb = C.c_int64(0)
+        self._chk(self.L.rvt_debug_partials(self.h, None, 0, C.byref(nb)))
+        rec = np.dtype([("d", "i4", (64, 96)), ("coll", "i8", (66,)), ("pad", "i8", (2,))])
+        buf = np.zeros(nb.value // rec.itemsize, dtype=rec)
+        self._chk(self.L.rvt_debug_partials(self.h, buf.ctypes.data, buf.nbytes, C.byref(nb)))
+        return buf
 
     def last_timing(self):
         t = np.zeros(4)
