@@ -138,6 +138,10 @@ int rvt_last_timing(const rvt_ctx* ctx, double out[4]);
 /* diagnostic: copy the raw sweep partials of the last flush's final batch (device layout, see
  * rvtests_b200/csrc/common.cuh SweepPartial) to the host; returns the byte count via *bytes */
 int rvt_debug_partials(rvt_ctx* ctx, void* out, int64_t cap_bytes, int64_t* bytes);
+/* diagnostic: with option "debug_phases"=1 the finalize kernel records SM cycle counts of its
+ * phases per gene: [0] split reduction, [1] K build, [2] eigenvalues, [3] Davies, [4] Liu+burden,
+ * [5] unused.  out: cap_genes x 6 int64 */
+int rvt_debug_phases(rvt_ctx* ctx, long long* out, int cap_genes);
 
 #ifdef __cplusplus
 }

@@ -106,6 +106,34 @@ struct BlockPar {
     a = sa;
     b = sb;
   }
+  __device__ __forceinline__ void allreduce4(double& a, double& b, double& c, double& d) const {
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) {
+      red[w] = a;
+      red[8 + w] = b;
+      red[16 + w] = c;
+      red[24 + w] = d;
+    }
+    __syncthreads();
+    double sa = 0.0, sb = 0.0, sc = 0.0, sd = 0.0;
+    for (int i = 0; i < nw; ++i) {
+      sa += red[i];
+      sb += red[8 + i];
+      sc += red[16 + i];
+      sd += red[24 + i];
+    }
+    a = sa;
+    b = sb;
+    c = sc;
+    d = sd;
+  }
 };
 
 }  // namespace rvt

@@ -25,6 +25,7 @@ struct SerialPar {
   RVT_HD int nt() const { return 1; }
   RVT_HD void sync() const {}
   RVT_HD void allreduce2(double&, double&) const {}
+  RVT_HD void allreduce4(double&, double&, double&, double&) const {}
 };
 
 struct QfState {
@@ -66,30 +67,36 @@ RVT_HD bool tick(QfState& s) {
   return s.over;
 }
 
-// qfc.c:128-147 with n_j = 1, nc_j = 0
-RVT_HD double errbd(QfState& s, double u, double* cx) {
+// qfc.c:128-147 with n_j = 1, nc_j = 0.  The r terms are dealt to the threads of the group
+// (serial group: j = r-1..0, the reference's order) and combined with one all-reduce.
+template <class Par>
+RVT_HD double errbd(QfState& s, double u, double* cx, const Par& par) {
   if (tick(s)) return 0.0;
   const double ncj = 0.0;
-  double xconst = u * s.sigsq;
-  double sum1 = u * xconst;
+  const double xc0 = u * s.sigsq;
+  const double s10 = u * xc0;
   u = 2.0 * u;
-  for (int j = s.r - 1; j >= 0; j--) {
+  double xconst = (par.tid() == 0) ? xc0 : 0.0;
+  double sum1 = (par.tid() == 0) ? s10 : 0.0;
+  for (int j = s.r - 1 - par.tid(); j >= 0; j -= par.nt()) {
     double lj = s.lb[j];
     double x = u * lj, y = 1.0 - x;
     xconst = xconst + lj * (ncj / y + 1) / y;
     sum1 = sum1 + ncj * sq(x / y) + (sq(x) / y + log1(-x, false));
   }
+  par.allreduce2(xconst, sum1);
   *cx = xconst;
   return exp1(-0.5 * sum1);
 }
 
 // qfc.c:149-174
-RVT_HD double ctff(QfState& s, double accx, double* upn) {
+template <class Par>
+RVT_HD double ctff(QfState& s, double accx, double* upn, const Par& par) {
   double u2 = *upn, u1 = 0.0, c1 = s.mean, c2 = 0.0, xconst = 0.0;
   double rb = 2.0 * ((u2 > 0.0) ? s.lmax : s.lmin);
   for (;;) {
     double u = u2 / (1.0 + u2 * rb);
-    double e = errbd(s, u, &c2);
+    double e = errbd(s, u, &c2, par);
     if (s.over) return 0.0;
     if (!(e > accx)) break;
     u1 = u2;
@@ -98,7 +105,7 @@ RVT_HD double ctff(QfState& s, double accx, double* upn) {
   }
   for (double u = (c1 - s.mean) / (c2 - s.mean); u < 0.9; u = (c1 - s.mean) / (c2 - s.mean)) {
     u = (u1 + u2) / 2.0;
-    double e = errbd(s, u / (1.0 + u * rb), &xconst);
+    double e = errbd(s, u / (1.0 + u * rb), &xconst, par);
     if (s.over) return 0.0;
     if (e > accx) {
       u1 = u;
@@ -112,26 +119,29 @@ RVT_HD double ctff(QfState& s, double accx, double* upn) {
   return c2;
 }
 
-// qfc.c:176-213 with n_j = 1, nc_j = 0
-RVT_HD double truncation(QfState& s, double u, double tausq) {
+// qfc.c:176-213 with n_j = 1, nc_j = 0; terms dealt to the group like errbd (serial: j = 0..r-1)
+template <class Par>
+RVT_HD double truncation(QfState& s, double u, double tausq, const Par& par) {
   if (tick(s)) return 0.0;
   const double ncj = 0.0;
   double sum1 = 0.0, prod2 = 0.0, prod3 = 0.0;
-  int ss = 0;
-  double sum2 = (s.sigsq + tausq) * sq(u);
-  double prod1 = 2.0 * sum2;
+  double ssd = 0.0;
+  const double sum2 = (s.sigsq + tausq) * sq(u);
+  double prod1 = (par.tid() == 0) ? 2.0 * sum2 : 0.0;
   u = 2.0 * u;
-  for (int j = 0; j < s.r; j++) {
+  for (int j = par.tid(); j < s.r; j += par.nt()) {
     double x = sq(u * s.lb[j]);
     sum1 = sum1 + ncj * x / (1.0 + x);
     if (x > 1.0) {
       prod2 = prod2 + log(x);
       prod3 = prod3 + log1(x, true);
-      ss = ss + 1;
+      ssd = ssd + 1.0;
     } else
       prod1 = prod1 + log1(x, true);
   }
-  sum1 = 0.5 * sum1;
+  par.allreduce4(prod1, prod2, prod3, ssd);
+  const int ss = (int)ssd;
+  sum1 = 0.5 * sum1;  // identically 0 on this path (nc_j = 0)
   prod2 = prod1 + prod2;
   prod3 = prod1 + prod3;
   double x = exp1(-sum1 - 0.25 * prod2) / kPi;
@@ -145,15 +155,16 @@ RVT_HD double truncation(QfState& s, double u, double tausq) {
 }
 
 // qfc.c:215-234
-RVT_HD void findu(QfState& s, double* utx, double accx) {
+template <class Par>
+RVT_HD void findu(QfState& s, double* utx, double accx, const Par& par) {
   const double divis[4] = {2.0, 1.4, 1.2, 1.1};
   double ut = *utx, u = ut / 4.0;
-  double t = truncation(s, u, 0.0);
+  double t = truncation(s, u, 0.0, par);
   if (s.over) return;
   if (t > accx) {
     for (;;) {
       u = ut;
-      t = truncation(s, u, 0.0);
+      t = truncation(s, u, 0.0, par);
       if (s.over) return;
       if (!(t > accx)) break;
       ut = ut * 4.0;
@@ -162,7 +173,7 @@ RVT_HD void findu(QfState& s, double* utx, double accx) {
     ut = u;
     for (;;) {
       u = u / 4.0;
-      t = truncation(s, u, 0.0);
+      t = truncation(s, u, 0.0, par);
       if (s.over) return;
       if (!(t <= accx)) break;
       ut = u;
@@ -170,7 +181,7 @@ RVT_HD void findu(QfState& s, double* utx, double accx) {
   }
   for (int i = 0; i < 4; i++) {
     u = ut / divis[i];
-    t = truncation(s, u, 0.0);
+    t = truncation(s, u, 0.0, par);
     if (s.over) return;
     if (t <= accx) ut = u;
   }
@@ -305,7 +316,7 @@ RVT_HDN double davies_qf(const double* lb, int r, double c1, int lim1, double ac
 
   double utx = 16.0 / sd, up = 4.5 / sd, un = -up;
   double tausq, intv = 0.0, xnt = 0.0;
-  findu(s, &utx, .5 * acc1);
+  findu(s, &utx, .5 * acc1, par);
   if (s.over) goto budget;
   if (s.c != 0.0 && (almx > 0.07 * sd)) {
     double cf = cfe(s, s.c, par);
@@ -314,11 +325,11 @@ RVT_HDN double davies_qf(const double* lb, int r, double c1, int lim1, double ac
     if (s.fail)
       s.fail = false;
     else {
-      double t = truncation(s, utx, tausq);
+      double t = truncation(s, utx, tausq, par);
       if (s.over) goto budget;
       if (t < .2 * acc1) {
         s.sigsq = s.sigsq + tausq;
-        findu(s, &utx, .25 * acc1);
+        findu(s, &utx, .25 * acc1, par);
         if (s.over) goto budget;
       }
     }
@@ -326,11 +337,11 @@ RVT_HDN double davies_qf(const double* lb, int r, double c1, int lim1, double ac
   acc1 = 0.5 * acc1;
 
   for (;;) {  // label l1 of qfc.c
-    double d1 = ctff(s, acc1, &up);
+    double d1 = ctff(s, acc1, &up, par);
     if (s.over) goto budget;
     d1 = d1 - s.c;
     if (d1 < 0.0) return 1.0;
-    double d2 = ctff(s, acc1, &un);
+    double d2 = ctff(s, acc1, &un, par);
     if (s.over) goto budget;
     d2 = s.c - d2;
     if (d2 < 0.0) return 0.0;
@@ -357,7 +368,7 @@ RVT_HDN double davies_qf(const double* lb, int r, double c1, int lim1, double ac
     integrate(s, ntm, intv1, tausq, false, par);
     xlim = xlim - xntm;
     s.sigsq = s.sigsq + tausq;
-    findu(s, &utx, .25 * acc1);
+    findu(s, &utx, .25 * acc1, par);
     if (s.over) goto budget;
     acc1 = 0.75 * acc1;
   }

@@ -20,8 +20,9 @@ namespace rvt {
 
 constexpr int kFinThreads = 128;
 constexpr int kKld = kTileRows + 1;  // padded leading dimension of K in shared memory
-// dynamic shared memory: reduced tile (int64) + K (fp64)
-constexpr int kFinSmem = kTileRows * kMaxNC * 8 + kTileRows * kKld * 8;
+// dynamic shared memory: K (fp64, 64 x 65) + the reduced gene x digit columns (int64, 64 x 32)
+constexpr int kFinSmem = kTileRows * kKld * 8 + kTileRows * kMaxER * 8;
+constexpr int kFinPhases = 6;  // debug cycle counters per gene
 
 __device__ __forceinline__ long long recombine4(const long long* d) {
   return d[0] + (d[1] << 8) + (d[2] << 16) + (d[3] << 24);
@@ -31,10 +32,12 @@ __global__ void __launch_bounds__(kFinThreads)
 k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __restrict__ rowflags,
            const double* __restrict__ af, const RowCounts* __restrict__ counts,
            const NullModel* __restrict__ nm, EngineParams prm, int S,
-           const SweepPartial* __restrict__ parts, rvt_gene_result* __restrict__ res) {
+           const SweepPartial* __restrict__ parts, rvt_gene_result* __restrict__ res,
+           long long* __restrict__ dbg /* nullable: [n_genes][kFinPhases] cycle counters */) {
   extern __shared__ __align__(16) uint8_t dyn[];
-  long long* D = reinterpret_cast<long long*>(dyn);                       // [64][NC]
-  double* K = reinterpret_cast<double*>(dyn + kTileRows * kMaxNC * 8);    // [64][kKld]
+  double* K = reinterpret_cast<double*>(dyn);                               // [64][kKld]
+  long long* De = reinterpret_cast<long long*>(dyn + kTileRows * kKld * 8); // [64][kMaxER] gene x digit sums
+  __shared__ long long s_ajj[kTileRows];
   __shared__ double s_red[64];
   __shared__ double s_cs[kTileRows + 2];
   __shared__ double s_ev[kTileRows], s_lam[kTileRows];
@@ -52,16 +55,31 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   const GeneDesc gd = genes[g];
   const int M = gd.M;
   const int64_t N = nm->N;
-  const int C = nm->C, ER = nm->ER, NC = kTileRows + ER;
+  const int C = nm->C, ER = nm->ER;
   const double sigma2 = nm->sigma2;
   BlockPar par{s_red};
 
-  // 1. reduce the splits (int64)
-  for (int idx = tid; idx < M * NC; idx += kFinThreads) {
-    const int i = idx / NC, j = idx - i * NC;
+  const SweepPartial* __restrict__ gp = parts + (size_t)g * S;
+  long long t_ph = clock64();
+  auto phase = [&](int k) {
+    if (dbg && tid == 0) {
+      long long now = clock64();
+      dbg[(size_t)g * kFinPhases + k] = now - t_ph;
+      t_ph = now;
+    }
+  };
+  // 1. reduce the splits (int64): gene x digit columns and the diagonal; the gene x gene block is
+  //    summed on the fly where K is built (each entry is needed exactly once)
+  for (int idx = tid; idx < M * ER; idx += kFinThreads) {
+    const int i = idx / ER, e = idx - i * ER;
     long long s = 0;
-    for (int sp = 0; sp < S; ++sp) s += parts[(size_t)g * S + sp].d[i][j];
-    D[i * NC + j] = s;
+    for (int sp = 0; sp < S; ++sp) s += gp[sp].d[i][kTileRows + e];
+    De[i * kMaxER + e] = s;
+  }
+  if (tid < M) {
+    long long s = 0;
+    for (int sp = 0; sp < S; ++sp) s += gp[sp].d[tid][tid];
+    s_ajj[tid] = s;
   }
   if (tid < 2 * (ER + 1)) {
     long long s = 0;
@@ -70,14 +88,15 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   }
   if (tid == 0) s_bad = 0;
   __syncthreads();
+  phase(0);
 
   // 2. per-variant counts -> flip / monomorphic, cross-checked with the flags the sweep used
   if (tid < M) {
     // intercept = vector 1 (X column 0): fixed-point image of 1.0 is 2^e exactly
-    long long cint = recombine4(&D[tid * NC + kTileRows + 4]);
+    long long cint = recombine4(&De[tid * kMaxER + 4]);
     double cd = (double)cint * nm->scale[1];
     long long c = llrint(cd);
-    long long ajj = D[tid * NC + tid];
+    long long ajj = s_ajj[tid];
     long long n2 = (ajj - c) / 2, n1 = c - 2 * n2, n0 = N - n1 - n2;
     int flip = c > N;
     int mono = (n0 == N) || (n1 == N) || (n2 == N);
@@ -102,11 +121,11 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   if (tid < Mp) {
     const int j = s_idx[tid];
     const int fl = s_flip[j];
-    long long sint = recombine4(&D[j * NC + kTileRows]);
+    long long sint = recombine4(&De[j * kMaxER]);
     if (fl) sint = 2 * nm->vsum[0] - sint;
     s_s[tid] = (double)sint * nm->scale[0];
     for (int l = 0; l < C; ++l) {
-      long long b = recombine4(&D[j * NC + kTileRows + 4 * (l + 1)]);
+      long long b = recombine4(&De[j * kMaxER + 4 * (l + 1)]);
       if (fl) b = 2 * nm->vsum[l + 1] - b;
       s_B[tid][l] = (double)b * nm->scale[l + 1];
     }
@@ -126,7 +145,8 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
     if (k < i) continue;
     const int ji = s_idx[i], jk = s_idx[k];
     const int fi = s_flip[ji], fk = s_flip[jk];
-    long long a = D[ji * NC + jk];
+    long long a = 0;
+    for (int sp = 0; sp < S; ++sp) a += gp[sp].d[ji][jk];
     const long long ci = s_craw[ji], ck = s_craw[jk];
     if (fi && fk)
       a = 4 * N - 2 * ci - 2 * ck + a;
@@ -145,6 +165,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
     K[k * kKld + i] = v;
   }
   __syncthreads();
+  phase(1);
 
   // 5. eigenvalues, descending, keep > 1e-30 from the top (Skat.cpp:84-98)
   double p_dav = -1.0, p_liu = 1.0, p_fin = 1.0, lam_max = 0.0;
@@ -155,12 +176,14 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
     if (tid < Mp) s_ev[tid] = K[tid * kKld + tid];
     __syncthreads();
     sort_descending(s_ev, Mp, s_lam, par);
+    phase(2);
     const int r_ub = (N < (int64_t)Mp) ? (int)N : Mp;
     while (r < r_ub && s_lam[r] > 1e-30) ++r;
     lam_max = r ? s_lam[0] : 0.0;
     // 6. p-value
     const double Q = s_Q;
     p_dav = mixchisq_pvalue(s_lam, r, Q, s_th, &fault, par);
+    phase(3);
     p_liu = liu_pvalue(s_lam, r, Q);
     p_fin = p_dav;
     if (p_fin <= 0.0 || p_fin == 1.0) p_fin = p_liu;
@@ -203,6 +226,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
       }
     }
     res[g] = o;
+    phase(4);
   }
 }
 

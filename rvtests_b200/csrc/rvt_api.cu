@@ -61,6 +61,9 @@ struct rvt_ctx {
   rvt_gene_result* d_res = nullptr;
   size_t cap_res = 0;
   unsigned int* d_counter = nullptr;
+  long long* d_dbg = nullptr;   // optional finalize phase counters (rvt_set_option "debug_phases")
+  size_t cap_dbg = 0;
+  bool want_dbg = false;
   // staging: one growable arena of int8 rows (row pitch stage_ld), TMA segment kSegStaged
   int8_t* d_stage = nullptr;
   int64_t stage_ld = 0, stage_cap_rows = 0, stage_used_rows = 0;
@@ -78,6 +81,7 @@ struct rvt_ctx {
   double t_sweep = 0, t_fin = 0, t_total = 0, n_launch = 0;
   int last_engine = 0, last_S = 0;
   int64_t last_parts = 0;
+  int last_n = 0;
 };
 
 #define CTX_FAIL(code, ...)                              \
@@ -198,7 +202,8 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg};
+  tc_destroy(&ctx->tc);
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& ev : ctx->ev)
@@ -221,6 +226,8 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "splits") {
     if (value < 0 || value > 64) CTX_FAIL(RVT_E_BADARG, "splits must be in 0..64");
     ctx->splits = (int)value;
+  } else if (k == "debug_phases") {
+    ctx->want_dbg = value != 0;
   } else
     CTX_FAIL(RVT_E_BADARG, "unknown option '%s'", key);
   return RVT_OK;
@@ -475,6 +482,14 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     if ((rc = ensure(ctx, (void**)&ctx->d_res, &ctx->cap_res, n, sizeof(rvt_gene_result)))) return rc;
     d_res = ctx->d_res;
   }
+  if (ctx->want_dbg) {
+    if ((rc = ensure(ctx, (void**)&ctx->d_dbg, &ctx->cap_dbg, (size_t)n * kFinPhases, sizeof(long long)))) return rc;
+  } else if (ctx->d_dbg) {
+    cudaFree(ctx->d_dbg);
+    ctx->d_dbg = nullptr;
+    ctx->cap_dbg = 0;
+  }
+  ctx->last_n = n;
   cudaStream_t st = ctx->stream;
   RVT_CUDA_OK(cudaEventRecord(ctx->ev[0], st));
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_genes, ctx->genes.data(), sizeof(GeneDesc) * n, cudaMemcpyHostToDevice, st));
@@ -511,7 +526,7 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     }
     RVT_CUDA_OK(cudaEventRecord(ctx->ev[3], st));
     k_finalize<<<nb, kFinThreads, kFinSmem, st>>>(ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S,
-                                                  ctx->d_parts, d_res + b0);
+                                                  ctx->d_parts, d_res + b0, ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr);
     RVT_CUDA_OK(cudaEventRecord(ctx->ev[4], st));
     RVT_CUDA_OK(cudaGetLastError());
     launches += 2;
@@ -637,6 +652,13 @@ int rvt_debug_partials(rvt_ctx* ctx, void* out, int64_t cap_bytes, int64_t* byte
   if (!out) return RVT_OK;
   if (cap_bytes < need) CTX_FAIL(RVT_E_BADARG, "partials need %lld bytes", (long long)need);
   RVT_CUDA_OK(cudaMemcpy(out, ctx->d_parts, (size_t)need, cudaMemcpyDeviceToHost));
+  return RVT_OK;
+}
+
+int rvt_debug_phases(rvt_ctx* ctx, long long* out, int cap_genes) {
+  if (!ctx || !out) return RVT_E_BADARG;
+  if (!ctx->d_dbg || cap_genes < ctx->last_n) CTX_FAIL(RVT_E_STATE, "phase counters not enabled (option debug_phases) or buffer too small");
+  RVT_CUDA_OK(cudaMemcpy(out, ctx->d_dbg, sizeof(long long) * kFinPhases * ctx->last_n, cudaMemcpyDeviceToHost));
   return RVT_OK;
 }
 

@@ -67,11 +67,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+// L2 eviction-priority policies (createpolicy encodings): genotypes stream through once,
+// the null-model digits E are re-read by every gene of the batch.
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                            uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;\n" ::"r"(
           smem_u32(smem_dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -113,7 +118,7 @@ __device__ __forceinline__ uint32_t sw128_word_off(int r, int w) {
 
 template <int ER>
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_sweep_tc(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_e,
+k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */, const __grid_constant__ CUtensorMap map_e,
            const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __restrict__ rowflags, int64_t N, int S,
            int64_t chunk, SweepPartial* __restrict__ out) {
   using Cfg = TcCfg<ER>;
@@ -126,7 +131,6 @@ k_sweep_tc(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CU
   uint64_t* tfull = bars + 2 * kTcStages;   // [2]
   uint64_t* tempty = tfull + 2;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  __shared__ uint32_t s_xf[4][kTileRows], s_mn[4][kTileRows], s_en[4][kTileRows];
   __shared__ unsigned long long s_coll[2][kCollapseN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -162,6 +166,11 @@ k_sweep_tc(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CU
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int gi = u / S, sp = u - gi * S;
         const int row0 = (int)genes[gi].row0;
+        const int Mg = genes[gi].M;
+        // the box of this gene holds exactly its M rows (no bytes of the neighbouring gene):
+        // rows M..63 of the smem tile keep stale data, which only feeds ignored rows/columns of D
+        const CUtensorMap* mg = maps_g + (Mg - 1);
+        const uint32_t stage_tx = (uint32_t)(kTcBoxes * (Mg + ER) * 128);
         const int64_t k0 = (int64_t)sp * chunk;
         int64_t k1 = k0 + chunk;
         if (k1 > N) k1 = N;
@@ -170,13 +179,13 @@ k_sweep_tc(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CU
           const int s = it % kTcStages;
           const uint32_t ph = (it / kTcStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], Cfg::kStageBytes);
+          mbar_expect_tx(&full[s], stage_tx);
           uint8_t* st = tiles + (size_t)s * Cfg::kStageBytes;
           const int kb = (int)(k0 + (int64_t)ks * kTcStageK);
 #pragma unroll
           for (int b = 0; b < kTcBoxes; ++b) {
-            tma_load_2d(st + b * Cfg::kBoxBytes, &map_g, kb + b * kTcBoxK, row0, &full[s]);
-            tma_load_2d(st + b * Cfg::kBoxBytes + kTileRows * 128, &map_e, kb + b * kTcBoxK, 0, &full[s]);
+            tma_load_2d(st + b * Cfg::kBoxBytes, mg, kb + b * kTcBoxK, row0, &full[s], kEvictFirst);
+            tma_load_2d(st + b * Cfg::kBoxBytes + kTileRows * 128, &map_e, kb + b * kTcBoxK, 0, &full[s], kEvictLast);
           }
         }
       }
@@ -234,13 +243,18 @@ k_sweep_tc(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CU
       int64_t k1 = k0 + chunk;
       if (k1 > N) k1 = N;
       const int nsteps = (k1 > k0) ? (int)((k1 - k0 + kTcStageK - 1) / kTcStageK) : 0;
-      for (int r = lane; r < kTileRows; r += 32) {
-        uint8_t f = (r < M) ? rowflags[gd.var0 + r] : (uint8_t)kRowSkip;
-        s_xf[cw][r] = (f == kRowFlipped) ? 0x01010101u : 0u;
-        s_mn[cw][r] = (f == kRowNormal) ? 0x01010101u : 0u;
-        s_en[cw][r] = (f == kRowSkip) ? 0u : 0x01010101u;
-      }
-      __syncwarp();
+      // per-row flags as two 64-bit masks held in registers (bit r: row r flipped / row r enabled)
+      const uint8_t f0 = (lane < M) ? rowflags[gd.var0 + lane] : (uint8_t)kRowSkip;
+      const uint8_t f1 = (lane + 32 < M) ? rowflags[gd.var0 + lane + 32] : (uint8_t)kRowSkip;
+      const unsigned long long fmask = (unsigned long long)__ballot_sync(0xffffffffu, f0 == kRowFlipped) |
+                                       ((unsigned long long)__ballot_sync(0xffffffffu, f1 == kRowFlipped) << 32);
+      const unsigned long long emask = (unsigned long long)__ballot_sync(0xffffffffu, f0 != kRowSkip) |
+                                       ((unsigned long long)__ballot_sync(0xffffffffu, f1 != kRowSkip) << 32);
+      const int Mr8 = (M + 7) & ~7;
+      // lane-constant swizzled offsets of word `lane` in rows j = 0..7 of an 8-row group
+      uint32_t woff[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) woff[j] = (uint32_t)(j * 128 + ((((lane >> 2) ^ j) << 4) | ((lane & 3) << 2)));
       int cz[ER + 1], cc[ER + 1];
 #pragma unroll
       for (int e = 0; e <= ER; ++e) cz[e] = cc[e] = 0;
@@ -251,9 +265,17 @@ k_sweep_tc(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CU
         const uint8_t* box = tiles + (size_t)s * Cfg::kStageBytes + cw * Cfg::kBoxBytes;
         const int64_t ksamp = k0 + (int64_t)ks * kTcStageK + cw * kTcBoxK + 4 * lane;
         uint32_t z = 0;
-        for (int r = 0; r < M; ++r) {
-          uint32_t w = *reinterpret_cast<const uint32_t*>(box + sw128_word_off(r, lane));
-          z += collapse_ind(w, s_xf[cw][r], s_mn[cw][r], s_en[cw][r]);
+        for (int r0 = 0; r0 < Mr8; r0 += 8) {
+          uint32_t w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[j] = *reinterpret_cast<const uint32_t*>(box + (r0 >> 3) * 1024 + woff[j]);
+          const uint32_t fb = (uint32_t)(fmask >> r0) & 0xFFu, eb = (uint32_t)(emask >> r0) & 0xFFu;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t en = ((eb >> j) & 1u) * 0x01010101u;   // rows >= M are disabled: stale smem never counts
+            const uint32_t xf = ((fb >> j) & 1u) * 0x01010101u;
+            z += collapse_ind(w[j], xf, en & ~xf, en);
+          }
         }
         int64_t rem = k1 - ksamp;
         uint32_t vm = rem >= 4 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - (int)rem))));
@@ -342,7 +364,13 @@ struct TcSegments {
   CUtensorMap map_e;
   static constexpr int kMaxSeg = 4;
   bool have_seg[kMaxSeg] = {false, false, false, false};
-  CUtensorMap map_seg[kMaxSeg];
+  // one tensor map per box height M = 1..64 over the same arena (encoded lazily, kept in HBM)
+  struct Seg {
+    const int8_t* base = nullptr;
+    int64_t rows = 0, N = 0, ld = 0;
+    bool have_m[kTileRows] = {};
+    CUtensorMap* d_maps = nullptr;   // [64] in device memory
+  } seg[kMaxSeg];
 };
 
 inline int tc_init(TcSegments* tc, char* err, size_t errlen) {
@@ -363,6 +391,14 @@ inline int tc_init(TcSegments* tc, char* err, size_t errlen) {
     return -2;
   }
   return 0;
+}
+
+inline void tc_destroy(TcSegments* tc) {
+  for (auto& sg : tc->seg)
+    if (sg.d_maps) {
+      cudaFree(sg.d_maps);
+      sg.d_maps = nullptr;
+    }
 }
 
 inline int tc_make_map(TcSegments* tc, CUtensorMap* map, const void* base, int64_t rows, int64_t N, int64_t ld, int box_rows,
@@ -402,9 +438,40 @@ inline int tc_bind_segment(TcSegments* tc, int seg, const int8_t* base, int64_t 
   if (!tc->encode || seg < 0 || seg >= TcSegments::kMaxSeg) return 0;
   tc->have_seg[seg] = false;
   if (rows <= 0) return 0;
-  int rc = tc_make_map(tc, &tc->map_seg[seg], base, rows, N, ld, kTileRows, err, errlen);
-  if (rc) return rc;
+  TcSegments::Seg& sg = tc->seg[seg];
+  sg.base = base;
+  sg.rows = rows;
+  sg.N = N;
+  sg.ld = ld;
+  for (bool& b : sg.have_m) b = false;
+  if (!sg.d_maps) {
+    cudaError_t e = cudaMalloc((void**)&sg.d_maps, sizeof(CUtensorMap) * kTileRows);
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "cudaMalloc(tensor maps): %s", cudaGetErrorString(e));
+      return -2;
+    }
+  }
   tc->have_seg[seg] = true;
+  return 0;
+}
+
+// make sure the segment has a tensor map for every box height present in this batch
+inline int tc_prepare_maps(TcSegments* tc, int seg, const GeneDesc* h_genes, int n, cudaStream_t st, char* err, size_t errlen) {
+  TcSegments::Seg& sg = tc->seg[seg];
+  for (int i = 0; i < n; ++i) {
+    const int M = h_genes[i].M;
+    if (sg.have_m[M - 1]) continue;
+    CUtensorMap m;
+    int rc = tc_make_map(tc, &m, sg.base, sg.rows, sg.N, sg.ld, M, err, errlen);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(sg.d_maps + (M - 1), &m, sizeof(m), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `m` is a stack temporary
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "tensor map upload: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    sg.have_m[M - 1] = true;
+  }
   return 0;
 }
 
@@ -436,10 +503,12 @@ inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_
     snprintf(err, errlen, "internal: chunk %lld is not a multiple of the TMA stage (%d)", (long long)chunk, kTcStageK);
     return -3;
   }
+  int rc = tc_prepare_maps(tc, seg, h_genes, n, st, err, errlen);
+  if (rc) return rc;
   if (ER == 16)
-    k_sweep_tc<16><<<grid, kTcThreads, TcCfg<16>::kSmem, st>>>(tc->map_seg[seg], tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+    k_sweep_tc<16><<<grid, kTcThreads, TcCfg<16>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
   else
-    k_sweep_tc<32><<<grid, kTcThreads, TcCfg<32>::kSmem, st>>>(tc->map_seg[seg], tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+    k_sweep_tc<32><<<grid, kTcThreads, TcCfg<32>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, errlen, "k_sweep_tc launch: %s", cudaGetErrorString(e));

@@ -51,6 +51,7 @@ EXPORTS = [
     "rvt_gene_push_f64", "rvt_gene_push_i8", "rvt_gene_push_dev_i8", "rvt_pending",
     "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded",
     "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
+    "rvt_debug_phases",
 ]
 
 _lib = None
@@ -89,6 +90,7 @@ def load_library(rebuild: bool = False):
     L.rvt_loaded_read.argtypes = [vp, C.c_int64, C.c_int, vp]
     L.rvt_last_timing.argtypes = [vp, _dp]
     L.rvt_debug_partials.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64)]
+    L.rvt_debug_phases.argtypes = [vp, vp, C.c_int]
     _lib = L
     return L
 
@@ -220,6 +222,11 @@ class GeneEngine:
         buf = np.zeros(nb.value // rec.itemsize, dtype=rec)
         self._chk(self.L.rvt_debug_partials(self.h, buf.ctypes.data, buf.nbytes, C.byref(nb)))
         return buf
+
+    def debug_phases(self, n):
+        out = np.zeros((n, 6), dtype=np.int64)
+        self._chk(self.L.rvt_debug_phases(self.h, out.ctypes.data, n))
+        return out
 
     def last_timing(self):
         t = np.zeros(4)
