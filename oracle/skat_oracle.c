@@ -1023,25 +1023,38 @@ typedef struct {
   int zeg_ok;
 } orc_gene_out;
 
-ORC_API int orc_gene(int64_t N, int M, int C, const double* G_raw, const double* af, const double* X,
-                     const double* resid, double sigma2, double beta1, double beta2,
-                     orc_gene_out* out, double* out_lambda /* M */) {
-  double* G = (double*)malloc(sizeof(double) * (size_t)N * M);
-  int* keep = (int*)malloc(sizeof(int) * M);
+/* scratch for one gene: the flipped copy (N*M), keep[], w, v, col */
+typedef struct {
+  double* G; int* keep; double* w; double* v; double* col; int64_t capN; int capM;
+} orc_scratch;
+static void orc_scratch_init(orc_scratch* s, int64_t N, int M) {
+  s->G = (double*)malloc(sizeof(double) * (size_t)N * M);
+  s->keep = (int*)malloc(sizeof(int) * M);
+  s->w = (double*)malloc(sizeof(double) * M);
+  s->v = (double*)malloc(sizeof(double) * N);
+  s->col = (double*)malloc(sizeof(double) * N);
+  s->capN = N; s->capM = M;
+}
+static void orc_scratch_free(orc_scratch* s) { free(s->G); free(s->keep); free(s->w); free(s->v); free(s->col); }
+
+static int orc_gene_with(orc_scratch* sc, int64_t N, int M, int C, const double* G_raw, const double* af, const double* X,
+                         const double* resid, double sigma2, double beta1, double beta2,
+                         orc_gene_out* out, double* out_lambda /* M */) {
+  double* G = sc->G;
+  int* keep = sc->keep;
   int mp = orc_flip_minor_polymorphic(N, M, G_raw, G, keep, NULL);
   memset(out, 0, sizeof(*out));
   out->m_poly = mp;
   if (mp == 0) {
     out->status = 2;
-    free(G); free(keep);
     return 0;
   }
-  double* w = (double*)malloc(sizeof(double) * mp);
+  double* w = sc->w;
   for (int i = 0; i < mp; ++i) w[i] = orc_skat_weight(af[i], beta1, beta2, 1);
-  double* v = (double*)malloc(sizeof(double) * N);
+  double* v = sc->v;
   for (int64_t i = 0; i < N; ++i) v[i] = sigma2;
   orc_skat_reduced64(N, mp, C, G, X, resid, v, w, &out->skat, out_lambda);
-  double* col = (double*)malloc(sizeof(double) * N);
+  double* col = sc->col;
   orc_cmc_collapse(N, mp, G, col);
   out->cmc_nonref = orc_nonref_sites(N, col);
   out->cmc_ok = orc_score_test_1(N, C, X, resid, sigma2, col, &out->cmc_U, &out->cmc_V,
@@ -1049,8 +1062,17 @@ ORC_API int orc_gene(int64_t N, int M, int C, const double* G_raw, const double*
   orc_zeggini_collapse(N, mp, G, col);
   out->zeg_ok = orc_score_test_1(N, C, X, resid, sigma2, col, &out->zeg_U, &out->zeg_V,
                                  &out->zeg_stat, &out->zeg_p) == 0;
-  free(G); free(keep); free(w); free(v); free(col);
   return 0;
+}
+
+ORC_API int orc_gene(int64_t N, int M, int C, const double* G_raw, const double* af, const double* X,
+                     const double* resid, double sigma2, double beta1, double beta2,
+                     orc_gene_out* out, double* out_lambda /* M */) {
+  orc_scratch sc;
+  orc_scratch_init(&sc, N, M);
+  int rc = orc_gene_with(&sc, N, M, C, G_raw, af, X, resid, sigma2, beta1, beta2, out, out_lambda);
+  orc_scratch_free(&sc);
+  return rc;
 }
 
 /* Batch driver for the CPU baseline: genes laid out back to back (each N x M col-major doubles),
@@ -1081,14 +1103,23 @@ ORC_API int orc_gene_batch_idx(int64_t N, int M, int C, int n_tasks, const int* 
                                int threads) {
 #ifdef _OPENMP
   if (threads > 0) omp_set_num_threads(threads);
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel
 #endif
-  for (int t = 0; t < n_tasks; ++t) {
-    const int g = index[t];
+  {
+    /* per-thread scratch allocated (and first-touched) once: the timed loop does no 200 MB mallocs */
+    orc_scratch sc;
+    orc_scratch_init(&sc, N, M);
     double* lam = (double*)malloc(sizeof(double) * M);
-    orc_gene(N, M, C, G_all + (size_t)g * N * M, af_all + (size_t)g * M, X, resid, sigma2, beta1,
-             beta2, &out[t], lam);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+    for (int t = 0; t < n_tasks; ++t) {
+      const int g = index[t];
+      orc_gene_with(&sc, N, M, C, G_all + (size_t)g * N * M, af_all + (size_t)g * M, X, resid, sigma2, beta1,
+                    beta2, &out[t], lam);
+    }
     free(lam);
+    orc_scratch_free(&sc);
   }
   return 0;
 }

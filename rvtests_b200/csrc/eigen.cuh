@@ -107,6 +107,114 @@ RVT_HDN int jacobi_eigenvalues(double* a, int n, int lda, double* cs, const Par&
   return sweeps;
 }
 
+// -----------------------------------------------------------------------------------------------
+// Faster path used by the kernels: Householder tridiagonalisation (parallel mat-vec and rank-2
+// update over the group) followed by Sturm-sequence bisection, one eigenvalue per thread.
+// ~n^3*4/3 flops and ~5n group barriers instead of ~10 Jacobi sweeps of 3(n-1) barriers each.
+// Accuracy: backward stable, |d lambda| <~ n eps ||A|| -- the same class as Jacobi for this path
+// (p-values depend on lambda / lambda_max).
+//
+// a: n x n symmetric, row-major, lda (destroyed).  d[n], e[n], v[n], p[n]: group-visible scratch.
+// out[n]: eigenvalues in DESCENDING order.
+template <class Par>
+RVT_HDN void sym_eigenvalues_tridiag(double* a, int n, int lda, double* d, double* e, double* v, double* p,
+                                     double* out, const Par& par) {
+  if (n == 1) {
+    if (par.tid() == 0) out[0] = a[0];
+    par.sync();
+    return;
+  }
+  for (int k = 0; k < n - 2; ++k) {
+    const int m = n - k - 1;          // size of the trailing block; x = a[k+1.., k]
+    double* x = a + (k + 1) * lda + k;  // stride lda
+    double ss = 0.0, dummy = 0.0;
+    for (int i = par.tid() + 1; i < m; i += par.nt()) ss += x[i * lda] * x[i * lda];
+    par.allreduce2(ss, dummy);
+    const double x0 = x[0];
+    if (ss == 0.0) {  // already tridiagonal in this column
+      if (par.tid() == 0) {
+        d[k] = a[k * lda + k];
+        e[k] = x0;
+      }
+      par.sync();
+      continue;
+    }
+    const double alpha = (x0 >= 0.0 ? -1.0 : 1.0) * sqrt(x0 * x0 + ss);
+    const double v0 = x0 - alpha;
+    const double beta = 2.0 / (v0 * v0 + ss);
+    for (int i = par.tid(); i < m; i += par.nt()) v[i] = (i == 0) ? v0 : x[i * lda];
+    par.sync();
+    // p = beta * A22 v
+    double* a22 = a + (k + 1) * lda + (k + 1);
+    for (int i = par.tid(); i < m; i += par.nt()) {
+      double s = 0.0;
+      const double* row = a22 + i * lda;
+      for (int j = 0; j < m; ++j) s += row[j] * v[j];
+      p[i] = beta * s;
+    }
+    par.sync();
+    double pv = 0.0;
+    dummy = 0.0;
+    for (int i = par.tid(); i < m; i += par.nt()) pv += p[i] * v[i];
+    par.allreduce2(pv, dummy);
+    const double kk = 0.5 * beta * pv;
+    // w = p - kk v (kept in p);  A22 -= v w' + w v'
+    for (int i = par.tid(); i < m; i += par.nt()) p[i] -= kk * v[i];
+    par.sync();
+    for (int idx = par.tid(); idx < m * m; idx += par.nt()) {
+      const int i = idx / m, j = idx - i * m;
+      a22[i * lda + j] -= v[i] * p[j] + p[i] * v[j];
+    }
+    if (par.tid() == 0) {
+      d[k] = a[k * lda + k];
+      e[k] = alpha;
+    }
+    par.sync();
+  }
+  if (par.tid() == 0) {
+    d[n - 2] = a[(n - 2) * lda + (n - 2)];
+    d[n - 1] = a[(n - 1) * lda + (n - 1)];
+    e[n - 2] = a[(n - 1) * lda + (n - 2)];
+    e[n - 1] = 0.0;
+  }
+  par.sync();
+  // Gershgorin interval and scale
+  double glo = d[0] - fabs(e[0]), ghi = d[0] + fabs(e[0]);
+  for (int i = 1; i < n; ++i) {
+    const double r = fabs(e[i - 1]) + ((i < n - 1) ? fabs(e[i]) : 0.0);
+    glo = fmin(glo, d[i] - r);
+    ghi = fmax(ghi, d[i] + r);
+  }
+  const double tnorm = fmax(fabs(glo), fabs(ghi));
+  const double pivmin = fmax(tnorm * tnorm * 1e-300, 1e-300);
+  glo -= 2.0 * tnorm * 2.3e-16 * n + 2.0 * pivmin;
+  ghi += 2.0 * tnorm * 2.3e-16 * n + 2.0 * pivmin;
+  // eigenvalue with ascending index kidx: bisection on #{eigenvalues < x} (Sturm count)
+  for (int kidx = par.tid(); kidx < n; kidx += par.nt()) {
+    double lo = glo, hi = ghi;
+    for (int it = 0; it < 120; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      if (mid <= lo || mid >= hi) break;  // interval is one ulp wide
+      int cnt = 0;
+      double q = d[0] - mid;
+      if (fabs(q) < pivmin) q = -pivmin;
+      cnt += (q < 0.0);
+      for (int i = 1; i < n; ++i) {
+        q = d[i] - mid - e[i - 1] * e[i - 1] / q;
+        if (fabs(q) < pivmin) q = -pivmin;
+        cnt += (q < 0.0);
+      }
+      if (cnt <= kidx)
+        lo = mid;
+      else
+        hi = mid;
+      if (hi - lo <= 4.0e-16 * tnorm) break;
+    }
+    out[n - 1 - kidx] = 0.5 * (lo + hi);
+  }
+  par.sync();
+}
+
 // Rank-sort ev[0..n) into out[0..n) in DESCENDING order (ties keep index order).
 template <class Par>
 RVT_HDN void sort_descending(const double* ev, int n, double* out, const Par& par) {

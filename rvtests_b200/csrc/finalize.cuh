@@ -39,7 +39,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   long long* De = reinterpret_cast<long long*>(dyn + kTileRows * kKld * 8); // [64][kMaxER] gene x digit sums
   __shared__ long long s_ajj[kTileRows];
   __shared__ double s_red[64];
-  __shared__ double s_cs[kTileRows + 2];
+  __shared__ double s_e[kTileRows + 2], s_v[kTileRows + 2], s_p[kTileRows + 2];
   __shared__ double s_ev[kTileRows], s_lam[kTileRows];
   __shared__ int s_th[kTileRows];
   __shared__ long long s_coll[kCollapseN];
@@ -171,11 +171,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   double p_dav = -1.0, p_liu = 1.0, p_fin = 1.0, lam_max = 0.0;
   int fault = 0, r = 0;
   if (Mp > 0) {
-    jacobi_eigenvalues(K, Mp, kKld, s_cs, par);
-    __syncthreads();
-    if (tid < Mp) s_ev[tid] = K[tid * kKld + tid];
-    __syncthreads();
-    sort_descending(s_ev, Mp, s_lam, par);
+    sym_eigenvalues_tridiag(K, Mp, kKld, s_ev, s_e, s_v, s_p, s_lam, par);
     phase(2);
     const int r_ub = (N < (int64_t)Mp) ? (int)N : Mp;
     while (r < r_ub && s_lam[r] > 1e-30) ++r;

@@ -250,7 +250,9 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
                                        ((unsigned long long)__ballot_sync(0xffffffffu, f1 == kRowFlipped) << 32);
       const unsigned long long emask = (unsigned long long)__ballot_sync(0xffffffffu, f0 != kRowSkip) |
                                        ((unsigned long long)__ballot_sync(0xffffffffu, f1 != kRowSkip) << 32);
-      const int Mr8 = (M + 7) & ~7;
+      const int Mr8 = (M + 7) & ~7, M8 = M & ~7;
+      // warp-uniform: every row of this gene is a normal (unflipped, polymorphic) row
+      const bool plain = (fmask == 0ull) && (emask == ((M >= 64) ? ~0ull : ((1ull << M) - 1ull)));
       // lane-constant swizzled offsets of word `lane` in rows j = 0..7 of an 8-row group
       uint32_t woff[8];
 #pragma unroll
@@ -265,16 +267,33 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
         const uint8_t* box = tiles + (size_t)s * Cfg::kStageBytes + cw * Cfg::kBoxBytes;
         const int64_t ksamp = k0 + (int64_t)ks * kTcStageK + cw * kTcBoxK + 4 * lane;
         uint32_t z = 0;
-        for (int r0 = 0; r0 < Mr8; r0 += 8) {
-          uint32_t w[8];
+        if (plain) {
+          // common case (no flipped / monomorphic row): indicator = (g | g>>1) & 1 per byte,
+          // 8 independent LDS in flight, 3 ALU ops per row
+          for (int r0 = 0; r0 < M8; r0 += 8) {
+            uint32_t w[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) w[j] = *reinterpret_cast<const uint32_t*>(box + (r0 >> 3) * 1024 + woff[j]);
-          const uint32_t fb = (uint32_t)(fmask >> r0) & 0xFFu, eb = (uint32_t)(emask >> r0) & 0xFFu;
+            for (int j = 0; j < 8; ++j) w[j] = *reinterpret_cast<const uint32_t*>(box + (r0 >> 3) * 1024 + woff[j]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t en = ((eb >> j) & 1u) * 0x01010101u;   // rows >= M are disabled: stale smem never counts
-            const uint32_t xf = ((fb >> j) & 1u) * 0x01010101u;
-            z += collapse_ind(w[j], xf, en & ~xf, en);
+            for (int j = 0; j < 8; j += 2)
+              z += (((w[j] >> 1) | w[j]) & 0x01010101u) + (((w[j + 1] >> 1) | w[j + 1]) & 0x01010101u);
+          }
+          for (int r = M8; r < M; ++r) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(box + (r >> 3) * 1024 + woff[r & 7]);
+            z += ((w >> 1) | w) & 0x01010101u;
+          }
+        } else {
+          for (int r0 = 0; r0 < Mr8; r0 += 8) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = *reinterpret_cast<const uint32_t*>(box + (r0 >> 3) * 1024 + woff[j]);
+            const uint32_t fb = (uint32_t)(fmask >> r0) & 0xFFu, eb = (uint32_t)(emask >> r0) & 0xFFu;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t en = ((eb >> j) & 1u) * 0x01010101u;   // rows >= M are disabled: stale smem never counts
+              const uint32_t xf = ((fb >> j) & 1u) * 0x01010101u;
+              z += collapse_ind(w[j], xf, en & ~xf, en);
+            }
           }
         }
         int64_t rem = k1 - ksamp;

@@ -47,6 +47,8 @@ def hostcheck():
     H.hc_qf.argtypes = [dp, C.c_int, C.c_double, C.c_int, C.c_double, C.POINTER(C.c_int)]
     H.hc_eigen.restype = C.c_int
     H.hc_eigen.argtypes = [dp, C.c_int, dp]
+    H.hc_eigen_tridiag.restype = C.c_int
+    H.hc_eigen_tridiag.argtypes = [dp, C.c_int, dp]
     return H
 
 

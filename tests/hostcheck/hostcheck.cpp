@@ -21,7 +21,14 @@ double hc_qf(const double* lam, int n, double Q, int lim, double acc, int* fault
   rvt::SerialPar par;
   return rvt::davies_qf(lam, n, Q, lim, acc, th.data(), fault, par);
 }
-// eigenvalues, descending
+// eigenvalues, descending, Householder + Sturm bisection (the path the kernels use)
+int hc_eigen_tridiag(const double* a_in, int n, double* out) {
+  std::vector<double> a(a_in, a_in + (size_t)n * n), d(n + 1), e(n + 1), v(n + 1), p(n + 1);
+  rvt::SerialPar par;
+  rvt::sym_eigenvalues_tridiag(a.data(), n, n, d.data(), e.data(), v.data(), p.data(), out, par);
+  return 0;
+}
+// eigenvalues, descending, parallel-ordered Jacobi (cross-check)
 int hc_eigen(const double* a_in, int n, double* out) {
   std::vector<double> a(a_in, a_in + (size_t)n * n), cs(n + 2), ev(n);
   rvt::SerialPar par;

@@ -78,3 +78,19 @@ def test_parallel_jacobi(hostcheck, n):
         ref = np.linalg.eigvalsh(A)[::-1]
         assert np.max(np.abs(out - ref)) <= 1e-12 * ref.max()
         assert np.all(np.diff(out) <= 0)
+        out2 = np.zeros(n)
+        hostcheck.hc_eigen_tridiag(_p(np.ascontiguousarray(A)), n, _p(out2))
+        assert np.max(np.abs(out2 - ref)) <= 1e-13 * ref.max(), (n, rank)
+        assert np.all(np.diff(out2) <= 0)
+
+
+def test_tridiag_special_matrices(hostcheck):
+    """diagonal, already-tridiagonal, repeated and zero eigenvalues"""
+    for A in (np.diag([3.0, 1.0, 2.0, 0.0]), np.diag([5.0] * 6), np.zeros((5, 5)),
+              np.diag([2.0] * 5) + np.diag([1.0] * 4, 1) + np.diag([1.0] * 4, -1),
+              np.ones((7, 7)), np.array([[2.0, -1.0], [-1.0, 2.0]])):
+        n = A.shape[0]
+        out = np.zeros(n)
+        hostcheck.hc_eigen_tridiag(_p(np.ascontiguousarray(A)), n, _p(out))
+        ref = np.linalg.eigvalsh(A)[::-1]
+        assert np.max(np.abs(out - ref)) <= 1e-13 * max(1.0, np.abs(ref).max()), A
