@@ -1106,9 +1106,16 @@ ORC_API int orc_gene_batch_idx(int64_t N, int M, int C, int n_tasks, const int* 
 #pragma omp parallel
 #endif
   {
-    /* per-thread scratch allocated (and first-touched) once: the timed loop does no 200 MB mallocs */
-    orc_scratch sc;
-    orc_scratch_init(&sc, N, M);
+    /* per-thread scratch, allocated and first-touched once per thread and kept across calls
+       (OpenMP keeps its worker threads): the timed loop does no 200 MB mallocs / page faults */
+    static __thread orc_scratch sc;
+    static __thread int sc_ready = 0;
+    if (!sc_ready || sc.capN < N || sc.capM < M) {
+      if (sc_ready) orc_scratch_free(&sc);
+      orc_scratch_init(&sc, N, M);
+      memset(sc.G, 0, sizeof(double) * (size_t)N * M);
+      sc_ready = 1;
+    }
     double* lam = (double*)malloc(sizeof(double) * M);
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 1)
@@ -1119,7 +1126,6 @@ ORC_API int orc_gene_batch_idx(int64_t N, int M, int C, int n_tasks, const int* 
                     beta2, &out[t], lam);
     }
     free(lam);
-    orc_scratch_free(&sc);
   }
   return 0;
 }

@@ -226,6 +226,14 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "splits") {
     if (value < 0 || value > 64) CTX_FAIL(RVT_E_BADARG, "splits must be in 0..64");
     ctx->splits = (int)value;
+  } else if (k == "tc_stages") {
+    if (value != 4 && value != 5) CTX_FAIL(RVT_E_BADARG, "tc_stages must be 4 or 5");
+    ctx->tc.stages = (int)value;
+  } else if (k == "tc_l2promo") {
+    if (value < 0 || value > 3) CTX_FAIL(RVT_E_BADARG, "tc_l2promo must be 0..3");
+    ctx->tc.l2promo = (int)value;
+    for (auto& sg : ctx->tc.seg)
+      for (bool& b : sg.have_m) b = false;  // re-encode lazily
   } else if (k == "debug_phases") {
     ctx->want_dbg = value != 0;
   } else

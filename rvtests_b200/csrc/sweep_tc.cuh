@@ -29,17 +29,17 @@
 namespace rvt {
 
 constexpr int kTcThreads = 192;
-constexpr int kTcStages = 4;
+constexpr int kTcMaxStages = 5;
 constexpr int kTcBoxes = 4;                 // boxes per stage == consumer warps
 constexpr int kTcBoxK = 128;                // samples per box (one 128-byte swizzle row)
 constexpr int kTcStageK = kTcBoxes * kTcBoxK;
 constexpr int kTcTmemCols = 256;            // 2 accumulators x 128 columns
 
-template <int ER>
+template <int ER, int STAGES>
 struct TcCfg {
   static constexpr int kBoxBytes = kTileRows * 128 + ER * 128;
   static constexpr int kStageBytes = kTcBoxes * kBoxBytes;
-  static constexpr int kSmem = kTcStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmem = STAGES * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kNC = kTileRows + ER;
 };
 
@@ -116,12 +116,12 @@ __device__ __forceinline__ uint32_t sw128_word_off(int r, int w) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((w >> 2) ^ (r & 7)) << 4) | ((w & 3) << 2)));
 }
 
-template <int ER>
+template <int ER, int kTcStages>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */, const __grid_constant__ CUtensorMap map_e,
            const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __restrict__ rowflags, int64_t N, int S,
            int64_t chunk, SweepPartial* __restrict__ out) {
-  using Cfg = TcCfg<ER>;
+  using Cfg = TcCfg<ER, kTcStages>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B (TMA destination and UMMA descriptors)
   uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -377,6 +377,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct TcSegments {
   void* encode = nullptr;   // cuTensorMapEncodeTiled through the runtime's driver entry point
+  int stages = 5;           // smem ring depth for ER=16 (4 or 5)
+  int l2promo = 2;          // CUtensorMapL2promotion: 0 none, 1 64B, 2 128B, 3 256B
   char why[128] = "";
   bool have_e = false;
   int ER = 0;
@@ -403,8 +405,9 @@ inline int tc_init(TcSegments* tc, char* err, size_t errlen) {
     return 0;  // the dp4a engine still works; an explicit engine=tc request fails loudly
   }
   tc->encode = fn;
-  e = cudaFuncSetAttribute(k_sweep_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16>::kSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32>::kSmem);
+  e = cudaFuncSetAttribute(k_sweep_tc<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 4>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4>::kSmem);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "cudaFuncSetAttribute(k_sweep_tc): %s", cudaGetErrorString(e));
     return -2;
@@ -428,7 +431,7 @@ inline int tc_make_map(TcSegments* tc, CUtensorMap* map, const void* base, int64
   cuuint32_t estr[2] = {1, 1};
   CUresult r = ((PFN_encodeTiled)tc->encode)(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box,
                                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                             (CUtensorMapL2promotion)tc->l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d) rows=%lld N=%lld ld=%lld", (int)r, (long long)rows, (long long)N,
              (long long)ld);
@@ -524,10 +527,12 @@ inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_
   }
   int rc = tc_prepare_maps(tc, seg, h_genes, n, st, err, errlen);
   if (rc) return rc;
-  if (ER == 16)
-    k_sweep_tc<16><<<grid, kTcThreads, TcCfg<16>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+  if (ER == 16 && tc->stages == 5)
+    k_sweep_tc<16, 5><<<grid, kTcThreads, TcCfg<16, 5>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+  else if (ER == 16)
+    k_sweep_tc<16, 4><<<grid, kTcThreads, TcCfg<16, 4>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
   else
-    k_sweep_tc<32><<<grid, kTcThreads, TcCfg<32>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+    k_sweep_tc<32, 4><<<grid, kTcThreads, TcCfg<32, 4>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, errlen, "k_sweep_tc launch: %s", cudaGetErrorString(e));
