@@ -15,6 +15,7 @@
 #include "../../include/rvtests_b200.h"
 #include "common.cuh"
 #include "eigen.cuh"
+#include "skato_tail.cuh"
 
 namespace rvt {
 
@@ -22,6 +23,14 @@ constexpr int kFinThreads = 128;
 constexpr int kKld = kTileRows + 1;  // padded leading dimension of K in shared memory
 // dynamic shared memory: K (fp64, 64 x 65) + the reduced gene x digit columns (int64, 64 x 32)
 constexpr int kFinSmem = kTileRows * kKld * 8 + kTileRows * kMaxER * 8;
+constexpr int kFinSmemSkato = kFinSmem + kTileRows * kKld * 8;   // + Wm = Z1'Z1 kept for the rho grid
+constexpr int kQagsLimit = 1000;   // Integration::limit (regression/GSLIntegration.cpp:7-15)
+
+// per-gene QAGS interval list in global memory (touched by one thread only)
+struct QagsScratch {
+  double a[kQagsLimit], b[kQagsLimit], r[kQagsLimit], e[kQagsLimit];
+  int order[kQagsLimit], level[kQagsLimit];
+};
 constexpr int kFinPhases = 6;  // debug cycle counters per gene
 
 __device__ __forceinline__ long long recombine4(const long long* d) {
@@ -33,10 +42,14 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
            const double* __restrict__ af, const RowCounts* __restrict__ counts,
            const NullModel* __restrict__ nm, EngineParams prm, int S,
            const SweepPartial* __restrict__ parts, rvt_gene_result* __restrict__ res,
-           long long* __restrict__ dbg /* nullable: [n_genes][kFinPhases] cycle counters */) {
+           long long* __restrict__ dbg /* nullable: [n_genes][kFinPhases] cycle counters */,
+           QagsScratch* __restrict__ qags /* nullable: [n_genes]; non-null enables SKAT-O */) {
   extern __shared__ __align__(16) uint8_t dyn[];
   double* K = reinterpret_cast<double*>(dyn);                               // [64][kKld]
   long long* De = reinterpret_cast<long long*>(dyn + kTileRows * kKld * 8); // [64][kMaxER] gene x digit sums
+  double* Wm = reinterpret_cast<double*>(dyn + kFinSmem);                   // [64][kKld], SKAT-O only
+  __shared__ QagsMachine s_mach;
+  __shared__ double s_fv[21], s_bcast[3], s_c[kTileRows + 2], s_lamz[kTileRows + 2], s_vw[kTileRows];
   __shared__ long long s_ajj[kTileRows];
   __shared__ double s_red[64];
   __shared__ double s_e[kTileRows + 2], s_v[kTileRows + 2], s_p[kTileRows + 2];
@@ -167,6 +180,18 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   __syncthreads();
   phase(1);
 
+  if (qags) {
+    // SKAT-O: Z1'Z1 = W (G'G - G'X (X'X)^-1 X'G) W / 2 with the UN-squared weights = K / (2 sigma2)
+    // (sqrt of the squared SKAT weight is the SKAT-O weight: src/Model.h:2652-2656 vs :2807-2809)
+    const double sc = 0.5 / sigma2;
+    for (int idx = tid; idx < Mp * Mp; idx += kFinThreads) {
+      const int i = idx / Mp, k = idx - i * Mp;
+      Wm[i * kKld + k] = K[i * kKld + k] * sc;
+    }
+    if (tid < Mp) s_vw[tid] = s_sw[tid] * s_s[tid];
+    __syncthreads();
+  }
+
   // 5. eigenvalues, descending, keep > 1e-30 from the top (Skat.cpp:84-98)
   double p_dav = -1.0, p_liu = 1.0, p_fin = 1.0, lam_max = 0.0;
   int fault = 0, r = 0;
@@ -185,6 +210,17 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
     if (p_fin <= 0.0 || p_fin == 1.0) p_fin = p_liu;
   }
 
+  // 6b. SKAT-O (SkatO.cpp:101-281) on the same statistics
+  SkatoOut so;
+  so.ok = 0;
+  so.Q = so.rho = so.pvalue = 0.0;
+  if (qags && Mp > 0) {
+    QagsWork work{qags[g].a, qags[g].b, qags[g].r, qags[g].e, qags[g].order, qags[g].level, kQagsLimit};
+    const double s2 = sigma2 * (double)N / (double)(N - 1);   // ||r||^2/(N-1), SkatO.cpp:136-137
+    so = skato_tail(Wm, K, Mp, kKld, s_vw, s2, s_ev, s_e, s_v, s_p, s_lamz, s_c, &s_mach, work, s_fv, s_bcast, s_th, par);
+    phase(5);
+  }
+
   // 7. burden score tests (m = 1)
   if (tid == 0) {
     rvt_gene_result o;
@@ -200,6 +236,10 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
     o.davies_fault = fault;
     o.n_lambda = r;
     o.lambda_max = lam_max;
+    o.skato_ok = so.ok;
+    o.skato_Q = so.Q;
+    o.skato_rho = so.rho;
+    o.skato_p = so.pvalue;
     for (int which = 0; which < 2; ++which) {  // 0 zeggini, 1 cmc
       const long long* cl = s_coll + which * (ER + 1);
       double U = (double)recombine4(cl) * nm->scale[0];

@@ -61,6 +61,9 @@ struct rvt_ctx {
   rvt_gene_result* d_res = nullptr;
   size_t cap_res = 0;
   unsigned int* d_counter = nullptr;
+  QagsScratch* d_qags = nullptr;   // SKAT-O interval lists, one per gene of a batch
+  size_t cap_qags = 0;
+  bool skato = false;
   long long* d_dbg = nullptr;   // optional finalize phase counters (rvt_set_option "debug_phases")
   size_t cap_dbg = 0;
   bool want_dbg = false;
@@ -190,7 +193,7 @@ int rvt_ctx_create(int device, rvt_ctx** out) {
   RVT_CUDA_OK(cudaMalloc((void**)&ctx->dbeta, sizeof(double) * kMaxC));
   RVT_CUDA_OK(cudaMalloc((void**)&ctx->dnull_part, sizeof(double) * kNullBlocks * kNullAcc));
   RVT_CUDA_OK(cudaFuncSetAttribute(k_sweep_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, kSimtSmem));
-  RVT_CUDA_OK(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinSmem));
+  RVT_CUDA_OK(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinSmemSkato));
   int rc = tc_init(&ctx->tc, ctx->err, sizeof(ctx->err));
   if (rc) return rc;
   return RVT_OK;
@@ -202,7 +205,7 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -226,6 +229,8 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "splits") {
     if (value < 0 || value > 64) CTX_FAIL(RVT_E_BADARG, "splits must be in 0..64");
     ctx->splits = (int)value;
+  } else if (k == "skato") {
+    ctx->skato = value != 0;
   } else if (k == "tc_stages") {
     if (value != 4 && value != 5) CTX_FAIL(RVT_E_BADARG, "tc_stages must be 4 or 5");
     ctx->tc.stages = (int)value;
@@ -490,6 +495,9 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     if ((rc = ensure(ctx, (void**)&ctx->d_res, &ctx->cap_res, n, sizeof(rvt_gene_result)))) return rc;
     d_res = ctx->d_res;
   }
+  if (ctx->skato) {
+    if ((rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)batch, sizeof(QagsScratch)))) return rc;
+  }
   if (ctx->want_dbg) {
     if ((rc = ensure(ctx, (void**)&ctx->d_dbg, &ctx->cap_dbg, (size_t)n * kFinPhases, sizeof(long long)))) return rc;
   } else if (ctx->d_dbg) {
@@ -533,8 +541,8 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       if (rc) return rc;
     }
     RVT_CUDA_OK(cudaEventRecord(ctx->ev[3], st));
-    k_finalize<<<nb, kFinThreads, kFinSmem, st>>>(ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S,
-                                                  ctx->d_parts, d_res + b0, ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr);
+    k_finalize<<<nb, kFinThreads, ctx->skato ? kFinSmemSkato : kFinSmem, st>>>(ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S,
+                                                  ctx->d_parts, d_res + b0, ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->skato ? ctx->d_qags : nullptr);
     RVT_CUDA_OK(cudaEventRecord(ctx->ev[4], st));
     RVT_CUDA_OK(cudaGetLastError());
     launches += 2;

@@ -47,6 +47,13 @@ def hostcheck():
     H.hc_qf.argtypes = [dp, C.c_int, C.c_double, C.c_int, C.c_double, C.POINTER(C.c_int)]
     H.hc_eigen.restype = C.c_int
     H.hc_eigen.argtypes = [dp, C.c_int, dp]
+    H.hc_chisq_qinv.restype = C.c_double
+    H.hc_chisq_qinv.argtypes = [C.c_double, C.c_double]
+    H.hc_qags.restype = C.c_int
+    H.hc_qags.argtypes = [C.CFUNCTYPE(C.c_double, C.c_double), C.c_double, C.c_double, C.c_double, C.c_double, dp, dp,
+                          C.POINTER(C.c_int)]
+    H.hc_skato_tail.restype = C.c_int
+    H.hc_skato_tail.argtypes = [dp, C.c_int, dp, C.c_double, dp]
     H.hc_eigen_tridiag.restype = C.c_int
     H.hc_eigen_tridiag.argtypes = [dp, C.c_int, dp]
     return H

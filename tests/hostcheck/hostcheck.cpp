@@ -21,6 +21,48 @@ double hc_qf(const double* lam, int n, double Q, int lim, double acc, int* fault
   rvt::SerialPar par;
   return rvt::davies_qf(lam, n, Q, lim, acc, th.data(), fault, par);
 }
+double hc_chisq_qinv(double q, double df) { return rvt::chisq_qinv(q, df); }
+
+// QAGS state machine driven with a plain C callback (limit 1000 as GSLIntegration.cpp:7-15)
+int hc_qags(double (*f)(double), double a, double b, double epsabs, double epsrel, double* result, double* abserr,
+            int* n_intervals) {
+  const int limit = 1000;
+  std::vector<double> wa(limit), wb(limit), wr(limit), we(limit);
+  std::vector<int> wo(limit), wl(limit);
+  rvt::QagsWork w{wa.data(), wb.data(), wr.data(), we.data(), wo.data(), wl.data(), limit};
+  rvt::QagsMachine m;
+  m.init(w, a, b, epsabs, epsrel);
+  double lo, hi, fv[21];
+  while (m.want(&lo, &hi)) {
+    const double c = 0.5 * (lo + hi), h = 0.5 * (hi - lo);
+    for (int i = 0; i < 21; ++i) fv[i] = f(c + h * rvt::gk21_node(i));
+    m.give(rvt::gk21_combine(fv, lo, hi));
+  }
+  *result = m.result;
+  *abserr = m.abserr;
+  if (n_intervals) *n_intervals = m.size;
+  return m.status;
+}
+
+// SKAT-O tail on the M x M statistics.  out[0..3] = Q, rho, pvalue, ok
+int hc_skato_tail(const double* Wm, int M, const double* v, double s2, double* out) {
+  const int limit = 1000, lda = M;
+  std::vector<double> Km((size_t)M * M), ev(M + 2), e(M + 2), vv(M + 2), pp(M + 2), lamz(M + 2), c(M + 2);
+  std::vector<double> wa(limit), wb(limit), wr(limit), we(limit);
+  std::vector<int> wo(limit), wl(limit), th(M + 2);
+  rvt::QagsWork w{wa.data(), wb.data(), wr.data(), we.data(), wo.data(), wl.data(), limit};
+  rvt::QagsMachine mach;
+  double fv[21], bcast[3];
+  rvt::SerialPar par;
+  rvt::SkatoOut o = rvt::skato_tail(Wm, Km.data(), M, lda, v, s2, ev.data(), e.data(), vv.data(), pp.data(), lamz.data(),
+                                    c.data(), &mach, w, fv, bcast, th.data(), par);
+  out[0] = o.Q;
+  out[1] = o.rho;
+  out[2] = o.pvalue;
+  out[3] = o.ok;
+  return 0;
+}
+
 // eigenvalues, descending, Householder + Sturm bisection (the path the kernels use)
 int hc_eigen_tridiag(const double* a_in, int n, double* out) {
   std::vector<double> a(a_in, a_in + (size_t)n * n), d(n + 1), e(n + 1), v(n + 1), p(n + 1);

@@ -94,3 +94,60 @@ def test_tridiag_special_matrices(hostcheck):
         hostcheck.hc_eigen_tridiag(_p(np.ascontiguousarray(A)), n, _p(out))
         ref = np.linalg.eigvalsh(A)[::-1]
         assert np.max(np.abs(out - ref)) <= 1e-13 * max(1.0, np.abs(ref).max()), A
+
+
+def test_chisq_quantile_vs_gsl(hostcheck, oracle):
+    G = oracle.ref_gsl()
+    if G is None:
+        pytest.skip("oracle/_ref/libgsl_ref.so not built")
+    for q in (0.999, 0.9, 0.5, 0.1, 1e-3, 1e-8, 1e-15):
+        for df in (0.3, 1.0, 2.5, 17.3, 120.0):
+            assert rel(hostcheck.hc_chisq_qinv(q, df), G.ref_gsl_cdf_chisq_Qinv(q, df)) <= 1e-10
+
+
+def test_qags_machine_matches_gsl_bitwise(hostcheck, oracle):
+    """the resumable QAGS machine must reproduce gsl_integration_qags (GSL 1.16) node for node"""
+    import math
+    G = oracle.ref_gsl()
+    if G is None:
+        pytest.skip("oracle/_ref/libgsl_ref.so not built")
+    CB = C.CFUNCTYPE(C.c_double, C.c_double)
+    fs = [lambda x: math.exp(-x) * math.sqrt(x), lambda x: 1 / math.sqrt(x) if x > 0 else 0.0,
+          lambda x: math.log(x) * math.sin(5 * x) if x > 0 else 0.0,
+          lambda x: math.exp(-0.5 * x) / math.sqrt(2 * math.pi * x), lambda x: 1.0 / (1e-4 + (x - 7.3) ** 2),
+          lambda x: abs(x - 13.1) ** 0.3]
+    for f in fs:
+        r, e, n = C.c_double(), C.c_double(), C.c_int()
+        st = hostcheck.hc_qags(CB(f), 0.0, 40.0, 1e-25, 0.0001220703, C.byref(r), C.byref(e), C.byref(n))
+        r2, e2, n2 = C.c_double(), C.c_double(), C.c_int()
+        st2 = G.ref_gsl_qags(oracle._QAGS_CB(lambda x, _: f(x)), None, 0.0, 40.0, 1e-25, 0.0001220703, 1000,
+                             C.byref(r2), C.byref(e2), C.byref(n2))
+        assert (st != 0) == (st2 != 0)
+        assert n.value == n2.value
+        assert r.value == r2.value and e.value == e2.value
+
+
+@pytest.mark.parametrize("case", [(1, 500, 5, 1), (2, 2000, 20, 3), (3, 3000, 50, 3), (4, 800, 1, 2), (5, 1500, 2, 3)])
+def test_skato_tail_vs_oracle(hostcheck, oracle, case):
+    """device SKAT-O tail (host build) on the M x M statistics vs the literal N x M numpy oracle"""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from util import af_of, make_problem
+    from oracle import skato_oracle as SO
+    O = oracle
+    seed, N, M, Cc = case
+    Gm, X, y = make_problem(O, seed, N, M, Cc, maf=np.linspace(0.01, 0.3, M))
+    nm = O.fit_null_linear(X, y)
+    ref = SO.skato_gene(Gm.astype(float), af_of(Gm), X, nm["resid"])
+    keep = [j for j in range(M) if Gm[:, j].min() != Gm[:, j].max()]
+    w = np.array([O.lib().orc_skat_weight(float(a), 1.0, 25.0, 0) for a in af_of(Gm)[: len(keep)]])
+    Gw = Gm[:, keep].astype(float) * w[None, :]
+    Wm = np.ascontiguousarray((Gw.T @ Gw - (Gw.T @ X) @ np.linalg.solve(X.T @ X, X.T @ Gw)) / 2)
+    v = np.ascontiguousarray(nm["resid"] @ Gw)
+    s2 = float(nm["resid"] @ nm["resid"]) / (N - 1)
+    out = np.zeros(4)
+    hostcheck.hc_skato_tail(_p(Wm), len(keep), _p(v), s2, _p(out))
+    assert out[3] == 1.0 and ref["ok"]
+    assert rel(out[0], ref["Q"]) <= 1e-10
+    assert out[1] == ref["rho"]
+    assert rel(out[2], ref["pvalue"]) <= 1e-8

@@ -162,6 +162,39 @@ def test_loaded_synthetic_cohort(eng, oracle, which):
         check_gene(res[g], ref, lam, ctx=f"loaded gene {g}")
 
 
+SKATO_CASES = [(40, 700, 1, 1), (41, 1500, 2, 3), (42, 2000, 12, 3), (43, 5000, 50, 3), (44, 3000, 64, 2), (45, 900, 7, 1)]
+
+
+@pytest.mark.parametrize("case", SKATO_CASES)
+def test_skato_vs_oracle(eng, oracle, case):
+    """SKAT-O (regression/SkatO.cpp) on the device vs the numpy + GSL 1.16 + reference-Davies oracle."""
+    from oracle import skato_oracle as SO
+    O = oracle
+    seed, N, M, C = case
+    G, X, y = make_problem(O, seed, N, M, C, maf=np.linspace(0.01, 0.35, M), n_flip=min(2, M - 1) if M > 1 else 0,
+                           n_mono=1 if M > 5 else 0)
+    eng.set_option("engine", 0)
+    eng.set_option("skato", 1)
+    try:
+        eng.set_null_model(X, y)
+        nm = O.fit_null_linear(X, y)
+        af = af_of(G)
+        eng.push_i8(G.T.copy(), af)
+        r = eng.flush()[0]
+    finally:
+        eng.set_option("skato", 0)
+    ref = SO.skato_gene(G.astype(float), af, X, nm["resid"])
+    assert int(r["skato_ok"]) == int(ref["ok"])
+    if ref["ok"]:
+        assert rel(r["skato_Q"], ref["Q"]) <= 1e-6, (r["skato_Q"], ref["Q"])
+        assert r["skato_rho"] == ref["rho"]
+        # SURVEY 8(d): SKAT-O p <= 1e-3 rel (QAGS epsrel is 1.2e-4); the port reproduces GSL's nodes
+        assert rel(r["skato_p"], ref["pvalue"]) <= 1e-5, (r["skato_p"], ref["pvalue"])
+    # the SKAT / burden columns are unaffected by enabling SKAT-O
+    ref2, lam = _oracle_gene(O, G, X, nm)
+    check_gene(r, ref2, lam, ctx=f"skat with skato on {case}")
+
+
 def test_bad_values_are_reported_not_computed(eng, oracle):
     O = oracle
     G, X, y = make_problem(O, 30, 500, 6, 1, maf=0.2)
