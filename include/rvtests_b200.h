@@ -11,7 +11,7 @@
  *   cmcCollapse / zegginiCollapse               src/Model.cpp:73-89, 115-130
  *   getFlippedToMinorPolymorphicGenotype        src/DataConsolidator.h:128-132, .cpp:46-142
  * The entry points below are what a C++ adapter with the ModelFitter signature binds instead of
- * those classes (rvtests_b200/host/*.h are such adapters; INTEGRATION.md shows the registration a
+ * those classes (rvtests_b200/host/rvt_fitters.h holds such adapters; INTEGRATION.md shows the registration a
  * maintainer adds to src/ModelManager.cpp).  Plain pointers and sizes only; no C++ / torch types.
  *
  * Threading: one host thread per context (the reference's model loop is single-threaded,

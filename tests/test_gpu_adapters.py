@@ -1,0 +1,80 @@
+"""GPU: the C++ ModelFitter-shaped adapters (rvtests_b200/host/rvt_fitters.h) driven like the
+reference's gene loop (src/Main.cpp:1221-1254) produce the .assoc lines the reference's own
+writeOutput would print ("%g" columns) for the oracle's numbers."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import af_of, make_problem
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build_demo():
+    exe = os.path.join(ROOT, "rvtests_b200", "host", "adapter_demo")
+    src = os.path.join(ROOT, "rvtests_b200", "host", "adapter_demo.cpp")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                    "-L", os.path.join(ROOT, "rvtests_b200"), "-lrvtests_b200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "rvtests_b200")], check=True)
+    return exe
+
+
+def g(v):
+    return "%g" % v
+
+
+@pytest.mark.parametrize("batch", [1, 3, 100])
+def test_adapters_match_reference_output_format(oracle, batch, tmp_path):
+    from oracle import skato_oracle as SO
+    import rvtests_b200
+    rvtests_b200.load_library()
+    O = oracle
+    N, C = 1200, 3
+    genes = []
+    X = y = None
+    for gi, (M, nm_, nf) in enumerate([(6, 0, 1), (1, 0, 0), (25, 2, 2), (4, 4, 0), (40, 1, 0)]):
+        G, X, y = make_problem(O, 77, N, M, C, maf=np.linspace(0.02, 0.4, M), n_mono=nm_, n_flip=nf)
+        rng = np.random.default_rng(gi)
+        G = G[:, rng.permutation(M)]
+        genes.append(G)
+    path = tmp_path / "problem.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("iii", N, C - 1, len(genes)))
+        f.write(np.ascontiguousarray(y).tobytes())
+        f.write(np.asfortranarray(X[:, 1:]).tobytes(order="F"))
+        for G in genes:
+            f.write(struct.pack("i", G.shape[1]))
+            f.write(np.asfortranarray(G.astype(np.float64)).tobytes(order="F"))
+            f.write(af_of(G).tobytes())
+    exe = build_demo()
+    out = subprocess.run([exe, str(path), str(batch)], capture_output=True, text=True, check=True).stdout
+    tables = {}
+    cur = None
+    for line in out.splitlines():
+        if line.startswith("#"):
+            cur = line[1:]
+            tables[cur] = []
+        else:
+            tables[cur].append(line.split("\t"))
+    assert tables["Skat"][0] == ["Range", "N_INFORMATIVE", "NumVar", "Q", "Pvalue"]
+    assert tables["SkatO"][0][-3:] == ["Q", "rho", "Pvalue"]
+    assert tables["CMC"][0][-2:] == ["NonRefSite", "Pvalue"]
+    assert tables["Zeggini"][0][-1:] == ["Pvalue"]
+    nm = O.fit_null_linear(X, y)
+    for gi, G in enumerate(genes):
+        ref, lam = O.gene(G.astype(float), af_of(G), X, nm["resid"], nm["sigma2"])
+        site = ["gene%d" % gi, str(N), str(G.shape[1])]
+        rs, ro, rc, rz = (tables[k][1 + gi] for k in ("Skat", "SkatO", "CMC", "Zeggini"))
+        assert rs[:3] == site and ro[:3] == site and rc[:3] == site and rz[:3] == site
+        if ref.status == 2:
+            assert rs[3:] == ["NA", "NA"] and ro[3:] == ["NA", "NA", "NA"] and rc[3:] == ["NA", "NA"] and rz[3:] == ["NA"]
+            continue
+        assert rs[3:] == [g(ref.skat.Q), g(ref.skat.pvalue)]
+        assert rc[3:] == [str(ref.cmc_nonref), g(ref.cmc_p)]
+        assert rz[3:] == [g(ref.zeg_p)]
+        so = SO.skato_gene(G.astype(float), af_of(G), X, nm["resid"])
+        assert ro[3:] == [g(so["Q"]), g(so["rho"]), g(so["pvalue"])]

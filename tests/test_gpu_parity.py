@@ -171,7 +171,10 @@ def test_skato_vs_oracle(eng, oracle, case):
     from oracle import skato_oracle as SO
     O = oracle
     seed, N, M, C = case
-    G, X, y = make_problem(O, seed, N, M, C, maf=np.linspace(0.01, 0.35, M), n_flip=min(2, M - 1) if M > 1 else 0,
+    # keep the carrier fraction well below 1: a constant CMC indicator is collinear with the
+    # intercept and makes the burden score test numerically undefined (in the reference as well)
+    hi = 0.35 if M <= 12 else 0.02
+    G, X, y = make_problem(O, seed, N, M, C, maf=np.linspace(0.002, hi, M), n_flip=min(2, M - 1) if M > 1 else 0,
                            n_mono=1 if M > 5 else 0)
     eng.set_option("engine", 0)
     eng.set_option("skato", 1)
