@@ -131,6 +131,39 @@ int rvt_run_loaded(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, int 
 /* copy rows [row0,row0+rows) x samples [0,N) of the loaded arena back to the host (tests) */
 int rvt_loaded_read(rvt_ctx* ctx, int64_t row0, int rows, int8_t* out /*rows x N*/);
 
+/* ---- single-variant meta-analysis statistics: --meta score,cov --------------------------------
+ * Replaces, for unrelated samples and a quantitative trait,
+ *   MetaScoreTest::fitWithGivenGenotype / writeOutput   src/Model.h:3188-3260, 3299-3365
+ *   MetaCovTest::fitWithGivenGenotype / printCovariance src/Model.cpp:844-1004 (window: src/Model.h:3954-3967)
+ * The pending pushes (rvt_gene_push_*; each push = a run of consecutive variants, raw ALT-allele
+ * coding, hard calls) are read as ONE ordered variant list v = 0..nv-1.
+ *   rvt_meta_plan : host only.  pos/chrom (nv each, sorted by chrom then pos), window in bp
+ *                   (ModelManager default 1000000, src/ModelManager.cpp:52,228) -> *wmax = the largest
+ *                   number of later variants any variant must be paired with.
+ *   rvt_meta_flush: vout[nv] = one rvt_variant_result per variant; band (may be NULL: score only) =
+ *                   nv x (wmax+1) doubles, band[v*(wmax+1)+d] = COV entry of variants (v, v+d) divided
+ *                   by N as the reference prints it; NaN where either variant is monomorphic (such
+ *                   variants are never queued by MetaCovTest) or v+d is outside v's window. */
+typedef struct rvt_variant_result {
+  double af;          /* AF                 GenotypeCounter::getAF */
+  double ac;          /* INFORMATIVE_ALT_AC GenotypeCounter::getAC */
+  double call_rate;   /* CALL_RATE */
+  double hwe_p;       /* HWE_PVALUE         SNPHWE */
+  int32_t n_ref, n_het, n_alt;   /* N_REF N_HET N_ALT */
+  int32_t ok;         /* fitOK: polymorphic and the score test succeeded (else the stats print NA) */
+  int32_t polymorphic;
+  int32_t pad;
+  double U;           /* U_STAT       = U / sigma2 */
+  double sqrtV;       /* SQRT_V_STAT  = sqrt(V / sigma2^2) */
+  double effect;      /* ALT_EFFSIZE */
+  double effect_se;   /* ALT_EFFSIZE_SE (tag "se") */
+  double pvalue;      /* PVALUE */
+} rvt_variant_result;
+
+int rvt_meta_plan(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64_t nv, int64_t window_bp, int* wmax);
+int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64_t window_bp,
+                   rvt_variant_result* vout, int64_t cap_variants, double* band, int64_t cap_band, int* wmax);
+
 /* ---- measurement hooks ----------------------------------------------------------------------- */
 /* device milliseconds of the last flush: [0] sweep kernel(s), [1] finalize kernel(s), [2] whole
  * flush on the context stream (CUDA events), [3] number of kernel launches */

@@ -1,0 +1,104 @@
+"""oracle/meta_oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+numpy restatement of `--meta score,cov` for unrelated samples and a quantitative trait:
+  MetaScoreTest::fitWithGivenGenotype / writeOutput + MetaUnrelatedQtl    src/Model.h:3188-3365, 3501-3555
+  GenotypeCounter                                                        src/GenotypeCounter.h:14-59
+  SNPHWE (Wigginton exact test)                                          libsrc/snp_hwe.cpp:25-122
+  LinearRegressionScoreTest::TestCovariate (Matrix overload, m = 1)      regression/LinearRegressionScoreTest.cpp:173-263
+  MetaCovTest window / printCovariance + MetaCovUnrelatedQtl             src/Model.h:3954-4020, src/Model.cpp:500-596, 844-1004
+The covariance follows the reference literally (centre the genotype, x~'x~/sigma2, covXZ, the LDLT
+pseudo-inverse of the centred-covariate Gram) in fp64; the reference itself computes it in float32,
+so parity is asserted at 1e-5.  Parity unpinned by the reference's tests (F6).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import oracle as O
+
+
+def snp_hwe(obs_hets, obs_hom1, obs_hom2):
+    obs_homc = max(obs_hom1, obs_hom2)
+    obs_homr = min(obs_hom1, obs_hom2)
+    rare = 2 * obs_homr + obs_hets
+    n = obs_hets + obs_homc + obs_homr
+    het = np.zeros(rare + 1)
+    mid = int(1.0 * rare * (2 * n - rare) / (2 * n))
+    if (rare & 1) ^ (mid & 1):
+        mid += 1
+    curr_hets, curr_homr = mid, (rare - mid) // 2
+    curr_homc = n - curr_hets - curr_homr
+    het[mid] = 1.0
+    s = het[mid]
+    h = mid
+    while h > 1:
+        het[h - 2] = het[h] * h * (h - 1.0) / (4.0 * (curr_homr + 1.0) * (curr_homc + 1.0))
+        s += het[h - 2]
+        curr_homr += 1
+        curr_homc += 1
+        h -= 2
+    curr_homr = (rare - mid) // 2
+    curr_homc = n - mid - curr_homr
+    h = mid
+    while h <= rare - 2:
+        het[h + 2] = het[h] * 4.0 * curr_homr * curr_homc / ((h + 2.0) * (h + 1.0))
+        s += het[h + 2]
+        curr_homr -= 1
+        curr_homc -= 1
+        h += 2
+    het /= s
+    p = het[het <= het[obs_hets]].sum()
+    return min(p, 1.0)
+
+
+def meta_score(g, X, resid, sigma2):
+    """one variant (N,) of hard calls -> dict of the MetaScore columns"""
+    N = len(g)
+    n0, n1, n2 = int((g == 0).sum()), int((g == 1).sum()), int((g == 2).sum())
+    out = dict(af=0.5 * g.sum() / N, ac=float(g.sum()), call_rate=1.0, n_ref=n0, n_het=n1, n_alt=n2,
+               hwe_p=snp_hwe(n1, n0, n2) if (n0 + n1 + n2) else 0.0)
+    mono = g.min() == g.max()
+    out["polymorphic"] = not mono
+    if mono:
+        out["ok"] = False
+        return out
+    U = float(g @ resid)
+    SZ = g @ X
+    SS = float(g @ g) - float(SZ @ np.linalg.solve(X.T @ X, SZ))
+    V = SS * sigma2
+    stat = U * (1.0 / SS / sigma2) * U
+    if stat < 0:
+        out["ok"] = False
+        return out
+    out.update(ok=True, U=U / sigma2, sqrtV=np.sqrt(V / sigma2 / sigma2), effect=(U / SS) if V != 0 else 0.0,
+               effect_se=(sigma2 / np.sqrt(V)) if V != 0 else 0.0, pvalue=O.lib().orc_chisq_q(stat, 1.0))
+    return out
+
+
+def meta_cov(G, pos, chrom, X, sigma2, window):
+    """G (N, nv) hard calls -> list over variants of (positions, cov values) as printCovariance
+    would emit when that variant reaches the head of the queue (None for monomorphic variants)."""
+    N, nv = G.shape
+    Gd = G.astype(np.float64)
+    Xc = X - X.mean(axis=0, keepdims=True)            # centerMatrix: intercept column -> exactly 0
+    covZZ = Xc.T @ Xc / sigma2
+    covZZInv = np.linalg.pinv(covZZ)                   # LDLT solve with zero pivots = pseudo-inverse
+    xt = Gd - Gd.mean(axis=0, keepdims=True)           # transformGenotype
+    covXZ = xt.T @ X / sigma2                          # calculateXZ uses the UNcentred cov
+    poly = [Gd[:, j].min() != Gd[:, j].max() for j in range(nv)]
+    out = []
+    for i in range(nv):
+        if not poly[i]:
+            out.append(None)
+            continue
+        ps, vals = [], []
+        for j in range(i, nv):
+            if chrom[j] != chrom[i] or pos[j] - pos[i] > window:
+                break
+            if not poly[j]:
+                continue
+            xx = float(xt[:, i] @ xt[:, j]) / sigma2
+            vals.append((xx - float(covXZ[i] @ covZZInv @ covXZ[j])) / N)
+            ps.append(int(pos[j]))
+        out.append((ps, vals))
+    return out

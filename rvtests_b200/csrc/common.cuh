@@ -40,6 +40,9 @@ struct GeneDesc {
   int64_t var0;      // offset of this gene's per-variant side arrays (flags, af)
   int32_t has_af;    // caller supplied allele frequencies (F9 quirk path)
   int32_t counted;   // the engine counted this gene's rows itself (RowCounts valid)
+  int64_t row0_b;    // meta-cov block pairs: first row of the B-operand tile (== row0 for a gene)
+  int32_t Mb;        // rows of the B tile (== M for a gene)
+  int32_t pad;
 };
 
 struct RowCounts {

@@ -13,6 +13,7 @@
 #include "../../include/rvtests_b200.h"
 #include "common.cuh"
 #include "finalize.cuh"
+#include "meta.cuh"
 #include "null_model.cuh"
 #include "prep.cuh"
 #include "sweep_simt.cuh"
@@ -369,6 +370,8 @@ static int push_common(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const 
   gd.var0 = ctx->n_var;
   gd.has_af = af ? 1 : 0;
   gd.counted = counted ? 1 : 0;
+  gd.row0_b = row0;
+  gd.Mb = M;
   ctx->genes.push_back(gd);
   ctx->count_slot.push_back(counted ? ctx->n_var : -1);
   for (int j = 0; j < M; ++j) {
@@ -580,6 +583,171 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
 int rvt_flush(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out) { return flush_impl(ctx, out, cap, n_out, false); }
 int rvt_flush_dev(rvt_ctx* ctx, rvt_gene_result* d_out, int cap, int* n_out) {
   return flush_impl(ctx, d_out, cap, n_out, true);
+}
+
+// last partner of every variant: jmax[i] = max { j >= i : chrom_j == chrom_i, pos_j - pos_i <= window }
+static int meta_jmax(const int32_t* pos, const int32_t* chrom, int64_t nv, int64_t window, std::vector<int>* jmax) {
+  jmax->resize(nv);
+  int64_t j = 0;
+  int wmax = 0;
+  for (int64_t i = 0; i < nv; ++i) {
+    if (j < i) j = i;
+    while (j + 1 < nv && chrom[j + 1] == chrom[i] && (int64_t)pos[j + 1] - (int64_t)pos[i] <= window) ++j;
+    // the list is sorted: a later variant on the same chromosome never has a smaller position
+    (*jmax)[i] = (int)j;
+    wmax = std::max<int>(wmax, (int)(j - i));
+  }
+  return wmax;
+}
+
+int rvt_meta_plan(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64_t nv, int64_t window_bp, int* wmax) {
+  if (!ctx || !pos || !chrom || !wmax || nv < 0) return RVT_E_BADARG;
+  std::vector<int> jm;
+  *wmax = meta_jmax(pos, chrom, nv, window_bp, &jm);
+  return RVT_OK;
+}
+
+int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64_t window_bp,
+                   rvt_variant_result* vout, int64_t cap_variants, double* band, int64_t cap_band, int* wmax_out) {
+  if (!ctx || !vout) return RVT_E_BADARG;
+  const int ngen = (int)ctx->genes.size();
+  const int64_t nv = ctx->n_var;
+  if (ngen == 0) return RVT_OK;
+  if (cap_variants < nv) CTX_FAIL(RVT_E_BADARG, "vout holds %lld records, %lld variants pending", (long long)cap_variants, (long long)nv);
+  if (band && (!pos || !chrom)) CTX_FAIL(RVT_E_BADARG, "the covariance band needs pos and chrom");
+  RVT_CUDA_OK(cudaSetDevice(ctx->device));
+  // the pushes must form one contiguous run of rows inside one TMA segment
+  const int seg = ctx->genes[0].seg;
+  const int64_t row_base = ctx->genes[0].row0;
+  {
+    int64_t r = row_base;
+    for (const auto& g : ctx->genes) {
+      if (g.seg != seg || g.row0 != r) CTX_FAIL(RVT_E_UNSUPPORTED, "meta: pending variant blocks are not contiguous in one segment");
+      r += g.M;
+    }
+  }
+  int rc;
+  if (seg == kSegStaged) {
+    if ((rc = tc_bind_segment(&ctx->tc, kSegStaged, ctx->d_stage, ctx->stage_used_rows, ctx->N, ctx->stage_ld, ctx->err, sizeof(ctx->err)))) return rc;
+  }
+  const int8_t* seg_base = (seg == kSegStaged) ? ctx->d_stage : ctx->d_loaded;
+  const int64_t seg_ld = (seg == kSegStaged) ? ctx->stage_ld : ctx->loaded_ld;
+  std::vector<int> jmax;
+  int wmax = 0;
+  if (band) {
+    wmax = meta_jmax(pos, chrom, nv, window_bp, &jmax);
+    if (cap_band < nv * (int64_t)(wmax + 1)) CTX_FAIL(RVT_E_BADARG, "band needs %lld doubles", (long long)(nv * (int64_t)(wmax + 1)));
+  } else {
+    jmax.assign(nv, 0);
+    for (int64_t i = 0; i < nv; ++i) jmax[i] = (int)i;
+  }
+  if (wmax_out) *wmax_out = wmax;
+  const int64_t N = ctx->N;
+  int S = ctx->splits;
+  if (S <= 0) S = (int)std::min<int64_t>(16, std::max<int64_t>(1, (N + 65535) / 65536));
+  int64_t chunk = (((N + S - 1) / S) + 511) & ~(int64_t)511;
+  S = (int)((N + chunk - 1) / chunk);
+  // tiles of 64 consecutive variants and the tile pairs inside the window
+  const int T = (int)((nv + kTileRows - 1) / kTileRows);
+  std::vector<GeneDesc> tiles(T), pairs;
+  for (int t = 0; t < T; ++t) {
+    GeneDesc g;
+    memset(&g, 0, sizeof(g));
+    g.row0 = g.row0_b = row_base + (int64_t)t * kTileRows;
+    g.M = g.Mb = (int)std::min<int64_t>(kTileRows, nv - (int64_t)t * kTileRows);
+    g.g = seg_base + (size_t)g.row0 * seg_ld;
+    g.ld = seg_ld;
+    g.seg = seg;
+    g.var0 = (int64_t)t * kTileRows;
+    tiles[t] = g;
+  }
+  if (band) {
+    for (int t = 0; t < T; ++t) {
+      int jm = 0;
+      for (int i = 0; i < tiles[t].M; ++i) jm = std::max(jm, jmax[(size_t)t * kTileRows + i]);
+      for (int u = t + 1; u <= jm / kTileRows; ++u) {
+        GeneDesc g = tiles[t];
+        g.row0_b = tiles[u].row0;
+        g.Mb = tiles[u].M;
+        pairs.push_back(g);
+      }
+    }
+  }
+  cudaStream_t st = ctx->stream;
+  // device buffers
+  int* d_jmax = nullptr;
+  double* d_B = nullptr;
+  uint8_t* d_poly = nullptr;
+  rvt_variant_result* d_v = nullptr;
+  double* d_band = nullptr;
+  GeneDesc* d_desc = nullptr;
+  uint8_t* d_flags0 = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_jmax); cudaFree(d_B); cudaFree(d_poly); cudaFree(d_v); cudaFree(d_band); cudaFree(d_desc); cudaFree(d_flags0);
+  };
+  const int batch = 1024;
+  const size_t ndesc = std::max<size_t>((size_t)T, pairs.size());
+  cudaError_t e = cudaMalloc((void**)&d_jmax, sizeof(int) * nv);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_B, sizeof(double) * nv * kMaxC);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_poly, nv);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_v, sizeof(rvt_variant_result) * nv);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_desc, sizeof(GeneDesc) * ndesc);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_flags0, (size_t)T * kTileRows);
+  if (e == cudaSuccess && band) e = cudaMalloc((void**)&d_band, sizeof(double) * nv * (size_t)(wmax + 1));
+  if (e != cudaSuccess) {
+    cleanup();
+    CTX_FAIL(RVT_E_CUDA, "meta: cudaMalloc: %s", cudaGetErrorString(e));
+  }
+  if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)batch * S, sizeof(SweepPartial)))) { cleanup(); return rc; }
+  RVT_CUDA_OK(cudaMemcpyAsync(d_jmax, jmax.data(), sizeof(int) * nv, cudaMemcpyHostToDevice, st));
+  RVT_CUDA_OK(cudaMemsetAsync(d_flags0, 0, (size_t)T * kTileRows, st));   // every row "normal": no flip in meta mode
+  if (band) {
+    // NaN-fill: entries outside a variant's window stay NaN
+    RVT_CUDA_OK(cudaMemsetAsync(d_band, 0xFF, sizeof(double) * nv * (size_t)(wmax + 1), st));
+  }
+  const bool tc_ok = ctx->tc.encode && ctx->tc.have_e && seg >= 0 && ctx->tc.have_seg[seg];
+  if (!pairs.empty() && !tc_ok) { cleanup(); CTX_FAIL(RVT_E_UNSUPPORTED, "meta cov needs the tensor-core engine (TMA segment unavailable)"); }
+  // phase 1: diagonal tiles
+  RVT_CUDA_OK(cudaMemcpyAsync(d_desc, tiles.data(), sizeof(GeneDesc) * T, cudaMemcpyHostToDevice, st));
+  for (int b0 = 0; b0 < T; b0 += batch) {
+    const int nb = std::min(batch, T - b0);
+    if (tc_ok) {
+      rc = tc_launch(&ctx->tc, d_desc + b0, tiles.data() + b0, nb, d_flags0, ctx->d_nm, N, ctx->ER, S, chunk, ctx->d_parts,
+                     ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), false);
+      if (rc) { cleanup(); return rc; }
+    } else {
+      RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), st));
+      k_sweep_simt<<<std::min(nb * S, ctx->sm_count * 3), kSimtThreads, kSimtSmem, st>>>(d_desc + b0, nb, d_flags0, ctx->d_nm, S, chunk,
+                                                                                       ctx->d_parts, ctx->d_counter);
+    }
+    k_meta_block<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, (int64_t)b0 * kTileRows, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, d_v,
+                                              d_B, d_poly, d_band);
+    RVT_CUDA_OK(cudaGetLastError());
+  }
+  // phase 2: tile pairs inside the window
+  if (!pairs.empty()) {
+    RVT_CUDA_OK(cudaStreamSynchronize(st));  // d_desc is rewritten
+    RVT_CUDA_OK(cudaMemcpyAsync(d_desc, pairs.data(), sizeof(GeneDesc) * pairs.size(), cudaMemcpyHostToDevice, st));
+    for (size_t b0 = 0; b0 < pairs.size(); b0 += batch) {
+      const int nb = (int)std::min<size_t>(batch, pairs.size() - b0);
+      rc = tc_launch(&ctx->tc, d_desc + b0, pairs.data() + b0, nb, d_flags0, ctx->d_nm, N, ctx->ER, S, chunk, ctx->d_parts,
+                     ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), true);
+      if (rc) { cleanup(); return rc; }
+      k_meta_pair<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, row_base, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, d_B, d_poly, d_band);
+      RVT_CUDA_OK(cudaGetLastError());
+    }
+  }
+  RVT_CUDA_OK(cudaMemcpyAsync(vout, d_v, sizeof(rvt_variant_result) * nv, cudaMemcpyDeviceToHost, st));
+  if (band) RVT_CUDA_OK(cudaMemcpyAsync(band, d_band, sizeof(double) * nv * (size_t)(wmax + 1), cudaMemcpyDeviceToHost, st));
+  RVT_CUDA_OK(cudaStreamSynchronize(st));
+  cleanup();
+  ctx->genes.clear();
+  ctx->userflags.clear();
+  ctx->af.clear();
+  ctx->count_slot.clear();
+  ctx->n_var = 0;
+  ctx->stage_used_rows = 0;
+  return RVT_OK;
 }
 
 int rvt_synth_load(rvt_ctx* ctx, int n_genes, int M, const uint64_t* keys, const uint32_t* t0, const uint32_t* t1) {

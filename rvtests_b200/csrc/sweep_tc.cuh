@@ -35,9 +35,15 @@ constexpr int kTcBoxK = 128;                // samples per box (one 128-byte swi
 constexpr int kTcStageK = kTcBoxes * kTcBoxK;
 constexpr int kTcTmemCols = 256;            // 2 accumulators x 128 columns
 
-template <int ER, int STAGES>
+// PAIR = the A operand (rows of block I) and the B operand (rows of block J) are different tiles:
+// the cross-block Gram of the meta-analysis covariance (src/Model.cpp:534-554 calculateXX for
+// every pair of variants in the sliding window).  Box = [A tile][B tile][E tile].
+template <int ER, int STAGES, bool PAIR = false>
 struct TcCfg {
-  static constexpr int kBoxBytes = kTileRows * 128 + ER * 128;
+  static constexpr int kAOff = 0;
+  static constexpr int kBOff = PAIR ? kTileRows * 128 : 0;
+  static constexpr int kEOff = kBOff + kTileRows * 128;
+  static constexpr int kBoxBytes = kEOff + ER * 128;
   static constexpr int kStageBytes = kTcBoxes * kBoxBytes;
   static constexpr int kSmem = STAGES * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kNC = kTileRows + ER;
@@ -116,12 +122,12 @@ __device__ __forceinline__ uint32_t sw128_word_off(int r, int w) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((w >> 2) ^ (r & 7)) << 4) | ((w & 3) << 2)));
 }
 
-template <int ER, int kTcStages>
+template <int ER, int kTcStages, bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */, const __grid_constant__ CUtensorMap map_e,
            const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __restrict__ rowflags, int64_t N, int S,
            int64_t chunk, SweepPartial* __restrict__ out) {
-  using Cfg = TcCfg<ER, kTcStages>;
+  using Cfg = TcCfg<ER, kTcStages, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B (TMA destination and UMMA descriptors)
   uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -170,7 +176,10 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
         // the box of this gene holds exactly its M rows (no bytes of the neighbouring gene):
         // rows M..63 of the smem tile keep stale data, which only feeds ignored rows/columns of D
         const CUtensorMap* mg = maps_g + (Mg - 1);
-        const uint32_t stage_tx = (uint32_t)(kTcBoxes * (Mg + ER) * 128);
+        const int row0b = (int)genes[gi].row0_b;
+        const int Mgb = genes[gi].Mb;
+        const CUtensorMap* mgb = maps_g + (Mgb - 1);
+        const uint32_t stage_tx = (uint32_t)(kTcBoxes * (Mg + (PAIR ? Mgb : 0) + ER) * 128);
         const int64_t k0 = (int64_t)sp * chunk;
         int64_t k1 = k0 + chunk;
         if (k1 > N) k1 = N;
@@ -184,8 +193,9 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
           const int kb = (int)(k0 + (int64_t)ks * kTcStageK);
 #pragma unroll
           for (int b = 0; b < kTcBoxes; ++b) {
-            tma_load_2d(st + b * Cfg::kBoxBytes, mg, kb + b * kTcBoxK, row0, &full[s], kEvictFirst);
-            tma_load_2d(st + b * Cfg::kBoxBytes + kTileRows * 128, &map_e, kb + b * kTcBoxK, 0, &full[s], kEvictLast);
+            tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kAOff, mg, kb + b * kTcBoxK, row0, &full[s], kEvictFirst);
+            if (PAIR) tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kBOff, mgb, kb + b * kTcBoxK, row0b, &full[s], kEvictFirst);
+            tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kEOff, &map_e, kb + b * kTcBoxK, 0, &full[s], kEvictLast);
           }
         }
       }
@@ -214,12 +224,12 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
           const uint32_t st = smem_u32(tiles + (size_t)s * Cfg::kStageBytes);
 #pragma unroll
           for (int b = 0; b < kTcBoxes; ++b) {
-            const uint64_t d0 = umma_desc_sw128(st + b * Cfg::kBoxBytes);
+            const uint64_t da0 = umma_desc_sw128(st + b * Cfg::kBoxBytes + Cfg::kAOff);
+            const uint64_t db0 = umma_desc_sw128(st + b * Cfg::kBoxBytes + Cfg::kBOff);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // advance 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-              const uint64_t d = d0 + (uint64_t)(2 * k);
-              umma_i8(tmem_d, d, d, idesc, (ks | b | k) ? 1u : 0u);
+              umma_i8(tmem_d, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, (ks | b | k) ? 1u : 0u);
             }
           }
           umma_commit(&empty[s]);
@@ -267,7 +277,9 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
         const uint8_t* box = tiles + (size_t)s * Cfg::kStageBytes + cw * Cfg::kBoxBytes;
         const int64_t ksamp = k0 + (int64_t)ks * kTcStageK + cw * kTcBoxK + 4 * lane;
         uint32_t z = 0;
-        if (plain) {
+        if (PAIR) {
+          // block pairs need the Gram only (no burden collapse)
+        } else if (plain) {
           // common case (no flipped / monomorphic row): indicator = (g | g>>1) & 1 per byte,
           // 8 independent LDS in flight, 3 ALU ops per row
           for (int r0 = 0; r0 < M8; r0 += 8) {
@@ -296,19 +308,21 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
             }
           }
         }
-        int64_t rem = k1 - ksamp;
-        uint32_t vm = rem >= 4 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - (int)rem))));
-        z &= vm;
-        const uint32_t c = ((z + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
-        const uint8_t* ebox = box + kTileRows * 128;
+        if (!PAIR) {
+          int64_t rem = k1 - ksamp;
+          uint32_t vm = rem >= 4 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - (int)rem))));
+          z &= vm;
+          const uint32_t c = ((z + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
+          const uint8_t* ebox = box + Cfg::kEOff;
 #pragma unroll
-        for (int e = 0; e < ER; ++e) {
-          int ew = *reinterpret_cast<const int*>(ebox + sw128_word_off(e, lane));
-          cz[e] = __dp4a((int)z, ew, cz[e]);
-          cc[e] = __dp4a((int)c, ew, cc[e]);
+          for (int e = 0; e < ER; ++e) {
+            int ew = *reinterpret_cast<const int*>(ebox + sw128_word_off(e, lane));
+            cz[e] = __dp4a((int)z, ew, cz[e]);
+            cc[e] = __dp4a((int)c, ew, cc[e]);
+          }
+          cz[ER] = __dp4a((int)z, (int)z, cz[ER]);
+          cc[ER] = __dp4a((int)c, (int)c, cc[ER]);
         }
-        cz[ER] = __dp4a((int)z, (int)z, cz[ER]);
-        cc[ER] = __dp4a((int)c, (int)c, cc[ER]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
       }
@@ -405,9 +419,11 @@ inline int tc_init(TcSegments* tc, char* err, size_t errlen) {
     return 0;  // the dp4a engine still works; an explicit engine=tc request fails loudly
   }
   tc->encode = fn;
-  e = cudaFuncSetAttribute(k_sweep_tc<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 4>::kSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5>::kSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4>::kSmem);
+  e = cudaFuncSetAttribute(k_sweep_tc<16, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 4>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 3, true>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 2, true>::kSmem);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "cudaFuncSetAttribute(k_sweep_tc): %s", cudaGetErrorString(e));
     return -2;
@@ -480,9 +496,9 @@ inline int tc_bind_segment(TcSegments* tc, int seg, const int8_t* base, int64_t 
 // make sure the segment has a tensor map for every box height present in this batch
 inline int tc_prepare_maps(TcSegments* tc, int seg, const GeneDesc* h_genes, int n, cudaStream_t st, char* err, size_t errlen) {
   TcSegments::Seg& sg = tc->seg[seg];
-  for (int i = 0; i < n; ++i) {
-    const int M = h_genes[i].M;
-    if (sg.have_m[M - 1]) continue;
+  for (int i = 0; i < 2 * n; ++i) {
+    const int M = (i < n) ? h_genes[i].M : h_genes[i - n].Mb;
+    if (M < 1 || M > kTileRows || sg.have_m[M - 1]) continue;
     CUtensorMap m;
     int rc = tc_make_map(tc, &m, sg.base, sg.rows, sg.N, sg.ld, M, err, errlen);
     if (rc) return rc;
@@ -518,7 +534,8 @@ inline bool tc_usable(TcSegments* tc, const GeneDesc* h_genes, int n) {
 
 inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_genes, int n, const uint8_t* d_flags,
                      const NullModel* /*d_nm*/, int64_t N, int ER, int S, int64_t chunk, SweepPartial* d_parts,
-                     unsigned int* /*counter*/, int sm_count, cudaStream_t st, char* err, size_t errlen) {
+                     unsigned int* /*counter*/, int sm_count, cudaStream_t st, char* err, size_t errlen,
+                     bool pair = false) {
   const int seg = h_genes[0].seg;
   const int grid = std::min(n * S, sm_count);
   if (chunk % kTcStageK != 0) {
@@ -527,12 +544,16 @@ inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_
   }
   int rc = tc_prepare_maps(tc, seg, h_genes, n, st, err, errlen);
   if (rc) return rc;
-  if (ER == 16 && tc->stages == 5)
-    k_sweep_tc<16, 5><<<grid, kTcThreads, TcCfg<16, 5>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+  if (pair && ER == 16)
+    k_sweep_tc<16, 3, true><<<grid, kTcThreads, TcCfg<16, 3, true>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+  else if (pair)
+    k_sweep_tc<32, 2, true><<<grid, kTcThreads, TcCfg<32, 2, true>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+  else if (ER == 16 && tc->stages == 5)
+    k_sweep_tc<16, 5, false><<<grid, kTcThreads, TcCfg<16, 5>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
   else if (ER == 16)
-    k_sweep_tc<16, 4><<<grid, kTcThreads, TcCfg<16, 4>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+    k_sweep_tc<16, 4, false><<<grid, kTcThreads, TcCfg<16, 4>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
   else
-    k_sweep_tc<32, 4><<<grid, kTcThreads, TcCfg<32, 4>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+    k_sweep_tc<32, 4, false><<<grid, kTcThreads, TcCfg<32, 4>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, errlen, "k_sweep_tc launch: %s", cudaGetErrorString(e));

@@ -52,7 +52,14 @@ EXPORTS = [
     "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded",
     "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
     "rvt_debug_phases",
+    "rvt_meta_plan", "rvt_meta_flush",
 ]
+
+VARIANT_DTYPE = np.dtype([
+    ("af", "f8"), ("ac", "f8"), ("call_rate", "f8"), ("hwe_p", "f8"),
+    ("n_ref", "i4"), ("n_het", "i4"), ("n_alt", "i4"), ("ok", "i4"), ("polymorphic", "i4"), ("pad", "i4"),
+    ("U", "f8"), ("sqrtV", "f8"), ("effect", "f8"), ("effect_se", "f8"), ("pvalue", "f8"),
+])
 
 _lib = None
 _dp = C.POINTER(C.c_double)
@@ -91,6 +98,8 @@ def load_library(rebuild: bool = False):
     L.rvt_last_timing.argtypes = [vp, _dp]
     L.rvt_debug_partials.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64)]
     L.rvt_debug_phases.argtypes = [vp, vp, C.c_int]
+    L.rvt_meta_plan.argtypes = [vp, vp, vp, C.c_int64, C.c_int64, C.POINTER(C.c_int)]
+    L.rvt_meta_flush.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -222,6 +231,23 @@ class GeneEngine:
         buf = np.zeros(nb.value // rec.itemsize, dtype=rec)
         self._chk(self.L.rvt_debug_partials(self.h, buf.ctypes.data, buf.nbytes, C.byref(nb)))
         return buf
+
+    def meta_flush(self, n_variants, pos=None, chrom=None, window_bp=1_000_000, want_cov=True):
+        """--meta score[,cov] over the pending variant blocks.  Returns (variant records, band, wmax)."""
+        vout = np.zeros(max(n_variants, 1), dtype=VARIANT_DTYPE)
+        wmax = C.c_int(0)
+        band = None
+        p = c = None
+        if want_cov:
+            p = np.ascontiguousarray(pos, dtype=np.int32)
+            c = np.ascontiguousarray(chrom, dtype=np.int32)
+            self._chk(self.L.rvt_meta_plan(self.h, p.ctypes.data, c.ctypes.data, len(p), int(window_bp), C.byref(wmax)))
+            band = np.zeros((n_variants, wmax.value + 1))
+        self._chk(self.L.rvt_meta_flush(self.h, None if p is None else p.ctypes.data, None if c is None else c.ctypes.data,
+                                        int(window_bp), vout.ctypes.data, len(vout),
+                                        None if band is None else band.ctypes.data, 0 if band is None else band.size,
+                                        C.byref(wmax)))
+        return vout[:n_variants], band, wmax.value
 
     def debug_phases(self, n):
         out = np.zeros((n, 6), dtype=np.int64)

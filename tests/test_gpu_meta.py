@@ -1,0 +1,95 @@
+"""GPU: --meta score,cov statistics (src/Model.h:3155-4096, src/Model.cpp:500-1004) against the
+numpy oracle: counts bit exact, score statistics 1e-6, HWE 1e-9, covariances 1e-5 (the reference
+is float32 there), window membership exact -- including tile pairs across the 64-variant tiles."""
+import numpy as np
+import pytest
+
+from util import rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _variants(O, seed, N, nv, maf_hi=0.4):
+    vid = np.arange(nv, dtype=np.uint64) + np.uint64(seed * 7919)
+    rng = np.random.default_rng(seed)
+    maf = 10 ** rng.uniform(np.log10(2.0 / N), np.log10(maf_hi), nv)
+    maf[rng.integers(0, nv, max(1, nv // 25))] = 0.9          # ALT-major variants stay unflipped in meta mode
+    G = O.synth_genotypes(seed, vid, N, maf=maf)                # (nv, N)
+    for j in rng.integers(0, nv, max(1, nv // 30)):
+        G[j] = 0                                                # monomorphic
+    return G
+
+
+@pytest.mark.parametrize("case", [(1, 3000, 50, 1, 400), (2, 5000, 200, 3, 3000), (3, 2500, 130, 2, 100000)])
+def test_meta_score_and_cov(engine_cls, oracle, case):
+    from oracle import meta_oracle as MO
+    O = oracle
+    seed, N, nv, C, window = case
+    G = _variants(O, seed, N, nv)
+    X, y = O.synth_covariates(seed, N, C)
+    rng = np.random.default_rng(seed + 100)
+    pos = np.cumsum(rng.integers(1, 60, nv)).astype(np.int32)
+    chrom = np.ones(nv, dtype=np.int32)
+    chrom[int(nv * 0.7):] = 2                                   # a chromosome change inside a tile
+    pos[int(nv * 0.7):] -= pos[int(nv * 0.7)] - 5
+    eng = engine_cls(0)
+    eng.set_null_model(X, y)
+    nm = O.fit_null_linear(X, y)
+    for b0 in range(0, nv, 37):                                 # pushes need not be tile aligned
+        eng.push_i8(G[b0:b0 + 37].copy(), None)
+    vout, band, wmax = eng.meta_flush(nv, pos, chrom, window)
+    ref_cov = MO.meta_cov(G.T, pos, chrom, X, nm["sigma2"], window)
+    n_cov = 0
+    for v in range(nv):
+        ref = MO.meta_score(G[v].astype(np.float64), X, nm["resid"], nm["sigma2"])
+        r = vout[v]
+        assert (int(r["n_ref"]), int(r["n_het"]), int(r["n_alt"])) == (ref["n_ref"], ref["n_het"], ref["n_alt"])
+        assert r["af"] == ref["af"] and r["ac"] == ref["ac"] and r["call_rate"] == 1.0
+        assert rel(r["hwe_p"], ref["hwe_p"]) <= 1e-9, (v, r["hwe_p"], ref["hwe_p"])
+        assert bool(r["ok"]) == ref["ok"] and bool(r["polymorphic"]) == ref["polymorphic"]
+        if ref["ok"]:
+            for k in ("U", "sqrtV", "effect", "effect_se"):
+                assert rel(r[k], ref[k]) <= 1e-6, (v, k, r[k], ref[k])
+            assert rel(r["pvalue"], ref["pvalue"]) <= 1e-6
+        # covariance row: the non-NaN entries of the band, in order, are the reference's COV list
+        row = band[v]
+        if ref_cov[v] is None:
+            assert np.all(np.isnan(row))
+            continue
+        ps, vals = ref_cov[v]
+        got = row[~np.isnan(row)]
+        got_pos = pos[v:v + wmax + 1][~np.isnan(row[: len(pos[v:v + wmax + 1])])]
+        assert list(got_pos) == ps
+        assert len(got) == len(vals)
+        scale = max(abs(vals[0]), 1e-300)                        # entry 0 is the variant's own variance
+        assert np.max(np.abs(got - np.array(vals))) <= 1e-5 * scale
+        n_cov += len(vals)
+    assert n_cov > nv
+    eng.close()
+
+
+def test_meta_score_only_and_hwe_extremes(engine_cls, oracle):
+    from oracle import meta_oracle as MO
+    O = oracle
+    N = 4000
+    rng = np.random.default_rng(5)
+    rows = []
+    for n1, n2 in ((0, 0), (1, 0), (0, 1), (N, 0), (0, N), (N // 2, N // 4), (17, 3), (1999, 1000), (N - 1, 0)):
+        g = np.zeros(N, dtype=np.int8)
+        idx = rng.permutation(N)
+        g[idx[:n1]] = 1
+        g[idx[n1:n1 + n2]] = 2
+        rows.append(g)
+    G = np.array(rows)
+    X, y = O.synth_covariates(9, N, 2)
+    eng = engine_cls(0)
+    eng.set_null_model(X, y)
+    nm = O.fit_null_linear(X, y)
+    eng.push_i8(G, None)
+    vout, band, wmax = eng.meta_flush(len(rows), want_cov=False)
+    assert band is None
+    for v in range(len(rows)):
+        ref = MO.meta_score(G[v].astype(np.float64), X, nm["resid"], nm["sigma2"])
+        assert rel(vout[v]["hwe_p"], ref["hwe_p"]) <= 1e-9
+        assert bool(vout[v]["ok"]) == ref["ok"]
+    eng.close()
