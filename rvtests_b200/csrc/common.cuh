@@ -1,11 +1,14 @@
 // common.cuh -- shared definitions of the B200 gene engine (device data layout + helpers).
 //
 // DATA LAYOUT IN HBM
-//   genotype block of one gene : int8 [M rows][ld bytes], "variant-major" (one row per variant,
-//       samples contiguous, hard calls 0/1/2) -- the orientation of a PLINK .bed and of the
-//       reference's column-major Matrix (base/MathMatrix.h:33-41) at one byte per call.
-//       Rows of consecutive genes are stacked in one arena so that ONE TMA tensor map
-//       [total_rows][N] serves every gene of a segment.
+//   genotype block of one gene : int8, hard calls 0/1/2, one byte per call, in the engine's TILED
+//       variant-major layout  [chunk c = sample/128][variant j][128 samples]  (zero padded to a
+//       whole chunk).  One sweep stage of 4 chunks is then ONE contiguous 4*M*128-byte run of HBM
+//       (a plain variant-major [M][N] block would scatter it over M DRAM pages, 128-512 B each,
+//       which capped the sweep at ~64 % of the HBM roofline).  All genes of a segment sit in one byte
+//       arena viewed as [bytes/128][128], so one family of TMA tensor maps (box = M x 128 B) serves
+//       every gene.  Caller-owned device blocks may stay plain variant-major [M][ld] (zero-copy,
+//       dp4a engine only).
 //   null-model digits "E"      : int8 [ER rows][ldE], ER = 4*(C+1) rounded up to 16.  Row 4*v+k is
 //       base-256 balanced digit k of the fixed-point image of vector v, v=0 the null residual r,
 //       v=1..C the covariate columns (column 0 = intercept).  value_i = (sum_k d_ik 256^k) 2^-e_v.
@@ -42,8 +45,15 @@ struct GeneDesc {
   int32_t counted;   // the engine counted this gene's rows itself (RowCounts valid)
   int64_t row0_b;    // meta-cov block pairs: first row of the B-operand tile (== row0 for a gene)
   int32_t Mb;        // rows of the B tile (== M for a gene)
-  int32_t pad;
+  int32_t tiled;     // 1: [chunk][M][128] layout (row0 = byte offset / 128 inside the segment); 0: [M][ld]
+  int64_t var0_b;    // meta: variant index of the B tile's first row
 };
+
+// address of (variant row r, sample k) inside a gene block
+__device__ __forceinline__ const int8_t* geno_ptr(const GeneDesc& gd, int r, int64_t k) {
+  return gd.tiled ? gd.g + ((size_t)(k >> 7) * gd.M + r) * 128 + (k & 127) : gd.g + (size_t)r * gd.ld + k;
+}
+static inline int64_t tiled_bytes(int64_t N, int M) { return ((N + 127) / 128) * (int64_t)M * 128; }
 
 struct RowCounts {
   int n1, n2, bad, pad;  // #het, #hom-alt, #values outside {0,1,2}

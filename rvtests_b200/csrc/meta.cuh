@@ -14,8 +14,8 @@
 //       (regression/EigenMatrixInterface.cpp:125-136), so this is (g_i'(I-H_X)g_j)/(sigma2 N)
 //       = (A_ij - B_i (X'X)^-1 B_j') / (sigma2 N): an entry of the same projected Gram the SKAT
 //       kernel builds, without weights.
-// Variants are tiled by 64 rows; tile pairs (I,J) inside the window come from the PAIR mode of the
-// tensor-core sweep (A tile = rows of I, B tile = rows of J).
+// Every push is one tile (<= 64 consecutive variants); tile pairs (I,J) inside the window come from
+// the PAIR mode of the tensor-core sweep (A tile = rows of I, B tile = rows of J).
 #pragma once
 #include "../../include/rvtests_b200.h"
 #include "common.cuh"
@@ -93,8 +93,7 @@ __device__ __forceinline__ long long recombine4m(const long long* d) {
 // One CTA per 64-variant tile: per-variant score statistics, the tile's B = G'X rows, and the
 // within-tile covariance band.  tiles[t]: row0 = first variant row, M = variants in the tile.
 __global__ void __launch_bounds__(kMetaThreads)
-k_meta_block(const GeneDesc* __restrict__ tiles, int n_tiles, int64_t v0 /*variant index of tile 0*/,
-             const NullModel* __restrict__ nm, int S, const SweepPartial* __restrict__ parts,
+k_meta_block(const GeneDesc* __restrict__ tiles, int n_tiles, const NullModel* __restrict__ nm, int S, const SweepPartial* __restrict__ parts,
              const int* __restrict__ jmax /*[nv] last partner (variant index)*/, int wmax,
              rvt_variant_result* __restrict__ vout, double* __restrict__ Bmat /*[nv][kMaxC]*/,
              uint8_t* __restrict__ poly /*[nv]*/, double* __restrict__ band /*[nv][wmax+1] or null*/) {
@@ -110,7 +109,7 @@ k_meta_block(const GeneDesc* __restrict__ tiles, int n_tiles, int64_t v0 /*varia
   const int C = nm->C, ER = nm->ER;
   const double sigma2 = nm->sigma2;
   const SweepPartial* __restrict__ gp = parts + (size_t)t * S;
-  const int64_t vbase = v0 + (int64_t)t * kTileRows;
+  const int64_t vbase = gd.var0;
   for (int idx = tid; idx < M * ER; idx += kMetaThreads) {
     const int i = idx / ER, e = idx - i * ER;
     long long s = 0;
@@ -193,15 +192,14 @@ k_meta_block(const GeneDesc* __restrict__ tiles, int n_tiles, int64_t v0 /*varia
 
 // One CTA per tile pair (I,J), J > I: the cross-tile part of the band.
 __global__ void __launch_bounds__(kMetaThreads)
-k_meta_pair(const GeneDesc* __restrict__ pairs, int n_pairs, int64_t row_base /*segment row of variant 0*/,
-            const NullModel* __restrict__ nm, int S, const SweepPartial* __restrict__ parts,
+k_meta_pair(const GeneDesc* __restrict__ pairs, int n_pairs, const NullModel* __restrict__ nm, int S, const SweepPartial* __restrict__ parts,
             const int* __restrict__ jmax, int wmax, const double* __restrict__ Bmat,
             const uint8_t* __restrict__ poly, double* __restrict__ band) {
   const int p = blockIdx.x, tid = threadIdx.x;
   if (p >= n_pairs) return;
   const GeneDesc gd = pairs[p];
   const int Ma = gd.M, Mb = gd.Mb;
-  const int64_t va = gd.row0 - row_base, vb = gd.row0_b - row_base;
+  const int64_t va = gd.var0, vb = gd.var0_b;
   const int C = nm->C;
   const double scale = 1.0 / (nm->sigma2 * (double)nm->N);
   const SweepPartial* __restrict__ gp = parts + (size_t)p * S;

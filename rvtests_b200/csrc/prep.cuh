@@ -19,15 +19,20 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
   return z ^ (z >> 31);
 }
 
-// grid: (ceil(ld/16/256), rows).  One thread = 16 consecutive samples of one row.
+// tiled address of (row r of an M-row gene, sample i): [chunk][M][128]
+__device__ __forceinline__ size_t tiled_off(int M, int r, int64_t i) { return ((size_t)(i >> 7) * M + r) * 128 + (i & 127); }
+
+// grid: (ceil(npad/16/256), rows), npad = N rounded up to 128.  One thread = 16 consecutive samples
+// of one row; row = gene*M + r, genes of equal M stacked back to back in the tiled layout.
 __global__ void __launch_bounds__(256)
-k_synth_rows(int8_t* __restrict__ arena, int64_t ld, int64_t N, const unsigned long long* __restrict__ keys,
+k_synth_rows(int8_t* __restrict__ arena, int M, int64_t gene_bytes, int64_t N, const unsigned long long* __restrict__ keys,
              const uint32_t* __restrict__ t0, const uint32_t* __restrict__ t1, RowCounts* __restrict__ counts) {
   const int64_t row = blockIdx.y;
   const int64_t c16 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i0 = c16 * 16;
+  const int64_t npad = (N + 127) & ~(int64_t)127;
   int n1 = 0, n2 = 0;
-  if (i0 < ld) {
+  if (i0 < npad) {
     const unsigned long long key = keys[row];
     const uint32_t a = t0[row], b = t1[row];
     uint32_t w[4];
@@ -48,7 +53,9 @@ k_synth_rows(int8_t* __restrict__ arena, int64_t ld, int64_t N, const unsigned l
       }
       w[q] = word;
     }
-    *reinterpret_cast<uint4*>(arena + (size_t)row * ld + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+    const int64_t gene = row / M;
+    const int r = (int)(row - gene * M);
+    *reinterpret_cast<uint4*>(arena + (size_t)gene * gene_bytes + tiled_off(M, r, i0)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
   for (int o = 16; o > 0; o >>= 1) {
     n1 += __shfl_xor_sync(0xffffffffu, n1, o);
@@ -101,14 +108,15 @@ k_count_rows(const int8_t* __restrict__ base, int64_t ld, int64_t N, RowCounts* 
   }
 }
 
-// grid: (ceil(ld/4/256), M).  src: N x M column-major doubles; dst: int8 [M][ld] (zero padded).
+// grid: (ceil(npad/4/256), M).  src: N x M column-major doubles; dst: tiled int8 block (zero padded).
 __global__ void __launch_bounds__(256)
-k_pack_f64(const double* __restrict__ src, int64_t N, int8_t* __restrict__ dst, int64_t ld,
+k_pack_f64(const double* __restrict__ src, int64_t N, int8_t* __restrict__ dst, int M,
            RowCounts* __restrict__ counts) {
   const int64_t row = blockIdx.y;
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int64_t npad = (N + 127) & ~(int64_t)127;
   int n1 = 0, n2 = 0, bad = 0;
-  if (i0 < ld) {
+  if (i0 < npad) {
     uint32_t word = 0;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -125,7 +133,7 @@ k_pack_f64(const double* __restrict__ src, int64_t N, int8_t* __restrict__ dst, 
       n2 += (gq == 2);
       word |= gq << (8 * s);
     }
-    *reinterpret_cast<uint32_t*>(dst + (size_t)row * ld + i0) = word;
+    *reinterpret_cast<uint32_t*>(dst + tiled_off(M, (int)row, i0)) = word;
   }
   for (int o = 16; o > 0; o >>= 1) {
     n1 += __shfl_xor_sync(0xffffffffu, n1, o);
@@ -137,6 +145,51 @@ k_pack_f64(const double* __restrict__ src, int64_t N, int8_t* __restrict__ dst, 
     atomicAdd(&counts[row].n2, n2);
     atomicAdd(&counts[row].bad, bad);
   }
+}
+
+// grid: (ceil(npad/16/256), M).  src: int8 [M][ld_src] variant-major; dst: tiled block; counts rows.
+__global__ void __launch_bounds__(256)
+k_tile_rows(const int8_t* __restrict__ src, int64_t ld_src, int64_t N, int8_t* __restrict__ dst, int M,
+            RowCounts* __restrict__ counts) {
+  const int64_t row = blockIdx.y;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  const int64_t npad = (N + 127) & ~(int64_t)127;
+  int n1 = 0, n2 = 0, bad = 0;
+  if (i0 < npad) {
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int s = 0; s < 16; ++s) {
+      const int64_t i = i0 + s;
+      uint32_t gq = 0;
+      if (i < N) gq = (uint8_t)src[(size_t)row * ld_src + i];
+      n1 += (gq == 1);
+      n2 += (gq == 2);
+      bad += (gq > 2);
+      w[s >> 2] |= gq << (8 * (s & 3));
+    }
+    *reinterpret_cast<uint4*>(dst + tiled_off(M, (int)row, i0)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (n1 | n2 | bad)) {
+    atomicAdd(&counts[row].n1, n1);
+    atomicAdd(&counts[row].n2, n2);
+    atomicAdd(&counts[row].bad, bad);
+  }
+}
+
+// grid: (ceil(N/16/256), rows).  Tiled blocks of equal M back to back -> plain [rows][N] (tests).
+__global__ void __launch_bounds__(256)
+k_untile(const int8_t* __restrict__ arena, int M, int64_t gene_bytes, int64_t row_first, int64_t N, int8_t* __restrict__ out) {
+  const int64_t lr = blockIdx.y, row = row_first + lr;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i0 >= N) return;
+  const int64_t gene = row / M;
+  const int r = (int)(row - gene * M);
+  const int8_t* p = arena + (size_t)gene * gene_bytes + tiled_off(M, r, i0);
+  for (int s = 0; s < 16 && i0 + s < N; ++s) out[(size_t)lr * N + i0 + s] = p[s];
 }
 
 // one thread per row

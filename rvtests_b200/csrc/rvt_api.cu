@@ -68,9 +68,11 @@ struct rvt_ctx {
   long long* d_dbg = nullptr;   // optional finalize phase counters (rvt_set_option "debug_phases")
   size_t cap_dbg = 0;
   bool want_dbg = false;
-  // staging: one growable arena of int8 rows (row pitch stage_ld), TMA segment kSegStaged
+  // staging: one growable byte arena of tiled gene blocks, TMA segment kSegStaged
   int8_t* d_stage = nullptr;
-  int64_t stage_ld = 0, stage_cap_rows = 0, stage_used_rows = 0;
+  int64_t stage_cap = 0, stage_used = 0;
+  int8_t* d_stage8 = nullptr;   // row-major landing buffer of rvt_gene_push_i8
+  size_t cap_stage8 = 0;
   double* d_stage64 = nullptr;
   size_t cap_stage64 = 0;
   // loaded synthetic cohort
@@ -134,32 +136,26 @@ static int ensure_var(rvt_ctx* ctx, size_t need) {
   return RVT_OK;
 }
 
-// rows for one staged gene; grows the arena (device-to-device copy, pending descriptors re-based)
-static int stage_alloc_rows(rvt_ctx* ctx, int M, int64_t ld, int64_t* row0) {
-  if (ctx->stage_ld != ld) {
-    if (ctx->stage_used_rows) CTX_FAIL(RVT_E_STATE, "internal: staging arena pitch changed with genes pending");
-    if (ctx->d_stage) cudaFree(ctx->d_stage);
-    ctx->d_stage = nullptr;
-    ctx->stage_cap_rows = 0;
-    ctx->stage_ld = ld;
-  }
-  if (ctx->stage_used_rows + M > ctx->stage_cap_rows) {
-    int64_t ncap = std::max<int64_t>(ctx->stage_used_rows + M, ctx->stage_cap_rows * 2);
-    ncap = std::max<int64_t>(ncap, std::max<int64_t>(256, ((int64_t)64 << 20) / ld));
+// bytes for one staged (tiled) gene block; grows the arena (device-to-device copy, pending
+// descriptors re-based).  Offsets are multiples of 128 so that they are whole TMA rows.
+static int stage_alloc(rvt_ctx* ctx, int64_t bytes, int64_t* off) {
+  if (ctx->stage_used + bytes > ctx->stage_cap) {
+    int64_t ncap = std::max<int64_t>(ctx->stage_used + bytes, ctx->stage_cap * 2);
+    ncap = std::max<int64_t>(ncap, (int64_t)64 << 20);
     int8_t* np = nullptr;
-    RVT_CUDA_OK(cudaMalloc((void**)&np, (size_t)ncap * ld));
+    RVT_CUDA_OK(cudaMalloc((void**)&np, (size_t)ncap));
     if (ctx->d_stage) {
-      RVT_CUDA_OK(cudaMemcpyAsync(np, ctx->d_stage, (size_t)ctx->stage_used_rows * ld, cudaMemcpyDeviceToDevice, ctx->stream));
+      RVT_CUDA_OK(cudaMemcpyAsync(np, ctx->d_stage, (size_t)ctx->stage_used, cudaMemcpyDeviceToDevice, ctx->stream));
       RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
       RVT_CUDA_OK(cudaFree(ctx->d_stage));
     }
     for (auto& g : ctx->genes)
-      if (g.seg == kSegStaged) g.g = np + (size_t)g.row0 * ld;
+      if (g.seg == kSegStaged) g.g = np + (size_t)g.row0 * 128;
     ctx->d_stage = np;
-    ctx->stage_cap_rows = ncap;
+    ctx->stage_cap = ncap;
   }
-  *row0 = ctx->stage_used_rows;
-  ctx->stage_used_rows += M;
+  *off = ctx->stage_used;
+  ctx->stage_used += bytes;
   return RVT_OK;
 }
 
@@ -206,7 +202,7 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_stage8};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -359,7 +355,7 @@ int rvt_get_null_model(rvt_ctx* ctx, double* resid, double* sigma2, double* xtx_
 
 // common tail of every push: append the descriptor and the per-variant side data
 static int push_common(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const double* af, const uint8_t* flags,
-                       bool counted, int seg, int64_t row0) {
+                       bool counted, int seg, int64_t row0, bool tiled) {
   GeneDesc gd;
   memset(&gd, 0, sizeof(gd));
   gd.g = dG;
@@ -372,6 +368,8 @@ static int push_common(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const 
   gd.counted = counted ? 1 : 0;
   gd.row0_b = row0;
   gd.Mb = M;
+  gd.tiled = tiled ? 1 : 0;
+  gd.var0_b = ctx->n_var;
   ctx->genes.push_back(gd);
   ctx->count_slot.push_back(counted ? ctx->n_var : -1);
   for (int j = 0; j < M; ++j) {
@@ -400,7 +398,7 @@ int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
   if (!ctx || !G) return RVT_E_BADARG;
   int rc = push_check(ctx, M);
   if (rc) return rc;
-  const int64_t N = ctx->N, ld = (N + 127) & ~(int64_t)127;
+  const int64_t N = ctx->N, npad = (N + 127) & ~(int64_t)127;
   size_t need = (size_t)N * M;
   if (need > ctx->cap_stage64) {
     if (ctx->d_stage64) {
@@ -410,36 +408,47 @@ int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
     RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_stage64, need * sizeof(double)));
     ctx->cap_stage64 = need;
   }
-  int64_t row0 = 0;
-  if ((rc = stage_alloc_rows(ctx, M, ld, &row0))) return rc;
-  int8_t* blk = ctx->d_stage + (size_t)row0 * ld;
+  int64_t off = 0;
+  if ((rc = stage_alloc(ctx, tiled_bytes(N, M), &off))) return rc;
+  int8_t* blk = ctx->d_stage + off;
   if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_stage64, G, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
-  dim3 grid((unsigned)((ld / 4 + 255) / 256), (unsigned)M);
-  k_pack_f64<<<grid, 256, 0, ctx->stream>>>(ctx->d_stage64, N, blk, ld, ctx->d_counts + ctx->n_var);
+  dim3 grid((unsigned)((npad / 4 + 255) / 256), (unsigned)M);
+  k_pack_f64<<<grid, 256, 0, ctx->stream>>>(ctx->d_stage64, N, blk, M, ctx->d_counts + ctx->n_var);
   RVT_CUDA_OK(cudaGetLastError());
   // the staging buffer is reused by the next push: wait (pageable H2D is synchronous anyway)
   RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  return push_common(ctx, blk, M, ld, af, nullptr, true, kSegStaged, row0);
+  return push_common(ctx, blk, M, 0, af, nullptr, true, kSegStaged, off / 128, true);
 }
 
 int rvt_gene_push_i8(rvt_ctx* ctx, const int8_t* G, int M, int64_t ld_in, const double* af) {
   if (!ctx || !G) return RVT_E_BADARG;
   int rc = push_check(ctx, M);
   if (rc) return rc;
-  const int64_t N = ctx->N, ld = (N + 127) & ~(int64_t)127;
+  const int64_t N = ctx->N, npad = (N + 127) & ~(int64_t)127;
   if (ld_in < N) CTX_FAIL(RVT_E_BADARG, "ld (%lld) < N (%lld)", (long long)ld_in, (long long)N);
-  int64_t row0 = 0;
-  if ((rc = stage_alloc_rows(ctx, M, ld, &row0))) return rc;
-  int8_t* blk = ctx->d_stage + (size_t)row0 * ld;
+  const size_t need = (size_t)M * N;
+  if (need > ctx->cap_stage8) {
+    if (ctx->d_stage8) {
+      RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_stage8);
+    }
+    const size_t cap = std::max(need, (size_t)kMaxM * N);   // one allocation serves every gene of this cohort
+    RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_stage8, cap));
+    ctx->cap_stage8 = cap;
+  }
+  int64_t off = 0;
+  if ((rc = stage_alloc(ctx, tiled_bytes(N, M), &off))) return rc;
+  int8_t* blk = ctx->d_stage + off;
   if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
-  RVT_CUDA_OK(cudaMemsetAsync(blk, 0, (size_t)M * ld, ctx->stream));
-  RVT_CUDA_OK(cudaMemcpy2DAsync(blk, ld, G, ld_in, N, M, cudaMemcpyHostToDevice, ctx->stream));
+  // land the caller's variant-major rows, then re-tile (and count) them on the device
+  RVT_CUDA_OK(cudaMemcpy2DAsync(ctx->d_stage8, N, G, ld_in, N, M, cudaMemcpyHostToDevice, ctx->stream));
   RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
-  launch_count(ctx, blk, M, ld, ctx->d_counts + ctx->n_var);
+  dim3 grid((unsigned)((npad / 16 + 255) / 256), (unsigned)M);
+  k_tile_rows<<<grid, 256, 0, ctx->stream>>>(ctx->d_stage8, N, N, blk, M, ctx->d_counts + ctx->n_var);
   RVT_CUDA_OK(cudaGetLastError());
-  return push_common(ctx, blk, M, ld, af, nullptr, true, kSegStaged, row0);
+  return push_common(ctx, blk, M, 0, af, nullptr, true, kSegStaged, off / 128, true);
 }
 
 int rvt_gene_push_dev_i8(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const double* af, const uint8_t* flags) {
@@ -454,7 +463,7 @@ int rvt_gene_push_dev_i8(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, cons
     launch_count(ctx, dG, M, ld, ctx->d_counts + ctx->n_var);
     RVT_CUDA_OK(cudaGetLastError());
   }
-  return push_common(ctx, dG, M, ld, af, flags, flags == nullptr, -1, 0);
+  return push_common(ctx, dG, M, ld, af, flags, flags == nullptr, -1, 0, false);
 }
 
 int rvt_pending(const rvt_ctx* ctx) { return ctx ? (int)ctx->genes.size() : 0; }
@@ -518,8 +527,9 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
                                                                          ctx->d_userflags, ctx->d_flags);
   int launches = 1;
   int engine = ctx->engine;
-  if (ctx->stage_used_rows > 0) {
-    rc = tc_bind_segment(&ctx->tc, kSegStaged, ctx->d_stage, ctx->stage_used_rows, N, ctx->stage_ld, ctx->err, sizeof(ctx->err));
+  if (ctx->stage_used > 0) {
+    // bind the whole capacity: the maps stay valid while the arena does not move
+    rc = tc_bind_segment(&ctx->tc, kSegStaged, ctx->d_stage, ctx->stage_cap, ctx->err, sizeof(ctx->err));
     if (rc) return rc;
   }
   bool tc_ok = tc_usable(&ctx->tc, ctx->genes.data(), n);
@@ -576,7 +586,7 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   ctx->af.clear();
   ctx->count_slot.clear();
   ctx->n_var = 0;
-  ctx->stage_used_rows = 0;
+  ctx->stage_used = 0;
   return RVT_OK;
 }
 
@@ -616,22 +626,14 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   if (cap_variants < nv) CTX_FAIL(RVT_E_BADARG, "vout holds %lld records, %lld variants pending", (long long)cap_variants, (long long)nv);
   if (band && (!pos || !chrom)) CTX_FAIL(RVT_E_BADARG, "the covariance band needs pos and chrom");
   RVT_CUDA_OK(cudaSetDevice(ctx->device));
-  // the pushes must form one contiguous run of rows inside one TMA segment
+  // every pending push is one tile (<= 64 consecutive variants, its own tiled block) of one segment
   const int seg = ctx->genes[0].seg;
-  const int64_t row_base = ctx->genes[0].row0;
-  {
-    int64_t r = row_base;
-    for (const auto& g : ctx->genes) {
-      if (g.seg != seg || g.row0 != r) CTX_FAIL(RVT_E_UNSUPPORTED, "meta: pending variant blocks are not contiguous in one segment");
-      r += g.M;
-    }
-  }
+  for (const auto& g : ctx->genes)
+    if (g.seg != seg || !g.tiled) CTX_FAIL(RVT_E_UNSUPPORTED, "meta: pending variant blocks must live in one engine-owned (tiled) segment");
   int rc;
   if (seg == kSegStaged) {
-    if ((rc = tc_bind_segment(&ctx->tc, kSegStaged, ctx->d_stage, ctx->stage_used_rows, ctx->N, ctx->stage_ld, ctx->err, sizeof(ctx->err)))) return rc;
+    if ((rc = tc_bind_segment(&ctx->tc, kSegStaged, ctx->d_stage, ctx->stage_cap, ctx->err, sizeof(ctx->err)))) return rc;
   }
-  const int8_t* seg_base = (seg == kSegStaged) ? ctx->d_stage : ctx->d_loaded;
-  const int64_t seg_ld = (seg == kSegStaged) ? ctx->stage_ld : ctx->loaded_ld;
   std::vector<int> jmax;
   int wmax = 0;
   if (band) {
@@ -647,28 +649,20 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   if (S <= 0) S = (int)std::min<int64_t>(16, std::max<int64_t>(1, (N + 65535) / 65536));
   int64_t chunk = (((N + S - 1) / S) + 511) & ~(int64_t)511;
   S = (int)((N + chunk - 1) / chunk);
-  // tiles of 64 consecutive variants and the tile pairs inside the window
-  const int T = (int)((nv + kTileRows - 1) / kTileRows);
-  std::vector<GeneDesc> tiles(T), pairs;
-  for (int t = 0; t < T; ++t) {
-    GeneDesc g;
-    memset(&g, 0, sizeof(g));
-    g.row0 = g.row0_b = row_base + (int64_t)t * kTileRows;
-    g.M = g.Mb = (int)std::min<int64_t>(kTileRows, nv - (int64_t)t * kTileRows);
-    g.g = seg_base + (size_t)g.row0 * seg_ld;
-    g.ld = seg_ld;
-    g.seg = seg;
-    g.var0 = (int64_t)t * kTileRows;
-    tiles[t] = g;
-  }
+  const int T = ngen;
+  std::vector<GeneDesc> tiles(ctx->genes), pairs;
+  std::vector<int> tile_of(nv);
+  for (int t = 0; t < T; ++t)
+    for (int i = 0; i < tiles[t].M; ++i) tile_of[tiles[t].var0 + i] = t;
   if (band) {
     for (int t = 0; t < T; ++t) {
       int jm = 0;
-      for (int i = 0; i < tiles[t].M; ++i) jm = std::max(jm, jmax[(size_t)t * kTileRows + i]);
-      for (int u = t + 1; u <= jm / kTileRows; ++u) {
+      for (int i = 0; i < tiles[t].M; ++i) jm = std::max(jm, jmax[tiles[t].var0 + i]);
+      for (int u = t + 1; u <= tile_of[jm]; ++u) {
         GeneDesc g = tiles[t];
         g.row0_b = tiles[u].row0;
         g.Mb = tiles[u].M;
+        g.var0_b = tiles[u].var0;
         pairs.push_back(g);
       }
     }
@@ -692,7 +686,7 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   if (e == cudaSuccess) e = cudaMalloc((void**)&d_poly, nv);
   if (e == cudaSuccess) e = cudaMalloc((void**)&d_v, sizeof(rvt_variant_result) * nv);
   if (e == cudaSuccess) e = cudaMalloc((void**)&d_desc, sizeof(GeneDesc) * ndesc);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_flags0, (size_t)T * kTileRows);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_flags0, (size_t)nv + kTileRows);
   if (e == cudaSuccess && band) e = cudaMalloc((void**)&d_band, sizeof(double) * nv * (size_t)(wmax + 1));
   if (e != cudaSuccess) {
     cleanup();
@@ -700,7 +694,7 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   }
   if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)batch * S, sizeof(SweepPartial)))) { cleanup(); return rc; }
   RVT_CUDA_OK(cudaMemcpyAsync(d_jmax, jmax.data(), sizeof(int) * nv, cudaMemcpyHostToDevice, st));
-  RVT_CUDA_OK(cudaMemsetAsync(d_flags0, 0, (size_t)T * kTileRows, st));   // every row "normal": no flip in meta mode
+  RVT_CUDA_OK(cudaMemsetAsync(d_flags0, 0, (size_t)nv + kTileRows, st));   // every row "normal": no flip in meta mode
   if (band) {
     // NaN-fill: entries outside a variant's window stay NaN
     RVT_CUDA_OK(cudaMemsetAsync(d_band, 0xFF, sizeof(double) * nv * (size_t)(wmax + 1), st));
@@ -720,8 +714,7 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
       k_sweep_simt<<<std::min(nb * S, ctx->sm_count * 3), kSimtThreads, kSimtSmem, st>>>(d_desc + b0, nb, d_flags0, ctx->d_nm, S, chunk,
                                                                                        ctx->d_parts, ctx->d_counter);
     }
-    k_meta_block<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, (int64_t)b0 * kTileRows, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, d_v,
-                                              d_B, d_poly, d_band);
+    k_meta_block<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, d_v, d_B, d_poly, d_band);
     RVT_CUDA_OK(cudaGetLastError());
   }
   // phase 2: tile pairs inside the window
@@ -733,7 +726,7 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
       rc = tc_launch(&ctx->tc, d_desc + b0, pairs.data() + b0, nb, d_flags0, ctx->d_nm, N, ctx->ER, S, chunk, ctx->d_parts,
                      ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), true);
       if (rc) { cleanup(); return rc; }
-      k_meta_pair<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, row_base, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, d_B, d_poly, d_band);
+      k_meta_pair<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, d_B, d_poly, d_band);
       RVT_CUDA_OK(cudaGetLastError());
     }
   }
@@ -746,7 +739,7 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   ctx->af.clear();
   ctx->count_slot.clear();
   ctx->n_var = 0;
-  ctx->stage_used_rows = 0;
+  ctx->stage_used = 0;
   return RVT_OK;
 }
 
@@ -754,13 +747,14 @@ int rvt_synth_load(rvt_ctx* ctx, int n_genes, int M, const uint64_t* keys, const
   if (!ctx || !keys || !t0 || !t1 || n_genes < 1) return RVT_E_BADARG;
   int rc = push_check(ctx, M);
   if (rc) return rc;
-  const int64_t N = ctx->N, ld = (N + 127) & ~(int64_t)127;
+  const int64_t N = ctx->N, npad = (N + 127) & ~(int64_t)127;
   const int64_t rows = (int64_t)n_genes * M;
+  const int64_t gene_bytes = tiled_bytes(N, M);
   if (ctx->d_loaded) {
     cudaFree(ctx->d_loaded);
     ctx->d_loaded = nullptr;
   }
-  RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_loaded, (size_t)rows * ld));
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_loaded, (size_t)n_genes * gene_bytes));
   unsigned long long* dk = nullptr;
   uint32_t *d0 = nullptr, *d1 = nullptr;
   RowCounts* dc = nullptr;
@@ -777,11 +771,13 @@ int rvt_synth_load(rvt_ctx* ctx, int n_genes, int M, const uint64_t* keys, const
   RVT_CUDA_OK(cudaMemcpyAsync(d0, t0, rows * 4, cudaMemcpyHostToDevice, st));
   RVT_CUDA_OK(cudaMemcpyAsync(d1, t1, rows * 4, cudaMemcpyHostToDevice, st));
   RVT_CUDA_OK(cudaMemsetAsync(dc, 0, rows * sizeof(RowCounts), st));
-  const unsigned per_row = (unsigned)((ld / 16 + 255) / 256);
-  for (int64_t r0 = 0; r0 < rows; r0 += 32768) {
-    const unsigned nr = (unsigned)std::min<int64_t>(32768, rows - r0);
-    k_synth_rows<<<dim3(per_row, nr), 256, 0, st>>>(ctx->d_loaded + (size_t)r0 * ld, ld, N, dk + r0, d0 + r0, d1 + r0,
-                                                    dc + r0);
+  const unsigned per_row = (unsigned)((npad / 16 + 255) / 256);
+  const int64_t genes_per_launch = std::max<int64_t>(1, 32768 / M);
+  for (int64_t g0 = 0; g0 < n_genes; g0 += genes_per_launch) {
+    const int64_t ng = std::min<int64_t>(genes_per_launch, n_genes - g0);
+    const int64_t r0 = g0 * M;
+    k_synth_rows<<<dim3(per_row, (unsigned)(ng * M)), 256, 0, st>>>(ctx->d_loaded + (size_t)g0 * gene_bytes, M, gene_bytes, N, dk + r0,
+                                                                    d0 + r0, d1 + r0, dc + r0);
   }
   k_flags_from_counts<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(rows, N, dc, dfl, daf);
   RVT_CUDA_OK(cudaGetLastError());
@@ -792,10 +788,10 @@ int rvt_synth_load(rvt_ctx* ctx, int n_genes, int M, const uint64_t* keys, const
   RVT_CUDA_OK(cudaStreamSynchronize(st));
   cudaFree(dk); cudaFree(d0); cudaFree(d1); cudaFree(dc); cudaFree(dfl); cudaFree(daf);
   ctx->loaded_rows = rows;
-  ctx->loaded_ld = ld;
+  ctx->loaded_ld = gene_bytes;   // bytes per gene block
   ctx->loaded_genes = n_genes;
   ctx->loaded_M = M;
-  rc = tc_bind_segment(&ctx->tc, kSegLoaded, ctx->d_loaded, rows, N, ld, ctx->err, sizeof(ctx->err));
+  rc = tc_bind_segment(&ctx->tc, kSegLoaded, ctx->d_loaded, (int64_t)n_genes * gene_bytes, ctx->err, sizeof(ctx->err));
   if (rc) return rc;
   return RVT_OK;
 }
@@ -814,8 +810,8 @@ int rvt_run_loaded(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, int 
   for (int g = 0; g < ctx->loaded_genes; ++g) {
     const int64_t row0 = (int64_t)g * M;
     // AF: the loader's counts, i.e. what GenotypeCounter::getAF hands to the fitters
-    push_common(ctx, ctx->d_loaded + (size_t)row0 * ctx->loaded_ld, M, ctx->loaded_ld, ctx->loaded_af.data() + row0,
-                ctx->loaded_flags.data() + row0, false, kSegLoaded, row0);
+    push_common(ctx, ctx->d_loaded + (size_t)g * ctx->loaded_ld, M, 0, ctx->loaded_af.data() + row0,
+                ctx->loaded_flags.data() + row0, false, kSegLoaded, ((int64_t)g * ctx->loaded_ld) / 128, true);
   }
   return flush_impl(ctx, out, cap, n_out, results_on_device != 0);
 }
@@ -823,9 +819,14 @@ int rvt_run_loaded(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, int 
 int rvt_loaded_read(rvt_ctx* ctx, int64_t row0, int rows, int8_t* out) {
   if (!ctx || !out) return RVT_E_BADARG;
   if (!ctx->d_loaded || row0 < 0 || row0 + rows > ctx->loaded_rows) CTX_FAIL(RVT_E_BADARG, "rows out of range");
-  RVT_CUDA_OK(cudaMemcpy2DAsync(out, ctx->N, ctx->d_loaded + (size_t)row0 * ctx->loaded_ld, ctx->loaded_ld, ctx->N,
-                                rows, cudaMemcpyDeviceToHost, ctx->stream));
+  int8_t* tmp = nullptr;
+  RVT_CUDA_OK(cudaMalloc((void**)&tmp, (size_t)rows * ctx->N));
+  dim3 grid((unsigned)((ctx->N / 16 + 256) / 256), (unsigned)rows);
+  k_untile<<<grid, 256, 0, ctx->stream>>>(ctx->d_loaded, ctx->loaded_M, ctx->loaded_ld, row0, ctx->N, tmp);
+  RVT_CUDA_OK(cudaGetLastError());
+  RVT_CUDA_OK(cudaMemcpyAsync(out, tmp, (size_t)rows * ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
   RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(tmp);
   return RVT_OK;
 }
 

@@ -98,7 +98,7 @@ k_sweep_simt(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __r
         const int8_t* src;
         if (row < kTileRows) {
           if (row >= M) nb = 0;
-          src = gd.g + (size_t)(row < M ? row : 0) * gd.ld + (nb ? k : 0);
+          src = geno_ptr(gd, row < M ? row : 0, nb ? k : 0);
         } else {
           src = E + (size_t)(row - kTileRows) * ldE + (nb ? k : 0);
         }

@@ -10,9 +10,10 @@
 // and the s32 accumulation is exact -- results do not depend on tiling or split order.
 //
 // CTA = 6 warps, persistent over units u = blockIdx.x + i*gridDim.x (static: units cost the same):
-//   warp 0      TMA producer: per stage 4 boxes of 128 samples, each box = gene tile 64 x 128 B
-//               (SWIZZLE_128B) immediately followed by the E tile ER x 128 B, so that the B operand
-//               of one UMMA is the contiguous (64+ER)-row tile.  OOB rows/samples are zero-filled.
+//   warp 0      TMA producer: per stage 4 boxes of 128 samples, each box = gene tile M x 128 B
+//               (SWIZZLE_128B; ONE contiguous M*128-byte run of HBM thanks to the tiled layout)
+//               followed at a fixed offset by the E tile ER x 128 B, so that the B operand of one
+//               UMMA is the contiguous (64+ER)-row tile.  OOB rows/samples are zero-filled.
 //   warp 1      MMA issuer: 4 UMMAs (K = 32 bytes) per box; tcgen05.commit frees the stage and,
 //               after the unit's last stage, publishes the TMEM accumulator (double-buffered).
 //   warps 2..5  consumers: (a) burden collapse of box (warp-2) of every stage straight from the
@@ -193,8 +194,11 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
           const int kb = (int)(k0 + (int64_t)ks * kTcStageK);
 #pragma unroll
           for (int b = 0; b < kTcBoxes; ++b) {
-            tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kAOff, mg, kb + b * kTcBoxK, row0, &full[s], kEvictFirst);
-            if (PAIR) tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kBOff, mgb, kb + b * kTcBoxK, row0b, &full[s], kEvictFirst);
+            // tiled genotype layout: chunk c of a gene is the contiguous run of M 128-byte rows
+            // starting at arena row  row0 + c*M  (arena viewed as [bytes/128][128])
+            const int ch = (kb >> 7) + b;
+            tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kAOff, mg, 0, row0 + ch * Mg, &full[s], kEvictFirst);
+            if (PAIR) tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kBOff, mgb, 0, row0b + ch * Mgb, &full[s], kEvictFirst);
             tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kEOff, &map_e, kb + b * kTcBoxK, 0, &full[s], kEvictLast);
           }
         }
@@ -402,7 +406,7 @@ struct TcSegments {
   // one tensor map per box height M = 1..64 over the same arena (encoded lazily, kept in HBM)
   struct Seg {
     const int8_t* base = nullptr;
-    int64_t rows = 0, N = 0, ld = 0;
+    int64_t rows = 0;   // arena bytes / 128
     bool have_m[kTileRows] = {};
     CUtensorMap* d_maps = nullptr;   // [64] in device memory
   } seg[kMaxSeg];
@@ -439,6 +443,8 @@ inline void tc_destroy(TcSegments* tc) {
     }
 }
 
+// 2-D map over [rows][row_bytes] with pitch ld: the genotype arena is [bytes/128][128] (ld = 128),
+// the null-model digits E are [ER][N] (ld = ldE).
 inline int tc_make_map(TcSegments* tc, CUtensorMap* map, const void* base, int64_t rows, int64_t N, int64_t ld, int box_rows,
                        char* err, size_t errlen) {
   cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows};
@@ -471,16 +477,21 @@ inline int tc_bind_null(TcSegments* tc, const int8_t* E, int ER, int64_t N, int6
   return 0;
 }
 
-inline int tc_bind_segment(TcSegments* tc, int seg, const int8_t* base, int64_t rows, int64_t N, int64_t ld, char* err,
-                           size_t errlen) {
+inline int tc_bind_segment(TcSegments* tc, int seg, const int8_t* base, int64_t bytes, char* err, size_t errlen) {
   if (!tc->encode || seg < 0 || seg >= TcSegments::kMaxSeg) return 0;
   tc->have_seg[seg] = false;
-  if (rows <= 0) return 0;
+  if (bytes <= 0) return 0;
+  if (bytes / 128 >= ((int64_t)1 << 31)) {
+    snprintf(tc->why, sizeof(tc->why), "segment larger than 2^31 TMA rows");
+    return 0;
+  }
   TcSegments::Seg& sg = tc->seg[seg];
+  if (sg.base == base && sg.rows == bytes / 128 && sg.d_maps) {   // unchanged: keep the encoded maps
+    tc->have_seg[seg] = true;
+    return 0;
+  }
   sg.base = base;
-  sg.rows = rows;
-  sg.N = N;
-  sg.ld = ld;
+  sg.rows = bytes / 128;
   for (bool& b : sg.have_m) b = false;
   if (!sg.d_maps) {
     cudaError_t e = cudaMalloc((void**)&sg.d_maps, sizeof(CUtensorMap) * kTileRows);
@@ -500,7 +511,7 @@ inline int tc_prepare_maps(TcSegments* tc, int seg, const GeneDesc* h_genes, int
     const int M = (i < n) ? h_genes[i].M : h_genes[i - n].Mb;
     if (M < 1 || M > kTileRows || sg.have_m[M - 1]) continue;
     CUtensorMap m;
-    int rc = tc_make_map(tc, &m, sg.base, sg.rows, sg.N, sg.ld, M, err, errlen);
+    int rc = tc_make_map(tc, &m, sg.base, sg.rows, 128, 128, M, err, errlen);
     if (rc) return rc;
     cudaError_t e = cudaMemcpyAsync(sg.d_maps + (M - 1), &m, sizeof(m), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `m` is a stack temporary
@@ -524,9 +535,9 @@ inline bool tc_usable(TcSegments* tc, const GeneDesc* h_genes, int n) {
     snprintf(tc->why, sizeof(tc->why), "genes are not in a TMA-mapped segment");
     return false;
   }
-  for (int i = 1; i < n; ++i)
-    if (h_genes[i].seg != seg) {
-      snprintf(tc->why, sizeof(tc->why), "genes span several segments");
+  for (int i = 0; i < n; ++i)
+    if (h_genes[i].seg != seg || !h_genes[i].tiled) {
+      snprintf(tc->why, sizeof(tc->why), "genes span several segments or are not in the tiled layout");
       return false;
     }
   return true;
