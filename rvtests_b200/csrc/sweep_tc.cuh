@@ -170,6 +170,8 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
+      const int nchunks = (int)((N + 127) >> 7);
+      constexpr int kOobRow = 0x7FFF0000;   // beyond any arena (< 2^31 rows of 128 B): TMA zero-fills
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int gi = u / S, sp = u - gi * S;
         const int row0 = (int)genes[gi].row0;
@@ -196,9 +198,13 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
           for (int b = 0; b < kTcBoxes; ++b) {
             // tiled genotype layout: chunk c of a gene is the contiguous run of M 128-byte rows
             // starting at arena row  row0 + c*M  (arena viewed as [bytes/128][128])
+            // a stage may run past the gene's last chunk: such a box is fetched from beyond the
+            // arena (row kOobRow), i.e. zero-filled by TMA, instead of from the next gene's block
             const int ch = (kb >> 7) + b;
-            tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kAOff, mg, 0, row0 + ch * Mg, &full[s], kEvictFirst);
-            if (PAIR) tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kBOff, mgb, 0, row0b + ch * Mgb, &full[s], kEvictFirst);
+            const bool in = ch < nchunks;
+            tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kAOff, mg, 0, in ? row0 + ch * Mg : kOobRow, &full[s], kEvictFirst);
+            if (PAIR)
+              tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kBOff, mgb, 0, in ? row0b + ch * Mgb : kOobRow, &full[s], kEvictFirst);
             tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kEOff, &map_e, kb + b * kTcBoxK, 0, &full[s], kEvictLast);
           }
         }
