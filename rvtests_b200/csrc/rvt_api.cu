@@ -231,6 +231,11 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "tc_stages") {
     if (value != 4 && value != 5) CTX_FAIL(RVT_E_BADARG, "tc_stages must be 4 or 5");
     ctx->tc.stages = (int)value;
+  } else if (k == "tc_boxes") {
+    if (value != 2 && value != 4) CTX_FAIL(RVT_E_BADARG, "tc_boxes must be 2 or 4");
+    ctx->tc.boxes = (int)value;
+  } else if (k == "tc_debug_skip") {
+    ctx->tc.dbg_skip = (int)value;
   } else if (k == "tc_l2promo") {
     if (value < 0 || value > 3) CTX_FAIL(RVT_E_BADARG, "tc_l2promo must be 0..3");
     ctx->tc.l2promo = (int)value;

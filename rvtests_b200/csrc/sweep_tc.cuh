@@ -16,9 +16,12 @@
 //               UMMA is the contiguous (64+ER)-row tile.  OOB rows/samples are zero-filled.
 //   warp 1      MMA issuer: 4 UMMAs (K = 32 bytes) per box; tcgen05.commit frees the stage and,
 //               after the unit's last stage, publishes the TMEM accumulator (double-buffered).
-//   warps 2..5  consumers: (a) burden collapse of box (warp-2) of every stage straight from the
-//               swizzled SMEM tile, (b) epilogue: tcgen05.ld the accumulator of the finished unit
-//               (UMMA M=64 layout: row m at lane (m%16)+32*(m/16)) and store the SweepPartial.
+//   warps 2..9  consumers, two groups of four: (a) burden collapse -- group g takes the stages with
+//               (it & 1) == g, warp (w & 3) the box of that number, straight from the swizzled SMEM
+//               tile (the collapse, not HBM, was the limiter with four warps: see profiles/);
+//               (b) epilogue: tcgen05.ld the accumulator of the finished unit (UMMA M=64 layout:
+//               row m at lane (m%16)+32*(m/16); the two warps of a TMEM lane quadrant split the
+//               column groups) and store the SweepPartial.
 // Roofline class: HBM sweep, 1 byte per genotype: the tensor pipe needs
 // 128*(64+ER)/256 = 40 cycles per 32-sample slice, i.e. ~64 B/clk/SM, ~3x what HBM can deliver.
 #pragma once
@@ -29,23 +32,25 @@
 
 namespace rvt {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcConsumerWarps = 8;             // two groups of 4: group g collapses the stages with (it & 1) == g
+constexpr int kTcThreads = 64 + 32 * kTcConsumerWarps;
 constexpr int kTcMaxStages = 5;
-constexpr int kTcBoxes = 4;                 // boxes per stage == consumer warps
 constexpr int kTcBoxK = 128;                // samples per box (one 128-byte swizzle row)
-constexpr int kTcStageK = kTcBoxes * kTcBoxK;
+constexpr int kTcChunkAlign = 512;          // split boundaries are multiples of this (>= any stage width)
 constexpr int kTcTmemCols = 256;            // 2 accumulators x 128 columns
 
 // PAIR = the A operand (rows of block I) and the B operand (rows of block J) are different tiles:
 // the cross-block Gram of the meta-analysis covariance (src/Model.cpp:534-554 calculateXX for
 // every pair of variants in the sliding window).  Box = [A tile][B tile][E tile].
-template <int ER, int STAGES, bool PAIR = false>
+template <int ER, int STAGES, bool PAIR = false, int BOXES = 4>
 struct TcCfg {
+  static constexpr int kBoxes = BOXES;          // boxes (of 128 samples) per pipeline stage
+  static constexpr int kStageK = BOXES * kTcBoxK;
   static constexpr int kAOff = 0;
   static constexpr int kBOff = PAIR ? kTileRows * 128 : 0;
   static constexpr int kEOff = kBOff + kTileRows * 128;
   static constexpr int kBoxBytes = kEOff + ER * 128;
-  static constexpr int kStageBytes = kTcBoxes * kBoxBytes;
+  static constexpr int kStageBytes = BOXES * kBoxBytes;
   static constexpr int kSmem = STAGES * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kNC = kTileRows + ER;
 };
@@ -123,12 +128,15 @@ __device__ __forceinline__ uint32_t sw128_word_off(int r, int w) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((w >> 2) ^ (r & 7)) << 4) | ((w & 3) << 2)));
 }
 
-template <int ER, int kTcStages, bool PAIR>
+template <int ER, int kTcStages, bool PAIR, int kTcBoxes>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */, const __grid_constant__ CUtensorMap map_e,
            const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __restrict__ rowflags, int64_t N, int S,
-           int64_t chunk, SweepPartial* __restrict__ out) {
-  using Cfg = TcCfg<ER, kTcStages, PAIR>;
+           int64_t chunk, SweepPartial* __restrict__ out, int dbg_skip /* timing experiments only: 1 no collapse,
+           2 no MMA, 4 no E loads; results are then meaningless */) {
+  using Cfg = TcCfg<ER, kTcStages, PAIR, kTcBoxes>;
+  constexpr int kTcStageK = Cfg::kStageK;
+  constexpr int kGroups = kTcConsumerWarps / kTcBoxes;   // consumer groups, one stage each in turn
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B (TMA destination and UMMA descriptors)
   uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -151,7 +159,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);
-        mbar_init(&tempty[a], 4);
+        mbar_init(&tempty[a], kTcConsumerWarps);
       }
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -182,7 +190,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
         const int row0b = (int)genes[gi].row0_b;
         const int Mgb = genes[gi].Mb;
         const CUtensorMap* mgb = maps_g + (Mgb - 1);
-        const uint32_t stage_tx = (uint32_t)(kTcBoxes * (Mg + (PAIR ? Mgb : 0) + ER) * 128);
+        const uint32_t stage_tx = (uint32_t)(kTcBoxes * (Mg + (PAIR ? Mgb : 0) + ((dbg_skip & 4) ? 0 : ER)) * 128);
         const int64_t k0 = (int64_t)sp * chunk;
         int64_t k1 = k0 + chunk;
         if (k1 > N) k1 = N;
@@ -205,7 +213,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
             tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kAOff, mg, 0, in ? row0 + ch * Mg : kOobRow, &full[s], kEvictFirst);
             if (PAIR)
               tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kBOff, mgb, 0, in ? row0b + ch * Mgb : kOobRow, &full[s], kEvictFirst);
-            tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kEOff, &map_e, kb + b * kTcBoxK, 0, &full[s], kEvictLast);
+            if (!(dbg_skip & 4)) tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kEOff, &map_e, kb + b * kTcBoxK, 0, &full[s], kEvictLast);
           }
         }
       }
@@ -233,7 +241,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
         if (lane == 0) {
           const uint32_t st = smem_u32(tiles + (size_t)s * Cfg::kStageBytes);
 #pragma unroll
-          for (int b = 0; b < kTcBoxes; ++b) {
+          for (int b = 0; b < ((dbg_skip & 2) ? 0 : kTcBoxes); ++b) {
             const uint64_t da0 = umma_desc_sw128(st + b * Cfg::kBoxBytes + Cfg::kAOff);
             const uint64_t db0 = umma_desc_sw128(st + b * Cfg::kBoxBytes + Cfg::kBOff);
 #pragma unroll
@@ -252,8 +260,10 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
     }
   } else {
     // ===================== consumers: collapse + epilogue =====================
-    const int cw = warp - 2;       // box handled in every stage
-    const int q = warp & 3;        // TMEM lane quadrant this warp may read
+    const int cw = (warp - 2) % kTcBoxes;   // box handled in this warp's stages
+    const int grp = (warp - 2) / kTcBoxes;  // which stages: it % kGroups == grp
+    const int egrp = (warp - 2) >> 2;       // epilogue: which of the quadrant's two warps
+    const int q = warp & 3;          // TMEM lane quadrant this warp may read
     uint32_t it = 0, ui = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
       const int gi = u / S, sp = u - gi * S;
@@ -281,13 +291,14 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
 #pragma unroll
       for (int e = 0; e <= ER; ++e) cz[e] = cc[e] = 0;
       for (int ks = 0; ks < nsteps; ++ks, ++it) {
+        if ((int)(it % (uint32_t)kGroups) != grp) continue;   // another consumer group owns this stage
         const int s = it % kTcStages;
         const uint32_t ph = (it / kTcStages) & 1;
         mbar_wait(&full[s], ph);
         const uint8_t* box = tiles + (size_t)s * Cfg::kStageBytes + cw * Cfg::kBoxBytes;
         const int64_t ksamp = k0 + (int64_t)ks * kTcStageK + cw * kTcBoxK + 4 * lane;
         uint32_t z = 0;
-        if (PAIR) {
+        if (PAIR || (dbg_skip & 1)) {
           // block pairs need the Gram only (no burden collapse)
         } else if (plain) {
           // common case (no flipped / monomorphic row): indicator = (g | g>>1) & 1 per byte,
@@ -318,7 +329,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
             }
           }
         }
-        if (!PAIR) {
+        if (!PAIR && !(dbg_skip & 1)) {
           int64_t rem = k1 - ksamp;
           uint32_t vm = rem >= 4 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - (int)rem))));
           z &= vm;
@@ -326,7 +337,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
           const uint8_t* ebox = box + Cfg::kEOff;
 #pragma unroll
           for (int e = 0; e < ER; ++e) {
-            int ew = *reinterpret_cast<const int*>(ebox + sw128_word_off(e, lane));
+            int ew = *reinterpret_cast<const int*>(ebox + (e >> 3) * 1024 + woff[e & 7]);
             cz[e] = __dp4a((int)z, ew, cz[e]);
             cc[e] = __dp4a((int)c, ew, cc[e]);
           }
@@ -357,7 +368,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
       SweepPartial* o = out + u;
       const uint32_t taddr = tmem_base + (uint32_t)a * 128u + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-      for (int c0 = 0; c0 < Cfg::kNC; c0 += 16) {
+      for (int c0 = 16 * egrp; c0 < Cfg::kNC; c0 += 32) {   // the quadrant's two warps alternate column groups
         uint32_t v[16];
         tmem_ld16(taddr + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -375,9 +386,9 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[a]);
-      // all 4 consumer warps have added their collapse sums -> one warp writes them out
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      if (cw == 0) {
+      // all consumer warps have added their collapse sums -> one warp writes them out
+      asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kTcConsumerWarps) : "memory");
+      if (warp == 2) {
         for (int i = lane; i < 2 * (ER + 1); i += 32) {
           o->coll[i] = (long long)s_coll[cb][i];
           s_coll[cb][i] = 0ull;
@@ -401,8 +412,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct TcSegments {
   void* encode = nullptr;   // cuTensorMapEncodeTiled through the runtime's driver entry point
-  int stages = 5;           // smem ring depth for ER=16 (4 or 5)
+  int stages = 5;           // (kept for the option parser; the ring depth is tied to `boxes`)
+  int boxes = 4;            // 128-sample boxes per pipeline stage for ER=16: 4 (5 stages) or 2 (10 stages)
   int l2promo = 2;          // CUtensorMapL2promotion: 0 none, 1 64B, 2 128B, 3 256B
+  int dbg_skip = 0;         // timing experiments (see k_sweep_tc)
   char why[128] = "";
   bool have_e = false;
   int ER = 0;
@@ -429,11 +442,11 @@ inline int tc_init(TcSegments* tc, char* err, size_t errlen) {
     return 0;  // the dp4a engine still works; an explicit engine=tc request fails loudly
   }
   tc->encode = fn;
-  e = cudaFuncSetAttribute(k_sweep_tc<16, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 4>::kSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5>::kSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4>::kSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 3, true>::kSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 2, true>::kSmem);
+  e = cudaFuncSetAttribute(k_sweep_tc<16, 5, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5, false, 4>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 10, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 10, false, 2>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4, false, 4>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 3, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 3, true, 4>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 2, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 2, true, 4>::kSmem);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "cudaFuncSetAttribute(k_sweep_tc): %s", cudaGetErrorString(e));
     return -2;
@@ -555,22 +568,26 @@ inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_
                      bool pair = false) {
   const int seg = h_genes[0].seg;
   const int grid = std::min(n * S, sm_count);
-  if (chunk % kTcStageK != 0) {
-    snprintf(err, errlen, "internal: chunk %lld is not a multiple of the TMA stage (%d)", (long long)chunk, kTcStageK);
+  if (chunk % kTcChunkAlign != 0) {
+    snprintf(err, errlen, "internal: chunk %lld is not a multiple of the TMA stage (%d)", (long long)chunk, kTcChunkAlign);
     return -3;
   }
   int rc = tc_prepare_maps(tc, seg, h_genes, n, st, err, errlen);
   if (rc) return rc;
+#define RVT_TC_LAUNCH(ER_, ST_, PAIR_, BX_)                                                                                  \
+  k_sweep_tc<ER_, ST_, PAIR_, BX_><<<grid, kTcThreads, TcCfg<ER_, ST_, PAIR_, BX_>::kSmem, st>>>(                           \
+      tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts, tc->dbg_skip)
   if (pair && ER == 16)
-    k_sweep_tc<16, 3, true><<<grid, kTcThreads, TcCfg<16, 3, true>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+    RVT_TC_LAUNCH(16, 3, true, 4);
   else if (pair)
-    k_sweep_tc<32, 2, true><<<grid, kTcThreads, TcCfg<32, 2, true>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
-  else if (ER == 16 && tc->stages == 5)
-    k_sweep_tc<16, 5, false><<<grid, kTcThreads, TcCfg<16, 5>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+    RVT_TC_LAUNCH(32, 2, true, 4);
+  else if (ER == 16 && tc->boxes == 2)
+    RVT_TC_LAUNCH(16, 10, false, 2);
   else if (ER == 16)
-    k_sweep_tc<16, 4, false><<<grid, kTcThreads, TcCfg<16, 4>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+    RVT_TC_LAUNCH(16, 5, false, 4);
   else
-    k_sweep_tc<32, 4, false><<<grid, kTcThreads, TcCfg<32, 4>::kSmem, st>>>(tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts);
+    RVT_TC_LAUNCH(32, 4, false, 4);
+#undef RVT_TC_LAUNCH
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, errlen, "k_sweep_tc launch: %s", cudaGetErrorString(e));

@@ -1,4 +1,5 @@
-"""GPU experiment: sweep-kernel time vs pipeline knobs (stages, L2 promotion, splits)."""
+"""GPU experiment: where does the tensor-core sweep spend its time?  Disables parts of the kernel
+(results are garbage in those runs; only the sweep time is read)."""
 import os
 import sys
 
@@ -15,19 +16,14 @@ X, y = synth.covariates(20260925, N, 3)
 eng = rvtests_b200.GeneEngine(0)
 eng.set_null_model(X, y)
 eng.synth_load(keys, t0, t1, ng, M)
-base = None
-for stages in (4, 5):
-    for promo in (3, 2, 0):
-        for splits in (8, 4, 16):
-            eng.set_option("tc_stages", stages)
-            eng.set_option("tc_l2promo", promo)
-            eng.set_option("splits", splits)
-            ts = []
-            for rep in range(4):
-                res = eng.run_loaded()
-                ts.append(eng.last_timing()["sweep_ms"])
-            if base is None:
-                base = res.tobytes()
-            ok = res.tobytes() == base
-            t = min(ts[1:])
-            print(f"stages {stages} l2promo {promo} splits {splits:2d}: sweep {t:7.3f} ms  {ng * N * M / t / 1e6:7.1f} GB/s  same={ok}", flush=True)
+names = {0: "full kernel", 1: "no collapse", 2: "no MMA", 4: "no E loads", 3: "no collapse, no MMA", 5: "no collapse, no E",
+         6: "no MMA, no E", 7: "TMA gene stream only"}
+for boxes, skip in ((4, 0), (2, 0), (4, 1), (2, 1), (4, 2), (2, 2)):
+    eng.set_option("tc_boxes", boxes)
+    eng.set_option("tc_debug_skip", skip)
+    ts = []
+    for rep in range(4):
+        eng.run_loaded()
+        ts.append(eng.last_timing()["sweep_ms"])
+    t = min(ts[1:])
+    print(f"boxes/stage {boxes} skip {skip} ({names[skip]:24s}): sweep {t:7.3f} ms  {ng * N * M / t / 1e6:7.1f} GB/s", flush=True)
