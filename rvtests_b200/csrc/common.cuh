@@ -76,6 +76,19 @@ struct NullModel {
   double xtx_inv[kMaxC * kMaxC];  // (X'X)^-1 row-major
   double scale[kMaxC + 1];        // 2^-e_v per vector v
   long long vsum[kMaxC + 1];      // sum_i fixed-point value of vector v (for flipped columns)
+  double rsum;                    // sum_i r_i  and  sum_i x_il  in fp64 (dosage path)
+  double xsum[kMaxC];
+};
+
+// Pre-digested per-gene statistics handed to the tail of k_finalize by the dosage path
+// (dosage.cuh): everything steps 1-4 of k_finalize would have produced.
+struct TailInput {
+  int Mp, status, nonref, pad;
+  double Q;
+  double K[kTileRows * kTileRows];   // Mp x Mp, row-major with leading dimension Mp
+  double vw[kTileRows];              // w_j (unsquared) * g_j'r   (SKAT-O)
+  double zegU, zegSS, zegSZ[kMaxC];  // burden score-test ingredients (before the covariate projection)
+  double cmcU, cmcSS, cmcSZ[kMaxC];
 };
 
 struct EngineParams {

@@ -43,7 +43,10 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
            const NullModel* __restrict__ nm, EngineParams prm, int S,
            const SweepPartial* __restrict__ parts, rvt_gene_result* __restrict__ res,
            long long* __restrict__ dbg /* nullable: [n_genes][kFinPhases] cycle counters */,
-           QagsScratch* __restrict__ qags /* nullable: [n_genes]; non-null enables SKAT-O */) {
+           QagsScratch* __restrict__ qags /* nullable: [n_genes]; non-null enables SKAT-O */,
+           const TailInput* __restrict__ tin /* nullable: [n_genes] pre-digested statistics (dosage path);
+                                                then `genes`/`parts` are unused and res is indexed through out_index */,
+           const int* __restrict__ out_index) {
   extern __shared__ __align__(16) uint8_t dyn[];
   double* K = reinterpret_cast<double*>(dyn);                               // [64][kKld]
   long long* De = reinterpret_cast<long long*>(dyn + kTileRows * kKld * 8); // [64][kMaxER] gene x digit sums
@@ -65,14 +68,18 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   const int g = blockIdx.x;
   if (g >= n_genes) return;
   const int tid = threadIdx.x;
-  const GeneDesc gd = genes[g];
+  GeneDesc gd;
+  if (tin)
+    memset(&gd, 0, sizeof(gd));
+  else
+    gd = genes[g];
   const int M = gd.M;
   const int64_t N = nm->N;
   const int C = nm->C, ER = nm->ER;
   const double sigma2 = nm->sigma2;
   BlockPar par{s_red};
 
-  const SweepPartial* __restrict__ gp = parts + (size_t)g * S;
+  const SweepPartial* __restrict__ gp = tin ? nullptr : parts + (size_t)g * S;
   long long t_ph = clock64();
   auto phase = [&](int k) {
     if (dbg && tid == 0) {
@@ -81,6 +88,27 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
       t_ph = now;
     }
   };
+  __shared__ double s_bur[2][2 + kMaxC];   // per burden test: U, SS (raw), SZ[]
+  __shared__ int s_nonref;
+  if (tin) {
+    // pre-digested statistics: load what steps 1-4 would have built
+    const TailInput& ti = tin[g];
+    if (tid == 0) {
+      s_Mp = ti.Mp;
+      s_bad = 0;
+      s_Q = ti.Q;
+      s_nonref = ti.nonref;
+      s_bur[0][0] = ti.zegU; s_bur[0][1] = ti.zegSS;
+      s_bur[1][0] = ti.cmcU; s_bur[1][1] = ti.cmcSS;
+      for (int l = 0; l < C; ++l) { s_bur[0][2 + l] = ti.zegSZ[l]; s_bur[1][2 + l] = ti.cmcSZ[l]; }
+    }
+    for (int idx = tid; idx < ti.Mp * ti.Mp; idx += kFinThreads) {
+      const int i = idx / ti.Mp, k = idx - i * ti.Mp;
+      K[i * kKld + k] = ti.K[idx];
+    }
+    if (tid < ti.Mp) s_vw[tid] = ti.vw[tid];
+    __syncthreads();
+  } else {
   // 1. reduce the splits (int64): gene x digit columns and the diagonal; the gene x gene block is
   //    summed on the fly where K is built (each entry is needed exactly once)
   for (int idx = tid; idx < M * ER; idx += kFinThreads) {
@@ -179,6 +207,18 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   }
   __syncthreads();
   phase(1);
+  if (tid == 0) {   // burden ingredients from the collapse digits
+    for (int which = 0; which < 2; ++which) {
+      const long long* cl = s_coll + which * (ER + 1);
+      s_bur[which][0] = (double)recombine4(cl) * nm->scale[0];
+      s_bur[which][1] = (double)cl[ER];
+      for (int l = 0; l < C; ++l) s_bur[which][2 + l] = (double)recombine4(cl + 4 * (l + 1)) * nm->scale[l + 1];
+    }
+    s_nonref = (int)s_coll[(ER + 1) + ER];
+  }
+  __syncthreads();
+  }  // !tin
+  const int Mp = s_Mp;
 
   if (qags) {
     // SKAT-O: Z1'Z1 = W (G'G - G'X (X'X)^-1 X'G) W / 2 with the UN-squared weights = K / (2 sigma2)
@@ -241,11 +281,9 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
     o.skato_rho = so.rho;
     o.skato_p = so.pvalue;
     for (int which = 0; which < 2; ++which) {  // 0 zeggini, 1 cmc
-      const long long* cl = s_coll + which * (ER + 1);
-      double U = (double)recombine4(cl) * nm->scale[0];
-      double SZ[kMaxC];
-      for (int l = 0; l < C; ++l) SZ[l] = (double)recombine4(cl + 4 * (l + 1)) * nm->scale[l + 1];
-      double SS = (double)cl[ER];
+      const double U = s_bur[which][0];
+      double SS = s_bur[which][1];
+      const double* SZ = &s_bur[which][2];
       double q = 0.0;
       for (int l = 0; l < C; ++l)
         for (int m = 0; m < C; ++m) q += SZ[l] * nm->xtx_inv[l * C + m] * SZ[m];
@@ -258,10 +296,11 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
         o.zeg_U = U; o.zeg_V = V; o.zeg_stat = stat; o.zeg_p = p; o.zeg_ok = ok;
       } else {
         o.cmc_U = U; o.cmc_V = V; o.cmc_stat = stat; o.cmc_p = p; o.cmc_ok = ok;
-        o.cmc_nonref = (int)cl[ER];
+        o.cmc_nonref = s_nonref;
       }
     }
-    res[g] = o;
+    if (tin && tin[g].status) o.status = tin[g].status;
+    res[out_index ? out_index[g] : g] = o;
     phase(4);
   }
 }

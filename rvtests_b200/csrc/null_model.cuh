@@ -117,6 +117,13 @@ __global__ void k_null_solve(int C, int nblocks, const double* __restrict__ part
     for (int b = 0; b < C; ++b) s += nm->xtx_inv[a * C + b] * xty[b];
     beta[a] = s;
   }
+  // column 0 is the intercept: X'X[0][l] = sum_i x_il, X'y[0] = sum_i y_i
+  double rs = xty[0];
+  for (int l = 0; l < C; ++l) {
+    nm->xsum[l] = xtx[0][l];
+    rs -= beta[l] * xtx[0][l];
+  }
+  nm->rsum = rs;
 }
 
 // stage 3: residuals + per-block RSS and max-abs of r and of every covariate column

@@ -12,6 +12,7 @@
 
 #include "../../include/rvtests_b200.h"
 #include "common.cuh"
+#include "dosage.cuh"
 #include "finalize.cuh"
 #include "meta.cuh"
 #include "null_model.cuh"
@@ -20,6 +21,16 @@
 #include "sweep_tc.cuh"
 
 using namespace rvt;
+
+namespace {
+struct DosGene {     // a pushed gene with non-hard-call values: handled by the fp64 path (dosage.cuh)
+  int gene_index;
+  int M;
+  double* dG;        // N x M column-major doubles, device
+  bool has_af;
+  std::vector<double> af;
+};
+}  // namespace
 
 constexpr int kSegLoaded = 0;  // the synthetic / loaded cohort arena
 constexpr int kSegStaged = 1;  // genes staged from host buffers
@@ -49,6 +60,7 @@ struct rvt_ctx {
   std::vector<uint8_t> userflags;  // per variant, 0xFF = derive from counts
   std::vector<double> af;          // per variant (valid when gene.has_af)
   std::vector<int64_t> count_slot; // per gene: offset into d_counts or -1
+  std::vector<DosGene> dos;        // pending genes that need the dosage path
   int64_t n_var = 0;
   // device side arrays (grown on demand)
   GeneDesc* d_genes = nullptr;
@@ -422,8 +434,26 @@ int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
   dim3 grid((unsigned)((npad / 4 + 255) / 256), (unsigned)M);
   k_pack_f64<<<grid, 256, 0, ctx->stream>>>(ctx->d_stage64, N, blk, M, ctx->d_counts + ctx->n_var);
   RVT_CUDA_OK(cudaGetLastError());
-  // the staging buffer is reused by the next push: wait (pageable H2D is synchronous anyway)
+  // the staging buffer is reused by the next push: wait (pageable H2D is synchronous anyway);
+  // the row counts also tell whether this gene holds anything but hard calls
+  std::vector<RowCounts> rc_host(M);
+  RVT_CUDA_OK(cudaMemcpyAsync(rc_host.data(), ctx->d_counts + ctx->n_var, sizeof(RowCounts) * M, cudaMemcpyDeviceToHost, ctx->stream));
   RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  bool dosage = false;
+  for (int j = 0; j < M; ++j) dosage |= rc_host[j].bad > 0;
+  if (dosage) {
+    // dosages / mean-imputed values: keep the fp64 matrix for the generic path and hand the
+    // staging buffer over to it (the next push allocates a fresh one)
+    DosGene dg;
+    dg.gene_index = (int)ctx->genes.size();
+    dg.M = M;
+    dg.dG = ctx->d_stage64;
+    dg.has_af = af != nullptr;
+    if (af) dg.af.assign(af, af + M);
+    ctx->dos.push_back(dg);
+    ctx->d_stage64 = nullptr;
+    ctx->cap_stage64 = 0;
+  }
   return push_common(ctx, blk, M, 0, af, nullptr, true, kSegStaged, off / 128, true);
 }
 
@@ -560,7 +590,7 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     }
     RVT_CUDA_OK(cudaEventRecord(ctx->ev[3], st));
     k_finalize<<<nb, kFinThreads, ctx->skato ? kFinSmemSkato : kFinSmem, st>>>(ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S,
-                                                  ctx->d_parts, d_res + b0, ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->skato ? ctx->d_qags : nullptr);
+                                                  ctx->d_parts, d_res + b0, ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->skato ? ctx->d_qags : nullptr, nullptr, nullptr);
     RVT_CUDA_OK(cudaEventRecord(ctx->ev[4], st));
     RVT_CUDA_OK(cudaGetLastError());
     launches += 2;
@@ -574,6 +604,39 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       ms_sweep += a;
       ms_fin += b;
     }
+  }
+  if (!ctx->dos.empty()) {
+    // genes with dosage / imputed values: fp64 statistics, then the same tail (eigen, Davies, SKAT-O, burden)
+    const int nd = (int)ctx->dos.size();
+    DosageStats* d_st = nullptr;
+    TailInput* d_tin = nullptr;
+    int* d_idx = nullptr;
+    double* d_afd = nullptr;
+    RVT_CUDA_OK(cudaMalloc((void**)&d_st, sizeof(DosageStats) * nd));
+    RVT_CUDA_OK(cudaMalloc((void**)&d_tin, sizeof(TailInput) * nd));
+    RVT_CUDA_OK(cudaMalloc((void**)&d_idx, sizeof(int) * nd));
+    RVT_CUDA_OK(cudaMalloc((void**)&d_afd, sizeof(double) * nd * kTileRows));
+    RVT_CUDA_OK(cudaMemsetAsync(d_st, 0, sizeof(DosageStats) * nd, st));
+    std::vector<int> idx(nd);
+    for (int i = 0; i < nd; ++i) {
+      const DosGene& dg = ctx->dos[i];
+      idx[i] = dg.gene_index;
+      RVT_CUDA_OK(cudaMemsetAsync(d_st[i].cmin, 0xFF, sizeof(unsigned long long) * kTileRows, st));
+      if (dg.has_af) RVT_CUDA_OK(cudaMemcpyAsync(d_afd + (size_t)i * kTileRows, dg.af.data(), sizeof(double) * dg.M, cudaMemcpyHostToDevice, st));
+      k_dosage_cols<<<ctx->sm_count, kDosThreads, 0, st>>>(dg.dG, N, dg.M, d_st + i);
+      k_dosage_stats<<<ctx->sm_count * 2, kDosThreads, 0, st>>>(dg.dG, N, dg.M, ctx->dX, ctx->C, ctx->dresid, d_st + i);
+      k_dosage_prepare<<<1, 64, 0, st>>>(d_st + i, dg.M, dg.has_af ? d_afd + (size_t)i * kTileRows : nullptr, ctx->d_nm, prm, d_tin + i);
+    }
+    RVT_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
+    if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)std::max(nd, batch), sizeof(QagsScratch)))) return rc;
+    k_finalize<<<nd, kFinThreads, ctx->skato ? kFinSmemSkato : kFinSmem, st>>>(nullptr, nd, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S,
+                                                                             nullptr, d_res, nullptr, ctx->skato ? ctx->d_qags : nullptr, d_tin, d_idx);
+    RVT_CUDA_OK(cudaGetLastError());
+    RVT_CUDA_OK(cudaStreamSynchronize(st));
+    launches += 3 * nd + 1;
+    cudaFree(d_st); cudaFree(d_tin); cudaFree(d_idx); cudaFree(d_afd);
+    for (auto& dg : ctx->dos) cudaFree(dg.dG);
+    ctx->dos.clear();
   }
   if (!to_device)
     RVT_CUDA_OK(cudaMemcpyAsync(out, d_res, sizeof(rvt_gene_result) * n, cudaMemcpyDeviceToHost, st));

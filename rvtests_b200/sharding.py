@@ -1,0 +1,34 @@
+"""Multi-GPU plumbing of the path: genes are independent, so each rank owns a
+contiguous shard of the gene list and the only collective is ONE gather of the fixed-size per-gene
+result records (168 B each).  Backend-agnostic (`dist` = torch.distributed with NCCL on GPUs, gloo in
+the CPU tests); no arithmetic here."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n_genes: int, rank: int, world: int):
+    """contiguous, balanced (sizes differ by at most one) shard [lo, hi) of rank `rank`"""
+    base, extra = divmod(n_genes, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_records(local: np.ndarray, dist, device=None) -> np.ndarray:
+    """all ranks end up with the records of every gene, in gene order.  `local` is a structured
+    numpy array (engine.RESULT_DTYPE); shards may differ in length by one (padded for the gather)."""
+    import torch
+    world = dist.get_world_size()
+    n_local = torch.tensor([len(local)], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local)
+    counts = [int(c.item()) for c in counts]
+    cap = max(counts) if counts else 0
+    item = local.dtype.itemsize
+    buf = torch.zeros(cap * item, dtype=torch.uint8, device=device)
+    if len(local):
+        buf[: len(local) * item] = torch.from_numpy(local.view(np.uint8).reshape(-1).copy()).to(buf.device)
+    out = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    parts = [np.frombuffer(o.cpu().numpy().tobytes(), dtype=local.dtype)[:c] for o, c in zip(out, counts)]
+    return np.concatenate(parts) if parts else local

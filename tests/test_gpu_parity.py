@@ -198,15 +198,50 @@ def test_skato_vs_oracle(eng, oracle, case):
     check_gene(r, ref2, lam, ctx=f"skat with skato on {case}")
 
 
-def test_bad_values_are_reported_not_computed(eng, oracle):
+@pytest.mark.parametrize("case", [(50, 700, 8, 1, 0.02), (51, 3000, 30, 3, 0.01), (52, 2000, 64, 2, 0.3)])
+def test_mean_imputed_and_dosage_genotypes(eng, oracle, case):
+    """A0: DataConsolidator::imputeGenotypeToMean (src/DataConsolidator.cpp:217-245) fills missing
+    calls with 2p -- not a hard call -- so such a gene takes the fp64 dosage path; same for dosages."""
+    O = oracle
+    seed, N, M, C, miss = case
+    G, X, y = make_problem(O, seed, N, M, C, maf=np.linspace(0.01, 0.3, M), n_flip=2, n_mono=1 if M > 8 else 0)
+    eng.set_option("engine", 0)
+    eng.set_null_model(X, y)
+    nm = O.fit_null_linear(X, y)
+    rng = np.random.default_rng(seed)
+    Gd = G.astype(np.float64)
+    af = np.zeros(M)
+    for j in range(M):
+        m = rng.random(N) < miss
+        obs = Gd[~m, j]
+        p = obs.sum() / (2 * len(obs)) if len(obs) else 0.0
+        Gd[m, j] = 2.0 * p                                    # imputeGenotypeToMean
+        af[j] = 0.5 * obs.sum() / N                            # GenotypeCounter::getAF divides by nSample incl. missing (F9)
+    Gdos = np.clip(G + rng.normal(0, 0.05, G.shape), 0, 2)      # genuine dosages
+    eng.push_f64(Gd, af)
+    eng.push_f64(Gdos, None)
+    eng.push_f64(G.astype(float), af_of(G))                    # a hard-call gene in the same flush
+    res = eng.flush()
+    ref, lam = O.gene(Gd, af, X, nm["resid"], nm["sigma2"])
+    check_gene(res[0], ref, lam, ctx=f"imputed {case}")
+    keep = [j for j in range(M) if Gdos[:, j].min() != Gdos[:, j].max()]
+    af2 = np.zeros(M)
+    af2[: len(keep)] = 0.5 * Gdos[:, keep].sum(axis=0) / N
+    ref2, lam2 = O.gene(Gdos, af2, X, nm["resid"], nm["sigma2"])
+    check_gene(res[1], ref2, lam2, ctx=f"dosage {case}")
+    ref3, lam3 = _oracle_gene(O, G, X, nm)
+    check_gene(res[2], ref3, lam3, ctx=f"hard calls {case}")
+
+
+def test_int8_path_rejects_non_hard_calls(eng, oracle):
     O = oracle
     G, X, y = make_problem(O, 30, 500, 6, 1, maf=0.2)
     eng.set_null_model(X, y)
-    Gd = G.astype(float)
-    Gd[3, 2] = 0.37  # an imputed dosage: not a hard call
-    eng.push_f64(Gd, af_of(G))
+    Gb = G.T.copy()
+    Gb[2, 3] = -1  # a missing code has no meaning in the packed hard-call format
+    eng.push_i8(Gb, af_of(G))
     r = eng.flush()[0]
-    assert int(r["status"]) == 5  # RVT_GENE_BADVALUE (hard-call path only in this build)
+    assert int(r["status"]) == 5  # RVT_GENE_BADVALUE: reported, never silently computed
 
 
 def test_errors_are_loud(eng):
