@@ -50,6 +50,8 @@ def check_gene(res, ref, lam_ref, tol_q=1e-6, tol_p=1e-4, ctx=""):
         ok = getattr(ref, pre + "_ok")
         assert int(res[pre + "_ok"]) == ok, f"{ctx} {pre}_ok"
         if ok:
-            assert rel(res[pre + "_U"], getattr(ref, pre + "_U")) <= 1e-6, f"{ctx} {pre}_U"
+            # U ~ N(0, V): judge the error on the scale of its standard deviation (U itself may be ~0)
+            u_ref, v_ref = getattr(ref, pre + "_U"), getattr(ref, pre + "_V")
+            assert abs(res[pre + "_U"] - u_ref) <= 1e-6 * max(abs(u_ref), np.sqrt(abs(v_ref))), f"{ctx} {pre}_U {res[pre + '_U']} vs {u_ref}"
             assert rel(res[pre + "_V"], getattr(ref, pre + "_V")) <= 1e-6, f"{ctx} {pre}_V"
             assert rel(res[pre + "_p"], getattr(ref, pre + "_p")) <= tol_p, f"{ctx} {pre}_p {res[pre + '_p']} vs {getattr(ref, pre + '_p')}"
