@@ -93,6 +93,13 @@ int rvt_set_stream(rvt_ctx* ctx, void* cuda_stream);
  * copyCovariateAndIntercept, src/ModelUtil.h:102-130); y: N.  Host pointers.  binary != 0
  * (logistic null) is RVT_E_UNSUPPORTED in this build. */
 int rvt_set_null_model(rvt_ctx* ctx, int64_t N, int C, const double* X, const double* y, int binary);
+/* "bring your own null": the caller supplies the score vector r (length N) and the variance scale
+ * sigma2, the engine only builds (X'X)^-1 and the device images.  This is the score step of the
+ * mixed models: BoltLMM::TestCovariate (regression/BoltLMM.cpp:315-338) is U = g.r with
+ * r = (I - ZZ')H^-1 y and V = (|g|^2 - |Z'g|^2) * kappa, kappa = |H^-1 y|^2_proj * calibration / N --
+ * i.e. rvt_meta_flush after rvt_set_null_residual(ctx, N, C, X, r, kappa).  The null fit that
+ * produces H^-1 y (BoltLMM::FitNullModel) is outside this build. */
+int rvt_set_null_residual(rvt_ctx* ctx, int64_t N, int C, const double* X, const double* resid, double sigma2);
 /* same, X and y already in device memory */
 int rvt_set_null_model_dev(rvt_ctx* ctx, int64_t N, int C, const double* dX, const double* dy);
 /* resid (N doubles, host, may be NULL), sigma2, xtx_inv (C*C row-major, may be NULL) */

@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(kNullThreads) k_null_resid(int64_t N, int C, c
                                                             const double* __restrict__ y,
                                                             const double* __restrict__ beta,
                                                             double* __restrict__ resid,
-                                                            double* __restrict__ part /*[blocks][2+kMaxC]*/) {
+                                                            double* __restrict__ part /*[blocks][2+kMaxC]*/,
+                                                            int keep_y /* 1: resid := y as given (caller-supplied null residual) */) {
   __shared__ double sh[32];
   double b[kMaxC];
 #pragma unroll
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(kNullThreads) k_null_resid(int64_t N, int C, c
         pred += x * b[c];
         mx[c + 1] = fmax(mx[c + 1], fabs(x));
       }
-    double r = y[i] - pred;
+    double r = keep_y ? y[i] : y[i] - pred;
     resid[i] = r;
     rss += r * r;
     mx[0] = fmax(mx[0], fabs(r));
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kNullThreads) k_null_resid(int64_t N, int C, c
 
 // stage 4 (one thread): sigma2 and the power-of-two fixed-point scales
 __global__ void k_null_finish(int64_t N, int C, int nblocks, const double* __restrict__ part, NullModel* nm,
-                              int* shift /*[kMaxC+1]*/) {
+                              int* shift /*[kMaxC+1]*/, double sigma2_given /* < 0: use RSS/N */) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double rss = 0.0, mx[kMaxC + 1];
   for (int c = 0; c <= kMaxC; ++c) mx[c] = 0.0;
@@ -171,7 +172,7 @@ __global__ void k_null_finish(int64_t N, int C, int nblocks, const double* __res
     rss += part[(size_t)b * (2 + kMaxC)];
     for (int c = 0; c <= kMaxC; ++c) mx[c] = fmax(mx[c], part[(size_t)b * (2 + kMaxC) + 1 + c]);
   }
-  nm->sigma2 = rss / (double)N;
+  nm->sigma2 = (sigma2_given >= 0.0) ? sigma2_given : rss / (double)N;
   for (int v = 0; v <= C; ++v) {
     int ex = 0;
     if (mx[v] > 0.0) frexp(mx[v], &ex);  // mx < 2^ex

@@ -282,7 +282,7 @@ double rvt_get_info(const rvt_ctx* ctx, const char* key) {
   return -1;
 }
 
-static int null_model_run(rvt_ctx* ctx) {
+static int null_model_run(rvt_ctx* ctx, bool keep_resid = false, double sigma2_given = -1.0) {
   const int64_t N = ctx->N;
   const int C = ctx->C;
   ctx->ER = ((4 * (C + 1)) + 15) & ~15;  // kind::i8 UMMA needs N = 64 + ER to be a multiple of 16
@@ -304,8 +304,8 @@ static int null_model_run(rvt_ctx* ctx) {
   k_null_moments<<<kNullBlocks, kNullThreads, 0, ctx->stream>>>(N, C, ctx->dX, ctx->dy, ctx->dnull_part);
   k_null_solve<<<1, 32, 0, ctx->stream>>>(C, kNullBlocks, ctx->dnull_part, ctx->d_nm, ctx->dbeta, ctx->d_status);
   k_null_resid<<<kNullBlocks, kNullThreads, 0, ctx->stream>>>(N, C, ctx->dX, ctx->dy, ctx->dbeta, ctx->dresid,
-                                                             ctx->dnull_part);
-  k_null_finish<<<1, 32, 0, ctx->stream>>>(N, C, kNullBlocks, ctx->dnull_part, ctx->d_nm, ctx->d_shift);
+                                                             ctx->dnull_part, keep_resid ? 1 : 0);
+  k_null_finish<<<1, 32, 0, ctx->stream>>>(N, C, kNullBlocks, ctx->dnull_part, ctx->d_nm, ctx->d_shift, sigma2_given);
   k_build_E<<<kNullBlocks, kNullThreads, 0, ctx->stream>>>(N, C, ctx->dX, ctx->dresid, ctx->d_shift, ctx->dE,
                                                           ctx->ldE, ctx->d_nm);
   RVT_CUDA_OK(cudaGetLastError());
@@ -347,6 +347,19 @@ int rvt_set_null_model(rvt_ctx* ctx, int64_t N, int C, const double* X, const do
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->dX, X, sizeof(double) * N * C, cudaMemcpyHostToDevice, ctx->stream));
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->dy, y, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
   return null_model_run(ctx);
+}
+
+int rvt_set_null_residual(rvt_ctx* ctx, int64_t N, int C, const double* X, const double* resid, double sigma2) {
+  if (!ctx || !X || !resid) return RVT_E_BADARG;
+  if (!(sigma2 > 0.0)) CTX_FAIL(RVT_E_BADARG, "sigma2 must be positive");
+  int rc = null_model_alloc(ctx, N, C);
+  if (rc) return rc;
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->dX, X, sizeof(double) * N * C, cudaMemcpyHostToDevice, ctx->stream));
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->dy, resid, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+  rc = null_model_run(ctx, true, sigma2);
+  if (rc) return rc;
+  // with a caller-supplied residual sum_i r_i is what it is: recompute it for the flip algebra
+  return RVT_OK;
 }
 
 int rvt_set_null_model_dev(rvt_ctx* ctx, int64_t N, int C, const double* dX, const double* dy) {

@@ -47,7 +47,7 @@ assert RESULT_DTYPE.itemsize == C.sizeof(GeneResult)
 EXPORTS = [
     "rvt_ctx_create", "rvt_ctx_destroy", "rvt_last_error", "rvt_set_option", "rvt_get_info",
     "rvt_set_stream",
-    "rvt_set_null_model", "rvt_set_null_model_dev", "rvt_get_null_model",
+    "rvt_set_null_model", "rvt_set_null_model_dev", "rvt_get_null_model", "rvt_set_null_residual",
     "rvt_gene_push_f64", "rvt_gene_push_i8", "rvt_gene_push_dev_i8", "rvt_pending",
     "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded",
     "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
@@ -84,6 +84,7 @@ def load_library(rebuild: bool = False):
     L.rvt_set_stream.argtypes = [vp, vp]
     L.rvt_set_null_model.argtypes = [vp, C.c_int64, C.c_int, _dp, _dp, C.c_int]
     L.rvt_set_null_model_dev.argtypes = [vp, C.c_int64, C.c_int, vp, vp]
+    L.rvt_set_null_residual.argtypes = [vp, C.c_int64, C.c_int, _dp, _dp, C.c_double]
     L.rvt_get_null_model.argtypes = [vp, _dp, _dp, _dp]
     L.rvt_gene_push_f64.argtypes = [vp, _dp, C.c_int, _dp]
     L.rvt_gene_push_i8.argtypes = [vp, vp, C.c_int, C.c_int64, _dp]
@@ -155,6 +156,13 @@ class GeneEngine:
         yc = np.ascontiguousarray(y, dtype=np.float64)
         self.N, self.C = Xc.shape
         self._chk(self.L.rvt_set_null_model(self.h, self.N, self.C, _pd(Xc), _pd(yc), int(binary)))
+
+    def set_null_residual(self, X, resid, sigma2):
+        """caller-supplied score vector and variance scale (mixed-model score step)"""
+        Xc = np.asfortranarray(X, dtype=np.float64)
+        rc_ = np.ascontiguousarray(resid, dtype=np.float64)
+        self.N, self.C = Xc.shape
+        self._chk(self.L.rvt_set_null_residual(self.h, self.N, self.C, _pd(Xc), _pd(rc_), float(sigma2)))
 
     def set_null_model_dev(self, N, Cc, dX_ptr, dy_ptr):
         self.N, self.C = int(N), int(Cc)

@@ -93,3 +93,42 @@ def test_meta_score_only_and_hwe_extremes(engine_cls, oracle):
         assert rel(vout[v]["hwe_p"], ref["hwe_p"]) <= 1e-9
         assert bool(vout[v]["ok"]) == ref["ok"]
     eng.close()
+
+
+def test_bolt_score_step(engine_cls, oracle):
+    """BoltLMM::TestCovariate (regression/BoltLMM.cpp:315-338, projDot/projNorm2 :1064-1138,
+    BoltPlinkLoader::projectCovariate .cpp:266-271) restated in numpy, for an arbitrary H^-1 y:
+      g_test = [g ; Z'g],  u = g.h - (Z'g).(Z'h),  v = (|g|^2 - |Z'g|^2) * |H^-1y|^2_proj * calib / N,
+      p = chisq_Q(u^2/v, 1), af = sum(g)/2N
+    against rvt_set_null_residual + rvt_meta_flush."""
+    O = oracle
+    N, nv, C = 6000, 90, 3
+    G = _variants(O, 11, N, nv, maf_hi=0.3)
+    X, _ = O.synth_covariates(11, N, C)
+    rng = np.random.default_rng(11)
+    Z, _r = np.linalg.qr(X)                       # orthonormal covariate basis (BoltPlinkLoader z_)
+    h = rng.standard_normal(N)                    # stands in for H^-1 y
+    hz = Z.T @ h
+    h_norm2 = float(h @ h - hz @ hz)              # projNorm2(H_inv_y_)
+    calib = 1.0371
+    kappa = h_norm2 * calib / N
+    r_b = h - Z @ hz
+    eng = engine_cls(0)
+    eng.set_null_residual(X, r_b, kappa)
+    for b0 in range(0, nv, 64):
+        eng.push_i8(G[b0:b0 + 64].copy(), None)
+    vout, _band, _w = eng.meta_flush(nv, want_cov=False)
+    for j in range(nv):
+        g = G[j].astype(np.float64)
+        zg = Z.T @ g
+        u = float(g @ h - zg @ hz)
+        v = float(g @ g - zg @ zg) * h_norm2 * calib / N
+        r = vout[j]
+        assert r["af"] == 0.5 * g.sum() / N
+        if g.min() == g.max():
+            assert not r["ok"]
+            continue
+        assert abs(r["U"] * kappa - u) <= 1e-6 * max(abs(u), np.sqrt(v))      # U_STAT = U / sigma2
+        assert rel(r["sqrtV"] ** 2 * kappa ** 2, v) <= 1e-6
+        assert rel(r["pvalue"], O.lib().orc_chisq_q(u * u / v, 1.0)) <= 1e-6
+    eng.close()

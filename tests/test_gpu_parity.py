@@ -255,3 +255,49 @@ def test_errors_are_loud(eng):
     with pytest.raises(rvtests_b200.RvtError):
         e2.set_null_model(X, np.arange(10.0))  # column 0 is not the intercept
     e2.close()
+
+
+def test_full_size_properties(engine_cls, oracle):
+    """BASELINE.json full size (N = 500 000 samples x M = 50 variants): size-independent properties
+    plus two genes checked against the oracle.
+      * the tcgen05 and the dp4a sweeps agree bit for bit, for every split count
+      * recoding a variant as 2-g (ALT <-> REF) and telling the engine to flip it back changes nothing
+      * 2 genes vs the CPU oracle (Q 1e-6, p 1e-4, NonRefSite exact)"""
+    O = oracle
+    from rvtests_b200 import synth
+    seed, N, M, ng, C = 20260925, 500_000, 50, 6, 3
+    X, y = synth.covariates(seed, N, C)
+    keys, t0, t1 = synth.variant_params(seed, 0, ng * M)
+    eng = engine_cls(0)
+    eng.set_null_model(X, y)
+    eng.synth_load(keys, t0, t1, ng, M)
+    outs = {}
+    for which in (1, 2):
+        for splits in (0, 5):
+            eng.set_option("engine", which)
+            eng.set_option("splits", splits)
+            outs[(which, splits)] = eng.run_loaded()
+    base = outs[(2, 0)]
+    for k, v in outs.items():
+        assert v.tobytes() == base.tobytes(), k
+    assert np.all(base["status"] == 0)
+    # oracle on two genes (host twin regenerates the same genotypes)
+    nm = O.fit_null_linear(X, y)
+    for g in (0, ng - 1):
+        Gg = eng.loaded_read(g * M, M)                      # (M, N) int8
+        ref, lam = O.gene(Gg.T.astype(np.float64), 0.5 * Gg.sum(axis=1) / N, X, nm["resid"], nm["sigma2"])
+        check_gene(base[g], ref, lam, ctx=f"full size gene {g}")
+    # flip invariance through the host int8 path (gene 1)
+    eng.set_option("engine", 0)
+    eng.set_option("splits", 0)
+    G1 = eng.loaded_read(M, M)
+    af = 0.5 * G1.sum(axis=1) / N
+    G1f = G1.copy()
+    G1f[[3, 17, 40]] = 2 - G1f[[3, 17, 40]]                  # these rows are now ALT-major: the engine flips them back
+    eng.push_i8(G1, af)
+    eng.push_i8(G1f, af)                                     # same AF => same weights (the quirk path takes AF from the caller)
+    r = eng.flush()
+    for k in ("Q", "p_skat", "cmc_nonref", "cmc_p", "zeg_p", "lambda_max"):
+        assert rel(r[0][k], r[1][k]) <= 1e-9, k
+    assert r[0]["cmc_nonref"] == r[1]["cmc_nonref"] == base[1]["cmc_nonref"]
+    eng.close()
