@@ -39,6 +39,10 @@ struct rvt_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t stream2 = nullptr;      // per-gene statistics of batch i overlap the sweep of batch i+1
+  bool overlap = true;
+  std::vector<cudaEvent_t> evpool;
+  int pending_timing_batches = 0;
   char err[512] = {0};
   int sm_count = 148;
   // options
@@ -194,6 +198,7 @@ int rvt_ctx_create(int device, rvt_ctx** out) {
              prop.major, prop.minor);
   RVT_CUDA_OK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
+  RVT_CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   for (auto& ev : ctx->ev) RVT_CUDA_OK(cudaEventCreate(&ev));
   RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_nm, sizeof(NullModel)));
   RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_counter, sizeof(unsigned int) * 4));
@@ -220,6 +225,8 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
     if (p) cudaFree(p);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& e : ctx->evpool) cudaEventDestroy(e);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -238,6 +245,8 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "splits") {
     if (value < 0 || value > 64) CTX_FAIL(RVT_E_BADARG, "splits must be in 0..64");
     ctx->splits = (int)value;
+  } else if (k == "overlap") {
+    ctx->overlap = value != 0;
   } else if (k == "skato") {
     ctx->skato = value != 0;
   } else if (k == "tc_stages") {
@@ -548,8 +557,14 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   int64_t chunk = (((N + S - 1) / S) + 511) & ~(int64_t)511;
   S = (int)((N + chunk - 1) / chunk);
   if (chunk > ((int64_t)1 << 22)) CTX_FAIL(RVT_E_UNSUPPORTED, "split of %lld samples exceeds the int32 accumulation bound; raise 'splits'", (long long)chunk);
-  const int batch = std::min(n, 2048);
-  if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)batch * S, sizeof(SweepPartial)))) return rc;
+  // Batches of genes flow through two streams: the sweep of batch i+1 (HBM-bound) runs on `st`
+  // while the per-gene statistics of batch i (latency / fp64-bound, no HBM traffic) run on `st2`;
+  // the partials are double-buffered.  With overlap off (or SKAT-O on: its finalize dwarfs the
+  // sweep) one big batch per launch is used instead.
+  const bool overlap = ctx->overlap && !ctx->skato && n > ctx->sm_count;
+  const int batch = overlap ? std::min(n, 2 * ctx->sm_count) : std::min(n, 2048);
+  const int nbuf = overlap ? 2 : 1;
+  if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)nbuf * batch * S, sizeof(SweepPartial)))) return rc;
   rvt_gene_result* d_res = out;
   if (!to_device) {
     if ((rc = ensure(ctx, (void**)&ctx->d_res, &ctx->cap_res, n, sizeof(rvt_gene_result)))) return rc;
@@ -567,6 +582,14 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   }
   ctx->last_n = n;
   cudaStream_t st = ctx->stream;
+  cudaStream_t st2 = overlap ? ctx->stream2 : st;
+  const int nbatch = (n + batch - 1) / batch;
+  // per batch: [0] sweep start, [1] sweep end, [2] finalize start, [3] finalize end
+  while ((int)ctx->evpool.size() < 4 * nbatch) {
+    cudaEvent_t e;
+    RVT_CUDA_OK(cudaEventCreate(&e));
+    ctx->evpool.push_back(e);
+  }
   RVT_CUDA_OK(cudaEventRecord(ctx->ev[0], st));
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_genes, ctx->genes.data(), sizeof(GeneDesc) * n, cudaMemcpyHostToDevice, st));
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_userflags, ctx->userflags.data(), ctx->n_var, cudaMemcpyHostToDevice, st));
@@ -587,37 +610,41 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   ctx->last_engine = engine;
   ctx->last_S = S;
   EngineParams prm{ctx->beta1, ctx->beta2};
-  float ms_sweep = 0.f, ms_fin = 0.f;
-  for (int b0 = 0; b0 < n; b0 += batch) {
+  if (engine == RVT_ENGINE_TC && (rc = tc_prepare_maps(&ctx->tc, ctx->genes[0].seg, ctx->genes.data(), n, st, ctx->err, sizeof(ctx->err))))
+    return rc;   // encode every box height up front: no host sync inside the pipelined loop
+  ctx->tc.overlap_smem = overlap;
+  for (int bi = 0; bi < nbatch; ++bi) {
+    const int b0 = bi * batch;
     const int nb = std::min(batch, n - b0);
+    SweepPartial* parts = ctx->d_parts + (size_t)(bi % nbuf) * batch * S;
+    cudaEvent_t* ev = &ctx->evpool[4 * bi];
+    if (overlap && bi >= 2) RVT_CUDA_OK(cudaStreamWaitEvent(st, ctx->evpool[4 * (bi - 2) + 3], 0));  // buffer free again
     RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), st));
-    RVT_CUDA_OK(cudaEventRecord(ctx->ev[2], st));
+    RVT_CUDA_OK(cudaEventRecord(ev[0], st));
     if (engine == RVT_ENGINE_SIMT) {
       const int grid = std::min(nb * S, ctx->sm_count * 3);
-      k_sweep_simt<<<grid, kSimtThreads, kSimtSmem, st>>>(ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_nm, S, chunk,
-                                                          ctx->d_parts, ctx->d_counter);
+      k_sweep_simt<<<grid, kSimtThreads, kSimtSmem, st>>>(ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_nm, S, chunk, parts, ctx->d_counter);
     } else {
       rc = tc_launch(&ctx->tc, ctx->d_genes + b0, ctx->genes.data() + b0, nb, ctx->d_flags, ctx->d_nm, N, ctx->ER,
-                     S, chunk, ctx->d_parts, ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err));
+                     S, chunk, parts, ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err));
       if (rc) return rc;
     }
-    RVT_CUDA_OK(cudaEventRecord(ctx->ev[3], st));
-    k_finalize<<<nb, kFinThreads, ctx->skato ? kFinSmemSkato : kFinSmem, st>>>(ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S,
-                                                  ctx->d_parts, d_res + b0, ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->skato ? ctx->d_qags : nullptr, nullptr, nullptr);
-    RVT_CUDA_OK(cudaEventRecord(ctx->ev[4], st));
+    RVT_CUDA_OK(cudaEventRecord(ev[1], st));
+    if (overlap) RVT_CUDA_OK(cudaStreamWaitEvent(st2, ev[1], 0));
+    RVT_CUDA_OK(cudaEventRecord(ev[2], st2));
+    k_finalize<<<nb, kFinThreads, ctx->skato ? kFinSmemSkato : kFinSmem, st2>>>(
+        ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S, parts, d_res + b0,
+        ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->skato ? ctx->d_qags : nullptr, nullptr, nullptr);
+    RVT_CUDA_OK(cudaEventRecord(ev[3], st2));
     RVT_CUDA_OK(cudaGetLastError());
     launches += 2;
     ctx->last_parts = (int64_t)nb * S;
-    if (n > batch || true) {
-      // per-batch timing needs the events resolved before they are re-recorded
-      RVT_CUDA_OK(cudaEventSynchronize(ctx->ev[4]));
-      float a = 0, b = 0;
-      RVT_CUDA_OK(cudaEventElapsedTime(&a, ctx->ev[2], ctx->ev[3]));
-      RVT_CUDA_OK(cudaEventElapsedTime(&b, ctx->ev[3], ctx->ev[4]));
-      ms_sweep += a;
-      ms_fin += b;
-    }
   }
+  if (overlap) {   // everything downstream on `st` (copies, the caller's collectives) follows the last statistics
+    RVT_CUDA_OK(cudaStreamWaitEvent(st, ctx->evpool[4 * (nbatch - 1) + 3], 0));
+    if (nbatch >= 2) RVT_CUDA_OK(cudaStreamWaitEvent(st, ctx->evpool[4 * (nbatch - 2) + 3], 0));
+  }
+  ctx->pending_timing_batches = nbatch;
   if (!ctx->dos.empty()) {
     // genes with dosage / imputed values: fp64 statistics, then the same tail (eigen, Davies, SKAT-O, burden)
     const int nd = (int)ctx->dos.size();
@@ -657,6 +684,14 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   RVT_CUDA_OK(cudaStreamSynchronize(st));
   float tot = 0;
   RVT_CUDA_OK(cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[1]));
+  float ms_sweep = 0.f, ms_fin = 0.f;
+  for (int bi = 0; bi < ctx->pending_timing_batches; ++bi) {
+    float a = 0, b = 0;
+    RVT_CUDA_OK(cudaEventElapsedTime(&a, ctx->evpool[4 * bi], ctx->evpool[4 * bi + 1]));
+    RVT_CUDA_OK(cudaEventElapsedTime(&b, ctx->evpool[4 * bi + 2], ctx->evpool[4 * bi + 3]));
+    ms_sweep += a;
+    ms_fin += b;
+  }
   ctx->t_sweep = ms_sweep;
   ctx->t_fin = ms_fin;
   ctx->t_total = tot;

@@ -416,6 +416,7 @@ struct TcSegments {
   int boxes = 4;            // 128-sample boxes per pipeline stage for ER=16: 4 (5 stages) or 2 (10 stages)
   int l2promo = 2;          // CUtensorMapL2promotion: 0 none, 1 64B, 2 128B, 3 256B
   int dbg_skip = 0;         // timing experiments (see k_sweep_tc)
+  bool overlap_smem = false; // leave room in SMEM for a co-resident k_finalize CTA (4-stage ring)
   char why[128] = "";
   bool have_e = false;
   int ER = 0;
@@ -443,6 +444,7 @@ inline int tc_init(TcSegments* tc, char* err, size_t errlen) {
   }
   tc->encode = fn;
   e = cudaFuncSetAttribute(k_sweep_tc<16, 5, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5, false, 4>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 4, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 4, false, 4>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 10, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 10, false, 2>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4, false, 4>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 3, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 3, true, 4>::kSmem);
@@ -583,6 +585,8 @@ inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_
     RVT_TC_LAUNCH(32, 2, true, 4);
   else if (ER == 16 && tc->boxes == 2)
     RVT_TC_LAUNCH(16, 10, false, 2);
+  else if (ER == 16 && tc->overlap_smem)
+    RVT_TC_LAUNCH(16, 4, false, 4);
   else if (ER == 16)
     RVT_TC_LAUNCH(16, 5, false, 4);
   else
