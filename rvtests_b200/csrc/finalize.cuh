@@ -57,7 +57,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   __shared__ double s_red[64];
   __shared__ double s_e[kTileRows + 2], s_v[kTileRows + 2], s_p[kTileRows + 2];
   __shared__ double s_ev[kTileRows], s_lam[kTileRows];
-  __shared__ int s_th[kTileRows];
+  __shared__ int s_th[(kFinThreads / 32) * kTileRows];   // Davies order scratch, one slice per warp
   __shared__ long long s_coll[kCollapseN];
   __shared__ long long s_craw[kTileRows];
   __shared__ int s_idx[kTileRows], s_flip[kTileRows];
@@ -257,7 +257,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   if (qags && Mp > 0) {
     QagsWork work{qags[g].a, qags[g].b, qags[g].r, qags[g].e, qags[g].order, qags[g].level, kQagsLimit};
     const double s2 = sigma2 * (double)N / (double)(N - 1);   // ||r||^2/(N-1), SkatO.cpp:136-137
-    so = skato_tail(Wm, K, Mp, kKld, s_vw, s2, s_ev, s_e, s_v, s_p, s_lamz, s_c, &s_mach, work, s_fv, s_bcast, s_th, par);
+    so = skato_tail(Wm, K, Mp, kKld, s_vw, s2, s_ev, s_e, s_v, s_p, s_lamz, s_c, &s_mach, work, s_fv, s_bcast, s_th, kTileRows, par);
     phase(5);
   }
 

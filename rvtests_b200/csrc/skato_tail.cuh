@@ -627,11 +627,36 @@ RVT_HDN double skato_integrand_liu(const SkatoParams& P, double x) {
   return chisq_p(Q, P.Df) * chisq_pdf(x, 1.0);
 }
 
+#if defined(__CUDACC__)
+// One warp as a cooperating group: barriers are __syncwarp, reductions are shuffles.  Used to
+// evaluate several quadrature nodes (one Davies evaluation each) concurrently inside a CTA.
+struct WarpPar {
+  __device__ __forceinline__ int tid() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int nt() const { return 32; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ void allreduce2(double& a, double& b) const {
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+  }
+  __device__ __forceinline__ void allreduce4(double& a, double& b, double& c, double& d) const {
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+  }
+};
+#endif
+
 // Cooperative QAGS of one of the two integrands over [0, 40].  `mach` and `fv` live in memory
 // visible to the whole group; thread 0 drives the machine.  Returns the status to every thread.
 template <class Par>
 RVT_HDN int skato_integrate(const SkatoParams& P, bool use_davies, QagsMachine* mach, const QagsWork& work,
-                            double* fv /*21*/, double* bcast /*3*/, int* th, double* result, const Par& par) {
+                            double* fv /*21*/, double* bcast /*3*/, int* th, int th_stride /* ints per warp, 0: one group */,
+                            double* result, const Par& par) {
   if (par.tid() == 0) mach->init(work, 0.0, 40.0, 1e-25, 0.0001220703);
   par.sync();
   for (;;) {
@@ -647,9 +672,23 @@ RVT_HDN int skato_integrate(const SkatoParams& P, bool use_davies, QagsMachine* 
     const double lo = bcast[1], hi = bcast[2];
     const double centre = 0.5 * (lo + hi), half = 0.5 * (hi - lo);
     if (use_davies) {
-      for (int i = 0; i < 21; ++i) {   // every node is a group-wide Davies evaluation
-        const double fx = skato_integrand_davies(P, centre + half * gk21_node(i), th, par);
-        if (par.tid() == 0) fv[i] = fx;
+#if defined(__CUDA_ARCH__)
+      if (th_stride > 0) {
+        // the 21 Kronrod nodes are independent: each warp of the CTA takes nodes w, w+nw, ... and
+        // runs its own Davies evaluation with warp-level reductions (no block barriers inside)
+        const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        WarpPar wp;
+        for (int i = w; i < 21; i += nw) {
+          const double fx = skato_integrand_davies(P, centre + half * gk21_node(i), th + w * th_stride, wp);
+          if (wp.tid() == 0) fv[i] = fx;
+        }
+      } else
+#endif
+      {
+        for (int i = 0; i < 21; ++i) {   // every node is a group-wide Davies evaluation
+          const double fx = skato_integrand_davies(P, centre + half * gk21_node(i), th, par);
+          if (par.tid() == 0) fv[i] = fx;
+        }
       }
     } else {
       for (int i = par.tid(); i < 21; i += par.nt()) fv[i] = skato_integrand_liu(P, centre + half * gk21_node(i));
@@ -675,7 +714,7 @@ struct SkatoOut {
 template <class Par>
 RVT_HDN SkatoOut skato_tail(const double* Wm, double* Km, int M, int lda, const double* v, double s2, double* ev,
                             double* e, double* vv, double* pp, double* lamz, double* c, QagsMachine* mach,
-                            const QagsWork& work, double* fv, double* bcast, int* th, const Par& par) {
+                            const QagsWork& work, double* fv, double* bcast, int* th, int th_stride, const Par& par) {
   SkatoOut out;
   out.Q = 0;
   out.rho = 0;
@@ -773,8 +812,8 @@ RVT_HDN SkatoOut skato_tail(const double* Wm, double* Km, int M, int lda, const 
     P.Qs_minP[i] = (q_org - mom[i].df) / sqrt(2. * mom[i].df) * sqrt(mom[i].varQ) + mom[i].muQ;
   }
   double integral = 0.0;
-  int st = skato_integrate(P, true, mach, work, fv, bcast, th, &integral, par);
-  if (st) st = skato_integrate(P, false, mach, work, fv, bcast, th, &integral, par);
+  int st = skato_integrate(P, true, mach, work, fv, bcast, th, th_stride, &integral, par);
+  if (st) st = skato_integrate(P, false, mach, work, fv, bcast, th, th_stride, &integral, par);
   double pvalue = 1.0 - integral;
   // sanity rules, SkatO.cpp:262-277 (nRho = 11 -> multi = 3)
   if (pvalue <= 0) {

@@ -55,7 +55,7 @@ int hc_skato_tail(const double* Wm, int M, const double* v, double s2, double* o
   double fv[21], bcast[3];
   rvt::SerialPar par;
   rvt::SkatoOut o = rvt::skato_tail(Wm, Km.data(), M, lda, v, s2, ev.data(), e.data(), vv.data(), pp.data(), lamz.data(),
-                                    c.data(), &mach, w, fv, bcast, th.data(), par);
+                                    c.data(), &mach, w, fv, bcast, th.data(), 0, par);
   out[0] = o.Q;
   out[1] = o.rho;
   out[2] = o.pvalue;
