@@ -186,6 +186,16 @@ def run_ours(args):
         alg_bytes = float(args.genes) * args.samples * args.variants  # 1 byte per genotype
         sweep_s = float(np.mean(sweep_ms)) * 1e-3
         achieved = alg_bytes / sweep_s / 1e9
+        # DRAM bytes of the dominant kernel from the committed ncu --set full capture (per launch,
+        # scaled from the captured launch by its traffic/algorithmic ratio)
+        traffic, traffic_src = None, None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
+            ratio = prof["k_sweep_tc"]["traffic_over_algorithmic"]
+            traffic = ratio * alg_bytes
+            traffic_src = "profiles/r01_ncu_summary.json: dram__bytes_read+write = %.4f x algorithmic bytes (ncu --set full, 512-gene launch)" % ratio
+        except Exception:
+            pass
         out = {
             "metric": METRIC, "value": value, "unit": "gene-sets/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -205,7 +215,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_sweep_tc" if int(eng.info("last_engine")) == 2 else "k_sweep_simt",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if pk else "fallback 6.65 TB/s (of fallback)",
-                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": None},
+                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": traffic, "traffic_source": traffic_src},
             "sanity": {"genes_ok": int((res["status"] == 0).sum()), "median_p_skat": float(np.median(res["p_skat"])),
                        "davies_fault_frac": float((res["davies_fault"] != 0).mean())},
         }
