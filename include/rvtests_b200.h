@@ -118,6 +118,14 @@ int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af);
 int rvt_gene_push_i8(rvt_ctx* ctx, const int8_t* G, int M, int64_t ld, const double* af);
 int rvt_gene_push_dev_i8(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const double* af,
                          const uint8_t* flags);
+/* rvt_gene_push_bed: M variants as PLINK .bed SNP-major rows on the host -- the 2-bit form the
+ *   reference itself keeps in RAM for large cohorts (regression/BoltPlinkLoader.cpp:164-264) and
+ *   decodes in libVcf/PlinkInputFile.cpp:23-47: sample p = bits 2(p&3)..2(p&3)+1 of byte p>>2 of
+ *   the variant's row, 00 -> 0, 10 -> 1, 11 -> 2, 01 -> missing; `stride` bytes between rows
+ *   (>= ceil(N/4)).  A quarter of the int8 bytes cross PCIe.  Missing calls are mean-imputed
+ *   exactly as DataConsolidator::imputeGenotypeToMean does (src/DataConsolidator.cpp:217-245);
+ *   such a gene then takes the fp64 path. */
+int rvt_gene_push_bed(rvt_ctx* ctx, const uint8_t* bed, int M, int64_t stride, const double* af);
 /* number of genes pushed and not yet flushed */
 int rvt_pending(const rvt_ctx* ctx);
 /* run the sweep + per-gene statistics for every pending gene; out: host array of `cap` records */

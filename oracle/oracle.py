@@ -346,3 +346,42 @@ def synth_covariates(seed, N, C=3):
     if C > 2:
         y = y - 0.3 * X[:, 2]
     return X, y
+
+
+# ---- PLINK 2-bit rows and mean imputation (checker for rvt_gene_push_bed) --------------------------
+def bed_decode(bed, N):
+    """PlinkInputFile::readIntoMatrix, SNP-major branch (libVcf/PlinkInputFile.cpp:23-47 with the
+    codes of PlinkInputFile.h:206-209): geno = (byte >> 2*(p&3)) & 3; 0 -> 0, 2 -> 1, 3 -> 2,
+    1 -> -9 (missing).  bed: (M, >= ceil(N/4)) uint8 -> (M, N) float64."""
+    bed = np.asarray(bed, dtype=np.uint8)
+    M = bed.shape[0]
+    out = np.empty((M, N), dtype=np.float64)
+    table = {0: 0.0, 2: 1.0, 3: 2.0, 1: -9.0}
+    for m in range(M):
+        for p in range(N):
+            out[m, p] = table[(int(bed[m, p >> 2]) >> ((p & 3) << 1)) & 3]
+    return out
+
+
+def bed_decode_fast(bed, N):
+    """vectorised twin of bed_decode (same table), for the larger test cases"""
+    bed = np.asarray(bed, dtype=np.uint8)
+    sh = (np.arange(N) & 3) << 1
+    code = (bed[:, np.arange(N) >> 2] >> sh.astype(np.uint8)) & 3
+    return np.array([0.0, -9.0, 1.0, 2.0])[code]
+
+
+def impute_mean(G):
+    """DataConsolidator::imputeGenotypeToMean (src/DataConsolidator.cpp:217-245): per column with a
+    missing (<0) entry, p = ac / an over the called entries (0 if none), fill 2p.  G: (N, M)."""
+    G = np.array(G, dtype=np.float64)
+    for i in range(G.shape[1]):
+        col = G[:, i]
+        called = col >= 0
+        if called.all():
+            continue
+        ac = int(col[called].sum())
+        an = 2 * int(called.sum())
+        p = 0.0 if an == 0 else 1.0 * ac / an
+        col[~called] = 2.0 * p
+    return G

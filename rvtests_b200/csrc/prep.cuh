@@ -180,6 +180,70 @@ k_tile_rows(const int8_t* __restrict__ src, int64_t ld_src, int64_t N, int8_t* _
   }
 }
 
+// PLINK .bed SNP-major rows -> tiled int8 block + counts.  Encoding as the reference decodes it
+// (libVcf/PlinkInputFile.cpp:23-47, PlinkInputFile.h:206-209): sample p sits in bits 2(p&3)..2(p&3)+1
+// of byte p>>2 of its variant's row; 00 -> 0 (HOM_REF), 10 -> 1 (HET), 11 -> 2 (HOM_ALT), 01 -> missing.
+// Missing calls are stored as 3 and counted in `bad`; a gene that has any is mean-imputed
+// (k_impute_tiled_f64) and takes the fp64 path at flush.
+// grid: (ceil(npad/16/256), M); src rows are 4-byte aligned (pitch a multiple of 4).
+__global__ void __launch_bounds__(256)
+k_unpack_bed(const uint8_t* __restrict__ src, int64_t pitch, int64_t N, int8_t* __restrict__ dst, int M,
+             RowCounts* __restrict__ counts) {
+  const int64_t row = blockIdx.y;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  const int64_t npad = (N + 127) & ~(int64_t)127;
+  int n1 = 0, n2 = 0, bad = 0;
+  if (i0 < npad) {
+    uint32_t packed = 0;
+    if (i0 < N) packed = *reinterpret_cast<const uint32_t*>(src + (size_t)row * pitch + (i0 >> 2));
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t x = (packed >> (8 * q)) & 0xFFu;
+      const uint32_t t = (x | (x << 6) | (x << 12) | (x << 18)) & 0x03030303u;   // byte k = code of sample 4q+k
+      const uint32_t b0 = t & 0x01010101u, b1 = (t >> 1) & 0x01010101u;
+      const uint32_t miss = b0 & ~b1;
+      uint32_t g = b1 + b0 + 2u * miss;                                         // 0, 3 (missing), 1, 2
+      const int64_t rem = N - (i0 + 4 * q);
+      const uint32_t vm = rem >= 4 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - (int)rem))));
+      g &= vm;
+      const uint32_t lo = g & 0x01010101u, hi = (g >> 1) & 0x01010101u;
+      n1 += __popc(lo & ~hi);
+      n2 += __popc(hi & ~lo);
+      bad += __popc(hi & lo);
+      w[q] = g;
+    }
+    *reinterpret_cast<uint4*>(dst + tiled_off(M, (int)row, i0)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (n1 | n2 | bad)) {
+    atomicAdd(&counts[row].n1, n1);
+    atomicAdd(&counts[row].n2, n2);
+    atomicAdd(&counts[row].bad, bad);
+  }
+}
+
+// DataConsolidator::imputeGenotypeToMean (src/DataConsolidator.cpp:217-245) for a gene that arrived
+// as hard calls with missing entries (code 3): column j gets g = 2 * ac / an over its non-missing
+// calls (p = 0 when nothing is called).  dst: N x M column-major doubles, the layout the fp64 path eats.
+// grid: (ceil(N/256), M)
+__global__ void __launch_bounds__(256)
+k_impute_tiled_f64(const int8_t* __restrict__ src, int M, int64_t N, const RowCounts* __restrict__ counts,
+                   double* __restrict__ dst) {
+  const int row = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const long long ac = (long long)counts[row].n1 + 2ll * counts[row].n2;
+  const long long an = 2ll * (N - counts[row].bad);
+  const double fill = an == 0 ? 0.0 : 2.0 * (1.0 * (double)ac / (double)an);
+  const int g = src[tiled_off(M, row, i)];
+  dst[(size_t)row * N + i] = (g == 3) ? fill : (double)g;
+}
+
 // grid: (ceil(N/16/256), rows).  Tiled blocks of equal M back to back -> plain [rows][N] (tests).
 __global__ void __launch_bounds__(256)
 k_untile(const int8_t* __restrict__ arena, int M, int64_t gene_bytes, int64_t row_first, int64_t N, int8_t* __restrict__ out) {

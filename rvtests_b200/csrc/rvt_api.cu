@@ -66,6 +66,7 @@ struct rvt_ctx {
   std::vector<double> af;          // per variant (valid when gene.has_af)
   std::vector<int64_t> count_slot; // per gene: offset into d_counts or -1
   std::vector<DosGene> dos;        // pending genes that need the dosage path
+  std::vector<int> bed_genes;      // pending genes pushed as PLINK 2-bit rows: checked for missing calls at flush
   int64_t n_var = 0;
   // device side arrays (grown on demand)
   GeneDesc* d_genes = nullptr;
@@ -509,6 +510,67 @@ int rvt_gene_push_i8(rvt_ctx* ctx, const int8_t* G, int M, int64_t ld_in, const 
   return push_common(ctx, blk, M, 0, af, nullptr, true, kSegStaged, off / 128, true);
 }
 
+int rvt_gene_push_bed(rvt_ctx* ctx, const uint8_t* bed, int M, int64_t stride, const double* af) {
+  if (!ctx || !bed) return RVT_E_BADARG;
+  int rc = push_check(ctx, M);
+  if (rc) return rc;
+  const int64_t N = ctx->N, npad = (N + 127) & ~(int64_t)127;
+  const int64_t rowb = (N + 3) / 4, pitch = (rowb + 3) & ~(int64_t)3;
+  if (stride < rowb) CTX_FAIL(RVT_E_BADARG, "stride (%lld) < ceil(N/4) (%lld)", (long long)stride, (long long)rowb);
+  const size_t need = (size_t)M * pitch;
+  if (need > ctx->cap_stage8) {
+    if (ctx->d_stage8) {
+      RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_stage8);
+    }
+    const size_t cap = std::max(need, (size_t)kMaxM * pitch);
+    RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_stage8, cap));
+    ctx->cap_stage8 = cap;
+  }
+  int64_t off = 0;
+  if ((rc = stage_alloc(ctx, tiled_bytes(N, M), &off))) return rc;
+  int8_t* blk = ctx->d_stage + off;
+  if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
+  // 2 bits per call over PCIe (a quarter of the int8 form), expanded + re-tiled + counted on the device
+  RVT_CUDA_OK(cudaMemcpy2DAsync(ctx->d_stage8, pitch, bed, stride, rowb, M, cudaMemcpyHostToDevice, ctx->stream));
+  RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
+  dim3 grid((unsigned)((npad / 16 + 255) / 256), (unsigned)M);
+  k_unpack_bed<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const uint8_t*>(ctx->d_stage8), pitch, N, blk, M,
+                                              ctx->d_counts + ctx->n_var);
+  RVT_CUDA_OK(cudaGetLastError());
+  ctx->bed_genes.push_back((int)ctx->genes.size());
+  return push_common(ctx, blk, M, 0, af, nullptr, true, kSegStaged, off / 128, true);
+}
+
+// genes that arrived as 2-bit rows may hold missing calls (code 01): the counts say which; those are
+// mean-imputed on the device (DataConsolidator::imputeGenotypeToMean) and handed to the fp64 path
+static int resolve_bed_missing(rvt_ctx* ctx) {
+  if (ctx->bed_genes.empty()) return RVT_OK;
+  const int64_t N = ctx->N;
+  std::vector<RowCounts> hc((size_t)ctx->n_var);
+  RVT_CUDA_OK(cudaMemcpyAsync(hc.data(), ctx->d_counts, sizeof(RowCounts) * ctx->n_var, cudaMemcpyDeviceToHost, ctx->stream));
+  RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  for (int gi : ctx->bed_genes) {
+    const GeneDesc& gd = ctx->genes[gi];
+    bool missing = false;
+    for (int j = 0; j < gd.M; ++j) missing |= hc[gd.var0 + j].bad > 0;
+    if (!missing) continue;
+    DosGene dg;
+    dg.gene_index = gi;
+    dg.M = gd.M;
+    dg.dG = nullptr;
+    RVT_CUDA_OK(cudaMalloc((void**)&dg.dG, sizeof(double) * (size_t)N * gd.M));
+    dim3 grid((unsigned)((N + 255) / 256), (unsigned)gd.M);
+    k_impute_tiled_f64<<<grid, 256, 0, ctx->stream>>>(gd.g, gd.M, N, ctx->d_counts + gd.var0, dg.dG);
+    RVT_CUDA_OK(cudaGetLastError());
+    dg.has_af = gd.has_af != 0;
+    if (dg.has_af) dg.af.assign(ctx->af.begin() + gd.var0, ctx->af.begin() + gd.var0 + gd.M);
+    ctx->dos.push_back(dg);
+  }
+  ctx->bed_genes.clear();
+  return RVT_OK;
+}
+
 int rvt_gene_push_dev_i8(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const double* af, const uint8_t* flags) {
   if (!ctx || !dG) return RVT_E_BADARG;
   int rc = push_check(ctx, M);
@@ -551,6 +613,7 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   int rc;
   if ((rc = ensure(ctx, (void**)&ctx->d_genes, &ctx->cap_genes, n, sizeof(GeneDesc)))) return rc;
   if ((rc = ensure_var(ctx, ctx->n_var))) return rc;
+  if ((rc = resolve_bed_missing(ctx))) return rc;
   const int64_t N = ctx->N;
   int S = ctx->splits;
   if (S <= 0) S = (int)std::min<int64_t>(16, std::max<int64_t>(1, (N + 65535) / 65536));
@@ -855,6 +918,7 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   ctx->userflags.clear();
   ctx->af.clear();
   ctx->count_slot.clear();
+  ctx->bed_genes.clear();
   ctx->n_var = 0;
   ctx->stage_used = 0;
   return RVT_OK;

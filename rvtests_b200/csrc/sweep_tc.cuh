@@ -83,6 +83,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // the null-model digits E are re-read by every gene of the batch.
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+// elect.sync: exactly one lane of the (converged) warp gets `true`.  Unlike `lane == 0` the compiler
+// KNOWS a single thread is active behind it, so tcgen05.mma / cp.async.bulk.tensor are emitted as bare
+// UTCIMMA / UTMALDG instead of being wrapped in an ELECT..BRA.U.ANY loop with R2UR.BROADCAST per
+// instruction (measured: ~110 instead of ~40 clk per 64x80x32 UMMA -- tools/umma_bench.cu).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n.reg .b32 %%rx;\n.reg .pred %%px;\nelect.sync %%rx|%%px, %2;\n@%%px mov.s32 %1, 1;\nmov.s32 %0, %%rx;\n}\n"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
                                             uint64_t policy) {
   asm volatile(
@@ -176,7 +188,8 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // warp-uniform loop; one elected lane issues the bulk copies of a stage
+    {
       uint32_t it = 0;
       const int nchunks = (int)((N + 127) >> 7);
       constexpr int kOobRow = 0x7FFF0000;   // beyond any arena (< 2^31 rows of 128 B): TMA zero-fills
@@ -199,22 +212,26 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
           const int s = it % kTcStages;
           const uint32_t ph = (it / kTcStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], stage_tx);
-          uint8_t* st = tiles + (size_t)s * Cfg::kStageBytes;
-          const int kb = (int)(k0 + (int64_t)ks * kTcStageK);
+          __syncwarp();
+          if (elect_one_sync()) {
+            mbar_expect_tx(&full[s], stage_tx);
+            uint8_t* st = tiles + (size_t)s * Cfg::kStageBytes;
+            const int kb = (int)(k0 + (int64_t)ks * kTcStageK);
 #pragma unroll
-          for (int b = 0; b < kTcBoxes; ++b) {
-            // tiled genotype layout: chunk c of a gene is the contiguous run of M 128-byte rows
-            // starting at arena row  row0 + c*M  (arena viewed as [bytes/128][128])
-            // a stage may run past the gene's last chunk: such a box is fetched from beyond the
-            // arena (row kOobRow), i.e. zero-filled by TMA, instead of from the next gene's block
-            const int ch = (kb >> 7) + b;
-            const bool in = ch < nchunks;
-            tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kAOff, mg, 0, in ? row0 + ch * Mg : kOobRow, &full[s], kEvictFirst);
-            if (PAIR)
-              tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kBOff, mgb, 0, in ? row0b + ch * Mgb : kOobRow, &full[s], kEvictFirst);
-            if (!(dbg_skip & 4)) tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kEOff, &map_e, kb + b * kTcBoxK, 0, &full[s], kEvictLast);
+            for (int b = 0; b < kTcBoxes; ++b) {
+              // tiled genotype layout: chunk c of a gene is the contiguous run of M 128-byte rows
+              // starting at arena row  row0 + c*M  (arena viewed as [bytes/128][128])
+              // a stage may run past the gene's last chunk: such a box is fetched from beyond the
+              // arena (row kOobRow), i.e. zero-filled by TMA, instead of from the next gene's block
+              const int ch = (kb >> 7) + b;
+              const bool in = ch < nchunks;
+              tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kAOff, mg, 0, in ? row0 + ch * Mg : kOobRow, &full[s], kEvictFirst);
+              if (PAIR)
+                tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kBOff, mgb, 0, in ? row0b + ch * Mgb : kOobRow, &full[s], kEvictFirst);
+              if (!(dbg_skip & 4)) tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kEOff, &map_e, kb + b * kTcBoxK, 0, &full[s], kEvictLast);
+            }
           }
+          __syncwarp();
         }
       }
     }
@@ -238,7 +255,8 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
         const uint32_t ph = (it / kTcStages) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        __syncwarp();
+        if (elect_one_sync()) {
           const uint32_t st = smem_u32(tiles + (size_t)s * Cfg::kStageBytes);
 #pragma unroll
           for (int b = 0; b < ((dbg_skip & 2) ? 0 : kTcBoxes); ++b) {
@@ -255,7 +273,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
         }
         __syncwarp();
       }
-      if (nsteps == 0 && lane == 0) umma_commit(&tfull[a]);  // degenerate unit: publish (stale) accumulator
+      if (nsteps == 0 && elect_one_sync()) umma_commit(&tfull[a]);  // degenerate unit: publish (stale) accumulator
       __syncwarp();
     }
   } else {

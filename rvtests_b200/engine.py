@@ -48,7 +48,7 @@ EXPORTS = [
     "rvt_ctx_create", "rvt_ctx_destroy", "rvt_last_error", "rvt_set_option", "rvt_get_info",
     "rvt_set_stream",
     "rvt_set_null_model", "rvt_set_null_model_dev", "rvt_get_null_model", "rvt_set_null_residual",
-    "rvt_gene_push_f64", "rvt_gene_push_i8", "rvt_gene_push_dev_i8", "rvt_pending",
+    "rvt_gene_push_f64", "rvt_gene_push_i8", "rvt_gene_push_dev_i8", "rvt_gene_push_bed", "rvt_pending",
     "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded",
     "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
     "rvt_debug_phases",
@@ -89,6 +89,7 @@ def load_library(rebuild: bool = False):
     L.rvt_gene_push_f64.argtypes = [vp, _dp, C.c_int, _dp]
     L.rvt_gene_push_i8.argtypes = [vp, vp, C.c_int, C.c_int64, _dp]
     L.rvt_gene_push_dev_i8.argtypes = [vp, vp, C.c_int, C.c_int64, _dp, vp]
+    L.rvt_gene_push_bed.argtypes = [vp, vp, C.c_int, C.c_int64, _dp]
     L.rvt_pending.argtypes = [vp]
     L.rvt_flush.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.rvt_flush_dev.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
@@ -186,6 +187,12 @@ class GeneEngine:
         Gc = np.ascontiguousarray(Gt, dtype=np.int8)
         afc = None if af is None else np.ascontiguousarray(af, dtype=np.float64)
         self._chk(self.L.rvt_gene_push_i8(self.h, Gc.ctypes.data, Gc.shape[0], Gc.shape[1], _pd(afc)))
+
+    def push_bed(self, bed, af=None):
+        """bed: (M, >= ceil(N/4)) uint8 PLINK SNP-major rows (00 -> 0, 10 -> 1, 11 -> 2, 01 -> missing)."""
+        assert bed.dtype == np.uint8 and bed.ndim == 2 and bed.strides[1] == 1, (bed.dtype, bed.shape, bed.strides)
+        afc = None if af is None else np.ascontiguousarray(af, dtype=np.float64)
+        self._chk(self.L.rvt_gene_push_bed(self.h, bed.ctypes.data, bed.shape[0], bed.strides[0], _pd(afc)))
 
     def push_dev_i8(self, dptr, M, ld, af=None, flags=None):
         afc = None if af is None else np.ascontiguousarray(af, dtype=np.float64)

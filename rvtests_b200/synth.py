@@ -43,3 +43,19 @@ def covariates(seed: int, N: int, C: int = 3):
     if C > 2:
         y = y - 0.3 * X[:, 2]
     return X, y
+
+
+def pack_bed(Gt, missing=None):
+    """Hard calls (M, N) in {0,1,2} -> PLINK .bed SNP-major rows (M, ceil(N/4)) uint8, the coding the
+    reference reads back in libVcf/PlinkInputFile.cpp:23-47: 0 -> 00, 1 -> 10, 2 -> 11, missing -> 01;
+    sample p occupies bits 2(p&3)..2(p&3)+1 of byte p>>2.  missing: optional boolean (M, N) mask."""
+    Gt = np.asarray(Gt)
+    M, N = Gt.shape
+    code = np.array([0, 2, 3], dtype=np.uint8)[Gt.astype(np.int64)]
+    if missing is not None:
+        code = np.where(missing, np.uint8(1), code)
+    pad = (-N) % 4
+    if pad:
+        code = np.concatenate([code, np.zeros((M, pad), dtype=np.uint8)], axis=1)
+    c = code.reshape(M, -1, 4)
+    return np.ascontiguousarray((c[:, :, 0] | (c[:, :, 1] << 2) | (c[:, :, 2] << 4) | (c[:, :, 3] << 6)).astype(np.uint8))
