@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                       "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -146,14 +146,19 @@ def run_ours(args):
         return n
 
     sweep_ms, fin_ms, launches = [], [], 0
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    # clocks / throttle reasons are sampled under load: from the warm-up steps through the timed region
+    # (the timed region alone is a few tens of ms, shorter than nvidia-smi's sampling period)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    t_w = time.perf_counter()
+    nw = 0
+    while nw < max(args.warmup, 3) or time.perf_counter() - t_w < 0.5:
+        step()
+        nw += 1
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     w0 = time.perf_counter()

@@ -257,6 +257,10 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "tc_boxes") {
     if (value != 2 && value != 4) CTX_FAIL(RVT_E_BADARG, "tc_boxes must be 2 or 4");
     ctx->tc.boxes = (int)value;
+  } else if (k == "tc_zc") {
+    ctx->tc.zc = value != 0;
+  } else if (k == "tc_wide") {
+    ctx->tc.wide = value != 0;
   } else if (k == "tc_debug_skip") {
     ctx->tc.dbg_skip = (int)value;
   } else if (k == "tc_l2promo") {
@@ -628,7 +632,20 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   const bool overlap = ctx->overlap && !ctx->skato && n > ctx->sm_count;
   const int batch = overlap ? std::min(n, 2 * ctx->sm_count) : std::min(n, 2048);
   const int nbuf = overlap ? 2 : 1;
-  if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)nbuf * batch * S, sizeof(SweepPartial)))) return rc;
+  int engine = ctx->engine;
+  if (ctx->stage_used > 0) {
+    // bind the whole capacity: the maps stay valid while the arena does not move
+    rc = tc_bind_segment(&ctx->tc, kSegStaged, ctx->d_stage, ctx->stage_cap, ctx->err, sizeof(ctx->err));
+    if (rc) return rc;
+  }
+  bool tc_ok = tc_usable(&ctx->tc, ctx->genes.data(), n);
+  if (engine == RVT_ENGINE_AUTO) engine = tc_ok ? RVT_ENGINE_TC : RVT_ENGINE_SIMT;
+  if (engine == RVT_ENGINE_TC && !tc_ok)
+    CTX_FAIL(RVT_E_UNSUPPORTED, "tensor-core engine requested but unavailable for these genes: %s", ctx->tc.why);
+  // the wide tensor-core sweep writes two partials per (gene, split): even and odd 128-sample boxes
+  const bool wide = engine == RVT_ENGINE_TC && tc_parts_per_unit(&ctx->tc) == 2;
+  const int Sp = wide ? 2 * S : S;
+  if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)nbuf * batch * Sp, sizeof(SweepPartial)))) return rc;
   rvt_gene_result* d_res = out;
   if (!to_device) {
     if ((rc = ensure(ctx, (void**)&ctx->d_res, &ctx->cap_res, n, sizeof(rvt_gene_result)))) return rc;
@@ -661,16 +678,6 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   k_resolve_flags<<<(unsigned)((ctx->n_var + 255) / 256), 256, 0, st>>>(ctx->n_var, N, ctx->d_counts,
                                                                          ctx->d_userflags, ctx->d_flags);
   int launches = 1;
-  int engine = ctx->engine;
-  if (ctx->stage_used > 0) {
-    // bind the whole capacity: the maps stay valid while the arena does not move
-    rc = tc_bind_segment(&ctx->tc, kSegStaged, ctx->d_stage, ctx->stage_cap, ctx->err, sizeof(ctx->err));
-    if (rc) return rc;
-  }
-  bool tc_ok = tc_usable(&ctx->tc, ctx->genes.data(), n);
-  if (engine == RVT_ENGINE_AUTO) engine = tc_ok ? RVT_ENGINE_TC : RVT_ENGINE_SIMT;
-  if (engine == RVT_ENGINE_TC && !tc_ok)
-    CTX_FAIL(RVT_E_UNSUPPORTED, "tensor-core engine requested but unavailable for these genes: %s", ctx->tc.why);
   ctx->last_engine = engine;
   ctx->last_S = S;
   EngineParams prm{ctx->beta1, ctx->beta2};
@@ -680,7 +687,7 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   for (int bi = 0; bi < nbatch; ++bi) {
     const int b0 = bi * batch;
     const int nb = std::min(batch, n - b0);
-    SweepPartial* parts = ctx->d_parts + (size_t)(bi % nbuf) * batch * S;
+    SweepPartial* parts = ctx->d_parts + (size_t)(bi % nbuf) * batch * Sp;
     cudaEvent_t* ev = &ctx->evpool[4 * bi];
     if (overlap && bi >= 2) RVT_CUDA_OK(cudaStreamWaitEvent(st, ctx->evpool[4 * (bi - 2) + 3], 0));  // buffer free again
     RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), st));
@@ -690,19 +697,19 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       k_sweep_simt<<<grid, kSimtThreads, kSimtSmem, st>>>(ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_nm, S, chunk, parts, ctx->d_counter);
     } else {
       rc = tc_launch(&ctx->tc, ctx->d_genes + b0, ctx->genes.data() + b0, nb, ctx->d_flags, ctx->d_nm, N, ctx->ER,
-                     S, chunk, parts, ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err));
+                     S, chunk, parts, ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), false, wide);
       if (rc) return rc;
     }
     RVT_CUDA_OK(cudaEventRecord(ev[1], st));
     if (overlap) RVT_CUDA_OK(cudaStreamWaitEvent(st2, ev[1], 0));
     RVT_CUDA_OK(cudaEventRecord(ev[2], st2));
     k_finalize<<<nb, kFinThreads, ctx->skato ? kFinSmemSkato : kFinSmem, st2>>>(
-        ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S, parts, d_res + b0,
+        ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, d_res + b0,
         ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->skato ? ctx->d_qags : nullptr, nullptr, nullptr);
     RVT_CUDA_OK(cudaEventRecord(ev[3], st2));
     RVT_CUDA_OK(cudaGetLastError());
     launches += 2;
-    ctx->last_parts = (int64_t)nb * S;
+    ctx->last_parts = (int64_t)nb * Sp;
   }
   if (overlap) {   // everything downstream on `st` (copies, the caller's collectives) follows the last statistics
     RVT_CUDA_OK(cudaStreamWaitEvent(st, ctx->evpool[4 * (nbatch - 1) + 3], 0));

@@ -37,22 +37,40 @@ constexpr int kTcThreads = 64 + 32 * kTcConsumerWarps;
 constexpr int kTcMaxStages = 5;
 constexpr int kTcBoxK = 128;                // samples per box (one 128-byte swizzle row)
 constexpr int kTcChunkAlign = 512;          // split boundaries are multiples of this (>= any stage width)
-constexpr int kTcTmemCols = 256;            // 2 accumulators x 128 columns
 
 // PAIR = the A operand (rows of block I) and the B operand (rows of block J) are different tiles:
 // the cross-block Gram of the meta-analysis covariance (src/Model.cpp:534-554 calculateXX for
 // every pair of variants in the sliding window).  Box = [A tile][B tile][E tile].
-template <int ER, int STAGES, bool PAIR = false, int BOXES = 4>
+// WIDE = one UMMA covers TWO boxes (256 samples x K=32 slices of each): A = [G box0 ; G box1] (M = 128),
+// B = [G box0 ; G box1 ; E box0 ; E box1] (N = 128 + 2 ER).  A tcgen05.mma.kind::i8 costs ~65 clk plus
+// ~0.35 clk per column of N whatever M is (tools/umma_bench.cu, profiles/r01_umma_bench.txt): 76 clk for
+// the 64 x 80 slice of one box but only 118 clk for the 128 x 160 slice of two, i.e. 59 clk per box
+// slice -- below the ~72 clk per slice at which HBM delivers the bytes.  The cross-box blocks of D are
+// garbage and ignored; lanes 0-63 hold the even boxes' sums, lanes 64-127 the odd boxes', written
+// as two SweepPartials per unit (exact integers: the split of the sum is invisible downstream).
+template <int ER, int STAGES, bool PAIR = false, int BOXES = 4, bool WIDE = false, bool ZC = false>
 struct TcCfg {
+  static_assert(!(PAIR && WIDE), "block pairs use the single-box UMMA");
+  static_assert(!WIDE || (BOXES % 2 == 0), "WIDE pairs boxes");
   static constexpr int kBoxes = BOXES;          // boxes (of 128 samples) per pipeline stage
   static constexpr int kStageK = BOXES * kTcBoxK;
   static constexpr int kAOff = 0;
   static constexpr int kBOff = PAIR ? kTileRows * 128 : 0;
   static constexpr int kEOff = kBOff + kTileRows * 128;
   static constexpr int kBoxBytes = kEOff + ER * 128;
+  static constexpr int kPairBytes = 2 * kBoxBytes;       // WIDE: [G b0][G b1][E b0][E b1]
   static constexpr int kStageBytes = BOXES * kBoxBytes;
-  static constexpr int kSmem = STAGES * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmem = STAGES * kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr int kNC = kTileRows + ER;
+  static constexpr int kAccCols = WIDE ? 2 * kNC : 128;  // TMEM columns of one accumulator
+  static constexpr int kTmemCols = WIDE ? 512 : 256;     // two accumulators, power of two
+  // byte offsets of box b's genotype tile / digit tile inside a stage
+  __host__ __device__ static constexpr int g_off(int b) {
+    return WIDE ? (b >> 1) * kPairBytes + (b & 1) * kTileRows * 128 : b * kBoxBytes + kAOff;
+  }
+  __host__ __device__ static constexpr int e_off(int b) {
+    return WIDE ? (b >> 1) * kPairBytes + 2 * kTileRows * 128 + (b & 1) * ER * 128 : b * kBoxBytes + kEOff;
+  }
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -140,13 +158,20 @@ __device__ __forceinline__ uint32_t sw128_word_off(int r, int w) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((w >> 2) ^ (r & 7)) << 4) | ((w & 3) << 2)));
 }
 
-template <int ER, int kTcStages, bool PAIR, int kTcBoxes>
+// ZC = the burden scores ride on the tensor core: the consumer warps write the per-sample Zeggini
+// count z and CMC indicator c of a box as two extra int8 ROWS (M and M+1) of the genotype tile, so
+// that D[M][64+e] = z.E_e, D[M][M] = z.z (rows M+1 likewise for c) come out of the same UMMAs.  The
+// consumers then never read the digit tile (16 LDS + 34 dp4a per lane and box less, a fifth of
+// their shared-memory wavefronts); the price is an extra hop TMA -> consumers -> UMMA per stage.
+// Needs M <= 62 and splits short enough for z.E_e to stay inside int32 (host checks both).
+template <int ER, int kTcStages, bool PAIR, int kTcBoxes, bool WIDE = false, bool ZC = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */, const __grid_constant__ CUtensorMap map_e,
            const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __restrict__ rowflags, int64_t N, int S,
            int64_t chunk, SweepPartial* __restrict__ out, int dbg_skip /* timing experiments only: 1 no collapse,
            2 no MMA, 4 no E loads; results are then meaningless */) {
-  using Cfg = TcCfg<ER, kTcStages, PAIR, kTcBoxes>;
+  using Cfg = TcCfg<ER, kTcStages, PAIR, kTcBoxes, WIDE, ZC>;
+  static_assert(!(ZC && PAIR), "block pairs carry no burden scores");
   constexpr int kTcStageK = Cfg::kStageK;
   constexpr int kGroups = kTcConsumerWarps / kTcBoxes;   // consumer groups, one stage each in turn
   extern __shared__ uint8_t smem_raw[];
@@ -157,7 +182,8 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
   uint64_t* empty = bars + kTcStages;       // [kTcStages]
   uint64_t* tfull = bars + 2 * kTcStages;   // [2]
   uint64_t* tempty = tfull + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* ready = tempty + 2;             // [kTcStages] ZC: the consumers have added the z / c rows
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + kTcStages);
   __shared__ unsigned long long s_coll[2][kCollapseN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -167,7 +193,8 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
     if (lane == 0) {
       for (int s = 0; s < kTcStages; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&empty[s], 1 + kTcBoxes);
+        mbar_init(&empty[s], ZC ? 1 : 1 + kTcBoxes);   // ZC: the UMMAs (which wait for the consumers) are the last readers
+        mbar_init(&ready[s], kTcBoxes);
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);
@@ -177,7 +204,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
     }
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
-                 "n"(kTcTmemCols));
+                 "n"(Cfg::kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
   if (threadIdx.x < 2 * kCollapseN) (&s_coll[0][0])[threadIdx.x] = 0ull;
@@ -225,10 +252,10 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
               // arena (row kOobRow), i.e. zero-filled by TMA, instead of from the next gene's block
               const int ch = (kb >> 7) + b;
               const bool in = ch < nchunks;
-              tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kAOff, mg, 0, in ? row0 + ch * Mg : kOobRow, &full[s], kEvictFirst);
+              tma_load_2d(st + Cfg::g_off(b), mg, 0, in ? row0 + ch * Mg : kOobRow, &full[s], kEvictFirst);
               if (PAIR)
                 tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kBOff, mgb, 0, in ? row0b + ch * Mgb : kOobRow, &full[s], kEvictFirst);
-              if (!(dbg_skip & 4)) tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kEOff, &map_e, kb + b * kTcBoxK, 0, &full[s], kEvictLast);
+              if (!(dbg_skip & 4)) tma_load_2d(st + Cfg::e_off(b), &map_e, kb + b * kTcBoxK, 0, &full[s], kEvictLast);
             }
           }
           __syncwarp();
@@ -238,7 +265,9 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 64, N = 64 + ER
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cfg::kNC >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
+    // WIDE: M = 128, N = 2 * (64 + ER)
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((WIDE ? 2 * Cfg::kNC : Cfg::kNC) >> 3) << 17) |
+                           ((uint32_t)((WIDE ? 2 * kTileRows : kTileRows) >> 4) << 24);
     uint32_t it = 0, ui = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
       const int gi = u / S, sp = u - gi * S;
@@ -249,23 +278,34 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
       const int a = ui & 1;
       mbar_wait(&tempty[a], ((ui >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)a * 128u;
+      const uint32_t tmem_d = tmem_base + (uint32_t)(a * Cfg::kAccCols);
       for (int ks = 0; ks < nsteps; ++ks, ++it) {
         const int s = it % kTcStages;
         const uint32_t ph = (it / kTcStages) & 1;
         mbar_wait(&full[s], ph);
+        if (ZC) mbar_wait(&ready[s], ph);
         tc_fence_after();
         __syncwarp();
         if (elect_one_sync()) {
           const uint32_t st = smem_u32(tiles + (size_t)s * Cfg::kStageBytes);
+          if constexpr (WIDE) {
 #pragma unroll
-          for (int b = 0; b < ((dbg_skip & 2) ? 0 : kTcBoxes); ++b) {
-            const uint64_t da0 = umma_desc_sw128(st + b * Cfg::kBoxBytes + Cfg::kAOff);
-            const uint64_t db0 = umma_desc_sw128(st + b * Cfg::kBoxBytes + Cfg::kBOff);
+            for (int p = 0; p < ((dbg_skip & 2) ? 0 : kTcBoxes / 2); ++p) {
+              // A = rows 0..127 of the pair (two genotype tiles), B = all 128 + 2 ER rows of it
+              const uint64_t d0 = umma_desc_sw128(st + p * Cfg::kPairBytes);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // advance 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-              umma_i8(tmem_d, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, (ks | b | k) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) umma_i8(tmem_d, d0 + (uint64_t)(2 * k), d0 + (uint64_t)(2 * k), idesc, (ks | p | k) ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int b = 0; b < ((dbg_skip & 2) ? 0 : kTcBoxes); ++b) {
+              const uint64_t da0 = umma_desc_sw128(st + b * Cfg::kBoxBytes + Cfg::kAOff);
+              const uint64_t db0 = umma_desc_sw128(st + b * Cfg::kBoxBytes + Cfg::kBOff);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                // advance 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+                umma_i8(tmem_d, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, (ks | b | k) ? 1u : 0u);
+              }
             }
           }
           umma_commit(&empty[s]);
@@ -313,7 +353,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
         const int s = it % kTcStages;
         const uint32_t ph = (it / kTcStages) & 1;
         mbar_wait(&full[s], ph);
-        const uint8_t* box = tiles + (size_t)s * Cfg::kStageBytes + cw * Cfg::kBoxBytes;
+        const uint8_t* box = tiles + (size_t)s * Cfg::kStageBytes + Cfg::g_off(cw);
         const int64_t ksamp = k0 + (int64_t)ks * kTcStageK + cw * kTcBoxK + 4 * lane;
         uint32_t z = 0;
         if (PAIR || (dbg_skip & 1)) {
@@ -347,12 +387,28 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
             }
           }
         }
+        if (ZC) {
+          // samples at/after k1 are zero-filled but a flipped row would count them: mask
+          int64_t rem = k1 - ksamp;
+          uint32_t vm = rem >= 4 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - (int)rem))));
+          z &= vm;
+          const uint32_t c = ((z + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
+          // rows M and M+1 of this box's genotype tile (never written by TMA: its box has M rows)
+          uint8_t* wbox = tiles + (size_t)s * Cfg::kStageBytes + Cfg::g_off(cw);
+          *reinterpret_cast<uint32_t*>(wbox + sw128_word_off(M, lane)) = z;
+          *reinterpret_cast<uint32_t*>(wbox + sw128_word_off(M + 1, lane)) = c;
+          // generic-proxy stores -> visible to the async proxy (UMMA operand fetch)
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready[s]);
+          continue;
+        }
         if (!PAIR && !(dbg_skip & 1)) {
           int64_t rem = k1 - ksamp;
           uint32_t vm = rem >= 4 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - (int)rem))));
           z &= vm;
           const uint32_t c = ((z + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
-          const uint8_t* ebox = box + Cfg::kEOff;
+          const uint8_t* ebox = tiles + (size_t)s * Cfg::kStageBytes + Cfg::e_off(cw);
 #pragma unroll
           for (int e = 0; e < ER; ++e) {
             int ew = *reinterpret_cast<const int*>(ebox + (e >> 3) * 1024 + woff[e & 7]);
@@ -367,24 +423,66 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
       }
       // ---- collapse sums of this unit: warp reduce (int64), combine the 4 warps through smem
       const int cb = ui & 1;
+      if constexpr (!ZC) {
 #pragma unroll
-      for (int e = 0; e <= ER; ++e) {
-        long long a = cz[e], b = cc[e];
-        for (int o = 16; o > 0; o >>= 1) {
-          a += __shfl_xor_sync(0xffffffffu, a, o);
-          b += __shfl_xor_sync(0xffffffffu, b, o);
-        }
-        if (lane == 0) {
-          atomicAdd(&s_coll[cb][e], (unsigned long long)a);
-          atomicAdd(&s_coll[cb][(ER + 1) + e], (unsigned long long)b);
+        for (int e = 0; e <= ER; ++e) {
+          long long a = cz[e], b = cc[e];
+          for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+          }
+          if (lane == 0) {
+            atomicAdd(&s_coll[cb][e], (unsigned long long)a);
+            atomicAdd(&s_coll[cb][(ER + 1) + e], (unsigned long long)b);
+          }
         }
       }
       // ---- epilogue: accumulator of this unit -> SweepPartial
       const int a = ui & 1;
       mbar_wait(&tfull[a], (ui >> 1) & 1);
       tc_fence_after();
-      SweepPartial* o = out + u;
-      const uint32_t taddr = tmem_base + (uint32_t)a * 128u + ((uint32_t)(q * 32) << 16);
+      SweepPartial* o = out + (WIDE ? 2 * (size_t)u : (size_t)u);
+      // ZC: rows M / M+1 of D are the Zeggini / CMC burden sums of this unit (digit columns, and the
+      // sum of squares on their own diagonal entry) -> coll[] of the partial, same slots as the dp4a path
+      auto zc_store = [&](SweepPartial* op, int row, int dcol, const uint32_t (&v)[16]) {
+        if (!ZC || (row != M && row != M + 1)) return;
+        const int base = (row == M) ? 0 : (ER + 1);
+        if (dcol >= kTileRows) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) op->coll[base + dcol - kTileRows + i] = nsteps ? (long long)(int)v[i] : 0ll;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (dcol + i == row) op->coll[base + ER] = nsteps ? (long long)(int)v[i] : 0ll;
+        }
+      };
+      if constexpr (WIDE) {
+        // UMMA M=128: row m of D lives in TMEM lane m.  Quadrants 0,1 = even boxes (rows 0..63 of the
+        // gene), quadrants 2,3 = odd boxes; each half goes to its own SweepPartial.
+        const int h = q >> 1;
+        const int row = 32 * (q & 1) + lane;
+        SweepPartial* oh = o + h;
+        const uint32_t taddr = tmem_base + (uint32_t)(a * Cfg::kAccCols) + ((uint32_t)(q * 32) << 16);
+        constexpr int nG = kTileRows / 16, nE = ER / 16;
+#pragma unroll
+        for (int gi2 = 0; gi2 < nG + nE; ++gi2) {
+          if ((gi2 & 1) != egrp) continue;   // the quadrant's two warps alternate column groups
+          const int col = gi2 < nG ? kTileRows * h + 16 * gi2 : 2 * kTileRows + ER * h + 16 * (gi2 - nG);
+          const int dcol = gi2 < nG ? 16 * gi2 : kTileRows + 16 * (gi2 - nG);
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)col, v);
+          tmem_ld_wait();
+          if (row < M) {
+            int4* dst = reinterpret_cast<int4*>(&oh->d[row][dcol]);
+            dst[0] = make_int4((int)v[0], (int)v[1], (int)v[2], (int)v[3]);
+            dst[1] = make_int4((int)v[4], (int)v[5], (int)v[6], (int)v[7]);
+            dst[2] = make_int4((int)v[8], (int)v[9], (int)v[10], (int)v[11]);
+            dst[3] = make_int4((int)v[12], (int)v[13], (int)v[14], (int)v[15]);
+          }
+          zc_store(oh, row, dcol, v);
+        }
+      } else {
+      const uint32_t taddr = tmem_base + (uint32_t)(a * Cfg::kAccCols) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
       for (int c0 = 16 * egrp; c0 < Cfg::kNC; c0 += 32) {   // the quadrant's two warps alternate column groups
         uint32_t v[16];
@@ -399,16 +497,19 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
             dst[2] = make_int4((int)v[8], (int)v[9], (int)v[10], (int)v[11]);
             dst[3] = make_int4((int)v[12], (int)v[13], (int)v[14], (int)v[15]);
           }
+          zc_store(o, row, c0, v);
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[a]);
       // all consumer warps have added their collapse sums -> one warp writes them out
-      asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kTcConsumerWarps) : "memory");
-      if (warp == 2) {
+      if constexpr (!ZC) asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kTcConsumerWarps) : "memory");
+      if (!ZC && warp == 2) {
         for (int i = lane; i < 2 * (ER + 1); i += 32) {
           o->coll[i] = (long long)s_coll[cb][i];
+          if (WIDE) o[1].coll[i] = 0ll;   // the collapse sums of a unit live in its first partial
           s_coll[cb][i] = 0ull;
         }
       }
@@ -419,7 +520,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(kTcTmemCols));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(Cfg::kTmemCols));
   }
 }
 
@@ -434,6 +535,9 @@ struct TcSegments {
   int boxes = 4;            // 128-sample boxes per pipeline stage for ER=16: 4 (5 stages) or 2 (10 stages)
   int l2promo = 2;          // CUtensorMapL2promotion: 0 none, 1 64B, 2 128B, 3 256B
   int dbg_skip = 0;         // timing experiments (see k_sweep_tc)
+  bool wide = false;        // M=128 two-box UMMAs (TcCfg WIDE; 2 partials per (gene, split)): measured no faster, the
+                            // sweep is bound by the shared-memory data pipe, not by UMMA issue (profiles/)
+  bool zc = true;           // burden scores through the UMMA (TcCfg ZC) when every gene has M <= 62
   bool overlap_smem = false; // leave room in SMEM for a co-resident k_finalize CTA (4-stage ring)
   char why[128] = "";
   bool have_e = false;
@@ -465,6 +569,13 @@ inline int tc_init(TcSegments* tc, char* err, size_t errlen) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 4, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 4, false, 4>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 10, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 10, false, 2>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4, false, 4>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 5, false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5, false, 4, true>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 4, false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 4, false, 4, true>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4, false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4, false, 4, true>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 5, false, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5, false, 4, false, true>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 5, false, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5, false, 4, true, true>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4, false, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4, false, 4, false, true>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4, false, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4, false, 4, true, true>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 3, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 3, true, 4>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 2, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 2, true, 4>::kSmem);
   if (e != cudaSuccess) {
@@ -563,6 +674,9 @@ inline int tc_prepare_maps(TcSegments* tc, int seg, const GeneDesc* h_genes, int
   return 0;
 }
 
+// SweepPartials written per (gene, split) by the gene sweep
+inline int tc_parts_per_unit(const TcSegments* tc) { return (tc->wide && tc->boxes == 4) ? 2 : 1; }
+
 inline bool tc_usable(TcSegments* tc, const GeneDesc* h_genes, int n) {
   if (!tc->encode) return false;
   if (!tc->have_e) {
@@ -585,7 +699,7 @@ inline bool tc_usable(TcSegments* tc, const GeneDesc* h_genes, int n) {
 inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_genes, int n, const uint8_t* d_flags,
                      const NullModel* /*d_nm*/, int64_t N, int ER, int S, int64_t chunk, SweepPartial* d_parts,
                      unsigned int* /*counter*/, int sm_count, cudaStream_t st, char* err, size_t errlen,
-                     bool pair = false) {
+                     bool pair = false, bool wide = false) {
   const int seg = h_genes[0].seg;
   const int grid = std::min(n * S, sm_count);
   if (chunk % kTcChunkAlign != 0) {
@@ -594,10 +708,27 @@ inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_
   }
   int rc = tc_prepare_maps(tc, seg, h_genes, n, st, err, errlen);
   if (rc) return rc;
-#define RVT_TC_LAUNCH(ER_, ST_, PAIR_, BX_)                                                                                  \
-  k_sweep_tc<ER_, ST_, PAIR_, BX_><<<grid, kTcThreads, TcCfg<ER_, ST_, PAIR_, BX_>::kSmem, st>>>(                           \
+#define RVT_TC_LAUNCH(ER_, ST_, PAIR_, BX_, ...)                                                                             \
+  k_sweep_tc<ER_, ST_, PAIR_, BX_, ##__VA_ARGS__><<<grid, kTcThreads, TcCfg<ER_, ST_, PAIR_, BX_, ##__VA_ARGS__>::kSmem, st>>>( \
       tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts, tc->dbg_skip)
-  if (pair && ER == 16)
+  // burden scores through the UMMA: two spare tile rows and |z . digit| sums that fit int32
+  bool zc = tc->zc && !pair && !tc->overlap_smem && tc->boxes == 4 && chunk <= 262144;
+  for (int i = 0; i < n && zc; ++i) zc = h_genes[i].M <= kTileRows - 2;
+  if (zc && wide && ER == 16)
+    RVT_TC_LAUNCH(16, 5, false, 4, true, true);
+  else if (zc && wide)
+    RVT_TC_LAUNCH(32, 4, false, 4, true, true);
+  else if (zc && ER == 16)
+    RVT_TC_LAUNCH(16, 5, false, 4, false, true);
+  else if (zc)
+    RVT_TC_LAUNCH(32, 4, false, 4, false, true);
+  else if (wide && !pair && ER == 16 && tc->overlap_smem)
+    RVT_TC_LAUNCH(16, 4, false, 4, true);
+  else if (wide && !pair && ER == 16)
+    RVT_TC_LAUNCH(16, 5, false, 4, true);
+  else if (wide && !pair)
+    RVT_TC_LAUNCH(32, 4, false, 4, true);
+  else if (pair && ER == 16)
     RVT_TC_LAUNCH(16, 3, true, 4);
   else if (pair)
     RVT_TC_LAUNCH(32, 2, true, 4);
