@@ -110,10 +110,43 @@ RVT_HDN int jacobi_eigenvalues(double* a, int n, int lda, double* cs, const Par&
 // -----------------------------------------------------------------------------------------------
 // Faster path used by the kernels: Householder tridiagonalisation (parallel mat-vec and rank-2
 // update over the group) followed by Sturm-sequence bisection, one eigenvalue per thread.
-// ~n^3*4/3 flops and ~5n group barriers instead of ~10 Jacobi sweeps of 3(n-1) barriers each.
+// ~n^3*4/3 flops and ~6n group barriers instead of ~10 Jacobi sweeps of 3(n-1) barriers each.
 // Accuracy: backward stable, |d lambda| <~ n eps ||A|| -- the same class as Jacobi for this path
 // (p-values depend on lambda / lambda_max).
-//
+
+// #{eigenvalues of the symmetric tridiagonal (d, e2 = e^2) that are < x}: sign changes of the
+// Sturm sequence p_0 = 1, p_1 = d_0 - x, p_{i+1} = (d_i - x) p_i - e_{i-1}^2 p_{i-1}.  The usual
+// ratio form q_i = p_i / p_{i-1} costs one fp64 DIVISION per step (a ~25-instruction dependent
+// chain on the GPU; 52 bisection steps x n of them per eigenvalue was two thirds of the solver's
+// time); the polynomial form costs two FMAs.  Its classical weakness -- over/underflow of p_i --
+// is handled by rescaling the pair (p_i, p_{i-1}), which leaves every ratio and hence every sign
+// unchanged.  An exact zero counts as a negative ratio, like q = -pivmin in the ratio form.
+// The caller scales the matrix so that |d_i - x| <= 4 and e2 <= 1.
+RVT_HD int sturm_count(const double* d, const double* e2, int n, double x) {
+  double pp = 1.0;          // p_{i-1}
+  double pm = d[0] - x;     // p_i
+  if (pm == 0.0) pm = -1e-300;
+  int cnt = pm < 0.0;
+  for (int i = 1; i < n; ++i) {
+    double p = (d[i] - x) * pm - e2[i - 1] * pp;
+    const double ap = fabs(p);
+    if (!(ap >= 1e-200 && ap <= 1e200)) {
+      if (p == 0.0) {
+        // zero pivot: a tiny value of the sign opposite to p_i
+        const double t = fmax(fabs(pm) * 1e-290, 1e-305);
+        p = (pm < 0.0) ? t : -t;
+      }
+      const double sc = (ap > 1.0) ? 1e-200 : 1e200;
+      p *= sc;
+      pm *= sc;
+    }
+    cnt += (p < 0.0) != (pm < 0.0);
+    pp = pm;
+    pm = p;
+  }
+  return cnt;
+}
+
 // a: n x n symmetric, row-major, lda (destroyed).  d[n], e[n], v[n], p[n]: group-visible scratch.
 // out[n]: eigenvalues in DESCENDING order.
 template <class Par>
@@ -124,6 +157,10 @@ RVT_HDN void sym_eigenvalues_tridiag(double* a, int n, int lda, double* d, doubl
     par.sync();
     return;
   }
+  // thread (ti, tj) of a W-wide grid over the group: rows are dealt to ti, columns to tj, so the
+  // inner loops run over consecutive addresses with no integer division
+  const int W = par.nt() < 32 ? par.nt() : 32;
+  const int ti = par.tid() / W, tj = par.tid() - ti * W, nti = par.nt() / W;
   for (int k = 0; k < n - 2; ++k) {
     const int m = n - k - 1;          // size of the trailing block; x = a[k+1.., k]
     double* x = a + (k + 1) * lda + k;  // stride lda
@@ -144,26 +181,33 @@ RVT_HDN void sym_eigenvalues_tridiag(double* a, int n, int lda, double* d, doubl
     const double beta = 2.0 / (v0 * v0 + ss);
     for (int i = par.tid(); i < m; i += par.nt()) v[i] = (i == 0) ? v0 : x[i * lda];
     par.sync();
-    // p = beta * A22 v
+    // p = beta * A22 v : one row per thread (rows are lda apart: an odd lda keeps the banks distinct)
     double* a22 = a + (k + 1) * lda + (k + 1);
-    for (int i = par.tid(); i < m; i += par.nt()) {
-      double s = 0.0;
-      const double* row = a22 + i * lda;
-      for (int j = 0; j < m; ++j) s += row[j] * v[j];
-      p[i] = beta * s;
-    }
-    par.sync();
     double pv = 0.0;
     dummy = 0.0;
-    for (int i = par.tid(); i < m; i += par.nt()) pv += p[i] * v[i];
-    par.allreduce2(pv, dummy);
+    for (int i = par.tid(); i < m; i += par.nt()) {
+      double s0 = 0.0, s1 = 0.0;
+      const double* row = a22 + i * lda;
+      int j = 0;
+      for (; j + 1 < m; j += 2) {
+        s0 += row[j] * v[j];
+        s1 += row[j + 1] * v[j + 1];
+      }
+      if (j < m) s0 += row[j] * v[j];
+      const double pi = beta * (s0 + s1);
+      p[i] = pi;
+      pv += pi * v[i];
+    }
+    par.allreduce2(pv, dummy);   // (its barriers also publish p)
     const double kk = 0.5 * beta * pv;
-    // w = p - kk v (kept in p);  A22 -= v w' + w v'
-    for (int i = par.tid(); i < m; i += par.nt()) p[i] -= kk * v[i];
-    par.sync();
-    for (int idx = par.tid(); idx < m * m; idx += par.nt()) {
-      const int i = idx / m, j = idx - i * m;
-      a22[i * lda + j] -= v[i] * p[j] + p[i] * v[j];
+    // w = p - kk v ;  A22 -= v w' + w v'   (w formed on the fly: p is read-only here)
+    for (int i = ti; i < m; i += nti) {
+      const double vi = v[i], wi = p[i] - kk * vi;
+      double* row = a22 + i * lda;
+      for (int j = tj; j < m; j += W) {
+        const double vj = v[j], wj = p[j] - kk * vj;
+        row[j] -= vi * wj + wi * vj;
+      }
     }
     if (par.tid() == 0) {
       d[k] = a[k * lda + k];
@@ -186,31 +230,34 @@ RVT_HDN void sym_eigenvalues_tridiag(double* a, int n, int lda, double* d, doubl
     ghi = fmax(ghi, d[i] + r);
   }
   const double tnorm = fmax(fabs(glo), fabs(ghi));
-  const double pivmin = fmax(tnorm * tnorm * 1e-300, 1e-300);
-  glo -= 2.0 * tnorm * 2.3e-16 * n + 2.0 * pivmin;
-  ghi += 2.0 * tnorm * 2.3e-16 * n + 2.0 * pivmin;
+  if (!(tnorm > 0.0)) {   // the zero matrix
+    for (int i = par.tid(); i < n; i += par.nt()) out[i] = 0.0;
+    par.sync();
+    return;
+  }
+  // work on T / tnorm (entries in [-1, 1], spectrum in [-3, 3]): v holds d / tnorm, p holds (e / tnorm)^2
+  const double inv = 1.0 / tnorm;
+  par.sync();
+  for (int i = par.tid(); i < n; i += par.nt()) {
+    v[i] = d[i] * inv;
+    const double es = e[i] * inv;
+    p[i] = es * es;
+  }
+  par.sync();
+  const double slo = glo * inv - 2.0 * 2.3e-16 * n - 1e-290, shi = ghi * inv + 2.0 * 2.3e-16 * n + 1e-290;
   // eigenvalue with ascending index kidx: bisection on #{eigenvalues < x} (Sturm count)
   for (int kidx = par.tid(); kidx < n; kidx += par.nt()) {
-    double lo = glo, hi = ghi;
+    double lo = slo, hi = shi;
     for (int it = 0; it < 120; ++it) {
       const double mid = 0.5 * (lo + hi);
       if (mid <= lo || mid >= hi) break;  // interval is one ulp wide
-      int cnt = 0;
-      double q = d[0] - mid;
-      if (fabs(q) < pivmin) q = -pivmin;
-      cnt += (q < 0.0);
-      for (int i = 1; i < n; ++i) {
-        q = d[i] - mid - e[i - 1] * e[i - 1] / q;
-        if (fabs(q) < pivmin) q = -pivmin;
-        cnt += (q < 0.0);
-      }
-      if (cnt <= kidx)
+      if (sturm_count(v, p, n, mid) <= kidx)
         lo = mid;
       else
         hi = mid;
-      if (hi - lo <= 4.0e-16 * tnorm) break;
+      if (hi - lo <= 4.0e-16) break;
     }
-    out[n - 1 - kidx] = 0.5 * (lo + hi);
+    out[n - 1 - kidx] = 0.5 * (lo + hi) * tnorm;
   }
   par.sync();
 }

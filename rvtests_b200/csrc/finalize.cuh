@@ -17,13 +17,24 @@
 #include "eigen.cuh"
 #include "skato_tail.cuh"
 
+#include <type_traits>
+
 namespace rvt {
 
-constexpr int kFinThreads = 128;
-constexpr int kKld = kTileRows + 1;  // padded leading dimension of K in shared memory
-// dynamic shared memory: K (fp64, 64 x 65) + the reduced gene x digit columns (int64, 64 x 32)
-constexpr int kFinSmem = kTileRows * kKld * 8 + kTileRows * kMaxER * 8;
-constexpr int kFinSmemSkato = kFinSmem + kTileRows * kKld * 8;   // + Wm = Z1'Z1 kept for the rho grid
+// Threads per gene: the per-gene tail is a chain of short dependent fp64 phases (latency-bound), so
+// what buys throughput is MANY resident genes per SM, not many threads per gene: 64 threads x <= 128
+// registers and ~30 KB of shared memory allow 8 genes per SM (it was 3 with 128 threads and 60 KB).
+// SKAT-O keeps 128 threads (one warp per Kronrod node group in its quadrature).
+constexpr int kFinThreads = 64;
+constexpr int kFinThreadsSkato = 128;
+// dynamic shared memory, sized by the widest gene of the launch (Mmax): K (fp64, Mmax x kld, kld odd
+// so that rows AND columns are bank-conflict free); the reduced gene x digit sums De (int64,
+// Mmax x ER) live in the same bytes (they are dead before K is built); SKAT-O adds Wm = Z1'Z1.
+static inline int fin_kld(int Mmax) { return Mmax | 1; }
+static inline int fin_smem(int Mmax, int ER, bool skato) {
+  const int k = Mmax * fin_kld(Mmax) * 8, de = Mmax * ER * 8;
+  return (k > de ? k : de) + (skato ? k : 0);
+}
 constexpr int kQagsLimit = 1000;   // Integration::limit (regression/GSLIntegration.cpp:7-15)
 
 // per-gene QAGS interval list in global memory (touched by one thread only)
@@ -37,8 +48,10 @@ __device__ __forceinline__ long long recombine4(const long long* d) {
   return d[0] + (d[1] << 8) + (d[2] << 16) + (d[3] << 24);
 }
 
-__global__ void __launch_bounds__(kFinThreads)
-k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __restrict__ rowflags,
+template <bool SKATO>
+__global__ void __launch_bounds__(SKATO ? kFinThreadsSkato : kFinThreads)
+k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(Mmax of this launch) */,
+           int wm_off /* byte offset of Wm inside the dynamic shared memory (SKAT-O) */, const uint8_t* __restrict__ rowflags,
            const double* __restrict__ af, const RowCounts* __restrict__ counts,
            const NullModel* __restrict__ nm, EngineParams prm, int S,
            const SweepPartial* __restrict__ parts, rvt_gene_result* __restrict__ res,
@@ -48,16 +61,21 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
                                                 then `genes`/`parts` are unused and res is indexed through out_index */,
            const int* __restrict__ out_index) {
   extern __shared__ __align__(16) uint8_t dyn[];
-  double* K = reinterpret_cast<double*>(dyn);                               // [64][kKld]
-  long long* De = reinterpret_cast<long long*>(dyn + kTileRows * kKld * 8); // [64][kMaxER] gene x digit sums
-  double* Wm = reinterpret_cast<double*>(dyn + kFinSmem);                   // [64][kKld], SKAT-O only
-  __shared__ QagsMachine s_mach;
-  __shared__ double s_fv[21], s_bcast[3], s_c[kTileRows + 2], s_lamz[kTileRows + 2], s_vw[kTileRows];
+  constexpr int NT = SKATO ? kFinThreadsSkato : kFinThreads;
+  double* K = reinterpret_cast<double*>(dyn);                // [Mmax][kld]
+  long long* De = reinterpret_cast<long long*>(dyn);         // [Mmax][ER] gene x digit sums, dead before K is written
+  double* Wm = reinterpret_cast<double*>(dyn + wm_off);      // [Mmax][kld], SKAT-O only
+  struct SkatoShared {   // SKAT-O only
+    QagsMachine mach;
+    double fv[21], bcast[3], c[kTileRows + 2], lamz[kTileRows + 2];
+  };
+  __shared__ typename std::conditional<SKATO, SkatoShared, int>::type s_sk;
+  __shared__ double s_vw[kTileRows];
   __shared__ long long s_ajj[kTileRows];
   __shared__ double s_red[64];
   __shared__ double s_e[kTileRows + 2], s_v[kTileRows + 2], s_p[kTileRows + 2];
   __shared__ double s_ev[kTileRows], s_lam[kTileRows];
-  __shared__ int s_th[(kFinThreads / 32) * kTileRows];   // Davies order scratch, one slice per warp
+  __shared__ int s_th[(NT / 32) * kTileRows];   // Davies order scratch, one slice per warp
   __shared__ long long s_coll[kCollapseN];
   __shared__ long long s_craw[kTileRows];
   __shared__ int s_idx[kTileRows], s_flip[kTileRows];
@@ -102,30 +120,30 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
       s_bur[1][0] = ti.cmcU; s_bur[1][1] = ti.cmcSS;
       for (int l = 0; l < C; ++l) { s_bur[0][2 + l] = ti.zegSZ[l]; s_bur[1][2 + l] = ti.cmcSZ[l]; }
     }
-    for (int idx = tid; idx < ti.Mp * ti.Mp; idx += kFinThreads) {
+    for (int idx = tid; idx < ti.Mp * ti.Mp; idx += NT) {
       const int i = idx / ti.Mp, k = idx - i * ti.Mp;
-      K[i * kKld + k] = ti.K[idx];
+      K[i * kld + k] = ti.K[idx];
     }
     if (tid < ti.Mp) s_vw[tid] = ti.vw[tid];
     __syncthreads();
   } else {
   // 1. reduce the splits (int64): gene x digit columns and the diagonal; the gene x gene block is
   //    summed on the fly where K is built (each entry is needed exactly once)
-  for (int idx = tid; idx < M * ER; idx += kFinThreads) {
+  for (int idx = tid; idx < M * ER; idx += NT) {
     const int i = idx / ER, e = idx - i * ER;
     long long s = 0;
     for (int sp = 0; sp < S; ++sp) s += gp[sp].d[i][kTileRows + e];
-    De[i * kMaxER + e] = s;
+    De[i * ER + e] = s;
   }
   if (tid < M) {
     long long s = 0;
     for (int sp = 0; sp < S; ++sp) s += gp[sp].d[tid][tid];
     s_ajj[tid] = s;
   }
-  if (tid < 2 * (ER + 1)) {
+  for (int i = tid; i < 2 * (ER + 1); i += NT) {
     long long s = 0;
-    for (int sp = 0; sp < S; ++sp) s += parts[(size_t)g * S + sp].coll[tid];
-    s_coll[tid] = s;
+    for (int sp = 0; sp < S; ++sp) s += parts[(size_t)g * S + sp].coll[i];
+    s_coll[i] = s;
   }
   if (tid == 0) s_bad = 0;
   __syncthreads();
@@ -134,7 +152,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   // 2. per-variant counts -> flip / monomorphic, cross-checked with the flags the sweep used
   if (tid < M) {
     // intercept = vector 1 (X column 0): fixed-point image of 1.0 is 2^e exactly
-    long long cint = recombine4(&De[tid * kMaxER + 4]);
+    long long cint = recombine4(&De[tid * ER + 4]);
     double cd = (double)cint * nm->scale[1];
     long long c = llrint(cd);
     long long ajj = s_ajj[tid];
@@ -162,11 +180,11 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   if (tid < Mp) {
     const int j = s_idx[tid];
     const int fl = s_flip[j];
-    long long sint = recombine4(&De[j * kMaxER]);
+    long long sint = recombine4(&De[j * ER]);
     if (fl) sint = 2 * nm->vsum[0] - sint;
     s_s[tid] = (double)sint * nm->scale[0];
     for (int l = 0; l < C; ++l) {
-      long long b = recombine4(&De[j * kMaxER + 4 * (l + 1)]);
+      long long b = recombine4(&De[j * ER + 4 * (l + 1)]);
       if (fl) b = 2 * nm->vsum[l + 1] - b;
       s_B[tid][l] = (double)b * nm->scale[l + 1];
     }
@@ -181,7 +199,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
     s_Q = q;
   }
   // 4. K = W^1/2 sigma2 (A' - B' (X'X)^-1 B'^T) W^1/2   (upper triangle, mirrored)
-  for (int idx = tid; idx < Mp * Mp; idx += kFinThreads) {
+  for (int idx = tid; idx < Mp * Mp; idx += NT) {
     const int i = idx / Mp, k = idx - i * Mp;
     if (k < i) continue;
     const int ji = s_idx[i], jk = s_idx[k];
@@ -202,8 +220,8 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
       t += s_B[i][l] * u;
     }
     double v = s_sw[i] * s_sw[k] * sigma2 * ((double)a - t);
-    K[i * kKld + k] = v;
-    K[k * kKld + i] = v;
+    K[i * kld + k] = v;
+    K[k * kld + i] = v;
   }
   __syncthreads();
   phase(1);
@@ -220,13 +238,13 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   }  // !tin
   const int Mp = s_Mp;
 
-  if (qags) {
+  if (SKATO && qags) {
     // SKAT-O: Z1'Z1 = W (G'G - G'X (X'X)^-1 X'G) W / 2 with the UN-squared weights = K / (2 sigma2)
     // (sqrt of the squared SKAT weight is the SKAT-O weight: src/Model.h:2652-2656 vs :2807-2809)
     const double sc = 0.5 / sigma2;
-    for (int idx = tid; idx < Mp * Mp; idx += kFinThreads) {
+    for (int idx = tid; idx < Mp * Mp; idx += NT) {
       const int i = idx / Mp, k = idx - i * Mp;
-      Wm[i * kKld + k] = K[i * kKld + k] * sc;
+      Wm[i * kld + k] = K[i * kld + k] * sc;
     }
     if (tid < Mp) s_vw[tid] = s_sw[tid] * s_s[tid];
     __syncthreads();
@@ -236,7 +254,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   double p_dav = -1.0, p_liu = 1.0, p_fin = 1.0, lam_max = 0.0;
   int fault = 0, r = 0;
   if (Mp > 0) {
-    sym_eigenvalues_tridiag(K, Mp, kKld, s_ev, s_e, s_v, s_p, s_lam, par);
+    sym_eigenvalues_tridiag(K, Mp, kld, s_ev, s_e, s_v, s_p, s_lam, par);
     phase(2);
     const int r_ub = (N < (int64_t)Mp) ? (int)N : Mp;
     while (r < r_ub && s_lam[r] > 1e-30) ++r;
@@ -254,11 +272,14 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __res
   SkatoOut so;
   so.ok = 0;
   so.Q = so.rho = so.pvalue = 0.0;
-  if (qags && Mp > 0) {
-    QagsWork work{qags[g].a, qags[g].b, qags[g].r, qags[g].e, qags[g].order, qags[g].level, kQagsLimit};
-    const double s2 = sigma2 * (double)N / (double)(N - 1);   // ||r||^2/(N-1), SkatO.cpp:136-137
-    so = skato_tail(Wm, K, Mp, kKld, s_vw, s2, s_ev, s_e, s_v, s_p, s_lamz, s_c, &s_mach, work, s_fv, s_bcast, s_th, kTileRows, par);
-    phase(5);
+  if constexpr (SKATO) {
+    if (qags && Mp > 0) {
+      QagsWork work{qags[g].a, qags[g].b, qags[g].r, qags[g].e, qags[g].order, qags[g].level, kQagsLimit};
+      const double s2 = sigma2 * (double)N / (double)(N - 1);   // ||r||^2/(N-1), SkatO.cpp:136-137
+      so = skato_tail(Wm, K, Mp, kld, s_vw, s2, s_ev, s_e, s_v, s_p, s_sk.lamz, s_sk.c, &s_sk.mach, work, s_sk.fv, s_sk.bcast, s_th,
+                      kTileRows, par);
+      phase(5);
+    }
   }
 
   // 7. burden score tests (m = 1)

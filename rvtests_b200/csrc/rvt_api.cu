@@ -39,9 +39,6 @@ struct rvt_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
-  cudaStream_t stream2 = nullptr;      // per-gene statistics of batch i overlap the sweep of batch i+1
-  bool overlap = false;   // measured on B200: co-resident finalize CTAs steal issue slots from the (issue-bound)
-                          // collapse warps of the sweep -- 17.8 ms/step overlapped vs 16.9 ms serial at 2 500 genes
   std::vector<cudaEvent_t> evpool;
   int pending_timing_batches = 0;
   char err[512] = {0};
@@ -200,7 +197,6 @@ int rvt_ctx_create(int device, rvt_ctx** out) {
              prop.major, prop.minor);
   RVT_CUDA_OK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
-  RVT_CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   for (auto& ev : ctx->ev) RVT_CUDA_OK(cudaEventCreate(&ev));
   RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_nm, sizeof(NullModel)));
   RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_counter, sizeof(unsigned int) * 4));
@@ -209,7 +205,8 @@ int rvt_ctx_create(int device, rvt_ctx** out) {
   RVT_CUDA_OK(cudaMalloc((void**)&ctx->dbeta, sizeof(double) * kMaxC));
   RVT_CUDA_OK(cudaMalloc((void**)&ctx->dnull_part, sizeof(double) * kNullBlocks * kNullAcc));
   RVT_CUDA_OK(cudaFuncSetAttribute(k_sweep_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, kSimtSmem));
-  RVT_CUDA_OK(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinSmemSkato));
+  RVT_CUDA_OK(cudaFuncSetAttribute(k_finalize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fin_smem(kTileRows, kMaxER, false)));
+  RVT_CUDA_OK(cudaFuncSetAttribute(k_finalize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fin_smem(kTileRows, kMaxER, true)));
   int rc = tc_init(&ctx->tc, ctx->err, sizeof(ctx->err));
   if (rc) return rc;
   return RVT_OK;
@@ -228,7 +225,6 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& e : ctx->evpool) cudaEventDestroy(e);
-  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -247,13 +243,8 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "splits") {
     if (value < 0 || value > 64) CTX_FAIL(RVT_E_BADARG, "splits must be in 0..64");
     ctx->splits = (int)value;
-  } else if (k == "overlap") {
-    ctx->overlap = value != 0;
   } else if (k == "skato") {
     ctx->skato = value != 0;
-  } else if (k == "tc_stages") {
-    if (value != 4 && value != 5) CTX_FAIL(RVT_E_BADARG, "tc_stages must be 4 or 5");
-    ctx->tc.stages = (int)value;
   } else if (k == "tc_boxes") {
     if (value != 2 && value != 4) CTX_FAIL(RVT_E_BADARG, "tc_boxes must be 2 or 4");
     ctx->tc.boxes = (int)value;
@@ -625,13 +616,12 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   int64_t chunk = (((N + S - 1) / S) + 511) & ~(int64_t)511;
   S = (int)((N + chunk - 1) / chunk);
   if (chunk > ((int64_t)1 << 22)) CTX_FAIL(RVT_E_UNSUPPORTED, "split of %lld samples exceeds the int32 accumulation bound; raise 'splits'", (long long)chunk);
-  // Batches of genes flow through two streams: the sweep of batch i+1 (HBM-bound) runs on `st`
-  // while the per-gene statistics of batch i (latency / fp64-bound, no HBM traffic) run on `st2`;
-  // the partials are double-buffered.  With overlap off (or SKAT-O on: its finalize dwarfs the
-  // sweep) one big batch per launch is used instead.
-  const bool overlap = ctx->overlap && !ctx->skato && n > ctx->sm_count;
-  const int batch = overlap ? std::min(n, 2 * ctx->sm_count) : std::min(n, 2048);
-  const int nbuf = overlap ? 2 : 1;
+  // One sweep launch + one statistics launch per batch of <= 2048 genes, back to back on the context
+  // stream.  (Running the statistics of batch i beside the sweep of batch i+1 on a second stream was
+  // built and measured twice -- 17.8 vs 16.9 ms/step with the first sweep, 12.9 vs 11.8 ms with the
+  // current one: the sweep needs its 5-stage ring, i.e. the whole shared memory -- and removed.)
+  const int batch = std::min(n, 2048);
+  const int nbuf = 1;
   int engine = ctx->engine;
   if (ctx->stage_used > 0) {
     // bind the whole capacity: the maps stay valid while the arena does not move
@@ -663,7 +653,7 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   }
   ctx->last_n = n;
   cudaStream_t st = ctx->stream;
-  cudaStream_t st2 = overlap ? ctx->stream2 : st;
+  cudaStream_t st2 = st;
   const int nbatch = (n + batch - 1) / batch;
   // per batch: [0] sweep start, [1] sweep end, [2] finalize start, [3] finalize end
   while ((int)ctx->evpool.size() < 4 * nbatch) {
@@ -683,13 +673,11 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   EngineParams prm{ctx->beta1, ctx->beta2};
   if (engine == RVT_ENGINE_TC && (rc = tc_prepare_maps(&ctx->tc, ctx->genes[0].seg, ctx->genes.data(), n, st, ctx->err, sizeof(ctx->err))))
     return rc;   // encode every box height up front: no host sync inside the pipelined loop
-  ctx->tc.overlap_smem = overlap;
   for (int bi = 0; bi < nbatch; ++bi) {
     const int b0 = bi * batch;
     const int nb = std::min(batch, n - b0);
     SweepPartial* parts = ctx->d_parts + (size_t)(bi % nbuf) * batch * Sp;
     cudaEvent_t* ev = &ctx->evpool[4 * bi];
-    if (overlap && bi >= 2) RVT_CUDA_OK(cudaStreamWaitEvent(st, ctx->evpool[4 * (bi - 2) + 3], 0));  // buffer free again
     RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), st));
     RVT_CUDA_OK(cudaEventRecord(ev[0], st));
     if (engine == RVT_ENGINE_SIMT) {
@@ -701,19 +689,22 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       if (rc) return rc;
     }
     RVT_CUDA_OK(cudaEventRecord(ev[1], st));
-    if (overlap) RVT_CUDA_OK(cudaStreamWaitEvent(st2, ev[1], 0));
     RVT_CUDA_OK(cudaEventRecord(ev[2], st2));
-    k_finalize<<<nb, kFinThreads, ctx->skato ? kFinSmemSkato : kFinSmem, st2>>>(
-        ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, d_res + b0,
-        ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->skato ? ctx->d_qags : nullptr, nullptr, nullptr);
+    int Mmax = 1;
+    for (int i = 0; i < nb; ++i) Mmax = std::max(Mmax, ctx->genes[b0 + i].M);
+    const int kld = fin_kld(Mmax), fsm = fin_smem(Mmax, ctx->ER, ctx->skato), wm_off = Mmax * kld * 8;
+    if (ctx->skato)
+      k_finalize<true><<<nb, kFinThreadsSkato, fsm, st2>>>(
+          ctx->d_genes + b0, nb, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, d_res + b0,
+          ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->d_qags, nullptr, nullptr);
+    else
+      k_finalize<false><<<nb, kFinThreads, fsm, st2>>>(
+          ctx->d_genes + b0, nb, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, d_res + b0,
+          ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, nullptr, nullptr, nullptr);
     RVT_CUDA_OK(cudaEventRecord(ev[3], st2));
     RVT_CUDA_OK(cudaGetLastError());
     launches += 2;
     ctx->last_parts = (int64_t)nb * Sp;
-  }
-  if (overlap) {   // everything downstream on `st` (copies, the caller's collectives) follows the last statistics
-    RVT_CUDA_OK(cudaStreamWaitEvent(st, ctx->evpool[4 * (nbatch - 1) + 3], 0));
-    if (nbatch >= 2) RVT_CUDA_OK(cudaStreamWaitEvent(st, ctx->evpool[4 * (nbatch - 2) + 3], 0));
   }
   ctx->pending_timing_batches = nbatch;
   if (!ctx->dos.empty()) {
@@ -740,8 +731,15 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     }
     RVT_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
     if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)std::max(nd, batch), sizeof(QagsScratch)))) return rc;
-    k_finalize<<<nd, kFinThreads, ctx->skato ? kFinSmemSkato : kFinSmem, st>>>(nullptr, nd, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S,
-                                                                             nullptr, d_res, nullptr, ctx->skato ? ctx->d_qags : nullptr, d_tin, d_idx);
+    {
+      const int kld = fin_kld(kTileRows), fsm = fin_smem(kTileRows, ctx->ER, ctx->skato), wm_off = kTileRows * kld * 8;
+      if (ctx->skato)
+        k_finalize<true><<<nd, kFinThreadsSkato, fsm, st>>>(nullptr, nd, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S,
+                                                             nullptr, d_res, nullptr, ctx->d_qags, d_tin, d_idx);
+      else
+        k_finalize<false><<<nd, kFinThreads, fsm, st>>>(nullptr, nd, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S,
+                                                         nullptr, d_res, nullptr, nullptr, d_tin, d_idx);
+    }
     RVT_CUDA_OK(cudaGetLastError());
     RVT_CUDA_OK(cudaStreamSynchronize(st));
     launches += 3 * nd + 1;

@@ -538,7 +538,6 @@ struct TcSegments {
   bool wide = false;        // M=128 two-box UMMAs (TcCfg WIDE; 2 partials per (gene, split)): measured no faster, the
                             // sweep is bound by the shared-memory data pipe, not by UMMA issue (profiles/)
   bool zc = true;           // burden scores through the UMMA (TcCfg ZC) when every gene has M <= 62
-  bool overlap_smem = false; // leave room in SMEM for a co-resident k_finalize CTA (4-stage ring)
   char why[128] = "";
   bool have_e = false;
   int ER = 0;
@@ -566,11 +565,9 @@ inline int tc_init(TcSegments* tc, char* err, size_t errlen) {
   }
   tc->encode = fn;
   e = cudaFuncSetAttribute(k_sweep_tc<16, 5, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5, false, 4>::kSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 4, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 4, false, 4>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 10, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 10, false, 2>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4, false, 4>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 5, false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5, false, 4, true>::kSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 4, false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 4, false, 4, true>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4, false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4, false, 4, true>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 5, false, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5, false, 4, false, true>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 5, false, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5, false, 4, true, true>::kSmem);
@@ -712,7 +709,7 @@ inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_
   k_sweep_tc<ER_, ST_, PAIR_, BX_, ##__VA_ARGS__><<<grid, kTcThreads, TcCfg<ER_, ST_, PAIR_, BX_, ##__VA_ARGS__>::kSmem, st>>>( \
       tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts, tc->dbg_skip)
   // burden scores through the UMMA: two spare tile rows and |z . digit| sums that fit int32
-  bool zc = tc->zc && !pair && !tc->overlap_smem && tc->boxes == 4 && chunk <= 262144;
+  bool zc = tc->zc && !pair && tc->boxes == 4 && chunk <= 262144;
   for (int i = 0; i < n && zc; ++i) zc = h_genes[i].M <= kTileRows - 2;
   if (zc && wide && ER == 16)
     RVT_TC_LAUNCH(16, 5, false, 4, true, true);
@@ -722,8 +719,6 @@ inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_
     RVT_TC_LAUNCH(16, 5, false, 4, false, true);
   else if (zc)
     RVT_TC_LAUNCH(32, 4, false, 4, false, true);
-  else if (wide && !pair && ER == 16 && tc->overlap_smem)
-    RVT_TC_LAUNCH(16, 4, false, 4, true);
   else if (wide && !pair && ER == 16)
     RVT_TC_LAUNCH(16, 5, false, 4, true);
   else if (wide && !pair)
@@ -734,8 +729,6 @@ inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_
     RVT_TC_LAUNCH(32, 2, true, 4);
   else if (ER == 16 && tc->boxes == 2)
     RVT_TC_LAUNCH(16, 10, false, 2);
-  else if (ER == 16 && tc->overlap_smem)
-    RVT_TC_LAUNCH(16, 4, false, 4);
   else if (ER == 16)
     RVT_TC_LAUNCH(16, 5, false, 4);
   else

@@ -151,3 +151,31 @@ def test_skato_tail_vs_oracle(hostcheck, oracle, case):
     assert rel(out[0], ref["Q"]) <= 1e-10
     assert out[1] == ref["rho"]
     assert rel(out[2], ref["pvalue"]) <= 1e-8
+
+
+def test_tridiag_hard_spectra(hostcheck):
+    """division-free Sturm counts (rescaled polynomial recurrence): graded, clustered, glued and
+    rank-deficient spectra, the shapes the SKAT kernel matrix W^1/2 (G'PG) W^1/2 produces"""
+    rng = np.random.default_rng(11)
+    mats = []
+    n = 21                                                    # Wilkinson W21+: pairs of close eigenvalues
+    mats.append(np.diag(np.abs(np.arange(n) - 10.0)) + np.diag(np.ones(n - 1), 1) + np.diag(np.ones(n - 1), -1))
+    for n in (8, 33, 50, 64):
+        Qm, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        mats.append((Qm * 10.0 ** np.linspace(0, -18, n)) @ Qm.T)          # graded over 18 decades
+        lam = np.concatenate([np.full(n // 2, 1.0) + 1e-13 * rng.standard_normal(n // 2), np.full(n - n // 2, 1e-9)])
+        mats.append((Qm * lam) @ Qm.T)                                       # two tight clusters
+        B = rng.standard_normal((n, 3))
+        mats.append(B @ B.T * 1e12)                                          # rank 3, huge scale
+        mats.append(B @ B.T * 1e-12)                                         # rank 3, tiny scale
+        D = np.diag(rng.uniform(0.5, 2, n))                                  # glued blocks, 1e-160 coupling
+        D[n // 2, n // 2 - 1] = D[n // 2 - 1, n // 2] = 1e-160
+        mats.append(D)
+    for A in mats:
+        A = 0.5 * (A + A.T)
+        n = A.shape[0]
+        out = np.zeros(n)
+        hostcheck.hc_eigen_tridiag(_p(np.ascontiguousarray(A)), n, _p(out))
+        ref = np.linalg.eigvalsh(A)[::-1]
+        assert np.max(np.abs(out - ref)) <= 2e-13 * np.abs(ref).max(), (n, np.max(np.abs(out - ref)) / np.abs(ref).max())
+        assert np.all(np.diff(out) <= 0)
