@@ -80,7 +80,9 @@ int rvt_ctx_create(int device, rvt_ctx** out);
 void rvt_ctx_destroy(rvt_ctx* ctx);
 const char* rvt_last_error(const rvt_ctx* ctx);
 /* keys: "beta1","beta2" (Beta weight, src/ModelManager.cpp:169-175), "engine", "splits" (0=auto),
- * "skato" (0/1) */
+ * "skato" (0/1), "stream_batch" (B > 0: every B host pushes the engine enqueues sweep + statistics for
+ * them right away, so the kernels run while the next genes are still crossing PCIe; rvt_flush then only
+ * waits for the tail.  0 = everything at flush.  Options apply to genes pushed after the call.) */
 int rvt_set_option(rvt_ctx* ctx, const char* key, double value);
 double rvt_get_info(const rvt_ctx* ctx, const char* key);
 /* run on a caller-owned CUDA stream (cudaStream_t), e.g. the framework's current stream, so that
@@ -113,7 +115,8 @@ int rvt_get_null_model(rvt_ctx* ctx, double* resid, double* sigma2, double* xtx_
  * rvt_gene_push_i8: same, hard calls as int8 [M][ld] variant-major on the host.
  * rvt_gene_push_dev_i8: block already in device memory (zero-copy; must stay valid until flush).
  *   flags: NULL (engine counts the rows itself) or M bytes 0 normal / 1 flip-to-minor / 2 skip.
- * Each push appends one gene; results come back from rvt_flush in push order. */
+ * Each push appends one gene; results come back from rvt_flush in push order.  Host buffers are copied
+ * asynchronously when they are page-locked: keep them valid and unchanged until rvt_flush returns. */
 int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af);
 int rvt_gene_push_i8(rvt_ctx* ctx, const int8_t* G, int M, int64_t ld, const double* af);
 int rvt_gene_push_dev_i8(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const double* af,

@@ -64,6 +64,17 @@ struct rvt_ctx {
   std::vector<int64_t> count_slot; // per gene: offset into d_counts or -1
   std::vector<DosGene> dos;        // pending genes that need the dosage path
   std::vector<int> bed_genes;      // pending genes pushed as PLINK 2-bit rows: checked for missing calls at flush
+  int launched = 0;                // pending genes [0, launched) already have their kernels enqueued (stream_batch)
+  int stream_batch = 0;            // option: enqueue sweep + statistics every this many host pushes (0 = only at flush)
+  bool flush_open = false;         // the timing window of the current flush has started
+  // host pushes land through a ring of buffers on a copy stream: the H2D copy of gene k+1 overlaps the
+  // unpack / re-tile kernel of gene k and the sweeps enqueued by stream_batch
+  static constexpr int kLandRing = 6;
+  cudaStream_t copy_stream = nullptr;
+  int8_t* d_land[kLandRing] = {};
+  size_t cap_land = 0;
+  cudaEvent_t ev_landed[kLandRing] = {}, ev_unpacked[kLandRing] = {};
+  unsigned long long land_seq = 0;
   int64_t n_var = 0;
   // device side arrays (grown on demand)
   GeneDesc* d_genes = nullptr;
@@ -86,8 +97,6 @@ struct rvt_ctx {
   // staging: one growable byte arena of tiled gene blocks, TMA segment kSegStaged
   int8_t* d_stage = nullptr;
   int64_t stage_cap = 0, stage_used = 0;
-  int8_t* d_stage8 = nullptr;   // row-major landing buffer of rvt_gene_push_i8
-  size_t cap_stage8 = 0;
   double* d_stage64 = nullptr;
   size_t cap_stage64 = 0;
   // loaded synthetic cohort
@@ -104,6 +113,19 @@ struct rvt_ctx {
   int64_t last_parts = 0;
   int last_n = 0;
 };
+
+static void pending_reset(rvt_ctx* ctx) {
+  ctx->genes.clear();
+  ctx->userflags.clear();
+  ctx->af.clear();
+  ctx->count_slot.clear();
+  ctx->bed_genes.clear();
+  ctx->n_var = 0;
+  ctx->stage_used = 0;
+  ctx->launched = 0;
+  ctx->pending_timing_batches = 0;
+  ctx->flush_open = false;
+}
 
 #define CTX_FAIL(code, ...)                              \
   do {                                                   \
@@ -198,6 +220,11 @@ int rvt_ctx_create(int device, rvt_ctx** out) {
   RVT_CUDA_OK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
   for (auto& ev : ctx->ev) RVT_CUDA_OK(cudaEventCreate(&ev));
+  RVT_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < rvt_ctx::kLandRing; ++i) {
+    RVT_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_landed[i], cudaEventDisableTiming));
+    RVT_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_unpacked[i], cudaEventDisableTiming));
+  }
   RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_nm, sizeof(NullModel)));
   RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_counter, sizeof(unsigned int) * 4));
   RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_shift, sizeof(int) * (kMaxC + 1)));
@@ -218,13 +245,22 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_stage8};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& e : ctx->evpool) cudaEventDestroy(e);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
+  for (int i = 0; i < rvt_ctx::kLandRing; ++i) {
+    if (ctx->d_land[i]) cudaFree(ctx->d_land[i]);
+    if (ctx->ev_landed[i]) cudaEventDestroy(ctx->ev_landed[i]);
+    if (ctx->ev_unpacked[i]) cudaEventDestroy(ctx->ev_unpacked[i]);
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -248,6 +284,9 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "tc_boxes") {
     if (value != 2 && value != 4) CTX_FAIL(RVT_E_BADARG, "tc_boxes must be 2 or 4");
     ctx->tc.boxes = (int)value;
+  } else if (k == "stream_batch") {
+    if (value < 0 || value > 65536) CTX_FAIL(RVT_E_BADARG, "stream_batch must be in 0..65536");
+    ctx->stream_batch = (int)value;
   } else if (k == "tc_zc") {
     ctx->tc.zc = value != 0;
   } else if (k == "tc_wide") {
@@ -430,6 +469,42 @@ static void launch_count(rvt_ctx* ctx, const int8_t* d, int M, int64_t ld, RowCo
   k_count_rows<<<grid, 256, 0, ctx->stream>>>(d, ld, ctx->N, counts);
 }
 
+// next landing buffer of the host->device ring (>= need bytes); the copy stream waits until the kernel
+// that consumed its previous content has run
+static int land_acquire(rvt_ctx* ctx, size_t need, int* slot) {
+  if (need > ctx->cap_land) {
+    RVT_CUDA_OK(cudaStreamSynchronize(ctx->copy_stream));
+    RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    for (auto& p : ctx->d_land) {
+      if (p) cudaFree(p);
+      p = nullptr;
+    }
+    for (auto& p : ctx->d_land) RVT_CUDA_OK(cudaMalloc((void**)&p, need));
+    ctx->cap_land = need;
+  }
+  *slot = (int)(ctx->land_seq++ % rvt_ctx::kLandRing);
+  RVT_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_unpacked[*slot], 0));
+  return RVT_OK;
+}
+// the copy is enqueued: make the context stream wait for it
+static int land_publish(rvt_ctx* ctx, int slot) {
+  RVT_CUDA_OK(cudaEventRecord(ctx->ev_landed[slot], ctx->copy_stream));
+  RVT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_landed[slot], 0));
+  return RVT_OK;
+}
+// the consuming kernel is enqueued: the slot may be overwritten once it has run; with option
+// "stream_batch" also enqueue sweep + statistics once enough genes are waiting
+static int land_release(rvt_ctx* ctx, int slot) {
+  RVT_CUDA_OK(cudaEventRecord(ctx->ev_unpacked[slot], ctx->stream));
+  return RVT_OK;
+}
+static int launch_range(rvt_ctx* ctx, int g0, int g1);
+static int maybe_stream(rvt_ctx* ctx) {
+  const int n = (int)ctx->genes.size();
+  if (ctx->stream_batch > 0 && n - ctx->launched >= ctx->stream_batch) return launch_range(ctx, ctx->launched, n);
+  return RVT_OK;
+}
+
 int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
   if (!ctx || !G) return RVT_E_BADARG;
   int rc = push_check(ctx, M);
@@ -482,27 +557,26 @@ int rvt_gene_push_i8(rvt_ctx* ctx, const int8_t* G, int M, int64_t ld_in, const 
   if (rc) return rc;
   const int64_t N = ctx->N, npad = (N + 127) & ~(int64_t)127;
   if (ld_in < N) CTX_FAIL(RVT_E_BADARG, "ld (%lld) < N (%lld)", (long long)ld_in, (long long)N);
-  const size_t need = (size_t)M * N;
-  if (need > ctx->cap_stage8) {
-    if (ctx->d_stage8) {
-      RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-      cudaFree(ctx->d_stage8);
-    }
-    const size_t cap = std::max(need, (size_t)kMaxM * N);   // one allocation serves every gene of this cohort
-    RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_stage8, cap));
-    ctx->cap_stage8 = cap;
-  }
+  int slot = 0;
+  if ((rc = land_acquire(ctx, (size_t)kMaxM * N, &slot))) return rc;   // one size serves every gene of this cohort
   int64_t off = 0;
   if ((rc = stage_alloc(ctx, tiled_bytes(N, M), &off))) return rc;
   int8_t* blk = ctx->d_stage + off;
   if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
-  // land the caller's variant-major rows, then re-tile (and count) them on the device
-  RVT_CUDA_OK(cudaMemcpy2DAsync(ctx->d_stage8, N, G, ld_in, N, M, cudaMemcpyHostToDevice, ctx->stream));
+  // land the caller's variant-major rows (copy stream), then re-tile and count them on the device
+  int8_t* land = ctx->d_land[slot];
+  if (ld_in == N)
+    RVT_CUDA_OK(cudaMemcpyAsync(land, G, (size_t)M * N, cudaMemcpyHostToDevice, ctx->copy_stream));
+  else
+    RVT_CUDA_OK(cudaMemcpy2DAsync(land, N, G, ld_in, N, M, cudaMemcpyHostToDevice, ctx->copy_stream));
+  if ((rc = land_publish(ctx, slot))) return rc;
   RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
   dim3 grid((unsigned)((npad / 16 + 255) / 256), (unsigned)M);
-  k_tile_rows<<<grid, 256, 0, ctx->stream>>>(ctx->d_stage8, N, N, blk, M, ctx->d_counts + ctx->n_var);
+  k_tile_rows<<<grid, 256, 0, ctx->stream>>>(land, N, N, blk, M, ctx->d_counts + ctx->n_var);
   RVT_CUDA_OK(cudaGetLastError());
-  return push_common(ctx, blk, M, 0, af, nullptr, true, kSegStaged, off / 128, true);
+  if ((rc = land_release(ctx, slot))) return rc;
+  if ((rc = push_common(ctx, blk, M, 0, af, nullptr, true, kSegStaged, off / 128, true))) return rc;
+  return maybe_stream(ctx);
 }
 
 int rvt_gene_push_bed(rvt_ctx* ctx, const uint8_t* bed, int M, int64_t stride, const double* af) {
@@ -512,29 +586,28 @@ int rvt_gene_push_bed(rvt_ctx* ctx, const uint8_t* bed, int M, int64_t stride, c
   const int64_t N = ctx->N, npad = (N + 127) & ~(int64_t)127;
   const int64_t rowb = (N + 3) / 4, pitch = (rowb + 3) & ~(int64_t)3;
   if (stride < rowb) CTX_FAIL(RVT_E_BADARG, "stride (%lld) < ceil(N/4) (%lld)", (long long)stride, (long long)rowb);
-  const size_t need = (size_t)M * pitch;
-  if (need > ctx->cap_stage8) {
-    if (ctx->d_stage8) {
-      RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-      cudaFree(ctx->d_stage8);
-    }
-    const size_t cap = std::max(need, (size_t)kMaxM * pitch);
-    RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_stage8, cap));
-    ctx->cap_stage8 = cap;
-  }
+  int slot = 0;
+  if ((rc = land_acquire(ctx, (size_t)kMaxM * pitch, &slot))) return rc;
   int64_t off = 0;
   if ((rc = stage_alloc(ctx, tiled_bytes(N, M), &off))) return rc;
   int8_t* blk = ctx->d_stage + off;
   if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
-  // 2 bits per call over PCIe (a quarter of the int8 form), expanded + re-tiled + counted on the device
-  RVT_CUDA_OK(cudaMemcpy2DAsync(ctx->d_stage8, pitch, bed, stride, rowb, M, cudaMemcpyHostToDevice, ctx->stream));
+  // 2 bits per call over PCIe (a quarter of the int8 form) on the copy stream; expanded, re-tiled and
+  // counted on the device
+  int8_t* land = ctx->d_land[slot];
+  if (stride == pitch)
+    RVT_CUDA_OK(cudaMemcpyAsync(land, bed, (size_t)M * pitch, cudaMemcpyHostToDevice, ctx->copy_stream));
+  else
+    RVT_CUDA_OK(cudaMemcpy2DAsync(land, pitch, bed, stride, rowb, M, cudaMemcpyHostToDevice, ctx->copy_stream));
+  if ((rc = land_publish(ctx, slot))) return rc;
   RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
   dim3 grid((unsigned)((npad / 16 + 255) / 256), (unsigned)M);
-  k_unpack_bed<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const uint8_t*>(ctx->d_stage8), pitch, N, blk, M,
-                                              ctx->d_counts + ctx->n_var);
+  k_unpack_bed<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const uint8_t*>(land), pitch, N, blk, M, ctx->d_counts + ctx->n_var);
   RVT_CUDA_OK(cudaGetLastError());
+  if ((rc = land_release(ctx, slot))) return rc;
   ctx->bed_genes.push_back((int)ctx->genes.size());
-  return push_common(ctx, blk, M, 0, af, nullptr, true, kSegStaged, off / 128, true);
+  if ((rc = push_common(ctx, blk, M, 0, af, nullptr, true, kSegStaged, off / 128, true))) return rc;
+  return maybe_stream(ctx);
 }
 
 // genes that arrived as 2-bit rows may hold missing calls (code 01): the counts say which; those are
@@ -598,86 +671,94 @@ __global__ void k_resolve_flags(int64_t n_var, int64_t N, const RowCounts* __res
   flags[r] = f;
 }
 
-static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, bool to_device) {
-  if (!ctx) return RVT_E_BADARG;
-  const int n = (int)ctx->genes.size();
-  if (n_out) *n_out = 0;
-  if (n == 0) return RVT_OK;
-  if (!out || cap < n) CTX_FAIL(RVT_E_BADARG, "result buffer too small: %d pending genes, cap %d", n, cap);
-  RVT_CUDA_OK(cudaSetDevice(ctx->device));
-  int rc;
-  if ((rc = ensure(ctx, (void**)&ctx->d_genes, &ctx->cap_genes, n, sizeof(GeneDesc)))) return rc;
-  if ((rc = ensure_var(ctx, ctx->n_var))) return rc;
-  if ((rc = resolve_bed_missing(ctx))) return rc;
+// splits of the sample axis: S units per gene, `chunk` samples each (a multiple of 512 = one TMA
+// stage of the tensor-core kernel = 2 simt tiles)
+static int split_plan(rvt_ctx* ctx, int* S_out, int64_t* chunk_out) {
   const int64_t N = ctx->N;
   int S = ctx->splits;
   if (S <= 0) S = (int)std::min<int64_t>(16, std::max<int64_t>(1, (N + 65535) / 65536));
-  // samples per split: multiple of 512 (one TMA stage of the tensor-core kernel; 2 simt tiles)
   int64_t chunk = (((N + S - 1) / S) + 511) & ~(int64_t)511;
   S = (int)((N + chunk - 1) / chunk);
   if (chunk > ((int64_t)1 << 22)) CTX_FAIL(RVT_E_UNSUPPORTED, "split of %lld samples exceeds the int32 accumulation bound; raise 'splits'", (long long)chunk);
-  // One sweep launch + one statistics launch per batch of <= 2048 genes, back to back on the context
-  // stream.  (Running the statistics of batch i beside the sweep of batch i+1 on a second stream was
-  // built and measured twice -- 17.8 vs 16.9 ms/step with the first sweep, 12.9 vs 11.8 ms with the
-  // current one: the sweep needs its 5-stage ring, i.e. the whole shared memory -- and removed.)
+  *S_out = S;
+  *chunk_out = chunk;
+  return RVT_OK;
+}
+
+// Enqueue sweep + statistics for the pending genes [g0, g1) on the context stream; records land in
+// ctx->d_res[g0..g1).  Nothing here waits for the device: with option "stream_batch" = B the pushes call
+// this every B genes, so the kernels of one range run while the next genes are still crossing PCIe on the
+// copy stream.  One sweep launch + one statistics launch per batch of <= 2048 genes, back to back.
+// (Running the statistics of batch i beside the sweep of batch i+1 on a second stream was built and
+// measured twice -- 17.8 vs 16.9 ms/step with the first sweep, 12.9 vs 11.8 ms with the current one: the
+// sweep needs its 5-stage ring, i.e. the whole shared memory -- and removed.)
+static int launch_range(rvt_ctx* ctx, int g0, int g1) {
+  const int n = g1 - g0;
+  if (n <= 0) return RVT_OK;
+  int rc;
+  const int64_t N = ctx->N;
+  const int n_total = (int)ctx->genes.size();
+  if ((rc = ensure(ctx, (void**)&ctx->d_genes, &ctx->cap_genes, n_total, sizeof(GeneDesc)))) return rc;
+  if ((rc = ensure_var(ctx, ctx->n_var))) return rc;
+  if ((rc = ensure(ctx, (void**)&ctx->d_res, &ctx->cap_res, n_total, sizeof(rvt_gene_result)))) return rc;
+  int S = 0;
+  int64_t chunk = 0;
+  if ((rc = split_plan(ctx, &S, &chunk))) return rc;
   const int batch = std::min(n, 2048);
-  const int nbuf = 1;
   int engine = ctx->engine;
   if (ctx->stage_used > 0) {
     // bind the whole capacity: the maps stay valid while the arena does not move
     rc = tc_bind_segment(&ctx->tc, kSegStaged, ctx->d_stage, ctx->stage_cap, ctx->err, sizeof(ctx->err));
     if (rc) return rc;
   }
-  bool tc_ok = tc_usable(&ctx->tc, ctx->genes.data(), n);
+  const GeneDesc* hg = ctx->genes.data() + g0;
+  bool tc_ok = tc_usable(&ctx->tc, hg, n);
   if (engine == RVT_ENGINE_AUTO) engine = tc_ok ? RVT_ENGINE_TC : RVT_ENGINE_SIMT;
   if (engine == RVT_ENGINE_TC && !tc_ok)
     CTX_FAIL(RVT_E_UNSUPPORTED, "tensor-core engine requested but unavailable for these genes: %s", ctx->tc.why);
   // the wide tensor-core sweep writes two partials per (gene, split): even and odd 128-sample boxes
   const bool wide = engine == RVT_ENGINE_TC && tc_parts_per_unit(&ctx->tc) == 2;
   const int Sp = wide ? 2 * S : S;
-  if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)nbuf * batch * Sp, sizeof(SweepPartial)))) return rc;
-  rvt_gene_result* d_res = out;
-  if (!to_device) {
-    if ((rc = ensure(ctx, (void**)&ctx->d_res, &ctx->cap_res, n, sizeof(rvt_gene_result)))) return rc;
-    d_res = ctx->d_res;
-  }
+  if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)batch * Sp, sizeof(SweepPartial)))) return rc;
   if (ctx->skato) {
     if ((rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)batch, sizeof(QagsScratch)))) return rc;
   }
   if (ctx->want_dbg) {
-    if ((rc = ensure(ctx, (void**)&ctx->d_dbg, &ctx->cap_dbg, (size_t)n * kFinPhases, sizeof(long long)))) return rc;
+    if ((rc = ensure(ctx, (void**)&ctx->d_dbg, &ctx->cap_dbg, (size_t)n_total * kFinPhases, sizeof(long long)))) return rc;
   } else if (ctx->d_dbg) {
     cudaFree(ctx->d_dbg);
     ctx->d_dbg = nullptr;
     ctx->cap_dbg = 0;
   }
-  ctx->last_n = n;
   cudaStream_t st = ctx->stream;
-  cudaStream_t st2 = st;
   const int nbatch = (n + batch - 1) / batch;
   // per batch: [0] sweep start, [1] sweep end, [2] finalize start, [3] finalize end
-  while ((int)ctx->evpool.size() < 4 * nbatch) {
+  while ((int)ctx->evpool.size() < 4 * (ctx->pending_timing_batches + nbatch)) {
     cudaEvent_t e;
     RVT_CUDA_OK(cudaEventCreate(&e));
     ctx->evpool.push_back(e);
   }
-  RVT_CUDA_OK(cudaEventRecord(ctx->ev[0], st));
-  RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_genes, ctx->genes.data(), sizeof(GeneDesc) * n, cudaMemcpyHostToDevice, st));
-  RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_userflags, ctx->userflags.data(), ctx->n_var, cudaMemcpyHostToDevice, st));
-  RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_af, ctx->af.data(), sizeof(double) * ctx->n_var, cudaMemcpyHostToDevice, st));
-  k_resolve_flags<<<(unsigned)((ctx->n_var + 255) / 256), 256, 0, st>>>(ctx->n_var, N, ctx->d_counts,
-                                                                         ctx->d_userflags, ctx->d_flags);
+  if (!ctx->flush_open) {
+    RVT_CUDA_OK(cudaEventRecord(ctx->ev[0], st));
+    ctx->flush_open = true;
+    ctx->n_launch = 0;
+  }
+  const int64_t v0 = ctx->genes[g0].var0, v1 = ctx->genes[g1 - 1].var0 + ctx->genes[g1 - 1].M, nv = v1 - v0;
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_genes + g0, hg, sizeof(GeneDesc) * n, cudaMemcpyHostToDevice, st));
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_userflags + v0, ctx->userflags.data() + v0, nv, cudaMemcpyHostToDevice, st));
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_af + v0, ctx->af.data() + v0, sizeof(double) * nv, cudaMemcpyHostToDevice, st));
+  k_resolve_flags<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(nv, N, ctx->d_counts + v0, ctx->d_userflags + v0, ctx->d_flags + v0);
   int launches = 1;
   ctx->last_engine = engine;
   ctx->last_S = S;
   EngineParams prm{ctx->beta1, ctx->beta2};
-  if (engine == RVT_ENGINE_TC && (rc = tc_prepare_maps(&ctx->tc, ctx->genes[0].seg, ctx->genes.data(), n, st, ctx->err, sizeof(ctx->err))))
-    return rc;   // encode every box height up front: no host sync inside the pipelined loop
+  if (engine == RVT_ENGINE_TC && (rc = tc_prepare_maps(&ctx->tc, hg[0].seg, hg, n, st, ctx->err, sizeof(ctx->err))))
+    return rc;   // encode every box height up front: no host sync inside the loop
   for (int bi = 0; bi < nbatch; ++bi) {
-    const int b0 = bi * batch;
-    const int nb = std::min(batch, n - b0);
-    SweepPartial* parts = ctx->d_parts + (size_t)(bi % nbuf) * batch * Sp;
-    cudaEvent_t* ev = &ctx->evpool[4 * bi];
+    const int b0 = g0 + bi * batch;
+    const int nb = std::min(batch, g1 - b0);
+    SweepPartial* parts = ctx->d_parts;
+    cudaEvent_t* ev = &ctx->evpool[4 * (ctx->pending_timing_batches + bi)];
     RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), st));
     RVT_CUDA_OK(cudaEventRecord(ev[0], st));
     if (engine == RVT_ENGINE_SIMT) {
@@ -689,26 +770,47 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       if (rc) return rc;
     }
     RVT_CUDA_OK(cudaEventRecord(ev[1], st));
-    RVT_CUDA_OK(cudaEventRecord(ev[2], st2));
+    RVT_CUDA_OK(cudaEventRecord(ev[2], st));
     int Mmax = 1;
     for (int i = 0; i < nb; ++i) Mmax = std::max(Mmax, ctx->genes[b0 + i].M);
     const int kld = fin_kld(Mmax), fsm = fin_smem(Mmax, ctx->ER, ctx->skato), wm_off = Mmax * kld * 8;
     if (ctx->skato)
-      k_finalize<true><<<nb, kFinThreadsSkato, fsm, st2>>>(
-          ctx->d_genes + b0, nb, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, d_res + b0,
+      k_finalize<true><<<nb, kFinThreadsSkato, fsm, st>>>(
+          ctx->d_genes + b0, nb, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, ctx->d_res + b0,
           ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->d_qags, nullptr, nullptr);
     else
-      k_finalize<false><<<nb, kFinThreads, fsm, st2>>>(
-          ctx->d_genes + b0, nb, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, d_res + b0,
+      k_finalize<false><<<nb, kFinThreads, fsm, st>>>(
+          ctx->d_genes + b0, nb, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, ctx->d_res + b0,
           ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, nullptr, nullptr, nullptr);
-    RVT_CUDA_OK(cudaEventRecord(ev[3], st2));
+    RVT_CUDA_OK(cudaEventRecord(ev[3], st));
     RVT_CUDA_OK(cudaGetLastError());
     launches += 2;
     ctx->last_parts = (int64_t)nb * Sp;
   }
-  ctx->pending_timing_batches = nbatch;
+  ctx->pending_timing_batches += nbatch;
+  ctx->n_launch += launches;
+  ctx->launched = g1;
+  return RVT_OK;
+}
+
+static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, bool to_device) {
+  if (!ctx) return RVT_E_BADARG;
+  const int n = (int)ctx->genes.size();
+  if (n_out) *n_out = 0;
+  if (n == 0) return RVT_OK;
+  if (!out || cap < n) CTX_FAIL(RVT_E_BADARG, "result buffer too small: %d pending genes, cap %d", n, cap);
+  RVT_CUDA_OK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = launch_range(ctx, ctx->launched, n))) return rc;
+  if ((rc = resolve_bed_missing(ctx))) return rc;
+  const int64_t N = ctx->N;
+  cudaStream_t st = ctx->stream;
+  rvt_gene_result* d_res = ctx->d_res;
+  EngineParams prm{ctx->beta1, ctx->beta2};
+  int launches = 0;
   if (!ctx->dos.empty()) {
-    // genes with dosage / imputed values: fp64 statistics, then the same tail (eigen, Davies, SKAT-O, burden)
+    // genes with dosage / imputed values: fp64 statistics, then the same tail (eigen, Davies, SKAT-O, burden);
+    // their records overwrite what the hard-call pipeline produced for the same slots
     const int nd = (int)ctx->dos.size();
     DosageStats* d_st = nullptr;
     TailInput* d_tin = nullptr;
@@ -730,14 +832,14 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       k_dosage_prepare<<<1, 64, 0, st>>>(d_st + i, dg.M, dg.has_af ? d_afd + (size_t)i * kTileRows : nullptr, ctx->d_nm, prm, d_tin + i);
     }
     RVT_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
-    if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)std::max(nd, batch), sizeof(QagsScratch)))) return rc;
+    if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nd, sizeof(QagsScratch)))) return rc;
     {
       const int kld = fin_kld(kTileRows), fsm = fin_smem(kTileRows, ctx->ER, ctx->skato), wm_off = kTileRows * kld * 8;
       if (ctx->skato)
-        k_finalize<true><<<nd, kFinThreadsSkato, fsm, st>>>(nullptr, nd, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S,
+        k_finalize<true><<<nd, kFinThreadsSkato, fsm, st>>>(nullptr, nd, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
                                                              nullptr, d_res, nullptr, ctx->d_qags, d_tin, d_idx);
       else
-        k_finalize<false><<<nd, kFinThreads, fsm, st>>>(nullptr, nd, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, S,
+        k_finalize<false><<<nd, kFinThreads, fsm, st>>>(nullptr, nd, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
                                                          nullptr, d_res, nullptr, nullptr, d_tin, d_idx);
     }
     RVT_CUDA_OK(cudaGetLastError());
@@ -747,8 +849,7 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     for (auto& dg : ctx->dos) cudaFree(dg.dG);
     ctx->dos.clear();
   }
-  if (!to_device)
-    RVT_CUDA_OK(cudaMemcpyAsync(out, d_res, sizeof(rvt_gene_result) * n, cudaMemcpyDeviceToHost, st));
+  RVT_CUDA_OK(cudaMemcpyAsync(out, d_res, sizeof(rvt_gene_result) * n, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   RVT_CUDA_OK(cudaEventRecord(ctx->ev[1], st));
   RVT_CUDA_OK(cudaStreamSynchronize(st));
   float tot = 0;
@@ -764,14 +865,10 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   ctx->t_sweep = ms_sweep;
   ctx->t_fin = ms_fin;
   ctx->t_total = tot;
-  ctx->n_launch = launches;
+  ctx->n_launch += launches;
+  ctx->last_n = n;
   if (n_out) *n_out = n;
-  ctx->genes.clear();
-  ctx->userflags.clear();
-  ctx->af.clear();
-  ctx->count_slot.clear();
-  ctx->n_var = 0;
-  ctx->stage_used = 0;
+  pending_reset(ctx);
   return RVT_OK;
 }
 
@@ -919,13 +1016,7 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   if (band) RVT_CUDA_OK(cudaMemcpyAsync(band, d_band, sizeof(double) * nv * (size_t)(wmax + 1), cudaMemcpyDeviceToHost, st));
   RVT_CUDA_OK(cudaStreamSynchronize(st));
   cleanup();
-  ctx->genes.clear();
-  ctx->userflags.clear();
-  ctx->af.clear();
-  ctx->count_slot.clear();
-  ctx->bed_genes.clear();
-  ctx->n_var = 0;
-  ctx->stage_used = 0;
+  pending_reset(ctx);
   return RVT_OK;
 }
 
