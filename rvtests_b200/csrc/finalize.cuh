@@ -31,10 +31,11 @@ constexpr int kFinThreadsSkato = 128;
 // so that rows AND columns are bank-conflict free); the reduced gene x digit sums De (int64,
 // Mmax x ER) live in the same bytes (they are dead before K is built); SKAT-O adds Wm = Z1'Z1.
 static inline int fin_kld(int Mmax) { return Mmax | 1; }
-static inline int fin_smem(int Mmax, int ER, bool skato) {
+static inline int fin_uk_off(int Mmax, int ER, bool skato) {
   const int k = Mmax * fin_kld(Mmax) * 8, de = Mmax * ER * 8;
   return (k > de ? k : de) + (skato ? k : 0);
 }
+static inline int fin_smem(int Mmax, int ER, bool skato) { return fin_uk_off(Mmax, ER, skato) + Mmax * kMaxC * 8; }
 constexpr int kQagsLimit = 1000;   // Integration::limit (regression/GSLIntegration.cpp:7-15)
 
 // per-gene QAGS interval list in global memory (touched by one thread only)
@@ -51,7 +52,8 @@ __device__ __forceinline__ long long recombine4(const long long* d) {
 template <bool SKATO>
 __global__ void __launch_bounds__(SKATO ? kFinThreadsSkato : kFinThreads)
 k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(Mmax of this launch) */,
-           int wm_off /* byte offset of Wm inside the dynamic shared memory (SKAT-O) */, const uint8_t* __restrict__ rowflags,
+           int wm_off /* byte offset of Wm inside the dynamic shared memory (SKAT-O) */, int uk_off /* ... of Uk */,
+           const uint8_t* __restrict__ rowflags,
            const double* __restrict__ af, const RowCounts* __restrict__ counts,
            const NullModel* __restrict__ nm, EngineParams prm, int S,
            const SweepPartial* __restrict__ parts, rvt_gene_result* __restrict__ res,
@@ -65,6 +67,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
   double* K = reinterpret_cast<double*>(dyn);                // [Mmax][kld]
   long long* De = reinterpret_cast<long long*>(dyn);         // [Mmax][ER] gene x digit sums, dead before K is written
   double* Wm = reinterpret_cast<double*>(dyn + wm_off);      // [Mmax][kld], SKAT-O only
+  double* Uk = reinterpret_cast<double*>(dyn + uk_off);      // [Mmax][C]  (X'X)^-1 B_k
   struct SkatoShared {   // SKAT-O only
     QagsMachine mach;
     double fv[21], bcast[3], c[kTileRows + 2], lamz[kTileRows + 2];
@@ -199,29 +202,44 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
     s_Q = q;
   }
   // 4. K = W^1/2 sigma2 (A' - B' (X'X)^-1 B'^T) W^1/2   (upper triangle, mirrored)
-  for (int idx = tid; idx < Mp * Mp; idx += NT) {
-    const int i = idx / Mp, k = idx - i * Mp;
-    if (k < i) continue;
-    const int ji = s_idx[i], jk = s_idx[k];
-    const int fi = s_flip[ji], fk = s_flip[jk];
-    long long a = 0;
-    for (int sp = 0; sp < S; ++sp) a += gp[sp].d[ji][jk];
-    const long long ci = s_craw[ji], ck = s_craw[jk];
-    if (fi && fk)
-      a = 4 * N - 2 * ci - 2 * ck + a;
-    else if (fi)
-      a = 2 * ck - a;
-    else if (fk)
-      a = 2 * ci - a;
-    double t = 0.0;
+  //    u_k = (X'X)^-1 B_k once per variant, then one dot product per entry
+  if (tid < Mp) {
     for (int l = 0; l < C; ++l) {
       double u = 0.0;
-      for (int m = 0; m < C; ++m) u += nm->xtx_inv[l * C + m] * s_B[k][m];
-      t += s_B[i][l] * u;
+      for (int m = 0; m < C; ++m) u += nm->xtx_inv[l * C + m] * s_B[tid][m];
+      Uk[tid * C + l] = u;
     }
-    double v = s_sw[i] * s_sw[k] * sigma2 * ((double)a - t);
-    K[i * kld + k] = v;
-    K[k * kld + i] = v;
+  }
+  __syncthreads();
+  //    rows r and Mp-1-r hold Mp+1 upper-triangle entries between them: one pass of the CTA per row pair
+  for (int r = 0; r < (Mp + 1) / 2; ++r) {
+    for (int t = tid; t < Mp + 1; t += NT) {
+      int i, k;
+      if (t < Mp - r) {
+        i = r;
+        k = r + t;
+      } else {
+        i = Mp - 1 - r;
+        if (i == r) continue;
+        k = i + (t - (Mp - r));
+      }
+      const int ji = s_idx[i], jk = s_idx[k];
+      const int fi = s_flip[ji], fk = s_flip[jk];
+      long long a = 0;
+      for (int sp = 0; sp < S; ++sp) a += gp[sp].d[ji][jk];
+      const long long ci = s_craw[ji], ck = s_craw[jk];
+      if (fi && fk)
+        a = 4 * N - 2 * ci - 2 * ck + a;
+      else if (fi)
+        a = 2 * ck - a;
+      else if (fk)
+        a = 2 * ci - a;
+      double tt = 0.0;
+      for (int l = 0; l < C; ++l) tt += s_B[i][l] * Uk[k * C + l];
+      const double v = s_sw[i] * s_sw[k] * sigma2 * ((double)a - tt);
+      K[i * kld + k] = v;
+      K[k * kld + i] = v;
+    }
   }
   __syncthreads();
   phase(1);

@@ -672,11 +672,19 @@ __global__ void k_resolve_flags(int64_t n_var, int64_t N, const RowCounts* __res
 }
 
 // splits of the sample axis: S units per gene, `chunk` samples each (a multiple of 512 = one TMA
-// stage of the tensor-core kernel = 2 simt tiles)
-static int split_plan(rvt_ctx* ctx, int* S_out, int64_t* chunk_out) {
+// stage of the tensor-core kernel = 2 simt tiles).  A unit must stay inside the int32 accumulation
+// bounds (2^22 samples for the Gram; 2^18 for the burden rows that ride on the UMMA); beyond that, only
+// as many splits as it takes to give every SM ~16 units: each extra split costs one more partial
+// (25 KB written by the sweep, read back by the statistics kernel) per gene.
+static int split_plan(rvt_ctx* ctx, int n_genes, int* S_out, int64_t* chunk_out) {
   const int64_t N = ctx->N;
   int S = ctx->splits;
-  if (S <= 0) S = (int)std::min<int64_t>(16, std::max<int64_t>(1, (N + 65535) / 65536));
+  if (S <= 0) {
+    const int64_t s_min = (N + 262143) / 262144;
+    const int64_t s_fill = (16 * (int64_t)ctx->sm_count + n_genes - 1) / std::max(1, n_genes);
+    S = (int)std::min<int64_t>(std::max<int64_t>(s_min, std::min<int64_t>(s_fill, (N + 65535) / 65536)), std::max<int64_t>(16, s_min));
+    S = std::max(S, 1);
+  }
   int64_t chunk = (((N + S - 1) / S) + 511) & ~(int64_t)511;
   S = (int)((N + chunk - 1) / chunk);
   if (chunk > ((int64_t)1 << 22)) CTX_FAIL(RVT_E_UNSUPPORTED, "split of %lld samples exceeds the int32 accumulation bound; raise 'splits'", (long long)chunk);
@@ -703,8 +711,8 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
   if ((rc = ensure(ctx, (void**)&ctx->d_res, &ctx->cap_res, n_total, sizeof(rvt_gene_result)))) return rc;
   int S = 0;
   int64_t chunk = 0;
-  if ((rc = split_plan(ctx, &S, &chunk))) return rc;
-  const int batch = std::min(n, 2048);
+  const int batch = (n + ((n + 2047) / 2048) - 1) / ((n + 2047) / 2048);   // equal batches of <= 2048 genes
+  if ((rc = split_plan(ctx, batch, &S, &chunk))) return rc;
   int engine = ctx->engine;
   if (ctx->stage_used > 0) {
     // bind the whole capacity: the maps stay valid while the arena does not move
@@ -776,11 +784,11 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
     const int kld = fin_kld(Mmax), fsm = fin_smem(Mmax, ctx->ER, ctx->skato), wm_off = Mmax * kld * 8;
     if (ctx->skato)
       k_finalize<true><<<nb, kFinThreadsSkato, fsm, st>>>(
-          ctx->d_genes + b0, nb, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, ctx->d_res + b0,
+          ctx->d_genes + b0, nb, kld, wm_off, fin_uk_off(Mmax, ctx->ER, ctx->skato), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, ctx->d_res + b0,
           ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->d_qags, nullptr, nullptr);
     else
       k_finalize<false><<<nb, kFinThreads, fsm, st>>>(
-          ctx->d_genes + b0, nb, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, ctx->d_res + b0,
+          ctx->d_genes + b0, nb, kld, wm_off, fin_uk_off(Mmax, ctx->ER, ctx->skato), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, ctx->d_res + b0,
           ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, nullptr, nullptr, nullptr);
     RVT_CUDA_OK(cudaEventRecord(ev[3], st));
     RVT_CUDA_OK(cudaGetLastError());
@@ -836,10 +844,10 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     {
       const int kld = fin_kld(kTileRows), fsm = fin_smem(kTileRows, ctx->ER, ctx->skato), wm_off = kTileRows * kld * 8;
       if (ctx->skato)
-        k_finalize<true><<<nd, kFinThreadsSkato, fsm, st>>>(nullptr, nd, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
+        k_finalize<true><<<nd, kFinThreadsSkato, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, ctx->skato), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
                                                              nullptr, d_res, nullptr, ctx->d_qags, d_tin, d_idx);
       else
-        k_finalize<false><<<nd, kFinThreads, fsm, st>>>(nullptr, nd, kld, wm_off, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
+        k_finalize<false><<<nd, kFinThreads, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, ctx->skato), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
                                                          nullptr, d_res, nullptr, nullptr, d_tin, d_idx);
     }
     RVT_CUDA_OK(cudaGetLastError());
