@@ -115,6 +115,10 @@ int rvt_get_null_model(rvt_ctx* ctx, double* resid, double* sigma2, double* xtx_
  * rvt_gene_push_i8: same, hard calls as int8 [M][ld] variant-major on the host.
  * rvt_gene_push_dev_i8: block already in device memory (zero-copy; must stay valid until flush).
  *   flags: NULL (engine counts the rows itself) or M bytes 0 normal / 1 flip-to-minor / 2 skip.
+ * Width: the host entry points (f64, i8, bed) take genes of 1..2048 variants -- the reference has no limit
+ *   (Skat::Fit / MixtureChiSquare size themselves to the gene); a gene of more than 64 variants is cut into
+ *   64-variant tiles and its Gram assembled from tile pairs (csrc/wide.cuh).  RVT_E_UNSUPPORTED beyond 2048,
+ *   for rvt_gene_push_dev_i8 beyond 64, and for a gene of more than 64 variants that holds dosages or missing calls.
  * Each push appends one gene; results come back from rvt_flush in push order.  Host buffers are copied
  * asynchronously when they are page-locked: keep them valid and unchanged until rvt_flush returns. */
 int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af);

@@ -49,6 +49,54 @@ __device__ __forceinline__ long long recombine4(const long long* d) {
   return d[0] + (d[1] << 8) + (d[2] << 16) + (d[3] << 24);
 }
 
+// Step 7 of the per-gene tail, shared by k_finalize and k_wide_finalize: the two burden score tests
+// (LinearRegressionScoreTest::TestCovariate with m = 1, regression/LinearRegressionScoreTest.cpp:229-261) from
+// bur[which] = {U, S'S, S'Z[0..C)} (which: 0 zeggini, 1 cmc), and the result record.
+__device__ inline void burden_and_store(rvt_gene_result* dst, int Mp, int bad, double Q, double p_fin, double p_dav, double p_liu, int fault,
+                                        int r, double lam_max, const SkatoOut& so, const double (*bur)[2 + kMaxC], int nonref,
+                                        const NullModel* __restrict__ nm, int status_override) {
+  const int C = nm->C;
+  const double sigma2 = nm->sigma2;
+  rvt_gene_result o;
+  memset(&o, 0, sizeof(o));
+  o.m_poly = Mp;
+  o.status = (Mp == 0) ? RVT_GENE_NA : RVT_GENE_OK;
+  if (bad == 1) o.status = RVT_GENE_BADFLAGS;
+  if (bad == 2) o.status = RVT_GENE_BADVALUE;
+  o.Q = Q;
+  o.p_skat = p_fin;
+  o.p_davies = p_dav;
+  o.p_liu = p_liu;
+  o.davies_fault = fault;
+  o.n_lambda = r;
+  o.lambda_max = lam_max;
+  o.skato_ok = so.ok;
+  o.skato_Q = so.Q;
+  o.skato_rho = so.rho;
+  o.skato_p = so.pvalue;
+  for (int which = 0; which < 2; ++which) {  // 0 zeggini, 1 cmc
+    const double U = bur[which][0];
+    double SS = bur[which][1];
+    const double* SZ = &bur[which][2];
+    double q = 0.0;
+    for (int l = 0; l < C; ++l)
+      for (int m = 0; m < C; ++m) q += SZ[l] * nm->xtx_inv[l * C + m] * SZ[m];
+    SS -= q;
+    double V = SS * sigma2;
+    double stat = U * ((1.0 / SS) / sigma2) * U;
+    int ok = (Mp > 0) && !(stat < 0.0) && (stat == stat);
+    double p = ok ? chisq_q(stat, 1.0) : nan("");
+    if (which == 0) {
+      o.zeg_U = U; o.zeg_V = V; o.zeg_stat = stat; o.zeg_p = p; o.zeg_ok = ok;
+    } else {
+      o.cmc_U = U; o.cmc_V = V; o.cmc_stat = stat; o.cmc_p = p; o.cmc_ok = ok;
+      o.cmc_nonref = nonref;
+    }
+  }
+  if (status_override) o.status = status_override;
+  *dst = o;
+}
+
 template <bool SKATO>
 __global__ void __launch_bounds__(SKATO ? kFinThreadsSkato : kFinThreads)
 k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(Mmax of this launch) */,
@@ -302,44 +350,8 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
 
   // 7. burden score tests (m = 1)
   if (tid == 0) {
-    rvt_gene_result o;
-    memset(&o, 0, sizeof(o));
-    o.m_poly = Mp;
-    o.status = (Mp == 0) ? RVT_GENE_NA : RVT_GENE_OK;
-    if (s_bad == 1) o.status = RVT_GENE_BADFLAGS;
-    if (s_bad == 2) o.status = RVT_GENE_BADVALUE;
-    o.Q = s_Q;
-    o.p_skat = p_fin;
-    o.p_davies = p_dav;
-    o.p_liu = p_liu;
-    o.davies_fault = fault;
-    o.n_lambda = r;
-    o.lambda_max = lam_max;
-    o.skato_ok = so.ok;
-    o.skato_Q = so.Q;
-    o.skato_rho = so.rho;
-    o.skato_p = so.pvalue;
-    for (int which = 0; which < 2; ++which) {  // 0 zeggini, 1 cmc
-      const double U = s_bur[which][0];
-      double SS = s_bur[which][1];
-      const double* SZ = &s_bur[which][2];
-      double q = 0.0;
-      for (int l = 0; l < C; ++l)
-        for (int m = 0; m < C; ++m) q += SZ[l] * nm->xtx_inv[l * C + m] * SZ[m];
-      SS -= q;
-      double V = SS * sigma2;
-      double stat = U * ((1.0 / SS) / sigma2) * U;
-      int ok = (Mp > 0) && !(stat < 0.0) && (stat == stat);
-      double p = ok ? chisq_q(stat, 1.0) : nan("");
-      if (which == 0) {
-        o.zeg_U = U; o.zeg_V = V; o.zeg_stat = stat; o.zeg_p = p; o.zeg_ok = ok;
-      } else {
-        o.cmc_U = U; o.cmc_V = V; o.cmc_stat = stat; o.cmc_p = p; o.cmc_ok = ok;
-        o.cmc_nonref = s_nonref;
-      }
-    }
-    if (tin && tin[g].status) o.status = tin[g].status;
-    res[out_index ? out_index[g] : g] = o;
+    burden_and_store(&res[out_index ? out_index[g] : g], Mp, s_bad, s_Q, p_fin, p_dav, p_liu, fault, r, lam_max, so, s_bur, s_nonref, nm,
+                     tin ? tin[g].status : 0);
     phase(4);
   }
 }

@@ -19,6 +19,7 @@
 #include "prep.cuh"
 #include "sweep_simt.cuh"
 #include "sweep_tc.cuh"
+#include "wide.cuh"
 
 using namespace rvt;
 
@@ -29,6 +30,18 @@ struct DosGene {     // a pushed gene with non-hard-call values: handled by the 
   double* dG;        // N x M column-major doubles, device
   bool has_af;
   std::vector<double> af;
+};
+struct WideGene {    // a pushed gene of more than kMaxM variants: T tiles of consecutive variants (wide.cuh)
+  int gene_index;    // its slot in the pending list (a placeholder descriptor = tile 0 sits there)
+  int M;
+  int64_t var0;
+  bool has_af;
+  std::vector<GeneDesc> tiles;
+};
+struct TilePlan {    // where the tiles of one pushed gene were staged
+  int T = 0;
+  std::vector<int64_t> off;
+  std::vector<int> rows, r0;
 };
 }  // namespace
 
@@ -63,6 +76,10 @@ struct rvt_ctx {
   std::vector<double> af;          // per variant (valid when gene.has_af)
   std::vector<int64_t> count_slot; // per gene: offset into d_counts or -1
   std::vector<DosGene> dos;        // pending genes that need the dosage path
+  std::vector<WideGene> wide;      // pending genes of more than kMaxM variants
+  std::vector<int> slots;          // per gene: per-variant slots it owns (== M except for the placeholder of a wide gene)
+  uint8_t* d_zero_flags = nullptr; // "every row normal" flags for the tile sweeps of wide genes
+  size_t cap_zero_flags = 0;
   std::vector<int> bed_genes;      // pending genes pushed as PLINK 2-bit rows: checked for missing calls at flush
   int launched = 0;                // pending genes [0, launched) already have their kernels enqueued (stream_batch)
   int stream_batch = 0;            // option: enqueue sweep + statistics every this many host pushes (0 = only at flush)
@@ -120,6 +137,8 @@ static void pending_reset(rvt_ctx* ctx) {
   ctx->af.clear();
   ctx->count_slot.clear();
   ctx->bed_genes.clear();
+  ctx->wide.clear();
+  ctx->slots.clear();
   ctx->n_var = 0;
   ctx->stage_used = 0;
   ctx->launched = 0;
@@ -188,6 +207,8 @@ static int stage_alloc(rvt_ctx* ctx, int64_t bytes, int64_t* off) {
     }
     for (auto& g : ctx->genes)
       if (g.seg == kSegStaged) g.g = np + (size_t)g.row0 * 128;
+    for (auto& w : ctx->wide)
+      for (auto& g : w.tiles) g.g = np + (size_t)g.row0 * 128;
     ctx->d_stage = np;
     ctx->stage_cap = ncap;
   }
@@ -245,7 +266,7 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_zero_flags};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -430,7 +451,8 @@ int rvt_get_null_model(rvt_ctx* ctx, double* resid, double* sigma2, double* xtx_
 
 // common tail of every push: append the descriptor and the per-variant side data
 static int push_common(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const double* af, const uint8_t* flags,
-                       bool counted, int seg, int64_t row0, bool tiled) {
+                       bool counted, int seg, int64_t row0, bool tiled, int slots = 0 /* per-variant slots owned; 0: M */) {
+  if (slots <= 0) slots = M;
   GeneDesc gd;
   memset(&gd, 0, sizeof(gd));
   gd.g = dG;
@@ -447,20 +469,65 @@ static int push_common(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const 
   gd.var0_b = ctx->n_var;
   ctx->genes.push_back(gd);
   ctx->count_slot.push_back(counted ? ctx->n_var : -1);
-  for (int j = 0; j < M; ++j) {
+  ctx->slots.push_back(slots);
+  for (int j = 0; j < slots; ++j) {
     ctx->userflags.push_back(flags ? flags[j] : (uint8_t)0xFF);
     ctx->af.push_back(af ? af[j] : 0.0);
   }
-  ctx->n_var += M;
+  ctx->n_var += slots;
   return RVT_OK;
 }
 
-static int push_check(rvt_ctx* ctx, int M) {
+static int push_check(rvt_ctx* ctx, int M, int max_m = kMaxM) {
   if (!ctx->have_null) CTX_FAIL(RVT_E_STATE, "set the null model before pushing genes");
   if (M < 1) CTX_FAIL(RVT_E_BADARG, "gene with no variant (the reference returns -1 / NA: src/Model.h:2637-2640)");
-  if (M > kMaxM) CTX_FAIL(RVT_E_UNSUPPORTED, "M=%d variants; this build handles genes of up to %d variants", M, kMaxM);
+  if (M > max_m) CTX_FAIL(RVT_E_UNSUPPORTED, "M=%d variants; this entry point handles genes of up to %d variants", M, max_m);
   RVT_CUDA_OK(cudaSetDevice(ctx->device));
   return RVT_OK;
+}
+
+// Stage room for a pushed gene: one tiled block if it fits a tensor-core tile, else T = ceil(M/64) blocks of
+// consecutive variants, balanced (wide.cuh).
+static int stage_tiles(rvt_ctx* ctx, int M, TilePlan* tp) {
+  const int T = (M + kTileRows - 1) / kTileRows;
+  tp->T = T;
+  tp->off.resize(T);
+  tp->rows.resize(T);
+  tp->r0.resize(T);
+  int r0 = 0;
+  for (int t = 0; t < T; ++t) {
+    const int rows = M / T + (t < M % T ? 1 : 0);
+    int rc = stage_alloc(ctx, tiled_bytes(ctx->N, rows), &tp->off[t]);
+    if (rc) return rc;
+    tp->rows[t] = rows;
+    tp->r0[t] = r0;
+    r0 += rows;
+  }
+  return RVT_OK;
+}
+
+// append a staged gene: an ordinary descriptor, or (T > 1) a wide gene whose placeholder descriptor is its tile 0
+static int push_staged(rvt_ctx* ctx, const TilePlan& tp, int M, const double* af) {
+  if (tp.T == 1) return push_common(ctx, ctx->d_stage + tp.off[0], M, 0, af, nullptr, true, kSegStaged, tp.off[0] / 128, true);
+  WideGene w;
+  w.gene_index = (int)ctx->genes.size();
+  w.M = M;
+  w.var0 = ctx->n_var;
+  w.has_af = af != nullptr;
+  for (int t = 0; t < tp.T; ++t) {
+    GeneDesc gd;
+    memset(&gd, 0, sizeof(gd));
+    gd.g = ctx->d_stage + tp.off[t];
+    gd.M = gd.Mb = tp.rows[t];
+    gd.seg = kSegStaged;
+    gd.row0 = gd.row0_b = tp.off[t] / 128;
+    gd.var0 = gd.var0_b = ctx->n_var + tp.r0[t];
+    gd.counted = 1;
+    gd.tiled = 1;
+    w.tiles.push_back(gd);
+  }
+  ctx->wide.push_back(w);
+  return push_common(ctx, ctx->d_stage + tp.off[0], tp.rows[0], 0, af, nullptr, true, kSegStaged, tp.off[0] / 128, true, M);
 }
 
 static void launch_count(rvt_ctx* ctx, const int8_t* d, int M, int64_t ld, RowCounts* counts) {
@@ -507,7 +574,7 @@ static int maybe_stream(rvt_ctx* ctx) {
 
 int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
   if (!ctx || !G) return RVT_E_BADARG;
-  int rc = push_check(ctx, M);
+  int rc = push_check(ctx, M, kWideMaxM);
   if (rc) return rc;
   const int64_t N = ctx->N, npad = (N + 127) & ~(int64_t)127;
   size_t need = (size_t)N * M;
@@ -519,14 +586,16 @@ int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
     RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_stage64, need * sizeof(double)));
     ctx->cap_stage64 = need;
   }
-  int64_t off = 0;
-  if ((rc = stage_alloc(ctx, tiled_bytes(N, M), &off))) return rc;
-  int8_t* blk = ctx->d_stage + off;
+  TilePlan tp;
+  if ((rc = stage_tiles(ctx, M, &tp))) return rc;
   if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_stage64, G, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
-  dim3 grid((unsigned)((npad / 4 + 255) / 256), (unsigned)M);
-  k_pack_f64<<<grid, 256, 0, ctx->stream>>>(ctx->d_stage64, N, blk, M, ctx->d_counts + ctx->n_var);
+  for (int t = 0; t < tp.T; ++t) {
+    dim3 grid((unsigned)((npad / 4 + 255) / 256), (unsigned)tp.rows[t]);
+    k_pack_f64<<<grid, 256, 0, ctx->stream>>>(ctx->d_stage64 + (size_t)tp.r0[t] * N, N, ctx->d_stage + tp.off[t], tp.rows[t],
+                                              ctx->d_counts + ctx->n_var + tp.r0[t]);
+  }
   RVT_CUDA_OK(cudaGetLastError());
   // the staging buffer is reused by the next push: wait (pageable H2D is synchronous anyway);
   // the row counts also tell whether this gene holds anything but hard calls
@@ -535,6 +604,8 @@ int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
   RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   bool dosage = false;
   for (int j = 0; j < M; ++j) dosage |= rc_host[j].bad > 0;
+  if (dosage && M > kMaxM)
+    CTX_FAIL(RVT_E_UNSUPPORTED, "gene of %d variants holds dosages / imputed values: the fp64 path handles up to %d variants", M, kMaxM);
   if (dosage) {
     // dosages / mean-imputed values: keep the fp64 matrix for the generic path and hand the
     // staging buffer over to it (the next push allocates a fresh one)
@@ -548,20 +619,19 @@ int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
     ctx->d_stage64 = nullptr;
     ctx->cap_stage64 = 0;
   }
-  return push_common(ctx, blk, M, 0, af, nullptr, true, kSegStaged, off / 128, true);
+  return push_staged(ctx, tp, M, af);
 }
 
 int rvt_gene_push_i8(rvt_ctx* ctx, const int8_t* G, int M, int64_t ld_in, const double* af) {
   if (!ctx || !G) return RVT_E_BADARG;
-  int rc = push_check(ctx, M);
+  int rc = push_check(ctx, M, kWideMaxM);
   if (rc) return rc;
   const int64_t N = ctx->N, npad = (N + 127) & ~(int64_t)127;
   if (ld_in < N) CTX_FAIL(RVT_E_BADARG, "ld (%lld) < N (%lld)", (long long)ld_in, (long long)N);
   int slot = 0;
-  if ((rc = land_acquire(ctx, (size_t)kMaxM * N, &slot))) return rc;   // one size serves every gene of this cohort
-  int64_t off = 0;
-  if ((rc = stage_alloc(ctx, tiled_bytes(N, M), &off))) return rc;
-  int8_t* blk = ctx->d_stage + off;
+  if ((rc = land_acquire(ctx, (size_t)std::max(M, kMaxM) * N, &slot))) return rc;   // one size serves every ordinary gene of this cohort
+  TilePlan tp;
+  if ((rc = stage_tiles(ctx, M, &tp))) return rc;
   if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
   // land the caller's variant-major rows (copy stream), then re-tile and count them on the device
   int8_t* land = ctx->d_land[slot];
@@ -571,26 +641,28 @@ int rvt_gene_push_i8(rvt_ctx* ctx, const int8_t* G, int M, int64_t ld_in, const 
     RVT_CUDA_OK(cudaMemcpy2DAsync(land, N, G, ld_in, N, M, cudaMemcpyHostToDevice, ctx->copy_stream));
   if ((rc = land_publish(ctx, slot))) return rc;
   RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
-  dim3 grid((unsigned)((npad / 16 + 255) / 256), (unsigned)M);
-  k_tile_rows<<<grid, 256, 0, ctx->stream>>>(land, N, N, blk, M, ctx->d_counts + ctx->n_var);
+  for (int t = 0; t < tp.T; ++t) {
+    dim3 grid((unsigned)((npad / 16 + 255) / 256), (unsigned)tp.rows[t]);
+    k_tile_rows<<<grid, 256, 0, ctx->stream>>>(land + (size_t)tp.r0[t] * N, N, N, ctx->d_stage + tp.off[t], tp.rows[t],
+                                               ctx->d_counts + ctx->n_var + tp.r0[t]);
+  }
   RVT_CUDA_OK(cudaGetLastError());
   if ((rc = land_release(ctx, slot))) return rc;
-  if ((rc = push_common(ctx, blk, M, 0, af, nullptr, true, kSegStaged, off / 128, true))) return rc;
+  if ((rc = push_staged(ctx, tp, M, af))) return rc;
   return maybe_stream(ctx);
 }
 
 int rvt_gene_push_bed(rvt_ctx* ctx, const uint8_t* bed, int M, int64_t stride, const double* af) {
   if (!ctx || !bed) return RVT_E_BADARG;
-  int rc = push_check(ctx, M);
+  int rc = push_check(ctx, M, kWideMaxM);
   if (rc) return rc;
   const int64_t N = ctx->N, npad = (N + 127) & ~(int64_t)127;
   const int64_t rowb = (N + 3) / 4, pitch = (rowb + 3) & ~(int64_t)3;
   if (stride < rowb) CTX_FAIL(RVT_E_BADARG, "stride (%lld) < ceil(N/4) (%lld)", (long long)stride, (long long)rowb);
   int slot = 0;
-  if ((rc = land_acquire(ctx, (size_t)kMaxM * pitch, &slot))) return rc;
-  int64_t off = 0;
-  if ((rc = stage_alloc(ctx, tiled_bytes(N, M), &off))) return rc;
-  int8_t* blk = ctx->d_stage + off;
+  if ((rc = land_acquire(ctx, (size_t)std::max(M, kMaxM) * pitch, &slot))) return rc;
+  TilePlan tp;
+  if ((rc = stage_tiles(ctx, M, &tp))) return rc;
   if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
   // 2 bits per call over PCIe (a quarter of the int8 form) on the copy stream; expanded, re-tiled and
   // counted on the device
@@ -601,12 +673,15 @@ int rvt_gene_push_bed(rvt_ctx* ctx, const uint8_t* bed, int M, int64_t stride, c
     RVT_CUDA_OK(cudaMemcpy2DAsync(land, pitch, bed, stride, rowb, M, cudaMemcpyHostToDevice, ctx->copy_stream));
   if ((rc = land_publish(ctx, slot))) return rc;
   RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
-  dim3 grid((unsigned)((npad / 16 + 255) / 256), (unsigned)M);
-  k_unpack_bed<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const uint8_t*>(land), pitch, N, blk, M, ctx->d_counts + ctx->n_var);
+  for (int t = 0; t < tp.T; ++t) {
+    dim3 grid((unsigned)((npad / 16 + 255) / 256), (unsigned)tp.rows[t]);
+    k_unpack_bed<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const uint8_t*>(land) + (size_t)tp.r0[t] * pitch, pitch, N,
+                                                ctx->d_stage + tp.off[t], tp.rows[t], ctx->d_counts + ctx->n_var + tp.r0[t]);
+  }
   RVT_CUDA_OK(cudaGetLastError());
   if ((rc = land_release(ctx, slot))) return rc;
   ctx->bed_genes.push_back((int)ctx->genes.size());
-  if ((rc = push_common(ctx, blk, M, 0, af, nullptr, true, kSegStaged, off / 128, true))) return rc;
+  if ((rc = push_staged(ctx, tp, M, af))) return rc;
   return maybe_stream(ctx);
 }
 
@@ -621,8 +696,11 @@ static int resolve_bed_missing(rvt_ctx* ctx) {
   for (int gi : ctx->bed_genes) {
     const GeneDesc& gd = ctx->genes[gi];
     bool missing = false;
-    for (int j = 0; j < gd.M; ++j) missing |= hc[gd.var0 + j].bad > 0;
+    for (int j = 0; j < ctx->slots[gi]; ++j) missing |= hc[gd.var0 + j].bad > 0;
     if (!missing) continue;
+    if (ctx->slots[gi] > kMaxM)
+      CTX_FAIL(RVT_E_UNSUPPORTED, "gene of %d variants holds missing calls: mean imputation (fp64 path) handles up to %d variants",
+               ctx->slots[gi], kMaxM);
     DosGene dg;
     dg.gene_index = gi;
     dg.M = gd.M;
@@ -751,7 +829,7 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
     ctx->flush_open = true;
     ctx->n_launch = 0;
   }
-  const int64_t v0 = ctx->genes[g0].var0, v1 = ctx->genes[g1 - 1].var0 + ctx->genes[g1 - 1].M, nv = v1 - v0;
+  const int64_t v0 = ctx->genes[g0].var0, v1 = ctx->genes[g1 - 1].var0 + ctx->slots[g1 - 1], nv = v1 - v0;
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_genes + g0, hg, sizeof(GeneDesc) * n, cudaMemcpyHostToDevice, st));
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_userflags + v0, ctx->userflags.data() + v0, nv, cudaMemcpyHostToDevice, st));
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_af + v0, ctx->af.data() + v0, sizeof(double) * nv, cudaMemcpyHostToDevice, st));
@@ -798,6 +876,99 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
   ctx->pending_timing_batches += nbatch;
   ctx->n_launch += launches;
   ctx->launched = g1;
+  return RVT_OK;
+}
+
+// Genes wider than one tile (wide.cuh): per gene, the T diagonal tile sweeps and the T(T-1)/2 tile-pair sweeps fill the
+// M x M integer Gram, one more pass computes the burden collapses over all M variants, then one CTA per gene runs the
+// O(M^3) tail on a global-memory workspace.  Their records overwrite what the placeholder descriptors produced.
+static int run_wide(rvt_ctx* ctx, rvt_gene_result* d_res, int* launches) {
+  if (ctx->wide.empty()) return RVT_OK;
+  int rc;
+  if ((rc = tc_bind_segment(&ctx->tc, kSegStaged, ctx->d_stage, ctx->stage_cap, ctx->err, sizeof(ctx->err)))) return rc;
+  if (!(ctx->tc.encode && ctx->tc.have_e && ctx->tc.have_seg[kSegStaged]))
+    CTX_FAIL(RVT_E_UNSUPPORTED, "genes of more than %d variants need the tensor-core sweep (TMA unavailable: %s)", kMaxM, ctx->tc.why);
+  cudaStream_t st = ctx->stream;
+  const int64_t N = ctx->N;
+  const int nw = (int)ctx->wide.size();
+  if ((rc = ensure(ctx, (void**)&ctx->d_zero_flags, &ctx->cap_zero_flags, (size_t)ctx->n_var + kTileRows, 1))) return rc;
+  RVT_CUDA_OK(cudaMemsetAsync(ctx->d_zero_flags, 0, (size_t)ctx->n_var + kTileRows, st));
+  if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nw, sizeof(QagsScratch)))) return rc;
+  EngineParams prm{ctx->beta1, ctx->beta2};
+  std::vector<WideJob> jobs(nw);
+  std::vector<void*> to_free;
+  auto cleanup = [&]() {
+    for (void* p : to_free) cudaFree(p);
+  };
+  WideJob* d_jobs = nullptr;
+  RVT_CUDA_OK(cudaMalloc((void**)&d_jobs, sizeof(WideJob) * nw));
+  to_free.push_back(d_jobs);
+  const int batch = 1024;
+  for (int wi = 0; wi < nw; ++wi) {
+    const WideGene& w = ctx->wide[wi];
+    const int T = (int)w.tiles.size();
+    std::vector<GeneDesc> units(w.tiles);
+    for (int t = 0; t < T; ++t)
+      for (int u = t + 1; u < T; ++u) {
+        GeneDesc g = w.tiles[t];
+        g.row0_b = w.tiles[u].row0;
+        g.Mb = w.tiles[u].M;
+        g.var0_b = w.tiles[u].var0;
+        units.push_back(g);
+      }
+    const int n_units = (int)units.size();
+    uint8_t* ws = nullptr;
+    GeneDesc* d_units = nullptr;
+    cudaError_t e = cudaMalloc((void**)&ws, wide_ws_bytes(w.M));
+    if (e == cudaSuccess) to_free.push_back(ws);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_units, sizeof(GeneDesc) * n_units);
+    if (e != cudaSuccess) {
+      cleanup();
+      CTX_FAIL(RVT_E_CUDA, "wide gene (M=%d): cudaMalloc: %s", w.M, cudaGetErrorString(e));
+    }
+    to_free.push_back(d_units);
+    WideJob jb = wide_job_make(ws, w.M);
+    jb.out_index = w.gene_index;
+    jb.var0 = w.var0;
+    jb.has_af = w.has_af ? 1 : 0;
+    jb.counted = 1;
+    jobs[wi] = jb;
+    RVT_CUDA_OK(cudaMemsetAsync(jb.coll, 0, sizeof(long long) * kCollapseN, st));
+    RVT_CUDA_OK(cudaMemcpyAsync(d_units, units.data(), sizeof(GeneDesc) * n_units, cudaMemcpyHostToDevice, st));
+    int S = 0;
+    int64_t chunk = 0;
+    if ((rc = split_plan(ctx, std::min(n_units, batch), &S, &chunk))) { cleanup(); return rc; }
+    if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)std::min(n_units, batch) * S, sizeof(SweepPartial)))) { cleanup(); return rc; }
+    for (int pass = 0; pass < 2; ++pass) {   // 0: diagonal tiles, 1: tile pairs
+      const int u0 = pass ? T : 0, u1 = pass ? n_units : T;
+      for (int b0 = u0; b0 < u1; b0 += batch) {
+        const int nb = std::min(batch, u1 - b0);
+        rc = tc_launch(&ctx->tc, d_units + b0, units.data() + b0, nb, ctx->d_zero_flags, ctx->d_nm, N, ctx->ER, S, chunk, ctx->d_parts,
+                       ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), pass == 1, false);
+        if (rc) { cleanup(); return rc; }
+        k_wide_gather<<<nb, kWideGatherThreads, 0, st>>>(d_units + b0, nb, w.var0, w.M, ctx->ER, S, ctx->d_parts, jb.A_raw, jb.De, pass);
+        *launches += 2;
+      }
+    }
+    const int64_t nchunks = (N + 127) / 128;
+    k_wide_collapse<<<(unsigned)std::min<int64_t>(nchunks, (int64_t)ctx->sm_count * 8), kWideCollapseThreads, 0, st>>>(
+        d_units, T, w.var0, w.M, ctx->d_flags, ctx->d_nm, jb.coll);
+    *launches += 1;
+    RVT_CUDA_OK(cudaGetLastError());
+    // `units` is a host temporary of this iteration: the copy above must have left it
+    RVT_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  RVT_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(WideJob) * nw, cudaMemcpyHostToDevice, st));
+  if (ctx->skato)
+    k_wide_finalize<true><<<nw, kWideThreads, 0, st>>>(d_jobs, nw, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, d_res, ctx->d_qags);
+  else
+    k_wide_finalize<false><<<nw, kWideThreads, 0, st>>>(d_jobs, nw, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, d_res, nullptr);
+  *launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "wide genes: %s", cudaGetErrorString(e));
+  ctx->wide.clear();
   return RVT_OK;
 }
 
@@ -857,6 +1028,7 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     for (auto& dg : ctx->dos) cudaFree(dg.dG);
     ctx->dos.clear();
   }
+  if ((rc = run_wide(ctx, d_res, &launches))) return rc;
   RVT_CUDA_OK(cudaMemcpyAsync(out, d_res, sizeof(rvt_gene_result) * n, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   RVT_CUDA_OK(cudaEventRecord(ctx->ev[1], st));
   RVT_CUDA_OK(cudaStreamSynchronize(st));
@@ -915,6 +1087,7 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   if (ngen == 0) return RVT_OK;
   if (cap_variants < nv) CTX_FAIL(RVT_E_BADARG, "vout holds %lld records, %lld variants pending", (long long)cap_variants, (long long)nv);
   if (band && (!pos || !chrom)) CTX_FAIL(RVT_E_BADARG, "the covariance band needs pos and chrom");
+  if (!ctx->wide.empty()) CTX_FAIL(RVT_E_UNSUPPORTED, "meta: push variant blocks of at most %d variants", kMaxM);
   RVT_CUDA_OK(cudaSetDevice(ctx->device));
   // every pending push is one tile (<= 64 consecutive variants, its own tiled block) of one segment
   const int seg = ctx->genes[0].seg;

@@ -1,0 +1,319 @@
+// wide.cuh -- genes wider than one tensor-core tile (M > 64 variants, up to kWideMaxM).
+//
+// The reference has no width limit: Skat::Fit (regression/Skat.cpp:29-105), SkatO::Fit
+// (regression/SkatO.cpp:101-281), cmcCollapse / zegginiCollapse (src/Model.cpp:73-130) take whatever N x M
+// matrix the gene file selects, and MixtureChiSquare grows its lambda array on demand
+// (regression/MixtureChiSquare.h:26-52).  A wide gene is cut into T = ceil(M/64) tiles of consecutive variants, each
+// staged as its own tiled block; its M x M Gram comes from the T diagonal sweeps plus the T(T-1)/2 tile pairs of the
+// PAIR mode of the tensor-core sweep (the same units `--meta cov` uses), still exact integers.  The burden collapses
+// are per-SAMPLE functions of all M variants (an OR and a count), so they take one extra pass over the tiles
+// (k_wide_collapse).  The O(M^3) tail is the same device code as k_finalize (eigen.cuh, davies.cuh, skato_tail.cuh)
+// run by one CTA per gene on a workspace in global memory instead of shared memory.
+#pragma once
+#include "../../include/rvtests_b200.h"
+#include "common.cuh"
+#include "finalize.cuh"
+
+namespace rvt {
+
+constexpr int kWideMaxM = 2048;     // workspace = 2 M^2 x 8 B = 64 MB per gene at the cap
+constexpr int kWideThreads = 256;
+constexpr int kWideGatherThreads = 128;
+constexpr int kWideCollapseThreads = 128;   // one thread per sample of a 128-sample chunk
+
+// per-gene workspace, carved from one allocation by wide_job_make()
+struct WideJob {
+  int M;               // variants of the gene (all tiles)
+  int out_index;       // slot of the gene in the result array
+  int64_t var0;        // first slot of the gene in the per-variant side arrays (flags, af, counts)
+  int has_af, counted;
+  long long* A_raw;    // [M][M] raw G'G (both triangles)
+  long long* De;       // [M][ER] gene x digit sums
+  long long* coll;     // [kCollapseN] burden sums, SweepPartial::coll layout
+  long long* craw;     // [M] column sums
+  double* K;           // [M][M]
+  double* Wm;          // [M][M], SKAT-O only: aliases A_raw (dead once K is built)
+  double* dws;         // doubles: see wide_dws_*
+  int* iws;            // ints: idx[M], flip[M], th[8][M]
+};
+static inline size_t wide_dws_count(int M) { return (size_t)M * (3 + 2 * kMaxC) + 7 * (size_t)(M + 2); }
+static inline size_t wide_iws_count(int M) { return (size_t)M * (2 + kWideThreads / 32); }
+static inline size_t wide_ws_bytes(int M) {
+  size_t b = 0;
+  b += (size_t)M * M * 8 * 2;               // A_raw, K
+  b += (size_t)M * kMaxER * 8;              // De
+  b += (size_t)kCollapseN * 8 + (size_t)M * 8;   // coll, craw
+  b += wide_dws_count(M) * 8 + wide_iws_count(M) * 4;
+  return (b + 255) & ~(size_t)255;
+}
+static inline WideJob wide_job_make(uint8_t* ws, int M) {
+  WideJob j;
+  memset(&j, 0, sizeof(j));
+  j.M = M;
+  uint8_t* p = ws;
+  j.A_raw = (long long*)p;  p += (size_t)M * M * 8;
+  j.K = (double*)p;         p += (size_t)M * M * 8;
+  j.De = (long long*)p;     p += (size_t)M * kMaxER * 8;
+  j.coll = (long long*)p;   p += (size_t)kCollapseN * 8;
+  j.craw = (long long*)p;   p += (size_t)M * 8;
+  j.dws = (double*)p;       p += wide_dws_count(M) * 8;
+  j.iws = (int*)p;
+  j.Wm = (double*)j.A_raw;
+  return j;
+}
+
+// One CTA per sweep unit (a diagonal tile or a tile pair) of ONE wide gene: sum the splits into the gene's M x M
+// integer Gram; diagonal tiles also deliver the gene x digit columns.
+__global__ void __launch_bounds__(kWideGatherThreads)
+k_wide_gather(const GeneDesc* __restrict__ units, int n_units, int64_t var_base, int M, int ER, int S,
+              const SweepPartial* __restrict__ parts, long long* __restrict__ A_raw, long long* __restrict__ De, int pair) {
+  const int u = blockIdx.x, tid = threadIdx.x;
+  if (u >= n_units) return;
+  const GeneDesc gd = units[u];
+  const int ri = (int)(gd.var0 - var_base), rj = (int)(gd.var0_b - var_base), Ma = gd.M, Mb = gd.Mb;
+  const SweepPartial* __restrict__ gp = parts + (size_t)u * S;
+  for (int idx = tid; idx < Ma * Mb; idx += kWideGatherThreads) {
+    const int i = idx / Mb, j = idx - i * Mb;
+    long long a = 0;
+    for (int sp = 0; sp < S; ++sp) a += gp[sp].d[i][j];
+    A_raw[(size_t)(ri + i) * M + (rj + j)] = a;
+    if (pair) A_raw[(size_t)(rj + j) * M + (ri + i)] = a;
+  }
+  if (!pair)
+    for (int idx = tid; idx < Ma * ER; idx += kWideGatherThreads) {
+      const int i = idx / ER, e = idx - i * ER;
+      long long s = 0;
+      for (int sp = 0; sp < S; ++sp) s += gp[sp].d[i][kTileRows + e];
+      De[(size_t)(ri + i) * ER + e] = s;
+    }
+}
+
+// cmcCollapse / zegginiCollapse over ALL tiles of a wide gene (src/Model.cpp:73-89, 115-130) and their dot products
+// with the null-model digit rows: thread = one sample of a 128-sample chunk, grid-stride over chunks.  Exact integers,
+// so the atomics make the result independent of the schedule.  coll[]: SweepPartial::coll layout.
+__global__ void __launch_bounds__(kWideCollapseThreads)
+k_wide_collapse(const GeneDesc* __restrict__ tiles, int T, int64_t var_base, int M, const uint8_t* __restrict__ rowflags,
+                const NullModel* __restrict__ nm, long long* __restrict__ coll) {
+  __shared__ uint8_t s_flag[kWideMaxM];
+  __shared__ unsigned long long s_red[kCollapseN];
+  const int tid = threadIdx.x;
+  const int64_t N = nm->N, ldE = nm->ldE;
+  const int ER = nm->ER;
+  const int8_t* __restrict__ E = nm->E;
+  for (int j = tid; j < M; j += kWideCollapseThreads) s_flag[j] = rowflags[var_base + j];
+  if (tid < kCollapseN) s_red[tid] = 0ull;
+  __syncthreads();
+  long long az[kMaxER + 1], ac[kMaxER + 1];
+#pragma unroll
+  for (int e = 0; e <= kMaxER; ++e) az[e] = ac[e] = 0;
+  const int64_t nchunks = (N + 127) >> 7;
+  for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int64_t i = (c << 7) + tid;
+    if (i >= N) continue;   // the padding of the last chunk is zero and would count under a flipped row
+    int z = 0;
+    for (int t = 0; t < T; ++t) {
+      const int Mt = tiles[t].M, r0 = (int)(tiles[t].var0 - var_base);
+      const int8_t* __restrict__ p = tiles[t].g + ((size_t)c * Mt) * 128 + tid;
+      for (int r = 0; r < Mt; ++r) {
+        const int g = p[(size_t)r * 128];
+        const uint8_t f = s_flag[r0 + r];
+        z += (f == kRowNormal) ? (g > 0) : (f == kRowFlipped) ? (g < 2) : 0;
+      }
+    }
+    const int cm = z > 0;
+#pragma unroll
+    for (int e = 0; e < kMaxER; ++e)
+      if (e < ER) {
+        const int d = E[(size_t)e * ldE + i];
+        az[e] += (long long)z * d;
+        ac[e] += cm * d;
+      }
+    az[kMaxER] += (long long)z * z;
+    ac[kMaxER] += cm;
+  }
+#pragma unroll
+  for (int e = 0; e <= kMaxER; ++e) {
+    if (e < ER || e == kMaxER) {
+      long long a = az[e], b = ac[e];
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if ((tid & 31) == 0) {
+        const int slot = (e == kMaxER) ? ER : e;
+        atomicAdd(&s_red[slot], (unsigned long long)a);
+        atomicAdd(&s_red[(ER + 1) + slot], (unsigned long long)b);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < 2 * (ER + 1)) atomicAdd(reinterpret_cast<unsigned long long*>(coll) + tid, s_red[tid]);
+}
+
+// One CTA per wide gene: steps 2-7 of k_finalize on the global-memory workspace.
+template <bool SKATO>
+__global__ void __launch_bounds__(kWideThreads)
+k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __restrict__ rowflags, const double* __restrict__ af,
+                const RowCounts* __restrict__ counts, const NullModel* __restrict__ nm, EngineParams prm,
+                rvt_gene_result* __restrict__ res, QagsScratch* __restrict__ qags) {
+  struct SkatoShared {
+    QagsMachine mach;
+    double fv[21], bcast[3];
+  };
+  __shared__ typename std::conditional<SKATO, SkatoShared, int>::type s_sk;
+  __shared__ double s_red[64];
+  __shared__ double s_bur[2][2 + kMaxC];
+  __shared__ int s_Mp, s_bad, s_nonref;
+  __shared__ double s_Q;
+  const int g = blockIdx.x, tid = threadIdx.x;
+  if (g >= n_jobs) return;
+  constexpr int NT = kWideThreads;
+  const WideJob jb = jobs[g];
+  const int M = jb.M;
+  const int64_t N = nm->N;
+  const int C = nm->C, ER = nm->ER;
+  const double sigma2 = nm->sigma2;
+  BlockPar par{s_red};
+  double* s_s = jb.dws;
+  double* s_sw = s_s + M;
+  double* s_vw = s_sw + M;
+  double* s_B = s_vw + M;              // [M][kMaxC]
+  double* Uk = s_B + (size_t)M * kMaxC;   // [M][kMaxC]
+  double* s_ev = Uk + (size_t)M * kMaxC;
+  double* s_e = s_ev + (M + 2);
+  double* s_v = s_e + (M + 2);
+  double* s_p = s_v + (M + 2);
+  double* s_lam = s_p + (M + 2);
+  double* s_c = s_lam + (M + 2);
+  double* s_lamz = s_c + (M + 2);
+  int* s_idx = jb.iws;
+  int* s_flip = s_idx + M;
+  int* s_th = s_flip + M;              // [NT/32][M]
+  long long* s_craw = jb.craw;
+  const long long* __restrict__ De = jb.De;
+  double* K = jb.K;
+  const int kld = M;
+
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  // 2. per-variant counts -> flip / monomorphic, cross-checked with the flags the collapse used
+  for (int j = tid; j < M; j += NT) {
+    const long long cint = recombine4(&De[(size_t)j * ER + 4]);
+    const long long c = llrint((double)cint * nm->scale[1]);
+    const long long ajj = jb.A_raw[(size_t)j * M + j];
+    const long long n2 = (ajj - c) / 2, n1 = c - 2 * n2, n0 = N - n1 - n2;
+    const int flip = c > N;
+    const int mono = (n0 == N) || (n1 == N) || (n2 == N);
+    const uint8_t expect = mono ? kRowSkip : (flip ? kRowFlipped : kRowNormal);
+    if (rowflags[jb.var0 + j] != expect) atomicExch(&s_bad, 1);
+    if ((ajj - c) & 1 || n0 < 0 || n1 < 0 || n2 < 0) atomicExch(&s_bad, 2);
+    if (jb.counted && counts[jb.var0 + j].bad > 0) atomicExch(&s_bad, 2);
+    s_craw[j] = c;
+    s_flip[j] = mono ? -1 : flip;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int mp = 0;
+    for (int j = 0; j < M; ++j)
+      if (s_flip[j] >= 0) s_idx[mp++] = j;
+    s_Mp = mp;
+  }
+  __syncthreads();
+  const int Mp = s_Mp;
+  // 3. score vector, covariate cross-products, weights (kept variants, minor-coded)
+  for (int t = tid; t < Mp; t += NT) {
+    const int j = s_idx[t];
+    const int fl = s_flip[j];
+    long long sint = recombine4(&De[(size_t)j * ER]);
+    if (fl) sint = 2 * nm->vsum[0] - sint;
+    s_s[t] = (double)sint * nm->scale[0];
+    for (int l = 0; l < C; ++l) {
+      long long b = recombine4(&De[(size_t)j * ER + 4 * (l + 1)]);
+      if (fl) b = 2 * nm->vsum[l + 1] - b;
+      s_B[t * kMaxC + l] = (double)b * nm->scale[l + 1];
+    }
+    // weight t of the kept columns uses af[t] in the caller's ORIGINAL order
+    const double freq = jb.has_af ? af[jb.var0 + t] : (double)s_craw[j] / (2.0 * (double)N);
+    s_sw[t] = sqrt(beta_weight(freq, prm.beta1, prm.beta2, true));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double q = 0.0;
+    for (int i = 0; i < Mp; ++i) q += (s_sw[i] * s_sw[i]) * s_s[i] * s_s[i];
+    s_Q = q;
+  }
+  // 4. K = W^1/2 sigma2 (A' - B' (X'X)^-1 B'^T) W^1/2
+  for (int t = tid; t < Mp; t += NT)
+    for (int l = 0; l < C; ++l) {
+      double u = 0.0;
+      for (int m = 0; m < C; ++m) u += nm->xtx_inv[l * C + m] * s_B[t * kMaxC + m];
+      Uk[t * kMaxC + l] = u;
+    }
+  __syncthreads();
+  for (size_t idx = tid; idx < (size_t)Mp * Mp; idx += NT) {
+    const int i = (int)(idx / Mp), k = (int)(idx - (size_t)i * Mp);
+    if (k < i) continue;
+    const int ji = s_idx[i], jk = s_idx[k];
+    const int fi = s_flip[ji], fk = s_flip[jk];
+    long long a = jb.A_raw[(size_t)ji * M + jk];
+    const long long ci = s_craw[ji], ck = s_craw[jk];
+    if (fi && fk)
+      a = 4 * N - 2 * ci - 2 * ck + a;
+    else if (fi)
+      a = 2 * ck - a;
+    else if (fk)
+      a = 2 * ci - a;
+    double tt = 0.0;
+    for (int l = 0; l < C; ++l) tt += s_B[i * kMaxC + l] * Uk[k * kMaxC + l];
+    const double v = s_sw[i] * s_sw[k] * sigma2 * ((double)a - tt);
+    K[(size_t)i * kld + k] = v;
+    K[(size_t)k * kld + i] = v;
+  }
+  if (tid == 0) {
+    for (int which = 0; which < 2; ++which) {
+      const long long* cl = jb.coll + which * (ER + 1);
+      s_bur[which][0] = (double)recombine4(cl) * nm->scale[0];
+      s_bur[which][1] = (double)cl[ER];
+      for (int l = 0; l < C; ++l) s_bur[which][2 + l] = (double)recombine4(cl + 4 * (l + 1)) * nm->scale[l + 1];
+    }
+    s_nonref = (int)jb.coll[(ER + 1) + ER];
+  }
+  __syncthreads();   // every read of A_raw is done: Wm may overwrite it
+
+  if (SKATO && qags) {
+    const double sc = 0.5 / sigma2;
+    for (size_t idx = tid; idx < (size_t)Mp * Mp; idx += NT) {
+      const int i = (int)(idx / Mp), k = (int)(idx - (size_t)i * Mp);
+      jb.Wm[(size_t)i * kld + k] = K[(size_t)i * kld + k] * sc;
+    }
+    for (int t = tid; t < Mp; t += NT) s_vw[t] = s_sw[t] * s_s[t];
+    __syncthreads();
+  }
+  // 5./6. eigenvalues, Davies / Liu
+  double p_dav = -1.0, p_liu = 1.0, p_fin = 1.0, lam_max = 0.0;
+  int fault = 0, r = 0;
+  if (Mp > 0) {
+    sym_eigenvalues_tridiag(K, Mp, kld, s_ev, s_e, s_v, s_p, s_lam, par);
+    const int r_ub = (N < (int64_t)Mp) ? (int)N : Mp;
+    while (r < r_ub && s_lam[r] > 1e-30) ++r;
+    lam_max = r ? s_lam[0] : 0.0;
+    p_dav = mixchisq_pvalue(s_lam, r, s_Q, s_th, &fault, par);
+    p_liu = liu_pvalue(s_lam, r, s_Q);
+    p_fin = p_dav;
+    if (p_fin <= 0.0 || p_fin == 1.0) p_fin = p_liu;
+  }
+  SkatoOut so;
+  so.ok = 0;
+  so.Q = so.rho = so.pvalue = 0.0;
+  if constexpr (SKATO) {
+    if (qags && Mp > 0) {
+      QagsWork work{qags[g].a, qags[g].b, qags[g].r, qags[g].e, qags[g].order, qags[g].level, kQagsLimit};
+      const double s2 = sigma2 * (double)N / (double)(N - 1);
+      so = skato_tail(jb.Wm, K, Mp, kld, s_vw, s2, s_ev, s_e, s_v, s_p, s_lamz, s_c, &s_sk.mach, work, s_sk.fv, s_sk.bcast, s_th, M, par);
+    }
+  }
+  if (tid == 0)
+    burden_and_store(&res[jb.out_index], Mp, s_bad, s_Q, p_fin, p_dav, p_liu, fault, r, lam_max, so, s_bur, s_nonref, nm, 0);
+}
+
+}  // namespace rvt

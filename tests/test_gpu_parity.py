@@ -301,3 +301,79 @@ def test_full_size_properties(engine_cls, oracle):
         assert rel(r[0][k], r[1][k]) <= 1e-9, k
     assert r[0]["cmc_nonref"] == r[1]["cmc_nonref"] == base[1]["cmc_nonref"]
     eng.close()
+
+
+WIDE_CASES = [
+    # seed, N, M, C, n_mono, n_flip  -- genes wider than one 64-variant tensor-core tile (wide.cuh)
+    (60, 3000, 65, 3, 1, 1),
+    (61, 3000, 150, 3, 2, 3),
+    (62, 5003, 300, 2, 0, 2),
+    (63, 70000, 129, 3, 1, 2),
+]
+
+
+@pytest.mark.parametrize("case", WIDE_CASES)
+def test_wide_genes_vs_oracle(eng, oracle, case):
+    """The reference has no limit on the variants of a gene (MixtureChiSquare grows its lambda array,
+    regression/MixtureChiSquare.h:26-52): M > 64 goes through tile pairs + a global-memory tail."""
+    from rvtests_b200.synth import pack_bed
+    if eng.info("tc_available") != 1:
+        pytest.skip("wide genes need the tensor-core sweep")
+    O = oracle
+    seed, N, M, C, n_mono, n_flip = case
+    G, X, y = make_problem(O, seed, N, M, C, maf=np.linspace(0.001, 0.02, M), n_mono=n_mono, n_flip=n_flip)
+    Gs, _, _ = make_problem(O, seed + 100, N, 20, C, maf=np.linspace(0.01, 0.1, 20))
+    eng.set_option("engine", 0)
+    eng.set_null_model(X, y)
+    nm = O.fit_null_linear(X, y)
+    af = af_of(G)
+    eng.push_i8(Gs.T.copy(), af_of(Gs))         # ordinary genes around the wide ones: record order is push order
+    eng.push_i8(G.T.copy(), af)
+    eng.push_bed(pack_bed(G.T), af)
+    eng.push_i8(Gs.T.copy(), af_of(Gs))
+    eng.push_f64(G.astype(float), af)
+    res = eng.flush()
+    assert len(res) == 5
+    ref, lam = _oracle_gene(O, G, X, nm)
+    refs, lams = _oracle_gene(O, Gs, X, nm)
+    for k in (1, 2, 4):
+        check_gene(res[k], ref, lam, ctx=f"wide[{k}] {case}")
+    assert res[1].tobytes() == res[2].tobytes() == res[4].tobytes()
+    for k in (0, 3):
+        check_gene(res[k], refs, lams, ctx=f"ordinary gene beside a wide one [{k}] {case}")
+    # (n_lambda is not compared: eigenvalues of duplicate rare variants are rounding noise around the 1e-30 cut)
+
+
+def test_wide_gene_skato_vs_oracle(eng, oracle):
+    from oracle import skato_oracle as SO
+    if eng.info("tc_available") != 1:
+        pytest.skip("wide genes need the tensor-core sweep")
+    O = oracle
+    seed, N, M, C = 64, 4000, 100, 3
+    G, X, y = make_problem(O, seed, N, M, C, maf=np.linspace(0.002, 0.02, M), n_flip=2, n_mono=1)
+    eng.set_option("engine", 0)
+    eng.set_option("skato", 1)
+    try:
+        eng.set_null_model(X, y)
+        nm = O.fit_null_linear(X, y)
+        af = af_of(G)
+        eng.push_i8(G.T.copy(), af)
+        r = eng.flush()[0]
+    finally:
+        eng.set_option("skato", 0)
+    ref = SO.skato_gene(G.astype(float), af, X, nm["resid"])
+    assert int(r["skato_ok"]) == int(ref["ok"]) == 1
+    assert rel(r["skato_Q"], ref["Q"]) <= 1e-6
+    assert r["skato_rho"] == ref["rho"]
+    assert rel(r["skato_p"], ref["pvalue"]) <= 1e-5, (r["skato_p"], ref["pvalue"])
+    ref2, lam = _oracle_gene(O, G, X, nm)
+    check_gene(r, ref2, lam, ctx="wide gene with skato on")
+
+
+def test_too_wide_gene_is_refused(eng, oracle):
+    import rvtests_b200
+    O = oracle
+    X, y = O.synth_covariates(5, 64, 1)
+    eng.set_null_model(X, y)
+    with pytest.raises(rvtests_b200.RvtError):
+        eng.push_i8(np.zeros((2049, 64), dtype=np.int8))
