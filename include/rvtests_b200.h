@@ -75,6 +75,23 @@ typedef struct rvt_gene_result {
   double lambda_max;   /* largest kept eigenvalue (diagnostic) */
 } rvt_gene_result;
 
+/* Permutation test of `--kernel skat[nPerm=..,alpha=..]` (the reference's default): one record per gene of the last
+ * flush, the columns Permutation::writeOutput prints (src/Permutation.h:118-139).  Enabled by
+ * rvt_set_option("perm", nPerm) [+ "perm_alpha"]; the shuffles replay glibc's default rand() stream exactly as the
+ * reference's serial gene loop consumes it (src/LinearAlgebra.h:8-21, no srand anywhere), starting at
+ * "perm_stream_pos" draws (0 in a fresh process) and advancing by ActualPerm * (N-1) per gene. */
+typedef struct rvt_perm_result {
+  int32_t num_perm;      /* NumPerm */
+  int32_t actual_perm;   /* ActualPerm */
+  int32_t num_greater;   /* NumGreater */
+  int32_t num_equal;     /* NumEqual */
+  double stat;           /* Stat: the observed Q */
+  double p_perm;         /* PermPvalue */
+  int64_t stream_pos;    /* rand() values consumed before this gene's first shuffle */
+  int32_t done;          /* 1: permutations ran; 0: gene NA (fit() == -1) or on a path the test does not cover */
+  int32_t pad;
+} rvt_perm_result;
+
 /* ---- lifetime ------------------------------------------------------------------------------- */
 int rvt_ctx_create(int device, rvt_ctx** out);
 void rvt_ctx_destroy(rvt_ctx* ctx);
@@ -82,7 +99,8 @@ const char* rvt_last_error(const rvt_ctx* ctx);
 /* keys: "beta1","beta2" (Beta weight, src/ModelManager.cpp:169-175), "engine", "splits" (0=auto),
  * "skato" (0/1), "stream_batch" (B > 0: every B host pushes the engine enqueues sweep + statistics for
  * them right away, so the kernels run while the next genes are still crossing PCIe; rvt_flush then only
- * waits for the tail.  0 = everything at flush.  Options apply to genes pushed after the call.) */
+ * waits for the tail.  0 = everything at flush.  Options apply to genes pushed after the call.),
+ * "perm" (nPerm, 0 = analytic p-value only), "perm_alpha" (0.05), "perm_stream_pos", "perm_seed", "perm_batch". */
 int rvt_set_option(rvt_ctx* ctx, const char* key, double value);
 double rvt_get_info(const rvt_ctx* ctx, const char* key);
 /* run on a caller-owned CUDA stream (cudaStream_t), e.g. the framework's current stream, so that
@@ -133,6 +151,11 @@ int rvt_gene_push_dev_i8(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, cons
  *   exactly as DataConsolidator::imputeGenotypeToMean does (src/DataConsolidator.cpp:217-245);
  *   such a gene then takes the fp64 path. */
 int rvt_gene_push_bed(rvt_ctx* ctx, const uint8_t* bed, int M, int64_t stride, const double* af);
+/* permutation records of the genes of the LAST rvt_flush / rvt_run_loaded, in the same order (empty unless option
+ * "perm" > 0).  out == NULL: only *n_out is set. */
+int rvt_perm_results(rvt_ctx* ctx, rvt_perm_result* out, int cap, int* n_out);
+/* diagnostics: with option "debug_perm_q" = 1, every permuted statistic of the last flush, in the order they ran */
+int rvt_perm_debug_q(rvt_ctx* ctx, double* out, int cap, int* n_out);
 /* number of genes pushed and not yet flushed */
 int rvt_pending(const rvt_ctx* ctx);
 /* run the sweep + per-gene statistics for every pending gene; out: host array of `cap` records */

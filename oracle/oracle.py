@@ -241,6 +241,36 @@ def gene(G_raw, af, X, resid, sigma2, beta1=1.0, beta2=25.0, native=False):
     return out, lam[: out.skat.n_lambda].copy()
 
 
+
+def gene_perm(G_raw, af, resid, obs, n_perm=10000, alpha=0.05, reseed=0, beta1=1.0, beta2=25.0, native=False):
+    """A6: the permutation loop of SkatTest::fit on one gene; consumes the process-wide glibc rand() stream
+    (reseed=1 restarts it as in a fresh process).  Returns dict(actual, greater, equal, p, q)."""
+    Gc = np.asfortranarray(G_raw, dtype=np.float64)
+    N, M = Gc.shape
+    af = np.ascontiguousarray(af, dtype=np.float64)
+    resid = np.ascontiguousarray(resid, dtype=np.float64)
+    out = (C.c_int * 3)()
+    p = C.c_double(1.0)
+    q = np.zeros(max(n_perm, 1))
+    L = lib(native)
+    L.orc_gene_perm.argtypes = [C.c_int64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_uint,
+                                C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.orc_gene_perm.restype = C.c_int
+    rc = L.orc_gene_perm(N, M, _p(Gc), _p(af), _p(resid), float(obs), float(beta1), float(beta2), int(n_perm),
+                         float(alpha), int(reseed), out, C.byref(p), _p(q))
+    return dict(rc=rc, actual=out[0], greater=out[1], equal=out[2], p=p.value, q=q[: out[0]].copy())
+
+
+def glibc_rand(n, reseed=0, skip=0, native=False):
+    """the next n values of glibc rand() (reseed=1: as in a fresh process)"""
+    out = np.zeros(n, dtype=np.int32)
+    L = lib(native)
+    L.orc_glibc_rand.argtypes = [C.c_uint, C.c_int64, C.c_int64, C.c_void_p]
+    L.orc_glibc_rand.restype = None
+    L.orc_glibc_rand(int(reseed), int(skip), int(n), out.ctypes.data)
+    return out
+
 def gene_batch(G_all, af_all, X, resid, sigma2, threads=1, beta1=1.0, beta2=25.0, native=False):
     """G_all: (n_genes, M, N) C-contiguous == each gene N x M column-major."""
     G_all = np.ascontiguousarray(G_all, dtype=np.float64)

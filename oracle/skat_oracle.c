@@ -1075,6 +1075,79 @@ ORC_API int orc_gene(int64_t N, int M, int C, const double* G_raw, const double*
   return rc;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * A6: the permutation p-value of SkatTest::fit (src/Model.h:2707-2717).
+ *   permute()                    src/LinearAlgebra.h:8-21   i = n-1..1, j = rand() % (i+1), swap -- glibc rand(),
+ *                                                           never seeded by the reference (default state == srand(1))
+ *   Skat::GetQFromNewResidual    regression/Skat.cpp:107-116  float32: res cast to float, K_sqrt = W^1/2 G' in float,
+ *                                                           (K_sqrt * res).squaredNorm()
+ *   Permutation init/next/add/getPvalue   src/Permutation.h:69-98   `int threshold = 1.0*numPerm*alpha*2`
+ * The shuffles are cumulative within a gene (permutedRes is shuffled again and again) and the rand() stream runs
+ * on from gene to gene.  `reseed` != 0 calls srand(reseed) first (srand(1) == a fresh process).
+ * G: the flipped/polymorphic N x mp matrix, w: the SQUARED Beta weights, obs: the observed statistic
+ * (Skat::GetQ).  out[0..2] = ActualPerm, NumGreater, NumEqual; *pval = PermPvalue.  q_out (nullable): the
+ * statistic of every permutation that ran.
+ * ---------------------------------------------------------------------------------------- */
+ORC_API int orc_skat_perm(int64_t N, int mp, const double* G, const double* w, const double* resid, double obs,
+                          int nPerm, double alpha, unsigned reseed, int* out, double* pval, double* q_out) {
+  if (reseed) srand(reseed);
+  float* K = (float*)malloc(sizeof(float) * (size_t)N * mp);   /* K_sqrt, row j = sqrt(w_j) g_j' */
+  float* rf = (float*)malloc(sizeof(float) * (size_t)N);
+  double* v = (double*)malloc(sizeof(double) * (size_t)N);
+  for (int j = 0; j < mp; ++j) {
+    const float sw = (float)sqrt(w[j]);                         /* w_sqrt is a VectorXf (Skat.cpp:41-45) */
+    for (int64_t i = 0; i < N; ++i) K[(size_t)j * N + i] = sw * (float)G[(size_t)j * N + i];
+  }
+  for (int64_t i = 0; i < N; ++i) v[i] = resid[i];              /* permutedRes = res */
+  int actual = 0, numX = 0, numEq = 0;
+  const int threshold = 1.0 * nPerm * alpha * 2;
+  while (actual < nPerm && numX + numEq < threshold) {
+    for (int64_t i = N - 1; i >= 1; --i) {
+      int j = rand() % (i + 1);
+      if (i != j) { double t = v[i]; v[i] = v[j]; v[j] = t; }
+    }
+    for (int64_t i = 0; i < N; ++i) rf[i] = (float)v[i];
+    float q = 0.f;
+    for (int j = 0; j < mp; ++j) {
+      float d = 0.f;
+      for (int64_t i = 0; i < N; ++i) d += K[(size_t)j * N + i] * rf[i];
+      q += d * d;
+    }
+    const double s = (double)q;
+    if (q_out) q_out[actual] = s;
+    ++actual;
+    if (s > obs) ++numX;
+    if (s == obs) ++numEq;
+  }
+  out[0] = actual; out[1] = numX; out[2] = numEq;
+  *pval = actual ? 1.0 * (numX + 0.5 * numEq) / actual : 1.0;
+  free(K); free(rf); free(v);
+  return 0;
+}
+
+/* gene-level wrapper: flip / drop monomorphic, weights (index quirk F9), then orc_skat_perm */
+ORC_API int orc_gene_perm(int64_t N, int M, const double* G_raw, const double* af, const double* resid, double obs,
+                          double beta1, double beta2, int nPerm, double alpha, unsigned reseed, int* out, double* pval,
+                          double* q_out) {
+  orc_scratch sc;
+  orc_scratch_init(&sc, N, M);
+  int mp = orc_flip_minor_polymorphic(N, M, G_raw, sc.G, sc.keep, NULL);
+  int rc = -1;
+  if (mp > 0) {
+    for (int i = 0; i < mp; ++i) sc.w[i] = orc_skat_weight(af[i], beta1, beta2, 1);
+    rc = orc_skat_perm(N, mp, sc.G, sc.w, resid, obs, nPerm, alpha, reseed, out, pval, q_out);
+  }
+  orc_scratch_free(&sc);
+  return rc;
+}
+
+/* the next n values of glibc rand() (after srand(reseed) when reseed != 0): pins the device generator */
+ORC_API void orc_glibc_rand(unsigned reseed, int64_t skip, int64_t n, int* out) {
+  if (reseed) srand(reseed);
+  for (int64_t i = 0; i < skip; ++i) (void)rand();
+  for (int64_t i = 0; i < n; ++i) out[i] = rand();
+}
+
 /* Batch driver for the CPU baseline: genes laid out back to back (each N x M col-major doubles),
  * OpenMP over genes on `threads` host threads (the reference's own gene loop is serial,
  * src/Main.cpp:1221-1254; threads=1 reproduces that). */

@@ -16,6 +16,7 @@
 #include "finalize.cuh"
 #include "meta.cuh"
 #include "null_model.cuh"
+#include "perm.cuh"
 #include "prep.cuh"
 #include "sweep_simt.cuh"
 #include "sweep_tc.cuh"
@@ -47,6 +48,7 @@ struct TilePlan {    // where the tiles of one pushed gene were staged
 
 constexpr int kSegLoaded = 0;  // the synthetic / loaded cohort arena
 constexpr int kSegStaged = 1;  // genes staged from host buffers
+constexpr int kSegPerm = 2;    // 16-permutation digit tiles of the permutation test (perm.cuh)
 
 struct rvt_ctx {
   int device = 0;
@@ -80,6 +82,18 @@ struct rvt_ctx {
   std::vector<int> slots;          // per gene: per-variant slots it owns (== M except for the placeholder of a wide gene)
   uint8_t* d_zero_flags = nullptr; // "every row normal" flags for the tile sweeps of wide genes
   size_t cap_zero_flags = 0;
+  // permutation test (perm.cuh): options, rand() stream position, scratch, records of the last flush
+  int perm_n = 0, perm_batch = 256;
+  double perm_alpha = 0.05;
+  uint64_t perm_pos = 0;           // rand() values consumed so far (the reference's process-wide stream)
+  uint32_t perm_seed = 1;          // glibc's default state == srand(1); the reference never seeds
+  LfgTables* d_lfg = nullptr;
+  uint8_t* d_perm = nullptr;       // one scratch allocation, carved per gene
+  size_t cap_perm = 0;
+  std::vector<rvt_perm_result> perm_out;
+  std::vector<char> is_dos;        // per pending gene: took the fp64 path
+  bool perm_log = false;           // option "debug_perm_q": keep every permuted statistic of the last flush
+  std::vector<double> perm_q_log;
   std::vector<int> bed_genes;      // pending genes pushed as PLINK 2-bit rows: checked for missing calls at flush
   int launched = 0;                // pending genes [0, launched) already have their kernels enqueued (stream_batch)
   int stream_batch = 0;            // option: enqueue sweep + statistics every this many host pushes (0 = only at flush)
@@ -266,7 +280,7 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_zero_flags};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -319,6 +333,22 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
     ctx->tc.l2promo = (int)value;
     for (auto& sg : ctx->tc.seg)
       for (bool& b : sg.have_m) b = false;  // re-encode lazily
+  } else if (k == "perm") {
+    if (value < 0 || value > 1e9) CTX_FAIL(RVT_E_BADARG, "perm (nPerm) must be in 0..1e9");
+    ctx->perm_n = (int)value;
+  } else if (k == "perm_alpha") {
+    ctx->perm_alpha = value;
+  } else if (k == "perm_batch") {
+    if (value < 16 || value > 4096 || ((int)value & 15)) CTX_FAIL(RVT_E_BADARG, "perm_batch must be a multiple of 16 in 16..4096");
+    ctx->perm_batch = (int)value;
+  } else if (k == "perm_stream_pos") {
+    if (value < 0) CTX_FAIL(RVT_E_BADARG, "perm_stream_pos must be >= 0");
+    ctx->perm_pos = (uint64_t)value;
+  } else if (k == "perm_seed") {
+    ctx->perm_seed = (uint32_t)value;
+    ctx->perm_pos = 0;
+  } else if (k == "debug_perm_q") {
+    ctx->perm_log = value != 0;
   } else if (k == "debug_phases") {
     ctx->want_dbg = value != 0;
   } else
@@ -345,6 +375,7 @@ double rvt_get_info(const rvt_ctx* ctx, const char* key) {
   if (k == "ER") return ctx->ER;
   if (k == "loaded_ld") return (double)ctx->loaded_ld;
   if (k == "tc_available") return ctx->tc.encode ? 1 : 0;
+  if (k == "perm_stream_pos") return (double)ctx->perm_pos;
   return -1;
 }
 
@@ -968,7 +999,155 @@ static int run_wide(rvt_ctx* ctx, rvt_gene_result* d_res, int* launches) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cleanup();
   if (e != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "wide genes: %s", cudaGetErrorString(e));
-  ctx->wide.clear();
+  return RVT_OK;
+}
+
+// A6 (perm.cuh): permutation p-values of the SKAT statistic, gene after gene in push order, consuming the glibc
+// rand() stream exactly as the reference's serial loop does (src/Model.h:2707-2717).  Runs after the analytic
+// results exist (the observed Q is the comparison value).
+static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* launches) {
+  ctx->perm_out.clear();
+  ctx->perm_q_log.clear();
+  if (ctx->perm_n <= 0) return RVT_OK;
+  if (!(ctx->tc.encode && ctx->tc.have_e))
+    CTX_FAIL(RVT_E_UNSUPPORTED, "the permutation test needs the tensor-core sweep (TMA unavailable: %s)", ctx->tc.why);
+  int rc;
+  cudaStream_t st = ctx->stream;
+  const int64_t N = ctx->N;
+  if (N < 2 || N > 0xFFFFFFF0ll) CTX_FAIL(RVT_E_UNSUPPORTED, "permutation test: N out of range");
+  std::vector<rvt_gene_result> hres(n);
+  RVT_CUDA_OK(cudaMemcpyAsync(hres.data(), d_res, sizeof(rvt_gene_result) * n, cudaMemcpyDeviceToHost, st));
+  RVT_CUDA_OK(cudaStreamSynchronize(st));
+  ctx->perm_out.assign(n, rvt_perm_result{});
+  if (!ctx->d_lfg) {   // jump tables of the rand() recurrence (constant)
+    std::vector<LfgTables> tab(1);
+    for (int k = 0; k < 32; ++k) tab[0].zblock[k] = lfg_pow((uint64_t)kLfgBlock << k);
+    for (int t = 0; t < kLfgThreads; ++t) tab[0].zthread[t] = lfg_pow((uint64_t)t * kLfgRun);
+    RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_lfg, sizeof(LfgTables)));
+    RVT_CUDA_OK(cudaMemcpy(ctx->d_lfg, tab.data(), sizeof(LfgTables), cudaMemcpyHostToDevice));
+  }
+  uint32_t y0[2 * kLfgDeg - 1];
+  lfg_seed_window(ctx->perm_seed, y0);
+  const int PB = ctx->perm_batch;                 // permutations per batch (multiple of 16)
+  const int64_t tile_b = tiled_bytes(N, kTileRows);
+  int Mmax = 1, Tmax = 1;
+  for (int g = 0; g < n; ++g) Mmax = std::max(Mmax, ctx->slots[g]);
+  for (auto& w : ctx->wide) Tmax = std::max<int>(Tmax, (int)w.tiles.size());
+  // scratch layout
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) & ~(size_t)1023; return o; };
+  const size_t o_tiles = carve((size_t)(PB / 16) * tile_b);
+  const size_t o_draws = carve((size_t)PB * (N - 1) * 4);
+  const size_t o_head = carve((size_t)PB * N * 4);
+  const size_t o_link = carve((size_t)PB * N * 4);
+  const size_t o_root = carve((size_t)PB * N * 4);
+  const size_t o_R0 = carve((size_t)N * 4), o_R1 = carve((size_t)N * 4);
+  const size_t o_w0 = carve(64 * 4);
+  const size_t o_sint = carve((size_t)PB * Mmax * 8);
+  const size_t o_w = carve((size_t)Mmax * 8);
+  const size_t o_Q = carve((size_t)PB * 8);
+  const size_t o_units = carve(sizeof(GeneDesc) * (size_t)Tmax * (PB / 16));
+  if (off > ctx->cap_perm) {
+    if (ctx->d_perm) cudaFree(ctx->d_perm);
+    ctx->d_perm = nullptr;
+    ctx->cap_perm = 0;
+    RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_perm, off));
+    ctx->cap_perm = off;
+  }
+  uint8_t* base = ctx->d_perm;
+  int8_t* d_tiles = (int8_t*)(base + o_tiles);
+  uint32_t *d_draws = (uint32_t*)(base + o_draws), *d_head = (uint32_t*)(base + o_head), *d_link = (uint32_t*)(base + o_link),
+           *d_root = (uint32_t*)(base + o_root), *d_R[2] = {(uint32_t*)(base + o_R0), (uint32_t*)(base + o_R1)},
+           *d_w0 = (uint32_t*)(base + o_w0);
+  long long* d_sint = (long long*)(base + o_sint);
+  double *d_w = (double*)(base + o_w), *d_Q = (double*)(base + o_Q);
+  GeneDesc* d_units = (GeneDesc*)(base + o_units);
+  if ((rc = tc_bind_segment(&ctx->tc, kSegPerm, d_tiles, (int64_t)(PB / 16) * tile_b, ctx->err, sizeof(ctx->err)))) return rc;
+  if ((rc = ensure(ctx, (void**)&ctx->d_zero_flags, &ctx->cap_zero_flags, (size_t)ctx->n_var + kTileRows, 1))) return rc;
+  RVT_CUDA_OK(cudaMemsetAsync(ctx->d_zero_flags, 0, (size_t)ctx->n_var + kTileRows, st));
+  EngineParams prm{ctx->beta1, ctx->beta2};
+  const int threshold = (int)(1.0 * ctx->perm_n * ctx->perm_alpha * 2);   // Permutation::init, `int threshold`
+  std::vector<double> hQ(PB);
+  std::vector<GeneDesc> units;
+  for (int g = 0; g < n; ++g) {
+    rvt_perm_result& rec = ctx->perm_out[g];
+    rec.num_perm = ctx->perm_n;
+    rec.stat = hres[g].Q;
+    rec.stream_pos = (int64_t)ctx->perm_pos;
+    rec.p_perm = 1.0;
+    const GeneDesc& gd = ctx->genes[g];
+    // fit() returned -1 (no polymorphic variant): the reference runs no permutation.  Genes on the fp64 path and
+    // caller-owned device blocks without the engine's own counts are not covered.
+    if (hres[g].status != RVT_GENE_OK || ctx->is_dos[g] || !gd.tiled || gd.seg < 0 || (!gd.has_af && !gd.counted)) continue;
+    const std::vector<GeneDesc>* tiles = nullptr;
+    std::vector<GeneDesc> one(1, gd);
+    for (auto& w : ctx->wide)
+      if (w.gene_index == g) tiles = &w.tiles;
+    if (!tiles) tiles = &one;
+    const int T = (int)tiles->size(), M = ctx->slots[g];
+    const double obs = hres[g].Q;
+    int actual = 0, numX = 0, numEq = 0, cur = 0;
+    k_perm_init<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ctx->d_nm, d_R[0]);
+    while (actual < ctx->perm_n && numX + numEq < threshold) {
+      const int Pb = std::min(PB, ctx->perm_n - actual), Pb16 = (Pb + 15) & ~15, G16 = Pb16 / 16;
+      const uint64_t pos0 = ctx->perm_pos + (uint64_t)actual * (uint64_t)(N - 1);
+      uint32_t w0[2 * kLfgDeg - 1];
+      lfg_window_at(lfg_pow(pos0 + kLfgWarm), y0, w0);
+      RVT_CUDA_OK(cudaMemcpyAsync(d_w0, w0, sizeof(w0), cudaMemcpyHostToDevice, st));   // (pageable: staged before return)
+      const uint64_t cnt = (uint64_t)Pb16 * (uint64_t)(N - 1);
+      k_lfg_draws<<<(unsigned)((cnt + kLfgBlock - 1) / kLfgBlock), kLfgThreads, 0, st>>>(ctx->d_lfg, d_w0, cnt, d_draws);
+      RVT_CUDA_OK(cudaMemsetAsync(d_head, 0xFF, (size_t)Pb16 * N * 4, st));
+      k_fy_link<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_draws, (uint32_t)N, Pb16, d_head, d_link);
+      k_fy_root<<<(unsigned)(((uint64_t)Pb16 * N + 255) / 256), 256, 0, st>>>(d_draws, (uint32_t)N, Pb16, d_head, d_link, d_root);
+      for (int p = 0; p < Pb16; ++p) {
+        k_perm_gather<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_R[cur], d_root + (size_t)p * N, (uint32_t)N, d_R[cur ^ 1],
+                                                                    d_tiles + (size_t)(p / 16) * tile_b, 4 * (p % 16));
+        cur ^= 1;
+      }
+      *launches += 4 + Pb16;
+      units.clear();
+      for (int t = 0; t < T; ++t)
+        for (int u = 0; u < G16; ++u) {
+          GeneDesc ud = (*tiles)[t];
+          ud.row0_b = (int64_t)u * tile_b / 128;
+          ud.Mb = kTileRows;
+          ud.var0_b = u;
+          units.push_back(ud);
+        }
+      const int n_units = (int)units.size();
+      RVT_CUDA_OK(cudaMemcpyAsync(d_units, units.data(), sizeof(GeneDesc) * n_units, cudaMemcpyHostToDevice, st));
+      const int batch = 1024;
+      int S = 0;
+      int64_t chunk = 0;
+      if ((rc = split_plan(ctx, std::min(n_units, batch), &S, &chunk))) return rc;
+      if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)std::min(n_units, batch) * S, sizeof(SweepPartial)))) return rc;
+      for (int b0 = 0; b0 < n_units; b0 += batch) {
+        const int nb = std::min(batch, n_units - b0);
+        rc = tc_launch(&ctx->tc, d_units + b0, units.data() + b0, nb, ctx->d_zero_flags, ctx->d_nm, N, ctx->ER, S, chunk, ctx->d_parts,
+                       ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), true, false, kSegPerm);
+        if (rc) return rc;
+        k_perm_sint<<<nb, 128, 0, st>>>(d_units + b0, nb, gd.var0, M, S, ctx->d_parts, d_sint);
+        *launches += 2;
+      }
+      k_perm_q<<<1, 256, 0, st>>>(Pb16, M, gd.var0, gd.has_af, d_sint, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, d_w, d_Q);
+      *launches += 1;
+      RVT_CUDA_OK(cudaGetLastError());
+      RVT_CUDA_OK(cudaMemcpyAsync(hQ.data(), d_Q, sizeof(double) * Pb16, cudaMemcpyDeviceToHost, st));
+      RVT_CUDA_OK(cudaStreamSynchronize(st));
+      for (int p = 0; p < Pb && actual < ctx->perm_n && numX + numEq < threshold; ++p) {   // Permutation::next / add
+        ++actual;
+        if (ctx->perm_log) ctx->perm_q_log.push_back(hQ[p]);
+        if (hQ[p] > obs) ++numX;
+        if (hQ[p] == obs) ++numEq;
+      }
+    }
+    ctx->perm_pos += (uint64_t)actual * (uint64_t)(N - 1);
+    rec.actual_perm = actual;
+    rec.num_greater = numX;
+    rec.num_equal = numEq;
+    rec.p_perm = actual ? 1.0 * (numX + 0.5 * numEq) / actual : 1.0;   // Permutation::getPvalue
+    rec.done = 1;
+  }
   return RVT_OK;
 }
 
@@ -987,6 +1166,8 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   rvt_gene_result* d_res = ctx->d_res;
   EngineParams prm{ctx->beta1, ctx->beta2};
   int launches = 0;
+  ctx->is_dos.assign(n, 0);
+  for (auto& dg : ctx->dos) ctx->is_dos[dg.gene_index] = 1;
   if (!ctx->dos.empty()) {
     // genes with dosage / imputed values: fp64 statistics, then the same tail (eigen, Davies, SKAT-O, burden);
     // their records overwrite what the hard-call pipeline produced for the same slots
@@ -1029,6 +1210,7 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     ctx->dos.clear();
   }
   if ((rc = run_wide(ctx, d_res, &launches))) return rc;
+  if ((rc = run_perm(ctx, d_res, n, &launches))) return rc;
   RVT_CUDA_OK(cudaMemcpyAsync(out, d_res, sizeof(rvt_gene_result) * n, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   RVT_CUDA_OK(cudaEventRecord(ctx->ev[1], st));
   RVT_CUDA_OK(cudaStreamSynchronize(st));
@@ -1053,6 +1235,24 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
 }
 
 int rvt_flush(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out) { return flush_impl(ctx, out, cap, n_out, false); }
+int rvt_perm_debug_q(rvt_ctx* ctx, double* out, int cap, int* n_out) {
+  if (!ctx || !n_out) return RVT_E_BADARG;
+  const int n = (int)ctx->perm_q_log.size();
+  *n_out = n;
+  if (!out) return RVT_OK;
+  if (cap < n) CTX_FAIL(RVT_E_BADARG, "permuted statistics: %d available, cap %d", n, cap);
+  if (n) memcpy(out, ctx->perm_q_log.data(), sizeof(double) * n);
+  return RVT_OK;
+}
+int rvt_perm_results(rvt_ctx* ctx, rvt_perm_result* out, int cap, int* n_out) {
+  if (!ctx || !n_out) return RVT_E_BADARG;
+  const int n = (int)ctx->perm_out.size();
+  *n_out = n;
+  if (!out) return RVT_OK;
+  if (cap < n) CTX_FAIL(RVT_E_BADARG, "permutation records: %d available, cap %d", n, cap);
+  if (n) memcpy(out, ctx->perm_out.data(), sizeof(rvt_perm_result) * n);
+  return RVT_OK;
+}
 int rvt_flush_dev(rvt_ctx* ctx, rvt_gene_result* d_out, int cap, int* n_out) {
   return flush_impl(ctx, d_out, cap, n_out, true);
 }

@@ -166,7 +166,9 @@ __device__ __forceinline__ uint32_t sw128_word_off(int r, int w) {
 // Needs M <= 62 and splits short enough for z.E_e to stay inside int32 (host checks both).
 template <int ER, int kTcStages, bool PAIR, int kTcBoxes, bool WIDE = false, bool ZC = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */, const __grid_constant__ CUtensorMap map_e,
+k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */,
+           const CUtensorMap* __restrict__ maps_b /* PAIR: the maps of the segment the B tiles live in (may equal maps_g) */,
+           const __grid_constant__ CUtensorMap map_e,
            const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __restrict__ rowflags, int64_t N, int S,
            int64_t chunk, SweepPartial* __restrict__ out, int dbg_skip /* timing experiments only: 1 no collapse,
            2 no MMA, 4 no E loads; results are then meaningless */) {
@@ -229,7 +231,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
         const CUtensorMap* mg = maps_g + (Mg - 1);
         const int row0b = (int)genes[gi].row0_b;
         const int Mgb = genes[gi].Mb;
-        const CUtensorMap* mgb = maps_g + (Mgb - 1);
+        const CUtensorMap* mgb = maps_b + (Mgb - 1);
         const uint32_t stage_tx = (uint32_t)(kTcBoxes * (Mg + (PAIR ? Mgb : 0) + ((dbg_skip & 4) ? 0 : ER)) * 128);
         const int64_t k0 = (int64_t)sp * chunk;
         int64_t k1 = k0 + chunk;
@@ -652,7 +654,12 @@ inline int tc_bind_segment(TcSegments* tc, int seg, const int8_t* base, int64_t 
 }
 
 // make sure the segment has a tensor map for every box height present in this batch
-inline int tc_prepare_maps(TcSegments* tc, int seg, const GeneDesc* h_genes, int n, cudaStream_t st, char* err, size_t errlen) {
+inline int tc_prepare_maps(TcSegments* tc, int seg, const GeneDesc* h_genes, int n, cudaStream_t st, char* err, size_t errlen,
+                           int seg_b = -1 /* PAIR: segment of the B tiles when it is not `seg` */) {
+  if (seg_b >= 0 && seg_b != seg) {
+    int rc = tc_prepare_maps(tc, seg_b, h_genes, n, st, err, errlen, -1);   // (encodes a few unused heights; harmless)
+    if (rc) return rc;
+  }
   TcSegments::Seg& sg = tc->seg[seg];
   for (int i = 0; i < 2 * n; ++i) {
     const int M = (i < n) ? h_genes[i].M : h_genes[i - n].Mb;
@@ -696,18 +703,19 @@ inline bool tc_usable(TcSegments* tc, const GeneDesc* h_genes, int n) {
 inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_genes, int n, const uint8_t* d_flags,
                      const NullModel* /*d_nm*/, int64_t N, int ER, int S, int64_t chunk, SweepPartial* d_parts,
                      unsigned int* /*counter*/, int sm_count, cudaStream_t st, char* err, size_t errlen,
-                     bool pair = false, bool wide = false) {
+                     bool pair = false, bool wide = false, int seg_b = -1) {
   const int seg = h_genes[0].seg;
+  if (seg_b < 0) seg_b = seg;
   const int grid = std::min(n * S, sm_count);
   if (chunk % kTcChunkAlign != 0) {
     snprintf(err, errlen, "internal: chunk %lld is not a multiple of the TMA stage (%d)", (long long)chunk, kTcChunkAlign);
     return -3;
   }
-  int rc = tc_prepare_maps(tc, seg, h_genes, n, st, err, errlen);
+  int rc = tc_prepare_maps(tc, seg, h_genes, n, st, err, errlen, seg_b);
   if (rc) return rc;
 #define RVT_TC_LAUNCH(ER_, ST_, PAIR_, BX_, ...)                                                                             \
   k_sweep_tc<ER_, ST_, PAIR_, BX_, ##__VA_ARGS__><<<grid, kTcThreads, TcCfg<ER_, ST_, PAIR_, BX_, ##__VA_ARGS__>::kSmem, st>>>( \
-      tc->seg[seg].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts, tc->dbg_skip)
+      tc->seg[seg].d_maps, tc->seg[seg_b].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts, tc->dbg_skip)
   // burden scores through the UMMA: two spare tile rows and |z . digit| sums that fit int32
   bool zc = tc->zc && !pair && tc->boxes == 4 && chunk <= 262144;
   for (int i = 0; i < n && zc; ++i) zc = h_genes[i].M <= kTileRows - 2;

@@ -52,8 +52,13 @@ EXPORTS = [
     "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded",
     "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
     "rvt_debug_phases",
-    "rvt_meta_plan", "rvt_meta_flush",
+    "rvt_meta_plan", "rvt_meta_flush", "rvt_perm_results", "rvt_perm_debug_q",
 ]
+
+PERM_DTYPE = np.dtype([
+    ("num_perm", "i4"), ("actual_perm", "i4"), ("num_greater", "i4"), ("num_equal", "i4"),
+    ("stat", "f8"), ("p_perm", "f8"), ("stream_pos", "i8"), ("done", "i4"), ("pad", "i4"),
+])
 
 VARIANT_DTYPE = np.dtype([
     ("af", "f8"), ("ac", "f8"), ("call_rate", "f8"), ("hwe_p", "f8"),
@@ -102,6 +107,8 @@ def load_library(rebuild: bool = False):
     L.rvt_debug_phases.argtypes = [vp, vp, C.c_int]
     L.rvt_meta_plan.argtypes = [vp, vp, vp, C.c_int64, C.c_int64, C.POINTER(C.c_int)]
     L.rvt_meta_flush.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.POINTER(C.c_int)]
+    L.rvt_perm_results.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
+    L.rvt_perm_debug_q.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -208,6 +215,21 @@ class GeneEngine:
         out = np.zeros(max(n, 1), dtype=RESULT_DTYPE)
         got = C.c_int(0)
         self._chk(self.L.rvt_flush(self.h, out.ctypes.data, len(out), C.byref(got)))
+        return out[: got.value]
+
+    def perm_results(self):
+        """permutation records (rvt_perm_result) of the genes of the last flush / run_loaded"""
+        got = C.c_int(0)
+        self._chk(self.L.rvt_perm_results(self.h, None, 0, C.byref(got)))
+        out = np.zeros(max(got.value, 1), dtype=PERM_DTYPE)
+        self._chk(self.L.rvt_perm_results(self.h, out.ctypes.data, len(out), C.byref(got)))
+        return out[: got.value]
+
+    def perm_debug_q(self):
+        got = C.c_int(0)
+        self._chk(self.L.rvt_perm_debug_q(self.h, None, 0, C.byref(got)))
+        out = np.zeros(max(got.value, 1))
+        self._chk(self.L.rvt_perm_debug_q(self.h, out.ctypes.data, len(out), C.byref(got)))
         return out[: got.value]
 
     def flush_dev(self, d_out_ptr, cap):

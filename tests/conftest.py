@@ -54,6 +54,10 @@ def hostcheck():
                           C.POINTER(C.c_int)]
     H.hc_skato_tail.restype = C.c_int
     H.hc_skato_tail.argtypes = [dp, C.c_int, dp, C.c_double, dp]
+    H.hc_lfg_draws.restype = None
+    H.hc_lfg_draws.argtypes = [C.c_uint, C.c_ulonglong, C.c_int, C.c_void_p]
+    H.hc_fy_roots.restype = None
+    H.hc_fy_roots.argtypes = [C.c_void_p, C.c_uint, C.c_void_p]
     H.hc_eigen_tridiag.restype = C.c_int
     H.hc_eigen_tridiag.argtypes = [dp, C.c_int, dp]
     return H

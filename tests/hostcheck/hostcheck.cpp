@@ -5,6 +5,7 @@
 #include <vector>
 #include "../../rvtests_b200/csrc/eigen.cuh"
 #include "../../rvtests_b200/csrc/skato_tail.cuh"
+#include "../../rvtests_b200/csrc/permlogic.cuh"
 
 extern "C" {
 double hc_gamma_q(double a, double x) { return rvt::gamma_q(a, x); }
@@ -78,5 +79,30 @@ int hc_eigen(const double* a_in, int n, double* out) {
   for (int i = 0; i < n; ++i) ev[i] = a[(size_t)i * n + i];
   rvt::sort_descending(ev.data(), n, out, par);
   return sweeps;
+}
+
+// glibc rand() by polynomial jump-ahead (permlogic.cuh): the n values from stream position pos after srand(seed)
+void hc_lfg_draws(unsigned seed, unsigned long long pos, int n, int* out) {
+  uint32_t y0[2 * rvt::kLfgDeg - 1], w[2 * rvt::kLfgDeg - 1];
+  rvt::lfg_seed_window(seed, y0);
+  rvt::lfg_window_at(rvt::lfg_pow(pos + rvt::kLfgWarm), y0, w);
+  uint32_t x[rvt::kLfgDeg];
+  for (int k = 0; k < rvt::kLfgDeg; ++k) x[k] = w[k];
+  for (int i = 0; i < n; ++i) {
+    const int k = i % rvt::kLfgDeg;
+    if (i >= rvt::kLfgDeg) x[k] += x[(k + rvt::kLfgDeg - 3) % rvt::kLfgDeg];
+    out[i] = (int)(x[k] >> 1);
+  }
+}
+// Fisher-Yates resolved as chains: root[i] for the shuffle driven by draws[0..n-2] (step s handles i = n-1-s)
+void hc_fy_roots(const unsigned* draws, unsigned n, unsigned* root) {
+  std::vector<uint32_t> head(n, rvt::kFyNil), link(n, rvt::kFyNil), j(n, 0);
+  for (unsigned s = 0; s + 1 < n; ++s) {
+    const unsigned i = n - 1 - s;
+    j[i] = draws[s] % (i + 1);
+    link[i] = head[j[i]];
+    head[j[i]] = i;
+  }
+  for (unsigned i = 0; i < n; ++i) root[i] = rvt::fy_root(head.data(), link.data(), i, j[i]);
 }
 }

@@ -1,0 +1,111 @@
+"""GPU (-m gpu): A6, the permutation p-value of `--kernel skat` (src/Model.h:2707-2717), against the oracle's literal
+loop (glibc rand() Fisher-Yates on the host, float32 statistic): the same shuffles, hence the same counts."""
+import numpy as np
+import pytest
+
+from util import af_of, make_problem, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(engine_cls):
+    e = engine_cls(0)
+    if e.info("tc_available") != 1:
+        pytest.skip("the permutation test needs the tensor-core sweep")
+    yield e
+    e.close()
+
+
+def _genes(O, N, C, specs):
+    X, y = None, None
+    out = []
+    for seed, M, kw in specs:
+        G, X, y = make_problem(O, seed, N, M, C, **kw)
+        out.append(G)
+    return out, X, y
+
+
+@pytest.mark.parametrize("case", [(80, 257, 1, 40, 0.3), (81, 3001, 3, 300, 0.05), (82, 20000, 3, 64, 0.5)])
+def test_perm_counts_equal_the_reference_loop(eng, oracle, case):
+    """three genes in a row (one of them wider than a tile, one with flipped + monomorphic variants): ActualPerm,
+    NumGreater, NumEqual and the stream position of every gene equal the serial host loop that calls rand()."""
+    O = oracle
+    seed, N, C, n_perm, alpha = case
+    genes, X, y = _genes(O, N, C, [(seed, 12, dict(maf=np.linspace(0.01, 0.2, 12), n_flip=2, n_mono=1)),
+                                   (seed, 70, dict(maf=np.linspace(0.005, 0.1, 70), n_flip=1)),
+                                   (seed, 5, dict(maf=0.1))])
+    eng.set_option("engine", 0)
+    eng.set_null_model(X, y)
+    nm = O.fit_null_linear(X, y)
+    eng.set_option("perm", n_perm)
+    eng.set_option("perm_alpha", alpha)
+    eng.set_option("perm_batch", 32)
+    eng.set_option("perm_seed", 1)            # the state of a fresh process (the reference never calls srand)
+    try:
+        for G in genes:
+            eng.push_i8(G.T.copy(), af_of(G))
+        res = eng.flush()
+        pr = eng.perm_results()
+    finally:
+        eng.set_option("perm", 0)
+    assert len(pr) == len(genes)
+    pos = 0
+    for g, G in enumerate(genes):
+        ref = O.gene_perm(G.astype(float), af_of(G), nm["resid"], float(res[g]["Q"]), n_perm=n_perm, alpha=alpha,
+                          reseed=1 if g == 0 else 0)
+        assert ref["rc"] == 0 and int(pr[g]["done"]) == 1
+        assert int(pr[g]["num_perm"]) == n_perm
+        assert int(pr[g]["stream_pos"]) == pos
+        assert pr[g]["stat"] == res[g]["Q"]
+        # the statistics of the very same shuffles: float32 in the reference, exact here
+        assert int(pr[g]["actual_perm"]) == ref["actual"], (g, pr[g], ref["actual"])
+        assert int(pr[g]["num_greater"]) == ref["greater"], (g, pr[g], ref["greater"])
+        assert int(pr[g]["num_equal"]) == ref["equal"]
+        assert rel(pr[g]["p_perm"], ref["p"]) <= 1e-12
+        pos += ref["actual"] * (N - 1)
+    assert eng.info("perm_stream_pos") == pos
+
+
+def test_perm_statistics_match_per_shuffle(eng, oracle):
+    """with alpha = 1 every permutation runs: compare each permuted statistic, not only the counts"""
+    O = oracle
+    N, C, n_perm = 5000, 2, 48
+    G, X, y = make_problem(O, 83, N, 30, C, maf=np.linspace(0.004, 0.1, 30), n_flip=2)
+    eng.set_option("engine", 0)
+    eng.set_null_model(X, y)
+    nm = O.fit_null_linear(X, y)
+    eng.set_option("perm", n_perm)
+    eng.set_option("perm_alpha", 1.0)
+    eng.set_option("perm_batch", 16)
+    eng.set_option("perm_seed", 1)
+    eng.set_option("debug_perm_q", 1)
+    try:
+        eng.push_i8(G.T.copy(), af_of(G))
+        res = eng.flush()
+        pr = eng.perm_results()
+        q = eng.perm_debug_q()
+    finally:
+        eng.set_option("perm", 0)
+        eng.set_option("debug_perm_q", 0)
+    ref = O.gene_perm(G.astype(float), af_of(G), nm["resid"], float(res[0]["Q"]), n_perm=n_perm, alpha=1.0, reseed=1)
+    assert int(pr[0]["actual_perm"]) == ref["actual"] == n_perm
+    assert len(q) == n_perm
+    assert np.max(np.abs(q - ref["q"]) / ref["q"]) <= 2e-5     # the reference's statistic is float32
+
+
+def test_perm_off_by_default_and_na_gene(eng, oracle):
+    O = oracle
+    G, X, y = make_problem(O, 84, 600, 4, 1, maf=0.2, n_mono=4)   # every variant monomorphic: fit() == -1
+    eng.set_null_model(X, y)
+    eng.push_i8(G.T.copy(), af_of(G))
+    eng.flush()
+    assert len(eng.perm_results()) == 0
+    eng.set_option("perm", 100)
+    try:
+        eng.push_i8(G.T.copy(), af_of(G))
+        eng.flush()
+        pr = eng.perm_results()
+    finally:
+        eng.set_option("perm", 0)
+    assert len(pr) == 1 and int(pr[0]["done"]) == 0 and int(pr[0]["actual_perm"]) == 0
