@@ -156,6 +156,9 @@ int rvt_gene_push_bed(rvt_ctx* ctx, const uint8_t* bed, int M, int64_t stride, c
 int rvt_perm_results(rvt_ctx* ctx, rvt_perm_result* out, int cap, int* n_out);
 /* diagnostics: with option "debug_perm_q" = 1, every permuted statistic of the last flush, in the order they ran */
 int rvt_perm_debug_q(rvt_ctx* ctx, double* out, int cap, int* n_out);
+/* diagnostics: the n values glibc's rand() returns from stream position `pos` after srand(seed), generated by the
+ * device kernel the permutation test uses (host array out[n]) */
+int rvt_debug_rand(rvt_ctx* ctx, uint32_t seed, uint64_t pos, int64_t n, int32_t* out);
 /* number of genes pushed and not yet flushed */
 int rvt_pending(const rvt_ctx* ctx);
 /* run the sweep + per-gene statistics for every pending gene; out: host array of `cap` records */

@@ -3,6 +3,7 @@
 // only (allocation, launches, copies); every number a test reports is computed on the GPU.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1002,6 +1003,17 @@ static int run_wide(rvt_ctx* ctx, rvt_gene_result* d_res, int* launches) {
   return RVT_OK;
 }
 
+// jump tables of the rand() recurrence (constant), uploaded once
+static int perm_tables(rvt_ctx* ctx) {
+  if (ctx->d_lfg) return RVT_OK;
+  std::vector<LfgTables> tab(1);
+  for (int k = 0; k < 32; ++k) tab[0].zblock[k] = lfg_pow((uint64_t)kLfgBlock << k);
+  for (int t = 0; t < kLfgThreads; ++t) tab[0].zthread[t] = lfg_pow((uint64_t)t * kLfgRun);
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_lfg, sizeof(LfgTables)));
+  RVT_CUDA_OK(cudaMemcpy(ctx->d_lfg, tab.data(), sizeof(LfgTables), cudaMemcpyHostToDevice));
+  return RVT_OK;
+}
+
 // A6 (perm.cuh): permutation p-values of the SKAT statistic, gene after gene in push order, consuming the glibc
 // rand() stream exactly as the reference's serial loop does (src/Model.h:2707-2717).  Runs after the analytic
 // results exist (the observed Q is the comparison value).
@@ -1019,13 +1031,7 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
   RVT_CUDA_OK(cudaMemcpyAsync(hres.data(), d_res, sizeof(rvt_gene_result) * n, cudaMemcpyDeviceToHost, st));
   RVT_CUDA_OK(cudaStreamSynchronize(st));
   ctx->perm_out.assign(n, rvt_perm_result{});
-  if (!ctx->d_lfg) {   // jump tables of the rand() recurrence (constant)
-    std::vector<LfgTables> tab(1);
-    for (int k = 0; k < 32; ++k) tab[0].zblock[k] = lfg_pow((uint64_t)kLfgBlock << k);
-    for (int t = 0; t < kLfgThreads; ++t) tab[0].zthread[t] = lfg_pow((uint64_t)t * kLfgRun);
-    RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_lfg, sizeof(LfgTables)));
-    RVT_CUDA_OK(cudaMemcpy(ctx->d_lfg, tab.data(), sizeof(LfgTables), cudaMemcpyHostToDevice));
-  }
+  if ((rc = perm_tables(ctx))) return rc;
   uint32_t y0[2 * kLfgDeg - 1];
   lfg_seed_window(ctx->perm_seed, y0);
   const int PB = ctx->perm_batch;                 // permutations per batch (multiple of 16)
@@ -1069,6 +1075,13 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
   const int threshold = (int)(1.0 * ctx->perm_n * ctx->perm_alpha * 2);   // Permutation::init, `int threshold`
   std::vector<double> hQ(PB);
   std::vector<GeneDesc> units;
+  const bool trace = getenv("RVT_PERM_TRACE") != nullptr;   // diagnostics: synchronise and report after every stage
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    cudaError_t e = cudaStreamSynchronize(st);
+    fprintf(stderr, "[perm] %s: %s\n", what, cudaGetErrorString(e));
+    fflush(stderr);
+  };
   for (int g = 0; g < n; ++g) {
     rvt_perm_result& rec = ctx->perm_out[g];
     rec.num_perm = ctx->perm_n;
@@ -1096,15 +1109,19 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
       RVT_CUDA_OK(cudaMemcpyAsync(d_w0, w0, sizeof(w0), cudaMemcpyHostToDevice, st));   // (pageable: staged before return)
       const uint64_t cnt = (uint64_t)Pb16 * (uint64_t)(N - 1);
       k_lfg_draws<<<(unsigned)((cnt + kLfgBlock - 1) / kLfgBlock), kLfgThreads, 0, st>>>(ctx->d_lfg, d_w0, cnt, d_draws);
+      mark("draws");
       RVT_CUDA_OK(cudaMemsetAsync(d_head, 0xFF, (size_t)Pb16 * N * 4, st));
       k_fy_link<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_draws, (uint32_t)N, Pb16, d_head, d_link);
+      mark("link");
       k_fy_root<<<(unsigned)(((uint64_t)Pb16 * N + 255) / 256), 256, 0, st>>>(d_draws, (uint32_t)N, Pb16, d_head, d_link, d_root);
+      mark("root");
       for (int p = 0; p < Pb16; ++p) {
         k_perm_gather<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_R[cur], d_root + (size_t)p * N, (uint32_t)N, d_R[cur ^ 1],
                                                                     d_tiles + (size_t)(p / 16) * tile_b, 4 * (p % 16));
         cur ^= 1;
       }
       *launches += 4 + Pb16;
+      mark("gather");
       units.clear();
       for (int t = 0; t < T; ++t)
         for (int u = 0; u < G16; ++u) {
@@ -1126,7 +1143,9 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
         rc = tc_launch(&ctx->tc, d_units + b0, units.data() + b0, nb, ctx->d_zero_flags, ctx->d_nm, N, ctx->ER, S, chunk, ctx->d_parts,
                        ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), true, false, kSegPerm);
         if (rc) return rc;
+        mark("sweep");
         k_perm_sint<<<nb, 128, 0, st>>>(d_units + b0, nb, gd.var0, M, S, ctx->d_parts, d_sint);
+        mark("sint");
         *launches += 2;
       }
       k_perm_q<<<1, 256, 0, st>>>(Pb16, M, gd.var0, gd.has_af, d_sint, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, d_w, d_Q);
@@ -1235,6 +1254,27 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
 }
 
 int rvt_flush(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out) { return flush_impl(ctx, out, cap, n_out, false); }
+int rvt_debug_rand(rvt_ctx* ctx, uint32_t seed, uint64_t pos, int64_t n, int32_t* out) {
+  if (!ctx || !out || n < 0) return RVT_E_BADARG;
+  RVT_CUDA_OK(cudaSetDevice(ctx->device));
+  int rc = perm_tables(ctx);
+  if (rc) return rc;
+  uint32_t y0[2 * kLfgDeg - 1], w0[2 * kLfgDeg - 1];
+  lfg_seed_window(seed, y0);
+  lfg_window_at(lfg_pow(pos + kLfgWarm), y0, w0);
+  uint32_t *d_w0 = nullptr, *d_out = nullptr;
+  RVT_CUDA_OK(cudaMalloc((void**)&d_w0, sizeof(w0)));
+  RVT_CUDA_OK(cudaMalloc((void**)&d_out, sizeof(uint32_t) * (size_t)std::max<int64_t>(n, 1)));
+  RVT_CUDA_OK(cudaMemcpyAsync(d_w0, w0, sizeof(w0), cudaMemcpyHostToDevice, ctx->stream));
+  if (n > 0) k_lfg_draws<<<(unsigned)((n + kLfgBlock - 1) / kLfgBlock), kLfgThreads, 0, ctx->stream>>>(ctx->d_lfg, d_w0, (uint64_t)n, d_out);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_w0);
+  cudaFree(d_out);
+  if (e != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "rvt_debug_rand: %s", cudaGetErrorString(e));
+  return RVT_OK;
+}
 int rvt_perm_debug_q(rvt_ctx* ctx, double* out, int cap, int* n_out) {
   if (!ctx || !n_out) return RVT_E_BADARG;
   const int n = (int)ctx->perm_q_log.size();

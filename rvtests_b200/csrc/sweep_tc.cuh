@@ -195,7 +195,9 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
     if (lane == 0) {
       for (int s = 0; s < kTcStages; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&empty[s], ZC ? 1 : 1 + kTcBoxes);   // ZC: the UMMAs (which wait for the consumers) are the last readers
+        // ZC: the UMMAs (which wait for the consumers) are the last readers.  PAIR: every consumer warp passes
+        // through every stage (see the consumer loop), so all of them release it.
+        mbar_init(&empty[s], PAIR ? 1 + kTcConsumerWarps : (ZC ? 1 : 1 + kTcBoxes));
         mbar_init(&ready[s], kTcBoxes);
       }
       for (int a = 0; a < 2; ++a) {
@@ -351,7 +353,14 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
 #pragma unroll
       for (int e = 0; e <= ER; ++e) cz[e] = cc[e] = 0;
       for (int ks = 0; ks < nsteps; ++ks, ++it) {
-        if ((int)(it % (uint32_t)kGroups) != grp) continue;   // another consumer group owns this stage
+        // Another consumer group owns this stage -- except in PAIR mode.  With the stage ring (3) not a multiple of
+        // the group count (2), successive uses of one stage belong to alternating groups, so a warp sees only every
+        // other phase of full[s]: a parity wait for use `it` is already satisfied by the completion of use
+        // it - 2*stages, and would fall through if the warp got there before use it - stages has landed.  Gene
+        // sweeps cannot get there (their consumers wait for the loads of the 3-4 stages in between); pair units have
+        // idle consumers that race ahead, and with ~64 CTAs in flight adjacent stage loads did complete out of order
+        // (hang at N = 200 000 x 16 pair units).  There every warp waits on, and releases, every stage.
+        if (!PAIR && (int)(it % (uint32_t)kGroups) != grp) continue;
         const int s = it % kTcStages;
         const uint32_t ph = (it / kTcStages) & 1;
         mbar_wait(&full[s], ph);

@@ -52,7 +52,7 @@ EXPORTS = [
     "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded",
     "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
     "rvt_debug_phases",
-    "rvt_meta_plan", "rvt_meta_flush", "rvt_perm_results", "rvt_perm_debug_q",
+    "rvt_meta_plan", "rvt_meta_flush", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand",
 ]
 
 PERM_DTYPE = np.dtype([
@@ -109,6 +109,7 @@ def load_library(rebuild: bool = False):
     L.rvt_meta_flush.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.POINTER(C.c_int)]
     L.rvt_perm_results.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.rvt_perm_debug_q.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
+    L.rvt_debug_rand.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_int64, vp]
     _lib = L
     return L
 
@@ -224,6 +225,11 @@ class GeneEngine:
         out = np.zeros(max(got.value, 1), dtype=PERM_DTYPE)
         self._chk(self.L.rvt_perm_results(self.h, out.ctypes.data, len(out), C.byref(got)))
         return out[: got.value]
+
+    def debug_rand(self, n, seed=1, pos=0):
+        out = np.zeros(max(int(n), 1), dtype=np.int32)
+        self._chk(self.L.rvt_debug_rand(self.h, int(seed), int(pos), int(n), out.ctypes.data))
+        return out[: int(n)]
 
     def perm_debug_q(self):
         got = C.c_int(0)

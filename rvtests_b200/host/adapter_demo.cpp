@@ -39,7 +39,9 @@ int main(int argc, char** argv) {
   if (C1) rd(f, &dc.cov.data[0], (size_t)N * C1);
   rvtb200::GeneBatcher<shim::DataConsolidator>::instance().setBatch(batch);
 
-  SkatTest skat;
+  const int nPerm = argc > 3 ? atoi(argv[3]) : 0;        // skat[nPerm=..,alpha=..]
+  const double alpha = argc > 4 ? atof(argv[4]) : 0.05;
+  SkatTest skat(nPerm, alpha);
   SkatOTest skato;
   CMCTest cmc;
   ZegginiTest zeg;

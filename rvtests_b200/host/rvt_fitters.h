@@ -14,8 +14,8 @@
 // are then written in arrival order -- the same deferred-output pattern as the in-tree MetaCovTest
 // (src/Model.cpp:828-834, writers outlive models: src/ModelManager.cpp:304-315).  The `siteInfo`
 // Result passed to writeOutput() is a reused buffer (src/Main.cpp:1085,1224), so its joined value
-// is snapshotted.  Permutation p-values (nPerm > 0) are not provided: construct the
-// adapter for `skat[nPerm=0]`.
+// is snapshotted.  Permutation p-values (`skat[nPerm=..,alpha=..]`, the reference's default nPerm = 10000) come
+// from the engine's device replay of the reference's rand()-driven shuffles (csrc/perm.cuh).
 #ifndef RVT_FITTERS_H_
 #define RVT_FITTERS_H_
 
@@ -43,6 +43,16 @@ class GeneBatcher {
   }
   void setBatch(int n) { batch_ = n > 0 ? n : 1; }
   void enableSkatO() { skato_ = true; }
+  void enablePerm(int nPerm, double alpha) {
+    perm_n_ = nPerm;
+    perm_alpha_ = alpha;
+  }
+  // permutation record of a ticket (NULL when the permutation test is off)
+  const rvt_perm_result* perm(int ticket) {
+    if (ticket < 0 || perm_n_ <= 0) return NULL;
+    if (ticket >= (int)results_.size() && !flush()) return NULL;
+    return ticket < (int)perms_.size() ? &perms_[ticket] : NULL;
+  }
   const char* error() const { return ctx_ ? rvt_last_error(ctx_) : "no context"; }
 
   // Called from fit(): returns the ticket of the CURRENT gene, uploading it on first sight.
@@ -74,12 +84,21 @@ class GeneBatcher {
       results_.resize(base);
       return false;
     }
+    perms_.resize(base + n);
+    for (int i = 0; i < n; ++i) memset(&perms_[base + i], 0, sizeof(rvt_perm_result));
+    if (perm_n_ > 0) {
+      int gotp = 0;
+      if (rvt_perm_results(ctx_, &perms_[base], n, &gotp) != RVT_OK || gotp != n) {
+        fprintf(stderr, "rvtests_b200: permutation records: %s\n", error());
+        return false;
+      }
+    }
     return true;
   }
   int newFitterId() { return next_id_++; }
 
  private:
-  GeneBatcher() : ctx_(NULL), batch_(256), skato_(false), current_(-1), next_id_(0), have_null_(false) {}
+  GeneBatcher() : ctx_(NULL), batch_(256), skato_(false), perm_n_(0), perm_alpha_(0.05), current_(-1), next_id_(0), have_null_(false) {}
   bool seen(int id) const {
     for (size_t i = 0; i < seen_.size(); ++i)
       if (seen_[i] == id) return true;
@@ -110,6 +129,10 @@ class GeneBatcher {
     for (int j = 0; j < cv.cols; ++j)
       for (int i = 0; i < n; ++i) X[(size_t)(j + 1) * n + i] = cv(i, j);
     if (skato_) rvt_set_option(ctx_, "skato", 1);
+    if (perm_n_ > 0) {
+      rvt_set_option(ctx_, "perm", perm_n_);
+      rvt_set_option(ctx_, "perm_alpha", perm_alpha_);
+    }
     if (rvt_set_null_model(ctx_, n, c, X.data(), y.data(), 0) != RVT_OK) {
       fprintf(stderr, "rvtests_b200: null model: %s\n", error());
       return false;
@@ -127,6 +150,9 @@ class GeneBatcher {
       // keep ticket numbering dense: pending genes first
       if (!flush()) return false;
       results_.push_back(na);
+      rvt_perm_result np;
+      memset(&np, 0, sizeof(np));
+      perms_.push_back(np);
       current_ = (int)results_.size() - 1;
       return true;
     }
@@ -143,10 +169,13 @@ class GeneBatcher {
   rvt_ctx* ctx_;
   int batch_;
   bool skato_;
+  int perm_n_;
+  double perm_alpha_;
   int current_, next_id_;
   bool have_null_;
   std::vector<int> seen_;
   std::vector<rvt_gene_result> results_;
+  std::vector<rvt_perm_result> perms_;
 };
 
 // Common machinery: ticket per gene, deferred lines.
@@ -181,13 +210,17 @@ class DeferredFitter {
 
  protected:
   virtual void formatLine(const rvt_gene_result* r, std::string* out) const = 0;
+  virtual void formatTicket(int ticket, std::string* out) const {
+    formatLine(GeneBatcher<DC>::instance().result(ticket), out);
+  }
   void drain() {
     if (!fp_) return;
     GeneBatcher<DC>& b = GeneBatcher<DC>::instance();
     for (size_t i = 0; i < pending_.size(); ++i) {
       std::string line = pending_[i].site;
       line += "\t";
-      formatLine(b.result(pending_[i].ticket), &line);
+      (void)b;
+      formatTicket(pending_[i].ticket, &line);
       line += "\n";
       fp_->write(line.c_str());
     }
@@ -214,11 +247,18 @@ class DeferredFitter {
 template <class DC, class FW, class RES>
 class SkatTestB200 : public DeferredFitter<DC, FW, RES> {
  public:
-  SkatTestB200() { this->modelName = "Skat"; }
+  // SkatTest(int nPerm, double alpha, double beta1, double beta2), src/Model.h:2615-2622 (beta1/beta2: engine options)
+  explicit SkatTestB200(int nPerm = 0, double alpha = 0.05) : usePermutation_(nPerm > 0) {
+    this->modelName = "Skat";
+    if (usePermutation_) GeneBatcher<DC>::instance().enablePerm(nPerm, alpha);
+  }
   ~SkatTestB200() { this->drain(); }
   void writeHeader(FW* fp, const RES& siteInfo) {
     siteInfo.writeHeaderTab(fp);
-    fp->write("Q\tPvalue\n");
+    if (!usePermutation_)
+      fp->write("Q\tPvalue\n");
+    else   // src/Model.h:2722-2731 + Permutation::writeHeader (src/Permutation.h:56-61)
+      fp->write("Q\tPvalue\tNumPerm\tActualPerm\tStat\tNumGreater\tNumEqual\tPermPvalue\n");
   }
 
  protected:
@@ -229,6 +269,24 @@ class SkatTestB200 : public DeferredFitter<DC, FW, RES> {
     }
     *out += this->g(r->Q) + "\t" + this->g(r->p_skat);
   }
+  void formatTicket(int ticket, std::string* out) const {
+    GeneBatcher<DC>& b = GeneBatcher<DC>::instance();
+    const rvt_gene_result* r = b.result(ticket);
+    formatLine(r, out);
+    if (!usePermutation_) return;
+    const rvt_perm_result* p = b.perm(ticket);
+    if (!r || r->status != RVT_GENE_OK || !p || !p->done) {   // src/Model.h:2736-2740
+      *out += "\tNA\tNA\tNA\tNA\tNA\tNA";
+      return;
+    }
+    char buf[160];   // Permutation::updateValue: ints via toString, doubles via floatToString (== %g)
+    snprintf(buf, sizeof(buf), "\t%d\t%d\t%g\t%d\t%d\t%g", p->num_perm, p->actual_perm, p->stat, p->num_greater, p->num_equal,
+             p->p_perm);
+    *out += buf;
+  }
+
+ private:
+  bool usePermutation_;
 };
 
 template <class DC, class FW, class RES>

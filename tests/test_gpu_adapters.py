@@ -79,3 +79,42 @@ def test_adapters_match_reference_output_format(oracle, batch, tmp_path):
         assert rz[3:] == [g(ref.zeg_p)]
         so = SO.skato_gene(G.astype(float), af_of(G), X, nm["resid"])
         assert ro[3:] == [g(so["Q"]), g(so["rho"]), g(so["pvalue"])]
+
+
+def test_skat_adapter_with_permutations(oracle, tmp_path):
+    """`--kernel skat[nPerm=300,alpha=0.1]`: the eight columns SkatTest::writeOutput prints with permutations
+    (src/Model.h:2722-2751, src/Permutation.h:118-139), against the oracle's rand()-driven loop."""
+    import rvtests_b200
+    rvtests_b200.load_library()
+    O = oracle
+    N, C, n_perm, alpha = 900, 2, 300, 0.1
+    genes = []
+    X = y = None
+    for gi, (M, nm_, nf) in enumerate([(6, 0, 1), (3, 3, 0), (25, 2, 2)]):
+        G, X, y = make_problem(O, 78, N, M, C, maf=np.linspace(0.004, 0.05, M), n_mono=nm_, n_flip=nf)
+        genes.append(G)
+    path = tmp_path / "problem.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("iii", N, C - 1, len(genes)))
+        f.write(np.ascontiguousarray(y).tobytes())
+        f.write(np.asfortranarray(X[:, 1:]).tobytes(order="F"))
+        for G in genes:
+            f.write(struct.pack("i", G.shape[1]))
+            f.write(np.asfortranarray(G.astype(np.float64)).tobytes(order="F"))
+            f.write(af_of(G).tobytes())
+    exe = build_demo()
+    out = subprocess.run([exe, str(path), "2", str(n_perm), str(alpha)], capture_output=True, text=True, check=True).stdout
+    rows = [l.split("\t") for l in out.split("#SkatO")[0].splitlines()[1:]]
+    assert rows[0][3:] == ["Q", "Pvalue", "NumPerm", "ActualPerm", "Stat", "NumGreater", "NumEqual", "PermPvalue"]
+    nm = O.fit_null_linear(X, y)
+    first = True
+    for gi, G in enumerate(genes):
+        ref, lam = O.gene(G.astype(float), af_of(G), X, nm["resid"], nm["sigma2"])
+        row = rows[1 + gi][3:]
+        if ref.status == 2:
+            assert row == ["NA"] * 8
+            continue
+        pr = O.gene_perm(G.astype(float), af_of(G), nm["resid"], ref.skat.Q, n_perm=n_perm, alpha=alpha, reseed=1 if first else 0)
+        first = False
+        assert row == [g(ref.skat.Q), g(ref.skat.pvalue), str(n_perm), str(pr["actual"]), g(ref.skat.Q), str(pr["greater"]),
+                       str(pr["equal"]), g(pr["p"])]

@@ -109,3 +109,15 @@ def test_perm_off_by_default_and_na_gene(eng, oracle):
     finally:
         eng.set_option("perm", 0)
     assert len(pr) == 1 and int(pr[0]["done"]) == 0 and int(pr[0]["actual_perm"]) == 0
+
+
+def test_device_rand_equals_glibc_rand(eng, oracle):
+    """k_lfg_draws (CTA + thread jump-ahead, state in registers) against glibc's own rand(): 60 M consecutive values
+    from a fresh stream, and a window at a far position"""
+    n = 60_000_000
+    ref = oracle.glibc_rand(n, reseed=1)
+    dev = eng.debug_rand(n, seed=1, pos=0)
+    bad = np.flatnonzero(dev != ref)
+    assert bad.size == 0, (bad[:5], dev[bad[:5]], ref[bad[:5]])
+    far = oracle.glibc_rand(100_000, reseed=7, skip=5_000_000)
+    assert np.array_equal(eng.debug_rand(100_000, seed=7, pos=5_000_000), far)
