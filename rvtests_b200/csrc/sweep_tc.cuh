@@ -48,6 +48,9 @@ constexpr int kTcChunkAlign = 512;          // split boundaries are multiples of
 // slice -- below the ~72 clk per slice at which HBM delivers the bytes.  The cross-box blocks of D are
 // garbage and ignored; lanes 0-63 hold the even boxes' sums, lanes 64-127 the odd boxes', written
 // as two SweepPartials per unit (exact integers: the split of the sum is invisible downstream).
+__host__ __device__ constexpr int tc_gcd(int a, int b) { return b == 0 ? a : tc_gcd(b, a % b); }
+__host__ __device__ constexpr int tc_lcm(int a, int b) { return a / tc_gcd(a, b) * b; }
+
 template <int ER, int STAGES, bool PAIR = false, int BOXES = 4, bool WIDE = false, bool ZC = false>
 struct TcCfg {
   static_assert(!(PAIR && WIDE), "block pairs use the single-box UMMA");
@@ -60,7 +63,7 @@ struct TcCfg {
   static constexpr int kBoxBytes = kEOff + ER * 128;
   static constexpr int kPairBytes = 2 * kBoxBytes;       // WIDE: [G b0][G b1][E b0][E b1]
   static constexpr int kStageBytes = BOXES * kBoxBytes;
-  static constexpr int kSmem = STAGES * kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int kSmem = STAGES * kStageBytes + 1024 /*align*/ + 1024 /*barriers*/;
   static constexpr int kNC = kTileRows + ER;
   static constexpr int kAccCols = WIDE ? 2 * kNC : 128;  // TMEM columns of one accumulator
   static constexpr int kTmemCols = WIDE ? 512 : 256;     // two accumulators, power of two
@@ -180,9 +183,20 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
   // 1024-byte alignment is required by SWIZZLE_128B (TMA destination and UMMA descriptors)
   uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + kTcStages * Cfg::kStageBytes);
-  uint64_t* full = bars;                    // [kTcStages]
-  uint64_t* empty = bars + kTcStages;       // [kTcStages]
-  uint64_t* tfull = bars + 2 * kTcStages;   // [2]
+  // "stage s holds the data of iteration `it`": ONE BARRIER PER (consumer group, stage).  When the ring depth is not a
+  // multiple of the group count, successive uses of a stage belong to alternating groups; with a single barrier per
+  // stage a consumer warp would see only every other phase, and a parity wait cannot tell "use it landed" from "use
+  // it - 2*stages landed, use it - stages still in flight".  With its own barrier per group every waiter (the MMA
+  // warp included) observes every phase of the barrier it waits on.  Uses of (group g, stage s) recur every
+  // lcm(stages, groups) iterations.  PAIR: one group (every consumer warp passes through every stage).
+  constexpr int kFullGroups = PAIR ? 1 : kGroups;
+  constexpr int kFullPeriod = tc_lcm(kTcStages, kFullGroups);
+  uint64_t* full = bars;                                  // [kFullGroups][kTcStages]
+  uint64_t* empty = bars + kFullGroups * kTcStages;       // [kTcStages]
+  uint64_t* tfull = empty + kTcStages;                    // [2]
+  auto full_bar = [&](uint32_t it_) { return &full[(it_ % kFullGroups) * kTcStages + (it_ % kTcStages)]; };
+  auto full_ph = [&](uint32_t it_) { return (it_ / (uint32_t)kFullPeriod) & 1u; };
+  static_assert((kFullGroups * kTcStages + 2 * kTcStages + 4) * 8 + 16 <= 1024, "barrier area");
   uint64_t* tempty = tfull + 2;             // [2]
   uint64_t* ready = tempty + 2;             // [kTcStages] ZC: the consumers have added the z / c rows
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + kTcStages);
@@ -193,8 +207,8 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
 
   if (warp == 0) {
     if (lane == 0) {
+      for (int s = 0; s < kFullGroups * kTcStages; ++s) mbar_init(&full[s], 1);
       for (int s = 0; s < kTcStages; ++s) {
-        mbar_init(&full[s], 1);
         // ZC: the UMMAs (which wait for the consumers) are the last readers.  PAIR: every consumer warp passes
         // through every stage (see the consumer loop), so all of them release it.
         mbar_init(&empty[s], PAIR ? 1 + kTcConsumerWarps : (ZC ? 1 : 1 + kTcBoxes));
@@ -245,7 +259,8 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
           mbar_wait(&empty[s], ph ^ 1);
           __syncwarp();
           if (elect_one_sync()) {
-            mbar_expect_tx(&full[s], stage_tx);
+            uint64_t* fb = full_bar(it);
+            mbar_expect_tx(fb, stage_tx);
             uint8_t* st = tiles + (size_t)s * Cfg::kStageBytes;
             const int kb = (int)(k0 + (int64_t)ks * kTcStageK);
 #pragma unroll
@@ -256,10 +271,10 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
               // arena (row kOobRow), i.e. zero-filled by TMA, instead of from the next gene's block
               const int ch = (kb >> 7) + b;
               const bool in = ch < nchunks;
-              tma_load_2d(st + Cfg::g_off(b), mg, 0, in ? row0 + ch * Mg : kOobRow, &full[s], kEvictFirst);
+              tma_load_2d(st + Cfg::g_off(b), mg, 0, in ? row0 + ch * Mg : kOobRow, fb, kEvictFirst);
               if (PAIR)
-                tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kBOff, mgb, 0, in ? row0b + ch * Mgb : kOobRow, &full[s], kEvictFirst);
-              if (!(dbg_skip & 4)) tma_load_2d(st + Cfg::e_off(b), &map_e, kb + b * kTcBoxK, 0, &full[s], kEvictLast);
+                tma_load_2d(st + b * Cfg::kBoxBytes + Cfg::kBOff, mgb, 0, in ? row0b + ch * Mgb : kOobRow, fb, kEvictFirst);
+              if (!(dbg_skip & 4)) tma_load_2d(st + Cfg::e_off(b), &map_e, kb + b * kTcBoxK, 0, fb, kEvictLast);
             }
           }
           __syncwarp();
@@ -286,7 +301,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
       for (int ks = 0; ks < nsteps; ++ks, ++it) {
         const int s = it % kTcStages;
         const uint32_t ph = (it / kTcStages) & 1;
-        mbar_wait(&full[s], ph);
+        mbar_wait(full_bar(it), full_ph(it));
         if (ZC) mbar_wait(&ready[s], ph);
         tc_fence_after();
         __syncwarp();
@@ -353,17 +368,13 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
 #pragma unroll
       for (int e = 0; e <= ER; ++e) cz[e] = cc[e] = 0;
       for (int ks = 0; ks < nsteps; ++ks, ++it) {
-        // Another consumer group owns this stage -- except in PAIR mode.  With the stage ring (3) not a multiple of
-        // the group count (2), successive uses of one stage belong to alternating groups, so a warp sees only every
-        // other phase of full[s]: a parity wait for use `it` is already satisfied by the completion of use
-        // it - 2*stages, and would fall through if the warp got there before use it - stages has landed.  Gene
-        // sweeps cannot get there (their consumers wait for the loads of the 3-4 stages in between); pair units have
-        // idle consumers that race ahead, and with ~64 CTAs in flight adjacent stage loads did complete out of order
-        // (hang at N = 200 000 x 16 pair units).  There every warp waits on, and releases, every stage.
+        // Another consumer group owns this stage -- except in PAIR mode, where the consumers have nothing to do but
+        // release the stage: there every warp waits on, and releases, every stage (one barrier group, see `full`).
+        // (Found as a hang at N = 200 000 x 16 pair units on 64 CTAs when the barrier was still per stage only: idle
+        // consumers raced ahead and a parity wait fell through while the previous use of the stage was in flight.)
         if (!PAIR && (int)(it % (uint32_t)kGroups) != grp) continue;
         const int s = it % kTcStages;
-        const uint32_t ph = (it / kTcStages) & 1;
-        mbar_wait(&full[s], ph);
+        mbar_wait(full_bar(it), full_ph(it));
         const uint8_t* box = tiles + (size_t)s * Cfg::kStageBytes + Cfg::g_off(cw);
         const int64_t ksamp = k0 + (int64_t)ks * kTcStageK + cw * kTcBoxK + 4 * lane;
         uint32_t z = 0;
