@@ -92,6 +92,16 @@ typedef struct rvt_perm_result {
   int32_t pad;
 } rvt_perm_result;
 
+/* One record per variant from rvt_lmm_flush: FastLMM::TestCovariate, score branch (regression/FastLMM.cpp:215-249) */
+typedef struct rvt_lmm_result {
+  double af;       /* allele frequency of the pushed hard calls */
+  double U, V;     /* Ustat, Vstat (FastLMM::GetUStat / GetVStat) */
+  double stat;     /* U^2 / V, or 0 when V <= 0 */
+  double pvalue;   /* gsl_cdf_chisq_Q(stat, 1), or 1 when V <= 0 */
+  int32_t ok;      /* 0: the block held values outside {0,1,2} */
+  int32_t pad;
+} rvt_lmm_result;
+
 /* ---- lifetime ------------------------------------------------------------------------------- */
 int rvt_ctx_create(int device, rvt_ctx** out);
 void rvt_ctx_destroy(rvt_ctx* ctx);
@@ -159,6 +169,16 @@ int rvt_perm_debug_q(rvt_ctx* ctx, double* out, int cap, int* n_out);
 /* diagnostics: the n values glibc's rand() returns from stream position `pos` after srand(seed), generated by the
  * device kernel the permutation test uses (host array out[n]) */
 int rvt_debug_rand(rvt_ctx* ctx, uint32_t seed, uint64_t pos, int64_t n, int32_t* out);
+/* ---- mixed-model (FastLMM) score step ---------------------------------------------------------
+ * rvt_lmm_set_null: what FastLMM::Impl::FitNullModel leaves behind (regression/FastLMM.cpp:27-140), computed by the caller:
+ *   U      N x N floats, column-major, column i = eigenvector i of the kinship (kinshipU.mat)
+ *   lambda N eigenvalues (kinshipS; absolute values are taken as the reference does), delta = sigma2_e / sigma2_g,
+ *   sigma2 = sigma2_g, uResid = U'y - U'X beta (N), ux = U'X (N x C column-major, intercept included).
+ * Then push blocks of <= 64 variants (rvt_gene_push_i8 / _bed, hard calls) and call rvt_lmm_flush: one record per
+ * pushed variant, in push order.  Replaces any linear null model set before. */
+int rvt_lmm_set_null(rvt_ctx* ctx, int64_t N, int C, const float* U, const float* lambda, double delta, double sigma2,
+                     const float* uResid, const float* ux);
+int rvt_lmm_flush(rvt_ctx* ctx, rvt_lmm_result* out, int64_t cap);
 /* number of genes pushed and not yet flushed */
 int rvt_pending(const rvt_ctx* ctx);
 /* run the sweep + per-gene statistics for every pending gene; out: host array of `cap` records */

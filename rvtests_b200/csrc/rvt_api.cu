@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "dosage.cuh"
 #include "finalize.cuh"
+#include "lmm.cuh"
 #include "meta.cuh"
 #include "null_model.cuh"
 #include "perm.cuh"
@@ -49,6 +50,7 @@ struct TilePlan {    // where the tiles of one pushed gene were staged
 
 constexpr int kSegLoaded = 0;  // the synthetic / loaded cohort arena
 constexpr int kSegStaged = 1;  // genes staged from host buffers
+constexpr int kSegLmm = 3;     // eigenvector digit tiles of the mixed-model score step (lmm.cuh)
 constexpr int kSegPerm = 2;    // 16-permutation digit tiles of the permutation test (perm.cuh)
 
 struct rvt_ctx {
@@ -93,6 +95,13 @@ struct rvt_ctx {
   size_t cap_perm = 0;
   std::vector<rvt_perm_result> perm_out;
   std::vector<char> is_dos;        // per pending gene: took the fp64 path
+  // FastLMM score step (lmm.cuh)
+  bool have_lmm = false;
+  LmmNull* d_lmm = nullptr;
+  LmmNull h_lmm;
+  int8_t* d_lmm_tiles = nullptr;
+  double* d_lmm_vec = nullptr;     // a, d, t (16 nb each), w (16 nb x kMaxC)
+  long long* d_lmm_tsum = nullptr;
   bool perm_log = false;           // option "debug_perm_q": keep every permuted statistic of the last flush
   std::vector<double> perm_q_log;
   std::vector<int> bed_genes;      // pending genes pushed as PLINK 2-bit rows: checked for missing calls at flush
@@ -281,7 +290,7 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1437,6 +1446,157 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   if (band) RVT_CUDA_OK(cudaMemcpyAsync(band, d_band, sizeof(double) * nv * (size_t)(wmax + 1), cudaMemcpyDeviceToHost, st));
   RVT_CUDA_OK(cudaStreamSynchronize(st));
   cleanup();
+  pending_reset(ctx);
+  return RVT_OK;
+}
+
+// ---- A13: FastLMM score step (lmm.cuh) -------------------------------------------------------------
+int rvt_lmm_set_null(rvt_ctx* ctx, int64_t N, int C, const float* U, const float* lambda, double delta, double sigma2,
+                     const float* uResid, const float* ux) {
+  if (!ctx || !U || !lambda || !uResid || !ux) return RVT_E_BADARG;
+  if (!(sigma2 > 0.0) || !(delta >= 0.0)) CTX_FAIL(RVT_E_BADARG, "lmm: sigma2 must be > 0 and delta >= 0");
+  if (C < 1 || C > kMaxC) CTX_FAIL(RVT_E_UNSUPPORTED, "lmm: C=%d covariate columns; this build supports 1..%d", C, kMaxC);
+  // the sweep needs a null-model image for its digit tile: a trivial one (intercept, zero residual)
+  int rc = null_model_alloc(ctx, N, 1);
+  if (rc) return rc;
+  {
+    std::vector<double> ones((size_t)N, 1.0), zeros((size_t)N, 0.0);
+    RVT_CUDA_OK(cudaMemcpy(ctx->dX, ones.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+    RVT_CUDA_OK(cudaMemcpy(ctx->dy, zeros.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+  }
+  if ((rc = null_model_run(ctx, true, 1.0))) return rc;
+  if (!(ctx->tc.encode && ctx->tc.have_e))
+    CTX_FAIL(RVT_E_UNSUPPORTED, "lmm: the score step needs the tensor-core sweep (TMA unavailable: %s)", ctx->tc.why);
+  ctx->have_lmm = false;
+  for (void* p : {(void*)ctx->d_lmm, (void*)ctx->d_lmm_tiles, (void*)ctx->d_lmm_vec, (void*)ctx->d_lmm_tsum})
+    if (p) cudaFree(p);
+  ctx->d_lmm = nullptr; ctx->d_lmm_tiles = nullptr; ctx->d_lmm_vec = nullptr; ctx->d_lmm_tsum = nullptr;
+  const int nb = (int)((N + 15) / 16);
+  const int64_t tile_b = tiled_bytes(N, kTileRows), nev = 16 * (int64_t)nb;
+  cudaStream_t st = ctx->stream;
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_lmm, sizeof(LmmNull)));
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_lmm_tiles, (size_t)nb * tile_b));
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_lmm_vec, sizeof(double) * nev * (3 + kMaxC)));
+  RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_lmm_tsum, sizeof(long long) * nev));
+  RVT_CUDA_OK(cudaMemsetAsync(ctx->d_lmm_tiles, 0, (size_t)nb * tile_b, st));
+  RVT_CUDA_OK(cudaMemsetAsync(ctx->d_lmm_vec, 0, sizeof(double) * nev * (3 + kMaxC), st));
+  RVT_CUDA_OK(cudaMemsetAsync(ctx->d_lmm_tsum, 0, sizeof(long long) * nev, st));
+  // eigenvectors, a panel of columns at a time
+  const int64_t pcols = std::max<int64_t>(1, std::min<int64_t>(N, ((int64_t)256 << 20) / (4 * N)));
+  float *d_panel = nullptr, *d_f = nullptr;
+  RVT_CUDA_OK(cudaMalloc((void**)&d_panel, sizeof(float) * pcols * N));
+  RVT_CUDA_OK(cudaMalloc((void**)&d_f, sizeof(float) * N * (2 + C)));
+  for (int64_t c0 = 0; c0 < N; c0 += pcols) {
+    const int64_t nc = std::min(pcols, N - c0);
+    RVT_CUDA_OK(cudaMemcpyAsync(d_panel, U + (size_t)c0 * N, sizeof(float) * nc * N, cudaMemcpyHostToDevice, st));
+    k_lmm_digits<<<(unsigned)nc, 256, 0, st>>>(d_panel, N, c0, ctx->d_lmm_tiles, tile_b, ctx->d_lmm_tsum);
+    RVT_CUDA_OK(cudaStreamSynchronize(st));   // the panel buffer is reused
+  }
+  RVT_CUDA_OK(cudaMemcpyAsync(d_f, lambda, sizeof(float) * N, cudaMemcpyHostToDevice, st));
+  RVT_CUDA_OK(cudaMemcpyAsync(d_f + N, uResid, sizeof(float) * N, cudaMemcpyHostToDevice, st));
+  RVT_CUDA_OK(cudaMemcpyAsync(d_f + 2 * N, ux, sizeof(float) * N * C, cudaMemcpyHostToDevice, st));
+  double *d_a = ctx->d_lmm_vec, *d_d = d_a + nev, *d_t = d_d + nev, *d_w = d_t + nev;
+  k_lmm_consts<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, C, d_f, d_f + N, d_f + 2 * N, ctx->d_lmm_tsum, delta, sigma2, d_a, d_d, d_t, d_w);
+  LmmNull h;
+  memset(&h, 0, sizeof(h));
+  h.N = N; h.C = C; h.nb = nb; h.delta = delta; h.sigma2 = sigma2;
+  h.a = d_a; h.d = d_d; h.t = d_t; h.w = d_w;
+  {   // (ux' D ux)^-1 in double (the reference: float .inverse(), FastLMM.cpp:133-137)
+    double A[kMaxC * kMaxC], I[kMaxC * kMaxC];
+    for (int l = 0; l < C; ++l)
+      for (int m = 0; m < C; ++m) {
+        double sacc = 0.0;
+        for (int64_t i = 0; i < N; ++i) sacc += (double)ux[(size_t)l * N + i] * (double)ux[(size_t)m * N + i] / ((double)fabsf(lambda[i]) + delta);
+        A[l * C + m] = sacc;
+        I[l * C + m] = (l == m) ? 1.0 : 0.0;
+      }
+    for (int k = 0; k < C; ++k) {   // Gauss-Jordan with partial pivoting
+      int piv = k;
+      for (int r = k + 1; r < C; ++r)
+        if (fabs(A[r * C + k]) > fabs(A[piv * C + k])) piv = r;
+      if (!(fabs(A[piv * C + k]) > 0.0)) {
+        cudaFree(d_panel); cudaFree(d_f);
+        CTX_FAIL(RVT_E_NUMERIC, "lmm: ux' D ux is singular");
+      }
+      for (int c = 0; c < C; ++c) { std::swap(A[k * C + c], A[piv * C + c]); std::swap(I[k * C + c], I[piv * C + c]); }
+      const double inv = 1.0 / A[k * C + k];
+      for (int c = 0; c < C; ++c) { A[k * C + c] *= inv; I[k * C + c] *= inv; }
+      for (int r = 0; r < C; ++r)
+        if (r != k) {
+          const double f = A[r * C + k];
+          for (int c = 0; c < C; ++c) { A[r * C + c] -= f * A[k * C + c]; I[r * C + c] -= f * I[k * C + c]; }
+        }
+    }
+    memcpy(h.xdx_inv, I, sizeof(double) * C * C);
+  }
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_lmm, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  k_lmm_consts2<<<1, 32, 0, st>>>(ctx->d_lmm);
+  RVT_CUDA_OK(cudaGetLastError());
+  RVT_CUDA_OK(cudaStreamSynchronize(st));
+  cudaFree(d_panel);
+  cudaFree(d_f);
+  ctx->h_lmm = h;
+  if ((rc = tc_bind_segment(&ctx->tc, kSegLmm, ctx->d_lmm_tiles, (int64_t)nb * tile_b, ctx->err, sizeof(ctx->err)))) return rc;
+  ctx->have_lmm = true;
+  return RVT_OK;
+}
+
+int rvt_lmm_flush(rvt_ctx* ctx, rvt_lmm_result* out, int64_t cap) {
+  if (!ctx || !out) return RVT_E_BADARG;
+  if (!ctx->have_lmm || ctx->h_lmm.N != ctx->N) CTX_FAIL(RVT_E_STATE, "lmm: call rvt_lmm_set_null first");
+  const int ngen = (int)ctx->genes.size();
+  const int64_t nv = ctx->n_var;
+  if (ngen == 0) return RVT_OK;
+  if (cap < nv) CTX_FAIL(RVT_E_BADARG, "lmm: out holds %lld records, %lld variants pending", (long long)cap, (long long)nv);
+  if (!ctx->wide.empty()) CTX_FAIL(RVT_E_UNSUPPORTED, "lmm: push variant blocks of at most %d variants", kMaxM);
+  for (const auto& g : ctx->genes)
+    if (g.seg != kSegStaged || !g.tiled) CTX_FAIL(RVT_E_UNSUPPORTED, "lmm: pending variant blocks must be host pushes (tiled, staged)");
+  RVT_CUDA_OK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = tc_bind_segment(&ctx->tc, kSegStaged, ctx->d_stage, ctx->stage_cap, ctx->err, sizeof(ctx->err)))) return rc;
+  cudaStream_t st = ctx->stream;
+  const int64_t N = ctx->N;
+  const int nb = ctx->h_lmm.nb;
+  const int64_t tile_b = tiled_bytes(N, kTileRows);
+  if ((rc = ensure(ctx, (void**)&ctx->d_zero_flags, &ctx->cap_zero_flags, (size_t)nv + kTileRows, 1))) return rc;
+  RVT_CUDA_OK(cudaMemsetAsync(ctx->d_zero_flags, 0, (size_t)nv + kTileRows, st));
+  const int batch = 1024;
+  int S = 0;
+  int64_t chunk = 0;
+  if ((rc = split_plan(ctx, std::min(nb, batch), &S, &chunk))) return rc;
+  if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)std::min(nb, batch) * S, sizeof(SweepPartial)))) return rc;
+  GeneDesc* d_units = nullptr;
+  double* d_acc = nullptr;
+  rvt_lmm_result* d_out = nullptr;
+  RVT_CUDA_OK(cudaMalloc((void**)&d_units, sizeof(GeneDesc) * nb));
+  RVT_CUDA_OK(cudaMalloc((void**)&d_acc, sizeof(double) * (size_t)nb * kTileRows * kLmmAcc));
+  RVT_CUDA_OK(cudaMalloc((void**)&d_out, sizeof(rvt_lmm_result) * nv));
+  auto cleanup = [&]() { cudaFree(d_units); cudaFree(d_acc); cudaFree(d_out); };
+  std::vector<GeneDesc> units(nb);
+  for (int g = 0; g < ngen; ++g) {
+    const GeneDesc& gd = ctx->genes[g];
+    for (int b = 0; b < nb; ++b) {
+      units[b] = gd;
+      units[b].row0_b = (int64_t)b * tile_b / 128;
+      units[b].Mb = kTileRows;
+      units[b].var0_b = b;
+    }
+    cudaError_t e = cudaMemcpyAsync(d_units, units.data(), sizeof(GeneDesc) * nb, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { cleanup(); CTX_FAIL(RVT_E_CUDA, "lmm: %s", cudaGetErrorString(e)); }
+    for (int b0 = 0; b0 < nb; b0 += batch) {
+      const int n = std::min(batch, nb - b0);
+      rc = tc_launch(&ctx->tc, d_units + b0, units.data() + b0, n, ctx->d_zero_flags, ctx->d_nm, N, ctx->ER, S, chunk, ctx->d_parts,
+                     ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), true, false, kSegLmm);
+      if (rc) { cleanup(); return rc; }
+      k_lmm_reduce<<<n, 64, 0, st>>>(d_units + b0, n, S, ctx->d_parts, ctx->d_lmm, d_acc + (size_t)b0 * kTileRows * kLmmAcc);
+    }
+    k_lmm_final<<<1, 64, 0, st>>>(gd.M, nb, d_acc, ctx->d_counts + gd.var0, ctx->d_lmm, d_out + gd.var0);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(rvt_lmm_result) * nv, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "lmm: %s", cudaGetErrorString(e));
   pending_reset(ctx);
   return RVT_OK;
 }

@@ -52,8 +52,10 @@ EXPORTS = [
     "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded",
     "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
     "rvt_debug_phases",
-    "rvt_meta_plan", "rvt_meta_flush", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand",
+    "rvt_meta_plan", "rvt_meta_flush", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand", "rvt_lmm_set_null", "rvt_lmm_flush",
 ]
+
+LMM_DTYPE = np.dtype([("af", "f8"), ("U", "f8"), ("V", "f8"), ("stat", "f8"), ("pvalue", "f8"), ("ok", "i4"), ("pad", "i4")])
 
 PERM_DTYPE = np.dtype([
     ("num_perm", "i4"), ("actual_perm", "i4"), ("num_greater", "i4"), ("num_equal", "i4"),
@@ -110,6 +112,8 @@ def load_library(rebuild: bool = False):
     L.rvt_perm_results.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.rvt_perm_debug_q.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.rvt_debug_rand.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_int64, vp]
+    L.rvt_lmm_set_null.argtypes = [vp, C.c_int64, C.c_int, vp, vp, C.c_double, C.c_double, vp, vp]
+    L.rvt_lmm_flush.argtypes = [vp, vp, C.c_int64]
     _lib = L
     return L
 
@@ -217,6 +221,23 @@ class GeneEngine:
         got = C.c_int(0)
         self._chk(self.L.rvt_flush(self.h, out.ctypes.data, len(out), C.byref(got)))
         return out[: got.value]
+
+    def lmm_set_null(self, U, lam, delta, sigma2, u_resid, ux):
+        """FastLMM score step: U (N, N) with eigenvectors in COLUMNS, lam (N,), uResid (N,), ux (N, C)"""
+        U = np.asfortranarray(U, dtype=np.float32)
+        lam = np.ascontiguousarray(lam, dtype=np.float32)
+        u_resid = np.ascontiguousarray(u_resid, dtype=np.float32)
+        ux = np.asfortranarray(ux, dtype=np.float32)
+        N = U.shape[0]
+        assert U.shape == (N, N) and lam.shape == (N,) and u_resid.shape == (N,) and ux.shape[0] == N
+        self._chk(self.L.rvt_lmm_set_null(self.h, N, ux.shape[1], U.ctypes.data, lam.ctypes.data, float(delta), float(sigma2),
+                                          u_resid.ctypes.data, ux.ctypes.data))
+
+    def lmm_flush(self, n_variants):
+        """one record per pushed variant (blocks of <= 64 variants pushed with push_i8 / push_bed)"""
+        out = np.zeros(max(int(n_variants), 1), dtype=LMM_DTYPE)
+        self._chk(self.L.rvt_lmm_flush(self.h, out.ctypes.data, len(out)))
+        return out[: int(n_variants)]
 
     def perm_results(self):
         """permutation records (rvt_perm_result) of the genes of the last flush / run_loaded"""
