@@ -134,6 +134,8 @@ int rvt_set_null_residual(rvt_ctx* ctx, int64_t N, int C, const double* X, const
 int rvt_set_null_model_dev(rvt_ctx* ctx, int64_t N, int C, const double* dX, const double* dy);
 /* resid (N doubles, host, may be NULL), sigma2, xtx_inv (C*C row-major, may be NULL) */
 int rvt_get_null_model(rvt_ctx* ctx, double* resid, double* sigma2, double* xtx_inv);
+/* beta (C doubles): LinearRegression::GetCovEst, printed in the ##NullModelEstimates block of MetaScore.assoc */
+int rvt_get_null_beta(rvt_ctx* ctx, double* beta);
 
 /* ---- genes ---------------------------------------------------------------------------------
  * rvt_gene_push_f64: the reference boundary -- G is dc->getGenotype(): N x M column-major doubles

@@ -490,6 +490,14 @@ int rvt_get_null_model(rvt_ctx* ctx, double* resid, double* sigma2, double* xtx_
   return RVT_OK;
 }
 
+int rvt_get_null_beta(rvt_ctx* ctx, double* beta) {
+  if (!ctx || !beta) return RVT_E_BADARG;
+  if (!ctx->have_null) CTX_FAIL(RVT_E_STATE, "no null model set");
+  RVT_CUDA_OK(cudaMemcpyAsync(beta, ctx->dbeta, sizeof(double) * ctx->C, cudaMemcpyDeviceToHost, ctx->stream));
+  RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return RVT_OK;
+}
+
 // common tail of every push: append the descriptor and the per-variant side data
 static int push_common(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, const double* af, const uint8_t* flags,
                        bool counted, int seg, int64_t row0, bool tiled, int slots = 0 /* per-variant slots owned; 0: M */) {

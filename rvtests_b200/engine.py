@@ -52,7 +52,7 @@ EXPORTS = [
     "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded",
     "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
     "rvt_debug_phases",
-    "rvt_meta_plan", "rvt_meta_flush", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand", "rvt_lmm_set_null", "rvt_lmm_flush",
+    "rvt_meta_plan", "rvt_meta_flush", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand", "rvt_lmm_set_null", "rvt_lmm_flush", "rvt_get_null_beta",
 ]
 
 LMM_DTYPE = np.dtype([("af", "f8"), ("U", "f8"), ("V", "f8"), ("stat", "f8"), ("pvalue", "f8"), ("ok", "i4"), ("pad", "i4")])

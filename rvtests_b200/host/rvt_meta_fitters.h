@@ -1,0 +1,437 @@
+// rvt_meta_fitters.h -- ModelFitter-shaped adapters for `--meta score,cov`, backed by rvt_meta_flush (include/rvtests_b200.h).
+// Same conventions as rvt_fitters.h (templated on the reference's DataConsolidator / FileWriter / Result so that the file
+// compiles inside rvtests and against host/shim.h here).
+//
+// Mirrors:
+//   MetaScoreTest  src/Model.h:3154-3365   modelName "MetaScore"; columns AF INFORMATIVE_ALT_AC CALL_RATE HWE_PVALUE N_REF
+//                  N_HET N_ALT U_STAT SQRT_V_STAT ALT_EFFSIZE [ALT_EFFSIZE_SE] PVALUE (:3263-3279); statistics of a
+//                  monomorphic or failed site print NA, its counts are still printed (:3290-3345); the
+//                  "##NullModelEstimates" block of MetaUnrelatedQtl::PrintNullModel (:3525-3541) precedes the header
+//   MetaCovTest    src/Model.cpp:807-1004, src/Model.h:3954-3967: one line per polymorphic variant, CHROM START_POS END_POS
+//                  NUM_MARKER MARKER_POS COV, listing every later polymorphic variant within windowSize bp on the same
+//                  chromosome (the loci queued when the head is popped), COV entries divided by N and printed as floats
+// Behavioural difference, by design (as in rvt_fitters.h): fit() only records the variant; variants are packed 64 to a block,
+// blocks are evaluated in segments, and the lines are written in arrival order when a segment is flushed (every
+// `segment` variants, at a chromosome change, in writeFootnote / the destructor).  A segment keeps the trailing variants
+// whose window is still open and re-submits them with the next segment, so covariance windows are never cut.
+// Not covered: binary traits, kinship (family) models, hemizygous regions, dosages (a site with a value outside {0,1,2}
+// prints NA statistics).
+#ifndef RVT_META_FITTERS_H_
+#define RVT_META_FITTERS_H_
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "rvtests_b200.h"
+
+namespace rvtb200 {
+
+template <class DC>
+class MetaBatcher {
+ public:
+  static MetaBatcher& instance() {
+    static MetaBatcher b;
+    return b;
+  }
+  ~MetaBatcher() {
+    if (ctx_) rvt_ctx_destroy(ctx_);
+  }
+  void setSegment(int nVariants) { segment_ = nVariants > 64 ? nVariants : 64; }
+  void setWindow(int bp) { window_ = bp; }
+  void enableCov() { want_cov_ = true; }
+  const char* error() const { return ctx_ ? rvt_last_error(ctx_) : "no context"; }
+  int newFitterId() { return next_id_++; }
+
+  struct Site {
+    int chrom, pos;
+    bool hard;           // every value in {0,1,2}
+    bool score_done, cov_done;
+    rvt_variant_result r;
+    std::string cov_line;   // empty: nothing to print (monomorphic)
+  };
+
+  // Called from fit(): ticket of the CURRENT variant, recorded on first sight (a fitter id seen twice = next variant)
+  int submit(int fitter_id, DC* dc) {
+    if (!ensureContext()) return -1;
+    if (current_ < 0 || seen(fitter_id)) {
+      if (!record(dc)) return -1;
+      seen_.clear();
+    }
+    seen_.push_back(fitter_id);
+    return current_;
+  }
+  const Site* site(int ticket, bool need_cov) {
+    if (ticket < 0 || ticket >= (int)sites_.size()) return NULL;
+    if (!sites_[ticket].score_done || (need_cov && !sites_[ticket].cov_done)) return NULL;
+    return &sites_[ticket];
+  }
+  // evaluate what is pending; final = no later variant will extend any window (end of input / destructor)
+  bool flush(bool final) {
+    if (!ctx_) return true;
+    // nothing new since the last evaluation, and no open window that `final` would close
+    if (pending_new_ == 0 && !(final && want_cov_ && !blocks_.empty())) return true;
+    closeBlock();
+    if (blocks_.empty()) return true;
+    std::vector<int> tix;
+    for (size_t b = 0; b < blocks_.size(); ++b) {
+      const Block& k = blocks_[b];
+      if (rvt_gene_push_i8(ctx_, k.g.data(), k.M, N_, NULL) != RVT_OK) return fail("push");
+      for (int j = 0; j < k.M; ++j) tix.push_back(k.first + j);
+    }
+    const int64_t nv = (int64_t)tix.size();
+    std::vector<int32_t> pos(nv), chrom(nv);
+    for (int64_t v = 0; v < nv; ++v) {
+      pos[v] = sites_[tix[v]].pos;
+      chrom[v] = sites_[tix[v]].chrom;
+    }
+    int wmax = 0;
+    std::vector<double> band;
+    if (want_cov_) {
+      if (rvt_meta_plan(ctx_, pos.data(), chrom.data(), nv, window_, &wmax) != RVT_OK) return fail("plan");
+      band.resize((size_t)nv * (wmax + 1));
+    }
+    std::vector<rvt_variant_result> vr(nv);
+    if (rvt_meta_flush(ctx_, pos.data(), chrom.data(), window_, vr.data(), nv, want_cov_ ? band.data() : NULL,
+                       (int64_t)band.size(), &wmax) != RVT_OK)
+      return fail("flush");
+    const int last_pos = pos[nv - 1], last_chrom = chrom[nv - 1];
+    int64_t first_open = nv;   // first variant whose window may still grow
+    for (int64_t v = 0; v < nv; ++v) {
+      Site& s = sites_[tix[v]];
+      if (!s.score_done) {
+        s.r = vr[v];
+        if (!s.hard) s.r.ok = 0;
+        s.score_done = true;
+      }
+      if (s.cov_done || !want_cov_) continue;
+      // the reference pops a head once a locus farther than windowSize (or on another chromosome) arrives
+      const bool closed = final || chrom[v] != last_chrom || abs(last_pos - pos[v]) > window_;
+      if (!closed) {
+        if (first_open == nv) first_open = v;
+        continue;
+      }
+      s.cov_done = true;
+      if (!vr[v].polymorphic || !s.hard) continue;   // never queued: no line
+      std::string mp, cv;
+      int n = 0;
+      char buf[64];
+      for (int d = 0; d <= wmax && v + d < nv; ++d) {
+        const double c = band[(size_t)v * (wmax + 1) + d];
+        if (c != c) continue;   // outside the window, or the partner is monomorphic
+        snprintf(buf, sizeof(buf), "%s%d", n ? "," : "", pos[v + d]);
+        mp += buf;
+        snprintf(buf, sizeof(buf), "%s%g", n ? "," : "", (double)(float)c);   // toString(float) (src/Model.h:4034-4041)
+        cv += buf;
+        ++n;
+        end_pos_ = pos[v + d];
+      }
+      snprintf(buf, sizeof(buf), "%d", n);
+      s.cov_line = chromName(chrom[v]) + "\t" + itoa(pos[v]) + "\t" + itoa(end_pos_) + "\t" + buf + "\t" + mp + "\t" + cv;
+    }
+    if (!want_cov_) first_open = nv;
+    // keep the blocks that still hold an open variant (a suffix), drop the rest
+    size_t keep_from = blocks_.size();
+    int64_t v0 = 0;
+    for (size_t b = 0; b < blocks_.size(); ++b) {
+      if (first_open < v0 + blocks_[b].M) {
+        keep_from = b;
+        break;
+      }
+      v0 += blocks_[b].M;
+    }
+    blocks_.erase(blocks_.begin(), blocks_.begin() + keep_from);
+    pending_new_ = 0;
+    return true;
+  }
+  bool shouldFlush() const { return pending_new_ >= segment_; }
+  // null model for the ##NullModelEstimates block (valid after the first submit)
+  bool nullModel(std::vector<double>* beta, std::vector<double>* var, double* sigma2) {
+    if (!ctx_ || C_ <= 0) return false;
+    beta->resize(C_);
+    std::vector<double> xtx((size_t)C_ * C_);
+    if (rvt_get_null_beta(ctx_, beta->data()) != RVT_OK) return false;
+    if (rvt_get_null_model(ctx_, NULL, sigma2, xtx.data()) != RVT_OK) return false;
+    var->resize(C_);
+    for (int i = 0; i < C_; ++i) (*var)[i] = xtx[(size_t)i * C_ + i] * *sigma2;   // covB = (X'X)^-1 sigma2, LinearRegression.cpp:62-66
+    return true;
+  }
+
+ private:
+  struct Block {
+    int first, M;             // ticket of row 0, rows
+    std::vector<int8_t> g;    // [M][N] variant-major hard calls
+  };
+  MetaBatcher()
+      : ctx_(NULL), N_(0), C_(0), segment_(4096), window_(1000000), want_cov_(false), current_(-1), next_id_(0), have_null_(false),
+        pending_new_(0), end_pos_(0) {}
+  bool fail(const char* what) {
+    fprintf(stderr, "rvtests_b200: meta %s failed: %s\n", what, error());
+    return false;
+  }
+  static std::string itoa(int v) {
+    char buf[32];
+    snprintf(buf, sizeof(buf), "%d", v);
+    return buf;
+  }
+  bool seen(int id) const {
+    for (size_t i = 0; i < seen_.size(); ++i)
+      if (seen_[i] == id) return true;
+    return false;
+  }
+  bool ensureContext() {
+    if (ctx_) return true;
+    if (rvt_ctx_create(0, &ctx_) != RVT_OK) {
+      fprintf(stderr, "rvtests_b200: %s\n", error());
+      if (ctx_) rvt_ctx_destroy(ctx_);
+      ctx_ = NULL;
+      return false;   // no CPU fallback
+    }
+    return true;
+  }
+  bool ensureNullModel(DC* dc) {
+    if (have_null_ && !dc->isPhenotypeUpdated() && !dc->isCovariateUpdated()) return true;
+    if (!flush(true)) return false;
+    const auto& ph = dc->getPhenotype();
+    const auto& cv = dc->getCovariate();
+    const int n = ph.rows, c = cv.cols + 1;
+    std::vector<double> X((size_t)n * c), y(n);
+    for (int i = 0; i < n; ++i) {
+      X[i] = 1.0;
+      y[i] = ph(i, 0);
+    }
+    for (int j = 0; j < cv.cols; ++j)
+      for (int i = 0; i < n; ++i) X[(size_t)(j + 1) * n + i] = cv(i, j);
+    if (rvt_set_null_model(ctx_, n, c, X.data(), y.data(), 0) != RVT_OK) return fail("null model");
+    N_ = n;
+    C_ = c;
+    have_null_ = true;
+    return true;
+  }
+  int chromId(const std::string& name) {
+    for (size_t i = 0; i < chroms_.size(); ++i)
+      if (chroms_[i] == name) return (int)i;
+    chroms_.push_back(name);
+    return (int)chroms_.size() - 1;
+  }
+  const std::string& chromName(int id) const { return chroms_[id]; }
+  void closeBlock() {
+    if (open_.M > 0) {
+      open_.g.resize((size_t)open_.M * N_);
+      blocks_.push_back(open_);
+      open_ = Block();
+      open_.M = 0;
+    }
+  }
+  bool record(DC* dc) {
+    if (!ensureNullModel(dc)) return false;
+    const auto& g = dc->getGenotype();   // N x 1
+    Site s;
+    memset(&s.r, 0, sizeof(s.r));
+    s.score_done = s.cov_done = false;
+    s.hard = g.cols == 1 && g.rows == N_;
+    const auto& info = dc->getResult();
+    s.chrom = chromId(info["CHROM"]);
+    s.pos = atoi(info["POS"].c_str());
+    // a chromosome change closes every window: evaluate what is pending first
+    if (!sites_.empty() && sites_.back().chrom != s.chrom && !flush(true)) return false;
+    if (open_.M == 0) {
+      open_.first = (int)sites_.size();
+      open_.g.assign((size_t)64 * N_, 0);
+    }
+    int8_t* row = open_.g.data() + (size_t)open_.M * N_;
+    if (s.hard)
+      for (int i = 0; i < N_; ++i) {
+        const double v = g(i, 0);
+        if (v == 0.0 || v == 1.0 || v == 2.0)
+          row[i] = (int8_t)v;
+        else {
+          s.hard = false;
+          break;
+        }
+      }
+    if (!s.hard) memset(row, 0, (size_t)N_);   // placeholder row (monomorphic): statistics print NA, never queued
+    sites_.push_back(s);
+    current_ = (int)sites_.size() - 1;
+    if (++open_.M == 64) closeBlock();
+    ++pending_new_;
+    return true;
+  }
+
+  rvt_ctx* ctx_;
+  int N_, C_, segment_, window_;
+  bool want_cov_;
+  int current_, next_id_;
+  bool have_null_;
+  int pending_new_, end_pos_;
+  std::vector<int> seen_;
+  std::vector<std::string> chroms_;
+  std::vector<Site> sites_;
+  std::deque<Block> blocks_;
+  Block open_ = Block{0, 0, std::vector<int8_t>()};
+};
+
+template <class DC, class FW, class RES>
+class MetaScoreTestB200 {
+ public:
+  explicit MetaScoreTestB200(bool outputSE = false) : outputSE_(outputSE), ticket_(-1), fp_(NULL), header_(false) {
+    modelName = "MetaScore";
+    id_ = MetaBatcher<DC>::instance().newFitterId();
+  }
+  ~MetaScoreTestB200() { drain(true); }
+  const std::string& getModelName() const { return modelName; }
+  bool needToIndexResult() const { return true; }   // indexResult = true, src/Model.h:3163
+  void reset() { ticket_ = -1; }
+  int fit(DC* dc) {
+    ticket_ = MetaBatcher<DC>::instance().submit(id_, dc);
+    return ticket_ >= 0 ? 0 : -1;
+  }
+  void writeHeader(FW*, const RES&) {}   // deferred: the header follows the null-model block (src/Model.h:3261-3281)
+  void writeOutput(FW* fp, const RES& siteInfo) {
+    fp_ = fp;
+    if (!header_) {
+      site_header_ = siteInfo.joinHeader();
+      header_ = true;
+    }
+    Pending p;
+    p.ticket = ticket_;
+    p.site = siteInfo.joinValue();
+    pending_.push_back(p);
+    if (MetaBatcher<DC>::instance().shouldFlush()) drain(false);
+  }
+  void writeFootnote(FW* fp) {
+    if (!fp_) fp_ = fp;
+    drain(true);
+  }
+
+ private:
+  static std::string g(double v) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%g", v);
+    return buf;
+  }
+  void printHeader() {
+    MetaBatcher<DC>& b = MetaBatcher<DC>::instance();
+    std::vector<double> beta, var;
+    double sigma2 = 0;
+    if (b.nullModel(&beta, &var, &sigma2)) {   // MetaUnrelatedQtl::PrintNullModel, src/Model.h:3525-3541
+      fp_->write("##NullModelEstimates\n");
+      fp_->write("## - Name\tBeta\tSD\n");
+      fp_->write(("## - Intercept\t" + g(beta[0]) + "\t" + g(var[0]) + "\n").c_str());
+      for (size_t i = 1; i < beta.size(); ++i) {
+        char nm[32];
+        snprintf(nm, sizeof(nm), "Cov%d", (int)i);   // the reference prints the covariate labels of its summary header
+        fp_->write((std::string("## - ") + nm + "\t" + g(beta[i]) + "\t" + g(var[i]) + "\n").c_str());
+      }
+      fp_->write(("## - Sigma2\t" + g(sigma2) + "\tNA\n").c_str());
+    }
+    std::string h = site_header_ + "\tAF\tINFORMATIVE_ALT_AC\tCALL_RATE\tHWE_PVALUE\tN_REF\tN_HET\tN_ALT\tU_STAT\tSQRT_V_STAT\tALT_EFFSIZE";
+    if (outputSE_) h += "\tALT_EFFSIZE_SE";
+    h += "\tPVALUE\n";
+    fp_->write(h.c_str());
+  }
+  void drain(bool final) {
+    if (!fp_ || pending_.empty()) return;
+    MetaBatcher<DC>& b = MetaBatcher<DC>::instance();
+    if (!b.flush(final)) return;
+    if (!printed_header_) {
+      printHeader();
+      printed_header_ = true;
+    }
+    size_t i = 0;
+    for (; i < pending_.size(); ++i) {
+      const typename MetaBatcher<DC>::Site* s = b.site(pending_[i].ticket, false);
+      if (!s && pending_[i].ticket >= 0) break;
+      std::string line = pending_[i].site + "\t";
+      if (!s) {
+        line += "NA\tNA\tNA\tNA\tNA\tNA\tNA\tNA\tNA\tNA";
+        if (outputSE_) line += "\tNA";
+        line += "\tNA";
+      } else {
+        const rvt_variant_result& r = s->r;
+        char buf[96];
+        snprintf(buf, sizeof(buf), "%d\t%d\t%d", r.n_ref, r.n_het, r.n_alt);
+        line += g(r.af) + "\t" + g(r.ac) + "\t" + g(r.call_rate) + "\t" + g(r.hwe_p) + "\t" + buf + "\t";
+        if (r.ok) {
+          line += g(r.U) + "\t" + g(r.sqrtV) + "\t" + g(r.effect);
+          if (outputSE_) line += "\t" + ((r.sqrtV > 0.0) ? g(r.effect_se) : std::string("NA"));
+          line += "\t" + g(r.pvalue);
+        } else {
+          line += "NA\tNA\tNA";
+          if (outputSE_) line += "\tNA";
+          line += "\tNA";
+        }
+      }
+      line += "\n";
+      fp_->write(line.c_str());
+    }
+    pending_.erase(pending_.begin(), pending_.begin() + i);
+  }
+  struct Pending {
+    int ticket;
+    std::string site;
+  };
+  std::string modelName, site_header_;
+  bool outputSE_;
+  int id_, ticket_;
+  FW* fp_;
+  bool header_, printed_header_ = false;
+  std::vector<Pending> pending_;
+};
+
+template <class DC, class FW, class RES>
+class MetaCovTestB200 {
+ public:
+  explicit MetaCovTestB200(int windowSize = 1000000) : ticket_(-1), fp_(NULL) {
+    modelName = "MetaCov";
+    MetaBatcher<DC>& b = MetaBatcher<DC>::instance();
+    id_ = b.newFitterId();
+    b.enableCov();
+    b.setWindow(windowSize);
+  }
+  ~MetaCovTestB200() { drain(true); }   // MetaCovTest::~MetaCovTest prints what is still queued (src/Model.cpp:828-834)
+  const std::string& getModelName() const { return modelName; }
+  bool needToIndexResult() const { return true; }
+  void reset() { ticket_ = -1; }
+  int fit(DC* dc) {
+    ticket_ = MetaBatcher<DC>::instance().submit(id_, dc);
+    return ticket_ >= 0 ? 0 : -1;
+  }
+  void writeHeader(FW* fp, const RES&) { fp->write("CHROM\tSTART_POS\tEND_POS\tNUM_MARKER\tMARKER_POS\tCOV\n"); }
+  void writeOutput(FW* fp, const RES&) {
+    fp_ = fp;
+    pending_.push_back(ticket_);
+    if (MetaBatcher<DC>::instance().shouldFlush()) drain(false);
+  }
+  void writeFootnote(FW* fp) {
+    if (!fp_) fp_ = fp;
+    drain(true);
+  }
+
+ private:
+  void drain(bool final) {
+    if (!fp_ || pending_.empty()) return;
+    MetaBatcher<DC>& b = MetaBatcher<DC>::instance();
+    if (!b.flush(final)) return;
+    size_t i = 0;
+    for (; i < pending_.size(); ++i) {
+      if (pending_[i] < 0) continue;
+      const typename MetaBatcher<DC>::Site* s = b.site(pending_[i], true);
+      if (!s) break;   // its window is still open
+      if (!s->cov_line.empty()) fp_->write((s->cov_line + "\n").c_str());
+    }
+    pending_.erase(pending_.begin(), pending_.begin() + i);
+  }
+  std::string modelName;
+  int id_, ticket_;
+  FW* fp_;
+  std::vector<int> pending_;
+};
+
+}  // namespace rvtb200
+#endif  // RVT_META_FITTERS_H_

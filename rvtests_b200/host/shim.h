@@ -39,6 +39,18 @@ struct Result {
   void writeHeaderTab(FileWriter* fp) const {
     for (size_t i = 0; i < keys.size(); ++i) fp->write((keys[i] + "\t").c_str());
   }
+  // siteInfo["CHROM"], siteInfo["POS"] (src/Result.h:218-238)
+  const std::string& operator[](const std::string& key) const {
+    static const std::string na = "NA";
+    for (size_t i = 0; i < keys.size(); ++i)
+      if (keys[i] == key) return values[i];
+    return na;
+  }
+  std::string joinHeader() const {
+    std::string s;
+    for (size_t i = 0; i < keys.size(); ++i) s += (i ? "\t" : "") + keys[i];
+    return s;
+  }
   std::string joinValue() const {
     std::string s;
     for (size_t i = 0; i < values.size(); ++i) s += (i ? "\t" : "") + values[i];
@@ -57,6 +69,8 @@ struct DataConsolidator {
   double getMarkerFrequency(int col) const { return af[col]; }
   bool isPhenotypeUpdated() const { return phenoUpdated; }
   bool isCovariateUpdated() const { return covUpdated; }
+  Result site;                                   // dc->getResult(): the site columns of the current variant
+  Result& getResult() { return site; }
 };
 
 }  // namespace shim

@@ -118,3 +118,77 @@ def test_skat_adapter_with_permutations(oracle, tmp_path):
         first = False
         assert row == [g(ref.skat.Q), g(ref.skat.pvalue), str(n_perm), str(pr["actual"]), g(ref.skat.Q), str(pr["greater"]),
                        str(pr["equal"]), g(pr["p"])]
+
+
+def build_meta_demo():
+    exe = os.path.join(ROOT, "rvtests_b200", "host", "meta_demo")
+    src = os.path.join(ROOT, "rvtests_b200", "host", "meta_demo.cpp")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                    "-L", os.path.join(ROOT, "rvtests_b200"), "-lrvtests_b200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "rvtests_b200")], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("segment", [64, 100, 100000])
+def test_meta_adapters_match_reference_output_format(oracle, segment, tmp_path):
+    """MetaScoreTest / MetaCovTest adapters (host/rvt_meta_fitters.h) driven variant by variant: the .assoc lines the
+    reference's writeOutput / printCovariance would print (src/Model.h:3282-3345, src/Model.cpp:942-1004) for the oracle's
+    numbers -- whatever the segment size (windows must survive segment boundaries and close at a chromosome change)."""
+    from oracle import meta_oracle as MO
+    import rvtests_b200
+    rvtests_b200.load_library()
+    O = oracle
+    seed, N, nv, C, window = 5, 1500, 230, 3, 900
+    vid = np.arange(nv, dtype=np.uint64) + np.uint64(seed * 7919)
+    rng = np.random.default_rng(seed)
+    maf = 10 ** rng.uniform(np.log10(2.0 / N), np.log10(0.4), nv)
+    G = O.synth_genotypes(seed, vid, N, maf=maf)                # (nv, N)
+    for j in rng.integers(0, nv, 8):
+        G[j] = 0                                                # monomorphic sites: NA statistics, no MetaCov line
+    X, y = O.synth_covariates(seed, N, C)
+    pos = np.cumsum(rng.integers(1, 40, nv)).astype(np.int32)
+    chrom = np.ones(nv, dtype=np.int32)
+    cut = int(nv * 0.6)
+    chrom[cut:] = 2
+    pos[cut:] -= pos[cut] - 7
+    path = tmp_path / "meta.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("iii", N, C - 1, nv))
+        f.write(np.ascontiguousarray(y).tobytes())
+        f.write(np.asfortranarray(X[:, 1:]).tobytes(order="F"))
+        for v in range(nv):
+            f.write(struct.pack("ii", int(chrom[v]), int(pos[v])))
+            f.write(G[v].astype(np.float64).tobytes())
+    exe = build_meta_demo()
+    out = subprocess.run([exe, str(path), str(segment), str(window)], capture_output=True, text=True, check=True).stdout
+    score_txt, cov_txt = out.split("#MetaCov\n")
+    score_lines = score_txt.splitlines()[1:]
+    nm = O.fit_null_linear(X, y)
+    # ##NullModelEstimates block, then the column header
+    assert score_lines[0] == "##NullModelEstimates" and score_lines[1] == "## - Name\tBeta\tSD"
+    beta = np.linalg.solve(X.T @ X, X.T @ y)
+    var = np.diag(nm["xtx_inv"]) * nm["sigma2"]
+    assert score_lines[2] == "## - Intercept\t%s\t%s" % (g(beta[0]), g(var[0]))
+    assert score_lines[2 + C] == "## - Sigma2\t%s\tNA" % g(nm["sigma2"])
+    hdr = score_lines[3 + C].split("\t")
+    assert hdr == ["CHROM", "POS", "REF", "ALT", "N_INFORMATIVE", "AF", "INFORMATIVE_ALT_AC", "CALL_RATE", "HWE_PVALUE", "N_REF",
+                   "N_HET", "N_ALT", "U_STAT", "SQRT_V_STAT", "ALT_EFFSIZE", "ALT_EFFSIZE_SE", "PVALUE"]
+    rows = [l.split("\t") for l in score_lines[4 + C:]]
+    assert len(rows) == nv
+    for v in range(nv):
+        ref = MO.meta_score(G[v].astype(np.float64), X, nm["resid"], nm["sigma2"])
+        exp = [str(chrom[v]), str(pos[v]), "A", "G", str(N), g(ref["af"]), g(ref["ac"]), "1", g(ref["hwe_p"]), str(ref["n_ref"]),
+               str(ref["n_het"]), str(ref["n_alt"])]
+        exp += [g(ref["U"]), g(ref["sqrtV"]), g(ref["effect"]), g(ref["effect_se"]), g(ref["pvalue"])] if ref["ok"] else ["NA"] * 5
+        assert rows[v] == exp, (v, rows[v], exp)
+    # MetaCov: one line per polymorphic variant, in order
+    cov_lines = cov_txt.splitlines()
+    assert cov_lines[0] == "CHROM\tSTART_POS\tEND_POS\tNUM_MARKER\tMARKER_POS\tCOV"
+    ref_cov = [(v, rc) for v, rc in enumerate(MO.meta_cov(G.T, pos, chrom, X, nm["sigma2"], window)) if rc is not None]
+    assert len(cov_lines) - 1 == len(ref_cov)
+    for line, (v, (ps, vals)) in zip(cov_lines[1:], ref_cov):
+        c = line.split("\t")
+        assert c[:5] == [str(chrom[v]), str(pos[v]), str(ps[-1]), str(len(ps)), ",".join(map(str, ps))], (v, c[:5])
+        got = np.array([float(x) for x in c[5].split(",")])
+        assert len(got) == len(vals)
+        assert np.all(np.abs(got - np.array(vals)) <= 2e-5 * np.maximum(np.abs(vals), 1e-12) + 1e-12)   # printed with 6 digits
