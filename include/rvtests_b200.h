@@ -102,6 +102,17 @@ typedef struct rvt_lmm_result {
   int32_t pad;
 } rvt_lmm_result;
 
+/* BoltLMM null-model fit (regression/BoltLMM.cpp:169-299): what FitNullModel leaves behind for TestCovariate */
+typedef struct rvt_bolt_null {
+  double delta;                  /* sigma2_e / sigma2_g at the end of the secant iteration */
+  double sigma2_g, sigma2_e, h2;
+  double h_inv_y_norm2;          /* projNorm2(H_inv_y_) */
+  double inf_stat_calibration;   /* infStatCalibration_ */
+  double xvx_xx_ratio;           /* xVx_xx_ratio_ (scales BoltLMM::GetCovXX) */
+  double log_delta[7], f[7];     /* the secant path: log(delta) tried and the MC-REML function there */
+  int32_t mc_trials, reml_evals, cg_iterations, n_covariates_kept;
+} rvt_bolt_null;
+
 /* ---- lifetime ------------------------------------------------------------------------------- */
 int rvt_ctx_create(int device, rvt_ctx** out);
 void rvt_ctx_destroy(rvt_ctx* ctx);
@@ -181,6 +192,15 @@ int rvt_debug_rand(rvt_ctx* ctx, uint32_t seed, uint64_t pos, int64_t n, int32_t
 int rvt_lmm_set_null(rvt_ctx* ctx, int64_t N, int C, const float* U, const float* lambda, double delta, double sigma2,
                      const float* uResid, const float* ux);
 int rvt_lmm_flush(rvt_ctx* ctx, rvt_lmm_result* out, int64_t cap);
+/* ---- BoltLMM null model -------------------------------------------------------------------------
+ * bed: the PLINK panel, M SNP-major 2-bit rows of `stride` >= ceil(N/4) bytes on the host (samples in phenotype order);
+ * y: N phenotypes; covar: N x C column-major, intercept first (the .covar file of BoltPlinkLoader); mc_trials: 0 = the
+ * reference's rule max(min(4e9/N^2, 15), 3).  h_inv_y (may be NULL) receives the N + n_covariates_kept values
+ * [H^-1 y / sigma2_g ; Z' of it]; Zout (may be NULL) the N x n_covariates_kept orthonormal covariate basis, column-major.
+ * The score step then is rvt_set_null_residual(ctx, N, C, X, h - Z Z'h, h_inv_y_norm2 * inf_stat_calibration / N) +
+ * rvt_meta_flush.  Random numbers: the reference's generator and seed (libsrc/Random.cpp, 12345). */
+int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t stride, int64_t N, const double* y, const double* covar,
+                      int C, int mc_trials, rvt_bolt_null* out, double* h_inv_y, double* Zout);
 /* number of genes pushed and not yet flushed */
 int rvt_pending(const rvt_ctx* ctx);
 /* run the sweep + per-gene statistics for every pending gene; out: host array of `cap` records */

@@ -1,0 +1,327 @@
+// bolt.cuh -- A15: the BoltLMM null-model fit (regression/BoltLMM.cpp:169-299, 463-859, 926-1214;
+// regression/BoltPlinkLoader.cpp:115-342) with the genotype panel resident on the GPU as PLINK 2-bit rows.
+//
+//   model        y = X beta + e,  beta ~ N(0, sigma2_g / M),  e ~ N(0, sigma2_e),  X = panel genotypes normalised to
+//                (g - 2p)/sqrt(2p(1-p)) (missing -> 0), covariates projected out of everything
+//   H            = X X' / M + delta I,  delta = sigma2_e / sigma2_g                      computeHx, BoltLMM.cpp:931-993
+//   solve        multi-RHS conjugate gradients on H, BOLT's tolerance 5e-4, <= min(N, 250) iterations   :745-859
+//   MC-REML      f(log delta) = log( (|beta^_data|^2/|e^_data|^2) / (sum_t |beta^_t|^2 / sum_t |e^_t|^2) ) over MCtrial
+//                simulated phenotypes X beta_rand + sqrt(delta) e_rand; secant iteration on log delta, <= 7 evaluations
+//                (evalREML :669-724, EstimateHeritabilityBolt :575-668)
+//   calibration  30 random panel SNPs: prospective x'V^-1y^2 / x'V^-1x against the uncalibrated retrospective
+//                statistic (EstimateInfStatCalibration :1141-1214)
+//   output       H^-1 y / sigma2_g, its projected squared norm, infStatCalibration -- what BoltLMM::TestCovariate
+//                (:315-338) needs, i.e. the inputs of rvt_set_null_residual + rvt_meta_flush (the A14 score step)
+//
+// The reference keeps every vector as [v ; Z'v] (N + C rows, Z = orthonormal covariate basis) so that projecting the
+// covariates out becomes a sign flip on the last C rows of every inner product (projDot / projNorm2 :1064-1138).  The same
+// layout is used here: vectors are (N + C) x R doubles, row-major (R right-hand sides side by side), the two O(N M R)
+// products of computeHx stream the 2-bit panel from HBM (N M / 4 bytes per pass) and decode it through a 4-entry table per
+// SNP held in shared memory.  The host drives the CG / secant logic (a few hundred scalars per iteration) and draws the
+// random numbers with the reference's own generator (MT19937 seeded 12345 + polar Box-Muller, libsrc/Random.cpp) so that
+// the Monte-Carlo path is the reference's path.  Arithmetic is fp64 where the reference uses float32.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace rvt {
+
+constexpr int kBoltMaxR = 32;        // right-hand sides per solve (MCtrial + 1 <= 16; 30 calibration SNPs)
+constexpr int kBoltSnpBlock = 64;    // SNPs per CTA in the X'v product
+constexpr int kBoltChunk = 1024;     // samples staged per step in the X'v product
+constexpr int kBoltRowPad = kBoltChunk / 4 + 4;   // bytes per staged row (65 words: conflict-free across rows)
+
+// libsrc/Random.cpp: MT19937 (InitMersenne :128-140, Next :146-183) and the polar Box-Muller Normal (:269-288)
+struct BoltRandom {
+  uint32_t mt[624];
+  int mti;
+  bool saved;
+  double store;
+  explicit BoltRandom(uint32_t s = 12345) { reset(s); }
+  void reset(uint32_t s) {
+    mt[0] = s;
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    mti = 624;
+    saved = false;
+  }
+  double next() {
+    if (mti >= 624) {
+      for (int kk = 0; kk < 624; ++kk) {
+        const uint32_t y = (mt[kk] & 0x80000000u) | (mt[(kk + 1) % 624] & 0x7FFFFFFFu);
+        mt[kk] = mt[(kk + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+      }
+      mti = 0;
+    }
+    uint32_t y = mt[mti++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9D2C5680u;
+    y ^= (y << 15) & 0xEFC60000u;
+    y ^= y >> 18;
+    return (1.0 / 4294967296.0) * ((double)y + 0.5);
+  }
+  double normal() {
+    if (saved) {
+      saved = false;
+      return store;
+    }
+    double v1, v2, rsq;
+    do {
+      v1 = 2.0 * next() - 1.0;
+      v2 = 2.0 * next() - 1.0;
+      rsq = v1 * v1 + v2 * v2;
+    } while (rsq >= 1.0 || rsq == 0.0);
+    const double fac = sqrt(-2.0 * log(rsq) / rsq);
+    store = v1 * fac;
+    saved = true;
+    return v2 * fac;
+  }
+};
+
+#if defined(__CUDACC__)
+// PLINK code of sample i in a row: 00 -> 0, 10 -> 1, 11 -> 2, 01 -> missing (libVcf/PlinkInputFile.cpp:23-47)
+__device__ __forceinline__ int bolt_code(const uint8_t* __restrict__ row, int64_t i) { return (row[i >> 2] >> (2 * (i & 3))) & 3; }
+
+// One CTA per SNP: allele / missing counts -> the 4-entry table (BoltPlinkLoader::prepareGenotype, .cpp:164-234), then
+// zg[c][m] = (Z'x_m)_c and gnorm2[m] = |x_m|^2 - |Z'x_m|^2 (:236-262).  tab[m][code].
+__global__ void __launch_bounds__(256)
+k_bolt_snp(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, int C, const double* __restrict__ Z /*[N][C]*/,
+           double* __restrict__ tab /*[M][4]*/, double* __restrict__ zg /*[M][C]*/, double* __restrict__ gnorm2) {
+  __shared__ double s_red[8][kMaxC + 2];
+  __shared__ double s_tab[4];
+  __shared__ long long s_cnt[8][2];
+  const int m = blockIdx.x, tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  const uint8_t* __restrict__ row = bed + (size_t)m * stride;
+  long long ac = 0, miss = 0;
+  for (int64_t i = tid; i < N; i += 256) {
+    const int c = bolt_code(row, i);
+    ac += (c == 2) ? 1 : (c == 3) ? 2 : 0;
+    miss += (c == 1);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ac += __shfl_xor_sync(0xffffffffu, ac, o);
+    miss += __shfl_xor_sync(0xffffffffu, miss, o);
+  }
+  if (l == 0) {
+    s_cnt[w][0] = ac;
+    s_cnt[w][1] = miss;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    long long a = 0, mi = 0;
+    for (int i = 0; i < 8; ++i) {
+      a += s_cnt[i][0];
+      mi += s_cnt[i][1];
+    }
+    const double af = (N - mi) > 0 ? 0.5 * (double)a / (double)(N - mi) : 0.0;
+    const double mean = af + af, sd = sqrt(2.0 * af * (1.0 - af));
+    const double inv = sd > 0.0 ? 1.0 / sd : 0.0;
+    s_tab[0] = (0.0 - mean) * inv;   // 00 hom ref
+    s_tab[1] = 0.0;                  // 01 missing
+    s_tab[2] = (1.0 - mean) * inv;   // 10 het
+    s_tab[3] = (2.0 - mean) * inv;   // 11 hom alt
+    for (int k = 0; k < 4; ++k) tab[(size_t)m * 4 + k] = s_tab[k];
+  }
+  __syncthreads();
+  double acc[kMaxC + 1];
+#pragma unroll
+  for (int c = 0; c <= kMaxC; ++c) acc[c] = 0.0;
+  for (int64_t i = tid; i < N; i += 256) {
+    const double x = s_tab[bolt_code(row, i)];
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c)
+      if (c < C) acc[c] += x * Z[(size_t)i * C + c];
+    acc[kMaxC] += x * x;
+  }
+#pragma unroll
+  for (int c = 0; c <= kMaxC; ++c) {
+    double v = acc[c];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (l == 0) s_red[w][c] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double n2 = 0.0, zz = 0.0;
+    for (int i = 0; i < 8; ++i) n2 += s_red[i][kMaxC];
+    for (int c = 0; c < C; ++c) {
+      double v = 0.0;
+      for (int i = 0; i < 8; ++i) v += s_red[i][c];
+      zg[(size_t)m * C + c] = v;
+      zz += v * v;
+    }
+    gnorm2[m] = n2 - zz;
+  }
+}
+
+// X'v over a split of the samples: part[split][m][r] = sum_{i in split} x_mi v[i][r].  One thread per SNP of a 64-SNP
+// block holds the R accumulators; the block's 2-bit rows are staged through shared memory chunk by chunk.
+template <int RMAX>
+__global__ void __launch_bounds__(kBoltSnpBlock)
+k_bolt_xtv(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, int M, const double* __restrict__ tab, const double* __restrict__ v,
+           int R, int64_t split_len, double* __restrict__ part /*[splits][M][R]*/) {
+  __shared__ __align__(16) uint8_t s_rows[kBoltSnpBlock][kBoltRowPad];
+  const int m = blockIdx.x * kBoltSnpBlock + threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.y * split_len;
+  int64_t i1 = i0 + split_len;
+  if (i1 > N) i1 = N;
+  double t4[4] = {0, 0, 0, 0};
+  if (m < M)
+    for (int k = 0; k < 4; ++k) t4[k] = tab[(size_t)m * 4 + k];
+  double acc[RMAX];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) acc[r] = 0.0;
+  for (int64_t c0 = i0; c0 < i1; c0 += kBoltChunk) {   // i0 and kBoltChunk are multiples of 4
+    const int64_t n_here = (i1 - c0 < kBoltChunk) ? (i1 - c0) : kBoltChunk;
+    const int nbytes = (int)((n_here + 3) >> 2);
+    __syncthreads();
+    for (int rr = 0; rr < kBoltSnpBlock; ++rr) {
+      const int mm = blockIdx.x * kBoltSnpBlock + rr;
+      if (mm >= M) break;
+      const uint8_t* __restrict__ src = bed + (size_t)mm * stride + (c0 >> 2);
+      for (int b = threadIdx.x; b < nbytes; b += kBoltSnpBlock) s_rows[rr][b] = src[b];
+    }
+    __syncthreads();
+    if (m < M) {
+      const uint8_t* __restrict__ my = s_rows[threadIdx.x];
+      for (int64_t k = 0; k < n_here; ++k) {
+        const double x = t4[(my[k >> 2] >> (2 * (k & 3))) & 3];
+        const double* __restrict__ vr = v + (size_t)(c0 + k) * R;   // warp-uniform address: one broadcast load
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r)
+          if (r < R) acc[r] += x * vr[r];
+      }
+    }
+  }
+  if (m < M) {
+    double* o = part + ((size_t)blockIdx.y * M + m) * R;
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r)
+      if (r < R) o[r] = acc[r];
+  }
+}
+
+// Xy[m][r] = sum over splits (index order) of part - sum_c zg[m][c] vbot[c][r]     (X_minus' y, BoltLMM.cpp:948-958)
+__global__ void k_bolt_xtv_finish(int M, int R, int C, int splits, const double* __restrict__ part, const double* __restrict__ zg,
+                                  const double* __restrict__ vbot /*[C][R]*/, double scale, double* __restrict__ Xy) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)M * R) return;
+  const int m = (int)(idx / R), r = (int)(idx - (int64_t)m * R);
+  double s = 0.0;
+  for (int sp = 0; sp < splits; ++sp) s += part[((size_t)sp * M + m) * R + r];
+  for (int c = 0; c < C; ++c) s -= zg[(size_t)m * C + c] * vbot[(size_t)c * R + r];
+  Xy[idx] = s * scale;
+}
+
+// out[i][r] = alpha * sum_m x_mi W[m][r] + beta * add[i][r]   (top rows; X_plus X_y / M + delta y, :960-975).
+// One thread per sample holds the R accumulators; W and the tables are staged per 64-SNP block.
+template <int RMAX>
+__global__ void __launch_bounds__(256)
+k_bolt_xw(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, int M, const double* __restrict__ tab, const double* __restrict__ W /*[M][R]*/,
+          int R, double alpha, double beta, const double* __restrict__ add, double* __restrict__ out) {
+  __shared__ double s_W[kBoltSnpBlock][RMAX];
+  __shared__ double s_tab[kBoltSnpBlock][4];
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  double acc[RMAX];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) acc[r] = 0.0;
+  for (int m0 = 0; m0 < M; m0 += kBoltSnpBlock) {
+    const int nm = (M - m0 < kBoltSnpBlock) ? (M - m0) : kBoltSnpBlock;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nm * R; idx += 256) s_W[idx / R][idx % R] = W[(size_t)m0 * R + idx];
+    for (int idx = threadIdx.x; idx < nm * 4; idx += 256) s_tab[idx >> 2][idx & 3] = tab[(size_t)m0 * 4 + idx];
+    __syncthreads();
+    if (i < N) {
+      const uint8_t* __restrict__ col = bed + (size_t)m0 * stride + (i >> 2);
+      const int sh = 2 * (int)(i & 3);
+      for (int mm = 0; mm < nm; ++mm) {
+        const double x = s_tab[mm][(col[(size_t)mm * stride] >> sh) & 3];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r)
+          if (r < R) acc[r] += x * s_W[mm][r];
+      }
+    }
+  }
+  if (i < N) {
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r)
+      if (r < R) out[(size_t)i * R + r] = alpha * acc[r] + (add ? beta * add[(size_t)i * R + r] : 0.0);
+  }
+}
+
+// bottom rows: out[c][r] = alpha * sum_m zg[m][c] W[m][r] + beta * add[c][r]   (one thread per (c, r), SNP order)
+__global__ void k_bolt_bot(int M, int R, int C, const double* __restrict__ zg, const double* __restrict__ W, double alpha, double beta,
+                           const double* __restrict__ add, double* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * R) return;
+  const int c = idx / R, r = idx - c * R;
+  double s = 0.0;
+  for (int m = 0; m < M; ++m) s += zg[(size_t)m * C + c] * W[(size_t)m * R + r];
+  out[idx] = alpha * s + (add ? beta * add[idx] : 0.0);
+}
+
+// bottom rows from top rows: vbot[c][r] = sum_i Z[i][c] v[i][r]  (projectCovariate, BoltPlinkLoader.cpp:266-271);
+// one CTA per (c, r), fixed-order tree
+__global__ void __launch_bounds__(256)
+k_bolt_project(int64_t N, int R, int C, const double* __restrict__ Z, const double* __restrict__ v, double* __restrict__ vbot) {
+  __shared__ double s[256];
+  const int c = blockIdx.x / R, r = blockIdx.x - c * R;
+  double a = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += 256) a += Z[(size_t)i * C + c] * v[(size_t)i * R + r];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) vbot[(size_t)c * R + r] = s[0];
+}
+
+// projected products of two (N + C) x R vectors: partial[cta][r] over the top rows (fixed grid, fixed-order trees);
+// the host adds the CTAs in order and subtracts the bottom rows (projDot, BoltLMM.cpp:1064-1097)
+constexpr int kBoltDotCtas = 256;
+__global__ void __launch_bounds__(256)
+k_bolt_dot(int64_t N, int R, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ partial /*[ctas][R]*/) {
+  __shared__ double s[256];
+  const int64_t total = N * R;
+  // thread t of CTA k owns the elements e = (k*256 + t) + j * (ctas*256): with R | 256*ctas the column of e is fixed
+  const int64_t step = (int64_t)gridDim.x * 256;
+  for (int r = 0; r < R; ++r) {
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < N; i += step) acc += a[(size_t)i * R + r] * b[(size_t)i * R + r];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * R + r] = s[0];
+    __syncthreads();
+  }
+  (void)total;
+}
+
+// elementwise column-scaled updates on all (N + C) rows:  y[i][r] = ca[r] * a[i][r] + cb[r] * b[i][r]
+__global__ void k_bolt_axpby(int64_t rows, int R, const double* __restrict__ ca, const double* __restrict__ a, const double* __restrict__ cb,
+                             const double* __restrict__ b, double* __restrict__ y) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * R) return;
+  const int r = (int)(idx % R);
+  y[idx] = ca[r] * a[idx] + (b ? cb[r] * b[idx] : 0.0);
+}
+
+// normalised genotype columns of chosen SNPs as top rows: out[i][k] = x_{idx[k], i}  (loadRandomSNPWithCov, .cpp:441-480)
+__global__ void k_bolt_columns(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, const int* __restrict__ idx, int K,
+                               const double* __restrict__ tab, double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * K) return;
+  const int64_t i = e / K;
+  const int k = (int)(e - i * K);
+  const int m = idx[k];
+  out[e] = tab[(size_t)m * 4 + bolt_code(bed + (size_t)m * stride, i)];
+}
+#endif  // __CUDACC__
+
+}  // namespace rvt

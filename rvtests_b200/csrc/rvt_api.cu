@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "dosage.cuh"
 #include "finalize.cuh"
+#include "bolt.cuh"
 #include "lmm.cuh"
 #include "meta.cuh"
 #include "null_model.cuh"
@@ -1606,6 +1607,343 @@ int rvt_lmm_flush(rvt_ctx* ctx, rvt_lmm_result* out, int64_t cap) {
   cleanup();
   if (e != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "lmm: %s", cudaGetErrorString(e));
   pending_reset(ctx);
+  return RVT_OK;
+}
+
+// ---- A15: BoltLMM null-model fit (bolt.cuh) ---------------------------------------------------------
+}  // extern "C"
+namespace {
+struct BoltDev {
+  int64_t N = 0, stride = 0, split_len = 0;
+  int M = 0, C = 0, splits = 1;
+  uint8_t* bed = nullptr;
+  double *Z = nullptr, *tab = nullptr, *zg = nullptr, *gnorm2 = nullptr, *part = nullptr, *Xy = nullptr, *dotp = nullptr, *coef = nullptr;
+  cudaStream_t st = nullptr;
+  std::vector<void*> owned;
+  cudaError_t err = cudaSuccess;
+  int cg_total = 0;
+  template <class T>
+  T* alloc(size_t n) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e != cudaSuccess) {
+      if (err == cudaSuccess) err = e;
+      return nullptr;
+    }
+    owned.push_back(p);
+    return (T*)p;
+  }
+  void note() {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && err == cudaSuccess) err = e;
+  }
+  ~BoltDev() {
+    for (void* p : owned) cudaFree(p);
+  }
+  size_t rows() const { return (size_t)(N + C); }
+  double* vec(int R) { return alloc<double>(rows() * R); }
+  // out = (X X'/M + delta I) v on [v ; Z'v]   (computeHx, BoltLMM.cpp:931-993)
+  void Hx(double delta, const double* v, double* out, int R) {
+    dim3 g1((unsigned)((M + kBoltSnpBlock - 1) / kBoltSnpBlock), (unsigned)splits);
+    if (R <= 16) k_bolt_xtv<16><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
+    else k_bolt_xtv<32><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
+    k_bolt_xtv_finish<<<(unsigned)(((int64_t)M * R + 255) / 256), 256, 0, st>>>(M, R, C, splits, part, zg, v + (size_t)N * R, 1.0, Xy);
+    XW(Xy, R, 1.0 / M, delta, v, out);
+  }
+  // out = alpha [X ; Z'X] W + beta add
+  void XW(const double* W, int R, double alpha, double beta, const double* add, double* out) {
+    const unsigned g2 = (unsigned)((N + 255) / 256);
+    if (R <= 16) k_bolt_xw<16><<<g2, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
+    else k_bolt_xw<32><<<g2, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
+    k_bolt_bot<<<(C * R + 63) / 64, 64, 0, st>>>(M, R, C, zg, W, alpha, beta, add ? add + (size_t)N * R : nullptr, out + (size_t)N * R);
+    note();
+  }
+  // X_minus' v / scale -> Xy (host copy optional)
+  void XtV(const double* v, int R, double scale) {
+    dim3 g1((unsigned)((M + kBoltSnpBlock - 1) / kBoltSnpBlock), (unsigned)splits);
+    if (R <= 16) k_bolt_xtv<16><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
+    else k_bolt_xtv<32><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
+    k_bolt_xtv_finish<<<(unsigned)(((int64_t)M * R + 255) / 256), 256, 0, st>>>(M, R, C, splits, part, zg, v + (size_t)N * R, scale, Xy);
+    note();
+  }
+  void project(double* v, int R) {   // bottom rows = Z' top rows
+    k_bolt_project<<<C * R, 256, 0, st>>>(N, R, C, Z, v, v + (size_t)N * R);
+    note();
+  }
+  // projDot / projNorm2 per column (BoltLMM.cpp:1064-1138)
+  void pdot(const double* a, const double* b, int R, double* out) {
+    k_bolt_dot<<<kBoltDotCtas, 256, 0, st>>>(N, R, a, b, dotp);
+    std::vector<double> hp((size_t)kBoltDotCtas * R), ha((size_t)C * R), hb((size_t)C * R);
+    cudaMemcpyAsync(hp.data(), dotp, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(ha.data(), a + (size_t)N * R, sizeof(double) * ha.size(), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(hb.data(), b + (size_t)N * R, sizeof(double) * hb.size(), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess && err == cudaSuccess) err = e;
+    for (int r = 0; r < R; ++r) {
+      double s = 0.0;
+      for (int k = 0; k < kBoltDotCtas; ++k) s += hp[(size_t)k * R + r];
+      for (int c = 0; c < C; ++c) s -= ha[(size_t)c * R + r] * hb[(size_t)c * R + r];
+      out[r] = s;
+    }
+  }
+  // y = ca .* a + cb .* b (columnwise coefficients), all N + C rows
+  void axpby(const double* ca, const double* a, const double* cb, const double* b, double* y, int R) {
+    cudaMemcpyAsync(coef, ca, sizeof(double) * R, cudaMemcpyHostToDevice, st);
+    if (b) cudaMemcpyAsync(coef + kBoltMaxR, cb, sizeof(double) * R, cudaMemcpyHostToDevice, st);
+    k_bolt_axpby<<<(unsigned)((rows() * R + 255) / 256), 256, 0, st>>>((int64_t)rows(), R, coef, a, coef + kBoltMaxR, b, y);
+    cudaStreamSynchronize(st);   // ca / cb are host temporaries
+    note();
+  }
+  // x = H^-1 y by conjugate gradients (solve, BoltLMM.cpp:745-859); r, p, ap: scratch vectors of the same shape
+  void solve(const double* y, double delta, double* x, double* r, double* p, double* ap, int R) {
+    std::vector<double> one(R, 1.0), c1(R), c2(R), rsold(R), rsnew(R), pap(R), alpha(R), ratio(R);
+    for (int k = 0; k < R; ++k) c1[k] = 1.0 / delta;
+    axpby(c1.data(), y, nullptr, nullptr, x, R);            // x = y / delta
+    Hx(delta, x, ap, R);
+    for (int k = 0; k < R; ++k) c2[k] = -1.0;
+    axpby(one.data(), y, c2.data(), ap, r, R);              // r = y - H x
+    axpby(one.data(), r, nullptr, nullptr, p, R);           // p = r
+    pdot(r, r, R, rsold.data());
+    const double tol = 5e-4;
+    const int maxIter = (int)std::min<int64_t>(N, 250);
+    for (int it = 0; it < maxIter && err == cudaSuccess; ++it) {
+      ++cg_total;
+      Hx(delta, p, ap, R);
+      pdot(p, ap, R, pap.data());
+      for (int k = 0; k < R; ++k) {
+        alpha[k] = rsold[k] / pap[k];
+        if (!std::isfinite(alpha[k])) alpha[k] = 0.0;
+      }
+      axpby(one.data(), x, alpha.data(), p, x, R);          // x += p alpha
+      for (int k = 0; k < R; ++k) c2[k] = -alpha[k];
+      axpby(one.data(), r, c2.data(), ap, r, R);            // r -= ap alpha
+      pdot(r, r, R, rsnew.data());
+      bool all_small = true;
+      double maxdiff = 0.0;
+      for (int k = 0; k < R; ++k) {
+        all_small = all_small && (rsnew[k] < tol);
+        maxdiff = std::max(maxdiff, fabs(rsnew[k] - rsold[k]));
+      }
+      if (all_small) break;          // "reach tolerence"
+      if (maxdiff < tol) break;      // "no improvement"
+      for (int k = 0; k < R; ++k) {
+        ratio[k] = rsnew[k] / rsold[k];
+        if (rsnew[k] < tol || !std::isfinite(ratio[k])) ratio[k] = 0.0;
+      }
+      axpby(one.data(), r, ratio.data(), p, p, R);          // p = r + p ratio
+      rsold = rsnew;
+    }
+  }
+};
+}  // namespace
+extern "C" {
+
+int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t stride, int64_t N, const double* y, const double* covar,
+                      int C, int mc_trials, rvt_bolt_null* out, double* h_inv_y, double* Zout) {
+  if (!ctx || !bed || !y || !covar || !out) return RVT_E_BADARG;
+  if (N < 2 || M < 1 || M > 0x7FFFFFF0ll || C < 1 || C > kMaxC) CTX_FAIL(RVT_E_BADARG, "bolt: N, M or C out of range");
+  if (stride < (N + 3) / 4) CTX_FAIL(RVT_E_BADARG, "bolt: stride (%lld) < ceil(N/4)", (long long)stride);
+  RVT_CUDA_OK(cudaSetDevice(ctx->device));
+  memset(out, 0, sizeof(*out));
+  // orthonormal covariate basis (BoltPlinkLoader::extractCovariateBasis keeps the left singular vectors above
+  // 1e-8 of the largest singular value; a modified Gram-Schmidt basis spans the same space, and only Z Z' matters)
+  std::vector<double> Zh;   // column-major N x Ck
+  int Ck = 0;
+  for (int c = 0; c < C; ++c) {
+    std::vector<double> v(covar + (size_t)c * N, covar + (size_t)(c + 1) * N);
+    double n0 = 0.0;
+    for (int64_t i = 0; i < N; ++i) n0 += v[i] * v[i];
+    for (int pass = 0; pass < 2; ++pass)
+      for (int k = 0; k < Ck; ++k) {
+        double d = 0.0;
+        const double* zk = Zh.data() + (size_t)k * N;
+        for (int64_t i = 0; i < N; ++i) d += zk[i] * v[i];
+        for (int64_t i = 0; i < N; ++i) v[i] -= d * zk[i];
+      }
+    double n1 = 0.0;
+    for (int64_t i = 0; i < N; ++i) n1 += v[i] * v[i];
+    if (!(n1 > 1e-16 * n0) || n0 == 0.0) continue;
+    const double inv = 1.0 / sqrt(n1);
+    for (int64_t i = 0; i < N; ++i) v[i] *= inv;
+    Zh.insert(Zh.end(), v.begin(), v.end());
+    ++Ck;
+  }
+  if (Ck < 1) CTX_FAIL(RVT_E_NUMERIC, "bolt: the covariate matrix has no usable column");
+  BoltDev B;
+  B.N = N; B.M = (int)M; B.C = Ck; B.stride = stride; B.st = ctx->stream;
+  const int mc = mc_trials > 0 ? std::min(mc_trials, 15) : std::max(std::min((int)(4e9 / (double)N / (double)N), 15), 3);   // BoltLMM.cpp:465
+  const int R1 = mc + 1;
+  const int nSnp = (int)std::min<int64_t>(30, M), Rmax = std::max(R1, nSnp);
+  // sample splits of the X'v product: enough CTAs to fill the device, each a multiple of the staged chunk
+  const int64_t nblk = (M + kBoltSnpBlock - 1) / kBoltSnpBlock;
+  int splits = (int)std::max<int64_t>(1, std::min<int64_t>((4 * (int64_t)ctx->sm_count + nblk - 1) / nblk, (N + kBoltChunk - 1) / kBoltChunk));
+  B.split_len = (((N + splits - 1) / splits) + kBoltChunk - 1) / kBoltChunk * kBoltChunk;
+  B.splits = (int)((N + B.split_len - 1) / B.split_len);
+  B.bed = B.alloc<uint8_t>((size_t)M * stride);
+  B.Z = B.alloc<double>((size_t)N * Ck);
+  B.tab = B.alloc<double>((size_t)M * 4);
+  B.zg = B.alloc<double>((size_t)M * Ck);
+  B.gnorm2 = B.alloc<double>((size_t)M);
+  B.part = B.alloc<double>((size_t)B.splits * M * Rmax);
+  B.Xy = B.alloc<double>((size_t)M * Rmax);
+  B.dotp = B.alloc<double>((size_t)kBoltDotCtas * Rmax);
+  B.coef = B.alloc<double>(2 * kBoltMaxR);
+  double *vy = B.vec(Rmax), *vx = B.vec(Rmax), *vr = B.vec(Rmax), *vp = B.vec(Rmax), *vap = B.vec(Rmax), *vxb = B.vec(mc), *ve = B.vec(mc);
+  if (B.err != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "bolt: cudaMalloc: %s", cudaGetErrorString(B.err));
+  cudaStream_t st = B.st;
+  RVT_CUDA_OK(cudaMemcpyAsync(B.bed, bed, (size_t)M * stride, cudaMemcpyHostToDevice, st));
+  {   // Z row-major [N][Ck] on the device
+    std::vector<double> zr((size_t)N * Ck);
+    for (int c = 0; c < Ck; ++c)
+      for (int64_t i = 0; i < N; ++i) zr[(size_t)i * Ck + c] = Zh[(size_t)c * N + i];
+    RVT_CUDA_OK(cudaMemcpy(B.Z, zr.data(), sizeof(double) * zr.size(), cudaMemcpyHostToDevice));
+  }
+  k_bolt_snp<<<(unsigned)M, 256, 0, st>>>(B.bed, stride, N, Ck, B.Z, B.tab, B.zg, B.gnorm2);
+  B.note();
+  // phenotype: centred (quantitative mode), bottom rows Z'y   (preparePhenotype, BoltPlinkLoader.cpp:143-163)
+  BoltRandom rng(12345);
+  const size_t rows = (size_t)(N + Ck);
+  std::vector<double> hy(rows, 0.0);
+  {
+    double mean = 0.0;
+    for (int64_t i = 0; i < N; ++i) mean += y[i];
+    mean /= (double)N;
+    for (int64_t i = 0; i < N; ++i) hy[i] = y[i] - mean;
+    for (int c = 0; c < Ck; ++c) {
+      double d = 0.0;
+      for (int64_t i = 0; i < N; ++i) d += Zh[(size_t)c * N + i] * hy[i];
+      hy[N + c] = d;
+    }
+  }
+  // WorkingData::init (BoltLMM.cpp:88-123): beta_rand ~ N(0, 1/M) row by row, x_beta = [X ; Z'X] beta_rand,
+  // e_rand ~ N(0, 1) row by row with its covariate rows
+  {
+    std::vector<double> hb((size_t)M * mc), he(rows * mc, 0.0);
+    const double sq = 1.0 / sqrt((double)M);
+    for (int64_t i = 0; i < M; ++i)
+      for (int j = 0; j < mc; ++j) hb[(size_t)i * mc + j] = rng.normal() * sq;
+    for (int64_t i = 0; i < N; ++i)
+      for (int j = 0; j < mc; ++j) he[(size_t)i * mc + j] = rng.normal();
+    RVT_CUDA_OK(cudaMemcpy(B.Xy, hb.data(), sizeof(double) * hb.size(), cudaMemcpyHostToDevice));
+    B.XW(B.Xy, mc, 1.0, 0.0, nullptr, vxb);
+    RVT_CUDA_OK(cudaMemcpy(ve, he.data(), sizeof(double) * he.size(), cudaMemcpyHostToDevice));
+    B.project(ve, mc);
+  }
+  std::vector<double> hxb(rows * mc), he(rows * mc), hY(rows * R1), hH(rows * R1), hbeta((size_t)M * R1);
+  RVT_CUDA_OK(cudaMemcpyAsync(hxb.data(), vxb, sizeof(double) * hxb.size(), cudaMemcpyDeviceToHost, st));
+  RVT_CUDA_OK(cudaMemcpyAsync(he.data(), ve, sizeof(double) * he.size(), cudaMemcpyDeviceToHost, st));
+  RVT_CUDA_OK(cudaStreamSynchronize(st));
+  int evals = 0;
+  auto evalREML = [&](double logDelta) -> double {   // BoltLMM.cpp:669-724
+    const double delta = exp(logDelta), sd = sqrt(delta);
+    for (size_t i = 0; i < rows; ++i) {
+      hY[i * R1] = hy[i];
+      for (int j = 0; j < mc; ++j) hY[i * R1 + 1 + j] = hxb[i * mc + j] + sd * he[i * mc + j];   // computeY :1046-1060
+    }
+    cudaMemcpy(vy, hY.data(), sizeof(double) * hY.size(), cudaMemcpyHostToDevice);
+    B.solve(vy, delta, vx, vr, vp, vap, R1);
+    B.XtV(vx, R1, 1.0 / (double)M);                  // beta_hat = [X ; Z'X]_minus' H^-1 y / M   (:734-742)
+    cudaMemcpyAsync(hbeta.data(), B.Xy, sizeof(double) * hbeta.size(), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(hH.data(), vx, sizeof(double) * hH.size(), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    ++evals;
+    double bn[kBoltMaxR], en[kBoltMaxR];
+    for (int r = 0; r < R1; ++r) bn[r] = en[r] = 0.0;
+    for (int64_t m = 0; m < M; ++m)
+      for (int r = 0; r < R1; ++r) bn[r] += hbeta[(size_t)m * R1 + r] * hbeta[(size_t)m * R1 + r];
+    for (size_t i = 0; i < rows; ++i)
+      for (int r = 0; r < R1; ++r) {
+        const double e = delta * hH[i * R1 + r];     // e_hat = delta H^-1 y
+        en[r] += (i < (size_t)N ? 1.0 : -1.0) * e * e;
+      }
+    double rb = 0.0, re = 0.0;
+    for (int r = 1; r < R1; ++r) {
+      rb += bn[r];
+      re += en[r];
+    }
+    return log((bn[0] / en[0]) / (rb / re));
+  };
+  // EstimateHeritabilityBolt (BoltLMM.cpp:575-668): secant iteration on log(delta)
+  double h2[7] = {0}, ld[7] = {0}, f[7] = {0};
+  int i = 0;
+  h2[0] = 0.25;
+  ld[0] = log((1.0 - h2[0]) / h2[0]);
+  f[0] = evalREML(ld[0]);
+  i = 1;
+  h2[1] = (f[0] < 0) ? 0.25 / 2 : std::min(0.25 * 2, 0.5 * 0.25 + 0.5);
+  ld[1] = log((1.0 - h2[1]) / h2[1]);
+  f[1] = evalREML(ld[1]);
+  for (i = 2; i < 7; ++i) {
+    ld[i] = (ld[i - 2] * f[i - 1] - ld[i - 1] * f[i - 2]) / (f[i - 1] - f[i - 2]);
+    if (!std::isfinite(ld[i])) {
+      --i;
+      break;
+    }
+    if (ld[i] > 5) ld[i] = 5;
+    if (ld[i] < -10) ld[i] = -10;
+    h2[i] = 1.0 / (1.0 + exp(ld[i]));
+    if (fabs(ld[i] - ld[i - 1]) < 0.01) break;
+    f[i] = evalREML(ld[i]);
+  }
+  if (i == 7) --i;
+  if (B.err != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "bolt: %s", cudaGetErrorString(B.err));
+  const double delta = exp(ld[i]);
+  double yh = 0.0;   // projDot(y, H^-1 y) of the LAST evaluation (the reference does not re-solve at the final delta)
+  for (size_t k = 0; k < rows; ++k) yh += (k < (size_t)N ? 1.0 : -1.0) * hy[k] * hH[k * R1];
+  const double sigma2_g = yh / (double)(N - Ck);
+  if (!(sigma2_g > 0.0)) CTX_FAIL(RVT_E_NUMERIC, "bolt: sigma2_g = %g is not positive", sigma2_g);
+  const double sigma2_e = delta * sigma2_g;
+  std::vector<double> hh(rows);
+  double hn2 = 0.0;
+  for (size_t k = 0; k < rows; ++k) {
+    hh[k] = hH[k * R1] / sigma2_g;                   // H_inv_y_
+    hn2 += (k < (size_t)N ? 1.0 : -1.0) * hh[k] * hh[k];
+  }
+  // EstimateInfStatCalibration (BoltLMM.cpp:1141-1214)
+  std::vector<int> idx(nSnp);
+  for (int k = 0; k < nSnp; ++k) idx[k] = (int)(size_t)(rng.next() * (double)M);
+  int* d_idx = B.alloc<int>(nSnp);
+  if (!d_idx) CTX_FAIL(RVT_E_CUDA, "bolt: cudaMalloc");
+  RVT_CUDA_OK(cudaMemcpy(d_idx, idx.data(), sizeof(int) * nSnp, cudaMemcpyHostToDevice));
+  k_bolt_columns<<<(unsigned)(((int64_t)N * nSnp + 255) / 256), 256, 0, st>>>(B.bed, stride, N, d_idx, nSnp, B.tab, vy);
+  B.project(vy, nSnp);
+  B.solve(vy, delta, vx, vr, vp, vap, nSnp);         // V^-1 x = H^-1 x / sigma2_g
+  std::vector<double> xVx(nSnp), xx(nSnp), xVy(nSnp), hg(rows * nSnp);
+  B.pdot(vy, vx, nSnp, xVx.data());
+  B.pdot(vy, vy, nSnp, xx.data());
+  RVT_CUDA_OK(cudaMemcpy(hg.data(), vy, sizeof(double) * hg.size(), cudaMemcpyDeviceToHost));
+  if (B.err != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "bolt: %s", cudaGetErrorString(B.err));
+  double r0 = 0.0, r1 = 0.0, sxVx = 0.0, sxx = 0.0;
+  for (int k = 0; k < nSnp; ++k) {
+    xVx[k] /= sigma2_g;
+    double d = 0.0;
+    for (size_t q = 0; q < rows; ++q) d += (q < (size_t)N ? 1.0 : -1.0) * hg[q * nSnp + k] * hh[q];
+    xVy[k] = d;
+    const double prosp = d * d / xVx[k], retro = (double)N * d * d / (xx[k] * hn2);
+    if (prosp < 5.0) {
+      r0 += retro;
+      r1 += prosp;
+    }
+    sxVx += xVx[k];
+    sxx += xx[k];
+  }
+  out->delta = delta;
+  out->sigma2_g = sigma2_g;
+  out->sigma2_e = sigma2_e;
+  out->h2 = h2[i];
+  out->h_inv_y_norm2 = hn2;
+  out->inf_stat_calibration = (r1 != 0.0) ? r0 / r1 : 1.0;
+  out->xvx_xx_ratio = std::isfinite(sxVx / sxx) ? sxVx / sxx : 1.0;
+  out->mc_trials = mc;
+  out->reml_evals = evals;
+  out->cg_iterations = B.cg_total;
+  out->n_covariates_kept = Ck;
+  for (int k = 0; k < 7; ++k) {
+    out->log_delta[k] = (k <= i) ? ld[k] : 0.0;
+    out->f[k] = (k < evals) ? f[k] : 0.0;
+  }
+  if (h_inv_y) memcpy(h_inv_y, hh.data(), sizeof(double) * rows);
+  if (Zout) memcpy(Zout, Zh.data(), sizeof(double) * (size_t)N * Ck);
   return RVT_OK;
 }
 

@@ -52,8 +52,12 @@ EXPORTS = [
     "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded",
     "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
     "rvt_debug_phases",
-    "rvt_meta_plan", "rvt_meta_flush", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand", "rvt_lmm_set_null", "rvt_lmm_flush", "rvt_get_null_beta",
+    "rvt_meta_plan", "rvt_meta_flush", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand", "rvt_lmm_set_null", "rvt_lmm_flush", "rvt_get_null_beta", "rvt_bolt_fit_null",
 ]
+
+BOLT_DTYPE = np.dtype([("delta", "f8"), ("sigma2_g", "f8"), ("sigma2_e", "f8"), ("h2", "f8"), ("h_inv_y_norm2", "f8"),
+                       ("inf_stat_calibration", "f8"), ("xvx_xx_ratio", "f8"), ("log_delta", "f8", (7,)), ("f", "f8", (7,)),
+                       ("mc_trials", "i4"), ("reml_evals", "i4"), ("cg_iterations", "i4"), ("n_covariates_kept", "i4")])
 
 LMM_DTYPE = np.dtype([("af", "f8"), ("U", "f8"), ("V", "f8"), ("stat", "f8"), ("pvalue", "f8"), ("ok", "i4"), ("pad", "i4")])
 
@@ -114,6 +118,7 @@ def load_library(rebuild: bool = False):
     L.rvt_debug_rand.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_int64, vp]
     L.rvt_lmm_set_null.argtypes = [vp, C.c_int64, C.c_int, vp, vp, C.c_double, C.c_double, vp, vp]
     L.rvt_lmm_flush.argtypes = [vp, vp, C.c_int64]
+    L.rvt_bolt_fit_null.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, _dp, _dp, C.c_int, C.c_int, vp, vp, vp]
     _lib = L
     return L
 
@@ -221,6 +226,21 @@ class GeneEngine:
         got = C.c_int(0)
         self._chk(self.L.rvt_flush(self.h, out.ctypes.data, len(out), C.byref(got)))
         return out[: got.value]
+
+    def bolt_fit_null(self, bed, N, y, covar, mc_trials=0):
+        """BoltLMM null fit on a PLINK panel: bed (M, >= ceil(N/4)) uint8 SNP-major rows, covar (N, C) with the intercept
+        first.  Returns (record, h [N + C'], Z [N, C'])."""
+        assert bed.dtype == np.uint8 and bed.ndim == 2 and bed.strides[1] == 1
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        cv = np.asfortranarray(covar, dtype=np.float64)
+        Cc = cv.shape[1]
+        rec = np.zeros(1, dtype=BOLT_DTYPE)
+        h = np.zeros(N + Cc)
+        Z = np.zeros((N, Cc), order="F")
+        self._chk(self.L.rvt_bolt_fit_null(self.h, bed.ctypes.data, bed.shape[0], bed.strides[0], int(N), _pd(y), _pd(cv), Cc,
+                                           int(mc_trials), rec.ctypes.data, h.ctypes.data, Z.ctypes.data))
+        k = int(rec[0]["n_covariates_kept"])
+        return rec[0], h[: N + k], np.ascontiguousarray(Z[:, :k])
 
     def lmm_set_null(self, U, lam, delta, sigma2, u_resid, ux):
         """FastLMM score step: U (N, N) with eigenvectors in COLUMNS, lam (N,), uResid (N,), ux (N, C)"""

@@ -1,0 +1,82 @@
+"""GPU (-m gpu): A15, the BoltLMM null-model fit (regression/BoltLMM.cpp:169-299, 463-859, 1141-1214) against the numpy
+restatement, which draws the reference's own random numbers (MT19937 seed 12345 + polar Box-Muller, libsrc/Random.cpp);
+then the fitted null drives the A14 score step (BoltLMM::TestCovariate) end to end."""
+import numpy as np
+import pytest
+
+from util import rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _panel(seed, N, M, miss=0.01):
+    rng = np.random.default_rng(seed)
+    maf = rng.uniform(0.05, 0.5, M)
+    G = rng.binomial(2, maf[:, None], size=(M, N)).astype(np.int8)
+    G[rng.random((M, N)) < miss] = -1                       # missing calls: code 01 in the .bed
+    G[3] = 0                                                # a monomorphic panel SNP (sd = 0 -> all-zero column)
+    return G
+
+
+def _pack(G):
+    """(M, N) int8 with -1 = missing -> PLINK 2-bit rows (00 -> 0, 10 -> 1, 11 -> 2, 01 -> missing)"""
+    code = np.where(G == 0, 0, np.where(G == 1, 2, np.where(G == 2, 3, 1))).astype(np.uint8)
+    M, N = G.shape
+    pad = (-N) % 4
+    code = np.pad(code, ((0, 0), (0, pad)))
+    c4 = code.reshape(M, -1, 4)
+    return (c4[:, :, 0] | (c4[:, :, 1] << 2) | (c4[:, :, 2] << 4) | (c4[:, :, 3] << 6)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("case", [(101, 800, 300, 3, 0.5), (102, 1200, 500, 2, 0.2)])
+def test_bolt_null_fit_vs_oracle(engine_cls, oracle, case):
+    from oracle import bolt_oracle as BO
+    seed, N, M, C, h2 = case
+    G = _panel(seed, N, M)
+    rng = np.random.default_rng(seed + 1)
+    covar = np.column_stack([np.ones(N)] + [rng.normal(size=N) for _ in range(C - 1)])
+    X, Z, _ = BO.prepare(G, covar, np.zeros(N))
+    y = X @ rng.normal(size=M) * np.sqrt(h2 / M) + rng.normal(size=N) * np.sqrt(1 - h2) + covar @ rng.normal(size=C)
+    X, Z, yc = BO.prepare(G, covar, y)
+    ref = BO.Fit(X, Z, yc).fit().calibrate()
+    eng = engine_cls(0)
+    rec, h, Zd = eng.bolt_fit_null(_pack(G), N, y, covar)
+    assert int(rec["mc_trials"]) == ref.mc == 15 and int(rec["n_covariates_kept"]) == C
+    # same covariate space
+    assert np.max(np.abs(Zd @ Zd.T - Z @ Z.T)) <= 1e-10
+    n_ld = len(ref.log_delta)
+    assert int(rec["reml_evals"]) == len(ref.f)
+    assert np.max(np.abs(rec["log_delta"][:n_ld] - np.array(ref.log_delta))) <= 1e-6, (rec["log_delta"], ref.log_delta)
+    assert np.max(np.abs(rec["f"][:len(ref.f)] - np.array(ref.f))) <= 1e-6
+    assert int(rec["cg_iterations"]) == sum(ref.cg_iters)
+    for k, v in (("delta", ref.delta), ("sigma2_g", ref.sigma2_g), ("sigma2_e", ref.sigma2_e), ("h2", ref.h2),
+                 ("h_inv_y_norm2", ref.h_norm2), ("inf_stat_calibration", ref.calibration), ("xvx_xx_ratio", ref.xvx_xx_ratio)):
+        assert rel(rec[k], v) <= 1e-6, (k, rec[k], v)
+    assert np.max(np.abs(h[:N] - ref.h)) <= 1e-7 * np.max(np.abs(ref.h))
+    assert 0.05 < rec["h2"] < 0.95
+    # the fitted null drives the score step (A14): u = g'Ph, v = g'Pg |h|^2_proj calib / N
+    hz = Zd.T @ h[:N]
+    r_b = h[:N] - Zd @ hz
+    kappa = float(rec["h_inv_y_norm2"] * rec["inf_stat_calibration"] / N)
+    eng.set_null_residual(covar, r_b, kappa)
+    Gt = rng.binomial(2, 0.2, size=(40, N)).astype(np.int8)
+    eng.push_i8(Gt, None)
+    vout, _b, _w = eng.meta_flush(40, want_cov=False)
+    for j in range(40):
+        g = Gt[j].astype(np.float64)
+        zg = Z.T @ g
+        u = float(g @ ref.h - zg @ (Z.T @ ref.h))
+        v = float(g @ g - zg @ zg) * ref.h_norm2 * ref.calibration / N
+        assert abs(vout[j]["U"] * kappa - u) <= 1e-6 * max(abs(u), np.sqrt(v))
+        assert rel(vout[j]["pvalue"], oracle.lib().orc_chisq_q(u * u / v, 1.0)) <= 1e-5
+    eng.close()
+
+
+def test_bolt_random_stream_is_the_reference_generator(oracle):
+    """MT19937(12345) first outputs -- the generator of libsrc/Random.cpp -- via numpy's legacy seeding"""
+    from oracle import bolt_oracle as BO
+    r = BO.Random(12345)
+    ref = np.random.RandomState(12345)                     # init_genrand(12345), the same seeding as InitMersenne
+    raw = ref.randint(0, 2**32, size=5, dtype=np.uint64)
+    got = [r.next() for _ in range(5)]
+    assert np.allclose(got, (raw.astype(np.float64) + 0.5) / 4294967296.0, rtol=0, atol=0)
