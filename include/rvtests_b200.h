@@ -131,8 +131,12 @@ int rvt_set_stream(rvt_ctx* ctx, void* cuda_stream);
 
 /* ---- null model: replaces LinearRegression::FitLinearModel(cov, phenoVec) -------------------
  * X: N x C column-major doubles INCLUDING the intercept as column 0 (the matrix produced by
- * copyCovariateAndIntercept, src/ModelUtil.h:102-130); y: N.  Host pointers.  binary != 0
- * (logistic null) is RVT_E_UNSUPPORTED in this build. */
+ * copyCovariateAndIntercept, src/ModelUtil.h:102-130); y: N.  Host pointers.
+ * binary != 0: y in {0,1}; LogisticRegression::FitLogisticModel(cov, phenoVec, 100) (regression/LogisticRegression.cpp:279-339)
+ *   on the device, then SKAT / CMC / Zeggini with r = y - p and the per-sample variance v = p(1-p) (src/Model.h:2673-2681,
+ *   LogisticRegressionScoreTest.cpp:219-302).  Such genes take the engine's fp64 path (<= 64 variants); SKAT-O and the
+ *   permutation test are not provided for a binary trait (skato_ok = 0 / done = 0).  rvt_get_null_model then returns
+ *   r, sigma2 = 1 and (X'VX)^-1. */
 int rvt_set_null_model(rvt_ctx* ctx, int64_t N, int C, const double* X, const double* y, int binary);
 /* "bring your own null": the caller supplies the score vector r (length N) and the variance scale
  * sigma2, the engine only builds (X'X)^-1 and the device images.  This is the score step of the

@@ -78,6 +78,12 @@ struct NullModel {
   long long vsum[kMaxC + 1];      // sum_i fixed-point value of vector v (for flipped columns)
   double rsum;                    // sum_i r_i  and  sum_i x_il  in fp64 (dosage path)
   double xsum[kMaxC];
+  // binary trait (logistic null, regression/LogisticRegression.cpp:279-339): r = y - p, per-sample variance
+  // v_i = p_i (1 - p_i), xtx_inv holds (X'VX)^-1 and sigma2 is 1 so that the quantitative formulas carry over
+  int32_t binary, pad_;
+  const double* vw;               // N variances (null for a quantitative trait: v == 1)
+  double vsum_w;                  // sum_i v_i
+  double xsum_w[kMaxC];           // sum_i v_i x_il
 };
 
 // Pre-digested per-gene statistics handed to the tail of k_finalize by the dosage path

@@ -19,6 +19,7 @@ namespace rvt {
 
 struct DosageStats {
   double csum[kTileRows];
+  double cw[kTileRows];   // sum_i v_i g_ij (binary trait; equals csum in exact arithmetic when v == 1)
   unsigned long long cmin[kTileRows], cmax[kTileRows];   // bit patterns of non-negative doubles (order preserving)
   double A[kTileRows][kTileRows];
   double s[kTileRows];
@@ -63,9 +64,10 @@ k_dosage_cols(const double* __restrict__ G, int64_t N, int M, DosageStats* __res
 // 64 x 64 block is dealt as 16 entries per thread: row = t >> 2, columns (t & 3) + 4*c, c = 0..15.
 __global__ void __launch_bounds__(kDosThreads)
 k_dosage_stats(const double* __restrict__ G, int64_t N, int M, const double* __restrict__ X, int C,
-               const double* __restrict__ resid, DosageStats* __restrict__ st) {
+               const double* __restrict__ resid, const double* __restrict__ vw /* per-sample variance, null: 1 */,
+               DosageStats* __restrict__ st) {
   __shared__ double sg[kTileRows][kDosTile + 1];
-  __shared__ double sr[kDosTile], sx[kMaxC][kDosTile];
+  __shared__ double sr[kDosTile], sx[kMaxC][kDosTile], sv[kDosTile];
   __shared__ int sflip[kTileRows], smono[kTileRows];
   const int tid = threadIdx.x;
   if (tid < kTileRows) {
@@ -76,7 +78,7 @@ k_dosage_stats(const double* __restrict__ G, int64_t N, int M, const double* __r
   double acc[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) acc[c] = 0.0;
-  double accs = 0.0, accB[kMaxC];
+  double accs = 0.0, accw = 0.0, accB[kMaxC];
 #pragma unroll
   for (int l = 0; l < kMaxC; ++l) accB[l] = 0.0;
   double bz[3 + kMaxC], bc[3 + kMaxC];   // U, SS, nonref, SZ[] for zeggini / cmc (thread < kDosTile only)
@@ -94,6 +96,7 @@ k_dosage_stats(const double* __restrict__ G, int64_t N, int M, const double* __r
     if (tid < kDosTile) {
       const int64_t i = i0 + tid;
       sr[tid] = (i < N) ? resid[i] : 0.0;
+      sv[tid] = (i < N) ? (vw ? vw[i] : 1.0) : 0.0;
       for (int l = 0; l < C; ++l) sx[l][tid] = (i < N) ? X[(size_t)l * N + i] : 0.0;
     }
     __syncthreads();
@@ -101,11 +104,13 @@ k_dosage_stats(const double* __restrict__ G, int64_t N, int M, const double* __r
       for (int k = 0; k < kDosTile; ++k) {
         const double g = sg[row][k];
         if (g == 0.0) continue;
+        const double gv = g * sv[k];   // G'VG, G'VX (Skat.cpp:55-76 with V = diag(v)); G'r stays unweighted
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] += g * sg[cb + 4 * c][k];
+        for (int c = 0; c < 16; ++c) acc[c] += gv * sg[cb + 4 * c][k];
         if (cb == 0) {
           accs += g * sr[k];
-          for (int l = 0; l < C; ++l) accB[l] += g * sx[l][k];
+          accw += gv;
+          for (int l = 0; l < C; ++l) accB[l] += gv * sx[l][k];
         }
       }
     }
@@ -118,12 +123,13 @@ k_dosage_stats(const double* __restrict__ G, int64_t N, int M, const double* __r
         if ((int)g > 0) z += 1.0;
       }
       const double c = (z > 0.0) ? 1.0 : 0.0;
-      const double r = sr[tid];
-      bz[0] += z * r;  bz[1] += z * z;  bz[2] += (z != 0.0);
-      bc[0] += c * r;  bc[1] += c * c;  bc[2] += (c != 0.0);
+      const double r = sr[tid], v = sv[tid];
+      // U = S'r, SS = S'VS, SZ = S'VZ (LinearRegressionScoreTest.cpp:209-217 with v == 1; LogisticRegressionScoreTest.cpp:266-269)
+      bz[0] += z * r;  bz[1] += v * z * z;  bz[2] += (z != 0.0);
+      bc[0] += c * r;  bc[1] += v * c * c;  bc[2] += (c != 0.0);
       for (int l = 0; l < C; ++l) {
-        bz[3 + l] += z * sx[l][tid];
-        bc[3 + l] += c * sx[l][tid];
+        bz[3 + l] += v * z * sx[l][tid];
+        bc[3 + l] += v * c * sx[l][tid];
       }
     }
   }
@@ -133,6 +139,7 @@ k_dosage_stats(const double* __restrict__ G, int64_t N, int M, const double* __r
       if (cb + 4 * c < M) atomicAdd(&st->A[row][cb + 4 * c], acc[c]);
     if (cb == 0) {
       atomicAdd(&st->s[row], accs);
+      atomicAdd(&st->cw[row], accw);
       for (int l = 0; l < C; ++l) atomicAdd(&st->B[row][l], accB[l]);
     }
   }
@@ -179,7 +186,7 @@ k_dosage_prepare(const DosageStats* __restrict__ st, int M, const double* __rest
   if (tid < Mp) {
     const int j = s_idx[tid], fl = s_flip[j];
     s_s[tid] = fl ? 2.0 * nm->rsum - st->s[j] : st->s[j];
-    for (int l = 0; l < C; ++l) s_B[tid][l] = fl ? 2.0 * nm->xsum[l] - st->B[j][l] : st->B[j][l];
+    for (int l = 0; l < C; ++l) s_B[tid][l] = fl ? 2.0 * (nm->binary ? nm->xsum_w[l] : nm->xsum[l]) - st->B[j][l] : st->B[j][l];
     // weight i of the kept columns uses af[i] in the caller's ORIGINAL order
     const double freq = af ? af[tid] : 0.5 * st->csum[j] / (double)N;
     s_sw[tid] = sqrt(beta_weight(freq, prm.beta1, prm.beta2, true));
@@ -190,9 +197,10 @@ k_dosage_prepare(const DosageStats* __restrict__ st, int M, const double* __rest
     const int ji = s_idx[i], jk = s_idx[k];
     const int fi = s_flip[ji], fk = s_flip[jk];
     double a = st->A[ji][jk];
-    const double ci = st->csum[ji], ck = st->csum[jk];
+    // g' = 2 - g under the weights v: (2-g_j)'V(2-g_k) = 4 sum v - 2 c^w_j - 2 c^w_k + A_jk, with c^w = G'v
+    const double ci = nm->binary ? st->cw[ji] : st->csum[ji], ck = nm->binary ? st->cw[jk] : st->csum[jk];
     if (fi && fk)
-      a = 4.0 * (double)N - 2.0 * ci - 2.0 * ck + a;
+      a = 4.0 * (nm->binary ? nm->vsum_w : (double)N) - 2.0 * ci - 2.0 * ck + a;
     else if (fi)
       a = 2.0 * ck - a;
     else if (fk)

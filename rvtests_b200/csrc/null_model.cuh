@@ -221,4 +221,53 @@ __global__ void __launch_bounds__(kNullThreads) k_build_E(int64_t N, int C, cons
     atomicAdd((unsigned long long*)&nm->vsum[threadIdx.x], ssum[threadIdx.x]);
 }
 
+// One Newton round of LogisticRegression::FitLogisticModel (regression/LogisticRegression.cpp:291-303) at the current beta:
+// p = 1/(1+exp(-X beta)), V = p(1-p) (both stored), and per block, in fixed order, the partial sums of
+// D = X'VX (C*C), r = X'(y-p) (C) and the log-likelihood of GetDeviance (:75-94).  part: [blocks][kLogitAcc]
+constexpr int kLogitAcc = kMaxC * kMaxC + kMaxC + 1;
+__global__ void __launch_bounds__(kNullThreads)
+k_logit_round(int64_t N, int C, const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ beta,
+              double* __restrict__ p_out, double* __restrict__ v_out, double* __restrict__ part) {
+  __shared__ double sh[kNullThreads];
+  double b[kMaxC];
+  for (int l = 0; l < C; ++l) b[l] = beta[l];
+  double acc[kLogitAcc];
+#pragma unroll
+  for (int q = 0; q < kLogitAcc; ++q) acc[q] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    double x[kMaxC], eta = 0.0;
+#pragma unroll
+    for (int l = 0; l < kMaxC; ++l)
+      if (l < C) {
+        x[l] = X[(size_t)l * N + i];
+        eta += x[l] * b[l];
+      }
+    const double p = 1.0 / (1.0 + exp(-eta));
+    const double v = p * (1.0 - p), yi = y[i];
+    p_out[i] = p;
+    v_out[i] = v;
+#pragma unroll
+    for (int l = 0; l < kMaxC; ++l)
+      if (l < C) {
+#pragma unroll
+        for (int m = 0; m < kMaxC; ++m)
+          if (m < C) acc[l * kMaxC + m] += v * x[l] * x[m];
+        acc[kMaxC * kMaxC + l] += x[l] * (yi - p);
+      }
+    acc[kLogitAcc - 1] += yi * log(p) + (1.0 - yi) * log(1.0 - p);
+  }
+  for (int q = 0; q < kLogitAcc; ++q) {
+    const int l = q / kMaxC, m = q % kMaxC;
+    const bool used = (q == kLogitAcc - 1) || (q >= kMaxC * kMaxC ? (q - kMaxC * kMaxC) < C : (l < C && m < C));
+    if (!used) continue;   // uniform
+    double sres = block_sum(acc[q], sh);
+    if (threadIdx.x == 0) part[(size_t)blockIdx.x * kLogitAcc + q] = sres;
+  }
+}
+// r = y - p into the buffer the linear path keeps its phenotype in
+__global__ void k_logit_resid(int64_t N, const double* __restrict__ y, const double* __restrict__ p, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[i] = y[i] - p[i];
+}
+
 }  // namespace rvt

@@ -96,6 +96,9 @@ struct rvt_ctx {
   size_t cap_perm = 0;
   std::vector<rvt_perm_result> perm_out;
   std::vector<char> is_dos;        // per pending gene: took the fp64 path
+  // binary trait (logistic null model)
+  bool binary = false;
+  double *d_p = nullptr, *d_vw = nullptr;
   // FastLMM score step (lmm.cuh)
   bool have_lmm = false;
   LmmNull* d_lmm = nullptr;
@@ -291,7 +294,7 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum, ctx->d_p, ctx->d_vw};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -444,17 +447,132 @@ static int null_model_alloc(rvt_ctx* ctx, int64_t N, int C) {
   ctx->N = N;
   ctx->C = C;
   ctx->have_null = false;
+  ctx->binary = false;
+  return RVT_OK;
+}
+
+// LogisticRegression::FitLogisticModel (regression/LogisticRegression.cpp:279-339): Newton rounds on the device (one
+// fixed-order reduction per round), the C x C solve and the stopping rule on the host.  Leaves p, v = p(1-p) of the LAST
+// round evaluated -- i.e. at the beta before the final update, exactly what GetPredicted / GetVariance return -- and
+// covB = (X'VX)^-1 of that round.
+static int logistic_null(rvt_ctx* ctx, double* covB /*C*C*/, double* vsum, double* xsum_w) {
+  const int64_t N = ctx->N;
+  const int C = ctx->C;
+  cudaStream_t st = ctx->stream;
+  for (double** p : {&ctx->d_p, &ctx->d_vw}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    RVT_CUDA_OK(cudaMalloc((void**)p, sizeof(double) * N));
+  }
+  double* d_part = nullptr;
+  RVT_CUDA_OK(cudaMalloc((void**)&d_part, sizeof(double) * kNullBlocks * kLogitAcc));
+  std::vector<double> part((size_t)kNullBlocks * kLogitAcc), beta(C, 0.0), D(C * C), r(C), L(C * C), dlt(C);
+  int rounds = 0;
+  double last = -99999, cur = -9999;
+  bool ok = false;
+  while (rounds < 100) {
+    RVT_CUDA_OK(cudaMemcpyAsync(ctx->dbeta, beta.data(), sizeof(double) * C, cudaMemcpyHostToDevice, st));
+    RVT_CUDA_OK(cudaMemsetAsync(d_part, 0, sizeof(double) * kNullBlocks * kLogitAcc, st));
+    k_logit_round<<<kNullBlocks, kNullThreads, 0, st>>>(N, C, ctx->dX, ctx->dy, ctx->dbeta, ctx->d_p, ctx->d_vw, d_part);
+    RVT_CUDA_OK(cudaMemcpyAsync(part.data(), d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, st));
+    RVT_CUDA_OK(cudaStreamSynchronize(st));
+    double ll = 0.0;
+    for (int l = 0; l < C; ++l) {
+      r[l] = 0.0;
+      for (int m = 0; m < C; ++m) D[l * C + m] = 0.0;
+    }
+    for (int b = 0; b < kNullBlocks; ++b) {
+      const double* pb = part.data() + (size_t)b * kLogitAcc;
+      for (int l = 0; l < C; ++l) {
+        for (int m = 0; m < C; ++m) D[l * C + m] += pb[l * kMaxC + m];
+        r[l] += pb[kMaxC * kMaxC + l];
+      }
+      ll += pb[kLogitAcc - 1];
+    }
+    // delta_beta = D.llt().solve(r)
+    for (int i = 0; i < C; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double sacc = D[i * C + j];
+        for (int k = 0; k < j; ++k) sacc -= L[i * C + k] * L[j * C + k];
+        if (i == j) {
+          if (!(sacc > 0.0)) { cudaFree(d_part); CTX_FAIL(RVT_E_NUMERIC, "logistic null model: X'VX is not positive definite"); }
+          L[i * C + i] = sqrt(sacc);
+        } else
+          L[i * C + j] = sacc / L[j * C + j];
+      }
+    for (int i = 0; i < C; ++i) {
+      double sacc = r[i];
+      for (int k = 0; k < i; ++k) sacc -= L[i * C + k] * dlt[k];
+      dlt[i] = sacc / L[i * C + i];
+    }
+    for (int i = C - 1; i >= 0; --i) {
+      double sacc = dlt[i];
+      for (int k = i + 1; k < C; ++k) sacc -= L[k * C + i] * dlt[k];
+      dlt[i] = sacc / L[i * C + i];
+    }
+    for (int l = 0; l < C; ++l) beta[l] += dlt[l];
+    cur = -2.0 * ll;
+    if (rounds > 1 && fabs(cur - last) < 1e-3) {
+      ok = true;
+      break;
+    }
+    if (!std::isnormal(cur)) break;   // "probably separation happens"
+    last = cur;
+    ++rounds;
+  }
+  cudaFree(d_part);
+  if (!ok) CTX_FAIL(RVT_E_NUMERIC, "logistic null model did not converge (separation, or more than 100 rounds)");
+  // covB = D^-1 through the Cholesky factor
+  for (int col = 0; col < C; ++col) {
+    std::vector<double> e(C, 0.0);
+    e[col] = 1.0;
+    for (int i = 0; i < C; ++i) {
+      double sacc = e[i];
+      for (int k = 0; k < i; ++k) sacc -= L[i * C + k] * e[k];
+      e[i] = sacc / L[i * C + i];
+    }
+    for (int i = C - 1; i >= 0; --i) {
+      double sacc = e[i];
+      for (int k = i + 1; k < C; ++k) sacc -= L[k * C + i] * e[k];
+      e[i] = sacc / L[i * C + i];
+    }
+    for (int i = 0; i < C; ++i) covB[i * C + col] = e[i];
+  }
+  *vsum = D[0];                                 // column 0 of X is the intercept: D[0][l] = sum v x_l
+  for (int l = 0; l < C; ++l) xsum_w[l] = D[l];
+  RVT_CUDA_OK(cudaMemcpyAsync(ctx->dbeta, beta.data(), sizeof(double) * C, cudaMemcpyHostToDevice, st));
   return RVT_OK;
 }
 
 int rvt_set_null_model(rvt_ctx* ctx, int64_t N, int C, const double* X, const double* y, int binary) {
   if (!ctx || !X || !y) return RVT_E_BADARG;
-  if (binary) CTX_FAIL(RVT_E_UNSUPPORTED, "binary traits (logistic null model) are not implemented in this build");
   int rc = null_model_alloc(ctx, N, C);
   if (rc) return rc;
+  ctx->binary = false;
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->dX, X, sizeof(double) * N * C, cudaMemcpyHostToDevice, ctx->stream));
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->dy, y, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
-  return null_model_run(ctx);
+  if (!binary) return null_model_run(ctx);
+  // binary trait: r = y - p and v = p(1-p) from the logistic fit; the linear machinery then runs on r with sigma2 = 1 and
+  // (X'VX)^-1 in place of (X'X)^-1 (src/Model.h:2673-2681: ynull = GetPredicted(), v = GetVariance())
+  for (int64_t i = 0; i < N; ++i)
+    if (y[i] != 0.0 && y[i] != 1.0) CTX_FAIL(RVT_E_BADARG, "binary trait: phenotype values must be 0 or 1");
+  double covB[kMaxC * kMaxC], vsum = 0.0, xsw[kMaxC];
+  if ((rc = logistic_null(ctx, covB, &vsum, xsw))) return rc;
+  std::vector<double> beta(C);
+  RVT_CUDA_OK(cudaMemcpy(beta.data(), ctx->dbeta, sizeof(double) * C, cudaMemcpyDeviceToHost));
+  k_logit_resid<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(N, ctx->dy, ctx->d_p, ctx->dy);
+  if ((rc = null_model_run(ctx, true, 1.0))) return rc;
+  NullModel h = ctx->h_nm;
+  memcpy(h.xtx_inv, covB, sizeof(double) * C * C);
+  h.binary = 1;
+  h.vw = ctx->d_vw;
+  h.vsum_w = vsum;
+  for (int l = 0; l < C; ++l) h.xsum_w[l] = xsw[l];
+  RVT_CUDA_OK(cudaMemcpy(ctx->d_nm, &h, sizeof(h), cudaMemcpyHostToDevice));
+  RVT_CUDA_OK(cudaMemcpy(ctx->dbeta, beta.data(), sizeof(double) * C, cudaMemcpyHostToDevice));   // (the linear fit overwrote it)
+  ctx->h_nm = h;
+  ctx->binary = true;
+  return RVT_OK;
 }
 
 int rvt_set_null_residual(rvt_ctx* ctx, int64_t N, int C, const double* X, const double* resid, double sigma2) {
@@ -1205,6 +1323,29 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   int launches = 0;
   ctx->is_dos.assign(n, 0);
   for (auto& dg : ctx->dos) ctx->is_dos[dg.gene_index] = 1;
+  if (ctx->binary) {
+    // binary trait: the Gram is weighted by the per-sample variance p(1-p), which the integer sweep does not carry:
+    // every gene takes the fp64 path (its hard-call tiles are expanded on the device)
+    if (!ctx->wide.empty())
+      CTX_FAIL(RVT_E_UNSUPPORTED, "binary trait: genes of more than %d variants are not supported", kMaxM);
+    for (int g = 0; g < n; ++g) {
+      if (ctx->is_dos[g]) continue;
+      const GeneDesc& gd = ctx->genes[g];
+      if (!gd.tiled) CTX_FAIL(RVT_E_UNSUPPORTED, "binary trait: caller-owned device blocks are not supported");
+      DosGene dg;
+      dg.gene_index = g;
+      dg.M = gd.M;
+      dg.dG = nullptr;
+      RVT_CUDA_OK(cudaMalloc((void**)&dg.dG, sizeof(double) * (size_t)N * gd.M));
+      dim3 grid((unsigned)((N + 255) / 256), (unsigned)gd.M);
+      k_impute_tiled_f64<<<grid, 256, 0, st>>>(gd.g, gd.M, N, ctx->d_counts + gd.var0, dg.dG);
+      RVT_CUDA_OK(cudaGetLastError());
+      dg.has_af = gd.has_af != 0;
+      if (dg.has_af) dg.af.assign(ctx->af.begin() + gd.var0, ctx->af.begin() + gd.var0 + gd.M);
+      ctx->dos.push_back(dg);
+      ctx->is_dos[g] = 1;
+    }
+  }
   if (!ctx->dos.empty()) {
     // genes with dosage / imputed values: fp64 statistics, then the same tail (eigen, Davies, SKAT-O, burden);
     // their records overwrite what the hard-call pipeline produced for the same slots
@@ -1225,14 +1366,14 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       RVT_CUDA_OK(cudaMemsetAsync(d_st[i].cmin, 0xFF, sizeof(unsigned long long) * kTileRows, st));
       if (dg.has_af) RVT_CUDA_OK(cudaMemcpyAsync(d_afd + (size_t)i * kTileRows, dg.af.data(), sizeof(double) * dg.M, cudaMemcpyHostToDevice, st));
       k_dosage_cols<<<ctx->sm_count, kDosThreads, 0, st>>>(dg.dG, N, dg.M, d_st + i);
-      k_dosage_stats<<<ctx->sm_count * 2, kDosThreads, 0, st>>>(dg.dG, N, dg.M, ctx->dX, ctx->C, ctx->dresid, d_st + i);
+      k_dosage_stats<<<ctx->sm_count * 2, kDosThreads, 0, st>>>(dg.dG, N, dg.M, ctx->dX, ctx->C, ctx->dresid, ctx->binary ? ctx->d_vw : nullptr, d_st + i);
       k_dosage_prepare<<<1, 64, 0, st>>>(d_st + i, dg.M, dg.has_af ? d_afd + (size_t)i * kTileRows : nullptr, ctx->d_nm, prm, d_tin + i);
     }
     RVT_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
     if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nd, sizeof(QagsScratch)))) return rc;
     {
       const int kld = fin_kld(kTileRows), fsm = fin_smem(kTileRows, ctx->ER, ctx->skato), wm_off = kTileRows * kld * 8;
-      if (ctx->skato)
+      if (ctx->skato && !ctx->binary)   // (SKAT-O for a binary trait is not provided: skato_ok stays 0)
         k_finalize<true><<<nd, kFinThreadsSkato, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, ctx->skato), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
                                                              nullptr, d_res, nullptr, ctx->d_qags, d_tin, d_idx);
       else

@@ -43,6 +43,11 @@ class GeneBatcher {
   }
   void setBatch(int n) { batch_ = n > 0 ? n : 1; }
   void enableSkatO() { skato_ = true; }
+  // setBinaryOutcome() of any adapter (ModelManager sets every model alike, src/ModelManager.cpp:274-282): logistic null
+  void setBinary(bool b) {
+    if (b != binary_) have_null_ = false;
+    binary_ = b;
+  }
   void enablePerm(int nPerm, double alpha) {
     perm_n_ = nPerm;
     perm_alpha_ = alpha;
@@ -98,7 +103,7 @@ class GeneBatcher {
   int newFitterId() { return next_id_++; }
 
  private:
-  GeneBatcher() : ctx_(NULL), batch_(256), skato_(false), perm_n_(0), perm_alpha_(0.05), current_(-1), next_id_(0), have_null_(false) {}
+  GeneBatcher() : ctx_(NULL), batch_(256), skato_(false), binary_(false), perm_n_(0), perm_alpha_(0.05), current_(-1), next_id_(0), have_null_(false) {}
   bool seen(int id) const {
     for (size_t i = 0; i < seen_.size(); ++i)
       if (seen_[i] == id) return true;
@@ -133,7 +138,7 @@ class GeneBatcher {
       rvt_set_option(ctx_, "perm", perm_n_);
       rvt_set_option(ctx_, "perm_alpha", perm_alpha_);
     }
-    if (rvt_set_null_model(ctx_, n, c, X.data(), y.data(), 0) != RVT_OK) {
+    if (rvt_set_null_model(ctx_, n, c, X.data(), y.data(), binary_ ? 1 : 0) != RVT_OK) {
       fprintf(stderr, "rvtests_b200: null model: %s\n", error());
       return false;
     }
@@ -168,7 +173,7 @@ class GeneBatcher {
 
   rvt_ctx* ctx_;
   int batch_;
-  bool skato_;
+  bool skato_, binary_;
   int perm_n_;
   double perm_alpha_;
   int current_, next_id_;
@@ -185,13 +190,18 @@ class DeferredFitter {
   DeferredFitter() : ticket_(-1), fp_(NULL), binary_(false) { id_ = GeneBatcher<DC>::instance().newFitterId(); }
   virtual ~DeferredFitter() {}
   const std::string& getModelName() const { return modelName; }
-  void setBinaryOutcome() { binary_ = true; }
-  void setQuantitativeOutcome() { binary_ = false; }
+  void setBinaryOutcome() {
+    binary_ = true;
+    GeneBatcher<DC>::instance().setBinary(true);
+  }
+  void setQuantitativeOutcome() {
+    binary_ = false;
+    GeneBatcher<DC>::instance().setBinary(false);
+  }
   bool isBinaryOutcome() const { return binary_; }
   bool needToIndexResult() const { return false; }
   void reset() { ticket_ = -1; }
   int fit(DC* dc) {
-    if (binary_) return -1;  // logistic null model: not in this build
     ticket_ = GeneBatcher<DC>::instance().submit(id_, dc);
     return ticket_ >= 0 ? 0 : -1;
   }

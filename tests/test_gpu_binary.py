@@ -1,0 +1,65 @@
+"""GPU (-m gpu): binary traits: logistic null model on the device + the variance-weighted SKAT / CMC /
+Zeggini statistics (src/Model.h:2673-2681, regression/LogisticRegression.cpp:279-339, LogisticRegressionScoreTest.cpp:219-302)
+against the numpy restatement."""
+import numpy as np
+import pytest
+
+from util import af_of, make_problem, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", [(110, 900, 12, 1, 0.3), (111, 4000, 40, 3, 0.05), (112, 2500, 64, 2, 0.1)])
+def test_binary_trait_vs_oracle(engine_cls, oracle, case):
+    from oracle import binary_oracle as BIN
+    from rvtests_b200.synth import pack_bed
+    O = oracle
+    seed, N, M, C, hi = case
+    G, X, _ = make_problem(O, seed, N, M, C, maf=np.linspace(0.004, hi, M), n_flip=2, n_mono=1 if M > 12 else 0)
+    rng = np.random.default_rng(seed)
+    eta = -0.8 + (X[:, 1:] @ np.full(C - 1, 0.5) if C > 1 else 0.0)
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(-eta))).astype(np.float64)
+    nm = BIN.fit_null_logistic(X, y)
+    eng = engine_cls(0)
+    eng.set_null_model(X, y, binary=True)
+    got = eng.get_null_model()
+    assert np.max(np.abs(got["resid"] - nm["resid"])) <= 1e-10           # y - p of the SAME Newton round
+    assert got["sigma2"] == 1.0
+    assert np.max(np.abs(got["xtx_inv"] - nm["covB"])) <= 1e-9 * np.max(np.abs(nm["covB"]))
+    af = af_of(G)
+    eng.push_i8(G.T.copy(), af)
+    eng.push_f64(G.astype(float), af)
+    eng.push_bed(pack_bed(G.T), af)
+    res = eng.flush()
+    ref = BIN.gene(G.astype(float), af, X, nm)
+    for k in range(3):
+        r = res[k]
+        assert int(r["m_poly"]) == ref["m_poly"] and int(r["status"]) == 0
+        assert rel(r["Q"], ref["Q"]) <= 1e-6
+        assert rel(r["lambda_max"], ref["lam"][0]) <= 1e-7
+        assert int(r["davies_fault"]) == ref["fault"]
+        assert rel(r["p_skat"], ref["p_skat"]) <= 1e-4
+        for pre in ("cmc", "zeg"):
+            b = ref[pre]
+            assert abs(r[pre + "_U"] - b["U"]) <= 1e-6 * max(abs(b["U"]), np.sqrt(b["V"]))
+            assert rel(r[pre + "_V"], b["V"]) <= 1e-6
+            assert rel(r[pre + "_p"], b["p"]) <= 1e-4
+        assert int(r["cmc_nonref"]) == ref["cmc"]["nonref"]
+    # back to a quantitative trait on the same context: the linear path is unaffected
+    Xq, yq = O.synth_covariates(seed, N, C)
+    eng.set_null_model(Xq, yq)
+    eng.push_i8(G.T.copy(), af)
+    rq = eng.flush()[0]
+    nmq = O.fit_null_linear(Xq, yq)
+    refq, lamq = O.gene(G.astype(float), af, Xq, nmq["resid"], nmq["sigma2"])
+    assert rel(rq["Q"], refq.skat.Q) <= 1e-6 and rel(rq["p_skat"], refq.skat.pvalue) <= 1e-4
+    eng.close()
+
+
+def test_binary_trait_rejects_other_codes(engine_cls):
+    import rvtests_b200
+    eng = engine_cls(0)
+    X = np.ones((10, 1))
+    with pytest.raises(rvtests_b200.RvtError):
+        eng.set_null_model(X, np.arange(10.0), binary=True)      # case/control must already be 0/1 at this boundary
+    eng.close()
