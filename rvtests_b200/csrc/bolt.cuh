@@ -322,6 +322,24 @@ __global__ void k_bolt_columns(const uint8_t* __restrict__ bed, int64_t stride, 
   const int m = idx[k];
   out[e] = tab[(size_t)m * 4 + bolt_code(bed + (size_t)m * stride, i)];
 }
+// second stage of k_bolt_dot: out[r] = sum over CTAs (index order) - sum_c abot[c][r] bbot[c][r]  (abot null: plain sum)
+__global__ void k_bolt_dot_finish(int ctas, int R, int C, const double* __restrict__ partial, const double* __restrict__ abot,
+                                  const double* __restrict__ bbot, double* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  double s = 0.0;
+  for (int k = 0; k < ctas; ++k) s += partial[(size_t)k * R + r];
+  if (abot)
+    for (int c = 0; c < C; ++c) s -= abot[(size_t)c * R + r] * bbot[(size_t)c * R + r];
+  out[r] = s;
+}
+
+// dst[i][k] = scale * src[i][col] for every k < K, all rows (one column of a vector replicated K times)
+__global__ void k_bolt_bcast(int64_t rows, int Rsrc, int col, int K, double scale, const double* __restrict__ src, double* __restrict__ dst) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * K) return;
+  dst[e] = scale * src[(size_t)(e / K) * Rsrc + col];
+}
 #endif  // __CUDACC__
 
 }  // namespace rvt

@@ -1372,12 +1372,13 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     RVT_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
     if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nd, sizeof(QagsScratch)))) return rc;
     {
-      const int kld = fin_kld(kTileRows), fsm = fin_smem(kTileRows, ctx->ER, ctx->skato), wm_off = kTileRows * kld * 8;
-      if (ctx->skato && !ctx->binary)   // (SKAT-O for a binary trait is not provided: skato_ok stays 0)
-        k_finalize<true><<<nd, kFinThreadsSkato, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, ctx->skato), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
+      const bool sk = ctx->skato && !ctx->binary;   // SKAT-O for a binary trait is not provided: skato_ok stays 0
+      const int kld = fin_kld(kTileRows), fsm = fin_smem(kTileRows, ctx->ER, sk), wm_off = kTileRows * kld * 8;
+      if (sk)
+        k_finalize<true><<<nd, kFinThreadsSkato, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, sk), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
                                                              nullptr, d_res, nullptr, ctx->d_qags, d_tin, d_idx);
       else
-        k_finalize<false><<<nd, kFinThreads, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, ctx->skato), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
+        k_finalize<false><<<nd, kFinThreads, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, sk), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
                                                          nullptr, d_res, nullptr, nullptr, d_tin, d_idx);
     }
     RVT_CUDA_OK(cudaGetLastError());
@@ -1811,21 +1812,23 @@ struct BoltDev {
     k_bolt_project<<<C * R, 256, 0, st>>>(N, R, C, Z, v, v + (size_t)N * R);
     note();
   }
-  // projDot / projNorm2 per column (BoltLMM.cpp:1064-1138)
+  // projDot / projNorm2 per column (BoltLMM.cpp:1064-1138): two fixed-order stages on the device, R scalars to the host
   void pdot(const double* a, const double* b, int R, double* out) {
     k_bolt_dot<<<kBoltDotCtas, 256, 0, st>>>(N, R, a, b, dotp);
-    std::vector<double> hp((size_t)kBoltDotCtas * R), ha((size_t)C * R), hb((size_t)C * R);
-    cudaMemcpyAsync(hp.data(), dotp, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(ha.data(), a + (size_t)N * R, sizeof(double) * ha.size(), cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(hb.data(), b + (size_t)N * R, sizeof(double) * hb.size(), cudaMemcpyDeviceToHost, st);
+    k_bolt_dot_finish<<<1, 64, 0, st>>>(kBoltDotCtas, R, C, dotp, a + (size_t)N * R, b + (size_t)N * R, coef + 2 * kBoltMaxR);
+    cudaMemcpyAsync(out, coef + 2 * kBoltMaxR, sizeof(double) * R, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess && err == cudaSuccess) err = e;
-    for (int r = 0; r < R; ++r) {
-      double s = 0.0;
-      for (int k = 0; k < kBoltDotCtas; ++k) s += hp[(size_t)k * R + r];
-      for (int c = 0; c < C; ++c) s -= ha[(size_t)c * R + r] * hb[(size_t)c * R + r];
-      out[r] = s;
-    }
+    note();
+  }
+  // column sums of squares of an M x R matrix (|beta_hat|^2 per right-hand side)
+  void colnorm2(const double* a, int64_t rows_, int R, double* out) {
+    k_bolt_dot<<<kBoltDotCtas, 256, 0, st>>>(rows_, R, a, a, dotp);
+    k_bolt_dot_finish<<<1, 64, 0, st>>>(kBoltDotCtas, R, 0, dotp, nullptr, nullptr, coef + 2 * kBoltMaxR);
+    cudaMemcpyAsync(out, coef + 2 * kBoltMaxR, sizeof(double) * R, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess && err == cudaSuccess) err = e;
+    note();
   }
   // y = ca .* a + cb .* b (columnwise coefficients), all N + C rows
   void axpby(const double* ca, const double* a, const double* cb, const double* b, double* y, int R) {
@@ -1928,7 +1931,7 @@ int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t strid
   B.part = B.alloc<double>((size_t)B.splits * M * Rmax);
   B.Xy = B.alloc<double>((size_t)M * Rmax);
   B.dotp = B.alloc<double>((size_t)kBoltDotCtas * Rmax);
-  B.coef = B.alloc<double>(2 * kBoltMaxR);
+  B.coef = B.alloc<double>(3 * kBoltMaxR);
   double *vy = B.vec(Rmax), *vx = B.vec(Rmax), *vr = B.vec(Rmax), *vp = B.vec(Rmax), *vap = B.vec(Rmax), *vxb = B.vec(mc), *ve = B.vec(mc);
   if (B.err != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "bolt: cudaMalloc: %s", cudaGetErrorString(B.err));
   cudaStream_t st = B.st;
@@ -1970,11 +1973,12 @@ int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t strid
     RVT_CUDA_OK(cudaMemcpy(ve, he.data(), sizeof(double) * he.size(), cudaMemcpyHostToDevice));
     B.project(ve, mc);
   }
-  std::vector<double> hxb(rows * mc), he(rows * mc), hY(rows * R1), hH(rows * R1), hbeta((size_t)M * R1);
+  std::vector<double> hxb(rows * mc), he(rows * mc), hY(rows * R1);
   RVT_CUDA_OK(cudaMemcpyAsync(hxb.data(), vxb, sizeof(double) * hxb.size(), cudaMemcpyDeviceToHost, st));
   RVT_CUDA_OK(cudaMemcpyAsync(he.data(), ve, sizeof(double) * he.size(), cudaMemcpyDeviceToHost, st));
   RVT_CUDA_OK(cudaStreamSynchronize(st));
   int evals = 0;
+  double last_hh = 0.0;   // |H^-1 y|^2_proj of the data column at the last evaluation
   auto evalREML = [&](double logDelta) -> double {   // BoltLMM.cpp:669-724
     const double delta = exp(logDelta), sd = sqrt(delta);
     for (size_t i = 0; i < rows; ++i) {
@@ -1984,19 +1988,12 @@ int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t strid
     cudaMemcpy(vy, hY.data(), sizeof(double) * hY.size(), cudaMemcpyHostToDevice);
     B.solve(vy, delta, vx, vr, vp, vap, R1);
     B.XtV(vx, R1, 1.0 / (double)M);                  // beta_hat = [X ; Z'X]_minus' H^-1 y / M   (:734-742)
-    cudaMemcpyAsync(hbeta.data(), B.Xy, sizeof(double) * hbeta.size(), cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(hH.data(), vx, sizeof(double) * hH.size(), cudaMemcpyDeviceToHost, st);
-    cudaStreamSynchronize(st);
     ++evals;
     double bn[kBoltMaxR], en[kBoltMaxR];
-    for (int r = 0; r < R1; ++r) bn[r] = en[r] = 0.0;
-    for (int64_t m = 0; m < M; ++m)
-      for (int r = 0; r < R1; ++r) bn[r] += hbeta[(size_t)m * R1 + r] * hbeta[(size_t)m * R1 + r];
-    for (size_t i = 0; i < rows; ++i)
-      for (int r = 0; r < R1; ++r) {
-        const double e = delta * hH[i * R1 + r];     // e_hat = delta H^-1 y
-        en[r] += (i < (size_t)N ? 1.0 : -1.0) * e * e;
-      }
+    B.colnorm2(B.Xy, M, R1, bn);                     // |beta_hat|^2 per right-hand side
+    B.pdot(vx, vx, R1, en);                          // e_hat = delta H^-1 y: |e_hat|^2_proj = delta^2 |H^-1 y|^2_proj
+    for (int r = 0; r < R1; ++r) en[r] *= delta * delta;
+    last_hh = en[0] / (delta * delta);
     double rb = 0.0, re = 0.0;
     for (int r = 1; r < R1; ++r) {
       rb += bn[r];
@@ -2029,17 +2026,20 @@ int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t strid
   if (i == 7) --i;
   if (B.err != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "bolt: %s", cudaGetErrorString(B.err));
   const double delta = exp(ld[i]);
-  double yh = 0.0;   // projDot(y, H^-1 y) of the LAST evaluation (the reference does not re-solve at the final delta)
-  for (size_t k = 0; k < rows; ++k) yh += (k < (size_t)N ? 1.0 : -1.0) * hy[k] * hH[k * R1];
-  const double sigma2_g = yh / (double)(N - Ck);
+  // projDot(y, H^-1 y) of the LAST evaluation (the reference does not re-solve at the final delta): vy / vx still hold them
+  double yhv[kBoltMaxR];
+  B.pdot(vy, vx, R1, yhv);
+  const double sigma2_g = yhv[0] / (double)(N - Ck);
   if (!(sigma2_g > 0.0)) CTX_FAIL(RVT_E_NUMERIC, "bolt: sigma2_g = %g is not positive", sigma2_g);
   const double sigma2_e = delta * sigma2_g;
-  std::vector<double> hh(rows);
-  double hn2 = 0.0;
-  for (size_t k = 0; k < rows; ++k) {
-    hh[k] = hH[k * R1] / sigma2_g;                   // H_inv_y_
-    hn2 += (k < (size_t)N ? 1.0 : -1.0) * hh[k] * hh[k];
-  }
+  const double hn2 = last_hh / (sigma2_g * sigma2_g);       // projNorm2(H_inv_y_), H_inv_y_ = H^-1 y / sigma2_g
+  const size_t rows_h = rows;
+  std::vector<double> hh(rows_h);
+  double* vh = B.vec(1);
+  if (!vh) CTX_FAIL(RVT_E_CUDA, "bolt: cudaMalloc");
+  k_bolt_bcast<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((int64_t)rows, R1, 0, 1, 1.0 / sigma2_g, vx, vh);
+  RVT_CUDA_OK(cudaMemcpyAsync(hh.data(), vh, sizeof(double) * rows, cudaMemcpyDeviceToHost, st));
+  RVT_CUDA_OK(cudaStreamSynchronize(st));
   // EstimateInfStatCalibration (BoltLMM.cpp:1141-1214)
   std::vector<int> idx(nSnp);
   for (int k = 0; k < nSnp; ++k) idx[k] = (int)(size_t)(rng.next() * (double)M);
@@ -2049,17 +2049,16 @@ int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t strid
   k_bolt_columns<<<(unsigned)(((int64_t)N * nSnp + 255) / 256), 256, 0, st>>>(B.bed, stride, N, d_idx, nSnp, B.tab, vy);
   B.project(vy, nSnp);
   B.solve(vy, delta, vx, vr, vp, vap, nSnp);         // V^-1 x = H^-1 x / sigma2_g
-  std::vector<double> xVx(nSnp), xx(nSnp), xVy(nSnp), hg(rows * nSnp);
+  std::vector<double> xVx(nSnp), xx(nSnp), xVy(nSnp);
   B.pdot(vy, vx, nSnp, xVx.data());
   B.pdot(vy, vy, nSnp, xx.data());
-  RVT_CUDA_OK(cudaMemcpy(hg.data(), vy, sizeof(double) * hg.size(), cudaMemcpyDeviceToHost));
+  k_bolt_bcast<<<(unsigned)((rows * nSnp + 255) / 256), 256, 0, st>>>((int64_t)rows, 1, 0, nSnp, 1.0, vh, vr);   // H_inv_y_ in every column
+  B.pdot(vy, vr, nSnp, xVy.data());
   if (B.err != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "bolt: %s", cudaGetErrorString(B.err));
   double r0 = 0.0, r1 = 0.0, sxVx = 0.0, sxx = 0.0;
-  for (int k = 0; k < nSnp; ++k) {
+  for (int k = 0; k < nSnp; ++k) {   // 30 scalars: the calibration ratio (BoltLMM.cpp:1166-1181)
     xVx[k] /= sigma2_g;
-    double d = 0.0;
-    for (size_t q = 0; q < rows; ++q) d += (q < (size_t)N ? 1.0 : -1.0) * hg[q * nSnp + k] * hh[q];
-    xVy[k] = d;
+    const double d = xVy[k];
     const double prosp = d * d / xVx[k], retro = (double)N * d * d / (xx[k] * hn2);
     if (prosp < 5.0) {
       r0 += retro;

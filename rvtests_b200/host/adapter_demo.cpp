@@ -41,10 +41,17 @@ int main(int argc, char** argv) {
 
   const int nPerm = argc > 3 ? atoi(argv[3]) : 0;        // skat[nPerm=..,alpha=..]
   const double alpha = argc > 4 ? atof(argv[4]) : 0.05;
+  const bool binary = argc > 5 && atoi(argv[5]) != 0;    // ModelManager: setBinaryOutcome() on every model
   SkatTest skat(nPerm, alpha);
   SkatOTest skato;
   CMCTest cmc;
   ZegginiTest zeg;
+  if (binary) {
+    skat.setBinaryOutcome();
+    skato.setBinaryOutcome();
+    cmc.setBinaryOutcome();
+    zeg.setBinaryOutcome();
+  }
   shim::FileWriter fw[4];
   shim::Result site;
   site.keys.push_back("Range");

@@ -192,3 +192,52 @@ def test_meta_adapters_match_reference_output_format(oracle, segment, tmp_path):
         got = np.array([float(x) for x in c[5].split(",")])
         assert len(got) == len(vals)
         assert np.all(np.abs(got - np.array(vals)) <= 2e-5 * np.maximum(np.abs(vals), 1e-12) + 1e-12)   # printed with 6 digits
+
+
+def test_adapters_binary_outcome(oracle, tmp_path):
+    """setBinaryOutcome(): the adapters switch to the logistic null model; Skat / CMC / Zeggini lines against the binary
+    oracle, SkatO prints NA (not provided for a binary trait)."""
+    from oracle import binary_oracle as BIN
+    import rvtests_b200
+    rvtests_b200.load_library()
+    O = oracle
+    N, C = 1500, 2
+    genes = []
+    X = None
+    for gi, (M, nm_, nf) in enumerate([(8, 0, 1), (30, 2, 2)]):
+        G, X, _ = make_problem(O, 79, N, M, C, maf=np.linspace(0.004, 0.05, M), n_mono=nm_, n_flip=nf)
+        genes.append(G)
+    rng = np.random.default_rng(79)
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(0.5 - 0.6 * X[:, 1]))).astype(np.float64)
+    path = tmp_path / "problem.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("iii", N, C - 1, len(genes)))
+        f.write(np.ascontiguousarray(y).tobytes())
+        f.write(np.asfortranarray(X[:, 1:]).tobytes(order="F"))
+        for G in genes:
+            f.write(struct.pack("i", G.shape[1]))
+            f.write(np.asfortranarray(G.astype(np.float64)).tobytes(order="F"))
+            f.write(af_of(G).tobytes())
+    exe = build_demo()
+    out = subprocess.run([exe, str(path), "8", "0", "0.05", "1"], capture_output=True, text=True, check=True).stdout
+    tables, cur = {}, None
+    for line in out.splitlines():
+        if line.startswith("#"):
+            cur = line[1:]
+            tables[cur] = []
+        else:
+            tables[cur].append(line.split("\t"))
+    nm = BIN.fit_null_logistic(X, y)
+
+    def close(txt, val, tol=2e-5):
+        return txt != "NA" and abs(float(txt) - val) <= tol * max(abs(val), 1e-300)
+
+    for gi, G in enumerate(genes):
+        ref = BIN.gene(G.astype(float), af_of(G), X, nm)
+        rs, ro, rc, rz = (tables[k][1 + gi][3:] for k in ("Skat", "SkatO", "CMC", "Zeggini"))
+        ctx = (gi, rs, ro, rc, rz, ref["Q"], ref["p_skat"], ref["cmc"], ref["zeg"])
+        # "%g" prints 6 digits; the statistics agree to ~1e-9, so compare the printed numbers numerically
+        assert close(rs[0], ref["Q"]) and close(rs[1], ref["p_skat"]), ctx
+        assert ro == ["NA", "NA", "NA"], ctx
+        assert rc[0] == str(ref["cmc"]["nonref"]) and close(rc[1], ref["cmc"]["p"]), ctx
+        assert close(rz[0], ref["zeg"]["p"]), ctx
