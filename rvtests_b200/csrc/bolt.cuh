@@ -156,50 +156,83 @@ k_bolt_snp(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, int C, co
   }
 }
 
-// X'v over a split of the samples: part[split][m][r] = sum_{i in split} x_mi v[i][r].  One thread per SNP of a 64-SNP
-// block holds the R accumulators; the block's 2-bit rows are staged through shared memory chunk by chunk.
+// X'v over a split of the samples: part[split][m][r] = sum_{i in split} x_mi v[i][r].  One thread holds the R accumulators
+// of TWO SNPs of a 128-SNP block (the loads of v are shared by both); the block's 2-bit rows are staged through shared
+// memory chunk by chunk.  v rows are read with 16-byte loads when R is even.
+constexpr int kBoltSnpPerThread = 2;
+constexpr int kBoltXtvBlock = kBoltSnpBlock * kBoltSnpPerThread;   // SNPs per CTA
 template <int RMAX>
 __global__ void __launch_bounds__(kBoltSnpBlock)
 k_bolt_xtv(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, int M, const double* __restrict__ tab, const double* __restrict__ v,
            int R, int64_t split_len, double* __restrict__ part /*[splits][M][R]*/) {
-  __shared__ __align__(16) uint8_t s_rows[kBoltSnpBlock][kBoltRowPad];
-  const int m = blockIdx.x * kBoltSnpBlock + threadIdx.x;
+  __shared__ __align__(16) uint8_t s_rows[kBoltXtvBlock][kBoltRowPad];
+  const int mA = blockIdx.x * kBoltXtvBlock + threadIdx.x, mB = mA + kBoltSnpBlock;
   const int64_t i0 = (int64_t)blockIdx.y * split_len;
   int64_t i1 = i0 + split_len;
   if (i1 > N) i1 = N;
-  double t4[4] = {0, 0, 0, 0};
-  if (m < M)
-    for (int k = 0; k < 4; ++k) t4[k] = tab[(size_t)m * 4 + k];
-  double acc[RMAX];
+  double tA[4] = {0, 0, 0, 0}, tB[4] = {0, 0, 0, 0};
+  for (int k = 0; k < 4; ++k) {
+    if (mA < M) tA[k] = tab[(size_t)mA * 4 + k];
+    if (mB < M) tB[k] = tab[(size_t)mB * 4 + k];
+  }
+  double accA[RMAX], accB[RMAX];
 #pragma unroll
-  for (int r = 0; r < RMAX; ++r) acc[r] = 0.0;
+  for (int r = 0; r < RMAX; ++r) accA[r] = accB[r] = 0.0;
+  const bool vec2 = (R == RMAX) && (RMAX % 2 == 0);   // full, even width: rows of v are 16-byte aligned
   for (int64_t c0 = i0; c0 < i1; c0 += kBoltChunk) {   // i0 and kBoltChunk are multiples of 4
     const int64_t n_here = (i1 - c0 < kBoltChunk) ? (i1 - c0) : kBoltChunk;
     const int nbytes = (int)((n_here + 3) >> 2);
     __syncthreads();
-    for (int rr = 0; rr < kBoltSnpBlock; ++rr) {
-      const int mm = blockIdx.x * kBoltSnpBlock + rr;
+    for (int rr = 0; rr < kBoltXtvBlock; ++rr) {
+      const int mm = blockIdx.x * kBoltXtvBlock + rr;
       if (mm >= M) break;
       const uint8_t* __restrict__ src = bed + (size_t)mm * stride + (c0 >> 2);
       for (int b = threadIdx.x; b < nbytes; b += kBoltSnpBlock) s_rows[rr][b] = src[b];
     }
     __syncthreads();
-    if (m < M) {
-      const uint8_t* __restrict__ my = s_rows[threadIdx.x];
-      for (int64_t k = 0; k < n_here; ++k) {
-        const double x = t4[(my[k >> 2] >> (2 * (k & 3))) & 3];
-        const double* __restrict__ vr = v + (size_t)(c0 + k) * R;   // warp-uniform address: one broadcast load
+    if (mA < M) {
+      const uint8_t* __restrict__ rowA = s_rows[threadIdx.x];
+      const uint8_t* __restrict__ rowB = s_rows[threadIdx.x + kBoltSnpBlock];   // (stale bytes when mB >= M: tB is all zero)
+      for (int64_t k4 = 0; k4 < n_here; k4 += 4) {
+        const unsigned bA = rowA[k4 >> 2], bB = rowB[k4 >> 2];
 #pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-          if (r < R) acc[r] += x * vr[r];
+        for (int q = 0; q < 4; ++q) {
+          if (k4 + q >= n_here) break;
+          const double xA = tA[(bA >> (2 * q)) & 3], xB = tB[(bB >> (2 * q)) & 3];
+          const double* __restrict__ vr = v + (size_t)(c0 + k4 + q) * R;   // warp-uniform address: broadcast loads
+          if (vec2) {
+#pragma unroll
+            for (int r = 0; r < RMAX; r += 2) {
+              const double2 vv = *reinterpret_cast<const double2*>(vr + r);
+              accA[r] += xA * vv.x;
+              accA[r + 1] += xA * vv.y;
+              accB[r] += xB * vv.x;
+              accB[r + 1] += xB * vv.y;
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r)
+              if (r < R) {
+                const double vv = vr[r];
+                accA[r] += xA * vv;
+                accB[r] += xB * vv;
+              }
+          }
+        }
       }
     }
   }
-  if (m < M) {
-    double* o = part + ((size_t)blockIdx.y * M + m) * R;
+  if (mA < M) {
+    double* o = part + ((size_t)blockIdx.y * M + mA) * R;
 #pragma unroll
     for (int r = 0; r < RMAX; ++r)
-      if (r < R) o[r] = acc[r];
+      if (r < R) o[r] = accA[r];
+  }
+  if (mB < M) {
+    double* o = part + ((size_t)blockIdx.y * M + mB) * R;
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r)
+      if (r < R) o[r] = accB[r];
   }
 }
 
@@ -216,39 +249,54 @@ __global__ void k_bolt_xtv_finish(int M, int R, int C, int splits, const double*
 }
 
 // out[i][r] = alpha * sum_m x_mi W[m][r] + beta * add[i][r]   (top rows; X_plus X_y / M + delta y, :960-975).
-// One thread per sample holds the R accumulators; W and the tables are staged per 64-SNP block.
-template <int RMAX>
+// One thread holds the R accumulators of SPT consecutive samples (SPT = 4: one whole byte of every SNP row per thread);
+// W and the decode tables are staged per 64-SNP block.
+template <int RMAX, int SPT>
 __global__ void __launch_bounds__(256)
 k_bolt_xw(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, int M, const double* __restrict__ tab, const double* __restrict__ W /*[M][R]*/,
           int R, double alpha, double beta, const double* __restrict__ add, double* __restrict__ out) {
+  static_assert(SPT == 1 || SPT == 4, "one sample or one byte per thread");
   __shared__ double s_W[kBoltSnpBlock][RMAX];
   __shared__ double s_tab[kBoltSnpBlock][4];
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  double acc[RMAX];
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * SPT;
+  double acc[SPT][RMAX];
 #pragma unroll
-  for (int r = 0; r < RMAX; ++r) acc[r] = 0.0;
+  for (int q = 0; q < SPT; ++q)
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) acc[q][r] = 0.0;
   for (int m0 = 0; m0 < M; m0 += kBoltSnpBlock) {
     const int nm = (M - m0 < kBoltSnpBlock) ? (M - m0) : kBoltSnpBlock;
     __syncthreads();
-    for (int idx = threadIdx.x; idx < nm * R; idx += 256) s_W[idx / R][idx % R] = W[(size_t)m0 * R + idx];
+    for (int idx = threadIdx.x; idx < nm * RMAX; idx += 256) {
+      const int mm = idx / RMAX, r = idx - mm * RMAX;
+      s_W[mm][r] = (r < R) ? W[(size_t)(m0 + mm) * R + r] : 0.0;
+    }
     for (int idx = threadIdx.x; idx < nm * 4; idx += 256) s_tab[idx >> 2][idx & 3] = tab[(size_t)m0 * 4 + idx];
     __syncthreads();
     if (i < N) {
       const uint8_t* __restrict__ col = bed + (size_t)m0 * stride + (i >> 2);
-      const int sh = 2 * (int)(i & 3);
+      const int sh = 2 * (int)(i & 3);   // 0 when SPT == 4
       for (int mm = 0; mm < nm; ++mm) {
-        const double x = s_tab[mm][(col[(size_t)mm * stride] >> sh) & 3];
+        const unsigned b = col[(size_t)mm * stride] >> sh;
+        double x[SPT];
 #pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-          if (r < R) acc[r] += x * s_W[mm][r];
+        for (int q = 0; q < SPT; ++q) x[q] = s_tab[mm][(b >> (2 * q)) & 3];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+          const double w = s_W[mm][r];
+#pragma unroll
+          for (int q = 0; q < SPT; ++q) acc[q][r] += x[q] * w;
+        }
       }
     }
   }
-  if (i < N) {
 #pragma unroll
-    for (int r = 0; r < RMAX; ++r)
-      if (r < R) out[(size_t)i * R + r] = alpha * acc[r] + (add ? beta * add[(size_t)i * R + r] : 0.0);
-  }
+  for (int q = 0; q < SPT; ++q)
+    if (i + q < N) {
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r)
+        if (r < R) out[(size_t)(i + q) * R + r] = alpha * acc[q][r] + (add ? beta * add[(size_t)(i + q) * R + r] : 0.0);
+    }
 }
 
 // bottom rows: out[c][r] = alpha * sum_m zg[m][c] W[m][r] + beta * add[c][r]   (one thread per (c, r), SNP order)

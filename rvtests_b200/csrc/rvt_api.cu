@@ -1784,27 +1784,32 @@ struct BoltDev {
   }
   size_t rows() const { return (size_t)(N + C); }
   double* vec(int R) { return alloc<double>(rows() * R); }
+  void launch_xtv(const double* v, int R) {
+    dim3 g1((unsigned)((M + kBoltXtvBlock - 1) / kBoltXtvBlock), (unsigned)splits);
+    if (R <= 4) k_bolt_xtv<4><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
+    else if (R <= 8) k_bolt_xtv<8><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
+    else if (R <= 16) k_bolt_xtv<16><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
+    else k_bolt_xtv<32><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
+  }
   // out = (X X'/M + delta I) v on [v ; Z'v]   (computeHx, BoltLMM.cpp:931-993)
   void Hx(double delta, const double* v, double* out, int R) {
-    dim3 g1((unsigned)((M + kBoltSnpBlock - 1) / kBoltSnpBlock), (unsigned)splits);
-    if (R <= 16) k_bolt_xtv<16><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
-    else k_bolt_xtv<32><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
+    launch_xtv(v, R);
     k_bolt_xtv_finish<<<(unsigned)(((int64_t)M * R + 255) / 256), 256, 0, st>>>(M, R, C, splits, part, zg, v + (size_t)N * R, 1.0, Xy);
     XW(Xy, R, 1.0 / M, delta, v, out);
   }
   // out = alpha [X ; Z'X] W + beta add
   void XW(const double* W, int R, double alpha, double beta, const double* add, double* out) {
-    const unsigned g2 = (unsigned)((N + 255) / 256);
-    if (R <= 16) k_bolt_xw<16><<<g2, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
-    else k_bolt_xw<32><<<g2, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
+    const unsigned g1 = (unsigned)((N + 255) / 256), g4 = (unsigned)((N + 1023) / 1024);
+    if (R <= 4) k_bolt_xw<4, 4><<<g4, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
+    else if (R <= 8) k_bolt_xw<8, 4><<<g4, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
+    else if (R <= 16) k_bolt_xw<16, 1><<<g1, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
+    else k_bolt_xw<32, 1><<<g1, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
     k_bolt_bot<<<(C * R + 63) / 64, 64, 0, st>>>(M, R, C, zg, W, alpha, beta, add ? add + (size_t)N * R : nullptr, out + (size_t)N * R);
     note();
   }
   // X_minus' v / scale -> Xy (host copy optional)
   void XtV(const double* v, int R, double scale) {
-    dim3 g1((unsigned)((M + kBoltSnpBlock - 1) / kBoltSnpBlock), (unsigned)splits);
-    if (R <= 16) k_bolt_xtv<16><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
-    else k_bolt_xtv<32><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
+    launch_xtv(v, R);
     k_bolt_xtv_finish<<<(unsigned)(((int64_t)M * R + 255) / 256), 256, 0, st>>>(M, R, C, splits, part, zg, v + (size_t)N * R, scale, Xy);
     note();
   }
@@ -1919,7 +1924,7 @@ int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t strid
   const int R1 = mc + 1;
   const int nSnp = (int)std::min<int64_t>(30, M), Rmax = std::max(R1, nSnp);
   // sample splits of the X'v product: enough CTAs to fill the device, each a multiple of the staged chunk
-  const int64_t nblk = (M + kBoltSnpBlock - 1) / kBoltSnpBlock;
+  const int64_t nblk = (M + kBoltXtvBlock - 1) / kBoltXtvBlock;
   int splits = (int)std::max<int64_t>(1, std::min<int64_t>((4 * (int64_t)ctx->sm_count + nblk - 1) / nblk, (N + kBoltChunk - 1) / kBoltChunk));
   B.split_len = (((N + splits - 1) / splits) + kBoltChunk - 1) / kBoltChunk * kBoltChunk;
   B.splits = (int)((N + B.split_len - 1) / B.split_len);
