@@ -920,14 +920,14 @@ __global__ void k_resolve_flags(int64_t n_var, int64_t N, const RowCounts* __res
 // splits of the sample axis: S units per gene, `chunk` samples each (a multiple of 512 = one TMA
 // stage of the tensor-core kernel = 2 simt tiles).  A unit must stay inside the int32 accumulation
 // bounds (2^22 samples for the Gram; 2^18 for the burden rows that ride on the UMMA); beyond that, only
-// as many splits as it takes to give every SM ~16 units: each extra split costs one more partial
+// as many splits as it takes to give every SM ~8 units: each extra split costs one more partial
 // (25 KB written by the sweep, read back by the statistics kernel) per gene.
 static int split_plan(rvt_ctx* ctx, int n_genes, int* S_out, int64_t* chunk_out) {
   const int64_t N = ctx->N;
   int S = ctx->splits;
   if (S <= 0) {
     const int64_t s_min = (N + 262143) / 262144;
-    const int64_t s_fill = (16 * (int64_t)ctx->sm_count + n_genes - 1) / std::max(1, n_genes);
+    const int64_t s_fill = (8 * (int64_t)ctx->sm_count + n_genes - 1) / std::max(1, n_genes);
     S = (int)std::min<int64_t>(std::max<int64_t>(s_min, std::min<int64_t>(s_fill, (N + 65535) / 65536)), std::max<int64_t>(16, s_min));
     S = std::max(S, 1);
   }
