@@ -1,6 +1,12 @@
 // rvt_api.cu -- the C ABI (include/rvtests_b200.h) of the B200 gene engine: context, null model,
-// gene queue, flush = [K0 flags] -> [K1 sweep] -> [K2/K3 finalize].  Host code here is plumbing
-// only (allocation, launches, copies); every number a test reports is computed on the GPU.
+// gene queue, flush = [K0 flags] -> [K1 sweep] -> [K2/K3 finalize], and the entry points of the rows built around it
+// (wide genes, permutation test, meta score/cov, FastLMM score step, BoltLMM null fit, binary traits).
+// Host code here is allocation, launches, copies and CONTROL FLOW on O(1)..O(C^2)..O(R) scalars: the per-gene and
+// per-variant statistics are computed on the GPU.  The places where the host does arithmetic are the ones whose inputs are
+// a handful of scalars per step: the Cholesky solve of the C x C logistic Newton step, the conjugate-gradient / secant
+// bookkeeping and the random draws of the Bolt fit (the reference's own MT19937 stream), its covariate basis (Gram-Schmidt
+// on the N x C covariates, as BoltPlinkLoader does on the host), (ux' D ux)^-1 of the FastLMM score step, the polynomial
+// jump of the rand() stream and the adaptive stop rule of the permutation test.  There is no CPU fallback of any kernel.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
