@@ -70,13 +70,3 @@ def test_bolt_null_fit_vs_oracle(engine_cls, oracle, case):
         assert abs(vout[j]["U"] * kappa - u) <= 1e-6 * max(abs(u), np.sqrt(v))
         assert rel(vout[j]["pvalue"], oracle.lib().orc_chisq_q(u * u / v, 1.0)) <= 1e-5
     eng.close()
-
-
-def test_bolt_random_stream_is_the_reference_generator(oracle):
-    """MT19937(12345) first outputs -- the generator of libsrc/Random.cpp -- via numpy's legacy seeding"""
-    from oracle import bolt_oracle as BO
-    r = BO.Random(12345)
-    ref = np.random.RandomState(12345)                     # init_genrand(12345), the same seeding as InitMersenne
-    raw = ref.randint(0, 2**32, size=5, dtype=np.uint64)
-    got = [r.next() for _ in range(5)]
-    assert np.allclose(got, (raw.astype(np.float64) + 0.5) / 4294967296.0, rtol=0, atol=0)
