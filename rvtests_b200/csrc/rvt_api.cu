@@ -37,7 +37,7 @@ namespace {
 struct DosGene {     // a pushed gene with non-hard-call values: handled by the fp64 path (dosage.cuh)
   int gene_index;
   int M;
-  double* dG;        // N x M column-major doubles, device
+  double* dG;        // N x M column-major doubles, device (null: expand the gene's hard-call tiles at flush)
   bool has_af;
   std::vector<double> af;
 };
@@ -1341,11 +1341,7 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       DosGene dg;
       dg.gene_index = g;
       dg.M = gd.M;
-      dg.dG = nullptr;
-      RVT_CUDA_OK(cudaMalloc((void**)&dg.dG, sizeof(double) * (size_t)N * gd.M));
-      dim3 grid((unsigned)((N + 255) / 256), (unsigned)gd.M);
-      k_impute_tiled_f64<<<grid, 256, 0, st>>>(gd.g, gd.M, N, ctx->d_counts + gd.var0, dg.dG);
-      RVT_CUDA_OK(cudaGetLastError());
+      dg.dG = nullptr;   // expanded into one shared scratch block inside the loop below (stream-ordered reuse)
       dg.has_af = gd.has_af != 0;
       if (dg.has_af) dg.af.assign(ctx->af.begin() + gd.var0, ctx->af.begin() + gd.var0 + gd.M);
       ctx->dos.push_back(dg);
@@ -1366,14 +1362,24 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     RVT_CUDA_OK(cudaMalloc((void**)&d_afd, sizeof(double) * nd * kTileRows));
     RVT_CUDA_OK(cudaMemsetAsync(d_st, 0, sizeof(DosageStats) * nd, st));
     std::vector<int> idx(nd);
+    double* d_expand = nullptr;   // scratch for genes that arrive as hard-call tiles (binary trait)
     for (int i = 0; i < nd; ++i) {
-      const DosGene& dg = ctx->dos[i];
+      DosGene& dg = ctx->dos[i];
       idx[i] = dg.gene_index;
+      const bool from_tiles = dg.dG == nullptr;
+      if (from_tiles) {
+        if (!d_expand) RVT_CUDA_OK(cudaMalloc((void**)&d_expand, sizeof(double) * (size_t)N * kMaxM));
+        const GeneDesc& gd = ctx->genes[dg.gene_index];
+        dim3 grid((unsigned)((N + 255) / 256), (unsigned)gd.M);
+        k_impute_tiled_f64<<<grid, 256, 0, st>>>(gd.g, gd.M, N, ctx->d_counts + gd.var0, d_expand);
+        dg.dG = d_expand;
+      }
       RVT_CUDA_OK(cudaMemsetAsync(d_st[i].cmin, 0xFF, sizeof(unsigned long long) * kTileRows, st));
       if (dg.has_af) RVT_CUDA_OK(cudaMemcpyAsync(d_afd + (size_t)i * kTileRows, dg.af.data(), sizeof(double) * dg.M, cudaMemcpyHostToDevice, st));
       k_dosage_cols<<<ctx->sm_count, kDosThreads, 0, st>>>(dg.dG, N, dg.M, d_st + i);
       k_dosage_stats<<<ctx->sm_count * 2, kDosThreads, 0, st>>>(dg.dG, N, dg.M, ctx->dX, ctx->C, ctx->dresid, ctx->binary ? ctx->d_vw : nullptr, d_st + i);
       k_dosage_prepare<<<1, 64, 0, st>>>(d_st + i, dg.M, dg.has_af ? d_afd + (size_t)i * kTileRows : nullptr, ctx->d_nm, prm, d_tin + i);
+      if (from_tiles) dg.dG = nullptr;   // not owned
     }
     RVT_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
     if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nd, sizeof(QagsScratch)))) return rc;
@@ -1391,7 +1397,9 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     RVT_CUDA_OK(cudaStreamSynchronize(st));
     launches += 3 * nd + 1;
     cudaFree(d_st); cudaFree(d_tin); cudaFree(d_idx); cudaFree(d_afd);
-    for (auto& dg : ctx->dos) cudaFree(dg.dG);
+    if (d_expand) cudaFree(d_expand);
+    for (auto& dg : ctx->dos)
+      if (dg.dG) cudaFree(dg.dG);
     ctx->dos.clear();
   }
   if ((rc = run_wide(ctx, d_res, &launches))) return rc;
@@ -1494,6 +1502,7 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   if (cap_variants < nv) CTX_FAIL(RVT_E_BADARG, "vout holds %lld records, %lld variants pending", (long long)cap_variants, (long long)nv);
   if (band && (!pos || !chrom)) CTX_FAIL(RVT_E_BADARG, "the covariance band needs pos and chrom");
   if (!ctx->wide.empty()) CTX_FAIL(RVT_E_UNSUPPORTED, "meta: push variant blocks of at most %d variants", kMaxM);
+  if (ctx->binary) CTX_FAIL(RVT_E_UNSUPPORTED, "meta score/cov for a binary trait (MetaUnrelatedBinary, src/Model.h:3557-3640) is not provided");
   RVT_CUDA_OK(cudaSetDevice(ctx->device));
   // every pending push is one tile (<= 64 consecutive variants, its own tiled block) of one segment
   const int seg = ctx->genes[0].seg;
