@@ -163,9 +163,8 @@ k_dosage_stats(const double* __restrict__ G, int64_t N, int M, const double* __r
 }
 
 // one CTA (64 threads) per dosage gene
-__global__ void __launch_bounds__(64)
-k_dosage_prepare(const DosageStats* __restrict__ st, int M, const double* __restrict__ af /*[M] or null*/,
-                 const NullModel* __restrict__ nm, EngineParams prm, TailInput* __restrict__ out) {
+__device__ inline void dosage_prepare(const DosageStats* __restrict__ st, int M, const double* __restrict__ af /*[M] or null*/,
+                                      const NullModel* __restrict__ nm, EngineParams prm, TailInput* __restrict__ out) {
   __shared__ int s_idx[kTileRows], s_flip[kTileRows];
   __shared__ double s_s[kTileRows], s_sw[kTileRows], s_B[kTileRows][kMaxC];
   __shared__ int s_Mp;
@@ -228,6 +227,232 @@ k_dosage_prepare(const DosageStats* __restrict__ st, int M, const double* __rest
       out->cmcSZ[l] = st->cmcSZ[l];
     }
   }
+}
+
+__global__ void __launch_bounds__(64)
+k_dosage_prepare(const DosageStats* __restrict__ st, int M, const double* __restrict__ af /*[M] or null*/,
+                 const NullModel* __restrict__ nm, EngineParams prm, TailInput* __restrict__ out) {
+  dosage_prepare(st, M, af, nm, prm, out);
+}
+
+// ---- genes whose values come from the engine's own hard-call tiles: missing calls (code 3) mean-imputed on the fly
+// (DataConsolidator::imputeGenotypeToMean, src/DataConsolidator.cpp:217-245), and every gene of a binary-trait run.
+// No N x M doubles are ever materialised: the statistics kernel reads the int8 tiles (1 byte per call) and many genes share
+// one launch (blockIdx.y = gene).
+struct TileGene {
+  const int8_t* g;    // tiled block [chunk][M][128]
+  int32_t M;
+  int32_t has_af;
+  int64_t var0;       // per-variant side arrays (counts, af)
+  int32_t slot;       // index into the DosageStats / TailInput arrays of this launch
+  int32_t allow_missing;   // 1: code 3 is a missing call to impute (2-bit pushes); 0: any value outside {0,1,2} is an error
+};
+
+// column sums / min / max of the imputed columns follow from the counts alone: no pass over the data
+__global__ void k_tile_cols(const TileGene* __restrict__ genes, int n_genes, int64_t N, const RowCounts* __restrict__ counts,
+                            DosageStats* __restrict__ st) {
+  const int gi = blockIdx.x, j = threadIdx.x;
+  if (gi >= n_genes) return;
+  const TileGene tg = genes[gi];
+  if (j >= tg.M) return;
+  const RowCounts rc = counts[tg.var0 + j];
+  const long long n1 = rc.n1, n2 = rc.n2, miss = rc.bad, n0 = N - n1 - n2 - miss, nobs = N - miss;
+  const double ac = (double)(n1 + 2 * n2);
+  const double fill = nobs > 0 ? 2.0 * (ac / (double)(2 * nobs)) : 0.0;     // 2 p^, p^ over the observed calls
+  double mn = 1e300, mx = -1e300;
+  if (n0 > 0) { mn = fmin(mn, 0.0); mx = fmax(mx, 0.0); }
+  if (n1 > 0) { mn = fmin(mn, 1.0); mx = fmax(mx, 1.0); }
+  if (n2 > 0) { mn = fmin(mn, 2.0); mx = fmax(mx, 2.0); }
+  if (miss > 0) { mn = fmin(mn, fill); mx = fmax(mx, fill); }
+  DosageStats* s = st + tg.slot;
+  if (miss > 0 && !tg.allow_missing) s->negative = 1;   // reported as RVT_GENE_BADVALUE, never silently computed
+  s->csum[j] = ac + (double)miss * fill;
+  s->cmin[j] = (unsigned long long)__double_as_longlong(mn);
+  s->cmax[j] = (unsigned long long)__double_as_longlong(mx);
+}
+
+// The statistics of k_dosage_stats on tiles, exploiting that rare-variant genotypes are almost all zero.  A thread owns 4
+// consecutive samples.  Pass 1 walks the gene's rows with one 32-bit load per row (4 calls) and only RECORDS the non-zero
+// calls in a short per-sample list; pass 2 does the arithmetic from the lists: products with r, v, X and with the other
+// non-zero calls of the same sample.  (A row-synchronous loop that accumulated directly made all lanes of a warp hit the
+// same shared-memory address at the same time: 435 us per gene; the lists decouple the lanes.)  Sums live in shared memory
+// (fp64 atomics on scattered addresses) and are flushed once per CTA.  Zero calls matter only to the burden scores of FLIPPED
+// rows (g' = 2 - g > 0): a per-gene constant F plus corrections at the non-zero calls.  A sample with more non-zero calls
+// than the list holds (common variants) is handled by re-reading its bytes.  grid (blocks, genes), 256 threads.
+constexpr int kSparseThreads = 256;
+constexpr int kSparseList = 12;
+__global__ void __launch_bounds__(kSparseThreads)
+k_tile_sparse(const TileGene* __restrict__ genes, int64_t N, const RowCounts* __restrict__ counts, const double* __restrict__ X, int C,
+              const double* __restrict__ resid, const double* __restrict__ vw, DosageStats* __restrict__ stats) {
+  __shared__ double sA[kTileRows][kTileRows + 1];
+  __shared__ double sS[kTileRows], sW[kTileRows], sB[kTileRows][kMaxC];
+  __shared__ double sfill[kTileRows];
+  __shared__ int8_t srole[kTileRows];   // 0 normal, 1 flipped, 2 monomorphic (ignored by the burden scores)
+  __shared__ int sF;
+  __shared__ double sbur[2][3 + kMaxC];
+  const TileGene tg = genes[blockIdx.y];
+  DosageStats* __restrict__ st = stats + tg.slot;
+  const int M = tg.M, tid = threadIdx.x;
+  for (int idx = tid; idx < kTileRows * (kTileRows + 1); idx += kSparseThreads) (&sA[0][0])[idx] = 0.0;
+  for (int idx = tid; idx < kTileRows * kMaxC; idx += kSparseThreads) (&sB[0][0])[idx] = 0.0;
+  if (tid < 2 * (3 + kMaxC)) (&sbur[0][0])[tid] = 0.0;
+  if (tid < kTileRows) {
+    sS[tid] = sW[tid] = 0.0;
+    double f = 0.0;
+    int role = 2;
+    if (tid < M) {
+      const RowCounts rc = counts[tg.var0 + tid];
+      const long long nobs = N - rc.bad;
+      f = nobs > 0 ? 2.0 * ((double)((long long)rc.n1 + 2ll * rc.n2) / (double)(2 * nobs)) : 0.0;
+      role = (st->cmin[tid] == st->cmax[tid]) ? 2 : ((st->csum[tid] > (double)N) ? 1 : 0);
+    }
+    sfill[tid] = f;
+    srole[tid] = (int8_t)role;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int F = 0;
+    for (int j = 0; j < M; ++j) F += (srole[j] == 1);
+    sF = F;
+  }
+  __syncthreads();
+  const int F = sF;
+  double bz[3 + kMaxC], bc[3 + kMaxC];   // per-thread burden partials: U, SS, nonref, SZ[]
+#pragma unroll
+  for (int l = 0; l < 3 + kMaxC; ++l) bz[l] = bc[l] = 0.0;
+  const int64_t nquads = (N + 3) >> 2;   // 4-sample groups; a chunk of 128 samples holds 32 of them
+  for (int64_t qd = (int64_t)blockIdx.x * kSparseThreads + tid; qd < nquads; qd += (int64_t)gridDim.x * kSparseThreads) {
+    const int64_t i0 = qd << 2;
+    const int8_t* __restrict__ base = tg.g + ((size_t)(i0 >> 7) * M) * 128 + (i0 & 127);   // row j at + j * 128
+    uint8_t lj[4][kSparseList], lc[4][kSparseList];
+    int cnt[4] = {0, 0, 0, 0};
+    // pass 1: record
+    for (int j = 0; j < M; ++j) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(base + (size_t)j * 128);
+      if (w == 0) continue;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t code = (w >> (8 * q)) & 0xFFu;
+        if (code == 0) continue;
+        if (cnt[q] < kSparseList) {
+          lj[q][cnt[q]] = (uint8_t)j;
+          lc[q][cnt[q]] = (uint8_t)code;
+        }
+        ++cnt[q];
+      }
+    }
+    // pass 2: arithmetic, sample by sample
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t i = i0 + q;
+      if (i >= N) continue;
+      const int n = cnt[q];
+      if (n == 0 && F == 0) continue;
+      const double r = resid[i], v = vw ? vw[i] : 1.0;
+      double x[kMaxC];
+#pragma unroll
+      for (int l = 0; l < kMaxC; ++l)
+        if (l < C) x[l] = X[(size_t)l * N + i];
+      int zc = 0;
+      const bool listed = n <= kSparseList;
+      // iterate the non-zero calls of this sample: from the list, or (overflow) by re-reading the sample's bytes
+      int a = 0, ja = -1;
+      for (;;) {
+        int code;
+        if (listed) {
+          if (a >= n) break;
+          ja = lj[q][a];
+          code = lc[q][a];
+        } else {
+          do { ++ja; } while (ja < M && base[(size_t)ja * 128 + q] == 0);
+          if (ja >= M) break;
+          code = base[(size_t)ja * 128 + q];
+        }
+        const double g = (code == 3) ? sfill[ja] : (double)code;
+        if (g != 0.0) {
+          const double gv = g * v;
+          atomicAdd(&sS[ja], g * r);
+          atomicAdd(&sW[ja], gv);
+#pragma unroll
+          for (int l = 0; l < kMaxC; ++l)
+            if (l < C) atomicAdd(&sB[ja][l], gv * x[l]);
+          atomicAdd(&sA[ja][ja], gv * g);
+          if (listed) {
+            for (int b = a + 1; b < n; ++b) {
+              const int jb = lj[q][b], cb = lc[q][b];
+              const double g2 = (cb == 3) ? sfill[jb] : (double)cb;
+              if (g2 != 0.0) atomicAdd(&sA[ja][jb], gv * g2);
+            }
+          } else {
+            for (int jb = ja + 1; jb < M; ++jb) {
+              const int cb = base[(size_t)jb * 128 + q];
+              if (cb == 0) continue;
+              const double g2 = (cb == 3) ? sfill[jb] : (double)cb;
+              if (g2 != 0.0) atomicAdd(&sA[ja][jb], gv * g2);
+            }
+          }
+          // burden indicator `(int)g' > 0` (src/Model.cpp:82-83) relative to a zero call of the same row
+          const int role = srole[ja];
+          if (role == 0) zc += ((int)g > 0);
+          else if (role == 1) zc -= !((int)(2.0 - g) > 0);
+        }
+        ++a;
+      }
+      const double z = (double)(F + zc);
+      if (z == 0.0) continue;
+      bz[0] += z * r;  bz[1] += v * z * z;  bz[2] += 1.0;
+      bc[0] += r;      bc[1] += v;          bc[2] += 1.0;
+#pragma unroll
+      for (int l = 0; l < kMaxC; ++l)
+        if (l < C) {
+          bz[3 + l] += v * z * x[l];
+          bc[3 + l] += v * x[l];
+        }
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < 3 + kMaxC; ++l) {
+    if (l >= 3 + C) break;
+    double a = bz[l], b = bc[l];
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((tid & 31) == 0) {
+      atomicAdd(&sbur[0][l], a);
+      atomicAdd(&sbur[1][l], b);
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < M * M; idx += kSparseThreads) {
+    const int a = idx / M, b = idx - a * M;
+    const double val = (a <= b) ? sA[a][b] : sA[b][a];   // only the upper triangle was accumulated
+    if (val != 0.0) atomicAdd(&st->A[a][b], val);
+  }
+  if (tid < M) {
+    if (sS[tid] != 0.0) atomicAdd(&st->s[tid], sS[tid]);
+    if (sW[tid] != 0.0) atomicAdd(&st->cw[tid], sW[tid]);
+    for (int l = 0; l < C; ++l)
+      if (sB[tid][l] != 0.0) atomicAdd(&st->B[tid][l], sB[tid][l]);
+  }
+  if (tid == 0) {
+    atomicAdd(&st->zegU, sbur[0][0]);  atomicAdd(&st->zegSS, sbur[0][1]);
+    atomicAdd(&st->cmcU, sbur[1][0]);  atomicAdd(&st->cmcSS, sbur[1][1]);
+    atomicAdd(&st->nonref, sbur[1][2]);
+    for (int l = 0; l < C; ++l) {
+      atomicAdd(&st->zegSZ[l], sbur[0][3 + l]);
+      atomicAdd(&st->cmcSZ[l], sbur[1][3 + l]);
+    }
+  }
+}
+
+// k_dosage_prepare for a batch of tile genes (blockIdx.x = gene)
+__global__ void __launch_bounds__(64)
+k_tile_prepare(const TileGene* __restrict__ genes, int n_genes, const DosageStats* __restrict__ st, const double* __restrict__ af,
+               const NullModel* __restrict__ nm, EngineParams prm, TailInput* __restrict__ out) {
+  if ((int)blockIdx.x >= n_genes) return;
+  const TileGene tg = genes[blockIdx.x];
+  dosage_prepare(st + tg.slot, tg.M, tg.has_af ? af + tg.var0 : nullptr, nm, prm, out + tg.slot);
 }
 
 }  // namespace rvt

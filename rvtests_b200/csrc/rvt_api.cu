@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <string>
 #include <vector>
@@ -39,6 +40,7 @@ struct DosGene {     // a pushed gene with non-hard-call values: handled by the 
   int M;
   double* dG;        // N x M column-major doubles, device (null: expand the gene's hard-call tiles at flush)
   bool has_af;
+  bool from_bed = false;   // arrived as 2-bit rows: code 3 in its tiles is a missing call to impute
   std::vector<double> af;
 };
 struct WideGene {    // a pushed gene of more than kMaxM variants: T tiles of consecutive variants (wide.cuh)
@@ -102,6 +104,9 @@ struct rvt_ctx {
   size_t cap_perm = 0;
   std::vector<rvt_perm_result> perm_out;
   std::vector<char> is_dos;        // per pending gene: took the fp64 path
+  // fp64 path: per-gene statistics / tail inputs, kept across flushes (cudaMalloc / cudaFree per flush cost 30-170 ms)
+  void *d_dos_st = nullptr, *d_dos_tin = nullptr, *d_dos_idx = nullptr, *d_dos_afd = nullptr, *d_dos_tg = nullptr;
+  size_t cap_dos_st = 0, cap_dos_tin = 0, cap_dos_idx = 0, cap_dos_afd = 0, cap_dos_tg = 0;
   // binary trait (logistic null model)
   bool binary = false;
   double *d_p = nullptr, *d_vw = nullptr;
@@ -300,7 +305,7 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum, ctx->d_p, ctx->d_vw};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum, ctx->d_p, ctx->d_vw, ctx->d_dos_st, ctx->d_dos_tin, ctx->d_dos_idx, ctx->d_dos_afd, ctx->d_dos_tg};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -461,7 +466,7 @@ static int null_model_alloc(rvt_ctx* ctx, int64_t N, int C) {
 // fixed-order reduction per round), the C x C solve and the stopping rule on the host.  Leaves p, v = p(1-p) of the LAST
 // round evaluated -- i.e. at the beta before the final update, exactly what GetPredicted / GetVariance return -- and
 // covB = (X'VX)^-1 of that round.
-static int logistic_null(rvt_ctx* ctx, double* covB /*C*C*/, double* vsum, double* xsum_w) {
+static int logistic_null(rvt_ctx* ctx, double* covB /*C*C*/, double* vsum, double* xsum_w, double* rsum) {
   const int64_t N = ctx->N;
   const int C = ctx->C;
   cudaStream_t st = ctx->stream;
@@ -544,6 +549,7 @@ static int logistic_null(rvt_ctx* ctx, double* covB /*C*C*/, double* vsum, doubl
     }
     for (int i = 0; i < C; ++i) covB[i * C + col] = e[i];
   }
+  *rsum = r[0];                                 // sum_i (y_i - p_i): not zero, p is one Newton step stale
   *vsum = D[0];                                 // column 0 of X is the intercept: D[0][l] = sum v x_l
   for (int l = 0; l < C; ++l) xsum_w[l] = D[l];
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->dbeta, beta.data(), sizeof(double) * C, cudaMemcpyHostToDevice, st));
@@ -562,8 +568,8 @@ int rvt_set_null_model(rvt_ctx* ctx, int64_t N, int C, const double* X, const do
   // (X'VX)^-1 in place of (X'X)^-1 (src/Model.h:2673-2681: ynull = GetPredicted(), v = GetVariance())
   for (int64_t i = 0; i < N; ++i)
     if (y[i] != 0.0 && y[i] != 1.0) CTX_FAIL(RVT_E_BADARG, "binary trait: phenotype values must be 0 or 1");
-  double covB[kMaxC * kMaxC], vsum = 0.0, xsw[kMaxC];
-  if ((rc = logistic_null(ctx, covB, &vsum, xsw))) return rc;
+  double covB[kMaxC * kMaxC], vsum = 0.0, xsw[kMaxC], rsum = 0.0;
+  if ((rc = logistic_null(ctx, covB, &vsum, xsw, &rsum))) return rc;
   std::vector<double> beta(C);
   RVT_CUDA_OK(cudaMemcpy(beta.data(), ctx->dbeta, sizeof(double) * C, cudaMemcpyDeviceToHost));
   k_logit_resid<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(N, ctx->dy, ctx->d_p, ctx->dy);
@@ -571,6 +577,7 @@ int rvt_set_null_model(rvt_ctx* ctx, int64_t N, int C, const double* X, const do
   NullModel h = ctx->h_nm;
   memcpy(h.xtx_inv, covB, sizeof(double) * C * C);
   h.binary = 1;
+  h.rsum = rsum;   // (the linear fit reports the sum of ITS residuals, ~0; the flip algebra of the fp64 path needs sum_i r_i)
   h.vw = ctx->d_vw;
   h.vsum_w = vsum;
   for (int l = 0; l < C; ++l) h.xsum_w[l] = xsw[l];
@@ -590,7 +597,14 @@ int rvt_set_null_residual(rvt_ctx* ctx, int64_t N, int C, const double* X, const
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->dy, resid, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
   rc = null_model_run(ctx, true, sigma2);
   if (rc) return rc;
-  // with a caller-supplied residual sum_i r_i is what it is: recompute it for the flip algebra
+  // with a caller-supplied residual sum_i r_i is what it is (the linear fit reports the sum of ITS residuals, ~0): the flip
+  // algebra of the fp64 path needs it.  It is the intercept component of X'r, which k_null_moments already reduced.
+  double rs = 0.0;
+  for (int64_t i = 0; i < N; ++i) rs += resid[i];
+  NullModel h = ctx->h_nm;
+  h.rsum = rs;
+  RVT_CUDA_OK(cudaMemcpy(ctx->d_nm, &h, sizeof(h), cudaMemcpyHostToDevice));
+  ctx->h_nm = h;
   return RVT_OK;
 }
 
@@ -863,7 +877,6 @@ int rvt_gene_push_bed(rvt_ctx* ctx, const uint8_t* bed, int M, int64_t stride, c
 // mean-imputed on the device (DataConsolidator::imputeGenotypeToMean) and handed to the fp64 path
 static int resolve_bed_missing(rvt_ctx* ctx) {
   if (ctx->bed_genes.empty()) return RVT_OK;
-  const int64_t N = ctx->N;
   std::vector<RowCounts> hc((size_t)ctx->n_var);
   RVT_CUDA_OK(cudaMemcpyAsync(hc.data(), ctx->d_counts, sizeof(RowCounts) * ctx->n_var, cudaMemcpyDeviceToHost, ctx->stream));
   RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -875,14 +888,11 @@ static int resolve_bed_missing(rvt_ctx* ctx) {
     if (ctx->slots[gi] > kMaxM)
       CTX_FAIL(RVT_E_UNSUPPORTED, "gene of %d variants holds missing calls: mean imputation (fp64 path) handles up to %d variants",
                ctx->slots[gi], kMaxM);
-    DosGene dg;
+    DosGene dg;   // stays in its int8 tiles: imputed on the fly by the tile statistics kernels (dosage.cuh)
     dg.gene_index = gi;
     dg.M = gd.M;
     dg.dG = nullptr;
-    RVT_CUDA_OK(cudaMalloc((void**)&dg.dG, sizeof(double) * (size_t)N * gd.M));
-    dim3 grid((unsigned)((N + 255) / 256), (unsigned)gd.M);
-    k_impute_tiled_f64<<<grid, 256, 0, ctx->stream>>>(gd.g, gd.M, N, ctx->d_counts + gd.var0, dg.dG);
-    RVT_CUDA_OK(cudaGetLastError());
+    dg.from_bed = true;
     dg.has_af = gd.has_af != 0;
     if (dg.has_af) dg.af.assign(ctx->af.begin() + gd.var0, ctx->af.begin() + gd.var0 + gd.M);
     ctx->dos.push_back(dg);
@@ -1314,14 +1324,25 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
 
 static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, bool to_device) {
   if (!ctx) return RVT_E_BADARG;
+  const bool trace = getenv("RVT_FLUSH_TRACE") != nullptr;   // diagnostics: host wall clock of the phases of a flush
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(ctx->stream);
+    fprintf(stderr, "[flush] %-24s %8.3f ms\n", what,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+  };
   const int n = (int)ctx->genes.size();
   if (n_out) *n_out = 0;
   if (n == 0) return RVT_OK;
   if (!out || cap < n) CTX_FAIL(RVT_E_BADARG, "result buffer too small: %d pending genes, cap %d", n, cap);
   RVT_CUDA_OK(cudaSetDevice(ctx->device));
   int rc;
+  mark("enter (copies landed)");
   if ((rc = launch_range(ctx, ctx->launched, n))) return rc;
+  mark("sweep + statistics");
   if ((rc = resolve_bed_missing(ctx))) return rc;
+  mark("missing-call check");
   const int64_t N = ctx->N;
   cudaStream_t st = ctx->stream;
   rvt_gene_result* d_res = ctx->d_res;
@@ -1352,21 +1373,35 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     // genes with dosage / imputed values: fp64 statistics, then the same tail (eigen, Davies, SKAT-O, burden);
     // their records overwrite what the hard-call pipeline produced for the same slots
     const int nd = (int)ctx->dos.size();
-    DosageStats* d_st = nullptr;
-    TailInput* d_tin = nullptr;
-    int* d_idx = nullptr;
-    double* d_afd = nullptr;
-    RVT_CUDA_OK(cudaMalloc((void**)&d_st, sizeof(DosageStats) * nd));
-    RVT_CUDA_OK(cudaMalloc((void**)&d_tin, sizeof(TailInput) * nd));
-    RVT_CUDA_OK(cudaMalloc((void**)&d_idx, sizeof(int) * nd));
-    RVT_CUDA_OK(cudaMalloc((void**)&d_afd, sizeof(double) * nd * kTileRows));
+    if ((rc = ensure(ctx, &ctx->d_dos_st, &ctx->cap_dos_st, (size_t)nd, sizeof(DosageStats)))) return rc;
+    if ((rc = ensure(ctx, &ctx->d_dos_tin, &ctx->cap_dos_tin, (size_t)nd, sizeof(TailInput)))) return rc;
+    if ((rc = ensure(ctx, &ctx->d_dos_idx, &ctx->cap_dos_idx, (size_t)nd, sizeof(int)))) return rc;
+    if ((rc = ensure(ctx, &ctx->d_dos_afd, &ctx->cap_dos_afd, (size_t)nd * kTileRows, sizeof(double)))) return rc;
+    DosageStats* d_st = (DosageStats*)ctx->d_dos_st;
+    TailInput* d_tin = (TailInput*)ctx->d_dos_tin;
+    int* d_idx = (int*)ctx->d_dos_idx;
+    double* d_afd = (double*)ctx->d_dos_afd;
     RVT_CUDA_OK(cudaMemsetAsync(d_st, 0, sizeof(DosageStats) * nd, st));
     std::vector<int> idx(nd);
-    double* d_expand = nullptr;   // scratch for genes that arrive as hard-call tiles (binary trait)
+    double* d_expand = nullptr;   // scratch for tile genes without the engine's own counts (loaded cohort, binary trait)
+    std::vector<TileGene> tgs;
     for (int i = 0; i < nd; ++i) {
       DosGene& dg = ctx->dos[i];
       idx[i] = dg.gene_index;
       const bool from_tiles = dg.dG == nullptr;
+      if (from_tiles && ctx->genes[dg.gene_index].counted) {
+        // statistics straight from the int8 tiles, all such genes in one batched launch below
+        const GeneDesc& gd = ctx->genes[dg.gene_index];
+        TileGene tg;
+        tg.g = gd.g;
+        tg.M = gd.M;
+        tg.has_af = gd.has_af;
+        tg.var0 = gd.var0;
+        tg.slot = i;
+        tg.allow_missing = dg.from_bed ? 1 : 0;
+        tgs.push_back(tg);
+        continue;
+      }
       if (from_tiles) {
         if (!d_expand) RVT_CUDA_OK(cudaMalloc((void**)&d_expand, sizeof(double) * (size_t)N * kMaxM));
         const GeneDesc& gd = ctx->genes[dg.gene_index];
@@ -1380,6 +1415,25 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       k_dosage_stats<<<ctx->sm_count * 2, kDosThreads, 0, st>>>(dg.dG, N, dg.M, ctx->dX, ctx->C, ctx->dresid, ctx->binary ? ctx->d_vw : nullptr, d_st + i);
       k_dosage_prepare<<<1, 64, 0, st>>>(d_st + i, dg.M, dg.has_af ? d_afd + (size_t)i * kTileRows : nullptr, ctx->d_nm, prm, d_tin + i);
       if (from_tiles) dg.dG = nullptr;   // not owned
+    }
+    TileGene* d_tg = nullptr;
+    if (!tgs.empty()) {
+      const int ntg = (int)tgs.size();
+      if ((rc = ensure(ctx, &ctx->d_dos_tg, &ctx->cap_dos_tg, (size_t)ntg, sizeof(TileGene)))) return rc;
+      d_tg = (TileGene*)ctx->d_dos_tg;
+      RVT_CUDA_OK(cudaMemcpyAsync(d_tg, tgs.data(), sizeof(TileGene) * ntg, cudaMemcpyHostToDevice, st));
+      const int64_t nblk = ((N + 3) / 4 + kSparseThreads - 1) / kSparseThreads;
+      const unsigned bx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nblk, (8 * (int64_t)ctx->sm_count + ntg - 1) / ntg));
+      for (int t0 = 0; t0 < ntg; t0 += 32768) {   // (grid.y limit)
+        const int nt = std::min(32768, ntg - t0);
+        k_tile_cols<<<nt, kTileRows, 0, st>>>(d_tg + t0, nt, N, ctx->d_counts, d_st);
+        k_tile_sparse<<<dim3(bx, (unsigned)nt), kSparseThreads, 0, st>>>(d_tg + t0, N, ctx->d_counts, ctx->dX, ctx->C, ctx->dresid,
+                                                                         ctx->binary ? ctx->d_vw : nullptr, d_st);
+        k_tile_prepare<<<nt, 64, 0, st>>>(d_tg + t0, nt, d_st, ctx->d_af, ctx->d_nm, prm, d_tin);
+        launches += 3;
+      }
+      RVT_CUDA_OK(cudaGetLastError());
+      RVT_CUDA_OK(cudaStreamSynchronize(st));   // `tgs` is a host temporary
     }
     RVT_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
     if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nd, sizeof(QagsScratch)))) return rc;
@@ -1396,12 +1450,12 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     RVT_CUDA_OK(cudaGetLastError());
     RVT_CUDA_OK(cudaStreamSynchronize(st));
     launches += 3 * nd + 1;
-    cudaFree(d_st); cudaFree(d_tin); cudaFree(d_idx); cudaFree(d_afd);
     if (d_expand) cudaFree(d_expand);
     for (auto& dg : ctx->dos)
       if (dg.dG) cudaFree(dg.dG);
     ctx->dos.clear();
   }
+  mark("fp64 path");
   if ((rc = run_wide(ctx, d_res, &launches))) return rc;
   if ((rc = run_perm(ctx, d_res, n, &launches))) return rc;
   RVT_CUDA_OK(cudaMemcpyAsync(out, d_res, sizeof(rvt_gene_result) * n, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));

@@ -63,3 +63,33 @@ def test_binary_trait_rejects_other_codes(engine_cls):
     with pytest.raises(rvtests_b200.RvtError):
         eng.set_null_model(X, np.arange(10.0), binary=True)      # case/control must already be 0/1 at this boundary
     eng.close()
+
+
+def test_dense_genotypes_take_the_rescan_path(engine_cls, oracle):
+    """common variants: most samples carry more non-zero calls than the per-sample list of k_tile_sparse holds, so the
+    kernel re-reads their bytes; SKAT and Zeggini against the oracle (the CMC indicator is constant here: skipped)"""
+    from oracle import binary_oracle as BIN
+    from rvtests_b200.synth import pack_bed
+    O = oracle
+    seed, N, M, C = 113, 1300, 40, 2
+    G, X, _ = make_problem(O, seed, N, M, C, maf=np.linspace(0.2, 0.45, M), n_flip=3)
+    rng = np.random.default_rng(seed)
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(0.3 - 0.5 * X[:, 1]))).astype(np.float64)
+    nm = BIN.fit_null_logistic(X, y)
+    assert np.median((G != 0).sum(axis=1)) > 14
+    eng = engine_cls(0)
+    eng.set_null_model(X, y, binary=True)
+    af = af_of(G)
+    eng.push_bed(pack_bed(G.T), af)
+    r = eng.flush()[0]
+    ref = BIN.gene(G.astype(float), af, X, nm)
+    assert int(r["status"]) == 0 and int(r["m_poly"]) == ref["m_poly"]
+    ctx = dict(Q=(r["Q"], ref["Q"]), lam=(r["lambda_max"], ref["lam"][0]), p=(r["p_skat"], ref["p_skat"]),
+               zegU=(r["zeg_U"], ref["zeg"]["U"]), zegV=(r["zeg_V"], ref["zeg"]["V"]))
+    assert rel(r["Q"], ref["Q"]) <= 1e-6, ctx
+    assert rel(r["lambda_max"], ref["lam"][0]) <= 1e-7, ctx
+    assert rel(r["p_skat"], ref["p_skat"]) <= 1e-4
+    assert abs(r["zeg_U"] - ref["zeg"]["U"]) <= 1e-6 * max(abs(ref["zeg"]["U"]), np.sqrt(ref["zeg"]["V"]))
+    assert rel(r["zeg_V"], ref["zeg"]["V"]) <= 1e-6 and rel(r["zeg_p"], ref["zeg"]["p"]) <= 1e-4
+    assert int(r["cmc_nonref"]) == ref["cmc"]["nonref"]
+    eng.close()
