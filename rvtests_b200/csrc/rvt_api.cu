@@ -107,6 +107,9 @@ struct rvt_ctx {
   // fp64 path: per-gene statistics / tail inputs, kept across flushes (cudaMalloc / cudaFree per flush cost 30-170 ms)
   void *d_dos_st = nullptr, *d_dos_tin = nullptr, *d_dos_idx = nullptr, *d_dos_afd = nullptr, *d_dos_tg = nullptr;
   size_t cap_dos_st = 0, cap_dos_tin = 0, cap_dos_idx = 0, cap_dos_afd = 0, cap_dos_tg = 0;
+  // scratch of the meta / mixed-model flushes, kept across calls for the same reason
+  void* d_scr[8] = {};
+  size_t cap_scr[8] = {};
   // binary trait (logistic null model)
   bool binary = false;
   double *d_p = nullptr, *d_vw = nullptr;
@@ -308,6 +311,8 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
                   ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum, ctx->d_p, ctx->d_vw, ctx->d_dos_st, ctx->d_dos_tin, ctx->d_dos_idx, ctx->d_dos_afd, ctx->d_dos_tg};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (void* p : ctx->d_scr)
     if (p) cudaFree(p);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
@@ -1608,21 +1613,28 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   double* d_band = nullptr;
   GeneDesc* d_desc = nullptr;
   uint8_t* d_flags0 = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(d_jmax); cudaFree(d_B); cudaFree(d_poly); cudaFree(d_v); cudaFree(d_band); cudaFree(d_desc); cudaFree(d_flags0);
-  };
+  auto cleanup = [&]() {};   // (the buffers below persist in the context)
   const int batch = 1024;
   const size_t ndesc = std::max<size_t>((size_t)T, pairs.size());
-  cudaError_t e = cudaMalloc((void**)&d_jmax, sizeof(int) * nv);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_B, sizeof(double) * nv * kMaxC);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_poly, nv);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_v, sizeof(rvt_variant_result) * nv);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_desc, sizeof(GeneDesc) * ndesc);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_flags0, (size_t)nv + kTileRows);
-  if (e == cudaSuccess && band) e = cudaMalloc((void**)&d_band, sizeof(double) * nv * (size_t)(wmax + 1));
-  if (e != cudaSuccess) {
-    cleanup();
-    CTX_FAIL(RVT_E_CUDA, "meta: cudaMalloc: %s", cudaGetErrorString(e));
+  {
+    const size_t need[7] = {sizeof(int) * (size_t)nv, sizeof(double) * (size_t)nv * kMaxC, (size_t)nv, sizeof(rvt_variant_result) * (size_t)nv,
+                            sizeof(GeneDesc) * ndesc, (size_t)nv + kTileRows, band ? sizeof(double) * (size_t)nv * (size_t)(wmax + 1) : 0};
+    for (int k = 0; k < 7; ++k)
+      if (need[k] > ctx->cap_scr[k]) {   // contents are rewritten every call: no copy on growth
+        if (ctx->d_scr[k]) cudaFree(ctx->d_scr[k]);
+        ctx->d_scr[k] = nullptr;
+        ctx->cap_scr[k] = 0;
+        cudaError_t e = cudaMalloc(&ctx->d_scr[k], need[k]);
+        if (e != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "meta: cudaMalloc: %s", cudaGetErrorString(e));
+        ctx->cap_scr[k] = need[k];
+      }
+    d_jmax = (int*)ctx->d_scr[0];
+    d_B = (double*)ctx->d_scr[1];
+    d_poly = (uint8_t*)ctx->d_scr[2];
+    d_v = (rvt_variant_result*)ctx->d_scr[3];
+    d_desc = (GeneDesc*)ctx->d_scr[4];
+    d_flags0 = (uint8_t*)ctx->d_scr[5];
+    d_band = band ? (double*)ctx->d_scr[6] : nullptr;
   }
   if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)batch * S, sizeof(SweepPartial)))) { cleanup(); return rc; }
   RVT_CUDA_OK(cudaMemcpyAsync(d_jmax, jmax.data(), sizeof(int) * nv, cudaMemcpyHostToDevice, st));

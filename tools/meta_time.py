@@ -19,17 +19,23 @@ eng.set_null_model(X, y)
 rng = np.random.default_rng(3)
 maf = 10 ** rng.uniform(-3, np.log10(0.3), nv)
 t = time.perf_counter()
-for b0 in range(0, nv, 64):                      # hard calls from two uniform bytes per genotype: P(g >= 1), P(g = 2)
+blocks = []
+for b0 in range(0, nv, 64):                      # hard calls from one uniform 16-bit draw per genotype: P(g >= 1), P(g = 2)
     m = maf[b0:b0 + 64, None]
     u = rng.integers(0, 65536, size=(64, N), dtype=np.uint16)
-    G = (u < (65536 * (1 - (1 - m) ** 2))).astype(np.int8) + (u < (65536 * m * m)).astype(np.int8)
-    eng.push_i8(G, None)
-print(f"{nv} variants x {N} samples generated and pushed in {time.perf_counter() - t:.1f} s", flush=True)
+    blocks.append((u < (65536 * (1 - (1 - m) ** 2))).astype(np.int8) + (u < (65536 * m * m)).astype(np.int8))
+print(f"{nv} variants x {N} samples generated in {time.perf_counter() - t:.1f} s", flush=True)
 pos = (1000 * np.arange(nv)).astype(np.int32)
 chrom = np.ones(nv, dtype=np.int32)
-t = time.perf_counter()
-vout, band, wmax = eng.meta_flush(nv, pos, chrom, window)
-dt = time.perf_counter() - t
+for rep in range(2):                             # the first flush pays the one-off allocations and tensor-map encodes
+    t = time.perf_counter()
+    for G in blocks:
+        eng.push_i8(G, None)
+    t_push = time.perf_counter() - t
+    t = time.perf_counter()
+    vout, band, wmax = eng.meta_flush(nv, pos, chrom, window)
+    dt = time.perf_counter() - t
+    print(f"rep {rep}: push {t_push:.3f} s (pageable host blocks), flush {dt:.3f} s", flush=True)
 pairs = int(np.sum(~np.isnan(band)))
 tiles = nv // 64
 units = tiles + sum(min(tiles - 1 - k, (wmax + 63) // 64 + 1) for k in range(tiles))
