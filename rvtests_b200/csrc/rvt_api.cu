@@ -209,6 +209,22 @@ static int ensure(rvt_ctx* ctx, void** p, size_t* cap, size_t need, size_t elem)
   return RVT_OK;
 }
 
+// scratch slot k of the context, at least `bytes` large; contents are NOT preserved on growth
+static int scratch(rvt_ctx* ctx, int k, size_t bytes, void** out) {
+  if (bytes > ctx->cap_scr[k]) {
+    if (ctx->d_scr[k]) {
+      RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_scr[k]);
+    }
+    ctx->d_scr[k] = nullptr;
+    ctx->cap_scr[k] = 0;
+    RVT_CUDA_OK(cudaMalloc(&ctx->d_scr[k], bytes));
+    ctx->cap_scr[k] = bytes;
+  }
+  *out = ctx->d_scr[k];
+  return RVT_OK;
+}
+
 // per-variant device arrays share one capacity
 static int ensure_var(rvt_ctx* ctx, size_t need) {
   if (need <= ctx->cap_var) return RVT_OK;
@@ -1800,10 +1816,10 @@ int rvt_lmm_flush(rvt_ctx* ctx, rvt_lmm_result* out, int64_t cap) {
   GeneDesc* d_units = nullptr;
   double* d_acc = nullptr;
   rvt_lmm_result* d_out = nullptr;
-  RVT_CUDA_OK(cudaMalloc((void**)&d_units, sizeof(GeneDesc) * nb));
-  RVT_CUDA_OK(cudaMalloc((void**)&d_acc, sizeof(double) * (size_t)nb * kTileRows * kLmmAcc));
-  RVT_CUDA_OK(cudaMalloc((void**)&d_out, sizeof(rvt_lmm_result) * nv));
-  auto cleanup = [&]() { cudaFree(d_units); cudaFree(d_acc); cudaFree(d_out); };
+  if ((rc = scratch(ctx, 0, sizeof(GeneDesc) * nb, (void**)&d_units))) return rc;
+  if ((rc = scratch(ctx, 1, sizeof(double) * (size_t)nb * kTileRows * kLmmAcc, (void**)&d_acc))) return rc;
+  if ((rc = scratch(ctx, 2, sizeof(rvt_lmm_result) * nv, (void**)&d_out))) return rc;
+  auto cleanup = [&]() {};   // (scratch slots persist in the context)
   std::vector<GeneDesc> units(nb);
   for (int g = 0; g < ngen; ++g) {
     const GeneDesc& gd = ctx->genes[g];
