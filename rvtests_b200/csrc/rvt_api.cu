@@ -95,7 +95,7 @@ struct rvt_ctx {
   uint8_t* d_zero_flags = nullptr; // "every row normal" flags for the tile sweeps of wide genes
   size_t cap_zero_flags = 0;
   // permutation test (perm.cuh): options, rand() stream position, scratch, records of the last flush
-  int perm_n = 0, perm_batch = 256;
+  int perm_n = 0, perm_batch = 512;   // (28.6 k perm/s at 256, 37.4 k at 1024 for 500 000 x 50: profiles/r01d_perm_time.txt)
   double perm_alpha = 0.05;
   uint64_t perm_pos = 0;           // rand() values consumed so far (the reference's process-wide stream)
   uint32_t perm_seed = 1;          // glibc's default state == srand(1); the reference never seeds
