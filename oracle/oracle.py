@@ -160,6 +160,94 @@ def ref_gsl():
     return _lib_cache["gsl"]
 
 
+def ref_skat():
+    """The reference's own Skat.cpp / SkatO.cpp / LinearRegression.cpp / LinearRegressionScoreTest.cpp,
+    compiled unmodified against oracle/eigen_standin + the vendored GSL (oracle/Makefile,
+    oracle/ref_skat_shim.cpp).  None when oracle/_ref was never built."""
+    if "skat" not in _lib_cache:
+        path = os.path.join(_HERE, "_ref", "libskat_ref.so")
+        if not os.path.exists(path):
+            _lib_cache["skat"] = None
+        else:
+            L = C.CDLL(path)
+            L.ref_skat_fit.restype = C.c_int
+            L.ref_skat_fit.argtypes = [C.c_int, C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p,
+                                       _dbl_p, _dbl_p, C.c_int, _dbl_p, _dbl_p]
+            L.ref_skato_fit.restype = C.c_int
+            L.ref_skato_fit.argtypes = [C.c_int, C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p,
+                                        C.c_char_p, _dbl_p, _dbl_p, _dbl_p]
+            L.ref_linear_fit.restype = C.c_int
+            L.ref_linear_fit.argtypes = [C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p]
+            L.ref_score_test.restype = C.c_int
+            L.ref_score_test.argtypes = [C.c_int, C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, C.c_int,
+                                         _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p]
+            _lib_cache["skat"] = L
+    return _lib_cache["skat"]
+
+
+def ref_skat_fit(res, v, X, G, w, res_perm=None):
+    """Skat::Fit of the reference build on (N,) res, (N,) v, (N,C) X, (N,M) G (already flipped to the minor
+    allele, polymorphic columns only), (M,) w (squared Beta densities, src/Model.h:2644-2661).
+    Returns dict(rc, Q, pvalue[, q_perm])."""
+    Gc = np.asfortranarray(G, dtype=np.float64)
+    Xc = np.asfortranarray(X, dtype=np.float64)
+    N, M = Gc.shape
+    res = np.ascontiguousarray(res, dtype=np.float64)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    Q, p = C.c_double(0), C.c_double(0)
+    n_perm, rp, qp = 0, None, None
+    if res_perm is not None:
+        rp = np.ascontiguousarray(res_perm, dtype=np.float64)
+        n_perm = rp.shape[0]
+        qp = np.zeros(n_perm)
+    rc = ref_skat().ref_skat_fit(N, M, Xc.shape[1], _p(res), _p(v), _p(Xc), _p(Gc), _p(w), C.byref(Q), C.byref(p),
+                                 n_perm, _p(rp) if n_perm else None, _p(qp) if n_perm else None)
+    out = dict(rc=rc, Q=Q.value, pvalue=p.value)
+    if n_perm:
+        out["q_perm"] = qp
+    return out
+
+
+def ref_skato_fit(res, v, X, G, w, binary=False):
+    """SkatO::Fit of the reference build; w are the UN-squared Beta densities (src/Model.h:2799-2813)."""
+    Gc = np.asfortranarray(G, dtype=np.float64)
+    Xc = np.asfortranarray(X, dtype=np.float64)
+    N, M = Gc.shape
+    res = np.ascontiguousarray(res, dtype=np.float64)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    Q, rho, p = C.c_double(0), C.c_double(0), C.c_double(0)
+    rc = ref_skat().ref_skato_fit(N, M, Xc.shape[1], _p(res), _p(v), _p(Xc), _p(Gc), _p(w), b"D" if binary else b"C",
+                                  C.byref(Q), C.byref(rho), C.byref(p))
+    return dict(rc=rc, Q=Q.value, rho=rho.value, pvalue=p.value)
+
+
+def ref_linear_fit(X, y):
+    """LinearRegression::FitLinearModel of the reference build."""
+    Xc = np.asfortranarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    N, Cc = Xc.shape
+    beta, resid, pred, covB = np.zeros(Cc), np.zeros(N), np.zeros(N), np.zeros((Cc, Cc), order="F")
+    s2 = C.c_double(0)
+    rc = ref_skat().ref_linear_fit(N, Cc, _p(Xc), _p(y), _p(beta), _p(resid), _p(pred), C.byref(s2), _p(covB))
+    return dict(rc=rc, beta=beta, resid=resid, predicted=pred, sigma2=s2.value, covB=covB)
+
+
+def ref_score_test(Xnull, y, Xcol, force_matrix=False):
+    """LinearRegressionScoreTest::FitNullModel + TestCovariate of the reference build; Xcol (N,) or (N, M)."""
+    Xc = np.asfortranarray(Xnull, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    g = np.asfortranarray(np.asarray(Xcol, dtype=np.float64).reshape(len(y), -1))
+    N, Cc = Xc.shape
+    M = g.shape[1]
+    U, V, beta = np.zeros(M), np.zeros((M, M), order="F"), np.zeros(M)
+    stat, p, s2 = C.c_double(0), C.c_double(0), C.c_double(0)
+    rc = ref_skat().ref_score_test(N, Cc, M, _p(Xc), _p(y), _p(g), int(force_matrix), _p(U), _p(V), _p(beta),
+                                   C.byref(stat), C.byref(p), C.byref(s2))
+    return dict(rc=rc, U=U, V=V, beta=beta, stat=stat.value, pvalue=p.value, sigma2=s2.value)
+
+
 # ------------------------------------------------------------------------------------------------
 # thin numpy-level helpers
 # ------------------------------------------------------------------------------------------------

@@ -1,0 +1,134 @@
+// oracle/ref_skat_shim.cpp -- TEST INFRASTRUCTURE ONLY.
+// extern "C" doors onto the REFERENCE's own per-gene statistics code, compiled UNMODIFIED from where
+// it lies under /root/reference into oracle/_ref/libskat_ref.so by oracle/Makefile:
+//   regression/Skat.cpp, SkatO.cpp, LinearRegression.cpp, LinearRegressionScoreTest.cpp,
+//   EigenMatrixInterface.cpp, GSLIntegration.cpp, MixtureChiSquare.cpp (+ qfc.c), cdflib.cpp,
+//   base/MathMatrix.cpp, base/MathVector.cpp (+ whatever of base/ they need to link),
+// against (i) GSL 1.16 built from the tarball the reference vendors and (ii) oracle/eigen_standin --
+// a from-scratch stand-in for the Eigen API those files use (Eigen itself is downloaded by the
+// reference's build and is absent here; see eigen_standin/third/eigen/Eigen/Core for what that
+// does and does not pin).  Nothing from the reference is copied into this repository: this file
+// only calls its public classes (regression/Skat.h:7-45, SkatO.h:7-47, LinearRegression.h:10-60,
+// LinearRegressionScoreTest.h:8-52).  All matrices cross the door column-major, like base/MathMatrix.h:34.
+#include <cstring>
+
+#include "base/MathMatrix.h"
+#include "base/MathVector.h"
+#include "regression/LinearRegression.h"
+#include "regression/LinearRegressionScoreTest.h"
+#include "regression/Skat.h"
+#include "regression/SkatO.h"
+
+namespace {
+void to_matrix(const double* p, int r, int c, Matrix* m) {
+  m->Dimension(r, c);
+  for (int j = 0; j < c; ++j)
+    for (int i = 0; i < r; ++i) (*m)(i, j) = p[(size_t)j * r + i];
+}
+void to_vector(const double* p, int n, Vector* v) {
+  v->Dimension(n);
+  for (int i = 0; i < n; ++i) (*v)[i] = p[i];
+}
+void from_matrix(const Matrix& m, double* p) {
+  for (int j = 0; j < m.cols; ++j)
+    for (int i = 0; i < m.rows; ++i) p[(size_t)j * m.rows + i] = m(i, j);
+}
+}  // namespace
+
+extern "C" {
+// Skat::Fit (regression/Skat.cpp:29-105) as SkatTest::fit calls it (src/Model.h:2700-2702);
+// q_perm[k] = Skat::GetQFromNewResidual (Skat.cpp:107-116) for n_perm further residual vectors.
+int ref_skat_fit(int N, int M, int C, const double* res, const double* v, const double* X,
+                 const double* G, const double* w, double* Q, double* p, int n_perm,
+                 const double* res_perm, double* q_perm) {
+  Vector res_G, v_G, w_G;
+  Matrix X_G, G_G;
+  to_vector(res, N, &res_G);
+  to_vector(v, N, &v_G);
+  to_vector(w, M, &w_G);
+  to_matrix(X, N, C, &X_G);
+  to_matrix(G, N, M, &G_G);
+  Skat skat;
+  skat.Reset();
+  const int rc = skat.Fit(res_G, v_G, X_G, G_G, w_G);
+  *Q = skat.GetQ();
+  *p = skat.GetPvalue();
+  for (int k = 0; k < n_perm; ++k) {
+    Vector r;
+    to_vector(res_perm + (size_t)k * N, N, &r);
+    q_perm[k] = skat.GetQFromNewResidual(r);
+  }
+  return rc;
+}
+
+// SkatO::Fit (regression/SkatO.cpp:497-516 -> :100-282) as SkatOTest::fit calls it (src/Model.h:2854-2858);
+// type "C" (quantitative) or "D" (binary).
+int ref_skato_fit(int N, int M, int C, const double* res, const double* v, const double* X,
+                  const double* G, const double* w, const char* type, double* Q, double* rho,
+                  double* p) {
+  Vector res_G, v_G, w_G;
+  Matrix X_G, G_G;
+  to_vector(res, N, &res_G);
+  to_vector(v, N, &v_G);
+  to_vector(w, M, &w_G);
+  to_matrix(X, N, C, &X_G);
+  to_matrix(G, N, M, &G_G);
+  SkatO skato;
+  skato.Reset();
+  const int rc = skato.Fit(res_G, v_G, X_G, G_G, w_G, type);
+  *Q = skato.GetQ();
+  *rho = skato.GetRho();
+  *p = skato.GetPvalue();
+  return rc;
+}
+
+// LinearRegression::FitLinearModel (regression/LinearRegression.cpp:20-69)
+int ref_linear_fit(int N, int C, const double* X, const double* y, double* beta, double* resid,
+                   double* predicted, double* sigma2, double* covB) {
+  Matrix X_G;
+  Vector y_G;
+  to_matrix(X, N, C, &X_G);
+  to_vector(y, N, &y_G);
+  LinearRegression lr;
+  const bool ok = lr.FitLinearModel(X_G, y_G);
+  for (int i = 0; i < C; ++i) beta[i] = lr.GetCovEst()[i];
+  for (int i = 0; i < N; ++i) {
+    resid[i] = lr.GetResiduals()[i];
+    predicted[i] = lr.GetPredicted()[i];
+  }
+  *sigma2 = lr.GetSigma2();
+  from_matrix(lr.GetCovB(), covB);
+  return ok ? 0 : -1;
+}
+
+// LinearRegressionScoreTest::FitNullModel + TestCovariate(Xnull, y, Xcol) -- the single-column form
+// the burden tests use (regression/LinearRegressionScoreTest.cpp:27-113; callers src/Model.h CMCTest /
+// ZegginiTest ::fit) -- and, when M > 1 or force_matrix, the matrix form (:173-263).
+int ref_score_test(int N, int C, int M, const double* Xnull, const double* y, const double* Xcol,
+                   int force_matrix, double* U, double* V, double* beta, double* stat, double* p,
+                   double* sigma2) {
+  Matrix Xn;
+  Vector y_G;
+  to_matrix(Xnull, N, C, &Xn);
+  to_vector(y, N, &y_G);
+  LinearRegressionScoreTest st;
+  if (!st.FitNullModel(Xn, y_G)) return -2;
+  bool ok;
+  if (M == 1 && !force_matrix) {
+    Vector xc;
+    to_vector(Xcol, N, &xc);
+    ok = st.TestCovariate(Xn, y_G, xc);
+  } else {
+    Matrix xc;
+    to_matrix(Xcol, N, M, &xc);
+    ok = st.TestCovariate((const Matrix&)Xn, (const Vector&)y_G, (const Matrix&)xc);
+  }
+  from_matrix(st.GetU(), U);
+  from_matrix(st.GetV(), V);
+  from_matrix(st.GetBeta(), beta);
+  *stat = st.GetStat();
+  *p = st.GetPvalue();
+  *sigma2 = st.GetSigma2();
+  return ok ? 0 : -1;
+}
+}
