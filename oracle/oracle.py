@@ -181,8 +181,28 @@ def ref_skat():
             L.ref_score_test.restype = C.c_int
             L.ref_score_test.argtypes = [C.c_int, C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, C.c_int,
                                          _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p]
+            L.ref_skat_perm.restype = C.c_int
+            L.ref_skat_perm.argtypes = [C.c_int, C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, C.c_int,
+                                        C.c_double, C.c_uint, _dbl_p, _int_p, _int_p, _int_p, _dbl_p, _dbl_p]
             _lib_cache["skat"] = L
     return _lib_cache["skat"]
+
+
+def ref_skat_perm(res, v, X, G, w, n_perm=10000, alpha=0.05, reseed=1):
+    """The permutation loop of SkatTest::fit (src/Model.h:2707-2717) run by the reference build: its own permute(),
+    Permutation and Skat::GetQFromNewResidual on the process-wide glibc rand() stream (reseed=1: fresh process)."""
+    Gc = np.asfortranarray(G, dtype=np.float64)
+    Xc = np.asfortranarray(X, dtype=np.float64)
+    N, M = Gc.shape
+    res = np.ascontiguousarray(res, dtype=np.float64)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    stat, p = C.c_double(0), C.c_double(0)
+    a, g, e = C.c_int(0), C.c_int(0), C.c_int(0)
+    q = np.zeros(max(n_perm, 1))
+    rc = ref_skat().ref_skat_perm(N, M, Xc.shape[1], _p(res), _p(v), _p(Xc), _p(Gc), _p(w), int(n_perm), float(alpha),
+                                  int(reseed), C.byref(stat), C.byref(a), C.byref(g), C.byref(e), C.byref(p), _p(q))
+    return dict(rc=rc, stat=stat.value, actual=a.value, greater=g.value, equal=e.value, p=p.value, q=q[: a.value].copy())
 
 
 def ref_skat_fit(res, v, X, G, w, res_perm=None):

@@ -132,3 +132,53 @@ int ref_score_test(int N, int C, int M, const double* Xnull, const double* y, co
   return ok ? 0 : -1;
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// A6: the permutation loop of SkatTest::fit (src/Model.h:2707-2717) with the reference's own
+// permute() (src/LinearAlgebra.h:8-21: Fisher-Yates on glibc rand()), Permutation bookkeeping
+// (src/Permutation.h:49-98: init/next/add/getPvalue, early stop at numPerm * alpha * 2) and
+// Skat::GetQFromNewResidual (regression/Skat.cpp:107-116).
+// ------------------------------------------------------------------------------------------------
+#include <cmath>
+#include <cstdlib>
+
+#include "third/eigen/Eigen/Core"
+#include "src/LinearAlgebra.h"
+#include "src/Permutation.h"
+
+extern "C" int ref_skat_perm(int N, int M, int C, const double* res, const double* v, const double* X,
+                             const double* G, const double* w, int n_perm, double alpha, unsigned reseed,
+                             double* stat, int* actual_perm, int* num_greater, int* num_equal,
+                             double* p_perm, double* q_out) {
+  Vector res_G, v_G, w_G;
+  Matrix X_G, G_G;
+  to_vector(res, N, &res_G);
+  to_vector(v, N, &v_G);
+  to_vector(w, M, &w_G);
+  to_matrix(X, N, C, &X_G);
+  to_matrix(G, N, M, &G_G);
+  if (reseed) srand(reseed);  // a fresh process starts as after srand(1)
+  Skat skat;
+  skat.Reset();
+  const int rc = skat.Fit(res_G, v_G, X_G, G_G, w_G);
+  *stat = skat.GetQ();
+  Permutation perm(n_perm, alpha);
+  Vector permutedRes = res_G;
+  perm.init(*stat);
+  int k = 0, greater = 0, equal = 0;
+  while (perm.next()) {
+    permute(&permutedRes);
+    const double s = skat.GetQFromNewResidual(permutedRes);
+    perm.add(s);
+    // Permutation keeps its counters private and only prints them: mirror add() for the caller
+    if (s > *stat) ++greater;
+    if (s == *stat) ++equal;
+    if (q_out) q_out[k] = s;
+    ++k;
+  }
+  *actual_perm = k;
+  *num_greater = greater;
+  *num_equal = equal;
+  *p_perm = perm.getPvalue();
+  return rc;
+}

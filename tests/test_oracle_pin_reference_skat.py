@@ -176,3 +176,37 @@ def test_live_reference_build(oracle, case):
             assert abs(out.cmc_U - sc["U"][0]) <= 1e-9 * max(abs(sc["U"][0]), np.sqrt(sc["V"][0, 0]))
             assert rel(out.cmc_V, sc["V"][0, 0]) <= 1e-9
             assert rel(out.cmc_p, sc["pvalue"]) <= 1e-8
+
+
+PERM = [(301, 200, 6, 1, 400, 0.05), (302, 1501, 20, 3, 300, 0.05), (303, 640, 11, 2, 250, 1.0)]
+
+
+def test_live_permutation_loop(oracle):
+    """A6: the oracle's permutation loop against the reference's own permute() + Permutation + Skat::GetQFromNewResidual
+    (src/LinearAlgebra.h:8-21, src/Permutation.h:49-98, regression/Skat.cpp:107-116) on the same glibc rand() stream:
+    identical shuffles => the same sequence of permuted Q (to the float32 noise of the reference side), hence the same
+    ActualPerm / NumGreater / NumEqual, across consecutive genes that continue one stream."""
+    O = oracle
+    if O.ref_skat() is None:
+        pytest.skip("oracle/_ref/libskat_ref.so not built (no /root/reference here)")
+    problems = []
+    for seed, N, M, Cc, n_perm, alpha in PERM:
+        G, X, y = make_problem(O, seed, N, M, Cc, maf=np.linspace(0.01, 0.3, M), n_flip=1)
+        problems.append((G, X, y, n_perm, alpha))
+    refs, orcs = [], []
+    for i, (G, X, y, n_perm, alpha) in enumerate(problems):  # the stream is process-wide: one pass per implementation
+        lin = O.ref_linear_fit(X, y)
+        Gf, w1 = _prep(O, G)
+        refs.append(O.ref_skat_perm(lin["resid"], np.full(len(y), lin["sigma2"]), X, Gf, w1 * w1, n_perm=n_perm, alpha=alpha,
+                                    reseed=1 if i == 0 else 0))
+    for i, (G, X, y, n_perm, alpha) in enumerate(problems):
+        nm = O.fit_null_linear(X, y)
+        out, _ = O.gene(G.astype(float), af_of(G), X, nm["resid"], nm["sigma2"])
+        orcs.append(O.gene_perm(G.astype(float), af_of(G), nm["resid"], out.skat.Q, n_perm=n_perm, alpha=alpha,
+                                reseed=1 if i == 0 else 0))
+    for i, (r, o) in enumerate(zip(refs, orcs)):
+        assert r["actual"] == o["actual"] and r["actual"] > 0, (i, r["actual"], o["actual"])
+        assert np.max(np.abs(r["q"] - o["q"]) / np.maximum(o["q"], 1e-300)) <= TOL_Q32, i
+        assert (r["greater"], r["equal"]) == (o["greater"], o["equal"]), i
+        assert r["p"] == pytest.approx(o["p"], rel=1e-12), i
+    assert any(r["actual"] < p[3] for r, p in zip(refs, problems))  # the early stop was exercised
