@@ -180,7 +180,12 @@ def ref_skat():
             L.ref_linear_fit.argtypes = [C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p]
             L.ref_score_test.restype = C.c_int
             L.ref_score_test.argtypes = [C.c_int, C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, C.c_int,
-                                         _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p]
+                                         _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p]
+            L.ref_fastlmm_score.restype = C.c_int
+            L.ref_fastlmm_score.argtypes = [C.c_int, C.c_int, C.c_int, _dbl_p, _dbl_p, C.c_void_p, C.c_void_p, _dbl_p,
+                                            _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p]
+            L.ref_genotype_counter.restype = None
+            L.ref_genotype_counter.argtypes = [C.c_int, _dbl_p, _dbl_p]
             L.ref_skat_perm.restype = C.c_int
             L.ref_skat_perm.argtypes = [C.c_int, C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, C.c_int,
                                         C.c_double, C.c_uint, _dbl_p, _int_p, _int_p, _int_p, _dbl_p, _dbl_p]
@@ -262,10 +267,36 @@ def ref_score_test(Xnull, y, Xcol, force_matrix=False):
     N, Cc = Xc.shape
     M = g.shape[1]
     U, V, beta = np.zeros(M), np.zeros((M, M), order="F"), np.zeros(M)
-    stat, p, s2 = C.c_double(0), C.c_double(0), C.c_double(0)
+    stat, p, s2, se = C.c_double(0), C.c_double(0), C.c_double(0), C.c_double(0)
     rc = ref_skat().ref_score_test(N, Cc, M, _p(Xc), _p(y), _p(g), int(force_matrix), _p(U), _p(V), _p(beta),
-                                   C.byref(stat), C.byref(p), C.byref(s2))
-    return dict(rc=rc, U=U, V=V, beta=beta, stat=stat.value, pvalue=p.value, sigma2=s2.value)
+                                   C.byref(stat), C.byref(p), C.byref(s2), C.byref(se))
+    return dict(rc=rc, U=U, V=V, beta=beta, stat=stat.value, pvalue=p.value, sigma2=s2.value, se_beta=se.value)
+
+
+def ref_fastlmm_score(X, y, U, S, G):
+    """FastLMM(SCORE, MLE)::FitNullModel + TestCovariate per column of G (N, M) of the reference build;
+    U (N, N) float32 kinship eigenvectors, S (N,) float32 eigenvalues."""
+    Xc = np.asfortranarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    Uf = np.asfortranarray(U, dtype=np.float32)
+    Sf = np.ascontiguousarray(S, dtype=np.float32)
+    Gc = np.asfortranarray(G, dtype=np.float64)
+    N, Cc = Xc.shape
+    M = Gc.shape[1]
+    delta, s2 = C.c_double(0), C.c_double(0)
+    beta, Us, Vs, ps = np.zeros(Cc), np.zeros(M), np.zeros(M), np.zeros(M)
+    rc = ref_skat().ref_fastlmm_score(N, Cc, M, _p(Xc), _p(y), Uf.ctypes.data, Sf.ctypes.data, _p(Gc), C.byref(delta),
+                                      C.byref(s2), _p(beta), _p(Us), _p(Vs), _p(ps))
+    return dict(rc=rc, delta=delta.value, sigma2=s2.value, beta=beta, U=Us, V=Vs, pvalue=ps)
+
+
+def ref_genotype_counter(g):
+    """GenotypeCounter of the reference build on one variant -> dict of the MetaScore site columns."""
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    out = np.zeros(8)
+    ref_skat().ref_genotype_counter(len(g), _p(g), _p(out))
+    return dict(n_ref=int(out[0]), n_het=int(out[1]), n_alt=int(out[2]), n_missing=int(out[3]), call_rate=out[4],
+                af=out[5], ac=out[6], hwe_p=out[7])
 
 
 # ------------------------------------------------------------------------------------------------

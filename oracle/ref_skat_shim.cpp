@@ -106,7 +106,7 @@ int ref_linear_fit(int N, int C, const double* X, const double* y, double* beta,
 // ZegginiTest ::fit) -- and, when M > 1 or force_matrix, the matrix form (:173-263).
 int ref_score_test(int N, int C, int M, const double* Xnull, const double* y, const double* Xcol,
                    int force_matrix, double* U, double* V, double* beta, double* stat, double* p,
-                   double* sigma2) {
+                   double* sigma2, double* se_beta) {
   Matrix Xn;
   Vector y_G;
   to_matrix(Xnull, N, C, &Xn);
@@ -129,6 +129,7 @@ int ref_score_test(int N, int C, int M, const double* Xnull, const double* y, co
   *stat = st.GetStat();
   *p = st.GetPvalue();
   *sigma2 = st.GetSigma2();
+  *se_beta = st.GetSEBeta(0);  // LinearRegressionScoreTest.cpp:365-376
   return ok ? 0 : -1;
 }
 }
@@ -181,4 +182,64 @@ extern "C" int ref_skat_perm(int N, int M, int C, const double* res, const doubl
   *num_equal = equal;
   *p_perm = perm.getPvalue();
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A13: FastLMM (regression/FastLMM.cpp): FitNullModel (:28-140: rotation by the kinship eigenvectors, the
+// 101-point grid + Brent search for delta, beta / sigma2 / uResid / scaledK) and the score branch of
+// TestCovariate (:215-249) for each of M variants.  U (N x N, column-major) and S (N) are the kinship
+// eigenvectors / eigenvalues in float, as the reference holds them (regression/EigenMatrix.h:9-12).
+// ------------------------------------------------------------------------------------------------
+#include "regression/EigenMatrix.h"
+#include "regression/FastLMM.h"
+
+extern "C" int ref_fastlmm_score(int N, int C, int M, const double* X, const double* y, const float* U,
+                                 const float* S, const double* G, double* delta, double* sigma_g2,
+                                 double* beta, double* Ustat, double* Vstat, double* pvalue) {
+  Matrix X_G, y_G;
+  to_matrix(X, N, C, &X_G);
+  to_matrix(y, N, 1, &y_G);
+  EigenMatrix kU, kS;
+  kU.mat.resize(N, N);
+  kS.mat.resize(N, 1);
+  for (int j = 0; j < N; ++j)
+    for (int i = 0; i < N; ++i) kU.mat(i, j) = U[(size_t)j * N + i];
+  for (int i = 0; i < N; ++i) kS.mat(i, 0) = S[i];
+  FastLMM lmm(FastLMM::SCORE, FastLMM::MLE);
+  const int rc = lmm.FitNullModel(X_G, y_G, kU, kS);
+  if (rc) return rc;
+  *delta = lmm.GetDelta();
+  *sigma_g2 = lmm.GetSigmaG2();
+  Vector b;
+  lmm.GetNullCovEst(&b);
+  for (int i = 0; i < C && i < b.Length(); ++i) beta[i] = b[i];
+  for (int k = 0; k < M; ++k) {
+    Matrix g;
+    to_matrix(G + (size_t)k * N, N, 1, &g);
+    if (lmm.TestCovariate(X_G, y_G, g, kU, kS)) return -100 - k;
+    Ustat[k] = lmm.GetUStat();
+    Vstat[k] = lmm.GetVStat();
+    pvalue[k] = lmm.GetPvalue();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A11: GenotypeCounter (src/GenotypeCounter.h:7-72, src/GenotypeCounter.cpp) with the exact HWE test
+// (libsrc/snp_hwe.cpp:25-122) as MetaScoreTest::fitWithGivenGenotype uses it (src/Model.h:3210-3240).
+// out = { nHomRef, nHet, nHomAlt, nMissing, callRate, AF, AC, HWE }
+// ------------------------------------------------------------------------------------------------
+#include "src/GenotypeCounter.h"
+
+extern "C" void ref_genotype_counter(int N, const double* g, double* out) {
+  GenotypeCounter c;
+  for (int i = 0; i < N; ++i) c.add(g[i]);
+  out[0] = c.getNumHomRef();
+  out[1] = c.getNumHet();
+  out[2] = c.getNumHomAlt();
+  out[3] = c.getNumMissing();
+  out[4] = c.getCallRate();
+  out[5] = c.getAF();
+  out[6] = c.getAC();
+  out[7] = c.getHWE();
 }

@@ -210,3 +210,66 @@ def test_live_permutation_loop(oracle):
         assert (r["greater"], r["equal"]) == (o["greater"], o["equal"]), i
         assert r["p"] == pytest.approx(o["p"], rel=1e-12), i
     assert any(r["actual"] < p[3] for r, p in zip(refs, problems))  # the early stop was exercised
+
+
+def test_live_fastlmm_score_step(oracle):
+    """A13: the FastLMM restatement (oracle/lmm_oracle.py) against the reference's own FastLMM.cpp: FitNullModel
+    (:28-140, delta by grid + Brent) then the score branch of TestCovariate (:215-249) per variant.  The restatement is
+    given the reference's delta (the device API takes the fitted null model from the caller, rvt_lmm_set_null) and must
+    reproduce beta, sigma2_g and every U / V / p; the reference computes in float32 => 2e-3 on the statistics."""
+    from oracle import lmm_oracle as LO
+    O = oracle
+    if O.ref_skat() is None:
+        pytest.skip("oracle/_ref/libskat_ref.so not built (no /root/reference here)")
+    rng = np.random.default_rng(5)
+    for N, Cc, h2 in ((240, 2, 0.5), (400, 3, 0.2)):
+        Zm = rng.binomial(2, 0.3, size=(N, 600)).astype(float)
+        Zm = (Zm - Zm.mean(0)) / Zm.std(0)
+        K = Zm @ Zm.T / Zm.shape[1]
+        lam, U = np.linalg.eigh(K)
+        U32, lam32 = U.astype(np.float32), lam.astype(np.float32)
+        X = np.c_[np.ones(N), rng.normal(size=(N, Cc - 1))]
+        y = X @ rng.normal(size=Cc) + np.linalg.cholesky(h2 * K + (1 - h2) * np.eye(N)) @ rng.normal(size=N)
+        G = rng.binomial(2, 0.15, size=(N, 12)).astype(float)
+        ref = O.ref_fastlmm_score(X, y, U32, lam32, G)
+        assert ref["rc"] == 0 and ref["delta"] > 0
+        nm = LO.fit_null_given_delta(U32, lam32, X, y, ref["delta"])
+        assert rel(nm["sigma2"], ref["sigma2"]) <= 2e-4, (nm["sigma2"], ref["sigma2"])
+        assert np.max(np.abs(nm["beta"] - ref["beta"])) <= 2e-4 * max(1.0, np.max(np.abs(ref["beta"])))
+        for j in range(G.shape[1]):
+            Us, Vs, st, p = LO.score(U32, nm, G[:, j])
+            assert abs(Us - ref["U"][j]) <= 2e-3 * max(abs(ref["U"][j]), np.sqrt(ref["V"][j])), (j, Us, ref["U"][j])
+            assert rel(Vs, ref["V"][j]) <= 2e-3, (j, Vs, ref["V"][j])
+            assert abs(p - ref["pvalue"][j]) <= 5e-3 * max(ref["pvalue"][j], 1e-3), (j, p, ref["pvalue"][j])
+
+
+def test_live_meta_score_columns(oracle):
+    """A11: the --meta score restatement (oracle/meta_oracle.py) against the reference's GenotypeCounter + SNPHWE
+    (src/GenotypeCounter.h, libsrc/snp_hwe.cpp) and LinearRegressionScoreTest (Matrix overload, as MetaUnrelatedQtl
+    calls it, src/Model.h:3516-3549: U / sigma2, V / sigma2^2, beta, sigma2 / sqrt(V), p)."""
+    from oracle import meta_oracle as MO
+    O = oracle
+    if O.ref_skat() is None:
+        pytest.skip("oracle/_ref/libskat_ref.so not built (no /root/reference here)")
+    G, X, y = make_problem(O, 401, 3000, 40, 3, maf=np.r_[np.linspace(0.0005, 0.5, 36), [0.7, 0.9, 0.98, 0.3]], n_mono=2)
+    nm = O.fit_null_linear(X, y)
+    seen_mono = False
+    for j in range(G.shape[1]):
+        g = G[:, j].astype(float)
+        o = MO.meta_score(g, X, nm["resid"], nm["sigma2"])
+        c = O.ref_genotype_counter(g)
+        assert (o["n_ref"], o["n_het"], o["n_alt"]) == (c["n_ref"], c["n_het"], c["n_alt"]) and c["n_missing"] == 0
+        assert o["af"] == c["af"] and o["ac"] == c["ac"] and o["call_rate"] == c["call_rate"]
+        assert o["hwe_p"] == pytest.approx(c["hwe_p"], rel=1e-12, abs=1e-300), j
+        if not o["polymorphic"]:
+            seen_mono = True
+            continue
+        s = O.ref_score_test(X, y, g, force_matrix=True)
+        assert o["ok"] == (s["rc"] == 0)
+        s2 = s["sigma2"]
+        assert abs(o["U"] - s["U"][0] / s2) <= 1e-9 * max(abs(o["U"]), o["sqrtV"])
+        assert rel(o["sqrtV"], np.sqrt(s["V"][0, 0] / s2 / s2)) <= 1e-9
+        assert abs(o["effect"] - s["beta"][0]) <= 1e-9 * max(abs(o["effect"]), o["effect_se"])
+        assert rel(o["effect_se"], s["se_beta"]) <= 1e-9
+        assert rel(o["pvalue"], s["pvalue"]) <= 1e-8
+    assert seen_mono
