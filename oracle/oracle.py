@@ -186,6 +186,10 @@ def ref_skat():
                                             _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p]
             L.ref_genotype_counter.restype = None
             L.ref_genotype_counter.argtypes = [C.c_int, _dbl_p, _dbl_p]
+            L.ref_logistic_fit.restype = C.c_int
+            L.ref_logistic_fit.argtypes = [C.c_int, C.c_int, _dbl_p, _dbl_p, C.c_int, _dbl_p, _dbl_p, _dbl_p, _dbl_p]
+            L.ref_logistic_score_test.restype = C.c_int
+            L.ref_logistic_score_test.argtypes = [C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p]
             L.ref_skat_perm.restype = C.c_int
             L.ref_skat_perm.argtypes = [C.c_int, C.c_int, C.c_int, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, C.c_int,
                                         C.c_double, C.c_uint, _dbl_p, _int_p, _int_p, _int_p, _dbl_p, _dbl_p]
@@ -288,6 +292,28 @@ def ref_fastlmm_score(X, y, U, S, G):
     rc = ref_skat().ref_fastlmm_score(N, Cc, M, _p(Xc), _p(y), Uf.ctypes.data, Sf.ctypes.data, _p(Gc), C.byref(delta),
                                       C.byref(s2), _p(beta), _p(Us), _p(Vs), _p(ps))
     return dict(rc=rc, delta=delta.value, sigma2=s2.value, beta=beta, U=Us, V=Vs, pvalue=ps)
+
+
+def ref_logistic_fit(X, y, rounds=100):
+    """LogisticRegression::FitLogisticModel of the reference build -> dict(rc, beta, p, v, covB)."""
+    Xc = np.asfortranarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    N, Cc = Xc.shape
+    beta, p, v, covB = np.zeros(Cc), np.zeros(N), np.zeros(N), np.zeros((Cc, Cc), order="F")
+    rc = ref_skat().ref_logistic_fit(N, Cc, _p(Xc), _p(y), int(rounds), _p(beta), _p(p), _p(v), _p(covB))
+    return dict(rc=rc, beta=beta, p=p, v=v, covB=covB)
+
+
+def ref_logistic_score_test(Xnull, y, xcol):
+    """LogisticRegressionScoreTest::FitNullModel + TestCovariate (Matrix overload) of the reference build;
+    intercept-only null models only (rc = -3 otherwise: the reference indexes out of bounds there)."""
+    Xc = np.asfortranarray(Xnull, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    g = np.ascontiguousarray(xcol, dtype=np.float64)
+    U, V, stat, p = C.c_double(0), C.c_double(0), C.c_double(0), C.c_double(0)
+    rc = ref_skat().ref_logistic_score_test(len(y), Xc.shape[1], _p(Xc), _p(y), _p(g), C.byref(U), C.byref(V),
+                                            C.byref(stat), C.byref(p))
+    return dict(rc=rc, U=U.value, V=V.value, stat=stat.value, pvalue=p.value)
 
 
 def ref_genotype_counter(g):

@@ -243,3 +243,48 @@ extern "C" void ref_genotype_counter(int N, const double* g, double* out) {
   out[6] = c.getAC();
   out[7] = c.getHWE();
 }
+
+// ------------------------------------------------------------------------------------------------
+// Binary traits: LogisticRegression::FitLogisticModel (regression/LogisticRegression.cpp:279-339)
+// as SkatTest::fit uses it (src/Model.h:2673-2681: ynull = GetPredicted(), v = GetVariance()), and
+// LogisticRegressionScoreTest::FitNullModel + TestCovariate(Matrix overload, :219-302) as CMCTest::fit uses it
+// (src/Model.h:841-848).  The latter solves its m x m `SS` against a d x d identity (:292-295): with covariates
+// (d > 1) that indexes out of bounds, so this door only runs it for d == 1 and returns -3 otherwise.
+// ------------------------------------------------------------------------------------------------
+#include "regression/LogisticRegression.h"
+#include "regression/LogisticRegressionScoreTest.h"
+
+extern "C" int ref_logistic_fit(int N, int C, const double* X, const double* y, int rounds, double* beta,
+                                double* p, double* V, double* covB) {
+  Matrix X_G;
+  Vector y_G;
+  to_matrix(X, N, C, &X_G);
+  to_vector(y, N, &y_G);
+  LogisticRegression lr;
+  if (!lr.FitLogisticModel(X_G, y_G, rounds)) return -1;
+  for (int i = 0; i < C; ++i) beta[i] = lr.GetCovEst()[i];
+  for (int i = 0; i < N; ++i) {
+    p[i] = lr.GetPredicted()[i];
+    V[i] = lr.GetVariance()[i];
+  }
+  from_matrix(lr.GetCovB(), covB);
+  return 0;
+}
+
+extern "C" int ref_logistic_score_test(int N, int C, const double* Xnull, const double* y, const double* Xcol,
+                                       double* U, double* V, double* stat, double* p) {
+  if (C != 1) return -3;
+  Matrix Xn, xc;
+  Vector y_G;
+  to_matrix(Xnull, N, C, &Xn);
+  to_vector(y, N, &y_G);
+  to_matrix(Xcol, N, 1, &xc);
+  LogisticRegressionScoreTest st;
+  if (!st.FitNullModel(Xn, y_G, 100)) return -2;
+  const bool ok = st.TestCovariate((const Matrix&)Xn, (const Vector&)y_G, (const Matrix&)xc);
+  *U = st.GetU()(0, 0);
+  *V = st.GetV()(0, 0);
+  *stat = st.GetStat();
+  *p = st.GetPvalue();
+  return ok ? 0 : -1;
+}

@@ -273,3 +273,41 @@ def test_live_meta_score_columns(oracle):
         assert rel(o["effect_se"], s["se_beta"]) <= 1e-9
         assert rel(o["pvalue"], s["pvalue"]) <= 1e-8
     assert seen_mono
+
+
+def test_live_binary_trait(oracle):
+    """the binary-trait restatement (oracle/binary_oracle.py) against the reference's own
+    LogisticRegression.cpp (Newton rounds, its stopping rule, and p / V left one step behind beta), Skat::Fit with
+    v = p(1-p), res = y - p (the general-covariate branch of P0, Skat.cpp:58-66) and, for an intercept-only null model,
+    LogisticRegressionScoreTest::TestCovariate on the CMC / Zeggini collapse."""
+    from oracle import binary_oracle as BIN
+    O = oracle
+    if O.ref_skat() is None:
+        pytest.skip("oracle/_ref/libskat_ref.so not built (no /root/reference here)")
+    for seed, N, M, Cc in ((501, 800, 10, 3), (502, 1500, 25, 2), (503, 600, 8, 1)):
+        G, X, _ = make_problem(O, seed, N, M, Cc, maf=np.linspace(0.005, 0.3 if M <= 12 else 0.03, M), n_flip=1, n_mono=1)
+        rng = np.random.default_rng(seed)
+        eta = X @ np.r_[-0.4, rng.normal(size=Cc - 1) * 0.5] + 0.4 * G[:, 0]
+        y = (rng.random(N) < 1 / (1 + np.exp(-eta))).astype(float)
+        nm = BIN.fit_null_logistic(X, y)
+        ref = O.ref_logistic_fit(X, y)
+        assert ref["rc"] == 0
+        assert np.max(np.abs(nm["beta"] - ref["beta"])) <= 1e-10
+        assert np.max(np.abs(nm["p"] - ref["p"])) <= 1e-12 and np.max(np.abs(nm["v"] - ref["v"])) <= 1e-12
+        # the quirk: p belongs to the beta of one Newton step earlier
+        assert np.max(np.abs(ref["p"] - 1 / (1 + np.exp(-(X @ ref["beta"]))))) > 0
+        assert np.max(np.abs(nm["covB"] - ref["covB"])) <= 1e-10 * np.max(np.abs(ref["covB"]))
+        out = BIN.gene(G.astype(float), af_of(G), X, nm)
+        Gf, w1 = _prep(O, G)
+        sk = O.ref_skat_fit(y - ref["p"], ref["v"], X, Gf, w1 * w1)
+        assert rel(out["Q"], sk["Q"]) <= TOL_Q32, (out["Q"], sk["Q"])
+        assert rel(out["p_skat"], sk["pvalue"]) <= TOL_P32, (out["p_skat"], sk["pvalue"])
+        if Cc == 1:
+            for name, S in (("cmc", (Gf > 0).any(1).astype(float)), ("zeg", (Gf > 0).sum(1).astype(float))):
+                st = O.ref_logistic_score_test(X, y, S)
+                assert st["rc"] == 0
+                assert abs(out[name]["U"] - st["U"]) <= 1e-10 * max(abs(st["U"]), np.sqrt(st["V"]))
+                assert rel(out[name]["V"], st["V"]) <= 1e-10
+                assert rel(out[name]["p"], st["pvalue"]) <= 1e-8
+        else:
+            assert O.ref_logistic_score_test(X, y, (Gf > 0).any(1).astype(float))["rc"] == -3
