@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE ONLY -- numpy restatement of the binary-trait path of SkatTest / CMCTest / ZegginiTest.
-parity unpinned (Eigen code that cannot be built here).
+Pinned on the reference's own LogisticRegression.cpp / LogisticRegressionScoreTest.cpp / Skat.cpp compiled against
+oracle/eigen_standin (oracle/_ref/libskat_ref.so): tests/test_oracle_pin_reference_skat.py::test_live_binary_trait.
 
   fit_null_logistic   LogisticRegression::FitLogisticModel (regression/LogisticRegression.cpp:279-339): Newton rounds from
                       beta = 0; GetDeviance (:75-94) is evaluated with the p of the round's START, the loop stops when two

@@ -1,6 +1,7 @@
-"""TEST INFRASTRUCTURE ONLY -- numpy restatement of the FastLMM score step.  parity unpinned:
-the reference computes this with Eigen 3.3.9 in float32 (absent here); this restatement follows its
-formulas line by line in float64 on the same float32 inputs.
+"""TEST INFRASTRUCTURE ONLY -- numpy restatement of the FastLMM score step.  Pinned on the
+reference's own FastLMM.cpp compiled against oracle/eigen_standin (oracle/_ref/libskat_ref.so,
+tests/test_oracle_pin_reference_skat.py::test_live_fastlmm_score_step; the reference computes in float32 => 2e-3);
+this restatement follows its formulas line by line in float64 on the same float32 inputs.
 
   fit_null_given_delta   FastLMM::Impl::getBetaSigma2 (regression/FastLMM.cpp:300-330, MLE: sigma2 = SSR / n) and the
                          members FitNullModel leaves behind: ux, uy rotated (:52-54), uResid (:126), scaledK (:131-138)

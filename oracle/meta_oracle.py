@@ -8,7 +8,10 @@ numpy restatement of `--meta score,cov` for unrelated samples and a quantitative
   MetaCovTest window / printCovariance + MetaCovUnrelatedQtl             src/Model.h:3954-4020, src/Model.cpp:500-596, 844-1004
 The covariance follows the reference literally (centre the genotype, x~'x~/sigma2, covXZ, the LDLT
 pseudo-inverse of the centred-covariate Gram) in fp64; the reference itself computes it in float32,
-so parity is asserted at 1e-5.  Parity unpinned by the reference's tests (F6).
+so parity is asserted at 1e-5.  The score columns are pinned on the reference's own
+GenotypeCounter / SNPHWE / LinearRegressionScoreTest (oracle/_ref/libskat_ref.so,
+tests/test_oracle_pin_reference_skat.py::test_live_meta_score_columns); the covariance window lives in src/Model.cpp,
+which cannot be compiled in isolation: parity unpinned by the reference for `--meta cov`.
 """
 from __future__ import annotations
 

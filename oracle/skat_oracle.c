@@ -15,10 +15,14 @@
  *   - Davies / Liu p-values: pinned against the reference's own MixtureChiSquare.cpp +
  *     qfc.c + cdflib.cpp compiled in place into oracle/_ref/ (tests/test_oracle_pin.py)
  *     and against the three known-answer vectors of regression/test/testMixtureChiSquare.cpp.
- *   - Q statistics / eigenvalues / burden p-values: the reference ships no golden vector
- *      => "parity unpinned" for those, anchored instead on (i) the literal
- *     float32 N x N restatement orc_skat_faithful32() of regression/Skat.cpp:29-105
- *     agreeing with the reduced fp64 algebra, and (ii) the C1 example anchor.
+ *   - Q statistics / burden U, V, p / null model / permutation loop: the reference ships no golden
+ *     vector, so its OWN sources (Skat.cpp, LinearRegression*.cpp, Permutation.h ...)
+ *     are compiled unmodified against oracle/eigen_standin into oracle/_ref/libskat_ref.so and run
+ *     beside this file (tests/test_oracle_pin_reference_skat.py, tests/golden/ref_skat_golden.npz);
+ *     also (i) the literal float32 N x N restatement orc_skat_faithful32() of
+ *     regression/Skat.cpp:29-105 agreeing with the reduced fp64 algebra, (ii) the C1 example anchor.
+ *   - flip-to-minor / collapse (src/DataConsolidator.cpp, src/Model.cpp): cannot be compiled in
+ *     isolation => "parity unpinned" for those integer steps.
  */
 #include <math.h>
 #include <setjmp.h>

@@ -10,7 +10,9 @@ Linear algebra is numpy (Eigen is not vendored by the reference); the special fu
 quadrature are the reference's OWN third-party code when oracle/_ref is built: GSL 1.16
 (gsl_cdf_chisq_Q/P/Qinv, gsl_ran_chisq_pdf, gsl_integration_qags) and the reference's
 MixtureChiSquare (Davies / Liu).  Without oracle/_ref it falls back to scipy + the C oracle and
-says so in `info["backend"]`.  Parity status: unpinned by the reference's tests.
+says so in `info["backend"]`.  Parity status: pinned on the reference's own SkatO.cpp compiled
+against oracle/eigen_standin (oracle/_ref/libskat_ref.so; Q / rho / p agree to ~1e-14,
+tests/test_oracle_pin_reference_skat.py and tests/golden/ref_skat_golden.npz).
 """
 from __future__ import annotations
 

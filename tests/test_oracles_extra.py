@@ -1,5 +1,6 @@
 """CPU: the numpy restatements added for the mixed-model and binary-trait rows are themselves checked against independent
-formulations (they are "parity unpinned" by the reference, whose Eigen code cannot be built here -- SURVEY 8(c))."""
+formulations (the FastLMM and binary-trait ones are additionally pinned on the reference build in
+test_oracle_pin_reference_skat.py; the Bolt null fit stays "parity unpinned": BoltLMM.cpp cannot be built here)."""
 import numpy as np
 import pytest
 
