@@ -332,21 +332,56 @@ def time_cpu(O, native, G, af, X, nm, threads, seconds):
     return len(idx) / dt, len(idx), dt, out
 
 
+def reference_wall(O, M, C, sizes=(2000, 4000, 8000)):
+    """SURVEY 8(d)(i): the reference's OWN Skat::Fit (regression/Skat.cpp:29-105, compiled unmodified into
+    oracle/_ref/libskat_ref.so against oracle/eigen_standin) forms the N x N float matrix P0 and costs 2 M N^2 flops
+    per gene: timed at small N to show the O(N^2) wall and why it cannot run at the metric's N.  The stand-in's
+    products are plain loops (Eigen's blocked GEMM would be a few times faster): the exponent and the 4 N^2 bytes of
+    P0 are the point, not the constant."""
+    if O.ref_skat() is None:
+        return {"unavailable": "oracle/_ref/libskat_ref.so not built"}
+    rng = np.random.default_rng(SEED)
+    rows = []
+    for N in sizes:
+        maf = rng.uniform(0.005, 0.05, M)
+        G = np.asfortranarray((rng.random((N, M)) < maf).astype(np.float64) + (rng.random((N, M)) < maf))
+        X = np.c_[np.ones(N), rng.normal(size=(N, C - 1))]
+        nm = O.fit_null_linear(X, rng.normal(size=N))
+        af = G.mean(axis=0) / 2
+        w = np.array([O.lib().orc_skat_weight(float(a), 1.0, 25.0, 1) for a in af])
+        t = time.perf_counter()
+        r = O.ref_skat_fit(nm["resid"], np.full(N, nm["sigma2"]), X, G, w)
+        dt = time.perf_counter() - t
+        rows.append({"N": N, "s_per_gene": dt, "p0_bytes": 4 * N * N, "Q": r["Q"]})
+    slope = float(np.polyfit(np.log([r_["N"] for r_ in rows]), np.log([r_["s_per_gene"] for r_ in rows]), 1)[0])
+    last = rows[-1]
+    return {"what": "Skat::Fit of the reference build (float32, explicit N x N P0), 1 thread, M=%d, C=%d" % (M, C),
+            "rows": rows, "fitted_exponent_in_N": slope,
+            "extrapolated_s_per_gene_at_500k": last["s_per_gene"] * (500_000 / last["N"]) ** 2,
+            "p0_bytes_at_500k": 4 * 500_000 ** 2}
+
+
 def cpu_baseline(args, threads):
     O, native, G, af, X, nm = cpu_problem(args)
+    try:
+        wall = reference_wall(O, args.variants, args.covariates)
+    except Exception as e:  # a reported side figure must never cost the bench line
+        wall = {"unavailable": repr(e)}
     v, ntask, dt, _ = time_cpu(O, native, G, af, X, nm, threads, args.cpu_seconds)
     v1, ntask1, dt1, _ = time_cpu(O, native, G, af, X, nm, 1, min(args.cpu_seconds, 6.0))
     return {"value": v, "unit": "gene-sets/s", "cores": threads, "kind": "port",
             "sample": f"{ntask} gene-tasks over {G.shape[0]} distinct genes of N={args.samples} x M={args.variants} "
-                      f"(fp64 column-major Matrix, 200 MB each) in {dt:.1f} s, OpenMP over genes, "
+                      f"(fp64 column-major Matrix, {args.samples * args.variants * 8 / 1e6:.0f} MB each) in {dt:.1f} s, OpenMP over genes, "
                       f"oracle/skat_oracle.c {'-march=native' if native else 'x86-64-v3'}: reduced O(N M^2) algebra "
                       "(the reference's own Skat.cpp is O(N^2) and cannot run at this N: SURVEY.md F2)",
-            "single_thread_value": v1, "single_thread_note": "the reference's gene loop is serial (src/Main.cpp:1221-1254)"}
+            "single_thread_value": v1, "single_thread_note": "the reference's gene loop is serial (src/Main.cpp:1221-1254)",
+            "reference_algorithm_wall": wall}
 
 
 def run_reference(args):
-    """reference arm: the reference algorithm (oracle port; Skat.cpp itself needs Eigen, absent) on all
-    host cores; rank 0 only."""
+    """reference arm: the reference algorithm on all host cores; rank 0 only.  The oracle port (reduced O(N M^2)
+    algebra) is timed: the reference's own Skat::Fit is built (oracle/_ref/libskat_ref.so) but forms an N x N matrix
+    -- 1 TB at N = 500 000 -- see cpu_baseline.reference_algorithm_wall of the main arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
