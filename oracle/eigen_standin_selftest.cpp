@@ -41,6 +41,8 @@ void st_solvers(int n, int m, const double* A, const double* B, double* inv, dou
   *det = a.determinant();
   *rank = (int)a.fullPivLu().rank();
 }
+// x = A.ldlt().solve(B) alone (A may be singular: Eigen applies the pseudo-inverse of D)
+void st_ldlt(int n, int m, const double* A, const double* B, double* x) { store(load<double>(A, n, n).ldlt().solve(load<double>(B, n, m)), x); }
 int st_rank(int r, int c, const double* A) { return (int)load<double>(A, r, c).fullPivLu().rank(); }
 // eigenvalues (increasing) and eigenvectors of a symmetric matrix, in double and in float
 void st_eigen(int n, const double* A, double* val64, double* vec64, double* val32) {

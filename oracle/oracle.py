@@ -325,6 +325,71 @@ def ref_genotype_counter(g):
                 af=out[5], ac=out[6], hwe_p=out[7])
 
 
+def ref_model():
+    """The reference's own model layer (src/Model.cpp + Model.h fitters, src/DataConsolidator.cpp ...) built into
+    oracle/_ref/libmodel_ref.so behind oracle/ref_model_shim.cpp.  None when oracle/_ref was never built."""
+    if "model" not in _lib_cache:
+        path = os.path.join(_HERE, "_ref", "libmodel_ref.so")
+        if not os.path.exists(path):
+            _lib_cache["model"] = None
+        else:
+            L = C.CDLL(path)
+            L.ref_run_gene_models.restype = C.c_int
+            L.ref_run_gene_models.argtypes = [C.c_int, C.c_int, _int_p, _dbl_p, C.c_int, _dbl_p, _dbl_p, C.c_int,
+                                              C.c_double, C.c_int, C.c_char_p]
+            L.ref_run_meta_models.restype = C.c_int
+            L.ref_run_meta_models.argtypes = [C.c_int, C.c_int, _dbl_p, _int_p, C.c_int, _dbl_p, _dbl_p, C.c_int,
+                                              C.c_char_p]
+            _lib_cache["model"] = L
+    return _lib_cache["model"]
+
+
+def _read_assoc(path):
+    """-> (comment lines, header fields, rows as lists of strings)"""
+    comments, rows, header = [], [], None
+    with open(path) as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if line.startswith("#"):
+                comments.append(line)
+            elif header is None:
+                header = line.split("\t")
+            else:
+                rows.append(line.split("\t"))
+    return comments, header, rows
+
+
+def ref_run_gene_models(genes, cov, pheno, prefix, n_perm=0, alpha=0.05, binary=False):
+    """Gene loop of src/Main.cpp:1221-1254 run by the reference build on `genes` (list of (N, M_k) raw genotype
+    matrices, missing < 0), cov (N, C-1) WITHOUT the intercept, pheno (N,).  Returns {model name: (comments, header, rows)}
+    parsed from the `.assoc` files the reference wrote under `prefix`."""
+    N = len(pheno)
+    flat = np.concatenate([np.asfortranarray(g, dtype=np.float64).ravel(order="F") for g in genes])
+    M = np.array([g.shape[1] for g in genes], dtype=np.int32)
+    covf = np.asfortranarray(np.asarray(cov, dtype=np.float64).reshape(N, -1))
+    y = np.ascontiguousarray(pheno, dtype=np.float64)
+    rc = ref_model().ref_run_gene_models(N, len(genes), _p(M, C.c_int), _p(flat), covf.shape[1], _p(covf), _p(y),
+                                         int(n_perm), float(alpha), int(binary), prefix.encode())
+    if rc:
+        raise RuntimeError(f"ref_run_gene_models rc={rc}")
+    return {m: _read_assoc(f"{prefix}.{m}.assoc") for m in ("Skat", "SkatO", "CMC", "Zeggini")}
+
+
+def ref_run_meta_models(G, pos, cov, pheno, window, prefix):
+    """Single-variant loop of src/Main.cpp:1092-1147 with MetaScoreTest + MetaCovTest(window) run by the reference build;
+    variant j = column j of G (N, n_var) at 1:pos[j]."""
+    Gc = np.asfortranarray(G, dtype=np.float64)
+    N, nv = Gc.shape
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    covf = np.asfortranarray(np.asarray(cov, dtype=np.float64).reshape(N, -1))
+    y = np.ascontiguousarray(pheno, dtype=np.float64)
+    rc = ref_model().ref_run_meta_models(N, nv, _p(Gc), _p(pos, C.c_int), covf.shape[1], _p(covf), _p(y), int(window),
+                                         prefix.encode())
+    if rc:
+        raise RuntimeError(f"ref_run_meta_models rc={rc}")
+    return {m: _read_assoc(f"{prefix}.{m}.assoc") for m in ("MetaScore", "MetaCov")}
+
+
 # ------------------------------------------------------------------------------------------------
 # thin numpy-level helpers
 # ------------------------------------------------------------------------------------------------

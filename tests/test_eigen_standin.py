@@ -54,6 +54,18 @@ def test_solvers(st):
         assert np.allclose(L, np.linalg.cholesky(A), rtol=1e-10, atol=1e-12)
         assert det.value == pytest.approx(np.linalg.det(A), rel=1e-9)
         assert rank.value == n
+    # LDLT of a matrix with an exactly-zero row / column (Z'Z of centred covariates incl. the intercept): pseudo-inverse
+    Z = rng.normal(size=(50, 3))
+    Z -= Z.mean(0)
+    Zc = np.c_[np.zeros(50), Z]
+    A, B, x = F(Zc.T @ Zc), F(np.eye(4)), F(np.zeros((4, 4)))
+    st.st_ldlt(4, 4, P(A), P(B), P(x))
+    assert np.all(np.isfinite(x)) and np.allclose(x, np.linalg.pinv(A), rtol=1e-9, atol=1e-12)
+    # and a matrix that needs the pivoting (leading zero on the diagonal, still non-singular after the permutation)
+    A2 = F(np.array([[0.0, 0.0, 0.0], [0.0, 4.0, 1.0], [0.0, 1.0, 3.0]]))
+    x2 = F(np.zeros((3, 3)))
+    st.st_ldlt(3, 3, P(A2), P(F(np.eye(3))), P(x2))
+    assert np.allclose(x2, np.linalg.pinv(A2), atol=1e-12)
     low = F(rng.normal(size=(9, 3)) @ rng.normal(size=(3, 7)))
     assert st.st_rank(9, 7, P(low)) == 3
 
