@@ -241,3 +241,37 @@ def test_adapters_binary_outcome(oracle, tmp_path):
         assert ro == ["NA", "NA", "NA"], ctx
         assert rc[0] == str(ref["cmc"]["nonref"]) and close(rc[1], ref["cmc"]["p"]), ctx
         assert close(rz[0], ref["zeg"]["p"]), ctx
+
+
+def test_adapters_vs_the_reference_model_layer_text(tmp_path):
+    """The C++ adapters on the device against the `.assoc` lines that the REFERENCE's own model layer printed for the same
+    five genes (tests/golden/ref_assoc_golden.npz: src/Model.cpp + Model.h fitters + DataConsolidator.cpp compiled
+    unmodified in the build container, tests/golden/make_golden_ref_assoc.py).  No oracle in between."""
+    import rvtests_b200
+    from test_oracle_pin_reference_model_layer import load_assoc_golden, model_columns_match
+    rvtests_b200.load_library()
+    X, y, genes, text = load_assoc_golden()
+    N = len(y)
+    path = tmp_path / "problem.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("iii", N, X.shape[1] - 1, len(genes)))
+        f.write(np.ascontiguousarray(y).tobytes())
+        f.write(np.asfortranarray(X[:, 1:]).tobytes(order="F"))
+        for G in genes:
+            f.write(struct.pack("i", G.shape[1]))
+            f.write(np.asfortranarray(G.astype(np.float64)).tobytes(order="F"))
+            f.write(af_of(G).tobytes())
+    exe = build_demo()
+    out = subprocess.run([exe, str(path), "3"], capture_output=True, text=True, check=True).stdout
+    tables, cur = {}, None
+    for line in out.splitlines():
+        if line.startswith("#"):
+            cur = line[1:]
+            tables[cur] = []
+        else:
+            tables[cur].append(line.split("\t"))
+    for m in ("Skat", "SkatO", "CMC", "Zeggini"):
+        w = {"Skat": 2, "SkatO": 3, "CMC": 2, "Zeggini": 1}[m]
+        assert tables[m][0][-w:] == text[m]["header"][-w:], (m, tables[m][0], text[m]["header"])
+    for k in range(len(genes)):
+        model_columns_match({m: text[m]["rows"][k] for m in text}, {m: tables[m][1 + k] for m in text})

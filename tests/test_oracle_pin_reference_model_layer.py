@@ -150,3 +150,51 @@ def test_single_variant_loop_meta_score_and_cov(ref, tmp_path):
         if o.get("ok"):
             for txt, key in zip(row[12:], ("U", "sqrtV", "effect", "pvalue")):
                 assert _close(txt, o[key], 1e-5), (j, key, txt, o[key])
+
+
+def model_columns_match(ref_rows, got, tol_skat_q=3e-6, tol_skat_p=5e-4, tol=1e-5):
+    """ref_rows: {model: row of the reference's .assoc text}; got: {model: the same model columns from another
+    implementation, as text}.  Model columns only: Skat Q,Pvalue | SkatO Q,rho,Pvalue | CMC NonRefSite,Pvalue | Zeggini Pvalue."""
+    width = {"Skat": 2, "SkatO": 3, "CMC": 2, "Zeggini": 1}
+    for m, w in width.items():
+        r, o = ref_rows[m][-w:], got[m][-w:]
+        if "NA" in r:
+            assert o == r, (m, r, o)
+            continue
+        for i, (a, b) in enumerate(zip(r, o)):
+            if a == b:
+                continue
+            if (m, i) in (("CMC", 0), ("SkatO", 1)):        # NonRefSite and rho: exact
+                assert float(a) == float(b), (m, r, o)
+            else:
+                t = (tol_skat_q if i == 0 else tol_skat_p) if m == "Skat" else tol
+                assert rel(float(a), float(b)) <= t + 1e-6, (m, r, o)   # + the rounding of "%g" itself
+
+
+def load_assoc_golden():
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_assoc_golden.npz"))
+    text = json.loads(str(g["assoc"]))
+    genes = [g[f"G{k}"] for k in range(len(text["Skat"]["rows"]))]
+    return g["X"], g["y"], genes, text
+
+
+def test_golden_assoc_text_vs_oracle(oracle):
+    """tests/golden/ref_assoc_golden.npz: the `.assoc` lines the reference's model layer printed for five genes
+    (tests/golden/make_golden_ref_assoc.py) against the oracle's numbers printed with "%g" -- runs without oracle/_ref.
+    The same file is what tests/test_gpu_adapters.py holds the C++ adapters on the device against."""
+    from oracle import skato_oracle as SO
+    O = oracle
+    X, y, genes, text = load_assoc_golden()
+    nm = O.fit_null_linear(X, y)
+    for k, G in enumerate(genes):
+        o, _ = O.gene(G.astype(float), _af_ref(G.astype(float)), X, nm["resid"], nm["sigma2"])
+        ref_rows = {m: text[m]["rows"][k] for m in text}
+        if o.status == 2:
+            got = {"Skat": ["NA", "NA"], "SkatO": ["NA"] * 3, "CMC": ["NA", "NA"], "Zeggini": ["NA"]}
+        else:
+            so = SO.skato_gene(G.astype(float), _af_ref(G.astype(float)), X, nm["resid"])
+            got = {"Skat": [_g(o.skat.Q), _g(o.skat.pvalue)], "SkatO": [_g(so["Q"]), _g(so["rho"]), _g(so["pvalue"])],
+                   "CMC": [str(o.cmc_nonref), _g(o.cmc_p)], "Zeggini": [_g(o.zeg_p)]}
+        model_columns_match(ref_rows, got)
