@@ -1,6 +1,6 @@
 """oracle/skato_oracle.py -- TEST INFRASTRUCTURE ONLY.
 
-numpy restatement of SKAT-O for quantitative traits, following the reference line by line:
+numpy restatement of SKAT-O (quantitative traits, and binary traits = type "D"), following the reference line by line:
   SkatOTest::fit          src/Model.h:2787-2860   (UN-squared Beta weights, OLS null, v = sigma2)
   SkatO::Fit / FitSKAT    regression/SkatO.cpp:101-281, 60-99
   getEigen/getMoment/getPvalByMoment/getQvalByMoment/capRhos   regression/SkatO.cpp:350-455
@@ -100,13 +100,18 @@ def get_moment(lam):
     return c[0], sigmaQ * sigmaQ, l
 
 
-def skato(G, w, X, res, be: _Backend | None = None):
-    """SkatO::Fit for a quantitative trait.  G (N, M) flipped/polymorphic, w unsquared weights,
-    X (N, C) incl. intercept, res null residuals.  Returns dict(ok, Q, rho, pvalue, info)."""
+def skato(G, w, X, res, be: _Backend | None = None, vv=None):
+    """SkatO::Fit.  G (N, M) flipped/polymorphic, w unsquared weights, X (N, C) incl. intercept,
+    res null residuals.  vv = None: quantitative trait (type "C"); vv = per-sample variance p(1-p)
+    of the logistic null: binary trait (type "D": s2 = 1, SkatO.cpp:133-134; Z1 = V^1/2 (G - X (X'VX)^-1 X'VG),
+    :150-158; FitSKAT :72-91).  Returns dict(ok, Q, rho, pvalue, info)."""
     be = be or _Backend()
     N, M = G.shape
     G = G.astype(np.float64) * w[None, :]
     info = {"backend": be.name}
+    binary = vv is not None
+    if binary:
+        vv = np.asarray(vv, dtype=np.float64)
 
     def davies(Q, lam):
         p, _ = O.mix_pvalue(lam, Q, be.mix)
@@ -118,9 +123,14 @@ def skato(G, w, X, res, be: _Backend | None = None):
     if M == 1:  # FitSKAT, SkatO.cpp:60-99
         temp = res @ G
         Q = float(temp @ temp)
-        s2 = float(res @ res) / (N - 1)
-        Q = Q / s2 / 2.0
-        W = G.T @ G - (G.T @ X) @ np.linalg.solve(X.T @ X, X.T @ G)
+        if not binary:
+            s2 = float(res @ res) / (N - 1)
+            Q = Q / s2
+            W = G.T @ G - (G.T @ X) @ np.linalg.solve(X.T @ X, X.T @ G)
+        else:
+            VG, VX = vv[:, None] * G, vv[:, None] * X
+            W = G.T @ VG - (G.T @ VX) @ np.linalg.solve(X.T @ VX, X.T @ VG)
+        Q = Q / 2.0
         W = W / 2
         lam = get_eigen(W)
         if lam is None:
@@ -129,11 +139,15 @@ def skato(G, w, X, res, be: _Backend | None = None):
 
     rhos_orig = np.array([i / 10 for i in range(11)])
     rhos = np.minimum(rhos_orig, 0.999)
-    s2 = float(np.linalg.norm(res) ** 2) / (N - 1)
+    s2 = 1.0 if binary else float(np.linalg.norm(res) ** 2) / (N - 1)
     v = res @ G
     Qs = np.array([(v @ ((1 - r) * np.eye(M) + r * np.ones((M, M)) - 0) @ v) if False else
                    float(v @ (np.where(np.eye(M) > 0, 1.0, r)) @ v) for r in rhos]) / s2 / 2.0
-    Z1 = (G - X @ np.linalg.solve(X.T @ X, X.T @ G)) / np.sqrt(2)
+    if not binary:
+        Z1 = (G - X @ np.linalg.solve(X.T @ X, X.T @ G)) / np.sqrt(2)
+    else:
+        vs = np.sqrt(vv)[:, None]
+        Z1 = (vs * G - vs * X @ np.linalg.solve(X.T @ (vv[:, None] * X), X.T @ (vv[:, None] * G))) / np.sqrt(2)
     lambdas = []
     for r in rhos:
         R = np.where(np.eye(M) > 0, 1.0, r)
@@ -217,9 +231,10 @@ def skato(G, w, X, res, be: _Backend | None = None):
     return dict(ok=True, Q=float(Q), rho=float(rho), pvalue=float(pvalue), info=info)
 
 
-def skato_gene(G_raw, af, X, resid, beta1=1.0, beta2=25.0):
+def skato_gene(G_raw, af, X, resid, beta1=1.0, beta2=25.0, vv=None):
     """SkatOTest::fit on one gene: flip/drop monomorphic (DataConsolidator.cpp:46-142), UN-squared
-    weights with the caller-order AF lookup (src/Model.h:2799-2813), then SkatO::Fit."""
+    weights with the caller-order AF lookup (src/Model.h:2799-2813), then SkatO::Fit -- type "C", or
+    type "D" when vv (the logistic null's p(1-p), src/Model.h:2833-2841, 2854-2858) is given."""
     Gc = np.asfortranarray(G_raw, dtype=np.float64)
     N, M = Gc.shape
     out = np.zeros((N, M), order="F")
@@ -229,4 +244,4 @@ def skato_gene(G_raw, af, X, resid, beta1=1.0, beta2=25.0):
     if mp == 0:
         return dict(ok=False, na=True)
     w = np.array([O.lib().orc_skat_weight(float(af[i]), beta1, beta2, 0) for i in range(mp)])
-    return skato(np.ascontiguousarray(out[:, :mp]), w, np.asarray(X, dtype=np.float64), np.asarray(resid))
+    return skato(np.ascontiguousarray(out[:, :mp]), w, np.asarray(X, dtype=np.float64), np.asarray(resid), vv=vv)

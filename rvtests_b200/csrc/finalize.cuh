@@ -312,7 +312,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
       const int i = idx / Mp, k = idx - i * Mp;
       Wm[i * kld + k] = K[i * kld + k] * sc;
     }
-    if (tid < Mp) s_vw[tid] = s_sw[tid] * s_s[tid];
+    if (!tin && tid < Mp) s_vw[tid] = s_sw[tid] * s_s[tid];   // (pre-digested genes bring their own W G'r: TailInput::vw)
     __syncthreads();
   }
 
@@ -341,7 +341,8 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
   if constexpr (SKATO) {
     if (qags && Mp > 0) {
       QagsWork work{qags[g].a, qags[g].b, qags[g].r, qags[g].e, qags[g].order, qags[g].level, kQagsLimit};
-      const double s2 = sigma2 * (double)N / (double)(N - 1);   // ||r||^2/(N-1), SkatO.cpp:136-137
+      // ||r||^2/(N-1), SkatO.cpp:136-137; a binary trait takes s2 = 1 (SkatO.cpp:133-134, FitSKAT :72-75)
+      const double s2 = nm->binary ? 1.0 : sigma2 * (double)N / (double)(N - 1);
       so = skato_tail(Wm, K, Mp, kld, s_vw, s2, s_ev, s_e, s_v, s_p, s_sk.lamz, s_sk.c, &s_sk.mach, work, s_sk.fv, s_sk.bcast, s_th,
                       kTileRows, par);
       phase(5);

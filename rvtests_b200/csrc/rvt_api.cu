@@ -150,6 +150,7 @@ struct rvt_ctx {
   QagsScratch* d_qags = nullptr;   // SKAT-O interval lists, one per gene of a batch
   size_t cap_qags = 0;
   bool skato = false;
+  bool skato_binary = false;   // SKAT-O for a binary trait (SkatO::Fit type "D"); opt-in, see include/rvtests_b200.h
   long long* d_dbg = nullptr;   // optional finalize phase counters (rvt_set_option "debug_phases")
   size_t cap_dbg = 0;
   bool want_dbg = false;
@@ -362,6 +363,8 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
     ctx->splits = (int)value;
   } else if (k == "skato") {
     ctx->skato = value != 0;
+  } else if (k == "skato_binary") {
+    ctx->skato_binary = value != 0;
   } else if (k == "tc_boxes") {
     if (value != 2 && value != 4) CTX_FAIL(RVT_E_BADARG, "tc_boxes must be 2 or 4");
     ctx->tc.boxes = (int)value;
@@ -1459,7 +1462,9 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     RVT_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
     if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nd, sizeof(QagsScratch)))) return rc;
     {
-      const bool sk = ctx->skato && !ctx->binary;   // SKAT-O for a binary trait is not provided: skato_ok stays 0
+      // SKAT-O for a binary trait (SkatO::Fit type "D": the same tail on the p(1-p)-weighted statistics with s2 = 1,
+      // finalize.cuh) runs only with "skato_binary" = 1; otherwise skato_ok stays 0
+      const bool sk = ctx->skato && (!ctx->binary || ctx->skato_binary);
       const int kld = fin_kld(kTileRows), fsm = fin_smem(kTileRows, ctx->ER, sk), wm_off = kTileRows * kld * 8;
       if (sk)
         k_finalize<true><<<nd, kFinThreadsSkato, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, sk), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,

@@ -153,6 +153,37 @@ def test_skato_tail_vs_oracle(hostcheck, oracle, case):
     assert rel(out[2], ref["pvalue"]) <= 1e-8
 
 
+@pytest.mark.parametrize("case", [(21, 800, 10, 3), (22, 1500, 25, 2), (23, 600, 1, 2), (24, 900, 2, 3), (25, 2500, 50, 3)])
+def test_skato_tail_binary_vs_oracle(hostcheck, oracle, case):
+    """binary trait (SkatO::Fit type "D"): the device tail with s2 = 1 on the p(1-p)-weighted M x M statistics the fp64
+    path hands it (K / 2 = W (G'VG - G'VX (X'VX)^-1 X'VG) W / 2, v = W G'(y - p)) vs the literal N x M oracle, itself
+    pinned on the reference's SkatO.cpp (tests/test_oracle_pin_reference_skat.py::test_live_binary_skato)"""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from util import af_of, make_problem
+    from oracle import binary_oracle as BIN
+    from oracle import skato_oracle as SO
+    O = oracle
+    seed, N, M, Cc = case
+    Gm, X, _ = make_problem(O, seed, N, M, Cc, maf=np.linspace(0.01, 0.3, M))
+    rng = np.random.default_rng(seed)
+    y = (rng.random(N) < 1 / (1 + np.exp(0.3 - 0.5 * X[:, -1]))).astype(float)
+    nm = BIN.fit_null_logistic(X, y)
+    ref = SO.skato_gene(Gm.astype(float), af_of(Gm), X, nm["resid"], vv=nm["v"])
+    keep = [j for j in range(M) if Gm[:, j].min() != Gm[:, j].max()]
+    w = np.array([O.lib().orc_skat_weight(float(a), 1.0, 25.0, 0) for a in af_of(Gm)[: len(keep)]])
+    Gw = Gm[:, keep].astype(float) * w[None, :]
+    VG, VX = nm["v"][:, None] * Gw, nm["v"][:, None] * X
+    Wm = np.ascontiguousarray((Gw.T @ VG - (Gw.T @ VX) @ np.linalg.solve(X.T @ VX, X.T @ VG)) / 2)
+    v = np.ascontiguousarray(nm["resid"] @ Gw)
+    out = np.zeros(4)
+    hostcheck.hc_skato_tail(_p(Wm), len(keep), _p(v), 1.0, _p(out))
+    assert out[3] == 1.0 and ref["ok"]
+    assert rel(out[0], ref["Q"]) <= 1e-10
+    assert out[1] == ref["rho"]
+    assert rel(out[2], ref["pvalue"]) <= 1e-8
+
+
 def test_tridiag_hard_spectra(hostcheck):
     """division-free Sturm counts (rescaled polynomial recurrence): graded, clustered, glued and
     rank-deficient spectra, the shapes the SKAT kernel matrix W^1/2 (G'PG) W^1/2 produces"""

@@ -1,0 +1,137 @@
+"""GPU (-m gpu): SKAT-O on genes that take the fp64 path (pre-digested statistics handed to k_finalize<true>):
+  * quantitative trait, genes with missing calls (mean-imputed on the device, A0) and dosage genes -- SkatO::Fit type "C";
+  * binary trait (option "skato_binary") -- SkatO::Fit type "D" (src/Model.h:2833-2841, 2854-2858; SkatO.cpp:72-91,
+    133-134, 150-158): the same tail on the p(1-p)-weighted statistics with s2 = 1.
+The oracle (oracle/skato_oracle.py) is pinned on the reference's own SkatO.cpp for both types
+(tests/test_oracle_pin_reference_skat.py::test_live_reference_build, ::test_live_binary_skato).
+This file sorts last on purpose: it was written after the round's GPU budget was spent, so the
+rest of the suite runs before it."""
+import numpy as np
+import pytest
+
+from util import af_of, check_gene, make_problem, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_skato(r, ref, ctx):
+    assert int(r["skato_ok"]) == int(ref["ok"]), ctx
+    if ref["ok"]:
+        assert rel(r["skato_Q"], ref["Q"]) <= 1e-6, (ctx, r["skato_Q"], ref["Q"])
+        assert r["skato_rho"] == ref["rho"], (ctx, r["skato_rho"], ref["rho"])
+        assert rel(r["skato_p"], ref["pvalue"]) <= 1e-5, (ctx, r["skato_p"], ref["pvalue"])
+
+
+@pytest.mark.parametrize("case", [(175, 700, 8, 1, 0.02), (171, 3001, 30, 3, 0.01), (172, 1200, 1, 2, 0.03)])
+def test_skato_on_genes_with_missing_calls(engine_cls, oracle, case):
+    from oracle import skato_oracle as SO
+    from rvtests_b200.synth import pack_bed
+    O = oracle
+    seed, N, M, C, miss = case
+    G, X, y = make_problem(O, seed, N, M, C, maf=np.linspace(0.004, 0.3 if M <= 8 else 0.03, M), n_flip=2 if M > 2 else 0)
+    rng = np.random.default_rng(seed)
+    mask = rng.random((M, N)) < miss
+    bed = pack_bed(G.T, mask)
+    raw = O.bed_decode_fast(bed, N).T
+    Gd = O.impute_mean(raw)
+    af = 0.5 * np.where(raw >= 0, raw, 0.0).sum(axis=0) / N
+    nm = O.fit_null_linear(X, y)
+    eng = engine_cls(0)
+    try:
+        eng.set_option("skato", 1)
+        eng.set_null_model(X, y)
+        eng.push_bed(bed, af)                       # missing calls -> fp64 path
+        eng.push_f64(Gd, af)                        # the same gene as dosages -> fp64 path
+        eng.push_bed(pack_bed(G.T), af_of(G))       # complete gene -> integer sweep, same flush
+        r = eng.flush()
+    finally:
+        eng.close()
+    ref = SO.skato_gene(Gd, af, X, nm["resid"])
+    _check_skato(r[0], ref, f"bed+missing {case}")
+    _check_skato(r[1], ref, f"dosage {case}")
+    _check_skato(r[2], SO.skato_gene(G.astype(float), af_of(G), X, nm["resid"]), f"complete {case}")
+    if M > 1:                                       # the SKAT / burden columns are unaffected by enabling SKAT-O
+        refs, lam = O.gene(Gd, af, X, nm["resid"], nm["sigma2"])
+        check_gene(r[0], refs, lam, ctx=f"skat columns with skato on, bed+missing {case}")
+        check_gene(r[1], refs, lam, ctx=f"skat columns with skato on, dosage {case}")
+
+
+@pytest.mark.parametrize("case", [(180, 900, 12, 1, 0.3), (181, 4000, 40, 3, 0.05), (182, 2500, 64, 2, 0.1), (183, 1500, 1, 2, 0.2),
+                                  (184, 1800, 2, 3, 0.2)])
+def test_binary_trait_skato_vs_oracle(engine_cls, oracle, case):
+    from oracle import binary_oracle as BIN
+    from oracle import skato_oracle as SO
+    from rvtests_b200.synth import pack_bed
+    O = oracle
+    seed, N, M, C, hi = case
+    G, X, _ = make_problem(O, seed, N, M, C, maf=np.linspace(0.004, hi, M), n_flip=2 if M > 2 else 0, n_mono=1 if M > 12 else 0)
+    rng = np.random.default_rng(seed)
+    eta = -0.8 + (X[:, 1:] @ np.full(C - 1, 0.5) if C > 1 else 0.0)
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(-eta))).astype(np.float64)
+    nm = BIN.fit_null_logistic(X, y)
+    af = af_of(G)
+    ref_skat = BIN.gene(G.astype(float), af, X, nm)
+    ref = SO.skato_gene(G.astype(float), af, X, nm["resid"], vv=nm["v"])
+    eng = engine_cls(0)
+    try:
+        eng.set_option("skato", 1)
+        eng.set_null_model(X, y, binary=True)
+        eng.push_i8(G.T.copy(), af)
+        off = eng.flush()[0]
+        assert int(off["skato_ok"]) == 0            # without the opt-in: not provided, NA
+        eng.set_option("skato_binary", 1)
+        eng.push_i8(G.T.copy(), af)
+        eng.push_bed(pack_bed(G.T), af)
+        res = eng.flush()
+    finally:
+        eng.close()
+    for k in range(2):
+        _check_skato(res[k], ref, f"binary {case} push {k}")
+        assert rel(res[k]["Q"], ref_skat["Q"]) <= 1e-6 and rel(res[k]["p_skat"], ref_skat["p_skat"]) <= 1e-4
+        assert rel(off["Q"], res[k]["Q"]) <= 1e-12
+
+
+def test_adapter_prints_skato_for_a_binary_trait(oracle, tmp_path):
+    """SkatOTest adapter with setBinaryOutcome() + enableSkatOBinary(): the Q / rho / Pvalue columns against the oracle
+    (adapter_demo argv[6] = 1); without the opt-in the line stays NA (tests/test_gpu_adapters.py)."""
+    import struct
+    import subprocess
+    from oracle import binary_oracle as BIN
+    from oracle import skato_oracle as SO
+    from test_gpu_adapters import build_demo
+    import rvtests_b200
+    rvtests_b200.load_library()
+    O = oracle
+    N, C = 1500, 2
+    genes = []
+    X = None
+    for gi, (M, nm_, nf) in enumerate([(8, 0, 1), (30, 2, 2), (1, 0, 0)]):
+        G, X, _ = make_problem(O, 79, N, M, C, maf=np.linspace(0.004, 0.05, M), n_mono=nm_, n_flip=nf)
+        genes.append(G)
+    rng = np.random.default_rng(79)
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(0.5 - 0.6 * X[:, 1]))).astype(np.float64)
+    path = tmp_path / "problem.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("iii", N, C - 1, len(genes)))
+        f.write(np.ascontiguousarray(y).tobytes())
+        f.write(np.asfortranarray(X[:, 1:]).tobytes(order="F"))
+        for G in genes:
+            f.write(struct.pack("i", G.shape[1]))
+            f.write(np.asfortranarray(G.astype(np.float64)).tobytes(order="F"))
+            f.write(af_of(G).tobytes())
+    exe = build_demo()
+    out = subprocess.run([exe, str(path), "8", "0", "0.05", "1", "1"], capture_output=True, text=True, check=True).stdout
+    tables, cur = {}, None
+    for line in out.splitlines():
+        if line.startswith("#"):
+            cur = line[1:]
+            tables[cur] = []
+        else:
+            tables[cur].append(line.split("\t"))
+    nm = BIN.fit_null_logistic(X, y)
+    for gi, G in enumerate(genes):
+        ref = SO.skato_gene(G.astype(float), af_of(G), X, nm["resid"], vv=nm["v"])
+        ro = tables["SkatO"][1 + gi][3:]
+        assert ref["ok"] and "NA" not in ro, (gi, ro)
+        # "%g" prints 6 significant digits
+        assert rel(float(ro[0]), ref["Q"]) <= 2e-5 and float(ro[1]) == ref["rho"] and rel(float(ro[2]), ref["pvalue"]) <= 3e-5, (gi, ro, ref)

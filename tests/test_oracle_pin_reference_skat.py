@@ -311,3 +311,43 @@ def test_live_binary_trait(oracle):
                 assert rel(out[name]["p"], st["pvalue"]) <= 1e-8
         else:
             assert O.ref_logistic_score_test(X, y, (Gf > 0).any(1).astype(float))["rc"] == -3
+
+
+def _binary_problem(O, seed, N, M, Cc):
+    G, X, _ = make_problem(O, seed, N, M, Cc, maf=np.linspace(0.005, 0.3 if M <= 12 else 0.03, M), n_flip=1 if M > 2 else 0,
+                           n_mono=1 if M > 2 else 0)
+    rng = np.random.default_rng(seed)
+    eta = X @ np.r_[-0.4, rng.normal(size=Cc - 1) * 0.5] + 0.4 * G[:, 0]
+    y = (rng.random(N) < 1 / (1 + np.exp(-eta))).astype(float)
+    return G, X, y
+
+
+BINARY_SKATO_CASES = ((511, 800, 10, 3), (512, 1500, 25, 2), (513, 600, 8, 1), (514, 700, 1, 2), (515, 900, 2, 3))
+
+
+@pytest.mark.parametrize("case", BINARY_SKATO_CASES)
+def test_live_binary_skato(oracle, case):
+    """SkatO::Fit type "D" (src/Model.h:2833-2841, 2854-2858; SkatO.cpp:72-91, 133-134, 150-158): the numpy restatement
+    (oracle/skato_oracle.py with vv = p(1-p)) against the reference's own SkatO.cpp driven with the reference's own
+    logistic null model, incl. the single-variant branch (FitSKAT) and a two-variant gene."""
+    from oracle import binary_oracle as BIN
+    from oracle import skato_oracle as SO
+    O = oracle
+    if O.ref_skat() is None:
+        pytest.skip("oracle/_ref/libskat_ref.so not built (no /root/reference here)")
+    seed, N, M, Cc = case
+    G, X, y = _binary_problem(O, seed, N, M, Cc)
+    ref = O.ref_logistic_fit(X, y)
+    assert ref["rc"] == 0
+    nm = BIN.fit_null_logistic(X, y)
+    Gf, w1 = _prep(O, G)
+    want = O.ref_skato_fit(y - ref["p"], ref["v"], X, Gf, w1, binary=True)
+    assert want["rc"] == 0
+    got = SO.skato_gene(G.astype(float), af_of(G), X, nm["resid"], vv=nm["v"])
+    assert got["ok"]
+    assert rel(got["Q"], want["Q"]) <= 1e-10, (got["Q"], want["Q"])
+    assert got["rho"] == want["rho"]
+    assert rel(got["pvalue"], want["pvalue"]) <= 1e-8, (got["pvalue"], want["pvalue"])
+    # and it is NOT the quantitative formula on the same inputs (s2 and the V-weighting both matter)
+    other = SO.skato_gene(G.astype(float), af_of(G), X, nm["resid"])
+    assert rel(other["Q"], want["Q"]) > 1e-3
