@@ -325,6 +325,85 @@ def ref_genotype_counter(g):
                 af=out[5], ac=out[6], hwe_p=out[7])
 
 
+def ref_vcf():
+    """The reference's own VCF record parser (libVcf/VCFRecord, VCFIndividual, VCFValue ... compiled unmodified into
+    oracle/_ref/libvcf_ref.so behind oracle/ref_vcf_shim.cpp).  None when oracle/_ref was never built."""
+    if "vcf" not in _lib_cache:
+        path = os.path.join(_HERE, "_ref", "libvcf_ref.so")
+        if not os.path.exists(path):
+            _lib_cache["vcf"] = None
+        else:
+            L = C.CDLL(path)
+            L.ref_vcf_genotypes.restype = C.c_int
+            L.ref_vcf_genotypes.argtypes = [C.c_char_p, C.c_char_p, _int_p, C.c_int, C.c_char_p, _int_p]
+            L.ref_vcf_gt.restype = C.c_int
+            L.ref_vcf_gt.argtypes = [C.c_char_p, C.c_int]
+            _lib_cache["vcf"] = L
+    return _lib_cache["vcf"]
+
+
+def ref_vcf_genotypes(header: str, record: str):
+    """One VCF data line through the reference's parser: (chrom, pos, genotypes per sample with -9 = missing)."""
+    L = ref_vcf()
+    cap = header.count("\t") + 1
+    out = np.zeros(cap, dtype=np.int32)
+    chrom = C.create_string_buffer(64)
+    pos = C.c_int(0)
+    n = L.ref_vcf_genotypes(header.encode(), record.encode(), out.ctypes.data_as(_int_p), cap, chrom, C.byref(pos))
+    if n < 0:
+        return None
+    return chrom.value.decode(), pos.value, out[:n].copy()
+
+
+def vcf_gt(s: str) -> int:
+    """VCFValue::getGenotype (libVcf/VCFValue.h:74-116) restated: the GT grammar of the default --inVcf path.
+    '0' / '1' haploid; a|b or a/b with single-digit alleles 0/1; '.' anywhere, any allele > 1 (multi-allelic), a wrong
+    separator or trailing characters -> missing (-9); a second allele below '0' (e.g. '-') is reported and IGNORED."""
+    c = s[0] if len(s) > 0 else "\0"
+    if c == "." or c < "0":
+        return -9
+    g = ord(c) - ord("0")
+    if g > 1:
+        return -9
+    if len(s) == 1:
+        return g
+    if s[1] not in "|/":
+        return -9
+    if len(s) == 2:
+        return -9
+    c = s[2]
+    if c == ".":
+        return -9
+    if not c < "0":
+        a2 = ord(c) - ord("0")
+        if a2 > 1:
+            return -9
+        g += a2
+    if len(s) != 3:
+        return -9
+    return g
+
+
+def vcf_record_genotypes(header: str, record: str):
+    """VCFRecord::parse + getFormatIndex("GT") (prefix match) + VCFIndividual::parse + justGet + getGenotype restated:
+    (chrom, pos, genotypes) or None for a record whose sample count differs from the header's."""
+    names = header.rstrip("\r\n").split("\t")[9:]
+    f = record.rstrip("\r\n").split("\t")
+    if len(f) < 10 or len(f) - 9 != len(names):
+        return None
+    idx = -1
+    for k, key in enumerate(f[8].split(":")):
+        if key.startswith("GT"):
+            idx = k
+            break
+    out = np.full(len(names), -9, dtype=np.int32)
+    if idx >= 0:
+        for i, col in enumerate(f[9:]):
+            sub = col.split(":")
+            out[i] = vcf_gt(sub[idx] if idx < len(sub) else "")
+    return f[0], int(f[1]) if f[1].lstrip("+-").isdigit() else 0, out
+
+
 def ref_model():
     """The reference's own model layer (src/Model.cpp + Model.h fitters, src/DataConsolidator.cpp ...) built into
     oracle/_ref/libmodel_ref.so behind oracle/ref_model_shim.cpp.  None when oracle/_ref was never built."""

@@ -1,0 +1,59 @@
+// oracle/ref_vcf_shim.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+// Drives the REFERENCE's own VCF record parser, compiled unmodified from /root/reference/libVcf
+// (VCFRecord.cpp, VCFIndividual.cpp, VCFInfo.cpp, VCFHeader.cpp, VCFBuffer.cpp, VCFValue.cpp, PeopleSet.cpp), the way
+// VCFGenotypeExtractor::extractMultipleGenotype does for hard calls outside hemizygous regions with no GD/GQ filter
+// (src/VCFGenotypeExtractor.cpp:29-140, 397-439): createIndividual(header) -> parse(line) -> getFormatIndex("GT") ->
+// people[i]->justGet(idx).getGenotype().  Output goes to oracle/_ref/libvcf_ref.so only.
+#include <string.h>
+
+#include <string>
+
+#include "libVcf/VCFRecord.h"
+
+// BufferedReader (base/IO.cpp needs bzip2/zlib trees that are not built here) is only reached from
+// include/excludePeopleFromFile, which this shim never calls
+#include <stdlib.h>
+static void unreachable(const char* w) {
+  fprintf(stderr, "ref_vcf_shim: %s reached\n", w);
+  abort();
+}
+BufferedReader::BufferedReader(const char*, int) { unreachable("BufferedReader"); }
+int BufferedReader::readLineBySep(std::vector<std::string>*, const char*) { unreachable("BufferedReader"); return 0; }
+bool BufferedReader::isEof() { return true; }
+void BufferedReader::close() {}
+int BufferedReader::getc() { return EOF; }
+int BufferedReader::read(void*, int) { return 0; }
+
+extern "C" {
+// header: the "#CHROM\tPOS..." line; record: one data line (no newline).  out[cap] receives the genotype per sample
+// (0/1/2, MISSING_GENOTYPE = -9); chrom (>= 64 bytes) and pos the site.  Returns the number of samples, < 0 on a parse error.
+int ref_vcf_genotypes(const char* header, const char* record, int* out, int cap, char* chrom, int* pos) {
+  VCFRecord r;
+  r.createIndividual(std::string(header));
+  r.includeAllPeople();
+  std::string line(record);
+  if (r.parse(&line)) {
+    r.deleteIndividual();
+    return -1;
+  }
+  const int idx = r.getFormatIndex("GT");
+  VCFPeople& people = r.getPeople();
+  const int n = (int)people.size();
+  for (int i = 0; i < n && i < cap; ++i) out[i] = idx >= 0 ? people[i]->justGet(idx).getGenotype() : MISSING_GENOTYPE;
+  strncpy(chrom, r.getChrom(), 63);
+  chrom[63] = 0;
+  *pos = r.getPos();
+  r.deleteIndividual();
+  return n;
+}
+
+// VCFValue::getGenotype on one GT string (libVcf/VCFValue.h:74-116)
+int ref_vcf_gt(const char* s, int len) {
+  char buf[64];
+  if (len > 63) len = 63;
+  memcpy(buf, s, len);
+  buf[len] = 0;
+  VCFValue v(buf, 0, len);
+  return v.getGenotype();
+}
+}

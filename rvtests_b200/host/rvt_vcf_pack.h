@@ -1,0 +1,297 @@
+// rvt_vcf_pack.h -- genotype ingestion for the engine: VCF text records -> PLINK 2-bit
+// SNP-major rows + the per-variant AF side table, i.e. exactly what rvt_gene_push_bed() takes, without ever building
+// the reference's N x M `Matrix` of doubles (24-200 MB per gene at the BASELINE sizes).
+//
+// What it replaces on the reference side (hard calls, autosomal / non-hemizygous sites, no GD/GQ filter, no dosage tag,
+// no multi-allelic expansion -- the default `--inVcf` path of a gene-based run):
+//   VCFRecord::parse / parseSite / parseIndividual        libVcf/VCFRecord.h:30-201     (tab-separated columns)
+//   VCFRecord::getFormatIndex("GT")                       libVcf/VCFRecord.h:280-306    (PREFIX match, first hit)
+//   VCFIndividual::parse + justGet(idx)                   libVcf/VCFIndividual.h:27-59, 95-100 (':'-separated subfields;
+//                                                         a column with too few subfields yields an empty value = missing)
+//   VCFValue::getGenotype                                 libVcf/VCFValue.h:74-116      (the GT grammar, quirks included)
+//   VCFGenotypeExtractor::extractMultipleGenotype         src/VCFGenotypeExtractor.cpp:29-140, getGenotype :397-439
+//   GenotypeCounter::add / getAF                          src/GenotypeCounter.h:14-52   (AF = 0.5 * sumAC / nSample, missing
+//                                                         calls stay in the denominator)
+//   RangeList "chr:beg-end[,chr:beg-end...]" sets          src/Main.cpp --setFile / --rangeList (1-based, inclusive ends)
+// Samples come out in VCF column order restricted to the kept names (VCFRecord::includePeople semantics); the caller
+// orders the phenotype accordingly, as DataLoader does.  Missing calls become the .bed code 01 and are mean-imputed on the
+// device (DataConsolidator::imputeGenotypeToMean).  Header-only, C++11, no dependency but the C ABI header.
+#ifndef RVT_VCF_PACK_H_
+#define RVT_VCF_PACK_H_
+
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <set>
+#include <string>
+#include <vector>
+
+#include "rvtests_b200.h"
+
+namespace rvtb200 {
+
+enum { kVcfMissing = -9 };  // MISSING_GENOTYPE, libVcf/VCFConstant.h:4
+
+// VCFValue::getGenotype (libVcf/VCFValue.h:74-116) on the GT subfield s[0, len).  Reading one past the end yields '\0'
+// like the reference's NUL-terminated in-place buffer.
+inline int vcfGenotype(const char* s, int len) {
+  int p = 0;
+  const char c0 = len > 0 ? s[0] : '\0';
+  if (c0 == '.') return kVcfMissing;
+  if (c0 < '0') return kVcfMissing;   // "Wrong genotype detected. [1]"
+  int g = c0 - '0';
+  if (g > 1) return kVcfMissing;      // multi-allelic (or any byte above '1')
+  p++;
+  if (p >= len) return g;             // haploid call
+  if (s[p] != '|' && s[p] != '/') return kVcfMissing;
+  p++;
+  if (p >= len) return kVcfMissing;   // "Wrong genotype length = 2"
+  if (s[p] == '.') return kVcfMissing;
+  if (s[p] < '0') {
+    // "Wrong genotype detected. [2]": the reference reports and carries on WITHOUT adding a second allele
+  } else {
+    const int a2 = s[p] - '0';
+    if (a2 > 1) return kVcfMissing;
+    g += a2;
+  }
+  p++;
+  if (p != len) return kVcfMissing;
+  return g;
+}
+
+// one or more "chr:beg-end" ranges (also "chr" = whole chromosome, "chr:pos" = one base); 1-based, inclusive
+class VcfRangeSet {
+ public:
+  void clear() { r_.clear(); }
+  bool empty() const { return r_.empty(); }
+  // returns the number of ranges added, < 0 on a malformed piece
+  int add(const std::string& spec) {
+    int added = 0;
+    size_t b = 0;
+    while (b <= spec.size()) {
+      size_t e = spec.find(',', b);
+      if (e == std::string::npos) e = spec.size();
+      if (e > b) {
+        Range r;
+        const std::string piece = spec.substr(b, e - b);
+        const size_t colon = piece.find(':');
+        if (colon == std::string::npos) {
+          r.chrom = piece;
+          r.beg = 0;
+          r.end = INT32_MAX;
+        } else {
+          r.chrom = piece.substr(0, colon);
+          const std::string rest = piece.substr(colon + 1);
+          const size_t dash = rest.find('-');
+          char* endp = NULL;
+          if (rest.empty()) return -1;
+          r.beg = (int)strtol(rest.c_str(), &endp, 10);
+          if (endp == rest.c_str()) return -1;
+          if (dash == std::string::npos) {
+            r.end = r.beg;
+          } else if (dash + 1 == rest.size()) {
+            r.end = INT32_MAX;   // "chr:beg-" = to the end of the chromosome
+          } else {
+            r.end = (int)strtol(rest.c_str() + dash + 1, &endp, 10);
+            if (endp == rest.c_str() + dash + 1) return -1;
+          }
+        }
+        if (r.chrom.empty() || r.end < r.beg) return -1;
+        r_.push_back(r);
+        ++added;
+      }
+      b = e + 1;
+    }
+    return added;
+  }
+  bool contains(const char* chrom, size_t chrom_len, int pos) const {
+    for (size_t i = 0; i < r_.size(); ++i)
+      if (r_[i].chrom.size() == chrom_len && memcmp(r_[i].chrom.data(), chrom, chrom_len) == 0 && pos >= r_[i].beg && pos <= r_[i].end)
+        return true;
+    return false;
+  }
+
+ private:
+  struct Range {
+    std::string chrom;
+    int beg, end;
+  };
+  std::vector<Range> r_;
+};
+
+class VcfGenePacker {
+ public:
+  VcfGenePacker() : ncol_(0), n_(0), stride_(0), m_(0) {}
+
+  // the "#CHROM\tPOS\t...\tFORMAT\tS1\tS2..." line.  keep: names to include (NULL or empty: everyone); samples are
+  // emitted in VCF column order (VCFRecord::createIndividual + includePeople, libVcf/VCFRecord.h:203-231).
+  // Returns the number of samples kept, < 0 when the line has no sample columns or repeats/misses a kept name.
+  int setHeader(const char* line, size_t len, const std::vector<std::string>* keep = NULL) {
+    while (len && (line[len - 1] == '\n' || line[len - 1] == '\r')) --len;
+    std::set<std::string> want;
+    if (keep) want.insert(keep->begin(), keep->end());
+    col_to_out_.clear();
+    names_.clear();
+    size_t b = 0;
+    int col = 0;
+    while (b <= len) {
+      const char* t = (const char*)memchr(line + b, '\t', len - b);
+      const size_t e = t ? (size_t)(t - line) : len;
+      if (col >= 9) {
+        const std::string name(line + b, e - b);
+        if (name.empty()) return -2;   // the reference exits on an empty column header
+        if (want.empty() || want.count(name)) {
+          col_to_out_.push_back((int)names_.size());
+          names_.push_back(name);
+        } else {
+          col_to_out_.push_back(-1);
+        }
+      }
+      ++col;
+      b = e + 1;
+    }
+    ncol_ = (int)col_to_out_.size();
+    n_ = (int64_t)names_.size();
+    stride_ = (n_ + 3) / 4;
+    clear();
+    if (ncol_ == 0) return -1;
+    if (!want.empty() && names_.size() != want.size()) return -3;
+    return (int)n_;
+  }
+
+  int64_t numSample() const { return n_; }
+  int64_t stride() const { return stride_; }
+  const std::vector<std::string>& sampleNames() const { return names_; }
+  VcfRangeSet& ranges() { return ranges_; }
+
+  // start the next gene: drops the rows collected so far (the range set stays; change it through ranges())
+  void clear() {
+    m_ = 0;
+    rows_.clear();
+    af_.clear();
+    counts_.clear();
+    names_var_.clear();
+  }
+
+  // One VCF line.  Returns 1 when the record became the next variant row of the current gene, 0 when it was skipped
+  // (meta/header line, or outside the range set when one is given), < 0 on a malformed record (fewer than 9 site
+  // columns, or a sample count different from the header's: VCFRecord::parseIndividual returns -1 for both).
+  int addRecord(const char* line, size_t len) {
+    while (len && (line[len - 1] == '\n' || line[len - 1] == '\r')) --len;
+    if (len == 0 || line[0] == '#') return 0;
+    if (ncol_ == 0) return -10;
+    // the nine site columns
+    size_t fb[9], fe[9];
+    size_t b = 0;
+    for (int c = 0; c < 9; ++c) {
+      if (b > len) return -1;
+      const char* t = (const char*)memchr(line + b, '\t', len - b);
+      if (!t && c < 8) return -1;
+      fb[c] = b;
+      fe[c] = t ? (size_t)(t - line) : len;
+      b = fe[c] + 1;
+    }
+    if (fe[8] >= len) return -1;   // no sample columns at all
+    const int pos = atoi(std::string(line + fb[1], fe[1] - fb[1]).c_str());
+    if (!ranges_.empty() && !ranges_.contains(line + fb[0], fe[0] - fb[0], pos)) return 0;
+    const int gt = formatIndex(line + fb[8], fe[8] - fb[8], "GT");
+
+    const size_t row0 = rows_.size();
+    rows_.resize(row0 + (size_t)stride_, 0);
+    uint8_t* row = &rows_[row0];
+    int cnt[4] = {0, 0, 0, 0};   // hom-ref, het, hom-alt, missing
+    int col = 0;
+    while (true) {
+      if (col >= ncol_) {   // "VCF header have LESS people than VCF content!"
+        rows_.resize(row0);
+        return -2;
+      }
+      const char* t = (const char*)memchr(line + b, '\t', len - b);
+      const size_t e = t ? (size_t)(t - line) : len;
+      const int o = col_to_out_[col];
+      if (o >= 0) {
+        int g = kVcfMissing;
+        if (gt >= 0) {
+          // the gt-th ':'-separated subfield; a column with fewer subfields reads as the empty value
+          size_t sb = b;
+          int k = 0;
+          while (k < gt && sb <= e) {
+            const char* cpos = (const char*)memchr(line + sb, ':', e - sb);
+            if (!cpos) {
+              sb = e + 1;
+              break;
+            }
+            sb = (size_t)(cpos - line) + 1;
+            ++k;
+          }
+          if (sb <= e && k == gt) {
+            const char* cpos = (const char*)memchr(line + sb, ':', e - sb);
+            const size_t se = cpos ? (size_t)(cpos - line) : e;
+            g = vcfGenotype(line + sb, (int)(se - sb));
+          }
+        }
+        // .bed codes, sample 0 in the low bits (libVcf/PlinkInputFile.h:206-209): 00 hom-ref, 10 het, 11 hom-alt, 01 missing
+        const unsigned code = g == 0 ? 0u : g == 1 ? 2u : g == 2 ? 3u : 1u;
+        row[o >> 2] |= (uint8_t)(code << ((o & 3) * 2));
+        ++cnt[g == 0 ? 0 : g == 1 ? 1 : g == 2 ? 2 : 3];
+      }
+      ++col;
+      if (!t) break;
+      b = e + 1;
+    }
+    if (col != ncol_) {   // "VCF header have MORE people than VCF content!"
+      rows_.resize(row0);
+      return -3;
+    }
+    // GenotypeCounter::getAF: 0.5 * sumAC / nSample, nSample counting the missing calls too
+    af_.push_back(n_ ? 0.5 * (double)(cnt[1] + 2 * cnt[2]) / (double)n_ : -1.0);
+    for (int k = 0; k < 4; ++k) counts_.push_back(cnt[k]);
+    names_var_.push_back(std::string(line + fb[0], fe[0] - fb[0]) + ":" + std::string(line + fb[1], fe[1] - fb[1]));
+    ++m_;
+    return 1;
+  }
+
+  int numVariant() const { return m_; }
+  const uint8_t* rows() const { return rows_.empty() ? NULL : &rows_[0]; }
+  const double* af() const { return af_.empty() ? NULL : &af_[0]; }
+  // [4 * j + k]: hom-ref, het, hom-alt, missing of variant j
+  const int* counts() const { return counts_.empty() ? NULL : &counts_[0]; }
+  const std::string& variantName(int j) const { return names_var_[j]; }   // "chrom:pos" (VCFGenotypeExtractor.cpp:113-116)
+
+  // hand the collected gene to the engine (rvt_gene_push_bed copies; the packer can be cleared right after)
+  int push(rvt_ctx* ctx) const {
+    if (m_ == 0) return RVT_E_BADARG;
+    return rvt_gene_push_bed(ctx, rows(), m_, stride_, af());
+  }
+
+ private:
+  // VCFRecord::getFormatIndex (libVcf/VCFRecord.h:280-306): index of the first FORMAT key that STARTS WITH `key`
+  static int formatIndex(const char* f, size_t len, const char* key) {
+    const size_t kl = strlen(key);
+    size_t b = 0;
+    int idx = 0;
+    while (b < len) {
+      if (kl <= len - b && memcmp(f + b, key, kl) == 0) return idx;
+      ++idx;
+      const char* c = (const char*)memchr(f + b, ':', len - b);
+      if (!c) return -1;
+      b = (size_t)(c - f) + 1;
+    }
+    return -1;
+  }
+
+  int ncol_;                      // sample columns in the header
+  int64_t n_, stride_;
+  int m_;
+  std::vector<int> col_to_out_;   // VCF sample column -> output sample index, -1 = not kept
+  std::vector<std::string> names_, names_var_;
+  std::vector<uint8_t> rows_;
+  std::vector<double> af_;
+  std::vector<int> counts_;
+  VcfRangeSet ranges_;
+};
+
+}  // namespace rvtb200
+
+#endif  // RVT_VCF_PACK_H_

@@ -67,3 +67,68 @@ def hostcheck():
 def engine_cls():
     import rvtests_b200
     return rvtests_b200.GeneEngine
+
+
+class VcfPacker:
+    """ctypes view of the product's host-side VCF packer (rvtests_b200/host/rvt_vcf_pack.h) through
+    tests/hostcheck/vcfpack_check.cpp."""
+
+    def __init__(self, lib):
+        import ctypes as C
+        self.L = lib
+        lib.vp_gt.argtypes = [C.c_char_p, C.c_int]
+        lib.vp_header.argtypes = [C.c_char_p, C.c_char_p]
+        lib.vp_set_range.argtypes = [C.c_char_p]
+        lib.vp_add.argtypes = [C.c_char_p, C.c_int]
+        lib.vp_stride.restype = C.c_longlong
+        lib.vp_num_sample.restype = C.c_longlong
+        lib.vp_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.vp_variant_name.restype = C.c_char_p
+        lib.vp_variant_name.argtypes = [C.c_int]
+        lib.vp_sample_name.restype = C.c_char_p
+        lib.vp_sample_name.argtypes = [C.c_int]
+
+    def gt(self, s):
+        b = s.encode("latin-1")
+        return self.L.vp_gt(b, len(b))
+
+    def header(self, line, keep=None):
+        return self.L.vp_header(line.encode(), None if keep is None else "\n".join(keep).encode())
+
+    def set_range(self, spec):
+        return self.L.vp_set_range((spec or "").encode())
+
+    def clear(self):
+        self.L.vp_clear()
+
+    def add(self, line):
+        b = line.encode("latin-1")
+        return self.L.vp_add(b, len(b))
+
+    def sample_names(self):
+        return [self.L.vp_sample_name(i).decode() for i in range(self.L.vp_num_sample())]
+
+    def gene(self):
+        """(rows uint8 (M, stride), af (M,), counts (M, 4) = hom-ref / het / hom-alt / missing, names)"""
+        import numpy as np
+        m, st = self.L.vp_num_variant(), self.L.vp_stride()
+        rows = np.zeros((m, st), dtype=np.uint8)
+        af = np.zeros(m)
+        counts = np.zeros((m, 4), dtype=np.int32)
+        if m:
+            self.L.vp_get(rows.ctypes.data, af.ctypes.data, counts.ctypes.data)
+        return rows, af, counts, [self.L.vp_variant_name(j).decode() for j in range(m)]
+
+
+@pytest.fixture(scope="session")
+def vcfpack():
+    import ctypes as C
+    import subprocess
+    d = os.path.join(ROOT, "tests", "hostcheck")
+    so = os.path.join(d, "libvcfpack_check.so")
+    deps = [os.path.join(d, "vcfpack_check.cpp"), os.path.join(ROOT, "rvtests_b200", "host", "rvt_vcf_pack.h"),
+            os.path.join(ROOT, "include", "rvtests_b200.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in deps):
+        subprocess.run(["g++", "-O2", "-std=c++11", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), deps[0], "-o", so],
+                       check=True)
+    return VcfPacker(C.CDLL(so))

@@ -1,0 +1,48 @@
+// tests/hostcheck/vcfpack_check.cpp -- C wrapper around the product's host-side VCF packer (rvtests_b200/host/rvt_vcf_pack.h)
+// so that the CPU tests can drive it through ctypes.  rvt_gene_push_bed is referenced by VcfGenePacker::push only; the
+// wrapper never calls it, and the test library is linked without the engine (the symbol stays an unused inline reference).
+#include <string>
+#include <vector>
+
+#include "../../rvtests_b200/host/rvt_vcf_pack.h"
+
+extern "C" int rvt_gene_push_bed(rvt_ctx*, const uint8_t*, int, int64_t, const double*) { return RVT_E_UNSUPPORTED; }
+
+static rvtb200::VcfGenePacker g_p;
+
+extern "C" {
+int vp_gt(const char* s, int len) { return rvtb200::vcfGenotype(s, len); }
+// keep: '\n'-separated names or NULL
+int vp_header(const char* line, const char* keep) {
+  std::vector<std::string> k;
+  if (keep) {
+    std::string s(keep);
+    size_t b = 0;
+    while (b < s.size()) {
+      size_t e = s.find('\n', b);
+      if (e == std::string::npos) e = s.size();
+      if (e > b) k.push_back(s.substr(b, e - b));
+      b = e + 1;
+    }
+  }
+  return g_p.setHeader(line, strlen(line), keep ? &k : NULL);
+}
+int vp_set_range(const char* spec) {
+  g_p.ranges().clear();
+  return spec && spec[0] ? g_p.ranges().add(spec) : 0;
+}
+void vp_clear() { g_p.clear(); }
+int vp_add(const char* line, int len) { return g_p.addRecord(line, (size_t)len); }
+int vp_num_variant() { return g_p.numVariant(); }
+long long vp_stride() { return g_p.stride(); }
+long long vp_num_sample() { return g_p.numSample(); }
+void vp_get(unsigned char* rows, double* af, int* counts) {
+  const int m = g_p.numVariant();
+  if (m == 0) return;
+  memcpy(rows, g_p.rows(), (size_t)m * g_p.stride());
+  memcpy(af, g_p.af(), sizeof(double) * m);
+  memcpy(counts, g_p.counts(), sizeof(int) * 4 * m);
+}
+const char* vp_variant_name(int j) { return g_p.variantName(j).c_str(); }
+const char* vp_sample_name(int i) { return g_p.sampleNames()[i].c_str(); }
+}

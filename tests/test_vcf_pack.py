@@ -1,0 +1,154 @@
+"""CPU: genotype ingestion -- the product's host-side VCF packer (rvtests_b200/host/rvt_vcf_pack.h: VCF text
+-> PLINK 2-bit rows + AF for rvt_gene_push_bed) against
+  * the REFERENCE's own VCF record parser compiled unmodified (oracle/_ref/libvcf_ref.so: libVcf/VCFRecord, VCFIndividual,
+    VCFValue::getGenotype ...), live when oracle/_ref is built,
+  * the committed golden vectors that build produced (tests/golden/vcf_golden.json, make_golden_vcf.py),
+  * the Python restatement (oracle.vcf_gt / vcf_record_genotypes), itself held against both."""
+import itertools
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "vcf_golden.json")
+ALPHABET = "012.|/-9a"
+
+
+def _all_gt_strings(maxlen=4):
+    for n in range(maxlen + 1):
+        for t in itertools.product(ALPHABET, repeat=n):
+            yield "".join(t)
+
+
+def test_gt_grammar_exhaustive(vcfpack, oracle, capfd):
+    """every string of up to 4 characters over '012.|/-9a': product == restatement == reference build"""
+    ref = oracle.ref_vcf()
+    n = 0
+    for s in _all_gt_strings():
+        want = oracle.vcf_gt(s)
+        assert vcfpack.gt(s) == want, s
+        if ref is not None:
+            assert ref.ref_vcf_gt(s.encode(), len(s)) == want, s
+        n += 1
+    capfd.readouterr()   # the reference REPORTs malformed calls on stderr
+    assert n == sum(len(ALPHABET) ** k for k in range(5))
+    # the quirks, spelled out (libVcf/VCFValue.h:74-116)
+    assert [oracle.vcf_gt(s) for s in ("0/1", "1|1", "0", "1", "./.", "0/2", "2/1", "0/", "1/.", "0/-", "0/1/1", "")] == \
+        [1, 2, 0, 1, -9, -9, -9, -9, -9, 0, -9, -9]
+
+
+def _random_record(rng, n, pos):
+    fmt_pool = [["GT"], ["GT", "GD", "GQ"], ["GD", "GT"], ["DS", "GQ", "GT"], ["GTX", "GT"], ["GD", "GQ"], ["PGT", "GT", "GL"]]
+    fmt = fmt_pool[int(rng.integers(len(fmt_pool)))]
+    gts = ["0/0", "0/1", "1/0", "1/1", "0|1", "1|1", "./.", ".", "0", "1", "0/2", "2/1", "1/.", "./1", "0/1/1", "0/", "00", "1-1"]
+    w = np.array([40, 10, 6, 4, 4, 2, 4, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1], dtype=float)
+    cols = []
+    for _ in range(n):
+        sub = []
+        for k in fmt:
+            if k in ("GT", "GTX", "PGT"):
+                sub.append(gts[int(rng.choice(len(gts), p=w / w.sum()))])
+            else:
+                sub.append(str(int(rng.integers(0, 99))))
+        keep = len(sub) if rng.random() > 0.08 else int(rng.integers(1, len(sub) + 1))   # truncated sample column
+        cols.append(":".join(sub[:keep]))
+    chrom = "1" if rng.random() < 0.7 else "X"
+    return "\t".join([chrom, str(pos), f"r{pos}", "A", "G", "100", "PASS", "DP=10;AF=0.1", ":".join(fmt)] + cols)
+
+
+def _header(n):
+    return "\t".join(["#CHROM", "POS", "ID", "REF", "ALT", "QUAL", "FILTER", "INFO", "FORMAT"] + [f"P{i + 1}" for i in range(n)])
+
+
+def _decode(oracle, rows, n):
+    return oracle.bed_decode_fast(rows, n) if len(rows) else np.zeros((0, n))
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 9, 64, 131])
+def test_records_vs_reference_parser(vcfpack, oracle, n, capfd):
+    rng = np.random.default_rng(1000 + n)
+    hdr = _header(n)
+    assert vcfpack.header(hdr) == n
+    vcfpack.set_range("")
+    vcfpack.clear()
+    want, afs, sites = [], [], []
+    for k in range(60):
+        rec = _random_record(rng, n, 10 * (k + 1))
+        exp = oracle.vcf_record_genotypes(hdr, rec)
+        if oracle.ref_vcf() is not None:
+            r = oracle.ref_vcf_genotypes(hdr, rec)
+            assert r is not None and r[0] == exp[0] and r[1] == exp[1]
+            assert np.array_equal(r[2], exp[2]), rec
+        assert vcfpack.add(rec + ("\n" if k % 3 == 0 else "")) == 1
+        want.append(exp[2])
+        # GenotypeCounter::add / getAF (src/GenotypeCounter.h:14-52): missing calls stay in the denominator
+        afs.append(0.5 * exp[2][exp[2] >= 0].sum() / n)
+        sites.append(f"{exp[0]}:{exp[1]}")
+    capfd.readouterr()
+    rows, af, counts, names = vcfpack.gene()
+    want = np.array(want)
+    assert rows.shape == (60, (n + 3) // 4)
+    got = _decode(oracle, rows, n)
+    assert np.array_equal(got, want.astype(float))
+    assert np.array_equal(af, np.array(afs))
+    assert names == sites
+    for k, key in enumerate((0, 1, 2, -9)):
+        assert np.array_equal(counts[:, k], (want == key).sum(axis=1))
+    # padding bits of the last byte are zero (the engine's staging kernel reads whole bytes)
+    if n % 4:
+        assert np.all(rows[:, -1] >> (2 * (n % 4)) == 0)
+
+
+def test_golden_vectors(vcfpack, oracle):
+    """tests/golden/vcf_golden.json: records + what the reference build returned for them (runs without oracle/_ref)"""
+    g = json.load(open(GOLD))
+    hdr = g["header"]
+    n = len(hdr.split("\t")) - 9
+    assert vcfpack.header(hdr) == n
+    vcfpack.set_range("")
+    vcfpack.clear()
+    for rec, exp in zip(g["records"], g["genotypes"]):
+        assert vcfpack.add(rec) == 1
+        assert list(oracle.vcf_record_genotypes(hdr, rec)[2]) == exp
+    rows, af, counts, names = vcfpack.gene()
+    assert np.array_equal(_decode(oracle, rows, n), np.array(g["genotypes"], dtype=float))
+    assert names == g["sites"]
+    for s, exp in g["gt_strings"].items():
+        assert vcfpack.gt(s) == exp and oracle.vcf_gt(s) == exp, s
+
+
+def test_sample_subset_ranges_and_malformed_lines(vcfpack, oracle):
+    n = 7
+    hdr = _header(n)
+    rng = np.random.default_rng(5)
+    recs = [_random_record(rng, n, p) for p in (5, 10, 20, 30, 31, 400)]
+    # keep-list: a SET of names, output in VCF column order (VCFRecord::includePeople)
+    assert vcfpack.header(hdr, keep=["P6", "P2", "P3"]) == 3
+    assert vcfpack.sample_names() == ["P2", "P3", "P6"]
+    assert vcfpack.header(hdr, keep=["P6", "nobody"]) < 0
+    assert vcfpack.header(hdr, keep=["P6", "P2", "P3"]) == 3
+    chrom = [r.split("\t")[0] for r in recs]
+    vcfpack.set_range("1:10-30,X:10-30")
+    vcfpack.clear()
+    taken = [vcfpack.add(r) for r in recs]
+    assert taken == [0, 1, 1, 1, 0, 0]
+    rows, af, counts, names = vcfpack.gene()
+    full = np.array([oracle.vcf_record_genotypes(hdr, r)[2] for r in recs[1:4]])
+    assert np.array_equal(_decode(oracle, rows, 3), full[:, [1, 2, 5]].astype(float))
+    assert names == [f"{c}:{p}" for c, p in zip(chrom[1:4], (10, 20, 30))]
+    assert np.array_equal(af, np.array([0.5 * r[r >= 0].sum() / 3 for r in full[:, [1, 2, 5]]]))
+    # other range spellings
+    assert vcfpack.set_range("1") == 1 and vcfpack.set_range("1:5") == 1 and vcfpack.set_range("1:5-") == 1
+    assert vcfpack.set_range("1:30-10") < 0 and vcfpack.set_range("1:x-3") < 0
+    vcfpack.set_range("")
+    # comment / meta lines are skipped; a record with a different sample count is an error and leaves no row behind
+    vcfpack.clear()
+    assert vcfpack.add("##fileformat=VCFv4.0") == 0 and vcfpack.add(hdr) == 0 and vcfpack.add("") == 0
+    short = "\t".join(recs[0].split("\t")[:-1])
+    assert vcfpack.add(short) < 0 and oracle.vcf_record_genotypes(hdr, short) is None
+    assert vcfpack.add(recs[0] + "\t0/1") < 0
+    assert vcfpack.add("1\t10\tr\tA\tG") < 0
+    assert vcfpack.gene()[0].shape[0] == 0
+    assert vcfpack.add(recs[0]) == 1 and vcfpack.gene()[0].shape[0] == 1
+    # (the reference's parseIndividual asserts / returns -1 on such a record, libVcf/VCFRecord.h:129-201: not driven here)
