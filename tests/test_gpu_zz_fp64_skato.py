@@ -178,3 +178,46 @@ def test_vcf_text_to_engine(engine_cls, oracle, vcfpack):
     for k, (Gd, af) in enumerate(refs):
         ref, lam = O.gene(Gd, af, X, nm["resid"], nm["sigma2"])
         check_gene(res[k], ref, lam, ctx=f"vcf gene {k}")
+
+
+@pytest.mark.parametrize("case", [(190, 5000, 24, 3), (191, 777, 1, 1), (192, 20011, 64, 2)])
+def test_zero_copy_entry_points(engine_cls, oracle, case):
+    """caller-owned device memory end to end: rvt_set_null_model_dev (X, y in HBM) + rvt_gene_push_dev_i8 ([M][ld] int8 block in
+    HBM, engine counts the rows itself) + rvt_flush_dev (records left in HBM) against the oracle and against the host entry
+    points on the same context"""
+    import torch
+    import rvtests_b200
+    O = oracle
+    seed, N, M, C = case
+    G, X, y = make_problem(O, seed, N, M, C, n_flip=min(2, M - 1), n_mono=1 if M > 3 else 0)
+    af = af_of(G)
+    nm = O.fit_null_linear(X, y)
+    ld = (N + 15) // 16 * 16 + 32
+    block = np.zeros((M, ld), dtype=np.int8)
+    block[:, :N] = G.T
+    dev = torch.device("cuda", 0)
+    dG = torch.from_numpy(block).to(dev)
+    dX = torch.from_numpy(np.asfortranarray(X).T.copy()).to(dev)      # column-major N x C = C contiguous columns
+    dy = torch.from_numpy(np.ascontiguousarray(y)).to(dev)
+    rec = rvtests_b200.engine.RESULT_DTYPE
+    d_out = torch.zeros(2 * rec.itemsize, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    eng = engine_cls(0)
+    try:
+        eng.set_null_model_dev(N, C, dX.data_ptr(), dy.data_ptr())
+        got = eng.get_null_model()
+        assert np.max(np.abs(got["resid"] - nm["resid"])) <= 1e-9 * max(1.0, np.max(np.abs(nm["resid"])))
+        assert rel(got["sigma2"], nm["sigma2"]) <= 1e-12
+        eng.push_dev_i8(dG.data_ptr(), M, ld, af)
+        eng.push_i8(G.T.copy(), af)
+        n = eng.flush_dev(d_out.data_ptr(), 2)
+        assert n == 2
+        torch.cuda.synchronize()
+        res = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=rec)
+    finally:
+        eng.close()
+    ref, lam = O.gene(G.astype(float), af, X, nm["resid"], nm["sigma2"])
+    check_gene(res[0], ref, lam, ctx=f"device block {case}")
+    check_gene(res[1], ref, lam, ctx=f"host block, records on the device {case}")
+    for k in ("Q", "cmc_nonref", "cmc_U", "zeg_U", "m_poly"):
+        assert res[0][k] == res[1][k], k       # same exact integer sums whichever way the block arrived
