@@ -338,6 +338,8 @@ def ref_vcf():
             L.ref_vcf_genotypes.argtypes = [C.c_char_p, C.c_char_p, _int_p, C.c_int, C.c_char_p, _int_p]
             L.ref_vcf_gt.restype = C.c_int
             L.ref_vcf_gt.argtypes = [C.c_char_p, C.c_int]
+            L.ref_vcf_dosages.restype = C.c_int
+            L.ref_vcf_dosages.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, _dbl_p, C.c_int]
             _lib_cache["vcf"] = L
     return _lib_cache["vcf"]
 
@@ -353,6 +355,69 @@ def ref_vcf_genotypes(header: str, record: str):
     if n < 0:
         return None
     return chrom.value.decode(), pos.value, out[:n].copy()
+
+
+def ref_vcf_dosages(header: str, record: str, tag: str):
+    """One VCF data line through the reference's parser in dosage mode: toDouble() of the `tag` subfield per sample."""
+    L = ref_vcf()
+    cap = header.count("\t") + 1
+    out = np.zeros(cap, dtype=np.float64)
+    n = L.ref_vcf_dosages(header.encode(), record.encode(), tag.encode(), _p(out), cap)
+    return None if n < 0 else out[:n].copy()
+
+
+def vcf_record_dosages(header: str, record: str, tag: str):
+    """dosage mode restated (src/VCFGenotypeExtractor.cpp:70-76, 404-406, 434-438): first FORMAT key that starts with `tag`;
+    value = C atof of the subfield ("." / garbage / an absent subfield -> 0.0); no such key -> -9 for everyone."""
+    import ctypes.util
+    libc = C.CDLL(ctypes.util.find_library("c"))
+    libc.atof.restype = C.c_double
+    libc.atof.argtypes = [C.c_char_p]
+    names = header.rstrip("\r\n").split("\t")[9:]
+    f = record.rstrip("\r\n").split("\t")
+    if len(f) < 10 or len(f) - 9 != len(names):
+        return None
+    idx = -1
+    for k, key in enumerate(f[8].split(":")):
+        if key.startswith(tag):
+            idx = k
+            break
+    out = np.full(len(names), -9.0)
+    if idx >= 0:
+        for i, col in enumerate(f[9:]):
+            sub = col.split(":")
+            out[i] = libc.atof((sub[idx] if idx < len(sub) else "").encode())
+    return out
+
+
+def genotype_counter(g):
+    """GenotypeCounter::add / getAF (src/GenotypeCounter.h:14-52) over one variant: (hom-ref, het, hom-alt, missing, AF)."""
+    g = np.asarray(g, dtype=np.float64)
+    miss = (g < 0) | (g > 2.0)
+    ref_ = ~miss & (g < 2.0 / 3)
+    het = ~miss & ~ref_ & (g < 4.0 / 3)
+    alt = ~miss & ~ref_ & ~het
+    s = 0.0
+    for x in g[~miss]:          # same summation order as the reference's running sumAC
+        s += x
+    return int(ref_.sum()), int(het.sum()), int(alt.sum()), int(miss.sum()), (0.5 * s / len(g) if len(g) else -1.0)
+
+
+def impute_mean_literal(G):
+    """DataConsolidator::imputeGenotypeToMean with its INTEGER accumulator (`int ac; ac += m(j, i)` truncates after every
+    addition, src/DataConsolidator.cpp:223-229): differs from impute_mean only for non-integer dosages."""
+    G = np.array(G, dtype=np.float64)
+    for i in range(G.shape[1]):
+        col = G[:, i]
+        if not (col < 0).any():
+            continue
+        ac, an = 0, 0
+        for x in col:
+            if x >= 0:
+                ac = int(ac + x)
+                an += 2
+        col[col < 0] = 2.0 * (0.0 if an == 0 else 1.0 * ac / an)
+    return G
 
 
 def vcf_gt(s: str) -> int:

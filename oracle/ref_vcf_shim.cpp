@@ -47,6 +47,25 @@ int ref_vcf_genotypes(const char* header, const char* record, int* out, int cap,
   return n;
 }
 
+// dosage mode (src/VCFGenotypeExtractor.cpp:70-76, 404-406): justGet(getFormatIndex(tag)).toDouble() per sample; no such key
+// -> MISSING_GENOTYPE (:434-438)
+int ref_vcf_dosages(const char* header, const char* record, const char* tag, double* out, int cap) {
+  VCFRecord r;
+  r.createIndividual(std::string(header));
+  r.includeAllPeople();
+  std::string line(record);
+  if (r.parse(&line)) {
+    r.deleteIndividual();
+    return -1;
+  }
+  const int idx = r.getFormatIndex(tag);
+  VCFPeople& people = r.getPeople();
+  const int n = (int)people.size();
+  for (int i = 0; i < n && i < cap; ++i) out[i] = idx >= 0 ? people[i]->justGet(idx).toDouble() : (double)MISSING_GENOTYPE;
+  r.deleteIndividual();
+  return n;
+}
+
 // VCFValue::getGenotype on one GT string (libVcf/VCFValue.h:74-116)
 int ref_vcf_gt(const char* s, int len) {
   char buf[64];

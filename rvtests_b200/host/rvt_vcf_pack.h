@@ -13,6 +13,9 @@
 //   GenotypeCounter::add / getAF                          src/GenotypeCounter.h:14-52   (AF = 0.5 * sumAC / nSample, missing
 //                                                         calls stay in the denominator)
 //   RangeList "chr:beg-end[,chr:beg-end...]" sets          src/Main.cpp --setFile / --rangeList (1-based, inclusive ends)
+// Dosage mode (`--dosage TAG`, VCFGenotypeExtractor.cpp:70-76, 404-406): setDosageTag("DS") makes every record contribute the
+// TAG subfield read with VCFValue::toDouble (= atof: "." and a truncated column read as 0.0, NOT missing) as one column of an
+// N x M column-major double block for rvt_gene_push_f64; negative entries are mean-imputed with the reference's rule first.
 // Samples come out in VCF column order restricted to the kept names (VCFRecord::includePeople semantics); the caller
 // orders the phenotype accordingly, as DataLoader does.  Missing calls become the .bed code 01 and are mean-imputed on the
 // device (DataConsolidator::imputeGenotypeToMean).  Header-only, C++11, no dependency but the C ABI header.
@@ -160,6 +163,12 @@ class VcfGenePacker {
     return (int)n_;
   }
 
+  // "" (default): hard calls from GT.  Otherwise the FORMAT key whose value is taken as the dosage.
+  void setDosageTag(const std::string& tag) {
+    dosage_tag_ = tag;
+    clear();
+  }
+  bool dosageMode() const { return !dosage_tag_.empty(); }
   int64_t numSample() const { return n_; }
   int64_t stride() const { return stride_; }
   const std::vector<std::string>& sampleNames() const { return names_; }
@@ -172,6 +181,7 @@ class VcfGenePacker {
     af_.clear();
     counts_.clear();
     names_var_.clear();
+    dos_.clear();
   }
 
   // One VCF line.  Returns 1 when the record became the next variant row of the current gene, 0 when it was skipped
@@ -195,22 +205,68 @@ class VcfGenePacker {
     if (fe[8] >= len) return -1;   // no sample columns at all
     const int pos = atoi(std::string(line + fb[1], fe[1] - fb[1]).c_str());
     if (!ranges_.empty() && !ranges_.contains(line + fb[0], fe[0] - fb[0], pos)) return 0;
-    const int gt = formatIndex(line + fb[8], fe[8] - fb[8], "GT");
+    const bool dosage = dosageMode();
+    const int gt = formatIndex(line + fb[8], fe[8] - fb[8], dosage ? dosage_tag_.c_str() : "GT");
 
-    const size_t row0 = rows_.size();
-    rows_.resize(row0 + (size_t)stride_, 0);
-    uint8_t* row = &rows_[row0];
+    const size_t row0 = rows_.size(), dos0 = dos_.size();
+    if (dosage)
+      dos_.resize(dos0 + (size_t)n_, (double)kVcfMissing);
+    else
+      rows_.resize(row0 + (size_t)stride_, 0);
+    uint8_t* row = dosage ? NULL : &rows_[row0];
+    double* drow = dosage ? &dos_[dos0] : NULL;
+    double sum_ac = 0.0;
     int cnt[4] = {0, 0, 0, 0};   // hom-ref, het, hom-alt, missing
     int col = 0;
     while (true) {
       if (col >= ncol_) {   // "VCF header have LESS people than VCF content!"
         rows_.resize(row0);
+        dos_.resize(dos0);
         return -2;
       }
       const char* t = (const char*)memchr(line + b, '\t', len - b);
       const size_t e = t ? (size_t)(t - line) : len;
       const int o = col_to_out_[col];
-      if (o >= 0) {
+      if (o >= 0 && dosage) {
+        // VCFIndividual::justGet(idx).toDouble(): atof of the subfield; an absent subfield is the empty string = 0.0;
+        // no such FORMAT key at all = MISSING_GENOTYPE (VCFGenotypeExtractor.cpp:434-438)
+        double g = (double)kVcfMissing;
+        if (gt >= 0) {
+          g = 0.0;
+          size_t sb = b;
+          int k = 0;
+          while (k < gt && sb <= e) {
+            const char* cpos = (const char*)memchr(line + sb, ':', e - sb);
+            if (!cpos) {
+              sb = e + 1;
+              break;
+            }
+            sb = (size_t)(cpos - line) + 1;
+            ++k;
+          }
+          if (sb <= e && k == gt) {
+            const char* cpos = (const char*)memchr(line + sb, ':', e - sb);
+            const size_t se = cpos ? (size_t)(cpos - line) : e;
+            g = atof(std::string(line + sb, se - sb).c_str());
+          }
+        }
+        drow[o] = g;
+        // GenotypeCounter::add (src/GenotypeCounter.h:14-33)
+        if (g < 0) {
+          ++cnt[3];
+        } else if (g < 2.0 / 3) {
+          ++cnt[0];
+          sum_ac += g;
+        } else if (g < 4.0 / 3) {
+          ++cnt[1];
+          sum_ac += g;
+        } else if (g <= 2.0) {
+          ++cnt[2];
+          sum_ac += g;
+        } else {
+          ++cnt[3];
+        }
+      } else if (o >= 0) {
         int g = kVcfMissing;
         if (gt >= 0) {
           // the gt-th ':'-separated subfield; a column with fewer subfields reads as the empty value
@@ -242,10 +298,12 @@ class VcfGenePacker {
     }
     if (col != ncol_) {   // "VCF header have MORE people than VCF content!"
       rows_.resize(row0);
+      dos_.resize(dos0);
       return -3;
     }
     // GenotypeCounter::getAF: 0.5 * sumAC / nSample, nSample counting the missing calls too
-    af_.push_back(n_ ? 0.5 * (double)(cnt[1] + 2 * cnt[2]) / (double)n_ : -1.0);
+    if (!dosage) sum_ac = (double)(cnt[1] + 2 * cnt[2]);
+    af_.push_back(n_ ? 0.5 * sum_ac / (double)n_ : -1.0);
     for (int k = 0; k < 4; ++k) counts_.push_back(cnt[k]);
     names_var_.push_back(std::string(line + fb[0], fe[0] - fb[0]) + ":" + std::string(line + fb[1], fe[1] - fb[1]));
     ++m_;
@@ -259,9 +317,40 @@ class VcfGenePacker {
   const int* counts() const { return counts_.empty() ? NULL : &counts_[0]; }
   const std::string& variantName(int j) const { return names_var_[j]; }   // "chrom:pos" (VCFGenotypeExtractor.cpp:113-116)
 
-  // hand the collected gene to the engine (rvt_gene_push_bed copies; the packer can be cleared right after)
-  int push(rvt_ctx* ctx) const {
+  // dosage mode: the N x M column-major block (variant j = entries [j * N, (j + 1) * N)), raw as read
+  const double* dosages() const { return dos_.empty() ? NULL : &dos_[0]; }
+
+  // DataConsolidator::imputeGenotypeToMean (src/DataConsolidator.cpp:217-245) on the dosage block, in place: in a column
+  // holding a negative entry those become 2 * ac / an, with the reference's INTEGER accumulator `int ac; ac += g`
+  // (truncation after every addition) over the non-negative entries.  Hard-call rows need none of this: code 01 is
+  // imputed on the device.
+  void imputeDosagesToMean() {
+    for (int j = 0; j < m_; ++j) {
+      double* c = &dos_[(size_t)j * (size_t)n_];
+      bool any = false;
+      int ac = 0, an = 0;
+      for (int64_t i = 0; i < n_; ++i) {
+        if (c[i] >= 0) {
+          ac = (int)(ac + c[i]);
+          an += 2;
+        } else {
+          any = true;
+        }
+      }
+      if (!any) continue;
+      const double g = 2.0 * (an == 0 ? 0.0 : 1.0 * ac / an);
+      for (int64_t i = 0; i < n_; ++i)
+        if (c[i] < 0) c[i] = g;
+    }
+  }
+
+  // hand the collected gene to the engine (the entry points copy; the packer can be cleared right after)
+  int push(rvt_ctx* ctx) {
     if (m_ == 0) return RVT_E_BADARG;
+    if (dosageMode()) {
+      imputeDosagesToMean();
+      return rvt_gene_push_f64(ctx, dosages(), m_, af());
+    }
     return rvt_gene_push_bed(ctx, rows(), m_, stride_, af());
   }
 
@@ -287,6 +376,8 @@ class VcfGenePacker {
   std::vector<int> col_to_out_;   // VCF sample column -> output sample index, -1 = not kept
   std::vector<std::string> names_, names_var_;
   std::vector<uint8_t> rows_;
+  std::vector<double> dos_;       // dosage mode: M columns of N doubles
+  std::string dosage_tag_;
   std::vector<double> af_;
   std::vector<int> counts_;
   VcfRangeSet ranges_;

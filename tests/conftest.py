@@ -87,6 +87,8 @@ class VcfPacker:
         lib.vp_variant_name.argtypes = [C.c_int]
         lib.vp_sample_name.restype = C.c_char_p
         lib.vp_sample_name.argtypes = [C.c_int]
+        lib.vp_set_dosage_tag.argtypes = [C.c_char_p]
+        lib.vp_get_dosages.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
 
     def gt(self, s):
         b = s.encode("latin-1")
@@ -107,6 +109,20 @@ class VcfPacker:
 
     def sample_names(self):
         return [self.L.vp_sample_name(i).decode() for i in range(self.L.vp_num_sample())]
+
+    def set_dosage_tag(self, tag):
+        self.L.vp_set_dosage_tag((tag or "").encode())
+
+    def dosage_gene(self, raw=True):
+        """dosage mode: (G (N, M) doubles, af (M,), counts (M, 4)); raw=False: after imputeDosagesToMean()"""
+        import numpy as np
+        m, n = self.L.vp_num_variant(), self.L.vp_num_sample()
+        G = np.zeros((m, n))
+        af = np.zeros(m)
+        counts = np.zeros((m, 4), dtype=np.int32)
+        if m:
+            self.L.vp_get_dosages(G.ctypes.data, af.ctypes.data, counts.ctypes.data, 1 if raw else 0)
+        return G.T.copy(), af, counts
 
     def gene(self):
         """(rows uint8 (M, stride), af (M,), counts (M, 4) = hom-ref / het / hom-alt / missing, names)"""

@@ -7,6 +7,7 @@
 #include "../../rvtests_b200/host/rvt_vcf_pack.h"
 
 extern "C" int rvt_gene_push_bed(rvt_ctx*, const uint8_t*, int, int64_t, const double*) { return RVT_E_UNSUPPORTED; }
+extern "C" int rvt_gene_push_f64(rvt_ctx*, const double*, int, const double*) { return RVT_E_UNSUPPORTED; }
 
 static rvtb200::VcfGenePacker g_p;
 
@@ -40,6 +41,16 @@ void vp_get(unsigned char* rows, double* af, int* counts) {
   const int m = g_p.numVariant();
   if (m == 0) return;
   memcpy(rows, g_p.rows(), (size_t)m * g_p.stride());
+  memcpy(af, g_p.af(), sizeof(double) * m);
+  memcpy(counts, g_p.counts(), sizeof(int) * 4 * m);
+}
+void vp_set_dosage_tag(const char* tag) { g_p.setDosageTag(tag ? tag : ""); }
+// raw != 0: as read; else after imputeDosagesToMean()
+void vp_get_dosages(double* out, double* af, int* counts, int raw) {
+  const int m = g_p.numVariant();
+  if (m == 0) return;
+  if (!raw) g_p.imputeDosagesToMean();
+  memcpy(out, g_p.dosages(), sizeof(double) * (size_t)m * (size_t)g_p.numSample());
   memcpy(af, g_p.af(), sizeof(double) * m);
   memcpy(counts, g_p.counts(), sizeof(int) * 4 * m);
 }

@@ -152,3 +152,67 @@ def test_sample_subset_ranges_and_malformed_lines(vcfpack, oracle):
     assert vcfpack.gene()[0].shape[0] == 0
     assert vcfpack.add(recs[0]) == 1 and vcfpack.gene()[0].shape[0] == 1
     # (the reference's parseIndividual asserts / returns -1 on such a record, libVcf/VCFRecord.h:129-201: not driven here)
+
+
+def _random_dosage_record(rng, n, pos):
+    fmt_pool = [["GT", "DS"], ["DS"], ["GT", "GQ", "DS"], ["DSX", "DS"], ["GT", "GQ"]]
+    fmt = fmt_pool[int(rng.integers(len(fmt_pool)))]
+    # (no EMPTY value: a sample column that ends in ':' makes VCFIndividual::parse call parseTill past the end, which
+    # returns -1 without touching the VCFValue, and the loop then writes a NUL at that value's STALE end offset from the
+    # previous record -- libVcf/VCFIndividual.h:39-53, VCFValue.h:262-263; the reference's result is then state-dependent.
+    # The packer reads such a subfield as the empty string.)
+    vals = ["0", "0.013", "1", "1.5", "2", "1.999", "0.666667", "1.333334", ".", "2.5", "-1", "1e-1", "0.5x", "nan"]
+    cols = []
+    for _ in range(n):
+        sub = []
+        for k in fmt:
+            if k in ("DS", "DSX"):
+                sub.append(vals[int(rng.integers(len(vals)))] if rng.random() < 0.4 else "%.3f" % rng.uniform(0, 2))
+            elif k == "GT":
+                sub.append("0/1")
+            else:
+                sub.append("30")
+        keep = len(sub) if rng.random() > 0.1 else int(rng.integers(1, len(sub) + 1))
+        cols.append(":".join(sub[:keep]))
+    return "\t".join(["2", str(pos), ".", "C", "T", "9", "PASS", ".", ":".join(fmt)] + cols)
+
+
+@pytest.mark.parametrize("n", [1, 6, 50])
+def test_dosage_mode_vs_reference_parser(vcfpack, oracle, n):
+    """--dosage DS: toDouble() of the tagged subfield (atof: '.', '' and a truncated column are 0.0, not missing; a record
+    without the key is all-missing), GenotypeCounter thresholds and AF, and the literal mean imputation of negative entries"""
+    rng = np.random.default_rng(2000 + n)
+    hdr = _header(n)
+    vcfpack.set_dosage_tag("DS")
+    try:
+        assert vcfpack.header(hdr) == n
+        vcfpack.set_range("")
+        vcfpack.clear()
+        want = []
+        for k in range(40):
+            rec = _random_dosage_record(rng, n, 3 * k + 1)
+            exp = oracle.vcf_record_dosages(hdr, rec, "DS")
+            if oracle.ref_vcf() is not None:
+                r = oracle.ref_vcf_dosages(hdr, rec, "DS")
+                assert np.array_equal(r, exp, equal_nan=True), rec
+            assert vcfpack.add(rec) == 1
+            want.append(exp)
+        want = np.array(want).T                                   # (N, M)
+        G, af, counts = vcfpack.dosage_gene(raw=True)
+        assert np.array_equal(G, want, equal_nan=True)
+        for j in range(want.shape[1]):
+            col = want[:, j]
+            if np.isnan(col).any():
+                continue                                          # ("nan" compares false everywhere: falls in the last branch)
+            r0, r1, r2, rm, a = oracle.genotype_counter(col)
+            assert list(counts[j]) == [r0, r1, r2, rm], j
+            assert af[j] == a, j
+        Gi, _, _ = vcfpack.dosage_gene(raw=False)
+        ok = ~np.isnan(want).any(axis=0)
+        assert np.array_equal(Gi[:, ok], oracle.impute_mean_literal(want[:, ok]))
+        # integer hard-call matrices: the literal rule equals the restatement the model-layer pin uses
+        H = rng.integers(-1, 3, size=(30, 5)).astype(float)
+        H[H < 0] = -9
+        assert np.array_equal(oracle.impute_mean_literal(H), oracle.impute_mean(H))
+    finally:
+        vcfpack.set_dosage_tag("")
