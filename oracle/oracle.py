@@ -338,6 +338,8 @@ def ref_vcf():
             L.ref_vcf_genotypes.argtypes = [C.c_char_p, C.c_char_p, _int_p, C.c_int, C.c_char_p, _int_p]
             L.ref_vcf_gt.restype = C.c_int
             L.ref_vcf_gt.argtypes = [C.c_char_p, C.c_int]
+            L.ref_vcf_genotypes_filtered.restype = C.c_int
+            L.ref_vcf_genotypes_filtered.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, _int_p, C.c_int]
             L.ref_vcf_dosages.restype = C.c_int
             L.ref_vcf_dosages.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, _dbl_p, C.c_int]
             _lib_cache["vcf"] = L
@@ -355,6 +357,15 @@ def ref_vcf_genotypes(header: str, record: str):
     if n < 0:
         return None
     return chrom.value.decode(), pos.value, out[:n].copy()
+
+
+def ref_vcf_genotypes_filtered(header: str, record: str, gd=(-1, -1), gq=(-1, -1)):
+    """hard calls through the reference's parser with --indvDepthMin/Max, --indvQualMin/Max (oracle/ref_vcf_shim.cpp)"""
+    L = ref_vcf()
+    cap = header.count("\t") + 1
+    out = np.zeros(cap, dtype=np.int32)
+    n = L.ref_vcf_genotypes_filtered(header.encode(), record.encode(), gd[0], gd[1], gq[0], gq[1], out.ctypes.data_as(_int_p), cap)
+    return None if n < 0 else out[:n].copy()
 
 
 def ref_vcf_dosages(header: str, record: str, tag: str):

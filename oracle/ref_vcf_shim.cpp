@@ -47,6 +47,41 @@ int ref_vcf_genotypes(const char* header, const char* record, int* out, int cap,
   return n;
 }
 
+// hard calls with the per-individual depth / quality filters of VCFGenotypeExtractor::getGenotype (:429-431).  checkGD /
+// checkGQ (:304-317) live in a file that cannot be built here (it pulls in the tabix / BCF readers), so their eight lines
+// are restated below ON TOP OF the reference's own parser values (justGet(idx).toInt()); negative min AND max = filter off.
+int ref_vcf_genotypes_filtered(const char* header, const char* record, int gd_min, int gd_max, int gq_min, int gq_max, int* out,
+                               int cap) {
+  VCFRecord r;
+  r.createIndividual(std::string(header));
+  r.includeAllPeople();
+  std::string line(record);
+  if (r.parse(&line)) {
+    r.deleteIndividual();
+    return -1;
+  }
+  const int idx = r.getFormatIndex("GT");
+  const int GDidx = r.getFormatIndex("GD");
+  const int GQidx = r.getFormatIndex("GQ");
+  const bool needGD = gd_min >= 0 && gd_max >= 0, needGQ = gq_min >= 0 && gq_max >= 0;
+  VCFPeople& people = r.getPeople();
+  const int n = (int)people.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    int g = idx >= 0 ? people[i]->justGet(idx).getGenotype() : MISSING_GENOTYPE;
+    if (idx >= 0 && needGD) {
+      const int gd = people[i]->justGet(GDidx).toInt();
+      if ((gd_min > 0 && gd < gd_min) || (gd_max > 0 && gd > gd_max)) g = MISSING_GENOTYPE;
+    }
+    if (idx >= 0 && needGQ) {
+      const int gq = people[i]->justGet(GQidx).toInt();
+      if ((gq_min > 0 && gq < gq_min) || (gq_max > 0 && gq > gq_max)) g = MISSING_GENOTYPE;
+    }
+    out[i] = g;
+  }
+  r.deleteIndividual();
+  return n;
+}
+
 // dosage mode (src/VCFGenotypeExtractor.cpp:70-76, 404-406): justGet(getFormatIndex(tag)).toDouble() per sample; no such key
 // -> MISSING_GENOTYPE (:434-438)
 int ref_vcf_dosages(const char* header, const char* record, const char* tag, double* out, int cap) {

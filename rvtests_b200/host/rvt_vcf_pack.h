@@ -125,7 +125,7 @@ class VcfRangeSet {
 
 class VcfGenePacker {
  public:
-  VcfGenePacker() : ncol_(0), n_(0), stride_(0), m_(0) {}
+  VcfGenePacker() : ncol_(0), n_(0), stride_(0), m_(0), need_gd_(false), need_gq_(false), gd_min_(0), gd_max_(0), gq_min_(0), gq_max_(0) {}
 
   // the "#CHROM\tPOS\t...\tFORMAT\tS1\tS2..." line.  keep: names to include (NULL or empty: everyone); samples are
   // emitted in VCF column order (VCFRecord::createIndividual + includePeople, libVcf/VCFRecord.h:203-231).
@@ -169,6 +169,20 @@ class VcfGenePacker {
     clear();
   }
   bool dosageMode() const { return !dosage_tag_.empty(); }
+  // --indvDepthMin/Max, --indvQualMin/Max (VCFGenotypeExtractor::checkGD / checkGQ, src/VCFGenotypeExtractor.cpp:304-333,
+  // 429-431): a call whose GD (GQ) subfield, read with atoi, lies below min or above max becomes missing; 0 = no bound on
+  // that side, and a negative pair switches the filter off.  With the filter on, a record WITHOUT the key reads 0 for
+  // everyone (justGet of index -1 is the empty value), so any min > 0 blanks the whole variant, as in the reference.
+  void setDepthFilter(int gd_min, int gd_max) {
+    need_gd_ = gd_min >= 0 && gd_max >= 0;
+    gd_min_ = gd_min;
+    gd_max_ = gd_max;
+  }
+  void setQualFilter(int gq_min, int gq_max) {
+    need_gq_ = gq_min >= 0 && gq_max >= 0;
+    gq_min_ = gq_min;
+    gq_max_ = gq_max;
+  }
   int64_t numSample() const { return n_; }
   int64_t stride() const { return stride_; }
   const std::vector<std::string>& sampleNames() const { return names_; }
@@ -208,6 +222,10 @@ class VcfGenePacker {
     const bool dosage = dosageMode();
     const int gt = formatIndex(line + fb[8], fe[8] - fb[8], dosage ? dosage_tag_.c_str() : "GT");
 
+    const int gd_idx = need_gd_ ? formatIndex(line + fb[8], fe[8] - fb[8], "GD") : -1;
+    const int gq_idx = need_gq_ ? formatIndex(line + fb[8], fe[8] - fb[8], "GQ") : -1;
+    const bool filtered = need_gd_ || need_gq_;
+
     const size_t row0 = rows_.size(), dos0 = dos_.size();
     if (dosage)
       dos_.resize(dos0 + (size_t)n_, (double)kVcfMissing);
@@ -232,23 +250,9 @@ class VcfGenePacker {
         // no such FORMAT key at all = MISSING_GENOTYPE (VCFGenotypeExtractor.cpp:434-438)
         double g = (double)kVcfMissing;
         if (gt >= 0) {
-          g = 0.0;
-          size_t sb = b;
-          int k = 0;
-          while (k < gt && sb <= e) {
-            const char* cpos = (const char*)memchr(line + sb, ':', e - sb);
-            if (!cpos) {
-              sb = e + 1;
-              break;
-            }
-            sb = (size_t)(cpos - line) + 1;
-            ++k;
-          }
-          if (sb <= e && k == gt) {
-            const char* cpos = (const char*)memchr(line + sb, ':', e - sb);
-            const size_t se = cpos ? (size_t)(cpos - line) : e;
-            g = atof(std::string(line + sb, se - sb).c_str());
-          }
+          size_t sb, se;
+          g = subfield(line, b, e, gt, &sb, &se) ? atof(std::string(line + sb, se - sb).c_str()) : 0.0;
+          if (filtered && !passFilters(line, b, e, gd_idx, gq_idx)) g = (double)kVcfMissing;
         }
         drow[o] = g;
         // GenotypeCounter::add (src/GenotypeCounter.h:14-33)
@@ -269,23 +273,10 @@ class VcfGenePacker {
       } else if (o >= 0) {
         int g = kVcfMissing;
         if (gt >= 0) {
-          // the gt-th ':'-separated subfield; a column with fewer subfields reads as the empty value
-          size_t sb = b;
-          int k = 0;
-          while (k < gt && sb <= e) {
-            const char* cpos = (const char*)memchr(line + sb, ':', e - sb);
-            if (!cpos) {
-              sb = e + 1;
-              break;
-            }
-            sb = (size_t)(cpos - line) + 1;
-            ++k;
-          }
-          if (sb <= e && k == gt) {
-            const char* cpos = (const char*)memchr(line + sb, ':', e - sb);
-            const size_t se = cpos ? (size_t)(cpos - line) : e;
-            g = vcfGenotype(line + sb, (int)(se - sb));
-          }
+          // the gt-th ':'-separated subfield; a column with fewer subfields reads as the empty value = missing
+          size_t sb, se;
+          if (subfield(line, b, e, gt, &sb, &se)) g = vcfGenotype(line + sb, (int)(se - sb));
+          if (filtered && !passFilters(line, b, e, gd_idx, gq_idx)) g = kVcfMissing;
         }
         // .bed codes, sample 0 in the low bits (libVcf/PlinkInputFile.h:206-209): 00 hom-ref, 10 het, 11 hom-alt, 01 missing
         const unsigned code = g == 0 ? 0u : g == 1 ? 2u : g == 2 ? 3u : 1u;
@@ -355,6 +346,42 @@ class VcfGenePacker {
   }
 
  private:
+  // the idx-th ':'-separated subfield of the sample column line[b, e) as [*sb, *se); false when the column has fewer
+  // subfields or idx < 0 (VCFIndividual::justGet then hands out the empty default value)
+  static bool subfield(const char* line, size_t b, size_t e, int idx, size_t* sb_out, size_t* se_out) {
+    if (idx < 0) return false;
+    size_t sb = b;
+    int k = 0;
+    while (k < idx) {
+      const char* cpos = (const char*)memchr(line + sb, ':', e - sb);
+      if (!cpos) return false;
+      sb = (size_t)(cpos - line) + 1;
+      ++k;
+    }
+    const char* cpos = (const char*)memchr(line + sb, ':', e - sb);
+    *sb_out = sb;
+    *se_out = cpos ? (size_t)(cpos - line) : e;
+    return true;
+  }
+  static int subfieldInt(const char* line, size_t b, size_t e, int idx) {
+    size_t sb, se;
+    if (!subfield(line, b, e, idx, &sb, &se)) return 0;   // atoi("")
+    return atoi(std::string(line + sb, se - sb).c_str());
+  }
+  bool passFilters(const char* line, size_t b, size_t e, int gd_idx, int gq_idx) const {
+    if (need_gd_) {
+      const int gd = subfieldInt(line, b, e, gd_idx);
+      if (gd_min_ > 0 && gd < gd_min_) return false;
+      if (gd_max_ > 0 && gd > gd_max_) return false;
+    }
+    if (need_gq_) {
+      const int gq = subfieldInt(line, b, e, gq_idx);
+      if (gq_min_ > 0 && gq < gq_min_) return false;
+      if (gq_max_ > 0 && gq > gq_max_) return false;
+    }
+    return true;
+  }
+
   // VCFRecord::getFormatIndex (libVcf/VCFRecord.h:280-306): index of the first FORMAT key that STARTS WITH `key`
   static int formatIndex(const char* f, size_t len, const char* key) {
     const size_t kl = strlen(key);
@@ -378,6 +405,8 @@ class VcfGenePacker {
   std::vector<uint8_t> rows_;
   std::vector<double> dos_;       // dosage mode: M columns of N doubles
   std::string dosage_tag_;
+  bool need_gd_, need_gq_;
+  int gd_min_, gd_max_, gq_min_, gq_max_;
   std::vector<double> af_;
   std::vector<int> counts_;
   VcfRangeSet ranges_;

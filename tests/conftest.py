@@ -110,6 +110,9 @@ class VcfPacker:
     def sample_names(self):
         return [self.L.vp_sample_name(i).decode() for i in range(self.L.vp_num_sample())]
 
+    def set_filters(self, gd=(-1, -1), gq=(-1, -1)):
+        self.L.vp_set_filters(int(gd[0]), int(gd[1]), int(gq[0]), int(gq[1]))
+
     def set_dosage_tag(self, tag):
         self.L.vp_set_dosage_tag((tag or "").encode())
 

@@ -44,6 +44,10 @@ void vp_get(unsigned char* rows, double* af, int* counts) {
   memcpy(af, g_p.af(), sizeof(double) * m);
   memcpy(counts, g_p.counts(), sizeof(int) * 4 * m);
 }
+void vp_set_filters(int gd_min, int gd_max, int gq_min, int gq_max) {
+  g_p.setDepthFilter(gd_min, gd_max);
+  g_p.setQualFilter(gq_min, gq_max);
+}
 void vp_set_dosage_tag(const char* tag) { g_p.setDosageTag(tag ? tag : ""); }
 // raw != 0: as read; else after imputeDosagesToMean()
 void vp_get_dosages(double* out, double* af, int* counts, int raw) {

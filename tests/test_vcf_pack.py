@@ -216,3 +216,37 @@ def test_dosage_mode_vs_reference_parser(vcfpack, oracle, n):
         assert np.array_equal(oracle.impute_mean_literal(H), oracle.impute_mean(H))
     finally:
         vcfpack.set_dosage_tag("")
+
+
+@pytest.mark.parametrize("flt", [((3, 0), (-1, -1)), ((-1, -1), (3, 0)), ((2, 40), (10, 90)), ((0, 50), (-1, -1)), ((0, 0), (0, 0))])
+def test_depth_and_quality_filters(vcfpack, oracle, flt, capfd):
+    """--indvDepthMin/Max, --indvQualMin/Max (the reference's own test/Makefile check3 / check4 use the two minima): calls
+    failing the GD / GQ bounds become missing; a record without the key reads 0 for everyone"""
+    if oracle.ref_vcf() is None:
+        pytest.skip("oracle/_ref/libvcf_ref.so not built (no /root/reference here)")
+    gd, gq = flt
+    n = 9
+    hdr = _header(n)
+    rng = np.random.default_rng(77)
+    vcfpack.set_filters(gd, gq)
+    try:
+        assert vcfpack.header(hdr) == n
+        vcfpack.set_range("")
+        vcfpack.clear()
+        want, plain = [], []
+        for k in range(50):
+            rec = _random_record(rng, n, k + 1)
+            want.append(oracle.ref_vcf_genotypes_filtered(hdr, rec, gd, gq))
+            plain.append(oracle.ref_vcf_genotypes(hdr, rec)[2])
+            assert vcfpack.add(rec) == 1
+        capfd.readouterr()
+        rows, af, counts, _ = vcfpack.gene()
+        want = np.array(want)
+        assert np.array_equal(_decode(oracle, rows, n), want.astype(float))
+        assert np.array_equal(counts[:, 3], (want == -9).sum(axis=1))
+        if gd[0] > 0 or gq[0] > 0:
+            assert (want == -9).sum() > (np.array(plain) == -9).sum()      # the filter did remove calls
+        if flt == ((0, 0), (0, 0)):
+            assert np.array_equal(want, np.array(plain))                    # switched on without bounds: nothing changes
+    finally:
+        vcfpack.set_filters()
