@@ -340,6 +340,12 @@ def ref_vcf():
             L.ref_vcf_gt.argtypes = [C.c_char_p, C.c_int]
             L.ref_vcf_genotypes_filtered.restype = C.c_int
             L.ref_vcf_genotypes_filtered.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, _int_p, C.c_int]
+            L.ref_vcf_gt_male02.restype = C.c_int
+            L.ref_vcf_gt_male02.argtypes = [C.c_char_p, C.c_int]
+            L.ref_par_is_hemi.restype = C.c_int
+            L.ref_par_is_hemi.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+            L.ref_vcf_genotypes_sex.restype = C.c_int
+            L.ref_vcf_genotypes_sex.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _int_p, C.c_char_p, _dbl_p, C.c_int]
             L.ref_vcf_dosages.restype = C.c_int
             L.ref_vcf_dosages.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, _dbl_p, C.c_int]
             _lib_cache["vcf"] = L
@@ -365,6 +371,17 @@ def ref_vcf_genotypes_filtered(header: str, record: str, gd=(-1, -1), gq=(-1, -1
     cap = header.count("\t") + 1
     out = np.zeros(cap, dtype=np.int32)
     n = L.ref_vcf_genotypes_filtered(header.encode(), record.encode(), gd[0], gd[1], gq[0], gq[1], out.ctypes.data_as(_int_p), cap)
+    return None if n < 0 else out[:n].copy()
+
+
+def ref_vcf_genotypes_sex(header: str, record: str, sex, x_label="", par_region="", dosage_tag=""):
+    """one VCF line with the X handling of VCFGenotypeExtractor::getGenotype over the reference's VCFValue + ParRegion"""
+    L = ref_vcf()
+    cap = header.count("\t") + 1
+    out = np.zeros(cap, dtype=np.float64)
+    sx = np.ascontiguousarray(sex, dtype=np.int32)
+    n = L.ref_vcf_genotypes_sex(header.encode(), record.encode(), x_label.encode(), par_region.encode(),
+                                sx.ctypes.data_as(_int_p), dosage_tag.encode(), _p(out), cap)
     return None if n < 0 else out[:n].copy()
 
 

@@ -8,6 +8,7 @@
 
 #include <string>
 
+#include "base/ParRegion.h"
 #include "libVcf/VCFRecord.h"
 
 // BufferedReader (base/IO.cpp needs bzip2/zlib trees that are not built here) is only reached from
@@ -75,6 +76,62 @@ int ref_vcf_genotypes_filtered(const char* header, const char* record, int gd_mi
     if (idx >= 0 && needGQ) {
       const int gq = people[i]->justGet(GQidx).toInt();
       if ((gq_min > 0 && gq < gq_min) || (gq_max > 0 && gq > gq_max)) g = MISSING_GENOTYPE;
+    }
+    out[i] = g;
+  }
+  r.deleteIndividual();
+  return n;
+}
+
+// VCFValue::getMaleNonParGenotype02 on one GT string (libVcf/VCFValue.h:125-142)
+int ref_vcf_gt_male02(const char* s, int len) {
+  char buf[64];
+  if (len > 63) len = 63;
+  memcpy(buf, s, len);
+  buf[len] = 0;
+  VCFValue v(buf, 0, len);
+  return v.getMaleNonParGenotype02();
+}
+
+// ParRegion::isHemiRegion (base/ParRegion.h) for the --xLabel / --xParRegion strings
+int ref_par_is_hemi(const char* xLabel, const char* parRegion, const char* chrom, int pos) {
+  ParRegion p(xLabel, parRegion);
+  return p.isHemiRegion(chrom, pos) ? 1 : 0;
+}
+
+// the sex / hemizygous-region branches of VCFGenotypeExtractor::getGenotype (src/VCFGenotypeExtractor.cpp:404-428), restated
+// over the reference's own VCFValue and ParRegion: dosage != 0 -> toDouble (male x 2 in a hemizygous region), else hard
+// calls (male: getMaleNonParGenotype02, female: getGenotype, unknown sex: missing).  out: doubles.
+int ref_vcf_genotypes_sex(const char* header, const char* record, const char* xLabel, const char* parRegion, const int* sex,
+                          const char* dosage_tag, double* out, int cap) {
+  VCFRecord r;
+  r.createIndividual(std::string(header));
+  r.includeAllPeople();
+  std::string line(record);
+  if (r.parse(&line)) {
+    r.deleteIndividual();
+    return -1;
+  }
+  const bool useDosage = dosage_tag && dosage_tag[0];
+  const int idx = r.getFormatIndex(useDosage ? dosage_tag : "GT");
+  ParRegion par(xLabel, parRegion);
+  const bool hemi = par.isHemiRegion(r.getChrom(), r.getPos());
+  VCFPeople& people = r.getPeople();
+  const int n = (int)people.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    double g = MISSING_GENOTYPE;
+    if (idx >= 0) {
+      VCFIndividual& indv = *people[i];
+      if (useDosage) {
+        g = indv.justGet(idx).toDouble();
+        if (hemi && sex[i] == PLINK_MALE) g *= 2.0;
+      } else if (!hemi) {
+        g = indv.justGet(idx).getGenotype();
+      } else if (sex[i] == PLINK_MALE) {
+        g = indv.justGet(idx).getMaleNonParGenotype02();
+      } else if (sex[i] == PLINK_FEMALE) {
+        g = indv.justGet(idx).getGenotype();
+      }
     }
     out[i] = g;
   }

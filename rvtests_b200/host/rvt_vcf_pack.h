@@ -26,8 +26,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <ctype.h>
+
 #include <set>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "rvtests_b200.h"
@@ -62,6 +65,84 @@ inline int vcfGenotype(const char* s, int len) {
   if (p != len) return kVcfMissing;
   return g;
 }
+
+// VCFValue::getMaleNonParGenotype02 (libVcf/VCFValue.h:125-142, getAllele1 / getAllele2 :159-179, isHaploid :242): a male's call
+// outside the pseudo-autosomal regions of X -- "0" / "1" or a homozygous diploid call -> 0 / 2, everything else missing.
+// (getAllele1/2 read a byte below '0' as allele 0 after a REPORT, and look at byte 2 without checking the separator.)
+inline int vcfGenotypeMale02(const char* s, int len) {
+  const char c0 = len > 0 ? s[0] : '\0';
+  if (c0 == '.') return kVcfMissing;
+  const int g = c0 < '0' ? 0 : c0 - '0';
+  if (len == 1) return g == 0 ? 0 : g == 1 ? 2 : kVcfMissing;
+  if (2 >= len) return kVcfMissing;
+  const char c2 = s[2];
+  if (c2 == '.') return kVcfMissing;
+  const int g2 = c2 < '0' ? 0 : c2 - '0';
+  if (g == g2) {
+    if (g == 0) return 0;
+    if (g == 1) return 2;
+  }
+  return kVcfMissing;
+}
+
+// ParRegion (base/ParRegion.h:18-147): X labels + pseudo-autosomal intervals; hemizygous = on an X label and outside them
+class VcfParRegion {
+ public:
+  VcfParRegion() { init("", ""); }   // Main.cpp passes --xLabel / --xParRegion, both empty by default: X,23 and hg19
+  void init(const std::string& xLabel, const std::string& parRegion) {
+    label_.clear();
+    region_.clear();
+    if (xLabel.empty()) {
+      label_.insert("X");
+      label_.insert("23");
+    } else {
+      size_t b = 0;
+      while (b <= xLabel.size()) {
+        size_t e = xLabel.find(',', b);
+        if (e == std::string::npos) e = xLabel.size();
+        label_.insert(xLabel.substr(b, e - b));
+        b = e + 1;
+      }
+    }
+    std::string r;
+    for (size_t i = 0; i < parRegion.size(); ++i) r += (char)tolower((unsigned char)parRegion[i]);
+    if (r.empty()) r = "hg19";
+    if (r == "hg19" || r == "b37" || r == "grch37") {
+      add(60001, 2699520);
+      add(154931044, 155260560);
+    } else if (r == "hg18" || r == "b36" || r == "grch36") {
+      add(1, 2709520);
+      add(154584238, 154913754);
+    } else if (r == "hg38" || r == "b38" || r == "grch38") {
+      add(10001, 2781479);
+      add(155701383, 156030895);
+    } else {
+      size_t b = 0;
+      while (b <= parRegion.size()) {
+        size_t e = parRegion.find(',', b);
+        if (e == std::string::npos) e = parRegion.size();
+        const std::string piece = parRegion.substr(b, e - b);
+        b = e + 1;
+        // stringTokenize(piece, "-"): exactly two fields, the first one not empty; an empty second = to the end
+        const size_t d = piece.find('-');
+        if (d == std::string::npos || piece.find('-', d + 1) != std::string::npos || d == 0) continue;
+        const std::string hi = piece.substr(d + 1);
+        add(atoi(piece.substr(0, d).c_str()), hi.empty() ? INT32_MAX : atoi(hi.c_str()));
+      }
+    }
+  }
+  bool isHemiRegion(const std::string& chrom, int pos) const {
+    if (!label_.count(chrom)) return false;
+    for (size_t i = 0; i < region_.size(); ++i)
+      if (pos >= region_[i].first && pos <= region_[i].second) return false;
+    return true;
+  }
+
+ private:
+  void add(int b, int e) { region_.push_back(std::make_pair(b, e)); }
+  std::set<std::string> label_;
+  std::vector<std::pair<int, int> > region_;
+};
 
 // one or more "chr:beg-end" ranges (also "chr" = whole chromosome, "chr:pos" = one base); 1-based, inclusive
 class VcfRangeSet {
@@ -169,6 +250,16 @@ class VcfGenePacker {
     clear();
   }
   bool dosageMode() const { return !dosage_tag_.empty(); }
+  // Sex of the KEPT samples in output order (PLINK coding: 1 male, 2 female, anything else unknown) switches on the
+  // reference's X handling (VCFGenotypeExtractor::getGenotype, src/VCFGenotypeExtractor.cpp:416-428, 404-415): at a site
+  // in a hemizygous region (parRegion()) a male is coded 0 / 2 (vcfGenotypeMale02; a dosage is doubled), a female as
+  // usual, unknown sex as missing (dosage: as read).  An empty vector (default) switches it off.
+  int setSex(const std::vector<int>& sex) {
+    if (!sex.empty() && (int64_t)sex.size() != n_) return -1;
+    sex_ = sex;
+    return 0;
+  }
+  VcfParRegion& parRegion() { return par_; }
   // --indvDepthMin/Max, --indvQualMin/Max (VCFGenotypeExtractor::checkGD / checkGQ, src/VCFGenotypeExtractor.cpp:304-333,
   // 429-431): a call whose GD (GQ) subfield, read with atoi, lies below min or above max becomes missing; 0 = no bound on
   // that side, and a negative pair switches the filter off.  With the filter on, a record WITHOUT the key reads 0 for
@@ -225,6 +316,7 @@ class VcfGenePacker {
     const int gd_idx = need_gd_ ? formatIndex(line + fb[8], fe[8] - fb[8], "GD") : -1;
     const int gq_idx = need_gq_ ? formatIndex(line + fb[8], fe[8] - fb[8], "GQ") : -1;
     const bool filtered = need_gd_ || need_gq_;
+    const bool hemi = !sex_.empty() && par_.isHemiRegion(std::string(line + fb[0], fe[0] - fb[0]), pos);
 
     const size_t row0 = rows_.size(), dos0 = dos_.size();
     if (dosage)
@@ -252,6 +344,7 @@ class VcfGenePacker {
         if (gt >= 0) {
           size_t sb, se;
           g = subfield(line, b, e, gt, &sb, &se) ? atof(std::string(line + sb, se - sb).c_str()) : 0.0;
+          if (hemi && sex_[o] == 1) g *= 2.0;   // imputed male dosages on X lie in [0, 1]
           if (filtered && !passFilters(line, b, e, gd_idx, gq_idx)) g = (double)kVcfMissing;
         }
         drow[o] = g;
@@ -275,7 +368,13 @@ class VcfGenePacker {
         if (gt >= 0) {
           // the gt-th ':'-separated subfield; a column with fewer subfields reads as the empty value = missing
           size_t sb, se;
-          if (subfield(line, b, e, gt, &sb, &se)) g = vcfGenotype(line + sb, (int)(se - sb));
+          const bool have = subfield(line, b, e, gt, &sb, &se);
+          if (!hemi || sex_[o] == 2)
+            g = have ? vcfGenotype(line + sb, (int)(se - sb)) : kVcfMissing;
+          else if (sex_[o] == 1)
+            g = have ? vcfGenotypeMale02(line + sb, (int)(se - sb)) : vcfGenotypeMale02("", 0);
+          else
+            g = kVcfMissing;
           if (filtered && !passFilters(line, b, e, gd_idx, gq_idx)) g = kVcfMissing;
         }
         // .bed codes, sample 0 in the low bits (libVcf/PlinkInputFile.h:206-209): 00 hom-ref, 10 het, 11 hom-alt, 01 missing
@@ -405,6 +504,8 @@ class VcfGenePacker {
   std::vector<uint8_t> rows_;
   std::vector<double> dos_;       // dosage mode: M columns of N doubles
   std::string dosage_tag_;
+  std::vector<int> sex_;
+  VcfParRegion par_;
   bool need_gd_, need_gq_;
   int gd_min_, gd_max_, gq_min_, gq_max_;
   std::vector<double> af_;

@@ -88,6 +88,9 @@ class VcfPacker:
         lib.vp_sample_name.restype = C.c_char_p
         lib.vp_sample_name.argtypes = [C.c_int]
         lib.vp_set_dosage_tag.argtypes = [C.c_char_p]
+        lib.vp_gt_male02.argtypes = [C.c_char_p, C.c_int]
+        lib.vp_par_is_hemi.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+        lib.vp_set_sex.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
         lib.vp_get_dosages.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
 
     def gt(self, s):
@@ -109,6 +112,20 @@ class VcfPacker:
 
     def sample_names(self):
         return [self.L.vp_sample_name(i).decode() for i in range(self.L.vp_num_sample())]
+
+    def gt_male02(self, s):
+        b = s.encode("latin-1")
+        return self.L.vp_gt_male02(b, len(b))
+
+    def par_is_hemi(self, x_label, par_region, chrom, pos):
+        return self.L.vp_par_is_hemi(x_label.encode(), par_region.encode(), chrom.encode(), int(pos))
+
+    def set_sex(self, sex=None, x_label="", par_region=""):
+        import numpy as np
+        if sex is None:
+            return self.L.vp_set_sex(None, 0, b"", b"")
+        sx = np.ascontiguousarray(sex, dtype=np.int32)
+        return self.L.vp_set_sex(sx.ctypes.data, len(sx), x_label.encode(), par_region.encode())
 
     def set_filters(self, gd=(-1, -1), gq=(-1, -1)):
         self.L.vp_set_filters(int(gd[0]), int(gd[1]), int(gq[0]), int(gq[1]))

@@ -44,6 +44,17 @@ void vp_get(unsigned char* rows, double* af, int* counts) {
   memcpy(af, g_p.af(), sizeof(double) * m);
   memcpy(counts, g_p.counts(), sizeof(int) * 4 * m);
 }
+int vp_gt_male02(const char* s, int len) { return rvtb200::vcfGenotypeMale02(s, len); }
+int vp_par_is_hemi(const char* xLabel, const char* parRegion, const char* chrom, int pos) {
+  rvtb200::VcfParRegion p;
+  p.init(xLabel, parRegion);
+  return p.isHemiRegion(chrom, pos) ? 1 : 0;
+}
+// sex == NULL: X handling off
+int vp_set_sex(const int* sex, int n, const char* xLabel, const char* parRegion) {
+  g_p.parRegion().init(xLabel ? xLabel : "", parRegion ? parRegion : "");
+  return g_p.setSex(sex ? std::vector<int>(sex, sex + n) : std::vector<int>());
+}
 void vp_set_filters(int gd_min, int gd_max, int gq_min, int gq_max) {
   g_p.setDepthFilter(gd_min, gd_max);
   g_p.setQualFilter(gq_min, gq_max);

@@ -250,3 +250,64 @@ def test_depth_and_quality_filters(vcfpack, oracle, flt, capfd):
             assert np.array_equal(want, np.array(plain))                    # switched on without bounds: nothing changes
     finally:
         vcfpack.set_filters()
+
+
+def test_male_hemizygous_grammar_and_par_regions(vcfpack, oracle, capfd):
+    """VCFValue::getMaleNonParGenotype02 on every short string, ParRegion::isHemiRegion for the built-in builds and custom
+    --xLabel / --xParRegion strings: product == reference build"""
+    if oracle.ref_vcf() is None:
+        pytest.skip("oracle/_ref/libvcf_ref.so not built (no /root/reference here)")
+    ref = oracle.ref_vcf()
+    for s in _all_gt_strings():
+        assert vcfpack.gt_male02(s) == ref.ref_vcf_gt_male02(s.encode(), len(s)), s
+    capfd.readouterr()
+    assert [vcfpack.gt_male02(s) for s in ("0", "1", "0/0", "1|1", "0/1", "2", "./.", "1", "1/", "")] == [0, 2, 0, 2, -9, -9, -9, 2, -9, -9]
+    probes = [1, 10000, 10001, 60000, 60001, 2699520, 2699521, 2709520, 2781479, 2781480, 154584238, 154931043, 154931044,
+              155260560, 155260561, 155701383, 156030895, 156030896, 2_000_000_000]
+    for xl in ("", "X", "chrX,X,chr23,23", "Z"):
+        for pr in ("", "hg19", "HG38", "b36", "grch37", "100-200", "100-200,5000-", "-100,300-400", "7-9-11,50-60", "junk"):
+            for chrom in ("X", "23", "chrX", "1", "Z"):
+                for pos in probes + [99, 100, 200, 201, 300, 400, 401, 5000, 55]:
+                    assert vcfpack.par_is_hemi(xl, pr, chrom, pos) == ref.ref_par_is_hemi(xl.encode(), pr.encode(), chrom.encode(), pos), \
+                        (xl, pr, chrom, pos)
+
+
+@pytest.mark.parametrize("dosage", [False, True])
+def test_records_on_x_with_sex(vcfpack, oracle, dosage, capfd):
+    """males 0 / 2 (dosage x 2) outside the pseudo-autosomal regions, females as usual, unknown sex missing; autosomes and
+    the PAR untouched"""
+    if oracle.ref_vcf() is None:
+        pytest.skip("oracle/_ref/libvcf_ref.so not built (no /root/reference here)")
+    n = 10
+    hdr = _header(n)
+    rng = np.random.default_rng(9)
+    sex = np.array([1, 2, 1, 2, 0, -9, 1, 2, 3, 1])
+    tag = "DS" if dosage else ""
+    vcfpack.set_dosage_tag(tag)
+    try:
+        assert vcfpack.header(hdr) == n
+        assert vcfpack.set_sex(sex[:3]) != 0 and vcfpack.set_sex(sex) == 0
+        vcfpack.set_range("")
+        vcfpack.clear()
+        want = []
+        for k, pos in enumerate([5, 60001, 100000, 2699520, 2699521, 3000000, 154931043, 154931044, 155260561] * 4):
+            rec = (_random_dosage_record if dosage else _random_record)(rng, n, pos)
+            f = rec.split("\t")
+            f[0] = ["X", "23", "1", "chrX"][k % 4]
+            rec = "\t".join(f)
+            want.append(oracle.ref_vcf_genotypes_sex(hdr, rec, sex, dosage_tag=tag))
+            assert vcfpack.add(rec) == 1
+        capfd.readouterr()
+        want = np.array(want)
+        if dosage:
+            G, _, _ = vcfpack.dosage_gene(raw=True)
+            assert np.array_equal(G.T, want, equal_nan=True)
+        else:
+            rows, _, _, _ = vcfpack.gene()
+            assert np.array_equal(_decode(oracle, rows, n), want)
+            hemi_rows = [k for k in range(len(want)) if k % 4 in (0, 1) and k % 9 in (0, 4, 5, 6, 8)]
+            assert np.all(want[hemi_rows][:, sex == 1] != 1)           # no heterozygous male there
+            assert np.all(want[hemi_rows][:, (sex != 1) & (sex != 2)] == -9)
+    finally:
+        vcfpack.set_dosage_tag("")
+        vcfpack.set_sex(None)
