@@ -346,6 +346,12 @@ def ref_vcf():
             L.ref_par_is_hemi.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
             L.ref_vcf_genotypes_sex.restype = C.c_int
             L.ref_vcf_genotypes_sex.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _int_p, C.c_char_p, _dbl_p, C.c_int]
+            L.ref_vcf_count_alt.restype = C.c_int
+            L.ref_vcf_count_alt.argtypes = [C.c_char_p, C.c_int, C.c_int]
+            L.ref_vcf_count_male_alt2.restype = C.c_int
+            L.ref_vcf_count_male_alt2.argtypes = [C.c_char_p, C.c_int, C.c_int]
+            L.ref_vcf_genotypes_alt.restype = C.c_int
+            L.ref_vcf_genotypes_alt.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _int_p, C.c_int, _int_p, C.c_int, _int_p]
             L.ref_vcf_dosages.restype = C.c_int
             L.ref_vcf_dosages.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, _dbl_p, C.c_int]
             _lib_cache["vcf"] = L
@@ -383,6 +389,20 @@ def ref_vcf_genotypes_sex(header: str, record: str, sex, x_label="", par_region=
     n = L.ref_vcf_genotypes_sex(header.encode(), record.encode(), x_label.encode(), par_region.encode(),
                                 sx.ctypes.data_as(_int_p), dosage_tag.encode(), _p(out), cap)
     return None if n < 0 else out[:n].copy()
+
+
+def ref_vcf_genotypes_alt(header: str, record: str, alt: int, sex=None, x_label="", par_region=""):
+    """--multipleAllele: copies of alt allele `alt` per sample through the reference's VCFValue (+ ParRegion / sex);
+    returns (genotypes, number of ALT alleles of the record)"""
+    L = ref_vcf()
+    cap = header.count("\t") + 1
+    out = np.zeros(cap, dtype=np.int32)
+    n_alt = C.c_int(0)
+    sx = None if sex is None else np.ascontiguousarray(sex, dtype=np.int32)
+    n = L.ref_vcf_genotypes_alt(header.encode(), record.encode(), x_label.encode(), par_region.encode(),
+                                None if sx is None else sx.ctypes.data_as(_int_p), int(alt), out.ctypes.data_as(_int_p), cap,
+                                C.byref(n_alt))
+    return (None, 0) if n < 0 else (out[:n].copy(), n_alt.value)
 
 
 def ref_vcf_dosages(header: str, record: str, tag: str):

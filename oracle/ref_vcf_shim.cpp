@@ -139,6 +139,61 @@ int ref_vcf_genotypes_sex(const char* header, const char* record, const char* xL
   return n;
 }
 
+// --multipleAllele: VCFValue::countAltAllele / countMaleNonParAltAllele2 on one GT string (libVcf/VCFValue.h:180-234)
+int ref_vcf_count_alt(const char* s, int len, int alt) {
+  char buf[64];
+  if (len > 63) len = 63;
+  memcpy(buf, s, len);
+  buf[len] = 0;
+  VCFValue v(buf, 0, len);
+  return v.countAltAllele(alt);
+}
+int ref_vcf_count_male_alt2(const char* s, int len, int alt) {
+  char buf[64];
+  if (len > 63) len = 63;
+  memcpy(buf, s, len);
+  buf[len] = 0;
+  VCFValue v(buf, 0, len);
+  return v.countMaleNonParAltAllele2(alt);
+}
+// hard-call branches of VCFGenotypeExtractor::getGenotypeForAltAllele (src/VCFGenotypeExtractor.cpp:459-473) for alt allele
+// `alt` of one record, over the reference's VCFValue and ParRegion; sex == NULL: nobody is in a hemizygous region.
+// n_alt receives the number of comma-separated ALT alleles (parseAltAllele, :393-395).
+int ref_vcf_genotypes_alt(const char* header, const char* record, const char* xLabel, const char* parRegion, const int* sex,
+                          int alt, int* out, int cap, int* n_alt) {
+  VCFRecord r;
+  r.createIndividual(std::string(header));
+  r.includeAllPeople();
+  std::string line(record);
+  if (r.parse(&line)) {
+    r.deleteIndividual();
+    return -1;
+  }
+  std::vector<std::string> alts;
+  stringTokenize(r.getAlt(), ",", &alts);
+  *n_alt = (int)alts.size();
+  const int idx = r.getFormatIndex("GT");
+  ParRegion par(xLabel, parRegion);
+  const bool hemi = sex && par.isHemiRegion(r.getChrom(), r.getPos());
+  VCFPeople& people = r.getPeople();
+  const int n = (int)people.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    int g = MISSING_GENOTYPE;
+    if (idx >= 0) {
+      VCFIndividual& indv = *people[i];
+      if (!hemi)
+        g = indv.justGet(idx).countAltAllele(alt);
+      else if (sex[i] == PLINK_MALE)
+        g = indv.justGet(idx).countMaleNonParAltAllele2(alt);
+      else if (sex[i] == PLINK_FEMALE)
+        g = indv.justGet(idx).countAltAllele(alt);
+    }
+    out[i] = g;
+  }
+  r.deleteIndividual();
+  return n;
+}
+
 // dosage mode (src/VCFGenotypeExtractor.cpp:70-76, 404-406): justGet(getFormatIndex(tag)).toDouble() per sample; no such key
 // -> MISSING_GENOTYPE (:434-438)
 int ref_vcf_dosages(const char* header, const char* record, const char* tag, double* out, int cap) {

@@ -85,6 +85,37 @@ inline int vcfGenotypeMale02(const char* s, int len) {
   return kVcfMissing;
 }
 
+// --multipleAllele: VCFValue::countAltAllele(alt) (libVcf/VCFValue.h:180-213): copies of alt allele `alt` (1-based) in the call.
+// Other alleles count 0 (so 0/2 is 0 for alt 1 and 1 for alt 2); '.', a wrong separator, a missing second allele or trailing
+// bytes -> missing; a non-digit allele is reported and counts 0.  An EMPTY value (truncated sample column) is read as
+// missing here -- the reference walks past the end of its one-byte default buffer in that case.
+inline int vcfCountAltAllele(const char* s, int len, int alt) {
+  if (len <= 0) return kVcfMissing;
+  if (s[0] == '.') return kVcfMissing;
+  int g = (s[0] - '0' == alt) ? 1 : 0;
+  if (len == 1) return g;
+  if (s[1] != '|' && s[1] != '/') return kVcfMissing;
+  if (len == 2) return kVcfMissing;
+  if (s[2] == '.') return kVcfMissing;
+  if (!(s[2] < '0' || s[2] > '9')) g += (s[2] - '0' == alt) ? 1 : 0;
+  if (len != 3) return kVcfMissing;
+  return g;
+}
+
+// VCFValue::countMaleNonParAltAllele2(alt) (libVcf/VCFValue.h:214-234): haploid call -> 2 if it is `alt` else 0; diploid
+// call with two equal alleles -> 2 if they are `alt` else 0; unequal alleles or a missing allele -> missing
+inline int vcfCountMaleAltAllele2(const char* s, int len, int alt) {
+  const char c0 = len > 0 ? s[0] : '\0';
+  if (c0 == '.') return kVcfMissing;
+  const int g = c0 < '0' ? 0 : c0 - '0';
+  if (len == 1) return g == alt ? 2 : 0;
+  if (2 >= len) return kVcfMissing;
+  if (s[2] == '.') return kVcfMissing;
+  const int g2 = s[2] < '0' ? 0 : s[2] - '0';
+  if (g == g2) return (g == alt ? 1 : 0) + (g2 == alt ? 1 : 0);
+  return kVcfMissing;
+}
+
 // ParRegion (base/ParRegion.h:18-147): X labels + pseudo-autosomal intervals; hemizygous = on an X label and outside them
 class VcfParRegion {
  public:
@@ -206,7 +237,7 @@ class VcfRangeSet {
 
 class VcfGenePacker {
  public:
-  VcfGenePacker() : ncol_(0), n_(0), stride_(0), m_(0), need_gd_(false), need_gq_(false), gd_min_(0), gd_max_(0), gq_min_(0), gq_max_(0) {}
+  VcfGenePacker() : ncol_(0), n_(0), stride_(0), m_(0), multi_(false), need_gd_(false), need_gq_(false), gd_min_(0), gd_max_(0), gq_min_(0), gq_max_(0) {}
 
   // the "#CHROM\tPOS\t...\tFORMAT\tS1\tS2..." line.  keep: names to include (NULL or empty: everyone); samples are
   // emitted in VCF column order (VCFRecord::createIndividual + includePeople, libVcf/VCFRecord.h:203-231).
@@ -250,6 +281,11 @@ class VcfGenePacker {
     clear();
   }
   bool dosageMode() const { return !dosage_tag_.empty(); }
+  // --multipleAllele (VCFGenotypeExtractor::extractMultipleGenotype, src/VCFGenotypeExtractor.cpp:44-50, 90-97, 113-122): a
+  // record with K comma-separated ALT alleles becomes K variant rows, row a counting the copies of alt allele a; the
+  // variant is then named "chrom:posREF/ALTa".  addRecord returns K.  (With a dosage tag the reference warns and keeps one
+  // row named after the LAST alt allele; so does this.)
+  void setMultiAllelic(bool on) { multi_ = on; }
   // Sex of the KEPT samples in output order (PLINK coding: 1 male, 2 female, anything else unknown) switches on the
   // reference's X handling (VCFGenotypeExtractor::getGenotype, src/VCFGenotypeExtractor.cpp:416-428, 404-415): at a site
   // in a hemizygous region (parRegion()) a male is coded 0 / 2 (vcfGenotypeMale02; a dosage is doubled), a female as
@@ -318,6 +354,24 @@ class VcfGenePacker {
     const bool filtered = need_gd_ || need_gq_;
     const bool hemi = !sex_.empty() && par_.isHemiRegion(std::string(line + fb[0], fe[0] - fb[0]), pos);
 
+    // alt alleles to expand (multi-allelic mode), else one pass with alt = 0 = the plain GT grammar
+    std::vector<std::string> alts;
+    if (multi_) {
+      size_t ab = fb[4];
+      while (ab <= fe[4]) {
+        const char* c = (const char*)memchr(line + ab, ',', fe[4] - ab);
+        const size_t ae = c ? (size_t)(c - line) : fe[4];
+        if (ae > ab) alts.push_back(std::string(line + ab, ae - ab));   // stringTokenize drops nothing but we skip empties
+        ab = ae + 1;
+      }
+      if (alts.empty()) alts.push_back(std::string());
+    }
+    const int n_pass = multi_ && !dosage ? (int)alts.size() : 1;
+    const size_t b_samples = b, row_first = rows_.size(), dos_first = dos_.size();
+    const int m_first = m_;
+    for (int pass = 0; pass < n_pass; ++pass) {
+    const int alt = multi_ && !dosage ? pass + 1 : 0;
+    b = b_samples;
     const size_t row0 = rows_.size(), dos0 = dos_.size();
     if (dosage)
       dos_.resize(dos0 + (size_t)n_, (double)kVcfMissing);
@@ -330,8 +384,7 @@ class VcfGenePacker {
     int col = 0;
     while (true) {
       if (col >= ncol_) {   // "VCF header have LESS people than VCF content!"
-        rows_.resize(row0);
-        dos_.resize(dos0);
+        rollback(row_first, dos_first, m_first);
         return -2;
       }
       const char* t = (const char*)memchr(line + b, '\t', len - b);
@@ -369,10 +422,12 @@ class VcfGenePacker {
           // the gt-th ':'-separated subfield; a column with fewer subfields reads as the empty value = missing
           size_t sb, se;
           const bool have = subfield(line, b, e, gt, &sb, &se);
+          const char* v = have ? line + sb : "";
+          const int vl = have ? (int)(se - sb) : 0;
           if (!hemi || sex_[o] == 2)
-            g = have ? vcfGenotype(line + sb, (int)(se - sb)) : kVcfMissing;
+            g = alt ? vcfCountAltAllele(v, vl, alt) : vcfGenotype(v, vl);
           else if (sex_[o] == 1)
-            g = have ? vcfGenotypeMale02(line + sb, (int)(se - sb)) : vcfGenotypeMale02("", 0);
+            g = alt ? vcfCountMaleAltAllele2(v, vl, alt) : vcfGenotypeMale02(v, vl);
           else
             g = kVcfMissing;
           if (filtered && !passFilters(line, b, e, gd_idx, gq_idx)) g = kVcfMissing;
@@ -387,17 +442,19 @@ class VcfGenePacker {
       b = e + 1;
     }
     if (col != ncol_) {   // "VCF header have MORE people than VCF content!"
-      rows_.resize(row0);
-      dos_.resize(dos0);
+      rollback(row_first, dos_first, m_first);
       return -3;
     }
     // GenotypeCounter::getAF: 0.5 * sumAC / nSample, nSample counting the missing calls too
     if (!dosage) sum_ac = (double)(cnt[1] + 2 * cnt[2]);
     af_.push_back(n_ ? 0.5 * sum_ac / (double)n_ : -1.0);
     for (int k = 0; k < 4; ++k) counts_.push_back(cnt[k]);
-    names_var_.push_back(std::string(line + fb[0], fe[0] - fb[0]) + ":" + std::string(line + fb[1], fe[1] - fb[1]));
+    std::string name = std::string(line + fb[0], fe[0] - fb[0]) + ":" + std::string(line + fb[1], fe[1] - fb[1]);
+    if (multi_) name += std::string(line + fb[3], fe[3] - fb[3]) + "/" + (dosage ? alts.back() : alts[pass]);
+    names_var_.push_back(name);
     ++m_;
-    return 1;
+    }  // pass
+    return n_pass;
   }
 
   int numVariant() const { return m_; }
@@ -445,6 +502,14 @@ class VcfGenePacker {
   }
 
  private:
+  void rollback(size_t rows_size, size_t dos_size, int m) {
+    rows_.resize(rows_size);
+    dos_.resize(dos_size);
+    af_.resize((size_t)m);
+    counts_.resize((size_t)m * 4);
+    names_var_.resize((size_t)m);
+    m_ = m;
+  }
   // the idx-th ':'-separated subfield of the sample column line[b, e) as [*sb, *se); false when the column has fewer
   // subfields or idx < 0 (VCFIndividual::justGet then hands out the empty default value)
   static bool subfield(const char* line, size_t b, size_t e, int idx, size_t* sb_out, size_t* se_out) {
@@ -506,7 +571,7 @@ class VcfGenePacker {
   std::string dosage_tag_;
   std::vector<int> sex_;
   VcfParRegion par_;
-  bool need_gd_, need_gq_;
+  bool multi_, need_gd_, need_gq_;
   int gd_min_, gd_max_, gq_min_, gq_max_;
   std::vector<double> af_;
   std::vector<int> counts_;

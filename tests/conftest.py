@@ -89,6 +89,8 @@ class VcfPacker:
         lib.vp_sample_name.argtypes = [C.c_int]
         lib.vp_set_dosage_tag.argtypes = [C.c_char_p]
         lib.vp_gt_male02.argtypes = [C.c_char_p, C.c_int]
+        lib.vp_count_alt.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        lib.vp_count_male_alt2.argtypes = [C.c_char_p, C.c_int, C.c_int]
         lib.vp_par_is_hemi.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         lib.vp_set_sex.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
         lib.vp_get_dosages.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -116,6 +118,17 @@ class VcfPacker:
     def gt_male02(self, s):
         b = s.encode("latin-1")
         return self.L.vp_gt_male02(b, len(b))
+
+    def count_alt(self, s, alt):
+        b = s.encode("latin-1")
+        return self.L.vp_count_alt(b, len(b), alt)
+
+    def count_male_alt2(self, s, alt):
+        b = s.encode("latin-1")
+        return self.L.vp_count_male_alt2(b, len(b), alt)
+
+    def set_multi(self, on):
+        self.L.vp_set_multi(1 if on else 0)
 
     def par_is_hemi(self, x_label, par_region, chrom, pos):
         return self.L.vp_par_is_hemi(x_label.encode(), par_region.encode(), chrom.encode(), int(pos))

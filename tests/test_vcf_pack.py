@@ -311,3 +311,64 @@ def test_records_on_x_with_sex(vcfpack, oracle, dosage, capfd):
     finally:
         vcfpack.set_dosage_tag("")
         vcfpack.set_sex(None)
+
+
+def test_multi_allelic_grammar_exhaustive(vcfpack, oracle, capfd):
+    """VCFValue::countAltAllele / countMaleNonParAltAllele2 for alt = 1, 2, 3 on every non-empty string of up to 4 characters
+    (the reference reads past its buffer on the empty value, and asserts on a first allele above '9' in the male form)"""
+    if oracle.ref_vcf() is None:
+        pytest.skip("oracle/_ref/libvcf_ref.so not built (no /root/reference here)")
+    ref = oracle.ref_vcf()
+    for s in _all_gt_strings():
+        if not s:
+            continue
+        for alt in (1, 2, 3):
+            assert vcfpack.count_alt(s, alt) == ref.ref_vcf_count_alt(s.encode(), len(s), alt), (s, alt)
+            if s[0] not in "a|":        # (bytes above '9': the reference asserts 0 <= g <= 9)
+                assert vcfpack.count_male_alt2(s, alt) == ref.ref_vcf_count_male_alt2(s.encode(), len(s), alt), (s, alt)
+    capfd.readouterr()
+    assert [vcfpack.count_alt(s, 2) for s in ("0/2", "2/2", "2|1", "1/1", "2", "./2", "0/", "")] == [1, 2, 1, 0, 1, -9, -9, -9]
+
+
+@pytest.mark.parametrize("with_sex", [False, True])
+def test_multi_allelic_records(vcfpack, oracle, with_sex, capfd):
+    """--multipleAllele: a record with K ALT alleles becomes K rows (copies of allele a), named chrom:posREF/ALTa"""
+    if oracle.ref_vcf() is None:
+        pytest.skip("oracle/_ref/libvcf_ref.so not built (no /root/reference here)")
+    n = 8
+    hdr = _header(n)
+    rng = np.random.default_rng(31)
+    sex = np.array([1, 2, 1, 2, 0, 1, 2, 1]) if with_sex else None
+    gts = ["0/0", "0/1", "1/1", "0/2", "1/2", "2/2", "2|0", "0", "1", "2", "./.", "3/1", "0/3", ".", "1/", "0/1/2"]
+    vcfpack.set_multi(True)
+    try:
+        assert vcfpack.header(hdr) == n
+        assert vcfpack.set_sex(sex) == 0
+        vcfpack.set_range("")
+        vcfpack.clear()
+        want, names = [], []
+        for k in range(40):
+            alts = ["G", "G,T", "G,T,<DEL>"][k % 3]
+            chrom, pos = ["X", "5"][k % 2], [70000, 5_000_000][(k // 2) % 2]
+            cols = [gts[int(rng.integers(len(gts)))] + ":7" for _ in range(n)]
+            rec = "\t".join([chrom, str(pos), ".", "AC", alts, "9", "PASS", ".", "GT:GQ"] + cols)
+            na = alts.count(",") + 1
+            assert vcfpack.add(rec) == na
+            for a in range(1, na + 1):
+                g, n_alt = oracle.ref_vcf_genotypes_alt(hdr, rec, a, sex)
+                assert n_alt == na
+                want.append(g)
+                names.append(f"{chrom}:{pos}AC/{alts.split(',')[a - 1]}")
+        capfd.readouterr()
+        rows, af, counts, got_names = vcfpack.gene()
+        want = np.array(want)
+        assert np.array_equal(_decode(oracle, rows, n), want.astype(float))
+        assert got_names == names
+        assert np.array_equal(af, np.array([0.5 * r[r >= 0].sum() / n for r in want]))
+        # a malformed record in this mode leaves nothing behind either
+        m0 = rows.shape[0]
+        assert vcfpack.add("\t".join(["5", "9", ".", "A", "C,G", "9", "PASS", ".", "GT"] + ["0/1"] * (n - 1))) < 0
+        assert vcfpack.gene()[0].shape[0] == m0
+    finally:
+        vcfpack.set_multi(False)
+        vcfpack.set_sex(None)
