@@ -237,7 +237,7 @@ class VcfRangeSet {
 
 class VcfGenePacker {
  public:
-  VcfGenePacker() : ncol_(0), n_(0), stride_(0), m_(0), multi_(false), need_gd_(false), need_gq_(false), gd_min_(0), gd_max_(0), gq_min_(0), gq_max_(0) {}
+  VcfGenePacker() : ncol_(0), n_(0), stride_(0), m_(0), multi_(false), freq_min_(0.0), freq_max_(0.0), need_gd_(false), need_gq_(false), gd_min_(0), gd_max_(0), gq_min_(0), gq_max_(0) {}
 
   // the "#CHROM\tPOS\t...\tFORMAT\tS1\tS2..." line.  keep: names to include (NULL or empty: everyone); samples are
   // emitted in VCF column order (VCFRecord::createIndividual + includePeople, libVcf/VCFRecord.h:203-231).
@@ -286,6 +286,13 @@ class VcfGenePacker {
   // variant is then named "chrom:posREF/ALTa".  addRecord returns K.  (With a dosage tag the reference warns and keeps one
   // row named after the LAST alt allele; so does this.)
   void setMultiAllelic(bool on) { multi_ = on; }
+  // --freqLower / --freqUpper (src/VCFGenotypeExtractor.cpp:98-110): a row whose MAF = min(AF, 1 - AF) (GenotypeCounter::
+  // getMAF, AF over ALL kept samples) lies below freq_min or above freq_max is dropped again; a bound <= 0 is off.
+  // addRecord then returns the number of rows that stayed.
+  void setFreqRange(double freq_min, double freq_max) {
+    freq_min_ = freq_min;
+    freq_max_ = freq_max;
+  }
   // Sex of the KEPT samples in output order (PLINK coding: 1 male, 2 female, anything else unknown) switches on the
   // reference's X handling (VCFGenotypeExtractor::getGenotype, src/VCFGenotypeExtractor.cpp:416-428, 404-415): at a site
   // in a hemizygous region (parRegion()) a male is coded 0 / 2 (vcfGenotypeMale02; a dosage is doubled), a female as
@@ -369,6 +376,7 @@ class VcfGenePacker {
     const int n_pass = multi_ && !dosage ? (int)alts.size() : 1;
     const size_t b_samples = b, row_first = rows_.size(), dos_first = dos_.size();
     const int m_first = m_;
+    int dropped = 0;
     for (int pass = 0; pass < n_pass; ++pass) {
     const int alt = multi_ && !dosage ? pass + 1 : 0;
     b = b_samples;
@@ -447,14 +455,22 @@ class VcfGenePacker {
     }
     // GenotypeCounter::getAF: 0.5 * sumAC / nSample, nSample counting the missing calls too
     if (!dosage) sum_ac = (double)(cnt[1] + 2 * cnt[2]);
-    af_.push_back(n_ ? 0.5 * sum_ac / (double)n_ : -1.0);
+    const double af_row = n_ ? 0.5 * sum_ac / (double)n_ : -1.0;
+    const double maf = af_row > 0.5 ? 1.0 - af_row : af_row;
+    if ((freq_min_ > 0. && freq_min_ > maf) || (freq_max_ > 0. && freq_max_ < maf)) {   // "undo loaded contents"
+      rows_.resize(row0);
+      dos_.resize(dos0);
+      ++dropped;
+      continue;
+    }
+    af_.push_back(af_row);
     for (int k = 0; k < 4; ++k) counts_.push_back(cnt[k]);
     std::string name = std::string(line + fb[0], fe[0] - fb[0]) + ":" + std::string(line + fb[1], fe[1] - fb[1]);
     if (multi_) name += std::string(line + fb[3], fe[3] - fb[3]) + "/" + (dosage ? alts.back() : alts[pass]);
     names_var_.push_back(name);
     ++m_;
     }  // pass
-    return n_pass;
+    return n_pass - dropped;
   }
 
   int numVariant() const { return m_; }
@@ -571,7 +587,9 @@ class VcfGenePacker {
   std::string dosage_tag_;
   std::vector<int> sex_;
   VcfParRegion par_;
-  bool multi_, need_gd_, need_gq_;
+  bool multi_;
+  double freq_min_, freq_max_;
+  bool need_gd_, need_gq_;
   int gd_min_, gd_max_, gq_min_, gq_max_;
   std::vector<double> af_;
   std::vector<int> counts_;

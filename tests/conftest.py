@@ -89,6 +89,7 @@ class VcfPacker:
         lib.vp_sample_name.argtypes = [C.c_int]
         lib.vp_set_dosage_tag.argtypes = [C.c_char_p]
         lib.vp_gt_male02.argtypes = [C.c_char_p, C.c_int]
+        lib.vp_set_freq.argtypes = [C.c_double, C.c_double]
         lib.vp_count_alt.argtypes = [C.c_char_p, C.c_int, C.c_int]
         lib.vp_count_male_alt2.argtypes = [C.c_char_p, C.c_int, C.c_int]
         lib.vp_par_is_hemi.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
@@ -126,6 +127,9 @@ class VcfPacker:
     def count_male_alt2(self, s, alt):
         b = s.encode("latin-1")
         return self.L.vp_count_male_alt2(b, len(b), alt)
+
+    def set_freq(self, lo=0.0, hi=0.0):
+        self.L.vp_set_freq(float(lo), float(hi))
 
     def set_multi(self, on):
         self.L.vp_set_multi(1 if on else 0)

@@ -58,6 +58,7 @@ int vp_set_sex(const int* sex, int n, const char* xLabel, const char* parRegion)
 int vp_count_alt(const char* s, int len, int alt) { return rvtb200::vcfCountAltAllele(s, len, alt); }
 int vp_count_male_alt2(const char* s, int len, int alt) { return rvtb200::vcfCountMaleAltAllele2(s, len, alt); }
 void vp_set_multi(int on) { g_p.setMultiAllelic(on != 0); }
+void vp_set_freq(double lo, double hi) { g_p.setFreqRange(lo, hi); }
 void vp_set_filters(int gd_min, int gd_max, int gq_min, int gq_max) {
   g_p.setDepthFilter(gd_min, gd_max);
   g_p.setQualFilter(gq_min, gq_max);

@@ -372,3 +372,33 @@ def test_multi_allelic_records(vcfpack, oracle, with_sex, capfd):
     finally:
         vcfpack.set_multi(False)
         vcfpack.set_sex(None)
+
+
+def test_maf_cut(vcfpack, oracle, capfd):
+    """--freqLower / --freqUpper (src/VCFGenotypeExtractor.cpp:98-110): rows outside [lo, hi] in MAF are undone"""
+    n = 40
+    hdr = _header(n)
+    rng = np.random.default_rng(3)
+    recs = [_random_record(rng, n, k + 1) for k in range(80)]
+    gen = [oracle.vcf_record_genotypes(hdr, r)[2] for r in recs]
+    maf = []
+    for g in gen:
+        a = 0.5 * g[g >= 0].sum() / n
+        maf.append(1 - a if a > 0.5 else a)
+    maf = np.array(maf)
+    assert vcfpack.header(hdr) == n
+    vcfpack.set_range("")
+    for lo, hi in ((0.0, 0.0), (0.1, 0.0), (0.0, 0.12), (0.08, 0.15)):
+        vcfpack.set_freq(lo, hi)
+        try:
+            vcfpack.clear()
+            kept = [vcfpack.add(r) for r in recs]
+        finally:
+            vcfpack.set_freq()
+        want = ~(((lo > 0) & (lo > maf)) | ((hi > 0) & (hi < maf)))
+        assert kept == [int(w) for w in want], (lo, hi)
+        rows, af, counts, names = vcfpack.gene()
+        assert rows.shape[0] == want.sum() == len(af) == len(names)
+        assert np.array_equal(_decode(oracle, rows, n), np.array(gen)[want].astype(float))
+    capfd.readouterr()
+    assert 0 < want.sum() < len(recs)
