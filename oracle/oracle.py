@@ -352,6 +352,8 @@ def ref_vcf():
             L.ref_vcf_count_male_alt2.argtypes = [C.c_char_p, C.c_int, C.c_int]
             L.ref_vcf_genotypes_alt.restype = C.c_int
             L.ref_vcf_genotypes_alt.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _int_p, C.c_int, _int_p, C.c_int, _int_p]
+            L.ref_parse_range.restype = C.c_int
+            L.ref_parse_range.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
             L.ref_vcf_dosages.restype = C.c_int
             L.ref_vcf_dosages.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, _dbl_p, C.c_int]
             _lib_cache["vcf"] = L

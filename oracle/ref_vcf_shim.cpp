@@ -9,6 +9,7 @@
 #include <string>
 
 #include "base/ParRegion.h"
+#include "base/RangeList.h"
 #include "libVcf/VCFRecord.h"
 
 // BufferedReader (base/IO.cpp needs bzip2/zlib trees that are not built here) is only reached from
@@ -24,6 +25,7 @@ bool BufferedReader::isEof() { return true; }
 void BufferedReader::close() {}
 int BufferedReader::getc() { return EOF; }
 int BufferedReader::read(void*, int) { return 0; }
+int BufferedReader::readLine(std::string*) { unreachable("BufferedReader"); return 0; }
 
 extern "C" {
 // header: the "#CHROM\tPOS..." line; record: one data line (no newline).  out[cap] receives the genotype per sample
@@ -81,6 +83,15 @@ int ref_vcf_genotypes_filtered(const char* header, const char* record, int gd_mi
   }
   r.deleteIndividual();
   return n;
+}
+
+// parseRangeFormat (base/RangeList.cpp:78-125): 0 = parsed
+int ref_parse_range(const char* s, char* chrom, unsigned int* beg, unsigned int* end) {
+  std::string c;
+  const int rc = parseRangeFormat(std::string(s), &c, beg, end);
+  strncpy(chrom, c.c_str(), 63);
+  chrom[63] = 0;
+  return rc;
 }
 
 // VCFValue::getMaleNonParGenotype02 on one GT string (libVcf/VCFValue.h:125-142)

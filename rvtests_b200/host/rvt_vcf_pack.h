@@ -23,6 +23,7 @@
 #define RVT_VCF_PACK_H_
 
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -175,50 +176,83 @@ class VcfParRegion {
   std::vector<std::pair<int, int> > region_;
 };
 
-// one or more "chr:beg-end" ranges (also "chr" = whole chromosome, "chr:pos" = one base); 1-based, inclusive
+// str2int (base/TypeConversion.cpp:55-135): blanks, an optional '-', blanks, then 1..10 digits (anything after them is
+// ignored); false when there is no digit or the value leaves the 32-bit range
+inline bool vcfStr2Int(const char* in, int* out) {
+  while (*in == ' ') ++in;
+  bool neg = false;
+  if (*in == '-') {
+    neg = true;
+    ++in;
+  }
+  if (*in == '\0') return false;
+  while (*in == ' ') ++in;
+  size_t len = 0;
+  while (in[len] >= '0' && in[len] <= '9') ++len;
+  if (len < 1 || len > 10) return false;
+  unsigned long v = 0;
+  for (size_t i = 0; i < len; ++i) v = v * 10 + (unsigned long)(in[i] - '0');
+  if (neg ? v > (unsigned long)INT32_MAX + 1 : v > (unsigned long)INT32_MAX) return false;
+  *out = neg ? (int)(-(long)v) : (int)v;
+  return true;
+}
+
+// parseRangeFormat (base/RangeList.cpp:78-125): "chr:beg-end" (1-based, inclusive); "chr:beg" and "chr:beg-" run to
+// 1 << 29 (tabix's constant); a piece without a usable begin, with a negative bound or with beg > end does not conform
+inline bool vcfParseRange(const std::string& s, std::string* chr, int* beg, int* end) {
+  size_t i = 0;
+  chr->clear();
+  while (i < s.size() && s[i] != ':') chr->push_back(s[i++]);
+  ++i;
+  std::string t;
+  while (i < s.size() && s[i] != '-') t.push_back(s[i++]);
+  int b = 0;
+  if (!vcfStr2Int(t.c_str(), &b) || b < 0) return false;
+  *beg = b;
+  if (i >= s.size()) {
+    *end = 1 << 29;
+    return true;
+  }
+  ++i;
+  if (i >= s.size()) {
+    *end = 1 << 29;
+    return true;
+  }
+  int e = 0;
+  if (!vcfStr2Int(s.c_str() + i, &e) || e < 0 || b > e) return false;
+  *end = e;
+  return true;
+}
+
+// a set of ranges as --rangeList / a --setFile line give them: "chr:beg-end[,chr:beg-end...]" (RangeList::addRangeList,
+// base/RangeList.cpp:134-150: pieces that do not conform are skipped) or chromosome + bounds (RangeList::addRange)
 class VcfRangeSet {
  public:
   void clear() { r_.clear(); }
   bool empty() const { return r_.empty(); }
-  // returns the number of ranges added, < 0 on a malformed piece
+  size_t size() const { return r_.size(); }
+  // returns the number of ranges added (malformed pieces are skipped, as in the reference)
   int add(const std::string& spec) {
     int added = 0;
     size_t b = 0;
     while (b <= spec.size()) {
       size_t e = spec.find(',', b);
       if (e == std::string::npos) e = spec.size();
-      if (e > b) {
-        Range r;
-        const std::string piece = spec.substr(b, e - b);
-        const size_t colon = piece.find(':');
-        if (colon == std::string::npos) {
-          r.chrom = piece;
-          r.beg = 0;
-          r.end = INT32_MAX;
-        } else {
-          r.chrom = piece.substr(0, colon);
-          const std::string rest = piece.substr(colon + 1);
-          const size_t dash = rest.find('-');
-          char* endp = NULL;
-          if (rest.empty()) return -1;
-          r.beg = (int)strtol(rest.c_str(), &endp, 10);
-          if (endp == rest.c_str()) return -1;
-          if (dash == std::string::npos) {
-            r.end = r.beg;
-          } else if (dash + 1 == rest.size()) {
-            r.end = INT32_MAX;   // "chr:beg-" = to the end of the chromosome
-          } else {
-            r.end = (int)strtol(rest.c_str() + dash + 1, &endp, 10);
-            if (endp == rest.c_str() + dash + 1) return -1;
-          }
-        }
-        if (r.chrom.empty() || r.end < r.beg) return -1;
+      Range r;
+      if (vcfParseRange(spec.substr(b, e - b), &r.chrom, &r.beg, &r.end)) {
         r_.push_back(r);
         ++added;
       }
       b = e + 1;
     }
     return added;
+  }
+  void addRange(const std::string& chrom, int beg, int end) {
+    Range r;
+    r.chrom = chrom;
+    r.beg = beg;
+    r.end = end;
+    r_.push_back(r);
   }
   bool contains(const char* chrom, size_t chrom_len, int pos) const {
     for (size_t i = 0; i < r_.size(); ++i)
@@ -233,6 +267,103 @@ class VcfRangeSet {
     int beg, end;
   };
   std::vector<Range> r_;
+};
+
+// --geneFile (refFlat) and --setFile: gene / set name -> ranges, names in order of first appearance
+// (loadGeneFile / loadRangeFile, src/Main.cpp:91-122, 138-173; OrderedMap keeps insertion order)
+class GeneRangeMap {
+ public:
+  size_t size() const { return names_.size(); }
+  const std::string& name(size_t i) const { return names_[i]; }
+  const VcfRangeSet& ranges(size_t i) const { return sets_[i]; }
+  void clear() {
+    names_.clear();
+    sets_.clear();
+  }
+  // refFlat lines "gene transcript chrom strand txStart txEnd ...", blank- or tab-separated: the gene's range is
+  // chopChr(chrom):txStart-txEnd, several lines of one gene add up.  only: comma-separated gene names to keep ("" = all).
+  // A line with fewer than 6 columns stops the reading (the reference logs an error and breaks).  Returns the number of
+  // genes, < 0 when the file cannot be opened.
+  int loadGeneFile(const std::string& path, const std::string& only = "") {
+    const std::set<std::string> keep = makeSet(only);
+    std::vector<std::string> fd;
+    return eachLine(path, [&](const std::string& line) -> bool {
+      split(line, &fd);
+      if (fd.size() < 6) return false;
+      if (!keep.empty() && !keep.count(fd[0])) return true;
+      std::string chr = fd[2];
+      if (chr.size() > 3 && (chr[0] == 'c' || chr[0] == 'C') && (chr[1] == 'h' || chr[1] == 'H') && (chr[2] == 'r' || chr[2] == 'R'))
+        chr = chr.substr(3);
+      slot(fd[0]).addRange(chr, atoi(fd[4].c_str()), atoi(fd[5].c_str()));
+      return true;
+    });
+  }
+  // "setName range[,range...]" lines; lines with fewer than 2 columns or an empty column are skipped
+  int loadRangeFile(const std::string& path, const std::string& only = "") {
+    const std::set<std::string> keep = makeSet(only);
+    std::vector<std::string> fd;
+    return eachLine(path, [&](const std::string& line) -> bool {
+      split(line, &fd);
+      if (fd.size() < 2) return true;
+      if (!keep.empty() && !keep.count(fd[0])) return true;
+      if (fd[0].empty() || fd[1].empty()) return true;
+      slot(fd[0]).add(fd[1]);
+      return true;
+    });
+  }
+
+ private:
+  VcfRangeSet& slot(const std::string& name) {
+    for (size_t i = 0; i < names_.size(); ++i)
+      if (names_[i] == name) return sets_[i];
+    names_.push_back(name);
+    sets_.push_back(VcfRangeSet());
+    return sets_.back();
+  }
+  static std::set<std::string> makeSet(const std::string& csv) {
+    std::set<std::string> out;
+    size_t b = 0;
+    while (b < csv.size()) {
+      size_t e = csv.find(',', b);
+      if (e == std::string::npos) e = csv.size();
+      if (e > b) out.insert(csv.substr(b, e - b));
+      b = e + 1;
+    }
+    return out;
+  }
+  static void split(const std::string& line, std::vector<std::string>* fd) {   // readLineBySep(&fd, "\t ")
+    fd->clear();
+    size_t b = 0;
+    while (true) {
+      const size_t e = line.find_first_of(" \t", b);
+      if (e == std::string::npos) {
+        fd->push_back(line.substr(b));
+        return;
+      }
+      fd->push_back(line.substr(b, e - b));
+      b = e + 1;
+    }
+  }
+  template <class F>
+  int eachLine(const std::string& path, F f) {
+    FILE* fp = fopen(path.c_str(), "rt");
+    if (!fp) return -1;
+    std::string line;
+    char buf[65536];
+    bool go = true;
+    while (go && fgets(buf, sizeof(buf), fp)) {
+      line += buf;
+      if (line.empty() || line[line.size() - 1] != '\n') continue;
+      while (!line.empty() && (line[line.size() - 1] == '\n' || line[line.size() - 1] == '\r')) line.erase(line.size() - 1);
+      go = f(line);
+      line.clear();
+    }
+    if (go && !line.empty()) f(line);
+    fclose(fp);
+    return (int)names_.size();
+  }
+  std::vector<std::string> names_;
+  std::vector<VcfRangeSet> sets_;
 };
 
 class VcfGenePacker {

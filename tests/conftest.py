@@ -89,6 +89,11 @@ class VcfPacker:
         lib.vp_sample_name.argtypes = [C.c_int]
         lib.vp_set_dosage_tag.argtypes = [C.c_char_p]
         lib.vp_gt_male02.argtypes = [C.c_char_p, C.c_int]
+        lib.vp_parse_range.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.vp_load_gene_file.argtypes = [C.c_char_p, C.c_char_p]
+        lib.vp_load_range_file.argtypes = [C.c_char_p, C.c_char_p]
+        lib.vp_map_name.restype = C.c_char_p
+        lib.vp_map_contains.argtypes = [C.c_int, C.c_char_p, C.c_int]
         lib.vp_set_freq.argtypes = [C.c_double, C.c_double]
         lib.vp_count_alt.argtypes = [C.c_char_p, C.c_int, C.c_int]
         lib.vp_count_male_alt2.argtypes = [C.c_char_p, C.c_int, C.c_int]
@@ -127,6 +132,13 @@ class VcfPacker:
     def count_male_alt2(self, s, alt):
         b = s.encode("latin-1")
         return self.L.vp_count_male_alt2(b, len(b), alt)
+
+    def parse_range(self, s):
+        import ctypes as C
+        chrom = C.create_string_buffer(64)
+        b, e = C.c_int(0), C.c_int(0)
+        rc = self.L.vp_parse_range(s.encode("latin-1"), chrom, C.byref(b), C.byref(e))
+        return None if rc else (chrom.value.decode("latin-1"), b.value, e.value)
 
     def set_freq(self, lo=0.0, hi=0.0):
         self.L.vp_set_freq(float(lo), float(hi))

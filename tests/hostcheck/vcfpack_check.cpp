@@ -59,6 +59,25 @@ int vp_count_alt(const char* s, int len, int alt) { return rvtb200::vcfCountAltA
 int vp_count_male_alt2(const char* s, int len, int alt) { return rvtb200::vcfCountMaleAltAllele2(s, len, alt); }
 void vp_set_multi(int on) { g_p.setMultiAllelic(on != 0); }
 void vp_set_freq(double lo, double hi) { g_p.setFreqRange(lo, hi); }
+int vp_parse_range(const char* s, char* chrom, int* beg, int* end) {
+  std::string c;
+  const bool ok = rvtb200::vcfParseRange(s, &c, beg, end);
+  strncpy(chrom, c.c_str(), 63);
+  chrom[63] = 0;
+  return ok ? 0 : -1;
+}
+static rvtb200::GeneRangeMap g_map;
+int vp_load_gene_file(const char* path, const char* only) {
+  g_map.clear();
+  return g_map.loadGeneFile(path, only ? only : "");
+}
+int vp_load_range_file(const char* path, const char* only) {
+  g_map.clear();
+  return g_map.loadRangeFile(path, only ? only : "");
+}
+const char* vp_map_name(int i) { return g_map.name(i).c_str(); }
+int vp_map_contains(int i, const char* chrom, int pos) { return g_map.ranges(i).contains(chrom, strlen(chrom), pos) ? 1 : 0; }
+int vp_map_nranges(int i) { return (int)g_map.ranges(i).size(); }
 void vp_set_filters(int gd_min, int gd_max, int gq_min, int gq_max) {
   g_p.setDepthFilter(gd_min, gd_max);
   g_p.setQualFilter(gq_min, gq_max);

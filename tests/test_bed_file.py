@@ -85,8 +85,8 @@ def test_fileset_rows_af_and_selection(bf, oracle, tmp_path, N):
     assert bf.bf_marker_index(b"nope") == -1
     sel = np.zeros(M, dtype=np.int32)
     assert bf.bf_select(b"1:200-400", sel.ctypes.data, M) == 3 and list(sel[:3]) == [1, 2, 3]
-    assert bf.bf_select(b"2:100-150,X", sel.ctypes.data, M) == 5 and list(sel[:5]) == [5, 6, 9, 10, 11]
-    assert bf.bf_select(b"3", sel.ctypes.data, M) == 0
+    assert bf.bf_select(b"2:100-150,X:1", sel.ctypes.data, M) == 5 and list(sel[:5]) == [5, 6, 9, 10, 11]
+    assert bf.bf_select(b"3:1", sel.ctypes.data, M) == 0 and bf.bf_select(b"X", sel.ctypes.data, M) == 0   # ("X" alone does not conform)
     # pushes: consecutive rows leave the mapping as they are, scattered rows are gathered; AF rides along
     for rows in ([1, 2, 3], [0, 5, 11], [7]):
         r = np.array(rows, dtype=np.int32)

@@ -138,9 +138,9 @@ def test_sample_subset_ranges_and_malformed_lines(vcfpack, oracle):
     assert np.array_equal(_decode(oracle, rows, 3), full[:, [1, 2, 5]].astype(float))
     assert names == [f"{c}:{p}" for c, p in zip(chrom[1:4], (10, 20, 30))]
     assert np.array_equal(af, np.array([0.5 * r[r >= 0].sum() / 3 for r in full[:, [1, 2, 5]]]))
-    # other range spellings
-    assert vcfpack.set_range("1") == 1 and vcfpack.set_range("1:5") == 1 and vcfpack.set_range("1:5-") == 1
-    assert vcfpack.set_range("1:30-10") < 0 and vcfpack.set_range("1:x-3") < 0
+    # other range spellings (parseRangeFormat): open-ended forms run to 1 << 29, pieces that do not conform are skipped
+    assert vcfpack.set_range("1:5") == 1 and vcfpack.set_range("1:5-") == 1 and vcfpack.set_range("1:5-9,2:1-2") == 2
+    assert vcfpack.set_range("1") == 0 and vcfpack.set_range("1:30-10") == 0 and vcfpack.set_range("1:x-3,1:4-5") == 1
     vcfpack.set_range("")
     # comment / meta lines are skipped; a record with a different sample count is an error and leaves no row behind
     vcfpack.clear()
@@ -402,3 +402,58 @@ def test_maf_cut(vcfpack, oracle, capfd):
         assert np.array_equal(_decode(oracle, rows, n), np.array(gen)[want].astype(float))
     capfd.readouterr()
     assert 0 < want.sum() < len(recs)
+
+
+def test_range_format_vs_reference(vcfpack, oracle):
+    """parseRangeFormat (base/RangeList.cpp:78-125) on every string of up to 6 characters over '1X:-0 9a' plus hand-made ones"""
+    import ctypes as C
+    if oracle.ref_vcf() is None:
+        pytest.skip("oracle/_ref/libvcf_ref.so not built (no /root/reference here)")
+    ref = oracle.ref_vcf()
+    cases = ["1:100-200", "X:150", "chr7:5-", "MT", "", ":", "1:", "1:-5", "1:5-3", "1:5-5", "1: 7-9", "1:7- 9", "1:12x-20y", "1:2147483647",
+             "1:2147483648", "1:99999999999", "1:5--6", "a:b-c", "1:1-2147483647", "22:0-0", "1:007-010"]
+    for n in range(1, 7):
+        for t in itertools.product("1X:-0 9a", repeat=n):
+            cases.append("".join(t))
+    chrom = C.create_string_buffer(64)
+    b, e = C.c_uint(0), C.c_uint(0)
+    n_ok = 0
+    for s in cases:
+        rc = ref.ref_parse_range(s.encode(), chrom, C.byref(b), C.byref(e))
+        got = vcfpack.parse_range(s)
+        if rc != 0:
+            assert got is None, s
+        else:
+            assert got == (chrom.value.decode(), b.value, e.value), (s, got)
+            n_ok += 1
+    assert n_ok > 1000
+
+
+def test_gene_file_and_set_file(vcfpack, tmp_path):
+    """--geneFile (refFlat) and --setFile readers (src/Main.cpp:91-122, 138-173), on the reference's own test/gene.txt layout"""
+    gf = tmp_path / "gene.txt"
+    gf.write_text("GENE1\ttran1\t1\t-\t10\t30\t10\t30\t1\t10\t30\n"
+                  "GENE2\ttran2\tchr1\t-\t40\t60\n"
+                  "GENE3 tran3 X + 50 110\n"
+                  "GENE1\ttran1b\t1\t-\t100\t130\n"
+                  "short\tline\n"
+                  "GENE9\ttran9\t2\t+\t1\t2\n")
+    L = vcfpack.L
+    assert L.vp_load_gene_file(str(gf).encode(), b"") == 3            # reading stops at the short line
+    assert [L.vp_map_name(i).decode() for i in range(3)] == ["GENE1", "GENE2", "GENE3"]
+    assert L.vp_map_nranges(0) == 2
+    assert [L.vp_map_contains(0, b"1", p) for p in (9, 10, 30, 31, 100, 131)] == [0, 1, 1, 0, 1, 0]
+    assert L.vp_map_contains(1, b"1", 50) == 1 and L.vp_map_contains(1, b"chr1", 50) == 0     # chopChr
+    assert L.vp_map_contains(2, b"X", 110) == 1
+    assert L.vp_load_gene_file(str(gf).encode(), b"GENE3,GENE2") == 2
+    assert [L.vp_map_name(i).decode() for i in range(2)] == ["GENE2", "GENE3"]
+    assert L.vp_load_gene_file(str(tmp_path / "nope").encode(), b"") < 0
+    sf = tmp_path / "setFile"
+    sf.write_text("set1 1:1-3\nset2\t1:10-20,2:5-6,junk\nlonely\n\nset1 X:7\nset3  1:1-2\n")
+    assert L.vp_load_range_file(str(sf).encode(), b"") == 2           # 'lonely', the blank line and the empty column are skipped
+    assert [L.vp_map_name(i).decode() for i in range(2)] == ["set1", "set2"]
+    assert L.vp_map_nranges(0) == 2 and L.vp_map_nranges(1) == 2
+    assert [L.vp_map_contains(0, b"1", p) for p in (0, 1, 3, 4)] == [0, 1, 1, 0]
+    assert L.vp_map_contains(0, b"X", 7) == 1 and L.vp_map_contains(0, b"X", 1 << 29) == 1 and L.vp_map_contains(0, b"X", 6) == 0
+    assert L.vp_map_contains(1, b"2", 6) == 1
+    assert L.vp_load_range_file(str(sf).encode(), b"set2") == 1
