@@ -22,6 +22,49 @@ def _check_skato(r, ref, ctx):
         assert rel(r["skato_p"], ref["pvalue"]) <= 1e-5, (ctx, r["skato_p"], ref["pvalue"])
 
 
+def test_vcf_text_to_engine(engine_cls, oracle, vcfpack):
+    """SURVEY 8(f) N2 end to end: VCF records -> rvt_vcf_pack.h (2-bit rows + AF) -> rvt_gene_push_bed -> device, against the
+    oracle run on the matrix the REFERENCE's parser semantics give (decode + imputeGenotypeToMean).  One gene with and one
+    without missing calls."""
+    from test_vcf_pack import _header
+    O = oracle
+    N, C = 1501, 3
+    X, y = O.synth_covariates(91, N, C)
+    nm = O.fit_null_linear(X, y)
+    rng = np.random.default_rng(91)
+    code = np.array(["0/0", "0/1", "1/1", "./.", "1|0", "0/2"])
+    eng = engine_cls(0)
+    try:
+        eng.set_null_model(X, y)
+        assert vcfpack.header(_header(N)) == N
+        vcfpack.set_range("7:100-200")
+        refs = []
+        for gene, with_missing in enumerate((False, True)):
+            vcfpack.clear()
+            M = 12
+            maf = np.linspace(0.01, 0.2, M)
+            for j in range(M + 3):
+                g = rng.binomial(2, maf[j % M], size=N)
+                if with_missing:
+                    g = np.where(rng.random(N) < 0.01, 3, g)
+                    g = np.where(rng.random(N) < 0.003, 5, g)      # multi-allelic call -> missing
+                g = np.where((g == 1) & (rng.random(N) < 0.5), 4, g)  # phased het, same value
+                pos = 100 + 5 * j if j < M else 300 + j               # the last three lie outside the range
+                rec = "\t".join(["7", str(pos), ".", "A", "G", "50", "PASS", ".", "GT:GQ"] + [c + ":9" for c in code[g]])
+                assert vcfpack.add(rec) == (1 if j < M else 0)
+            rows, af, counts, names = vcfpack.gene()
+            assert rows.shape == (M, (N + 3) // 4) and (counts[:, 3].sum() > 0) == with_missing
+            raw = O.bed_decode_fast(rows, N).T
+            refs.append((O.impute_mean(raw), af.copy()))
+            eng.push_bed(rows, af)
+        res = eng.flush()
+    finally:
+        eng.close()
+    for k, (Gd, af) in enumerate(refs):
+        ref, lam = O.gene(Gd, af, X, nm["resid"], nm["sigma2"])
+        check_gene(res[k], ref, lam, ctx=f"vcf gene {k}")
+
+
 @pytest.mark.parametrize("case", [(175, 700, 8, 1, 0.02), (171, 3001, 30, 3, 0.01), (172, 1200, 1, 2, 0.03)])
 def test_skato_on_genes_with_missing_calls(engine_cls, oracle, case):
     from oracle import skato_oracle as SO
@@ -135,49 +178,6 @@ def test_adapter_prints_skato_for_a_binary_trait(oracle, tmp_path):
         assert ref["ok"] and "NA" not in ro, (gi, ro)
         # "%g" prints 6 significant digits
         assert rel(float(ro[0]), ref["Q"]) <= 2e-5 and float(ro[1]) == ref["rho"] and rel(float(ro[2]), ref["pvalue"]) <= 3e-5, (gi, ro, ref)
-
-
-def test_vcf_text_to_engine(engine_cls, oracle, vcfpack):
-    """SURVEY 8(f) N2 end to end: VCF records -> rvt_vcf_pack.h (2-bit rows + AF) -> rvt_gene_push_bed -> device, against the
-    oracle run on the matrix the REFERENCE's parser semantics give (decode + imputeGenotypeToMean).  One gene with and one
-    without missing calls."""
-    from test_vcf_pack import _header
-    O = oracle
-    N, C = 1501, 3
-    X, y = O.synth_covariates(91, N, C)
-    nm = O.fit_null_linear(X, y)
-    rng = np.random.default_rng(91)
-    code = np.array(["0/0", "0/1", "1/1", "./.", "1|0", "0/2"])
-    eng = engine_cls(0)
-    try:
-        eng.set_null_model(X, y)
-        assert vcfpack.header(_header(N)) == N
-        vcfpack.set_range("7:100-200")
-        refs = []
-        for gene, with_missing in enumerate((False, True)):
-            vcfpack.clear()
-            M = 12
-            maf = np.linspace(0.01, 0.2, M)
-            for j in range(M + 3):
-                g = rng.binomial(2, maf[j % M], size=N)
-                if with_missing:
-                    g = np.where(rng.random(N) < 0.01, 3, g)
-                    g = np.where(rng.random(N) < 0.003, 5, g)      # multi-allelic call -> missing
-                g = np.where((g == 1) & (rng.random(N) < 0.5), 4, g)  # phased het, same value
-                pos = 100 + 5 * j if j < M else 300 + j               # the last three lie outside the range
-                rec = "\t".join(["7", str(pos), ".", "A", "G", "50", "PASS", ".", "GT:GQ"] + [c + ":9" for c in code[g]])
-                assert vcfpack.add(rec) == (1 if j < M else 0)
-            rows, af, counts, names = vcfpack.gene()
-            assert rows.shape == (M, (N + 3) // 4) and (counts[:, 3].sum() > 0) == with_missing
-            raw = O.bed_decode_fast(rows, N).T
-            refs.append((O.impute_mean(raw), af.copy()))
-            eng.push_bed(rows, af)
-        res = eng.flush()
-    finally:
-        eng.close()
-    for k, (Gd, af) in enumerate(refs):
-        ref, lam = O.gene(Gd, af, X, nm["resid"], nm["sigma2"])
-        check_gene(res[k], ref, lam, ctx=f"vcf gene {k}")
 
 
 @pytest.mark.parametrize("case", [(190, 5000, 24, 3), (191, 777, 1, 1), (192, 20011, 64, 2)])
