@@ -221,3 +221,68 @@ def test_zero_copy_entry_points(engine_cls, oracle, case):
     check_gene(res[1], ref, lam, ctx=f"host block, records on the device {case}")
     for k in ("Q", "cmc_nonref", "cmc_U", "zeg_U", "m_poly"):
         assert res[0][k] == res[1][k], k       # same exact integer sums whichever way the block arrived
+
+
+def test_ingest_demo_vcf_and_bed(oracle, tmp_path):
+    """rvtests_b200/host/ingest_demo.cpp: setFile + plain-text VCF (rvt_vcf_pack.h) and setFile + PLINK fileset
+    (rvt_bed_file.h) through the C ABI in C++, one flush each, against the oracle (intercept-only null model)"""
+    import os
+    import subprocess
+    from rvtests_b200.synth import pack_bed
+    from test_vcf_pack import _header
+    O = oracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "rvtests_b200", "host", "ingest_demo")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(root, "include"), "-I", os.path.join(root, "rvtests_b200", "host"),
+                    os.path.join(root, "rvtests_b200", "host", "ingest_demo.cpp"), "-o", exe, "-L", os.path.join(root, "rvtests_b200"),
+                    "-lrvtests_b200", "-Wl,-rpath," + os.path.join(root, "rvtests_b200")], check=True)
+    N, M = 1203, 30
+    rng = np.random.default_rng(404)
+    maf = np.linspace(0.01, 0.2, M)
+    G = rng.binomial(2, maf[None, :], size=(N, M)).astype(np.int8)
+    miss = rng.random((N, M)) < 0.004
+    miss[:, :20] = False                                   # set A (first 10 variants) and B (next 10) complete, C with missing calls
+    y = rng.normal(size=N) + 0.3 * G[:, 3]
+    pos = 100 + 10 * np.arange(M)
+    sets = {"A": "1:100-190", "B": "1:200-290", "C": "1:300-390", "EMPTY": "2:1-5"}
+    sf = tmp_path / "sets.txt"
+    sf.write_text("".join(f"{k} {v}\n" for k, v in sets.items()))
+    # --- VCF
+    code = np.array(["0/0", "0/1", "1/1"])
+    with open(tmp_path / "g.vcf", "w") as f:
+        f.write("##fileformat=VCFv4.1\n" + _header(N) + "\n")
+        for j in range(M):
+            gt = np.where(miss[:, j], "./.", code[G[:, j]])
+            f.write("\t".join(["1", str(pos[j]), ".", "A", "G", "9", "PASS", ".", "GT"] + list(gt)) + "\n")
+    with open(tmp_path / "ph.txt", "w") as f:
+        for i in range(N):
+            f.write(f"P{i + 1} {float(y[i])!r}\n")
+    # --- PLINK fileset (same calls)
+    prefix = str(tmp_path / "fs")
+    with open(prefix + ".bed", "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01]))
+        f.write(pack_bed(G.T, miss.T).tobytes())
+    with open(prefix + ".bim", "w") as f:
+        for j in range(M):
+            f.write(f"1\trs{j}\t0\t{pos[j]}\tA\tG\n")
+    with open(prefix + ".fam", "w") as f:
+        for i in range(N):
+            f.write(f"F{i} P{i + 1} 0 0 1 {float(y[i])!r}\n")
+    X = np.ones((N, 1))
+    nm = O.fit_null_linear(X, y)
+    raw = np.where(miss, -9.0, G.astype(float))
+    want = {}
+    for k, (a, b) in {"A": (0, 10), "B": (10, 20), "C": (20, 30)}.items():
+        Gd = O.impute_mean(raw[:, a:b])
+        af = 0.5 * np.where(raw[:, a:b] >= 0, raw[:, a:b], 0.0).sum(axis=0) / N
+        want[k] = O.gene(Gd, af, X, nm["resid"], nm["sigma2"])[0]
+    for argv in (["vcf", str(tmp_path / "g.vcf"), str(sf), str(tmp_path / "ph.txt")], ["bed", prefix, str(sf)]):
+        out = subprocess.run([exe] + argv, capture_output=True, text=True, check=True).stdout.splitlines()
+        assert out[0].split("\t") == ["Set", "NumPolyVar", "Q", "Pvalue", "NonRefSite", "CMC_P", "Zeggini_P"]
+        rows = [l.split("\t") for l in out[1:]]
+        assert [r[0] for r in rows] == ["A", "B", "C"], argv[0]                 # the empty set is not pushed
+        for r in rows:
+            ref = want[r[0]]
+            assert int(r[4]) == ref.cmc_nonref
+            # "%g": 6 significant digits
+            assert rel(float(r[2]), ref.skat.Q) <= 2e-5 and rel(float(r[3]), ref.skat.pvalue) <= 2e-4, (argv[0], r, ref.skat.Q, ref.skat.pvalue)
