@@ -509,97 +509,97 @@ class VcfGenePacker {
     const int m_first = m_;
     int dropped = 0;
     for (int pass = 0; pass < n_pass; ++pass) {
-    const int alt = multi_ && !dosage ? pass + 1 : 0;
-    b = b_samples;
-    const size_t row0 = rows_.size(), dos0 = dos_.size();
-    if (dosage)
-      dos_.resize(dos0 + (size_t)n_, (double)kVcfMissing);
-    else
-      rows_.resize(row0 + (size_t)stride_, 0);
-    uint8_t* row = dosage ? NULL : &rows_[row0];
-    double* drow = dosage ? &dos_[dos0] : NULL;
-    double sum_ac = 0.0;
-    int cnt[4] = {0, 0, 0, 0};   // hom-ref, het, hom-alt, missing
-    int col = 0;
-    while (true) {
-      if (col >= ncol_) {   // "VCF header have LESS people than VCF content!"
+      const int alt = multi_ && !dosage ? pass + 1 : 0;
+      b = b_samples;
+      const size_t row0 = rows_.size(), dos0 = dos_.size();
+      if (dosage)
+        dos_.resize(dos0 + (size_t)n_, (double)kVcfMissing);
+      else
+        rows_.resize(row0 + (size_t)stride_, 0);
+      uint8_t* row = dosage ? NULL : &rows_[row0];
+      double* drow = dosage ? &dos_[dos0] : NULL;
+      double sum_ac = 0.0;
+      int cnt[4] = {0, 0, 0, 0};   // hom-ref, het, hom-alt, missing
+      int col = 0;
+      while (true) {
+        if (col >= ncol_) {   // "VCF header have LESS people than VCF content!"
+          rollback(row_first, dos_first, m_first);
+          return -2;
+        }
+        const char* t = (const char*)memchr(line + b, '\t', len - b);
+        const size_t e = t ? (size_t)(t - line) : len;
+        const int o = col_to_out_[col];
+        if (o >= 0 && dosage) {
+          // VCFIndividual::justGet(idx).toDouble(): atof of the subfield; an absent subfield is the empty string = 0.0;
+          // no such FORMAT key at all = MISSING_GENOTYPE (VCFGenotypeExtractor.cpp:434-438)
+          double g = (double)kVcfMissing;
+          if (gt >= 0) {
+            size_t sb, se;
+            g = subfield(line, b, e, gt, &sb, &se) ? atof(std::string(line + sb, se - sb).c_str()) : 0.0;
+            if (hemi && sex_[o] == 1) g *= 2.0;   // imputed male dosages on X lie in [0, 1]
+            if (filtered && !passFilters(line, b, e, gd_idx, gq_idx)) g = (double)kVcfMissing;
+          }
+          drow[o] = g;
+          // GenotypeCounter::add (src/GenotypeCounter.h:14-33)
+          if (g < 0) {
+            ++cnt[3];
+          } else if (g < 2.0 / 3) {
+            ++cnt[0];
+            sum_ac += g;
+          } else if (g < 4.0 / 3) {
+            ++cnt[1];
+            sum_ac += g;
+          } else if (g <= 2.0) {
+            ++cnt[2];
+            sum_ac += g;
+          } else {
+            ++cnt[3];
+          }
+        } else if (o >= 0) {
+          int g = kVcfMissing;
+          if (gt >= 0) {
+            // the gt-th ':'-separated subfield; a column with fewer subfields reads as the empty value = missing
+            size_t sb, se;
+            const bool have = subfield(line, b, e, gt, &sb, &se);
+            const char* v = have ? line + sb : "";
+            const int vl = have ? (int)(se - sb) : 0;
+            if (!hemi || sex_[o] == 2)
+              g = alt ? vcfCountAltAllele(v, vl, alt) : vcfGenotype(v, vl);
+            else if (sex_[o] == 1)
+              g = alt ? vcfCountMaleAltAllele2(v, vl, alt) : vcfGenotypeMale02(v, vl);
+            else
+              g = kVcfMissing;
+            if (filtered && !passFilters(line, b, e, gd_idx, gq_idx)) g = kVcfMissing;
+          }
+          // .bed codes, sample 0 in the low bits (libVcf/PlinkInputFile.h:206-209): 00 hom-ref, 10 het, 11 hom-alt, 01 missing
+          const unsigned code = g == 0 ? 0u : g == 1 ? 2u : g == 2 ? 3u : 1u;
+          row[o >> 2] |= (uint8_t)(code << ((o & 3) * 2));
+          ++cnt[g == 0 ? 0 : g == 1 ? 1 : g == 2 ? 2 : 3];
+        }
+        ++col;
+        if (!t) break;
+        b = e + 1;
+      }
+      if (col != ncol_) {   // "VCF header have MORE people than VCF content!"
         rollback(row_first, dos_first, m_first);
-        return -2;
+        return -3;
       }
-      const char* t = (const char*)memchr(line + b, '\t', len - b);
-      const size_t e = t ? (size_t)(t - line) : len;
-      const int o = col_to_out_[col];
-      if (o >= 0 && dosage) {
-        // VCFIndividual::justGet(idx).toDouble(): atof of the subfield; an absent subfield is the empty string = 0.0;
-        // no such FORMAT key at all = MISSING_GENOTYPE (VCFGenotypeExtractor.cpp:434-438)
-        double g = (double)kVcfMissing;
-        if (gt >= 0) {
-          size_t sb, se;
-          g = subfield(line, b, e, gt, &sb, &se) ? atof(std::string(line + sb, se - sb).c_str()) : 0.0;
-          if (hemi && sex_[o] == 1) g *= 2.0;   // imputed male dosages on X lie in [0, 1]
-          if (filtered && !passFilters(line, b, e, gd_idx, gq_idx)) g = (double)kVcfMissing;
-        }
-        drow[o] = g;
-        // GenotypeCounter::add (src/GenotypeCounter.h:14-33)
-        if (g < 0) {
-          ++cnt[3];
-        } else if (g < 2.0 / 3) {
-          ++cnt[0];
-          sum_ac += g;
-        } else if (g < 4.0 / 3) {
-          ++cnt[1];
-          sum_ac += g;
-        } else if (g <= 2.0) {
-          ++cnt[2];
-          sum_ac += g;
-        } else {
-          ++cnt[3];
-        }
-      } else if (o >= 0) {
-        int g = kVcfMissing;
-        if (gt >= 0) {
-          // the gt-th ':'-separated subfield; a column with fewer subfields reads as the empty value = missing
-          size_t sb, se;
-          const bool have = subfield(line, b, e, gt, &sb, &se);
-          const char* v = have ? line + sb : "";
-          const int vl = have ? (int)(se - sb) : 0;
-          if (!hemi || sex_[o] == 2)
-            g = alt ? vcfCountAltAllele(v, vl, alt) : vcfGenotype(v, vl);
-          else if (sex_[o] == 1)
-            g = alt ? vcfCountMaleAltAllele2(v, vl, alt) : vcfGenotypeMale02(v, vl);
-          else
-            g = kVcfMissing;
-          if (filtered && !passFilters(line, b, e, gd_idx, gq_idx)) g = kVcfMissing;
-        }
-        // .bed codes, sample 0 in the low bits (libVcf/PlinkInputFile.h:206-209): 00 hom-ref, 10 het, 11 hom-alt, 01 missing
-        const unsigned code = g == 0 ? 0u : g == 1 ? 2u : g == 2 ? 3u : 1u;
-        row[o >> 2] |= (uint8_t)(code << ((o & 3) * 2));
-        ++cnt[g == 0 ? 0 : g == 1 ? 1 : g == 2 ? 2 : 3];
+      // GenotypeCounter::getAF: 0.5 * sumAC / nSample, nSample counting the missing calls too
+      if (!dosage) sum_ac = (double)(cnt[1] + 2 * cnt[2]);
+      const double af_row = n_ ? 0.5 * sum_ac / (double)n_ : -1.0;
+      const double maf = af_row > 0.5 ? 1.0 - af_row : af_row;
+      if ((freq_min_ > 0. && freq_min_ > maf) || (freq_max_ > 0. && freq_max_ < maf)) {   // "undo loaded contents"
+        rows_.resize(row0);
+        dos_.resize(dos0);
+        ++dropped;
+        continue;
       }
-      ++col;
-      if (!t) break;
-      b = e + 1;
-    }
-    if (col != ncol_) {   // "VCF header have MORE people than VCF content!"
-      rollback(row_first, dos_first, m_first);
-      return -3;
-    }
-    // GenotypeCounter::getAF: 0.5 * sumAC / nSample, nSample counting the missing calls too
-    if (!dosage) sum_ac = (double)(cnt[1] + 2 * cnt[2]);
-    const double af_row = n_ ? 0.5 * sum_ac / (double)n_ : -1.0;
-    const double maf = af_row > 0.5 ? 1.0 - af_row : af_row;
-    if ((freq_min_ > 0. && freq_min_ > maf) || (freq_max_ > 0. && freq_max_ < maf)) {   // "undo loaded contents"
-      rows_.resize(row0);
-      dos_.resize(dos0);
-      ++dropped;
-      continue;
-    }
-    af_.push_back(af_row);
-    for (int k = 0; k < 4; ++k) counts_.push_back(cnt[k]);
-    std::string name = std::string(line + fb[0], fe[0] - fb[0]) + ":" + std::string(line + fb[1], fe[1] - fb[1]);
-    if (multi_) name += std::string(line + fb[3], fe[3] - fb[3]) + "/" + (dosage ? alts.back() : alts[pass]);
-    names_var_.push_back(name);
-    ++m_;
+      af_.push_back(af_row);
+      for (int k = 0; k < 4; ++k) counts_.push_back(cnt[k]);
+      std::string name = std::string(line + fb[0], fe[0] - fb[0]) + ":" + std::string(line + fb[1], fe[1] - fb[1]);
+      if (multi_) name += std::string(line + fb[3], fe[3] - fb[3]) + "/" + (dosage ? alts.back() : alts[pass]);
+      names_var_.push_back(name);
+      ++m_;
     }  // pass
     return n_pass - dropped;
   }
