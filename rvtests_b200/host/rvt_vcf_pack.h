@@ -520,14 +520,16 @@ class VcfGenePacker {
       double* drow = dosage ? &dos_[dos0] : NULL;
       double sum_ac = 0.0;
       int cnt[4] = {0, 0, 0, 0};   // hom-ref, het, hom-alt, missing
+      const bool plain = gt == 0 && !hemi && !filtered && alt == 0;   // GT first, no X / filter / allele expansion
       int col = 0;
       while (true) {
         if (col >= ncol_) {   // "VCF header have LESS people than VCF content!"
           rollback(row_first, dos_first, m_first);
           return -2;
         }
-        const char* t = (const char*)memchr(line + b, '\t', len - b);
-        const size_t e = t ? (size_t)(t - line) : len;
+        size_t e = b;   // sample columns are a few bytes long: a plain scan beats a library call here
+        while (e < len && line[e] != '\t') ++e;
+        const bool t = e < len;
         const int o = col_to_out_[col];
         if (o >= 0 && dosage) {
           // VCFIndividual::justGet(idx).toDouble(): atof of the subfield; an absent subfield is the empty string = 0.0;
@@ -557,7 +559,10 @@ class VcfGenePacker {
           }
         } else if (o >= 0) {
           int g = kVcfMissing;
-          if (gt >= 0) {
+          if (plain && e - b >= 3 && (b + 3 == e || line[b + 3] == ':') && (line[b] == '0' || line[b] == '1') &&
+              (line[b + 1] == '/' || line[b + 1] == '|') && (line[b + 2] == '0' || line[b + 2] == '1')) {
+            g = (line[b] - '0') + (line[b + 2] - '0');   // the common case, same value as the general grammar below
+          } else if (gt >= 0) {
             // the gt-th ':'-separated subfield; a column with fewer subfields reads as the empty value = missing
             size_t sb, se;
             const bool have = subfield(line, b, e, gt, &sb, &se);
