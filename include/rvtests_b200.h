@@ -40,6 +40,10 @@ extern "C" {
 #define RVT_GENE_NA 2           /* no polymorphic variant: fit() == -1, output "NA" (src/Model.h:2637-2640) */
 #define RVT_GENE_BADFLAGS 4     /* caller-supplied flip/skip flags contradict the data */
 #define RVT_GENE_BADVALUE 5     /* a genotype outside {0,1,2} reached the hard-call path */
+#define RVT_GENE_UNSUPPORTED 7  /* this gene is outside what the engine computes (more than 64 variants AND missing calls);
+                                   the other genes of the flush are unaffected */
+#define RVT_GENE_TIMEOUT 6      /* device watchdog: the SKAT-O quadrature of this gene exceeded its cycle budget
+                                   (option "watchdog_ms", default 4000); skato_ok = 0, the other columns are valid */
 
 /* engine selection for rvt_set_option("engine") */
 #define RVT_ENGINE_AUTO 0

@@ -99,6 +99,7 @@ struct TailInput {
 
 struct EngineParams {
   double beta1, beta2;   // Beta weight parameters (src/ModelManager.cpp:169-175 defaults 1, 25)
+  long long wd_cycles;   // device watchdog of the per-gene tail (SKAT-O quadrature), SM cycles; 0 = off
 };
 
 #define RVT_CUDA_OK(expr)                                                              \

@@ -52,12 +52,23 @@ RVT_HD double log1(double x, bool first) {
   double k = 3.0;
   double s = (first ? 2.0 : -x) * y;
   y = y * y;
-  for (double s1 = s + term / k; s1 != s; s1 = s + term / k) {
+  // |y^2| <= (0.1/1.9)^2: the series is down to one ulp after < 12 terms.  The cap makes a NaN argument (s1 != s
+  // for ever) return NaN instead of spinning -- on the device that spin was a hang.
+  int guard = 0;
+  for (double s1 = s + term / k; s1 != s && guard < 64; s1 = s + term / k, ++guard) {
     k = k + 2.0;
     term = term * y;
     s = s1;
   }
   return s;
+}
+
+// (int) of a double the way the reference's x86 build converts it (cvttsd2si): NaN and values outside int range give
+// INT_MIN, where the GPU's cvt.rzi would give 0 / saturate.  qf() reaches this with xnt = NaN when its argument c is NaN:
+// INT_MIN terms = an empty trapezoid sum on the CPU; 0 on the device meant ONE term evaluated at u = NaN.
+RVT_HD int to_int_x86(double x) {
+  if (!(x > -2147483649.0 && x < 2147483648.0)) return (-2147483647 - 1);
+  return (int)x;
 }
 
 // budget tick (qfc.c:77-83); returns true when the budget is exhausted
@@ -244,6 +255,7 @@ RVT_HD void integrate(QfState& s, int nterm, double interv, double tausq, bool m
   const double ncj = 0.0;
   double inpi = interv / kPi;
   double a_intl = 0.0, a_ersm = 0.0;
+  if (nterm < 0) nterm = -1;   // (INT_MIN from to_int_x86: no term; and nterm - tid must not wrap)
   for (int k = nterm - par.tid(); k >= 0; k -= par.nt()) {
     double u = (k + 0.5) * interv;
     double sum1 = -2.0 * u * s.c;
@@ -354,7 +366,7 @@ RVT_HDN double davies_qf(const double* lb, int r, double c1, int lim1, double ac
       *ifault = 1;
       return qfval;
     }
-    int ntm = (int)floor(xntm + 0.5);
+    int ntm = to_int_x86(floor(xntm + 0.5));
     double intv1 = utx / ntm;
     double x = 2.0 * kPi / intv1;
     if (x <= fabs(s.c)) break;
@@ -379,7 +391,7 @@ RVT_HDN double davies_qf(const double* lb, int r, double c1, int lim1, double ac
     return qfval;
   }
   {
-    int nt = (int)floor(xnt + 0.5);
+    int nt = to_int_x86(floor(xnt + 0.5));
     integrate(s, nt, intv, 0.0, true, par);
     qfval = 0.5 - s.intl;
     // round-off test, radix 8/16 allowance (qfc.c:444-446)

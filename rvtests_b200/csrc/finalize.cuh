@@ -218,6 +218,20 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
     s_flip[tid] = mono ? -1 : flip;
   }
   __syncthreads();
+  if (s_bad == 2) {
+    // values outside {0,1,2} (missing calls, dosages) reached the integer sweep: its sums are meaningless, and the
+    // gene's record is (re)written by the fp64 path (dosage.cuh) or stays BADVALUE.  Do not run the O(M^3) tail --
+    // least of all SKAT-O's quadrature -- on garbage (CTA-uniform exit: s_bad is shared and published above).
+    if (tid == 0) {
+      rvt_gene_result o;
+      memset(&o, 0, sizeof(o));
+      o.status = RVT_GENE_BADVALUE;
+      o.p_skat = o.p_liu = 1.0;
+      o.p_davies = -1.0;
+      res[g] = o;
+    }
+    return;
+  }
   if (tid == 0) {
     int mp = 0;
     for (int j = 0; j < M; ++j)
@@ -337,10 +351,12 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
   // 6b. SKAT-O (SkatO.cpp:101-281) on the same statistics
   SkatoOut so;
   so.ok = 0;
+  so.timed_out = 0;
   so.Q = so.rho = so.pvalue = 0.0;
   if constexpr (SKATO) {
     if (qags && Mp > 0) {
       QagsWork work{qags[g].a, qags[g].b, qags[g].r, qags[g].e, qags[g].order, qags[g].level, kQagsLimit};
+      work.deadline = prm.wd_cycles > 0 ? clock64() + prm.wd_cycles : 0;
       // ||r||^2/(N-1), SkatO.cpp:136-137; a binary trait takes s2 = 1 (SkatO.cpp:133-134, FitSKAT :72-75)
       const double s2 = nm->binary ? 1.0 : sigma2 * (double)N / (double)(N - 1);
       so = skato_tail(Wm, K, Mp, kld, s_vw, s2, s_ev, s_e, s_v, s_p, s_sk.lamz, s_sk.c, &s_sk.mach, work, s_sk.fv, s_sk.bcast, s_th,
@@ -352,7 +368,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
   // 7. burden score tests (m = 1)
   if (tid == 0) {
     burden_and_store(&res[out_index ? out_index[g] : g], Mp, s_bad, s_Q, p_fin, p_dav, p_liu, fault, r, lam_max, so, s_bur, s_nonref, nm,
-                     tin ? tin[g].status : 0);
+                     so.timed_out ? RVT_GENE_TIMEOUT : (tin ? tin[g].status : 0));
     phase(4);
   }
 }

@@ -123,6 +123,7 @@ struct rvt_ctx {
   bool perm_log = false;           // option "debug_perm_q": keep every permuted statistic of the last flush
   std::vector<double> perm_q_log;
   std::vector<int> bed_genes;      // pending genes pushed as PLINK 2-bit rows: checked for missing calls at flush
+  std::vector<int> unsupported;    // pending genes the flush cannot compute (wide + missing calls): record status only
   int launched = 0;                // pending genes [0, launched) already have their kernels enqueued (stream_batch)
   int stream_batch = 0;            // option: enqueue sweep + statistics every this many host pushes (0 = only at flush)
   bool flush_open = false;         // the timing window of the current flush has started
@@ -149,6 +150,7 @@ struct rvt_ctx {
   unsigned int* d_counter = nullptr;
   QagsScratch* d_qags = nullptr;   // SKAT-O interval lists, one per gene of a batch
   size_t cap_qags = 0;
+  long long wd_cycles = 8000000000ll;   // device watchdog of the per-gene tail, SM cycles (option "watchdog_ms"; ~4 s)
   bool skato = false;
   bool skato_binary = false;   // SKAT-O for a binary trait (SkatO::Fit type "D"); opt-in, see include/rvtests_b200.h
   long long* d_dbg = nullptr;   // optional finalize phase counters (rvt_set_option "debug_phases")
@@ -180,6 +182,7 @@ static void pending_reset(rvt_ctx* ctx) {
   ctx->af.clear();
   ctx->count_slot.clear();
   ctx->bed_genes.clear();
+  ctx->unsupported.clear();
   ctx->wide.clear();
   ctx->slots.clear();
   ctx->n_var = 0;
@@ -363,6 +366,9 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
     ctx->splits = (int)value;
   } else if (k == "skato") {
     ctx->skato = value != 0;
+  } else if (k == "watchdog_ms") {
+    if (value < 0 || value > 3.6e6) CTX_FAIL(RVT_E_BADARG, "watchdog_ms must be in 0..3600000 (0 = off)");
+    ctx->wd_cycles = (long long)(value * 2.0e6);   // ~2 GHz SM clock
   } else if (k == "skato_binary") {
     ctx->skato_binary = value != 0;
   } else if (k == "tc_boxes") {
@@ -694,6 +700,10 @@ static int push_check(rvt_ctx* ctx, int M, int max_m = kMaxM) {
   if (!ctx->have_null) CTX_FAIL(RVT_E_STATE, "set the null model before pushing genes");
   if (M < 1) CTX_FAIL(RVT_E_BADARG, "gene with no variant (the reference returns -1 / NA: src/Model.h:2637-2640)");
   if (M > max_m) CTX_FAIL(RVT_E_UNSUPPORTED, "M=%d variants; this entry point handles genes of up to %d variants", M, max_m);
+  // what the flush could not handle is refused HERE, while the queue is still consistent (a flush that failed half-way
+  // used to leave the context stuck: ADVICE r01)
+  if (ctx->binary && M > kMaxM)
+    CTX_FAIL(RVT_E_UNSUPPORTED, "binary trait: genes of more than %d variants are not supported (M=%d)", kMaxM, M);
   RVT_CUDA_OK(cudaSetDevice(ctx->device));
   return RVT_OK;
 }
@@ -799,6 +809,7 @@ int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
     ctx->cap_stage64 = need;
   }
   TilePlan tp;
+  const int64_t stage_mark = ctx->stage_used;
   if ((rc = stage_tiles(ctx, M, &tp))) return rc;
   if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_stage64, G, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -816,8 +827,10 @@ int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
   RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   bool dosage = false;
   for (int j = 0; j < M; ++j) dosage |= rc_host[j].bad > 0;
-  if (dosage && M > kMaxM)
+  if (dosage && M > kMaxM) {
+    ctx->stage_used = stage_mark;   // nothing of this gene stays queued
     CTX_FAIL(RVT_E_UNSUPPORTED, "gene of %d variants holds dosages / imputed values: the fp64 path handles up to %d variants", M, kMaxM);
+  }
   if (dosage) {
     // dosages / mean-imputed values: keep the fp64 matrix for the generic path and hand the
     // staging buffer over to it (the next push allocates a fresh one)
@@ -879,8 +892,8 @@ int rvt_gene_push_bed(rvt_ctx* ctx, const uint8_t* bed, int M, int64_t stride, c
   // 2 bits per call over PCIe (a quarter of the int8 form) on the copy stream; expanded, re-tiled and
   // counted on the device
   int8_t* land = ctx->d_land[slot];
-  if (stride == pitch)
-    RVT_CUDA_OK(cudaMemcpyAsync(land, bed, (size_t)M * pitch, cudaMemcpyHostToDevice, ctx->copy_stream));
+  if (stride == pitch)   // the last row holds only rowb valid bytes (e.g. the tail of a mapped .bed file)
+    RVT_CUDA_OK(cudaMemcpyAsync(land, bed, (size_t)(M - 1) * pitch + rowb, cudaMemcpyHostToDevice, ctx->copy_stream));
   else
     RVT_CUDA_OK(cudaMemcpy2DAsync(land, pitch, bed, stride, rowb, M, cudaMemcpyHostToDevice, ctx->copy_stream));
   if ((rc = land_publish(ctx, slot))) return rc;
@@ -909,9 +922,17 @@ static int resolve_bed_missing(rvt_ctx* ctx) {
     bool missing = false;
     for (int j = 0; j < ctx->slots[gi]; ++j) missing |= hc[gd.var0 + j].bad > 0;
     if (!missing) continue;
-    if (ctx->slots[gi] > kMaxM)
-      CTX_FAIL(RVT_E_UNSUPPORTED, "gene of %d variants holds missing calls: mean imputation (fp64 path) handles up to %d variants",
-               ctx->slots[gi], kMaxM);
+    if (ctx->slots[gi] > kMaxM) {
+      // mean imputation (fp64 path) handles up to kMaxM variants: this ONE gene is reported RVT_GENE_UNSUPPORTED in its
+      // record; the rest of the batch is computed (a failed batch would print NA for every later gene of the run)
+      ctx->unsupported.push_back(gi);
+      for (size_t w = 0; w < ctx->wide.size(); ++w)
+        if (ctx->wide[w].gene_index == gi) {
+          ctx->wide.erase(ctx->wide.begin() + (long)w);
+          break;
+        }
+      continue;
+    }
     DosGene dg;   // stays in its int8 tiles: imputed on the fly by the tile statistics kernels (dosage.cuh)
     dg.gene_index = gi;
     dg.M = gd.M;
@@ -931,6 +952,7 @@ int rvt_gene_push_dev_i8(rvt_ctx* ctx, const int8_t* dG, int M, int64_t ld, cons
   if (rc) return rc;
   if (ld < ctx->N || (ld & 15) || ((uintptr_t)dG & 15))
     CTX_FAIL(RVT_E_BADARG, "device block must be 16-byte aligned with ld a multiple of 16 and >= N");
+  if (ctx->binary) CTX_FAIL(RVT_E_UNSUPPORTED, "binary trait: caller-owned device blocks are not supported (push host rows instead)");
   if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
   if (!flags) {
     RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
@@ -1045,7 +1067,7 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
   int launches = 1;
   ctx->last_engine = engine;
   ctx->last_S = S;
-  EngineParams prm{ctx->beta1, ctx->beta2};
+  EngineParams prm{ctx->beta1, ctx->beta2, ctx->wd_cycles};
   if (engine == RVT_ENGINE_TC && (rc = tc_prepare_maps(&ctx->tc, hg[0].seg, hg, n, st, ctx->err, sizeof(ctx->err))))
     return rc;   // encode every box height up front: no host sync inside the loop
   for (int bi = 0; bi < nbatch; ++bi) {
@@ -1055,6 +1077,15 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
     cudaEvent_t* ev = &ctx->evpool[4 * (ctx->pending_timing_batches + bi)];
     RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), st));
     RVT_CUDA_OK(cudaEventRecord(ev[0], st));
+    // binary trait: every gene takes the fp64 path at flush (the Gram is weighted by p(1-p), which the integer sweep does
+    // not carry) -- the unweighted sweep and its tail would be wasted work on statistics that mean nothing (and SKAT-O's
+    // quadrature on such an indefinite K is where the r01 hang sat)
+    if (ctx->binary) {
+      RVT_CUDA_OK(cudaEventRecord(ev[1], st));
+      RVT_CUDA_OK(cudaEventRecord(ev[2], st));
+      RVT_CUDA_OK(cudaEventRecord(ev[3], st));
+      continue;
+    }
     if (engine == RVT_ENGINE_SIMT) {
       const int grid = std::min(nb * S, ctx->sm_count * 3);
       k_sweep_simt<<<grid, kSimtThreads, kSimtSmem, st>>>(ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_nm, S, chunk, parts, ctx->d_counter);
@@ -1102,7 +1133,7 @@ static int run_wide(rvt_ctx* ctx, rvt_gene_result* d_res, int* launches) {
   if ((rc = ensure(ctx, (void**)&ctx->d_zero_flags, &ctx->cap_zero_flags, (size_t)ctx->n_var + kTileRows, 1))) return rc;
   RVT_CUDA_OK(cudaMemsetAsync(ctx->d_zero_flags, 0, (size_t)ctx->n_var + kTileRows, st));
   if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nw, sizeof(QagsScratch)))) return rc;
-  EngineParams prm{ctx->beta1, ctx->beta2};
+  EngineParams prm{ctx->beta1, ctx->beta2, ctx->wd_cycles};
   std::vector<WideJob> jobs(nw);
   std::vector<void*> to_free;
   auto cleanup = [&]() {
@@ -1247,7 +1278,7 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
   if ((rc = tc_bind_segment(&ctx->tc, kSegPerm, d_tiles, (int64_t)(PB / 16) * tile_b, ctx->err, sizeof(ctx->err)))) return rc;
   if ((rc = ensure(ctx, (void**)&ctx->d_zero_flags, &ctx->cap_zero_flags, (size_t)ctx->n_var + kTileRows, 1))) return rc;
   RVT_CUDA_OK(cudaMemsetAsync(ctx->d_zero_flags, 0, (size_t)ctx->n_var + kTileRows, st));
-  EngineParams prm{ctx->beta1, ctx->beta2};
+  EngineParams prm{ctx->beta1, ctx->beta2, ctx->wd_cycles};
   const int threshold = (int)(1.0 * ctx->perm_n * ctx->perm_alpha * 2);   // Permutation::init, `int threshold`
   std::vector<double> hQ(PB);
   std::vector<GeneDesc> units;
@@ -1346,7 +1377,26 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
   return RVT_OK;
 }
 
+static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, bool to_device);
+// A flush that fails must not leave the queue half-consumed (every later flush failed again and the adapters
+// printed NA for the rest of the run): whatever the reason, the pending genes are dropped and the fp64-path buffers freed;
+// rvt_last_error() keeps the message of the failure.  (A too-small result buffer is the caller's to retry: nothing is dropped.)
 static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, bool to_device) {
+  if (!ctx) return RVT_E_BADARG;
+  if (!ctx->genes.empty() && (!out || cap < (int)ctx->genes.size()))
+    CTX_FAIL(RVT_E_BADARG, "result buffer too small: %d pending genes, cap %d", (int)ctx->genes.size(), cap);
+  const int rc = flush_body(ctx, out, cap, n_out, to_device);
+  if (rc != RVT_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& dg : ctx->dos)
+      if (dg.dG) cudaFree(dg.dG);
+    ctx->dos.clear();
+    pending_reset(ctx);
+  }
+  return rc;
+}
+
+static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, bool to_device) {
   if (!ctx) return RVT_E_BADARG;
   const bool trace = getenv("RVT_FLUSH_TRACE") != nullptr;   // diagnostics: host wall clock of the phases of a flush
   const auto t_begin = std::chrono::steady_clock::now();
@@ -1370,7 +1420,7 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   const int64_t N = ctx->N;
   cudaStream_t st = ctx->stream;
   rvt_gene_result* d_res = ctx->d_res;
-  EngineParams prm{ctx->beta1, ctx->beta2};
+  EngineParams prm{ctx->beta1, ctx->beta2, ctx->wd_cycles};
   int launches = 0;
   ctx->is_dos.assign(n, 0);
   for (auto& dg : ctx->dos) ctx->is_dos[dg.gene_index] = 1;
@@ -1484,6 +1534,15 @@ static int flush_impl(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   mark("fp64 path");
   if ((rc = run_wide(ctx, d_res, &launches))) return rc;
   if ((rc = run_perm(ctx, d_res, n, &launches))) return rc;
+  if (!ctx->unsupported.empty()) {
+    static rvt_gene_result na;   // (static: outlives the asynchronous copies)
+    memset(&na, 0, sizeof(na));
+    na.status = RVT_GENE_UNSUPPORTED;
+    na.p_skat = na.p_liu = 1.0;
+    na.p_davies = -1.0;
+    for (int gi : ctx->unsupported)
+      RVT_CUDA_OK(cudaMemcpyAsync(d_res + gi, &na, sizeof(na), cudaMemcpyHostToDevice, st));
+  }
   RVT_CUDA_OK(cudaMemcpyAsync(out, d_res, sizeof(rvt_gene_result) * n, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   RVT_CUDA_OK(cudaEventRecord(ctx->ev[1], st));
   RVT_CUDA_OK(cudaStreamSynchronize(st));

@@ -64,6 +64,7 @@ struct QagsWork {   // `limit` entries each; owned by ONE thread
   double *a, *b, *r, *e;
   int *order, *level;
   int limit;
+  long long deadline;       // device watchdog: clock64() value after which the quadrature gives up (0 = none)
 };
 
 constexpr double kDblEps = 2.2204460492503131e-16;
@@ -661,6 +662,14 @@ RVT_HDN int skato_integrate(const SkatoParams& P, bool use_davies, QagsMachine* 
   par.sync();
   for (;;) {
     if (par.tid() == 0) {
+#if defined(__CUDA_ARCH__)
+      // watchdog (status 8): the machine is bounded by `limit` bisections of 42 budgeted Davies evaluations each, which
+      // is finite but can be minutes; a gene that exceeds its cycle budget is reported, not waited for
+      if (mach->stage != 3 && mach->w.deadline != 0 && clock64() > mach->w.deadline) {
+        mach->status = 8;
+        mach->stage = 3;
+      }
+#endif
       double lo = 0, hi = 0;
       const bool more = mach->want(&lo, &hi);
       bcast[0] = more ? 1.0 : 0.0;
@@ -706,6 +715,7 @@ RVT_HDN int skato_integrate(const SkatoParams& P, bool use_davies, QagsMachine* 
 struct SkatoOut {
   double Q, rho, pvalue;
   int ok;
+  int timed_out;       // the quadrature hit the device watchdog (QagsWork::deadline): ok = 0, record status RVT_GENE_TIMEOUT
 };
 
 // Wm: M x M (lda), symmetric, = Z1'Z1 (kept intact).  Km: M x M scratch (lda).  v[M] = w_j * (g_j'r).
@@ -720,6 +730,7 @@ RVT_HDN SkatoOut skato_tail(const double* Wm, double* Km, int M, int lda, const 
   out.rho = 0;
   out.pvalue = -999.0;
   out.ok = 0;
+  out.timed_out = 0;
   if (M == 1) {  // FitSKAT, SkatO.cpp:60-99 / :118-120
     const double Q = v[0] * v[0] / s2 / 2.0;
     const double lam1 = Wm[0];
@@ -814,6 +825,10 @@ RVT_HDN SkatoOut skato_tail(const double* Wm, double* Km, int M, int lda, const 
   double integral = 0.0;
   int st = skato_integrate(P, true, mach, work, fv, bcast, th, th_stride, &integral, par);
   if (st) st = skato_integrate(P, false, mach, work, fv, bcast, th, th_stride, &integral, par);
+  if (st == 8) {
+    out.timed_out = 1;
+    return out;
+  }
   double pvalue = 1.0 - integral;
   // sanity rules, SkatO.cpp:262-277 (nRho = 11 -> multi = 3)
   if (pvalue <= 0) {

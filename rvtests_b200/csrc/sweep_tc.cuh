@@ -87,18 +87,38 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// Device watchdog: a wait that does not complete within kMbarBudgetCycles (~2 s; a whole sweep launch is ~10 ms) can only
+// be a protocol bug.  It ends the kernel with __trap() -- the next CUDA call of the host reports a launch failure -- instead
+// of spinning until the box is killed ("no watchdog anywhere").  The spin itself stays a tight PTX
+// loop; the clock is read once per 4096 failed tries.
+constexpr long long kMbarBudgetCycles = 4000000000ll;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
+  long long t0 = 0;
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "mov.u32 %0, 1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "@p bra WAIT_DONE;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 q, n, 4096;\n"
+        "@q bra WAIT_LOOP;\n"
+        "mov.u32 %0, 0;\n"
+        "WAIT_DONE:\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    if (now - t0 > kMbarBudgetCycles) __trap();
+  }
 }
 // L2 eviction-priority policies (createpolicy encodings): genotypes stream through once,
 // the null-model digits E are re-read by every gene of the batch.

@@ -304,16 +304,18 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
   }
   SkatoOut so;
   so.ok = 0;
+  so.timed_out = 0;
   so.Q = so.rho = so.pvalue = 0.0;
   if constexpr (SKATO) {
     if (qags && Mp > 0) {
       QagsWork work{qags[g].a, qags[g].b, qags[g].r, qags[g].e, qags[g].order, qags[g].level, kQagsLimit};
+      work.deadline = prm.wd_cycles > 0 ? clock64() + prm.wd_cycles : 0;
       const double s2 = sigma2 * (double)N / (double)(N - 1);
       so = skato_tail(jb.Wm, K, Mp, kld, s_vw, s2, s_ev, s_e, s_v, s_p, s_lamz, s_c, &s_sk.mach, work, s_sk.fv, s_sk.bcast, s_th, M, par);
     }
   }
   if (tid == 0)
-    burden_and_store(&res[jb.out_index], Mp, s_bad, s_Q, p_fin, p_dav, p_liu, fault, r, lam_max, so, s_bur, s_nonref, nm, 0);
+    burden_and_store(&res[jb.out_index], Mp, s_bad, s_Q, p_fin, p_dav, p_liu, fault, r, lam_max, so, s_bur, s_nonref, nm, so.timed_out ? RVT_GENE_TIMEOUT : 0);
 }
 
 }  // namespace rvt

@@ -12,6 +12,33 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _cuda_device_present():
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except Exception:
+        return os.path.exists("/dev/nvidia0")
+
+
+# per-test wall-clock limit of the GPU tests.  The device code has its own watchdogs (an mbarrier wait or a SKAT-O
+# quadrature that exceeds its cycle budget ends the kernel with an error, csrc/sweep_tc.cuh / skato_tail.cuh); this is the
+# backstop: pytest-timeout's thread method ends the PROCESS, because a host thread blocked in cudaStreamSynchronize never
+# sees a signal.  One hung test then costs two minutes instead of the whole GPU run.
+GPU_TEST_TIMEOUT_S = 150
+
+
+def pytest_collection_modifyitems(config, items):
+    have = _cuda_device_present()
+    skip = pytest.mark.skip(reason="no CUDA device (the engine has no CPU fallback)")
+    for it in items:
+        if "gpu" not in it.keywords:
+            continue
+        if not have:
+            it.add_marker(skip)
+        elif it.get_closest_marker("timeout") is None:
+            it.add_marker(pytest.mark.timeout(GPU_TEST_TIMEOUT_S, method="thread"))
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import oracle as O
