@@ -122,9 +122,9 @@ int rvt_ctx_create(int device, rvt_ctx** out);
 void rvt_ctx_destroy(rvt_ctx* ctx);
 const char* rvt_last_error(const rvt_ctx* ctx);
 /* keys: "beta1","beta2" (Beta weight, src/ModelManager.cpp:169-175), "engine", "splits" (0=auto),
- * "skato" (0/1), "skato_binary" (0/1, default 0: with a binary null model SKAT-O = SkatO::Fit type "D",
- * src/Model.h:2854-2858, regression/SkatO.cpp:72-91,133-134,150-158, is computed only when this is 1;
- * otherwise skato_ok stays 0 for a binary trait), "stream_batch" (B > 0: every B host pushes the engine enqueues sweep + statistics for
+ * "skato" (0/1), "skato_binary" (0/1, default 1: with a binary null model SKAT-O = SkatO::Fit type "D",
+ * src/Model.h:2854-2858, regression/SkatO.cpp:72-91,133-134,150-158; 0 leaves skato_ok = 0 for a binary trait), "watchdog_ms"
+ * (device watchdog of the per-gene SKAT-O quadrature, default 4000; 0 = off), "stream_batch" (B > 0: every B host pushes the engine enqueues sweep + statistics for
  * them right away, so the kernels run while the next genes are still crossing PCIe; rvt_flush then only
  * waits for the tail.  0 = everything at flush.  Options apply to genes pushed after the call.),
  * "perm" (nPerm, 0 = analytic p-value only), "perm_alpha" (0.05), "perm_stream_pos", "perm_seed", "perm_batch". */
@@ -140,8 +140,8 @@ int rvt_set_stream(rvt_ctx* ctx, void* cuda_stream);
  * copyCovariateAndIntercept, src/ModelUtil.h:102-130); y: N.  Host pointers.
  * binary != 0: y in {0,1}; LogisticRegression::FitLogisticModel(cov, phenoVec, 100) (regression/LogisticRegression.cpp:279-339)
  *   on the device, then SKAT / CMC / Zeggini with r = y - p and the per-sample variance v = p(1-p) (src/Model.h:2673-2681,
- *   LogisticRegressionScoreTest.cpp:219-302).  Such genes take the engine's fp64 path (<= 64 variants); SKAT-O needs
- *   the "skato_binary" option (else skato_ok = 0) and the permutation test is not provided for a binary trait (done = 0).  rvt_get_null_model then returns
+ *   LogisticRegressionScoreTest.cpp:219-302).  Such genes take the engine's fp64 path (<= 64 variants); SKAT-O is type "D"
+ *   (option "skato_binary", default on) and the permutation test is not provided for a binary trait (done = 0).  rvt_get_null_model then returns
  *   r, sigma2 = 1 and (X'VX)^-1. */
 int rvt_set_null_model(rvt_ctx* ctx, int64_t N, int C, const double* X, const double* y, int binary);
 /* "bring your own null": the caller supplies the score vector r (length N) and the variance scale

@@ -15,11 +15,12 @@
 #include "../../include/rvtests_b200.h"
 #include "common.cuh"
 #include "eigen.cuh"
-#include "skato_tail.cuh"
+#include "skato_fast.cuh"
 
 #include <type_traits>
 
 namespace rvt {
+static_assert(kSkatoMaxLam == kTileRows, "SkatoJob::lam holds the spectrum of a one-tile gene");
 
 // Threads per gene: the per-gene tail is a chain of short dependent fp64 phases (latency-bound), so
 // what buys throughput is MANY resident genes per SM, not many threads per gene: 64 threads x <= 128
@@ -36,13 +37,6 @@ static inline int fin_uk_off(int Mmax, int ER, bool skato) {
   return (k > de ? k : de) + (skato ? k : 0);
 }
 static inline int fin_smem(int Mmax, int ER, bool skato) { return fin_uk_off(Mmax, ER, skato) + Mmax * kMaxC * 8; }
-constexpr int kQagsLimit = 1000;   // Integration::limit (regression/GSLIntegration.cpp:7-15)
-
-// per-gene QAGS interval list in global memory (touched by one thread only)
-struct QagsScratch {
-  double a[kQagsLimit], b[kQagsLimit], r[kQagsLimit], e[kQagsLimit];
-  int order[kQagsLimit], level[kQagsLimit];
-};
 constexpr int kFinPhases = 6;  // debug cycle counters per gene
 
 __device__ __forceinline__ long long recombine4(const long long* d) {
@@ -106,7 +100,8 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
            const NullModel* __restrict__ nm, EngineParams prm, int S,
            const SweepPartial* __restrict__ parts, rvt_gene_result* __restrict__ res,
            long long* __restrict__ dbg /* nullable: [n_genes][kFinPhases] cycle counters */,
-           QagsScratch* __restrict__ qags /* nullable: [n_genes]; non-null enables SKAT-O */,
+           SkatoJob* __restrict__ jobs /* nullable: [n_genes]; non-null enables SKAT-O: everything before the quadrature runs
+                                          here, the quadrature itself in k_skato_qags (skato_fast.cuh), launched next */,
            const TailInput* __restrict__ tin /* nullable: [n_genes] pre-digested statistics (dosage path);
                                                 then `genes`/`parts` are unused and res is indexed through out_index */,
            const int* __restrict__ out_index) {
@@ -117,8 +112,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
   double* Wm = reinterpret_cast<double*>(dyn + wm_off);      // [Mmax][kld], SKAT-O only
   double* Uk = reinterpret_cast<double*>(dyn + uk_off);      // [Mmax][C]  (X'X)^-1 B_k
   struct SkatoShared {   // SKAT-O only
-    QagsMachine mach;
-    double fv[21], bcast[3], c[kTileRows + 2], lamz[kTileRows + 2];
+    double c[kTileRows + 2], lamz[kTileRows + 2];
   };
   __shared__ typename std::conditional<SKATO, SkatoShared, int>::type s_sk;
   __shared__ double s_vw[kTileRows];
@@ -318,7 +312,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
   }  // !tin
   const int Mp = s_Mp;
 
-  if (SKATO && qags) {
+  if (SKATO && jobs) {
     // SKAT-O: Z1'Z1 = W (G'G - G'X (X'X)^-1 X'G) W / 2 with the UN-squared weights = K / (2 sigma2)
     // (sqrt of the squared SKAT weight is the SKAT-O weight: src/Model.h:2652-2656 vs :2807-2809)
     const double sc = 0.5 / sigma2;
@@ -348,19 +342,25 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
     if (p_fin <= 0.0 || p_fin == 1.0) p_fin = p_liu;
   }
 
-  // 6b. SKAT-O (SkatO.cpp:101-281) on the same statistics
+  // 6b. SKAT-O (SkatO.cpp:101-281) on the same statistics: everything up to the quadrature; the record's skato_* fields
+  //     are written by k_skato_qags
   SkatoOut so;
   so.ok = 0;
   so.timed_out = 0;
   so.Q = so.rho = so.pvalue = 0.0;
   if constexpr (SKATO) {
-    if (qags && Mp > 0) {
-      QagsWork work{qags[g].a, qags[g].b, qags[g].r, qags[g].e, qags[g].order, qags[g].level, kQagsLimit};
-      work.deadline = prm.wd_cycles > 0 ? clock64() + prm.wd_cycles : 0;
-      // ||r||^2/(N-1), SkatO.cpp:136-137; a binary trait takes s2 = 1 (SkatO.cpp:133-134, FitSKAT :72-75)
-      const double s2 = nm->binary ? 1.0 : sigma2 * (double)N / (double)(N - 1);
-      so = skato_tail(Wm, K, Mp, kld, s_vw, s2, s_ev, s_e, s_v, s_p, s_sk.lamz, s_sk.c, &s_sk.mach, work, s_sk.fv, s_sk.bcast, s_th,
-                      kTileRows, par);
+    if (jobs) {
+      if (Mp > 0) {
+        // ||r||^2/(N-1), SkatO.cpp:136-137; a binary trait takes s2 = 1 (SkatO.cpp:133-134, FitSKAT :72-75)
+        const double s2 = nm->binary ? 1.0 : sigma2 * (double)N / (double)(N - 1);
+        // Wm = K / (2 sigma2): its smallest eigenvalue is known from step 5 when all Mp are positive
+        const double lam_min_w = (r == Mp) ? s_lam[Mp - 1] * (0.5 / sigma2) : 0.0;
+        skato_prepare(Wm, K, Mp, kld, s_vw, s2, lam_min_w, s_ev, s_e, s_v, s_p, s_sk.lamz, s_sk.c, s_th, &jobs[g], par);
+      } else if (tid == 0) {
+        jobs[g].run = 0;
+        jobs[g].ok = 0;
+        jobs[g].Q = jobs[g].rho = jobs[g].pvalue = 0.0;
+      }
       phase(5);
     }
   }
@@ -368,7 +368,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
   // 7. burden score tests (m = 1)
   if (tid == 0) {
     burden_and_store(&res[out_index ? out_index[g] : g], Mp, s_bad, s_Q, p_fin, p_dav, p_liu, fault, r, lam_max, so, s_bur, s_nonref, nm,
-                     so.timed_out ? RVT_GENE_TIMEOUT : (tin ? tin[g].status : 0));
+                     tin ? tin[g].status : 0);
     phase(4);
   }
 }

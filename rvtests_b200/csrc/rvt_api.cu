@@ -150,9 +150,18 @@ struct rvt_ctx {
   unsigned int* d_counter = nullptr;
   QagsScratch* d_qags = nullptr;   // SKAT-O interval lists, one per gene of a batch
   size_t cap_qags = 0;
+  SkatoJob* d_jobs = nullptr;      // SKAT-O: what k_finalize hands to k_skato_qags, one per gene of a batch
+  size_t cap_jobs = 0;
+  // statistics (K2/K3/K4) of batch i on a second stream UNDER the sweep of batch i+1 (option "overlap"): needs the sweep to
+  // leave shared memory free ("tc_stages" 4 or 3) and the partials double-buffered
+  int overlap = 0;                 // 0 off, else the number of batches a flush is cut into
+  cudaStream_t fin_stream = nullptr;
+  cudaEvent_t ev_swept[2] = {nullptr, nullptr}, ev_fin_done[2] = {nullptr, nullptr};
+  bool fin_busy[2] = {false, false};
+  unsigned long long batch_seq = 0;
   long long wd_cycles = 8000000000ll;   // device watchdog of the per-gene tail, SM cycles (option "watchdog_ms"; ~4 s)
   bool skato = false;
-  bool skato_binary = false;   // SKAT-O for a binary trait (SkatO::Fit type "D"); opt-in, see include/rvtests_b200.h
+  bool skato_binary = true;    // SKAT-O for a binary trait (SkatO::Fit type "D"); on by default, see include/rvtests_b200.h
   long long* d_dbg = nullptr;   // optional finalize phase counters (rvt_set_option "debug_phases")
   size_t cap_dbg = 0;
   bool want_dbg = false;
@@ -304,6 +313,11 @@ int rvt_ctx_create(int device, rvt_ctx** out) {
   ctx->stream = ctx->own_stream;
   for (auto& ev : ctx->ev) RVT_CUDA_OK(cudaEventCreate(&ev));
   RVT_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  RVT_CUDA_OK(cudaStreamCreateWithFlags(&ctx->fin_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    RVT_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_swept[i], cudaEventDisableTiming));
+    RVT_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_fin_done[i], cudaEventDisableTiming));
+  }
   for (int i = 0; i < rvt_ctx::kLandRing; ++i) {
     RVT_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_landed[i], cudaEventDisableTiming));
     RVT_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_unpacked[i], cudaEventDisableTiming));
@@ -328,7 +342,7 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum, ctx->d_p, ctx->d_vw, ctx->d_dos_st, ctx->d_dos_tin, ctx->d_dos_idx, ctx->d_dos_afd, ctx->d_dos_tg};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_jobs, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum, ctx->d_p, ctx->d_vw, ctx->d_dos_st, ctx->d_dos_tin, ctx->d_dos_idx, ctx->d_dos_afd, ctx->d_dos_tg};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -340,6 +354,14 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
+  }
+  if (ctx->fin_stream) {
+    cudaStreamSynchronize(ctx->fin_stream);
+    cudaStreamDestroy(ctx->fin_stream);
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_swept[i]) cudaEventDestroy(ctx->ev_swept[i]);
+    if (ctx->ev_fin_done[i]) cudaEventDestroy(ctx->ev_fin_done[i]);
   }
   for (int i = 0; i < rvt_ctx::kLandRing; ++i) {
     if (ctx->d_land[i]) cudaFree(ctx->d_land[i]);
@@ -366,6 +388,12 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
     ctx->splits = (int)value;
   } else if (k == "skato") {
     ctx->skato = value != 0;
+  } else if (k == "overlap") {
+    if (value < 0 || value > 64) CTX_FAIL(RVT_E_BADARG, "overlap must be in 0..64 (batches per flush; 0 = off)");
+    ctx->overlap = (int)value;
+  } else if (k == "tc_stages") {
+    if (value != 3 && value != 4 && value != 5) CTX_FAIL(RVT_E_BADARG, "tc_stages must be 3, 4 or 5");
+    ctx->tc.stages = (int)value;
   } else if (k == "watchdog_ms") {
     if (value < 0 || value > 3.6e6) CTX_FAIL(RVT_E_BADARG, "watchdog_ms must be in 0..3600000 (0 = off)");
     ctx->wd_cycles = (long long)(value * 2.0e6);   // ~2 GHz SM clock
@@ -1004,10 +1032,11 @@ static int split_plan(rvt_ctx* ctx, int n_genes, int* S_out, int64_t* chunk_out)
 // Enqueue sweep + statistics for the pending genes [g0, g1) on the context stream; records land in
 // ctx->d_res[g0..g1).  Nothing here waits for the device: with option "stream_batch" = B the pushes call
 // this every B genes, so the kernels of one range run while the next genes are still crossing PCIe on the
-// copy stream.  One sweep launch + one statistics launch per batch of <= 2048 genes, back to back.
-// (Running the statistics of batch i beside the sweep of batch i+1 on a second stream was built and
-// measured twice -- 17.8 vs 16.9 ms/step with the first sweep, 12.9 vs 11.8 ms with the current one: the
-// sweep needs its 5-stage ring, i.e. the whole shared memory -- and removed.)
+// copy stream.  One sweep launch + one statistics launch per batch of <= 2048 genes, back to back -- or, with option
+// "overlap" = B, B batches per call with the statistics of batch i on a second stream under the sweep of batch i+1.
+// (r01 measured that overlap slower twice -- 17.8 vs 16.9 and 12.9 vs 11.8 ms/step: the sweep's 5-stage ring takes
+// 200 KB, so no statistics CTA ever fitted beside a sweep CTA and the two kernels only took turns.  With "tc_stages" 4
+// or 3 the ring leaves 65 / 105 KB per SM for them.)
 static int launch_range(rvt_ctx* ctx, int g0, int g1) {
   const int n = g1 - g0;
   if (n <= 0) return RVT_OK;
@@ -1019,7 +1048,9 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
   if ((rc = ensure(ctx, (void**)&ctx->d_res, &ctx->cap_res, n_total, sizeof(rvt_gene_result)))) return rc;
   int S = 0;
   int64_t chunk = 0;
-  const int batch = (n + ((n + 2047) / 2048) - 1) / ((n + 2047) / 2048);   // equal batches of <= 2048 genes
+  int nbat = (n + 2047) / 2048;   // equal batches of <= 2048 genes
+  if (ctx->overlap > 0 && !ctx->binary) nbat = std::max(nbat, std::min(ctx->overlap, std::max(1, n / ctx->sm_count)));
+  const int batch = (n + nbat - 1) / nbat;
   if ((rc = split_plan(ctx, batch, &S, &chunk))) return rc;
   int engine = ctx->engine;
   if (ctx->stage_used > 0) {
@@ -1035,9 +1066,11 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
   // the wide tensor-core sweep writes two partials per (gene, split): even and odd 128-sample boxes
   const bool wide = engine == RVT_ENGINE_TC && tc_parts_per_unit(&ctx->tc) == 2;
   const int Sp = wide ? 2 * S : S;
-  if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)batch * Sp, sizeof(SweepPartial)))) return rc;
+  const bool ovl = ctx->overlap > 0 && !ctx->binary;
+  if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)batch * Sp * (ovl ? 2 : 1), sizeof(SweepPartial)))) return rc;
   if (ctx->skato) {
     if ((rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)batch, sizeof(QagsScratch)))) return rc;
+    if ((rc = ensure(ctx, (void**)&ctx->d_jobs, &ctx->cap_jobs, (size_t)batch, sizeof(SkatoJob)))) return rc;
   }
   if (ctx->want_dbg) {
     if ((rc = ensure(ctx, (void**)&ctx->d_dbg, &ctx->cap_dbg, (size_t)n_total * kFinPhases, sizeof(long long)))) return rc;
@@ -1073,7 +1106,10 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
   for (int bi = 0; bi < nbatch; ++bi) {
     const int b0 = g0 + bi * batch;
     const int nb = std::min(batch, g1 - b0);
-    SweepPartial* parts = ctx->d_parts;
+    // overlap: two partial buffers in turn; buffer k is free again once the statistics kernels that read it have run
+    const int pb = ovl ? (int)(ctx->batch_seq++ & 1) : 0;
+    SweepPartial* parts = ctx->d_parts + (size_t)pb * batch * Sp;
+    if (ovl && ctx->fin_busy[pb]) RVT_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_fin_done[pb], 0));
     cudaEvent_t* ev = &ctx->evpool[4 * (ctx->pending_timing_batches + bi)];
     RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), st));
     RVT_CUDA_OK(cudaEventRecord(ev[0], st));
@@ -1095,22 +1131,40 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
       if (rc) return rc;
     }
     RVT_CUDA_OK(cudaEventRecord(ev[1], st));
-    RVT_CUDA_OK(cudaEventRecord(ev[2], st));
+    cudaStream_t fs = st;   // the stream the statistics kernels of this batch run on
+    if (ovl) {
+      fs = ctx->fin_stream;
+      RVT_CUDA_OK(cudaEventRecord(ctx->ev_swept[pb], st));
+      RVT_CUDA_OK(cudaStreamWaitEvent(fs, ctx->ev_swept[pb], 0));
+    }
+    RVT_CUDA_OK(cudaEventRecord(ev[2], fs));
     int Mmax = 1;
     for (int i = 0; i < nb; ++i) Mmax = std::max(Mmax, ctx->genes[b0 + i].M);
     const int kld = fin_kld(Mmax), fsm = fin_smem(Mmax, ctx->ER, ctx->skato), wm_off = Mmax * kld * 8;
-    if (ctx->skato)
-      k_finalize<true><<<nb, kFinThreadsSkato, fsm, st>>>(
+    if (ctx->skato) {
+      k_finalize<true><<<nb, kFinThreadsSkato, fsm, fs>>>(
           ctx->d_genes + b0, nb, kld, wm_off, fin_uk_off(Mmax, ctx->ER, ctx->skato), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, ctx->d_res + b0,
-          ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->d_qags, nullptr, nullptr);
-    else
-      k_finalize<false><<<nb, kFinThreads, fsm, st>>>(
+          ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->d_jobs, nullptr, nullptr);
+      k_skato_qags<<<nb, kQagsThreads, 0, fs>>>(ctx->d_jobs, nb, ctx->d_qags, ctx->d_res + b0, nullptr, ctx->wd_cycles);
+      launches += 1;
+    } else
+      k_finalize<false><<<nb, kFinThreads, fsm, fs>>>(
           ctx->d_genes + b0, nb, kld, wm_off, fin_uk_off(Mmax, ctx->ER, ctx->skato), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, ctx->d_res + b0,
           ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, nullptr, nullptr, nullptr);
-    RVT_CUDA_OK(cudaEventRecord(ev[3], st));
+    RVT_CUDA_OK(cudaEventRecord(ev[3], fs));
+    if (ovl) {
+      RVT_CUDA_OK(cudaEventRecord(ctx->ev_fin_done[pb], fs));
+      ctx->fin_busy[pb] = true;
+    }
     RVT_CUDA_OK(cudaGetLastError());
     launches += 2;
     ctx->last_parts = (int64_t)nb * Sp;
+  }
+  if (ovl) {
+    // everything enqueued on the context stream after this call (the fp64 path, wide genes, the copy of the records, the
+    // next pushes' kernels) is ordered after the statistics of these batches
+    for (int k = 0; k < 2; ++k)
+      if (ctx->fin_busy[k]) RVT_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_fin_done[k], 0));
   }
   ctx->pending_timing_batches += nbatch;
   ctx->n_launch += launches;
@@ -1511,15 +1565,18 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     }
     RVT_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
     if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nd, sizeof(QagsScratch)))) return rc;
+    if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_jobs, &ctx->cap_jobs, (size_t)nd, sizeof(SkatoJob)))) return rc;
     {
       // SKAT-O for a binary trait (SkatO::Fit type "D": the same tail on the p(1-p)-weighted statistics with s2 = 1,
       // finalize.cuh) runs only with "skato_binary" = 1; otherwise skato_ok stays 0
       const bool sk = ctx->skato && (!ctx->binary || ctx->skato_binary);
       const int kld = fin_kld(kTileRows), fsm = fin_smem(kTileRows, ctx->ER, sk), wm_off = kTileRows * kld * 8;
-      if (sk)
+      if (sk) {
         k_finalize<true><<<nd, kFinThreadsSkato, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, sk), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
-                                                             nullptr, d_res, nullptr, ctx->d_qags, d_tin, d_idx);
-      else
+                                                             nullptr, d_res, nullptr, ctx->d_jobs, d_tin, d_idx);
+        k_skato_qags<<<nd, kQagsThreads, 0, st>>>(ctx->d_jobs, nd, ctx->d_qags, d_res, d_idx, ctx->wd_cycles);
+        launches += 1;
+      } else
         k_finalize<false><<<nd, kFinThreads, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, sk), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
                                                          nullptr, d_res, nullptr, nullptr, d_tin, d_idx);
     }

@@ -67,6 +67,14 @@ struct QagsWork {   // `limit` entries each; owned by ONE thread
   long long deadline;       // device watchdog: clock64() value after which the quadrature gives up (0 = none)
 };
 
+constexpr int kQagsLimit = 1000;   // Integration::limit (regression/GSLIntegration.cpp:7-15)
+
+// per-gene QAGS interval list in global memory (touched by one thread only)
+struct QagsScratch {
+  double a[kQagsLimit], b[kQagsLimit], r[kQagsLimit], e[kQagsLimit];
+  int order[kQagsLimit], level[kQagsLimit];
+};
+
 constexpr double kDblEps = 2.2204460492503131e-16;
 constexpr double kDblMin = 2.2250738585072014e-308;
 constexpr double kDblMax = 1.7976931348623157e+308;

@@ -88,37 +88,53 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 // Device watchdog: a wait that does not complete within kMbarBudgetCycles (~2 s; a whole sweep launch is ~10 ms) can only
-// be a protocol bug.  It ends the kernel with __trap() -- the next CUDA call of the host reports a launch failure -- instead
-// of spinning until the box is killed ("no watchdog anywhere").  The spin itself stays a tight PTX
-// loop; the clock is read once per 4096 failed tries.
-constexpr long long kMbarBudgetCycles = 4000000000ll;
+// be a protocol bug.  It ends the kernel with `trap` -- the next CUDA call of the host reports a launch failure -- instead
+// of spinning until the box is killed ("no watchdog anywhere").  The whole wait is ONE opaque PTX
+// block, as before: the spin stays a tight try_wait loop and the clock is read once per 4096 failed tries.
+// -DRVT_MBAR_WATCHDOG=0 builds the plain spin (A/B timing of the watchdog's cost).
+#ifndef RVT_MBAR_WATCHDOG
+#define RVT_MBAR_WATCHDOG 1
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  long long t0 = 0;
-  for (;;) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p, q;\n"
-        ".reg .u32 n;\n"
-        "mov.u32 n, 0;\n"
-        "mov.u32 %0, 1;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "@p bra WAIT_DONE;\n"
-        "add.u32 n, n, 1;\n"
-        "setp.lt.u32 q, n, 4096;\n"
-        "@q bra WAIT_LOOP;\n"
-        "mov.u32 %0, 0;\n"
-        "WAIT_DONE:\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (done) return;
-    const long long now = clock64();
-    if (t0 == 0) t0 = now;
-    if (now - t0 > kMbarBudgetCycles) __trap();
-  }
+#if RVT_MBAR_WATCHDOG
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .u32 n, m;\n"
+      ".reg .u64 t0, t1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "mov.u32 n, 0;\n"
+      "mov.u64 t0, %%clock64;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "add.u32 n, n, 1;\n"
+      "and.b32 m, n, 4095;\n"
+      "setp.ne.u32 q, m, 0;\n"
+      "@q bra WAIT_LOOP;\n"
+      "mov.u64 t1, %%clock64;\n"
+      "sub.u64 t1, t1, t0;\n"
+      "setp.lt.u64 q, t1, 4000000000;\n"
+      "@q bra WAIT_LOOP;\n"
+      "trap;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+#else
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+#endif
 }
 // L2 eviction-priority policies (createpolicy encodings): genotypes stream through once,
 // the null-model digits E are re-read by every gene of the batch.
@@ -573,7 +589,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct TcSegments {
   void* encode = nullptr;   // cuTensorMapEncodeTiled through the runtime's driver entry point
-  int stages = 5;           // (kept for the option parser; the ring depth is tied to `boxes`)
+  int stages = 5;           // ring depth of the ZC gene sweep: 5 (200 KB), 4 (160 KB) or 3 (120 KB of shared memory)
   int boxes = 4;            // 128-sample boxes per pipeline stage for ER=16: 4 (5 stages) or 2 (10 stages)
   int l2promo = 2;          // CUtensorMapL2promotion: 0 none, 1 64B, 2 128B, 3 256B
   int dbg_skip = 0;         // timing experiments (see k_sweep_tc)
@@ -613,6 +629,11 @@ inline int tc_init(TcSegments* tc, char* err, size_t errlen) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4, false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4, false, 4, true>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 5, false, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5, false, 4, false, true>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 5, false, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 5, false, 4, true, true>::kSmem);
+  // shallower rings (option "tc_stages"): 160 / 120 KB instead of 200 KB, so that the statistics kernels of the previous
+  // batch fit on the same SMs and run UNDER the sweep (rvt_api.cu: launch_range, option "overlap")
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 4, false, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 4, false, 4, false, true>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 3, false, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 3, false, 4, false, true>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 3, false, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 3, false, 4, false, true>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4, false, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4, false, 4, false, true>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<32, 4, false, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32, 4, false, 4, true, true>::kSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tc<16, 3, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<16, 3, true, 4>::kSmem);
@@ -763,8 +784,14 @@ inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_
     RVT_TC_LAUNCH(16, 5, false, 4, true, true);
   else if (zc && wide)
     RVT_TC_LAUNCH(32, 4, false, 4, true, true);
+  else if (zc && ER == 16 && tc->stages == 4)
+    RVT_TC_LAUNCH(16, 4, false, 4, false, true);
+  else if (zc && ER == 16 && tc->stages == 3)
+    RVT_TC_LAUNCH(16, 3, false, 4, false, true);
   else if (zc && ER == 16)
     RVT_TC_LAUNCH(16, 5, false, 4, false, true);
+  else if (zc && tc->stages <= 3)
+    RVT_TC_LAUNCH(32, 3, false, 4, false, true);
   else if (zc)
     RVT_TC_LAUNCH(32, 4, false, 4, false, true);
   else if (wide && !pair && ER == 16)

@@ -3,6 +3,7 @@ the C ABI one to one).  No arithmetic happens here."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -82,6 +83,8 @@ def load_library(rebuild: bool = False):
     if _lib is not None and not rebuild:
         return _lib
     path = _build.build_lib(force=rebuild)
+    # diagnostics only (A/B timing of build variants, tools/): an alternate build of the same sources
+    path = os.environ.get("RVT_B200_LIB_VARIANT", path)
     L = C.CDLL(path)
     vp = C.c_void_p
     L.rvt_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]

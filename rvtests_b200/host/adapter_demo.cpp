@@ -42,7 +42,7 @@ int main(int argc, char** argv) {
   const int nPerm = argc > 3 ? atoi(argv[3]) : 0;        // skat[nPerm=..,alpha=..]
   const double alpha = argc > 4 ? atof(argv[4]) : 0.05;
   const bool binary = argc > 5 && atoi(argv[5]) != 0;    // ModelManager: setBinaryOutcome() on every model
-  if (argc > 6 && atoi(argv[6]) != 0) rvtb200::GeneBatcher<shim::DataConsolidator>::instance().enableSkatOBinary();
+  if (argc > 6) rvtb200::GeneBatcher<shim::DataConsolidator>::instance().enableSkatOBinary(atoi(argv[6]) != 0);   // default: on
   SkatTest skat(nPerm, alpha);
   SkatOTest skato;
   CMCTest cmc;

@@ -43,9 +43,9 @@ class GeneBatcher {
   }
   void setBatch(int n) { batch_ = n > 0 ? n : 1; }
   void enableSkatO() { skato_ = true; }
-  // SkatO::Fit type "D" (src/Model.h:2854-2858) on the engine's "skato_binary" option; until it has been confirmed on the
-  // hardware the default stays NA for a binary trait
-  void enableSkatOBinary() { skato_binary_ = true; }
+  // SkatO::Fit type "D" (src/Model.h:2854-2858) = the engine's "skato_binary" option: on by default (as the reference
+  // computes it); enableSkatOBinary(false) prints NA for a binary trait instead
+  void enableSkatOBinary(bool on = true) { skato_binary_ = on; }
   // setBinaryOutcome() of any adapter (ModelManager sets every model alike, src/ModelManager.cpp:274-282): logistic null
   void setBinary(bool b) {
     if (b != binary_) have_null_ = false;
@@ -106,7 +106,7 @@ class GeneBatcher {
   int newFitterId() { return next_id_++; }
 
  private:
-  GeneBatcher() : ctx_(NULL), batch_(256), skato_(false), skato_binary_(false), binary_(false), perm_n_(0), perm_alpha_(0.05), current_(-1), next_id_(0), have_null_(false) {}
+  GeneBatcher() : ctx_(NULL), batch_(256), skato_(false), skato_binary_(true), binary_(false), perm_n_(0), perm_alpha_(0.05), current_(-1), next_id_(0), have_null_(false) {}
   bool seen(int id) const {
     for (size_t i = 0; i < seen_.size(); ++i)
       if (seen_[i] == id) return true;
@@ -137,7 +137,7 @@ class GeneBatcher {
     for (int j = 0; j < cv.cols; ++j)
       for (int i = 0; i < n; ++i) X[(size_t)(j + 1) * n + i] = cv(i, j);
     if (skato_) rvt_set_option(ctx_, "skato", 1);
-    if (skato_ && skato_binary_) rvt_set_option(ctx_, "skato_binary", 1);
+    rvt_set_option(ctx_, "skato_binary", skato_binary_ ? 1 : 0);
     if (perm_n_ > 0) {
       rvt_set_option(ctx_, "perm", perm_n_);
       rvt_set_option(ctx_, "perm_alpha", perm_alpha_);

@@ -81,6 +81,12 @@ def hostcheck():
                           C.POINTER(C.c_int)]
     H.hc_skato_tail.restype = C.c_int
     H.hc_skato_tail.argtypes = [dp, C.c_int, dp, C.c_double, dp]
+    H.hc_qf_fast.restype = C.c_double
+    H.hc_qf_fast.argtypes = [dp, C.c_int, C.c_double, C.c_int, C.c_double, C.POINTER(C.c_int)]
+    H.hc_qf_fast_many.restype = None
+    H.hc_qf_fast_many.argtypes = [dp, C.c_int, dp, C.c_int, dp, C.POINTER(C.c_int)]
+    H.hc_skato_fast.restype = C.c_int
+    H.hc_skato_fast.argtypes = [dp, C.c_int, dp, C.c_double, C.c_double, dp]
     H.hc_lfg_draws.restype = None
     H.hc_lfg_draws.argtypes = [C.c_uint, C.c_ulonglong, C.c_int, C.c_void_p]
     H.hc_fy_roots.restype = None

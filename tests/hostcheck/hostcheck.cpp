@@ -5,6 +5,7 @@
 #include <vector>
 #include "../../rvtests_b200/csrc/eigen.cuh"
 #include "../../rvtests_b200/csrc/skato_tail.cuh"
+#include "../../rvtests_b200/csrc/skato_fast.cuh"
 #include "../../rvtests_b200/csrc/permlogic.cuh"
 
 extern "C" {
@@ -22,6 +23,49 @@ double hc_qf(const double* lam, int n, double Q, int lim, double acc, int* fault
   rvt::SerialPar par;
   return rvt::davies_qf(lam, n, Q, lim, acc, th.data(), fault, par);
 }
+// the serial product-form Davies of the SKAT-O quadrature (davies_fast.cuh): prepare once per spectrum, then evaluate
+double hc_qf_fast(const double* lam, int n, double Q, int lim, double acc, int* fault) {
+  std::vector<int> th(n > 0 ? n : 1);
+  rvt::DaviesPre pre;
+  rvt::davies_prepare(lam, n, lim, acc, th.data(), &pre);
+  return rvt::davies_qf_fast(lam, pre, th.data(), Q, lim, acc, fault);
+}
+// many points c on one prepared spectrum (what the quadrature does)
+void hc_qf_fast_many(const double* lam, int n, const double* Q, int nq, double* out, int* faults) {
+  std::vector<int> th(n > 0 ? n : 1);
+  rvt::DaviesPre pre;
+  rvt::davies_prepare(lam, n, 10000, 0.000001, th.data(), &pre);
+  for (int i = 0; i < nq; ++i) out[i] = rvt::davies_qf_fast(lam, pre, th.data(), Q[i], 10000, 0.000001, &faults[i]);
+}
+// SKAT-O through skato_prepare (trace moments) + the serial form of k_skato_qags.  out[0..3] = Q, rho, pvalue, ok;
+// out[4] = 1 when the quadrature ran.  lam_min_w <= 0 forces the eigen-solve for every rho.
+int hc_skato_fast(const double* Wm, int M, const double* v, double s2, double lam_min_w, double* out) {
+  const int limit = 1000, lda = M;
+  std::vector<double> Km((size_t)M * M), ev(M + 2), e(M + 2), vv(M + 2), pp(M + 2), lamz(M + 2), c(M + 2);
+  std::vector<double> wa(limit), wb(limit), wr(limit), we(limit);
+  std::vector<int> wo(limit), wl(limit), th(M + 2);
+  rvt::QagsWork w{wa.data(), wb.data(), wr.data(), we.data(), wo.data(), wl.data(), limit};
+  rvt::SerialPar par;
+  rvt::SkatoJob job;
+  const int run = rvt::skato_prepare(Wm, Km.data(), M, lda, v, s2, lam_min_w, ev.data(), e.data(), vv.data(), pp.data(), lamz.data(),
+                                     c.data(), th.data(), &job, par);
+  out[4] = run;
+  if (!run) {
+    out[0] = job.Q;
+    out[1] = job.rho;
+    out[2] = job.pvalue;
+    out[3] = job.ok;
+    return 0;
+  }
+  rvt::SkatoOut o;
+  rvt::skato_quadrature_serial(job, w, th.data(), &o);
+  out[0] = o.Q;
+  out[1] = o.rho;
+  out[2] = o.pvalue;
+  out[3] = o.ok;
+  return 0;
+}
+
 double hc_chisq_qinv(double q, double df) { return rvt::chisq_qinv(q, df); }
 
 // QAGS state machine driven with a plain C callback (limit 1000 as GSLIntegration.cpp:7-15)

@@ -196,7 +196,8 @@ def test_meta_adapters_match_reference_output_format(oracle, segment, tmp_path):
 
 def test_adapters_binary_outcome(oracle, tmp_path):
     """setBinaryOutcome(): the adapters switch to the logistic null model; Skat / CMC / Zeggini lines against the binary
-    oracle, SkatO prints NA (not provided for a binary trait)."""
+    oracle; with enableSkatOBinary(false) (adapter_demo argv[6] = 0) SkatO prints NA -- the default prints the type "D"
+    columns (tests/test_gpu_zz_fp64_skato.py::test_adapter_prints_skato_for_a_binary_trait)."""
     from oracle import binary_oracle as BIN
     import rvtests_b200
     rvtests_b200.load_library()
@@ -219,7 +220,7 @@ def test_adapters_binary_outcome(oracle, tmp_path):
             f.write(np.asfortranarray(G.astype(np.float64)).tobytes(order="F"))
             f.write(af_of(G).tobytes())
     exe = build_demo()
-    out = subprocess.run([exe, str(path), "8", "0", "0.05", "1"], capture_output=True, text=True, check=True).stdout
+    out = subprocess.run([exe, str(path), "8", "0", "0.05", "1", "0"], capture_output=True, text=True, check=True).stdout
     tables, cur = {}, None
     for line in out.splitlines():
         if line.startswith("#"):

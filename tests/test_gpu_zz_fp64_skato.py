@@ -118,11 +118,12 @@ def test_binary_trait_skato_vs_oracle(engine_cls, oracle, case):
     eng = engine_cls(0)
     try:
         eng.set_option("skato", 1)
+        eng.set_option("skato_binary", 0)
         eng.set_null_model(X, y, binary=True)
         eng.push_i8(G.T.copy(), af)
         off = eng.flush()[0]
-        assert int(off["skato_ok"]) == 0            # without the opt-in: not provided, NA
-        eng.set_option("skato_binary", 1)
+        assert int(off["skato_ok"]) == 0            # switched off: NA
+        eng.set_option("skato_binary", 1)           # (the default)
         eng.push_i8(G.T.copy(), af)
         eng.push_bed(pack_bed(G.T), af)
         res = eng.flush()
@@ -135,8 +136,8 @@ def test_binary_trait_skato_vs_oracle(engine_cls, oracle, case):
 
 
 def test_adapter_prints_skato_for_a_binary_trait(oracle, tmp_path):
-    """SkatOTest adapter with setBinaryOutcome() + enableSkatOBinary(): the Q / rho / Pvalue columns against the oracle
-    (adapter_demo argv[6] = 1); without the opt-in the line stays NA (tests/test_gpu_adapters.py)."""
+    """SkatOTest adapter with setBinaryOutcome() (SKAT-O type "D" is on by default): the Q / rho / Pvalue columns against
+    the oracle; with enableSkatOBinary(false) the line is NA (tests/test_gpu_adapters.py)."""
     import struct
     import subprocess
     from oracle import binary_oracle as BIN
@@ -163,7 +164,7 @@ def test_adapter_prints_skato_for_a_binary_trait(oracle, tmp_path):
             f.write(np.asfortranarray(G.astype(np.float64)).tobytes(order="F"))
             f.write(af_of(G).tobytes())
     exe = build_demo()
-    out = subprocess.run([exe, str(path), "8", "0", "0.05", "1", "1"], capture_output=True, text=True, check=True).stdout
+    out = subprocess.run([exe, str(path), "8", "0", "0.05", "1"], capture_output=True, text=True, check=True).stdout
     tables, cur = {}, None
     for line in out.splitlines():
         if line.startswith("#"):
