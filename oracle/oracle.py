@@ -16,6 +16,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -46,7 +47,8 @@ def build(native: bool = False) -> str:
     """Compile the checker (make -C oracle).  `native` additionally builds liboracle_native.so
     with -march=native on THIS machine (used by the CPU-baseline timing legs)."""
     targets = ["all"] + (["liboracle_native.so"] if native else [])
-    subprocess.run(["make", "-s", "-C", _HERE] + targets, check=True)
+    # make's chatter goes to stderr: bench.py's stdout is ONE JSON line
+    subprocess.run(["make", "-s", "-C", _HERE] + targets, check=True, stdout=sys.stderr)
     return os.path.join(_HERE, "liboracle_native.so" if native else "liboracle.so")
 
 
@@ -566,6 +568,41 @@ def ref_run_gene_models(genes, cov, pheno, prefix, n_perm=0, alpha=0.05, binary=
                                          int(n_perm), float(alpha), int(binary), prefix.encode())
     if rc:
         raise RuntimeError(f"ref_run_gene_models rc={rc}")
+    return {m: _read_assoc(f"{prefix}.{m}.assoc") for m in ("Skat", "SkatO", "CMC", "Zeggini")}
+
+
+def ref_dropin():
+    """oracle/_ref/libdropin_ref.so: the reference's own ModelManager (registration patch of rvtests_b200/host/ModelB200.h
+    applied) + Main.cpp's gene loop (oracle/ref_dropin_shim.cpp), linked with the reference model layer AND the product's
+    C ABI.  None when oracle/_ref was never built."""
+    if "dropin" not in _lib_cache:
+        path = os.path.join(_HERE, "_ref", "libdropin_ref.so")
+        if not os.path.exists(path):
+            _lib_cache["dropin"] = None
+        else:
+            # its DT_NEEDED entries (libmodel_ref.so, librvtests_b200.so) resolve through $ORIGIN rpaths
+            L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+            L.dropin_run_gene_models.restype = C.c_int
+            L.dropin_run_gene_models.argtypes = [C.c_int, C.c_int, _int_p, _dbl_p, C.c_int, _dbl_p, _dbl_p, C.c_char_p,
+                                                 C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
+            _lib_cache["dropin"] = L
+    return _lib_cache["dropin"]
+
+
+def dropin_run_gene_models(genes, cov, pheno, prefix, use_b200, kernel="skat[nPerm=0],skato", burden="cmc,zeggini",
+                           binary=False, batch=0):
+    """`--kernel <kernel> --burden <burden>` through the reference's ModelManager and gene loop; use_b200 selects the
+    reference's own fitters (False) or the B200 adapters registered behind the same names (True)."""
+    N = len(pheno)
+    flat = np.concatenate([np.asfortranarray(g, dtype=np.float64).ravel(order="F") for g in genes])
+    M = np.array([g.shape[1] for g in genes], dtype=np.int32)
+    covf = np.asfortranarray(np.asarray(cov, dtype=np.float64).reshape(N, -1))
+    y = np.ascontiguousarray(pheno, dtype=np.float64)
+    rc = ref_dropin().dropin_run_gene_models(N, len(genes), _p(M, C.c_int), _p(flat), covf.shape[1], _p(covf), _p(y),
+                                             kernel.encode(), burden.encode(), int(binary), int(use_b200), int(batch),
+                                             prefix.encode())
+    if rc:
+        raise RuntimeError(f"dropin_run_gene_models rc={rc}")
     return {m: _read_assoc(f"{prefix}.{m}.assoc") for m in ("Skat", "SkatO", "CMC", "Zeggini")}
 
 

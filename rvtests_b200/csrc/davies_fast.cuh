@@ -17,6 +17,20 @@
 #pragma once
 #include "davies.cuh"
 
+// inner-loop variants (A/B-timed on the B200, profiles/r02_davies_variants.txt): 1 = terms in blocks with independent chains
+#ifndef RVT_DF_ERRBD4
+#define RVT_DF_ERRBD4 0
+#endif
+#ifndef RVT_DF_TRUNC2
+#define RVT_DF_TRUNC2 1   // measured: 57.1 -> 51.1 ms per 2 500 genes (ERRBD4: 61.7, INT2: 64.3 -- register pressure)
+#endif
+#ifndef RVT_DF_INT2
+#define RVT_DF_INT2 0
+#endif
+#ifndef RVT_DF_RCP
+#define RVT_DF_RCP 0      // 1: errbd's reciprocals as rcp.approx + two Newton steps instead of an IEEE division
+#endif
+
 namespace rvt {
 
 struct DaviesPre {
@@ -58,6 +72,23 @@ struct Prod {
   RVT_HD double ln() const { return log(m) + (double)e * kLnBig; }
 };
 
+// 1 / y to ~1 ulp without the IEEE division's special-case path (device; the host build divides)
+RVT_HD double rcp_fast(double y) {
+#if defined(__CUDA_ARCH__) && RVT_DF_RCP
+  if (!(fabs(y) > 1e-290 && fabs(y) < 1e290)) return 1.0 / y;
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+  double e = fma(-y, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-y, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-y, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1.0 / y;
+#endif
+}
+
 struct St {
   double sigsq, lmax, lmin, mean, c;
   double intl, ersm;
@@ -73,7 +104,10 @@ RVT_HD bool tick(St& s) {
   return s.over;
 }
 
-// qfc.c:128-147.  sum1 = u^2 sigsq + sum_j [x_j^2 / y_j + log(1 - x_j) + x_j],  x_j = 2 u lb_j, y_j = 1 - x_j
+#if RVT_DF_ERRBD4
+// qfc.c:128-147.  sum1 = u^2 sigsq + sum_j [x_j^2 / y_j + log(1 - x_j) + x_j],  x_j = 2 u lb_j, y_j = 1 - x_j.
+// Terms go four at a time: the four reciprocals are independent instruction chains (the kernel is latency-bound: a few
+// warps per scheduler, each thread a serial Davies evaluation), and the product takes one range check per block.
 RVT_HD double errbd(St& s, double u, double* cx) {
   if (tick(s)) return 0.0;
   double xconst = u * s.sigsq;
@@ -83,7 +117,33 @@ RVT_HD double errbd(St& s, double u, double* cx) {
   p.init();
   double sx = 0.0;
   bool neg = false;
-  for (int j = s.r - 1; j >= 0; j--) {
+  int j = s.r - 1;
+  for (; j >= 3; j -= 4) {
+    const double l0 = s.lb[j], l1 = s.lb[j - 1], l2 = s.lb[j - 2], l3 = s.lb[j - 3];
+    const double x0 = u * l0, x1 = u * l1, x2 = u * l2, x3 = u * l3;
+    const double y0 = 1.0 - x0, y1 = 1.0 - x1, y2 = 1.0 - x2, y3 = 1.0 - x3;
+    const double i0 = 1.0 / y0, i1 = 1.0 / y1, i2 = 1.0 / y2, i3 = 1.0 / y3;
+    xconst = xconst + l0 * i0;
+    xconst = xconst + l1 * i1;
+    xconst = xconst + l2 * i2;
+    xconst = xconst + l3 * i3;
+    sum1 = sum1 + sq(x0) * i0;
+    sum1 = sum1 + sq(x1) * i1;
+    sum1 = sum1 + sq(x2) * i2;
+    sum1 = sum1 + sq(x3) * i3;
+    sx += (x0 + x1) + (x2 + x3);
+    neg |= !(y0 > 0.0) | !(y1 > 0.0) | !(y2 > 0.0) | !(y3 > 0.0);
+    const double a0 = fabs(y0), a1 = fabs(y1), a2 = fabs(y2), a3 = fabs(y3);
+    if (fmax(fmax(a0, a1), fmax(a2, a3)) < 1e30 && fmin(fmin(a0, a1), fmin(a2, a3)) > 1e-30)
+      p.mul((a0 * a1) * (a2 * a3));   // |block| in (1e-120, 1e120): one range check
+    else {
+      p.mul(a0);
+      p.mul(a1);
+      p.mul(a2);
+      p.mul(a3);
+    }
+  }
+  for (; j >= 0; j--) {
     const double lj = s.lb[j];
     const double x = u * lj, y = 1.0 - x;
     const double inv = 1.0 / y;
@@ -99,6 +159,34 @@ RVT_HD double errbd(St& s, double u, double* cx) {
   return exp1(-0.5 * sum1);
 }
 
+#else
+// qfc.c:128-147.  sum1 = u^2 sigsq + sum_j [x_j^2 / y_j + log(1 - x_j) + x_j],  x_j = 2 u lb_j, y_j = 1 - x_j
+RVT_HD double errbd(St& s, double u, double* cx) {
+  if (tick(s)) return 0.0;
+  double xconst = u * s.sigsq;
+  double sum1 = u * xconst;
+  u = 2.0 * u;
+  Prod p;
+  p.init();
+  double sx = 0.0;
+  bool neg = false;
+  for (int j = s.r - 1; j >= 0; j--) {
+    const double lj = s.lb[j];
+    const double x = u * lj, y = 1.0 - x;
+    const double inv = rcp_fast(y);
+    xconst = xconst + lj * inv;
+    sum1 = sum1 + sq(x) * inv;
+    sx += x;
+    neg |= !(y > 0.0);
+    p.mul(fabs(y));
+  }
+  // (a non-positive y makes the reference's log NaN; keep that outcome)
+  sum1 = sum1 + (sx + (neg ? nan("") : p.ln()));
+  *cx = xconst;
+  return exp1(-0.5 * sum1);
+}
+
+#endif
 // qfc.c:149-174
 RVT_HD double ctff(St& s, double accx, double* upn) {
   double u2 = *upn, u1 = 0.0, c1 = s.mean, c2 = 0.0, xconst = 0.0;
@@ -134,6 +222,40 @@ RVT_HD double truncation(St& s, double u, double tausq) {
   if (tick(s)) return 0.0;
   const double sum2 = (s.sigsq + tausq) * sq(u);
   u = 2.0 * u;
+#if RVT_DF_TRUNC2
+  Prod p1, p2, p3;
+  p1.init();
+  p2.init();
+  p3.init();
+  int ss = 0;
+  // branch-free: the threads of a warp share lb but not u, so (x > 1) differs from lane to lane
+  int j = 0;
+  for (; j + 1 < s.r; j += 2) {
+    const double xa = sq(u * s.lb[j]), xb = sq(u * s.lb[j + 1]);
+    const bool ba = xa > 1.0, bb = xb > 1.0;
+    ss += (int)ba + (int)bb;
+    if (xa < 1e60 && xb < 1e60) {
+      p1.mul((ba ? 1.0 : 1.0 + xa) * (bb ? 1.0 : 1.0 + xb));
+      p2.mul((ba ? xa : 1.0) * (bb ? xb : 1.0));
+      p3.mul((ba ? 1.0 + xa : 1.0) * (bb ? 1.0 + xb : 1.0));
+    } else {
+      p1.mul(ba ? 1.0 : 1.0 + xa);
+      p1.mul(bb ? 1.0 : 1.0 + xb);
+      p2.mul(ba ? xa : 1.0);
+      p2.mul(bb ? xb : 1.0);
+      p3.mul(ba ? 1.0 + xa : 1.0);
+      p3.mul(bb ? 1.0 + xb : 1.0);
+    }
+  }
+  for (; j < s.r; j++) {
+    const double x = sq(u * s.lb[j]);
+    const bool b = x > 1.0;
+    ss += (int)b;
+    p1.mul(b ? 1.0 : 1.0 + x);
+    p2.mul(b ? x : 1.0);
+    p3.mul(b ? 1.0 + x : 1.0);
+  }
+#else
   Prod p1, p2, p3;
   p1.init();
   p2.init();
@@ -148,6 +270,7 @@ RVT_HD double truncation(St& s, double u, double tausq) {
     } else
       p1.mul(1.0 + x);
   }
+#endif
   const double prod1 = 2.0 * sum2 + p1.ln();
   const double prod2 = prod1 + (ss ? p2.ln() : 0.0);
   const double prod3 = prod1 + (ss ? p3.ln() : 0.0);
@@ -222,6 +345,94 @@ RVT_HD double cfe(St& s, double x) {
   return pow(2.0, (sum1 / 4.0)) / (kPi * sq(axl));
 }
 
+#if RVT_DF_INT2
+// qfc.c:237-268.  Per term k: prod_j (1 + i x_j), x_j = 2 lb_j u, gives sum_j atan(x_j) as its (unwrapped) argument and
+// sum_j log(1 + x_j^2) as the log of its squared modulus.  Positive and negative coefficients are kept in two products
+// (the error sum needs sum_j |atan x_j|): `p` multiplies (1 + i x_j) for x_j >= 0, `n` multiplies (1 + i |x_j|) for
+// x_j < 0 (its argument enters with a minus sign).  Each product is held in the first quadrant by a quarter turn back
+// whenever it leaves it -- one factor turns it by less than pi/2 -- and the turns are counted.
+struct Cprod {
+  double r, i;
+  int q, e;   // quarter turns taken back, exponent in units of 1e150
+  RVT_HD void init() {
+    r = 1.0;
+    i = 0.0;
+    q = 0;
+    e = 0;
+  }
+  RVT_HD void mul(double x /* >= 0 */) {
+    const double tr = r - i * x, ti = i + r * x;   // argument now in [0, pi)
+    const bool turn = tr <= 0.0;                   // past pi/2: multiply by -i
+    r = turn ? ti : tr;
+    i = turn ? -tr : ti;
+    q += (int)turn;
+    if (r + i > kBig) {
+      r *= kSmall;
+      i *= kSmall;
+      ++e;
+    }
+  }
+  RVT_HD double arg() const { return (double)q * (0.5 * 3.14159265358979323846) + atan2(i, r); }
+  RVT_HD double mod2() const { return r * r + i * i; }
+};
+
+RVT_HD void integrate_term(St& s, double u, const Cprod& p, const Cprod& n, double inpi, double tausq, bool mainx) {
+  double sum1 = -2.0 * u * s.c;
+  double sum2 = fabs(sum1);
+  double sum3 = -0.5 * s.sigsq * sq(u);
+  const double thp = p.arg(), thn = n.arg();   // both >= 0
+  const double lmod2 = log(p.mod2() * n.mod2()) + 2.0 * (double)(p.e + n.e) * kLnBig;
+  sum3 = sum3 - 0.25 * lmod2;
+  sum1 = sum1 + (thp - thn);
+  sum2 = sum2 + (thp + thn);
+  double x = inpi * exp1(sum3) / u;
+  if (!mainx) x = x * (1.0 - exp1(-0.5 * tausq * sq(u)));
+  s.intl = s.intl + sin(0.5 * sum1) * x;
+  s.ersm = s.ersm + 0.5 * sum2 * x;
+}
+
+// two trapezoid terms per pass over the coefficients: two independent product chains (and the sign branch on lb_j is
+// the same for every thread of the warp); the sums are accumulated in the reference's order k = nterm .. 0
+RVT_HD void integrate(St& s, int nterm, double interv, double tausq, bool mainx) {
+  const double inpi = interv / kPi;
+  int k = nterm;
+  for (; k >= 1; k -= 2) {
+    const double ua = (k + 0.5) * interv, ub = (k - 0.5) * interv;
+    const double ua2 = 2.0 * ua, ub2 = 2.0 * ub;
+    Cprod pa, na, pb, nb;
+    pa.init();
+    na.init();
+    pb.init();
+    nb.init();
+    for (int j = s.r - 1; j >= 0; j--) {
+      const double l = s.lb[j];
+      if (l >= 0.0) {
+        pa.mul(l * ua2);
+        pb.mul(l * ub2);
+      } else {
+        na.mul(-l * ua2);
+        nb.mul(-l * ub2);
+      }
+    }
+    integrate_term(s, ua, pa, na, inpi, tausq, mainx);
+    integrate_term(s, ub, pb, nb, inpi, tausq, mainx);
+  }
+  if (k == 0) {
+    const double u = 0.5 * interv, u2 = 2.0 * u;
+    Cprod p, n;
+    p.init();
+    n.init();
+    for (int j = s.r - 1; j >= 0; j--) {
+      const double l = s.lb[j];
+      if (l >= 0.0)
+        p.mul(l * u2);
+      else
+        n.mul(-l * u2);
+    }
+    integrate_term(s, u, p, n, inpi, tausq, mainx);
+  }
+}
+#else
 // qfc.c:237-268.  Per term k: prod_j (1 + i x_j), x_j = 2 lb_j u, gives sum_j atan(x_j) as its (unwrapped) argument and
 // sum_j log(1 + x_j^2) as the log of its squared modulus.  Positive and negative coefficients are kept in two products
 // (the error sum needs sum_j |atan x_j|); each is held in the first / fourth quadrant by a quarter turn whenever it
@@ -282,6 +493,7 @@ RVT_HD void integrate(St& s, int nterm, double interv, double tausq, bool mainx)
     s.ersm = s.ersm + 0.5 * sum2 * x;
   }
 }
+#endif
 }  // namespace qff
 
 // what qf() computes before it looks at c, once per spectrum.  th: r ints, receives the order of |lb| (descending)

@@ -159,6 +159,7 @@ struct rvt_ctx {
   cudaEvent_t ev_swept[2] = {nullptr, nullptr}, ev_fin_done[2] = {nullptr, nullptr};
   bool fin_busy[2] = {false, false};
   unsigned long long batch_seq = 0;
+  int qags_pack = 1;               // SKAT-O quadrature: 1 = three genes per persistent 128-thread CTA (k_skato_qags_packed)
   long long wd_cycles = 8000000000ll;   // device watchdog of the per-gene tail, SM cycles (option "watchdog_ms"; ~4 s)
   bool skato = false;
   bool skato_binary = true;    // SKAT-O for a binary trait (SkatO::Fit type "D"); on by default, see include/rvtests_b200.h
@@ -394,6 +395,8 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "tc_stages") {
     if (value != 3 && value != 4 && value != 5) CTX_FAIL(RVT_E_BADARG, "tc_stages must be 3, 4 or 5");
     ctx->tc.stages = (int)value;
+  } else if (k == "qags_pack") {
+    ctx->qags_pack = value != 0;
   } else if (k == "watchdog_ms") {
     if (value < 0 || value > 3.6e6) CTX_FAIL(RVT_E_BADARG, "watchdog_ms must be in 0..3600000 (0 = off)");
     ctx->wd_cycles = (long long)(value * 2.0e6);   // ~2 GHz SM clock
@@ -816,6 +819,18 @@ static int land_release(rvt_ctx* ctx, int slot) {
   return RVT_OK;
 }
 static int launch_range(rvt_ctx* ctx, int g0, int g1);
+// SKAT-O quadrature of the nb genes whose jobs sit in ctx->d_jobs (records at d_res[out_index ? out_index[i] : i])
+static int launch_qags(rvt_ctx* ctx, int nb, rvt_gene_result* d_res, const int* d_index, cudaStream_t st) {
+  if (!ctx->qags_pack) {
+    k_skato_qags<<<nb, kQagsThreads, 0, st>>>(ctx->d_jobs, nb, ctx->d_qags, d_res, d_index, ctx->wd_cycles);
+  } else {
+    const int grid = std::max(1, std::min((nb + kQagsSlots - 1) / kQagsSlots, 6 * ctx->sm_count));
+    RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(unsigned int), st));
+    k_skato_qags_packed<<<grid, kQagsPackThreads, 0, st>>>(ctx->d_jobs, nb, ctx->d_qags, d_res, d_index, ctx->wd_cycles, ctx->d_counter + 1);
+  }
+  RVT_CUDA_OK(cudaGetLastError());
+  return RVT_OK;
+}
 static int maybe_stream(rvt_ctx* ctx) {
   const int n = (int)ctx->genes.size();
   if (ctx->stream_batch > 0 && n - ctx->launched >= ctx->stream_batch) return launch_range(ctx, ctx->launched, n);
@@ -1069,7 +1084,7 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
   const bool ovl = ctx->overlap > 0 && !ctx->binary;
   if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)batch * Sp * (ovl ? 2 : 1), sizeof(SweepPartial)))) return rc;
   if (ctx->skato) {
-    if ((rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)batch, sizeof(QagsScratch)))) return rc;
+    if ((rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)batch + kQagsSlots, sizeof(QagsScratch)))) return rc;
     if ((rc = ensure(ctx, (void**)&ctx->d_jobs, &ctx->cap_jobs, (size_t)batch, sizeof(SkatoJob)))) return rc;
   }
   if (ctx->want_dbg) {
@@ -1145,7 +1160,7 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
       k_finalize<true><<<nb, kFinThreadsSkato, fsm, fs>>>(
           ctx->d_genes + b0, nb, kld, wm_off, fin_uk_off(Mmax, ctx->ER, ctx->skato), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, ctx->d_res + b0,
           ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->d_jobs, nullptr, nullptr);
-      k_skato_qags<<<nb, kQagsThreads, 0, fs>>>(ctx->d_jobs, nb, ctx->d_qags, ctx->d_res + b0, nullptr, ctx->wd_cycles);
+      if ((rc = launch_qags(ctx, nb, ctx->d_res + b0, nullptr, fs))) return rc;
       launches += 1;
     } else
       k_finalize<false><<<nb, kFinThreads, fsm, fs>>>(
@@ -1564,7 +1579,7 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       RVT_CUDA_OK(cudaStreamSynchronize(st));   // `tgs` is a host temporary
     }
     RVT_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
-    if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nd, sizeof(QagsScratch)))) return rc;
+    if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nd + kQagsSlots, sizeof(QagsScratch)))) return rc;
     if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_jobs, &ctx->cap_jobs, (size_t)nd, sizeof(SkatoJob)))) return rc;
     {
       // SKAT-O for a binary trait (SkatO::Fit type "D": the same tail on the p(1-p)-weighted statistics with s2 = 1,
@@ -1574,7 +1589,7 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       if (sk) {
         k_finalize<true><<<nd, kFinThreadsSkato, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, sk), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
                                                              nullptr, d_res, nullptr, ctx->d_jobs, d_tin, d_idx);
-        k_skato_qags<<<nd, kQagsThreads, 0, st>>>(ctx->d_jobs, nd, ctx->d_qags, d_res, d_idx, ctx->wd_cycles);
+        if ((rc = launch_qags(ctx, nd, d_res, d_idx, st))) return rc;
         launches += 1;
       } else
         k_finalize<false><<<nd, kFinThreads, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, sk), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
@@ -1720,7 +1735,16 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   if (wmax_out) *wmax_out = wmax;
   const int64_t N = ctx->N;
   int S = ctx->splits;
-  if (S <= 0) S = (int)std::min<int64_t>(16, std::max<int64_t>(1, (N + 65535) / 65536));
+  if (S <= 0) {
+    S = (int)std::min<int64_t>(16, std::max<int64_t>(1, (N + 65535) / 65536));
+    if (band) {
+      // the pair sweeps walk the band split-major (sweep_tc.cuh): one sample chunk of the tiles a window spans -- the
+      // partners of a tile plus the tile itself, 64 bytes per sample each -- should sit in L2 (126 MB) with room to spare
+      const int64_t wt = (wmax + kTileRows - 1) / kTileRows + 2;
+      const int64_t s_l2 = (N * kTileRows * wt + (48ll << 20) - 1) / (48ll << 20);
+      S = (int)std::min<int64_t>(64, std::max<int64_t>(S, s_l2));
+    }
+  }
   int64_t chunk = (((N + S - 1) / S) + 511) & ~(int64_t)511;
   S = (int)((N + chunk - 1) / chunk);
   const int T = ngen;
@@ -1783,6 +1807,7 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   const bool tc_ok = ctx->tc.encode && ctx->tc.have_e && seg >= 0 && ctx->tc.have_seg[seg];
   if (!pairs.empty() && !tc_ok) { cleanup(); CTX_FAIL(RVT_E_UNSUPPORTED, "meta cov needs the tensor-core engine (TMA segment unavailable)"); }
   // phase 1: diagonal tiles
+  RVT_CUDA_OK(cudaEventRecord(ctx->ev[0], st));
   RVT_CUDA_OK(cudaMemcpyAsync(d_desc, tiles.data(), sizeof(GeneDesc) * T, cudaMemcpyHostToDevice, st));
   for (int b0 = 0; b0 < T; b0 += batch) {
     const int nb = std::min(batch, T - b0);
@@ -1798,7 +1823,10 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
     k_meta_block<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, d_v, d_B, d_poly, d_band);
     RVT_CUDA_OK(cudaGetLastError());
   }
+  k_meta_hwe<<<(unsigned)nv, kHweThreads, 0, st>>>(nv, d_v);
+  RVT_CUDA_OK(cudaGetLastError());
   // phase 2: tile pairs inside the window
+  RVT_CUDA_OK(cudaEventRecord(ctx->ev[2], st));
   if (!pairs.empty()) {
     RVT_CUDA_OK(cudaStreamSynchronize(st));  // d_desc is rewritten
     RVT_CUDA_OK(cudaMemcpyAsync(d_desc, pairs.data(), sizeof(GeneDesc) * pairs.size(), cudaMemcpyHostToDevice, st));
@@ -1811,9 +1839,24 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
       RVT_CUDA_OK(cudaGetLastError());
     }
   }
+  RVT_CUDA_OK(cudaEventRecord(ctx->ev[3], st));
   RVT_CUDA_OK(cudaMemcpyAsync(vout, d_v, sizeof(rvt_variant_result) * nv, cudaMemcpyDeviceToHost, st));
   if (band) RVT_CUDA_OK(cudaMemcpyAsync(band, d_band, sizeof(double) * nv * (size_t)(wmax + 1), cudaMemcpyDeviceToHost, st));
+  RVT_CUDA_OK(cudaEventRecord(ctx->ev[1], st));
   RVT_CUDA_OK(cudaStreamSynchronize(st));
+  {
+    // rvt_last_timing of a meta flush: [0] the tile-pair sweeps + band assembly (phase 2), [1] the diagonal tiles + score
+    // statistics (phase 1), [2] the whole flush incl. the copies of the results
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&b, ctx->ev[0], ctx->ev[2]);
+    cudaEventElapsedTime(&c, ctx->ev[0], ctx->ev[1]);
+    ctx->t_sweep = a;
+    ctx->t_fin = b;
+    ctx->t_total = c;
+    ctx->n_launch = (double)pairs.size();
+    ctx->last_S = S;
+  }
   cleanup();
   pending_reset(ctx);
   return RVT_OK;

@@ -344,7 +344,10 @@ RVT_HDN void skato_quadrature_serial(const SkatoJob& job, const QagsWork& work, 
 constexpr int kQagsThreads = 64;
 
 // One CTA per gene; thread t < 42 owns Kronrod node t % 21 of half t / 21 of the current bisection.
-__global__ void __launch_bounds__(kQagsThreads)
+#ifndef RVT_QAGS_MINBLOCKS
+#define RVT_QAGS_MINBLOCKS 12
+#endif
+__global__ void __launch_bounds__(kQagsThreads, RVT_QAGS_MINBLOCKS)
 k_skato_qags(const SkatoJob* __restrict__ jobs, int n_genes, QagsScratch* __restrict__ qags, rvt_gene_result* __restrict__ res,
              const int* __restrict__ out_index, long long wd_cycles) {
   __shared__ SkatoParams P;
@@ -425,6 +428,136 @@ k_skato_qags(const SkatoJob* __restrict__ jobs, int n_genes, QagsScratch* __rest
       dst->skato_rho = (job.rhos[job.min_index] >= 0.999) ? 1.0 : job.rhos[job.min_index];
       dst->skato_p = skato_final_p(mach.result, job.minP, job.pvals);
     }
+  }
+}
+
+// Packed form: the 42 nodes of a bisection fill 1.3 warps, so the kernel above keeps a third of its lanes idle.  Here a
+// CTA of 128 threads runs THREE quadratures side by side -- slot s owns lanes 42 s .. 42 s + 41 -- and is persistent: a slot
+// whose gene is finished takes the next one from a global counter, so the lanes stay busy until the queue is empty.
+// All slots step together (sample -> barrier -> give -> barrier); the serial parts (machine update, per-gene set-up)
+// are done by the slot's first lane while the others wait at the barrier (~1 % of a step).
+constexpr int kQagsSlots = 3;
+constexpr int kQagsPackThreads = 128;
+
+__global__ void __launch_bounds__(kQagsPackThreads, 6)
+k_skato_qags_packed(const SkatoJob* __restrict__ jobs, int n_genes, QagsScratch* __restrict__ qags /* [gridDim.x * kQagsSlots] */,
+                    rvt_gene_result* __restrict__ res, const int* __restrict__ out_index, long long wd_cycles,
+                    unsigned int* __restrict__ next /* zeroed by the host */) {
+  struct Slot {
+    SkatoParams P;
+    double lam[kSkatoMaxLam];
+    int th[kSkatoMaxLam];
+    DaviesPre pre;
+    QagsMachine mach;
+    double fv[42], bc[5];
+    int gene;   // -1: no more work
+    int pass;   // 0 Davies integrand, 1 Liu integrand
+    int nint;   // intervals to sample in this step (0: nothing)
+  };
+  __shared__ Slot sl[kQagsSlots];
+  __shared__ int s_live;
+  const int tid = threadIdx.x;
+  const int s = tid / 42, t = tid - 42 * s;
+  const bool leader = s < kQagsSlots && t == 0;
+  if (leader) sl[s].gene = -2;   // -2: idle, fetch
+  if (tid == 0) s_live = 1;
+  __syncthreads();
+  for (;;) {
+    if (leader) {
+      Slot& S = sl[s];
+      // fetch + set up the next gene(s) until one needs the quadrature or the queue is empty
+      while (S.gene == -2) {
+        const unsigned int g = atomicAdd(next, 1u);
+        if (g >= (unsigned int)n_genes) {
+          S.gene = -1;
+          break;
+        }
+        const SkatoJob& job = jobs[g];
+        rvt_gene_result* dst = &res[out_index ? out_index[g] : (int)g];
+        if (!job.run) {
+          dst->skato_ok = job.ok;
+          dst->skato_Q = job.Q;
+          dst->skato_rho = job.rho;
+          dst->skato_p = job.pvalue;
+          continue;
+        }
+        const int nl = job.n_lam;
+        for (int i = 0; i < nl; ++i) S.lam[i] = job.lam[i];
+        skato_params_from_job(job, S.lam, &S.P);
+        S.pre.degenerate = 0;
+        if (nl >= 2) davies_prepare(S.lam, nl, 10000, 0.000001, S.th, &S.pre);
+        QagsScratch& q = qags[(size_t)blockIdx.x * kQagsSlots + s];
+        QagsWork work{q.a, q.b, q.r, q.e, q.order, q.level, kQagsLimit};
+        work.deadline = wd_cycles > 0 ? clock64() + wd_cycles : 0;
+        S.mach.init(work, 0.0, 40.0, 1e-25, 0.0001220703);
+        S.gene = (int)g;
+        S.pass = 0;
+      }
+      S.nint = 0;
+      if (S.gene >= 0) {
+        QagsMachine& m = S.mach;
+        if (m.stage != 3 && m.w.deadline != 0 && clock64() > m.w.deadline) {   // watchdog, status 8
+          m.status = 8;
+          m.stage = 3;
+        }
+        double lo = 0, hi = 0;
+        if (m.want(&lo, &hi)) {
+          S.nint = m.stage == 1 ? 2 : 1;
+          S.bc[1] = lo;
+          S.bc[2] = hi;
+          S.bc[3] = m.a2;
+          S.bc[4] = m.b2;
+        }
+      }
+    }
+    if (tid == 0) {
+      // (written before the barrier by thread 0 only; the leaders of slots 1, 2 publish through sl[].gene)
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int live = 0;
+      for (int k = 0; k < kQagsSlots; ++k) live |= (sl[k].gene != -1);
+      s_live = live;
+    }
+    if (s < kQagsSlots) {
+      Slot& S = sl[s];
+      if (t < 21 * S.nint) {
+        const int h = t >= 21;
+        const double lo = h ? S.bc[3] : S.bc[1], hi = h ? S.bc[4] : S.bc[2];
+        const double x = 0.5 * (lo + hi) + 0.5 * (hi - lo) * gk21_node(t - 21 * h);
+        S.fv[t] = S.pass == 0 ? skato_node_davies(S.P, S.pre, S.th, x) : skato_integrand_liu(S.P, x);
+      }
+    }
+    __syncthreads();
+    if (!s_live) break;
+    if (leader && sl[s].gene >= 0) {
+      Slot& S = sl[s];
+      QagsMachine& m = S.mach;
+      if (S.nint >= 1) m.give(gk21_combine(S.fv, S.bc[1], S.bc[2]));
+      if (S.nint == 2) m.give(gk21_combine(S.fv + 21, S.bc[3], S.bc[4]));
+      if (m.stage == 3) {
+        const int st = m.status;
+        if (st != 0 && st != 8 && S.pass == 0) {   // the Davies integrand failed: Liu integrand (SkatO.cpp:243-255)
+          QagsWork work = m.w;
+          m.init(work, 0.0, 40.0, 1e-25, 0.0001220703);
+          S.pass = 1;
+        } else {
+          const SkatoJob& job = jobs[S.gene];
+          rvt_gene_result* dst = &res[out_index ? out_index[S.gene] : S.gene];
+          if (st == 8) {
+            dst->skato_ok = 0;
+            dst->status = RVT_GENE_TIMEOUT;
+          } else {
+            dst->skato_ok = 1;
+            dst->skato_Q = job.Qs[job.min_index];
+            dst->skato_rho = (job.rhos[job.min_index] >= 0.999) ? 1.0 : job.rhos[job.min_index];
+            dst->skato_p = skato_final_p(m.result, job.minP, job.pvals);
+          }
+          S.gene = -2;
+        }
+      }
+    }
+    // (the next step's leader section runs before any lane touches fv / bc again: ordered by the barrier at its end)
   }
 }
 #endif

@@ -38,6 +38,9 @@ constexpr int kTcMaxStages = 5;
 constexpr int kTcBoxK = 128;                // samples per box (one 128-byte swizzle row)
 constexpr int kTcChunkAlign = 512;          // split boundaries are multiples of this (>= any stage width)
 
+// PAIR units are walked SPLIT-MAJOR (all pairs of sample chunk 0, then chunk 1, ...): a tile takes part in up to 2 W pairs
+// of the band (W partner tiles), and with the pairs of one chunk adjacent in time its chunk (64 x N/S bytes) stays in the
+// 126 MB L2 between its uses instead of being re-read from HBM for every partner.
 // PAIR = the A operand (rows of block I) and the B operand (rows of block J) are different tiles:
 // the cross-block Gram of the meta-analysis covariance (src/Model.cpp:534-554 calculateXX for
 // every pair of variants in the sliding window).  Box = [A tile][B tile][E tile].
@@ -275,7 +278,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
       const int nchunks = (int)((N + 127) >> 7);
       constexpr int kOobRow = 0x7FFF0000;   // beyond any arena (< 2^31 rows of 128 B): TMA zero-fills
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int gi = u / S, sp = u - gi * S;
+        const int gi = PAIR ? u % n_genes : u / S, sp = PAIR ? u / n_genes : u - gi * S;   // PAIR: split-major (L2 reuse, below)
         const int row0 = (int)genes[gi].row0;
         const int Mg = genes[gi].M;
         // the box of this gene holds exactly its M rows (no bytes of the neighbouring gene):
@@ -325,7 +328,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
                            ((uint32_t)((WIDE ? 2 * kTileRows : kTileRows) >> 4) << 24);
     uint32_t it = 0, ui = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-      const int gi = u / S, sp = u - gi * S;
+      const int gi = PAIR ? u % n_genes : u / S, sp = PAIR ? u / n_genes : u - gi * S;   // PAIR: split-major (L2 reuse, below)
       const int64_t k0 = (int64_t)sp * chunk;
       int64_t k1 = k0 + chunk;
       if (k1 > N) k1 = N;
@@ -379,7 +382,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
     const int q = warp & 3;          // TMEM lane quadrant this warp may read
     uint32_t it = 0, ui = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-      const int gi = u / S, sp = u - gi * S;
+      const int gi = PAIR ? u % n_genes : u / S, sp = PAIR ? u / n_genes : u - gi * S;   // PAIR: split-major (L2 reuse, below)
       const GeneDesc gd = genes[gi];
       const int M = gd.M;
       const int64_t k0 = (int64_t)sp * chunk;
@@ -499,7 +502,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
       const int a = ui & 1;
       mbar_wait(&tfull[a], (ui >> 1) & 1);
       tc_fence_after();
-      SweepPartial* o = out + (WIDE ? 2 * (size_t)u : (size_t)u);
+      SweepPartial* o = out + (WIDE ? 2 * (size_t)u : (PAIR ? (size_t)gi * S + sp : (size_t)u));
       // ZC: rows M / M+1 of D are the Zeggini / CMC burden sums of this unit (digit columns, and the
       // sum of squares on their own diagonal entry) -> coll[] of the partial, same slots as the dp4a path
       auto zc_store = [&](SweepPartial* op, int row, int dcol, const uint32_t (&v)[16]) {

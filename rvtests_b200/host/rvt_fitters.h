@@ -12,7 +12,12 @@
 // Behavioural difference, by design: fit() only ENQUEUES the gene; statistics materialise when the
 // batch is flushed (every `batch` genes, or in writeFootnote()/the destructor) and the output lines
 // are then written in arrival order -- the same deferred-output pattern as the in-tree MetaCovTest
-// (src/Model.cpp:828-834, writers outlive models: src/ModelManager.cpp:304-315).  The `siteInfo`
+// (src/Model.cpp:828-834, writers outlive models: src/ModelManager.cpp:304-315).
+// Every adapter takes a 4th template parameter BASE: inside rvtests it is the reference's own ModelFitter
+// (src/ModelFitter.h:17-75) -- fit / writeHeader / writeOutput / writeFootnote / reset then OVERRIDE its virtuals and the
+// objects sit in ModelManager's std::vector<ModelFitter*> like any other model (rvtests_b200/host/ModelB200.h; built
+// against the real headers and run next to the reference's fitters by oracle/ref_dropin_shim.cpp).  Stand-alone
+// (shim.h, the adapter demos) BASE defaults to a small struct with the same members.  The `siteInfo`
 // Result passed to writeOutput() is a reused buffer (src/Main.cpp:1085,1224), so its joined value
 // is snapshotted.  Permutation p-values (`skat[nPerm=..,alpha=..]`, the reference's default nPerm = 10000) come
 // from the engine's device replay of the reference's rand()-driven shuffles (csrc/perm.cuh).
@@ -20,17 +25,39 @@
 #define RVT_FITTERS_H_
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rvtests_b200.h"
 
 namespace rvtb200 {
 
-// One engine context per process, shared by every adapter so that a gene is uploaded once even
-// when several tests (skat, skato, cmc, zeggini) run on it.
+// what the adapters use of ModelFitter, for builds without the reference tree
+struct StandaloneBase {
+  StandaloneBase() : modelName("UninitializedModel"), binaryOutcome(false) {}
+  virtual ~StandaloneBase() {}
+  const std::string& getModelName() const { return modelName; }
+  bool isBinaryOutcome() const { return binaryOutcome; }
+  void setBinaryOutcome() { binaryOutcome = true; }
+  void setQuantitativeOutcome() { binaryOutcome = false; }
+  bool needToIndexResult() const { return false; }
+  virtual void reset() {}
+
+ protected:
+  std::string modelName;
+  bool binaryOutcome;
+};
+
+// One engine per process, shared by every adapter so that a gene is uploaded once even when several tests (skat, skato,
+// cmc, zeggini) run on it.  It drives ONE CONTEXT PER DEVICE: setDevices(n) / $RVTESTS_B200_DEVICES = n (default 1) deals
+// the genes round-robin over devices first .. first + n - 1 ($RVTESTS_B200_DEVICE = first, default 0); a flush runs the
+// contexts concurrently, one host thread each (the C ABI's rule: one thread per context), and hands the records back in
+// arrival order.  The permutation test replays ONE rand() stream in gene order (csrc/perm.cuh), so with nPerm > 0 a
+// single device is used.
 template <class DC>
 class GeneBatcher {
  public:
@@ -39,9 +66,19 @@ class GeneBatcher {
     return b;
   }
   ~GeneBatcher() {
-    if (ctx_) rvt_ctx_destroy(ctx_);
+    for (size_t k = 0; k < ctx_.size(); ++k)
+      if (ctx_[k]) rvt_ctx_destroy(ctx_[k]);
   }
   void setBatch(int n) { batch_ = n > 0 ? n : 1; }
+  // Beta(MAF; beta1, beta2) weights of --kernel skat[beta1=..,beta2=..] / skato[..] (src/ModelManager.cpp:169-185): one
+  // engine serves every adapter, so the pair is process-wide (the reference's default 1, 25 unless a model says otherwise)
+  void setBeta(double b1, double b2) {
+    if (b1 != beta1_ || b2 != beta2_) have_null_ = false;
+    beta1_ = b1;
+    beta2_ = b2;
+  }
+  void setDevice(int first) { device_ = first; }      // before the first fit(); default $RVTESTS_B200_DEVICE or 0
+  void setDevices(int n) { n_devices_ = n; }          // before the first fit(); default $RVTESTS_B200_DEVICES or 1
   void enableSkatO() { skato_ = true; }
   // SkatO::Fit type "D" (src/Model.h:2854-2858) = the engine's "skato_binary" option: on by default (as the reference
   // computes it); enableSkatOBinary(false) prints NA for a binary trait instead
@@ -61,7 +98,7 @@ class GeneBatcher {
     if (ticket >= (int)results_.size() && !flush()) return NULL;
     return ticket < (int)perms_.size() ? &perms_[ticket] : NULL;
   }
-  const char* error() const { return ctx_ ? rvt_last_error(ctx_) : "no context"; }
+  const char* error() const { return last_error_.c_str(); }
 
   // Called from fit(): returns the ticket of the CURRENT gene, uploading it on first sight.
   // A fitter id seen twice means the caller's gene loop has advanced (src/Main.cpp:1249-1253).
@@ -80,52 +117,121 @@ class GeneBatcher {
     if (ticket >= (int)results_.size() && !flush()) return NULL;
     return ticket < (int)results_.size() ? &results_[ticket] : NULL;
   }
-  bool shouldFlush() const { return rvt_pending(ctx_) >= batch_; }
+  bool shouldFlush() const { return (int)owner_.size() >= batch_; }
   bool flush() {
-    int n = ctx_ ? rvt_pending(ctx_) : 0;
+    const int n = (int)owner_.size();
     if (n == 0) return true;
-    size_t base = results_.size();
-    results_.resize(base + n);
-    int got = 0;
-    if (rvt_flush(ctx_, &results_[base], n, &got) != RVT_OK || got != n) {
-      fprintf(stderr, "rvtests_b200: flush failed: %s\n", error());
-      results_.resize(base);
-      return false;
+    const int nc = (int)ctx_.size();
+    std::vector<std::vector<rvt_gene_result> > res(nc);
+    std::vector<std::vector<rvt_perm_result> > prm(nc);
+    std::vector<int> ok(nc, 1);
+    std::vector<std::thread> th;
+    for (int k = 0; k < nc; ++k) {
+      if (nc == 1)
+        flushOne(k, &res[k], &prm[k], &ok[k]);
+      else
+        th.push_back(std::thread(&GeneBatcher::flushOne, this, k, &res[k], &prm[k], &ok[k]));
     }
-    perms_.resize(base + n);
-    for (int i = 0; i < n; ++i) memset(&perms_[base + i], 0, sizeof(rvt_perm_result));
-    if (perm_n_ > 0) {
-      int gotp = 0;
-      if (rvt_perm_results(ctx_, &perms_[base], n, &gotp) != RVT_OK || gotp != n) {
-        fprintf(stderr, "rvtests_b200: permutation records: %s\n", error());
-        return false;
+    for (size_t k = 0; k < th.size(); ++k) th[k].join();
+    bool all = true;
+    for (int k = 0; k < nc; ++k)
+      if (!ok[k]) {
+        last_error_ = rvt_last_error(ctx_[k]);
+        fprintf(stderr, "rvtests_b200: flush failed on device %d: %s\n", device_ + k, last_error_.c_str());
+        all = false;
       }
+    // hand the records back in arrival order; a failed device leaves NA records (status != OK) for its genes
+    std::vector<size_t> at(nc, 0);
+    for (int i = 0; i < n; ++i) {
+      const int k = owner_[i];
+      rvt_gene_result r;
+      rvt_perm_result p;
+      memset(&r, 0, sizeof(r));
+      memset(&p, 0, sizeof(p));
+      r.status = RVT_GENE_NA;
+      if (ok[k] && at[k] < res[k].size()) {
+        r = res[k][at[k]];
+        if (at[k] < prm[k].size()) p = prm[k][at[k]];
+      }
+      ++at[k];
+      results_.push_back(r);
+      perms_.push_back(p);
     }
-    return true;
+    owner_.clear();
+    return all;
   }
   int newFitterId() { return next_id_++; }
+  // adapters register for their lifetime: when the last one is gone (ModelManager::close deletes the models,
+  // src/ModelManager.cpp:304-315) the batcher forgets the run -- tickets, the current gene, the null model -- so that a
+  // second ModelManager in the same process starts clean
+  void attach() { ++n_attached_; }
+  void detach() {
+    if (--n_attached_ > 0) return;
+    if (!owner_.empty()) flush();
+    results_.clear();
+    perms_.clear();
+    seen_.clear();
+    current_ = -1;
+    have_null_ = false;
+    skato_ = false;
+    perm_n_ = 0;
+  }
 
  private:
-  GeneBatcher() : ctx_(NULL), batch_(256), skato_(false), skato_binary_(true), binary_(false), perm_n_(0), perm_alpha_(0.05), current_(-1), next_id_(0), have_null_(false) {}
+  GeneBatcher()
+      : n_attached_(0), device_(-1), n_devices_(-1), beta1_(1.0), beta2_(25.0), batch_(256), skato_(false), skato_binary_(true),
+        binary_(false), perm_n_(0), perm_alpha_(0.05), current_(-1), next_id_(0), next_ctx_(0), have_null_(false) {}
   bool seen(int id) const {
     for (size_t i = 0; i < seen_.size(); ++i)
       if (seen_[i] == id) return true;
     return false;
   }
+  void flushOne(int k, std::vector<rvt_gene_result>* res, std::vector<rvt_perm_result>* prm, int* ok) {
+    const int n = rvt_pending(ctx_[k]);
+    res->resize(n);
+    prm->clear();
+    if (n == 0) return;
+    int got = 0;
+    if (rvt_flush(ctx_[k], res->data(), n, &got) != RVT_OK || got != n) {
+      *ok = 0;
+      return;
+    }
+    if (perm_n_ > 0) {
+      prm->resize(n);
+      int gotp = 0;
+      if (rvt_perm_results(ctx_[k], prm->data(), n, &gotp) != RVT_OK || gotp != n) *ok = 0;
+    }
+  }
   bool ensureContext() {
-    if (ctx_) return true;
-    if (rvt_ctx_create(0, &ctx_) != RVT_OK) {
-      fprintf(stderr, "rvtests_b200: %s\n", error());
-      if (ctx_) rvt_ctx_destroy(ctx_);
-      ctx_ = NULL;
-      return false;  // no CPU fallback: the adapters report fit() == -1 and print NA
+    if (!ctx_.empty()) return true;
+    if (device_ < 0) {
+      const char* e = getenv("RVTESTS_B200_DEVICE");
+      device_ = e ? atoi(e) : 0;
+    }
+    if (n_devices_ < 1) {
+      const char* e = getenv("RVTESTS_B200_DEVICES");
+      n_devices_ = e ? atoi(e) : 1;
+      if (n_devices_ < 1) n_devices_ = 1;
+    }
+    if (perm_n_ > 0) n_devices_ = 1;   // one rand() stream in gene order
+    for (int k = 0; k < n_devices_; ++k) {
+      rvt_ctx* c = NULL;
+      if (rvt_ctx_create(device_ + k, &c) != RVT_OK) {
+        last_error_ = c ? rvt_last_error(c) : "context allocation failed";
+        fprintf(stderr, "rvtests_b200: %s\n", last_error_.c_str());
+        if (c) rvt_ctx_destroy(c);
+        for (size_t j = 0; j < ctx_.size(); ++j) rvt_ctx_destroy(ctx_[j]);
+        ctx_.clear();
+        return false;  // no CPU fallback: the adapters report fit() == -1 and print NA
+      }
+      ctx_.push_back(c);
     }
     return true;
   }
-  // copyCovariateAndIntercept + FitLinearModel (src/ModelUtil.h:102-130, src/Model.h:2672-2699)
+  // copyCovariateAndIntercept + FitLinearModel (src/ModelUtil.h:102-130, src/Model.h:2672-2699), on every device
   bool ensureNullModel(DC* dc) {
     if (have_null_ && !dc->isPhenotypeUpdated() && !dc->isCovariateUpdated()) return true;
-    if (rvt_pending(ctx_) > 0 && !flush()) return false;
+    if (!owner_.empty() && !flush()) return false;
     const auto& ph = dc->getPhenotype();
     const auto& cv = dc->getCovariate();
     const int n = ph.rows, c = cv.cols + 1;
@@ -136,15 +242,19 @@ class GeneBatcher {
     }
     for (int j = 0; j < cv.cols; ++j)
       for (int i = 0; i < n; ++i) X[(size_t)(j + 1) * n + i] = cv(i, j);
-    if (skato_) rvt_set_option(ctx_, "skato", 1);
-    rvt_set_option(ctx_, "skato_binary", skato_binary_ ? 1 : 0);
-    if (perm_n_ > 0) {
-      rvt_set_option(ctx_, "perm", perm_n_);
-      rvt_set_option(ctx_, "perm_alpha", perm_alpha_);
-    }
-    if (rvt_set_null_model(ctx_, n, c, X.data(), y.data(), binary_ ? 1 : 0) != RVT_OK) {
-      fprintf(stderr, "rvtests_b200: null model: %s\n", error());
-      return false;
+    for (size_t k = 0; k < ctx_.size(); ++k) {
+      rvt_ctx* c_ = ctx_[k];
+      rvt_set_option(c_, "skato", skato_ ? 1 : 0);
+      rvt_set_option(c_, "skato_binary", skato_binary_ ? 1 : 0);
+      rvt_set_option(c_, "beta1", beta1_);
+      rvt_set_option(c_, "beta2", beta2_);
+      rvt_set_option(c_, "perm", perm_n_ > 0 ? perm_n_ : 0);
+      if (perm_n_ > 0) rvt_set_option(c_, "perm_alpha", perm_alpha_);
+      if (rvt_set_null_model(c_, n, c, X.data(), y.data(), binary_ ? 1 : 0) != RVT_OK) {
+        last_error_ = rvt_last_error(c_);
+        fprintf(stderr, "rvtests_b200: null model: %s\n", last_error_.c_str());
+        return false;
+      }
     }
     have_null_ = true;
     return true;
@@ -167,49 +277,57 @@ class GeneBatcher {
     }
     std::vector<double> af(g.cols);
     for (int j = 0; j < g.cols; ++j) af[j] = dc->getMarkerFrequency(j);
-    if (rvt_gene_push_f64(ctx_, &g.data[0], g.cols, af.data()) != RVT_OK) {
-      fprintf(stderr, "rvtests_b200: push: %s\n", error());
+    const int k = next_ctx_;
+    if (rvt_gene_push_f64(ctx_[k], &g.data[0], g.cols, af.data()) != RVT_OK) {
+      last_error_ = rvt_last_error(ctx_[k]);
+      fprintf(stderr, "rvtests_b200: push: %s\n", last_error_.c_str());
       return false;
     }
-    current_ = (int)results_.size() + rvt_pending(ctx_) - 1;
+    next_ctx_ = (next_ctx_ + 1) % (int)ctx_.size();
+    owner_.push_back(k);
+    current_ = (int)results_.size() + (int)owner_.size() - 1;
     return true;
   }
 
-  rvt_ctx* ctx_;
+  int n_attached_;
+  std::vector<rvt_ctx*> ctx_;
+  int device_, n_devices_;
+  double beta1_, beta2_;
   int batch_;
   bool skato_, skato_binary_, binary_;
   int perm_n_;
   double perm_alpha_;
-  int current_, next_id_;
+  int current_, next_id_, next_ctx_;
   bool have_null_;
+  std::string last_error_;
   std::vector<int> seen_;
+  std::vector<int> owner_;   // pending genes in arrival order: the context each one was pushed to
   std::vector<rvt_gene_result> results_;
   std::vector<rvt_perm_result> perms_;
 };
 
 // Common machinery: ticket per gene, deferred lines.
-template <class DC, class FW, class RES>
-class DeferredFitter {
+template <class DC, class FW, class RES, class BASE = StandaloneBase>
+class DeferredFitter : public BASE {
  public:
-  DeferredFitter() : ticket_(-1), fp_(NULL), binary_(false) { id_ = GeneBatcher<DC>::instance().newFitterId(); }
-  virtual ~DeferredFitter() {}
-  const std::string& getModelName() const { return modelName; }
-  void setBinaryOutcome() {
-    binary_ = true;
-    GeneBatcher<DC>::instance().setBinary(true);
+  DeferredFitter() : ticket_(-1), fp_(NULL) {
+    id_ = GeneBatcher<DC>::instance().newFitterId();
+    GeneBatcher<DC>::instance().attach();
   }
-  void setQuantitativeOutcome() {
-    binary_ = false;
-    GeneBatcher<DC>::instance().setBinary(false);
+  virtual ~DeferredFitter() { GeneBatcher<DC>::instance().detach(); }
+  // ModelFitter::reset() clears the model's own Result (src/ModelFitter.h:46); the adapters keep none
+  virtual void reset() {
+    BASE::reset();
+    ticket_ = -1;
   }
-  bool isBinaryOutcome() const { return binary_; }
-  bool needToIndexResult() const { return false; }
-  void reset() { ticket_ = -1; }
-  int fit(DC* dc) {
+  virtual int fit(DC* dc) {
+    // ModelManager flips the (non-virtual) outcome flag of every model alike (src/ModelManager.cpp:274-282): read it here
+    GeneBatcher<DC>::instance().setBinary(this->isBinaryOutcome());
     ticket_ = GeneBatcher<DC>::instance().submit(id_, dc);
     return ticket_ >= 0 ? 0 : -1;
   }
-  void writeOutput(FW* fp, const RES& siteInfo) {
+  virtual void writeHeader(FW* fp, const RES& siteInfo) = 0;
+  virtual void writeOutput(FW* fp, const RES& siteInfo) {
     fp_ = fp;
     Pending p;
     p.ticket = ticket_;
@@ -217,7 +335,7 @@ class DeferredFitter {
     pending_.push_back(p);
     if (GeneBatcher<DC>::instance().shouldFlush()) drain();
   }
-  void writeFootnote(FW* fp) {
+  virtual void writeFootnote(FW* fp) {
     if (!fp_) fp_ = fp;
     drain();
   }
@@ -229,11 +347,9 @@ class DeferredFitter {
   }
   void drain() {
     if (!fp_) return;
-    GeneBatcher<DC>& b = GeneBatcher<DC>::instance();
     for (size_t i = 0; i < pending_.size(); ++i) {
       std::string line = pending_[i].site;
       line += "\t";
-      (void)b;
       formatTicket(pending_[i].ticket, &line);
       line += "\n";
       fp_->write(line.c_str());
@@ -245,7 +361,6 @@ class DeferredFitter {
     snprintf(buf, sizeof(buf), "%g", v);
     return buf;
   }
-  std::string modelName;
 
  private:
   struct Pending {
@@ -254,16 +369,16 @@ class DeferredFitter {
   };
   int id_, ticket_;
   FW* fp_;
-  bool binary_;
   std::vector<Pending> pending_;
 };
 
-template <class DC, class FW, class RES>
-class SkatTestB200 : public DeferredFitter<DC, FW, RES> {
+template <class DC, class FW, class RES, class BASE = StandaloneBase>
+class SkatTestB200 : public DeferredFitter<DC, FW, RES, BASE> {
  public:
   // SkatTest(int nPerm, double alpha, double beta1, double beta2), src/Model.h:2615-2622 (beta1/beta2: engine options)
-  explicit SkatTestB200(int nPerm = 0, double alpha = 0.05) : usePermutation_(nPerm > 0) {
+  explicit SkatTestB200(int nPerm = 0, double alpha = 0.05, double beta1 = 1.0, double beta2 = 25.0) : usePermutation_(nPerm > 0) {
     this->modelName = "Skat";
+    GeneBatcher<DC>::instance().setBeta(beta1, beta2);
     if (usePermutation_) GeneBatcher<DC>::instance().enablePerm(nPerm, alpha);
   }
   ~SkatTestB200() { this->drain(); }
@@ -303,11 +418,12 @@ class SkatTestB200 : public DeferredFitter<DC, FW, RES> {
   bool usePermutation_;
 };
 
-template <class DC, class FW, class RES>
-class SkatOTestB200 : public DeferredFitter<DC, FW, RES> {
+template <class DC, class FW, class RES, class BASE = StandaloneBase>
+class SkatOTestB200 : public DeferredFitter<DC, FW, RES, BASE> {
  public:
-  SkatOTestB200() {
+  explicit SkatOTestB200(double beta1 = 1.0, double beta2 = 25.0) {   // SkatOTest(beta1, beta2), src/Model.h:2776-2783
     this->modelName = "SkatO";
+    GeneBatcher<DC>::instance().setBeta(beta1, beta2);
     GeneBatcher<DC>::instance().enableSkatO();
   }
   ~SkatOTestB200() { this->drain(); }
@@ -326,8 +442,8 @@ class SkatOTestB200 : public DeferredFitter<DC, FW, RES> {
   }
 };
 
-template <class DC, class FW, class RES>
-class CMCTestB200 : public DeferredFitter<DC, FW, RES> {
+template <class DC, class FW, class RES, class BASE = StandaloneBase>
+class CMCTestB200 : public DeferredFitter<DC, FW, RES, BASE> {
  public:
   CMCTestB200() { this->modelName = "CMC"; }
   ~CMCTestB200() { this->drain(); }
@@ -348,8 +464,8 @@ class CMCTestB200 : public DeferredFitter<DC, FW, RES> {
   }
 };
 
-template <class DC, class FW, class RES>
-class ZegginiTestB200 : public DeferredFitter<DC, FW, RES> {
+template <class DC, class FW, class RES, class BASE = StandaloneBase>
+class ZegginiTestB200 : public DeferredFitter<DC, FW, RES, BASE> {
  public:
   ZegginiTestB200() { this->modelName = "Zeggini"; }
   ~ZegginiTestB200() { this->drain(); }

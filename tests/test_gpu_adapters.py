@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def build_demo():
     exe = os.path.join(ROOT, "rvtests_b200", "host", "adapter_demo")
     src = os.path.join(ROOT, "rvtests_b200", "host", "adapter_demo.cpp")
-    subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+    subprocess.run(["g++", "-std=c++11", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
                     "-L", os.path.join(ROOT, "rvtests_b200"), "-lrvtests_b200",
                     "-Wl,-rpath," + os.path.join(ROOT, "rvtests_b200")], check=True)
     return exe
@@ -123,7 +123,7 @@ def test_skat_adapter_with_permutations(oracle, tmp_path):
 def build_meta_demo():
     exe = os.path.join(ROOT, "rvtests_b200", "host", "meta_demo")
     src = os.path.join(ROOT, "rvtests_b200", "host", "meta_demo.cpp")
-    subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+    subprocess.run(["g++", "-std=c++11", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
                     "-L", os.path.join(ROOT, "rvtests_b200"), "-lrvtests_b200",
                     "-Wl,-rpath," + os.path.join(ROOT, "rvtests_b200")], check=True)
     return exe

@@ -35,7 +35,10 @@ for rep in range(2):                             # the first flush pays the one-
     t = time.perf_counter()
     vout, band, wmax = eng.meta_flush(nv, pos, chrom, window)
     dt = time.perf_counter() - t
-    print(f"rep {rep}: push {t_push:.3f} s (pageable host blocks), flush {dt:.3f} s", flush=True)
+    tm = eng.last_timing()
+    print(f"rep {rep}: push {t_push:.3f} s (pageable host blocks), flush {dt:.3f} s; device: diagonal tiles + score statistics "
+          f"{tm['finalize_ms']:.1f} ms, {int(tm['launches'])} tile pairs + band {tm['sweep_ms']:.1f} ms, total {tm['total_ms']:.1f} ms, "
+          f"S = {int(eng.info('last_splits'))}", flush=True)
 pairs = int(np.sum(~np.isnan(band)))
 tiles = nv // 64
 units = tiles + sum(min(tiles - 1 - k, (wmax + 63) // 64 + 1) for k in range(tiles))
@@ -43,4 +46,8 @@ print(f"meta score+cov: {dt:.3f} s for {nv} variants, wmax = {wmax}, {pairs} cov
       f"-> {nv / dt:.0f} variants/s, {pairs / dt / 1e6:.1f} M cov entries/s (each a length-{N} dot product: "
       f"{2 * N * pairs / dt / 1e12:.1f} Tflop/s equivalent); ~{units} sweep units x <= {2 * 64 * N / 1e6:.0f} MB")
 print(f"  median p {np.median(vout['pvalue'][vout['ok'] == 1]):.3f}, polymorphic {int(vout['polymorphic'].sum())}/{nv}")
+pair_bytes = tm["launches"] * 2 * 64 * N
+print(f"  pair phase: {pair_bytes / 1e9:.1f} GB of operand bytes through the tensor core in {tm['sweep_ms']:.1f} ms = "
+      f"{pair_bytes / tm['sweep_ms'] / 1e9:.2f} TB/s operand rate (HBM copy peak 6.45 TB/s: above it = served from L2); "
+      f"{2.0 * 64 * 64 * N * tm['launches'] / tm['sweep_ms'] / 1e9:.0f} T-op/s int8")
 print(f"  extrapolation to 1 M variants: {1e6 / (nv / dt) / 60:.1f} min on one B200 (data streamed in segments), /8 on eight")
