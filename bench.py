@@ -49,6 +49,10 @@ def parse():
     ap.add_argument("--e2e-genes", type=int, default=256, help="genes per step of the host-buffer (e2e) leg (a quarter of it for the int8 form)")
     ap.add_argument("--cpu-genes", type=int, default=16, help="distinct genes of the CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
+    ap.add_argument("--workload", default="skat", choices=["skat", "meta"],
+                    help="skat: the headline metric (default).  meta: --meta score,cov at the BASELINE configs[3] shape")
+    ap.add_argument("--meta-variants", type=int, default=8192, help="variants per GPU and step of --workload meta")
+    ap.add_argument("--meta-spacing", type=int, default=1000, help="bp between consecutive variants (window 1 Mb)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -593,9 +597,245 @@ def run_reference(args):
     }))
 
 
+# ---------------------------------------------------------------------------------------------------
+META_METRIC = "variants/sec (--meta score,cov, 500k samples, MetaCov window 1 Mb)"
+
+
+def meta_config(args):
+    return {"workload": f"--meta score,cov: N={args.samples} samples, {args.meta_variants} variants per GPU and step, one variant "
+                        f"every {args.meta_spacing} bp, window 1 Mb (BASELINE configs[3] in blocks + one-window halo), C={args.covariates}",
+            "samples": args.samples, "variants_per_gpu": args.meta_variants, "spacing_bp": args.meta_spacing,
+            "window_bp": 1_000_000, "covariates_incl_intercept": args.covariates,
+            "l2_policy": "the covariance band is walked sample-chunk by sample-chunk so that a window's tiles are re-used from "
+                         "L2 BY DESIGN (that reuse is the algorithm); every step starts from HBM: 4.6 GB of genotypes per step "
+                         ">> 126 MB L2"}
+
+
+def run_meta(args):
+    """--meta score,cov: per rank a block of consecutive variants plus a one-window halo (the variants of the next block
+    that the last variants of this one pair with), all resident as 64-variant tiles; a step = score statistics + exact HWE
+    of every variant + the covariance band of the block; N > 1: one NCCL all_gather of the bands."""
+    import torch
+    import torch.distributed as dist
+    import rvtests_b200
+    from rvtests_b200.synth import variant_params, covariates
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    numa = bind_numa(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    N, nv, window = args.samples, args.meta_variants, 1_000_000
+    halo = ((window // args.meta_spacing + 63) // 64) * 64          # variants of the next block inside the last window
+    nall = nv + halo
+    keys, t0, t1 = variant_params(SEED, rank * nv, nall)            # (the halo IS the next rank's first variants)
+    X, y = covariates(SEED, N, args.covariates)
+    eng = rvtests_b200.GeneEngine(local)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_null_model(X, y)
+    eng.synth_load(keys, t0, t1, nall // 64, 64)
+    pos = (args.meta_spacing * (rank * nv + np.arange(nall))).astype(np.int32)
+    chrom = np.ones(nall, dtype=np.int32)
+    eng.push_loaded()
+    _, _, wmax = eng.meta_flush(nall, pos, chrom, window)             # plan + first-use allocations (host outputs)
+    rec = rvtests_b200.engine.VARIANT_DTYPE.itemsize
+    d_v = torch.empty(nall * rec, dtype=torch.uint8, device=dev)
+    d_band = torch.empty(nall * (wmax + 1), dtype=torch.float64, device=dev)
+    d_all = torch.empty(world * nv * (wmax + 1), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        eng.push_loaded()
+        eng.meta_flush_dev(nall, pos, chrom, window, d_v.data_ptr(), d_band.data_ptr(), d_band.numel())
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_band[: nv * (wmax + 1)])
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_w, nw = time.perf_counter(), 0
+    while nw < max(args.warmup, 3) or time.perf_counter() - t_w < 0.5:
+        step()
+        nw += 1
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pair_ms, diag_ms, pairs = [], [], 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+        t = eng.last_timing()
+        pair_ms.append(t["sweep_ms"])
+        diag_ms.append(t["finalize_ms"])
+        pairs = t["launches"]
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item()) / args.steps
+    # ---- e2e: 2-bit rows from pinned host memory in, records + band to pinned host memory out
+    from rvtests_b200.synth import pack_bed
+    calls = eng.loaded_read(0, nall)
+    host = torch.empty((nall, (N + 3) // 4), dtype=torch.uint8, pin_memory=True)
+    host.numpy()[:] = pack_bed(calls)
+    hn = host.numpy()
+    h_v = torch.empty(nall * rec, dtype=torch.uint8, pin_memory=True)
+    h_band = torch.empty(nall * (wmax + 1), dtype=torch.float64, pin_memory=True)
+
+    def e2e_step():
+        for b0 in range(0, nall, 64):
+            eng.push_bed(hn[b0:b0 + 64], None)
+        eng.meta_flush_dev(nall, pos, chrom, window, h_v.data_ptr(), h_band.data_ptr(), h_band.numel())
+
+    e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = 2
+    tw = time.perf_counter()
+    for _ in range(reps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - tw], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_s = float(dt.item()) / reps
+    if rank == 0:
+        vout = np.frombuffer(d_v.cpu().numpy().tobytes(), dtype=rvtests_b200.engine.VARIANT_DTYPE)
+        band = d_band.cpu().numpy().reshape(nall, wmax + 1)
+        pk = peaks()
+        pair_s = float(np.mean(pair_ms)) * 1e-3
+        ops = 2.0 * 64 * 64 * N * pairs                         # every tile pair is a 64 x 64 x N int8 GEMM
+        tens_peak = (pk.get("bf16_tflops_sustained") or pk.get("bf16_tflops")) if pk else 1590.0
+        operand_bytes = 2.0 * 64 * N * pairs
+        alg_bytes = float(nall) * N                             # every genotype byte once
+        out = {
+            "metric": META_METRIC, "value": world * nv / (ms * 1e-3), "unit": "variants/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "s8 x s8 -> s32 (exact) + f64 tail", "data": "synthetic", "config": meta_config(args),
+            "kernel_ms_per_step": {"tile pairs (k_sweep_tc PAIR) + band assembly": float(np.mean(pair_ms)),
+                                   "diagonal tiles + score statistics + exact HWE": float(np.mean(diag_ms))},
+            "tile_pairs_per_step": int(pairs), "cov_entries_per_step": int(np.sum(~np.isnan(band[:nv]))),
+            "gpu_launches": int(args.steps * (2 * ((nall // 64 + 1023) // 1024) + 1 + 2 * ((pairs + 1023) // 1024))),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "k_sweep_tc (PAIR mode)", "achieved": ops / pair_s / 1e12, "peak": tens_peak,
+                         "unit": "TFLOP/s", "frac": ops / pair_s / 1e12 / tens_peak,
+                         "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if pk else "fallback (of fallback)"),
+                         "note": "s8 tcgen05 operations counted as flops against the dense bf16 peak (the int8 pipe's own peak is "
+                                 "twice that); 64 x 64 x 32 UMMAs, whose issue cost (~76 clk) is the limit of this tiling",
+                         "algorithmic_flops_per_launch": ops,
+                         "operand_tb_per_s": operand_bytes / pair_s / 1e12,
+                         "operand_note": "bytes of A and B tiles fed to the tensor core per second; above the HBM copy peak "
+                                         "means the band is served from L2 (split-major walk of the pair units)",
+                         "traffic": None},
+            "engine": {"splits": int(eng.info("last_splits")), "numa": numa,
+                       "parallelism": f"variant blocks + one-window halo over {world} rank(s), one NCCL all_gather of the band"},
+            "sanity": {"variants_ok": int(vout["ok"][:nv].sum()), "median_p": float(np.median(vout["pvalue"][:nv][vout["ok"][:nv] == 1])),
+                       "median_hwe_p": float(np.median(vout["hwe_p"][:nv]))},
+            "e2e": {"value": world * nv / e2e_s, "unit": "variants/s",
+                    "h2d_bytes_per_step": int(world * nall * hn.shape[1]),
+                    "d2h_bytes_per_step": int(world * (nall * rec + nall * (wmax + 1) * 8)),
+                    "host_format": "PLINK .bed 2-bit rows in pinned host memory -> rvt_gene_push_bed; records and the covariance band "
+                                   "copied back to pinned host memory", "timing": "host wall clock, max over ranks"},
+        }
+        if not args.no_cpu and world == 1:
+            out["parity"], out["cpu_baseline"] = meta_cpu_leg(args, eng, vout, band, pos, chrom, window, X, y)
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def meta_cpu_leg(args, eng, vout, band, pos, chrom, window, X, y, n_check=96):
+    """oracle/meta_oracle.py (numpy restatement of MetaScoreTest / MetaCovTest, pinned on the reference model layer) on the
+    first n_check variants with a window cut to them: checker of the records of the timed steps AND the timed CPU baseline."""
+    from oracle import oracle as O
+    from oracle import meta_oracle as MO
+    O.build()
+    N = args.samples
+    G = eng.loaded_read(0, n_check).T.astype(np.float64)          # (N, n_check)
+    nm = O.fit_null_linear(X, y)
+    t = time.perf_counter()
+    sc = [MO.meta_score(G[:, j], X, nm["resid"], nm["sigma2"]) for j in range(n_check)]
+    cv = MO.meta_cov(G, pos[:n_check], chrom[:n_check], X, nm["sigma2"], window)
+    dt = time.perf_counter() - t
+
+    def rel(a, b):
+        a, b = float(a), float(b)
+        return 0.0 if a == b else abs(a - b) / max(abs(a), abs(b), 1e-300)
+
+    worst = {"U": 0.0, "sqrtV": 0.0, "pvalue": 0.0, "hwe_p": 0.0, "cov": 0.0}
+    exact = True
+    for j in range(n_check):
+        r, o = vout[j], sc[j]
+        exact &= (int(r["n_ref"]), int(r["n_het"]), int(r["n_alt"])) == (o["n_ref"], o["n_het"], o["n_alt"])
+        worst["hwe_p"] = max(worst["hwe_p"], rel(r["hwe_p"], o["hwe_p"]))
+        if o.get("ok"):
+            for k in ("U", "sqrtV", "pvalue"):
+                worst[k] = max(worst[k], rel(r[k], o[k]))
+        if cv[j] is not None:
+            for pj, val in zip(*cv[j]):
+                d = (pj - int(pos[j])) // args.meta_spacing
+                worst["cov"] = max(worst["cov"], abs(band[j, d] - val) / max(abs(val), abs(cv[j][1][0]) * 1e-6, 1e-300))
+    ok = exact and worst["U"] <= 1e-6 and worst["sqrtV"] <= 1e-6 and worst["pvalue"] <= 1e-4 and worst["hwe_p"] <= 1e-9 and worst["cov"] <= 1e-5
+    parity = {"variants_checked": n_check, "pass": bool(ok), "max_rel_err": worst, "counts_exact": bool(exact),
+              "tolerances": {"U, sqrtV": 1e-6, "pvalue": 1e-4, "hwe_p": 1e-9, "cov (relative to the variant's variance)": 1e-5},
+              "checker": "oracle/meta_oracle.py (pinned on the reference's MetaScoreTest / MetaCovTest text)"}
+    cpu = {"value": n_check / dt, "unit": "variants/s", "cores": 1, "kind": "port",
+           "sample": f"{n_check} variants of N={N} with all their pairs inside the sample ({n_check * (n_check + 1) // 2} covariances) in {dt:.1f} s: "
+                     "numpy restatement of MetaScoreTest + MetaCovTest (oracle/meta_oracle.py), single thread; the full window "
+                     f"({window // args.meta_spacing} partners per variant) would cost ~{window // args.meta_spacing / (n_check / 2):.0f}x more per variant"}
+    return parity, cpu
+
+
+def run_reference_meta(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from oracle import meta_oracle as MO
+    O.build()
+    from rvtests_b200.synth import variant_params, covariates
+    N, n_s = args.samples, 64
+    keys, t0, t1 = variant_params(SEED, 0, n_s)
+    G = O.synth_rows_f64(keys, t0, t1, N, threads=0).reshape(n_s, N).T.copy()
+    X, y = covariates(SEED, N, args.covariates)
+    nm = O.fit_null_linear(X, y)
+    pos = (args.meta_spacing * np.arange(n_s)).astype(np.int32)
+    chrom = np.ones(n_s, dtype=np.int32)
+    vals = []
+    for k in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        [MO.meta_score(G[:, j], X, nm["resid"], nm["sigma2"]) for j in range(n_s)]
+        MO.meta_cov(G, pos, chrom, X, nm["sigma2"], 1_000_000)
+        dt = time.perf_counter() - t
+        if k >= args.warmup:
+            vals.append((n_s / dt, dt))
+    value = float(np.mean([v[0] for v in vals]))
+    sample = (f"each step = {n_s} variants of N={N} with the {n_s * (n_s + 1) // 2} covariances among them "
+              f"(the full 1 Mb window has {1_000_000 // args.meta_spacing} partners per variant, ~{1_000_000 // args.meta_spacing / (n_s / 2):.0f}x the work), "
+              "oracle/meta_oracle.py (numpy), single thread")
+    print(json.dumps({
+        "impl": "reference", "metric": META_METRIC, "value": value, "unit": "variants/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean([v[1] for v in vals])) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": meta_config(args),
+        "cpu_baseline": {"value": value, "unit": "variants/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
-        run_reference(a)
+        run_reference_meta(a) if a.workload == "meta" else run_reference(a)
+    elif a.workload == "meta":
+        run_meta(a)
     else:
         run_ours(a)

@@ -83,7 +83,10 @@ typedef struct rvt_gene_result {
  * flush, the columns Permutation::writeOutput prints (src/Permutation.h:118-139).  Enabled by
  * rvt_set_option("perm", nPerm) [+ "perm_alpha"]; the shuffles replay glibc's default rand() stream exactly as the
  * reference's serial gene loop consumes it (src/LinearAlgebra.h:8-21, no srand anywhere), starting at
- * "perm_stream_pos" draws (0 in a fresh process) and advancing by ActualPerm * (N-1) per gene. */
+ * "perm_stream_pos" draws (0 in a fresh process) and advancing by ActualPerm * (N-1) per gene.  Quantitative and binary
+ * traits alike (src/Model.h:2673-2717).  NOT covered: a gene with dosages or missing calls (done = 0, NA columns); the
+ * reference would have shuffled for it, so from such a gene on the stream position -- hence NumGreater / NumEqual of the
+ * LATER genes -- no longer replays the reference's.  rvt_perm_result.stream_pos tells where each gene started. */
 typedef struct rvt_perm_result {
   int32_t num_perm;      /* NumPerm */
   int32_t actual_perm;   /* ActualPerm */
@@ -141,7 +144,7 @@ int rvt_set_stream(rvt_ctx* ctx, void* cuda_stream);
  * binary != 0: y in {0,1}; LogisticRegression::FitLogisticModel(cov, phenoVec, 100) (regression/LogisticRegression.cpp:279-339)
  *   on the device, then SKAT / CMC / Zeggini with r = y - p and the per-sample variance v = p(1-p) (src/Model.h:2673-2681,
  *   LogisticRegressionScoreTest.cpp:219-302).  Such genes take the engine's fp64 path (<= 64 variants); SKAT-O is type "D"
- *   (option "skato_binary", default on) and the permutation test is not provided for a binary trait (done = 0).  rvt_get_null_model then returns
+ *   (option "skato_binary", default on); the permutation test runs as for a quantitative trait.  rvt_get_null_model then returns
  *   r, sigma2 = 1 and (X'VX)^-1. */
 int rvt_set_null_model(rvt_ctx* ctx, int64_t N, int C, const double* X, const double* y, int binary);
 /* "bring your own null": the caller supplies the score vector r (length N) and the variance scale
@@ -227,6 +230,9 @@ int rvt_flush_dev(rvt_ctx* ctx, rvt_gene_result* d_out, int cap, int* n_out);
 int rvt_synth_load(rvt_ctx* ctx, int n_genes, int M, const uint64_t* keys, const uint32_t* t0,
                    const uint32_t* t1);
 int rvt_loaded_genes(const rvt_ctx* ctx);
+/* queue every loaded gene (zero-copy) without flushing: followed by rvt_flush, or -- the genes then being 64-variant tiles of
+ * consecutive variants -- by rvt_meta_flush (bench.py --workload meta) */
+int rvt_push_loaded(rvt_ctx* ctx);
 int rvt_run_loaded(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, int results_on_device);
 /* copy rows [row0,row0+rows) x samples [0,N) of the loaded arena back to the host (tests) */
 int rvt_loaded_read(rvt_ctx* ctx, int64_t row0, int rows, int8_t* out /*rows x N*/);
@@ -243,7 +249,11 @@ int rvt_loaded_read(rvt_ctx* ctx, int64_t row0, int rows, int8_t* out /*rows x N
  *   rvt_meta_flush: vout[nv] = one rvt_variant_result per variant; band (may be NULL: score only) =
  *                   nv x (wmax+1) doubles, band[v*(wmax+1)+d] = COV entry of variants (v, v+d) divided
  *                   by N as the reference prints it; NaN where either variant is monomorphic (such
- *                   variants are never queued by MetaCovTest) or v+d is outside v's window. */
+ *                   variants are never queued by MetaCovTest) or v+d is outside v's window.
+ *                   vout / band may be host or device pointers.
+ * Mixed-model band: after rvt_set_null_residual (Bolt score step) set option "meta_cov_scale" = rvt_bolt_null.xvx_xx_ratio:
+ *                   the entries are then BoltLMM::GetCovXX / N = g_v'(I - ZZ')g_{v+d} * xVx_xx_ratio / N
+ *                   (regression/BoltLMM.cpp:435-460, MetaCovFamQtlBolt, src/Model.cpp:780-805); 0 restores the default. */
 typedef struct rvt_variant_result {
   double af;          /* AF                 GenotypeCounter::getAF */
   double ac;          /* INFORMATIVE_ALT_AC GenotypeCounter::getAC */

@@ -119,4 +119,83 @@ int dropin_run_gene_models(int N, int n_genes, const int* M, const double* G, in
   }   // ModelManager::close: writeFootnote + delete models, then the writers
   return 0;
 }
+
+// Single-variant loop of src/Main.cpp:1092-1147 through ModelManager::create("meta", "score[se],cov[windowSize=..]"): variant j
+// is column j of G (N x n_var column-major raw genotypes) at 1:pos[j].  Writes <prefix>.MetaScore.assoc.gz and
+// <prefix>.MetaCov.assoc.gz -- plain text here: the writer behind FileWriter(.., BGZIP) is the stdio stand-in of
+// ref_model_shim.cpp, and the tabix step of ModelManager::close is stubbed.
+int dropin_run_meta_models(int N, int n_var, const double* G, const int* pos, int n_cov, const double* cov, const double* pheno,
+                           const char* meta, int use_b200, int segment, const char* prefix) {
+  if (!logger) logger = new Logger((std::string(prefix) + ".log").c_str());
+  {
+    delete g_SummaryHeader;   // the trait / covariate summaries MetaScoreTest prints in its header (src/Main.cpp:775-780)
+    g_SummaryHeader = new SummaryHeader;
+    SimpleMatrix m(N, n_cov);
+    std::vector<std::string> names;
+    for (int j = 0; j < n_cov; ++j) {
+      for (int i = 0; i < N; ++i) m[i][j] = cov[(size_t)j * N + i];
+      char b[32];
+      snprintf(b, sizeof b, "cov%d", j);
+      names.push_back(b);
+    }
+    m.setColName(names);
+    g_SummaryHeader->recordCovariate(m);
+    g_SummaryHeader->recordPhenotype("Trait", std::vector<double>(pheno, pheno + N));
+  }
+  if (use_b200)
+    setenv("RVTESTS_B200", "1", 1);
+  else
+    unsetenv("RVTESTS_B200");
+  if (use_b200 && segment > 0) rvtb200::MetaBatcher<DataConsolidator>::instance().setSegment(segment);
+  Matrix phenotypeMatrix, covariate;
+  fill(pheno, N, 1, &phenotypeMatrix);
+  fill(cov, N, n_cov, &covariate);
+  for (int j = 0; j < n_cov; ++j) {
+    char b[32];
+    snprintf(b, sizeof b, "cov%d", j);
+    covariate.SetColumnLabel(j, b);
+  }
+  ParRegion par;
+  DataConsolidator dc;
+  dc.setStrategy(DataConsolidator::IMPUTE_MEAN);
+  dc.setParRegion(&par);
+  {
+    ModelManager modelManager(prefix);
+    modelManager.setQuantitativeOutcome();
+    modelManager.create("meta", meta);
+    const std::vector<ModelFitter*>& model = modelManager.getModel();
+    const std::vector<FileWriter*>& fOuts = modelManager.getResultFile();
+    const size_t numModel = model.size();
+    Result& buf = dc.getResult();
+    buf.addHeader("CHROM");
+    buf.addHeader("POS");
+    buf.addHeader("REF");
+    buf.addHeader("ALT");
+    buf.addHeader("N_INFORMATIVE");
+    for (size_t m = 0; m < numModel; m++) model[m]->writeHeader(fOuts[m], buf);
+    Matrix& genotype = dc.getOriginalGenotype();
+    for (int j = 0; j < n_var; ++j) {
+      fill(G + (size_t)j * N, N, 1, &genotype);
+      char b[32];
+      snprintf(b, sizeof b, "1:%d", pos[j]);
+      genotype.SetColumnLabel(0, b);
+      std::vector<GenotypeCounter> counter(1);
+      for (int i = 0; i < N; ++i) counter[0].add(genotype(i, 0));
+      dc.setGenotypeCounter(counter);
+      buf.clearValue();
+      buf.updateValue("CHROM", "1");
+      buf.updateValue("POS", pos[j]);
+      buf.updateValue("REF", "A");
+      buf.updateValue("ALT", "C");
+      dc.consolidate(phenotypeMatrix, covariate, genotype);
+      buf.updateValue("N_INFORMATIVE", toString(genotype.rows));
+      for (size_t m = 0; m != numModel; m++) {
+        model[m]->reset();
+        model[m]->fit(&dc);
+        model[m]->writeOutput(fOuts[m], buf);
+      }
+    }
+  }
+  return 0;
+}
 }

@@ -223,6 +223,14 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
       o.p_skat = o.p_liu = 1.0;
       o.p_davies = -1.0;
       res[g] = o;
+      if constexpr (SKATO) {
+        if (jobs) {   // nothing for k_skato_qags to do (an unset job would be read as garbage)
+          jobs[g].run = 0;
+          jobs[g].ok = 0;
+          jobs[g].n_lam = 0;
+          jobs[g].Q = jobs[g].rho = jobs[g].pvalue = 0.0;
+        }
+      }
     }
     return;
   }

@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(kMetaThreads)
 k_meta_block(const GeneDesc* __restrict__ tiles, int n_tiles, const NullModel* __restrict__ nm, int S, const SweepPartial* __restrict__ parts,
              const int* __restrict__ jmax /*[nv] last partner (variant index)*/, int wmax,
              rvt_variant_result* __restrict__ vout, double* __restrict__ Bmat /*[nv][kMaxC]*/,
-             uint8_t* __restrict__ poly /*[nv]*/, double* __restrict__ band /*[nv][wmax+1] or null*/) {
+             uint8_t* __restrict__ poly /*[nv]*/, double* __restrict__ band /*[nv][wmax+1] or null*/,
+             double band_scale /* > 0: entries are (projected Gram) * band_scale instead of / (sigma2 N) */) {
   __shared__ long long De[kTileRows][kMaxER];
   __shared__ long long s_ajj[kTileRows];
   __shared__ double s_B[kTileRows][kMaxC];
@@ -231,7 +232,7 @@ k_meta_block(const GeneDesc* __restrict__ tiles, int n_tiles, const NullModel* _
   __syncthreads();
   if (!band) return;
   // within-tile covariance band
-  const double scale = 1.0 / (sigma2 * (double)N);
+  const double scale = band_scale > 0.0 ? band_scale : 1.0 / (sigma2 * (double)N);
   for (int idx = tid; idx < M * M; idx += kMetaThreads) {
     const int i = idx / M, j = idx - i * M;
     if (j < i) continue;
@@ -257,14 +258,14 @@ k_meta_block(const GeneDesc* __restrict__ tiles, int n_tiles, const NullModel* _
 __global__ void __launch_bounds__(kMetaThreads)
 k_meta_pair(const GeneDesc* __restrict__ pairs, int n_pairs, const NullModel* __restrict__ nm, int S, const SweepPartial* __restrict__ parts,
             const int* __restrict__ jmax, int wmax, const double* __restrict__ Bmat,
-            const uint8_t* __restrict__ poly, double* __restrict__ band) {
+            const uint8_t* __restrict__ poly, double* __restrict__ band, double band_scale) {
   const int p = blockIdx.x, tid = threadIdx.x;
   if (p >= n_pairs) return;
   const GeneDesc gd = pairs[p];
   const int Ma = gd.M, Mb = gd.Mb;
   const int64_t va = gd.var0, vb = gd.var0_b;
   const int C = nm->C;
-  const double scale = 1.0 / (nm->sigma2 * (double)nm->N);
+  const double scale = band_scale > 0.0 ? band_scale : 1.0 / (nm->sigma2 * (double)nm->N);
   const SweepPartial* __restrict__ gp = parts + (size_t)p * S;
   for (int idx = tid; idx < Ma * Mb; idx += kMetaThreads) {
     const int i = idx / Mb, j = idx - i * Mb;

@@ -159,6 +159,7 @@ struct rvt_ctx {
   cudaEvent_t ev_swept[2] = {nullptr, nullptr}, ev_fin_done[2] = {nullptr, nullptr};
   bool fin_busy[2] = {false, false};
   unsigned long long batch_seq = 0;
+  double meta_cov_scale = 0.0;     // > 0: mixed-model (Bolt) covariance band, see rvt_meta_flush
   int qags_pack = 1;               // SKAT-O quadrature: 1 = three genes per persistent 128-thread CTA (k_skato_qags_packed)
   long long wd_cycles = 8000000000ll;   // device watchdog of the per-gene tail, SM cycles (option "watchdog_ms"; ~4 s)
   bool skato = false;
@@ -395,6 +396,9 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "tc_stages") {
     if (value != 3 && value != 4 && value != 5) CTX_FAIL(RVT_E_BADARG, "tc_stages must be 3, 4 or 5");
     ctx->tc.stages = (int)value;
+  } else if (k == "meta_cov_scale") {
+    if (value < 0) CTX_FAIL(RVT_E_BADARG, "meta_cov_scale must be >= 0");
+    ctx->meta_cov_scale = value;
   } else if (k == "qags_pack") {
     ctx->qags_pack = value != 0;
   } else if (k == "watchdog_ms") {
@@ -819,18 +823,30 @@ static int land_release(rvt_ctx* ctx, int slot) {
   return RVT_OK;
 }
 static int launch_range(rvt_ctx* ctx, int g0, int g1);
-// SKAT-O quadrature of the nb genes whose jobs sit in ctx->d_jobs (records at d_res[out_index ? out_index[i] : i])
-static int launch_qags(rvt_ctx* ctx, int nb, rvt_gene_result* d_res, const int* d_index, cudaStream_t st) {
+// SKAT-O quadrature of nb genes (jobs[i] -> record d_res[out_index ? out_index[i] : i]).  One launch for as many genes as
+// possible: the kernel is latency-bound (serial Davies evaluations), so what it needs is resident warps -- 2 500 genes in
+// one launch run at 6 CTAs per SM where two launches of 1 250 ran at 3 (profiles/r02g_qags_ncu.txt).
+static size_t qags_scratch_entries(const rvt_ctx* ctx, int nb) {
+  if (!ctx->qags_pack) return (size_t)std::min(nb, 2048);
+  return (size_t)std::max(1, std::min((nb + kQagsSlots - 1) / kQagsSlots, 6 * ctx->sm_count)) * kQagsSlots;
+}
+static int launch_qags(rvt_ctx* ctx, const SkatoJob* jobs, int nb, rvt_gene_result* d_res, const int* d_index, cudaStream_t st) {
+  if (nb <= 0) return RVT_OK;
   if (!ctx->qags_pack) {
-    k_skato_qags<<<nb, kQagsThreads, 0, st>>>(ctx->d_jobs, nb, ctx->d_qags, d_res, d_index, ctx->wd_cycles);
+    for (int b0 = 0; b0 < nb; b0 += 2048) {   // one interval list per gene: bounded scratch
+      const int n = std::min(2048, nb - b0);
+      k_skato_qags<<<n, kQagsThreads, 0, st>>>(jobs + b0, n, ctx->d_qags, d_index ? d_res : d_res + b0, d_index ? d_index + b0 : nullptr,
+                                               ctx->wd_cycles);
+    }
   } else {
-    const int grid = std::max(1, std::min((nb + kQagsSlots - 1) / kQagsSlots, 6 * ctx->sm_count));
+    const int grid = (int)(qags_scratch_entries(ctx, nb) / kQagsSlots);
     RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(unsigned int), st));
-    k_skato_qags_packed<<<grid, kQagsPackThreads, 0, st>>>(ctx->d_jobs, nb, ctx->d_qags, d_res, d_index, ctx->wd_cycles, ctx->d_counter + 1);
+    k_skato_qags_packed<<<grid, kQagsPackThreads, 0, st>>>(jobs, nb, ctx->d_qags, d_res, d_index, ctx->wd_cycles, ctx->d_counter + 1);
   }
   RVT_CUDA_OK(cudaGetLastError());
   return RVT_OK;
 }
+
 static int maybe_stream(rvt_ctx* ctx) {
   const int n = (int)ctx->genes.size();
   if (ctx->stream_batch > 0 && n - ctx->launched >= ctx->stream_batch) return launch_range(ctx, ctx->launched, n);
@@ -1084,8 +1100,8 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
   const bool ovl = ctx->overlap > 0 && !ctx->binary;
   if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)batch * Sp * (ovl ? 2 : 1), sizeof(SweepPartial)))) return rc;
   if (ctx->skato) {
-    if ((rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)batch + kQagsSlots, sizeof(QagsScratch)))) return rc;
-    if ((rc = ensure(ctx, (void**)&ctx->d_jobs, &ctx->cap_jobs, (size_t)batch, sizeof(SkatoJob)))) return rc;
+    if ((rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, qags_scratch_entries(ctx, n), sizeof(QagsScratch)))) return rc;
+    if ((rc = ensure(ctx, (void**)&ctx->d_jobs, &ctx->cap_jobs, (size_t)n, sizeof(SkatoJob)))) return rc;
   }
   if (ctx->want_dbg) {
     if ((rc = ensure(ctx, (void**)&ctx->d_dbg, &ctx->cap_dbg, (size_t)n_total * kFinPhases, sizeof(long long)))) return rc;
@@ -1159,9 +1175,11 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
     if (ctx->skato) {
       k_finalize<true><<<nb, kFinThreadsSkato, fsm, fs>>>(
           ctx->d_genes + b0, nb, kld, wm_off, fin_uk_off(Mmax, ctx->ER, ctx->skato), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, ctx->d_res + b0,
-          ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->d_jobs, nullptr, nullptr);
-      if ((rc = launch_qags(ctx, nb, ctx->d_res + b0, nullptr, fs))) return rc;
-      launches += 1;
+          ctx->d_dbg ? ctx->d_dbg + (size_t)b0 * kFinPhases : nullptr, ctx->d_jobs + (b0 - g0), nullptr, nullptr);
+      if (bi == nbatch - 1) {   // the quadrature of the whole range in one launch (see launch_qags)
+        if ((rc = launch_qags(ctx, ctx->d_jobs, n, ctx->d_res + g0, nullptr, fs))) return rc;
+        launches += 1;
+      }
     } else
       k_finalize<false><<<nb, kFinThreads, fsm, fs>>>(
           ctx->d_genes + b0, nb, kld, wm_off, fin_uk_off(Mmax, ctx->ER, ctx->skato), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, ctx->d_res + b0,
@@ -1365,9 +1383,13 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
     rec.stream_pos = (int64_t)ctx->perm_pos;
     rec.p_perm = 1.0;
     const GeneDesc& gd = ctx->genes[g];
-    // fit() returned -1 (no polymorphic variant): the reference runs no permutation.  Genes on the fp64 path and
-    // caller-owned device blocks without the engine's own counts are not covered.
-    if (hres[g].status != RVT_GENE_OK || ctx->is_dos[g] || !gd.tiled || gd.seg < 0 || (!gd.has_af && !gd.counted)) continue;
+    // fit() returned -1 (no polymorphic variant): the reference runs no permutation.  Genes with dosages / missing calls
+    // (fp64 path) and caller-owned device blocks without the engine's own counts are not covered: their record says
+    // done = 0 and -- the reference WOULD have shuffled for them -- the rand() stream of the genes after them no longer
+    // lines up with the reference's (documented in include/rvtests_b200.h).  A binary trait is covered: its permuted
+    // statistic is sum_j w_j (g_j' r_pi)^2 with r = y - p, hard calls and digits of r as for a quantitative trait
+    // (src/Model.h:2673-2717: one loop for both outcomes).
+    if (hres[g].status != RVT_GENE_OK || ctx->is_dos[g] == 1 || !gd.tiled || gd.seg < 0 || (!gd.has_af && !gd.counted)) continue;
     const std::vector<GeneDesc>* tiles = nullptr;
     std::vector<GeneDesc> one(1, gd);
     for (auto& w : ctx->wide)
@@ -1509,7 +1531,7 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       dg.has_af = gd.has_af != 0;
       if (dg.has_af) dg.af.assign(ctx->af.begin() + gd.var0, ctx->af.begin() + gd.var0 + gd.M);
       ctx->dos.push_back(dg);
-      ctx->is_dos[g] = 1;
+      ctx->is_dos[g] = 2;   // hard calls, on the fp64 path only because of the weighted Gram: the permutation test still applies
     }
   }
   if (!ctx->dos.empty()) {
@@ -1579,7 +1601,7 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       RVT_CUDA_OK(cudaStreamSynchronize(st));   // `tgs` is a host temporary
     }
     RVT_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
-    if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nd + kQagsSlots, sizeof(QagsScratch)))) return rc;
+    if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, qags_scratch_entries(ctx, nd), sizeof(QagsScratch)))) return rc;
     if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_jobs, &ctx->cap_jobs, (size_t)nd, sizeof(SkatoJob)))) return rc;
     {
       // SKAT-O for a binary trait (SkatO::Fit type "D": the same tail on the p(1-p)-weighted statistics with s2 = 1,
@@ -1589,7 +1611,7 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       if (sk) {
         k_finalize<true><<<nd, kFinThreadsSkato, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, sk), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
                                                              nullptr, d_res, nullptr, ctx->d_jobs, d_tin, d_idx);
-        if ((rc = launch_qags(ctx, nd, d_res, d_idx, st))) return rc;
+        if ((rc = launch_qags(ctx, ctx->d_jobs, nd, d_res, d_idx, st))) return rc;
         launches += 1;
       } else
         k_finalize<false><<<nd, kFinThreads, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, sk), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
@@ -1806,6 +1828,10 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   }
   const bool tc_ok = ctx->tc.encode && ctx->tc.have_e && seg >= 0 && ctx->tc.have_seg[seg];
   if (!pairs.empty() && !tc_ok) { cleanup(); CTX_FAIL(RVT_E_UNSUPPORTED, "meta cov needs the tensor-core engine (TMA segment unavailable)"); }
+  // BoltLMM::GetCovXX (regression/BoltLMM.cpp:435-460; MetaCovFamQtlBolt::calculateXX, src/Model.cpp:780-805): the entry
+  // is g1'(I - ZZ')g2 * xVx_xx_ratio / N -- the projected Gram of this band times a scalar -- where the unrelated-sample
+  // model divides by sigma2 N (option "meta_cov_scale" = xVx_xx_ratio of rvt_bolt_fit_null; 0 = unrelated samples)
+  const double band_scale = ctx->meta_cov_scale > 0.0 ? ctx->meta_cov_scale / (double)N : 0.0;
   // phase 1: diagonal tiles
   RVT_CUDA_OK(cudaEventRecord(ctx->ev[0], st));
   RVT_CUDA_OK(cudaMemcpyAsync(d_desc, tiles.data(), sizeof(GeneDesc) * T, cudaMemcpyHostToDevice, st));
@@ -1820,7 +1846,7 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
       k_sweep_simt<<<std::min(nb * S, ctx->sm_count * 3), kSimtThreads, kSimtSmem, st>>>(d_desc + b0, nb, d_flags0, ctx->d_nm, S, chunk,
                                                                                        ctx->d_parts, ctx->d_counter);
     }
-    k_meta_block<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, d_v, d_B, d_poly, d_band);
+    k_meta_block<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, d_v, d_B, d_poly, d_band, band_scale);
     RVT_CUDA_OK(cudaGetLastError());
   }
   k_meta_hwe<<<(unsigned)nv, kHweThreads, 0, st>>>(nv, d_v);
@@ -1835,13 +1861,14 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
       rc = tc_launch(&ctx->tc, d_desc + b0, pairs.data() + b0, nb, d_flags0, ctx->d_nm, N, ctx->ER, S, chunk, ctx->d_parts,
                      ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), true);
       if (rc) { cleanup(); return rc; }
-      k_meta_pair<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, d_B, d_poly, d_band);
+      k_meta_pair<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, d_B, d_poly, d_band, band_scale);
       RVT_CUDA_OK(cudaGetLastError());
     }
   }
   RVT_CUDA_OK(cudaEventRecord(ctx->ev[3], st));
-  RVT_CUDA_OK(cudaMemcpyAsync(vout, d_v, sizeof(rvt_variant_result) * nv, cudaMemcpyDeviceToHost, st));
-  if (band) RVT_CUDA_OK(cudaMemcpyAsync(band, d_band, sizeof(double) * nv * (size_t)(wmax + 1), cudaMemcpyDeviceToHost, st));
+  // (vout / band may be host or device pointers: unified addressing tells)
+  RVT_CUDA_OK(cudaMemcpyAsync(vout, d_v, sizeof(rvt_variant_result) * nv, cudaMemcpyDefault, st));
+  if (band) RVT_CUDA_OK(cudaMemcpyAsync(band, d_band, sizeof(double) * nv * (size_t)(wmax + 1), cudaMemcpyDefault, st));
   RVT_CUDA_OK(cudaEventRecord(ctx->ev[1], st));
   RVT_CUDA_OK(cudaStreamSynchronize(st));
   {
@@ -2408,7 +2435,7 @@ int rvt_synth_load(rvt_ctx* ctx, int n_genes, int M, const uint64_t* keys, const
 
 int rvt_loaded_genes(const rvt_ctx* ctx) { return ctx ? ctx->loaded_genes : 0; }
 
-int rvt_run_loaded(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, int results_on_device) {
+int rvt_push_loaded(rvt_ctx* ctx) {
   if (!ctx) return RVT_E_BADARG;
   if (!ctx->d_loaded) CTX_FAIL(RVT_E_STATE, "no cohort loaded (rvt_synth_load)");
   if (!ctx->genes.empty()) CTX_FAIL(RVT_E_STATE, "flush pending genes first");
@@ -2423,6 +2450,12 @@ int rvt_run_loaded(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, int 
     push_common(ctx, ctx->d_loaded + (size_t)g * ctx->loaded_ld, M, 0, ctx->loaded_af.data() + row0,
                 ctx->loaded_flags.data() + row0, false, kSegLoaded, ((int64_t)g * ctx->loaded_ld) / 128, true);
   }
+  return RVT_OK;
+}
+
+int rvt_run_loaded(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, int results_on_device) {
+  int rc = rvt_push_loaded(ctx);
+  if (rc) return rc;
   return flush_impl(ctx, out, cap, n_out, results_on_device != 0);
 }
 

@@ -360,7 +360,7 @@ k_skato_qags(const SkatoJob* __restrict__ jobs, int n_genes, QagsScratch* __rest
   if (g >= n_genes) return;
   const SkatoJob& job = jobs[g];
   rvt_gene_result* dst = &res[out_index ? out_index[g] : g];
-  if (!job.run) {
+  if (job.run != 1) {
     if (tid == 0) {
       dst->skato_ok = job.ok;
       dst->skato_Q = job.Q;
@@ -369,7 +369,7 @@ k_skato_qags(const SkatoJob* __restrict__ jobs, int n_genes, QagsScratch* __rest
     }
     return;
   }
-  const int nl = job.n_lam;
+  const int nl = min(max(job.n_lam, 0), kSkatoMaxLam);
   for (int i = tid; i < nl; i += kQagsThreads) s_lam[i] = job.lam[i];
   if (tid == 0) skato_params_from_job(job, s_lam, &P);
   __syncthreads();
@@ -474,14 +474,14 @@ k_skato_qags_packed(const SkatoJob* __restrict__ jobs, int n_genes, QagsScratch*
         }
         const SkatoJob& job = jobs[g];
         rvt_gene_result* dst = &res[out_index ? out_index[g] : (int)g];
-        if (!job.run) {
+        if (job.run != 1) {
           dst->skato_ok = job.ok;
           dst->skato_Q = job.Q;
           dst->skato_rho = job.rho;
           dst->skato_p = job.pvalue;
           continue;
         }
-        const int nl = job.n_lam;
+        const int nl = min(max(job.n_lam, 0), kSkatoMaxLam);
         for (int i = 0; i < nl; ++i) S.lam[i] = job.lam[i];
         skato_params_from_job(job, S.lam, &S.P);
         S.pre.degenerate = 0;

@@ -50,7 +50,7 @@ EXPORTS = [
     "rvt_set_stream",
     "rvt_set_null_model", "rvt_set_null_model_dev", "rvt_get_null_model", "rvt_set_null_residual",
     "rvt_gene_push_f64", "rvt_gene_push_i8", "rvt_gene_push_dev_i8", "rvt_gene_push_bed", "rvt_pending",
-    "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded",
+    "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded", "rvt_push_loaded",
     "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
     "rvt_debug_phases",
     "rvt_meta_plan", "rvt_meta_flush", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand", "rvt_lmm_set_null", "rvt_lmm_flush", "rvt_get_null_beta", "rvt_bolt_fit_null",
@@ -110,6 +110,7 @@ def load_library(rebuild: bool = False):
     L.rvt_synth_load.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.rvt_loaded_genes.argtypes = [vp]
     L.rvt_run_loaded.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.c_int]
+    L.rvt_push_loaded.argtypes = [vp]
     L.rvt_loaded_read.argtypes = [vp, C.c_int64, C.c_int, vp]
     L.rvt_last_timing.argtypes = [vp, _dp]
     L.rvt_debug_partials.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64)]
@@ -335,6 +336,18 @@ class GeneEngine:
                                         None if band is None else band.ctypes.data, 0 if band is None else band.size,
                                         C.byref(wmax)))
         return vout[:n_variants], band, wmax.value
+
+    def push_loaded(self):
+        self._chk(self.L.rvt_push_loaded(self.h))
+
+    def meta_flush_dev(self, n_variants, pos, chrom, window_bp, d_vout, d_band, band_elems):
+        """as meta_flush with the outputs left in device memory (d_vout: n_variants records, d_band: band_elems doubles)"""
+        p = np.ascontiguousarray(pos, dtype=np.int32)
+        c = np.ascontiguousarray(chrom, dtype=np.int32)
+        wmax = C.c_int(0)
+        self._chk(self.L.rvt_meta_flush(self.h, p.ctypes.data, c.ctypes.data, int(window_bp), C.c_void_p(d_vout), int(n_variants),
+                                        C.c_void_p(d_band), int(band_elems), C.byref(wmax)))
+        return wmax.value
 
     def debug_phases(self, n):
         out = np.zeros((n, 6), dtype=np.int64)

@@ -12,6 +12,10 @@
 //     } else if (modelType == "kernel") {
 //       RVT_B200_KERNEL_MODELS(modelName, parser, model)        // <- added
 //       if (modelName == "skat") {
+//     ...
+//     } else if (modelType == "meta") {
+//       RVT_B200_META_MODELS(modelName, parser, model)          // <- added
+//       if (modelName == "score") {
 //
 // The B200 models are created when the environment variable RVTESTS_B200 is set to a non-empty value other than "0"
 // (a maintainer would add a command-line flag next to the other ones in src/Main.cpp); otherwise the stock models run.
@@ -32,11 +36,14 @@
 #include "src/Result.h"
 
 #include "rvt_fitters.h"
+#include "rvt_meta_fitters.h"
 
 typedef rvtb200::SkatTestB200<DataConsolidator, FileWriter, Result, ModelFitter> SkatTestB200;
 typedef rvtb200::SkatOTestB200<DataConsolidator, FileWriter, Result, ModelFitter> SkatOTestB200;
 typedef rvtb200::CMCTestB200<DataConsolidator, FileWriter, Result, ModelFitter> CMCTestB200;
 typedef rvtb200::ZegginiTestB200<DataConsolidator, FileWriter, Result, ModelFitter> ZegginiTestB200;
+typedef rvtb200::MetaScoreTestB200<DataConsolidator, FileWriter, Result, ModelFitter> MetaScoreTestB200;
+typedef rvtb200::MetaCovTestB200<DataConsolidator, FileWriter, Result, ModelFitter> MetaCovTestB200;
 
 namespace rvtb200 {
 inline bool enabled() {
@@ -63,6 +70,16 @@ inline bool enabled() {
     double beta1B200 = 1.0, beta2B200 = 25.0;                                              \
     (parser).assign("beta1", &beta1B200, 1.0).assign("beta2", &beta2B200, 25.0);           \
     (model).push_back(new SkatOTestB200(beta1B200, beta2B200));                            \
+  } else
+
+// --meta score[se],cov[windowSize=..]  (src/ModelManager.cpp:208-236), quantitative trait, unrelated samples
+#define RVT_B200_META_MODELS(modelName, parser, model)                               \
+  if (rvtb200::enabled() && (modelName) == "score") {                                \
+    (model).push_back(new MetaScoreTestB200((parser).hasTag("se")));                 \
+  } else if (rvtb200::enabled() && (modelName) == "cov") {                           \
+    int windowSizeB200 = 1000000;                                                    \
+    (parser).assign("windowSize", &windowSizeB200, 1000000);                         \
+    (model).push_back(new MetaCovTestB200(windowSizeB200));                          \
   } else
 
 #endif  // RVT_MODEL_B200_H_

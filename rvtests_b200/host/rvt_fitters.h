@@ -38,18 +38,18 @@ namespace rvtb200 {
 
 // what the adapters use of ModelFitter, for builds without the reference tree
 struct StandaloneBase {
-  StandaloneBase() : modelName("UninitializedModel"), binaryOutcome(false) {}
+  StandaloneBase() : modelName("UninitializedModel"), binaryOutcome(false), indexResult(false) {}
   virtual ~StandaloneBase() {}
   const std::string& getModelName() const { return modelName; }
   bool isBinaryOutcome() const { return binaryOutcome; }
   void setBinaryOutcome() { binaryOutcome = true; }
   void setQuantitativeOutcome() { binaryOutcome = false; }
-  bool needToIndexResult() const { return false; }
+  bool needToIndexResult() const { return indexResult; }
   virtual void reset() {}
 
  protected:
   std::string modelName;
-  bool binaryOutcome;
+  bool binaryOutcome, indexResult;
 };
 
 // One engine per process, shared by every adapter so that a gene is uploaded once even when several tests (skat, skato,

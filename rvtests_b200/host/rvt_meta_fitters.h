@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "rvtests_b200.h"
+#include "rvt_fitters.h"   // StandaloneBase
 
 namespace rvtb200 {
 
@@ -276,23 +277,26 @@ class MetaBatcher {
   Block open_ = Block{0, 0, std::vector<int8_t>()};
 };
 
-template <class DC, class FW, class RES>
-class MetaScoreTestB200 {
+// BASE: the reference's ModelFitter inside rvtests (ModelB200.h), StandaloneBase otherwise -- see rvt_fitters.h
+template <class DC, class FW, class RES, class BASE = StandaloneBase>
+class MetaScoreTestB200 : public BASE {
  public:
   explicit MetaScoreTestB200(bool outputSE = false) : outputSE_(outputSE), ticket_(-1), fp_(NULL), header_(false) {
-    modelName = "MetaScore";
+    this->modelName = "MetaScore";
+    this->indexResult = true;   // src/Model.h:3163: ModelManager opens a bgzipped, tabix-indexed writer for this model
     id_ = MetaBatcher<DC>::instance().newFitterId();
   }
   ~MetaScoreTestB200() { drain(true); }
-  const std::string& getModelName() const { return modelName; }
-  bool needToIndexResult() const { return true; }   // indexResult = true, src/Model.h:3163
-  void reset() { ticket_ = -1; }
-  int fit(DC* dc) {
+  virtual void reset() {
+    BASE::reset();
+    ticket_ = -1;
+  }
+  virtual int fit(DC* dc) {
     ticket_ = MetaBatcher<DC>::instance().submit(id_, dc);
     return ticket_ >= 0 ? 0 : -1;
   }
-  void writeHeader(FW*, const RES&) {}   // deferred: the header follows the null-model block (src/Model.h:3261-3281)
-  void writeOutput(FW* fp, const RES& siteInfo) {
+  virtual void writeHeader(FW*, const RES&) {}   // deferred: the header follows the null-model block (src/Model.h:3261-3281)
+  virtual void writeOutput(FW* fp, const RES& siteInfo) {
     fp_ = fp;
     if (!header_) {
       site_header_ = siteInfo.joinHeader();
@@ -304,7 +308,7 @@ class MetaScoreTestB200 {
     pending_.push_back(p);
     if (MetaBatcher<DC>::instance().shouldFlush()) drain(false);
   }
-  void writeFootnote(FW* fp) {
+  virtual void writeFootnote(FW* fp) {
     if (!fp_) fp_ = fp;
     drain(true);
   }
@@ -376,7 +380,7 @@ class MetaScoreTestB200 {
     int ticket;
     std::string site;
   };
-  std::string modelName, site_header_;
+  std::string site_header_;
   bool outputSE_;
   int id_, ticket_;
   FW* fp_;
@@ -384,31 +388,33 @@ class MetaScoreTestB200 {
   std::vector<Pending> pending_;
 };
 
-template <class DC, class FW, class RES>
-class MetaCovTestB200 {
+template <class DC, class FW, class RES, class BASE = StandaloneBase>
+class MetaCovTestB200 : public BASE {
  public:
   explicit MetaCovTestB200(int windowSize = 1000000) : ticket_(-1), fp_(NULL) {
-    modelName = "MetaCov";
+    this->modelName = "MetaCov";
+    this->indexResult = true;
     MetaBatcher<DC>& b = MetaBatcher<DC>::instance();
     id_ = b.newFitterId();
     b.enableCov();
     b.setWindow(windowSize);
   }
   ~MetaCovTestB200() { drain(true); }   // MetaCovTest::~MetaCovTest prints what is still queued (src/Model.cpp:828-834)
-  const std::string& getModelName() const { return modelName; }
-  bool needToIndexResult() const { return true; }
-  void reset() { ticket_ = -1; }
-  int fit(DC* dc) {
+  virtual void reset() {
+    BASE::reset();
+    ticket_ = -1;
+  }
+  virtual int fit(DC* dc) {
     ticket_ = MetaBatcher<DC>::instance().submit(id_, dc);
     return ticket_ >= 0 ? 0 : -1;
   }
-  void writeHeader(FW* fp, const RES&) { fp->write("CHROM\tSTART_POS\tEND_POS\tNUM_MARKER\tMARKER_POS\tCOV\n"); }
-  void writeOutput(FW* fp, const RES&) {
+  virtual void writeHeader(FW* fp, const RES&) { fp->write("CHROM\tSTART_POS\tEND_POS\tNUM_MARKER\tMARKER_POS\tCOV\n"); }
+  virtual void writeOutput(FW* fp, const RES&) {
     fp_ = fp;
     pending_.push_back(ticket_);
     if (MetaBatcher<DC>::instance().shouldFlush()) drain(false);
   }
-  void writeFootnote(FW* fp) {
+  virtual void writeFootnote(FW* fp) {
     if (!fp_) fp_ = fp;
     drain(true);
   }
@@ -427,7 +433,6 @@ class MetaCovTestB200 {
     }
     pending_.erase(pending_.begin(), pending_.begin() + i);
   }
-  std::string modelName;
   int id_, ticket_;
   FW* fp_;
   std::vector<int> pending_;

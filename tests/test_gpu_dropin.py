@@ -78,3 +78,55 @@ def test_dropin_binary(oracle, tmp_path):
     ref = O.dropin_run_gene_models(genes, X[:, 1:], y, str(tmp_path / "ref"), use_b200=False, binary=True)
     b2 = O.dropin_run_gene_models(genes, X[:, 1:], y, str(tmp_path / "b200"), use_b200=True, binary=True, batch=4)
     _compare(ref, b2, {"Skat": 5e-5, "SkatO": 2e-5, "CMC": 2e-5, "Zeggini": 2e-5})
+
+
+def _meta_problem(O, seed, N, nv, C):
+    rng = np.random.default_rng(seed)
+    maf = 10 ** rng.uniform(-2.3, np.log10(0.4), nv)
+    u = rng.random((N, nv))
+    G = (u < (1 - (1 - maf) ** 2)[None, :]).astype(np.float64) + (u < (maf * maf)[None, :])
+    G[:, 7] = 0.0                                   # a monomorphic variant: NA statistics, never queued by MetaCov
+    X, y = O.synth_covariates(seed, N, C)
+    pos = np.cumsum(rng.integers(50, 900, nv)).astype(np.int32)
+    return G, pos, X, y
+
+
+def _compare_meta(ref, b2):
+    cr, hr, rr = ref["MetaScore"]
+    cb, hb, rb = b2["MetaScore"]
+    assert hr == hb and len(rr) == len(rb) and len(rr) > 0
+    exact = {"AF", "INFORMATIVE_ALT_AC", "CALL_RATE", "N_REF", "N_HET", "N_ALT"}
+    for lr, lb in zip(rr, rb):
+        assert lr[:5] == lb[:5], (lr, lb)
+        for k in range(5, len(hr)):
+            a, b = _num(lr[k]), _num(lb[k])
+            assert (a is None) == (b is None), (hr[k], lr, lb)
+            if a is None:
+                continue
+            if hr[k] in exact:
+                assert a == b, (hr[k], lr, lb)
+            else:
+                assert abs(a - b) <= 3e-5 * max(abs(a), abs(b), 1e-300), (hr[k], lr, lb)
+    _, hcr, rcr = ref["MetaCov"]
+    _, hcb, rcb = b2["MetaCov"]
+    assert hcr == hcb and len(rcr) == len(rcb) and len(rcr) > 0
+    for lr, lb in zip(rcr, rcb):
+        assert lr[:5] == lb[:5], (lr, lb)             # CHROM START_POS END_POS NUM_MARKER MARKER_POS: the window logic
+        ca = np.array([float(x) for x in lr[5].split(",")])
+        cb_ = np.array([float(x) for x in lb[5].split(",")])
+        assert len(ca) == len(cb_)
+        # the reference accumulates the products in float32 (FloatMatrixRef, src/Model.cpp:534-554)
+        assert np.all(np.abs(ca - cb_) <= 2e-4 * np.maximum(np.abs(ca), ca[0] * 1e-2)), (lr[:4], ca, cb_)
+
+
+def test_dropin_meta_score_cov(oracle, tmp_path):
+    """--meta score[se],cov[windowSize=..] created by name through the reference's ModelManager: MetaScoreTest / MetaCovTest vs
+    MetaScoreTestB200 / MetaCovTestB200 (ModelFitter subclasses) in the reference's single-variant loop.  Intercept-only
+    model: with covariates the reference's computeQuadraticForm multiplies non-conforming shapes."""
+    O = oracle
+    if O.ref_dropin() is None:
+        pytest.skip("oracle/_ref/libdropin_ref.so not built")
+    G, pos, X, y = _meta_problem(O, 311, 1800, 150, 1)
+    ref = O.dropin_run_meta_models(G, pos, X[:, 1:], y, 4000, str(tmp_path / "ref"), use_b200=False, se=True)
+    b2 = O.dropin_run_meta_models(G, pos, X[:, 1:], y, 4000, str(tmp_path / "b200"), use_b200=True, se=True, segment=64)
+    _compare_meta(ref, b2)

@@ -132,3 +132,48 @@ def test_bolt_score_step(engine_cls, oracle):
         assert rel(r["sqrtV"] ** 2 * kappa ** 2, v) <= 1e-6
         assert rel(r["pvalue"], O.lib().orc_chisq_q(u * u / v, 1.0)) <= 1e-6
     eng.close()
+
+
+def test_bolt_covariance_band(engine_cls, oracle):
+    """BoltLMM::GetCovXX (regression/BoltLMM.cpp:435-460) as MetaCovFamQtlBolt::calculateXX uses it (src/Model.cpp:780-805),
+    printed divided by N (printCovariance, :990-996): g1'(I - ZZ')g2 * xVx_xx_ratio / N, restated in numpy, against the band of
+    rvt_meta_flush with option "meta_cov_scale"."""
+    O = oracle
+    N, nv, C, ratio = 5000, 130, 3, 0.8731
+    G = _variants(O, 12, N, nv, maf_hi=0.3)
+    X, _ = O.synth_covariates(12, N, C)
+    Z, _r = np.linalg.qr(X)
+    rng = np.random.default_rng(12)
+    h = rng.standard_normal(N)
+    r_b = h - Z @ (Z.T @ h)
+    pos = (500 * np.arange(nv)).astype(np.int32)
+    chrom = np.ones(nv, dtype=np.int32)
+    window = 20_000
+    eng = engine_cls(0)
+    try:
+        eng.set_null_residual(X, r_b, 1.3)
+        eng.set_option("meta_cov_scale", ratio)
+        for b0 in range(0, nv, 64):
+            eng.push_i8(G[b0:b0 + 64].copy(), None)
+        vout, band, wmax = eng.meta_flush(nv, pos, chrom, window)
+    finally:
+        eng.close()
+    Gd = G.astype(np.float64)
+    PG = Gd - (Gd @ Z) @ Z.T                      # rows projected off the covariates
+    poly = Gd.min(axis=1) != Gd.max(axis=1)
+    checked = 0
+    for i in range(nv):
+        for d in range(wmax + 1):
+            j = i + d
+            if j >= nv or pos[j] - pos[i] > window:
+                continue
+            if not (poly[i] and poly[j]):
+                assert np.isnan(band[i, d])
+                continue
+            want = float(PG[i] @ Gd[j]) * ratio / N
+            # an entry is a small difference of two large sums (A_ij - B_i (X'X)^-1 B_j'): judge the error on the scale
+            # of the two variants' variances (the covariates enter through 2^-30 fixed-point digits)
+            scale = np.sqrt(float(PG[i] @ Gd[i]) * float(PG[j] @ Gd[j])) * ratio / N
+            assert abs(band[i, d] - want) <= 1e-7 * scale, (i, d, band[i, d], want, scale)
+            checked += 1
+    assert checked > 1000

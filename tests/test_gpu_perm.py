@@ -67,6 +67,39 @@ def test_perm_counts_equal_the_reference_loop(eng, oracle, case):
     assert eng.info("perm_stream_pos") == pos
 
 
+def test_perm_binary_trait(engine_cls, oracle):
+    """binary trait: the same loop on r = y - p of the logistic null (src/Model.h:2673-2717) -- counts and stream positions
+    of two genes against the serial host loop"""
+    from oracle import binary_oracle as BIN
+    O = oracle
+    N, C, n_perm, alpha = 2500, 2, 200, 0.1
+    genes, X, _ = _genes(O, N, C, [(85, 12, dict(maf=np.linspace(0.01, 0.2, 12), n_flip=2, n_mono=1)), (85, 30, dict(maf=0.05))])
+    rng = np.random.default_rng(85)
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(0.4 - 0.5 * X[:, 1]))).astype(np.float64)
+    nm = BIN.fit_null_logistic(X, y)
+    e = engine_cls(0)
+    try:
+        e.set_option("perm", n_perm)
+        e.set_option("perm_alpha", alpha)
+        e.set_option("perm_batch", 32)
+        e.set_option("perm_seed", 1)
+        e.set_null_model(X, y, binary=True)
+        for G in genes:
+            e.push_i8(G.T.copy(), af_of(G))
+        res = e.flush()
+        pr = e.perm_results()
+    finally:
+        e.close()
+    pos = 0
+    for g, G in enumerate(genes):
+        ref = O.gene_perm(G.astype(float), af_of(G), nm["resid"], float(res[g]["Q"]), n_perm=n_perm, alpha=alpha,
+                          reseed=1 if g == 0 else 0)
+        assert ref["rc"] == 0 and int(pr[g]["done"]) == 1, (g, pr[g])
+        assert int(pr[g]["stream_pos"]) == pos
+        assert (int(pr[g]["actual_perm"]), int(pr[g]["num_greater"]), int(pr[g]["num_equal"])) == (ref["actual"], ref["greater"], ref["equal"]), (g, pr[g], ref)
+        pos += ref["actual"] * (N - 1)
+
+
 def test_perm_statistics_match_per_shuffle(eng, oracle):
     """with alpha = 1 every permutation runs: compare each permuted statistic, not only the counts"""
     O = oracle

@@ -16,7 +16,7 @@ X, y = synth.covariates(20260925, N, 3)
 eng = rvtests_b200.GeneEngine(0)
 eng.set_null_model(X, y)
 eng.synth_load(keys, t0, t1, ng, M)
-eng.set_option("qags_pack", int(os.environ.get("RVT_QAGS_PACK", "0")))
+eng.set_option("qags_pack", int(os.environ.get("RVT_QAGS_PACK", "1")))
 base = None
 quick = len(sys.argv) > 2 and sys.argv[2] == "quick"
 for skato in (0, 1):
