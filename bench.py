@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--meta-spacing", type=int, default=1000, help="bp between consecutive variants (window 1 Mb)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-skato", action="store_true", help="skip the SKAT-O arm (profiler captures of the headline step)")
     return ap.parse_args()
 
 
@@ -290,9 +291,9 @@ def run_ours(args):
                        "davies_fault_frac": float((res["davies_fault"] != 0).mean())},
         }
     # ---- the same step with SKAT-O on: BASELINE configs[2] is `--kernel skat,skato --burden cmc,zeggini`
-    skato = run_skato_arm(args, eng, torch, dist, world, rank, dev, stream, d_res, d_all)
+    skato = None if args.no_skato else run_skato_arm(args, eng, torch, dist, world, rank, dev, stream, d_res, d_all)
     res_skato = None
-    if rank == 0:
+    if rank == 0 and skato is not None:
         res_skato = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=rvtests_b200.engine.RESULT_DTYPE).copy()
     # ---- e2e: HOST buffers through the C ABI, H2D + D2H inside the timed region (rank-local, all ranks)
     e2e = None
