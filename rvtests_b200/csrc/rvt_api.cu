@@ -30,6 +30,7 @@
 #include "prep.cuh"
 #include "sweep_simt.cuh"
 #include "sweep_tc.cuh"
+#include "sweep_aug.cuh"
 #include "wide.cuh"
 
 using namespace rvt;
@@ -159,6 +160,7 @@ struct rvt_ctx {
   cudaEvent_t ev_swept[2] = {nullptr, nullptr}, ev_fin_done[2] = {nullptr, nullptr};
   bool fin_busy[2] = {false, false};
   unsigned long long batch_seq = 0;
+  int aug = 1;                     // genes with missing calls on the augmented tensor-core sweep (sweep_aug.cuh); 0: sparse kernel
   double meta_cov_scale = 0.0;     // > 0: mixed-model (Bolt) covariance band, see rvt_meta_flush
   int qags_pack = 1;               // SKAT-O quadrature: 1 = three genes per persistent 128-thread CTA (k_skato_qags_packed)
   long long wd_cycles = 8000000000ll;   // device watchdog of the per-gene tail, SM cycles (option "watchdog_ms"; ~4 s)
@@ -182,7 +184,7 @@ struct rvt_ctx {
   // timing
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double t_sweep = 0, t_fin = 0, t_total = 0, n_launch = 0;
-  int last_engine = 0, last_S = 0;
+  int last_engine = 0, last_S = 0, last_aug = 0;
   int64_t last_parts = 0;
   int last_n = 0;
 };
@@ -335,6 +337,7 @@ int rvt_ctx_create(int device, rvt_ctx** out) {
   RVT_CUDA_OK(cudaFuncSetAttribute(k_finalize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fin_smem(kTileRows, kMaxER, true)));
   int rc = tc_init(&ctx->tc, ctx->err, sizeof(ctx->err));
   if (rc) return rc;
+  if (ctx->tc.encode && (rc = aug_init(ctx->err, sizeof(ctx->err)))) return rc;
   return RVT_OK;
 }
 
@@ -396,6 +399,8 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "tc_stages") {
     if (value != 3 && value != 4 && value != 5) CTX_FAIL(RVT_E_BADARG, "tc_stages must be 3, 4 or 5");
     ctx->tc.stages = (int)value;
+  } else if (k == "aug") {
+    ctx->aug = value != 0;
   } else if (k == "meta_cov_scale") {
     if (value < 0) CTX_FAIL(RVT_E_BADARG, "meta_cov_scale must be >= 0");
     ctx->meta_cov_scale = value;
@@ -460,6 +465,7 @@ double rvt_get_info(const rvt_ctx* ctx, const char* key) {
   if (k == "sm_count") return ctx->sm_count;
   if (k == "last_engine") return ctx->last_engine;
   if (k == "last_splits") return ctx->last_S;
+  if (k == "last_aug") return ctx->last_aug;
   if (k == "N") return (double)ctx->N;
   if (k == "C") return ctx->C;
   if (k == "ER") return ctx->ER;
@@ -1158,7 +1164,8 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
       k_sweep_simt<<<grid, kSimtThreads, kSimtSmem, st>>>(ctx->d_genes + b0, nb, ctx->d_flags, ctx->d_nm, S, chunk, parts, ctx->d_counter);
     } else {
       rc = tc_launch(&ctx->tc, ctx->d_genes + b0, ctx->genes.data() + b0, nb, ctx->d_flags, ctx->d_nm, N, ctx->ER,
-                     S, chunk, parts, ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), false, wide);
+                     S, chunk, parts, ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), false, wide, -1,
+                     ctx->aug ? ctx->d_counts : nullptr);
       if (rc) return rc;
     }
     RVT_CUDA_OK(cudaEventRecord(ev[1], st));
@@ -1583,22 +1590,79 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
     }
     TileGene* d_tg = nullptr;
     if (!tgs.empty()) {
+      // Genes with missing calls of a quantitative trait ride the AUGMENTED tensor-core sweep (sweep_aug.cuh: the imputed
+      // matrix is H + M diag(delta), every sum an exact integer product over the rows [H ; M]); what it does not cover --
+      // a binary trait (weighted Gram), tiles of 63 / 64 variants (no spare rows), another segment, no TMA -- keeps the
+      // sparse CUDA-core kernel.  The augmented genes are put first so that both sets are contiguous sub-lists.
+      const bool aug_ok = ctx->aug && !ctx->binary && ctx->tc.encode && ctx->tc.have_e && (ctx->ER == 16 || ctx->ER == 32);
+      auto is_aug = [&](const TileGene& tg) {
+        const GeneDesc& gd = ctx->genes[ctx->dos[tg.slot].gene_index];
+        return aug_ok && tg.allow_missing && tg.M <= kTileRows - 2 && gd.tiled && gd.seg == kSegStaged;
+      };
+      std::stable_partition(tgs.begin(), tgs.end(), is_aug);
+      int n_aug = 0;
+      while (n_aug < (int)tgs.size() && is_aug(tgs[n_aug])) ++n_aug;
       const int ntg = (int)tgs.size();
       if ((rc = ensure(ctx, &ctx->d_dos_tg, &ctx->cap_dos_tg, (size_t)ntg, sizeof(TileGene)))) return rc;
       d_tg = (TileGene*)ctx->d_dos_tg;
       RVT_CUDA_OK(cudaMemcpyAsync(d_tg, tgs.data(), sizeof(TileGene) * ntg, cudaMemcpyHostToDevice, st));
-      const int64_t nblk = ((N + 3) / 4 + kSparseThreads - 1) / kSparseThreads;
-      const unsigned bx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nblk, (8 * (int64_t)ctx->sm_count + ntg - 1) / ntg));
-      for (int t0 = 0; t0 < ntg; t0 += 32768) {   // (grid.y limit)
+      for (int t0 = 0; t0 < ntg; t0 += 32768) {   // (grid limit)
         const int nt = std::min(32768, ntg - t0);
         k_tile_cols<<<nt, kTileRows, 0, st>>>(d_tg + t0, nt, N, ctx->d_counts, d_st);
-        k_tile_sparse<<<dim3(bx, (unsigned)nt), kSparseThreads, 0, st>>>(d_tg + t0, N, ctx->d_counts, ctx->dX, ctx->C, ctx->dresid,
-                                                                         ctx->binary ? ctx->d_vw : nullptr, d_st);
+        launches += 1;
+      }
+      std::vector<GeneDesc> aug_desc;   // (host temporaries: the stream is synchronised below)
+      std::vector<AugGene> aug_genes;
+      if (n_aug > 0) {
+        if ((rc = tc_bind_segment(&ctx->tc, kSegStaged, ctx->d_stage, ctx->stage_cap, ctx->err, sizeof(ctx->err)))) return rc;
+        aug_desc.resize(n_aug);
+        aug_genes.resize(n_aug);
+        for (int i = 0; i < n_aug; ++i) {
+          aug_desc[i] = ctx->genes[ctx->dos[tgs[i].slot].gene_index];
+          aug_genes[i].M = tgs[i].M;
+          aug_genes[i].slot = tgs[i].slot;
+          aug_genes[i].var0 = tgs[i].var0;
+        }
+        const int abatch = std::min(n_aug, 1024);
+        int S = 0;
+        int64_t chunk = 0;
+        if ((rc = split_plan(ctx, abatch, &S, &chunk))) return rc;
+        void *d_adesc = nullptr, *d_agenes = nullptr;
+        if ((rc = scratch(ctx, 6, sizeof(GeneDesc) * (size_t)n_aug, &d_adesc))) return rc;
+        if ((rc = scratch(ctx, 7, sizeof(AugGene) * (size_t)n_aug, &d_agenes))) return rc;
+        if ((rc = ensure(ctx, (void**)&ctx->d_parts, &ctx->cap_parts, (size_t)abatch * S * kAugParts, sizeof(SweepPartial)))) return rc;
+        RVT_CUDA_OK(cudaMemcpyAsync(d_adesc, aug_desc.data(), sizeof(GeneDesc) * n_aug, cudaMemcpyHostToDevice, st));
+        RVT_CUDA_OK(cudaMemcpyAsync(d_agenes, aug_genes.data(), sizeof(AugGene) * n_aug, cudaMemcpyHostToDevice, st));
+        k_aug_flags<<<n_aug, kTileRows, 0, st>>>((const AugGene*)d_agenes, n_aug, N, d_st, ctx->d_flags);
+        for (int b0 = 0; b0 < n_aug; b0 += abatch) {
+          const int nb = std::min(abatch, n_aug - b0);
+          if ((rc = aug_launch(&ctx->tc, kSegStaged, (const GeneDesc*)d_adesc + b0, aug_desc.data() + b0, nb, ctx->d_flags, N, ctx->ER, S, chunk,
+                               ctx->d_parts, ctx->sm_count, st, ctx->err, sizeof(ctx->err))))
+            return rc;
+          k_aug_stats<<<nb, 128, 0, st>>>((const AugGene*)d_agenes + b0, nb, S, ctx->d_parts, ctx->d_flags, ctx->d_counts, ctx->d_nm, d_st);
+          launches += 2;
+        }
+        launches += 1;
+      }
+      const int nsp = ntg - n_aug;
+      if (nsp > 0) {
+        const int64_t nblk = ((N + 3) / 4 + kSparseThreads - 1) / kSparseThreads;
+        const unsigned bx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nblk, (8 * (int64_t)ctx->sm_count + nsp - 1) / nsp));
+        for (int t0 = n_aug; t0 < ntg; t0 += 32768) {   // (grid.y limit)
+          const int nt = std::min(32768, ntg - t0);
+          k_tile_sparse<<<dim3(bx, (unsigned)nt), kSparseThreads, 0, st>>>(d_tg + t0, N, ctx->d_counts, ctx->dX, ctx->C, ctx->dresid,
+                                                                           ctx->binary ? ctx->d_vw : nullptr, d_st);
+          launches += 1;
+        }
+      }
+      for (int t0 = 0; t0 < ntg; t0 += 32768) {
+        const int nt = std::min(32768, ntg - t0);
         k_tile_prepare<<<nt, 64, 0, st>>>(d_tg + t0, nt, d_st, ctx->d_af, ctx->d_nm, prm, d_tin);
-        launches += 3;
+        launches += 1;
       }
       RVT_CUDA_OK(cudaGetLastError());
-      RVT_CUDA_OK(cudaStreamSynchronize(st));   // `tgs` is a host temporary
+      RVT_CUDA_OK(cudaStreamSynchronize(st));   // `tgs`, `aug_desc`, `aug_genes` are host temporaries
+      ctx->last_aug = n_aug;
     }
     RVT_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nd, cudaMemcpyHostToDevice, st));
     if (ctx->skato && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, qags_scratch_entries(ctx, nd), sizeof(QagsScratch)))) return rc;

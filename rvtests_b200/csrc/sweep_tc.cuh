@@ -213,7 +213,10 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
            const __grid_constant__ CUtensorMap map_e,
            const GeneDesc* __restrict__ genes, int n_genes, const uint8_t* __restrict__ rowflags, int64_t N, int S,
            int64_t chunk, SweepPartial* __restrict__ out, int dbg_skip /* timing experiments only: 1 no collapse,
-           2 no MMA, 4 no E loads; results are then meaningless */) {
+           2 no MMA, 4 no E loads; results are then meaningless */,
+           const RowCounts* __restrict__ counts /* nullable.  Gene sweeps: a gene whose rows hold values outside {0,1,2}
+           (missing calls of a 2-bit push, counted at push time) is not swept here at all -- its units run zero stages; the
+           statistics kernel reports it from the same counts and the augmented sweep (sweep_aug.cuh) computes it */) {
   using Cfg = TcCfg<ER, kTcStages, PAIR, kTcBoxes, WIDE, ZC>;
   static_assert(!(ZC && PAIR), "block pairs carry no burden scores");
   constexpr int kTcStageK = Cfg::kStageK;
@@ -243,6 +246,14 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = n_genes * S;
+  // warp-uniform (every lane of the calling warp must be active): does gene gi hold non-hard-call values?
+  auto gene_skipped = [&](int gi) -> bool {
+    if (PAIR || counts == nullptr || !genes[gi].counted) return false;
+    const int Mg = genes[gi].M;
+    const int64_t v0 = genes[gi].var0;
+    const int b0 = (lane < Mg) ? counts[v0 + lane].bad : 0, b1 = (lane + 32 < Mg) ? counts[v0 + lane + 32].bad : 0;
+    return __any_sync(0xffffffffu, (b0 | b1) != 0);
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -291,7 +302,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
         const int64_t k0 = (int64_t)sp * chunk;
         int64_t k1 = k0 + chunk;
         if (k1 > N) k1 = N;
-        const int nsteps = (k1 > k0) ? (int)((k1 - k0 + kTcStageK - 1) / kTcStageK) : 0;
+        const int nsteps = (k1 > k0 && !gene_skipped(gi)) ? (int)((k1 - k0 + kTcStageK - 1) / kTcStageK) : 0;
         for (int ks = 0; ks < nsteps; ++ks, ++it) {
           const int s = it % kTcStages;
           const uint32_t ph = (it / kTcStages) & 1;
@@ -332,7 +343,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
       const int64_t k0 = (int64_t)sp * chunk;
       int64_t k1 = k0 + chunk;
       if (k1 > N) k1 = N;
-      const int nsteps = (k1 > k0) ? (int)((k1 - k0 + kTcStageK - 1) / kTcStageK) : 0;
+      const int nsteps = (k1 > k0 && !gene_skipped(gi)) ? (int)((k1 - k0 + kTcStageK - 1) / kTcStageK) : 0;
       const int a = ui & 1;
       mbar_wait(&tempty[a], ((ui >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -388,7 +399,7 @@ k_sweep_tc(const CUtensorMap* __restrict__ maps_g /* [64]: box rows = index+1 */
       const int64_t k0 = (int64_t)sp * chunk;
       int64_t k1 = k0 + chunk;
       if (k1 > N) k1 = N;
-      const int nsteps = (k1 > k0) ? (int)((k1 - k0 + kTcStageK - 1) / kTcStageK) : 0;
+      const int nsteps = (k1 > k0 && !gene_skipped(gi)) ? (int)((k1 - k0 + kTcStageK - 1) / kTcStageK) : 0;
       // per-row flags as two 64-bit masks held in registers (bit r: row r flipped / row r enabled)
       const uint8_t f0 = (lane < M) ? rowflags[gd.var0 + lane] : (uint8_t)kRowSkip;
       const uint8_t f1 = (lane + 32 < M) ? rowflags[gd.var0 + lane + 32] : (uint8_t)kRowSkip;
@@ -767,7 +778,7 @@ inline bool tc_usable(TcSegments* tc, const GeneDesc* h_genes, int n) {
 inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_genes, int n, const uint8_t* d_flags,
                      const NullModel* /*d_nm*/, int64_t N, int ER, int S, int64_t chunk, SweepPartial* d_parts,
                      unsigned int* /*counter*/, int sm_count, cudaStream_t st, char* err, size_t errlen,
-                     bool pair = false, bool wide = false, int seg_b = -1) {
+                     bool pair = false, bool wide = false, int seg_b = -1, const RowCounts* d_counts = nullptr) {
   const int seg = h_genes[0].seg;
   if (seg_b < 0) seg_b = seg;
   const int grid = std::min(n * S, sm_count);
@@ -779,7 +790,7 @@ inline int tc_launch(TcSegments* tc, const GeneDesc* d_genes, const GeneDesc* h_
   if (rc) return rc;
 #define RVT_TC_LAUNCH(ER_, ST_, PAIR_, BX_, ...)                                                                             \
   k_sweep_tc<ER_, ST_, PAIR_, BX_, ##__VA_ARGS__><<<grid, kTcThreads, TcCfg<ER_, ST_, PAIR_, BX_, ##__VA_ARGS__>::kSmem, st>>>( \
-      tc->seg[seg].d_maps, tc->seg[seg_b].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts, tc->dbg_skip)
+      tc->seg[seg].d_maps, tc->seg[seg_b].d_maps, tc->map_e, d_genes, n, d_flags, N, S, chunk, d_parts, tc->dbg_skip, d_counts)
   // burden scores through the UMMA: two spare tile rows and |z . digit| sums that fit int32
   bool zc = tc->zc && !pair && tc->boxes == 4 && chunk <= 262144;
   for (int i = 0; i < n && zc; ++i) zc = h_genes[i].M <= kTileRows - 2;

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 import rvtests_b200  # noqa: E402
 from rvtests_b200 import synth  # noqa: E402
 
-N, M, ng = int(os.environ.get("IMP_N", 500_000)), 50, int(os.environ.get("IMP_GENES", 64))
+N, M, ng = int(os.environ.get("IMP_N", 500_000)), 50, int(os.environ.get("IMP_GENES", 128))
 X, y = synth.covariates(20260925, N, 3)
 rng = np.random.default_rng(11)
 maf = 10 ** rng.uniform(-4, np.log10(0.05), (ng, M))
@@ -34,7 +34,8 @@ for name, miss in (("complete", 0.0), ("1% missing", 0.01)):
 eng = rvtests_b200.GeneEngine(0)
 
 
-def run(tag, bed, binary):
+def run(tag, bed, binary, aug=1):
+    eng.set_option("aug", aug)
     if binary:
         yb = (np.random.default_rng(1).random(N) < 0.3).astype(np.float64)
         eng.set_null_model(X, yb, binary=True)
@@ -44,11 +45,16 @@ def run(tag, bed, binary):
         t = time.perf_counter()
         for g in range(ng):
             eng.push_bed(bed[g], None)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
         res = eng.flush()
         dt = time.perf_counter() - t
-    print(f"{tag:42s}: {ng / dt:8.0f} genes/s end to end ({dt * 1e3:.1f} ms for {ng} genes), status ok {int((res['status'] == 0).sum())}/{ng}", flush=True)
+        dflush = time.perf_counter() - t1
+    print(f"{tag:52s}: {ng / dt:8.0f} genes/s end to end ({dt * 1e3:.1f} ms for {ng} genes); flush alone (tiles resident) "
+          f"{dflush * 1e3:.2f} ms = {ng / dflush:8.0f} genes/s; augmented genes {int(eng.info('last_aug'))}; status ok {int((res['status'] == 0).sum())}/{ng}", flush=True)
 
 
 run("complete hard calls (integer sweep)", beds["complete"], False)
-run("1% missing calls -> mean imputed (fp64 path)", beds["1% missing"], False)
+run("1% missing calls -> augmented tensor-core sweep", beds["1% missing"], False)
+run("1% missing calls -> sparse CUDA-core kernel (r01)", beds["1% missing"], False, aug=0)
 run("binary trait, complete calls (fp64 path)", beds["complete"], True)
