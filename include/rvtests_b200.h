@@ -84,8 +84,9 @@ typedef struct rvt_gene_result {
  * rvt_set_option("perm", nPerm) [+ "perm_alpha"]; the shuffles replay glibc's default rand() stream exactly as the
  * reference's serial gene loop consumes it (src/LinearAlgebra.h:8-21, no srand anywhere), starting at
  * "perm_stream_pos" draws (0 in a fresh process) and advancing by ActualPerm * (N-1) per gene.  Quantitative and binary
- * traits alike (src/Model.h:2673-2717).  NOT covered: a gene with dosages or missing calls (done = 0, NA columns); the
- * reference would have shuffled for it, so from such a gene on the stream position -- hence NumGreater / NumEqual of the
+ * traits alike (src/Model.h:2673-2717), genes with missing calls (2-bit pushes, mean-imputed) included.  NOT covered: a gene
+ * with dosages pushed as doubles, a gene with missing calls of a binary-trait run or of 63-64 variants (done = 0, NA columns);
+ * the reference would have shuffled for it, so from such a gene on the stream position -- hence NumGreater / NumEqual of the
  * LATER genes -- no longer replays the reference's.  rvt_perm_result.stream_pos tells where each gene started. */
 typedef struct rvt_perm_result {
   int32_t num_perm;      /* NumPerm */

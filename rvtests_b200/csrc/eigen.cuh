@@ -126,6 +126,39 @@ RVT_HD int sturm_count(const double* d, const double* e2, int n, double x) {
   double pp = 1.0;          // p_{i-1}
   double pm = d[0] - x;     // p_i
   if (pm == 0.0) pm = -1e-300;
+#if defined(__CUDA_ARCH__)
+  // Device form of the loop below, same arithmetic (hence the same counts), fewer instructions per term: this loop is
+  // ~60 % of the instructions k_finalize executes (ncu source page, profiles/r02_finalize_hot.txt).  The magnitude test
+  // first reads the exponent field (biased exponent in 360..1686 => 1e-200 < |p| < 1e200 for sure), the sign change is
+  // an XOR of the sign bits.
+  int hm = __double2hiint(pm);
+  unsigned int cnt = (unsigned int)hm >> 31;
+#pragma unroll 4
+  for (int i = 1; i < n; ++i) {
+    double p = (d[i] - x) * pm - e2[i - 1] * pp;
+    int hp = __double2hiint(p);
+    const unsigned int ex = ((unsigned int)hp >> 20) & 0x7FFu;
+    if (ex - 360u > 1326u) {   // binades that straddle a bound take the exact test: same decisions as the host form
+      const double ap = fabs(p);
+      if (!(ap >= 1e-200 && ap <= 1e200)) {
+        if (p == 0.0) {
+          const double t = fmax(fabs(pm) * 1e-290, 1e-305);
+          p = (pm < 0.0) ? t : -t;
+        }
+        const double sc = (ap > 1.0) ? 1e-200 : 1e200;
+        p *= sc;
+        pm *= sc;
+        hp = __double2hiint(p);
+        hm = __double2hiint(pm);
+      }
+    }
+    cnt += (unsigned int)(hp ^ hm) >> 31;
+    pp = pm;
+    pm = p;
+    hm = hp;
+  }
+  return (int)cnt;
+#else
   int cnt = pm < 0.0;
   for (int i = 1; i < n; ++i) {
     double p = (d[i] - x) * pm - e2[i - 1] * pp;
@@ -145,18 +178,12 @@ RVT_HD int sturm_count(const double* d, const double* e2, int n, double x) {
     pm = p;
   }
   return cnt;
+#endif
 }
 
-// a: n x n symmetric, row-major, lda (destroyed).  d[n], e[n], v[n], p[n]: group-visible scratch.
-// out[n]: eigenvalues in DESCENDING order.
+// Householder tridiagonalisation alone: d[0..n) the diagonal, e[0..n-1) the sub-diagonal (e[n-1] = 0).  n >= 2.
 template <class Par>
-RVT_HDN void sym_eigenvalues_tridiag(double* a, int n, int lda, double* d, double* e, double* v, double* p,
-                                     double* out, const Par& par) {
-  if (n == 1) {
-    if (par.tid() == 0) out[0] = a[0];
-    par.sync();
-    return;
-  }
+RVT_HDN void householder_tridiag(double* a, int n, int lda, double* d, double* e, double* v, double* p, const Par& par) {
   // thread (ti, tj) of a W-wide grid over the group: rows are dealt to ti, columns to tj, so the
   // inner loops run over consecutive addresses with no integer division
   const int W = par.nt() < 32 ? par.nt() : 32;
@@ -222,6 +249,13 @@ RVT_HDN void sym_eigenvalues_tridiag(double* a, int n, int lda, double* d, doubl
     e[n - 1] = 0.0;
   }
   par.sync();
+}
+
+// Eigenvalues of the symmetric tridiagonal (d, e) by Sturm bisection, one eigenvalue per thread; out[n] DESCENDING.
+// v[n], p[n]: group-visible scratch.  n >= 2.  (Needs ~2 n doubles of shared memory and few registers: k_fin_sturm runs it
+// at many CTAs per SM, where the all-in-one statistics kernel is held to 6 by the M x M matrix.)
+template <class Par>
+RVT_HDN void tridiag_eigenvalues(const double* d, const double* e, int n, double* v, double* p, double* out, const Par& par) {
   // Gershgorin interval and scale
   double glo = d[0] - fabs(e[0]), ghi = d[0] + fabs(e[0]);
   for (int i = 1; i < n; ++i) {
@@ -260,6 +294,20 @@ RVT_HDN void sym_eigenvalues_tridiag(double* a, int n, int lda, double* d, doubl
     out[n - 1 - kidx] = 0.5 * (lo + hi) * tnorm;
   }
   par.sync();
+}
+
+// a: n x n symmetric, row-major, lda (destroyed).  d[n], e[n], v[n], p[n]: group-visible scratch.
+// out[n]: eigenvalues in DESCENDING order.
+template <class Par>
+RVT_HDN void sym_eigenvalues_tridiag(double* a, int n, int lda, double* d, double* e, double* v, double* p,
+                                     double* out, const Par& par) {
+  if (n == 1) {
+    if (par.tid() == 0) out[0] = a[0];
+    par.sync();
+    return;
+  }
+  householder_tridiag(a, n, lda, d, e, v, p, par);
+  tridiag_eigenvalues(d, e, n, v, p, out, par);
 }
 
 // Rank-sort ev[0..n) into out[0..n) in DESCENDING order (ties keep index order).

@@ -91,7 +91,21 @@ __device__ inline void burden_and_store(rvt_gene_result* dst, int Mp, int bad, d
   *dst = o;
 }
 
-template <bool SKATO>
+// Split form of the statistics (option "fin_split", default on, SKAT-O off): the all-in-one kernel is held to 6 CTAs per
+// SM by the M x M matrix in shared memory, and at that occupancy its serial fp64 chains -- the Sturm bisection above all,
+// ~60 % of its instructions -- leave the SM idle three cycles in four (ncu: 24 % issue-active, 0.27 eligible warps per
+// cycle).  Only the FRONT needs the matrix: split reduction, K, Householder.  It hands a FinMid record (the tridiagonal
+// form and a few scalars, 1.7 KB) to k_fin_sturm (bisection: 2 KB of shared memory, few registers, many CTAs per SM) and
+// k_fin_tail (Davies / Liu / burden score tests).
+struct FinMid {
+  int Mp, bad, nonref, status;   // Mp < 0: the front already wrote the record (bad-value gene)
+  double Q;
+  double bur[2][2 + kMaxC];
+  double d[kTileRows], e[kTileRows];   // tridiagonal form of K (Mp >= 2)
+  double lam[kTileRows];                // eigenvalues, descending (k_fin_sturm; Mp == 1: K itself, by the front)
+};
+
+template <bool SKATO, bool FRONT = false>
 __global__ void __launch_bounds__(SKATO ? kFinThreadsSkato : kFinThreads)
 k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(Mmax of this launch) */,
            int wm_off /* byte offset of Wm inside the dynamic shared memory (SKAT-O) */, int uk_off /* ... of Uk */,
@@ -104,7 +118,8 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
                                           here, the quadrature itself in k_skato_qags (skato_fast.cuh), launched next */,
            const TailInput* __restrict__ tin /* nullable: [n_genes] pre-digested statistics (dosage path);
                                                 then `genes`/`parts` are unused and res is indexed through out_index */,
-           const int* __restrict__ out_index) {
+           const int* __restrict__ out_index, FinMid* __restrict__ mid = nullptr /* FRONT: [n_genes] */) {
+  static_assert(!(SKATO && FRONT), "the split form serves the statistics without SKAT-O");
   extern __shared__ __align__(16) uint8_t dyn[];
   constexpr int NT = SKATO ? kFinThreadsSkato : kFinThreads;
   double* K = reinterpret_cast<double*>(dyn);                // [Mmax][kld]
@@ -223,6 +238,7 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
       o.p_skat = o.p_liu = 1.0;
       o.p_davies = -1.0;
       res[g] = o;
+      if constexpr (FRONT) mid[g].Mp = -1;
       if constexpr (SKATO) {
         if (jobs) {   // nothing for k_skato_qags to do (an unset job would be read as garbage)
           jobs[g].run = 0;
@@ -332,6 +348,27 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
     __syncthreads();
   }
 
+  if constexpr (FRONT) {
+    FinMid* __restrict__ m = &mid[g];
+    if (Mp >= 2) {
+      householder_tridiag(K, Mp, kld, s_ev, s_e, s_v, s_p, par);
+      for (int i = tid; i < Mp; i += NT) {
+        m->d[i] = s_ev[i];
+        m->e[i] = s_e[i];
+      }
+    }
+    if (tid == 0) {
+      m->Mp = Mp;
+      m->bad = s_bad;
+      m->nonref = s_nonref;
+      m->status = tin ? tin[g].status : 0;
+      m->Q = s_Q;
+      for (int w = 0; w < 2; ++w)
+        for (int l = 0; l < 2 + kMaxC; ++l) m->bur[w][l] = s_bur[w][l];
+      if (Mp == 1) m->lam[0] = K[0];
+    }
+    return;
+  }
   // 5. eigenvalues, descending, keep > 1e-30 from the top (Skat.cpp:84-98)
   double p_dav = -1.0, p_liu = 1.0, p_fin = 1.0, lam_max = 0.0;
   int fault = 0, r = 0;
@@ -378,6 +415,62 @@ k_finalize(const GeneDesc* __restrict__ genes, int n_genes, int kld /* fin_kld(M
     burden_and_store(&res[out_index ? out_index[g] : g], Mp, s_bad, s_Q, p_fin, p_dav, p_liu, fault, r, lam_max, so, s_bur, s_nonref, nm,
                      tin ? tin[g].status : 0);
     phase(4);
+  }
+}
+
+// bisection of the tridiagonal forms (one CTA per gene, one eigenvalue per thread)
+__global__ void __launch_bounds__(kFinThreads, 16)
+k_fin_sturm(FinMid* __restrict__ mid, int n_genes) {
+  __shared__ double s_d[kTileRows + 2], s_e[kTileRows + 2], s_v[kTileRows + 2], s_p[kTileRows + 2], s_lam[kTileRows];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  if (g >= n_genes) return;
+  FinMid* __restrict__ m = &mid[g];
+  const int Mp = m->Mp;
+  if (Mp < 2) return;
+  for (int i = tid; i < Mp; i += kFinThreads) {
+    s_d[i] = m->d[i];
+    s_e[i] = m->e[i];
+  }
+  __syncthreads();
+  BlockPar par{nullptr};   // (no reduction in this phase)
+  tridiag_eigenvalues(s_d, s_e, Mp, s_v, s_p, s_lam, par);
+  for (int i = tid; i < Mp; i += kFinThreads) m->lam[i] = s_lam[i];
+}
+
+// steps 5b-7 of k_finalize from the FinMid record: kept eigenvalues, Davies -> Liu, burden score tests, the record
+__global__ void __launch_bounds__(kFinThreads)
+k_fin_tail(const FinMid* __restrict__ mid, int n_genes, const NullModel* __restrict__ nm, rvt_gene_result* __restrict__ res,
+           const int* __restrict__ out_index) {
+  __shared__ double s_lam[kTileRows], s_red[64];
+  __shared__ int s_th[(kFinThreads / 32) * kTileRows];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  if (g >= n_genes) return;
+  const FinMid* __restrict__ m = &mid[g];
+  const int Mp = m->Mp;
+  if (Mp < 0) return;   // the front wrote the record
+  const int64_t N = nm->N;
+  for (int i = tid; i < Mp; i += kFinThreads) s_lam[i] = m->lam[i];
+  __syncthreads();
+  BlockPar par{s_red};
+  double p_dav = -1.0, p_liu = 1.0, p_fin = 1.0, lam_max = 0.0;
+  int fault = 0, r = 0;
+  const double Q = m->Q;
+  if (Mp > 0) {
+    const int r_ub = (N < (int64_t)Mp) ? (int)N : Mp;
+    while (r < r_ub && s_lam[r] > 1e-30) ++r;
+    lam_max = r ? s_lam[0] : 0.0;
+    p_dav = mixchisq_pvalue(s_lam, r, Q, s_th, &fault, par);
+    p_liu = liu_pvalue(s_lam, r, Q);
+    p_fin = p_dav;
+    if (p_fin <= 0.0 || p_fin == 1.0) p_fin = p_liu;
+  }
+  if (tid == 0) {
+    SkatoOut so;
+    so.ok = 0;
+    so.timed_out = 0;
+    so.Q = so.rho = so.pvalue = 0.0;
+    burden_and_store(&res[out_index ? out_index[g] : g], Mp, m->bad, Q, p_fin, p_dav, p_liu, fault, r, lam_max, so, m->bur, m->nonref, nm,
+                     m->status);
   }
 }
 

@@ -210,6 +210,62 @@ k_perm_q(int P, int M, int64_t var_base, int has_af, const long long* __restrict
     Qout[p] = q;
   }
 }
+// ---- genes with missing calls (mean-imputed: G = H + M diag(delta), sweep_aug.cuh) -------------------------------------
+// k_split_hm writes the two operand tiles the permuted products need -- H (hard calls, missing -> fill) and M (0/1 missing
+// indicators) -- as tiled blocks; the sweep units then pair both with the permutation tiles, sint holds H'r_pi in columns
+// 0..M-1 and M'r_pi in columns M..2M-1, and k_perm_q_aug combines them: s = H'r_pi + delta (M'r_pi).
+// grid: (ceil(nchunk*32/256), M); one thread = one 4-sample word of one row of one 128-sample chunk
+__global__ void __launch_bounds__(256)
+k_split_hm(const int8_t* __restrict__ g, int M, int64_t N, const uint8_t* __restrict__ rowflags /* of this gene */,
+           int8_t* __restrict__ H, int8_t* __restrict__ Mt) {
+  const int r = blockIdx.y;
+  const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // word index along the samples
+  const int64_t nchunk = (N + 127) >> 7;
+  if (wi >= nchunk * 32) return;
+  const size_t off = ((size_t)(wi >> 5) * M + r) * 128 + (size_t)(wi & 31) * 4;
+  const uint32_t w = *reinterpret_cast<const uint32_t*>(g + off);
+  const uint32_t m = w & (w >> 1) & 0x01010101u;
+  const uint32_t fill2 = (rowflags[r] == kRowFlipped) ? 0x02020202u : 0u;
+  *reinterpret_cast<uint32_t*>(H + off) = (w & ~(m | (m << 1))) | ((m << 1) & fill2);
+  *reinterpret_cast<uint32_t*>(Mt + off) = m;
+}
+
+__global__ void __launch_bounds__(256)
+k_perm_q_aug(int P, int M, int64_t var_base, int has_af, const long long* __restrict__ sint /*[P][2M]*/, const uint8_t* __restrict__ rowflags,
+             const double* __restrict__ af, const RowCounts* __restrict__ counts, const NullModel* __restrict__ nm, EngineParams prm,
+             double* __restrict__ w /*[2M] scratch: weights, then deltas*/, double* __restrict__ Qout /*[P]*/) {
+  const int tid = threadIdx.x;
+  const double N = (double)nm->N;
+  if (tid == 0) {
+    int t = 0;
+    for (int j = 0; j < M; ++j) {
+      const RowCounts rc = counts[var_base + j];
+      const double nobs = N - (double)rc.bad, ac = (double)((long long)rc.n1 + 2ll * rc.n2);
+      const double fill = nobs > 0 ? 2.0 * (ac / (2.0 * nobs)) : 0.0;          // imputeGenotypeToMean (as k_tile_cols)
+      w[M + j] = fill - ((rowflags[var_base + j] == kRowFlipped) ? 2.0 : 0.0);
+      if (rowflags[var_base + j] == kRowSkip) {
+        w[j] = -1.0;
+        continue;
+      }
+      const double freq = has_af ? af[var_base + t] : 0.5 * (ac + (double)rc.bad * fill) / N;   // dosage_prepare's frequency
+      w[j] = beta_weight(freq, prm.beta1, prm.beta2, true);
+      ++t;
+    }
+  }
+  __syncthreads();
+  const double rsum = (double)nm->vsum[0] * nm->scale[0];   // sum_i r_pi(i) = sum_i r_i
+  for (int p = tid; p < P; p += blockDim.x) {
+    double q = 0.0;
+    for (int j = 0; j < M; ++j) {
+      if (w[j] < 0.0) continue;
+      double sd = ((double)sint[(size_t)p * 2 * M + j] + w[M + j] * (double)sint[(size_t)p * 2 * M + M + j]) * nm->scale[0];
+      if (rowflags[var_base + j] == kRowFlipped) sd = 2.0 * rsum - sd;
+      const double sw = sqrt(w[j]);
+      q += (sw * sw) * sd * sd;
+    }
+    Qout[p] = q;
+  }
+}
 #endif  // __CUDACC__
 
 }  // namespace rvt

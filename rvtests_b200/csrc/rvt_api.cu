@@ -62,6 +62,7 @@ constexpr int kSegLoaded = 0;  // the synthetic / loaded cohort arena
 constexpr int kSegStaged = 1;  // genes staged from host buffers
 constexpr int kSegLmm = 3;     // eigenvector digit tiles of the mixed-model score step (lmm.cuh)
 constexpr int kSegPerm = 2;    // 16-permutation digit tiles of the permutation test (perm.cuh)
+constexpr int kSegAux = 4;     // H / M operand tiles of a gene with missing calls (permutation test)
 
 struct rvt_ctx {
   int device = 0;
@@ -160,6 +161,9 @@ struct rvt_ctx {
   cudaEvent_t ev_swept[2] = {nullptr, nullptr}, ev_fin_done[2] = {nullptr, nullptr};
   bool fin_busy[2] = {false, false};
   unsigned long long batch_seq = 0;
+  int fin_split = 1;               // statistics as front / bisection / tail kernels (finalize.cuh); 0: the all-in-one kernel
+  FinMid* d_mid = nullptr;
+  size_t cap_mid = 0;
   int aug = 1;                     // genes with missing calls on the augmented tensor-core sweep (sweep_aug.cuh); 0: sparse kernel
   double meta_cov_scale = 0.0;     // > 0: mixed-model (Bolt) covariance band, see rvt_meta_flush
   int qags_pack = 1;               // SKAT-O quadrature: 1 = three genes per persistent 128-thread CTA (k_skato_qags_packed)
@@ -335,6 +339,7 @@ int rvt_ctx_create(int device, rvt_ctx** out) {
   RVT_CUDA_OK(cudaFuncSetAttribute(k_sweep_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, kSimtSmem));
   RVT_CUDA_OK(cudaFuncSetAttribute(k_finalize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fin_smem(kTileRows, kMaxER, false)));
   RVT_CUDA_OK(cudaFuncSetAttribute(k_finalize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fin_smem(kTileRows, kMaxER, true)));
+  RVT_CUDA_OK(cudaFuncSetAttribute(k_finalize<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fin_smem(kTileRows, kMaxER, false)));
   int rc = tc_init(&ctx->tc, ctx->err, sizeof(ctx->err));
   if (rc) return rc;
   if (ctx->tc.encode && (rc = aug_init(ctx->err, sizeof(ctx->err)))) return rc;
@@ -347,7 +352,7 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_jobs, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum, ctx->d_p, ctx->d_vw, ctx->d_dos_st, ctx->d_dos_tin, ctx->d_dos_idx, ctx->d_dos_afd, ctx->d_dos_tg};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_jobs, ctx->d_mid, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum, ctx->d_p, ctx->d_vw, ctx->d_dos_st, ctx->d_dos_tin, ctx->d_dos_idx, ctx->d_dos_afd, ctx->d_dos_tg};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -399,6 +404,8 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "tc_stages") {
     if (value != 3 && value != 4 && value != 5) CTX_FAIL(RVT_E_BADARG, "tc_stages must be 3, 4 or 5");
     ctx->tc.stages = (int)value;
+  } else if (k == "fin_split") {
+    ctx->fin_split = value != 0;
   } else if (k == "aug") {
     ctx->aug = value != 0;
   } else if (k == "meta_cov_scale") {
@@ -1187,6 +1194,14 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
         if ((rc = launch_qags(ctx, ctx->d_jobs, n, ctx->d_res + g0, nullptr, fs))) return rc;
         launches += 1;
       }
+    } else if (ctx->fin_split && !ctx->d_dbg) {
+      if ((rc = ensure(ctx, (void**)&ctx->d_mid, &ctx->cap_mid, (size_t)nb, sizeof(FinMid)))) return rc;
+      k_finalize<false, true><<<nb, kFinThreads, fsm, fs>>>(
+          ctx->d_genes + b0, nb, kld, wm_off, fin_uk_off(Mmax, ctx->ER, false), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, ctx->d_res + b0,
+          nullptr, nullptr, nullptr, nullptr, ctx->d_mid);
+      k_fin_sturm<<<nb, kFinThreads, 0, fs>>>(ctx->d_mid, nb);
+      k_fin_tail<<<nb, kFinThreads, 0, fs>>>(ctx->d_mid, nb, ctx->d_nm, ctx->d_res + b0, nullptr);
+      launches += 2;
     } else
       k_finalize<false><<<nb, kFinThreads, fsm, fs>>>(
           ctx->d_genes + b0, nb, kld, wm_off, fin_uk_off(Mmax, ctx->ER, ctx->skato), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, Sp, parts, ctx->d_res + b0,
@@ -1337,9 +1352,12 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
   lfg_seed_window(ctx->perm_seed, y0);
   const int PB = ctx->perm_batch;                 // permutations per batch (multiple of 16)
   const int64_t tile_b = tiled_bytes(N, kTileRows);
-  int Mmax = 1, Tmax = 1;
+  int Mmax = 1, Tmax = 2;
   for (int g = 0; g < n; ++g) Mmax = std::max(Mmax, ctx->slots[g]);
+  Mmax = std::max(Mmax, 2 * kTileRows);   // a gene with missing calls: columns for H'r and M'r
   for (auto& w : ctx->wide) Tmax = std::max<int>(Tmax, (int)w.tiles.size());
+  bool any_aug = false;
+  for (int g = 0; g < n; ++g) any_aug |= ctx->is_dos[g] == 3;
   // scratch layout
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) & ~(size_t)1023; return o; };
@@ -1351,9 +1369,10 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
   const size_t o_R0 = carve((size_t)N * 4), o_R1 = carve((size_t)N * 4);
   const size_t o_w0 = carve(64 * 4);
   const size_t o_sint = carve((size_t)PB * Mmax * 8);
-  const size_t o_w = carve((size_t)Mmax * 8);
+  const size_t o_w = carve((size_t)2 * Mmax * 8);
   const size_t o_Q = carve((size_t)PB * 8);
   const size_t o_units = carve(sizeof(GeneDesc) * (size_t)Tmax * (PB / 16));
+  const size_t o_aux = carve(any_aug ? 2 * (size_t)tile_b : 0);   // H and M tiles of one gene with missing calls
   if (off > ctx->cap_perm) {
     if (ctx->d_perm) cudaFree(ctx->d_perm);
     ctx->d_perm = nullptr;
@@ -1370,6 +1389,8 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
   double *d_w = (double*)(base + o_w), *d_Q = (double*)(base + o_Q);
   GeneDesc* d_units = (GeneDesc*)(base + o_units);
   if ((rc = tc_bind_segment(&ctx->tc, kSegPerm, d_tiles, (int64_t)(PB / 16) * tile_b, ctx->err, sizeof(ctx->err)))) return rc;
+  int8_t* d_aux = (int8_t*)(base + o_aux);
+  if (any_aug && (rc = tc_bind_segment(&ctx->tc, kSegAux, d_aux, 2 * tile_b, ctx->err, sizeof(ctx->err)))) return rc;
   if ((rc = ensure(ctx, (void**)&ctx->d_zero_flags, &ctx->cap_zero_flags, (size_t)ctx->n_var + kTileRows, 1))) return rc;
   RVT_CUDA_OK(cudaMemsetAsync(ctx->d_zero_flags, 0, (size_t)ctx->n_var + kTileRows, st));
   EngineParams prm{ctx->beta1, ctx->beta2, ctx->wd_cycles};
@@ -1397,12 +1418,29 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
     // statistic is sum_j w_j (g_j' r_pi)^2 with r = y - p, hard calls and digits of r as for a quantitative trait
     // (src/Model.h:2673-2717: one loop for both outcomes).
     if (hres[g].status != RVT_GENE_OK || ctx->is_dos[g] == 1 || !gd.tiled || gd.seg < 0 || (!gd.has_af && !gd.counted)) continue;
+    const bool aug = ctx->is_dos[g] == 3;   // missing calls: two operand tiles, H (fills applied) and M (indicators)
     const std::vector<GeneDesc>* tiles = nullptr;
     std::vector<GeneDesc> one(1, gd);
     for (auto& w : ctx->wide)
       if (w.gene_index == g) tiles = &w.tiles;
     if (!tiles) tiles = &one;
-    const int T = (int)tiles->size(), M = ctx->slots[g];
+    if (aug) {
+      const int Mg = gd.M;
+      const int64_t nwords = ((N + 127) >> 7) * 32;
+      const int64_t hb = tiled_bytes(N, Mg);
+      k_split_hm<<<dim3((unsigned)((nwords + 255) / 256), (unsigned)Mg), 256, 0, st>>>(gd.g, Mg, N, ctx->d_flags + gd.var0, d_aux, d_aux + tile_b);
+      one.assign(2, gd);
+      one[0].g = d_aux;
+      one[0].seg = kSegAux;
+      one[0].row0 = one[0].row0_b = 0;
+      one[1].g = d_aux + tile_b;
+      one[1].seg = kSegAux;
+      one[1].row0 = one[1].row0_b = tile_b / 128;
+      one[1].var0 = one[1].var0_b = gd.var0 + Mg;   // columns M..2M-1 of sint
+      (void)hb;
+      tiles = &one;
+    }
+    const int T = (int)tiles->size(), M = aug ? 2 * gd.M : ctx->slots[g];
     const double obs = hres[g].Q;
     int actual = 0, numX = 0, numEq = 0, cur = 0;
     k_perm_init<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ctx->d_nm, d_R[0]);
@@ -1453,7 +1491,10 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
         mark("sint");
         *launches += 2;
       }
-      k_perm_q<<<1, 256, 0, st>>>(Pb16, M, gd.var0, gd.has_af, d_sint, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, d_w, d_Q);
+      if (aug)
+        k_perm_q_aug<<<1, 256, 0, st>>>(Pb16, gd.M, gd.var0, gd.has_af, d_sint, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, d_w, d_Q);
+      else
+        k_perm_q<<<1, 256, 0, st>>>(Pb16, M, gd.var0, gd.has_af, d_sint, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, d_w, d_Q);
       *launches += 1;
       RVT_CUDA_OK(cudaGetLastError());
       RVT_CUDA_OK(cudaMemcpyAsync(hQ.data(), d_Q, sizeof(double) * Pb16, cudaMemcpyDeviceToHost, st));
@@ -1618,6 +1659,7 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
         aug_desc.resize(n_aug);
         aug_genes.resize(n_aug);
         for (int i = 0; i < n_aug; ++i) {
+          ctx->is_dos[ctx->dos[tgs[i].slot].gene_index] = 3;   // (the permutation test covers these: run_perm)
           aug_desc[i] = ctx->genes[ctx->dos[tgs[i].slot].gene_index];
           aug_genes[i].M = tgs[i].M;
           aug_genes[i].slot = tgs[i].slot;
@@ -1677,6 +1719,13 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
                                                              nullptr, d_res, nullptr, ctx->d_jobs, d_tin, d_idx);
         if ((rc = launch_qags(ctx, ctx->d_jobs, nd, d_res, d_idx, st))) return rc;
         launches += 1;
+      } else if (ctx->fin_split) {
+        if ((rc = ensure(ctx, (void**)&ctx->d_mid, &ctx->cap_mid, (size_t)nd, sizeof(FinMid)))) return rc;
+        k_finalize<false, true><<<nd, kFinThreads, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, false), ctx->d_flags, ctx->d_af, ctx->d_counts,
+                                                               ctx->d_nm, prm, 1, nullptr, d_res, nullptr, nullptr, d_tin, d_idx, ctx->d_mid);
+        k_fin_sturm<<<nd, kFinThreads, 0, st>>>(ctx->d_mid, nd);
+        k_fin_tail<<<nd, kFinThreads, 0, st>>>(ctx->d_mid, nd, ctx->d_nm, d_res, d_idx);
+        launches += 2;
       } else
         k_finalize<false><<<nd, kFinThreads, fsm, st>>>(nullptr, nd, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, sk), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, 1,
                                                          nullptr, d_res, nullptr, nullptr, d_tin, d_idx);

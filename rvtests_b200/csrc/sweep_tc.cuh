@@ -614,8 +614,8 @@ struct TcSegments {
   bool have_e = false;
   int ER = 0;
   CUtensorMap map_e;
-  static constexpr int kMaxSeg = 4;
-  bool have_seg[kMaxSeg] = {false, false, false, false};
+  static constexpr int kMaxSeg = 5;
+  bool have_seg[kMaxSeg] = {false, false, false, false, false};
   // one tensor map per box height M = 1..64 over the same arena (encoded lazily, kept in HBM)
   struct Seg {
     const int8_t* base = nullptr;

@@ -100,6 +100,50 @@ def test_perm_binary_trait(engine_cls, oracle):
         pos += ref["actual"] * (N - 1)
 
 
+def test_perm_genes_with_missing_calls(engine_cls, oracle):
+    """a gene with missing calls (mean-imputed, augmented sweep) between two complete genes: its permutations run -- on the
+    operand tiles H and M, s = H'r_pi + delta M'r_pi -- and consume the rand() stream as the reference's loop does, so the
+    counts AND stream positions of the genes after it still replay the serial host loop."""
+    from rvtests_b200.synth import pack_bed
+    O = oracle
+    N, C, n_perm, alpha = 3001, 3, 150, 0.2
+    genes, X, y = _genes(O, N, C, [(87, 10, dict(maf=np.linspace(0.01, 0.2, 10))),
+                                   (88, 30, dict(maf=np.linspace(0.005, 0.1, 30), n_flip=2, n_mono=1)),
+                                   (89, 6, dict(maf=0.1))])
+    nm = O.fit_null_linear(X, y)
+    rng = np.random.default_rng(87)
+    mask = rng.random((30, N)) < 0.02
+    mask[3, : N // 4] = True
+    bed1 = pack_bed(genes[1].T, mask)
+    raw = O.bed_decode_fast(bed1, N).T
+    Gd1 = O.impute_mean(raw)
+    af1 = 0.5 * np.where(raw >= 0, raw, 0.0).sum(axis=0) / N
+    mats = [genes[0].astype(float), Gd1, genes[2].astype(float)]
+    afs = [af_of(genes[0]), af1, af_of(genes[2])]
+    e = engine_cls(0)
+    try:
+        e.set_option("perm", n_perm)
+        e.set_option("perm_alpha", alpha)
+        e.set_option("perm_batch", 32)
+        e.set_option("perm_seed", 1)
+        e.set_null_model(X, y)
+        e.push_bed(pack_bed(genes[0].T), afs[0])
+        e.push_bed(bed1, af1)
+        e.push_bed(pack_bed(genes[2].T), afs[2])
+        res = e.flush()
+        pr = e.perm_results()
+        assert int(e.info("last_aug")) == 1
+    finally:
+        e.close()
+    pos = 0
+    for g in range(3):
+        ref = O.gene_perm(mats[g], afs[g], nm["resid"], float(res[g]["Q"]), n_perm=n_perm, alpha=alpha, reseed=1 if g == 0 else 0)
+        assert ref["rc"] == 0 and int(pr[g]["done"]) == 1, (g, pr[g])
+        assert int(pr[g]["stream_pos"]) == pos, (g, pr[g], pos)
+        assert (int(pr[g]["actual_perm"]), int(pr[g]["num_greater"]), int(pr[g]["num_equal"])) == (ref["actual"], ref["greater"], ref["equal"]), (g, pr[g], ref)
+        pos += ref["actual"] * (N - 1)
+
+
 def test_perm_statistics_match_per_shuffle(eng, oracle):
     """with alpha = 1 every permutation runs: compare each permuted statistic, not only the counts"""
     O = oracle
