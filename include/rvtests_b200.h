@@ -206,6 +206,13 @@ int rvt_debug_rand(rvt_ctx* ctx, uint32_t seed, uint64_t pos, int64_t n, int32_t
 int rvt_lmm_set_null(rvt_ctx* ctx, int64_t N, int C, const float* U, const float* lambda, double delta, double sigma2,
                      const float* uResid, const float* ux);
 int rvt_lmm_flush(rvt_ctx* ctx, rvt_lmm_result* out, int64_t cap);
+/* The same flush plus the covariance band of `--meta cov` for related samples: MetaCovFamQtl (src/Model.cpp:437-498) =
+ * FastLMM::TransformCentered / GetCovXX / GetCovXZ / GetCovZZ (regression/FastLMM.cpp:538-625) through
+ * MetaCovTest::printCovariance (src/Model.cpp:934-1004).  pos / chrom / window_bp / band / wmax as in rvt_meta_flush:
+ * band[v*(wmax+1)+d] = (x~_v' D x~_w / sigma2 - covXZ_v covZZ^-1 covXZ_w') / N for w = v + d inside v's window, NaN where
+ * either variant is monomorphic or w is outside the window.  band may be a host or a device pointer. */
+int rvt_lmm_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64_t window_bp, rvt_lmm_result* out, int64_t cap,
+                       double* band, int64_t cap_band, int* wmax);
 /* ---- BoltLMM null model -------------------------------------------------------------------------
  * bed: the PLINK panel, M SNP-major 2-bit rows of `stride` >= ceil(N/4) bytes on the host (samples in phenotype order);
  * y: N phenotypes; covar: N x C column-major, intercept first (the .covar file of BoltPlinkLoader); mc_trials: 0 = the

@@ -36,3 +36,31 @@ def score(U, nm, g):
         stat = Ustat * Ustat / Vstat
         return Ustat, Vstat, stat, float(stats.chi2.sf(stat, 1))
     return Ustat, Vstat, 0.0, 1.0
+
+
+def meta_cov(U, nm, G, pos, chrom, window):
+    """MetaCovFamQtl (src/Model.cpp:437-498) through MetaCovTest::printCovariance (:934-1004) for the variants in the columns
+    of G (N, nv): TransformCentered x~ = U'(g - gbar) (regression/FastLMM.cpp:611-625), covXX = x~_v' D x~_w / sigma2 (:538-551),
+    covXZ = x~' D ux / sigma2 (:552-595), covZZ = ux' D ux / sigma2, entry = (covXX - covXZ_v covZZ^-1 covXZ_w') / N.
+    Returns a dict {(v, w): value} for w >= v inside v's window, both polymorphic (monomorphic variants are never queued)."""
+    U = np.asarray(U, dtype=np.float64)
+    N, nv = G.shape
+    d = 1.0 / (nm["lam"] + nm["delta"])
+    ux = nm["ux"]
+    Xt = U.T @ (G - G.mean(axis=0, keepdims=True))            # (N, nv)
+    covZZ = ux.T @ (d[:, None] * ux) / nm["sigma2"]
+    covZZInv = np.linalg.inv(covZZ)
+    covXZ = (Xt * d[:, None]).T @ ux / nm["sigma2"]           # (nv, C)
+    poly = [G[:, j].min() != G[:, j].max() for j in range(nv)]
+    out = {}
+    for v in range(nv):
+        if not poly[v]:
+            continue
+        for w in range(v, nv):
+            if chrom[w] != chrom[v] or pos[w] - pos[v] > window:
+                break
+            if not poly[w]:
+                continue
+            xx = float(np.sum(Xt[:, v] * d * Xt[:, w])) / nm["sigma2"]
+            out[(v, w)] = (xx - float(covXZ[v] @ covZZInv @ covXZ[w])) / N
+    return out

@@ -13,6 +13,16 @@
 // 64-row tile in the engine's tiled layout, and U'G for a block of <= 64 variants is N/16 tile-PAIR units of the
 // tensor-core sweep (kind::i8, exact integers): u~ comes out exact for the fixed-point image, i.e. more accurate than
 // the reference's float32 product.  Centring is applied afterwards: U'(g - gbar 1) = U'g - gbar t, t = U'1.
+//
+// Covariance band of `--meta cov` for related samples -- MetaCovFamQtl (src/Model.cpp:437-498) on FastLMM::TransformCentered,
+// GetCovXX, GetCovXZ, GetCovZZ (regression/FastLMM.cpp:538-625):
+//   x~_v = U'(g_v - gbar_v)                                     TransformCentered
+//   covXX(v, w) = x~_v' D x~_w / sigma2,  covXZ(v) = x~_v' D ux / sigma2,  covZZ = ux' D ux / sigma2
+//   entry = (covXX - covXZ_v covZZ^-1 covXZ_w') / N             MetaCovTest::printCovariance (src/Model.cpp:990-996)
+// The rotated vectors t_v = U'g_v come out of the same tensor-core units as the score step and are KEPT, scaled by
+// sqrt(d_i), as rows of Y (nv x N doubles); the band is then a plain fp64 Gram of rows of Y over the tile pairs inside the
+// window (k_lmm_gram) plus the centring / projection corrections, which need only per-variant scalars the score step already
+// has (gbar, t'D u1, t'D ux):   x~_v' D x~_w = y_v.y_w - gbar_w s3_v - gbar_v s3_w + gbar_v gbar_w (u1' D u1).
 #pragma once
 #include "../../include/rvtests_b200.h"
 #include "common.cuh"
@@ -97,7 +107,8 @@ __global__ void k_lmm_consts2(LmmNull* nm) {   // <<<1, 32>>>: sums in index ord
 // acc: [n_units][64][kLmmAcc]
 __global__ void __launch_bounds__(64)
 k_lmm_reduce(const GeneDesc* __restrict__ units, int n_units, int S, const SweepPartial* __restrict__ parts, const LmmNull* __restrict__ nm,
-             double* __restrict__ acc) {
+             double* __restrict__ acc, double* __restrict__ Y /* nullable: [nv][ldY] rotated rows scaled by sqrt(d) */, int64_t ldY,
+             int64_t v0 /* variant index of the tile's first row */) {
   const int u = blockIdx.x, j = threadIdx.x;
   if (u >= n_units) return;
   const GeneDesc gd = units[u];
@@ -114,6 +125,7 @@ k_lmm_reduce(const GeneDesc* __restrict__ units, int n_units, int S, const Sweep
       const double ut = ldexp((double)(dg[0] + (dg[1] << 8) + (dg[2] << 16) + (dg[3] << 24)), -kLmmShift);
       const int i = 16 * b + il;
       const double di = nm->d[i], ti = nm->t[i];
+      if (Y) Y[(size_t)(v0 + j) * ldY + i] = ut * sqrt(di);
       s1 += ut * nm->a[i];
       s2 += ut * ut * di;
       s3 += ut * ti * di;
@@ -128,9 +140,14 @@ k_lmm_reduce(const GeneDesc* __restrict__ units, int n_units, int S, const Sweep
 }
 
 // One thread per variant of the tile: sum the eigenvector tiles in index order, centre, finish the statistics.
+struct LmmVar {   // per variant, for the covariance band
+  double gbar, s3, q[kMaxC];   // mean genotype, t'D u1, t'D ux - gbar u1'D ux
+  int32_t poly, pad;
+};
+
 __global__ void __launch_bounds__(64)
 k_lmm_final(int M, int nb, const double* __restrict__ acc /*[nb][64][kLmmAcc]*/, const RowCounts* __restrict__ counts, const LmmNull* __restrict__ nm,
-            rvt_lmm_result* __restrict__ out) {
+            rvt_lmm_result* __restrict__ out, LmmVar* __restrict__ vars /* nullable: [M] */) {
   const int j = threadIdx.x;
   if (j >= M) return;
   const int C = nm->C;
@@ -150,6 +167,16 @@ k_lmm_final(int M, int nb, const double* __restrict__ acc /*[nb][64][kLmmAcc]*/,
   for (int l = 0; l < C; ++l)
     for (int m = 0; m < C; ++m) proj += q[l] * nm->xdx_inv[l * C + m] * q[m];
   const double V = (quad - proj) / nm->sigma2;
+  if (vars) {
+    LmmVar lv;
+    lv.gbar = gbar;
+    lv.s3 = s[2];
+    for (int l = 0; l < kMaxC; ++l) lv.q[l] = l < C ? q[l] : 0.0;
+    const long long n1 = counts[j].n1, n2 = counts[j].n2, n0 = nm->N - n1 - n2;
+    lv.poly = !(n0 == nm->N || n1 == nm->N || n2 == nm->N) && counts[j].bad == 0;
+    lv.pad = 0;
+    vars[j] = lv;
+  }
   rvt_lmm_result r;
   memset(&r, 0, sizeof(r));
   r.af = 0.5 * ac / N;
@@ -169,6 +196,81 @@ k_lmm_final(int M, int nb, const double* __restrict__ acc /*[nb][64][kLmmAcc]*/,
     r.pvalue = 1.0;
   }
   out[j] = r;
+}
+
+// fp64 Gram of two 64-row tiles of Y: G[a][b] = sum_k Y[va + a][k] Y[vb + b][k].  One CTA (256 threads) per tile pair, each
+// thread a 4 x 4 block of the 64 x 64 result; K walks the N eigen-coordinates 32 at a time through shared memory.
+struct LmmPair {
+  int64_t va, vb;
+  int32_t Ma, Mb;
+};
+__global__ void __launch_bounds__(256)
+k_lmm_gram(const LmmPair* __restrict__ pairs, int n_pairs, const double* __restrict__ Y, int64_t ldY, int64_t K, double* __restrict__ G /*[n_pairs][64][64]*/) {
+  __shared__ double sA[32][kTileRows + 1], sB[32][kTileRows + 1];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  if (p >= n_pairs) return;
+  const LmmPair pr = pairs[p];
+  const int ty = tid >> 4, tx = tid & 15;   // rows 4 ty .. 4 ty + 3 of A, rows 4 tx .. of B
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int64_t k0 = 0; k0 < K; k0 += 32) {
+    for (int idx = tid; idx < 32 * kTileRows; idx += 256) {
+      const int r = idx >> 5, kk = idx & 31;   // consecutive threads walk K: coalesced rows of Y
+      const int64_t k = k0 + kk;
+      sA[kk][r] = (r < pr.Ma && k < K) ? Y[(size_t)(pr.va + r) * ldY + k] : 0.0;
+      sB[kk][r] = (r < pr.Mb && k < K) ? Y[(size_t)(pr.vb + r) * ldY + k] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = sA[kk][4 * ty + i];
+        b[i] = sB[kk][4 * tx + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+  double* out = G + (size_t)p * kTileRows * kTileRows;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[(4 * ty + i) * kTileRows + 4 * tx + j] = acc[i][j];
+}
+
+// band entries of the pairs: centring + covariate projection + the reference's scaling (header)
+__global__ void __launch_bounds__(128)
+k_lmm_band(const LmmPair* __restrict__ pairs, int n_pairs, const double* __restrict__ G, const LmmVar* __restrict__ vars, const LmmNull* __restrict__ nm,
+           const int* __restrict__ jmax, int wmax, double* __restrict__ band) {
+  const int p = blockIdx.x, tid = threadIdx.x;
+  if (p >= n_pairs) return;
+  const LmmPair pr = pairs[p];
+  const int C = nm->C;
+  const double scale = 1.0 / (nm->sigma2 * (double)nm->N);
+  const double* g = G + (size_t)p * kTileRows * kTileRows;
+  for (int idx = tid; idx < pr.Ma * pr.Mb; idx += 128) {
+    const int a = idx / pr.Mb, b = idx - a * pr.Mb;
+    const int64_t vi = pr.va + a, vj = pr.vb + b;
+    if (vj < vi || vj > jmax[vi]) continue;
+    double val = nan("");
+    const LmmVar x = vars[vi], y = vars[vj];
+    if (x.poly && y.poly) {
+      const double xx = g[a * kTileRows + b] - y.gbar * x.s3 - x.gbar * y.s3 + x.gbar * y.gbar * nm->ttd;
+      double proj = 0.0;
+      for (int l = 0; l < C; ++l)
+        for (int m = 0; m < C; ++m) proj += x.q[l] * nm->xdx_inv[l * C + m] * y.q[m];
+      val = (xx - proj) * scale;
+    }
+    band[(size_t)vi * (wmax + 1) + (vj - vi)] = val;
+  }
 }
 
 }  // namespace rvt

@@ -2093,7 +2093,18 @@ int rvt_lmm_set_null(rvt_ctx* ctx, int64_t N, int C, const float* U, const float
   return RVT_OK;
 }
 
-int rvt_lmm_flush(rvt_ctx* ctx, rvt_lmm_result* out, int64_t cap) {
+static int meta_jmax(const int32_t* pos, const int32_t* chrom, int64_t nv, int64_t window, std::vector<int>* jmax);
+static int lmm_flush_impl(rvt_ctx* ctx, rvt_lmm_result* out, int64_t cap, const int32_t* pos, const int32_t* chrom, int64_t window_bp,
+                          double* band, int64_t cap_band, int* wmax_out);
+int rvt_lmm_flush(rvt_ctx* ctx, rvt_lmm_result* out, int64_t cap) { return lmm_flush_impl(ctx, out, cap, nullptr, nullptr, 0, nullptr, 0, nullptr); }
+int rvt_lmm_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64_t window_bp, rvt_lmm_result* out, int64_t cap, double* band,
+                       int64_t cap_band, int* wmax) {
+  if (!pos || !chrom || !band) return RVT_E_BADARG;
+  return lmm_flush_impl(ctx, out, cap, pos, chrom, window_bp, band, cap_band, wmax);
+}
+
+static int lmm_flush_impl(rvt_ctx* ctx, rvt_lmm_result* out, int64_t cap, const int32_t* pos, const int32_t* chrom, int64_t window_bp,
+                          double* band, int64_t cap_band, int* wmax_out) {
   if (!ctx || !out) return RVT_E_BADARG;
   if (!ctx->have_lmm || ctx->h_lmm.N != ctx->N) CTX_FAIL(RVT_E_STATE, "lmm: call rvt_lmm_set_null first");
   const int ngen = (int)ctx->genes.size();
@@ -2124,6 +2135,22 @@ int rvt_lmm_flush(rvt_ctx* ctx, rvt_lmm_result* out, int64_t cap) {
   if ((rc = scratch(ctx, 1, sizeof(double) * (size_t)nb * kTileRows * kLmmAcc, (void**)&d_acc))) return rc;
   if ((rc = scratch(ctx, 2, sizeof(rvt_lmm_result) * nv, (void**)&d_out))) return rc;
   auto cleanup = [&]() {};   // (scratch slots persist in the context)
+  // covariance band (MetaCovFamQtl): keep the rotated rows, plan the tile pairs of the window
+  std::vector<int> jmax;
+  int wmax = 0;
+  double *d_Y = nullptr, *d_band = nullptr;
+  LmmVar* d_vars = nullptr;
+  const int64_t ldY = 16 * (int64_t)nb;
+  if (band) {
+    wmax = meta_jmax(pos, chrom, nv, window_bp, &jmax);
+    if (wmax_out) *wmax_out = wmax;
+    if (cap_band < nv * (int64_t)(wmax + 1)) CTX_FAIL(RVT_E_BADARG, "lmm: band needs %lld doubles", (long long)(nv * (int64_t)(wmax + 1)));
+    if ((double)nv * (double)ldY * 8.0 > 48e9) CTX_FAIL(RVT_E_UNSUPPORTED, "lmm: %lld variants x %lld eigenvectors of rotated genotypes exceed the 48 GB kept for them; flush in segments", (long long)nv, (long long)ldY);
+    if ((rc = scratch(ctx, 3, sizeof(double) * (size_t)nv * ldY, (void**)&d_Y))) return rc;
+    if ((rc = scratch(ctx, 4, sizeof(LmmVar) * (size_t)nv, (void**)&d_vars))) return rc;
+    if ((rc = scratch(ctx, 5, sizeof(double) * (size_t)nv * (wmax + 1), (void**)&d_band))) return rc;
+    RVT_CUDA_OK(cudaMemsetAsync(d_band, 0xFF, sizeof(double) * (size_t)nv * (wmax + 1), st));   // NaN: outside the window
+  }
   std::vector<GeneDesc> units(nb);
   for (int g = 0; g < ngen; ++g) {
     const GeneDesc& gd = ctx->genes[g];
@@ -2140,9 +2167,38 @@ int rvt_lmm_flush(rvt_ctx* ctx, rvt_lmm_result* out, int64_t cap) {
       rc = tc_launch(&ctx->tc, d_units + b0, units.data() + b0, n, ctx->d_zero_flags, ctx->d_nm, N, ctx->ER, S, chunk, ctx->d_parts,
                      ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), true, false, kSegLmm);
       if (rc) { cleanup(); return rc; }
-      k_lmm_reduce<<<n, 64, 0, st>>>(d_units + b0, n, S, ctx->d_parts, ctx->d_lmm, d_acc + (size_t)b0 * kTileRows * kLmmAcc);
+      k_lmm_reduce<<<n, 64, 0, st>>>(d_units + b0, n, S, ctx->d_parts, ctx->d_lmm, d_acc + (size_t)b0 * kTileRows * kLmmAcc, d_Y, ldY, gd.var0);
     }
-    k_lmm_final<<<1, 64, 0, st>>>(gd.M, nb, d_acc, ctx->d_counts + gd.var0, ctx->d_lmm, d_out + gd.var0);
+    k_lmm_final<<<1, 64, 0, st>>>(gd.M, nb, d_acc, ctx->d_counts + gd.var0, ctx->d_lmm, d_out + gd.var0, d_vars ? d_vars + gd.var0 : nullptr);
+  }
+  if (band) {
+    // tile pairs inside the window (diagonal pairs included), fp64 Gram of the kept rows, band assembly
+    std::vector<LmmPair> pairs;
+    std::vector<int> tile_of(nv);
+    for (int t = 0; t < ngen; ++t)
+      for (int i = 0; i < ctx->genes[t].M; ++i) tile_of[ctx->genes[t].var0 + i] = t;
+    for (int t = 0; t < ngen; ++t) {
+      int jm = 0;
+      for (int i = 0; i < ctx->genes[t].M; ++i) jm = std::max(jm, jmax[ctx->genes[t].var0 + i]);
+      for (int u = t; u <= tile_of[jm]; ++u) pairs.push_back(LmmPair{ctx->genes[t].var0, ctx->genes[u].var0, ctx->genes[t].M, ctx->genes[u].M});
+    }
+    LmmPair* d_pairs = nullptr;
+    int* d_jmax = nullptr;
+    double* d_G = nullptr;
+    const int pbatch = 2048;
+    if ((rc = scratch(ctx, 6, sizeof(LmmPair) * pairs.size(), (void**)&d_pairs))) return rc;
+    if ((rc = scratch(ctx, 7, sizeof(int) * (size_t)nv, (void**)&d_jmax))) return rc;
+    if ((rc = scratch(ctx, 1, sizeof(double) * (size_t)std::min<size_t>(pairs.size(), pbatch) * kTileRows * kTileRows, (void**)&d_G))) return rc;   // (d_acc is dead)
+    RVT_CUDA_OK(cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(LmmPair) * pairs.size(), cudaMemcpyHostToDevice, st));
+    RVT_CUDA_OK(cudaMemcpyAsync(d_jmax, jmax.data(), sizeof(int) * (size_t)nv, cudaMemcpyHostToDevice, st));
+    for (size_t p0 = 0; p0 < pairs.size(); p0 += pbatch) {
+      const int np = (int)std::min<size_t>(pbatch, pairs.size() - p0);
+      k_lmm_gram<<<np, 256, 0, st>>>(d_pairs + p0, np, d_Y, ldY, N, d_G);
+      k_lmm_band<<<np, 128, 0, st>>>(d_pairs + p0, np, d_G, d_vars, ctx->d_lmm, d_jmax, wmax, d_band);
+    }
+    RVT_CUDA_OK(cudaGetLastError());
+    RVT_CUDA_OK(cudaMemcpyAsync(band, d_band, sizeof(double) * (size_t)nv * (wmax + 1), cudaMemcpyDefault, st));
+    RVT_CUDA_OK(cudaStreamSynchronize(st));   // `pairs`, `jmax` are host temporaries
   }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(rvt_lmm_result) * nv, cudaMemcpyDeviceToHost, st);

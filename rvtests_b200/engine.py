@@ -53,7 +53,7 @@ EXPORTS = [
     "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded", "rvt_push_loaded",
     "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
     "rvt_debug_phases",
-    "rvt_meta_plan", "rvt_meta_flush", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand", "rvt_lmm_set_null", "rvt_lmm_flush", "rvt_get_null_beta", "rvt_bolt_fit_null",
+    "rvt_meta_plan", "rvt_meta_flush", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand", "rvt_lmm_set_null", "rvt_lmm_flush", "rvt_lmm_meta_flush", "rvt_get_null_beta", "rvt_bolt_fit_null",
 ]
 
 BOLT_DTYPE = np.dtype([("delta", "f8"), ("sigma2_g", "f8"), ("sigma2_e", "f8"), ("h2", "f8"), ("h_inv_y_norm2", "f8"),
@@ -111,6 +111,7 @@ def load_library(rebuild: bool = False):
     L.rvt_loaded_genes.argtypes = [vp]
     L.rvt_run_loaded.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.c_int]
     L.rvt_push_loaded.argtypes = [vp]
+    L.rvt_lmm_meta_flush.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.POINTER(C.c_int)]
     L.rvt_loaded_read.argtypes = [vp, C.c_int64, C.c_int, vp]
     L.rvt_last_timing.argtypes = [vp, _dp]
     L.rvt_debug_partials.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64)]
@@ -262,6 +263,18 @@ class GeneEngine:
         out = np.zeros(max(int(n_variants), 1), dtype=LMM_DTYPE)
         self._chk(self.L.rvt_lmm_flush(self.h, out.ctypes.data, len(out)))
         return out[: int(n_variants)]
+
+    def lmm_meta_flush(self, n_variants, pos, chrom, window_bp):
+        """score records + the MetaCovFamQtl covariance band -> (records, band (nv, wmax+1), wmax)"""
+        p = np.ascontiguousarray(pos, dtype=np.int32)
+        c = np.ascontiguousarray(chrom, dtype=np.int32)
+        wmax = C.c_int(0)
+        self._chk(self.L.rvt_meta_plan(self.h, p.ctypes.data, c.ctypes.data, len(p), int(window_bp), C.byref(wmax)))
+        out = np.zeros(max(int(n_variants), 1), dtype=LMM_DTYPE)
+        band = np.zeros((int(n_variants), wmax.value + 1))
+        self._chk(self.L.rvt_lmm_meta_flush(self.h, p.ctypes.data, c.ctypes.data, int(window_bp), out.ctypes.data, len(out),
+                                            band.ctypes.data, band.size, C.byref(wmax)))
+        return out[: int(n_variants)], band, wmax.value
 
     def perm_results(self):
         """permutation records (rvt_perm_result) of the genes of the last flush / run_loaded"""

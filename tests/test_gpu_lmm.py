@@ -49,3 +49,50 @@ def test_fastlmm_score_step(engine_cls, oracle, case):
             assert abs(r["stat"] - st) <= 1e-4 * max(st, 1e-3), (j, r["stat"], st)
             assert abs(r["pvalue"] - p) <= 1e-4 * max(p, 1e-12) + 1e-12, (j, r["pvalue"], p)
     eng.close()
+
+
+def test_fastlmm_covariance_band(engine_cls, oracle):
+    """MetaCovFamQtl: FastLMM::TransformCentered / GetCovXX / GetCovXZ / GetCovZZ (regression/FastLMM.cpp:538-625) through
+    MetaCovTest::printCovariance -- the band of rvt_lmm_meta_flush against the numpy restatement (oracle/lmm_oracle.py)."""
+    from oracle import lmm_oracle as LO
+    O = oracle
+    seed, N, C, delta, nv = 95, 900, 2, 0.6, 150
+    eng = engine_cls(0)
+    if eng.info("tc_available") != 1:
+        pytest.skip("the mixed-model score step needs the tensor-core sweep")
+    rng = np.random.default_rng(seed)
+    Z = rng.binomial(2, 0.3, size=(N, 3 * N // 2)).astype(np.float64)
+    Z = (Z - Z.mean(axis=0)) / Z.std(axis=0)
+    K = Z @ Z.T / Z.shape[1]
+    lam, U = np.linalg.eigh(K)
+    G, X, y = make_problem(O, seed, N, nv, C, maf=np.linspace(0.01, 0.4, nv), n_mono=1)
+    U32, lam32 = U.astype(np.float32), lam.astype(np.float32)
+    nm = LO.fit_null_given_delta(U32, lam32, X, y, delta)
+    eng.lmm_set_null(U32, lam32, delta, nm["sigma2"], nm["uResid"], nm["ux"])
+    nm32 = dict(nm, uResid=nm["uResid"].astype(np.float32).astype(np.float64), ux=nm["ux"].astype(np.float32).astype(np.float64),
+                lam=np.abs(lam32.astype(np.float64)))
+    pos = np.cumsum(rng.integers(100, 900, nv)).astype(np.int32)
+    chrom = np.ones(nv, dtype=np.int32)
+    chrom[110:] = 2
+    window = 6000
+    for b0 in range(0, nv, 64):
+        eng.push_i8(G[:, b0:b0 + 64].T.copy())
+    res, band, wmax = eng.lmm_meta_flush(nv, pos, chrom, window)
+    eng.close()
+    ref = LO.meta_cov(U32, nm32, G.astype(np.float64), pos, chrom, window)
+    assert len(ref) > 500
+    seen = 0
+    for v in range(nv):
+        for dd in range(wmax + 1):
+            w = v + dd
+            val = band[v, dd]
+            if (v, w) in ref:
+                scale = np.sqrt(abs(ref[(v, v)] * ref[(w, w)]))
+                assert abs(val - ref[(v, w)]) <= 1e-6 * scale, (v, w, val, ref[(v, w)])
+                seen += 1
+            else:
+                assert np.isnan(val), (v, w, val)
+    assert seen == len(ref)
+    # the score records are those of rvt_lmm_flush
+    Us, Vs, st, p = LO.score(U32, nm32, G[:, 5].astype(np.float64))
+    assert abs(res[5]["U"] - Us) <= 1e-5 * max(abs(Us), np.sqrt(abs(Vs)))
