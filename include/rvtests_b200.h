@@ -281,6 +281,23 @@ typedef struct rvt_variant_result {
 int rvt_meta_plan(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64_t nv, int64_t window_bp, int* wmax);
 int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64_t window_bp,
                    rvt_variant_result* vout, int64_t cap_variants, double* band, int64_t cap_band, int* wmax);
+/* Binary trait (rvt_set_null_model(.., binary = 1)): rvt_meta_flush evaluates MetaUnrelatedBinary (src/Model.h:3669-3784:
+ * U = g'(y - p), V = g'Wg - g'WZ (Z'WZ)^-1 Z'Wg with W = diag(p(1 - p)) of the logistic null model, U_STAT = U,
+ * SQRT_V_STAT = sqrt(V), ALT_EFFSIZE = U / V, SE = 1 / sqrt(V); LogisticRegressionScoreTest.cpp:219-302 with the intended
+ * 1 x 1 solve) and MetaCovUnrelatedBinary (src/Model.cpp:695-778: band entries (g_i'W g_j - covXZ_i covZZ^-1 covXZ_j') / N on
+ * the raw genotypes).  The columns MetaScoreTest / MetaCovTest print only for a binary trait come from
+ * rvt_meta_binary_extras, for the variants of the LAST rvt_meta_flush:
+ *   cc[v]                 genotype counts and exact HWE p among the cases [0] and the controls [1] (the all:case:control
+ *                         columns, src/Model.h:3300-3330; AF / AC / call rate follow from the counts)
+ *   cov_xz[v*C + l]       covXZ of variant v = g_v'W Z (printCovariance appends covXZ / N of the head variant and
+ *   cov_zz[l*C + m]       covZZ / N = Z'WZ / N after the band, src/Model.cpp:985-994)
+ * Any of the three pointers may be NULL. */
+typedef struct rvt_variant_cc {
+  int32_t n[2];                              /* cases, controls */
+  int32_t n_ref[2], n_het[2], n_alt[2];
+  double hwe_p[2];
+} rvt_variant_cc;
+int rvt_meta_binary_extras(rvt_ctx* ctx, rvt_variant_cc* cc, double* cov_xz, double* cov_zz, int64_t cap_variants);
 
 /* ---- measurement hooks ----------------------------------------------------------------------- */
 /* device milliseconds of the last flush: [0] sweep kernel(s), [1] finalize kernel(s), [2] whole

@@ -105,3 +105,65 @@ def meta_cov(G, pos, chrom, X, sigma2, window):
             ps.append(int(pos[j]))
         out.append((ps, vals))
     return out
+
+
+def meta_score_binary(g, y, X, nm):
+    """MetaUnrelatedBinary (src/Model.h:3669-3784) on one variant (N,) of hard calls.  nm = binary_oracle.fit_null_logistic
+    (p and v of the round before the last update, as GetPredicted / GetVariance return them).
+    LogisticRegressionScoreTest::TestCovariate(Xnull, y, Xcol), regression/LogisticRegressionScoreTest.cpp:219-302:
+    U = g'(y - p), V = g'Wg - g'WZ (Z'WZ)^-1 Z'Wg; U_STAT = U, SQRT_V_STAT = sqrt(V), ALT_EFFSIZE = U / V, SE = 1 / sqrt(V).
+    (With covariates the reference solves its 1 x 1 SS against a d x d identity, :292-295; the intended statistic is used.)
+    The all:case:control site columns come from GenotypeCounter on the three sample sets (src/Model.h:3220-3232)."""
+    g = np.asarray(g, dtype=np.float64)
+    out = meta_score(g, X, y - nm["p"], 1.0)
+    cc = {}
+    for name, sel in (("case", y == 1), ("ctrl", y == 0)):
+        gs = g[sel]
+        n0, n1, n2 = int((gs == 0).sum()), int((gs == 1).sum()), int((gs == 2).sum())
+        cc[name] = dict(n=int(sel.sum()), n_ref=n0, n_het=n1, n_alt=n2, hwe_p=snp_hwe(n1, n0, n2) if (n0 + n1 + n2) else 0.0)
+    out["cc"] = cc
+    for k in ("U", "sqrtV", "effect", "effect_se", "pvalue"):
+        out.pop(k, None)
+    if not out["polymorphic"]:
+        out["ok"] = False
+        return out
+    v = nm["v"]
+    U = float(g @ (y - nm["p"]))
+    xz = (g * v) @ X
+    V = float(g @ (v * g)) - float(xz @ nm["covB"] @ xz)
+    out["cov_xz"] = xz
+    stat = U * U / V
+    if not (V > 0) or stat < 0:
+        out["ok"] = False
+        return out
+    out.update(ok=True, U=U, sqrtV=np.sqrt(V), effect=(U / V) if U != 0 else 0.0, effect_se=1.0 / np.sqrt(V),
+               pvalue=O.lib().orc_chisq_q(stat, 1.0))
+    return out
+
+
+def meta_cov_binary(G, pos, chrom, X, nm, window):
+    """MetaCovUnrelatedBinary (src/Model.cpp:695-778) through MetaCovTest::printCovariance (:942-1004): raw genotypes,
+    covXX = g_i'W g_j, covXZ = g'W Z, covZZ = Z'WZ, entry = (covXX - covXZ_i covZZ^-1 covXZ_j') / N.  Same return shape as
+    meta_cov."""
+    N, nv = G.shape
+    Gd = G.astype(np.float64)
+    v = nm["v"]
+    covZZInv = np.linalg.inv(X.T @ (v[:, None] * X))
+    covXZ = (Gd * v[:, None]).T @ X
+    poly = [Gd[:, j].min() != Gd[:, j].max() for j in range(nv)]
+    out = []
+    for i in range(nv):
+        if not poly[i]:
+            out.append(None)
+            continue
+        ps, vals = [], []
+        for j in range(i, nv):
+            if chrom[j] != chrom[i] or pos[j] - pos[i] > window:
+                break
+            if not poly[j]:
+                continue
+            xx = float(Gd[:, i] @ (v * Gd[:, j]))
+            vals.append((xx - float(covXZ[i] @ covZZInv @ covXZ[j])) / N)
+            ps.append(int(pos[j]))
+        out.append((ps, vals))
+    return out

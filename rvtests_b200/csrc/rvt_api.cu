@@ -110,6 +110,10 @@ struct rvt_ctx {
   void *d_dos_st = nullptr, *d_dos_tin = nullptr, *d_dos_idx = nullptr, *d_dos_afd = nullptr, *d_dos_tg = nullptr;
   size_t cap_dos_st = 0, cap_dos_tin = 0, cap_dos_idx = 0, cap_dos_afd = 0, cap_dos_tg = 0;
   // scratch of the meta / mixed-model flushes, kept across calls for the same reason
+  double h_xvx[kMaxC * kMaxC] = {};   // binary trait: X'VX of the logistic null model
+  int64_t metab_nv = 0;               // variants of the last binary-trait meta flush (rvt_meta_binary_extras)
+  void* d_metab[6] = {};              // its scratch: digits, scaled tiles, band sums, per-variant sums, case/control counts, covXZ
+  size_t cap_metab[6] = {};
   void* d_scr[8] = {};
   size_t cap_scr[8] = {};
   // binary trait (logistic null model)
@@ -355,6 +359,8 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
                   ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_jobs, ctx->d_mid, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum, ctx->d_p, ctx->d_vw, ctx->d_dos_st, ctx->d_dos_tin, ctx->d_dos_idx, ctx->d_dos_afd, ctx->d_dos_tg};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (void* p : ctx->d_metab)
     if (p) cudaFree(p);
   for (void* p : ctx->d_scr)
     if (p) cudaFree(p);
@@ -627,6 +633,7 @@ static int logistic_null(rvt_ctx* ctx, double* covB /*C*C*/, double* vsum, doubl
     }
     for (int i = 0; i < C; ++i) covB[i * C + col] = e[i];
   }
+  for (int l = 0; l < C * C; ++l) ctx->h_xvx[l] = D[l];   // Z'WZ of that round = covZZ of MetaCovUnrelatedBinary
   *rsum = r[0];                                 // sum_i (y_i - p_i): not zero, p is one Newton step stale
   *vsum = D[0];                                 // column 0 of X is the intercept: D[0][l] = sum v x_l
   for (int l = 0; l < C; ++l) xsum_w[l] = D[l];
@@ -1848,7 +1855,6 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   if (cap_variants < nv) CTX_FAIL(RVT_E_BADARG, "vout holds %lld records, %lld variants pending", (long long)cap_variants, (long long)nv);
   if (band && (!pos || !chrom)) CTX_FAIL(RVT_E_BADARG, "the covariance band needs pos and chrom");
   if (!ctx->wide.empty()) CTX_FAIL(RVT_E_UNSUPPORTED, "meta: push variant blocks of at most %d variants", kMaxM);
-  if (ctx->binary) CTX_FAIL(RVT_E_UNSUPPORTED, "meta score/cov for a binary trait (MetaUnrelatedBinary, src/Model.h:3557-3640) is not provided");
   RVT_CUDA_OK(cudaSetDevice(ctx->device));
   // every pending push is one tile (<= 64 consecutive variants, its own tiled block) of one segment
   const int seg = ctx->genes[0].seg;
@@ -1880,6 +1886,8 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
       S = (int)std::min<int64_t>(64, std::max<int64_t>(S, s_l2));
     }
   }
+  // binary trait: an s32 accumulator holds |g d_k e| <= 128 * 127 per sample for 2^31 / 16256 = 132 104 samples
+  if (ctx->binary) S = (int)std::max<int64_t>(S, (N + 65535) / 65536);
   int64_t chunk = (((N + S - 1) / S) + 511) & ~(int64_t)511;
   S = (int)((N + chunk - 1) / chunk);
   const int T = ngen;
@@ -1911,7 +1919,7 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   uint8_t* d_flags0 = nullptr;
   auto cleanup = [&]() {};   // (the buffers below persist in the context)
   const int batch = 1024;
-  const size_t ndesc = std::max<size_t>((size_t)T, pairs.size());
+  const size_t ndesc = ctx->binary ? (size_t)T + pairs.size() : std::max<size_t>((size_t)T, pairs.size());
   {
     const size_t need[7] = {sizeof(int) * (size_t)nv, sizeof(double) * (size_t)nv * kMaxC, (size_t)nv, sizeof(rvt_variant_result) * (size_t)nv,
                             sizeof(GeneDesc) * ndesc, (size_t)nv + kTileRows, band ? sizeof(double) * (size_t)nv * (size_t)(wmax + 1) : 0};
@@ -1941,6 +1949,40 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
   }
   const bool tc_ok = ctx->tc.encode && ctx->tc.have_e && seg >= 0 && ctx->tc.have_seg[seg];
   if (!pairs.empty() && !tc_ok) { cleanup(); CTX_FAIL(RVT_E_UNSUPPORTED, "meta cov needs the tensor-core engine (TMA segment unavailable)"); }
+  // binary trait: scratch of the digit passes
+  int8_t *d_dig = nullptr, *d_aux = nullptr;
+  double *d_acc = nullptr, *d_covxz = nullptr, *d_uraw = nullptr;
+  MetabVar* d_mv = nullptr;
+  rvt_variant_cc* d_cc = nullptr;
+  unsigned long long* d_ncase = nullptr;
+  std::vector<int64_t> aux_off(T + 1, 0);
+  const int64_t ldd = ((N + 127) >> 7) * 128;
+  ctx->metab_nv = 0;
+  if (ctx->binary) {
+    if (!tc_ok) { cleanup(); CTX_FAIL(RVT_E_UNSUPPORTED, "meta score/cov for a binary trait needs the tensor-core engine"); }
+    for (int t = 0; t < T; ++t) aux_off[t + 1] = aux_off[t] + tiled_bytes(N, tiles[t].M);
+    const size_t need[6] = {(size_t)(kMetabDigits + 1) * ldd, (size_t)aux_off[T], sizeof(double) * (size_t)nv * (size_t)(wmax + 1),
+                            sizeof(MetabVar) * (size_t)nv + sizeof(double) * (size_t)nv + 16, sizeof(rvt_variant_cc) * (size_t)nv,
+                            sizeof(double) * (size_t)nv * kMaxC};
+    for (int k = 0; k < 6; ++k)
+      if (need[k] > ctx->cap_metab[k]) {
+        if (ctx->d_metab[k]) cudaFree(ctx->d_metab[k]);
+        ctx->d_metab[k] = nullptr;
+        ctx->cap_metab[k] = 0;
+        cudaError_t e = cudaMalloc(&ctx->d_metab[k], need[k]);
+        if (e != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "meta (binary trait): cudaMalloc of %zu bytes: %s", need[k], cudaGetErrorString(e));
+        ctx->cap_metab[k] = need[k];
+      }
+    d_dig = (int8_t*)ctx->d_metab[0];
+    d_aux = (int8_t*)ctx->d_metab[1];
+    d_acc = (double*)ctx->d_metab[2];
+    d_mv = (MetabVar*)ctx->d_metab[3];
+    d_uraw = (double*)((char*)ctx->d_metab[3] + sizeof(MetabVar) * (size_t)nv);
+    d_ncase = (unsigned long long*)(d_uraw + nv);
+    d_cc = (rvt_variant_cc*)ctx->d_metab[4];
+    d_covxz = (double*)ctx->d_metab[5];
+    if ((rc = tc_bind_segment(&ctx->tc, kSegAux, d_aux, aux_off[T], ctx->err, sizeof(ctx->err)))) { cleanup(); return rc; }
+  }
   // BoltLMM::GetCovXX (regression/BoltLMM.cpp:435-460; MetaCovFamQtlBolt::calculateXX, src/Model.cpp:780-805): the entry
   // is g1'(I - ZZ')g2 * xVx_xx_ratio / N -- the projected Gram of this band times a scalar -- where the unrelated-sample
   // model divides by sigma2 N (option "meta_cov_scale" = xVx_xx_ratio of rvt_bolt_fit_null; 0 = unrelated samples)
@@ -1959,14 +2001,61 @@ int rvt_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, int64
       k_sweep_simt<<<std::min(nb * S, ctx->sm_count * 3), kSimtThreads, kSimtSmem, st>>>(d_desc + b0, nb, d_flags0, ctx->d_nm, S, chunk,
                                                                                        ctx->d_parts, ctx->d_counter);
     }
-    k_meta_block<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, d_v, d_B, d_poly, d_band, band_scale);
+    k_meta_block<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, d_v, d_B, d_poly,
+                                              ctx->binary ? nullptr : d_band, band_scale, d_uraw);
     RVT_CUDA_OK(cudaGetLastError());
   }
   k_meta_hwe<<<(unsigned)nv, kHweThreads, 0, st>>>(nv, d_v);
   RVT_CUDA_OK(cudaGetLastError());
   // phase 2: tile pairs inside the window
   RVT_CUDA_OK(cudaEventRecord(ctx->ev[2], st));
-  if (!pairs.empty()) {
+  if (ctx->binary) {
+    // digit passes (meta.cuh): A operand = G o d_k in kSegAux, B operand = the plain tiles; units = the diagonal pairs
+    // (t, t) followed by the window's pairs; pass kMetabDigits (d = y) needs the diagonal pairs only
+    std::vector<GeneDesc> units((size_t)T + pairs.size());
+    for (int t = 0; t < T; ++t) {
+      GeneDesc g = tiles[t];
+      g.row0_b = tiles[t].row0;
+      g.Mb = tiles[t].M;
+      g.var0_b = tiles[t].var0;
+      units[t] = g;
+    }
+    for (size_t p = 0; p < pairs.size(); ++p) units[(size_t)T + p] = pairs[p];
+    for (auto& u : units) {   // the A tile lives in the scaled copy
+      const int t = tile_of[u.var0];
+      u.g = d_aux + aux_off[t];
+      u.seg = kSegAux;
+      u.row0 = aux_off[t] / 128;
+    }
+    RVT_CUDA_OK(cudaStreamSynchronize(st));  // d_desc is rewritten
+    RVT_CUDA_OK(cudaMemcpyAsync(d_desc, units.data(), sizeof(GeneDesc) * units.size(), cudaMemcpyHostToDevice, st));
+    RVT_CUDA_OK(cudaMemsetAsync(d_ncase, 0, sizeof(unsigned long long), st));
+    k_metab_digits<<<(unsigned)((ldd + 255) / 256), 256, 0, st>>>(N, ctx->d_vw, ctx->dresid, d_dig, ldd, d_ncase);
+    const int64_t nwords = ((N + 127) >> 7) * 32;
+    for (int k = 0; k <= kMetabDigits; ++k) {
+      for (int t = 0; t < T; ++t)
+        k_metab_scale<<<dim3((unsigned)((nwords + 255) / 256), (unsigned)tiles[t].M), 256, 0, st>>>(tiles[t].g, tiles[t].M, N, d_dig + (size_t)k * ldd,
+                                                                                                  d_aux + aux_off[t]);
+      RVT_CUDA_OK(cudaGetLastError());
+      const size_t nu = (k == kMetabDigits) ? (size_t)T : units.size();
+      for (size_t b0 = 0; b0 < nu; b0 += batch) {
+        const int nb = (int)std::min<size_t>(batch, nu - b0);
+        rc = tc_launch(&ctx->tc, d_desc + b0, units.data() + b0, nb, d_flags0, ctx->d_nm, N, ctx->ER, S, chunk, ctx->d_parts,
+                       ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), true, false, seg);
+        if (rc) { cleanup(); return rc; }
+        k_metab_acc<<<nb, kMetaThreads, 0, st>>>(d_desc + b0, nb, ctx->d_nm, S, ctx->d_parts, d_jmax, wmax, k, d_acc, d_mv);
+        RVT_CUDA_OK(cudaGetLastError());
+      }
+    }
+    k_metab_final<<<(unsigned)((nv + 127) / 128), 128, 0, st>>>(nv, ctx->d_nm, d_acc, wmax, d_mv, d_uraw, d_ncase, d_v, d_cc, d_covxz);
+    k_meta_hwe_cc<<<(unsigned)(2 * nv), kHweThreads, 0, st>>>(nv, d_cc);
+    if (band) {
+      const int64_t ne = nv * (int64_t)(wmax + 1);
+      k_metab_band<<<(unsigned)((ne + 127) / 128), 128, 0, st>>>(nv, ctx->d_nm, d_acc, d_covxz, d_poly, d_jmax, wmax, d_band);
+    }
+    RVT_CUDA_OK(cudaGetLastError());
+    ctx->metab_nv = nv;
+  } else if (!pairs.empty()) {
     RVT_CUDA_OK(cudaStreamSynchronize(st));  // d_desc is rewritten
     RVT_CUDA_OK(cudaMemcpyAsync(d_desc, pairs.data(), sizeof(GeneDesc) * pairs.size(), cudaMemcpyHostToDevice, st));
     for (size_t b0 = 0; b0 < pairs.size(); b0 += batch) {
@@ -2090,6 +2179,27 @@ int rvt_lmm_set_null(rvt_ctx* ctx, int64_t N, int C, const float* U, const float
   ctx->h_lmm = h;
   if ((rc = tc_bind_segment(&ctx->tc, kSegLmm, ctx->d_lmm_tiles, (int64_t)nb * tile_b, ctx->err, sizeof(ctx->err)))) return rc;
   ctx->have_lmm = true;
+  return RVT_OK;
+}
+
+int rvt_meta_binary_extras(rvt_ctx* ctx, rvt_variant_cc* cc, double* cov_xz, double* cov_zz, int64_t cap_variants) {
+  if (!ctx) return RVT_E_BADARG;
+  if (!ctx->binary || ctx->metab_nv == 0) CTX_FAIL(RVT_E_STATE, "no binary-trait rvt_meta_flush to report on");
+  const int64_t nv = ctx->metab_nv;
+  const int C = ctx->C;
+  if ((cc || cov_xz) && cap_variants < nv) CTX_FAIL(RVT_E_BADARG, "%lld variants in the last flush, room for %lld", (long long)nv, (long long)cap_variants);
+  RVT_CUDA_OK(cudaSetDevice(ctx->device));
+  if (cc) RVT_CUDA_OK(cudaMemcpyAsync(cc, ctx->d_metab[4], sizeof(rvt_variant_cc) * (size_t)nv, cudaMemcpyDefault, ctx->stream));
+  if (cov_xz) {
+    std::vector<double> h((size_t)nv * kMaxC);
+    RVT_CUDA_OK(cudaMemcpyAsync(h.data(), ctx->d_metab[5], sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    for (int64_t v = 0; v < nv; ++v)
+      for (int l = 0; l < C; ++l) cov_xz[v * C + l] = h[(size_t)v * kMaxC + l];
+  }
+  if (cov_zz)
+    for (int l = 0; l < C * C; ++l) cov_zz[l] = ctx->h_xvx[l];
+  RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return RVT_OK;
 }
 

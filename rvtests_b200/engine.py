@@ -53,7 +53,7 @@ EXPORTS = [
     "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded", "rvt_push_loaded",
     "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
     "rvt_debug_phases",
-    "rvt_meta_plan", "rvt_meta_flush", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand", "rvt_lmm_set_null", "rvt_lmm_flush", "rvt_lmm_meta_flush", "rvt_get_null_beta", "rvt_bolt_fit_null",
+    "rvt_meta_plan", "rvt_meta_flush", "rvt_meta_binary_extras", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand", "rvt_lmm_set_null", "rvt_lmm_flush", "rvt_lmm_meta_flush", "rvt_get_null_beta", "rvt_bolt_fit_null",
 ]
 
 BOLT_DTYPE = np.dtype([("delta", "f8"), ("sigma2_g", "f8"), ("sigma2_e", "f8"), ("h2", "f8"), ("h_inv_y_norm2", "f8"),
@@ -67,6 +67,7 @@ PERM_DTYPE = np.dtype([
     ("stat", "f8"), ("p_perm", "f8"), ("stream_pos", "i8"), ("done", "i4"), ("pad", "i4"),
 ])
 
+CC_DTYPE = np.dtype([("n", "i4", 2), ("n_ref", "i4", 2), ("n_het", "i4", 2), ("n_alt", "i4", 2), ("hwe_p", "f8", 2)])
 VARIANT_DTYPE = np.dtype([
     ("af", "f8"), ("ac", "f8"), ("call_rate", "f8"), ("hwe_p", "f8"),
     ("n_ref", "i4"), ("n_het", "i4"), ("n_alt", "i4"), ("ok", "i4"), ("polymorphic", "i4"), ("pad", "i4"),
@@ -111,6 +112,7 @@ def load_library(rebuild: bool = False):
     L.rvt_loaded_genes.argtypes = [vp]
     L.rvt_run_loaded.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.c_int]
     L.rvt_push_loaded.argtypes = [vp]
+    L.rvt_meta_binary_extras.argtypes = [vp, vp, vp, vp, C.c_int64]
     L.rvt_lmm_meta_flush.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.POINTER(C.c_int)]
     L.rvt_loaded_read.argtypes = [vp, C.c_int64, C.c_int, vp]
     L.rvt_last_timing.argtypes = [vp, _dp]
@@ -352,6 +354,14 @@ class GeneEngine:
 
     def push_loaded(self):
         self._chk(self.L.rvt_push_loaded(self.h))
+
+    def meta_binary_extras(self, n_variants, n_cov):
+        """case / control counts, covXZ (nv, C) and covZZ (C, C) of the last binary-trait meta_flush"""
+        cc = np.zeros(max(int(n_variants), 1), dtype=CC_DTYPE)
+        xz = np.zeros((max(int(n_variants), 1), int(n_cov)))
+        zz = np.zeros((int(n_cov), int(n_cov)))
+        self._chk(self.L.rvt_meta_binary_extras(self.h, cc.ctypes.data, xz.ctypes.data, zz.ctypes.data, len(cc)))
+        return cc[: int(n_variants)], xz[: int(n_variants)], zz
 
     def meta_flush_dev(self, n_variants, pos, chrom, window_bp, d_vout, d_band, band_elems):
         """as meta_flush with the outputs left in device memory (d_vout: n_variants records, d_band: band_elems doubles)"""

@@ -177,3 +177,80 @@ def test_bolt_covariance_band(engine_cls, oracle):
             assert abs(band[i, d] - want) <= 1e-7 * scale, (i, d, band[i, d], want, scale)
             checked += 1
     assert checked > 1000
+
+
+def _binary_problem(O, seed, N, nv, C):
+    G = _variants(O, seed, N, nv)
+    X, _y = O.synth_covariates(seed, N, C)
+    rng = np.random.default_rng(seed + 7)
+    eta = -0.4 + (0.5 * X[:, 1] if C > 1 else 0.0) + 0.3 * (G[3] - G[3].mean())
+    y = (rng.uniform(size=N) < 1.0 / (1.0 + np.exp(-eta))).astype(np.float64)
+    return G, X, y
+
+
+@pytest.mark.parametrize("case", [(11, 3000, 50, 1, 400), (12, 5000, 200, 3, 3000), (13, 70000, 90, 2, 100000)])
+def test_meta_binary_trait_score_and_cov(engine_cls, oracle, case):
+    """MetaUnrelatedBinary (src/Model.h:3669-3784) + MetaCovUnrelatedBinary (src/Model.cpp:695-778): the weighted sums come
+    off the integer tensor-core sweep through base-128 digits of the weights (csrc/meta.cuh); counts among cases / controls
+    exact, statistics 1e-6 (the weights are rounded to 2^-28), band 1e-6 of the variant's own variance."""
+    from oracle import meta_oracle as MO
+    from oracle import binary_oracle as BIN
+    O = oracle
+    seed, N, nv, C, window = case
+    G, X, y = _binary_problem(O, seed, N, nv, C)
+    rng = np.random.default_rng(seed + 100)
+    pos = np.cumsum(rng.integers(1, 60, nv)).astype(np.int32)
+    chrom = np.ones(nv, dtype=np.int32)
+    chrom[int(nv * 0.7):] = 2
+    pos[int(nv * 0.7):] -= pos[int(nv * 0.7)] - 5
+    eng = engine_cls(0)
+    if eng.info("tc_available") != 1:
+        pytest.skip("binary-trait meta statistics need the tensor-core sweep")
+    eng.set_null_model(X, y, binary=True)
+    nm = BIN.fit_null_logistic(X, y)
+    for b0 in range(0, nv, 37):
+        eng.push_i8(G[b0:b0 + 37].copy(), None)
+    vout, band, wmax = eng.meta_flush(nv, pos, chrom, window)
+    cc, xz, zz = eng.meta_binary_extras(nv, C)
+    assert np.max(np.abs(zz - X.T @ (nm["v"][:, None] * X))) <= 1e-9 * np.max(np.abs(zz))
+    ref_cov = MO.meta_cov_binary(G.T, pos, chrom, X, nm, window)
+    n_cov = n_ok = 0
+    for v in range(nv):
+        ref = MO.meta_score_binary(G[v].astype(np.float64), y, X, nm)
+        r = vout[v]
+        assert (int(r["n_ref"]), int(r["n_het"]), int(r["n_alt"])) == (ref["n_ref"], ref["n_het"], ref["n_alt"])
+        assert r["af"] == ref["af"] and r["ac"] == ref["ac"]
+        assert rel(r["hwe_p"], ref["hwe_p"]) <= 1e-9
+        for w, name in enumerate(("case", "ctrl")):
+            rc = ref["cc"][name]
+            assert (int(cc[v]["n"][w]), int(cc[v]["n_ref"][w]), int(cc[v]["n_het"][w]), int(cc[v]["n_alt"][w])) == \
+                (rc["n"], rc["n_ref"], rc["n_het"], rc["n_alt"]), (v, name)
+            assert rel(cc[v]["hwe_p"][w], rc["hwe_p"]) <= 1e-9, (v, name, cc[v]["hwe_p"][w], rc["hwe_p"])
+        assert bool(r["ok"]) == ref["ok"] and bool(r["polymorphic"]) == ref["polymorphic"], (v, r, ref)
+        if ref["ok"]:
+            n_ok += 1
+            assert abs(r["U"] - ref["U"]) <= 1e-6 * max(abs(ref["U"]), ref["sqrtV"]), (v, r["U"], ref["U"])
+            for k in ("sqrtV", "effect_se"):
+                assert rel(r[k], ref[k]) <= 1e-6, (v, k, r[k], ref[k])
+            assert abs(r["effect"] - ref["effect"]) <= 1e-6 * max(abs(ref["effect"]), ref["effect_se"])
+            assert abs(r["pvalue"] - ref["pvalue"]) <= 1e-6 * max(ref["pvalue"], 1e-12) + 1e-9
+            assert np.max(np.abs(xz[v] - ref["cov_xz"])) <= 1e-6 * max(np.max(np.abs(ref["cov_xz"])), 1e-12)
+        row = band[v]
+        if ref_cov[v] is None:
+            assert np.all(np.isnan(row))
+            continue
+        ps, vals = ref_cov[v]
+        got = row[~np.isnan(row)]
+        got_pos = pos[v:v + wmax + 1][~np.isnan(row[: len(pos[v:v + wmax + 1])])]
+        assert list(got_pos) == ps
+        scale = max(abs(vals[0]), 1e-300)
+        assert np.max(np.abs(got - np.array(vals))) <= 1e-6 * scale, (v, got[:4], vals[:4])
+        n_cov += len(vals)
+    assert n_cov > nv and n_ok > nv // 2
+    # score only: no band, same records
+    for b0 in range(0, nv, 64):
+        eng.push_i8(G[b0:b0 + 64].copy(), None)
+    vout2, _b, _w = eng.meta_flush(nv, want_cov=False)
+    for k in ("U", "sqrtV", "pvalue"):
+        assert np.allclose(vout2[k], vout[k], rtol=1e-12, atol=0)
+    eng.close()
