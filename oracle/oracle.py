@@ -587,12 +587,12 @@ def ref_dropin():
                                                  C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
             L.dropin_run_meta_models.restype = C.c_int
             L.dropin_run_meta_models.argtypes = [C.c_int, C.c_int, _dbl_p, _int_p, C.c_int, _dbl_p, _dbl_p, C.c_char_p, C.c_int,
-                                                 C.c_int, C.c_char_p]
+                                                 C.c_int, C.c_char_p, C.c_int]
             _lib_cache["dropin"] = L
     return _lib_cache["dropin"]
 
 
-def dropin_run_meta_models(G, pos, cov, pheno, window, prefix, use_b200, se=False, segment=0):
+def dropin_run_meta_models(G, pos, cov, pheno, window, prefix, use_b200, se=False, segment=0, binary=False):
     """`--meta score[se],cov[windowSize=window]` through the reference's ModelManager and single-variant loop (see
     dropin_run_gene_models); the files carry ModelManager's `.assoc.gz` names but are plain text in this build."""
     Gc = np.asfortranarray(G, dtype=np.float64)
@@ -602,7 +602,7 @@ def dropin_run_meta_models(G, pos, cov, pheno, window, prefix, use_b200, se=Fals
     y = np.ascontiguousarray(pheno, dtype=np.float64)
     spec = "score%s,cov[windowSize=%d]" % ("[se]" if se else "", int(window))
     rc = ref_dropin().dropin_run_meta_models(N, nv, _p(Gc), _p(pos, C.c_int), covf.shape[1], _p(covf), _p(y), spec.encode(),
-                                             int(use_b200), int(segment), prefix.encode())
+                                             int(use_b200), int(segment), prefix.encode(), int(binary))
     if rc:
         raise RuntimeError(f"dropin_run_meta_models rc={rc}")
     return {m: _read_assoc(f"{prefix}.{m}.assoc.gz") for m in ("MetaScore", "MetaCov")}

@@ -125,7 +125,7 @@ int dropin_run_gene_models(int N, int n_genes, const int* M, const double* G, in
 // <prefix>.MetaCov.assoc.gz -- plain text here: the writer behind FileWriter(.., BGZIP) is the stdio stand-in of
 // ref_model_shim.cpp, and the tabix step of ModelManager::close is stubbed.
 int dropin_run_meta_models(int N, int n_var, const double* G, const int* pos, int n_cov, const double* cov, const double* pheno,
-                           const char* meta, int use_b200, int segment, const char* prefix) {
+                           const char* meta, int use_b200, int segment, const char* prefix, int binary) {
   if (!logger) logger = new Logger((std::string(prefix) + ".log").c_str());
   {
     delete g_SummaryHeader;   // the trait / covariate summaries MetaScoreTest prints in its header (src/Main.cpp:775-780)
@@ -161,7 +161,10 @@ int dropin_run_meta_models(int N, int n_var, const double* G, const int* pos, in
   dc.setParRegion(&par);
   {
     ModelManager modelManager(prefix);
-    modelManager.setQuantitativeOutcome();
+    if (binary)
+      modelManager.setBinaryOutcome();   // MetaUnrelatedBinary / MetaCovUnrelatedBinary (phenotype already 0 / 1)
+    else
+      modelManager.setQuantitativeOutcome();
     modelManager.create("meta", meta);
     const std::vector<ModelFitter*>& model = modelManager.getModel();
     const std::vector<FileWriter*>& fOuts = modelManager.getResultFile();

@@ -14,6 +14,7 @@
 //       (regression/EigenMatrixInterface.cpp:125-136), so this is (g_i'(I-H_X)g_j)/(sigma2 N)
 //       = (A_ij - B_i (X'X)^-1 B_j') / (sigma2 N): an entry of the same projected Gram the SKAT
 //       kernel builds, without weights.
+//   MetaUnrelatedBinary / MetaCovUnrelatedBinary (binary trait)   src/Model.h:3669-3784, src/Model.cpp:695-778  (end of file)
 // Every push is one tile (<= 64 consecutive variants); tile pairs (I,J) inside the window come from
 // the PAIR mode of the tensor-core sweep (A tile = rows of I, B tile = rows of J).
 #pragma once

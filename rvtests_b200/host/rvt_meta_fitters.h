@@ -14,7 +14,10 @@
 // blocks are evaluated in segments, and the lines are written in arrival order when a segment is flushed (every
 // `segment` variants, at a chromosome change, in writeFootnote / the destructor).  A segment keeps the trailing variants
 // whose window is still open and re-submits them with the next segment, so covariance windows are never cut.
-// Not covered: binary traits, kinship (family) models, hemizygous regions, dosages (a site with a value outside {0,1,2}
+// Binary traits (the fitter's isBinaryOutcome(), read at fit time): MetaUnrelatedBinary / MetaCovUnrelatedBinary -- the site
+// columns become all:case:control triples (src/Model.h:3300-3330), the null-model block prints Sigma2 NA NA (:3733-3747),
+// and every MetaCov line carries ":covXZ/N:covZZ/N" of its head variant after the band (src/Model.cpp:985-994).
+// Not covered: kinship (family) models, hemizygous regions, dosages (a site with a value outside {0,1,2}
 // prints NA statistics).
 #ifndef RVT_META_FITTERS_H_
 #define RVT_META_FITTERS_H_
@@ -48,18 +51,44 @@ class MetaBatcher {
   void enableCov() { want_cov_ = true; }
   const char* error() const { return ctx_ ? rvt_last_error(ctx_) : "no context"; }
   int newFitterId() { return next_id_++; }
+  // every adapter attaches in its constructor and detaches in its destructor (after draining its own lines): when the last
+  // one of a run is gone the batcher forgets the run, so that a second ModelManager in the same process starts clean
+  void attach() { ++n_attached_; }
+  void detach() {
+    if (--n_attached_ > 0) return;
+    sites_.clear();
+    blocks_.clear();
+    open_ = Block{0, 0, std::vector<int8_t>()};
+    seen_.clear();
+    chroms_.clear();
+    current_ = -1;
+    pending_new_ = 0;
+    have_null_ = false;
+    want_cov_ = false;
+    binary_ = false;
+    if (ctx_ && rvt_pending(ctx_) > 0) {   // (a failed flush left pushes behind)
+      rvt_ctx_destroy(ctx_);
+      ctx_ = NULL;
+    }
+  }
 
   struct Site {
     int chrom, pos;
     bool hard;           // every value in {0,1,2}
     bool score_done, cov_done;
     rvt_variant_result r;
+    rvt_variant_cc cc;      // binary trait: cases [0] / controls [1]
     std::string cov_line;   // empty: nothing to print (monomorphic)
   };
 
   // Called from fit(): ticket of the CURRENT variant, recorded on first sight (a fitter id seen twice = next variant)
-  int submit(int fitter_id, DC* dc) {
+  int submit(int fitter_id, DC* dc, bool binary = false) {
     if (!ensureContext()) return -1;
+    if (binary != binary_) {   // the outcome type changed: a new null model
+      if (!flush(true)) return -1;
+      binary_ = binary;
+      have_null_ = false;
+    }
     if (current_ < 0 || seen(fitter_id)) {
       if (!record(dc)) return -1;
       seen_.clear();
@@ -101,12 +130,21 @@ class MetaBatcher {
     if (rvt_meta_flush(ctx_, pos.data(), chrom.data(), window_, vr.data(), nv, want_cov_ ? band.data() : NULL,
                        (int64_t)band.size(), &wmax) != RVT_OK)
       return fail("flush");
+    std::vector<rvt_variant_cc> cc;
+    std::vector<double> xz, zz;
+    if (binary_) {
+      cc.resize(nv);
+      xz.resize((size_t)nv * C_);
+      zz.resize((size_t)C_ * C_);
+      if (rvt_meta_binary_extras(ctx_, cc.data(), xz.data(), zz.data(), nv) != RVT_OK) return fail("binary extras");
+    }
     const int last_pos = pos[nv - 1], last_chrom = chrom[nv - 1];
     int64_t first_open = nv;   // first variant whose window may still grow
     for (int64_t v = 0; v < nv; ++v) {
       Site& s = sites_[tix[v]];
       if (!s.score_done) {
         s.r = vr[v];
+        if (binary_) s.cc = cc[v];
         if (!s.hard) s.r.ok = 0;
         s.score_done = true;
       }
@@ -131,6 +169,20 @@ class MetaBatcher {
         cv += buf;
         ++n;
         end_pos_ = pos[v + d];
+      }
+      if (binary_) {   // printCovariance: s += ':' covXZ / n  ':' lower triangle of covZZ / n (src/Model.cpp:985-994)
+        const float scale = 1.0f / (float)N_;
+        cv += ':';
+        for (int l = 0; l < C_; ++l) {
+          snprintf(buf, sizeof(buf), "%s%g", l ? "," : "", (double)((float)xz[(size_t)v * C_ + l] * scale));
+          cv += buf;
+        }
+        cv += ':';
+        for (int i = 0; i < C_; ++i)
+          for (int j = 0; j <= i; ++j) {
+            snprintf(buf, sizeof(buf), "%s%g", (i || j) ? "," : "", zz[(size_t)i * C_ + j] * (double)scale);
+            cv += buf;
+          }
       }
       snprintf(buf, sizeof(buf), "%d", n);
       s.cov_line = chromName(chrom[v]) + "\t" + itoa(pos[v]) + "\t" + itoa(end_pos_) + "\t" + buf + "\t" + mp + "\t" + cv;
@@ -160,8 +212,9 @@ class MetaBatcher {
     if (rvt_get_null_model(ctx_, NULL, sigma2, xtx.data()) != RVT_OK) return false;
     var->resize(C_);
     for (int i = 0; i < C_; ++i) (*var)[i] = xtx[(size_t)i * C_ + i] * *sigma2;   // covB = (X'X)^-1 sigma2, LinearRegression.cpp:62-66
-    return true;
+    return true;                                                                   // (binary: (X'VX)^-1 of the logistic fit, sigma2 = 1)
   }
+  bool binary() const { return binary_; }
 
  private:
   struct Block {
@@ -208,7 +261,7 @@ class MetaBatcher {
     }
     for (int j = 0; j < cv.cols; ++j)
       for (int i = 0; i < n; ++i) X[(size_t)(j + 1) * n + i] = cv(i, j);
-    if (rvt_set_null_model(ctx_, n, c, X.data(), y.data(), 0) != RVT_OK) return fail("null model");
+    if (rvt_set_null_model(ctx_, n, c, X.data(), y.data(), binary_ ? 1 : 0) != RVT_OK) return fail("null model");
     N_ = n;
     C_ = c;
     have_null_ = true;
@@ -234,6 +287,7 @@ class MetaBatcher {
     const auto& g = dc->getGenotype();   // N x 1
     Site s;
     memset(&s.r, 0, sizeof(s.r));
+    memset(&s.cc, 0, sizeof(s.cc));
     s.score_done = s.cov_done = false;
     s.hard = g.cols == 1 && g.rows == N_;
     const auto& info = dc->getResult();
@@ -266,7 +320,8 @@ class MetaBatcher {
 
   rvt_ctx* ctx_;
   int N_, C_, segment_, window_;
-  bool want_cov_;
+  bool want_cov_, binary_ = false;
+  int n_attached_ = 0;
   int current_, next_id_;
   bool have_null_;
   int pending_new_, end_pos_;
@@ -285,14 +340,18 @@ class MetaScoreTestB200 : public BASE {
     this->modelName = "MetaScore";
     this->indexResult = true;   // src/Model.h:3163: ModelManager opens a bgzipped, tabix-indexed writer for this model
     id_ = MetaBatcher<DC>::instance().newFitterId();
+    MetaBatcher<DC>::instance().attach();
   }
-  ~MetaScoreTestB200() { drain(true); }
+  ~MetaScoreTestB200() {
+    drain(true);
+    MetaBatcher<DC>::instance().detach();
+  }
   virtual void reset() {
     BASE::reset();
     ticket_ = -1;
   }
   virtual int fit(DC* dc) {
-    ticket_ = MetaBatcher<DC>::instance().submit(id_, dc);
+    ticket_ = MetaBatcher<DC>::instance().submit(id_, dc, this->isBinaryOutcome());
     return ticket_ >= 0 ? 0 : -1;
   }
   virtual void writeHeader(FW*, const RES&) {}   // deferred: the header follows the null-model block (src/Model.h:3261-3281)
@@ -332,7 +391,7 @@ class MetaScoreTestB200 : public BASE {
         snprintf(nm, sizeof(nm), "Cov%d", (int)i);   // the reference prints the covariate labels of its summary header
         fp_->write((std::string("## - ") + nm + "\t" + g(beta[i]) + "\t" + g(var[i]) + "\n").c_str());
       }
-      fp_->write(("## - Sigma2\t" + g(sigma2) + "\tNA\n").c_str());
+      fp_->write(b.binary() ? "## - Sigma2\tNA\tNA\n" : ("## - Sigma2\t" + g(sigma2) + "\tNA\n").c_str());
     }
     std::string h = site_header_ + "\tAF\tINFORMATIVE_ALT_AC\tCALL_RATE\tHWE_PVALUE\tN_REF\tN_HET\tN_ALT\tU_STAT\tSQRT_V_STAT\tALT_EFFSIZE";
     if (outputSE_) h += "\tALT_EFFSIZE_SE";
@@ -358,9 +417,24 @@ class MetaScoreTestB200 : public BASE {
         line += "\tNA";
       } else {
         const rvt_variant_result& r = s->r;
-        char buf[96];
-        snprintf(buf, sizeof(buf), "%d\t%d\t%d", r.n_ref, r.n_het, r.n_alt);
-        line += g(r.af) + "\t" + g(r.ac) + "\t" + g(r.call_rate) + "\t" + g(r.hwe_p) + "\t" + buf + "\t";
+        char buf[160];
+        if (!b.binary()) {
+          snprintf(buf, sizeof(buf), "%d\t%d\t%d", r.n_ref, r.n_het, r.n_alt);
+          line += g(r.af) + "\t" + g(r.ac) + "\t" + g(r.call_rate) + "\t" + g(r.hwe_p) + "\t" + buf + "\t";
+        } else {   // all:case:control (src/Model.h:3300-3330); complete hard calls, so GenotypeCounter reduces to the counts
+          const rvt_variant_cc& q = s->cc;
+          double ac[2], af[2], cr[2];
+          for (int w = 0; w < 2; ++w) {
+            ac[w] = (double)q.n_het[w] + 2.0 * (double)q.n_alt[w];
+            af[w] = q.n[w] ? 0.5 * ac[w] / (double)q.n[w] : -1.0;   // GenotypeCounter::getAF / getCallRate of an empty set
+            cr[w] = q.n[w] ? 1.0 : 0.0;
+          }
+          line += g(r.af) + ":" + g(af[0]) + ":" + g(af[1]) + "\t" + g(r.ac) + ":" + g(ac[0]) + ":" + g(ac[1]) + "\t" + g(r.call_rate) + ":" + g(cr[0]) +
+                  ":" + g(cr[1]) + "\t" + g(r.hwe_p) + ":" + g(q.hwe_p[0]) + ":" + g(q.hwe_p[1]) + "\t";
+          snprintf(buf, sizeof(buf), "%d:%d:%d\t%d:%d:%d\t%d:%d:%d\t", r.n_ref, q.n_ref[0], q.n_ref[1], r.n_het, q.n_het[0], q.n_het[1], r.n_alt,
+                   q.n_alt[0], q.n_alt[1]);
+          line += buf;
+        }
         if (r.ok) {
           line += g(r.U) + "\t" + g(r.sqrtV) + "\t" + g(r.effect);
           if (outputSE_) line += "\t" + ((r.sqrtV > 0.0) ? g(r.effect_se) : std::string("NA"));
@@ -396,16 +470,20 @@ class MetaCovTestB200 : public BASE {
     this->indexResult = true;
     MetaBatcher<DC>& b = MetaBatcher<DC>::instance();
     id_ = b.newFitterId();
+    b.attach();
     b.enableCov();
     b.setWindow(windowSize);
   }
-  ~MetaCovTestB200() { drain(true); }   // MetaCovTest::~MetaCovTest prints what is still queued (src/Model.cpp:828-834)
+  ~MetaCovTestB200() {   // MetaCovTest::~MetaCovTest prints what is still queued (src/Model.cpp:828-834)
+    drain(true);
+    MetaBatcher<DC>::instance().detach();
+  }
   virtual void reset() {
     BASE::reset();
     ticket_ = -1;
   }
   virtual int fit(DC* dc) {
-    ticket_ = MetaBatcher<DC>::instance().submit(id_, dc);
+    ticket_ = MetaBatcher<DC>::instance().submit(id_, dc, this->isBinaryOutcome());
     return ticket_ >= 0 ? 0 : -1;
   }
   virtual void writeHeader(FW* fp, const RES&) { fp->write("CHROM\tSTART_POS\tEND_POS\tNUM_MARKER\tMARKER_POS\tCOV\n"); }

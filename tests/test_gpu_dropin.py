@@ -99,24 +99,35 @@ def _compare_meta(ref, b2):
     for lr, lb in zip(rr, rb):
         assert lr[:5] == lb[:5], (lr, lb)
         for k in range(5, len(hr)):
-            a, b = _num(lr[k]), _num(lb[k])
-            assert (a is None) == (b is None), (hr[k], lr, lb)
-            if a is None:
-                continue
-            if hr[k] in exact:
-                assert a == b, (hr[k], lr, lb)
-            else:
-                assert abs(a - b) <= 3e-5 * max(abs(a), abs(b), 1e-300), (hr[k], lr, lb)
+            fa, fb = lr[k].split(":"), lb[k].split(":")     # binary trait: all:case:control
+            assert len(fa) == len(fb), (hr[k], lr, lb)
+            for xa, xb in zip(fa, fb):
+                a, b = _num(xa), _num(xb)
+                assert (a is None) == (b is None), (hr[k], lr, lb)
+                if a is None:
+                    continue
+                if hr[k] in exact:
+                    assert a == b, (hr[k], lr, lb)
+                else:
+                    assert abs(a - b) <= 3e-5 * max(abs(a), abs(b), 1e-300), (hr[k], lr, lb)
     _, hcr, rcr = ref["MetaCov"]
     _, hcb, rcb = b2["MetaCov"]
     assert hcr == hcb and len(rcr) == len(rcb) and len(rcr) > 0
     for lr, lb in zip(rcr, rcb):
         assert lr[:5] == lb[:5], (lr, lb)             # CHROM START_POS END_POS NUM_MARKER MARKER_POS: the window logic
-        ca = np.array([float(x) for x in lr[5].split(",")])
-        cb_ = np.array([float(x) for x in lb[5].split(",")])
+        pa, pb = lr[5].split(":"), lb[5].split(":")    # binary trait: band ':' covXZ / n ':' covZZ / n
+        assert len(pa) == len(pb), (lr, lb)
+        ca = np.array([float(x) for x in pa[0].split(",")])
+        cb_ = np.array([float(x) for x in pb[0].split(",")])
         assert len(ca) == len(cb_)
-        # the reference accumulates the products in float32 (FloatMatrixRef, src/Model.cpp:534-554)
-        assert np.all(np.abs(ca - cb_) <= 2e-4 * np.maximum(np.abs(ca), ca[0] * 1e-2)), (lr[:4], ca, cb_)
+        # the reference accumulates the products in float32 (FloatMatrixRef, src/Model.cpp:534-554); a binary trait works on
+        # UNcentred genotypes, so g_i'W g_j and the projection term cancel to a small entry: wider floor there
+        floor = 5e-2 if len(pa) > 1 else 1e-2
+        assert np.all(np.abs(ca - cb_) <= 2e-4 * np.maximum(np.abs(ca), ca[0] * floor)), (lr[:4], ca, cb_)
+        for xa, xb in zip(pa[1:], pb[1:]):
+            va = np.array([float(x) for x in xa.split(",")])
+            vb = np.array([float(x) for x in xb.split(",")])
+            assert len(va) == len(vb) and np.all(np.abs(va - vb) <= 2e-4 * np.max(np.abs(va))), (lr[:4], xa, xb)
 
 
 def test_dropin_meta_score_cov(oracle, tmp_path):
@@ -129,4 +140,22 @@ def test_dropin_meta_score_cov(oracle, tmp_path):
     G, pos, X, y = _meta_problem(O, 311, 1800, 150, 1)
     ref = O.dropin_run_meta_models(G, pos, X[:, 1:], y, 4000, str(tmp_path / "ref"), use_b200=False, se=True)
     b2 = O.dropin_run_meta_models(G, pos, X[:, 1:], y, 4000, str(tmp_path / "b200"), use_b200=True, se=True, segment=64)
+    _compare_meta(ref, b2)
+
+
+def test_dropin_meta_binary_trait(oracle, tmp_path):
+    """A case/control phenotype through the reference's ModelManager::setBinaryOutcome: MetaUnrelatedBinary /
+    MetaCovUnrelatedBinary (src/Model.h:3669-3784, src/Model.cpp:695-778) vs the B200 adapters, which read isBinaryOutcome() at
+    fit time -- all:case:control site columns, the ':covXZ:covZZ' tail of every MetaCov line.  Intercept-only model: with
+    covariates the reference's score test solves a 1 x 1 matrix against a d x d identity (LogisticRegressionScoreTest.cpp:292)."""
+    O = oracle
+    if O.ref_dropin() is None:
+        pytest.skip("oracle/_ref/libdropin_ref.so not built")
+    G, pos, X, _y = _meta_problem(O, 312, 1500, 140, 1)
+    rng = np.random.default_rng(9)
+    eta = -0.5 + 0.4 * (G[:, 20] - G[:, 20].mean())
+    y = (rng.random(len(eta)) < 1.0 / (1.0 + np.exp(-eta))).astype(np.float64)
+    ref = O.dropin_run_meta_models(G, pos, X[:, 1:], y, 4000, str(tmp_path / "ref"), use_b200=False, se=True, binary=True)
+    b2 = O.dropin_run_meta_models(G, pos, X[:, 1:], y, 4000, str(tmp_path / "b200"), use_b200=True, se=True, segment=64, binary=True)
+    assert ":" in ref["MetaScore"][2][0][5]
     _compare_meta(ref, b2)
