@@ -2,15 +2,27 @@
 // (src/Main.cpp:1084-1117: for each variant { consolidate; for each model { reset; fit; writeOutput } }; then
 // ModelManager::close -> writeFootnote, models deleted before the writers) and prints both .assoc tables.
 //   input: int32 N, C1, nVar; double y[N]; double cov[N*C1] (col-major); per variant: int32 chrom, pos; double g[N]
-//   usage: meta_demo problem.bin segment window
+//   usage: meta_demo problem.bin segment window [prefix [binary]]
+// With a prefix the tables are ALSO written the way ModelManager writes a model with needToIndexResult()
+// (src/ModelManager.cpp:285-327): "<prefix>.MetaScore.assoc.gz" / "<prefix>.MetaCov.assoc.gz", bgzipped, and tabix-indexed
+// when the writers close (rvt_bgzf.h).  binary = 1: setBinaryOutcome() on both models (case / control phenotype, 0 / 1).
 #include <stdio.h>
 #include <stdlib.h>
 
+#include "rvt_bgzf.h"
 #include "rvt_meta_fitters.h"
 #include "shim.h"
 
-typedef rvtb200::MetaScoreTestB200<shim::DataConsolidator, shim::FileWriter, shim::Result> MetaScoreTest;
-typedef rvtb200::MetaCovTestB200<shim::DataConsolidator, shim::FileWriter, shim::Result> MetaCovTest;
+struct DemoWriter : shim::FileWriter {   // FileWriter(fn, BGZIP) of base/IO.h next to the in-memory copy the tests read
+  rvtb200::IndexedAssocWriter gz;
+  bool on = false;
+  int write(const char* s) {
+    if (on) gz.write(s);
+    return shim::FileWriter::write(s);
+  }
+};
+typedef rvtb200::MetaScoreTestB200<shim::DataConsolidator, DemoWriter, shim::Result> MetaScoreTest;
+typedef rvtb200::MetaCovTestB200<shim::DataConsolidator, DemoWriter, shim::Result> MetaCovTest;
 
 template <class T>
 static void rd(FILE* f, T* p, size_t n) {
@@ -35,10 +47,21 @@ int main(int argc, char** argv) {
   dc.cov.Dimension(N, C1);
   if (C1) rd(f, &dc.cov.data[0], (size_t)N * C1);
   rvtb200::MetaBatcher<shim::DataConsolidator>::instance().setSegment(segment);
-  shim::FileWriter fw[2];
+  DemoWriter fw[2];
+  if (argc > 4) {
+    const std::string prefix = argv[4];
+    fw[0].on = fw[0].gz.open((prefix + ".MetaScore.assoc.gz").c_str());
+    fw[1].on = fw[1].gz.open((prefix + ".MetaCov.assoc.gz").c_str());
+    if (!fw[0].on || !fw[1].on) return 3;
+  }
+  int rc_close = 0;
   {
     MetaScoreTest score(true);   // --meta score[se]
     MetaCovTest cov(window);
+    if (argc > 5 && atoi(argv[5])) {
+      score.setBinaryOutcome();
+      cov.setBinaryOutcome();
+    }
     const char* keys[5] = {"CHROM", "POS", "REF", "ALT", "N_INFORMATIVE"};
     for (int k = 0; k < 5; ++k) dc.site.keys.push_back(keys[k]);
     dc.site.values.resize(5);
@@ -66,7 +89,10 @@ int main(int argc, char** argv) {
     score.writeFootnote(&fw[0]);
     cov.writeFootnote(&fw[1]);
   }
+  // ModelManager::close: the writers close after the models are gone, then createIndex()
+  for (int k = 0; k < 2; ++k)
+    if (fw[k].on && fw[k].gz.close() != 0) rc_close = 4;
   printf("#MetaScore\n%s#MetaCov\n%s", fw[0].out.c_str(), fw[1].out.c_str());
   fclose(f);
-  return 0;
+  return rc_close;
 }

@@ -124,7 +124,7 @@ def build_meta_demo():
     exe = os.path.join(ROOT, "rvtests_b200", "host", "meta_demo")
     src = os.path.join(ROOT, "rvtests_b200", "host", "meta_demo.cpp")
     subprocess.run(["g++", "-std=c++11", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
-                    "-L", os.path.join(ROOT, "rvtests_b200"), "-lrvtests_b200",
+                    "-L", os.path.join(ROOT, "rvtests_b200"), "-lrvtests_b200", "-lz",
                     "-Wl,-rpath," + os.path.join(ROOT, "rvtests_b200")], check=True)
     return exe
 
@@ -160,8 +160,20 @@ def test_meta_adapters_match_reference_output_format(oracle, segment, tmp_path):
             f.write(struct.pack("ii", int(chrom[v]), int(pos[v])))
             f.write(G[v].astype(np.float64).tobytes())
     exe = build_meta_demo()
-    out = subprocess.run([exe, str(path), str(segment), str(window)], capture_output=True, text=True, check=True).stdout
+    prefix = str(tmp_path / "out")
+    out = subprocess.run([exe, str(path), str(segment), str(window), prefix], capture_output=True, text=True, check=True).stdout
     score_txt, cov_txt = out.split("#MetaCov\n")
+    # the bgzipped + tabix-indexed files ModelManager would leave behind (rvt_bgzf.h; format checks in tests/test_bgzf_tabix.py)
+    import gzip
+    assert gzip.open(prefix + ".MetaScore.assoc.gz", "rt").read() == score_txt.split("#MetaScore\n", 1)[1]
+    assert gzip.open(prefix + ".MetaCov.assoc.gz", "rt").read() == cov_txt
+    for m in ("MetaScore", "MetaCov"):
+        tbi = gzip.open(prefix + "." + m + ".assoc.gz.tbi", "rb").read()
+        # two chromosomes + the column header line, which carries no '#' and which tabix therefore indexes as a sequence
+        # named CHROM -- in the reference's own files too
+        assert tbi[:4] == b"TBI\x01" and struct.unpack_from("<i", tbi, 4)[0] == 3
+        assert tbi[36:].startswith(b"CHROM\x001\x002\x00")
+        assert struct.unpack_from("<6i", tbi, 8) == (0, 1, 2, 0, ord("#"), 0)
     score_lines = score_txt.splitlines()[1:]
     nm = O.fit_null_linear(X, y)
     # ##NullModelEstimates block, then the column header
