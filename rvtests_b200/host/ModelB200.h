@@ -45,7 +45,34 @@ typedef rvtb200::ZegginiTestB200<DataConsolidator, FileWriter, Result, ModelFitt
 typedef rvtb200::MetaScoreTestB200<DataConsolidator, FileWriter, Result, ModelFitter> MetaScoreTestB200;
 typedef rvtb200::MetaCovTestB200<DataConsolidator, FileWriter, Result, ModelFitter> MetaCovTestB200;
 
+#include "src/Summary.h"
+extern SummaryHeader* g_SummaryHeader;   // src/Main.cpp / src/Model.cpp
+
 namespace rvtb200 {
+// the reference's own summary block and covariate labels, read when the first line is written
+struct RefSummaryHook : SummaryHook<FileWriter> {
+  virtual void outputHeader(FileWriter* fp) {
+    if (g_SummaryHeader) g_SummaryHeader->outputHeader(fp);
+  }
+  virtual const std::vector<std::string>& getCovLabel() const {
+    static const std::vector<std::string> none;
+    return g_SummaryHeader ? g_SummaryHeader->getCovLabel() : none;
+  }
+  static RefSummaryHook* instance() {
+    static RefSummaryHook h;
+    return &h;
+  }
+};
+inline ::MetaScoreTestB200* newMetaScore(bool se) {
+  ::MetaScoreTestB200* m = new ::MetaScoreTestB200(se);
+  m->setSummaryHeader(RefSummaryHook::instance());
+  return m;
+}
+inline ::MetaCovTestB200* newMetaCov(int windowSize) {
+  ::MetaCovTestB200* m = new ::MetaCovTestB200(windowSize);
+  m->setSummaryHeader(RefSummaryHook::instance());
+  return m;
+}
 inline bool enabled() {
   const char* e = getenv("RVTESTS_B200");
   return e && e[0] && !(e[0] == '0' && e[1] == 0);
@@ -72,14 +99,14 @@ inline bool enabled() {
     (model).push_back(new SkatOTestB200(beta1B200, beta2B200));                            \
   } else
 
-// --meta score[se],cov[windowSize=..]  (src/ModelManager.cpp:208-236), quantitative trait, unrelated samples
+// --meta score[se],cov[windowSize=..]  (src/ModelManager.cpp:208-236), quantitative or binary trait, unrelated samples
 #define RVT_B200_META_MODELS(modelName, parser, model)                               \
   if (rvtb200::enabled() && (modelName) == "score") {                                \
-    (model).push_back(new MetaScoreTestB200((parser).hasTag("se")));                 \
+    (model).push_back(rvtb200::newMetaScore((parser).hasTag("se")));                 \
   } else if (rvtb200::enabled() && (modelName) == "cov") {                           \
     int windowSizeB200 = 1000000;                                                    \
     (parser).assign("windowSize", &windowSizeB200, 1000000);                         \
-    (model).push_back(new MetaCovTestB200(windowSizeB200));                          \
+    (model).push_back(rvtb200::newMetaCov(windowSizeB200));                          \
   } else
 
 #endif  // RVT_MODEL_B200_H_

@@ -33,6 +33,7 @@
 
 #include "rvtests_b200.h"
 #include "rvt_fitters.h"   // StandaloneBase
+#include "rvt_summary.h"   // SummaryHook
 
 namespace rvtb200 {
 
@@ -371,6 +372,9 @@ class MetaScoreTestB200 : public BASE {
     if (!fp_) fp_ = fp;
     drain(true);
   }
+  // g_SummaryHeader of the reference (src/Main.cpp:775-780): its block opens the file and its covariate labels name the rows of
+  // the null-model estimates (MetaScoreTest::writeSummaryAndHeader, src/Model.h:3283-3297).  Not owned.
+  void setSummaryHeader(SummaryHook<FW>* h) { summary_ = h; }
 
  private:
   static std::string g(double v) {
@@ -382,14 +386,17 @@ class MetaScoreTestB200 : public BASE {
     MetaBatcher<DC>& b = MetaBatcher<DC>::instance();
     std::vector<double> beta, var;
     double sigma2 = 0;
+    if (summary_) summary_->outputHeader(fp_);
+    const std::vector<std::string>* labels = summary_ ? &summary_->getCovLabel() : NULL;
     if (b.nullModel(&beta, &var, &sigma2)) {   // MetaUnrelatedQtl::PrintNullModel, src/Model.h:3525-3541
       fp_->write("##NullModelEstimates\n");
       fp_->write("## - Name\tBeta\tSD\n");
       fp_->write(("## - Intercept\t" + g(beta[0]) + "\t" + g(var[0]) + "\n").c_str());
       for (size_t i = 1; i < beta.size(); ++i) {
         char nm[32];
-        snprintf(nm, sizeof(nm), "Cov%d", (int)i);   // the reference prints the covariate labels of its summary header
-        fp_->write((std::string("## - ") + nm + "\t" + g(beta[i]) + "\t" + g(var[i]) + "\n").c_str());
+        snprintf(nm, sizeof(nm), "Cov%d", (int)i);   // (no summary header recorded: placeholder names)
+        if (labels && i - 1 >= labels->size()) break;   // PrintNullModel stops at the last label
+        fp_->write((std::string("## - ") + (labels ? (*labels)[i - 1] : std::string(nm)) + "\t" + g(beta[i]) + "\t" + g(var[i]) + "\n").c_str());
       }
       fp_->write(b.binary() ? "## - Sigma2\tNA\tNA\n" : ("## - Sigma2\t" + g(sigma2) + "\tNA\n").c_str());
     }
@@ -455,6 +462,7 @@ class MetaScoreTestB200 : public BASE {
     std::string site;
   };
   std::string site_header_;
+  SummaryHook<FW>* summary_ = NULL;
   bool outputSE_;
   int id_, ticket_;
   FW* fp_;
@@ -486,7 +494,12 @@ class MetaCovTestB200 : public BASE {
     ticket_ = MetaBatcher<DC>::instance().submit(id_, dc, this->isBinaryOutcome());
     return ticket_ >= 0 ? 0 : -1;
   }
-  virtual void writeHeader(FW* fp, const RES&) { fp->write("CHROM\tSTART_POS\tEND_POS\tNUM_MARKER\tMARKER_POS\tCOV\n"); }
+  // MetaCovTest::writeHeader: the summary block, then the column names (src/Model.h:3944-3953)
+  virtual void writeHeader(FW* fp, const RES&) {
+    if (summary_) summary_->outputHeader(fp);
+    fp->write("CHROM\tSTART_POS\tEND_POS\tNUM_MARKER\tMARKER_POS\tCOV\n");
+  }
+  void setSummaryHeader(SummaryHook<FW>* h) { summary_ = h; }
   virtual void writeOutput(FW* fp, const RES&) {
     fp_ = fp;
     pending_.push_back(ticket_);
@@ -513,6 +526,7 @@ class MetaCovTestB200 : public BASE {
   }
   int id_, ticket_;
   FW* fp_;
+  SummaryHook<FW>* summary_ = NULL;
   std::vector<int> pending_;
 };
 

@@ -23,3 +23,33 @@ int bz_printf_check(const char* path) {
 }
 int bz_reg2bin(unsigned beg, unsigned end) { return rvtb200::TabixIndex::reg2bin(beg, end); }
 }
+
+// ---- rvt_summary.h --------------------------------------------------------------------------------------------------
+#include "rvt_summary.h"
+namespace {
+struct StrWriter {
+  std::string out;
+  int write(const char* s) {
+    out += s;
+    return (int)strlen(s);
+  }
+};
+}  // namespace
+extern "C" int sh_render(int N, int n_cov, const double* y, const double* cov /* col-major */, const char* version, char* out, int cap) {
+  rvtb200::SummaryHeaderB200<StrWriter> sh(version);
+  sh.recordPhenotype("Trait", std::vector<double>(y, y + N));
+  std::vector<std::string> labels;
+  std::vector<std::vector<double> > cols;
+  for (int j = 0; j < n_cov; ++j) {
+    char b[32];
+    snprintf(b, sizeof b, "cov%d", j);
+    labels.push_back(b);
+    cols.push_back(std::vector<double>(cov + (size_t)j * N, cov + (size_t)(j + 1) * N));
+  }
+  sh.recordCovariate(labels, cols);
+  StrWriter w;
+  sh.outputHeader(&w);
+  if ((int)w.out.size() + 1 > cap) return -1;
+  memcpy(out, w.out.c_str(), w.out.size() + 1);
+  return (int)w.out.size();
+}

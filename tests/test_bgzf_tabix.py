@@ -178,3 +178,27 @@ def test_unsorted_input_reports_an_index_error_but_keeps_the_data(bz, tmp_path):
     path = str(tmp_path / "u.assoc.gz")
     assert bz.bz_write_indexed(path.encode(), text, len(text), 5) == -2
     assert gzip.open(path, "rb").read() == text and not os.path.exists(path + ".tbi")
+
+
+@pytest.mark.parametrize("n_cov", [0, 2])
+def test_summary_header_matches_the_reference_block(bz, tmp_path, n_cov):
+    """SummaryHeaderB200 (rvtests_b200/host/rvt_summary.h) against the '##' block the reference's own SummaryHeader
+    (src/Summary.h) writes at the top of its MetaScore file -- the reference model layer run on the CPU
+    (oracle/_ref/libdropin_ref.so with the stock fitters)."""
+    from oracle import oracle as O
+    if O.ref_dropin() is None:
+        pytest.skip("oracle/_ref/libdropin_ref.so not built")
+    rng = np.random.default_rng(17 + n_cov)
+    N, nv = 403, 3
+    G = rng.binomial(2, 0.3, (N, nv)).astype(np.float64)
+    y = rng.normal(size=N) * 3 + 1
+    cov = rng.normal(size=(N, n_cov))
+    pos = np.array([10, 20, 30], dtype=np.int32)
+    ref = O.dropin_run_meta_models(G, pos, cov, y, 1000, str(tmp_path / "ref"), use_b200=False)
+    block = [c for c in ref["MetaScore"][0] if not c.startswith("##NullModel") and not c.startswith("## - ")]
+    bz.sh_render.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+    out = C.create_string_buffer(1 << 16)
+    covf = np.asfortranarray(cov)
+    n = bz.sh_render(N, n_cov, y.ctypes.data, covf.ctypes.data if n_cov else None, b"reference-build-under-test", out, len(out))
+    assert n > 0
+    assert out.value.decode().splitlines() == block

@@ -91,9 +91,27 @@ def _meta_problem(O, seed, N, nv, C):
     return G, pos, X, y
 
 
+def _compare_comments(cr, cb):
+    """the '##' block: the summary header verbatim, the null-model estimates to the printed precision"""
+    assert len(cr) == len(cb) and len(cr) > 0, (cr, cb)
+    for a, b in zip(cr, cb):
+        if a.startswith("## - "):
+            fa, fb = a.split("\t"), b.split("\t")
+            assert fa[0] == fb[0] and len(fa) == len(fb), (a, b)
+            for xa, xb in zip(fa[1:], fb[1:]):
+                if _num(xa) is None or xa in ("Beta", "SD"):
+                    assert xa == xb, (a, b)
+                else:
+                    assert abs(float(xa) - float(xb)) <= 2e-5 * max(abs(float(xa)), 1e-300), (a, b)
+        else:
+            assert a == b, (a, b)
+
+
 def _compare_meta(ref, b2):
     cr, hr, rr = ref["MetaScore"]
     cb, hb, rb = b2["MetaScore"]
+    _compare_comments(cr, cb)
+    _compare_comments(ref["MetaCov"][0], b2["MetaCov"][0])
     assert hr == hb and len(rr) == len(rb) and len(rr) > 0
     exact = {"AF", "INFORMATIVE_ALT_AC", "CALL_RATE", "N_REF", "N_HET", "N_ALT"}
     for lr, lb in zip(rr, rb):
