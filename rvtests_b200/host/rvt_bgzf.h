@@ -1,4 +1,5 @@
-// rvt_bgzf.h -- the output side of `--meta`: a BGZF (blocked gzip) writer and a tabix index builder, header-only C++11 + zlib.
+// rvt_bgzf.h -- BGZF (blocked gzip) + tabix, header-only C++11 + zlib: the writer and index builder of the `--meta` outputs, and
+// (second half) the reader of bgzipped, tabix-indexed input text.
 //
 // Replaces, for a host that does not link the reference's base/ and third/tabix:
 //   FileWriter(fn, BGZIP) = BGZipFileWriter       base/IO.h:645-676 (bgzf_open(fn, "w"), bgzf_write, bgzf_close)
@@ -28,6 +29,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/types.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -413,6 +415,315 @@ class IndexedAssocWriter {
   bool open_;
   std::string path_, line_, index_error_;
   uint64_t line_start_;
+};
+
+// ---- the input side: bgzipped, tabix-indexed text (the reference's --inVcf file.vcf.gz with --rangeList / --setFile) ---------
+//   VCFInputFile in range mode      libVcf/VCFInputFile.cpp:20-120 (ti_open, ti_queryi per range, ti_read), base/IO.h BGZipFileReader
+//   third/tabix-0.2.6/index.c       ti_index_load, reg2bins, ti_iter_first / ti_iter_read: the bins a region overlaps, their chunks
+//                                   with end > the linear-index offset of the region's first 16 kb window, sorted and merged;
+//                                   lines are read from each chunk and kept when they overlap the region
+// BgzfReader inflates one member at a time (a member is at most 64 KiB either way) and addresses by virtual offset.
+class BgzfReader {
+ public:
+  BgzfReader() : fp_(NULL), addr_(0), next_addr_(0), off_(0), eof_(false) {}
+  ~BgzfReader() { close(); }
+  bool open(const char* path) {
+    close();
+    fp_ = fopen(path, "rb");
+    addr_ = next_addr_ = 0;
+    off_ = 0;
+    block_.clear();
+    eof_ = false;
+    error_.clear();
+    return fp_ != NULL;
+  }
+  void close() {
+    if (fp_) fclose(fp_);
+    fp_ = NULL;
+  }
+  bool seek(uint64_t voffset) {
+    if (!fp_) return false;
+    const uint64_t a = voffset >> 16;
+    if (a != addr_ || block_.empty()) {
+      next_addr_ = a;
+      eof_ = false;
+      if (!readMember()) return false;
+    }
+    off_ = (size_t)(voffset & 0xffff);
+    return off_ <= block_.size();
+  }
+  // as bgzf_tell of a reader that has just consumed up to here: a position at the end of a member is (next member, 0)
+  uint64_t tell() const { return off_ >= block_.size() ? next_addr_ << 16 : (addr_ << 16) | off_; }
+  // one line without its '\n' (a trailing '\r' is kept, as bgzf_getline does); false at the end of the file
+  bool getline(std::string* line) {
+    line->clear();
+    bool any = false;
+    while (true) {
+      if (off_ >= block_.size()) {
+        if (eof_ || !readMember()) return any;
+        if (block_.empty()) continue;   // empty member (the EOF marker, or a flush)
+      }
+      const char* b = (const char*)block_.data() + off_;
+      const char* nl = (const char*)memchr(b, '\n', block_.size() - off_);
+      any = true;
+      if (nl) {
+        line->append(b, nl - b);
+        off_ += (size_t)(nl - b) + 1;
+        return true;
+      }
+      line->append(b, block_.size() - off_);
+      off_ = block_.size();
+    }
+  }
+  // the whole remaining payload (small files: the .tbi)
+  bool readAll(std::vector<uint8_t>* out) {
+    out->clear();
+    while (true) {
+      if (off_ < block_.size()) out->insert(out->end(), block_.begin() + off_, block_.end());
+      off_ = block_.size();
+      if (eof_ || !readMember()) break;
+    }
+    return error_.empty();
+  }
+  const std::string& error() const { return error_; }
+
+ private:
+  bool readMember() {
+    block_.clear();
+    off_ = 0;
+    addr_ = next_addr_;
+    if (fseeko(fp_, (off_t)addr_, SEEK_SET) != 0) return fail("seek");
+    uint8_t h[18];
+    const size_t got = fread(h, 1, 18, fp_);
+    if (got == 0) {
+      eof_ = true;
+      return false;
+    }
+    if (got != 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return fail("not a BGZF member");
+    const unsigned xlen = h[10] | (h[11] << 8);
+    if (xlen != 6 || h[12] != 'B' || h[13] != 'C') return fail("BGZF member without the BC subfield first");   // as bgzf.c checks
+    const unsigned bsize = (h[16] | (h[17] << 8)) + 1u;
+    if (bsize < 26) return fail("short BGZF member");
+    std::vector<uint8_t> c(bsize - 18);
+    if (fread(c.data(), 1, c.size(), fp_) != c.size()) return fail("truncated BGZF member");
+    const size_t clen = c.size() - 8;
+    const uint32_t isize = c[clen + 4] | (c[clen + 5] << 8) | (c[clen + 6] << 16) | ((uint32_t)c[clen + 7] << 24);
+    block_.resize(isize);
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return fail("inflateInit2");
+    zs.next_in = c.data();
+    zs.avail_in = (uInt)clen;
+    zs.next_out = block_.data();
+    zs.avail_out = isize;
+    const int rc = isize ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END || (isize && zs.total_out != isize)) return fail("inflate");
+    next_addr_ = addr_ + bsize;
+    return true;
+  }
+  bool fail(const char* what) {
+    error_ = what;
+    eof_ = true;
+    block_.clear();
+    return false;
+  }
+  FILE* fp_;
+  uint64_t addr_, next_addr_;
+  size_t off_;
+  bool eof_;
+  std::vector<uint8_t> block_;
+  std::string error_;
+};
+
+class TabixReader {
+ public:
+  // opens <path> and <path>.tbi
+  bool open(const char* path) {
+    names_.clear();
+    refs_.clear();
+    if (!data_.open(path)) return fail("cannot open the data file");
+    BgzfReader ix;
+    std::vector<uint8_t> b;
+    if (!ix.open((std::string(path) + ".tbi").c_str()) || !ix.readAll(&b)) return fail("cannot read the .tbi index");
+    size_t o = 0;
+    if (b.size() < 36 || memcmp(b.data(), "TBI\1", 4) != 0) return fail("wrong magic number in the index");
+    const int32_t n_ref = get32(b, 4);
+    memcpy(&conf_, b.data() + 8, 24);
+    const int32_t l_nm = get32(b, 32);
+    o = 36;
+    if (o + (size_t)l_nm > b.size()) return fail("truncated index");
+    for (size_t i = o, st = o; i < o + (size_t)l_nm; ++i)
+      if (b[i] == 0) {
+        names_.push_back(std::string((const char*)b.data() + st, i - st));
+        st = i + 1;
+      }
+    o += l_nm;
+    refs_.resize(n_ref);
+    for (int32_t t = 0; t < n_ref; ++t) {
+      if (o + 4 > b.size()) return fail("truncated index");
+      const int32_t n_bin = get32(b, o);
+      o += 4;
+      for (int32_t k = 0; k < n_bin; ++k) {
+        if (o + 8 > b.size()) return fail("truncated index");
+        const uint32_t bin = (uint32_t)get32(b, o);
+        const int32_t n_chunk = get32(b, o + 4);
+        o += 8;
+        if (o + 16 * (size_t)n_chunk > b.size()) return fail("truncated index");
+        std::vector<Chunk>& c = refs_[t].bins[bin];
+        c.resize(n_chunk);
+        if (n_chunk) memcpy(c.data(), b.data() + o, 16 * (size_t)n_chunk);
+        o += 16 * (size_t)n_chunk;
+      }
+      if (o + 4 > b.size()) return fail("truncated index");
+      const int32_t n_intv = get32(b, o);
+      o += 4;
+      if (o + 8 * (size_t)n_intv > b.size()) return fail("truncated index");
+      refs_[t].lidx.resize(n_intv);
+      if (n_intv) memcpy(refs_[t].lidx.data(), b.data() + o, 8 * (size_t)n_intv);
+      o += 8 * (size_t)n_intv;
+    }
+    return true;
+  }
+  const std::vector<std::string>& names() const { return names_; }
+  // header = the leading lines that start with the meta character (ti_query before any region: "#..." lines of a VCF)
+  bool readHeader(std::vector<std::string>* lines) {
+    lines->clear();
+    if (!data_.seek(0)) return false;
+    std::string l;
+    while (true) {
+      const uint64_t at = data_.tell();
+      if (!data_.getline(&l)) break;
+      if (l.empty() || l[0] != (char)conf_.meta_char) {
+        data_.seek(at);
+        break;
+      }
+      lines->push_back(l);
+    }
+    return true;
+  }
+  // region in the reference's convention: 1-based, inclusive [beg, end] (RangeList); false when the sequence is unknown
+  bool query(const std::string& chrom, int beg1, int end1) {
+    chunks_.clear();
+    cur_ = 0;
+    active_ = false;
+    tid_ = -1;
+    for (size_t i = 0; i < names_.size(); ++i)
+      if (names_[i] == chrom) tid_ = (int)i;
+    if (tid_ < 0) return false;
+    qbeg_ = beg1 > 0 ? beg1 - 1 : 0;   // 0-based half-open
+    qend_ = end1 < 1 ? 1 : end1;
+    if (qend_ > (1 << 29)) qend_ = 1 << 29;
+    if (qbeg_ >= qend_) return true;   // nothing can overlap
+    const Ref& r = refs_[tid_];
+    uint64_t min_off = 0;
+    if (!r.lidx.empty()) {
+      const size_t w = (size_t)(qbeg_ >> 14);
+      min_off = w >= r.lidx.size() ? r.lidx.back() : r.lidx[w];
+    }
+    static const int first[6] = {0, 1, 9, 73, 585, 4681}, shift[6] = {29, 26, 23, 20, 17, 14};
+    for (int lv = 0; lv < 6; ++lv)
+      for (int bn = first[lv] + (qbeg_ >> shift[lv]); bn <= first[lv] + ((qend_ - 1) >> shift[lv]); ++bn) {
+        std::map<uint32_t, std::vector<Chunk> >::const_iterator it = r.bins.find((uint32_t)bn);
+        if (it == r.bins.end()) continue;
+        for (size_t c = 0; c < it->second.size(); ++c)
+          if (it->second[c].v > min_off) chunks_.push_back(it->second[c]);
+      }
+    std::sort(chunks_.begin(), chunks_.end(), chunkLess);
+    size_t m = 0;   // merge chunks that overlap or touch
+    for (size_t l = 1; l < chunks_.size(); ++l) {
+      if (chunks_[l].u <= chunks_[m].v) {
+        if (chunks_[l].v > chunks_[m].v) chunks_[m].v = chunks_[l].v;
+      } else
+        chunks_[++m] = chunks_[l];
+    }
+    if (!chunks_.empty()) chunks_.resize(m + 1);
+    return true;
+  }
+  // the next line overlapping the queried region, in file order
+  bool next(std::string* line) {
+    while (cur_ < chunks_.size()) {
+      if (!active_) {
+        if (!data_.seek(chunks_[cur_].u)) return false;
+        active_ = true;
+      }
+      if (data_.tell() >= chunks_[cur_].v || !data_.getline(line)) {
+        ++cur_;
+        active_ = false;
+        continue;
+      }
+      if (!line->empty() && (*line)[0] == (char)conf_.meta_char) continue;
+      std::string nm;
+      long b, e;
+      if (!interval(*line, &nm, &b, &e)) continue;
+      if (nm != names_[tid_]) continue;
+      if (b >= qend_) {   // sorted: nothing further in this chunk can overlap
+        ++cur_;
+        active_ = false;
+        continue;
+      }
+      if (e > qbeg_) return true;
+    }
+    return false;
+  }
+  const std::string& error() const { return error_; }
+
+ private:
+  struct Chunk {
+    uint64_t u, v;
+  };
+  struct Ref {
+    std::map<uint32_t, std::vector<Chunk> > bins;
+    std::vector<uint64_t> lidx;
+  };
+  static bool chunkLess(const Chunk& a, const Chunk& b) { return a.u < b.u; }
+  static int32_t get32(const std::vector<uint8_t>& b, size_t o) {
+    int32_t v;
+    memcpy(&v, b.data() + o, 4);
+    return v;
+  }
+  bool fail(const char* what) {
+    error_ = what;
+    return false;
+  }
+  // ti_get_intv for the generic and VCF presets (0-based half-open)
+  bool interval(const std::string& line, std::string* name, long* beg, long* end) const {
+    size_t b = 0;
+    int id = 1;
+    *beg = *end = -1;
+    bool have_name = false;
+    const int preset = conf_.preset & 0xffff;
+    for (size_t i = 0; i <= line.size(); ++i) {
+      if (i == line.size() || line[i] == '\t') {
+        if (id == conf_.sc) {
+          name->assign(line, b, i - b);
+          have_name = true;
+        } else if (id == conf_.bc) {
+          *beg = *end = strtol(line.substr(b, i - b).c_str(), NULL, 0);
+          if (!(conf_.preset & 0x10000)) --*beg; else ++*end;
+          if (*beg < 0) *beg = 0;
+          if (*end < 1) *end = 1;
+        } else if (preset == 0 && id == conf_.ec) {
+          *end = strtol(line.substr(b, i - b).c_str(), NULL, 0);
+        } else if (preset == 2 && id == 4 && b < i) {   // VCF: the REF allele spans the record
+          *end = *beg + (long)(i - b);
+        }
+        b = i + 1;
+        ++id;
+      }
+    }
+    return have_name && *beg >= 0 && *end >= 0;
+  }
+  BgzfReader data_;
+  TabixConf conf_;
+  std::vector<std::string> names_;
+  std::vector<Ref> refs_;
+  std::vector<Chunk> chunks_;
+  size_t cur_ = 0;
+  bool active_ = false;
+  int tid_ = -1;
+  long qbeg_ = 0, qend_ = 0;
+  std::string error_;
 };
 
 }  // namespace rvtb200

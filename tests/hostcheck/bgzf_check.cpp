@@ -53,3 +53,40 @@ extern "C" int sh_render(int N, int n_cov, const double* y, const double* cov /*
   memcpy(out, w.out.c_str(), w.out.size() + 1);
   return (int)w.out.size();
 }
+
+// ---- readers --------------------------------------------------------------------------------------------------------
+// lines of <path> overlapping chrom:beg-end (1-based inclusive) joined by '\n' -> length, -1 unknown sequence, -2 open error
+extern "C" long bz_query(const char* path, const char* chrom, int beg, int end, char* out, long cap) {
+  rvtb200::TabixReader r;
+  if (!r.open(path)) return -2;
+  if (!r.query(chrom, beg, end)) return -1;
+  std::string all, line;
+  while (r.next(&line)) all += line + "\n";
+  if ((long)all.size() + 1 > cap) return -3;
+  memcpy(out, all.c_str(), all.size() + 1);
+  return (long)all.size();
+}
+extern "C" long bz_header(const char* path, char* out, long cap) {
+  rvtb200::TabixReader r;
+  if (!r.open(path)) return -2;
+  std::vector<std::string> h;
+  r.readHeader(&h);
+  std::string all;
+  for (size_t i = 0; i < h.size(); ++i) all += h[i] + "\n";
+  if ((long)all.size() + 1 > cap) return -3;
+  memcpy(out, all.c_str(), all.size() + 1);
+  return (long)all.size();
+}
+// sequential read of a BGZF file through BgzfReader::getline -> number of lines, bytes summed into *nbytes
+extern "C" long bz_count_lines(const char* path, long* nbytes) {
+  rvtb200::BgzfReader r;
+  if (!r.open(path)) return -2;
+  std::string l;
+  long n = 0;
+  *nbytes = 0;
+  while (r.getline(&l)) {
+    ++n;
+    *nbytes += (long)l.size() + 1;
+  }
+  return r.error().empty() ? n : -4;
+}

@@ -202,3 +202,84 @@ def test_summary_header_matches_the_reference_block(bz, tmp_path, n_cov):
     n = bz.sh_render(N, n_cov, y.ctypes.data, covf.ctypes.data if n_cov else None, b"reference-build-under-test", out, len(out))
     assert n > 0
     assert out.value.decode().splitlines() == block
+
+
+def _tabix_query_ref(T, path, region):
+    T.ti_open.restype = C.c_void_p
+    T.ti_open.argtypes = [C.c_char_p, C.c_char_p]
+    T.ti_querys.restype = C.c_void_p
+    T.ti_querys.argtypes = [C.c_void_p, C.c_char_p]
+    T.ti_read.restype = C.c_char_p
+    T.ti_read.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    T.ti_iter_destroy.argtypes = [C.c_void_p]
+    T.ti_close.argtypes = [C.c_void_p]
+    t = T.ti_open(path.encode(), None)
+    it = T.ti_querys(t, region.encode())
+    out = []
+    if it:
+        n = C.c_int(0)
+        while True:
+            s = T.ti_read(t, it, C.byref(n))
+            if s is None:
+                break
+            out.append(s.decode())
+        T.ti_iter_destroy(it)
+    T.ti_close(t)
+    return out
+
+
+def _query(bz, path, chrom, beg, end):
+    bz.bz_query.restype = C.c_long
+    bz.bz_query.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_long]
+    out = C.create_string_buffer(1 << 24)
+    n = bz.bz_query(path.encode(), chrom.encode(), beg, end, out, len(out))
+    assert n >= -1, n
+    return None if n == -1 else out.value.decode().splitlines()
+
+
+def test_tabix_reader_on_own_files(bz, tmp_path):
+    text = _assoc_text(5, 3000)
+    path = str(tmp_path / "q.assoc.gz")
+    assert bz.bz_write_indexed(path.encode(), text, len(text), 1000) == 0
+    nb = C.c_long(0)
+    bz.bz_count_lines.restype = C.c_long
+    bz.bz_count_lines.argtypes = [C.c_char_p, C.POINTER(C.c_long)]
+    assert bz.bz_count_lines(path.encode(), C.byref(nb)) == text.count(b"\n") and nb.value == len(text)
+    rows = [ln for ln in text.decode().splitlines() if not ln.startswith("#")]
+    T = _tabix_ref()
+    rng = np.random.default_rng(1)
+    assert _query(bz, path, "nope", 1, 10) is None
+    for _ in range(25):
+        name = ["1", "2", "X"][int(rng.integers(0, 3))]
+        beg = int(rng.integers(1, 3_000_000))
+        end = beg + int(rng.integers(0, 200_000))
+        want = [r for r in rows if r.split("\t")[0] == name and beg <= int(r.split("\t")[1]) <= end]
+        got = _query(bz, path, name, beg, end)
+        assert got == want
+        if T is not None:
+            assert _tabix_query_ref(T, path, f"{name}:{beg}-{end}") == want
+
+
+def test_tabix_reader_on_the_reference_example_vcf(bz):
+    """example/example.vcf.gz + .tbi of the reference (written by the stock bgzip / tabix -p vcf): header lines and region
+    queries against a plain gzip scan -- and against tabix 0.2.6's own ti_querys."""
+    path = "/root/reference/example/example.vcf.gz"
+    if not os.path.exists(path):
+        pytest.skip("no /root/reference here")
+    text = gzip.open(path, "rt").read().splitlines()
+    bz.bz_header.restype = C.c_long
+    bz.bz_header.argtypes = [C.c_char_p, C.c_char_p, C.c_long]
+    out = C.create_string_buffer(1 << 20)
+    assert bz.bz_header(path.encode(), out, len(out)) > 0
+    assert out.value.decode().splitlines() == [l for l in text if l.startswith("#")]
+    recs = [l for l in text if not l.startswith("#")]
+    assert len(recs) > 0
+    T = _tabix_ref()
+    pos = sorted(int(r.split("\t")[1]) for r in recs)
+    chrom = recs[0].split("\t")[0]
+    for beg, end in [(1, 10 ** 8), (pos[0], pos[0]), (pos[1], pos[-2]), (pos[-1] + 1, pos[-1] + 5), (pos[2] - 1, pos[2] - 1)]:
+        want = [r for r in recs if r.split("\t")[0] == chrom and int(r.split("\t")[1]) <= end
+                and int(r.split("\t")[1]) + len(r.split("\t")[3]) - 1 >= beg]
+        assert _query(bz, path, chrom, beg, end) == want
+        if T is not None:
+            assert _tabix_query_ref(T, path, f"{chrom}:{beg}-{end}") == want
