@@ -254,6 +254,10 @@ class VcfRangeSet {
     r.end = end;
     r_.push_back(r);
   }
+  // the i-th range (for index / region queries: TabixReader::query, BgenReader::setRange)
+  const std::string& chrom(size_t i) const { return r_[i].chrom; }
+  int begin(size_t i) const { return r_[i].beg; }
+  int end(size_t i) const { return r_[i].end; }
   bool contains(const char* chrom, size_t chrom_len, int pos) const {
     for (size_t i = 0; i < r_.size(); ++i)
       if (r_[i].chrom.size() == chrom_len && memcmp(r_[i].chrom.data(), chrom, chrom_len) == 0 && pos >= r_[i].beg && pos <= r_[i].end)

@@ -18,8 +18,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def bz():
+def load_bgzf_check():
     d = os.path.join(ROOT, "tests", "hostcheck")
     so = os.path.join(d, "libbgzfcheck.so")
     src = os.path.join(d, "bgzf_check.cpp")
@@ -31,6 +30,11 @@ def bz():
     L.bz_printf_check.argtypes = [C.c_char_p]
     L.bz_reg2bin.argtypes = [C.c_uint, C.c_uint]
     return L
+
+
+@pytest.fixture(scope="module")
+def bz():
+    return load_bgzf_check()
 
 
 def _tabix_ref():

@@ -236,7 +236,7 @@ def test_ingest_demo_vcf_and_bed(oracle, tmp_path):
     exe = os.path.join(root, "rvtests_b200", "host", "ingest_demo")
     subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(root, "include"), "-I", os.path.join(root, "rvtests_b200", "host"),
                     os.path.join(root, "rvtests_b200", "host", "ingest_demo.cpp"), "-o", exe, "-L", os.path.join(root, "rvtests_b200"),
-                    "-lrvtests_b200", "-Wl,-rpath," + os.path.join(root, "rvtests_b200")], check=True)
+                    "-lrvtests_b200", "-lz", "-ldl", "-Wl,-rpath," + os.path.join(root, "rvtests_b200")], check=True)
     N, M = 1203, 30
     rng = np.random.default_rng(404)
     maf = np.linspace(0.01, 0.2, M)
@@ -277,7 +277,14 @@ def test_ingest_demo_vcf_and_bed(oracle, tmp_path):
         Gd = O.impute_mean(raw[:, a:b])
         af = 0.5 * np.where(raw[:, a:b] >= 0, raw[:, a:b], 0.0).sum(axis=0) / N
         want[k] = O.gene(Gd, af, X, nm["resid"], nm["sigma2"])[0]
-    for argv in (["vcf", str(tmp_path / "g.vcf"), str(sf), str(tmp_path / "ph.txt")], ["bed", prefix, str(sf)]):
+    # --- the same VCF bgzipped + tabix-indexed (rvt_bgzf.h writes it, the demo reads it back by region queries)
+    from test_bgzf_tabix import load_bgzf_check
+    bzl = load_bgzf_check()
+    text = open(tmp_path / "g.vcf", "rb").read()
+    gz = str(tmp_path / "g.vcf.gz")
+    assert bzl.bz_write_indexed(gz.encode(), text, len(text), 1 << 16) == 0
+    for argv in (["vcf", str(tmp_path / "g.vcf"), str(sf), str(tmp_path / "ph.txt")], ["bed", prefix, str(sf)],
+                 ["vcfgz", gz, str(sf), str(tmp_path / "ph.txt")]):
         out = subprocess.run([exe] + argv, capture_output=True, text=True, check=True).stdout.splitlines()
         assert out[0].split("\t") == ["Set", "NumPolyVar", "Q", "Pvalue", "NonRefSite", "CMC_P", "Zeggini_P"]
         rows = [l.split("\t") for l in out[1:]]
@@ -287,3 +294,79 @@ def test_ingest_demo_vcf_and_bed(oracle, tmp_path):
             assert int(r[4]) == ref.cmc_nonref
             # "%g": 6 significant digits
             assert rel(float(r[2]), ref.skat.Q) <= 2e-5 and rel(float(r[3]), ref.skat.pvalue) <= 2e-4, (argv[0], r, ref.skat.Q, ref.skat.pvalue)
+
+
+def _write_bgen(path, ids, chrom, pos, P0, P1, miss, bits=16):
+    """BGEN v1.2 (layout 2, zlib, unphased diploid bi-allelic): P0 / P1 = integer numerators of p(hom ref) / p(het), (M, N)"""
+    import struct
+    import zlib
+    N, M = len(ids), len(pos)
+    sblock = struct.pack("<II", 8 + sum(2 + len(s) for s in ids), N) + b"".join(struct.pack("<H", len(s)) + s.encode() for s in ids)
+    header = struct.pack("<III4sI", 20, M, N, b"bgen", 1 | (2 << 2) | (1 << 31))
+    out = struct.pack("<I", len(header) + len(sblock)) + header + sblock
+    dt = {8: "<u1", 16: "<u2", 32: "<u4"}[bits]
+    for j in range(M):
+        def s2(x):
+            return struct.pack("<H", len(x)) + x.encode()
+        ident = s2(f"v{j}") + s2(f"rs{j}") + s2(chrom) + struct.pack("<IH", int(pos[j]), 2) + struct.pack("<I", 1) + b"A" + struct.pack("<I", 1) + b"G"
+        pm = (2 | (miss[j].astype(np.uint8) << 7)).astype(np.uint8).tobytes()
+        probs = np.stack([P0[j], P1[j]], axis=1).astype(dt).tobytes()
+        payload = struct.pack("<IHBB", N, 2, 2, 2) + pm + struct.pack("<BB", 0, bits) + probs
+        comp = zlib.compress(payload)
+        out += ident + struct.pack("<II", len(comp) + 4, len(payload)) + comp
+    open(path, "wb").write(out)
+
+
+def test_ingest_demo_bgen_dosages(oracle, tmp_path):
+    """BGEN (rvt_bgen.h) -> dosages -> mean imputation -> rvt_gene_push_f64 in C++ (ingest_demo bgen), against the oracle on
+    the dosages the reference's float arithmetic gives (BitReader: numerator * float(1 / (2^B - 1)); remainder in float;
+    p(het) + 2 p(hom alt) in double)."""
+    import os
+    import subprocess
+    O = oracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "rvtests_b200", "host", "ingest_demo")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(root, "include"), "-I", os.path.join(root, "rvtests_b200", "host"),
+                    os.path.join(root, "rvtests_b200", "host", "ingest_demo.cpp"), "-o", exe, "-L", os.path.join(root, "rvtests_b200"),
+                    "-lrvtests_b200", "-lz", "-ldl", "-Wl,-rpath," + os.path.join(root, "rvtests_b200")], check=True)
+    N, M, bits = 907, 24, 16
+    rng = np.random.default_rng(808)
+    top = (1 << bits) - 1
+    maf = np.linspace(0.02, 0.3, M)
+    g = rng.binomial(2, maf[:, None], size=(M, N))
+    # imputed-looking probabilities around the call
+    noise = rng.dirichlet([0.3, 0.3, 0.3], size=(M, N))
+    pr = 0.85 * np.eye(3)[g] + 0.15 * noise
+    P0 = np.floor(pr[..., 0] * top).astype(np.int64)
+    P1 = np.minimum(np.floor(pr[..., 1] * top).astype(np.int64), top - P0)
+    miss = rng.random((M, N)) < 0.01
+    miss[:8] = False
+    ids = [f"S{i}" for i in range(N)]
+    pos = 1000 + 7 * np.arange(M)
+    path = str(tmp_path / "d.bgen")
+    _write_bgen(path, ids, "7", pos, P0, P1, miss, bits)
+    scale = np.float32(1.0 / np.float32(top))                # BitReader: float scale = 1 / (2^B - 1)
+    p0 = P0.astype(np.float32) * scale
+    p1 = P1.astype(np.float32) * scale
+    p2 = (np.float32(1.0) - p0) - p1
+    D = p1.astype(np.float64) + p2.astype(np.float64) * 2.0
+    D[miss] = -9.0
+    y = rng.normal(size=N) + 0.4 * D[2].clip(0)
+    with open(tmp_path / "ph.txt", "w") as f:
+        for i in range(N):
+            f.write(f"{ids[i]} {float(y[i])!r}\n")
+    sf = tmp_path / "sets.txt"
+    sf.write_text(f"A 7:{pos[0]}-{pos[7]}\nB 7:{pos[8]}-{pos[15]},7:{pos[20]}-{pos[23]}\nNONE 8:1-100\n")
+    out = subprocess.run([exe, "bgen", path, str(sf), str(tmp_path / "ph.txt")], capture_output=True, text=True, check=True).stdout.splitlines()
+    rows = [l.split("\t") for l in out[1:]]
+    assert [r[0] for r in rows] == ["A", "B"]
+    X = np.ones((N, 1))
+    nm = O.fit_null_linear(X, y)
+    for r, cols in zip(rows, (list(range(0, 8)), list(range(8, 16)) + list(range(20, 24)))):
+        raw = D[cols].T                                        # (N, M)
+        Gd = O.impute_mean_literal(raw)
+        af = 0.5 * np.where(raw >= 0, raw, 0.0).sum(axis=0) / N
+        ref = O.gene(Gd, af, X, nm["resid"], nm["sigma2"])[0]
+        assert int(r[1]) == ref.m_poly
+        assert rel(float(r[2]), ref.skat.Q) <= 2e-5 and rel(float(r[3]), ref.skat.pvalue) <= 2e-4, (r, ref.skat.Q, ref.skat.pvalue)
+        assert rel(float(r[5]), ref.cmc_p) <= 2e-4 and rel(float(r[6]), ref.zeg_p) <= 2e-4
