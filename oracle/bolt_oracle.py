@@ -177,11 +177,15 @@ class Fit:
         if i == 7:
             i -= 1
         self.log_delta, self.f = ld, f
-        self.delta = float(np.exp(ld[i]))
+        return self.finish(float(np.exp(ld[i])), h2[i])
+
+    def finish(self, delta, h2):
+        """BoltLMM.cpp:649-666: the variance components from the LAST solve (which may be one secant step behind delta)"""
+        self.delta = delta
         y0, H0 = self.yc[:, None], self.H_inv_y[:, :1]
         self.sigma2_g = float(self.pdot(y0, H0)[0] / (self.N - self.C))
         self.sigma2_e = self.delta * self.sigma2_g
-        self.h2 = h2[i]
+        self.h2 = h2
         self.h = self.H_inv_y[:, 0] / self.sigma2_g      # H_inv_y_
         self.h_norm2 = float(self.pdot(self.h[:, None], self.h[:, None])[0])
         return self

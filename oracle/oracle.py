@@ -895,3 +895,96 @@ def impute_mean(G):
         p = 0.0 if an == 0 else 1.0 * ac / an
         col[~called] = 2.0 * p
     return G
+
+
+# ------------------------------------------------------------------ the reference's own BoltLMM (oracle/_ref/libbolt_ref.so)
+_ref_bolt = [False]
+
+
+def ref_bolt():
+    """The reference's own regression/BoltLMM.cpp + BoltPlinkLoader.cpp (+ PlinkInputFile, base/IO.cpp, cnpy), compiled
+    unmodified against oracle/eigen_standin behind oracle/ref_bolt_shim.cpp.  None when oracle/_ref was never built."""
+    if _ref_bolt[0] is False:
+        path = os.path.join(_HERE, "_ref", "libbolt_ref.so")
+        if not os.path.exists(path):
+            _ref_bolt[0] = None
+        else:
+            L = C.CDLL(path)
+            L.bolt_ref_fit.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+            L.bolt_ref_test.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+            L.bolt_ref_covxx.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            L.bolt_ref_free.restype = None
+            _ref_bolt[0] = L
+    return _ref_bolt[0]
+
+
+def pack_plink(G):
+    """(M, N) int8 hard calls with -1 = missing -> PLINK 2-bit SNP-major rows (00 hom-ref, 10 het, 11 hom-alt, 01 missing:
+    libVcf/PlinkInputFile.h:14-20)."""
+    G = np.asarray(G)
+    code = np.where(G == 0, 0, np.where(G == 1, 2, np.where(G == 2, 3, 1))).astype(np.uint8)
+    M, N = G.shape
+    code = np.pad(code, ((0, 0), (0, (-N) % 4)))
+    c4 = code.reshape(M, -1, 4)
+    return (c4[:, :, 0] | (c4[:, :, 1] << 2) | (c4[:, :, 2] << 4) | (c4[:, :, 3] << 6)).astype(np.uint8)
+
+
+def write_bolt_fileset(prefix, G, y, covar):
+    """prefix.bed/.bim/.fam (+ .covar when there is more than the intercept) as `--boltPlink prefix` reads them
+    (BoltPlinkLoader::open / loadCovariate, regression/BoltPlinkLoader.cpp:37-117)."""
+    M, N = np.asarray(G).shape
+    with open(prefix + ".bed", "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 1]) + pack_plink(G).tobytes())
+    with open(prefix + ".bim", "w") as f:
+        for j in range(M):
+            f.write(f"1\trs{j}\t0\t{100 + j}\tA\tG\n")
+    with open(prefix + ".fam", "w") as f:
+        for i in range(N):
+            f.write(f"F{i} S{i} 0 0 1 {y[i]:.9g}\n")
+    covar = np.asarray(covar)
+    if covar.shape[1] > 1:
+        with open(prefix + ".covar", "w") as f:
+            f.write("FID IID " + " ".join(f"c{k}" for k in range(1, covar.shape[1])) + "\n")
+            for i in range(N):
+                f.write(f"F{i} S{i} " + " ".join(f"{covar[i, k]:.9g}" for k in range(1, covar.shape[1])) + "\n")
+
+
+def ref_bolt_fit(prefix, npz, log, pheno=None, binary=False):
+    """BoltLMM::FitNullModel(prefix, phenotype) of the reference build; returns what the reference exports through
+    BOLTLMM_SAVE_NULL_MODEL plus the secant path parsed from its BOLTLMM_DEBUG log."""
+    import re
+    L = ref_bolt()
+    ph = None if pheno is None else np.ascontiguousarray(pheno, dtype=np.float64)
+    rc = L.bolt_ref_fit(prefix.encode(), None if ph is None else ph.ctypes.data, 0 if ph is None else ph.size,
+                        npz.encode(), log.encode(), int(binary))
+    if rc != 0:
+        raise RuntimeError(f"reference BoltLMM::FitNullModel returned {rc}")
+    z = np.load(npz)
+    text = open(log).read()
+    ld, f = [], []
+    for m in re.finditer(r"^i = (\d+)\tlogDelta = (\S+)\tf = (\S+)\tdelta = (\S+)\th2 = (\S+)$", text, re.M):
+        ld.append(float(m.group(2)))
+        f.append(float(m.group(3)))
+    fin = re.search(r"^i = (\d+), delta = (\S+), sigma2_g = (\S+), sigma2_e = (\S+), h2 = (\S+)$", text, re.M)
+    return dict(H_inv_y=np.array(z["H_inv_y"]).reshape(-1), H_inv_y_norm2=float(z["H_inv_y_norm2"][0]),
+                infStatCalibration=float(z["infStatCalibration"][0]), xVx_xx_ratio=float(z["xVx_xx_ratio"][0]),
+                log_delta=np.array(ld), f=np.array(f), final_i=int(fin.group(1)), delta=float(fin.group(2)),
+                sigma2_g=float(fin.group(3)), sigma2_e=float(fin.group(4)), h2=float(fin.group(5)),
+                n_solves=text.count("=> Enter solve()"))
+
+
+def ref_bolt_test(g):
+    """BoltLMM::TestCovariate on one variant: (af, U, V, effect, pvalue)"""
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    out = np.zeros(5)
+    ref_bolt().bolt_ref_test(g.ctypes.data, g.size, out.ctypes.data)
+    return out
+
+
+def ref_bolt_covxx(g1, g2):
+    """BoltLMM::GetCovXX, both overloads: (vector<double> form, FloatMatrixRef form)"""
+    a = np.ascontiguousarray(g1, dtype=np.float64)
+    b = np.ascontiguousarray(g2, dtype=np.float64)
+    out = np.zeros(2)
+    ref_bolt().bolt_ref_covxx(a.ctypes.data, b.ctypes.data, a.size, out.ctypes.data)
+    return out

@@ -70,3 +70,53 @@ def test_bolt_null_fit_vs_oracle(engine_cls, oracle, case):
         assert abs(vout[j]["U"] * kappa - u) <= 1e-6 * max(abs(u), np.sqrt(v))
         assert rel(vout[j]["pvalue"], oracle.lib().orc_chisq_q(u * u / v, 1.0)) <= 1e-5
     eng.close()
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_bolt_device_vs_reference_golden(engine_cls, oracle, k):
+    """The device against outputs of the REFERENCE's own BoltLMM (regression/BoltLMM.cpp + BoltPlinkLoader.cpp compiled
+    unmodified: tests/golden/ref_bolt_golden.npz, generator tests/golden/make_golden_ref_bolt.py), nothing in between:
+    A15 the null fit (secant path, variance components, H^-1 y, calibration, xVx/xx), then A14 on top of the DEVICE's own
+    fit -- TestCovariate (:315-338) per variant through rvt_set_null_residual + rvt_meta_flush, GetCovXX (:414-460) per pair
+    through the band with option meta_cov_scale.  The reference is float32 and its secant steps amplify that noise
+    (tests/test_oracle_pin_reference_bolt.py holds the path step by step): 5e-3 on what follows from log-delta, float32
+    tolerances on the score step."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_bolt_golden.npz"))
+    _seed, N, M, C, _h2 = (int(v) if i < 4 else v for i, v in enumerate(z[f"c{k}_case"]))
+    bed, y, covar, Gt = z[f"c{k}_bed"], z[f"c{k}_y"], z[f"c{k}_covar"], z[f"c{k}_gtest"]
+    ref = {key[len(f"c{k}_"):]: z[key] for key in z.files if key.startswith(f"c{k}_")}
+    eng = engine_cls(0)
+    try:
+        rec, h, Zd = eng.bolt_fit_null(np.ascontiguousarray(bed), N, y, covar)
+        n = len(ref["f"])
+        assert int(rec["reml_evals"]) == n and int(rec["n_covariates_kept"]) == C and int(rec["mc_trials"]) == 15
+        assert np.max(np.abs(rec["log_delta"][:n] - ref["log_delta"])) <= 5e-3
+        assert np.max(np.abs(rec["f"][:n] - ref["f"])) <= 5e-3
+        for mine, key in (("delta", "delta"), ("sigma2_g", "sigma2_g"), ("sigma2_e", "sigma2_e"), ("h2", "h2"),
+                          ("h_inv_y_norm2", "H_inv_y_norm2"), ("inf_stat_calibration", "infStatCalibration"),
+                          ("xvx_xx_ratio", "xVx_xx_ratio")):
+            assert rel(rec[mine], float(ref[key])) <= 5e-3, (mine, rec[mine], float(ref[key]))
+        assert np.max(np.abs(h[:N] - ref["H_inv_y"][:N])) <= 5e-3 * np.max(np.abs(ref["H_inv_y"][:N]))
+        # A14 on the device's fit
+        r_b = h[:N] - Zd @ (Zd.T @ h[:N])
+        kappa = float(rec["h_inv_y_norm2"] * rec["inf_stat_calibration"] / N)
+        eng.set_null_residual(covar, r_b, kappa)
+        eng.set_option("meta_cov_scale", float(rec["xvx_xx_ratio"]))
+        nv = Gt.shape[0]
+        eng.push_i8(np.ascontiguousarray(Gt), None)
+        pos = (100 * np.arange(nv)).astype(np.int32)
+        vout, band, wmax = eng.meta_flush(nv, pos, np.ones(nv, dtype=np.int32), 100 * nv)
+        for j in range(nv):
+            af, ru, rv, reff, rp = ref["tests"][j]
+            u, v = vout[j]["U"] * kappa, vout[j]["V"] * kappa * kappa        # U = g'r / kappa, V = g'Pg / kappa as MetaScore prints
+            assert abs(u - ru) <= 5e-3 * np.sqrt(rv) and rel(v, rv) <= 5e-3, (j, u, ru, v, rv)
+            assert rel(vout[j]["pvalue"], rp) <= 2e-2 or abs(vout[j]["pvalue"] - rp) <= 1e-6
+        assert wmax >= nv - 1
+        for (a, b), (c64, c32) in zip(ref["pairs"], ref["covxx"]):
+            i, j = (int(a), int(b)) if a <= b else (int(b), int(a))
+            got = band[i, j - i] * N                                   # printed divided by N (src/Model.cpp:990-996)
+            scale = np.sqrt(band[i, 0] * band[j, 0]) * N
+            assert abs(got - c64) <= 5e-3 * scale and abs(got - c32) <= 5e-3 * scale, (a, b, got, c64, c32)
+    finally:
+        eng.close()
