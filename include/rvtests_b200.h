@@ -222,6 +222,19 @@ int rvt_lmm_meta_flush(rvt_ctx* ctx, const int32_t* pos, const int32_t* chrom, i
  * rvt_meta_flush.  Random numbers: the reference's generator and seed (libsrc/Random.cpp, 12345). */
 int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t stride, int64_t N, const double* y, const double* covar,
                       int C, int mc_trials, rvt_bolt_null* out, double* h_inv_y, double* Zout);
+/* The same fit with the panel's SNPs sharded over ranks (BASELINE configs[4] on 8 GPUs; the reference has no
+ * multi-device path, its OpenMP loops over the 64 SNPs of a batch are what this replaces, BoltPlinkLoader.cpp:305-440).
+ * This rank holds rows [m_offset, m_offset + M) of the M_total SNP rows (bed, host or DEVICE pointer -- a device panel is
+ * used in place); y / covar are replicated.  Every product that sums over SNPs -- the X X'v half of computeHx
+ * (BoltLMM.cpp:956-966), |beta_hat|^2 (:689-692), the calibration columns -- is a local partial followed by ONE call of
+ * `allreduce`: an in-place SUM over ranks of `count` doubles at DEVICE pointer `buf`, ordered on `cuda_stream` (the context's
+ * stream, a cudaStream_t) like ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, comm, stream); return 0 on success.  One
+ * call per H-product of the conjugate gradients.  Every rank draws the same random stream and returns the same record /
+ * h_inv_y.  allreduce may be NULL only when M == M_total. */
+typedef int (*rvt_allreduce_fn)(void* user, double* buf, int64_t count, void* cuda_stream);
+int rvt_bolt_fit_null_sharded(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t stride, int64_t N, const double* y, const double* covar,
+                              int C, int mc_trials, int64_t M_total, int64_t m_offset, rvt_allreduce_fn allreduce, void* user,
+                              rvt_bolt_null* out, double* h_inv_y, double* Zout);
 /* number of genes pushed and not yet flushed */
 int rvt_pending(const rvt_ctx* ctx);
 /* run the sweep + per-gene statistics for every pending gene; out: host array of `cap` records */

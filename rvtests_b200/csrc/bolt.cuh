@@ -360,7 +360,14 @@ __global__ void k_bolt_axpby(int64_t rows, int R, const double* __restrict__ ca,
   y[idx] = ca[r] * a[idx] + (b ? cb[r] * b[idx] : 0.0);
 }
 
-// normalised genotype columns of chosen SNPs as top rows: out[i][k] = x_{idx[k], i}  (loadRandomSNPWithCov, .cpp:441-480)
+// y[e] += beta * a[e]   (the "+ delta y" term of computeHx after the sum over ranks of the sharded product)
+__global__ void k_bolt_axpy(int64_t n, double beta, const double* __restrict__ a, double* __restrict__ y) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) y[e] += beta * a[e];
+}
+
+// normalised genotype columns of chosen SNPs as top rows: out[i][k] = x_{idx[k], i}  (loadRandomSNPWithCov, .cpp:441-480);
+// idx[k] < 0: the SNP lives on another rank, the column is zero here (the sum over ranks fills it)
 __global__ void k_bolt_columns(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, const int* __restrict__ idx, int K,
                                const double* __restrict__ tab, double* __restrict__ out) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -368,7 +375,7 @@ __global__ void k_bolt_columns(const uint8_t* __restrict__ bed, int64_t stride, 
   const int64_t i = e / K;
   const int k = (int)(e - i * K);
   const int m = idx[k];
-  out[e] = tab[(size_t)m * 4 + bolt_code(bed + (size_t)m * stride, i)];
+  out[e] = m < 0 ? 0.0 : tab[(size_t)m * 4 + bolt_code(bed + (size_t)m * stride, i)];
 }
 // second stage of k_bolt_dot: out[r] = sum over CTAs (index order) - sum_c abot[c][r] bbot[c][r]  (abot null: plain sum)
 __global__ void k_bolt_dot_finish(int ctas, int R, int C, const double* __restrict__ partial, const double* __restrict__ abot,

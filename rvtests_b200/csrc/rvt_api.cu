@@ -2331,6 +2331,18 @@ struct BoltDev {
   std::vector<void*> owned;
   cudaError_t err = cudaSuccess;
   int cg_total = 0;
+  // variant sharding: this rank holds SNP rows [m_off, m_off + M) of M_total; every product that sums over
+  // SNPs is a local partial followed by ONE sum over ranks through the caller's collective (ncclAllReduce on `st`)
+  int64_t M_total = 0, m_off = 0;
+  rvt_allreduce_fn ar = nullptr;
+  void* ar_user = nullptr;
+  int ar_calls = 0;
+  int ar_rc = 0;
+  void allreduce(double* buf, int64_t n) {
+    if (!ar || err != cudaSuccess || ar_rc) return;
+    ++ar_calls;
+    ar_rc = ar(ar_user, buf, n, (void*)st);
+  }
   template <class T>
   T* alloc(size_t n) {
     void* p = nullptr;
@@ -2362,17 +2374,31 @@ struct BoltDev {
   void Hx(double delta, const double* v, double* out, int R) {
     launch_xtv(v, R);
     k_bolt_xtv_finish<<<(unsigned)(((int64_t)M * R + 255) / 256), 256, 0, st>>>(M, R, C, splits, part, zg, v + (size_t)N * R, 1.0, Xy);
-    XW(Xy, R, 1.0 / M, delta, v, out);
+    XW(Xy, R, 1.0 / (double)M_total, delta, v, out);
   }
   // out = alpha [X ; Z'X] W + beta add
   void XW(const double* W, int R, double alpha, double beta, const double* add, double* out) {
     const unsigned g1 = (unsigned)((N + 255) / 256), g4 = (unsigned)((N + 1023) / 1024);
+    if (ar) {   // sharded: local partial over this rank's SNPs, one sum over ranks, then the + beta add term
+      const double* add0 = add;
+      const double beta0 = beta;
+      add = nullptr;
+      beta = 0.0;
+      launch_xw(g1, g4, W, R, alpha, beta, add, out);
+      allreduce(out, (int64_t)rows() * R);
+      if (add0) k_bolt_axpy<<<(unsigned)((rows() * R + 255) / 256), 256, 0, st>>>((int64_t)rows() * R, beta0, add0, out);
+      note();
+      return;
+    }
+    launch_xw(g1, g4, W, R, alpha, beta, add, out);
+    note();
+  }
+  void launch_xw(unsigned g1, unsigned g4, const double* W, int R, double alpha, double beta, const double* add, double* out) {
     if (R <= 4) k_bolt_xw<4, 4><<<g4, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
     else if (R <= 8) k_bolt_xw<8, 4><<<g4, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
     else if (R <= 16) k_bolt_xw<16, 1><<<g1, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
     else k_bolt_xw<32, 1><<<g1, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
     k_bolt_bot<<<(C * R + 63) / 64, 64, 0, st>>>(M, R, C, zg, W, alpha, beta, add ? add + (size_t)N * R : nullptr, out + (size_t)N * R);
-    note();
   }
   // X_minus' v / scale -> Xy (host copy optional)
   void XtV(const double* v, int R, double scale) {
@@ -2394,9 +2420,10 @@ struct BoltDev {
     note();
   }
   // column sums of squares of an M x R matrix (|beta_hat|^2 per right-hand side)
-  void colnorm2(const double* a, int64_t rows_, int R, double* out) {
+  void colnorm2(const double* a, int64_t rows_, int R, double* out, bool over_snps = true) {
     k_bolt_dot<<<kBoltDotCtas, 256, 0, st>>>(rows_, R, a, a, dotp);
     k_bolt_dot_finish<<<1, 64, 0, st>>>(kBoltDotCtas, R, 0, dotp, nullptr, nullptr, coef + 2 * kBoltMaxR);
+    if (over_snps) allreduce(coef + 2 * kBoltMaxR, R);
     cudaMemcpyAsync(out, coef + 2 * kBoltMaxR, sizeof(double) * R, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess && err == cudaSuccess) err = e;
@@ -2456,8 +2483,16 @@ extern "C" {
 
 int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t stride, int64_t N, const double* y, const double* covar,
                       int C, int mc_trials, rvt_bolt_null* out, double* h_inv_y, double* Zout) {
+  return rvt_bolt_fit_null_sharded(ctx, bed, M, stride, N, y, covar, C, mc_trials, M, 0, nullptr, nullptr, out, h_inv_y, Zout);
+}
+
+int rvt_bolt_fit_null_sharded(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t stride, int64_t N, const double* y, const double* covar,
+                              int C, int mc_trials, int64_t M_total, int64_t m_offset, rvt_allreduce_fn allreduce, void* user,
+                              rvt_bolt_null* out, double* h_inv_y, double* Zout) {
   if (!ctx || !bed || !y || !covar || !out) return RVT_E_BADARG;
   if (N < 2 || M < 1 || M > 0x7FFFFFF0ll || C < 1 || C > kMaxC) CTX_FAIL(RVT_E_BADARG, "bolt: N, M or C out of range");
+  if (m_offset < 0 || m_offset + M > M_total || M_total > 0x7FFFFFF0ll) CTX_FAIL(RVT_E_BADARG, "bolt: shard [%lld, %lld) outside 0..%lld", (long long)m_offset, (long long)(m_offset + M), (long long)M_total);
+  if (M != M_total && !allreduce) CTX_FAIL(RVT_E_BADARG, "bolt: a shard of the panel needs the sum-over-ranks callback");
   if (stride < (N + 3) / 4) CTX_FAIL(RVT_E_BADARG, "bolt: stride (%lld) < ceil(N/4)", (long long)stride);
   RVT_CUDA_OK(cudaSetDevice(ctx->device));
   memset(out, 0, sizeof(*out));
@@ -2487,15 +2522,20 @@ int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t strid
   if (Ck < 1) CTX_FAIL(RVT_E_NUMERIC, "bolt: the covariate matrix has no usable column");
   BoltDev B;
   B.N = N; B.M = (int)M; B.C = Ck; B.stride = stride; B.st = ctx->stream;
+  B.M_total = M_total; B.m_off = m_offset; B.ar = allreduce; B.ar_user = user;
   const int mc = mc_trials > 0 ? std::min(mc_trials, 15) : std::max(std::min((int)(4e9 / (double)N / (double)N), 15), 3);   // BoltLMM.cpp:465
   const int R1 = mc + 1;
-  const int nSnp = (int)std::min<int64_t>(30, M), Rmax = std::max(R1, nSnp);
+  const int nSnp = (int)std::min<int64_t>(30, M_total), Rmax = std::max(R1, nSnp);
   // sample splits of the X'v product: enough CTAs to fill the device, each a multiple of the staged chunk
   const int64_t nblk = (M + kBoltXtvBlock - 1) / kBoltXtvBlock;
   int splits = (int)std::max<int64_t>(1, std::min<int64_t>((4 * (int64_t)ctx->sm_count + nblk - 1) / nblk, (N + kBoltChunk - 1) / kBoltChunk));
   B.split_len = (((N + splits - 1) / splits) + kBoltChunk - 1) / kBoltChunk * kBoltChunk;
   B.splits = (int)((N + B.split_len - 1) / B.split_len);
-  B.bed = B.alloc<uint8_t>((size_t)M * stride);
+  // the panel: copied when it lives on the host, used in place when the caller already holds it in device memory
+  cudaPointerAttributes pattr;
+  const bool bed_on_device = cudaPointerGetAttributes(&pattr, bed) == cudaSuccess && pattr.type == cudaMemoryTypeDevice;
+  cudaGetLastError();
+  B.bed = bed_on_device ? const_cast<uint8_t*>(bed) : B.alloc<uint8_t>((size_t)M * stride);
   B.Z = B.alloc<double>((size_t)N * Ck);
   B.tab = B.alloc<double>((size_t)M * 4);
   B.zg = B.alloc<double>((size_t)M * Ck);
@@ -2507,7 +2547,7 @@ int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t strid
   double *vy = B.vec(Rmax), *vx = B.vec(Rmax), *vr = B.vec(Rmax), *vp = B.vec(Rmax), *vap = B.vec(Rmax), *vxb = B.vec(mc), *ve = B.vec(mc);
   if (B.err != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "bolt: cudaMalloc: %s", cudaGetErrorString(B.err));
   cudaStream_t st = B.st;
-  RVT_CUDA_OK(cudaMemcpyAsync(B.bed, bed, (size_t)M * stride, cudaMemcpyHostToDevice, st));
+  if (!bed_on_device) RVT_CUDA_OK(cudaMemcpyAsync(B.bed, bed, (size_t)M * stride, cudaMemcpyHostToDevice, st));
   {   // Z row-major [N][Ck] on the device
     std::vector<double> zr((size_t)N * Ck);
     for (int c = 0; c < Ck; ++c)
@@ -2535,9 +2575,12 @@ int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t strid
   // e_rand ~ N(0, 1) row by row with its covariate rows
   {
     std::vector<double> hb((size_t)M * mc), he(rows * mc, 0.0);
-    const double sq = 1.0 / sqrt((double)M);
-    for (int64_t i = 0; i < M; ++i)
-      for (int j = 0; j < mc; ++j) hb[(size_t)i * mc + j] = rng.normal() * sq;
+    const double sq = 1.0 / sqrt((double)M_total);
+    for (int64_t i = 0; i < M_total; ++i)           // every rank draws the whole stream and keeps its own SNP rows
+      for (int j = 0; j < mc; ++j) {
+        const double v = rng.normal() * sq;
+        if (i >= m_offset && i < m_offset + M) hb[(size_t)(i - m_offset) * mc + j] = v;
+      }
     for (int64_t i = 0; i < N; ++i)
       for (int j = 0; j < mc; ++j) he[(size_t)i * mc + j] = rng.normal();
     RVT_CUDA_OK(cudaMemcpy(B.Xy, hb.data(), sizeof(double) * hb.size(), cudaMemcpyHostToDevice));
@@ -2559,7 +2602,7 @@ int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t strid
     }
     cudaMemcpy(vy, hY.data(), sizeof(double) * hY.size(), cudaMemcpyHostToDevice);
     B.solve(vy, delta, vx, vr, vp, vap, R1);
-    B.XtV(vx, R1, 1.0 / (double)M);                  // beta_hat = [X ; Z'X]_minus' H^-1 y / M   (:734-742)
+    B.XtV(vx, R1, 1.0 / (double)M_total);            // beta_hat = [X ; Z'X]_minus' H^-1 y / M   (:734-742)
     ++evals;
     double bn[kBoltMaxR], en[kBoltMaxR];
     B.colnorm2(B.Xy, M, R1, bn);                     // |beta_hat|^2 per right-hand side
@@ -2614,11 +2657,15 @@ int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t strid
   RVT_CUDA_OK(cudaStreamSynchronize(st));
   // EstimateInfStatCalibration (BoltLMM.cpp:1141-1214)
   std::vector<int> idx(nSnp);
-  for (int k = 0; k < nSnp; ++k) idx[k] = (int)(size_t)(rng.next() * (double)M);
+  for (int k = 0; k < nSnp; ++k) {
+    const int64_t g = (int64_t)(size_t)(rng.next() * (double)M_total);
+    idx[k] = (g >= m_offset && g < m_offset + M) ? (int)(g - m_offset) : -1;   // columns of other ranks' SNPs arrive with the sum
+  }
   int* d_idx = B.alloc<int>(nSnp);
   if (!d_idx) CTX_FAIL(RVT_E_CUDA, "bolt: cudaMalloc");
   RVT_CUDA_OK(cudaMemcpy(d_idx, idx.data(), sizeof(int) * nSnp, cudaMemcpyHostToDevice));
   k_bolt_columns<<<(unsigned)(((int64_t)N * nSnp + 255) / 256), 256, 0, st>>>(B.bed, stride, N, d_idx, nSnp, B.tab, vy);
+  B.allreduce(vy, (int64_t)N * nSnp);
   B.project(vy, nSnp);
   B.solve(vy, delta, vx, vr, vp, vap, nSnp);         // V^-1 x = H^-1 x / sigma2_g
   std::vector<double> xVx(nSnp), xx(nSnp), xVy(nSnp);
@@ -2650,6 +2697,7 @@ int rvt_bolt_fit_null(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64_t strid
   out->reml_evals = evals;
   out->cg_iterations = B.cg_total;
   out->n_covariates_kept = Ck;
+  if (B.ar_rc) CTX_FAIL(RVT_E_CUDA, "bolt: the sum-over-ranks callback returned %d", B.ar_rc);
   for (int k = 0; k < 7; ++k) {
     out->log_delta[k] = (k <= i) ? ld[k] : 0.0;
     out->f[k] = (k < evals) ? f[k] : 0.0;

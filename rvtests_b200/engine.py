@@ -53,9 +53,11 @@ EXPORTS = [
     "rvt_flush", "rvt_flush_dev", "rvt_synth_load", "rvt_loaded_genes", "rvt_run_loaded", "rvt_push_loaded",
     "rvt_loaded_read", "rvt_last_timing", "rvt_debug_partials",
     "rvt_debug_phases",
-    "rvt_meta_plan", "rvt_meta_flush", "rvt_meta_binary_extras", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand", "rvt_lmm_set_null", "rvt_lmm_flush", "rvt_lmm_meta_flush", "rvt_get_null_beta", "rvt_bolt_fit_null",
+    "rvt_meta_plan", "rvt_meta_flush", "rvt_meta_binary_extras", "rvt_perm_results", "rvt_perm_debug_q", "rvt_debug_rand", "rvt_lmm_set_null", "rvt_lmm_flush", "rvt_lmm_meta_flush", "rvt_get_null_beta", "rvt_bolt_fit_null", "rvt_bolt_fit_null_sharded",
 ]
 
+# rvt_allreduce_fn (include/rvtests_b200.h): int (*)(void* user, double* buf, int64_t count, void* cuda_stream)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 BOLT_DTYPE = np.dtype([("delta", "f8"), ("sigma2_g", "f8"), ("sigma2_e", "f8"), ("h2", "f8"), ("h_inv_y_norm2", "f8"),
                        ("inf_stat_calibration", "f8"), ("xvx_xx_ratio", "f8"), ("log_delta", "f8", (7,)), ("f", "f8", (7,)),
                        ("mc_trials", "i4"), ("reml_evals", "i4"), ("cg_iterations", "i4"), ("n_covariates_kept", "i4")])
@@ -126,6 +128,8 @@ def load_library(rebuild: bool = False):
     L.rvt_lmm_set_null.argtypes = [vp, C.c_int64, C.c_int, vp, vp, C.c_double, C.c_double, vp, vp]
     L.rvt_lmm_flush.argtypes = [vp, vp, C.c_int64]
     L.rvt_bolt_fit_null.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, _dp, _dp, C.c_int, C.c_int, vp, vp, vp]
+    L.rvt_bolt_fit_null_sharded.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, _dp, _dp, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                            ALLREDUCE_FN, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -234,18 +238,41 @@ class GeneEngine:
         self._chk(self.L.rvt_flush(self.h, out.ctypes.data, len(out), C.byref(got)))
         return out[: got.value]
 
-    def bolt_fit_null(self, bed, N, y, covar, mc_trials=0):
+    def bolt_fit_null(self, bed, N, y, covar, mc_trials=0, M_total=None, m_offset=0, allreduce=None, bed_dev=None):
         """BoltLMM null fit on a PLINK panel: bed (M, >= ceil(N/4)) uint8 SNP-major rows, covar (N, C) with the intercept
-        first.  Returns (record, h [N + C'], Z [N, C'])."""
-        assert bed.dtype == np.uint8 and bed.ndim == 2 and bed.strides[1] == 1
+        first.  Returns (record, h [N + C'], Z [N, C']).
+        Sharded over ranks (rvt_bolt_fit_null_sharded): bed holds rows [m_offset, m_offset + M) of M_total and `allreduce`
+        is a Python callable (dev_ptr, count, cuda_stream) -> 0 that sums `count` doubles in place over the ranks
+        (rvtests_b200.sharding.torch_allreduce).  bed_dev = (device_ptr, M, stride): a panel already in device memory."""
+        if bed_dev is not None:
+            bed_ptr, M, stride = int(bed_dev[0]), int(bed_dev[1]), int(bed_dev[2])
+        else:
+            assert bed.dtype == np.uint8 and bed.ndim == 2 and bed.strides[1] == 1
+            bed_ptr, M, stride = bed.ctypes.data, bed.shape[0], bed.strides[0]
         y = np.ascontiguousarray(y, dtype=np.float64)
         cv = np.asfortranarray(covar, dtype=np.float64)
         Cc = cv.shape[1]
         rec = np.zeros(1, dtype=BOLT_DTYPE)
         h = np.zeros(N + Cc)
         Z = np.zeros((N, Cc), order="F")
-        self._chk(self.L.rvt_bolt_fit_null(self.h, bed.ctypes.data, bed.shape[0], bed.strides[0], int(N), _pd(y), _pd(cv), Cc,
-                                           int(mc_trials), rec.ctypes.data, h.ctypes.data, Z.ctypes.data))
+        if M_total is None and allreduce is None:
+            self._chk(self.L.rvt_bolt_fit_null(self.h, bed_ptr, M, stride, int(N), _pd(y), _pd(cv), Cc,
+                                               int(mc_trials), rec.ctypes.data, h.ctypes.data, Z.ctypes.data))
+        else:
+            def _cb(_user, buf, count, stream):
+                try:
+                    return int(allreduce(int(buf), int(count), int(stream or 0)) or 0)
+                except Exception as e:            # an exception must not unwind through the C frames
+                    self._cb_error = e
+                    return 1
+            cb = ALLREDUCE_FN(_cb) if allreduce is not None else C.cast(None, ALLREDUCE_FN)
+            self._cb_error = None
+            rc = self.L.rvt_bolt_fit_null_sharded(self.h, bed_ptr, M, stride, int(N), _pd(y), _pd(cv), Cc, int(mc_trials),
+                                                  int(M if M_total is None else M_total), int(m_offset), cb, None,
+                                                  rec.ctypes.data, h.ctypes.data, Z.ctypes.data)
+            if self._cb_error is not None:
+                raise self._cb_error
+            self._chk(rc)
         k = int(rec[0]["n_covariates_kept"])
         return rec[0], h[: N + k], np.ascontiguousarray(Z[:, :k])
 

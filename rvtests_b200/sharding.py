@@ -32,3 +32,40 @@ def gather_records(local: np.ndarray, dist, device=None) -> np.ndarray:
     dist.all_gather(out, buf)
     parts = [np.frombuffer(o.cpu().numpy().tobytes(), dtype=local.dtype)[:c] for o, c in zip(out, counts)]
     return np.concatenate(parts) if parts else local
+
+
+def snp_shard(m_total: int, rank: int, world: int):
+    """BoltLMM null fit (BASELINE configs[4]): the panel's SNP rows are sharded, [lo, hi) of rank `rank`"""
+    return shard_range(m_total, rank, world)
+
+
+class _DevView:
+    """a device buffer of doubles as an object torch.as_tensor understands (__cuda_array_interface__, no copy)"""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def torch_allreduce(dist, device=None, staged: bool = False):
+    """The rvt_allreduce_fn of rvt_bolt_fit_null_sharded on torch.distributed: (dev_ptr, count, cuda_stream) -> 0.
+    NCCL: the device buffer is wrapped in place and summed by ncclAllReduce, ordered on the engine's stream (handed to the
+    callback).  staged=True (gloo, the CPU-side tests with two ranks on one GPU): the
+    buffer goes through host memory."""
+    import torch
+
+    def fn(ptr: int, count: int, stream: int) -> int:
+        t = torch.as_tensor(_DevView(ptr, count), device=device)
+        if staged:
+            torch.cuda.synchronize()
+            h = t.cpu()
+            dist.all_reduce(h)
+            t.copy_(h)
+            torch.cuda.synchronize()
+        elif stream:
+            with torch.cuda.stream(torch.cuda.ExternalStream(stream)):   # ordered on the engine's own stream
+                dist.all_reduce(t)
+        else:
+            dist.all_reduce(t)
+        return 0
+
+    return fn

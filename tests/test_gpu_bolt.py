@@ -120,3 +120,76 @@ def test_bolt_device_vs_reference_golden(engine_cls, oracle, k):
             assert abs(got - c64) <= 5e-3 * scale and abs(got - c32) <= 5e-3 * scale, (a, b, got, c64, c32)
     finally:
         eng.close()
+
+
+def _bolt_rank(rank, world, port, case, q):
+    """one rank of the SNP-sharded fit; both ranks share cuda:0, so the sum over ranks is staged through gloo"""
+    import os
+    import sys
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from rvtests_b200 import engine, sharding
+    from oracle import bolt_oracle as BO
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seed, N, M, C, h2 = case
+    G = _panel(seed, N, M)
+    rng = np.random.default_rng(seed + 1)
+    covar = np.column_stack([np.ones(N)] + [rng.normal(size=N) for _ in range(C - 1)])
+    X, _, _ = BO.prepare(G, covar, np.zeros(N))
+    y = X @ rng.normal(size=M) * np.sqrt(h2 / M) + rng.normal(size=N) * np.sqrt(1 - h2) + covar @ rng.normal(size=C)
+    bed = _pack(G)
+    lo, hi = sharding.snp_shard(M, rank, world)
+    eng = engine.GeneEngine(0)
+    calls = [0]
+    ar = sharding.torch_allreduce(dist, device="cuda:0", staged=True)
+
+    def counted(ptr, count, stream):
+        calls[0] += 1
+        return ar(ptr, count, stream)
+
+    rec, h, _Z = eng.bolt_fit_null(np.ascontiguousarray(bed[lo:hi]), N, y, covar, M_total=M, m_offset=lo, allreduce=counted)
+    out = {k: (rec[k].tolist() if hasattr(rec[k], "tolist") else rec[k]) for k in rec.dtype.names}
+    if rank == 0:
+        full, hf, _ = eng.bolt_fit_null(bed, N, y, covar)
+        out["full"] = {k: (full[k].tolist() if hasattr(full[k], "tolist") else full[k]) for k in full.dtype.names}
+        out["h_err"] = float(np.max(np.abs(h - hf)) / np.max(np.abs(hf)))
+    eng.close()
+    q.put((rank, calls[0], out, h[:8].tolist()))
+    dist.destroy_process_group()
+
+
+def test_bolt_snp_sharded_two_ranks_equals_unsharded():
+    """rvt_bolt_fit_null_sharded with the panel's SNPs split over two ranks (two processes on this GPU, the sum over ranks
+    through the callback) against the unsharded fit: same secant path, same CG iteration counts, same H^-1 y; one
+    collective per H-product (+ one per |beta_hat|^2, + the calibration columns)."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    case = (105, 640, 333, 2, 0.4)
+    ps = [ctx.Process(target=_bolt_rank, args=(r, 2, port, case, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    outs = sorted((q.get(timeout=140) for _ in ps), key=lambda o: o[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, calls0, o0, h0), (r1, calls1, o1, h1) = outs
+    full = o0["full"]
+    assert calls0 == calls1 > 0
+    assert o0["cg_iterations"] == o1["cg_iterations"] == full["cg_iterations"]
+    assert o0["reml_evals"] == o1["reml_evals"] == full["reml_evals"]
+    # H-products: one per CG iteration + one per solve start; |beta_hat|^2 once per REML evaluation; x_beta_rand; the columns
+    n_solves = full["reml_evals"] + 1
+    assert calls0 == full["cg_iterations"] + n_solves + full["reml_evals"] + 2
+    for k in ("delta", "sigma2_g", "sigma2_e", "h_inv_y_norm2", "inf_stat_calibration", "xvx_xx_ratio"):
+        assert rel(o0[k], full[k]) <= 1e-9 and o0[k] == o1[k], (k, o0[k], o1[k], full[k])
+    assert np.max(np.abs(np.array(o0["log_delta"]) - np.array(full["log_delta"]))) <= 1e-9
+    assert o0["h_err"] <= 1e-9 and h0 == h1

@@ -65,3 +65,53 @@ def test_two_rank_gather_gloo():
     for rank, lo, hi, Q, mp_ in outs:
         assert Q == list(range(n))          # every rank holds all records, in gene order
         assert mp_ == [0] * 7 + [1] * 6     # 13 genes: ranks own 7 and 6
+
+
+def _bolt_worker(rank, world, port, q):
+    """SNP-sharded H-product of the BoltLMM null fit (BASELINE configs[4]): each rank holds a slice of the
+    panel's SNPs, computes its partial of X X'v / M and the ONE sum over ranks gives the full product -- the host-side
+    logic of rvt_bolt_fit_null_sharded, here in numpy over gloo."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from rvtests_b200 import sharding
+    from oracle import bolt_oracle as BO
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)
+    N, M, C, R = 240, 131, 2, 5
+    G = rng.binomial(2, rng.uniform(0.05, 0.5, M)[:, None], size=(M, N)).astype(np.int8)
+    G[rng.random((M, N)) < 0.02] = -1
+    covar = np.column_stack([np.ones(N), rng.normal(size=N)])
+    X, Z, _ = BO.prepare(G, covar, np.zeros(N))
+    v = rng.normal(size=(N, R))
+    lo, hi = sharding.snp_shard(M, rank, world)
+    Xl = X[:, lo:hi]
+    # local: X_l' (I - ZZ') v, then X_l (.)  -- the partial of the top rows; Z'X_l (.) the partial of the covariate rows
+    xy = Xl.T @ v - (Xl.T @ Z) @ (Z.T @ v)
+    part = np.vstack([Xl @ xy, (Z.T @ Xl) @ xy]) / M
+    t = torch.from_numpy(part.copy())
+    dist.all_reduce(t)                                   # the one collective per H-product
+    full = BO.Fit(X, Z, np.zeros(N), mc_trials=3)
+    want = full.Hx(0.0, v)
+    got = t.numpy()
+    q.put((rank, lo, hi, float(np.max(np.abs(got[:N] - want))), float(np.max(np.abs(got[N:] - Z.T @ want)))))
+    dist.destroy_process_group()
+
+
+def test_two_rank_bolt_snp_sharding_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_bolt_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    outs = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [(o[1], o[2]) for o in outs] == [(0, 66), (66, 131)]
+    for _rank, _lo, _hi, e_top, e_bot in outs:
+        assert e_top <= 1e-10 and e_bot <= 1e-10
