@@ -49,8 +49,13 @@ def parse():
     ap.add_argument("--e2e-genes", type=int, default=256, help="genes per step of the host-buffer (e2e) leg (a quarter of it for the int8 form)")
     ap.add_argument("--cpu-genes", type=int, default=16, help="distinct genes of the CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
-    ap.add_argument("--workload", default="skat", choices=["skat", "meta"],
-                    help="skat: the headline metric (default).  meta: --meta score,cov at the BASELINE configs[3] shape")
+    ap.add_argument("--workload", default="skat", choices=["skat", "meta", "bolt"],
+                    help="skat: the headline metric (default).  meta: --meta score,cov at the BASELINE configs[3] shape.  "
+                         "bolt: the BoltLMM null fit (BASELINE configs[4]), panel SNPs sharded over the ranks (tools/bolt_bench.py)")
+    ap.add_argument("--bolt-samples", type=int, default=200_000, help="N of --workload bolt")
+    ap.add_argument("--bolt-snps", type=int, default=20_000, help="panel SNPs of --workload bolt (whole job)")
+    ap.add_argument("--bolt-ref-samples", type=int, default=4000, help="N of the bounded sample of --impl reference --workload bolt")
+    ap.add_argument("--bolt-ref-snps", type=int, default=4000, help="panel SNPs of that sample")
     ap.add_argument("--meta-variants", type=int, default=8192, help="variants per GPU and step of --workload meta")
     ap.add_argument("--meta-spacing", type=int, default=1000, help="bp between consecutive variants (window 1 Mb)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -846,7 +851,14 @@ def run_reference_meta(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.workload == "bolt":
+        from tools import bolt_bench
+        if "--steps" not in sys.argv:
+            a.steps = 2                       # a step is a whole null fit
+        if "--warmup" not in sys.argv:
+            a.warmup = 1
+        bolt_bench.run_reference_bolt(a) if a.impl == "reference" else bolt_bench.run_bolt(a, ClockSampler, bind_numa)
+    elif a.impl == "reference":
         run_reference_meta(a) if a.workload == "meta" else run_reference(a)
     elif a.workload == "meta":
         run_meta(a)

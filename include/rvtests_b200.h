@@ -119,6 +119,12 @@ typedef struct rvt_bolt_null {
   double xvx_xx_ratio;           /* xVx_xx_ratio_ (scales BoltLMM::GetCovXX) */
   double log_delta[7], f[7];     /* the secant path: log(delta) tried and the MC-REML function there */
   int32_t mc_trials, reml_evals, cg_iterations, n_covariates_kept;
+  /* measurement: device time (CUDA events on the context stream) of the two panel products over the whole fit -- X'v
+   * (BoltLMM.cpp:942-952) and X w (:956-966) --, the number of H-products (computeHx calls) and of sum-over-ranks calls */
+  double ms_xtv, ms_xw;
+  int32_t h_products, allreduce_calls;
+  int32_t h_products_calibration;   /* of h_products, those of the calibration solve (30 right-hand sides instead of MCtrial + 1) */
+  int32_t pad;
 } rvt_bolt_null;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -131,6 +137,7 @@ const char* rvt_last_error(const rvt_ctx* ctx);
  * (device watchdog of the per-gene SKAT-O quadrature, default 4000; 0 = off), "stream_batch" (B > 0: every B host pushes the engine enqueues sweep + statistics for
  * them right away, so the kernels run while the next genes are still crossing PCIe; rvt_flush then only
  * waits for the tail.  0 = everything at flush.  Options apply to genes pushed after the call.),
+ * "bolt_kernels" (2 = second-generation panel products of rvt_bolt_fit_null, 1 = the first; same results to rounding),
  * "perm" (nPerm, 0 = analytic p-value only), "perm_alpha" (0.05), "perm_stream_pos", "perm_seed", "perm_batch". */
 int rvt_set_option(rvt_ctx* ctx, const char* key, double value);
 double rvt_get_info(const rvt_ctx* ctx, const char* key);

@@ -299,6 +299,149 @@ k_bolt_xw(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, int M, con
     }
 }
 
+// ---- second generation of the two panel products (option "bolt_kernels" = 2, the default) ----------------------------
+// Both are bound by the fp64 pipe (2 N M R multiply-adds per pass against N M / 4 bytes), so what matters is how many
+// non-DFMA instructions ride along with each DFMA.  k_bolt_xw2: a thread owns FOUR consecutive samples (one byte of every
+// SNP row) and 16 right-hand sides -- 64 accumulators; per SNP it spends one byte load, four table look-ups (the four
+// codes of a SNP sit in one 32-byte line of shared memory: one wavefront whatever the codes are) and 8 LDS.128 of W for
+// 64 DFMA.  64-thread CTAs so that N / 256 CTAs fill the device from N ~ 40 000 on.  r0: first column of the window
+// (a 30-column solve runs as two windows).
+template <int RMAX>
+__global__ void __launch_bounds__(64)
+k_bolt_xw2(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, int M, const double* __restrict__ tab, const double* __restrict__ W /*[M][R]*/,
+           int R, int r0, double alpha, double beta, const double* __restrict__ add, double* __restrict__ out) {
+  __shared__ __align__(16) double s_W[kBoltSnpBlock][RMAX];
+  __shared__ __align__(16) double s_tab[kBoltSnpBlock][4];
+  const int64_t i = ((int64_t)blockIdx.x * 64 + threadIdx.x) * 4;
+  double acc[4][RMAX];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) acc[q][r] = 0.0;
+  const int nr = (R - r0 < RMAX) ? (R - r0) : RMAX;
+  for (int m0 = 0; m0 < M; m0 += kBoltSnpBlock) {
+    const int nm = (M - m0 < kBoltSnpBlock) ? (M - m0) : kBoltSnpBlock;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nm * RMAX; idx += 64) {
+      const int mm = idx / RMAX, r = idx - mm * RMAX;
+      s_W[mm][r] = (r < nr) ? W[(size_t)(m0 + mm) * R + r0 + r] : 0.0;
+    }
+    for (int idx = threadIdx.x; idx < nm * 4; idx += 64) s_tab[idx >> 2][idx & 3] = tab[(size_t)m0 * 4 + idx];
+    __syncthreads();
+    if (i < N) {
+      const uint8_t* __restrict__ col = bed + (size_t)m0 * stride + (i >> 2);
+#pragma unroll 2
+      for (int mm = 0; mm < nm; ++mm) {
+        const unsigned b = col[(size_t)mm * stride];
+        const double x0 = s_tab[mm][b & 3], x1 = s_tab[mm][(b >> 2) & 3], x2 = s_tab[mm][(b >> 4) & 3], x3 = s_tab[mm][(b >> 6) & 3];
+#pragma unroll
+        for (int r = 0; r < RMAX; r += 2) {
+          const double2 w = *reinterpret_cast<const double2*>(&s_W[mm][r]);
+          acc[0][r] += x0 * w.x; acc[0][r + 1] += x0 * w.y;
+          acc[1][r] += x1 * w.x; acc[1][r + 1] += x1 * w.y;
+          acc[2][r] += x2 * w.x; acc[2][r + 1] += x2 * w.y;
+          acc[3][r] += x3 * w.x; acc[3][r + 1] += x3 * w.y;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (i + q < N) {
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r)
+        if (r < nr) out[(size_t)(i + q) * R + r0 + r] = alpha * acc[q][r] + (add ? beta * add[(size_t)(i + q) * R + r0 + r] : 0.0);
+    }
+}
+
+// k_bolt_xtv2: a thread owns FOUR SNPs (rows t, t+64, t+128, t+192 of a 256-SNP block) and 16 right-hand sides; a row of v
+// (warp-uniform address: 8 broadcast LDG.128) now serves 64 DFMA instead of 32, and the decode goes through a table in
+// shared memory instead of a dynamically indexed register array (which the compiler keeps in local memory).
+constexpr int kBoltXtv2Snps = 4;
+constexpr int kBoltXtv2Block = kBoltSnpBlock * kBoltXtv2Snps;   // SNPs per CTA
+constexpr int kBoltXtv2Chunk = 512;                            // samples staged per step
+constexpr int kBoltXtv2RowPad = kBoltXtv2Chunk / 4 + 4;
+template <int RMAX>
+__global__ void __launch_bounds__(kBoltSnpBlock)
+k_bolt_xtv2(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, int M, const double* __restrict__ tab, const double* __restrict__ v,
+            int R, int r0, int64_t split_len, double* __restrict__ part /*[splits][M][R]*/) {
+  __shared__ __align__(16) uint8_t s_rows[kBoltXtv2Block][kBoltXtv2RowPad];
+  __shared__ __align__(16) double s_tab[4][kBoltXtv2Block];   // [code][SNP]: lane t reads word t of a code's row -- no bank conflict whatever the codes
+  const int mbase = blockIdx.x * kBoltXtv2Block;
+  const int64_t i0 = (int64_t)blockIdx.y * split_len;
+  int64_t i1 = i0 + split_len;
+  if (i1 > N) i1 = N;
+  for (int idx = threadIdx.x; idx < kBoltXtv2Block * 4; idx += kBoltSnpBlock) {
+    const int mm = mbase + (idx >> 2);
+    s_tab[idx & 3][idx >> 2] = (mm < M) ? tab[(size_t)mm * 4 + (idx & 3)] : 0.0;
+  }
+  const int nr = (R - r0 < RMAX) ? (R - r0) : RMAX;
+  double acc[kBoltXtv2Snps][RMAX];
+#pragma unroll
+  for (int k = 0; k < kBoltXtv2Snps; ++k)
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) acc[k][r] = 0.0;
+  const bool vec2 = (nr == RMAX) && (((size_t)R * 8) % 16 == 0) && (((size_t)r0 * 8) % 16 == 0);
+  for (int64_t c0 = i0; c0 < i1; c0 += kBoltXtv2Chunk) {   // i0 and the chunk are multiples of 4
+    const int64_t n_here = (i1 - c0 < kBoltXtv2Chunk) ? (i1 - c0) : kBoltXtv2Chunk;
+    const int nbytes = (int)((n_here + 3) >> 2);
+    __syncthreads();
+    for (int rr = 0; rr < kBoltXtv2Block; ++rr) {
+      const int mm = mbase + rr;
+      if (mm >= M) {   // rows beyond the panel decode through an all-zero table; keep the bytes defined
+        for (int b = threadIdx.x; b < nbytes; b += kBoltSnpBlock) s_rows[rr][b] = 0;
+        continue;
+      }
+      const uint8_t* __restrict__ src = bed + (size_t)mm * stride + (c0 >> 2);
+      for (int b = threadIdx.x; b < nbytes; b += kBoltSnpBlock) s_rows[rr][b] = src[b];
+    }
+    __syncthreads();
+    const uint8_t* __restrict__ row0 = s_rows[threadIdx.x];
+    for (int64_t k4 = 0; k4 < n_here; k4 += 4) {
+      unsigned bb[kBoltXtv2Snps];
+#pragma unroll
+      for (int k = 0; k < kBoltXtv2Snps; ++k) bb[k] = row0[(size_t)k * kBoltSnpBlock * kBoltXtv2RowPad + (k4 >> 2)];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (k4 + q >= n_here) break;
+        double x[kBoltXtv2Snps];
+#pragma unroll
+        for (int k = 0; k < kBoltXtv2Snps; ++k) x[k] = s_tab[(bb[k] >> (2 * q)) & 3][threadIdx.x + k * kBoltSnpBlock];
+        const double* __restrict__ vr = v + (size_t)(c0 + k4 + q) * R + r0;   // warp-uniform address: broadcast loads
+        if (vec2) {
+#pragma unroll
+          for (int r = 0; r < RMAX; r += 2) {
+            const double2 vv = *reinterpret_cast<const double2*>(vr + r);
+#pragma unroll
+            for (int k = 0; k < kBoltXtv2Snps; ++k) {
+              acc[k][r] += x[k] * vv.x;
+              acc[k][r + 1] += x[k] * vv.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < RMAX; ++r)
+            if (r < nr) {
+              const double vv = vr[r];
+#pragma unroll
+              for (int k = 0; k < kBoltXtv2Snps; ++k) acc[k][r] += x[k] * vv;
+            }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kBoltXtv2Snps; ++k) {
+    const int mm = mbase + threadIdx.x + k * kBoltSnpBlock;
+    if (mm < M) {
+      double* o = part + ((size_t)blockIdx.y * M + mm) * R + r0;
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r)
+        if (r < nr) o[r] = acc[k][r];
+    }
+  }
+}
+
 // bottom rows: out[c][r] = alpha * sum_m zg[m][c] W[m][r] + beta * add[c][r]   (one thread per (c, r), SNP order)
 __global__ void k_bolt_bot(int M, int R, int C, const double* __restrict__ zg, const double* __restrict__ W, double alpha, double beta,
                            const double* __restrict__ add, double* __restrict__ out) {

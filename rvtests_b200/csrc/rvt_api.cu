@@ -173,6 +173,7 @@ struct rvt_ctx {
   int qags_pack = 1;               // SKAT-O quadrature: 1 = three genes per persistent 128-thread CTA (k_skato_qags_packed)
   long long wd_cycles = 8000000000ll;   // device watchdog of the per-gene tail, SM cycles (option "watchdog_ms"; ~4 s)
   bool skato = false;
+  int bolt_kernels = 2;        // generation of the panel-product kernels of rvt_bolt_fit_null (bolt.cuh)
   bool skato_binary = true;    // SKAT-O for a binary trait (SkatO::Fit type "D"); on by default, see include/rvtests_b200.h
   long long* d_dbg = nullptr;   // optional finalize phase counters (rvt_set_option "debug_phases")
   size_t cap_dbg = 0;
@@ -422,6 +423,8 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "watchdog_ms") {
     if (value < 0 || value > 3.6e6) CTX_FAIL(RVT_E_BADARG, "watchdog_ms must be in 0..3600000 (0 = off)");
     ctx->wd_cycles = (long long)(value * 2.0e6);   // ~2 GHz SM clock
+  } else if (k == "bolt_kernels") {
+    ctx->bolt_kernels = (value >= 2.0) ? 2 : 1;
   } else if (k == "skato_binary") {
     ctx->skato_binary = value != 0;
   } else if (k == "tc_boxes") {
@@ -2363,7 +2366,43 @@ struct BoltDev {
   }
   size_t rows() const { return (size_t)(N + C); }
   double* vec(int R) { return alloc<double>(rows() * R); }
+  int gen = 2;                        // option "bolt_kernels": 1 = first-generation product kernels, 2 = k_bolt_xtv2 / k_bolt_xw2
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_xtv, ev_xw;   // per-launch events of the two panel products
+  double ms_xtv = 0.0, ms_xw = 0.0;
+  int n_hx = 0;
+  cudaEvent_t tick() {
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    return e;
+  }
+  void collect_times() {             // after a stream synchronize
+    for (int w = 0; w < 2; ++w) {
+      auto& ev = w ? ev_xw : ev_xtv;
+      for (auto& pr : ev) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) (w ? ms_xw : ms_xtv) += ms;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+      }
+      ev.clear();
+    }
+  }
   void launch_xtv(const double* v, int R) {
+    cudaEvent_t e0 = tick();
+    launch_xtv_(v, R);
+    ev_xtv.push_back({e0, tick()});
+  }
+  void launch_xtv_(const double* v, int R) {
+    if (gen >= 2) {
+      dim3 g2((unsigned)((M + kBoltXtv2Block - 1) / kBoltXtv2Block), (unsigned)splits);
+      for (int r0 = 0; r0 < R; r0 += 16) {
+        if (R - r0 <= 4) k_bolt_xtv2<4><<<g2, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, r0, split_len, part);
+        else if (R - r0 <= 8) k_bolt_xtv2<8><<<g2, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, r0, split_len, part);
+        else k_bolt_xtv2<16><<<g2, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, r0, split_len, part);
+      }
+      return;
+    }
     dim3 g1((unsigned)((M + kBoltXtvBlock - 1) / kBoltXtvBlock), (unsigned)splits);
     if (R <= 4) k_bolt_xtv<4><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
     else if (R <= 8) k_bolt_xtv<8><<<g1, kBoltSnpBlock, 0, st>>>(bed, stride, N, M, tab, v, R, split_len, part);
@@ -2372,6 +2411,7 @@ struct BoltDev {
   }
   // out = (X X'/M + delta I) v on [v ; Z'v]   (computeHx, BoltLMM.cpp:931-993)
   void Hx(double delta, const double* v, double* out, int R) {
+    ++n_hx;
     launch_xtv(v, R);
     k_bolt_xtv_finish<<<(unsigned)(((int64_t)M * R + 255) / 256), 256, 0, st>>>(M, R, C, splits, part, zg, v + (size_t)N * R, 1.0, Xy);
     XW(Xy, R, 1.0 / (double)M_total, delta, v, out);
@@ -2394,6 +2434,21 @@ struct BoltDev {
     note();
   }
   void launch_xw(unsigned g1, unsigned g4, const double* W, int R, double alpha, double beta, const double* add, double* out) {
+    cudaEvent_t e0 = tick();
+    launch_xw_(g1, g4, W, R, alpha, beta, add, out);
+    ev_xw.push_back({e0, tick()});
+  }
+  void launch_xw_(unsigned g1, unsigned g4, const double* W, int R, double alpha, double beta, const double* add, double* out) {
+    if (gen >= 2) {
+      const unsigned g = (unsigned)((N + 255) / 256);
+      for (int r0 = 0; r0 < R; r0 += 16) {
+        if (R - r0 <= 4) k_bolt_xw2<4><<<g, 64, 0, st>>>(bed, stride, N, M, tab, W, R, r0, alpha, beta, add, out);
+        else if (R - r0 <= 8) k_bolt_xw2<8><<<g, 64, 0, st>>>(bed, stride, N, M, tab, W, R, r0, alpha, beta, add, out);
+        else k_bolt_xw2<16><<<g, 64, 0, st>>>(bed, stride, N, M, tab, W, R, r0, alpha, beta, add, out);
+      }
+      k_bolt_bot<<<(C * R + 63) / 64, 64, 0, st>>>(M, R, C, zg, W, alpha, beta, add ? add + (size_t)N * R : nullptr, out + (size_t)N * R);
+      return;
+    }
     if (R <= 4) k_bolt_xw<4, 4><<<g4, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
     else if (R <= 8) k_bolt_xw<8, 4><<<g4, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
     else if (R <= 16) k_bolt_xw<16, 1><<<g1, 256, 0, st>>>(bed, stride, N, M, tab, W, R, alpha, beta, add, out);
@@ -2527,7 +2582,9 @@ int rvt_bolt_fit_null_sharded(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64
   const int R1 = mc + 1;
   const int nSnp = (int)std::min<int64_t>(30, M_total), Rmax = std::max(R1, nSnp);
   // sample splits of the X'v product: enough CTAs to fill the device, each a multiple of the staged chunk
-  const int64_t nblk = (M + kBoltXtvBlock - 1) / kBoltXtvBlock;
+  B.gen = ctx->bolt_kernels;
+  const int64_t xtv_block = B.gen >= 2 ? kBoltXtv2Block : kBoltXtvBlock;
+  const int64_t nblk = (M + xtv_block - 1) / xtv_block;
   int splits = (int)std::max<int64_t>(1, std::min<int64_t>((4 * (int64_t)ctx->sm_count + nblk - 1) / nblk, (N + kBoltChunk - 1) / kBoltChunk));
   B.split_len = (((N + splits - 1) / splits) + kBoltChunk - 1) / kBoltChunk * kBoltChunk;
   B.splits = (int)((N + B.split_len - 1) / B.split_len);
@@ -2667,6 +2724,7 @@ int rvt_bolt_fit_null_sharded(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64
   k_bolt_columns<<<(unsigned)(((int64_t)N * nSnp + 255) / 256), 256, 0, st>>>(B.bed, stride, N, d_idx, nSnp, B.tab, vy);
   B.allreduce(vy, (int64_t)N * nSnp);
   B.project(vy, nSnp);
+  const int hx_before_cal = B.n_hx;
   B.solve(vy, delta, vx, vr, vp, vap, nSnp);         // V^-1 x = H^-1 x / sigma2_g
   std::vector<double> xVx(nSnp), xx(nSnp), xVy(nSnp);
   B.pdot(vy, vx, nSnp, xVx.data());
@@ -2697,6 +2755,13 @@ int rvt_bolt_fit_null_sharded(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64
   out->reml_evals = evals;
   out->cg_iterations = B.cg_total;
   out->n_covariates_kept = Ck;
+  cudaStreamSynchronize(st);
+  B.collect_times();
+  out->ms_xtv = B.ms_xtv;
+  out->ms_xw = B.ms_xw;
+  out->h_products = B.n_hx;
+  out->h_products_calibration = B.n_hx - hx_before_cal;
+  out->allreduce_calls = B.ar_calls;
   if (B.ar_rc) CTX_FAIL(RVT_E_CUDA, "bolt: the sum-over-ranks callback returned %d", B.ar_rc);
   for (int k = 0; k < 7; ++k) {
     out->log_delta[k] = (k <= i) ? ld[k] : 0.0;

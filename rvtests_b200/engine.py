@@ -60,7 +60,9 @@ EXPORTS = [
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 BOLT_DTYPE = np.dtype([("delta", "f8"), ("sigma2_g", "f8"), ("sigma2_e", "f8"), ("h2", "f8"), ("h_inv_y_norm2", "f8"),
                        ("inf_stat_calibration", "f8"), ("xvx_xx_ratio", "f8"), ("log_delta", "f8", (7,)), ("f", "f8", (7,)),
-                       ("mc_trials", "i4"), ("reml_evals", "i4"), ("cg_iterations", "i4"), ("n_covariates_kept", "i4")])
+                       ("mc_trials", "i4"), ("reml_evals", "i4"), ("cg_iterations", "i4"), ("n_covariates_kept", "i4"),
+                       ("ms_xtv", "f8"), ("ms_xw", "f8"), ("h_products", "i4"), ("allreduce_calls", "i4"),
+                       ("h_products_calibration", "i4"), ("pad", "i4")])
 
 LMM_DTYPE = np.dtype([("af", "f8"), ("U", "f8"), ("V", "f8"), ("stat", "f8"), ("pvalue", "f8"), ("ok", "i4"), ("pad", "i4")])
 
