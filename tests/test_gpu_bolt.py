@@ -109,7 +109,7 @@ def test_bolt_device_vs_reference_golden(engine_cls, oracle, k):
         vout, band, wmax = eng.meta_flush(nv, pos, np.ones(nv, dtype=np.int32), 100 * nv)
         for j in range(nv):
             af, ru, rv, reff, rp = ref["tests"][j]
-            u, v = vout[j]["U"] * kappa, vout[j]["V"] * kappa * kappa        # U = g'r / kappa, V = g'Pg / kappa as MetaScore prints
+            u, v = vout[j]["U"] * kappa, (vout[j]["sqrtV"] * kappa) ** 2     # U = g'r / kappa, V = g'Pg / kappa as MetaScore prints
             assert abs(u - ru) <= 5e-3 * np.sqrt(rv) and rel(v, rv) <= 5e-3, (j, u, ru, v, rv)
             assert rel(vout[j]["pvalue"], rp) <= 2e-2 or abs(vout[j]["pvalue"] - rp) <= 1e-6
         assert wmax >= nv - 1
