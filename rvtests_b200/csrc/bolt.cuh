@@ -442,6 +442,208 @@ k_bolt_xtv2(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, int M, c
   }
 }
 
+// ---- third generation (option "bolt_kernels" = 3, the default): the same thread decompositions with the global loads taken
+// off the critical path.  ncu of generation 2 (profiles/r02t_bolt_ncu.txt): 70 % of the warp samples wait on a long
+// scoreboard -- the strided byte loads of k_bolt_xw2 and the staging / v-row loads of k_bolt_xtv2 --, the fp64 pipe is 7-16 %
+// busy.  Here every byte a CTA needs for the NEXT block arrives by cp.async into the other half of a double buffer while
+// the current block is multiplied; the inner loops touch shared memory only.
+__device__ __forceinline__ void bolt_cp4(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g));
+}
+__device__ __forceinline__ void bolt_cp8(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g));
+}
+__device__ __forceinline__ void bolt_cp16(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g));
+}
+__device__ __forceinline__ void bolt_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void bolt_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// X w: 128 threads, a thread owns four consecutive samples (one byte per SNP row) and RMAX right-hand sides; per 64-SNP block
+// the CTA's 128-byte row segments, the block's rows of W and its decode tables are staged by cp.async (double buffer).
+// Requires stride % 4 == 0 and a 4-byte aligned panel (the engine's own copy has a 16-byte pitch).
+constexpr int kBoltXw3Threads = 128;
+template <int RMAX>
+struct BoltXw3Smem {
+  uint8_t rows[2][kBoltSnpBlock][kBoltXw3Threads];
+  double W[2][kBoltSnpBlock][RMAX];
+  double tab[2][kBoltSnpBlock][4];
+};
+template <int RMAX>
+__global__ void __launch_bounds__(kBoltXw3Threads)
+k_bolt_xw3(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, int M, const double* __restrict__ tab, const double* __restrict__ W /*[M][R]*/,
+           int R, int r0, double alpha, double beta, const double* __restrict__ add, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char bolt_smem_raw[];
+  BoltXw3Smem<RMAX>& sm = *reinterpret_cast<BoltXw3Smem<RMAX>*>(bolt_smem_raw);
+  const int tid = threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.x * (kBoltXw3Threads * 4);
+  const int64_t i = i0 + (int64_t)tid * 4;
+  const int64_t byte0 = i0 >> 2;
+  const int64_t rowb = (N + 3) >> 2;
+  int words = (int)((rowb - byte0 + 3) >> 2);                   // 4-byte words of this CTA's segment inside a row
+  if (words > kBoltXw3Threads / 4) words = kBoltXw3Threads / 4;
+  const int nr = (R - r0 < RMAX) ? (R - r0) : RMAX;
+  const int nblk = (M + kBoltSnpBlock - 1) / kBoltSnpBlock;
+  auto stage = [&](int b, int buf) {
+    const int m0 = b * kBoltSnpBlock;
+    const int nm = (M - m0 < kBoltSnpBlock) ? (M - m0) : kBoltSnpBlock;
+    for (int idx = tid; idx < kBoltSnpBlock * (kBoltXw3Threads / 4); idx += kBoltXw3Threads) {
+      const int rr = idx / (kBoltXw3Threads / 4), wd = idx - rr * (kBoltXw3Threads / 4);
+      if (rr < nm && wd < words) bolt_cp4(&sm.rows[buf][rr][wd * 4], bed + (size_t)(m0 + rr) * stride + byte0 + wd * 4);
+    }
+    for (int idx = tid; idx < nm * RMAX; idx += kBoltXw3Threads) {
+      const int mm = idx / RMAX, r = idx - mm * RMAX;
+      if (r < nr) bolt_cp8(&sm.W[buf][mm][r], W + (size_t)(m0 + mm) * R + r0 + r);
+      else sm.W[buf][mm][r] = 0.0;
+    }
+    for (int idx = tid; idx < nm * 4; idx += kBoltXw3Threads) bolt_cp8(&sm.tab[buf][idx >> 2][idx & 3], tab + (size_t)m0 * 4 + idx);
+    bolt_cp_commit();
+  };
+  double acc[4][RMAX];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) acc[q][r] = 0.0;
+  stage(0, 0);
+  for (int b = 0; b < nblk; ++b) {
+    const int buf = b & 1;
+    if (b + 1 < nblk) {
+      stage(b + 1, buf ^ 1);
+      bolt_cp_wait<1>();
+    } else {
+      bolt_cp_wait<0>();
+    }
+    __syncthreads();
+    const int nm = (M - b * kBoltSnpBlock < kBoltSnpBlock) ? (M - b * kBoltSnpBlock) : kBoltSnpBlock;
+    if (i < N) {
+#pragma unroll 4
+      for (int mm = 0; mm < nm; ++mm) {
+        const unsigned bb = sm.rows[buf][mm][tid];
+        const double x0 = sm.tab[buf][mm][bb & 3], x1 = sm.tab[buf][mm][(bb >> 2) & 3], x2 = sm.tab[buf][mm][(bb >> 4) & 3],
+                     x3 = sm.tab[buf][mm][(bb >> 6) & 3];
+#pragma unroll
+        for (int r = 0; r < RMAX; r += 2) {
+          const double2 w = *reinterpret_cast<const double2*>(&sm.W[buf][mm][r]);
+          acc[0][r] += x0 * w.x; acc[0][r + 1] += x0 * w.y;
+          acc[1][r] += x1 * w.x; acc[1][r + 1] += x1 * w.y;
+          acc[2][r] += x2 * w.x; acc[2][r + 1] += x2 * w.y;
+          acc[3][r] += x3 * w.x; acc[3][r + 1] += x3 * w.y;
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (i + q < N) {
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r)
+        if (r < nr) out[(size_t)(i + q) * R + r0 + r] = alpha * acc[q][r] + (add ? beta * add[(size_t)(i + q) * R + r0 + r] : 0.0);
+    }
+}
+
+// X'v: 64 threads, a thread owns four SNPs (rows t, t+64, t+128, t+192 of a 256-SNP block) and RMAX right-hand sides; per chunk of
+// CHUNK samples the 256 row segments (pitch CHUNK/4 + 4 bytes: conflict-free word reads) and the chunk's rows of v are staged by
+// cp.async (double buffer); the decode table sits transposed in shared memory.  Same alignment requirement as k_bolt_xw3.
+template <int RMAX, int CHUNK>
+struct BoltXtv3Smem {
+  double v[2][CHUNK][RMAX];
+  double tab[4][kBoltXtv2Block];
+  uint32_t rows[2][kBoltXtv2Block][CHUNK / 16 + 1];
+};
+template <int RMAX, int CHUNK>
+__global__ void __launch_bounds__(kBoltSnpBlock)
+k_bolt_xtv3(const uint8_t* __restrict__ bed, int64_t stride, int64_t N, int M, const double* __restrict__ tab, const double* __restrict__ v,
+            int R, int r0, int64_t split_len, double* __restrict__ part /*[splits][M][R]*/) {
+  extern __shared__ __align__(16) unsigned char bolt_smem_raw[];
+  typedef BoltXtv3Smem<RMAX, CHUNK> Smem;
+  Smem& sm = *reinterpret_cast<Smem*>(bolt_smem_raw);
+  constexpr int kWords = CHUNK / 16;
+  const int tid = threadIdx.x;
+  const int mbase = blockIdx.x * kBoltXtv2Block;
+  const int64_t i0 = (int64_t)blockIdx.y * split_len;          // a multiple of CHUNK
+  int64_t i1 = i0 + split_len;
+  if (i1 > N) i1 = N;
+  const int64_t rowb = (N + 3) >> 2;
+  const int nr = (R - r0 < RMAX) ? (R - r0) : RMAX;
+  for (int idx = tid; idx < kBoltXtv2Block * 4; idx += kBoltSnpBlock) {
+    const int mm = mbase + (idx >> 2);
+    sm.tab[idx & 3][idx >> 2] = (mm < M) ? tab[(size_t)mm * 4 + (idx & 3)] : 0.0;
+  }
+  const int nchunk = (int)((i1 - i0 + CHUNK - 1) / CHUNK);
+  auto stage = [&](int c, int buf) {
+    const int64_t c0 = i0 + (int64_t)c * CHUNK;
+    const int64_t n_here = (i1 - c0 < CHUNK) ? (i1 - c0) : CHUNK;
+    const int64_t byte0 = c0 >> 2;
+    int words = (int)((rowb - byte0 + 3) >> 2);
+    if (words > kWords) words = kWords;
+    for (int idx = tid; idx < kBoltXtv2Block * kWords; idx += kBoltSnpBlock) {
+      const int rr = idx / kWords, wd = idx - rr * kWords;
+      const int mm = mbase + rr;
+      if (mm < M && wd < words) bolt_cp4(&sm.rows[buf][rr][wd], bed + (size_t)mm * stride + byte0 + wd * 4);
+      else sm.rows[buf][rr][wd] = 0u;
+    }
+    for (int idx = tid; idx < (int)n_here * RMAX; idx += kBoltSnpBlock) {
+      const int ii = idx / RMAX, r = idx - ii * RMAX;
+      if (r < nr) bolt_cp8(&sm.v[buf][ii][r], v + (size_t)(c0 + ii) * R + r0 + r);
+      else sm.v[buf][ii][r] = 0.0;
+    }
+    bolt_cp_commit();
+  };
+  double acc[kBoltXtv2Snps][RMAX];
+#pragma unroll
+  for (int k = 0; k < kBoltXtv2Snps; ++k)
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) acc[k][r] = 0.0;
+  if (nchunk > 0) stage(0, 0);
+  for (int c = 0; c < nchunk; ++c) {
+    const int buf = c & 1;
+    if (c + 1 < nchunk) {
+      stage(c + 1, buf ^ 1);
+      bolt_cp_wait<1>();
+    } else {
+      bolt_cp_wait<0>();
+    }
+    __syncthreads();
+    const int64_t c0 = i0 + (int64_t)c * CHUNK;
+    const int n_here = (int)((i1 - c0 < CHUNK) ? (i1 - c0) : CHUNK);
+    for (int k16 = 0; k16 < n_here; k16 += 16) {
+      uint32_t wv[kBoltXtv2Snps];
+#pragma unroll
+      for (int k = 0; k < kBoltXtv2Snps; ++k) wv[k] = sm.rows[buf][tid + k * kBoltSnpBlock][k16 >> 4];
+      const int lim = (n_here - k16 < 16) ? (n_here - k16) : 16;
+#pragma unroll 4
+      for (int q = 0; q < 16; ++q) {
+        if (q >= lim) break;
+        double x[kBoltXtv2Snps];
+#pragma unroll
+        for (int k = 0; k < kBoltXtv2Snps; ++k) x[k] = sm.tab[(wv[k] >> (2 * q)) & 3][tid + k * kBoltSnpBlock];
+#pragma unroll
+        for (int r = 0; r < RMAX; r += 2) {
+          const double2 vv = *reinterpret_cast<const double2*>(&sm.v[buf][k16 + q][r]);   // warp-uniform: broadcast
+#pragma unroll
+          for (int k = 0; k < kBoltXtv2Snps; ++k) {
+            acc[k][r] += x[k] * vv.x;
+            acc[k][r + 1] += x[k] * vv.y;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < kBoltXtv2Snps; ++k) {
+    const int mm = mbase + tid + k * kBoltSnpBlock;
+    if (mm < M) {
+      double* o = part + ((size_t)blockIdx.y * M + mm) * R + r0;
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r)
+        if (r < nr) o[r] = acc[k][r];
+    }
+  }
+}
+
 // bottom rows: out[c][r] = alpha * sum_m zg[m][c] W[m][r] + beta * add[c][r]   (one thread per (c, r), SNP order)
 __global__ void k_bolt_bot(int M, int R, int C, const double* __restrict__ zg, const double* __restrict__ W, double alpha, double beta,
                            const double* __restrict__ add, double* __restrict__ out) {

@@ -173,7 +173,7 @@ struct rvt_ctx {
   int qags_pack = 1;               // SKAT-O quadrature: 1 = three genes per persistent 128-thread CTA (k_skato_qags_packed)
   long long wd_cycles = 8000000000ll;   // device watchdog of the per-gene tail, SM cycles (option "watchdog_ms"; ~4 s)
   bool skato = false;
-  int bolt_kernels = 2;        // generation of the panel-product kernels of rvt_bolt_fit_null (bolt.cuh)
+  int bolt_kernels = 3;        // generation of the panel-product kernels of rvt_bolt_fit_null (bolt.cuh)
   bool skato_binary = true;    // SKAT-O for a binary trait (SkatO::Fit type "D"); on by default, see include/rvtests_b200.h
   long long* d_dbg = nullptr;   // optional finalize phase counters (rvt_set_option "debug_phases")
   size_t cap_dbg = 0;
@@ -424,7 +424,7 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
     if (value < 0 || value > 3.6e6) CTX_FAIL(RVT_E_BADARG, "watchdog_ms must be in 0..3600000 (0 = off)");
     ctx->wd_cycles = (long long)(value * 2.0e6);   // ~2 GHz SM clock
   } else if (k == "bolt_kernels") {
-    ctx->bolt_kernels = (value >= 2.0) ? 2 : 1;
+    ctx->bolt_kernels = (value >= 3.0) ? 3 : (value >= 2.0) ? 2 : 1;
   } else if (k == "skato_binary") {
     ctx->skato_binary = value != 0;
   } else if (k == "tc_boxes") {
@@ -2366,7 +2366,7 @@ struct BoltDev {
   }
   size_t rows() const { return (size_t)(N + C); }
   double* vec(int R) { return alloc<double>(rows() * R); }
-  int gen = 2;                        // option "bolt_kernels": 1 = first-generation product kernels, 2 = k_bolt_xtv2 / k_bolt_xw2
+  int gen = 3;                        // option "bolt_kernels": 1 = first-generation product kernels, 2 = k_bolt_xtv2 / k_bolt_xw2, 3 = the cp.async-pipelined k_bolt_xtv3 / k_bolt_xw3
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_xtv, ev_xw;   // per-launch events of the two panel products
   double ms_xtv = 0.0, ms_xw = 0.0;
   int n_hx = 0;
@@ -2393,7 +2393,31 @@ struct BoltDev {
     launch_xtv_(v, R);
     ev_xtv.push_back({e0, tick()});
   }
+  template <int RMAX, int CHUNK>
+  void xtv3(dim3 g, const double* v, int R, int r0) {
+    typedef BoltXtv3Smem<RMAX, CHUNK> Smem;
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_bolt_xtv3<RMAX, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+      attr_set = true;
+    }
+    k_bolt_xtv3<RMAX, CHUNK><<<g, kBoltSnpBlock, sizeof(Smem), st>>>(bed, stride, N, M, tab, v, R, r0, split_len, part);
+  }
+  template <int RMAX>
+  void xw3(const double* W, int R, int r0, double alpha, double beta, const double* add, double* out) {
+    const unsigned g = (unsigned)((N + kBoltXw3Threads * 4 - 1) / (kBoltXw3Threads * 4));
+    k_bolt_xw3<RMAX><<<g, kBoltXw3Threads, sizeof(BoltXw3Smem<RMAX>), st>>>(bed, stride, N, M, tab, W, R, r0, alpha, beta, add, out);
+  }
   void launch_xtv_(const double* v, int R) {
+    if (gen >= 3) {
+      dim3 g2((unsigned)((M + kBoltXtv2Block - 1) / kBoltXtv2Block), (unsigned)splits);
+      for (int r0 = 0; r0 < R; r0 += 16) {
+        if (R - r0 <= 4) xtv3<4, 512>(g2, v, R, r0);
+        else if (R - r0 <= 8) xtv3<8, 256>(g2, v, R, r0);
+        else xtv3<16, 256>(g2, v, R, r0);
+      }
+      return;
+    }
     if (gen >= 2) {
       dim3 g2((unsigned)((M + kBoltXtv2Block - 1) / kBoltXtv2Block), (unsigned)splits);
       for (int r0 = 0; r0 < R; r0 += 16) {
@@ -2439,6 +2463,15 @@ struct BoltDev {
     ev_xw.push_back({e0, tick()});
   }
   void launch_xw_(unsigned g1, unsigned g4, const double* W, int R, double alpha, double beta, const double* add, double* out) {
+    if (gen >= 3) {
+      for (int r0 = 0; r0 < R; r0 += 16) {
+        if (R - r0 <= 4) xw3<4>(W, R, r0, alpha, beta, add, out);
+        else if (R - r0 <= 8) xw3<8>(W, R, r0, alpha, beta, add, out);
+        else xw3<16>(W, R, r0, alpha, beta, add, out);
+      }
+      k_bolt_bot<<<(C * R + 63) / 64, 64, 0, st>>>(M, R, C, zg, W, alpha, beta, add ? add + (size_t)N * R : nullptr, out + (size_t)N * R);
+      return;
+    }
     if (gen >= 2) {
       const unsigned g = (unsigned)((N + 255) / 256);
       for (int r0 = 0; r0 < R; r0 += 16) {
@@ -2592,7 +2625,10 @@ int rvt_bolt_fit_null_sharded(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64
   cudaPointerAttributes pattr;
   const bool bed_on_device = cudaPointerGetAttributes(&pattr, bed) == cudaSuccess && pattr.type == cudaMemoryTypeDevice;
   cudaGetLastError();
-  B.bed = bed_on_device ? const_cast<uint8_t*>(bed) : B.alloc<uint8_t>((size_t)M * stride);
+  const int64_t pitch = bed_on_device ? stride : ((stride + 15) / 16) * 16;   // the engine's own copy: 16-byte row pitch
+  B.bed = bed_on_device ? const_cast<uint8_t*>(bed) : B.alloc<uint8_t>((size_t)M * pitch);
+  B.stride = pitch;
+  if (B.gen >= 3 && (pitch % 4 != 0 || ((uintptr_t)B.bed & 3) != 0)) B.gen = 2;   // cp.async needs 4-byte aligned row segments
   B.Z = B.alloc<double>((size_t)N * Ck);
   B.tab = B.alloc<double>((size_t)M * 4);
   B.zg = B.alloc<double>((size_t)M * Ck);
@@ -2604,14 +2640,17 @@ int rvt_bolt_fit_null_sharded(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64
   double *vy = B.vec(Rmax), *vx = B.vec(Rmax), *vr = B.vec(Rmax), *vp = B.vec(Rmax), *vap = B.vec(Rmax), *vxb = B.vec(mc), *ve = B.vec(mc);
   if (B.err != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "bolt: cudaMalloc: %s", cudaGetErrorString(B.err));
   cudaStream_t st = B.st;
-  if (!bed_on_device) RVT_CUDA_OK(cudaMemcpyAsync(B.bed, bed, (size_t)M * stride, cudaMemcpyHostToDevice, st));
+  if (!bed_on_device) {
+    if (pitch != stride) RVT_CUDA_OK(cudaMemsetAsync(B.bed, 0, (size_t)M * pitch, st));
+    RVT_CUDA_OK(cudaMemcpy2DAsync(B.bed, (size_t)pitch, bed, (size_t)stride, (size_t)((N + 3) / 4), (size_t)M, cudaMemcpyHostToDevice, st));
+  }
   {   // Z row-major [N][Ck] on the device
     std::vector<double> zr((size_t)N * Ck);
     for (int c = 0; c < Ck; ++c)
       for (int64_t i = 0; i < N; ++i) zr[(size_t)i * Ck + c] = Zh[(size_t)c * N + i];
     RVT_CUDA_OK(cudaMemcpy(B.Z, zr.data(), sizeof(double) * zr.size(), cudaMemcpyHostToDevice));
   }
-  k_bolt_snp<<<(unsigned)M, 256, 0, st>>>(B.bed, stride, N, Ck, B.Z, B.tab, B.zg, B.gnorm2);
+  k_bolt_snp<<<(unsigned)M, 256, 0, st>>>(B.bed, B.stride, N, Ck, B.Z, B.tab, B.zg, B.gnorm2);
   B.note();
   // phenotype: centred (quantitative mode), bottom rows Z'y   (preparePhenotype, BoltPlinkLoader.cpp:143-163)
   BoltRandom rng(12345);
@@ -2721,7 +2760,7 @@ int rvt_bolt_fit_null_sharded(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64
   int* d_idx = B.alloc<int>(nSnp);
   if (!d_idx) CTX_FAIL(RVT_E_CUDA, "bolt: cudaMalloc");
   RVT_CUDA_OK(cudaMemcpy(d_idx, idx.data(), sizeof(int) * nSnp, cudaMemcpyHostToDevice));
-  k_bolt_columns<<<(unsigned)(((int64_t)N * nSnp + 255) / 256), 256, 0, st>>>(B.bed, stride, N, d_idx, nSnp, B.tab, vy);
+  k_bolt_columns<<<(unsigned)(((int64_t)N * nSnp + 255) / 256), 256, 0, st>>>(B.bed, B.stride, N, d_idx, nSnp, B.tab, vy);
   B.allreduce(vy, (int64_t)N * nSnp);
   B.project(vy, nSnp);
   const int hx_before_cal = B.n_hx;
