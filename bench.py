@@ -52,8 +52,8 @@ def parse():
     ap.add_argument("--workload", default="skat", choices=["skat", "meta", "bolt"],
                     help="skat: the headline metric (default).  meta: --meta score,cov at the BASELINE configs[3] shape.  "
                          "bolt: the BoltLMM null fit (BASELINE configs[4]), panel SNPs sharded over the ranks (tools/bolt_bench.py)")
-    ap.add_argument("--bolt-samples", type=int, default=200_000, help="N of --workload bolt")
-    ap.add_argument("--bolt-snps", type=int, default=20_000, help="panel SNPs of --workload bolt (whole job)")
+    ap.add_argument("--bolt-samples", type=int, default=1_000_000, help="N of --workload bolt (BASELINE configs[4]: 1M samples)")
+    ap.add_argument("--bolt-snps", type=int, default=16_384, help="panel SNPs of --workload bolt (whole job; 4.1 GB of 2-bit rows at 1M samples)")
     ap.add_argument("--bolt-ref-samples", type=int, default=4000, help="N of the bounded sample of --impl reference --workload bolt")
     ap.add_argument("--bolt-ref-snps", type=int, default=4000, help="panel SNPs of that sample")
     ap.add_argument("--meta-variants", type=int, default=8192, help="variants per GPU and step of --workload meta")

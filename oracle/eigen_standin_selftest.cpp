@@ -89,3 +89,41 @@ void st_misc(int n, int m, const double* A, double* rowsum, double* colmean, dou
   scalars[7] = a.maxCoeff();
 }
 }
+
+// ---- what regression/BoltLMM.cpp / BoltPlinkLoader.cpp use on top (blocks of blocks, write-through block arrays,
+// projected column products, comparisons, thin SVD)
+extern "C" void st_bolt_api(int n, int c, int k, const double* A /* (n+c) x k */, const double* B /* (n+c) x k */, const double* Zc /* n x c */,
+                            double* projdot /* k */, double* projnorm /* k */, double* centred /* n */, double* proj /* (n+c) x k */,
+                            double* colhead /* n */, int* all_lt, int* any_lt, double* sv /* c */, double* U /* n x c */, double* blkdiv /* n */) {
+  using namespace Eigen;
+  Map<const MatrixXd> a(A, n + c, k), b(B, n + c, k), z(Zc, n, c);
+  MatrixXd v1 = a, v2 = b, Z = z;
+  // projDot / projNorm2 exactly as BoltLMM.cpp:1088-1098, 1134-1137 spell them
+  RowVectorXd pd = (v1.topRows(n).array() * v2.topRows(n).array()).eval().matrix().colwise().sum() -
+                   (v1.bottomRows(c).array() * v2.bottomRows(c).array()).eval().matrix().colwise().sum();
+  RowVectorXd pn = v1.topRows(n).cwiseAbs2().eval().colwise().sum() - v1.bottomRows(c).cwiseAbs2().eval().colwise().sum();
+  for (int j = 0; j < k; ++j) { projdot[j] = pd(j); projnorm[j] = pn(j); }
+  // preparePhenotype (BoltPlinkLoader.cpp:156-160): centre the top rows through a block array, then the covariate rows
+  MatrixXd y = v1.col(0);
+  double avg = y.topLeftCorner(n, 1).sum() / n;
+  y.topLeftCorner(n, 1).array() -= avg;
+  y.bottomLeftCorner(c, 1).noalias() = Z.transpose() * y.topLeftCorner(n, 1);
+  for (int i = 0; i < n; ++i) centred[i] = y(i, 0);
+  // projectCovariate (:266-271) on all columns
+  MatrixXd m = v2;
+  m.bottomRows(c).noalias() = Z.transpose() * m.topRows(n);
+  for (int i = 0; i < (n + c) * k; ++i) proj[i] = m.data()[i];
+  // g.col(0).head(N) = other.col(0)  (BoltLMM.cpp:449) and block / scalar (:569)
+  MatrixXd g(n + c, 2);
+  g.setZero();
+  g.col(1).head(n) = v2.col(0).head(n);
+  for (int i = 0; i < n; ++i) colhead[i] = g(i, 1);
+  MatrixXd hd = v1.col(0) / 4.0;
+  for (int i = 0; i < n; ++i) blkdiv[i] = hd(i, 0);
+  *all_lt = (pn.array() < 1e300).all() ? 1 : 0;
+  *any_lt = (pn.array() < -1e300).any() ? 1 : 0;
+  BDCSVD<MatrixXd> svd(Z, ComputeThinU);
+  for (int j = 0; j < c; ++j) sv[j] = svd.singularValues()[j];
+  MatrixXd u = svd.matrixU().leftCols(c);
+  for (int i = 0; i < n * c; ++i) U[i] = u.data()[i];
+}

@@ -2412,9 +2412,11 @@ struct BoltDev {
     if (gen >= 3) {
       dim3 g2((unsigned)((M + kBoltXtv2Block - 1) / kBoltXtv2Block), (unsigned)splits);
       for (int r0 = 0; r0 < R; r0 += 16) {
-        if (R - r0 <= 4) xtv3<4, 512>(g2, v, R, r0);
-        else if (R - r0 <= 8) xtv3<8, 256>(g2, v, R, r0);
-        else xtv3<16, 256>(g2, v, R, r0);
+        // 128-sample chunks: 34 / 42 / 58 KB of shared memory per CTA, i.e. 6 / 5 / 3 CTAs per SM (512-sample chunks left
+        // one warp per scheduler: 27 % of the fp64 pipe, "wait" stalls -- profiles/r02t_bolt_ncu.txt)
+        if (R - r0 <= 4) xtv3<4, 128>(g2, v, R, r0);
+        else if (R - r0 <= 8) xtv3<8, 128>(g2, v, R, r0);
+        else xtv3<16, 128>(g2, v, R, r0);
       }
       return;
     }

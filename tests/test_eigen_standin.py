@@ -109,3 +109,28 @@ def test_reductions_blocks_comma_map(st):
     assert np.allclose(vfr, A.sum(0)) and (sc[4], sc[5]) == (m, 1)
     assert np.allclose(sc[:4], [A.sum(), (A * A).sum(), np.sqrt((A * A).sum()), np.trace(A)])
     assert (sc[6], sc[7]) == (A.min(), A.max())
+
+
+def test_bolt_api_blocks_arrays_and_svd(st):
+    """the part of the API regression/BoltLMM.cpp and BoltPlinkLoader.cpp add: blocks of blocks, block arrays that write
+    through, the projected column products as the reference spells them, array comparisons, the thin SVD"""
+    rng = np.random.default_rng(5)
+    n, c, k = 41, 3, 4
+    A, B = F(rng.normal(size=(n + c, k))), F(rng.normal(size=(n + c, k)))
+    Z = F(np.column_stack([np.ones(n), rng.normal(size=(n, c - 1))]))
+    pd, pn, cen, proj = np.zeros(k), np.zeros(k), np.zeros(n), F(np.zeros((n + c, k)))
+    colhead, blkdiv, sv, U = np.zeros(n), np.zeros(n), np.zeros(c), F(np.zeros((n, c)))
+    all_lt, any_lt = C.c_int(-1), C.c_int(-1)
+    st.st_bolt_api(n, c, k, P(A), P(B), P(Z), P(pd), P(pn), P(cen), P(proj), P(colhead), C.byref(all_lt), C.byref(any_lt), P(sv), P(U), P(blkdiv))
+    assert np.allclose(pd, (A[:n] * B[:n]).sum(0) - (A[n:] * B[n:]).sum(0), rtol=1e-13, atol=1e-13)
+    assert np.allclose(pn, (A[:n] ** 2).sum(0) - (A[n:] ** 2).sum(0), rtol=1e-13, atol=1e-13)
+    assert np.allclose(cen, A[:n, 0] - A[:n, 0].mean(), rtol=1e-13, atol=1e-13)
+    want = B.copy()
+    want[n:] = Z.T @ B[:n]
+    assert np.allclose(proj, want, rtol=1e-12, atol=1e-12)
+    assert np.allclose(colhead, B[:n, 0]) and np.allclose(blkdiv, A[:n, 0] / 4.0)
+    assert all_lt.value == 1 and any_lt.value == 0
+    s_np = np.linalg.svd(Z, compute_uv=False)
+    assert np.allclose(sv, s_np, rtol=1e-12)
+    assert np.allclose(U.T @ U, np.eye(c), atol=1e-12)                       # orthonormal
+    assert np.allclose(U @ (U.T @ Z), Z, atol=1e-10)                         # spans the columns of Z

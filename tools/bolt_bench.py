@@ -34,7 +34,7 @@ def bolt_config(args):
                         "(BASELINE configs[4] null fit; the score step is --workload meta's path)",
             "samples": args.bolt_samples, "panel_snps": args.bolt_snps, "covariates_incl_intercept": args.covariates,
             "l2_policy": "every pass streams the 2-bit panel (N M / 4 bytes) and the N x R vectors; inputs >> 126 MB L2 at the "
-                         "default size (1.0 GB panel + 26 MB per vector), no flush"}
+                         "default size (4.1 GB panel + 32 MB per vector), no flush"}
 
 
 def synth_rows(torch, dev, N, lo, hi, miss=0.01):
