@@ -2615,7 +2615,7 @@ int rvt_bolt_fit_null_sharded(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64
   B.M_total = M_total; B.m_off = m_offset; B.ar = allreduce; B.ar_user = user;
   const int mc = mc_trials > 0 ? std::min(mc_trials, 15) : std::max(std::min((int)(4e9 / (double)N / (double)N), 15), 3);   // BoltLMM.cpp:465
   const int R1 = mc + 1;
-  const int nSnp = (int)std::min<int64_t>(30, M_total), Rmax = std::max(R1, nSnp);
+  const int nSnp = (int)std::min<int64_t>(30, M_total), Rmax = std::max(std::max(R1, nSnp), Ck);
   // sample splits of the X'v product: enough CTAs to fill the device, each a multiple of the staged chunk
   B.gen = ctx->bolt_kernels;
   const int64_t xtv_block = B.gen >= 2 ? kBoltXtv2Block : kBoltXtvBlock;
@@ -2652,7 +2652,15 @@ int rvt_bolt_fit_null_sharded(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64
       for (int64_t i = 0; i < N; ++i) zr[(size_t)i * Ck + c] = Zh[(size_t)c * N + i];
     RVT_CUDA_OK(cudaMemcpy(B.Z, zr.data(), sizeof(double) * zr.size(), cudaMemcpyHostToDevice));
   }
-  k_bolt_snp<<<(unsigned)M, 256, 0, st>>>(B.bed, B.stride, N, Ck, B.Z, B.tab, B.zg, B.gnorm2);
+  if (B.gen >= 3) {
+    // counts -> tables by popcount; Z'X as one pass of the X'v product with v = Z (row-major [N][Ck] is the layout of a vector)
+    k_bolt_count<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(B.bed, B.stride, N, (int)M, B.tab, B.gnorm2);
+    B.launch_xtv_(B.Z, Ck);
+    k_bolt_xtv_finish<<<(unsigned)(((int64_t)M * Ck + 255) / 256), 256, 0, st>>>((int)M, Ck, 0, B.splits, B.part, nullptr, nullptr, 1.0, B.Xy);
+    k_bolt_gnorm<<<(unsigned)((M + 255) / 256), 256, 0, st>>>((int)M, Ck, B.Xy, B.zg, B.gnorm2);
+  } else {
+    k_bolt_snp<<<(unsigned)M, 256, 0, st>>>(B.bed, B.stride, N, Ck, B.Z, B.tab, B.zg, B.gnorm2);
+  }
   B.note();
   // phenotype: centred (quantitative mode), bottom rows Z'y   (preparePhenotype, BoltPlinkLoader.cpp:143-163)
   BoltRandom rng(12345);

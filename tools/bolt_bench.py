@@ -30,7 +30,7 @@ CHUNK = 256
 
 def bolt_config(args):
     return {"workload": f"BoltLMM null fit (MC-REML secant + multi-RHS CG + calibration): N={args.bolt_samples} samples x "
-                        f"M_panel={args.bolt_snps} SNPs (2-bit PLINK rows), C={args.covariates}, 15 MC trials "
+                        f"M_panel={args.bolt_snps} SNPs (2-bit PLINK rows), C={args.covariates}, {max(min(int(4e9 / args.bolt_samples / args.bolt_samples), 15), 3)} MC trials "
                         "(BASELINE configs[4] null fit; the score step is --workload meta's path)",
             "samples": args.bolt_samples, "panel_snps": args.bolt_snps, "covariates_incl_intercept": args.covariates,
             "l2_policy": "every pass streams the 2-bit panel (N M / 4 bytes) and the N x R vectors; inputs >> 126 MB L2 at the "
@@ -195,7 +195,7 @@ def run_bolt(args, ClockSampler, bind_numa):
         "gpu_launches": int(2 * hx * (2 if R1 > 16 else 1) + 12 * hx),
         "clocks": clocks,
         "roofline": {"bound": "fp64 pipe (CUDA cores; no GEMM shape: a 4-entry table decode per genotype feeds R multiply-adds)",
-                     "kernel": "k_bolt_xtv2 + k_bolt_xw2", "achieved": flops / (ms_x * 1e-3) / 1e12, "peak": fp64_peak,
+                     "kernel": "k_bolt_xtv3 + k_bolt_xw3", "achieved": flops / (ms_x * 1e-3) / 1e12, "peak": fp64_peak,
                      "unit": "TFLOP/s", "frac": flops / (ms_x * 1e-3) / 1e12 / fp64_peak,
                      "peak_source": "148 SMs x 64 fp64 lanes x 2 x 1.965 GHz (nominal; MEASURED_PEAKS.json holds no fp64 figure)",
                      "hbm": {"achieved": bytes_alg / (ms_x * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
