@@ -127,6 +127,19 @@ def bind_numa(local):
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
         info.update({"gpu_pci": bdf, "gpu_numa_node": node})
         if node < 0:
+            node = _numa_from_topo(local, info)
+        if node < 0:
+            # no placement information at all (virtualised PCI tree): at least spread this job's pinned pages over every
+            # memory node the cpuset allows, so that N ranks do not all pull their H2D copies from one socket's DRAM
+            nodes = _allowed_mem_nodes()
+            info["mem_nodes_allowed"] = nodes
+            if len(nodes) > 1:
+                libc = ctypes.CDLL(None, use_errno=True)
+                mask = (ctypes.c_ulong * 16)()
+                for nd in nodes:
+                    mask[nd // 64] |= 1 << (nd % 64)
+                rc = libc.syscall(238, 3, mask, 16 * 64 + 1)   # set_mempolicy(MPOL_INTERLEAVE)
+                info["mempolicy"] = "interleave over %s" % nodes if rc == 0 else "set_mempolicy errno %d" % ctypes.get_errno()
             return info
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
@@ -148,6 +161,45 @@ def bind_numa(local):
     except Exception as e:   # never let a placement hint cost the bench line
         info["error"] = repr(e)
     return info
+
+
+def _allowed_mem_nodes():
+    try:
+        for line in open("/proc/self/status"):
+            if line.startswith("Mems_allowed_list:"):
+                out = []
+                for part in line.split(":", 1)[1].strip().split(","):
+                    a, _, b = part.partition("-")
+                    out.extend(range(int(a), int(b or a) + 1))
+                return out
+    except Exception:
+        pass
+    return []
+
+
+def _numa_from_topo(local, info):
+    """`nvidia-smi topo -m` prints a NUMA Affinity column even where sysfs says -1"""
+    try:
+        txt = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        head = None
+        for line in txt.splitlines():
+            cells = [c.strip() for c in line.split("\t") if c.strip()]
+            if not cells:
+                continue
+            if head is None and any("NUMA Affinity" in c for c in cells):
+                head = cells
+                continue
+            if head and cells[0] == f"GPU{local}":
+                # the data row has one more leading cell (the row label) than the header
+                idx = [i for i, c in enumerate(head) if "NUMA Affinity" in c][0] + 1
+                if idx < len(cells) and cells[idx].split(",")[0].split("-")[0].isdigit():
+                    node = int(cells[idx].split(",")[0].split("-")[0])
+                    if node in _allowed_mem_nodes():
+                        info["gpu_numa_node_from_topo"] = node
+                        return node
+    except Exception as e:
+        info["topo_error"] = repr(e)
+    return -1
 
 
 def peaks():
