@@ -404,6 +404,7 @@ class VcfGenePacker {
     ncol_ = (int)col_to_out_.size();
     n_ = (int64_t)names_.size();
     stride_ = (n_ + 3) / 4;
+    if ((int64_t)sex_.size() != n_) sex_.clear();   // a sex vector belongs to one kept-sample set: call setSex again after setHeader
     clear();
     if (ncol_ == 0) return -1;
     if (!want.empty() && names_.size() != want.size()) return -3;
@@ -494,7 +495,7 @@ class VcfGenePacker {
     const int gd_idx = need_gd_ ? formatIndex(line + fb[8], fe[8] - fb[8], "GD") : -1;
     const int gq_idx = need_gq_ ? formatIndex(line + fb[8], fe[8] - fb[8], "GQ") : -1;
     const bool filtered = need_gd_ || need_gq_;
-    const bool hemi = !sex_.empty() && par_.isHemiRegion(std::string(line + fb[0], fe[0] - fb[0]), pos);
+    const bool hemi = (int64_t)sex_.size() == n_ && n_ > 0 && par_.isHemiRegion(std::string(line + fb[0], fe[0] - fb[0]), pos);
 
     // alt alleles to expand (multi-allelic mode), else one pass with alt = 0 = the plain GT grammar
     std::vector<std::string> alts;
@@ -503,7 +504,7 @@ class VcfGenePacker {
       while (ab <= fe[4]) {
         const char* c = (const char*)memchr(line + ab, ',', fe[4] - ab);
         const size_t ae = c ? (size_t)(c - line) : fe[4];
-        if (ae > ab) alts.push_back(std::string(line + ab, ae - ab));   // stringTokenize drops nothing but we skip empties
+        alts.push_back(std::string(line + ab, ae - ab));   // empty tokens kept, as stringTokenize keeps them: "A,,T" is three alleles
         ab = ae + 1;
       }
       if (alts.empty()) alts.push_back(std::string());

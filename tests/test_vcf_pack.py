@@ -348,7 +348,7 @@ def test_multi_allelic_records(vcfpack, oracle, with_sex, capfd):
         vcfpack.clear()
         want, names = [], []
         for k in range(40):
-            alts = ["G", "G,T", "G,T,<DEL>"][k % 3]
+            alts = ["G", "G,T", "G,T,<DEL>", "G,,T"][k % 4]          # "G,,T": the empty token is an allele of its own (stringTokenize keeps it)
             chrom, pos = ["X", "5"][k % 2], [70000, 5_000_000][(k // 2) % 2]
             cols = [gts[int(rng.integers(len(gts)))] + ":7" for _ in range(n)]
             rec = "\t".join([chrom, str(pos), ".", "AC", alts, "9", "PASS", ".", "GT:GQ"] + cols)
