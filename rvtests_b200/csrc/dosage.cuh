@@ -326,19 +326,29 @@ k_tile_sparse(const TileGene* __restrict__ genes, int64_t N, const RowCounts* __
     const int8_t* __restrict__ base = tg.g + ((size_t)(i0 >> 7) * M) * 128 + (i0 & 127);   // row j at + j * 128
     uint8_t lj[4][kSparseList], lc[4][kSparseList];
     int cnt[4] = {0, 0, 0, 0};
-    // pass 1: record
-    for (int j = 0; j < M; ++j) {
-      const uint32_t w = *reinterpret_cast<const uint32_t*>(base + (size_t)j * 128);
-      if (w == 0) continue;
+    // pass 1: record.  The rows' words are fetched sixteen at a time BEFORE anything branches on them: with one load per
+    // iteration behind `if (w == 0) continue` the loop ran at one HBM latency per row (ncu: 51 % long-scoreboard stalls;
+    // 83 -> 63 us per 25 MB gene).  Tried and dropped (profiles/r02u_binary_path.txt): the per-variant sums in a separate
+    // variant-major kernel without shared-memory atomics -- its gathers of r, v, X are as latency-bound as the atomics were.
+    for (int j0 = 0; j0 < M; j0 += 16) {
+      uint32_t wv[16];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t code = (w >> (8 * q)) & 0xFFu;
-        if (code == 0) continue;
-        if (cnt[q] < kSparseList) {
-          lj[q][cnt[q]] = (uint8_t)j;
-          lc[q][cnt[q]] = (uint8_t)code;
+      for (int k = 0; k < 16; ++k) wv[k] = (j0 + k < M) ? __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)(j0 + k) * 128)) : 0u;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const uint32_t w = wv[k];
+        if (w == 0) continue;
+        const int j = j0 + k;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t code = (w >> (8 * q)) & 0xFFu;
+          if (code == 0) continue;
+          if (cnt[q] < kSparseList) {
+            lj[q][cnt[q]] = (uint8_t)j;
+            lc[q][cnt[q]] = (uint8_t)code;
+          }
+          ++cnt[q];
         }
-        ++cnt[q];
       }
     }
     // pass 2: arithmetic, sample by sample
