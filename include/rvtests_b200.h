@@ -87,7 +87,8 @@ typedef struct rvt_gene_result {
  * traits alike (src/Model.h:2673-2717), genes with missing calls (2-bit pushes, mean-imputed) included.  NOT covered: a gene
  * with dosages pushed as doubles, a gene with missing calls of a binary-trait run or of 63-64 variants (done = 0, NA columns);
  * the reference would have shuffled for it, so from such a gene on the stream position -- hence NumGreater / NumEqual of the
- * LATER genes -- no longer replays the reference's.  rvt_perm_result.stream_pos tells where each gene started. */
+ * LATER genes -- no longer replays the reference's: those records carry stream_ok = 0.  rvt_perm_result.stream_pos tells where
+ * each gene started. */
 typedef struct rvt_perm_result {
   int32_t num_perm;      /* NumPerm */
   int32_t actual_perm;   /* ActualPerm */
@@ -97,7 +98,10 @@ typedef struct rvt_perm_result {
   double p_perm;         /* PermPvalue */
   int64_t stream_pos;    /* rand() values consumed before this gene's first shuffle */
   int32_t done;          /* 1: permutations ran; 0: gene NA (fit() == -1) or on a path the test does not cover */
-  int32_t pad;
+  int32_t stream_ok;     /* 1: stream_pos is where the reference's serial loop stands at this gene; 0: an EARLIER gene of this
+                          * context (since "perm_stream_pos" / "perm_seed" was last set) was testable in the reference but not
+                          * covered here (done = 0 with status OK), so this gene's shuffles -- NumGreater, NumEqual, PermPvalue --
+                          * are valid permutation statistics but not the reference's own draws */
 } rvt_perm_result;
 
 /* One record per variant from rvt_lmm_flush: FastLMM::TestCovariate, score branch (regression/FastLMM.cpp:215-249) */

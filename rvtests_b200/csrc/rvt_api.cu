@@ -173,6 +173,7 @@ struct rvt_ctx {
   int qags_pack = 1;               // SKAT-O quadrature: 1 = three genes per persistent 128-thread CTA (k_skato_qags_packed)
   long long wd_cycles = 8000000000ll;   // device watchdog of the per-gene tail, SM cycles (option "watchdog_ms"; ~4 s)
   bool skato = false;
+  bool perm_stream_lost = false;   // a gene the reference would have permuted was skipped: later stream positions are not the reference's
   int bolt_kernels = 3;        // generation of the panel-product kernels of rvt_bolt_fit_null (bolt.cuh)
   bool skato_binary = true;    // SKAT-O for a binary trait (SkatO::Fit type "D"); on by default, see include/rvtests_b200.h
   long long* d_dbg = nullptr;   // optional finalize phase counters (rvt_set_option "debug_phases")
@@ -455,9 +456,11 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "perm_stream_pos") {
     if (value < 0) CTX_FAIL(RVT_E_BADARG, "perm_stream_pos must be >= 0");
     ctx->perm_pos = (uint64_t)value;
+    ctx->perm_stream_lost = false;
   } else if (k == "perm_seed") {
     ctx->perm_seed = (uint32_t)value;
     ctx->perm_pos = 0;
+    ctx->perm_stream_lost = false;
   } else if (k == "debug_perm_q") {
     ctx->perm_log = value != 0;
   } else if (k == "debug_phases") {
@@ -1427,7 +1430,13 @@ static int run_perm(rvt_ctx* ctx, const rvt_gene_result* d_res, int n, int* laun
     // lines up with the reference's (documented in include/rvtests_b200.h).  A binary trait is covered: its permuted
     // statistic is sum_j w_j (g_j' r_pi)^2 with r = y - p, hard calls and digits of r as for a quantitative trait
     // (src/Model.h:2673-2717: one loop for both outcomes).
-    if (hres[g].status != RVT_GENE_OK || ctx->is_dos[g] == 1 || !gd.tiled || gd.seg < 0 || (!gd.has_af && !gd.counted)) continue;
+    rec.stream_ok = ctx->perm_stream_lost ? 0 : 1;
+    if (hres[g].status != RVT_GENE_OK || ctx->is_dos[g] == 1 || !gd.tiled || gd.seg < 0 || (!gd.has_af && !gd.counted)) {
+      // status OK: the reference's SkatTest::fit would have run its permutation loop here and consumed ActualPerm * (N - 1)
+      // draws we cannot know -- every later record of this context says so (stream_ok = 0) until the position is set again
+      if (hres[g].status == RVT_GENE_OK) ctx->perm_stream_lost = true;
+      continue;
+    }
     const bool aug = ctx->is_dos[g] == 3;   // missing calls: two operand tiles, H (fills applied) and M (indicators)
     const std::vector<GeneDesc>* tiles = nullptr;
     std::vector<GeneDesc> one(1, gd);

@@ -68,7 +68,7 @@ LMM_DTYPE = np.dtype([("af", "f8"), ("U", "f8"), ("V", "f8"), ("stat", "f8"), ("
 
 PERM_DTYPE = np.dtype([
     ("num_perm", "i4"), ("actual_perm", "i4"), ("num_greater", "i4"), ("num_equal", "i4"),
-    ("stat", "f8"), ("p_perm", "f8"), ("stream_pos", "i8"), ("done", "i4"), ("pad", "i4"),
+    ("stat", "f8"), ("p_perm", "f8"), ("stream_pos", "i8"), ("done", "i4"), ("stream_ok", "i4"),
 ])
 
 CC_DTYPE = np.dtype([("n", "i4", 2), ("n_ref", "i4", 2), ("n_het", "i4", 2), ("n_alt", "i4", 2), ("hwe_p", "f8", 2)])

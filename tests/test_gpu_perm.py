@@ -198,3 +198,39 @@ def test_device_rand_equals_glibc_rand(eng, oracle):
     assert bad.size == 0, (bad[:5], dev[bad[:5]], ref[bad[:5]])
     far = oracle.glibc_rand(100_000, reseed=7, skip=5_000_000)
     assert np.array_equal(eng.debug_rand(100_000, seed=7, pos=5_000_000), far)
+
+
+def test_perm_reports_lost_stream_parity_after_an_uncovered_gene(engine_cls, oracle):
+    """A gene with dosages pushed as doubles is not permuted (done = 0) although the reference would have shuffled for it:
+    every LATER record of the context says stream_ok = 0 (valid permutation statistics, but not the reference's own draws)
+    until the stream position is set again; a gene the reference itself skips (fit() == -1) costs nothing."""
+    O = oracle
+    N = 500
+    G1, X, y = make_problem(O, 91, N, 6, 1, maf=0.2)
+    Gm, _, _ = make_problem(O, 92, N, 4, 1, maf=0.2, n_mono=4)
+    G2, _, _ = make_problem(O, 93, N, 7, 1, maf=0.2)
+    Gd = G2.astype(np.float64)
+    Gd[::7, 0] = 0.37                                   # dosages: the fp64 path
+    eng = engine_cls(0)
+    try:
+        eng.set_null_model(X, y)
+        eng.set_option("perm", 200)
+        eng.push_i8(G1.T.copy(), af_of(G1))
+        eng.push_i8(Gm.T.copy(), af_of(Gm))             # NA in the reference too: no draws consumed
+        eng.push_f64(Gd, af_of(G2))                     # testable in the reference, not covered here
+        eng.push_i8(G2.T.copy(), af_of(G2))
+        res = eng.flush()
+        pr = eng.perm_results()
+        assert [int(r["status"]) for r in res][0] == 0 and int(res[2]["status"]) == 0
+        assert [int(p["done"]) for p in pr] == [1, 0, 0, 1]
+        assert [int(p["stream_ok"]) for p in pr] == [1, 1, 1, 0]
+        eng.push_i8(G1.T.copy(), af_of(G1))
+        eng.flush()
+        assert int(eng.perm_results()[0]["stream_ok"]) == 0          # sticky across flushes
+        eng.set_option("perm_stream_pos", 0)
+        eng.push_i8(G1.T.copy(), af_of(G1))
+        eng.flush()
+        p2 = eng.perm_results()[0]
+        assert int(p2["stream_ok"]) == 1 and int(p2["num_greater"]) == int(pr[0]["num_greater"]) and int(p2["actual_perm"]) == int(pr[0]["actual_perm"])
+    finally:
+        eng.close()
