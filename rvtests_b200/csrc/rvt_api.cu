@@ -129,6 +129,17 @@ struct rvt_ctx {
   bool perm_log = false;           // option "debug_perm_q": keep every permuted statistic of the last flush
   std::vector<double> perm_q_log;
   std::vector<int> bed_genes;      // pending genes pushed as PLINK 2-bit rows: checked for missing calls at flush
+  // binary trait: tile genes whose fp64 statistics + tail were enqueued right behind their copies (launch_range), so that they
+  // run under the PCIe transfers of the following genes instead of all at flush: 0 no, 1 done (hard calls / missing unknown yet)
+  std::vector<char> bin_streamed;
+  std::vector<char> is_bed;        // per pending gene: pushed as 2-bit rows (code 3 = a missing call to impute)
+  std::vector<TileGene> bs_tg;     // host staging of one streamed batch
+  std::vector<int> bs_idx;
+  cudaStream_t bin_s = nullptr;
+  cudaEvent_t ev_bin_in = nullptr, ev_bin_out = nullptr;
+  bool bin_pending = false;
+  void *d_bs_st = nullptr, *d_bs_tin = nullptr, *d_bs_idx = nullptr, *d_bs_tg = nullptr;
+  size_t cap_bs_st = 0, cap_bs_tin = 0, cap_bs_idx = 0, cap_bs_tg = 0;
   std::vector<int> unsupported;    // pending genes the flush cannot compute (wide + missing calls): record status only
   int launched = 0;                // pending genes [0, launched) already have their kernels enqueued (stream_batch)
   int stream_batch = 0;            // option: enqueue sweep + statistics every this many host pushes (0 = only at flush)
@@ -173,6 +184,7 @@ struct rvt_ctx {
   int qags_pack = 1;               // SKAT-O quadrature: 1 = three genes per persistent 128-thread CTA (k_skato_qags_packed)
   long long wd_cycles = 8000000000ll;   // device watchdog of the per-gene tail, SM cycles (option "watchdog_ms"; ~4 s)
   bool skato = false;
+  bool bin_stream = true;      // option "binary_stream": binary-trait tile genes are computed in launch_range (behind their copies), not at flush
   bool perm_stream_lost = false;   // a gene the reference would have permuted was skipped: later stream positions are not the reference's
   int bolt_kernels = 3;        // generation of the panel-product kernels of rvt_bolt_fit_null (bolt.cuh)
   bool skato_binary = true;    // SKAT-O for a binary trait (SkatO::Fit type "D"); on by default, see include/rvtests_b200.h
@@ -200,11 +212,15 @@ struct rvt_ctx {
 };
 
 static void pending_reset(rvt_ctx* ctx) {
+  if (ctx->bin_pending && ctx->bin_s) cudaStreamSynchronize(ctx->bin_s);   // (a failed flush drops the queue: nothing may still run on it)
+  ctx->bin_pending = false;
   ctx->genes.clear();
   ctx->userflags.clear();
   ctx->af.clear();
   ctx->count_slot.clear();
   ctx->bed_genes.clear();
+  ctx->bin_streamed.clear();
+  ctx->is_bed.clear();
   ctx->unsupported.clear();
   ctx->wide.clear();
   ctx->slots.clear();
@@ -358,7 +374,7 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_jobs, ctx->d_mid, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum, ctx->d_p, ctx->d_vw, ctx->d_dos_st, ctx->d_dos_tin, ctx->d_dos_idx, ctx->d_dos_afd, ctx->d_dos_tg};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_jobs, ctx->d_mid, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum, ctx->d_p, ctx->d_vw, ctx->d_dos_st, ctx->d_dos_tin, ctx->d_dos_idx, ctx->d_dos_afd, ctx->d_dos_tg, ctx->d_bs_st, ctx->d_bs_tin, ctx->d_bs_idx, ctx->d_bs_tg};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -373,6 +389,12 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
   }
+  if (ctx->bin_s) {
+    cudaStreamSynchronize(ctx->bin_s);
+    cudaStreamDestroy(ctx->bin_s);
+  }
+  if (ctx->ev_bin_in) cudaEventDestroy(ctx->ev_bin_in);
+  if (ctx->ev_bin_out) cudaEventDestroy(ctx->ev_bin_out);
   if (ctx->fin_stream) {
     cudaStreamSynchronize(ctx->fin_stream);
     cudaStreamDestroy(ctx->fin_stream);
@@ -424,6 +446,8 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "watchdog_ms") {
     if (value < 0 || value > 3.6e6) CTX_FAIL(RVT_E_BADARG, "watchdog_ms must be in 0..3600000 (0 = off)");
     ctx->wd_cycles = (long long)(value * 2.0e6);   // ~2 GHz SM clock
+  } else if (k == "binary_stream") {
+    ctx->bin_stream = value != 0;
   } else if (k == "bolt_kernels") {
     ctx->bolt_kernels = (value >= 3.0) ? 3 : (value >= 2.0) ? 2 : 1;
   } else if (k == "skato_binary") {
@@ -873,9 +897,100 @@ static int launch_qags(rvt_ctx* ctx, const SkatoJob* jobs, int nb, rvt_gene_resu
   return RVT_OK;
 }
 
+// Binary trait: the fp64 statistics (dosage.cuh) and the tail of the tile genes of [b0, b0 + nb), enqueued now -- right behind
+// their copies -- instead of at flush, where they used to run after the last byte had crossed PCIe (profiles/r02u: copies
+// 125 us + statistics 63 us per gene in series = 5.3 k genes/s end to end against 8.1 k for a quantitative trait).  Same
+// kernels, same records; genes this does not take (doubles with dosages, blocks without the engine's own counts, wide genes)
+// keep the flush path.
+static int binary_stream_batch(rvt_ctx* ctx, int b0, int nb, const EngineParams& prm, int* launches) {
+  const int64_t N = ctx->N;
+  int rc;
+  // On a stream of their own: behind the context's stream the 2 ms of statistics of a 32-gene batch held up the unpack
+  // kernels of the following genes, the landing ring filled and the copy engine idled (measured: no gain at all).
+  if (!ctx->bin_s) {
+    RVT_CUDA_OK(cudaStreamCreateWithFlags(&ctx->bin_s, cudaStreamNonBlocking));
+    RVT_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_bin_in, cudaEventDisableTiming));
+    RVT_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_bin_out, cudaEventDisableTiming));
+  }
+  RVT_CUDA_OK(cudaEventRecord(ctx->ev_bin_in, ctx->stream));      // tiles unpacked, counts / flags / af of this range in place
+  cudaStream_t st = ctx->bin_s;
+  RVT_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_bin_in, 0));
+  ctx->bin_streamed.resize(ctx->genes.size(), 0);
+  ctx->is_bed.resize(ctx->genes.size(), 0);
+  ctx->bs_tg.clear();
+  ctx->bs_idx.clear();
+  for (int g = b0; g < b0 + nb; ++g) {
+    const GeneDesc& gd = ctx->genes[g];
+    if (!gd.tiled || !gd.counted || gd.M > kMaxM || ctx->slots[g] > kMaxM) continue;
+    bool f64 = false;
+    for (auto& dg : ctx->dos) f64 |= dg.gene_index == g;
+    for (auto& w : ctx->wide) f64 |= w.gene_index == g;
+    if (f64) continue;
+    TileGene tg;
+    tg.g = gd.g;
+    tg.M = gd.M;
+    tg.has_af = gd.has_af;
+    tg.var0 = gd.var0;
+    tg.slot = (int)ctx->bs_tg.size();
+    tg.allow_missing = ctx->is_bed[g] ? 1 : 0;
+    ctx->bs_tg.push_back(tg);
+    ctx->bs_idx.push_back(g);
+    ctx->bin_streamed[g] = 1;
+  }
+  const int nt = (int)ctx->bs_tg.size();
+  if (nt == 0) return RVT_OK;
+  if ((size_t)nt > ctx->cap_bs_st || (size_t)nt > ctx->cap_bs_tin || (size_t)nt > ctx->cap_bs_idx || (size_t)nt > ctx->cap_bs_tg ||
+      (size_t)nt > ctx->cap_jobs || (size_t)nt > ctx->cap_mid || qags_scratch_entries(ctx, nt) > ctx->cap_qags)
+    RVT_CUDA_OK(cudaStreamSynchronize(st));   // a buffer is about to move: nothing of the previous batch may still read it
+  if ((rc = ensure(ctx, &ctx->d_bs_st, &ctx->cap_bs_st, (size_t)nt, sizeof(DosageStats)))) return rc;
+  if ((rc = ensure(ctx, &ctx->d_bs_tin, &ctx->cap_bs_tin, (size_t)nt, sizeof(TailInput)))) return rc;
+  if ((rc = ensure(ctx, &ctx->d_bs_idx, &ctx->cap_bs_idx, (size_t)nt, sizeof(int)))) return rc;
+  if ((rc = ensure(ctx, &ctx->d_bs_tg, &ctx->cap_bs_tg, (size_t)nt, sizeof(TileGene)))) return rc;
+  DosageStats* d_st = (DosageStats*)ctx->d_bs_st;
+  TailInput* d_tin = (TailInput*)ctx->d_bs_tin;
+  int* d_idx = (int*)ctx->d_bs_idx;
+  TileGene* d_tg = (TileGene*)ctx->d_bs_tg;
+  RVT_CUDA_OK(cudaMemsetAsync(d_st, 0, sizeof(DosageStats) * nt, st));
+  RVT_CUDA_OK(cudaMemcpyAsync(d_tg, ctx->bs_tg.data(), sizeof(TileGene) * nt, cudaMemcpyHostToDevice, st));   // (pageable: staged before the call returns)
+  RVT_CUDA_OK(cudaMemcpyAsync(d_idx, ctx->bs_idx.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, st));
+  k_tile_cols<<<nt, kTileRows, 0, st>>>(d_tg, nt, N, ctx->d_counts, d_st);
+  const int64_t nblk = ((N + 3) / 4 + kSparseThreads - 1) / kSparseThreads;
+  const unsigned bx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nblk, (8 * (int64_t)ctx->sm_count + nt - 1) / nt));
+  k_tile_sparse<<<dim3(bx, (unsigned)nt), kSparseThreads, 0, st>>>(d_tg, N, ctx->d_counts, ctx->dX, ctx->C, ctx->dresid, ctx->d_vw, d_st);
+  k_tile_prepare<<<nt, 64, 0, st>>>(d_tg, nt, d_st, ctx->d_af, ctx->d_nm, prm, d_tin);
+  const bool sk = ctx->skato && ctx->skato_binary;
+  const int kld = fin_kld(kTileRows), fsm = fin_smem(kTileRows, ctx->ER, sk), wm_off = kTileRows * kld * 8;
+  if (sk) {
+    if ((rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, qags_scratch_entries(ctx, nt), sizeof(QagsScratch)))) return rc;
+    if ((rc = ensure(ctx, (void**)&ctx->d_jobs, &ctx->cap_jobs, (size_t)nt, sizeof(SkatoJob)))) return rc;
+    k_finalize<true><<<nt, kFinThreadsSkato, fsm, st>>>(nullptr, nt, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, sk), ctx->d_flags, ctx->d_af, ctx->d_counts,
+                                                         ctx->d_nm, prm, 1, nullptr, ctx->d_res, nullptr, ctx->d_jobs, d_tin, d_idx);
+    if ((rc = launch_qags(ctx, ctx->d_jobs, nt, ctx->d_res, d_idx, st))) return rc;
+    *launches += 1;
+  } else if (ctx->fin_split) {
+    if ((rc = ensure(ctx, (void**)&ctx->d_mid, &ctx->cap_mid, (size_t)nt, sizeof(FinMid)))) return rc;
+    k_finalize<false, true><<<nt, kFinThreads, fsm, st>>>(nullptr, nt, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, false), ctx->d_flags, ctx->d_af, ctx->d_counts,
+                                                           ctx->d_nm, prm, 1, nullptr, ctx->d_res, nullptr, nullptr, d_tin, d_idx, ctx->d_mid);
+    k_fin_sturm<<<nt, kFinThreads, 0, st>>>(ctx->d_mid, nt);
+    k_fin_tail<<<nt, kFinThreads, 0, st>>>(ctx->d_mid, nt, ctx->d_nm, ctx->d_res, d_idx);
+    *launches += 2;
+  } else {
+    k_finalize<false><<<nt, kFinThreads, fsm, st>>>(nullptr, nt, kld, wm_off, fin_uk_off(kTileRows, ctx->ER, sk), ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm,
+                                                     prm, 1, nullptr, ctx->d_res, nullptr, nullptr, d_tin, d_idx);
+  }
+  RVT_CUDA_OK(cudaGetLastError());
+  RVT_CUDA_OK(cudaEventRecord(ctx->ev_bin_out, st));
+  ctx->bin_pending = true;     // flush waits for ev_bin_out before it reads the records
+  *launches += 4;
+  return RVT_OK;
+}
+
 static int maybe_stream(rvt_ctx* ctx) {
   const int n = (int)ctx->genes.size();
-  if (ctx->stream_batch > 0 && n - ctx->launched >= ctx->stream_batch) return launch_range(ctx, ctx->launched, n);
+  // binary trait: the statistics of a batch occupy the SMs for ~60 us per gene; small batches keep them out of the way of the
+  // unpack kernels that free the landing ring (8 / 32 / 64 genes: 6.85 / 6.20 / 5.80 k genes/s end to end, profiles/r02u)
+  const int sb = (ctx->binary && ctx->bin_stream) ? std::min(ctx->stream_batch, 8) : ctx->stream_batch;
+  if (ctx->stream_batch > 0 && n - ctx->launched >= sb) return launch_range(ctx, ctx->launched, n);
   return RVT_OK;
 }
 
@@ -991,6 +1106,8 @@ int rvt_gene_push_bed(rvt_ctx* ctx, const uint8_t* bed, int M, int64_t stride, c
   RVT_CUDA_OK(cudaGetLastError());
   if ((rc = land_release(ctx, slot))) return rc;
   ctx->bed_genes.push_back((int)ctx->genes.size());
+  ctx->is_bed.resize(ctx->genes.size() + 1, 0);
+  ctx->is_bed[ctx->genes.size()] = 1;
   if ((rc = push_staged(ctx, tp, M, af))) return rc;
   return maybe_stream(ctx);
 }
@@ -1006,6 +1123,10 @@ static int resolve_bed_missing(rvt_ctx* ctx) {
     const GeneDesc& gd = ctx->genes[gi];
     bool missing = false;
     for (int j = 0; j < ctx->slots[gi]; ++j) missing |= hc[gd.var0 + j].bad > 0;
+    if ((size_t)gi < ctx->bin_streamed.size() && ctx->bin_streamed[gi]) {
+      ctx->bin_streamed[gi] = missing ? 2 : 1;   // computed behind its copy (imputed on the fly); 2: the permutation test does not cover it
+      continue;
+    }
     if (!missing) continue;
     if (ctx->slots[gi] > kMaxM) {
       // mean imputation (fp64 path) handles up to kMaxM variants: this ONE gene is reported RVT_GENE_UNSUPPORTED in its
@@ -1102,6 +1223,7 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
   const int n_total = (int)ctx->genes.size();
   if ((rc = ensure(ctx, (void**)&ctx->d_genes, &ctx->cap_genes, n_total, sizeof(GeneDesc)))) return rc;
   if ((rc = ensure_var(ctx, ctx->n_var))) return rc;
+  if (ctx->bin_pending && (size_t)n_total > ctx->cap_res) RVT_CUDA_OK(cudaStreamSynchronize(ctx->bin_s));   // records in flight: the buffer must not move under them
   if ((rc = ensure(ctx, (void**)&ctx->d_res, &ctx->cap_res, n_total, sizeof(rvt_gene_result)))) return rc;
   int S = 0;
   int64_t chunk = 0;
@@ -1176,6 +1298,7 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
     if (ctx->binary) {
       RVT_CUDA_OK(cudaEventRecord(ev[1], st));
       RVT_CUDA_OK(cudaEventRecord(ev[2], st));
+      if (ctx->bin_stream && (rc = binary_stream_batch(ctx, b0, nb, prm, &launches))) return rc;
       RVT_CUDA_OK(cudaEventRecord(ev[3], st));
       continue;
     }
@@ -1572,6 +1695,10 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   int rc;
   mark("enter (copies landed)");
   if ((rc = launch_range(ctx, ctx->launched, n))) return rc;
+  if (ctx->bin_pending) {
+    RVT_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_bin_out, 0));
+    ctx->bin_pending = false;
+  }
   mark("sweep + statistics");
   if ((rc = resolve_bed_missing(ctx))) return rc;
   mark("missing-call check");
@@ -1589,6 +1716,10 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
       CTX_FAIL(RVT_E_UNSUPPORTED, "binary trait: genes of more than %d variants are not supported", kMaxM);
     for (int g = 0; g < n; ++g) {
       if (ctx->is_dos[g]) continue;
+      if ((size_t)g < ctx->bin_streamed.size() && ctx->bin_streamed[g]) {
+        ctx->is_dos[g] = ctx->bin_streamed[g] == 2 ? 1 : 2;   // statistics + tail ran in launch_range; 2 = hard calls: the permutation test applies
+        continue;
+      }
       const GeneDesc& gd = ctx->genes[g];
       if (!gd.tiled) CTX_FAIL(RVT_E_UNSUPPORTED, "binary trait: caller-owned device blocks are not supported");
       DosGene dg;

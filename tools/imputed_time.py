@@ -36,6 +36,10 @@ eng = rvtests_b200.GeneEngine(0)
 
 def run(tag, bed, binary, aug=1):
     eng.set_option("aug", aug)
+    if os.environ.get("IMP_STREAM"):
+        eng.set_option("stream_batch", int(os.environ["IMP_STREAM"]))     # sweep / statistics enqueued under the following copies, as bench.py's e2e leg does
+    if os.environ.get("IMP_BINSTREAM"):
+        eng.set_option("binary_stream", int(os.environ["IMP_BINSTREAM"]))
     if binary:
         yb = (np.random.default_rng(1).random(N) < 0.3).astype(np.float64)
         eng.set_null_model(X, yb, binary=True)
