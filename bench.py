@@ -359,12 +359,14 @@ def run_ours(args):
         e2e_i8 = run_e2e(args, eng, torch, dist, world, rank, dev, "i8")
         e2e_f64 = run_e2e(args, eng, torch, dist, world, rank, dev, "f64")
         e2e_miss = run_e2e(args, eng, torch, dist, world, rank, dev, "bed_missing")
+        e2e_bin = run_e2e(args, eng, torch, dist, world, rank, dev, "bed_binary")
     if rank == 0:
         out["e2e"] = e2e
         if e2e is not None:
             out["e2e_int8"] = e2e_i8
             out["e2e_f64"] = e2e_f64
             out["e2e_missing_calls"] = e2e_miss
+            out["e2e_binary_trait"] = e2e_bin
         out["skato"] = skato
         if not args.no_cpu and world == 1:
             # the oracle as CHECKER of the very records the timed steps produced (parity gates measured in
@@ -489,16 +491,26 @@ def run_e2e(args, eng, torch, dist, world, rank, dev, fmt="bed"):
     copied back).  H2D of every gene and D2H of the records are inside the timed region."""
     import rvtests_b200
     from rvtests_b200.synth import pack_bed
-    ng, M, N = (args.e2e_genes if fmt in ("bed", "bed_missing") else max(16, args.e2e_genes // 4)), args.variants, args.samples
+    ng, M, N = (args.e2e_genes if fmt in ("bed", "bed_missing", "bed_binary") else max(16, args.e2e_genes // 4)), args.variants, args.samples
     if fmt == "f64":
         ng = max(4, args.e2e_genes // 32)               # 200 MB per gene: the reference's own Matrix boundary
     ng = min(ng, args.genes)
     nd = min(ng, {"f64": 4, "bed_missing": 16}.get(fmt, 64))   # distinct genes held on the host, cycled
     calls = eng.loaded_read(0, nd * M)                  # the same genotypes as the first resident genes
     af = 0.5 * calls.reshape(nd, M, N).sum(axis=2, dtype=np.int64) / N
-    if fmt in ("bed", "bed_missing"):
+    src_eng = eng
+    if fmt == "bed_binary":
+        # a binary trait (logistic null on the device, p(1-p)-weighted statistics through the fp64 path, enqueued behind the
+        # copies: option binary_stream) on an engine of its own, so that the resident cohort keeps its quantitative null
+        from rvtests_b200.synth import covariates
+        X, _y = covariates(SEED, N, args.covariates)
+        yb = (np.random.default_rng(SEED).random(N) < 0.3).astype(np.float64)
+        eng = rvtests_b200.GeneEngine(torch.cuda.current_device())
+        eng.set_stream(torch.cuda.current_stream().cuda_stream)
+        eng.set_null_model(X, yb, binary=True)
+    if fmt in ("bed", "bed_missing", "bed_binary"):
         host = torch.empty((nd * M, (N + 3) // 4), dtype=torch.uint8, pin_memory=True)
-        if fmt == "bed":
+        if fmt in ("bed", "bed_binary"):
             host.numpy()[:] = pack_bed(calls)
         else:   # 1 % of the calls missing (PLINK code 01): mean-imputed on the device, augmented tensor-core sweep
             rng = np.random.default_rng(SEED + rank)
@@ -520,7 +532,7 @@ def run_e2e(args, eng, torch, dist, world, rank, dev, fmt="bed"):
             blk = hn[k * M:(k + 1) * M]
             if fmt == "bed_missing":
                 eng.push_bed(blk, None)
-            elif fmt == "bed":
+            elif fmt in ("bed", "bed_binary"):
                 eng.push_bed(blk, af[k])
             elif fmt == "i8":
                 eng.push_i8(blk, af[k])
@@ -546,12 +558,16 @@ def run_e2e(args, eng, torch, dist, world, rank, dev, fmt="bed"):
     sec = float(dt.item()) / reps
     eng.set_option("stream_batch", 0)
     assert int((r["status"] == 0).sum()) == ng
+    if eng is not src_eng:
+        eng.close()
     return {"value": world * ng / sec, "unit": "gene-sets/s",
             "h2d_bytes_per_step": int(world * ng * M * hn.shape[1] * hn.itemsize), "d2h_bytes_per_step": int(world * ng * rvtests_b200.engine.RESULT_DTYPE.itemsize),
             "genes_per_step_per_gpu": ng,
             "host_format": {"bed": "PLINK .bed 2-bit SNP-major rows, pinned host memory (rvt_gene_push_bed)",
                             "bed_missing": "PLINK .bed 2-bit rows with 1 % of the calls missing (mean-imputed on the device: augmented "
                                            "tensor-core sweep), pinned host memory (rvt_gene_push_bed)",
+                            "bed_binary": "PLINK .bed 2-bit rows, BINARY trait (logistic null; every gene takes the p(1-p)-weighted fp64 "
+                                          "statistics, enqueued behind the copies), pinned host memory (rvt_gene_push_bed)",
                             "i8": "int8 variant-major hard calls, pinned host memory (rvt_gene_push_i8)",
                             "f64": "N x M column-major doubles = dc->getGenotype(), the ModelFitter::fit boundary itself, "
                                    "pinned host memory (rvt_gene_push_f64)"}[fmt],
