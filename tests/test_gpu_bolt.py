@@ -193,3 +193,38 @@ def test_bolt_snp_sharded_two_ranks_equals_unsharded():
         assert rel(o0[k], full[k]) <= 1e-9 and o0[k] == o1[k], (k, o0[k], o1[k], full[k])
     assert np.max(np.abs(np.array(o0["log_delta"]) - np.array(full["log_delta"]))) <= 1e-9
     assert o0["h_err"] <= 1e-9 and h0 == h1
+
+
+def test_bolt_odd_stride_tail_bits_and_device_resident_panel(engine_cls, oracle):
+    """N = 810: two samples in the last byte of a row (the padding bits stay out of every count), a row stride of 203 bytes.
+    The engine's own copy of a host panel gets a 16-byte pitch (cp.async kernels); a panel that already lives in device memory
+    is used in place, and with this stride that means the fall-back to the second-generation kernels -- same fit either way,
+    and the fit of the restatement."""
+    import torch
+    from oracle import bolt_oracle as BO
+    seed, N, M, C, h2 = 131, 810, 257, 2, 0.35
+    G = _panel(seed, N, M, miss=0.03)
+    rng = np.random.default_rng(seed + 1)
+    covar = np.column_stack([np.ones(N), rng.normal(size=N)])
+    X, Z, _ = BO.prepare(G, covar, np.zeros(N))
+    y = X @ rng.normal(size=M) * np.sqrt(h2 / M) + rng.normal(size=N) * np.sqrt(1 - h2)
+    X, Z, yc = BO.prepare(G, covar, y)
+    ref = BO.Fit(X, Z, yc).fit().calibrate()
+    bed = _pack(G)
+    assert bed.shape[1] == 203
+    eng = engine_cls(0)
+    try:
+        rec, h, _ = eng.bolt_fit_null(bed, N, y, covar)
+        dev = torch.from_numpy(bed).cuda()
+        rec_d, h_d, _ = eng.bolt_fit_null(None, N, y, covar, bed_dev=(dev.data_ptr(), M, dev.stride(0)))
+        eng.set_option("bolt_kernels", 1)
+        rec_1, h_1, _ = eng.bolt_fit_null(bed, N, y, covar)
+    finally:
+        eng.close()
+    for r_, h_ in ((rec, h), (rec_d, h_d), (rec_1, h_1)):
+        assert int(r_["reml_evals"]) == len(ref.f) and int(r_["cg_iterations"]) == sum(ref.cg_iters)
+        assert np.max(np.abs(r_["log_delta"][:len(ref.log_delta)] - np.array(ref.log_delta))) <= 1e-6
+        for k, v in (("delta", ref.delta), ("sigma2_g", ref.sigma2_g), ("h_inv_y_norm2", ref.h_norm2),
+                     ("inf_stat_calibration", ref.calibration), ("xvx_xx_ratio", ref.xvx_xx_ratio)):
+            assert rel(r_[k], v) <= 1e-6, (k, r_[k], v)
+        assert np.max(np.abs(h_[:N] - ref.h)) <= 1e-7 * np.max(np.abs(ref.h))
