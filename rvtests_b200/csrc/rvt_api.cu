@@ -2783,7 +2783,7 @@ int rvt_bolt_fit_null_sharded(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64
   if (B.err != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "bolt: cudaMalloc: %s", cudaGetErrorString(B.err));
   cudaStream_t st = B.st;
   if (!bed_on_device) {
-    if (pitch != stride) RVT_CUDA_OK(cudaMemsetAsync(B.bed, 0, (size_t)M * pitch, st));
+    if (pitch != (N + 3) / 4) RVT_CUDA_OK(cudaMemsetAsync(B.bed, 0, (size_t)M * pitch, st));   // the bytes between a row's end and its pitch are read as words
     RVT_CUDA_OK(cudaMemcpy2DAsync(B.bed, (size_t)pitch, bed, (size_t)stride, (size_t)((N + 3) / 4), (size_t)M, cudaMemcpyHostToDevice, st));
   }
   {   // Z row-major [N][Ck] on the device
