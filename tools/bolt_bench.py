@@ -168,6 +168,44 @@ def run_bolt(args, ClockSampler, bind_numa):
         e2e = {"value": work / 2.0 / (float(tm.item()) * 1e-3), "unit": "multiply-adds/s", "h2d_bytes_per_step": int(hb.nbytes + 8 * N * (C + 1)),
                "d2h_bytes_per_step": int(8 * (N + C) + rec.nbytes), "wall_ms": (time.perf_counter() - t) * 1e3,
                "what": "rvt_bolt_fit_null(_sharded) with the 2-bit panel in pinned host memory; H^-1 y and the record back to the host"}
+    # ---- the other half of BASELINE configs[4]: the score test of the variants of this rank's shard on the fitted null
+    # (BoltLMM::TestCovariate, regression/BoltLMM.cpp:315-338 = rvt_set_null_residual + rvt_meta_flush, score columns only)
+    score = None
+    if not getattr(args, "no_score", False):
+        from rvtests_b200.synth import variant_params
+        nv = args.meta_variants
+        hN = h[:N]
+        r_b = hN - Z @ (Z.T @ hN)
+        kappa = float(rec["h_inv_y_norm2"] * rec["inf_stat_calibration"] / N)
+        eng.set_null_residual(covar, r_b, kappa)
+        keys, t0v, t1v = variant_params(SEED, rank * nv, nv)
+        eng.synth_load(keys, t0v, t1v, nv // 64, 64)
+        for _ in range(2):
+            eng.push_loaded()
+            vout, _b, _w = eng.meta_flush(nv, want_cov=False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        reps = 5
+        e0.record(stream)
+        for _ in range(reps):
+            eng.push_loaded()
+            vout, _b, _w = eng.meta_flush(nv, want_cov=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ts = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ms_s = float(ts.item()) / reps
+        score = {"value": world * nv / (ms_s * 1e-3), "unit": "variants/s", "variants_per_gpu_per_step": nv, "ms_per_step": ms_s,
+                 "what": "BoltLMM::TestCovariate on resident 64-variant tiles of N samples: rvt_set_null_residual(H^-1 y projected, kappa) "
+                         "+ rvt_meta_flush (score columns, exact HWE, records to the host); 500 000 variants = "
+                         f"{500000 / max(world * nv / (ms_s * 1e-3), 1e-9):.2f} s on {world} GPU(s)",
+                 "ok": int((vout["ok"] == 1).sum()), "median_p": float(np.median(vout["pvalue"])),
+                 "note": "the test variants are independent of phenotype and panel; infStatCalibration is estimated on IN-PANEL SNPs "
+                         "(the reference's rule, BoltLMM.cpp:1141-1186) and falls far below 1 when the panel is small against N "
+                         f"(here M/N = {M / N:.3f}, calibration {float(rec['inf_stat_calibration']):.3f}), which inflates the statistics of "
+                         "out-of-panel variants: a property of this synthetic shape under the reference's algorithm, not of the kernels"}
     if rank != 0:
         return
     peaks = {}
@@ -202,6 +240,7 @@ def run_bolt(args, ClockSampler, bind_numa):
                              "frac": bytes_alg / (ms_x * 1e-3) / 1e9 / hbm, "algorithmic_bytes_per_step": bytes_alg},
                      "traffic": None, "share_of_step": ms_x / ms},
         "e2e": e2e,
+        "score_test": score,
     }
     print(json.dumps(line))
 
