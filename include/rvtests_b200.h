@@ -85,7 +85,7 @@ typedef struct rvt_gene_result {
  * reference's serial gene loop consumes it (src/LinearAlgebra.h:8-21, no srand anywhere), starting at
  * "perm_stream_pos" draws (0 in a fresh process) and advancing by ActualPerm * (N-1) per gene.  Quantitative and binary
  * traits alike (src/Model.h:2673-2717), genes with missing calls (2-bit pushes, mean-imputed) included.  NOT covered: a gene
- * with dosages pushed as doubles, a gene with missing calls of a binary-trait run or of 63-64 variants (done = 0, NA columns);
+ * with dosages pushed as doubles, a gene with missing calls of a binary-trait run, of 63-64 or of more than 64 variants (done = 0, NA columns);
  * the reference would have shuffled for it, so from such a gene on the stream position -- hence NumGreater / NumEqual of the
  * LATER genes -- no longer replays the reference's: those records carry stream_ok = 0.  rvt_perm_result.stream_pos tells where
  * each gene started. */

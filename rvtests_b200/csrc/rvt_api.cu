@@ -49,6 +49,7 @@ struct WideGene {    // a pushed gene of more than kMaxM variants: T tiles of co
   int M;
   int64_t var0;
   bool has_af;
+  bool imputed = false;   // pushed as 2-bit rows and holds missing calls: mean-imputed through the rows [H ; Mi] (run_wide)
   std::vector<GeneDesc> tiles;
 };
 struct TilePlan {    // where the tiles of one pushed gene were staged
@@ -1129,14 +1130,20 @@ static int resolve_bed_missing(rvt_ctx* ctx) {
     }
     if (!missing) continue;
     if (ctx->slots[gi] > kMaxM) {
-      // mean imputation (fp64 path) handles up to kMaxM variants: this ONE gene is reported RVT_GENE_UNSUPPORTED in its
-      // record; the rest of the batch is computed (a failed batch would print NA for every later gene of the run)
-      ctx->unsupported.push_back(gi);
+      // a wide gene with missing calls: the tensor-core pair sweep on the rows [H ; Mi] of every tile (run_wide, wide.cuh).
+      // Without the tensor-core engine (or for a binary trait, refused at push) this ONE gene is reported
+      // RVT_GENE_UNSUPPORTED in its record; the rest of the batch is computed
+      const bool can = ctx->tc.encode && ctx->tc.have_e && !ctx->binary;
       for (size_t w = 0; w < ctx->wide.size(); ++w)
         if (ctx->wide[w].gene_index == gi) {
-          ctx->wide.erase(ctx->wide.begin() + (long)w);
+          if (can) {
+            ctx->wide[w].imputed = true;
+          } else {
+            ctx->wide.erase(ctx->wide.begin() + (long)w);
+          }
           break;
         }
+      if (!can) ctx->unsupported.push_back(gi);
       continue;
     }
     DosGene dg;   // stays in its int8 tiles: imputed on the fly by the tile statistics kernels (dosage.cuh)
@@ -1390,20 +1397,59 @@ static int run_wide(rvt_ctx* ctx, rvt_gene_result* d_res, int* launches) {
   const int batch = 1024;
   for (int wi = 0; wi < nw; ++wi) {
     const WideGene& w = ctx->wide[wi];
-    const int T = (int)w.tiles.size();
-    std::vector<GeneDesc> units(w.tiles);
+    const int T0 = (int)w.tiles.size();
+    // Missing calls (mean-imputed, G = H + Mi diag(delta)): every tile is split into its operand tiles H (hard calls, the
+    // fill 0 / 2 at missing entries) and Mi (0/1 indicators) in an auxiliary segment, and the gene is swept as the 2M rows
+    // [H_1 .. H_T ; Mi_1 .. Mi_T]: the same diagonal + pair units, exact integers; k_wide_finalize combines them.
+    std::vector<GeneDesc> tiles(w.tiles);
+    int8_t* d_hm = nullptr;
+    if (w.imputed) {
+      std::vector<int64_t> off(2 * T0 + 1, 0);
+      for (int t = 0; t < 2 * T0; ++t) off[t + 1] = off[t] + tiled_bytes(N, w.tiles[t % T0].M);
+      cudaError_t ea = cudaMalloc((void**)&d_hm, (size_t)off[2 * T0]);
+      if (ea != cudaSuccess) {
+        cleanup();
+        CTX_FAIL(RVT_E_CUDA, "wide gene with missing calls (M=%d): cudaMalloc of the operand tiles (%lld bytes): %s", w.M, (long long)off[2 * T0],
+                 cudaGetErrorString(ea));
+      }
+      to_free.push_back(d_hm);
+      k_wide_imp_flags<<<(unsigned)((w.M + 255) / 256), 256, 0, st>>>(w.var0, w.M, N, ctx->d_counts, ctx->d_flags);
+      const int64_t nwords = ((N + 127) >> 7) * 32;
+      tiles.resize(2 * T0);
+      for (int t = 0; t < T0; ++t) {
+        const GeneDesc& src = w.tiles[t];
+        k_split_hm<<<dim3((unsigned)((nwords + 255) / 256), (unsigned)src.M), 256, 0, st>>>(src.g, src.M, N, ctx->d_flags + src.var0, d_hm + off[t],
+                                                                                         d_hm + off[T0 + t]);
+        GeneDesc h = src, m = src;
+        h.g = d_hm + off[t];
+        h.seg = kSegAux;
+        h.row0 = h.row0_b = off[t] / 128;
+        m.g = d_hm + off[T0 + t];
+        m.seg = kSegAux;
+        m.row0 = m.row0_b = off[T0 + t] / 128;
+        m.var0 = m.var0_b = src.var0 + w.M;        // rows M .. 2M-1 of the doubled gene
+        tiles[t] = h;
+        tiles[T0 + t] = m;
+      }
+      if ((rc = tc_bind_segment(&ctx->tc, kSegAux, d_hm, (size_t)off[2 * T0], ctx->err, sizeof(ctx->err)))) { cleanup(); return rc; }
+      if ((rc = ensure(ctx, (void**)&ctx->d_zero_flags, &ctx->cap_zero_flags, (size_t)ctx->n_var + 2 * (size_t)w.M + kTileRows, 1))) { cleanup(); return rc; }
+      RVT_CUDA_OK(cudaMemsetAsync(ctx->d_zero_flags, 0, (size_t)ctx->n_var + 2 * (size_t)w.M + kTileRows, st));
+    }
+    const int T = (int)tiles.size();
+    const int Mw = w.imputed ? 2 * w.M : w.M;      // rows of the swept Gram
+    std::vector<GeneDesc> units(tiles);
     for (int t = 0; t < T; ++t)
       for (int u = t + 1; u < T; ++u) {
-        GeneDesc g = w.tiles[t];
-        g.row0_b = w.tiles[u].row0;
-        g.Mb = w.tiles[u].M;
-        g.var0_b = w.tiles[u].var0;
+        GeneDesc g = tiles[t];
+        g.row0_b = tiles[u].row0;
+        g.Mb = tiles[u].M;
+        g.var0_b = tiles[u].var0;
         units.push_back(g);
       }
     const int n_units = (int)units.size();
     uint8_t* ws = nullptr;
     GeneDesc* d_units = nullptr;
-    cudaError_t e = cudaMalloc((void**)&ws, wide_ws_bytes(w.M));
+    cudaError_t e = cudaMalloc((void**)&ws, wide_ws_bytes(Mw));
     if (e == cudaSuccess) to_free.push_back(ws);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_units, sizeof(GeneDesc) * n_units);
     if (e != cudaSuccess) {
@@ -1411,7 +1457,9 @@ static int run_wide(rvt_ctx* ctx, rvt_gene_result* d_res, int* launches) {
       CTX_FAIL(RVT_E_CUDA, "wide gene (M=%d): cudaMalloc: %s", w.M, cudaGetErrorString(e));
     }
     to_free.push_back(d_units);
-    WideJob jb = wide_job_make(ws, w.M);
+    WideJob jb = wide_job_make(ws, Mw);
+    jb.M = w.M;
+    jb.imp = w.imputed ? 1 : 0;
     jb.out_index = w.gene_index;
     jb.var0 = w.var0;
     jb.has_af = w.has_af ? 1 : 0;
@@ -1430,13 +1478,13 @@ static int run_wide(rvt_ctx* ctx, rvt_gene_result* d_res, int* launches) {
         rc = tc_launch(&ctx->tc, d_units + b0, units.data() + b0, nb, ctx->d_zero_flags, ctx->d_nm, N, ctx->ER, S, chunk, ctx->d_parts,
                        ctx->d_counter, ctx->sm_count, st, ctx->err, sizeof(ctx->err), pass == 1, false);
         if (rc) { cleanup(); return rc; }
-        k_wide_gather<<<nb, kWideGatherThreads, 0, st>>>(d_units + b0, nb, w.var0, w.M, ctx->ER, S, ctx->d_parts, jb.A_raw, jb.De, pass);
+        k_wide_gather<<<nb, kWideGatherThreads, 0, st>>>(d_units + b0, nb, w.var0, Mw, ctx->ER, S, ctx->d_parts, jb.A_raw, jb.De, pass);
         *launches += 2;
       }
     }
     const int64_t nchunks = (N + 127) / 128;
     k_wide_collapse<<<(unsigned)std::min<int64_t>(nchunks, (int64_t)ctx->sm_count * 8), kWideCollapseThreads, 0, st>>>(
-        d_units, T, w.var0, w.M, ctx->d_flags, ctx->d_nm, jb.coll);
+        d_units, T0, w.var0, w.M, ctx->d_flags, ctx->d_nm, jb.coll);   // (imputed: the H tiles -- an imputed value never counts, the fill sees to it)
     *launches += 1;
     RVT_CUDA_OK(cudaGetLastError());
     // `units` is a host temporary of this iteration: the copy above must have left it
@@ -1709,6 +1757,8 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   int launches = 0;
   ctx->is_dos.assign(n, 0);
   for (auto& dg : ctx->dos) ctx->is_dos[dg.gene_index] = 1;
+  for (auto& w : ctx->wide)
+    if (w.imputed) ctx->is_dos[w.gene_index] = 1;   // (computed by run_wide; the permutation test does not cover it)
   if (ctx->binary) {
     // binary trait: the Gram is weighted by the per-sample variance p(1-p), which the integer sweep does not carry:
     // every gene takes the fp64 path (its hard-call tiles are expanded on the device)

@@ -27,6 +27,9 @@ struct WideJob {
   int out_index;       // slot of the gene in the result array
   int64_t var0;        // first slot of the gene in the per-variant side arrays (flags, af, counts)
   int has_af, counted;
+  int imp, pad;        // imp = 1: a gene with MISSING calls (mean-imputed, G = H + Mi diag(delta)): A_raw is the (2M x 2M) Gram of the rows
+                       // [H ; Mi] (H = hard calls with the fill 0 / 2 at missing entries, Mi = 0/1 indicators), De their (2M x ER)
+                       // digit sums; the workspace is the one of a 2M-variant gene
   long long* A_raw;    // [M][M] raw G'G (both triangles)
   long long* De;       // [M][ER] gene x digit sums
   long long* coll;     // [kCollapseN] burden sums, SweepPartial::coll layout
@@ -150,6 +153,25 @@ k_wide_collapse(const GeneDesc* __restrict__ tiles, int T, int64_t var_base, int
   if (tid < 2 * (ER + 1)) atomicAdd(reinterpret_cast<unsigned long long*>(coll) + tid, s_red[tid]);
 }
 
+// Flags of a wide gene with missing calls from its counts, with the imputation folded in -- the decisions k_tile_cols +
+// k_aug_flags take for a single tile (DataConsolidator.cpp:46-142 on the mean-imputed matrix): the column sum above N flips,
+// all values equal drops.  They steer k_split_hm (fill 0 / 2), the collapse and the tail alike.
+__global__ void k_wide_imp_flags(int64_t var0, int M, int64_t N, const RowCounts* __restrict__ counts, uint8_t* __restrict__ rowflags) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const RowCounts rc = counts[var0 + j];
+  const long long n1 = rc.n1, n2 = rc.n2, miss = rc.bad, n0 = N - n1 - n2 - miss, nobs = N - miss;
+  const double ac = (double)(n1 + 2 * n2);
+  const double fill = nobs > 0 ? 2.0 * (ac / (double)(2 * nobs)) : 0.0;
+  double mn = 1e300, mx = -1e300;
+  if (n0 > 0) { mn = fmin(mn, 0.0); mx = fmax(mx, 0.0); }
+  if (n1 > 0) { mn = fmin(mn, 1.0); mx = fmax(mx, 1.0); }
+  if (n2 > 0) { mn = fmin(mn, 2.0); mx = fmax(mx, 2.0); }
+  if (miss > 0) { mn = fmin(mn, fill); mx = fmax(mx, fill); }
+  const double csum = ac + (double)miss * fill;
+  rowflags[var0 + j] = (mn == mx) ? kRowSkip : ((csum > (double)N) ? kRowFlipped : kRowNormal);
+}
+
 // One CTA per wide gene: steps 2-7 of k_finalize on the global-memory workspace.
 template <bool SKATO>
 __global__ void __launch_bounds__(kWideThreads)
@@ -193,10 +215,38 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
   const long long* __restrict__ De = jb.De;
   double* K = jb.K;
   const int kld = M;
+  const bool imp = jb.imp != 0;
+  const int lda = imp ? 2 * M : M;          // leading dimension of A_raw
+  double* s_delta = s_lamz + (M + 2);       // imp: delta_j = fill_j - (flipped ? 2 : 0); the workspace of a 2M gene has the room
+  double* s_csum = s_delta + M;             // imp: column sums of the imputed matrix
 
   if (tid == 0) s_bad = 0;
   __syncthreads();
   // 2. per-variant counts -> flip / monomorphic, cross-checked with the flags the collapse used
+  if (imp) {
+    for (int j = tid; j < M; j += NT) {
+      const RowCounts rc = counts[jb.var0 + j];
+      const long long n1 = rc.n1, n2 = rc.n2, miss = rc.bad, n0 = N - n1 - n2 - miss, nobs = N - miss;
+      const double ac = (double)(n1 + 2 * n2);
+      const double fill = nobs > 0 ? 2.0 * (ac / (double)(2 * nobs)) : 0.0;   // imputeGenotypeToMean: 2 p^ (as k_tile_cols)
+      double mn = 1e300, mx = -1e300;
+      if (n0 > 0) { mn = fmin(mn, 0.0); mx = fmax(mx, 0.0); }
+      if (n1 > 0) { mn = fmin(mn, 1.0); mx = fmax(mx, 1.0); }
+      if (n2 > 0) { mn = fmin(mn, 2.0); mx = fmax(mx, 2.0); }
+      if (miss > 0) { mn = fmin(mn, fill); mx = fmax(mx, fill); }
+      const double csum = ac + (double)miss * fill;
+      const int mono = mn == mx, flip = csum > (double)N;
+      const uint8_t expect = mono ? kRowSkip : (flip ? kRowFlipped : kRowNormal);
+      if (rowflags[jb.var0 + j] != expect) atomicExch(&s_bad, 1);
+      // the integer sums must be those of the rows [H ; Mi]: H'H_jj = n1 + 4 n2 (+ 4 miss in a flipped row), Mi'Mi_jj = miss
+      const long long hjj = jb.A_raw[(size_t)j * lda + j], mjj = jb.A_raw[(size_t)(M + j) * lda + (M + j)];
+      if (mjj != miss || hjj != n1 + 4 * n2 + (flip && !mono ? 4 * miss : 0)) atomicExch(&s_bad, 2);
+      s_craw[j] = 0;
+      s_csum[j] = csum;
+      s_delta[j] = fill - (flip && !mono ? 2.0 : 0.0);
+      s_flip[j] = mono ? -1 : flip;
+    }
+  } else
   for (int j = tid; j < M; j += NT) {
     const long long cint = recombine4(&De[(size_t)j * ER + 4]);
     const long long c = llrint((double)cint * nm->scale[1]);
@@ -224,6 +274,19 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
   for (int t = tid; t < Mp; t += NT) {
     const int j = s_idx[t];
     const int fl = s_flip[j];
+    if (imp) {
+      // G'v = H'v + delta (Mi'v) for v = r, X_l; a flipped column is 2 - g
+      const double dj = s_delta[j];
+      double sv = ((double)recombine4(&De[(size_t)j * ER]) + dj * (double)recombine4(&De[(size_t)(M + j) * ER])) * nm->scale[0];
+      if (fl) sv = 2.0 * (double)nm->vsum[0] * nm->scale[0] - sv;
+      s_s[t] = sv;
+      for (int l = 0; l < C; ++l) {
+        double b = ((double)recombine4(&De[(size_t)j * ER + 4 * (l + 1)]) + dj * (double)recombine4(&De[(size_t)(M + j) * ER + 4 * (l + 1)])) *
+                   nm->scale[l + 1];
+        if (fl) b = 2.0 * (double)nm->vsum[l + 1] * nm->scale[l + 1] - b;
+        s_B[t * kMaxC + l] = b;
+      }
+    } else {
     long long sint = recombine4(&De[(size_t)j * ER]);
     if (fl) sint = 2 * nm->vsum[0] - sint;
     s_s[t] = (double)sint * nm->scale[0];
@@ -232,8 +295,9 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
       if (fl) b = 2 * nm->vsum[l + 1] - b;
       s_B[t * kMaxC + l] = (double)b * nm->scale[l + 1];
     }
+    }
     // weight t of the kept columns uses af[t] in the caller's ORIGINAL order
-    const double freq = jb.has_af ? af[jb.var0 + t] : (double)s_craw[j] / (2.0 * (double)N);
+    const double freq = jb.has_af ? af[jb.var0 + t] : (imp ? s_csum[j] : (double)s_craw[j]) / (2.0 * (double)N);
     s_sw[t] = sqrt(beta_weight(freq, prm.beta1, prm.beta2, true));
   }
   __syncthreads();
@@ -255,6 +319,22 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
     if (k < i) continue;
     const int ji = s_idx[i], jk = s_idx[k];
     const int fi = s_flip[ji], fk = s_flip[jk];
+    double ad;
+    if (imp) {
+      // G'G = H'H + H'Mi D + D Mi'H + D Mi'Mi D   (D = diag delta), then the same flip identities on the imputed column sums
+      const double di = s_delta[ji], dk = s_delta[jk];
+      ad = (double)jb.A_raw[(size_t)ji * lda + jk] + dk * (double)jb.A_raw[(size_t)ji * lda + (M + jk)] +
+           di * (double)jb.A_raw[(size_t)(M + ji) * lda + jk] + di * dk * (double)jb.A_raw[(size_t)(M + ji) * lda + (M + jk)];
+      // (H carries the fill 2 of a flipped row, i.e. ad is the Gram of the UNflipped imputed columns only for normal rows:
+      //  for a flipped row H + Mi delta = g with g_missing = 2 + (fill - 2) = fill as well -- both cases are the raw imputed g)
+      const double ci = s_csum[ji], ck = s_csum[jk];
+      if (fi && fk)
+        ad = 4.0 * (double)N - 2.0 * ci - 2.0 * ck + ad;
+      else if (fi)
+        ad = 2.0 * ck - ad;
+      else if (fk)
+        ad = 2.0 * ci - ad;
+    } else {
     long long a = jb.A_raw[(size_t)ji * M + jk];
     const long long ci = s_craw[ji], ck = s_craw[jk];
     if (fi && fk)
@@ -263,9 +343,11 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
       a = 2 * ck - a;
     else if (fk)
       a = 2 * ci - a;
+    ad = (double)a;
+    }
     double tt = 0.0;
     for (int l = 0; l < C; ++l) tt += s_B[i * kMaxC + l] * Uk[k * kMaxC + l];
-    const double v = s_sw[i] * s_sw[k] * sigma2 * ((double)a - tt);
+    const double v = s_sw[i] * s_sw[k] * sigma2 * (ad - tt);
     K[(size_t)i * kld + k] = v;
     K[(size_t)k * kld + i] = v;
   }

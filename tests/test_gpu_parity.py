@@ -377,3 +377,55 @@ def test_too_wide_gene_is_refused(eng, oracle):
     eng.set_null_model(X, y)
     with pytest.raises(rvtests_b200.RvtError):
         eng.push_i8(np.zeros((2049, 64), dtype=np.int8))
+
+
+@pytest.mark.parametrize("case", [(161, 3000, 100, 3, 0.01, 2, 1), (162, 2500, 200, 2, 0.02, 3, 2), (163, 700, 65, 1, 0.05, 1, 0)])
+def test_wide_genes_with_missing_calls_vs_oracle(eng, oracle, case):
+    """A gene of more than 64 variants WITH missing calls (PLINK code 01): the reference imputes to the mean
+    (DataConsolidator::imputeGenotypeToMean, src/DataConsolidator.cpp:217-245) whatever the width.  Here every tile is split
+    into H (hard calls + fill) and Mi (indicators), the gene is swept as the 2M rows [H ; Mi] (diagonal + pair units, exact
+    integers) and the tail combines G = H + Mi diag(delta).  Flipped and monomorphic columns with missing calls, SKAT + burden
+    + SKAT-O, an ordinary gene and a complete wide gene in the same flush."""
+    from rvtests_b200.synth import pack_bed
+    from oracle import skato_oracle as SO
+    if eng.info("tc_available") != 1:
+        pytest.skip("wide genes need the tensor-core sweep")
+    O = oracle
+    seed, N, M, C, miss, n_flip, n_mono = case
+    G, X, y = make_problem(O, seed, N, M, C, maf=np.linspace(0.002, 0.03, M), n_mono=n_mono, n_flip=n_flip)
+    Gs, _, _ = make_problem(O, seed + 100, N, 20, C, maf=np.linspace(0.01, 0.1, 20))
+    rng = np.random.default_rng(seed)
+    mask = rng.random((M, N)) < miss
+    mask[5] = False                                              # a fully called variant among them
+    mask[M - 1, : N // 3] = True                                 # a third of the last variant missing
+    bed = pack_bed(G.T, mask)
+    raw = O.bed_decode_fast(bed, N).T
+    Gd = O.impute_mean(raw)
+    af = 0.5 * np.where(raw >= 0, raw, 0.0).sum(axis=0) / N      # GenotypeCounter::getAF over nSample (SURVEY F9)
+    eng.set_option("engine", 0)
+    eng.set_option("skato", 1)
+    try:
+        eng.set_null_model(X, y)
+        nm = O.fit_null_linear(X, y)
+        eng.push_i8(Gs.T.copy(), af_of(Gs))
+        eng.push_bed(bed, af)
+        eng.push_bed(pack_bed(G.T), af_of(G))                    # the same gene fully called
+        eng.push_bed(bed, None)                                  # frequencies left to the engine
+        res = eng.flush()
+    finally:
+        eng.set_option("skato", 0)
+    assert len(res) == 4 and [int(r["status"]) for r in res] == [0, 0, 0, 0]
+    ref, lam = O.gene(Gd, af, X, nm["resid"], nm["sigma2"])
+    check_gene(res[1], ref, lam, ctx=f"wide+missing {case}")
+    ref_c, lam_c = _oracle_gene(O, G, X, nm)
+    check_gene(res[2], ref_c, lam_c, ctx=f"wide complete beside it {case}")
+    refs, lams = _oracle_gene(O, Gs, X, nm)
+    check_gene(res[0], refs, lams, ctx=f"ordinary gene beside it {case}")
+    so = SO.skato_gene(Gd, af, X, nm["resid"])
+    assert int(res[1]["skato_ok"]) == int(so["ok"]) == 1
+    assert rel(res[1]["skato_Q"], so["Q"]) <= 1e-6 and res[1]["skato_rho"] == so["rho"]
+    assert rel(res[1]["skato_p"], so["pvalue"]) <= 1e-5
+    # no frequencies supplied: the weights come from the imputed column sums
+    af_imp = Gd.sum(axis=0) / (2.0 * N)
+    ref_n, lam_n = O.gene(Gd, af_imp, X, nm["resid"], nm["sigma2"])
+    check_gene(res[3], ref_n, lam_n, ctx=f"wide+missing, engine frequencies {case}")
