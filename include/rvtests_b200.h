@@ -40,8 +40,8 @@ extern "C" {
 #define RVT_GENE_NA 2           /* no polymorphic variant: fit() == -1, output "NA" (src/Model.h:2637-2640) */
 #define RVT_GENE_BADFLAGS 4     /* caller-supplied flip/skip flags contradict the data */
 #define RVT_GENE_BADVALUE 5     /* a genotype outside {0,1,2} reached the hard-call path */
-#define RVT_GENE_UNSUPPORTED 7  /* this gene is outside what the engine computes (more than 64 variants AND missing calls);
-                                   the other genes of the flush are unaffected */
+#define RVT_GENE_UNSUPPORTED 7  /* this gene is outside what the engine computes (more than 64 variants AND missing calls when the
+                                   tensor-core engine is unavailable); the other genes of the flush are unaffected */
 #define RVT_GENE_TIMEOUT 6      /* device watchdog: the SKAT-O quadrature of this gene exceeded its cycle budget
                                    (option "watchdog_ms", default 4000); skato_ok = 0, the other columns are valid */
 
@@ -186,7 +186,9 @@ int rvt_get_null_beta(rvt_ctx* ctx, double* beta);
  * Width: the host entry points (f64, i8, bed) take genes of 1..2048 variants -- the reference has no limit
  *   (Skat::Fit / MixtureChiSquare size themselves to the gene); a gene of more than 64 variants is cut into
  *   64-variant tiles and its Gram assembled from tile pairs (csrc/wide.cuh).  RVT_E_UNSUPPORTED beyond 2048,
- *   for rvt_gene_push_dev_i8 beyond 64, and for a gene of more than 64 variants that holds dosages or missing calls.
+ *   for rvt_gene_push_dev_i8 beyond 64, for a gene of more than 64 variants that holds dosages (pushed as doubles), and for such a
+ *   gene in a binary-trait run.  Missing calls of a wide gene pushed as 2-bit rows are mean-imputed like those of any gene
+ *   (src/DataConsolidator.cpp:217-245): its tiles are split into hard-call and indicator tiles and swept as 2M rows.
  * Each push appends one gene; results come back from rvt_flush in push order.  Host buffers are copied
  * asynchronously when they are page-locked: keep them valid and unchanged until rvt_flush returns. */
 int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af);
