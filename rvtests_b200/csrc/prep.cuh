@@ -109,13 +109,19 @@ k_count_rows(const int8_t* __restrict__ base, int64_t ld, int64_t N, RowCounts* 
 }
 
 // grid: (ceil(npad/4/256), M).  src: N x M column-major doubles; dst: tiled int8 block (zero padded).
+// Values outside {0,1,2} are stored as code 3 and their range per row is kept in frac[row] = {min, max} (bit patterns of
+// positive doubles order like the values; anything else -- negative, NaN -- sets max to all ones).  The Matrix that
+// ModelFitter::fit() sees has ALREADY been through DataConsolidator::imputeGenotypeToMean (src/DataConsolidator.cpp:217-245): a
+// column whose non-integer entries all equal 2 p^ of its observed calls is a hard-call column with missing calls, and the host
+// then treats the gene exactly like a 2-bit push with code 01 (augmented sweep / wide operand tiles) instead of as dosages.
 __global__ void __launch_bounds__(256)
 k_pack_f64(const double* __restrict__ src, int64_t N, int8_t* __restrict__ dst, int M,
-           RowCounts* __restrict__ counts) {
+           RowCounts* __restrict__ counts, unsigned long long* __restrict__ frac /* [rows][2] or null */) {
   const int64_t row = blockIdx.y;
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int64_t npad = (N + 127) & ~(int64_t)127;
   int n1 = 0, n2 = 0, bad = 0;
+  unsigned long long fmn = ~0ull, fmx = 0ull;
   if (i0 < npad) {
     uint32_t word = 0;
 #pragma unroll
@@ -127,7 +133,13 @@ k_pack_f64(const double* __restrict__ src, int64_t N, int8_t* __restrict__ dst, 
         if (v == 0.0) gq = 0;
         else if (v == 1.0) gq = 1;
         else if (v == 2.0) gq = 2;
-        else { gq = 0; bad += 1; }
+        else {
+          gq = 3;
+          bad += 1;
+          const unsigned long long b = (v > 0.0 && v < 1e300) ? (unsigned long long)__double_as_longlong(v) : ~0ull;
+          fmn = b < fmn ? b : fmn;
+          fmx = b > fmx ? b : fmx;
+        }
       }
       n1 += (gq == 1);
       n2 += (gq == 2);
@@ -139,6 +151,13 @@ k_pack_f64(const double* __restrict__ src, int64_t N, int8_t* __restrict__ dst, 
     n1 += __shfl_xor_sync(0xffffffffu, n1, o);
     n2 += __shfl_xor_sync(0xffffffffu, n2, o);
     bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    const unsigned long long a = __shfl_xor_sync(0xffffffffu, fmn, o), b = __shfl_xor_sync(0xffffffffu, fmx, o);
+    fmn = a < fmn ? a : fmn;
+    fmx = b > fmx ? b : fmx;
+  }
+  if (frac && (threadIdx.x & 31) == 0 && bad) {
+    atomicMin(&frac[2 * row], fmn);
+    atomicMax(&frac[2 * row + 1], fmx);
   }
   if ((threadIdx.x & 31) == 0 && (n1 | n2 | bad)) {
     atomicAdd(&counts[row].n1, n1);

@@ -186,6 +186,8 @@ struct rvt_ctx {
   long long wd_cycles = 8000000000ll;   // device watchdog of the per-gene tail, SM cycles (option "watchdog_ms"; ~4 s)
   bool skato = false;
   bool bin_stream = true;      // option "binary_stream": binary-trait tile genes are computed in launch_range (behind their copies), not at flush
+  bool f64_imputed = true;     // option "f64_imputed": rvt_gene_push_f64 recognises mean-imputed hard calls and routes them like a 2-bit push with missing calls
+  unsigned long long* d_frac = nullptr;   // per-row {min, max} of the non-integer values of the last rvt_gene_push_f64
   bool perm_stream_lost = false;   // a gene the reference would have permuted was skipped: later stream positions are not the reference's
   int bolt_kernels = 3;        // generation of the panel-product kernels of rvt_bolt_fit_null (bolt.cuh)
   bool skato_binary = true;    // SKAT-O for a binary trait (SkatO::Fit type "D"); on by default, see include/rvtests_b200.h
@@ -375,7 +377,7 @@ void rvt_ctx_destroy(rvt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->dX, ctx->dy, ctx->dresid, ctx->dnull_part, ctx->dbeta, ctx->dE, ctx->d_nm,
                   ctx->d_shift, ctx->d_status, ctx->d_genes, ctx->d_flags, ctx->d_userflags, ctx->d_af,
-                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_jobs, ctx->d_mid, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum, ctx->d_p, ctx->d_vw, ctx->d_dos_st, ctx->d_dos_tin, ctx->d_dos_idx, ctx->d_dos_afd, ctx->d_dos_tg, ctx->d_bs_st, ctx->d_bs_tin, ctx->d_bs_idx, ctx->d_bs_tg};
+                  ctx->d_counts, ctx->d_parts, ctx->d_res, ctx->d_counter, ctx->d_stage64, ctx->d_loaded, ctx->d_stage, ctx->d_dbg, ctx->d_qags, ctx->d_jobs, ctx->d_mid, ctx->d_zero_flags, ctx->d_lfg, ctx->d_perm, ctx->d_lmm, ctx->d_lmm_tiles, ctx->d_lmm_vec, ctx->d_lmm_tsum, ctx->d_p, ctx->d_vw, ctx->d_dos_st, ctx->d_dos_tin, ctx->d_dos_idx, ctx->d_dos_afd, ctx->d_dos_tg, ctx->d_bs_st, ctx->d_bs_tin, ctx->d_bs_idx, ctx->d_bs_tg, ctx->d_frac};
   tc_destroy(&ctx->tc);
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -447,6 +449,8 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
   } else if (k == "watchdog_ms") {
     if (value < 0 || value > 3.6e6) CTX_FAIL(RVT_E_BADARG, "watchdog_ms must be in 0..3600000 (0 = off)");
     ctx->wd_cycles = (long long)(value * 2.0e6);   // ~2 GHz SM clock
+  } else if (k == "f64_imputed") {
+    ctx->f64_imputed = value != 0;
   } else if (k == "binary_stream") {
     ctx->bin_stream = value != 0;
   } else if (k == "bolt_kernels") {
@@ -1015,10 +1019,16 @@ int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
   if ((rc = ensure_var(ctx, ctx->n_var + M))) return rc;
   RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_stage64, G, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   RVT_CUDA_OK(cudaMemsetAsync(ctx->d_counts + ctx->n_var, 0, sizeof(RowCounts) * M, ctx->stream));
+  if (!ctx->d_frac) RVT_CUDA_OK(cudaMalloc((void**)&ctx->d_frac, sizeof(unsigned long long) * 2 * kWideMaxM));
+  {
+    std::vector<unsigned long long> init(2 * (size_t)M);
+    for (int j = 0; j < M; ++j) { init[2 * j] = ~0ull; init[2 * j + 1] = 0ull; }
+    RVT_CUDA_OK(cudaMemcpyAsync(ctx->d_frac, init.data(), sizeof(unsigned long long) * 2 * M, cudaMemcpyHostToDevice, ctx->stream));   // (pageable: staged)
+  }
   for (int t = 0; t < tp.T; ++t) {
     dim3 grid((unsigned)((npad / 4 + 255) / 256), (unsigned)tp.rows[t]);
     k_pack_f64<<<grid, 256, 0, ctx->stream>>>(ctx->d_stage64 + (size_t)tp.r0[t] * N, N, ctx->d_stage + tp.off[t], tp.rows[t],
-                                              ctx->d_counts + ctx->n_var + tp.r0[t]);
+                                              ctx->d_counts + ctx->n_var + tp.r0[t], ctx->d_frac + 2 * (size_t)tp.r0[t]);
   }
   RVT_CUDA_OK(cudaGetLastError());
   // the staging buffer is reused by the next push: wait (pageable H2D is synchronous anyway);
@@ -1028,6 +1038,29 @@ int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
   RVT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   bool dosage = false;
   for (int j = 0; j < M; ++j) dosage |= rc_host[j].bad > 0;
+  if (dosage && ctx->f64_imputed) {
+    // Is every non-integer entry the mean-imputed value of its column?  Then this is a hard-call gene with missing calls --
+    // what DataConsolidator hands to fit() under the default --impute -- and it takes the integer paths of a 2-bit push with
+    // code 01 (the tiles hold code 3 there): augmented sweep, wide operand tiles, permutation test included.
+    std::vector<unsigned long long> fr(2 * (size_t)M);
+    RVT_CUDA_OK(cudaMemcpy(fr.data(), ctx->d_frac, sizeof(unsigned long long) * 2 * M, cudaMemcpyDeviceToHost));
+    bool pattern = true;
+    for (int j = 0; j < M && pattern; ++j) {
+      if (rc_host[j].bad == 0) continue;
+      const long long nobs = N - rc_host[j].bad;
+      const double ac = (double)((long long)rc_host[j].n1 + 2ll * rc_host[j].n2);
+      const double fill = nobs > 0 ? 2.0 * (ac / (double)(2 * nobs)) : 0.0;
+      double v;
+      memcpy(&v, &fr[2 * j], sizeof(v));
+      pattern = fr[2 * j] == fr[2 * j + 1] && fr[2 * j] != ~0ull && fabs(v - fill) <= 1e-12 * std::max(1.0, fill);
+    }
+    if (pattern) {
+      dosage = false;
+      ctx->bed_genes.push_back((int)ctx->genes.size());
+      ctx->is_bed.resize(ctx->genes.size() + 1, 0);
+      ctx->is_bed[ctx->genes.size()] = 1;
+    }
+  }
   if (dosage && M > kMaxM) {
     ctx->stage_used = stage_mark;   // nothing of this gene stays queued
     CTX_FAIL(RVT_E_UNSUPPORTED, "gene of %d variants holds dosages / imputed values: the fp64 path handles up to %d variants", M, kMaxM);

@@ -433,3 +433,50 @@ def test_wide_genes_with_missing_calls_vs_oracle(eng, oracle, case):
     af_q[: len(kept)] = af_imp[kept]
     ref_n, lam_n = O.gene(Gd, af_q, X, nm["resid"], nm["sigma2"])
     check_gene(res[3], ref_n, lam_n, ctx=f"wide+missing, engine frequencies {case}")
+
+
+def test_push_f64_of_a_mean_imputed_matrix_takes_the_integer_paths(eng, oracle):
+    """ModelFitter::fit() sees the genotype Matrix AFTER DataConsolidator::imputeGenotypeToMean (src/DataConsolidator.cpp:217-245):
+    hard calls plus, per column, ONE fractional value 2 p^ at the missing entries.  rvt_gene_push_f64 recognises that pattern and
+    routes the gene like a 2-bit push with code 01 -- augmented tensor-core sweep, wide operand tiles -- so the literal drop-in
+    gets the same records as the 2-bit form, bit for bit; anything else (a real dosage) keeps the fp64 path."""
+    import rvtests_b200
+    from rvtests_b200.synth import pack_bed
+    if eng.info("tc_available") != 1:
+        pytest.skip("needs the tensor-core sweep")
+    O = oracle
+    N, C = 2600, 3
+    X, y = O.synth_covariates(171, N, C)
+    eng.set_option("engine", 0)
+    eng.set_null_model(X, y)
+    nm = O.fit_null_linear(X, y)
+    rng = np.random.default_rng(171)
+    for M in (40, 100):
+        G, _, _ = make_problem(O, 172 + M, N, M, C, maf=np.linspace(0.003, 0.04, M), n_flip=2, n_mono=1)
+        mask = rng.random((M, N)) < 0.015
+        mask[3] = False
+        bed = pack_bed(G.T, mask)
+        raw = O.bed_decode_fast(bed, N).T
+        Gd = O.impute_mean(raw)
+        af = 0.5 * np.where(raw >= 0, raw, 0.0).sum(axis=0) / N
+        eng.push_f64(Gd, af)
+        eng.push_bed(bed, af)
+        r = eng.flush()
+        assert [int(v) for v in r["status"]] == [0, 0]
+        assert r[0].tobytes() == r[1].tobytes(), f"M={M}: Matrix form and 2-bit form differ"
+        if M <= 62:
+            assert int(eng.info("last_aug")) == 2                      # both rode the augmented sweep
+        ref, lam = O.gene(Gd, af, X, nm["resid"], nm["sigma2"])
+        check_gene(r[0], ref, lam, ctx=f"imputed Matrix M={M}")
+        # a real dosage in one entry: not the pattern -> the generic fp64 path (or refused beyond 64 variants)
+        Gx = Gd.copy()
+        Gx[7, 2] = 0.61
+        if M <= 62:
+            eng.push_f64(Gx, af)
+            rx = eng.flush()
+            assert int(eng.info("last_aug")) == 0
+            refx, lamx = O.gene(Gx, af, X, nm["resid"], nm["sigma2"])
+            check_gene(rx[0], refx, lamx, ctx=f"dosage Matrix M={M}")
+        else:
+            with pytest.raises(rvtests_b200.RvtError):
+                eng.push_f64(Gx, af)
