@@ -18,7 +18,8 @@ def _genes(O, seed, N, C):
     genes = []
     X = None
     for gi, (M, nm_, nf, miss) in enumerate([(8, 0, 1, 0.0), (30, 2, 2, 0.0), (1, 0, 0, 0.0), (50, 1, 3, 0.01), (12, 0, 0, 0.03),
-                                              (3, 3, 0, 0.0), (64, 0, 4, 0.0)]):
+                                              (3, 3, 0, 0.0), (64, 0, 4, 0.0),
+                                              (70, 0, 1, 0.0), (90, 1, 2, 0.01)]):       # wider than a tile; the last with missing calls
         G, X, y = make_problem(O, seed + gi, N, M, C, maf=np.linspace(0.004, 0.06, M), n_mono=nm_, n_flip=nf)
         G = G.astype(np.float64)
         if miss > 0:
