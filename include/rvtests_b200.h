@@ -180,6 +180,10 @@ int rvt_get_null_beta(rvt_ctx* ctx, double* beta);
  *   on the host, imputed, NOT yet flipped (the engine performs convertToMinorAlleleCount +
  *   removeMonomorphicMarker itself).  af: M allele frequencies in the caller's column order
  *   (GenotypeCounter::getAF) or NULL (then AF = column mean / 2 of the kept columns).
+ *   Mean-imputed missing calls (DataConsolidator::imputeGenotypeToMean, src/DataConsolidator.cpp:217-245: hard calls plus, per
+ *   column, ONE fractional value 2 p^ of its observed calls) are recognised on the device and such a gene is computed exactly like
+ *   a 2-bit push with code 01 -- augmented tensor-core sweep, wide operand tiles, permutation test -- with records equal to that
+ *   form bit for bit (option "f64_imputed", default 1); any other non-integer value makes it a dosage gene (fp64 path, <= 64 variants).
  * rvt_gene_push_i8: same, hard calls as int8 [M][ld] variant-major on the host.
  * rvt_gene_push_dev_i8: block already in device memory (zero-copy; must stay valid until flush).
  *   flags: NULL (engine counts the rows itself) or M bytes 0 normal / 1 flip-to-minor / 2 skip.
