@@ -93,3 +93,64 @@ def test_dense_genotypes_take_the_rescan_path(engine_cls, oracle):
     assert rel(r["zeg_V"], ref["zeg"]["V"]) <= 1e-6 and rel(r["zeg_p"], ref["zeg"]["p"]) <= 1e-4
     assert int(r["cmc_nonref"]) == ref["cmc"]["nonref"]
     eng.close()
+
+
+def test_binary_streaming_is_invisible_in_the_results(engine_cls, oracle):
+    """options binary_stream / stream_batch: with a binary null model the fp64 statistics and the tail of the tile genes are
+    enqueued behind their copies (batches of <= 8, a stream of their own) instead of at flush.  Same records in the same order
+    -- a gene with missing calls (imputed on the fly), a mean-imputed Matrix push, a dosage gene (which keeps the flush path) and
+    SKAT-O included -- whether streamed, streamed in small batches or all at flush.  (fp64 shared-memory atomics make the last
+    bits of the sums schedule-dependent: 1e-10, not bitwise.)"""
+    from oracle import binary_oracle as BIN
+    from rvtests_b200.synth import pack_bed
+    O = oracle
+    N, C = 6001, 3
+    rng = np.random.default_rng(191)
+    X, _ = O.synth_covariates(191, N, C)
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(0.7 - 0.4 * X[:, 1]))).astype(np.float64)
+    Ms = [5, 50, 64, 1, 33, 62, 17, 40, 8, 21, 12]
+    genes = []
+    for g, M in enumerate(Ms):
+        G, _, _ = make_problem(O, 1910 + g, N, M, C, maf=np.linspace(0.004, 0.06, M), n_flip=1 if M > 1 else 0)
+        genes.append(G)
+    mask = rng.random((Ms[4], N)) < 0.02
+    raw = O.bed_decode_fast(pack_bed(genes[6].T, rng.random((Ms[6], N)) < 0.01), N).T
+    G6 = O.impute_mean(raw)                                        # the Matrix form of a gene with missing calls
+    G9 = genes[9].astype(np.float64)
+    G9[11, 3] = 0.4                                                 # a real dosage
+
+    def run(stream_batch, binary_stream):
+        eng = engine_cls(0)
+        try:
+            eng.set_null_model(X, y, binary=True)
+            eng.set_option("skato", 1)
+            eng.set_option("stream_batch", stream_batch)
+            eng.set_option("binary_stream", binary_stream)
+            for g, G in enumerate(genes):
+                if g == 4:
+                    eng.push_bed(pack_bed(G.T, mask), af_of(G))
+                elif g == 6:
+                    eng.push_f64(G6, af_of(genes[6]))
+                elif g == 9:
+                    eng.push_f64(G9, af_of(G))
+                elif g % 3 == 1:
+                    eng.push_i8(G.T.copy(), af_of(G))
+                else:
+                    eng.push_bed(pack_bed(G.T), af_of(G))
+            return eng.flush()
+        finally:
+            eng.close()
+
+    base = run(0, 0)
+    assert len(base) == len(Ms) and np.all(base["status"] == 0)
+    nm = BIN.fit_null_logistic(X, y)
+    ref = BIN.gene(genes[1].astype(float), af_of(genes[1]), X, nm)
+    assert rel(base[1]["Q"], ref["Q"]) <= 1e-6
+    for sb, bs in ((0, 1), (3, 1), (64, 1), (3, 0)):
+        r = run(sb, bs)
+        assert len(r) == len(Ms)
+        for k in range(len(Ms)):
+            for f in ("status", "m_poly", "cmc_nonref", "davies_fault", "skato_ok"):
+                assert int(r[k][f]) == int(base[k][f]), (sb, bs, k, f)
+            for f in ("Q", "p_skat", "cmc_p", "zeg_p", "skato_Q", "skato_p", "skato_rho"):
+                assert rel(r[k][f], base[k][f]) <= 1e-9, (sb, bs, k, f, r[k][f], base[k][f])
