@@ -157,7 +157,7 @@ int rvt_set_stream(rvt_ctx* ctx, void* cuda_stream);
  * copyCovariateAndIntercept, src/ModelUtil.h:102-130); y: N.  Host pointers.
  * binary != 0: y in {0,1}; LogisticRegression::FitLogisticModel(cov, phenoVec, 100) (regression/LogisticRegression.cpp:279-339)
  *   on the device, then SKAT / CMC / Zeggini with r = y - p and the per-sample variance v = p(1-p) (src/Model.h:2673-2681,
- *   LogisticRegressionScoreTest.cpp:219-302).  Such genes take the engine's fp64 path (<= 64 variants); SKAT-O is type "D"
+ *   LogisticRegressionScoreTest.cpp:219-302).  Such genes take the engine's fp64 paths (any width up to 2048); SKAT-O is type "D"
  *   (option "skato_binary", default on); the permutation test runs as for a quantitative trait.  rvt_get_null_model then returns
  *   r, sigma2 = 1 and (X'VX)^-1. */
 int rvt_set_null_model(rvt_ctx* ctx, int64_t N, int C, const double* X, const double* y, int binary);
@@ -190,9 +190,10 @@ int rvt_get_null_beta(rvt_ctx* ctx, double* beta);
  * Width: the host entry points (f64, i8, bed) take genes of 1..2048 variants -- the reference has no limit
  *   (Skat::Fit / MixtureChiSquare size themselves to the gene); a gene of more than 64 variants is cut into
  *   64-variant tiles and its Gram assembled from tile pairs (csrc/wide.cuh).  RVT_E_UNSUPPORTED beyond 2048,
- *   for rvt_gene_push_dev_i8 beyond 64, for a gene of more than 64 variants that holds dosages (pushed as doubles), and for such a
- *   gene in a binary-trait run.  Missing calls of a wide gene pushed as 2-bit rows are mean-imputed like those of any gene
- *   (src/DataConsolidator.cpp:217-245): its tiles are split into hard-call and indicator tiles and swept as 2M rows.
+ *   for rvt_gene_push_dev_i8 beyond 64, and for a gene of more than 64 variants that holds dosages (pushed as doubles).  Missing calls of a wide gene pushed as 2-bit rows are mean-imputed like those of any gene
+ *   (src/DataConsolidator.cpp:217-245): its tiles are split into hard-call and indicator tiles and swept as 2M rows.  With a
+ *   binary null model a wide gene takes fp64 statistics computed from its tiles (csrc/wide.cuh: k_wide_sparse), missing calls
+ *   included; the permutation test does not cover it.
  * Each push appends one gene; results come back from rvt_flush in push order.  Host buffers are copied
  * asynchronously when they are page-locked: keep them valid and unchanged until rvt_flush returns. */
 int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af);

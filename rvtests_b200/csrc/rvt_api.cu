@@ -792,8 +792,6 @@ static int push_check(rvt_ctx* ctx, int M, int max_m = kMaxM) {
   if (M > max_m) CTX_FAIL(RVT_E_UNSUPPORTED, "M=%d variants; this entry point handles genes of up to %d variants", M, max_m);
   // what the flush could not handle is refused HERE, while the queue is still consistent (a flush that failed half-way
   // used to leave the context stuck: ADVICE r01)
-  if (ctx->binary && M > kMaxM)
-    CTX_FAIL(RVT_E_UNSUPPORTED, "binary trait: genes of more than %d variants are not supported (M=%d)", kMaxM, M);
   RVT_CUDA_OK(cudaSetDevice(ctx->device));
   return RVT_OK;
 }
@@ -1166,7 +1164,7 @@ static int resolve_bed_missing(rvt_ctx* ctx) {
       // a wide gene with missing calls: the tensor-core pair sweep on the rows [H ; Mi] of every tile (run_wide, wide.cuh).
       // Without the tensor-core engine (or for a binary trait, refused at push) this ONE gene is reported
       // RVT_GENE_UNSUPPORTED in its record; the rest of the batch is computed
-      const bool can = ctx->tc.encode && ctx->tc.have_e && !ctx->binary;
+      const bool can = ctx->binary || (ctx->tc.encode && ctx->tc.have_e);   // (binary: k_wide_sparse imputes code 3 on the fly)
       for (size_t w = 0; w < ctx->wide.size(); ++w)
         if (ctx->wide[w].gene_index == gi) {
           if (can) {
@@ -1406,8 +1404,74 @@ static int launch_range(rvt_ctx* ctx, int g0, int g1) {
 // Genes wider than one tile (wide.cuh): per gene, the T diagonal tile sweeps and the T(T-1)/2 tile-pair sweeps fill the
 // M x M integer Gram, one more pass computes the burden collapses over all M variants, then one CTA per gene runs the
 // O(M^3) tail on a global-memory workspace.  Their records overwrite what the placeholder descriptors produced.
+// Wide genes of a binary-trait run: the p(1-p)-weighted statistics by k_wide_sparse (fp64, from the int8 tiles, missing calls
+// imputed on the fly), then the same tail (k_wide_finalize, fp64 mode).
+static int run_wide_binary(rvt_ctx* ctx, rvt_gene_result* d_res, int* launches) {
+  cudaStream_t st = ctx->stream;
+  const int64_t N = ctx->N;
+  const int nw = (int)ctx->wide.size();
+  int rc;
+  const bool sk = ctx->skato && ctx->skato_binary;
+  if (sk && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nw, sizeof(QagsScratch)))) return rc;
+  EngineParams prm{ctx->beta1, ctx->beta2, ctx->wd_cycles};
+  std::vector<WideJob> jobs(nw);
+  std::vector<void*> to_free;
+  auto cleanup = [&]() {
+    for (void* p : to_free) cudaFree(p);
+  };
+  WideJob* d_jobs = nullptr;
+  RVT_CUDA_OK(cudaMalloc((void**)&d_jobs, sizeof(WideJob) * nw));
+  to_free.push_back(d_jobs);
+  for (int wi = 0; wi < nw; ++wi) {
+    const WideGene& w = ctx->wide[wi];
+    const int T = (int)w.tiles.size();
+    uint8_t* ws = nullptr;
+    GeneDesc* d_tiles = nullptr;
+    cudaError_t e = cudaMalloc((void**)&ws, wide_ws_bytes(w.M));
+    if (e == cudaSuccess) to_free.push_back(ws);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_tiles, sizeof(GeneDesc) * T);
+    if (e != cudaSuccess) {
+      cleanup();
+      CTX_FAIL(RVT_E_CUDA, "wide gene (M=%d, binary trait): cudaMalloc: %s", w.M, cudaGetErrorString(e));
+    }
+    to_free.push_back(d_tiles);
+    WideJob jb = wide_job_make(ws, w.M);
+    jb.imp = 2;
+    jb.out_index = w.gene_index;
+    jb.var0 = w.var0;
+    jb.has_af = w.has_af ? 1 : 0;
+    jb.counted = 1;
+    jobs[wi] = jb;
+    // accumulators: A (as doubles over A_raw), {S, CW, B} (over De), the burden sums (over coll)
+    RVT_CUDA_OK(cudaMemsetAsync(jb.A_raw, 0, sizeof(double) * (size_t)w.M * w.M, st));
+    RVT_CUDA_OK(cudaMemsetAsync(jb.De, 0, sizeof(double) * (size_t)w.M * kMaxER, st));
+    RVT_CUDA_OK(cudaMemsetAsync(jb.coll, 0, sizeof(long long) * kCollapseN, st));
+    RVT_CUDA_OK(cudaMemcpyAsync(d_tiles, w.tiles.data(), sizeof(GeneDesc) * T, cudaMemcpyHostToDevice, st));   // (pageable: staged)
+    k_wide_imp_flags<<<(unsigned)((w.M + 255) / 256), 256, 0, st>>>(w.var0, w.M, N, ctx->d_counts, ctx->d_flags);
+    const int64_t nchunks = (N + 127) / 128;
+    const size_t smem = (size_t)w.M * (sizeof(double) + 3);
+    k_wide_sparse<<<(unsigned)std::min<int64_t>(nchunks, (int64_t)ctx->sm_count * 8), kWideCollapseThreads, smem, st>>>(
+        d_tiles, T, w.var0, w.M, ctx->d_flags, ctx->d_counts, ctx->d_nm, ctx->dX, ctx->d_vw, reinterpret_cast<double*>(jb.A_raw),
+        reinterpret_cast<double*>(jb.De), reinterpret_cast<double*>(jb.coll));
+    *launches += 2;
+    RVT_CUDA_OK(cudaGetLastError());
+  }
+  RVT_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(WideJob) * nw, cudaMemcpyHostToDevice, st));
+  if (sk)
+    k_wide_finalize<true><<<nw, kWideThreads, 0, st>>>(d_jobs, nw, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, d_res, ctx->d_qags);
+  else
+    k_wide_finalize<false><<<nw, kWideThreads, 0, st>>>(d_jobs, nw, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, d_res, nullptr);
+  *launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  if (e != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "wide genes (binary trait): %s", cudaGetErrorString(e));
+  return RVT_OK;
+}
+
 static int run_wide(rvt_ctx* ctx, rvt_gene_result* d_res, int* launches) {
   if (ctx->wide.empty()) return RVT_OK;
+  if (ctx->binary) return run_wide_binary(ctx, d_res, launches);
   int rc;
   if ((rc = tc_bind_segment(&ctx->tc, kSegStaged, ctx->d_stage, ctx->stage_cap, ctx->err, sizeof(ctx->err)))) return rc;
   if (!(ctx->tc.encode && ctx->tc.have_e && ctx->tc.have_seg[kSegStaged]))
@@ -1795,8 +1859,7 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   if (ctx->binary) {
     // binary trait: the Gram is weighted by the per-sample variance p(1-p), which the integer sweep does not carry:
     // every gene takes the fp64 path (its hard-call tiles are expanded on the device)
-    if (!ctx->wide.empty())
-      CTX_FAIL(RVT_E_UNSUPPORTED, "binary trait: genes of more than %d variants are not supported", kMaxM);
+    for (auto& w : ctx->wide) ctx->is_dos[w.gene_index] = 1;   // wide genes: run_wide_binary (fp64 statistics from the tiles); no permutation test
     for (int g = 0; g < n; ++g) {
       if (ctx->is_dos[g]) continue;
       if ((size_t)g < ctx->bin_streamed.size() && ctx->bin_streamed[g]) {

@@ -153,6 +153,157 @@ k_wide_collapse(const GeneDesc* __restrict__ tiles, int T, int64_t var_base, int
   if (tid < 2 * (ER + 1)) atomicAdd(reinterpret_cast<unsigned long long*>(coll) + tid, s_red[tid]);
 }
 
+// ---- binary trait (or any weighted Gram): the fp64 statistics of a wide gene from its int8 tiles ---------------------------
+// The p(1-p)-weighted Gram G'VG is not an integer product, so a wide gene of a binary-trait run cannot use the pair sweep as
+// it is; it gets what k_tile_sparse does for a single tile, generalised to T tiles and to accumulators in global memory:
+// a thread owns one sample, records the non-zero calls of that sample over ALL M variants (rare variants: a handful), and
+// adds their products with r, v, v x_l and with each other -- A (upper triangle), S, CW, B -- by fp64 atomics in global memory
+// (native on sm_100a); a sample with more calls than the list holds re-reads its bytes.  Missing calls (code 3) are imputed on
+// the fly to 2 p^ of the observed calls (DataConsolidator.cpp:217-245).  The burden scores follow src/Model.cpp:73-130 on the
+// minor-coded matrix as in k_tile_sparse.  WideJob fields re-used as doubles in this mode (imp == 2): A_raw -> A[M][M],
+// De -> per variant {S, CW, B[0..C)} at stride kMaxER, craw -> imputed column sums, coll -> burden sums [2][3 + kMaxC].
+constexpr int kWideSparseList = 48;
+__global__ void __launch_bounds__(kWideCollapseThreads)
+k_wide_sparse(const GeneDesc* __restrict__ tiles, int T, int64_t var_base, int M, const uint8_t* __restrict__ rowflags,
+              const RowCounts* __restrict__ counts, const NullModel* __restrict__ nm, const double* __restrict__ X,
+              const double* __restrict__ vw, double* __restrict__ A, double* __restrict__ SB, double* __restrict__ bur) {
+  extern __shared__ __align__(16) unsigned char ws_smem[];
+  double* s_fill = reinterpret_cast<double*>(ws_smem);                   // [M]
+  uint8_t* s_role = reinterpret_cast<uint8_t*>(s_fill + M);              // [M] 0 normal, 1 flipped, 2 monomorphic
+  uint8_t* s_tile = s_role + M;                                          // [M] tile of variant j
+  uint8_t* s_row = s_tile + M;                                           // [M] its row inside the tile
+  __shared__ int s_F;
+  __shared__ double s_bur[2][3 + kMaxC];
+  const int tid = threadIdx.x;
+  const int64_t N = nm->N;
+  const int C = nm->C;
+  const double* __restrict__ resid = nm->resid;
+  for (int t = 0; t < T; ++t) {
+    const int r0 = (int)(tiles[t].var0 - var_base), Mt = tiles[t].M;
+    for (int r = tid; r < Mt; r += kWideCollapseThreads) {
+      const int j = r0 + r;
+      s_tile[j] = (uint8_t)t;
+      s_row[j] = (uint8_t)r;
+      const RowCounts rc = counts[var_base + j];
+      const long long nobs = N - rc.bad;
+      s_fill[j] = nobs > 0 ? 2.0 * ((double)((long long)rc.n1 + 2ll * rc.n2) / (double)(2 * nobs)) : 0.0;
+      const uint8_t f = rowflags[var_base + j];
+      s_role[j] = (f == kRowNormal) ? 0 : (f == kRowFlipped) ? 1 : 2;
+    }
+  }
+  if (tid < 2 * (3 + kMaxC)) (&s_bur[0][0])[tid] = 0.0;
+  __syncthreads();
+  if (tid == 0) {
+    int F = 0;
+    for (int j = 0; j < M; ++j) F += (s_role[j] == 1);
+    s_F = F;
+  }
+  __syncthreads();
+  const int F = s_F;
+  double bz[3 + kMaxC], bc[3 + kMaxC];
+#pragma unroll
+  for (int l = 0; l < 3 + kMaxC; ++l) bz[l] = bc[l] = 0.0;
+  const int64_t nchunks = (N + 127) >> 7;
+  for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int64_t i = (c << 7) + tid;
+    if (i >= N) continue;
+    uint16_t lj[kWideSparseList];
+    uint8_t lc[kWideSparseList];
+    int n = 0;
+    for (int t = 0; t < T; ++t) {
+      const int Mt = tiles[t].M, r0 = (int)(tiles[t].var0 - var_base);
+      const int8_t* __restrict__ p = tiles[t].g + ((size_t)c * Mt) * 128 + tid;
+      for (int r = 0; r < Mt; ++r) {
+        const int code = p[(size_t)r * 128];
+        if (code == 0) continue;
+        if (n < kWideSparseList) {
+          lj[n] = (uint16_t)(r0 + r);
+          lc[n] = (uint8_t)code;
+        }
+        ++n;
+      }
+    }
+    if (n == 0 && F == 0) continue;
+    const double r = resid[i], v = vw ? vw[i] : 1.0;
+    double x[kMaxC];
+#pragma unroll
+    for (int l = 0; l < kMaxC; ++l)
+      if (l < C) x[l] = X[(size_t)l * N + i];
+    const bool listed = n <= kWideSparseList;
+    auto code_at = [&](int j) -> int { const int t = s_tile[j]; return tiles[t].g[((size_t)c * tiles[t].M + s_row[j]) * 128 + tid]; };
+    int zc = 0, a = 0, ja = -1;
+    for (;;) {
+      int code;
+      if (listed) {
+        if (a >= n) break;
+        ja = lj[a];
+        code = lc[a];
+      } else {
+        do { ++ja; } while (ja < M && code_at(ja) == 0);
+        if (ja >= M) break;
+        code = code_at(ja);
+      }
+      const double g = (code == 3) ? s_fill[ja] : (double)code;
+      if (g != 0.0) {
+        const double gv = g * v;
+        double* sb = SB + (size_t)ja * kMaxER;
+        atomicAdd(&sb[0], g * r);
+        atomicAdd(&sb[1], gv);
+#pragma unroll
+        for (int l = 0; l < kMaxC; ++l)
+          if (l < C) atomicAdd(&sb[2 + l], gv * x[l]);
+        atomicAdd(&A[(size_t)ja * M + ja], gv * g);
+        if (listed) {
+          for (int b = a + 1; b < n; ++b) {
+            const int jb = lj[b], cb = lc[b];
+            const double g2 = (cb == 3) ? s_fill[jb] : (double)cb;
+            if (g2 != 0.0) atomicAdd(&A[(size_t)ja * M + jb], gv * g2);
+          }
+        } else {
+          for (int jb = ja + 1; jb < M; ++jb) {
+            const int cb = code_at(jb);
+            if (cb == 0) continue;
+            const double g2 = (cb == 3) ? s_fill[jb] : (double)cb;
+            if (g2 != 0.0) atomicAdd(&A[(size_t)ja * M + jb], gv * g2);
+          }
+        }
+        const int role = s_role[ja];
+        if (role == 0) zc += ((int)g > 0);
+        else if (role == 1) zc -= !((int)(2.0 - g) > 0);
+      }
+      ++a;
+    }
+    const double z = (double)(F + zc);
+    if (z == 0.0) continue;
+    bz[0] += z * r;  bz[1] += v * z * z;  bz[2] += 1.0;
+    bc[0] += r;      bc[1] += v;          bc[2] += 1.0;
+#pragma unroll
+    for (int l = 0; l < kMaxC; ++l)
+      if (l < C) {
+        bz[3 + l] += v * z * x[l];
+        bc[3 + l] += v * x[l];
+      }
+  }
+#pragma unroll
+  for (int l = 0; l < 3 + kMaxC; ++l) {
+    if (l >= 3 + C) break;
+    double a = bz[l], b = bc[l];
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((tid & 31) == 0) {
+      atomicAdd(&s_bur[0][l], a);
+      atomicAdd(&s_bur[1][l], b);
+    }
+  }
+  __syncthreads();
+  if (tid < 2 * (3 + kMaxC)) {
+    const double val = (&s_bur[0][0])[tid];
+    if (val != 0.0) atomicAdd(&bur[tid], val);
+  }
+}
+
 // Flags of a wide gene with missing calls from its counts, with the imputation folded in -- the decisions k_tile_cols +
 // k_aug_flags take for a single tile (DataConsolidator.cpp:46-142 on the mean-imputed matrix): the column sum above N flips,
 // all values equal drops.  They steer k_split_hm (fill 0 / 2), the collapse and the tail alike.
@@ -215,7 +366,11 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
   const long long* __restrict__ De = jb.De;
   double* K = jb.K;
   const int kld = M;
-  const bool imp = jb.imp != 0;
+  const bool imp = jb.imp == 1;
+  const bool f64 = jb.imp == 2;             // fp64 statistics from k_wide_sparse (binary trait): A, {S, CW, B}, burden sums as doubles
+  const double* __restrict__ Ad = reinterpret_cast<const double*>(jb.A_raw);
+  const double* __restrict__ SBd = reinterpret_cast<const double*>(jb.De);
+  const double* __restrict__ burd = reinterpret_cast<const double*>(jb.coll);
   const int lda = imp ? 2 * M : M;          // leading dimension of A_raw
   double* s_delta = s_lamz + (M + 2);       // imp: delta_j = fill_j - (flipped ? 2 : 0); the workspace of a 2M gene has the room
   double* s_csum = s_delta + M;             // imp: column sums of the imputed matrix
@@ -223,7 +378,7 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
   if (tid == 0) s_bad = 0;
   __syncthreads();
   // 2. per-variant counts -> flip / monomorphic, cross-checked with the flags the collapse used
-  if (imp) {
+  if (imp || f64) {
     for (int j = tid; j < M; j += NT) {
       const RowCounts rc = counts[jb.var0 + j];
       const long long n1 = rc.n1, n2 = rc.n2, miss = rc.bad, n0 = N - n1 - n2 - miss, nobs = N - miss;
@@ -239,8 +394,10 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
       const uint8_t expect = mono ? kRowSkip : (flip ? kRowFlipped : kRowNormal);
       if (rowflags[jb.var0 + j] != expect) atomicExch(&s_bad, 1);
       // the integer sums must be those of the rows [H ; Mi]: H'H_jj = n1 + 4 n2 (+ 4 miss in a flipped row), Mi'Mi_jj = miss
-      const long long hjj = jb.A_raw[(size_t)j * lda + j], mjj = jb.A_raw[(size_t)(M + j) * lda + (M + j)];
-      if (mjj != miss || hjj != n1 + 4 * n2 + (flip && !mono ? 4 * miss : 0)) atomicExch(&s_bad, 2);
+      if (imp) {
+        const long long hjj = jb.A_raw[(size_t)j * lda + j], mjj = jb.A_raw[(size_t)(M + j) * lda + (M + j)];
+        if (mjj != miss || hjj != n1 + 4 * n2 + (flip && !mono ? 4 * miss : 0)) atomicExch(&s_bad, 2);
+      }
       s_craw[j] = 0;
       s_csum[j] = csum;
       s_delta[j] = fill - (flip && !mono ? 2.0 : 0.0);
@@ -274,7 +431,12 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
   for (int t = tid; t < Mp; t += NT) {
     const int j = s_idx[t];
     const int fl = s_flip[j];
-    if (imp) {
+    if (f64) {
+      // (2 - g)'r = 2 sum r - g'r, (2 - g)'V x_l = 2 sum v x_l - g'V x_l   (dosage_prepare)
+      const double* sb = SBd + (size_t)j * kMaxER;
+      s_s[t] = fl ? 2.0 * nm->rsum - sb[0] : sb[0];
+      for (int l = 0; l < C; ++l) s_B[t * kMaxC + l] = fl ? 2.0 * (nm->binary ? nm->xsum_w[l] : nm->xsum[l]) - sb[2 + l] : sb[2 + l];
+    } else if (imp) {
       // G'v = H'v + delta (Mi'v) for v = r, X_l; a flipped column is 2 - g
       const double dj = s_delta[j];
       double sv = ((double)recombine4(&De[(size_t)j * ER]) + dj * (double)recombine4(&De[(size_t)(M + j) * ER])) * nm->scale[0];
@@ -297,7 +459,7 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
     }
     }
     // weight t of the kept columns uses af[t] in the caller's ORIGINAL order
-    const double freq = jb.has_af ? af[jb.var0 + t] : (imp ? s_csum[j] : (double)s_craw[j]) / (2.0 * (double)N);
+    const double freq = jb.has_af ? af[jb.var0 + t] : ((imp || f64) ? s_csum[j] : (double)s_craw[j]) / (2.0 * (double)N);
     s_sw[t] = sqrt(beta_weight(freq, prm.beta1, prm.beta2, true));
   }
   __syncthreads();
@@ -320,7 +482,17 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
     const int ji = s_idx[i], jk = s_idx[k];
     const int fi = s_flip[ji], fk = s_flip[jk];
     double ad;
-    if (imp) {
+    if (f64) {
+      // the weighted Gram (upper triangle accumulated); g' = 2 - g under the weights: 4 sum v - 2 c^w_j - 2 c^w_k + A_jk, c^w = G'v
+      ad = Ad[(size_t)(ji < jk ? ji : jk) * M + (ji < jk ? jk : ji)];
+      const double ci = nm->binary ? SBd[(size_t)ji * kMaxER + 1] : s_csum[ji], ck = nm->binary ? SBd[(size_t)jk * kMaxER + 1] : s_csum[jk];
+      if (fi && fk)
+        ad = 4.0 * (nm->binary ? nm->vsum_w : (double)N) - 2.0 * ci - 2.0 * ck + ad;
+      else if (fi)
+        ad = 2.0 * ck - ad;
+      else if (fk)
+        ad = 2.0 * ci - ad;
+    } else if (imp) {
       // G'G = H'H + H'Mi D + D Mi'H + D Mi'Mi D   (D = diag delta), then the same flip identities on the imputed column sums
       const double di = s_delta[ji], dk = s_delta[jk];
       ad = (double)jb.A_raw[(size_t)ji * lda + jk] + dk * (double)jb.A_raw[(size_t)ji * lda + (M + jk)] +
@@ -351,7 +523,15 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
     K[(size_t)i * kld + k] = v;
     K[(size_t)k * kld + i] = v;
   }
-  if (tid == 0) {
+  if (tid == 0 && f64) {
+    for (int which = 0; which < 2; ++which) {
+      const double* b = burd + which * (3 + kMaxC);          // U, SS, count, SZ[]
+      s_bur[which][0] = b[0];
+      s_bur[which][1] = b[1];
+      for (int l = 0; l < C; ++l) s_bur[which][2 + l] = b[3 + l];
+    }
+    s_nonref = (int)llrint(burd[(3 + kMaxC) + 2]);
+  } else if (tid == 0) {
     for (int which = 0; which < 2; ++which) {
       const long long* cl = jb.coll + which * (ER + 1);
       s_bur[which][0] = (double)recombine4(cl) * nm->scale[0];
@@ -392,7 +572,7 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
     if (qags && Mp > 0) {
       QagsWork work{qags[g].a, qags[g].b, qags[g].r, qags[g].e, qags[g].order, qags[g].level, kQagsLimit};
       work.deadline = prm.wd_cycles > 0 ? clock64() + prm.wd_cycles : 0;
-      const double s2 = sigma2 * (double)N / (double)(N - 1);
+      const double s2 = nm->binary ? 1.0 : sigma2 * (double)N / (double)(N - 1);   // SkatO.cpp:133-137 (type "D": s2 = 1)
       so = skato_tail(jb.Wm, K, Mp, kld, s_vw, s2, s_ev, s_e, s_v, s_p, s_lamz, s_c, &s_sk.mach, work, s_sk.fv, s_sk.bcast, s_th, M, par);
     }
   }

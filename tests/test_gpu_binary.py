@@ -154,3 +154,63 @@ def test_binary_streaming_is_invisible_in_the_results(engine_cls, oracle):
                 assert int(r[k][f]) == int(base[k][f]), (sb, bs, k, f)
             for f in ("Q", "p_skat", "cmc_p", "zeg_p", "skato_Q", "skato_p", "skato_rho"):
                 assert rel(r[k][f], base[k][f]) <= 1e-9, (sb, bs, k, f, r[k][f], base[k][f])
+
+
+@pytest.mark.parametrize("case", [(141, 3000, 100, 3, 0.0), (142, 2200, 180, 2, 0.01), (143, 900, 65, 1, 0.03)])
+def test_binary_trait_wide_genes_vs_oracle(engine_cls, oracle, case):
+    """A binary trait with a gene of more than 64 variants (the reference has no width limit: Skat::Fit sizes itself to the
+    gene, regression/Skat.cpp:29-105): the p(1-p)-weighted statistics come from k_wide_sparse (fp64, from the int8 tiles of all
+    T tiles, missing calls imputed on the fly), the tail is k_wide_finalize's.  SKAT, CMC, Zeggini and SKAT-O (type "D") against
+    the numpy restatements; hard calls through all three host forms, missing calls through the 2-bit form and through the
+    mean-imputed Matrix; an ordinary gene in the same flush."""
+    from oracle import binary_oracle as BIN
+    from oracle import skato_oracle as SO
+    from rvtests_b200.synth import pack_bed
+    O = oracle
+    seed, N, M, C, miss = case
+    G, X, _ = make_problem(O, seed, N, M, C, maf=np.linspace(0.003, 0.05, M), n_flip=2, n_mono=1)
+    Gs, _, _ = make_problem(O, seed + 50, N, 20, C, maf=np.linspace(0.01, 0.1, 20))
+    rng = np.random.default_rng(seed)
+    eta = -0.7 + (X[:, 1:] @ np.full(C - 1, 0.4) if C > 1 else 0.0)
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(-eta))).astype(np.float64)
+    nm = BIN.fit_null_logistic(X, y)
+    if miss > 0:
+        mask = rng.random((M, N)) < miss
+        mask[2] = False
+        bed = pack_bed(G.T, mask)
+        raw = O.bed_decode_fast(bed, N).T
+        Gd = O.impute_mean(raw)
+        af = 0.5 * np.where(raw >= 0, raw, 0.0).sum(axis=0) / N
+    else:
+        bed, Gd, af = pack_bed(G.T), G.astype(np.float64), af_of(G)
+    eng = engine_cls(0)
+    try:
+        eng.set_null_model(X, y, binary=True)
+        eng.set_option("skato", 1)
+        eng.push_i8(Gs.T.copy(), af_of(Gs))
+        eng.push_bed(bed, af)
+        eng.push_f64(Gd, af)
+        if miss == 0:
+            eng.push_i8(G.T.copy(), af)
+        res = eng.flush()
+    finally:
+        eng.close()
+    assert np.all(res["status"] == 0)
+    ref = BIN.gene(Gd, af, X, nm)
+    so = SO.skato_gene(Gd, af, X, nm["resid"], vv=nm["v"])
+    for r in res[1:]:
+        assert int(r["m_poly"]) == ref["m_poly"]
+        assert rel(r["Q"], ref["Q"]) <= 1e-6
+        assert int(r["davies_fault"]) == ref["fault"]
+        assert rel(r["p_skat"], ref["p_skat"]) <= 1e-4
+        for pre in ("cmc", "zeg"):
+            b = ref[pre]
+            assert abs(r[pre + "_U"] - b["U"]) <= 1e-6 * max(abs(b["U"]), np.sqrt(b["V"]))
+            assert rel(r[pre + "_V"], b["V"]) <= 1e-6
+            assert rel(r[pre + "_p"], b["p"]) <= 1e-4
+        assert int(r["cmc_nonref"]) == ref["cmc"]["nonref"]
+        assert int(r["skato_ok"]) == int(so["ok"]) == 1
+        assert rel(r["skato_Q"], so["Q"]) <= 1e-6 and r["skato_rho"] == so["rho"]
+        assert rel(r["skato_p"], so["pvalue"]) <= 1e-5
+    refs = BIN.gene(Gs.astype(float), af_of(Gs), X, nm)
+    assert rel(res[0]["Q"], refs["Q"]) <= 1e-6 and rel(res[0]["p_skat"], refs["p_skat"]) <= 1e-4
