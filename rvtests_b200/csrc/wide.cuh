@@ -373,7 +373,8 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
   const double* __restrict__ burd = reinterpret_cast<const double*>(jb.coll);
   const int lda = imp ? 2 * M : M;          // leading dimension of A_raw
   double* s_delta = s_lamz + (M + 2);       // imp: delta_j = fill_j - (flipped ? 2 : 0); the workspace of a 2M gene has the room
-  double* s_csum = s_delta + M;             // imp: column sums of the imputed matrix
+  // column sums of the imputed matrix: imp -- behind s_delta (2M workspace); f64 -- the craw slots (the workspace is M-sized there)
+  double* s_csum = f64 ? reinterpret_cast<double*>(jb.craw) : s_delta + M;
 
   if (tid == 0) s_bad = 0;
   __syncthreads();
@@ -398,9 +399,11 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
         const long long hjj = jb.A_raw[(size_t)j * lda + j], mjj = jb.A_raw[(size_t)(M + j) * lda + (M + j)];
         if (mjj != miss || hjj != n1 + 4 * n2 + (flip && !mono ? 4 * miss : 0)) atomicExch(&s_bad, 2);
       }
-      s_craw[j] = 0;
       s_csum[j] = csum;
-      s_delta[j] = fill - (flip && !mono ? 2.0 : 0.0);
+      if (imp) {
+        s_craw[j] = 0;
+        s_delta[j] = fill - (flip && !mono ? 2.0 : 0.0);
+      }
       s_flip[j] = mono ? -1 : flip;
     }
   } else
