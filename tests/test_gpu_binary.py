@@ -205,6 +205,9 @@ def test_binary_trait_wide_genes_vs_oracle(engine_cls, oracle, case):
         assert rel(r["p_skat"], ref["p_skat"]) <= 1e-4
         for pre in ("cmc", "zeg"):
             b = ref[pre]
+            if b["V"] <= 1e-9 * N:     # with this many variants nearly every sample carries one: the CMC indicator is the intercept,
+                assert abs(r[pre + "_V"]) <= 1e-9 * N                  # its variance rounding noise around zero on both sides
+                continue
             assert abs(r[pre + "_U"] - b["U"]) <= 1e-6 * max(abs(b["U"]), np.sqrt(b["V"]))
             assert rel(r[pre + "_V"], b["V"]) <= 1e-6
             assert rel(r[pre + "_p"], b["p"]) <= 1e-4
