@@ -143,6 +143,8 @@ const char* rvt_last_error(const rvt_ctx* ctx);
  * waits for the tail.  0 = everything at flush.  Options apply to genes pushed after the call.),
  * "binary_stream" (default 1: with a binary null model and "stream_batch" > 0 the fp64 statistics and the tail of the tile genes
  * are enqueued -- on a stream of their own -- right behind their copies instead of at flush; 0 = everything at flush),
+ * "bolt_binary" (1: rvt_bolt_fit_null in BoltLMM::enableBinaryMode -- the phenotype is not centred, BoltPlinkLoader.cpp:155-158;
+ * the saddle-point calibration of that mode is compiled out upstream: useSaddlePoint = false, BoltLMM.cpp:160),
  * "bolt_kernels" (2 = second-generation panel products of rvt_bolt_fit_null, 1 = the first; same results to rounding),
  * "perm" (nPerm, 0 = analytic p-value only), "perm_alpha" (0.05), "perm_stream_pos", "perm_seed", "perm_batch". */
 int rvt_set_option(rvt_ctx* ctx, const char* key, double value);

@@ -61,15 +61,16 @@ class Random:
         return v2 * fac
 
 
-def prepare(G, covar, y):
+def prepare(G, covar, y, binary=False):
     """G: (M, N) int8 hard calls, -1 = missing; covar: (N, C) with the intercept in column 0; y: (N,).
-    Returns X (N, M) normalised, Z (N, C') orthonormal, yc (centred phenotype)."""
+    Returns X (N, M) normalised, Z (N, C') orthonormal, yc (centred phenotype; binary: as it is -- enableBinaryMode,
+    BoltPlinkLoader.cpp:155-158)."""
     G = np.asarray(G)
     M, N = G.shape
     U, s, _ = np.linalg.svd(np.asarray(covar, dtype=np.float64), full_matrices=False)
     keep = 1 + int(np.sum(s[1:] > s[0] * 1e-8))
     Z = U[:, :keep]
-    yc = np.asarray(y, dtype=np.float64) - np.mean(y)
+    yc = np.asarray(y, dtype=np.float64) - (0.0 if binary else np.mean(y))
     X = np.zeros((N, M))
     for m in range(M):
         g = G[m].astype(np.float64)

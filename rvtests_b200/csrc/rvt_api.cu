@@ -189,6 +189,7 @@ struct rvt_ctx {
   bool f64_imputed = true;     // option "f64_imputed": rvt_gene_push_f64 recognises mean-imputed hard calls and routes them like a 2-bit push with missing calls
   unsigned long long* d_frac = nullptr;   // per-row {min, max} of the non-integer values of the last rvt_gene_push_f64
   bool perm_stream_lost = false;   // a gene the reference would have permuted was skipped: later stream positions are not the reference's
+  bool bolt_binary = false;    // option "bolt_binary": the null fit of a binary trait (BoltLMM::enableBinaryMode: the phenotype is not centred)
   int bolt_kernels = 3;        // generation of the panel-product kernels of rvt_bolt_fit_null (bolt.cuh)
   bool skato_binary = true;    // SKAT-O for a binary trait (SkatO::Fit type "D"); on by default, see include/rvtests_b200.h
   long long* d_dbg = nullptr;   // optional finalize phase counters (rvt_set_option "debug_phases")
@@ -453,6 +454,8 @@ int rvt_set_option(rvt_ctx* ctx, const char* key, double value) {
     ctx->f64_imputed = value != 0;
   } else if (k == "binary_stream") {
     ctx->bin_stream = value != 0;
+  } else if (k == "bolt_binary") {
+    ctx->bolt_binary = value != 0;
   } else if (k == "bolt_kernels") {
     ctx->bolt_kernels = (value >= 3.0) ? 3 : (value >= 2.0) ? 2 : 1;
   } else if (k == "skato_binary") {
@@ -2956,6 +2959,7 @@ int rvt_bolt_fit_null_sharded(rvt_ctx* ctx, const uint8_t* bed, int64_t M, int64
     double mean = 0.0;
     for (int64_t i = 0; i < N; ++i) mean += y[i];
     mean /= (double)N;
+    if (ctx->bolt_binary) mean = 0.0;   // BoltLMM::enableBinaryMode: "no need to center phenotype for binary trait" (BoltPlinkLoader.cpp:155-158)
     for (int64_t i = 0; i < N; ++i) hy[i] = y[i] - mean;
     for (int c = 0; c < Ck; ++c) {
       double d = 0.0;

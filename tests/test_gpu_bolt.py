@@ -228,3 +228,37 @@ def test_bolt_odd_stride_tail_bits_and_device_resident_panel(engine_cls, oracle)
                      ("inf_stat_calibration", ref.calibration), ("xvx_xx_ratio", ref.xvx_xx_ratio)):
             assert rel(r_[k], v) <= 1e-6, (k, r_[k], v)
         assert np.max(np.abs(h_[:N] - ref.h)) <= 1e-7 * np.max(np.abs(ref.h))
+
+
+def test_bolt_binary_mode_vs_oracle(engine_cls, oracle):
+    """option bolt_binary = BoltLMM::enableBinaryMode (BASELINE configs[4]): the 0/1 phenotype is not centred
+    (BoltPlinkLoader.cpp:155-158); the restatement in that mode is pinned on the reference's own build
+    (tests/test_oracle_pin_reference_bolt.py::test_bolt_binary_mode_vs_live_reference_build)."""
+    from oracle import bolt_oracle as BO
+    seed, N, M, C = 151, 1000, 320, 3
+    G = _panel(seed, N, M)
+    rng = np.random.default_rng(seed + 1)
+    covar = np.column_stack([np.ones(N)] + [rng.normal(size=N) for _ in range(C - 1)])
+    X, Z, _ = BO.prepare(G, covar, np.zeros(N))
+    liab = X @ rng.normal(size=M) * np.sqrt(0.5 / M) + rng.normal(size=N) * np.sqrt(0.5) + 0.3 * covar[:, 1]
+    y = (liab > 0.5).astype(np.float64)
+    X, Z, yc = BO.prepare(G, covar, y, binary=True)
+    ref = BO.Fit(X, Z, yc).fit().calibrate()
+    eng = engine_cls(0)
+    try:
+        eng.set_option("bolt_binary", 1)
+        rec, h, Zd = eng.bolt_fit_null(_pack(G), N, y, covar)
+        eng.set_option("bolt_binary", 0)
+        rec_c, h_c, _ = eng.bolt_fit_null(_pack(G), N, y, covar)
+    finally:
+        eng.close()
+    assert int(rec["reml_evals"]) == len(ref.f) and int(rec["cg_iterations"]) == sum(ref.cg_iters)
+    assert np.max(np.abs(rec["log_delta"][:len(ref.log_delta)] - np.array(ref.log_delta))) <= 1e-6
+    for k, v in (("delta", ref.delta), ("sigma2_g", ref.sigma2_g), ("h_inv_y_norm2", ref.h_norm2),
+                 ("inf_stat_calibration", ref.calibration), ("xvx_xx_ratio", ref.xvx_xx_ratio)):
+        assert rel(rec[k], v) <= 1e-6, (k, rec[k], v)
+    assert np.max(np.abs(h[:N] - ref.h)) <= 1e-7 * np.max(np.abs(ref.h))
+    # the two modes differ only inside the covariate space: the projected H^-1 y -- what the score step uses -- is the same
+    pb, pc = h[:N] - Zd @ (Zd.T @ h[:N]), h_c[:N] - Zd @ (Zd.T @ h_c[:N])
+    assert np.max(np.abs(pb - pc)) <= 1e-6 * np.max(np.abs(pb))
+    assert np.max(np.abs(h[:N] - h_c[:N])) > 1e-3 * np.max(np.abs(h[:N]))

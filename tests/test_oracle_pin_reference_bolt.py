@@ -139,3 +139,31 @@ def test_bolt_restatement_vs_live_reference_build(tmp_path):
     assert Z.shape[1] == C
     _check(ref, BO.Fit(X, Z, yc), Gt, N)
     _free_run(ref, BO.Fit(X, Z, yc).fit().calibrate())
+
+
+def test_bolt_binary_mode_vs_live_reference_build(tmp_path):
+    """BoltLMM::enableBinaryMode (BASELINE configs[4]: a binary trait): the phenotype is not centred
+    (BoltPlinkLoader.cpp:155-158); the saddle-point branch is compiled out upstream (useSaddlePoint = false, BoltLMM.cpp:160).
+    The restatement with binary=True against the reference build in that mode."""
+    if orc.ref_bolt() is None:
+        pytest.skip("oracle/_ref/libbolt_ref.so not built")
+    seed, N, M, C = 221, 800, 256, 2
+    rng = np.random.default_rng(seed)
+    G = rng.binomial(2, rng.uniform(0.05, 0.5, M)[:, None], size=(M, N)).astype(np.int8)
+    G[rng.random((M, N)) < 0.01] = -1
+    covar = np.column_stack([np.ones(N), rng.normal(size=N)])
+    X, _, _ = BO.prepare(G, covar, np.zeros(N))
+    liab = X @ rng.normal(size=M) * np.sqrt(0.5 / M) + rng.normal(size=N) * np.sqrt(0.5)
+    y = (liab > 0.4).astype(np.float64)
+    covar = np.array([[float("%.9g" % v) for v in row] for row in covar])
+    prefix = str(tmp_path / "panel")
+    orc.write_bolt_fileset(prefix, G, y, covar)
+    ref = orc.ref_bolt_fit(prefix, npz=str(tmp_path / "null.npz"), log=str(tmp_path / "log.txt"), binary=True)
+    Gt = rng.binomial(2, 0.3, size=(6, N)).astype(np.int8)
+    ref["tests"] = np.array([orc.ref_bolt_test(Gt[j].astype(np.float64)) for j in range(6)])
+    ref["pairs"] = np.array([(0, 1), (2, 3), (4, 4)])
+    ref["covxx"] = np.array([orc.ref_bolt_covxx(Gt[a].astype(np.float64), Gt[b].astype(np.float64)) for a, b in ref["pairs"]])
+    orc.ref_bolt().bolt_ref_free()
+    X, Z, yc = BO.prepare(G, covar, y, binary=True)
+    assert abs(yc.mean() - y.mean()) < 1e-15 and y.mean() > 0.1
+    _check(ref, BO.Fit(X, Z, yc), Gt, N)

@@ -31,7 +31,7 @@ CHUNK = 256
 def bolt_config(args):
     return {"workload": f"BoltLMM null fit (MC-REML secant + multi-RHS CG + calibration): N={args.bolt_samples} samples x "
                         f"M_panel={args.bolt_snps} SNPs (2-bit PLINK rows), C={args.covariates}, {max(min(int(4e9 / args.bolt_samples / args.bolt_samples), 15), 3)} MC trials "
-                        "(BASELINE configs[4] null fit; the score step is --workload meta's path)",
+                        "(BASELINE configs[4]: binary trait = 30 % cases of a liability with 256 causal panel SNPs, BoltLMM::enableBinaryMode; null fit + score test)",
             "samples": args.bolt_samples, "panel_snps": args.bolt_snps, "covariates_incl_intercept": args.covariates,
             "l2_policy": "every pass streams the 2-bit panel (N M / 4 bytes) and the N x R vectors; inputs >> 126 MB L2 at the "
                          "default size (4.1 GB panel + 32 MB per vector), no flush"}
@@ -63,7 +63,7 @@ def synth_rows(torch, dev, N, lo, hi, miss=0.01):
     return out
 
 
-def phenotype(torch, dev, N, M, C, h2=0.4):
+def phenotype(torch, dev, N, M, C, h2=0.4, binary=True):
     """y = sum of 256 causal panel SNPs (normalised) * effect + covariates + noise, replicated on every rank"""
     rng = np.random.default_rng(SEED)
     causal = np.unique(np.linspace(0, M - 1, 256).astype(np.int64))
@@ -80,6 +80,8 @@ def phenotype(torch, dev, N, M, C, h2=0.4):
         g += b * x.cpu().numpy()
     covar = np.column_stack([np.ones(N)] + [rng.normal(size=N) for _ in range(C - 1)])
     y = g + rng.normal(size=N) * np.sqrt(1 - h2) + covar @ rng.normal(size=C)
+    if binary:   # BASELINE configs[4] is a binary trait: cases = the upper 30 % of the liability
+        y = (y > np.quantile(y, 0.7)).astype(np.float64)
     return y, covar
 
 
@@ -104,6 +106,7 @@ def run_bolt(args, ClockSampler, bind_numa):
     y, covar = phenotype(torch, dev, N, M, C)
     eng = rvtests_b200.GeneEngine(local)
     eng.set_stream(stream.cuda_stream)
+    eng.set_option("bolt_binary", 1)     # BoltLMM::enableBinaryMode (the phenotype is 0/1 and stays uncentred)
     if os.environ.get("RVT_BOLT_KERNELS"):
         eng.set_option("bolt_kernels", float(os.environ["RVT_BOLT_KERNELS"]))      # A/B of the product kernels (profiles/)
     ar = sharding.torch_allreduce(dist, device=dev) if world > 1 else None
