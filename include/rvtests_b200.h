@@ -192,7 +192,8 @@ int rvt_get_null_beta(rvt_ctx* ctx, double* beta);
  * Width: the host entry points (f64, i8, bed) take genes of 1..2048 variants -- the reference has no limit
  *   (Skat::Fit / MixtureChiSquare size themselves to the gene); a gene of more than 64 variants is cut into
  *   64-variant tiles and its Gram assembled from tile pairs (csrc/wide.cuh).  RVT_E_UNSUPPORTED beyond 2048,
- *   for rvt_gene_push_dev_i8 beyond 64, and for a gene of more than 64 variants that holds dosages (pushed as doubles).  Missing calls of a wide gene pushed as 2-bit rows are mean-imputed like those of any gene
+ *   for rvt_gene_push_dev_i8 beyond 64.  A wide gene pushed as doubles that holds real dosages keeps its matrix on the device
+ *   for dense fp64 statistics (csrc/wide.cuh: k_wide_dos_*).  Missing calls of a wide gene pushed as 2-bit rows are mean-imputed like those of any gene
  *   (src/DataConsolidator.cpp:217-245): its tiles are split into hard-call and indicator tiles and swept as 2M rows.  With a
  *   binary null model a wide gene takes fp64 statistics computed from its tiles (csrc/wide.cuh: k_wide_sparse), missing calls
  *   included; the permutation test does not cover it.

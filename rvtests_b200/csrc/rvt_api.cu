@@ -50,6 +50,7 @@ struct WideGene {    // a pushed gene of more than kMaxM variants: T tiles of co
   int64_t var0;
   bool has_af;
   bool imputed = false;   // pushed as 2-bit rows and holds missing calls: mean-imputed through the rows [H ; Mi] (run_wide)
+  double* dG = nullptr;   // real dosages: the pushed N x M doubles, kept on the device for the dense statistics (owned)
   std::vector<GeneDesc> tiles;
 };
 struct TilePlan {    // where the tiles of one pushed gene were staged
@@ -218,6 +219,8 @@ struct rvt_ctx {
 static void pending_reset(rvt_ctx* ctx) {
   if (ctx->bin_pending && ctx->bin_s) cudaStreamSynchronize(ctx->bin_s);   // (a failed flush drops the queue: nothing may still run on it)
   ctx->bin_pending = false;
+  for (auto& w : ctx->wide)
+    if (w.dG) cudaFree(w.dG);
   ctx->genes.clear();
   ctx->userflags.clear();
   ctx->af.clear();
@@ -1063,8 +1066,19 @@ int rvt_gene_push_f64(rvt_ctx* ctx, const double* G, int M, const double* af) {
     }
   }
   if (dosage && M > kMaxM) {
-    ctx->stage_used = stage_mark;   // nothing of this gene stays queued
-    CTX_FAIL(RVT_E_UNSUPPORTED, "gene of %d variants holds dosages / imputed values: the fp64 path handles up to %d variants", M, kMaxM);
+    // real dosages in a gene wider than a tile: the matrix stays on the device for the dense fp64 statistics of run_wide
+    // (k_wide_dos_*); the staged tiles only keep the gene's slot
+    (void)stage_mark;
+    double* keep = ctx->d_stage64;
+    ctx->d_stage64 = nullptr;
+    ctx->cap_stage64 = 0;
+    rc = push_staged(ctx, tp, M, af);
+    if (rc) {
+      cudaFree(keep);
+      return rc;
+    }
+    ctx->wide.back().dG = keep;
+    return RVT_OK;
   }
   if (dosage) {
     // dosages / mean-imputed values: keep the fp64 matrix for the generic path and hand the
@@ -1472,7 +1486,86 @@ static int run_wide_binary(rvt_ctx* ctx, rvt_gene_result* d_res, int* launches) 
   return RVT_OK;
 }
 
+// Wide genes pushed as doubles that hold REAL dosages: dense fp64 statistics (k_wide_dos_cols / _gram / _burden), then the fp64
+// mode of the tail.  Quantitative and binary traits alike (vw = null for the former).
+static int run_wide_dosage(rvt_ctx* ctx, rvt_gene_result* d_res, int* launches) {
+  cudaStream_t st = ctx->stream;
+  const int64_t N = ctx->N;
+  int nw = 0;
+  for (auto& w : ctx->wide) nw += w.dG != nullptr;
+  if (nw == 0) return RVT_OK;
+  int rc;
+  const bool sk = ctx->skato && (!ctx->binary || ctx->skato_binary);
+  if (sk && (rc = ensure(ctx, (void**)&ctx->d_qags, &ctx->cap_qags, (size_t)nw, sizeof(QagsScratch)))) return rc;
+  EngineParams prm{ctx->beta1, ctx->beta2, ctx->wd_cycles};
+  std::vector<WideJob> jobs;
+  std::vector<void*> to_free;
+  auto cleanup = [&]() {
+    for (void* p : to_free) cudaFree(p);
+  };
+  const double* vw = ctx->binary ? ctx->d_vw : nullptr;
+  for (auto& w : ctx->wide) {
+    if (!w.dG) continue;
+    uint8_t* ws = nullptr;
+    cudaError_t e = cudaMalloc((void**)&ws, wide_ws_bytes(w.M));
+    if (e != cudaSuccess) {
+      cleanup();
+      CTX_FAIL(RVT_E_CUDA, "wide gene (M=%d, dosages): cudaMalloc: %s", w.M, cudaGetErrorString(e));
+    }
+    to_free.push_back(ws);
+    WideJob jb = wide_job_make(ws, w.M);
+    jb.imp = 3;
+    jb.out_index = w.gene_index;
+    jb.var0 = w.var0;
+    jb.has_af = w.has_af ? 1 : 0;
+    jb.counted = 1;
+    jobs.push_back(jb);
+    double* A = reinterpret_cast<double*>(jb.A_raw);
+    double* SB = reinterpret_cast<double*>(jb.De);
+    double* bur = reinterpret_cast<double*>(jb.coll);
+    double* csum = reinterpret_cast<double*>(jb.craw);
+    RVT_CUDA_OK(cudaMemsetAsync(A, 0, sizeof(double) * (size_t)w.M * w.M, st));
+    RVT_CUDA_OK(cudaMemsetAsync(jb.coll, 0, sizeof(long long) * kCollapseN, st));
+    k_wide_dos_cols<<<w.M, kWideDosThreads, 0, st>>>(w.dG, N, w.M, w.var0, ctx->d_nm, ctx->dX, vw, SB, csum, ctx->d_flags);
+    const int nblk = (w.M + 63) / 64;
+    const int npair = nblk * (nblk + 1) / 2;
+    const int splits = (int)std::max<int64_t>(1, std::min<int64_t>((N + 4095) / 4096, (4 * (int64_t)ctx->sm_count + npair - 1) / npair));
+    const int64_t split_len = (((N + splits - 1) / splits) + 31) / 32 * 32;
+    k_wide_dos_gram<<<dim3((unsigned)npair, (unsigned)((N + split_len - 1) / split_len)), 256, 0, st>>>(w.dG, N, w.M, vw, nblk, split_len, A);
+    k_wide_dos_burden<<<(unsigned)std::min<int64_t>((N + kWideDosThreads - 1) / kWideDosThreads, (int64_t)ctx->sm_count * 8), kWideDosThreads, (size_t)w.M, st>>>(
+        w.dG, N, w.M, w.var0, ctx->d_flags, ctx->d_nm, ctx->dX, vw, bur);
+    *launches += 3;
+    RVT_CUDA_OK(cudaGetLastError());
+  }
+  WideJob* d_jobs = nullptr;
+  RVT_CUDA_OK(cudaMalloc((void**)&d_jobs, sizeof(WideJob) * nw));
+  to_free.push_back(d_jobs);
+  RVT_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(WideJob) * nw, cudaMemcpyHostToDevice, st));
+  if (sk)
+    k_wide_finalize<true><<<nw, kWideThreads, 0, st>>>(d_jobs, nw, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, d_res, ctx->d_qags);
+  else
+    k_wide_finalize<false><<<nw, kWideThreads, 0, st>>>(d_jobs, nw, ctx->d_flags, ctx->d_af, ctx->d_counts, ctx->d_nm, prm, d_res, nullptr);
+  *launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cleanup();
+  // the dosage matrices are done with; what is left in ctx->wide are the genes of the integer / sparse paths
+  for (size_t k = 0; k < ctx->wide.size();) {
+    if (ctx->wide[k].dG) {
+      cudaFree(ctx->wide[k].dG);
+      ctx->wide.erase(ctx->wide.begin() + (long)k);
+    } else {
+      ++k;
+    }
+  }
+  if (e != cudaSuccess) CTX_FAIL(RVT_E_CUDA, "wide genes (dosages): %s", cudaGetErrorString(e));
+  return RVT_OK;
+}
+
 static int run_wide(rvt_ctx* ctx, rvt_gene_result* d_res, int* launches) {
+  if (ctx->wide.empty()) return RVT_OK;
+  int rc0 = run_wide_dosage(ctx, d_res, launches);
+  if (rc0) return rc0;
   if (ctx->wide.empty()) return RVT_OK;
   if (ctx->binary) return run_wide_binary(ctx, d_res, launches);
   int rc;
@@ -1858,7 +1951,7 @@ static int flush_body(rvt_ctx* ctx, rvt_gene_result* out, int cap, int* n_out, b
   ctx->is_dos.assign(n, 0);
   for (auto& dg : ctx->dos) ctx->is_dos[dg.gene_index] = 1;
   for (auto& w : ctx->wide)
-    if (w.imputed) ctx->is_dos[w.gene_index] = 1;   // (computed by run_wide; the permutation test does not cover it)
+    if (w.imputed || w.dG) ctx->is_dos[w.gene_index] = 1;   // (computed by run_wide; the permutation test does not cover it)
   if (ctx->binary) {
     // binary trait: the Gram is weighted by the per-sample variance p(1-p), which the integer sweep does not carry:
     // every gene takes the fp64 path (its hard-call tiles are expanded on the device)

@@ -304,6 +304,159 @@ k_wide_sparse(const GeneDesc* __restrict__ tiles, int T, int64_t var_base, int M
   }
 }
 
+// ---- a wide gene whose genotypes are REAL dosages (N x M column-major doubles, e.g. from BGEN): dense fp64 statistics ------
+// k_wide_dos_cols: one CTA per column -- sum, min, max -> flag (all values equal drops, column sum above N flips; a negative
+// value poisons the sum: RVT_GENE_BADVALUE), and the dot products S = g'r, CW = g'v, B = g'(v x_l).
+constexpr int kWideDosThreads = 256;
+__global__ void __launch_bounds__(kWideDosThreads)
+k_wide_dos_cols(const double* __restrict__ G, int64_t N, int M, int64_t var0, const NullModel* __restrict__ nm, const double* __restrict__ X,
+                const double* __restrict__ vw, double* __restrict__ SB, double* __restrict__ csum, uint8_t* __restrict__ rowflags) {
+  __shared__ double s_red[kWideDosThreads];
+  const int j = blockIdx.x, tid = threadIdx.x;
+  const int C = nm->C;
+  const double* __restrict__ g = G + (size_t)j * N;
+  const double* __restrict__ resid = nm->resid;
+  double acc[5 + kMaxC];   // sum, min, max, S, CW, B[]
+  acc[0] = 0.0; acc[1] = 1e300; acc[2] = -1e300; acc[3] = acc[4] = 0.0;
+#pragma unroll
+  for (int l = 0; l < kMaxC; ++l) acc[5 + l] = 0.0;
+  for (int64_t i = tid; i < N; i += kWideDosThreads) {
+    const double x = g[i], v = vw ? vw[i] : 1.0, xv = x * v;
+    acc[0] += x;
+    acc[1] = fmin(acc[1], x);
+    acc[2] = fmax(acc[2], x);
+    acc[3] += x * resid[i];
+    acc[4] += xv;
+#pragma unroll
+    for (int l = 0; l < kMaxC; ++l)
+      if (l < C) acc[5 + l] += xv * X[(size_t)l * N + i];
+  }
+  double out[5 + kMaxC];
+  for (int q = 0; q < 5 + C; ++q) {
+    s_red[tid] = acc[q];
+    __syncthreads();
+    for (int o = kWideDosThreads / 2; o > 0; o >>= 1) {
+      if (tid < o) s_red[tid] = (q == 1) ? fmin(s_red[tid], s_red[tid + o]) : (q == 2) ? fmax(s_red[tid], s_red[tid + o]) : s_red[tid] + s_red[tid + o];
+      __syncthreads();
+    }
+    out[q] = s_red[0];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const double sum = out[0], mn = out[1], mx = out[2];
+    csum[j] = (mn < 0.0) ? nan("") : sum;
+    rowflags[var0 + j] = (mn == mx) ? kRowSkip : ((sum > (double)N) ? kRowFlipped : kRowNormal);
+    double* sb = SB + (size_t)j * kMaxER;
+    sb[0] = out[3];
+    sb[1] = out[4];
+    for (int l = 0; l < C; ++l) sb[2 + l] = out[5 + l];
+  }
+}
+// k_wide_dos_gram: A[ja..ja+64)[jb..jb+64) += sum over a sample range of v g_a g_b; grid (block pairs a <= b, sample splits),
+// 256 threads, each a 4 x 4 patch of the 64 x 64 block; the two column tiles of 32 samples staged in shared memory.
+__global__ void __launch_bounds__(256)
+k_wide_dos_gram(const double* __restrict__ G, int64_t N, int M, const double* __restrict__ vw, int nblk, int64_t split_len, double* __restrict__ A) {
+  __shared__ double sa[32][64 + 1], sb[32][64 + 1];
+  // unrank the pair index into (a, b), a <= b
+  int a = 0, rem = blockIdx.x;
+  while (rem >= nblk - a) { rem -= nblk - a; ++a; }
+  const int b = a + rem;
+  const int ja = a * 64, jb = b * 64;
+  const int tid = threadIdx.x, tr = (tid >> 4) * 4, tc = (tid & 15) * 4;
+  const int64_t i0 = (int64_t)blockIdx.y * split_len;
+  int64_t i1 = i0 + split_len;
+  if (i1 > N) i1 = N;
+  double acc[4][4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
+  for (int64_t c0 = i0; c0 < i1; c0 += 32) {
+    for (int idx = tid; idx < 32 * 64; idx += 256) {
+      const int col = idx >> 5, ii = idx & 31;                 // consecutive threads: consecutive samples of one column
+      const int64_t i = c0 + ii;
+      const bool in = i < i1;
+      const double v = in ? (vw ? vw[i] : 1.0) : 0.0;
+      sa[ii][col] = (in && ja + col < M) ? G[(size_t)(ja + col) * N + i] * v : 0.0;
+      sb[ii][col] = (in && jb + col < M) ? G[(size_t)(jb + col) * N + i] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int ii = 0; ii < 32; ++ii) {
+      double xa[4], xb[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) { xa[p] = sa[ii][tr + p]; xb[p] = sb[ii][tc + p]; }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] += xa[p] * xb[q];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = ja + tr + p, c = jb + tc + q;
+      if (r < M && c < M && r <= c && acc[p][q] != 0.0) atomicAdd(&A[(size_t)r * M + c], acc[p][q]);
+    }
+}
+// k_wide_dos_burden: thread = one sample over all M columns (coalesced across samples): the collapses of src/Model.cpp:73-130 on
+// the minor-coded matrix, `(int)g' > 0`, and their sums with r, v, v x_l.  bur: [2][3 + kMaxC] as k_wide_sparse.
+__global__ void __launch_bounds__(kWideDosThreads)
+k_wide_dos_burden(const double* __restrict__ G, int64_t N, int M, int64_t var0, const uint8_t* __restrict__ rowflags, const NullModel* __restrict__ nm,
+                  const double* __restrict__ X, const double* __restrict__ vw, double* __restrict__ bur) {
+  __shared__ double s_bur[2][3 + kMaxC];
+  extern __shared__ uint8_t s_roleb[];   // [M]
+  const int tid = threadIdx.x;
+  const int C = nm->C;
+  const double* __restrict__ resid = nm->resid;
+  for (int j = tid; j < M; j += kWideDosThreads) s_roleb[j] = rowflags[var0 + j];
+  if (tid < 2 * (3 + kMaxC)) (&s_bur[0][0])[tid] = 0.0;
+  __syncthreads();
+  double bz[3 + kMaxC], bc[3 + kMaxC];
+#pragma unroll
+  for (int l = 0; l < 3 + kMaxC; ++l) bz[l] = bc[l] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * kWideDosThreads + tid; i < N; i += (int64_t)gridDim.x * kWideDosThreads) {
+    int zi = 0;
+    for (int j = 0; j < M; ++j) {
+      const uint8_t f = s_roleb[j];
+      if (f == kRowSkip) continue;
+      const double g = G[(size_t)j * N + i];
+      zi += (f == kRowFlipped) ? ((int)(2.0 - g) > 0) : ((int)g > 0);
+    }
+    if (zi == 0) continue;
+    const double z = (double)zi, r = resid[i], v = vw ? vw[i] : 1.0;
+    bz[0] += z * r;  bz[1] += v * z * z;  bz[2] += 1.0;
+    bc[0] += r;      bc[1] += v;          bc[2] += 1.0;
+#pragma unroll
+    for (int l = 0; l < kMaxC; ++l)
+      if (l < C) {
+        const double x = X[(size_t)l * N + i];
+        bz[3 + l] += v * z * x;
+        bc[3 + l] += v * x;
+      }
+  }
+#pragma unroll
+  for (int l = 0; l < 3 + kMaxC; ++l) {
+    if (l >= 3 + C) break;
+    double a = bz[l], b = bc[l];
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((tid & 31) == 0) {
+      atomicAdd(&s_bur[0][l], a);
+      atomicAdd(&s_bur[1][l], b);
+    }
+  }
+  __syncthreads();
+  if (tid < 2 * (3 + kMaxC)) {
+    const double val = (&s_bur[0][0])[tid];
+    if (val != 0.0) atomicAdd(&bur[tid], val);
+  }
+}
+
 // Flags of a wide gene with missing calls from its counts, with the imputation folded in -- the decisions k_tile_cols +
 // k_aug_flags take for a single tile (DataConsolidator.cpp:46-142 on the mean-imputed matrix): the column sum above N flips,
 // all values equal drops.  They steer k_split_hm (fill 0 / 2), the collapse and the tail alike.
@@ -367,7 +520,8 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
   double* K = jb.K;
   const int kld = M;
   const bool imp = jb.imp == 1;
-  const bool f64 = jb.imp == 2;             // fp64 statistics from k_wide_sparse (binary trait): A, {S, CW, B}, burden sums as doubles
+  const bool dos = jb.imp == 3;             // real dosages: as f64, with the column sums (craw slots) and the flags computed by k_wide_dos_cols
+  const bool f64 = jb.imp == 2 || dos;      // fp64 statistics (k_wide_sparse: binary trait; k_wide_dos_*: dosages): A, {S, CW, B}, burden sums as doubles
   const double* __restrict__ Ad = reinterpret_cast<const double*>(jb.A_raw);
   const double* __restrict__ SBd = reinterpret_cast<const double*>(jb.De);
   const double* __restrict__ burd = reinterpret_cast<const double*>(jb.coll);
@@ -379,7 +533,13 @@ k_wide_finalize(const WideJob* __restrict__ jobs, int n_jobs, const uint8_t* __r
   if (tid == 0) s_bad = 0;
   __syncthreads();
   // 2. per-variant counts -> flip / monomorphic, cross-checked with the flags the collapse used
-  if (imp || f64) {
+  if (dos) {
+    for (int j = tid; j < M; j += NT) {
+      const uint8_t f = rowflags[jb.var0 + j];
+      if (!(s_csum[j] == s_csum[j])) atomicExch(&s_bad, 2);   // a negative value (a missing call that was never imputed) reached fit()
+      s_flip[j] = (f == kRowSkip) ? -1 : (f == kRowFlipped);
+    }
+  } else if (imp || f64) {
     for (int j = tid; j < M; j += NT) {
       const RowCounts rc = counts[jb.var0 + j];
       const long long n1 = rc.n1, n2 = rc.n2, miss = rc.bad, n0 = N - n1 - n2 - miss, nobs = N - miss;

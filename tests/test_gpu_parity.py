@@ -476,6 +476,69 @@ def test_push_f64_of_a_mean_imputed_matrix_takes_the_integer_paths(eng, oracle):
             rx = eng.flush()
             refx, lamx = O.gene(Gx, af, X, nm["resid"], nm["sigma2"])
             check_gene(rx[0], refx, lamx, ctx=f"dosage Matrix M={M}")
+        else:   # beyond 64 variants the matrix stays on the device for the dense statistics
+            eng.push_f64(Gx, af)
+            rx = eng.flush()
+            refx, lamx = O.gene(Gx, af, X, nm["resid"], nm["sigma2"])
+            check_gene(rx[0], refx, lamx, ctx=f"wide dosage Matrix M={M}")
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_wide_genes_with_real_dosages_vs_oracle(engine_cls, oracle, binary):
+    """A gene of more than 64 variants pushed as doubles with REAL dosages (BGEN): the matrix stays on the device and the
+    statistics are dense fp64 (k_wide_dos_cols / _gram / _burden) into the same tail; quantitative and binary trait, flipped and
+    monomorphic columns, SKAT + burden + SKAT-O, an ordinary gene and a hard-call wide gene in the same flush."""
+    from oracle import binary_oracle as BIN
+    from oracle import skato_oracle as SO
+    import rvtests_b200
+    O = oracle
+    seed, N, M, C = 181, 2100, 150, 3
+    G, X, yq = make_problem(O, seed, N, M, C, maf=np.linspace(0.004, 0.05, M), n_flip=2, n_mono=1)
+    Gs, _, _ = make_problem(O, seed + 1, N, 20, C, maf=np.linspace(0.01, 0.1, 20))
+    rng = np.random.default_rng(seed)
+    Gd = G.astype(np.float64)
+    soft = rng.random(Gd.shape) < 0.05
+    Gd[soft] = np.clip(Gd[soft] + rng.normal(scale=0.2, size=int(soft.sum())), 0.0, 2.0)     # imputation uncertainty
+    poly = [j for j in range(M) if G[:, j].min() != G[:, j].max()]
+    mono = [j for j in range(M) if j not in poly]
+    Gd[:, mono] = G[:, mono]                                      # the monomorphic column stays monomorphic
+    af = 0.5 * Gd.mean(axis=0)
+    eng = engine_cls(0)
+    if eng.info("tc_available") != 1:
+        eng.close()
+        pytest.skip("wide genes need the tensor-core sweep")
+    try:
+        if binary:
+            y = (rng.random(N) < 1.0 / (1.0 + np.exp(0.6 - 0.4 * X[:, 1]))).astype(np.float64)
+            eng.set_null_model(X, y, binary=True)
+            nm = BIN.fit_null_logistic(X, y)
         else:
-            with pytest.raises(rvtests_b200.RvtError):
-                eng.push_f64(Gx, af)
+            eng.set_null_model(X, yq)
+            nm = O.fit_null_linear(X, yq)
+        eng.set_option("skato", 1)
+        eng.push_i8(Gs.T.copy(), af_of(Gs))
+        eng.push_f64(Gd, af)
+        eng.push_i8(G.T.copy(), af_of(G))
+        res = eng.flush()
+    finally:
+        eng.close()
+    assert [int(v) for v in res["status"]] == [0, 0, 0]
+    r = res[1]
+    if binary:
+        ref = BIN.gene(Gd, af, X, nm)
+        so = SO.skato_gene(Gd, af, X, nm["resid"], vv=nm["v"])
+        assert int(r["m_poly"]) == ref["m_poly"] and rel(r["Q"], ref["Q"]) <= 1e-6 and rel(r["p_skat"], ref["p_skat"]) <= 1e-4
+        for pre in ("cmc", "zeg"):
+            b = ref[pre]
+            assert abs(r[pre + "_U"] - b["U"]) <= 1e-6 * max(abs(b["U"]), np.sqrt(b["V"])) and rel(r[pre + "_V"], b["V"]) <= 1e-6
+        assert int(r["cmc_nonref"]) == ref["cmc"]["nonref"]
+        refh = BIN.gene(G.astype(float), af_of(G), X, nm)
+        assert rel(res[2]["Q"], refh["Q"]) <= 1e-6
+    else:
+        ref, lam = O.gene(Gd, af, X, nm["resid"], nm["sigma2"])
+        check_gene(r, ref, lam, ctx="wide dosage gene")
+        so = SO.skato_gene(Gd, af, X, nm["resid"])
+        refh, lamh = _oracle_gene(O, G, X, nm)
+        check_gene(res[2], refh, lamh, ctx="hard-call wide gene beside it")
+    assert int(r["skato_ok"]) == int(so["ok"]) == 1
+    assert rel(r["skato_Q"], so["Q"]) <= 1e-6 and r["skato_rho"] == so["rho"] and rel(r["skato_p"], so["pvalue"]) <= 1e-5
