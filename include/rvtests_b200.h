@@ -85,7 +85,8 @@ typedef struct rvt_gene_result {
  * reference's serial gene loop consumes it (src/LinearAlgebra.h:8-21, no srand anywhere), starting at
  * "perm_stream_pos" draws (0 in a fresh process) and advancing by ActualPerm * (N-1) per gene.  Quantitative and binary
  * traits alike (src/Model.h:2673-2717), genes with missing calls (2-bit pushes, mean-imputed) included.  NOT covered: a gene
- * with dosages pushed as doubles, a gene with missing calls of a binary-trait run, of 63-64 or of more than 64 variants (done = 0, NA columns);
+ * with real dosages pushed as doubles, a gene with missing calls of a binary-trait run, of 63-64 or of more than 64 variants, any gene
+ * of more than 64 variants of a binary-trait run (done = 0, NA columns);
  * the reference would have shuffled for it, so from such a gene on the stream position -- hence NumGreater / NumEqual of the
  * LATER genes -- no longer replays the reference's: those records carry stream_ok = 0.  rvt_perm_result.stream_pos tells where
  * each gene started. */
@@ -185,7 +186,7 @@ int rvt_get_null_beta(rvt_ctx* ctx, double* beta);
  *   Mean-imputed missing calls (DataConsolidator::imputeGenotypeToMean, src/DataConsolidator.cpp:217-245: hard calls plus, per
  *   column, ONE fractional value 2 p^ of its observed calls) are recognised on the device and such a gene is computed exactly like
  *   a 2-bit push with code 01 -- augmented tensor-core sweep, wide operand tiles, permutation test -- with records equal to that
- *   form bit for bit (option "f64_imputed", default 1); any other non-integer value makes it a dosage gene (fp64 path, <= 64 variants).
+ *   form bit for bit (option "f64_imputed", default 1); any other non-integer value makes it a dosage gene (fp64 paths).
  * rvt_gene_push_i8: same, hard calls as int8 [M][ld] variant-major on the host.
  * rvt_gene_push_dev_i8: block already in device memory (zero-copy; must stay valid until flush).
  *   flags: NULL (engine counts the rows itself) or M bytes 0 normal / 1 flip-to-minor / 2 skip.
