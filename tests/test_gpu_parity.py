@@ -544,34 +544,3 @@ def test_wide_genes_with_real_dosages_vs_oracle(engine_cls, oracle, binary):
     assert int(r["skato_ok"]) == int(so["ok"]) == 1
     assert rel(r["skato_Q"], so["Q"]) <= 1e-6 and r["skato_rho"] == so["rho"] and rel(r["skato_p"], so["pvalue"]) <= 1e-5
 
-
-def test_a_failed_flush_drops_the_queue_and_the_context_lives_on(eng, oracle):
-    """a flush that fails must not leave the context stuck.  Forced here by asking the dp4a engine for a gene wider than
-    a tile (which needs the tensor-core pair sweep): the flush raises, the pending genes are dropped, and the next flush on the
-    same context computes as if nothing had happened."""
-    import rvtests_b200
-    O = oracle
-    if eng.info("tc_available") != 1:
-        pytest.skip("needs both engines")
-    N, C = 1500, 2
-    G, X, y = make_problem(O, 201, N, 90, C, maf=np.linspace(0.004, 0.05, 90))
-    Gs, _, _ = make_problem(O, 202, N, 12, C, maf=0.05)
-    eng.set_null_model(X, y)
-    nm = O.fit_null_linear(X, y)
-    eng.set_option("engine", 1)
-    try:
-        eng.push_i8(Gs.T.copy(), af_of(Gs))
-        eng.push_i8(G.T.copy(), af_of(G))
-        with pytest.raises(rvtests_b200.RvtError):
-            eng.flush()
-        assert eng.pending() == 0
-    finally:
-        eng.set_option("engine", 0)
-    eng.push_i8(Gs.T.copy(), af_of(Gs))
-    eng.push_i8(G.T.copy(), af_of(G))
-    r = eng.flush()
-    assert len(r) == 2
-    refs, lams = _oracle_gene(O, Gs, X, nm)
-    check_gene(r[0], refs, lams, ctx="after a failed flush")
-    ref, lam = _oracle_gene(O, G, X, nm)
-    check_gene(r[1], ref, lam, ctx="the wide gene, on the engine that can take it")
