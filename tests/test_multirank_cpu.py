@@ -115,3 +115,24 @@ def test_two_rank_bolt_snp_sharding_gloo():
     assert [(o[1], o[2]) for o in outs] == [(0, 66), (66, 131)]
     for _rank, _lo, _hi, e_top, e_bot in outs:
         assert e_top <= 1e-10 and e_bot <= 1e-10
+
+
+def test_bolt_bench_panel_shards_hold_the_same_bytes_at_every_world_size():
+    """bench.py --workload bolt synthesises the panel in 256-row chunks keyed by the GLOBAL row index: a rank's shard of the SNP
+    rows is the same bytes whatever the number of ranks (the strong-scaling runs at 1, 2, 4, 8 GPUs fit the same cohort)."""
+    import torch
+    sys.path.insert(0, ROOT)
+    from tools import bolt_bench
+    from rvtests_b200 import sharding
+    dev = torch.device("cpu")
+    N, M = 1003, 700
+    full = bolt_bench.synth_rows(torch, dev, N, 0, M)
+    assert full.shape == (M, (N + 3) // 4) and full.dtype == torch.uint8
+    for world in (2, 3, 8):
+        parts = [bolt_bench.synth_rows(torch, dev, N, *sharding.snp_shard(M, r, world)) for r in range(world)]
+        assert torch.equal(torch.cat(parts), full), world
+    # padding bits of the last byte are 00, missing calls are code 01 at about 1 %
+    codes = torch.stack([(full >> s) & 3 for s in (0, 2, 4, 6)], dim=2).reshape(M, -1)
+    assert int(codes[:, N:].sum()) == 0
+    frac_missing = float((codes[:, :N] == 1).float().mean())
+    assert 0.005 < frac_missing < 0.02
